@@ -1,0 +1,150 @@
+/* regcn_b200 -- C ABI of the B200 (sm_100a) kernels behind RE-GCN's per-snapshot evolution and
+ * all-entity scoring path.  The reference (sgxxyyds/RE-GCN) has no FFI layer: its boundary is the
+ * Python nn.Module surface.  The Python mirror in regcn_b200/*.py keeps those
+ * signatures and reaches this library through ctypes; every entry point below names the reference
+ * code (file:line under the reference root) whose device work it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (16-byte aligned for float rows);
+ *     the library never allocates, frees or retains device memory;
+ *   - ids on the device are int32, triples are the reference's int64 (T,3) row-major layout;
+ *   - float matrices are dense row-major fp32;
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered and asynchronous;
+ *   - return 0 on success, <0 argument error (-1 null pointer, -2 bad dimension/alignment,
+ *     -3 workspace too small, -4 unsupported shape), >0 a cudaError_t from the launch;
+ *     regcn_last_error_string() describes the last failure on the calling thread.
+ */
+#ifndef REGCN_B200_H_
+#define REGCN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define REGCN_API __attribute__((visibility("default")))
+#else
+#define REGCN_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+REGCN_API int regcn_version(void);
+REGCN_API const char* regcn_last_error_string(void);
+/* 1 if the calling process sees a CUDA device of compute capability 10.x, else 0 */
+REGCN_API int regcn_device_ok(void);
+
+/* ---- K1 edge index: rgcn/utils.py:100-134 (build_sub_graph), :78-97 (r2e) ---------------------
+ * triples (T,3) int64 -> E = 2T edges [src;dst]->[dst;src], type [rel;rel+R]; in-degree; norm;
+ * CSR by destination (stable in edge id): rowptr (N+1), src_sorted/etype_sorted/eperm (E);
+ * virtual rows for the aggregate kernels: vptr/sptr (N+1), vrow_row (N + E/256 + 1);
+ * relation->entity CSR shared by r and r+R: rel_rowptr (R+1), rel_ents (<= 2T, sorted per relation);
+ * counts[4] = {n_virtual_rows, n_split_chunks, n_rel_ents, max_hub_degree}.                      */
+REGCN_API size_t regcn_csr_build_workspace_bytes(int T, int N, int R);
+REGCN_API int regcn_csr_build(const int64_t* triples, int T, int N, int R,
+                    int32_t* src, int32_t* dst, int32_t* etype, int32_t* indeg, float* norm,
+                    int32_t* rowptr, int32_t* src_sorted, int32_t* etype_sorted, int32_t* eperm,
+                    int32_t* vptr, int32_t* sptr, int32_t* vrow_row,
+                    int32_t* rel_rowptr, int32_t* rel_ents, int32_t* counts,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K2 relation mean-pool: src/rrgcn.py:161-166, hyperbolic_model.py:802-812 -----------------
+ * out (2R,d): out[r] = out[r+R] = mean of h rows in ents(r); zero rows for absent relations.
+ * nsplit > 1 splits every relation over nsplit CTAs (partial: R*nsplit*d floats).               */
+REGCN_API int regcn_rel_mean_pool(const float* h, const int32_t* rel_rowptr, const int32_t* rel_ents, int R, int d,
+                        int nsplit, float* out, float* partial, void* stream);
+
+/* ---- K4 union aggregate: rgcn/layers.py:257-279; hyperbolic_layers.py:222-240 ------------------
+ * out[v] = norm[v] * sum_{(u,r)->v} w_uv (h[u] + rel[r]);  w_uv = exp(-gamma |radius[u]-radius[v]|)
+ * when radius != NULL else 1.  partial: n_split_chunks*d floats (NULL when n_split_chunks == 0). */
+REGCN_API int regcn_union_aggregate(const float* h, const float* rel, const int32_t* rowptr, const int32_t* src_sorted,
+                          const int32_t* etype_sorted, const float* norm, const int32_t* vptr,
+                          const int32_t* sptr, const int32_t* vrow_row, int n_vrows, int n_split_chunks,
+                          const float* radius, float gamma, int N, int d, float* out, float* partial,
+                          void* stream);
+
+/* ---- K6 block-diagonal aggregate: rgcn/layers.py:167-179; hyperbolic_layers.py:87-109 ----------
+ * out[v] = norm[v] * sum_in blockdiag(W[type]) . h[src];  W (num_rels, nb*(d_in/nb)*(d_out/nb)). */
+REGCN_API int regcn_block_aggregate(const float* h, const float* W, const int32_t* rowptr, const int32_t* src_sorted,
+                          const int32_t* etype_sorted, const float* norm, int N, int d_in, int d_out, int nb,
+                          float* out, void* stream);
+
+/* ---- K7 Lorentz centroid aggregate: hyperbolic_layers.py:589-625,665-672; hyperbolic_ops.py:477-518,563-581
+ * ht tangent input; out = clamp(log_0(to_poincare(centroid)), +-10), zero rows for in-degree 0.  */
+REGCN_API int regcn_lorentz_aggregate(const float* ht, const float* W, const float* rel, const int32_t* rowptr,
+                            const int32_t* src_sorted, const int32_t* etype_sorted, const float* norm, int N,
+                            int d, int nb, double c, float* out, void* stream);
+
+/* ---- dense contraction (fp32 CUDA cores): torch.mm / F.linear call sites on the path -----------
+ * C[M,N] (+)= A[M,K] . op(B) (+ bias[N]); op(B) = B[K,N] if !transB else B[N,K]^T.
+ * K, lda, ldb multiples of 4; split_k > 1 needs regcn_gemm_f32_workspace_bytes(M,N,split_k).     */
+REGCN_API size_t regcn_gemm_f32_workspace_bytes(int M, int N, int split_k);
+REGCN_API int regcn_gemm_f32(const float* A, int lda, const float* B, int ldb, int transB, float* C, int ldc, int M,
+                   int N, int K, const float* bias, int accumulate, int split_k, float* workspace,
+                   size_t workspace_bytes, void* stream);
+
+/* ---- row maps: F.normalize / tanh / log_0 / exp_0 / project (hyperbolic_ops.py:38-116) ---------
+ * mode 0 normalize, 1 tanh, 2 0.9 tanh(log_0 x)+0.1 log_0 x, 3 log_0, 4 exp_0, 5 project,
+ * 6 exp_0(normalize(log_0 x)), 7 identity; sumsq (optional, M): |out|^2 per row; out may be NULL
+ * when only sumsq is wanted.                                                                    */
+REGCN_API int regcn_row_map(const float* x, float* out, int M, int d, int mode, double c, float* sumsq, void* stream);
+
+/* ---- K3 GRU gates: nn.GRUCell at src/rrgcn.py:133,168-174; hyperbolic_model.py:408,815-824 ----- */
+REGCN_API int regcn_gru_gate(const float* gi, const float* gh, const float* hprev, float* out, int M, int d,
+                   int normalize, void* stream);
+
+/* ---- K5 self-loop combine: rgcn/layers.py:226-255; hyperbolic_layers.py:273-323,649-694 -------- */
+REGCN_API int regcn_union_combine(const float* P, const float* L, const int32_t* indeg, const float* S,
+                        const float* skip_bias, const float* prev, int N, int d, int act, int hyper, double c,
+                        float* out, float* ht_next, float* radius_next, void* stream);
+
+/* ---- K9 time gate (Euclidean): src/rrgcn.py:176-178 -------------------------------------------- */
+REGCN_API int regcn_time_gate(const float* G, const float* bias, const float* cur, const float* h, float* out, int N,
+                    int d, int normalize_cur, void* stream);
+
+/* ---- K8/K9 hyperbolic: hyperbolic_model.py:715-720,773-782,802,829-867; hyperbolic_ops.py:395-435 */
+REGCN_API int regcn_hyp_init(const float* emb, const float* radius_static, int N, int d, int normalize, int on_manifold,
+                   double c, float radius_min, float radius_max, float* out, void* stream);
+REGCN_API int regcn_hyp_tangent(const float* h, int N, int d, double c, float* ht, float* pt, float* radius, void* stream);
+REGCN_API int regcn_hyp_time_gate(const float* h2, const float* pt, const float* G, const float* bias,
+                        const float* radius_static, const float* radius_w, float radius_b, int N, int d,
+                        int layer_norm, int residual, double c, float radius_min, float radius_max, float beta,
+                        float eps_r, float* out, void* stream);
+
+/* ---- K10 ConvTransE/ConvTransR tower: src/decoder.py:29-52,78-95; hyperbolic_decoder.py:376-406 - */
+REGCN_API int regcn_convtranse_features(const float* ent, const float* second, const int64_t* triples, int col0, int col1,
+                              int B, int d, int C, int ksz, const float* bn0_scale, const float* bn0_shift,
+                              const float* conv_w, const float* conv_b, const float* bn1_scale,
+                              const float* bn1_shift, float* F, void* stream);
+REGCN_API int regcn_affine_relu(float* x, const float* scale, const float* shift, int M, int d, int relu, void* stream);
+
+/* ---- K12 RotH / MuRP / RotHRel query builder: hyperbolic_decoder.py:744-765,1064-1086,1243-1251 - */
+REGCN_API int regcn_gather_log0(const float* E, const int64_t* triples, int col, int B, int d, int project, double c,
+                      float* out, void* stream);
+REGCN_API int regcn_hyp_query(const float* s_tan, const float* ang, const float* trans, const float* E,
+                    const int64_t* triples, int B, int d, int kind, double c, float* Q, float* q_sumsq,
+                    void* stream);
+
+/* ---- K13 hyperbolic score epilogue on a dense <q,e> matrix: hyperbolic_decoder.py:89-179 -------- */
+REGCN_API int regcn_hyp_score_epilogue(float* S, int ld, int B, int N, const float* q_sumsq, const float* e_sumsq,
+                             const float* bias, const float* qbias, double c, const float* scale_margin,
+                             void* stream);
+
+/* ---- K14 rank / filter: rgcn/utils.py:21-25,51-75,136-166 --------------------------------------
+ * S (B, ld) scores of a shard of N candidate columns starting at global column col_offset.
+ * filt_ptr (B+1)/filt_idx: per-query sorted global ids of the other true answers (all_ans).      */
+REGCN_API int regcn_gather_target_score(const float* S, int64_t ld, int B, int N, const int64_t* triples, int target_col,
+                              int col_offset, float* target_score, void* stream);
+REGCN_API int regcn_rank_count(const float* S, int64_t ld, int B, int N, const int64_t* triples, int target_col,
+                     const int32_t* filt_ptr, const int32_t* filt_idx, int col_offset, const float* target_score,
+                     int32_t* raw_count, int32_t* filt_count, void* stream);
+REGCN_API int regcn_counts_to_ranks(const int32_t* raw_count, const int32_t* filt_count, int B, int64_t* rank,
+                          int64_t* filt_rank, void* stream);
+REGCN_API int regcn_apply_filter(float* S, int64_t ld, int B, int N, const int64_t* triples, int target_col,
+                       const int32_t* filt_ptr, const int32_t* filt_idx, int col_offset, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REGCN_B200_H_ */

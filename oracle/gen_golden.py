@@ -1,0 +1,145 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.npz by executing the UNMODIFIED reference.
+
+Runs only in the build container (needs /root/reference, which does not exist on the GPU box):
+
+    python oracle/gen_golden.py            # regenerate every fixture
+
+The reference modules (src/rrgcn.py, rgcn/{layers,utils}.py, src/decoder.py, hyperbolic_src/*) are imported as
+they lie under /root/reference with the DGL stand-in of oracle/fake_dgl.py; inputs and parameters come from
+oracle/synth.py (numpy default_rng, reproducible anywhere), so a fixture stores only its config, seed and the
+reference's outputs.  Large cases store a seeded subsample of rows / columns plus the full integer outputs.
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = os.environ.get("REGCN_REFERENCE", "/root/reference")
+sys.path.insert(0, ROOT)
+
+from oracle import fake_dgl, synth  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+# fixture name -> config
+CASES = {
+    "regcn_tiny_s0": dict(kind="regcn", shape="tiny", seed=0, layer_norm=True),
+    "regcn_tiny_s1_noln": dict(kind="regcn", shape="tiny", seed=1, layer_norm=False),
+    "regcn_small_s2": dict(kind="regcn", shape="small", seed=2, layer_norm=True),
+    "regcn_c1_s0": dict(kind="regcn", shape="c1", seed=0, layer_norm=True, sub=96),
+    "regcn_c3_s1": dict(kind="regcn", shape="c3", seed=1, layer_norm=True, sub=64),
+    "hyp_uv_convtranse_tiny_s0": dict(kind="hyp", shape="tiny", seed=0, encoder="hyperbolic_uvrgcn",
+                                      decoder="hyperbolic_convtranse", layer_norm=False, gamma=0.15),
+    "hyp_uv_convtranse_tiny_s1_ln": dict(kind="hyp", shape="tiny", seed=1, encoder="hyperbolic_uvrgcn",
+                                         decoder="hyperbolic_convtranse", layer_norm=True, gamma=1.0),
+    "hyp_uv_murp_tiny_s2": dict(kind="hyp", shape="tiny", seed=2, encoder="hyperbolic_uvrgcn", decoder="murp",
+                                layer_norm=False, gamma=0.15),
+    "hyp_lgcn_roth_tiny_s0": dict(kind="hyp", shape="tiny_l", seed=0, encoder="lgcn", decoder="roth",
+                                  layer_norm=False, gamma=0.15),
+    "hyp_lgcn_roth_small_s1": dict(kind="hyp", shape="small_l", seed=1, encoder="lgcn", decoder="roth",
+                                   layer_norm=False, gamma=0.15),
+    "hyp_lgcn_roth_c1_s0": dict(kind="hyp", shape="c1", seed=0, encoder="lgcn", decoder="roth", layer_norm=False,
+                                gamma=0.15, sub=96),
+    "hyp_uv_roth_c1_s1": dict(kind="hyp", shape="c1", seed=1, encoder="hyperbolic_uvrgcn", decoder="roth",
+                              layer_norm=True, gamma=0.15, sub=96),
+}
+H_DIM = 200
+N_BASES = 100
+N_LAYERS = 2
+CURV = 0.01
+
+
+def _import_reference():
+    if not os.path.isdir(REF):
+        raise SystemExit(f"{REF} not present: golden fixtures can only be regenerated in the build container")
+    fake_dgl.install()
+    sys.path.insert(0, REF)
+    import logging
+    logging.disable(logging.CRITICAL)
+    from rgcn import utils as ref_utils
+    from src.rrgcn import RecurrentRGCN
+    from hyperbolic_src.hyperbolic_model import HyperbolicRecurrentRGCN
+    return ref_utils, RecurrentRGCN, HyperbolicRecurrentRGCN
+
+
+def build_reference_model(cfg, n, r, RecurrentRGCN, HyperbolicRecurrentRGCN):
+    if cfg["kind"] == "regcn":
+        m = RecurrentRGCN("convtranse", "uvrgcn", n, r, 0, 0, H_DIM, "sub", 3, num_bases=N_BASES, num_basis=-1,
+                          num_hidden_layers=N_LAYERS, dropout=0.2, self_loop=True, skip_connect=False,
+                          layer_norm=cfg["layer_norm"], input_dropout=0.2, hidden_dropout=0.2, feat_dropout=0.2,
+                          entity_prediction=True, relation_prediction=True, use_cuda=False, gpu="cpu")
+    else:
+        m = HyperbolicRecurrentRGCN(cfg["decoder"], cfg["encoder"], n, r, 0, 0, H_DIM, "sub", 3, num_bases=N_BASES,
+                                    num_hidden_layers=N_LAYERS, dropout=0.2, c=CURV, self_loop=True,
+                                    skip_connect=False, layer_norm=cfg["layer_norm"], input_dropout=0.2,
+                                    hidden_dropout=0.2, feat_dropout=0.2, entity_prediction=True,
+                                    relation_prediction=True, use_cuda=False, gpu="cpu",
+                                    radius_msg_gamma=cfg["gamma"], hyp_init_scale=1e-3)
+    m.load_state_dict(synth.fill_state_dict(m.state_dict(), cfg["seed"]))
+    m.eval()
+    return m
+
+
+def run_case(name, cfg, ref_utils, RecurrentRGCN, HyperbolicRecurrentRGCN):
+    case = synth.make_case(cfg["shape"], cfg["seed"])
+    n, r = case["num_ents"], case["num_rels"]
+    model = build_reference_model(cfg, n, r, RecurrentRGCN, HyperbolicRecurrentRGCN)
+    glist = [ref_utils.build_sub_graph(n, r, snap, False, "cpu") for snap in case["history"]]
+    out = {"config": np.array(json.dumps(cfg))}
+    # ---- integer outputs of build_sub_graph / r2e (rgcn/utils.py:78-134) for every snapshot
+    for i, g in enumerate(glist):
+        src, dst = g.edges()
+        out[f"g{i}_src"] = src.numpy().astype(np.int32)
+        out[f"g{i}_dst"] = dst.numpy().astype(np.int32)
+        out[f"g{i}_type"] = g.edata["type"].numpy().astype(np.int32)
+        out[f"g{i}_norm"] = g.ndata["norm"].view(-1).numpy().astype(np.float32)
+        out[f"g{i}_uniq_r"] = np.asarray(g.uniq_r, dtype=np.int32)
+        out[f"g{i}_r_len"] = np.asarray(g.r_len, dtype=np.int32).reshape(-1, 2)
+        out[f"g{i}_r_to_e"] = np.asarray([int(x) for x in g.r_to_e], dtype=np.int32)
+    test = torch.from_numpy(case["test"])
+    t0 = time.time()
+    with torch.no_grad():
+        all_triples, score, score_rel = model.predict(glist, r, None, test, False)
+        hist, _, h0, _, _ = model.forward(glist, None, False)
+    dt = time.time() - t0
+    all_ans = ref_utils.load_all_answers_for_filter(case["test"], r, False)
+    all_ans_r = ref_utils.load_all_answers_for_filter(case["test"], r, True)
+    fm, m, rank, frank = ref_utils.get_total_rank(all_triples, score.clone(), all_ans, eval_bz=1000, rel_predict=0)
+    fmr, mr, rank_r, frank_r = ref_utils.get_total_rank(all_triples, score_rel.clone(), all_ans_r, eval_bz=1000,
+                                                          rel_predict=1)
+    out.update(all_triples=all_triples.numpy().astype(np.int64), rank=rank.numpy(), filter_rank=frank.numpy(),
+               rank_rel=rank_r.numpy(), filter_rank_rel=frank_r.numpy(),
+               mrr=np.array([fm, m, fmr, mr], dtype=np.float64), h0=h0.numpy())
+    sub = cfg.get("sub")
+    if sub:
+        rng = np.random.default_rng(777 + cfg["seed"])
+        rows = np.sort(rng.choice(n, size=sub, replace=False))
+        qrows = np.sort(rng.choice(score.shape[0], size=min(sub, score.shape[0]), replace=False))
+        out.update(sub_rows=rows, sub_qrows=qrows, hist_last_rows=hist[-1][rows].numpy(),
+                   hist_first_rows=hist[0][rows].numpy(), score_block=score[qrows][:, rows].numpy(),
+                   score_rel_qrows=score_rel[qrows].numpy(),
+                   score_rowsum=score.double().sum(1).numpy(), score_absmax=score.abs().max(1).values.numpy())
+    else:
+        out.update(hist=np.stack([h.numpy() for h in hist]), score=score.numpy(), score_rel=score_rel.numpy())
+    os.makedirs(GOLDEN, exist_ok=True)
+    path = os.path.join(GOLDEN, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: reference ran in {dt:.2f}s -> {path} ({os.path.getsize(path) / 1e6:.2f} MB), "
+          f"mrr(filter/raw)={fm:.4f}/{m:.4f}")
+
+
+def main(argv):
+    ref_utils, RecurrentRGCN, HyperbolicRecurrentRGCN = _import_reference()
+    torch.set_num_threads(os.cpu_count() or 1)
+    names = argv[1:] or list(CASES)
+    for name in names:
+        run_case(name, CASES[name], ref_utils, RecurrentRGCN, HyperbolicRecurrentRGCN)
+
+
+if __name__ == "__main__":
+    main(sys.argv)

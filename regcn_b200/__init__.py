@@ -1,0 +1,18 @@
+"""regcn_b200 -- B200 (sm_100a) implementation of RE-GCN's per-snapshot evolution and all-entity
+scoring path behind the reference's own module signatures.  See DESIGN.md for the path and its boundary.
+
+The kernels live in libregcn_b200.so (C ABI: include/regcn_b200.h); there is no CPU or eager fallback.
+"""
+from . import _lib  # noqa: F401
+from .graph import SnapshotGraph, build_sub_graph  # noqa: F401
+from .layers import RGCNBlockLayer, UnionRGCNLayer  # noqa: F401
+from .rrgcn import RecurrentRGCN, RGCNCell  # noqa: F401
+from .decoder import ConvTransE, ConvTransR  # noqa: F401
+from .hyperbolic_layers import (HyperbolicRGCNCell, HyperbolicUnionRGCNLayer, LorentzRGCNCell,  # noqa: F401
+                                LorentzRGCNLayer)
+from .hyperbolic_decoder import (HyperbolicConvTransE, HyperbolicConvTransR, HyperbolicMuRP,  # noqa: F401
+                                 HyperbolicMuRPRel, HyperbolicRotH, HyperbolicRotHRel)
+from .hyperbolic_model import HyperbolicRecurrentRGCN  # noqa: F401
+from . import utils  # noqa: F401
+
+__version__ = "0.1.0"

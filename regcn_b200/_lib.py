@@ -1,0 +1,105 @@
+"""ctypes binding of libregcn_b200.so (the C ABI declared in include/regcn_b200.h).
+
+There is deliberately no fallback: if the shared library is missing, or a kernel entry point is
+called without a B200-class device, the call raises.  PyTorch is used only to own device memory
+and the stream; every pointer handed to the library is `tensor.data_ptr()`.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libregcn_b200.so")
+
+_p = ctypes.c_void_p
+_i = ctypes.c_int
+_i64 = ctypes.c_int64
+_f = ctypes.c_float
+_d = ctypes.c_double
+_sz = ctypes.c_size_t
+
+# name -> (restype, argtypes); must list every symbol of include/regcn_b200.h (tests check this)
+SIGNATURES = {
+    "regcn_version": (_i, []),
+    "regcn_last_error_string": (ctypes.c_char_p, []),
+    "regcn_device_ok": (_i, []),
+    "regcn_csr_build_workspace_bytes": (_sz, [_i, _i, _i]),
+    "regcn_csr_build": (_i, [_p, _i, _i, _i] + [_p] * 15 + [_p, _sz, _p]),
+    "regcn_rel_mean_pool": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p]),
+    "regcn_union_aggregate": (_i, [_p] * 9 + [_i, _i, _p, _f, _i, _i, _p, _p, _p]),
+    "regcn_block_aggregate": (_i, [_p] * 6 + [_i, _i, _i, _i, _p, _p]),
+    "regcn_lorentz_aggregate": (_i, [_p] * 7 + [_i, _i, _i, _d, _p, _p]),
+    "regcn_gemm_f32_workspace_bytes": (_sz, [_i, _i, _i]),
+    "regcn_gemm_f32": (_i, [_p, _i, _p, _i, _i, _p, _i, _i, _i, _i, _p, _i, _i, _p, _sz, _p]),
+    "regcn_row_map": (_i, [_p, _p, _i, _i, _i, _d, _p, _p]),
+    "regcn_gru_gate": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
+    "regcn_union_combine": (_i, [_p] * 6 + [_i, _i, _i, _i, _d, _p, _p, _p, _p]),
+    "regcn_time_gate": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p]),
+    "regcn_hyp_init": (_i, [_p, _p, _i, _i, _i, _i, _d, _f, _f, _p, _p]),
+    "regcn_hyp_tangent": (_i, [_p, _i, _i, _d, _p, _p, _p, _p]),
+    "regcn_hyp_time_gate": (_i, [_p] * 6 + [_f, _i, _i, _i, _i, _d, _f, _f, _f, _f, _p, _p]),
+    "regcn_convtranse_features": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i] + [_p] * 7 + [_p]),
+    "regcn_affine_relu": (_i, [_p, _p, _p, _i, _i, _i, _p]),
+    "regcn_gather_log0": (_i, [_p, _p, _i, _i, _i, _i, _d, _p, _p]),
+    "regcn_hyp_query": (_i, [_p] * 5 + [_i, _i, _i, _d, _p, _p, _p]),
+    "regcn_hyp_score_epilogue": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _d, _p, _p]),
+    "regcn_gather_target_score": (_i, [_p, _i64, _i, _i, _p, _i, _i, _p, _p]),
+    "regcn_rank_count": (_i, [_p, _i64, _i, _i, _p, _i, _p, _p, _i, _p, _p, _p, _p]),
+    "regcn_counts_to_ranks": (_i, [_p, _p, _i, _p, _p, _p]),
+    "regcn_apply_filter": (_i, [_p, _i64, _i, _i, _p, _i, _p, _p, _i, _p]),
+}
+
+_lib = None
+launch_count = 0  # kernels-launching C-ABI calls made by this process (bench.py reports it)
+
+
+def load():
+    """Load the shared library (raises if it was not built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"regcn_b200: {LIB_PATH} is missing -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C regcn_b200/csrc`; there is no CPU fallback")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def last_error():
+    return load().regcn_last_error_string().decode("utf-8", "replace")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL); refuses CPU tensors and non-contiguous layouts."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("regcn_b200: kernels take CUDA tensors only (no CPU fallback)")
+    if not t.is_contiguous():
+        raise RuntimeError("regcn_b200: tensor must be contiguous")
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args):
+    """Invoke a kernel entry point on torch's current stream; raise on a non-zero status."""
+    global launch_count
+    lib = load()
+    rc = getattr(lib, name)(*args, stream())
+    launch_count += 1
+    if rc != 0:
+        raise RuntimeError(f"{name} failed with status {rc}: {last_error()}")
+
+
+def require_device():
+    if not torch.cuda.is_available() or not load().regcn_device_ok():
+        raise RuntimeError("regcn_b200: no sm_100 (B200) CUDA device visible -- the product path has no CPU fallback")

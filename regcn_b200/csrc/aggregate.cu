@@ -1,0 +1,381 @@
+// Memory-bound edge path: CSR-by-destination gather / segmented sum kernels.
+//   K4  union aggregate      rgcn/layers.py:257-279 (msg_func/apply_func), hyperbolic_layers.py:222-240
+//   K6  block-diag aggregate rgcn/layers.py:167-179, hyperbolic_layers.py:87-109
+//   K7  Lorentz centroid     hyperbolic_layers.py:589-625, hyperbolic_ops.py:477-518,563-581
+//   K2  relation mean-pool   src/rrgcn.py:161-166, hyperbolic_model.py:802-812
+// One warp owns one (virtual) destination row: lanes cover the row's float4 chunks (coalesced
+// 128-bit loads of whole 800-byte entity rows), edges of the row are walked in CSR order and
+// summed in registers -- a warp-segmented reduction, no atomics, deterministic.
+#include "common.cuh"
+
+namespace regcn {
+
+constexpr int kAggChunk = 256;  // must match graph_build.cu
+
+// ---------------------------------------------------------------------------
+// K4: agg[v] = norm[v] * sum_{(u,r)->v} w_uv * (h[u] + rel[r]),  w_uv = exp(-gamma*|rad[u]-rad[v]|) or 1.
+// The d x d neighbour transform is applied afterwards by the node GEMM (the message is linear in
+// (h[u] + rel[r]), so aggregate-then-transform is exact up to fp32 re-association).
+// ---------------------------------------------------------------------------
+template <int RV, bool RADIUS>
+__global__ void __launch_bounds__(256) union_aggregate_kernel(
+    const float* __restrict__ h, const float* __restrict__ rel, const int* __restrict__ rowptr,
+    const int* __restrict__ src_sorted, const int* __restrict__ etype_sorted, const float* __restrict__ norm,
+    const int* __restrict__ vptr, const int* __restrict__ sptr, const int* __restrict__ vrow_row, int nv,
+    const float* __restrict__ radius, float gamma, int d, float* __restrict__ out, float* __restrict__ partial) {
+  const int lane = threadIdx.x & 31;
+  const int w = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+  if (w >= nv) return;
+  const int nvec = d >> 2;
+  const int row = __ldg(vrow_row + w);
+  const int v0 = __ldg(vptr + row), v1 = __ldg(vptr + row + 1);
+  const int k = w - v0;
+  const int rbeg = __ldg(rowptr + row), rend = __ldg(rowptr + row + 1);
+  const int beg = rbeg + k * kAggChunk;
+  const int end = min(beg + kAggChunk, rend);
+  float r_dst = 0.f;
+  if (RADIUS) r_dst = __ldg(radius + row);
+
+  WarpRow<RV> acc;
+  acc.zero();
+  for (int base = beg; base < end; base += kWarp) {
+    const int e = base + lane;
+    int s = 0, t = 0;
+    float wgt = 1.f;
+    if (e < end) {
+      s = __ldg(src_sorted + e);
+      t = __ldg(etype_sorted + e);
+      if (RADIUS) wgt = expf(-gamma * fabsf(__ldg(radius + s) - r_dst));
+    }
+    const int cnt = min(kWarp, end - base);
+    int j = 0;
+    for (; j + 4 <= cnt; j += 4) {  // 4 edges in flight per lane: 8 independent 16-byte row loads
+      int sj[4], tj[4];
+      float wj[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        sj[u] = __shfl_sync(0xffffffffu, s, j + u);
+        tj[u] = __shfl_sync(0xffffffffu, t, j + u);
+        wj[u] = RADIUS ? __shfl_sync(0xffffffffu, wgt, j + u) : 1.f;
+      }
+      float4 hv[4][RV], rv[4][RV];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int i = 0; i < RV; ++i) {
+          int c = lane + i * kWarp;
+          if (c < nvec) {
+            hv[u][i] = ldg4(h + (size_t)sj[u] * d + 4 * c);
+            rv[u][i] = ldg4(rel + (size_t)tj[u] * d + 4 * c);
+          } else {
+            hv[u][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            rv[u][i] = hv[u][i];
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int i = 0; i < RV; ++i) {
+          float4 m = f4_add(hv[u][i], rv[u][i]);
+          acc.v[i] = RADIUS ? f4_fma(wj[u], m, acc.v[i]) : f4_add(acc.v[i], m);
+        }
+      }
+    }
+    for (; j < cnt; ++j) {
+      int sj = __shfl_sync(0xffffffffu, s, j);
+      int tj = __shfl_sync(0xffffffffu, t, j);
+      float wj = RADIUS ? __shfl_sync(0xffffffffu, wgt, j) : 1.f;
+#pragma unroll
+      for (int i = 0; i < RV; ++i) {
+        int c = lane + i * kWarp;
+        if (c < nvec) {
+          float4 m = f4_add(ldg4(h + (size_t)sj * d + 4 * c), ldg4(rel + (size_t)tj * d + 4 * c));
+          acc.v[i] = RADIUS ? f4_fma(wj, m, acc.v[i]) : f4_add(acc.v[i], m);
+        }
+      }
+    }
+  }
+  if (v1 - v0 == 1) {
+    acc.scale(__ldg(norm + row));
+    acc.store(out + (size_t)row * d, nvec, lane);
+  } else {
+    acc.store(partial + (size_t)(__ldg(sptr + row) + k) * d, nvec, lane);
+  }
+}
+
+// Rows that were split into several chunks: sum the chunk partials in chunk order, apply norm.
+template <int RV>
+__global__ void __launch_bounds__(256) aggregate_fixup_kernel(
+    const int* __restrict__ vptr, const int* __restrict__ sptr, const float* __restrict__ norm, int N, int d,
+    const float* __restrict__ partial, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int row = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+  if (row >= N) return;
+  const int nch = __ldg(vptr + row + 1) - __ldg(vptr + row);
+  if (nch <= 1) return;
+  const int nvec = d >> 2;
+  const int s0 = __ldg(sptr + row);
+  WarpRow<RV> acc, p;
+  acc.zero();
+  for (int k = 0; k < nch; ++k) {
+    p.load_plain(partial + (size_t)(s0 + k) * d, nvec, lane);
+#pragma unroll
+    for (int i = 0; i < RV; ++i) acc.v[i] = f4_add(acc.v[i], p.v[i]);
+  }
+  acc.scale(__ldg(norm + row));
+  acc.store(out + (size_t)row * d, nvec, lane);
+}
+
+int union_aggregate(const float* h, const float* rel, const int* rowptr, const int* src_sorted,
+                    const int* etype_sorted, const float* norm, const int* vptr, const int* sptr,
+                    const int* vrow_row, int nv, int nsplit, const float* radius, float gamma, int N, int d,
+                    float* out, float* partial, cudaStream_t st) {
+  if (!h || !rel || !rowptr || !src_sorted || !etype_sorted || !norm || !vptr || !sptr || !vrow_row || !out) {
+    set_last_error("union_aggregate: null pointer"); return REGCN_ERR_NULL;
+  }
+  if (d <= 0 || (d & 3) || d > 256) { set_last_error("union_aggregate: d=%d unsupported (need d%%4==0, d<=256)", d); return REGCN_ERR_UNSUPPORTED; }
+  if (nsplit > 0 && !partial) { set_last_error("union_aggregate: split rows need a partial buffer"); return REGCN_ERR_WORKSPACE; }
+  if (nv <= 0) return REGCN_OK;
+  const int TB = 256;
+  const unsigned grid = (unsigned)(((size_t)nv * 32 + TB - 1) / TB);
+  const bool small = d <= 128;
+  if (radius) {
+    if (small) union_aggregate_kernel<1, true><<<grid, TB, 0, st>>>(h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, radius, gamma, d, out, partial);
+    else union_aggregate_kernel<2, true><<<grid, TB, 0, st>>>(h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, radius, gamma, d, out, partial);
+  } else {
+    if (small) union_aggregate_kernel<1, false><<<grid, TB, 0, st>>>(h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, nullptr, 0.f, d, out, partial);
+    else union_aggregate_kernel<2, false><<<grid, TB, 0, st>>>(h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, nullptr, 0.f, d, out, partial);
+  }
+  if (nsplit > 0) {
+    const unsigned g2 = (unsigned)(((size_t)N * 32 + TB - 1) / TB);
+    if (small) aggregate_fixup_kernel<1><<<g2, TB, 0, st>>>(vptr, sptr, norm, N, d, partial, out);
+    else aggregate_fixup_kernel<2><<<g2, TB, 0, st>>>(vptr, sptr, norm, N, d, partial, out);
+  }
+  return check_launch("union_aggregate");
+}
+
+// ---------------------------------------------------------------------------
+// K6: block-diagonal relation transform, agg[v] = norm[v] * sum_in blockdiag(W[type]) . h[src].
+// W is (num_rels, nb*si*so); output column j = b*so+o reads inputs b*si .. b*si+si-1.
+// One warp per destination row, lanes stride over output columns (coalesced).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) block_aggregate_kernel(
+    const float* __restrict__ h, const float* __restrict__ W, const float* __restrict__ rel_add,
+    const int* __restrict__ rowptr, const int* __restrict__ src_sorted, const int* __restrict__ etype_sorted,
+    const float* __restrict__ norm, int N, int d_in, int d_out, int nb, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int row = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+  if (row >= N) return;
+  const int si = d_in / nb, so = d_out / nb;
+  const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+  const float nrm = __ldg(norm + row);
+  for (int j0 = 0; j0 < d_out; j0 += kWarp) {
+    const int j = j0 + lane;
+    float acc = 0.f;
+    if (j < d_out) {
+      const int b = j / so, o = j - b * so;
+      for (int e = beg; e < end; ++e) {
+        const int s = __ldg(src_sorted + e), t = __ldg(etype_sorted + e);
+        const float* hp = h + (size_t)s * d_in + b * si;
+        const float* wp = W + (size_t)t * ((size_t)nb * si * so) + (size_t)b * si * so + o;
+        float m = 0.f;
+        for (int i = 0; i < si; ++i) m = fmaf(__ldg(hp + i), __ldg(wp + i * so), m);
+        if (rel_add) m += __ldg(rel_add + (size_t)t * d_out + j);
+        acc += m;
+      }
+      out[(size_t)row * d_out + j] = acc * nrm;
+    }
+  }
+}
+
+int block_aggregate(const float* h, const float* W, const int* rowptr, const int* src_sorted,
+                    const int* etype_sorted, const float* norm, int N, int d_in, int d_out, int nb,
+                    float* out, cudaStream_t st) {
+  if (!h || !W || !rowptr || !src_sorted || !etype_sorted || !norm || !out) { set_last_error("block_aggregate: null pointer"); return REGCN_ERR_NULL; }
+  if (nb <= 0 || d_in % nb || d_out % nb) { set_last_error("block_aggregate: num_bases=%d must divide d_in=%d and d_out=%d", nb, d_in, d_out); return REGCN_ERR_UNSUPPORTED; }
+  const int TB = 256;
+  const unsigned grid = (unsigned)(((size_t)N * 32 + TB - 1) / TB);
+  block_aggregate_kernel<<<grid, TB, 0, st>>>(h, W, nullptr, rowptr, src_sorted, etype_sorted, norm, N, d_in, d_out, nb, out);
+  return check_launch("block_aggregate");
+}
+
+// ---------------------------------------------------------------------------
+// K7: Lorentz-centroid aggregation (lgcn encoder).  Per edge (tangent space input ht):
+//   m  = blockdiag(W[type]) . ht[src] + rel[type]            hyperbolic_layers.py:593-606
+//   p  = exp_0(m);  mL = to_lorentz(p) = [(1+c|p|^2)/(sqrt_c*D), 2p/D], D = max(1-c|p|^2, eps)   :609-610, ops:492-499
+// Per node v with K = indeg(v) > 0:
+//   w_i = norm_v / (K*norm_v + 1e-6)  (all equal), then lorentz_centroid: w <- w/(sum w + eps),
+//   cbar = sum w_i mL_i ; cbar /= sqrt(max(-<cbar,cbar>_L * c, eps))                              :613-625, ops:576-581
+//   out = clamp(log_0(to_poincare(cbar)), +-10)                                                   :670-672
+// indeg 0 -> exact zero row (DGL zero fill; to_poincare(0)=0, log_0(0)=0).
+// Requires si == so == 2 or generic; lanes own float4 chunks of the d-vector like K4.
+// ---------------------------------------------------------------------------
+template <int RV>
+__global__ void __launch_bounds__(256) lorentz_aggregate_kernel(
+    const float* __restrict__ ht, const float* __restrict__ W, const float* __restrict__ rel,
+    const int* __restrict__ rowptr, const int* __restrict__ src_sorted, const int* __restrict__ etype_sorted,
+    const float* __restrict__ norm, int N, int d, int nb, Curv cv, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int row = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+  if (row >= N) return;
+  const int nvec = d >> 2;
+  const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+  WarpRow<RV> acc;
+  acc.zero();
+  if (beg == end) { acc.store(out + (size_t)row * d, nvec, lane); return; }
+  const int K = end - beg;
+  const int sb = d / nb;  // square blocks: submat_in == submat_out == sb (in_feat == out_feat)
+  const float nv = __ldg(norm + row);
+  // reduce_func weights (:620): norms / (norms.sum() + 1e-6); torch sums K equal fp32 values
+  float wsum = 0.f;
+  for (int i = 0; i < K; ++i) wsum += nv;
+  const float w0 = nv / (wsum + 1e-6f);
+  // lorentz_centroid (:576): w = weights / (weights.sum() + eps)
+  float w0sum = 0.f;
+  for (int i = 0; i < K; ++i) w0sum += w0;
+  const float wgt = w0 / (w0sum + kEps);
+  float acc0 = 0.f;  // time component of the centroid
+  for (int e = beg; e < end; ++e) {
+    const int s = __ldg(src_sorted + e), t = __ldg(etype_sorted + e);
+    const float* hp = ht + (size_t)s * d;
+    const float* wp = W + (size_t)t * ((size_t)nb * sb * sb);
+    WarpRow<RV> m;
+#pragma unroll
+    for (int i = 0; i < RV; ++i) {
+      const int c = lane + i * kWarp;
+      float o4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (c < nvec) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int j = 4 * c + q;
+          const int b = j / sb, o = j - b * sb;
+          float a = 0.f;
+          for (int ii = 0; ii < sb; ++ii) a = fmaf(__ldg(hp + b * sb + ii), __ldg(wp + ((size_t)b * sb + ii) * sb + o), a);
+          o4[q] = a;
+        }
+        float4 r4 = rel ? ldg4(rel + (size_t)t * d + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        m.v[i] = make_float4(o4[0] + r4.x, o4[1] + r4.y, o4[2] + r4.z, o4[3] + r4.w);
+      } else {
+        m.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    row_exp0(m, cv);
+    const float nsq = m.sumsq();
+    const float D = fmaxf(1.0f - cv.c * nsq, kEps);
+    const float x0 = (1.0f + cv.c * nsq) / (cv.sqrt_c * D);
+    acc0 = fmaf(wgt, x0, acc0);
+#pragma unroll
+    for (int i = 0; i < RV; ++i) {
+      float4 xi = make_float4(2.0f * m.v[i].x / D, 2.0f * m.v[i].y / D, 2.0f * m.v[i].z / D, 2.0f * m.v[i].w / D);
+      acc.v[i] = f4_fma(wgt, xi, acc.v[i]);
+    }
+  }
+  const float ip = -acc0 * acc0 + acc.sumsq();
+  const float scale = sqrtf(fmaxf(-ip * cv.c, kEps));
+  const float y0 = acc0 / scale;
+  const float den = fmaxf(1.0f + y0 * cv.sqrt_c, kEps);
+  acc.map([=](float a) { return (a / scale) / den; });
+  row_log0(acc, cv);
+  acc.map([](float a) { return clampf_(a, -10.f, 10.f); });
+  acc.store(out + (size_t)row * d, nvec, lane);
+}
+
+int lorentz_aggregate(const float* ht, const float* W, const float* rel, const int* rowptr,
+                      const int* src_sorted, const int* etype_sorted, const float* norm, int N, int d, int nb,
+                      double c, float* out, cudaStream_t st) {
+  if (!ht || !W || !rowptr || !src_sorted || !etype_sorted || !norm || !out) { set_last_error("lorentz_aggregate: null pointer"); return REGCN_ERR_NULL; }
+  if (d <= 0 || (d & 3) || d > 256 || nb <= 0 || d % nb) { set_last_error("lorentz_aggregate: d=%d nb=%d unsupported", d, nb); return REGCN_ERR_UNSUPPORTED; }
+  const int TB = 256;
+  const unsigned grid = (unsigned)(((size_t)N * 32 + TB - 1) / TB);
+  Curv cv = make_curv(c);
+  if (d <= 128) lorentz_aggregate_kernel<1><<<grid, TB, 0, st>>>(ht, W, rel, rowptr, src_sorted, etype_sorted, norm, N, d, nb, cv, out);
+  else lorentz_aggregate_kernel<2><<<grid, TB, 0, st>>>(ht, W, rel, rowptr, src_sorted, etype_sorted, norm, N, d, nb, cv, out);
+  return check_launch("lorentz_aggregate");
+}
+
+// ---------------------------------------------------------------------------
+// K2: x_input[r] = x_input[r+R] = mean_{e in ents(r)} h[e]; absent relations stay zero.
+// grid = (R, nsplit): each block reduces a slice of the relation's entity list.
+// ---------------------------------------------------------------------------
+template <int RV>
+__global__ void __launch_bounds__(256) rel_mean_pool_kernel(
+    const float* __restrict__ h, const int* __restrict__ rel_rowptr, const int* __restrict__ rel_ents,
+    int R, int d, int nsplit, float* __restrict__ out, float* __restrict__ partial) {
+  __shared__ float4 red[8][RV * 32];
+  const int r = blockIdx.x, sp = blockIdx.y;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int nvec = d >> 2;
+  const int beg = __ldg(rel_rowptr + r), end = __ldg(rel_rowptr + r + 1);
+  const int n = end - beg;
+  const int per = (n + nsplit - 1) / nsplit;
+  const int b = beg + sp * per, e = min(b + per, end);
+  WarpRow<RV> acc, row;
+  acc.zero();
+  for (int i = b + wid; i < e; i += nw) {
+    row.load(h + (size_t)__ldg(rel_ents + i) * d, nvec, lane);
+#pragma unroll
+    for (int q = 0; q < RV; ++q) acc.v[q] = f4_add(acc.v[q], row.v[q]);
+  }
+#pragma unroll
+  for (int q = 0; q < RV; ++q) red[wid][q * 32 + lane] = acc.v[q];
+  __syncthreads();
+  if (wid == 0) {
+    for (int w2 = 1; w2 < nw; ++w2) {
+#pragma unroll
+      for (int q = 0; q < RV; ++q) acc.v[q] = f4_add(acc.v[q], red[w2][q * 32 + lane]);
+    }
+    if (nsplit == 1) {
+      if (n > 0) {
+        const float fn = (float)n;
+        acc.map([=](float a) { return a / fn; });
+      }
+      acc.store(out + (size_t)r * d, nvec, lane);
+      acc.store(out + (size_t)(r + R) * d, nvec, lane);
+    } else {
+      acc.store(partial + ((size_t)r * nsplit + sp) * d, nvec, lane);
+    }
+  }
+}
+
+template <int RV>
+__global__ void rel_mean_finalize_kernel(const float* __restrict__ partial, const int* __restrict__ rel_rowptr,
+                                         int R, int d, int nsplit, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int r = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+  if (r >= R) return;
+  const int nvec = d >> 2;
+  const int n = __ldg(rel_rowptr + r + 1) - __ldg(rel_rowptr + r);
+  WarpRow<RV> acc, p;
+  acc.zero();
+  for (int s = 0; s < nsplit; ++s) {
+    p.load_plain(partial + ((size_t)r * nsplit + s) * d, nvec, lane);
+#pragma unroll
+    for (int q = 0; q < RV; ++q) acc.v[q] = f4_add(acc.v[q], p.v[q]);
+  }
+  if (n > 0) {
+    const float fn = (float)n;
+    acc.map([=](float a) { return a / fn; });
+  }
+  acc.store(out + (size_t)r * d, nvec, lane);
+  acc.store(out + (size_t)(r + R) * d, nvec, lane);
+}
+
+int rel_mean_pool(const float* h, const int* rel_rowptr, const int* rel_ents, int R, int d, int nsplit,
+                  float* out, float* partial, cudaStream_t st) {
+  if (!h || !rel_rowptr || !rel_ents || !out) { set_last_error("rel_mean_pool: null pointer"); return REGCN_ERR_NULL; }
+  if (d <= 0 || (d & 3) || d > 256) { set_last_error("rel_mean_pool: d=%d unsupported", d); return REGCN_ERR_UNSUPPORTED; }
+  if (nsplit < 1) nsplit = 1;
+  if (nsplit > 1 && !partial) { set_last_error("rel_mean_pool: nsplit>1 needs a partial buffer"); return REGCN_ERR_WORKSPACE; }
+  dim3 grid(R, nsplit);
+  if (d <= 128) rel_mean_pool_kernel<1><<<grid, 256, 0, st>>>(h, rel_rowptr, rel_ents, R, d, nsplit, out, partial);
+  else rel_mean_pool_kernel<2><<<grid, 256, 0, st>>>(h, rel_rowptr, rel_ents, R, d, nsplit, out, partial);
+  if (nsplit > 1) {
+    const unsigned g2 = (unsigned)(((size_t)R * 32 + 255) / 256);
+    if (d <= 128) rel_mean_finalize_kernel<1><<<g2, 256, 0, st>>>(partial, rel_rowptr, R, d, nsplit, out);
+    else rel_mean_finalize_kernel<2><<<g2, 256, 0, st>>>(partial, rel_rowptr, R, d, nsplit, out);
+  }
+  return check_launch("rel_mean_pool");
+}
+
+}  // namespace regcn

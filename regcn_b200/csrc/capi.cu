@@ -1,0 +1,148 @@
+// extern "C" surface of libregcn_b200.so (declared in include/regcn_b200.h).
+#include "../../include/regcn_b200.h"
+#include "common.cuh"
+#include "internal.h"
+#include <stdarg.h>
+#include <stdio.h>
+
+namespace regcn {
+static thread_local char g_err[512] = "";
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_last_error("%s: CUDA error %d (%s)", what, (int)e, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return REGCN_OK;
+}
+}  // namespace regcn
+
+using namespace regcn;
+#define ST(s) ((cudaStream_t)(s))
+
+extern "C" {
+
+int regcn_version(void) { return 100; }
+const char* regcn_last_error_string(void) { return g_err; }
+int regcn_device_ok(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return 0; }
+  int dev = 0, major = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  return major == 10 ? 1 : 0;
+}
+
+size_t regcn_csr_build_workspace_bytes(int T, int N, int R) { return csr_build_workspace_bytes(T, N, R); }
+int regcn_csr_build(const int64_t* triples, int T, int N, int R, int32_t* src, int32_t* dst, int32_t* etype,
+                    int32_t* indeg, float* norm, int32_t* rowptr, int32_t* src_sorted, int32_t* etype_sorted,
+                    int32_t* eperm, int32_t* vptr, int32_t* sptr, int32_t* vrow_row, int32_t* rel_rowptr,
+                    int32_t* rel_ents, int32_t* counts, void* workspace, size_t workspace_bytes, void* stream) {
+  return csr_build(triples, T, N, R, src, dst, etype, indeg, norm, rowptr, src_sorted, etype_sorted, eperm, vptr, sptr,
+                   vrow_row, rel_rowptr, rel_ents, counts, workspace, workspace_bytes, ST(stream));
+}
+int regcn_rel_mean_pool(const float* h, const int32_t* rel_rowptr, const int32_t* rel_ents, int R, int d, int nsplit,
+                        float* out, float* partial, void* stream) {
+  return rel_mean_pool(h, rel_rowptr, rel_ents, R, d, nsplit, out, partial, ST(stream));
+}
+int regcn_union_aggregate(const float* h, const float* rel, const int32_t* rowptr, const int32_t* src_sorted,
+                          const int32_t* etype_sorted, const float* norm, const int32_t* vptr, const int32_t* sptr,
+                          const int32_t* vrow_row, int n_vrows, int n_split_chunks, const float* radius, float gamma,
+                          int N, int d, float* out, float* partial, void* stream) {
+  return union_aggregate(h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, n_vrows, n_split_chunks,
+                         radius, gamma, N, d, out, partial, ST(stream));
+}
+int regcn_block_aggregate(const float* h, const float* W, const int32_t* rowptr, const int32_t* src_sorted,
+                          const int32_t* etype_sorted, const float* norm, int N, int d_in, int d_out, int nb, float* out,
+                          void* stream) {
+  return block_aggregate(h, W, rowptr, src_sorted, etype_sorted, norm, N, d_in, d_out, nb, out, ST(stream));
+}
+int regcn_lorentz_aggregate(const float* ht, const float* W, const float* rel, const int32_t* rowptr,
+                            const int32_t* src_sorted, const int32_t* etype_sorted, const float* norm, int N, int d,
+                            int nb, double c, float* out, void* stream) {
+  return lorentz_aggregate(ht, W, rel, rowptr, src_sorted, etype_sorted, norm, N, d, nb, c, out, ST(stream));
+}
+size_t regcn_gemm_f32_workspace_bytes(int M, int N, int split_k) { return gemm_f32_workspace_bytes(M, N, split_k); }
+int regcn_gemm_f32(const float* A, int lda, const float* B, int ldb, int transB, float* C, int ldc, int M, int N, int K,
+                   const float* bias, int accumulate, int split_k, float* workspace, size_t workspace_bytes,
+                   void* stream) {
+  return gemm_f32(A, lda, B, ldb, transB, C, ldc, M, N, K, bias, accumulate, split_k, workspace, workspace_bytes,
+                  ST(stream));
+}
+int regcn_row_map(const float* x, float* out, int M, int d, int mode, double c, float* sumsq, void* stream) {
+  return row_map(x, out, M, d, mode, c, sumsq, ST(stream));
+}
+int regcn_gru_gate(const float* gi, const float* gh, const float* hprev, float* out, int M, int d, int normalize,
+                   void* stream) {
+  return gru_gate(gi, gh, hprev, out, M, d, normalize, ST(stream));
+}
+int regcn_union_combine(const float* P, const float* L, const int32_t* indeg, const float* S, const float* skip_bias,
+                        const float* prev, int N, int d, int act, int hyper, double c, float* out, float* ht_next,
+                        float* radius_next, void* stream) {
+  return union_combine(P, L, indeg, S, skip_bias, prev, N, d, act, hyper, c, out, ht_next, radius_next, ST(stream));
+}
+int regcn_time_gate(const float* G, const float* bias, const float* cur, const float* h, float* out, int N, int d,
+                    int normalize_cur, void* stream) {
+  return time_gate(G, bias, cur, h, out, N, d, normalize_cur, ST(stream));
+}
+int regcn_hyp_init(const float* emb, const float* radius_static, int N, int d, int normalize, int on_manifold, double c,
+                   float radius_min, float radius_max, float* out, void* stream) {
+  return hyp_init(emb, radius_static, N, d, normalize, on_manifold, c, radius_min, radius_max, out, ST(stream));
+}
+int regcn_hyp_tangent(const float* h, int N, int d, double c, float* ht, float* pt, float* radius, void* stream) {
+  return hyp_tangent(h, N, d, c, ht, pt, radius, ST(stream));
+}
+int regcn_hyp_time_gate(const float* h2, const float* pt, const float* G, const float* bias, const float* radius_static,
+                        const float* radius_w, float radius_b, int N, int d, int layer_norm, int residual, double c,
+                        float radius_min, float radius_max, float beta, float eps_r, float* out, void* stream) {
+  return hyp_time_gate(h2, pt, G, bias, radius_static, radius_w, radius_b, N, d, layer_norm, residual, c, radius_min,
+                       radius_max, beta, eps_r, out, ST(stream));
+}
+int regcn_convtranse_features(const float* ent, const float* second, const int64_t* triples, int col0, int col1, int B,
+                              int d, int C, int ksz, const float* bn0_scale, const float* bn0_shift,
+                              const float* conv_w, const float* conv_b, const float* bn1_scale, const float* bn1_shift,
+                              float* F, void* stream) {
+  return convtranse_features(ent, second, triples, col0, col1, B, d, C, ksz, bn0_scale, bn0_shift, conv_w, conv_b,
+                             bn1_scale, bn1_shift, F, ST(stream));
+}
+int regcn_affine_relu(float* x, const float* scale, const float* shift, int M, int d, int relu, void* stream) {
+  return affine_relu(x, scale, shift, M, d, relu, ST(stream));
+}
+int regcn_gather_log0(const float* E, const int64_t* triples, int col, int B, int d, int project, double c, float* out,
+                      void* stream) {
+  return gather_log0(E, triples, col, B, d, project, c, out, ST(stream));
+}
+int regcn_hyp_query(const float* s_tan, const float* ang, const float* trans, const float* E, const int64_t* triples,
+                    int B, int d, int kind, double c, float* Q, float* q_sumsq, void* stream) {
+  return hyp_query(s_tan, ang, trans, E, triples, B, d, kind, c, Q, q_sumsq, ST(stream));
+}
+int regcn_hyp_score_epilogue(float* S, int ld, int B, int N, const float* q_sumsq, const float* e_sumsq,
+                             const float* bias, const float* qbias, double c, const float* scale_margin, void* stream) {
+  return hyp_score_epilogue(S, ld, B, N, q_sumsq, e_sumsq, bias, qbias, c, scale_margin, ST(stream));
+}
+int regcn_gather_target_score(const float* S, int64_t ld, int B, int N, const int64_t* triples, int target_col,
+                              int col_offset, float* target_score, void* stream) {
+  return gather_target_score(S, ld, B, N, triples, target_col, col_offset, target_score, ST(stream));
+}
+int regcn_rank_count(const float* S, int64_t ld, int B, int N, const int64_t* triples, int target_col,
+                     const int32_t* filt_ptr, const int32_t* filt_idx, int col_offset, const float* target_score,
+                     int32_t* raw_count, int32_t* filt_count, void* stream) {
+  return rank_count(S, ld, B, N, triples, target_col, filt_ptr, filt_idx, col_offset, target_score, raw_count,
+                    filt_count, ST(stream));
+}
+int regcn_counts_to_ranks(const int32_t* raw_count, const int32_t* filt_count, int B, int64_t* rank, int64_t* filt_rank,
+                          void* stream) {
+  return counts_to_ranks(raw_count, filt_count, B, rank, filt_rank, ST(stream));
+}
+int regcn_apply_filter(float* S, int64_t ld, int B, int N, const int64_t* triples, int target_col,
+                       const int32_t* filt_ptr, const int32_t* filt_idx, int col_offset, void* stream) {
+  return apply_filter(S, ld, B, N, triples, target_col, filt_ptr, filt_idx, col_offset, ST(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,168 @@
+// Shared device helpers for the regcn_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#define REGCN_OK 0
+#define REGCN_ERR_NULL (-1)
+#define REGCN_ERR_DIM (-2)
+#define REGCN_ERR_WORKSPACE (-3)
+#define REGCN_ERR_UNSUPPORTED (-4)
+
+namespace regcn {
+
+void set_last_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+constexpr int kWarp = 32;
+constexpr float kEps = 1e-6f;                   // HyperbolicOps.EPS (hyperbolic_ops.py:28)
+constexpr float kRReluSlope = (1.0f / 8.0f + 1.0f / 3.0f) * 0.5f;  // F.rrelu eval slope, 11/48
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float rreluf_(float x) { return x >= 0.f ? x : x * kRReluSlope; }
+__device__ __forceinline__ float clampf_(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 f4_fma(float s, float4 a, float4 acc) {
+  return make_float4(fmaf(s, a.x, acc.x), fmaf(s, a.y, acc.y), fmaf(s, a.z, acc.z), fmaf(s, a.w, acc.w));
+}
+__device__ __forceinline__ float4 f4_scale(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+__device__ __forceinline__ float f4_dot(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+
+// ---------------------------------------------------------------------------
+// A row of d floats (d % 4 == 0, d <= 4*32*RV) held by one warp: lane l owns the
+// float4 chunks l, l+32, ...  RV = 2 covers d <= 256 (d = 200 -> 50 chunks).
+// ---------------------------------------------------------------------------
+template <int RV>
+struct WarpRow {
+  float4 v[RV];
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int i = 0; i < RV; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __device__ __forceinline__ void load(const float* row, int nvec, int lane) {
+#pragma unroll
+    for (int i = 0; i < RV; ++i) {
+      int c = lane + i * kWarp;
+      v[i] = c < nvec ? ldg4(row + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  __device__ __forceinline__ void load_plain(const float* row, int nvec, int lane) {
+#pragma unroll
+    for (int i = 0; i < RV; ++i) {
+      int c = lane + i * kWarp;
+      v[i] = c < nvec ? *reinterpret_cast<const float4*>(row + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  __device__ __forceinline__ void store(float* row, int nvec, int lane) const {
+#pragma unroll
+    for (int i = 0; i < RV; ++i) {
+      int c = lane + i * kWarp;
+      if (c < nvec) st4(row + 4 * c, v[i]);
+    }
+  }
+  __device__ __forceinline__ float sumsq() const {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < RV; ++i) s += f4_dot(v[i], v[i]);
+    return warp_sum(s);
+  }
+  __device__ __forceinline__ float dot(const WarpRow& o) const {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < RV; ++i) s += f4_dot(v[i], o.v[i]);
+    return warp_sum(s);
+  }
+  __device__ __forceinline__ void scale(float s) {
+#pragma unroll
+    for (int i = 0; i < RV; ++i) v[i] = f4_scale(v[i], s);
+  }
+  template <typename F>
+  __device__ __forceinline__ void map(F f) {
+#pragma unroll
+    for (int i = 0; i < RV; ++i) {
+      v[i].x = f(v[i].x); v[i].y = f(v[i].y); v[i].z = f(v[i].z); v[i].w = f(v[i].w);
+    }
+  }
+  template <typename F>
+  __device__ __forceinline__ void zip(const WarpRow& o, F f) {
+#pragma unroll
+    for (int i = 0; i < RV; ++i) {
+      v[i].x = f(v[i].x, o.v[i].x); v[i].y = f(v[i].y, o.v[i].y);
+      v[i].z = f(v[i].z, o.v[i].z); v[i].w = f(v[i].w, o.v[i].w);
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------
+// Poincare-ball row maps, restating hyperbolic_ops.py:38-233 exactly
+// (same clamp order, same epsilons).  All take sqrt_c and c as fp32.
+// ---------------------------------------------------------------------------
+struct Curv {
+  float c, sqrt_c;
+  float proj_max;    // (1/sqrt(c) - eps) - eps : clamp bound inside clamp_norm via project_to_ball (:51-53,:72-74)
+  float radius_max;  // 1/sqrt(c) - eps         : apply_radius upper clamp (:229-230)
+};
+// Bounds are formed in double like the reference's python-float arithmetic, then rounded to fp32.
+inline Curv make_curv(double c) {
+  Curv k;
+  k.c = (float)c;
+  k.sqrt_c = (float)sqrt(c);
+  k.proj_max = (float)(1.0 / sqrt(c) - 1e-6 - 1e-6);
+  k.radius_max = (float)(1.0 / sqrt(c) - 1e-6);
+  return k;
+}
+
+// clamp_norm(x, max_norm): n = max(|x|, eps); x * (min(n, max_norm - eps) / n)   (:51-53)
+template <int RV>
+__device__ __forceinline__ void row_project(WarpRow<RV>& x, const Curv& k) {
+  float n = fmaxf(sqrtf(x.sumsq()), kEps);
+  float cn = fminf(n, k.proj_max);
+  x.scale(cn / n);
+}
+// exp_map_zero (:91-95): project( tanh(sqrt_c*n) * (v/n) / sqrt_c )
+template <int RV>
+__device__ __forceinline__ void row_exp0(WarpRow<RV>& v, const Curv& k) {
+  float n = fmaxf(sqrtf(v.sumsq()), kEps);
+  float t = tanhf(k.sqrt_c * n);
+  const float sc = k.sqrt_c;
+  v.map([=](float a) { return t * (a / n) / sc; });
+  row_project(v, k);
+}
+// log_map_zero (:112-116): atanh(min(sqrt_c*n, 1-eps)) * x / (sqrt_c*n)
+template <int RV>
+__device__ __forceinline__ void row_log0(WarpRow<RV>& x, const Curv& k) {
+  float n = fmaxf(sqrtf(x.sumsq()), kEps);
+  float sn = fminf(k.sqrt_c * n, 1.0f - kEps);
+  float a = atanhf(sn);
+  float den = k.sqrt_c * n;
+  x.map([=](float e) { return a * e / den; });
+}
+// apply_radius (:222-233): x / max(|x|,eps) * clamp(r, eps, 1/sqrt(c) - eps)
+template <int RV>
+__device__ __forceinline__ void row_apply_radius(WarpRow<RV>& x, float r, const Curv& k) {
+  float n = fmaxf(sqrtf(x.sumsq()), kEps);
+  float rr = clampf_(r, kEps, k.radius_max);
+  x.map([=](float e) { return e / n * rr; });
+}
+// F.normalize: x / max(|x|, 1e-12)
+template <int RV>
+__device__ __forceinline__ void row_l2normalize(WarpRow<RV>& x) {
+  float n = fmaxf(sqrtf(x.sumsq()), 1e-12f);
+  x.map([=](float e) { return e / n; });
+}
+
+}  // namespace regcn

@@ -1,0 +1,236 @@
+// Decoder-side kernels.
+//   K10 ConvTransE / ConvTransR query tower   src/decoder.py:29-52,78-95; hyperbolic_decoder.py:376-406,478-507
+//   K12 RotH / MuRP query builder             hyperbolic_decoder.py:1064-1086 (RotH), :744-765 (MuRP), :1243-1251 (RotHRel)
+//   K13 hyperbolic score epilogue             hyperbolic_decoder.py:89-179 (proxy-distance branch) in norm/dot form
+// The dense contractions between these stages (FC 50d->d, the d->d projections, Q.E^T) run on the GEMM kernels.
+#include "common.cuh"
+
+namespace regcn {
+
+// ---- K10a: feature map  F[b, c*d + i] = relu(bn1(conv1d(bn0([x0;x1]))))  (eval-mode BatchNorm) --------
+// x0 = ent[idx0[b]], x1 = second[idx1[b]] (relation row for ConvTransE, object row for ConvTransR).
+// bn params are pre-folded on the host into scale/shift: y = x*scale + shift.
+__global__ void __launch_bounds__(256) convtranse_features_kernel(
+    const float* __restrict__ ent, const float* __restrict__ second, const int64_t* __restrict__ triples,
+    int col0, int col1, int B, int d, int C, int ksz,
+    const float* __restrict__ bn0_scale, const float* __restrict__ bn0_shift,   // (2)
+    const float* __restrict__ conv_w, const float* __restrict__ conv_b,         // (C,2,ksz), (C)
+    const float* __restrict__ bn1_scale, const float* __restrict__ bn1_shift,   // (C)
+    float* __restrict__ F) {
+  extern __shared__ float sm[];
+  const int pad = ksz / 2;
+  const int ld = d + 2 * pad;
+  float* y0 = sm;            // padded, bn0 applied
+  float* y1 = sm + ld;
+  float* wsm = sm + 2 * ld;  // C*2*ksz weights, then C conv bias, C bn1 scale, C bn1 shift
+  const int b = blockIdx.x;
+  const int64_t i0 = triples[3 * (size_t)b + col0];
+  const int64_t i1 = triples[3 * (size_t)b + col1];
+  const float s0 = bn0_scale[0], t0 = bn0_shift[0], s1 = bn0_scale[1], t1 = bn0_shift[1];
+  for (int i = threadIdx.x; i < ld; i += blockDim.x) {
+    const int j = i - pad;
+    const bool in = j >= 0 && j < d;
+    y0[i] = in ? fmaf(__ldg(ent + (size_t)i0 * d + j), s0, t0) : 0.f;
+    y1[i] = in ? fmaf(__ldg(second + (size_t)i1 * d + j), s1, t1) : 0.f;
+  }
+  const int nw = C * 2 * ksz;
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) wsm[i] = conv_w[i];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    wsm[nw + i] = conv_b[i];
+    wsm[nw + C + i] = bn1_scale[i];
+    wsm[nw + 2 * C + i] = bn1_shift[i];
+  }
+  __syncthreads();
+  float* Fb = F + (size_t)b * C * d;
+  for (int o = threadIdx.x; o < C * d; o += blockDim.x) {
+    const int c = o / d, i = o - c * d;
+    const float* w = wsm + c * 2 * ksz;
+    float acc = wsm[nw + c];
+    for (int k = 0; k < ksz; ++k) acc = fmaf(w[k], y0[i + k], acc);
+    for (int k = 0; k < ksz; ++k) acc = fmaf(w[ksz + k], y1[i + k], acc);
+    acc = fmaf(acc, wsm[nw + C + c], wsm[nw + 2 * C + c]);
+    Fb[o] = fmaxf(acc, 0.f);
+  }
+}
+
+int convtranse_features(const float* ent, const float* second, const int64_t* triples, int col0, int col1, int B,
+                        int d, int C, int ksz, const float* bn0_scale, const float* bn0_shift, const float* conv_w,
+                        const float* conv_b, const float* bn1_scale, const float* bn1_shift, float* F, cudaStream_t st) {
+  if (!ent || !second || !triples || !bn0_scale || !bn0_shift || !conv_w || !conv_b || !bn1_scale || !bn1_shift || !F) {
+    set_last_error("convtranse_features: null pointer"); return REGCN_ERR_NULL;
+  }
+  if (B <= 0) return REGCN_OK;
+  if (d <= 0 || C <= 0 || ksz <= 0 || !(ksz & 1)) { set_last_error("convtranse_features: bad dims d=%d C=%d k=%d", d, C, ksz); return REGCN_ERR_DIM; }
+  const size_t smem = ((size_t)2 * (d + 2 * (ksz / 2)) + (size_t)C * 2 * ksz + 3 * (size_t)C) * sizeof(float);
+  if (smem > 48 * 1024) { set_last_error("convtranse_features: shared memory %zu too large", smem); return REGCN_ERR_UNSUPPORTED; }
+  convtranse_features_kernel<<<B, 256, smem, st>>>(ent, second, triples, col0, col1, B, d, C, ksz, bn0_scale, bn0_shift,
+                                                   conv_w, conv_b, bn1_scale, bn1_shift, F);
+  return check_launch("convtranse_features");
+}
+
+// ---- K10b: x = relu(x*scale + shift) per feature (bn2 folded; scale==null -> plain relu, the B==1 case) ----
+__global__ void affine_relu_kernel(float* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
+                                   size_t total, int d, int relu) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int j = (int)(i % d);
+  float v = x[i];
+  if (scale) v = fmaf(v, __ldg(scale + j), __ldg(shift + j));
+  x[i] = relu ? fmaxf(v, 0.f) : v;
+}
+
+int affine_relu(float* x, const float* scale, const float* shift, int M, int d, int relu, cudaStream_t st) {
+  if (!x || (scale && !shift)) { set_last_error("affine_relu: null pointer"); return REGCN_ERR_NULL; }
+  const size_t total = (size_t)M * d;
+  if (!total) return REGCN_OK;
+  affine_relu_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, scale, shift, total, d, relu);
+  return check_launch("affine_relu");
+}
+
+// ---- K12a: gather + tangent map of the query subjects:  out[b] = log_0(project?(E[idx[b]])) ----
+template <int RV>
+__global__ void __launch_bounds__(256) gather_log0_kernel(const float* __restrict__ E, const int64_t* __restrict__ triples,
+                                                          int col, int B, int d, int project, Curv cv, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int row = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+  if (row >= B) return;
+  const int nvec = d >> 2;
+  WarpRow<RV> r;
+  r.load(E + (size_t)triples[3 * (size_t)row + col] * d, nvec, lane);
+  if (project) row_project(r, cv);
+  row_log0(r, cv);
+  r.store(out + (size_t)row * d, nvec, lane);
+}
+
+int gather_log0(const float* E, const int64_t* triples, int col, int B, int d, int project, double c, float* out, cudaStream_t st) {
+  if (!E || !triples || !out) { set_last_error("gather_log0: null pointer"); return REGCN_ERR_NULL; }
+  if (d <= 0 || (d & 3) || d > 256) { set_last_error("gather_log0: d=%d unsupported", d); return REGCN_ERR_UNSUPPORTED; }
+  if (B <= 0) return REGCN_OK;
+  Curv cv = make_curv(c);
+  const unsigned grid = (unsigned)(((size_t)B * 32 + 255) / 256);
+  if (d <= 128) gather_log0_kernel<1><<<grid, 256, 0, st>>>(E, triples, col, B, d, project, cv, out);
+  else gather_log0_kernel<2><<<grid, 256, 0, st>>>(E, triples, col, B, d, project, cv, out);
+  return check_launch("gather_log0");
+}
+
+// ---- K12b: query = project(exp_0(rot(s_tan))) (+)_c project(exp_0(v_r)) ----------------------------------
+// kind 0 RotH   : rot = Givens(s_tan[b], ang[r_b])   ang (2R, d/2), trans (2R, d)       hyperbolic_decoder.py:1074-1085
+// kind 1 MuRP   : rot = diag[r_b] * s_tan[b]         ang = diag (2R, d)                  :751-764
+// kind 2 RotHRel: rot = Givens(s_tan[b], global_rot (d/2)); query = (-exp_0(rot)) (+)_c E[o_b]   :1247-1251
+// Pair (x_{2i}, x_{2i+1}) lives inside one float4, so the rotation needs no shuffles.
+__device__ __forceinline__ float4 givens4(float4 x, float a0, float a1) {
+  float s0, c0, s1, c1;
+  sincosf(a0, &s0, &c0);
+  sincosf(a1, &s1, &c1);
+  return make_float4(c0 * x.x - s0 * x.y, s0 * x.x + c0 * x.y, c1 * x.z - s1 * x.w, s1 * x.z + c1 * x.w);
+}
+
+template <int RV>
+__device__ __forceinline__ void row_mobius_add(WarpRow<RV>& x, const WarpRow<RV>& y, const Curv& cv) {
+  // mobius_add (hyperbolic_ops.py:135-143)
+  const float x_sq = x.sumsq(), y_sq = y.sumsq(), xy = x.dot(y);
+  const float c = cv.c;
+  const float a = 1.0f + 2.0f * c * xy + c * y_sq;
+  const float b = 1.0f - c * x_sq;
+  const float den = 1.0f + 2.0f * c * xy + c * c * x_sq * y_sq + kEps;
+  x.zip(y, [=](float xx, float yy) { return (a * xx + b * yy) / den; });
+  row_project(x, cv);
+}
+
+template <int RV>
+__global__ void __launch_bounds__(256) hyp_query_kernel(
+    const float* __restrict__ s_tan, const float* __restrict__ ang, const float* __restrict__ trans,
+    const float* __restrict__ E, const int64_t* __restrict__ triples, int B, int d, int kind, Curv cv,
+    float* __restrict__ Q, float* __restrict__ q_sumsq) {
+  const int lane = threadIdx.x & 31;
+  const int row = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+  if (row >= B) return;
+  const int nvec = d >> 2;
+  const int64_t r = triples[3 * (size_t)row + 1];
+  WarpRow<RV> x, y;
+  x.load_plain(s_tan + (size_t)row * d, nvec, lane);
+#pragma unroll
+  for (int i = 0; i < RV; ++i) {
+    const int cidx = lane + i * kWarp;
+    if (cidx < nvec) {
+      if (kind == 1) {
+        float4 dg = ldg4(ang + (size_t)r * d + 4 * cidx);
+        x.v[i] = make_float4(dg.x * x.v[i].x, dg.y * x.v[i].y, dg.z * x.v[i].z, dg.w * x.v[i].w);
+      } else {
+        const float* ap = kind == 0 ? ang + (size_t)r * (d / 2) + 2 * cidx : ang + 2 * cidx;
+        x.v[i] = givens4(x.v[i], __ldg(ap), __ldg(ap + 1));
+      }
+    }
+  }
+  row_exp0(x, cv);
+  if (kind == 2) {
+    x.map([](float a) { return -a; });
+    y.load(E + (size_t)triples[3 * (size_t)row + 2] * d, nvec, lane);
+  } else {
+    row_project(x, cv);
+    y.load(trans + (size_t)r * d, nvec, lane);
+    row_exp0(y, cv);
+    row_project(y, cv);
+  }
+  row_mobius_add(x, y, cv);
+  x.store(Q + (size_t)row * d, nvec, lane);
+  if (q_sumsq) {
+    const float s = x.sumsq();
+    if (lane == 0) q_sumsq[row] = s;
+  }
+}
+
+int hyp_query(const float* s_tan, const float* ang, const float* trans, const float* E, const int64_t* triples, int B,
+              int d, int kind, double c, float* Q, float* q_sumsq, cudaStream_t st) {
+  if (!s_tan || !ang || !triples || !Q || (kind != 2 && !trans) || (kind == 2 && !E)) { set_last_error("hyp_query: null pointer"); return REGCN_ERR_NULL; }
+  if (d <= 0 || (d & 3) || d > 256 || kind < 0 || kind > 2) { set_last_error("hyp_query: d=%d kind=%d unsupported", d, kind); return REGCN_ERR_UNSUPPORTED; }
+  if (B <= 0) return REGCN_OK;
+  Curv cv = make_curv(c);
+  const unsigned grid = (unsigned)(((size_t)B * 32 + 255) / 256);
+  if (d <= 128) hyp_query_kernel<1><<<grid, 256, 0, st>>>(s_tan, ang, trans, E, triples, B, d, kind, cv, Q, q_sumsq);
+  else hyp_query_kernel<2><<<grid, 256, 0, st>>>(s_tan, ang, trans, E, triples, B, d, kind, cv, Q, q_sumsq);
+  return check_launch("hyp_query");
+}
+
+// ---- K13: score epilogue on a dense dot-product matrix -------------------------------------------------
+// In:  S[b,n] = <q_b, e_n>.  Out: scale*(margin - |project((-q_b) (+)_c e_n)|^2) + bias[n] + qbias[b]
+// with x = -q: x_sq = |q|^2, y_sq = |e|^2, xy = -<q,e>; A = 1+2c*xy+c*y_sq; Bc = 1-c*x_sq;
+// |num|^2 = A^2 x_sq + 2 A Bc xy + Bc^2 y_sq; den = 1+2c*xy+c^2 x_sq y_sq + eps; n = sqrt(|num|^2)/den,
+// clamp_norm -> min(n, proj_max) (for n >= eps).                       hyperbolic_decoder.py:164-172, ops:135-143
+__device__ __forceinline__ float hyp_score_from_dot(float dot, float x_sq, float y_sq, float c, float proj_max,
+                                                    float scale, float margin) {
+  const float xy = -dot;
+  const float a = 1.0f + 2.0f * c * xy + c * y_sq;
+  const float b = 1.0f - c * x_sq;
+  const float num_sq = fmaxf(a * a * x_sq + 2.0f * a * b * xy + b * b * y_sq, 0.f);
+  const float den = 1.0f + 2.0f * c * xy + c * c * x_sq * y_sq + kEps;
+  float n = sqrtf(num_sq) / fabsf(den);
+  n = fminf(n, proj_max);
+  return scale * (margin - n * n);
+}
+
+__global__ void hyp_score_epilogue_kernel(float* __restrict__ S, size_t ld, int B, int N, const float* __restrict__ q_sumsq,
+                                          const float* __restrict__ e_sumsq, const float* __restrict__ bias,
+                                          const float* __restrict__ qbias, Curv cv, const float* __restrict__ scale_margin) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (n >= N) return;
+  const float scale = scale_margin[0], margin = scale_margin[1];
+  float v = hyp_score_from_dot(S[(size_t)b * ld + n], __ldg(q_sumsq + b), __ldg(e_sumsq + n), cv.c, cv.proj_max, scale, margin);
+  if (bias) v += __ldg(bias + n);
+  if (qbias) v += __ldg(qbias + b);
+  S[(size_t)b * ld + n] = v;
+}
+
+int hyp_score_epilogue(float* S, int ld, int B, int N, const float* q_sumsq, const float* e_sumsq, const float* bias,
+                       const float* qbias, double c, const float* scale_margin, cudaStream_t st) {
+  if (!S || !q_sumsq || !e_sumsq || !scale_margin) { set_last_error("hyp_score_epilogue: null pointer"); return REGCN_ERR_NULL; }
+  if (B <= 0 || N <= 0) return REGCN_OK;
+  if (B > 65535) { set_last_error("hyp_score_epilogue: B=%d > 65535 (chunk the queries)", B); return REGCN_ERR_DIM; }
+  Curv cv = make_curv(c);
+  dim3 grid((N + 255) / 256, B);
+  hyp_score_epilogue_kernel<<<grid, 256, 0, st>>>(S, (size_t)ld, B, N, q_sumsq, e_sumsq, bias, qbias, cv, scale_margin);
+  return check_launch("hyp_score_epilogue");
+}
+
+}  // namespace regcn

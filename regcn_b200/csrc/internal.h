@@ -1,0 +1,56 @@
+// Internal C++ declarations of the kernel launchers (one per extern "C" entry in include/regcn_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace regcn {
+size_t csr_build_workspace_bytes(int T, int N, int R);
+int csr_build(const int64_t* triples, int T, int N, int R, int* src, int* dst, int* etype, int* indeg, float* norm,
+              int* rowptr, int* src_sorted, int* etype_sorted, int* eperm, int* vptr, int* sptr, int* vrow_row,
+              int* rel_rowptr, int* rel_ents, int* counts, void* ws, size_t ws_bytes, cudaStream_t st);
+int rel_mean_pool(const float* h, const int* rel_rowptr, const int* rel_ents, int R, int d, int nsplit, float* out,
+                  float* partial, cudaStream_t st);
+int union_aggregate(const float* h, const float* rel, const int* rowptr, const int* src_sorted, const int* etype_sorted,
+                    const float* norm, const int* vptr, const int* sptr, const int* vrow_row, int nv, int nsplit,
+                    const float* radius, float gamma, int N, int d, float* out, float* partial, cudaStream_t st);
+int block_aggregate(const float* h, const float* W, const int* rowptr, const int* src_sorted, const int* etype_sorted,
+                    const float* norm, int N, int d_in, int d_out, int nb, float* out, cudaStream_t st);
+int lorentz_aggregate(const float* ht, const float* W, const float* rel, const int* rowptr, const int* src_sorted,
+                      const int* etype_sorted, const float* norm, int N, int d, int nb, double c, float* out,
+                      cudaStream_t st);
+size_t gemm_f32_workspace_bytes(int M, int N, int split_k);
+int gemm_f32(const float* A, int lda, const float* B, int ldb, int transB, float* C, int ldc, int M, int N, int K,
+             const float* bias, int accumulate, int split_k, float* ws, size_t ws_bytes, cudaStream_t st);
+int row_map(const float* x, float* out, int M, int d, int mode, double c, float* sumsq, cudaStream_t st);
+int gru_gate(const float* gi, const float* gh, const float* hprev, float* out, int M, int d, int normalize, cudaStream_t st);
+int union_combine(const float* P, const float* L, const int* indeg, const float* S, const float* skip_bias,
+                  const float* prev, int N, int d, int act, int hyper, double c, float* out, float* ht_next,
+                  float* radius_next, cudaStream_t st);
+int time_gate(const float* G, const float* bias, const float* cur, const float* h, float* out, int N, int d,
+              int normalize_cur, cudaStream_t st);
+int hyp_init(const float* emb, const float* radius_static, int N, int d, int normalize, int on_manifold, double c,
+             float rmin, float rmax, float* out, cudaStream_t st);
+int hyp_tangent(const float* h, int N, int d, double c, float* ht, float* pt, float* radius, cudaStream_t st);
+int hyp_time_gate(const float* h2, const float* pt, const float* G, const float* bias, const float* radius_static,
+                  const float* rw, float rb, int N, int d, int layer_norm, int residual, double c, float rmin,
+                  float rmax, float beta, float eps_r, float* out, cudaStream_t st);
+int convtranse_features(const float* ent, const float* second, const int64_t* triples, int col0, int col1, int B,
+                        int d, int C, int ksz, const float* bn0_scale, const float* bn0_shift, const float* conv_w,
+                        const float* conv_b, const float* bn1_scale, const float* bn1_shift, float* F, cudaStream_t st);
+int affine_relu(float* x, const float* scale, const float* shift, int M, int d, int relu, cudaStream_t st);
+int gather_log0(const float* E, const int64_t* triples, int col, int B, int d, int project, double c, float* out,
+                cudaStream_t st);
+int hyp_query(const float* s_tan, const float* ang, const float* trans, const float* E, const int64_t* triples, int B,
+              int d, int kind, double c, float* Q, float* q_sumsq, cudaStream_t st);
+int hyp_score_epilogue(float* S, int ld, int B, int N, const float* q_sumsq, const float* e_sumsq, const float* bias,
+                       const float* qbias, double c, const float* scale_margin, cudaStream_t st);
+int gather_target_score(const float* S, int64_t ld, int B, int N, const int64_t* triples, int target_col,
+                        int col_offset, float* target_score, cudaStream_t st);
+int rank_count(const float* S, int64_t ld, int B, int N, const int64_t* triples, int target_col, const int* filt_ptr,
+               const int* filt_idx, int col_offset, const float* target_score, int* raw_count, int* filt_count,
+               cudaStream_t st);
+int counts_to_ranks(const int* raw_count, const int* filt_count, int B, int64_t* rank, int64_t* filt_rank, cudaStream_t st);
+int apply_filter(float* S, int64_t ld, int B, int N, const int64_t* triples, int target_col, const int* filt_ptr,
+                 const int* filt_idx, int col_offset, cudaStream_t st);
+}  // namespace regcn

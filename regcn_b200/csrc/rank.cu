@@ -1,0 +1,125 @@
+// K14: raw + time-filtered rank of the target among all candidates, without sorting.
+// Restates rgcn/utils.py:21-25 (sort_and_rank), :51-75 (filter_score / filter_score_r), :136-166.
+//   reference rank (0-based) = position of the target after a descending sort of the row
+//   here                     = #{j : s_j > s_t} + #{j < t : s_j == s_t}   (the stable-sort position)
+// which is identical whenever the target's score is unique in the row (ties only occur among the
+// -1e7 filtered entries, which sit below any real target score).  Filtered variant: every other
+// true answer j in filt(b) \ {t} is scored -10000000 (utils.py:60,74) before ranking.
+// Output ranks are 1-based int64 like the reference (utils.py:162-163).
+#include "common.cuh"
+
+namespace regcn {
+
+constexpr float kFilterScore = -10000000.0f;
+
+__device__ __forceinline__ int rank_contrib(float s, int j, float st, int t) {
+  return (s > st || (s == st && j < t)) ? 1 : 0;
+}
+
+// One CTA per query row: counts over the dense row, then corrects for the (short, sorted) filter list.
+__global__ void __launch_bounds__(256) rank_rows_kernel(
+    const float* __restrict__ S, size_t ld, int B, int N, const int64_t* __restrict__ triples, int target_col,
+    const int* __restrict__ filt_ptr, const int* __restrict__ filt_idx, int col_offset,
+    int* __restrict__ raw_count, int* __restrict__ filt_count, float* __restrict__ target_score) {
+  __shared__ int red[8];
+  const int b = blockIdx.x;
+  const float* row = S + (size_t)b * ld;
+  const int t = (int)triples[3 * (size_t)b + target_col] - col_offset;  // local column of the target (may be outside this shard)
+  const float st = target_score[b];
+  int cnt = 0;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    if (j != t) cnt += rank_contrib(row[j], j, st, t);
+  }
+  // filter correction: entries of filt(b) inside this shard, excluding the target itself
+  int corr = 0;
+  if (filt_ptr) {
+    const int fb = filt_ptr[b], fe = filt_ptr[b + 1];
+    for (int i = fb + threadIdx.x; i < fe; i += blockDim.x) {
+      const int j = filt_idx[i] - col_offset;
+      if (j < 0 || j >= N || j == t) continue;
+      corr += rank_contrib(kFilterScore, j, st, t) - rank_contrib(row[j], j, st, t);
+    }
+  }
+  cnt = warp_sum_i(cnt);
+  corr = warp_sum_i(corr);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) red[wid] = cnt;
+  __syncthreads();
+  int tot = 0;
+  if (threadIdx.x == 0) { for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += red[i]; }
+  __syncthreads();
+  if (lane == 0) red[wid] = corr;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tc = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tc += red[i];
+    raw_count[b] = tot;
+    if (filt_count) filt_count[b] = tot + tc;
+  }
+}
+
+// target_score[b] = S[b, t_b] read from the dense matrix (exactly the value the counts compare against)
+__global__ void gather_target_score_kernel(const float* __restrict__ S, size_t ld, int B, int N,
+                                           const int64_t* __restrict__ triples, int target_col, int col_offset,
+                                           float* __restrict__ target_score) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int t = (int)triples[3 * (size_t)b + target_col] - col_offset;
+  if (t >= 0 && t < N) target_score[b] = S[(size_t)b * ld + t];
+}
+
+__global__ void counts_to_ranks_kernel(const int* __restrict__ raw_count, const int* __restrict__ filt_count, int B,
+                                       int64_t* __restrict__ rank, int64_t* __restrict__ filt_rank) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  rank[b] = (int64_t)raw_count[b] + 1;
+  if (filt_rank) filt_rank[b] = (int64_t)(filt_count ? filt_count[b] : raw_count[b]) + 1;
+}
+
+// Optionally reproduce the reference's in-place side effect: score[b][ans \ {t}] = -1e7 (utils.py:60).
+__global__ void apply_filter_kernel(float* __restrict__ S, size_t ld, int B, int N, const int64_t* __restrict__ triples,
+                                    int target_col, const int* __restrict__ filt_ptr, const int* __restrict__ filt_idx,
+                                    int col_offset) {
+  const int b = blockIdx.x;
+  const int t = (int)triples[3 * (size_t)b + target_col] - col_offset;
+  for (int i = filt_ptr[b] + threadIdx.x; i < filt_ptr[b + 1]; i += blockDim.x) {
+    const int j = filt_idx[i] - col_offset;
+    if (j >= 0 && j < N && j != t) S[(size_t)b * ld + j] = kFilterScore;
+  }
+}
+
+int gather_target_score(const float* S, int64_t ld, int B, int N, const int64_t* triples, int target_col, int col_offset,
+                        float* target_score, cudaStream_t st) {
+  if (!S || !triples || !target_score) { set_last_error("gather_target_score: null pointer"); return REGCN_ERR_NULL; }
+  if (B <= 0) return REGCN_OK;
+  gather_target_score_kernel<<<(B + 255) / 256, 256, 0, st>>>(S, (size_t)ld, B, N, triples, target_col, col_offset, target_score);
+  return check_launch("gather_target_score");
+}
+
+int rank_count(const float* S, int64_t ld, int B, int N, const int64_t* triples, int target_col, const int* filt_ptr,
+               const int* filt_idx, int col_offset, const float* target_score, int* raw_count, int* filt_count,
+               cudaStream_t st) {
+  if (!S || !triples || !target_score || !raw_count || (filt_ptr && !filt_idx)) { set_last_error("rank_count: null pointer"); return REGCN_ERR_NULL; }
+  if (target_col < 0 || target_col > 2 || ld < N) { set_last_error("rank_count: bad target_col=%d or ld", target_col); return REGCN_ERR_DIM; }
+  if (B <= 0) return REGCN_OK;
+  rank_rows_kernel<<<B, 256, 0, st>>>(S, (size_t)ld, B, N, triples, target_col, filt_ptr, filt_idx, col_offset, raw_count,
+                                      filt_count, const_cast<float*>(target_score));
+  return check_launch("rank_count");
+}
+
+int counts_to_ranks(const int* raw_count, const int* filt_count, int B, int64_t* rank, int64_t* filt_rank, cudaStream_t st) {
+  if (!raw_count || !rank) { set_last_error("counts_to_ranks: null pointer"); return REGCN_ERR_NULL; }
+  if (B <= 0) return REGCN_OK;
+  counts_to_ranks_kernel<<<(B + 255) / 256, 256, 0, st>>>(raw_count, filt_count, B, rank, filt_rank);
+  return check_launch("counts_to_ranks");
+}
+
+int apply_filter(float* S, int64_t ld, int B, int N, const int64_t* triples, int target_col, const int* filt_ptr,
+                 const int* filt_idx, int col_offset, cudaStream_t st) {
+  if (!S || !triples || !filt_ptr || !filt_idx) { set_last_error("apply_filter: null pointer"); return REGCN_ERR_NULL; }
+  if (B <= 0) return REGCN_OK;
+  apply_filter_kernel<<<B, 128, 0, st>>>(S, (size_t)ld, B, N, triples, target_col, filt_ptr, filt_idx, col_offset);
+  return check_launch("apply_filter");
+}
+
+}  // namespace regcn

@@ -1,0 +1,138 @@
+"""SnapshotGraph: the device-resident edge index of one history snapshot.
+
+Replaces the DGL graph object produced by the reference's `build_sub_graph`
+(rgcn/utils.py:100-134) and the python `r2e` loop (rgcn/utils.py:78-97).  The index is built by one
+C-ABI call (`regcn_csr_build`) and kept in HBM as CSR-by-destination plus a relation->entity CSR; the
+attributes the reference's modules read from `g` (`ndata['id'|'norm']`, `edata['type']`, `in_degrees`,
+`number_of_nodes`, `uniq_r`, `r_to_e`, `r_len`, `to`) are provided as lazily materialised views so
+code written against the reference keeps working.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import call, ptr
+
+I32 = torch.int32
+AGG_CHUNK = 256  # must match csrc/graph_build.cu kAggChunk
+
+
+class _Frame(dict):
+    pass
+
+
+class SnapshotGraph:
+    def __init__(self, num_nodes, num_rels, triples_dev):
+        self.num_nodes = int(num_nodes)
+        self.num_rels = int(num_rels)
+        self.triples = triples_dev  # (T,3) int64 on the device, reference layout
+        self.device = triples_dev.device
+        T = int(triples_dev.shape[0])
+        N, R, E = self.num_nodes, self.num_rels, 2 * T
+        self.num_edges = E
+        dev = self.device
+
+        def i32(n):
+            return torch.empty(max(int(n), 1), device=dev, dtype=I32)
+
+        self.src, self.dst, self.etype = i32(E), i32(E), i32(E)
+        self.indeg = i32(N)
+        self.norm = torch.empty(N, device=dev, dtype=torch.float32)
+        self.rowptr = i32(N + 1)
+        self.src_sorted, self.etype_sorted, self.eperm = i32(E), i32(E), i32(E)
+        self.vptr, self.sptr = i32(N + 1), i32(N + 1)
+        self.vrow_row = i32(N + E // AGG_CHUNK + 1)
+        self.rel_rowptr = i32(R + 1)
+        self.rel_ents = i32(E)
+        counts = torch.zeros(4, device=dev, dtype=I32)
+        ws_bytes = _lib.load().regcn_csr_build_workspace_bytes(T, N, R)
+        ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+        call("regcn_csr_build", ptr(triples_dev), T, N, R, ptr(self.src), ptr(self.dst), ptr(self.etype),
+             ptr(self.indeg), ptr(self.norm), ptr(self.rowptr), ptr(self.src_sorted), ptr(self.etype_sorted),
+             ptr(self.eperm), ptr(self.vptr), ptr(self.sptr), ptr(self.vrow_row), ptr(self.rel_rowptr),
+             ptr(self.rel_ents), ptr(counts), ptr(ws), ws_bytes)
+        c = counts.tolist()  # the one host sync of graph construction
+        self.n_vrows, self.n_split_chunks, self.n_rel_ents, self.max_hub_degree = c
+        self._ndata = None
+        self._edata = None
+        self._r2e = None
+
+    # ---- the slice of the DGL surface the reference modules use -----------------
+    def number_of_nodes(self):
+        return self.num_nodes
+
+    def number_of_edges(self):
+        return self.num_edges
+
+    def in_degrees(self, v=None):
+        deg = self.indeg[: self.num_nodes].long()
+        if v is None or isinstance(v, range):
+            return deg
+        return deg[torch.as_tensor(v, device=self.device, dtype=torch.long)]
+
+    def to(self, device):
+        return self
+
+    @property
+    def ndata(self):
+        if self._ndata is None:
+            f = _Frame()
+            f["id"] = torch.arange(self.num_nodes, device=self.device, dtype=torch.long).view(-1, 1)
+            f["norm"] = self.norm.view(-1, 1)
+            self._ndata = f
+        return self._ndata
+
+    @property
+    def edata(self):
+        if self._edata is None:
+            f = _Frame()
+            f["type"] = self.etype[: self.num_edges].long()
+            self._edata = f
+        return self._edata
+
+    def edges(self):
+        return self.src[: self.num_edges].long(), self.dst[: self.num_edges].long()
+
+    def _host_r2e(self):
+        if self._r2e is None:
+            R = self.num_rels
+            rp = self.rel_rowptr.cpu().numpy().astype(np.int64)
+            ents = self.rel_ents[: self.n_rel_ents].cpu().numpy().astype(np.int64)
+            present = np.nonzero(rp[1:] > rp[:-1])[0]
+            uniq_r = np.concatenate((present, present + R))
+            r_len, e_idx, idx = [], [], 0
+            for r in uniq_r:
+                b, e = rp[r % R], rp[r % R + 1]
+                r_len.append((idx, idx + int(e - b)))
+                e_idx.extend(ents[b:e].tolist())
+                idx += int(e - b)
+            self._r2e = (uniq_r, r_len, torch.as_tensor(e_idx, dtype=torch.long, device=self.device))
+        return self._r2e
+
+    @property
+    def uniq_r(self):
+        return self._host_r2e()[0]
+
+    @property
+    def r_len(self):
+        return self._host_r2e()[1]
+
+    @property
+    def r_to_e(self):
+        return self._host_r2e()[2]
+
+
+def build_sub_graph(num_nodes, num_rels, triples, use_cuda=True, gpu=0):
+    """Drop-in for rgcn/utils.py:100 `build_sub_graph(num_nodes, num_rels, triples, use_cuda, gpu)`.
+
+    `triples` is the reference's (T,3) int numpy array (or a tensor).  The index is always built on
+    the device (`use_cuda=False` is refused: the product path has no CPU implementation)."""
+    if not use_cuda:
+        raise RuntimeError("regcn_b200.build_sub_graph: use_cuda=False is not supported (no CPU path)")
+    _lib.require_device()
+    dev = torch.device("cuda", gpu) if isinstance(gpu, int) else torch.device(gpu)
+    if isinstance(triples, torch.Tensor):
+        t = triples.to(device=dev, dtype=torch.int64)
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(np.asarray(triples, dtype=np.int64)).reshape(-1, 3)).to(dev)
+    return SnapshotGraph(num_nodes, num_rels, t.contiguous())

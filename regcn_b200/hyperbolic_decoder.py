@@ -1,0 +1,298 @@
+"""Hyperbolic decoders with the reference's signatures and parameter names on the sm_100a kernels:
+HyperbolicConvTransE / ConvTransR (hyperbolic_src/hyperbolic_decoder.py:310-510), HyperbolicMuRP (:647-817),
+HyperbolicRotH (:931-1138) and HyperbolicRotHRel (:1141-1280).
+
+The all-entity hyperbolic score (:89-179, proxy-distance branch) is evaluated in norm/dot form: one dense
+contraction <q_b, e_n> followed by an epilogue that needs only |q_b|^2 and |e_n|^2, instead of
+the reference's B*N*d Mobius-add temporaries.
+Not implemented in this round (raise): entity Euclidean bias, relation-specific curvature (both default off,
+hyperbolic_main.py:803-810), the streaming-CE `loss` heads (training), AttH / MuRPRel.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.nn.parameter import Parameter
+
+from . import ops
+from .decoder import _fold_bn
+
+SCORE_SCALE_EPSILON = 1e-6
+
+
+class _HypConvBase(nn.Module):
+    def __init__(self, n_bias, embedding_dim, c, input_dropout, hidden_dropout, feature_map_dropout, channels,
+                 kernel_size):
+        super().__init__()
+        self.embedding_dim = embedding_dim
+        self.c = c
+        self.inp_drop = nn.Dropout(input_dropout)
+        self.hidden_drop = nn.Dropout(hidden_dropout)
+        self.feature_map_drop = nn.Dropout(feature_map_dropout)
+        self.conv1 = nn.Conv1d(2, channels, kernel_size, stride=1, padding=int(math.floor(kernel_size / 2)))
+        self.bn0 = nn.BatchNorm1d(2)
+        self.bn1 = nn.BatchNorm1d(channels)
+        self.bn2 = nn.BatchNorm1d(embedding_dim)
+        self.fc = nn.Linear(embedding_dim * channels, embedding_dim)
+        self.register_parameter('b', Parameter(torch.zeros(n_bias)))
+
+    def _tower(self, ent_act, second, triplets, col0, col1, always_bn2):
+        if self.training:
+            raise NotImplementedError("regcn_b200 decoders: training mode needs the backward kernels; call .eval()")
+        B = len(triplets)
+        feats = ops.convtranse_features(ent_act, second, triplets, col0, col1, _fold_bn(self.bn0),
+                                        self.conv1.weight.detach(), self.conv1.bias.detach(), _fold_bn(self.bn1))
+        split_k = max(1, min(16, (148 * 2) // max(1, ((B + 127) // 128) * ((self.fc.out_features + 127) // 128))))
+        x = ops.gemm(feats, self.fc.weight.detach(), trans_b=True, bias=self.fc.bias.detach(), split_k=split_k)
+        if always_bn2 or B > 1:
+            s, t = _fold_bn(self.bn2)
+            ops.affine_relu_(x, s, t, relu=True)
+        else:
+            ops.affine_relu_(x, None, None, relu=True)
+        return x
+
+
+class HyperbolicConvTransE(_HypConvBase):
+    """hyperbolic_decoder.py:310-413."""
+
+    def __init__(self, num_entities, embedding_dim, c=0.01, input_dropout=0.0, hidden_dropout=0.0,
+                 feature_map_dropout=0.0, channels=50, kernel_size=3):
+        super().__init__(num_entities, embedding_dim, c, input_dropout, hidden_dropout, feature_map_dropout, channels,
+                         kernel_size)
+        self.num_entities = num_entities
+
+    @torch.no_grad()
+    def forward(self, entity_embedding, rel_embedding, triplets, mode="train"):
+        et = ops.row_map(entity_embedding, ops.ROW_LEAKY_TANH_LOG0, c=self.c)
+        q = self._tower(et, rel_embedding.contiguous(), triplets, 0, 1, always_bn2=False)
+        return ops.gemm(q, et, trans_b=True, bias=self.b.detach())
+
+
+class HyperbolicConvTransR(_HypConvBase):
+    """hyperbolic_decoder.py:416-510."""
+
+    def __init__(self, num_relations, embedding_dim, c=0.01, input_dropout=0.0, hidden_dropout=0.0,
+                 feature_map_dropout=0.0, channels=50, kernel_size=3):
+        super().__init__(num_relations * 2, embedding_dim, c, input_dropout, hidden_dropout, feature_map_dropout,
+                         channels, kernel_size)
+        self.num_relations = num_relations
+
+    @torch.no_grad()
+    def forward(self, entity_embedding, rel_embedding, triplets, mode="train"):
+        et = ops.row_map(entity_embedding, ops.ROW_LEAKY_TANH_LOG0, c=self.c)
+        q = self._tower(et, et, triplets, 0, 2, always_bn2=True)
+        return ops.gemm(q, rel_embedding.contiguous(), trans_b=True, bias=self.b.detach())
+
+
+class _HypDistBase(nn.Module):
+    """Shared scoring tail of the distance decoders: scale*(margin - |(-q)(+)e|^2) + bias  (:164-172)."""
+
+    def _score_scale(self):
+        return F.softplus(self.score_scale_raw) + SCORE_SCALE_EPSILON
+
+    def _scale_margin(self):
+        return torch.stack((self._score_scale().detach(), self.score_margin.detach())).float().contiguous()
+
+    def _unsupported_flags(self):
+        if getattr(self, "use_entity_euclidean_bias", False) or getattr(self, "use_relation_specific_curvature", False):
+            raise NotImplementedError("entity Euclidean bias / relation-specific curvature are not implemented yet "
+                                      "(default-off flags, SURVEY.md 8f-3)")
+        if self.training and self.dropout.p > 0:
+            raise NotImplementedError("regcn_b200 decoders: training mode needs the backward kernels; call .eval()")
+
+    def _dist_scores(self, query, q_sumsq, cand, bias):
+        e_sumsq = ops.row_sumsq(cand)
+        S = ops.gemm(query, cand, trans_b=True)                                  # <q_b, e_n>
+        return ops.hyp_score_epilogue_(S, q_sumsq, e_sumsq, bias, None, self.c, self._scale_margin())
+
+
+class HyperbolicRotH(_HypDistBase):
+    """hyperbolic_decoder.py:931-1138."""
+
+    def __init__(self, num_entities, num_relations, embedding_dim, c=0.01, dropout=0.0, query_chunk_size=128,
+                 candidate_chunk_size=256, init_scale=1e-3, score_scale_init=1.0, score_margin_init=1.0,
+                 use_entity_euclidean_bias=False, use_relation_specific_curvature=False):
+        super().__init__()
+        assert embedding_dim % 2 == 0, "embedding_dim must be even (required for Givens rotation)"
+        self.num_entities = num_entities
+        self.embedding_dim = embedding_dim
+        self.half_dim = embedding_dim // 2
+        self.c = c
+        self.query_chunk_size = query_chunk_size
+        self.candidate_chunk_size = candidate_chunk_size
+        self.num_relations = num_relations
+        self.use_entity_euclidean_bias = use_entity_euclidean_bias
+        self.use_relation_specific_curvature = use_relation_specific_curvature
+        self.rot_proj = nn.Linear(embedding_dim, self.half_dim)
+        self.trans_proj = nn.Linear(embedding_dim, embedding_dim)
+        self.reshape_fc1 = nn.Linear(embedding_dim, embedding_dim)
+        self.reshape_fc2 = nn.Linear(embedding_dim, embedding_dim)
+        for lin in (self.rot_proj, self.trans_proj, self.reshape_fc1, self.reshape_fc2):
+            nn.init.uniform_(lin.weight, -init_scale, init_scale)
+            nn.init.zeros_(lin.bias)
+        if use_entity_euclidean_bias:
+            self.entity_bias = nn.Parameter(torch.zeros(num_entities))
+        else:
+            self.register_parameter("entity_bias", None)
+        if use_relation_specific_curvature:
+            self.rel_curvature_raw = nn.Parameter(torch.zeros(num_relations))
+        else:
+            self.register_parameter("rel_curvature_raw", None)
+        self.rel_curvature_max = float(c) if use_relation_specific_curvature else None
+        self.score_scale_raw = nn.Parameter(torch.tensor(float(score_scale_init)))
+        self.score_margin = nn.Parameter(torch.tensor(float(score_margin_init)))
+        self.dropout = nn.Dropout(dropout)
+
+    @torch.no_grad()
+    def query(self, entity_embedding, rel_embedding, triplets):
+        """K12: (B,d) query points and their squared norms."""
+        self._unsupported_flags()
+        s_tan = ops.gather_log0(entity_embedding, triplets, 0, True, self.c)                     # :1066-1070
+        h1 = ops.gemm(s_tan, self.reshape_fc1.weight.detach(), trans_b=True, bias=self.reshape_fc1.bias.detach())
+        ops.affine_relu_(h1, None, None, relu=True)
+        ops.gemm(h1, self.reshape_fc2.weight.detach(), trans_b=True, bias=self.reshape_fc2.bias.detach(),
+                 out=s_tan, accumulate=True)                                                      # x + fc2(relu(fc1 x))
+        rel = rel_embedding.contiguous()
+        ang = ops.gemm(rel, self.rot_proj.weight.detach(), trans_b=True, bias=self.rot_proj.bias.detach())      # (2R, d/2)
+        trans = ops.gemm(rel, self.trans_proj.weight.detach(), trans_b=True, bias=self.trans_proj.bias.detach())  # (2R, d)
+        return ops.hyp_query(s_tan, ang, trans, None, triplets, 0, self.c)
+
+    @torch.no_grad()
+    def forward(self, entity_embedding, rel_embedding, triplets, mode="train"):
+        q, qss = self.query(entity_embedding, rel_embedding, triplets)
+        return self._dist_scores(q, qss, entity_embedding.contiguous(), None)
+
+    def loss(self, *a, **k):
+        raise NotImplementedError("streaming-CE training head is SURVEY.md 8f rank 1 (next)")
+
+
+class HyperbolicMuRP(_HypDistBase):
+    """hyperbolic_decoder.py:647-817."""
+
+    def __init__(self, num_entities, num_relations, embedding_dim, c=0.01, dropout=0.0, query_chunk_size=128,
+                 candidate_chunk_size=256, init_scale=1e-3, score_scale_init=1.0, score_margin_init=1.0,
+                 use_entity_euclidean_bias=False, use_relation_specific_curvature=False):
+        super().__init__()
+        self.num_entities = num_entities
+        self.embedding_dim = embedding_dim
+        self.c = c
+        self.query_chunk_size = query_chunk_size
+        self.candidate_chunk_size = candidate_chunk_size
+        self.num_relations = num_relations
+        self.use_entity_euclidean_bias = use_entity_euclidean_bias
+        self.use_relation_specific_curvature = use_relation_specific_curvature
+        self.rot_proj = nn.Linear(embedding_dim, embedding_dim)
+        self.trans_proj = nn.Linear(embedding_dim, embedding_dim)
+        for lin in (self.rot_proj, self.trans_proj):
+            nn.init.uniform_(lin.weight, -init_scale, init_scale)
+            nn.init.zeros_(lin.bias)
+        if use_entity_euclidean_bias:
+            self.entity_bias = nn.Parameter(torch.zeros(num_entities))
+        else:
+            self.register_parameter("entity_bias", None)
+        if use_relation_specific_curvature:
+            self.rel_curvature_raw = nn.Parameter(torch.zeros(num_relations))
+        else:
+            self.register_parameter("rel_curvature_raw", None)
+        self.rel_curvature_max = float(c) if use_relation_specific_curvature else None
+        self.score_scale_raw = nn.Parameter(torch.tensor(float(score_scale_init)))
+        self.score_margin = nn.Parameter(torch.tensor(float(score_margin_init)))
+        self.dropout = nn.Dropout(dropout)
+
+    @torch.no_grad()
+    def query(self, entity_embedding, rel_embedding, triplets):
+        self._unsupported_flags()
+        s_tan = ops.gather_log0(entity_embedding, triplets, 0, True, self.c)
+        rel = rel_embedding.contiguous()
+        diag = ops.gemm(rel, self.rot_proj.weight.detach(), trans_b=True, bias=self.rot_proj.bias.detach())
+        trans = ops.gemm(rel, self.trans_proj.weight.detach(), trans_b=True, bias=self.trans_proj.bias.detach())
+        return ops.hyp_query(s_tan, diag, trans, None, triplets, 1, self.c)
+
+    @torch.no_grad()
+    def forward(self, entity_embedding, rel_embedding, triplets, mode="train"):
+        q, qss = self.query(entity_embedding, rel_embedding, triplets)
+        return self._dist_scores(q, qss, entity_embedding.contiguous(), None)
+
+    def loss(self, *a, **k):
+        raise NotImplementedError("streaming-CE training head is SURVEY.md 8f rank 1 (next)")
+
+
+class HyperbolicRotHRel(_HypDistBase):
+    """hyperbolic_decoder.py:1141-1280."""
+
+    def __init__(self, num_relations, embedding_dim, c=0.01, dropout=0.0, query_chunk_size=128,
+                 candidate_chunk_size=256, init_scale=1e-3, score_scale_init=1.0, score_margin_init=1.0):
+        super().__init__()
+        assert embedding_dim % 2 == 0, "embedding_dim must be even (required for Givens rotation)"
+        self.num_relations = num_relations
+        self.embedding_dim = embedding_dim
+        self.half_dim = embedding_dim // 2
+        self.c = c
+        self.query_chunk_size = query_chunk_size
+        self.candidate_chunk_size = candidate_chunk_size
+        self.global_rot = nn.Parameter(torch.Tensor(self.half_dim))
+        nn.init.uniform_(self.global_rot, -math.pi, math.pi)
+        self.reshape_fc1 = nn.Linear(embedding_dim, embedding_dim)
+        self.reshape_fc2 = nn.Linear(embedding_dim, embedding_dim)
+        for lin in (self.reshape_fc1, self.reshape_fc2):
+            nn.init.uniform_(lin.weight, -init_scale, init_scale)
+            nn.init.zeros_(lin.bias)
+        self.rel_bias = nn.Parameter(torch.zeros(num_relations * 2))
+        self.score_scale_raw = nn.Parameter(torch.tensor(float(score_scale_init)))
+        self.score_margin = nn.Parameter(torch.tensor(float(score_margin_init)))
+        self.dropout = nn.Dropout(dropout)
+
+    @torch.no_grad()
+    def forward(self, entity_embedding, rel_embedding, triplets, mode="train"):
+        self._unsupported_flags()
+        E = entity_embedding.contiguous()
+        s_tan = ops.gather_log0(E, triplets, 0, False, self.c)
+        h1 = ops.gemm(s_tan, self.reshape_fc1.weight.detach(), trans_b=True, bias=self.reshape_fc1.bias.detach())
+        ops.affine_relu_(h1, None, None, relu=True)
+        ops.gemm(h1, self.reshape_fc2.weight.detach(), trans_b=True, bias=self.reshape_fc2.bias.detach(), out=s_tan,
+                 accumulate=True)
+        q, qss = ops.hyp_query(s_tan, self.global_rot.detach(), None, E, triplets, 2, self.c)
+        rel_hyp, rss = ops.row_map(rel_embedding.contiguous(), ops.ROW_EXP0, c=self.c, want_sumsq=True)
+        S = ops.gemm(q, rel_hyp, trans_b=True)
+        return ops.hyp_score_epilogue_(S, qss, rss, self.rel_bias.detach(), None, self.c, self._scale_margin())
+
+    def loss(self, *a, **k):
+        raise NotImplementedError("streaming-CE training head is SURVEY.md 8f rank 1 (next)")
+
+
+class HyperbolicMuRPRel(_HypDistBase):
+    """hyperbolic_decoder.py:820-928: query = exp_0(log_0(h_s) W_s + log_0(h_o) W_o), scored against exp_0(rel)
+    with no scale / margin (score = -|(-q)(+)r|^2 + rel_bias)."""
+
+    def __init__(self, num_relations, embedding_dim, c=0.01, dropout=0.0, query_chunk_size=128,
+                 candidate_chunk_size=256):
+        super().__init__()
+        self.num_relations = num_relations
+        self.embedding_dim = embedding_dim
+        self.c = c
+        self.query_chunk_size = query_chunk_size
+        self.candidate_chunk_size = candidate_chunk_size
+        self.W_s = nn.Parameter(torch.Tensor(embedding_dim, embedding_dim))
+        nn.init.xavier_uniform_(self.W_s)
+        self.W_o = nn.Parameter(torch.Tensor(embedding_dim, embedding_dim))
+        nn.init.xavier_uniform_(self.W_o)
+        self.rel_bias = nn.Parameter(torch.zeros(num_relations * 2))
+        self.dropout = nn.Dropout(dropout)
+
+    @torch.no_grad()
+    def forward(self, entity_embedding, rel_embedding, triplets, mode="train"):
+        self._unsupported_flags()
+        E = entity_embedding.contiguous()
+        s_tan = ops.gather_log0(E, triplets, 0, False, self.c)
+        o_tan = ops.gather_log0(E, triplets, 2, False, self.c)
+        q_tan = ops.gemm(s_tan, self.W_s.detach())
+        ops.gemm(o_tan, self.W_o.detach(), out=q_tan, accumulate=True)
+        q, qss = ops.row_map(q_tan, ops.ROW_EXP0, c=self.c, want_sumsq=True)
+        rel_hyp, rss = ops.row_map(rel_embedding.contiguous(), ops.ROW_EXP0, c=self.c, want_sumsq=True)
+        S = ops.gemm(q, rel_hyp, trans_b=True)
+        sm = torch.tensor([1.0, 0.0], device=S.device, dtype=torch.float32)
+        return ops.hyp_score_epilogue_(S, qss, rss, self.rel_bias.detach(), None, self.c, sm)
+
+    def loss(self, *a, **k):
+        raise NotImplementedError("streaming-CE training head is SURVEY.md 8f rank 1 (next)")

@@ -1,0 +1,217 @@
+"""HyperbolicRecurrentRGCN with the reference's constructor / forward / predict signatures and state-dict names
+(hyperbolic_src/hyperbolic_model.py:157-1088), evolving snapshots on the sm_100a kernels.
+
+Per history snapshot (hyperbolic_model.py:797-888):
+  tangent prep (log_0 h, |h|)  -> relation mean-pool (K2) -> relation GRU (K3)
+  -> 2 x {HyperbolicUnionRGCNLayer | LorentzRGCNLayer}  (K4/K7 aggregate + node GEMMs + K5 combine with exp_0)
+  -> tangent-space time gate + projection + residual radius evolution (K9 + K8, one fused row kernel).
+The five unconditional `.item()` host syncs of the reference's TemporalRadiusEvolution (hyperbolic_ops.py:426-434)
+do not exist here.  Not in this round: EST add-ons, FHNN/HGAT encoders, AttH decoders, geoopt ManifoldParameter,
+learnable curvature, the training losses (all default-off or SURVEY.md 8f "next").
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .hyperbolic_decoder import (HyperbolicConvTransE, HyperbolicConvTransR, HyperbolicMuRP, HyperbolicMuRPRel,
+                                 HyperbolicRotH, HyperbolicRotHRel)
+from .hyperbolic_layers import HyperbolicRGCNCell, LorentzRGCNCell
+from .layers import RGCNBlockLayer
+
+
+class TemporalRadiusEvolution(nn.Module):
+    """Parameter holder for hyperbolic_ops.py:364-435 (the arithmetic is fused into the time-gate kernel)."""
+
+    def __init__(self, dim, c=0.01, epsilon=0.1, anchor_beta=1.0):
+        super().__init__()
+        if anchor_beta < 0.0 or anchor_beta > 1.0:
+            raise ValueError("anchor_beta must be in [0, 1]")
+        self.dim, self.c, self.epsilon, self.anchor_beta = dim, c, epsilon, float(anchor_beta)
+        self.radius_mlp = nn.Linear(dim, 1)
+        nn.init.xavier_uniform_(self.radius_mlp.weight, gain=0.1)
+        nn.init.zeros_(self.radius_mlp.bias)
+        self.last_evolution_stats = None
+
+    def get_evolution_stats(self):
+        return self.last_evolution_stats
+
+
+class HyperbolicRecurrentRGCN(nn.Module):
+    def __init__(self, decoder_name, encoder_name, num_ents, num_rels, num_static_rels, num_words, h_dim, opn,
+                 sequence_len, num_bases=-1, num_hidden_layers=1, dropout=0, c=0.01, self_loop=False,
+                 skip_connect=False, layer_norm=False, input_dropout=0, hidden_dropout=0, feat_dropout=0, weight=1,
+                 discount=0, angle=0, use_static=False, entity_prediction=False, relation_prediction=False,
+                 use_cuda=False, gpu=0, analysis=False, learn_curvature=False, use_residual_evolution=True,
+                 radius_target=None, radius_lambda=0.02, radius_min=0.5, radius_max=3.0, radius_epsilon=0.1,
+                 radius_anchor_beta=1.0, curvature_min=1e-4, curvature_max=1e-1, num_heads=4, query_chunk_size=128,
+                 candidate_chunk_size=256, hyp_init_scale=1e-3, hyp_score_scale_init=1.0, hyp_score_margin_init=1.0,
+                 use_entity_euclidean_bias=False, use_relation_specific_curvature=False, use_est=False,
+                 est_state_alpha=0.2, est_encoder="gru", use_time_aware_negative=False, radius_msg_gamma=1.0):
+        super().__init__()
+        if learn_curvature or use_est or use_time_aware_negative:
+            raise NotImplementedError("learnable curvature / EST add-ons are out of this round's scope (default-off flags)")
+        self.decoder_name, self.encoder_name = decoder_name, encoder_name
+        self.num_rels, self.num_ents = num_rels, num_ents
+        self.opn = opn
+        self.num_words, self.num_static_rels = num_words, num_static_rels
+        self.sequence_len = sequence_len
+        self.h_dim = h_dim
+        self.layer_norm = layer_norm
+        self.h = None
+        self.run_analysis = analysis
+        self.weight, self.discount, self.use_static, self.angle = weight, discount, use_static, angle
+        self.relation_prediction, self.entity_prediction = relation_prediction, entity_prediction
+        self.gpu = gpu
+        self.learn_curvature = learn_curvature
+        self.use_residual_evolution = use_residual_evolution
+        self.radius_lambda = radius_lambda
+        self.radius_min, self.radius_max = radius_min, radius_max
+        self.radius_anchor_beta = radius_anchor_beta
+        self.curvature_min, self.curvature_max = curvature_min, curvature_max
+        self.num_heads = num_heads
+        self.query_chunk_size, self.candidate_chunk_size = query_chunk_size, candidate_chunk_size
+        self.use_entity_euclidean_bias = use_entity_euclidean_bias
+        self.use_relation_specific_curvature = use_relation_specific_curvature
+        self.radius_msg_gamma = radius_msg_gamma
+        self.use_est = use_est
+        self._c_float = float(c)
+
+        self.register_buffer('c', torch.tensor(c))
+        self.dynamic_emb = nn.Parameter(torch.Tensor(num_ents, h_dim))
+        nn.init.normal_(self.dynamic_emb, std=1.0)
+        self.emb_rel = nn.Parameter(torch.Tensor(num_rels * 2, h_dim))
+        nn.init.xavier_normal_(self.emb_rel)
+        self.temporal_radius_evolution = TemporalRadiusEvolution(h_dim, c=c, epsilon=radius_epsilon,
+                                                                 anchor_beta=radius_anchor_beta)
+        self.w1 = nn.Parameter(torch.Tensor(h_dim, h_dim))
+        nn.init.xavier_normal_(self.w1)
+        self.w2 = nn.Parameter(torch.Tensor(h_dim, h_dim))
+        nn.init.xavier_normal_(self.w2)
+        if self.use_static:
+            self.words_emb = nn.Parameter(torch.Tensor(num_words, h_dim))
+            nn.init.xavier_normal_(self.words_emb)
+            self.static_rgcn_layer = RGCNBlockLayer(h_dim, h_dim, num_static_rels * 2, num_bases, activation=F.rrelu,
+                                                    dropout=dropout, self_loop=False, skip_connect=False)
+            self.static_loss = nn.MSELoss()
+        self.loss_r = nn.CrossEntropyLoss()
+        self.loss_e = nn.CrossEntropyLoss()
+
+        if encoder_name == "hyperbolic_uvrgcn":
+            self.rgcn = HyperbolicRGCNCell(num_ents, h_dim, h_dim, num_rels * 2, num_bases, num_hidden_layers, dropout,
+                                           c=c, self_loop=self_loop, skip_connect=skip_connect,
+                                           encoder_name=encoder_name, rel_emb=self.emb_rel, use_cuda=use_cuda,
+                                           analysis=analysis, radius_msg_gamma=radius_msg_gamma)
+        elif encoder_name == "lgcn":
+            self.rgcn = LorentzRGCNCell(num_ents, h_dim, h_dim, num_rels * 2, num_bases, num_hidden_layers, dropout,
+                                        c=c, self_loop=self_loop, skip_connect=skip_connect, encoder_name=encoder_name,
+                                        rel_emb=self.emb_rel, use_cuda=use_cuda, analysis=analysis)
+        else:
+            raise NotImplementedError(f"Encoder '{encoder_name}' not implemented here (hyperbolic_uvrgcn, lgcn)")
+
+        self.time_gate_weight = nn.Parameter(torch.Tensor(h_dim, h_dim))
+        nn.init.xavier_uniform_(self.time_gate_weight, gain=nn.init.calculate_gain('relu'))
+        self.time_gate_bias = nn.Parameter(torch.zeros(h_dim))
+        self.relation_gru = nn.GRUCell(h_dim * 2, h_dim)
+
+        dist_kw = dict(c=c, dropout=input_dropout, query_chunk_size=query_chunk_size,
+                       candidate_chunk_size=candidate_chunk_size)
+        ent_kw = dict(init_scale=hyp_init_scale, score_scale_init=hyp_score_scale_init,
+                      score_margin_init=hyp_score_margin_init, use_entity_euclidean_bias=use_entity_euclidean_bias,
+                      use_relation_specific_curvature=use_relation_specific_curvature)
+        if decoder_name == "hyperbolic_convtranse":
+            self.decoder_ob = HyperbolicConvTransE(num_ents, h_dim, c=c, input_dropout=input_dropout,
+                                                   hidden_dropout=hidden_dropout, feature_map_dropout=feat_dropout)
+            self.rdecoder = HyperbolicConvTransR(num_rels, h_dim, c=c, input_dropout=input_dropout,
+                                                 hidden_dropout=hidden_dropout, feature_map_dropout=feat_dropout)
+        elif decoder_name == "murp":
+            self.decoder_ob = HyperbolicMuRP(num_ents, num_rels * 2, h_dim, **dist_kw, **ent_kw)
+            self.rdecoder = HyperbolicMuRPRel(num_rels, h_dim, **dist_kw)
+        elif decoder_name == "roth":
+            self.decoder_ob = HyperbolicRotH(num_ents, num_rels * 2, h_dim, **dist_kw, **ent_kw)
+            self.rdecoder = HyperbolicRotHRel(num_rels, h_dim, **dist_kw, init_scale=hyp_init_scale,
+                                              score_scale_init=hyp_score_scale_init,
+                                              score_margin_init=hyp_score_margin_init)
+        else:
+            raise NotImplementedError(f"Decoder '{decoder_name}' not implemented here (hyperbolic_convtranse, murp, roth)")
+
+        if radius_target is None:
+            target = torch.full((num_ents,), 0.5 * (radius_min + radius_max))
+        else:
+            target = torch.as_tensor(radius_target, dtype=torch.float)
+        self.register_buffer("radius_target", target)
+        self.radius_static = nn.Parameter(self.radius_target.clone())
+
+    def get_curvature(self):
+        return self.c
+
+    def _relation_step(self, g, ht, h0_prev):
+        cell, d = self.relation_gru, self.h_dim
+        x_mean = ops.rel_mean_pool(ht, g)
+        w_ih = cell.weight_ih.detach()
+        gi = ops.gemm(self.emb_rel.detach(), w_ih[:, :d], trans_b=True, bias=cell.bias_ih.detach())
+        ops.gemm(x_mean, w_ih[:, d:], trans_b=True, out=gi, accumulate=True)
+        gh = ops.gemm(h0_prev, cell.weight_hh.detach(), trans_b=True, bias=cell.bias_hh.detach())
+        return ops.gru_gate(gi, gh, h0_prev, self.layer_norm)
+
+    @torch.no_grad()
+    def forward(self, g_list, static_graph, use_cuda):
+        gate_list, degree_list = [], []
+        c = self._c_float
+        rs_raw = self.radius_static.detach()
+        if self.use_static and static_graph is not None:
+            static_graph = static_graph.to(self.gpu)
+            static_graph.ndata['h'] = torch.cat((self.dynamic_emb, self.words_emb), dim=0).detach()
+            self.static_rgcn_layer(static_graph, [])
+            static_emb = static_graph.ndata.pop('h')[:self.num_ents, :].contiguous()
+            static_emb = ops.row_map(static_emb, ops.ROW_NORMALIZE) if self.layer_norm else static_emb
+            self.h = ops.hyp_init(static_emb, rs_raw, False, False, c, self.radius_min, self.radius_max)
+        else:
+            self.h = ops.hyp_init(self.dynamic_emb.detach(), rs_raw, self.layer_norm, False, c, self.radius_min,
+                                  self.radius_max)
+            static_emb = None
+
+        tre = self.temporal_radius_evolution
+        rw = tre.radius_mlp.weight.detach().view(-1).contiguous()
+        rb = float(tre.radius_mlp.bias.detach().item()) if not hasattr(self, "_rb_cache") else self._rb_cache
+        self._rb_cache = rb
+        history_embs = []
+        for i, g in enumerate(g_list):
+            g = g.to(self.gpu)
+            ht, pt, radius = ops.hyp_tangent(self.h, c, want_clamped=True, want_radius=True)
+            h0_prev = self.emb_rel.detach() if i == 0 else self.h_0
+            self.h_0 = self._relation_step(g, ht, h0_prev)
+            current_h = self.rgcn.forward(g, self.h, [self.h_0, self.h_0], _tangent=ht, _radius=radius)
+            G = ops.gemm(pt, self.time_gate_weight.detach())
+            self.h = ops.hyp_time_gate(current_h, pt, G, self.time_gate_bias.detach(), rs_raw, rw, rb, self.layer_norm,
+                                       self.use_residual_evolution, c, self.radius_min, self.radius_max,
+                                       tre.anchor_beta, tre.epsilon)
+            history_embs.append(self.h)
+        return history_embs, static_emb, self.h_0, gate_list, degree_list
+
+    @torch.no_grad()
+    def predict(self, test_graph, num_rels, static_graph, test_triplets, use_cuda):
+        inverse_test_triplets = test_triplets[:, [2, 1, 0]]
+        inverse_test_triplets[:, 1] = inverse_test_triplets[:, 1] + num_rels
+        all_triples = torch.cat((test_triplets, inverse_test_triplets)).contiguous()
+        evolve_embs, _, r_emb, _, _ = self.forward(test_graph, static_graph, use_cuda)
+        embedding = evolve_embs[-1]
+        if self.layer_norm:
+            embedding = ops.row_map(embedding, ops.ROW_TANGENT_NORMALIZE, c=self._c_float)
+        score = self.decoder_ob.forward(embedding, r_emb, all_triples, mode="test")
+        score_rel = self.rdecoder.forward(embedding, r_emb, all_triples, mode="test")
+        return all_triples, score, score_rel
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        out = super().load_state_dict(state_dict, strict=strict, **kw)
+        self._c_float = float(self.c.item())
+        if hasattr(self, "_rb_cache"):
+            del self._rb_cache
+        return out
+
+    def get_loss(self, glist, triples, static_graph, use_cuda, query_time=None):
+        raise NotImplementedError(
+            "regcn_b200.HyperbolicRecurrentRGCN.get_loss: the training step (backward kernels, SURVEY.md 8f rank 1) "
+            "is not part of this round's hot path; forward()/predict() are")

@@ -1,0 +1,258 @@
+"""Thin tensor-level wrappers over the C ABI (one per kernel entry point).
+
+Each wrapper allocates its outputs with torch (device memory ownership stays with the caller's
+framework), validates dtypes, and launches on torch's current stream.  No arithmetic happens here.
+"""
+import torch
+
+from . import _lib
+from ._lib import call, ptr
+
+F32 = torch.float32
+I32 = torch.int32
+I64 = torch.int64
+
+
+def _f32(t, name):
+    if t.dtype != F32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def _rowmajor(t, name):
+    """fp32 2-D tensor with unit column stride (row slices / column blocks of a bigger matrix are fine)."""
+    if t.dtype != F32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    if t.dim() != 2:
+        raise ValueError(f"{name} must be 2-D")
+    if not t.is_cuda:
+        raise RuntimeError("regcn_b200: kernels take CUDA tensors only (no CPU fallback)")
+    if t.stride(1) != 1 or t.stride(0) % 4 or t.data_ptr() % 16:
+        t = t.contiguous()
+    return t
+
+
+# --------------------------------------------------------------------------- dense contractions
+_GEMM_IMPL = {"impl": "simt"}
+
+
+def gemm(a, b, trans_b=False, bias=None, out=None, accumulate=False, split_k=1):
+    """C[M,N] (+)= A[M,K] @ (B[K,N] | B[N,K]^T) (+ bias).  torch.mm / F.linear call sites of the path."""
+    a = _rowmajor(a, "a")
+    b = _rowmajor(b, "b")
+    M, K = a.shape
+    N = b.shape[0] if trans_b else b.shape[1]
+    if (b.shape[1] if trans_b else b.shape[0]) != K:
+        raise ValueError(f"gemm: inner dims differ {tuple(a.shape)} x {tuple(b.shape)} trans_b={trans_b}")
+    if out is None:
+        if accumulate:
+            raise ValueError("gemm: accumulate needs out")
+        out = torch.empty((M, N), device=a.device, dtype=F32)
+    elif not out.is_cuda or out.dtype != F32 or out.stride(1) != 1:
+        raise ValueError("gemm: out must be a CUDA float32 matrix with unit column stride")
+    ldc = out.stride(0)
+    ws = None
+    ws_bytes = 0
+    if split_k > 1:
+        ws_bytes = _lib.load().regcn_gemm_f32_workspace_bytes(M, N, split_k)
+        ws = torch.empty(ws_bytes // 4, device=a.device, dtype=F32)
+    call("regcn_gemm_f32", a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), int(trans_b), out.data_ptr(), ldc, M, N, K,
+         ptr(bias), int(accumulate), split_k, ptr(ws), ws_bytes)
+    return out
+
+
+# --------------------------------------------------------------------------- edge path
+def rel_mean_pool(h, g, nsplit=None):
+    h = _f32(h, "h")
+    R, d = g.num_rels, h.shape[1]
+    out = torch.empty((2 * R, d), device=h.device, dtype=F32)
+    if nsplit is None:
+        nsplit = max(1, min(64, g.n_rel_ents // (R * 512)))
+    partial = torch.empty((R * nsplit, d), device=h.device, dtype=F32) if nsplit > 1 else None
+    call("regcn_rel_mean_pool", ptr(h), ptr(g.rel_rowptr), ptr(g.rel_ents), R, d, nsplit, ptr(out), ptr(partial))
+    return out
+
+
+def union_aggregate(h, rel, g, radius=None, gamma=0.0, out=None):
+    h = _f32(h, "h")
+    rel = _f32(rel, "rel")
+    N, d = h.shape
+    if out is None:
+        out = torch.empty((N, d), device=h.device, dtype=F32)
+    partial = torch.empty((g.n_split_chunks, d), device=h.device, dtype=F32) if g.n_split_chunks > 0 else None
+    call("regcn_union_aggregate", ptr(h), ptr(rel), ptr(g.rowptr), ptr(g.src_sorted), ptr(g.etype_sorted), ptr(g.norm),
+         ptr(g.vptr), ptr(g.sptr), ptr(g.vrow_row), g.n_vrows, g.n_split_chunks, ptr(radius), float(gamma), N, d,
+         ptr(out), ptr(partial))
+    return out
+
+
+def block_aggregate(h, weight, g, num_bases, d_out):
+    h = _f32(h, "h")
+    weight = _f32(weight, "weight")
+    N, d_in = h.shape
+    out = torch.empty((N, d_out), device=h.device, dtype=F32)
+    call("regcn_block_aggregate", ptr(h), ptr(weight), ptr(g.rowptr), ptr(g.src_sorted), ptr(g.etype_sorted),
+         ptr(g.norm), N, d_in, d_out, num_bases, ptr(out))
+    return out
+
+
+def lorentz_aggregate(ht, weight, rel, g, num_bases, c):
+    ht = _f32(ht, "ht")
+    N, d = ht.shape
+    out = torch.empty((N, d), device=ht.device, dtype=F32)
+    call("regcn_lorentz_aggregate", ptr(ht), ptr(_f32(weight, "weight")), ptr(rel), ptr(g.rowptr), ptr(g.src_sorted),
+         ptr(g.etype_sorted), ptr(g.norm), N, d, num_bases, float(c), ptr(out))
+    return out
+
+
+# --------------------------------------------------------------------------- row maps
+ROW_NORMALIZE, ROW_TANH, ROW_LEAKY_TANH_LOG0, ROW_LOG0, ROW_EXP0, ROW_PROJECT, ROW_TANGENT_NORMALIZE, ROW_IDENTITY = range(8)
+
+
+def row_sumsq(x):
+    """|x_n|^2 per row (the e_sumsq operand of the norm/dot score form)."""
+    x = _f32(x, "x")
+    M, d = x.shape
+    ss = torch.empty(M, device=x.device, dtype=F32)
+    call("regcn_row_map", ptr(x), None, M, d, ROW_IDENTITY, 1.0, ptr(ss))
+    return ss
+
+
+def row_map(x, mode, c=1.0, want_sumsq=False, out=None):
+    x = _f32(x, "x")
+    M, d = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    ss = torch.empty(M, device=x.device, dtype=F32) if want_sumsq else None
+    call("regcn_row_map", ptr(x), ptr(out), M, d, mode, float(c), ptr(ss))
+    return (out, ss) if want_sumsq else out
+
+
+def gru_gate(gi, gh, hprev, normalize):
+    M, d = hprev.shape
+    out = torch.empty((M, d), device=hprev.device, dtype=F32)
+    call("regcn_gru_gate", ptr(gi), ptr(gh), ptr(_f32(hprev, "hprev")), ptr(out), M, d, int(normalize))
+    return out
+
+
+def union_combine(P, L, indeg, act=1, hyper=False, c=1.0, skip=None, skip_bias=None, prev=None,
+                  want_tangent=False, want_radius=False):
+    N, d = P.shape
+    out = torch.empty((N, d), device=P.device, dtype=F32)
+    ht = torch.empty((N, d), device=P.device, dtype=F32) if want_tangent else None
+    rad = torch.empty(N, device=P.device, dtype=F32) if want_radius else None
+    call("regcn_union_combine", ptr(P), ptr(L), ptr(indeg), ptr(skip), ptr(skip_bias), ptr(prev), N, d, act,
+         int(hyper), float(c), ptr(out), ptr(ht), ptr(rad))
+    return out, ht, rad
+
+
+def time_gate(G, bias, cur, h, normalize_cur):
+    N, d = h.shape
+    out = torch.empty((N, d), device=h.device, dtype=F32)
+    call("regcn_time_gate", ptr(G), ptr(_f32(bias, "bias")), ptr(cur), ptr(_f32(h, "h")), ptr(out), N, d,
+         int(normalize_cur))
+    return out
+
+
+def hyp_init(emb, radius_static, normalize, on_manifold, c, rmin, rmax):
+    emb = _f32(emb, "emb")
+    N, d = emb.shape
+    out = torch.empty((N, d), device=emb.device, dtype=F32)
+    call("regcn_hyp_init", ptr(emb), ptr(radius_static), N, d, int(normalize), int(on_manifold), float(c), float(rmin),
+         float(rmax), ptr(out))
+    return out
+
+
+def hyp_tangent(h, c, want_clamped=True, want_radius=True):
+    h = _f32(h, "h")
+    N, d = h.shape
+    ht = torch.empty((N, d), device=h.device, dtype=F32)
+    pt = torch.empty((N, d), device=h.device, dtype=F32) if want_clamped else None
+    rad = torch.empty(N, device=h.device, dtype=F32) if want_radius else None
+    call("regcn_hyp_tangent", ptr(h), N, d, float(c), ptr(ht), ptr(pt), ptr(rad))
+    return ht, pt, rad
+
+
+def hyp_time_gate(h2, pt, G, bias, radius_static, radius_w, radius_b, layer_norm, residual, c, rmin, rmax, beta, eps_r):
+    N, d = h2.shape
+    out = torch.empty((N, d), device=h2.device, dtype=F32)
+    call("regcn_hyp_time_gate", ptr(h2), ptr(pt), ptr(G), ptr(_f32(bias, "bias")), ptr(_f32(radius_static, "rs")),
+         ptr(radius_w), float(radius_b), N, d, int(layer_norm), int(residual), float(c), float(rmin), float(rmax),
+         float(beta), float(eps_r), ptr(out))
+    return out
+
+
+# --------------------------------------------------------------------------- decoders
+def convtranse_features(ent, second, triples, col0, col1, bn0, conv_w, conv_b, bn1):
+    """bn0 / bn1 = (scale, shift) folded eval-mode BatchNorm."""
+    B = triples.shape[0]
+    d = ent.shape[1]
+    C, _, ksz = conv_w.shape
+    out = torch.empty((B, C * d), device=ent.device, dtype=F32)
+    call("regcn_convtranse_features", ptr(ent), ptr(second), ptr(triples), col0, col1, B, d, C, ksz, ptr(bn0[0]),
+         ptr(bn0[1]), ptr(conv_w.contiguous()), ptr(conv_b), ptr(bn1[0]), ptr(bn1[1]), ptr(out))
+    return out
+
+
+def affine_relu_(x, scale, shift, relu=True):
+    M, d = x.shape
+    call("regcn_affine_relu", ptr(x), ptr(scale), ptr(shift), M, d, int(relu))
+    return x
+
+
+def gather_log0(E, triples, col, project, c):
+    B = triples.shape[0]
+    d = E.shape[1]
+    out = torch.empty((B, d), device=E.device, dtype=F32)
+    call("regcn_gather_log0", ptr(E), ptr(triples), col, B, d, int(project), float(c), ptr(out))
+    return out
+
+
+def hyp_query(s_tan, ang, trans, E, triples, kind, c):
+    B, d = s_tan.shape
+    Q = torch.empty((B, d), device=s_tan.device, dtype=F32)
+    qss = torch.empty(B, device=s_tan.device, dtype=F32)
+    call("regcn_hyp_query", ptr(s_tan), ptr(ang), ptr(trans), ptr(E), ptr(triples), B, d, kind, float(c), ptr(Q),
+         ptr(qss))
+    return Q, qss
+
+
+def hyp_score_epilogue_(S, q_sumsq, e_sumsq, bias, qbias, c, scale_margin):
+    B, N = S.shape
+    step = 65535
+    for b0 in range(0, B, step):
+        b1 = min(B, b0 + step)
+        call("regcn_hyp_score_epilogue", S[b0:b1].data_ptr(), S.stride(0), b1 - b0, N, q_sumsq[b0:b1].data_ptr(),
+             ptr(e_sumsq), ptr(bias), None if qbias is None else qbias[b0:b1].data_ptr(), float(c), ptr(scale_margin))
+    return S
+
+
+# --------------------------------------------------------------------------- ranking
+def rank_dense(score, triples, target_col, filt_ptr=None, filt_idx=None, col_offset=0, target_score=None):
+    """Counts for a (B, N_shard) dense score block.  Returns (raw_count, filt_count, target_score) int32/int32/f32."""
+    B, N = score.shape
+    dev = score.device
+    if target_score is None:
+        target_score = torch.zeros(B, device=dev, dtype=F32)
+        call("regcn_gather_target_score", ptr(score), score.stride(0), B, N, ptr(triples), target_col, col_offset,
+             ptr(target_score))
+    raw = torch.empty(B, device=dev, dtype=I32)
+    filt = torch.empty(B, device=dev, dtype=I32) if filt_ptr is not None else None
+    call("regcn_rank_count", score.data_ptr(), score.stride(0), B, N, ptr(triples), target_col, ptr(filt_ptr),
+         ptr(filt_idx), col_offset, ptr(target_score), ptr(raw), ptr(filt))
+    return raw, filt, target_score
+
+
+def counts_to_ranks(raw, filt):
+    B = raw.shape[0]
+    rank = torch.empty(B, device=raw.device, dtype=I64)
+    frank = torch.empty(B, device=raw.device, dtype=I64)
+    call("regcn_counts_to_ranks", ptr(raw), ptr(filt), B, ptr(rank), ptr(frank))
+    return rank, frank
+
+
+def apply_filter_(score, triples, target_col, filt_ptr, filt_idx, col_offset=0):
+    B, N = score.shape
+    call("regcn_apply_filter", score.data_ptr(), score.stride(0), B, N, ptr(triples), target_col, ptr(filt_ptr),
+         ptr(filt_idx), col_offset)
+    return score

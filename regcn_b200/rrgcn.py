@@ -1,0 +1,159 @@
+"""RecurrentRGCN with the reference's constructor / forward / predict / get_loss signatures
+(src/rrgcn.py:14-248) and state-dict names, evolving snapshots on the sm_100a kernels.
+
+Per history snapshot (src/rrgcn.py:159-179): relation mean-pool (K2) -> relation GRU (K3) ->
+2 x UnionRGCNLayer (K4 aggregate + node GEMMs + K5 combine) -> time gate (K9).
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .decoder import ConvTransE, ConvTransR
+from .layers import RGCNBlockLayer, UnionRGCNLayer
+from .model import BaseRGCN
+
+
+class RGCNCell(BaseRGCN):
+    """src/rrgcn.py:14-54."""
+
+    def build_hidden_layer(self, idx):
+        act = F.rrelu
+        if idx:
+            self.num_basis = 0
+        sc = bool(self.skip_connect and idx != 0)
+        if self.encoder_name == "uvrgcn":
+            return UnionRGCNLayer(self.h_dim, self.h_dim, self.num_rels, self.num_bases, activation=act,
+                                  dropout=self.dropout, self_loop=self.self_loop, skip_connect=sc,
+                                  rel_emb=self.rel_emb)
+        raise NotImplementedError
+
+    def forward(self, g, init_ent_emb, init_rel_emb):
+        if self.encoder_name != "uvrgcn":
+            raise NotImplementedError
+        # ndata['id'] is arange(N) (rgcn/utils.py:122), so init_ent_emb[node_id] is the identity gather
+        g.ndata['h'] = init_ent_emb
+        for i, layer in enumerate(self.layers):
+            layer(g, [], init_rel_emb[i])
+        return g.ndata.pop('h')
+
+
+class RecurrentRGCN(nn.Module):
+    def __init__(self, decoder_name, encoder_name, num_ents, num_rels, num_static_rels, num_words, h_dim, opn,
+                 sequence_len, num_bases=-1, num_basis=-1, num_hidden_layers=1, dropout=0, self_loop=False,
+                 skip_connect=False, layer_norm=False, input_dropout=0, hidden_dropout=0, feat_dropout=0,
+                 aggregation='cat', weight=1, discount=0, angle=0, use_static=False, entity_prediction=False,
+                 relation_prediction=False, use_cuda=False, gpu=0, analysis=False):
+        super().__init__()
+        self.decoder_name = decoder_name
+        self.encoder_name = encoder_name
+        self.num_rels = num_rels
+        self.num_ents = num_ents
+        self.opn = opn
+        self.num_words = num_words
+        self.num_static_rels = num_static_rels
+        self.sequence_len = sequence_len
+        self.h_dim = h_dim
+        self.layer_norm = layer_norm
+        self.h = None
+        self.run_analysis = analysis
+        self.aggregation = aggregation
+        self.relation_evolve = False
+        self.weight = weight
+        self.discount = discount
+        self.use_static = use_static
+        self.angle = angle
+        self.relation_prediction = relation_prediction
+        self.entity_prediction = entity_prediction
+        self.emb_rel = None
+        self.gpu = gpu
+
+        self.w1 = nn.Parameter(torch.Tensor(h_dim, h_dim))
+        nn.init.xavier_normal_(self.w1)
+        self.w2 = nn.Parameter(torch.Tensor(h_dim, h_dim))
+        nn.init.xavier_normal_(self.w2)
+        self.emb_rel = nn.Parameter(torch.Tensor(num_rels * 2, h_dim))
+        nn.init.xavier_normal_(self.emb_rel)
+        self.dynamic_emb = nn.Parameter(torch.Tensor(num_ents, h_dim))
+        nn.init.normal_(self.dynamic_emb)
+
+        if self.use_static:
+            self.words_emb = nn.Parameter(torch.Tensor(num_words, h_dim))
+            nn.init.xavier_normal_(self.words_emb)
+            self.statci_rgcn_layer = RGCNBlockLayer(h_dim, h_dim, num_static_rels * 2, num_bases, activation=F.rrelu,
+                                                    dropout=dropout, self_loop=False, skip_connect=False)
+            self.static_loss = nn.MSELoss()
+
+        self.loss_r = nn.CrossEntropyLoss()
+        self.loss_e = nn.CrossEntropyLoss()
+
+        self.rgcn = RGCNCell(num_ents, h_dim, h_dim, num_rels * 2, num_bases, num_basis, num_hidden_layers, dropout,
+                             self_loop, skip_connect, encoder_name, self.opn, self.emb_rel, use_cuda, analysis)
+
+        self.time_gate_weight = nn.Parameter(torch.Tensor(h_dim, h_dim))
+        nn.init.xavier_uniform_(self.time_gate_weight, gain=nn.init.calculate_gain('relu'))
+        self.time_gate_bias = nn.Parameter(torch.Tensor(h_dim))
+        nn.init.zeros_(self.time_gate_bias)
+
+        self.relation_cell_1 = nn.GRUCell(h_dim * 2, h_dim)
+
+        if decoder_name == "convtranse":
+            self.decoder_ob = ConvTransE(num_ents, h_dim, input_dropout, hidden_dropout, feat_dropout)
+            self.rdecoder = ConvTransR(num_rels, h_dim, input_dropout, hidden_dropout, feat_dropout)
+        else:
+            raise NotImplementedError
+
+    # ------------------------------------------------------------------ relation GRU (K2 + K3)
+    def _relation_step(self, g, h, h0_prev):
+        cell = self.relation_cell_1
+        d = self.h_dim
+        x_mean = ops.rel_mean_pool(h, g)                                       # (2R, d)
+        w_ih = cell.weight_ih.detach()                                         # (3d, 2d): [emb_rel | x_mean] halves
+        gi = ops.gemm(self.emb_rel.detach(), w_ih[:, :d], trans_b=True, bias=cell.bias_ih.detach())
+        ops.gemm(x_mean, w_ih[:, d:], trans_b=True, out=gi, accumulate=True)
+        gh = ops.gemm(h0_prev, cell.weight_hh.detach(), trans_b=True, bias=cell.bias_hh.detach())
+        return ops.gru_gate(gi, gh, h0_prev, self.layer_norm)
+
+    @torch.no_grad()
+    def forward(self, g_list, static_graph, use_cuda):
+        gate_list, degree_list = [], []
+        if self.use_static:
+            static_graph = static_graph.to(self.gpu)
+            static_graph.ndata['h'] = torch.cat((self.dynamic_emb, self.words_emb), dim=0).detach()
+            self.statci_rgcn_layer(static_graph, [])
+            static_emb = static_graph.ndata.pop('h')[:self.num_ents, :].contiguous()
+            static_emb = ops.row_map(static_emb, ops.ROW_NORMALIZE) if self.layer_norm else static_emb
+            self.h = static_emb
+        else:
+            dyn = self.dynamic_emb.detach()
+            self.h = ops.row_map(dyn, ops.ROW_NORMALIZE) if self.layer_norm else dyn
+            static_emb = None
+
+        history_embs = []
+        for i, g in enumerate(g_list):
+            g = g.to(self.gpu)
+            h0_prev = self.emb_rel.detach() if i == 0 else self.h_0
+            self.h_0 = self._relation_step(g, self.h, h0_prev)
+            current_h = self.rgcn.forward(g, self.h, [self.h_0, self.h_0])
+            G = ops.gemm(self.h, self.time_gate_weight.detach())
+            self.h = ops.time_gate(G, self.time_gate_bias.detach(), current_h, self.h, self.layer_norm)
+            history_embs.append(self.h)
+        return history_embs, static_emb, self.h_0, gate_list, degree_list
+
+    @torch.no_grad()
+    def predict(self, test_graph, num_rels, static_graph, test_triplets, use_cuda):
+        inverse_test_triplets = test_triplets[:, [2, 1, 0]]
+        inverse_test_triplets[:, 1] = inverse_test_triplets[:, 1] + num_rels
+        all_triples = torch.cat((test_triplets, inverse_test_triplets)).contiguous()
+
+        evolve_embs, _, r_emb, _, _ = self.forward(test_graph, static_graph, use_cuda)
+        embedding = ops.row_map(evolve_embs[-1], ops.ROW_NORMALIZE) if self.layer_norm else evolve_embs[-1]
+
+        score = self.decoder_ob.forward(embedding, r_emb, all_triples, mode="test")
+        score_rel = self.rdecoder.forward(embedding, r_emb, all_triples, mode="test")
+        return all_triples, score, score_rel
+
+    def get_loss(self, glist, triples, static_graph, use_cuda):
+        raise NotImplementedError(
+            "regcn_b200.RecurrentRGCN.get_loss: the training step (backward kernels, SURVEY.md 8f rank 1) is not "
+            "part of this round's hot path; forward()/predict() are")

@@ -1,0 +1,142 @@
+"""Evaluation utilities with the reference's names and return values (rgcn/utils.py).
+
+`get_total_rank` (rgcn/utils.py:136-166) keeps its signature and returns; the two full sorts and the
+per-query python filter loop (utils.py:21-25, 51-75) are replaced by the count-based rank kernels
+(regcn_b200/csrc/rank.cu).  Host-side helpers that only shape python data (answer dictionaries,
+`split_by_time`) are restated here so callers of the reference find them.
+"""
+import numpy as np
+import torch
+
+from . import ops
+from .graph import build_sub_graph  # noqa: F401  (same import site as the reference: utils.build_sub_graph)
+
+
+# ------------------------------------------------------------------------------ answer sets
+def _add(d, k1, k2, v):
+    d.setdefault(k1, {}).setdefault(k2, set()).add(v)
+
+
+def load_all_answers_for_filter(total_data, num_rel, rel_p=False):
+    """rgcn/utils.py:264-283: {e1: {r: {e2}}} incl. inverse queries, or {e1: {e2: {r}}} when rel_p."""
+    all_ans = {}
+    for line in total_data:
+        s, r, o = (int(x) for x in line[:3])
+        if rel_p:
+            _add(all_ans, s, o, r)
+            _add(all_ans, o, s, r + num_rel)
+        else:
+            _add(all_ans, o, r + num_rel, s)
+            _add(all_ans, s, r, o)
+    return all_ans
+
+
+def split_by_time(data):
+    """rgcn/utils.py:306-339 (without the sanity print): list of (T_i,3) arrays, one per timestamp."""
+    data = np.asarray(data)
+    snapshot_list, snapshot, latest_t = [], [], 0
+    for i in range(len(data)):
+        t = data[i][3]
+        if latest_t != t:
+            latest_t = t
+            if len(snapshot):
+                snapshot_list.append(np.array(snapshot).copy())
+            snapshot = []
+        snapshot.append(data[i][:3])
+    if len(snapshot) > 0:
+        snapshot_list.append(np.array(snapshot).copy())
+    return snapshot_list
+
+
+def load_all_answers_for_time_filter(total_data, num_rels, num_nodes, rel_p=False):
+    """rgcn/utils.py:286-304."""
+    return [load_all_answers_for_filter(snap, num_rels, rel_p) for snap in split_by_time(total_data)]
+
+
+# ------------------------------------------------------------------------------ filter CSR
+class FilterCSR:
+    """Per-query sorted ids of the true answers (the reference's all_ans[h][r] / all_ans[h][t] sets) on the device."""
+
+    def __init__(self, ptr_t, idx_t):
+        self.ptr, self.idx = ptr_t, idx_t
+
+
+def filter_csr_from_dict(test_triples, all_ans, rel_predict=0, device=None):
+    """Build the CSR from the reference's nested dict (one pass over the queries on the host)."""
+    tt = test_triples.detach().cpu().numpy()
+    ptr_l, idx_l = [0], []
+    for h, r, t in tt:
+        key2 = int(t) if rel_predict else int(r)
+        ans = sorted(all_ans[int(h)][key2])
+        idx_l.extend(ans)
+        ptr_l.append(len(idx_l))
+    dev = device if device is not None else test_triples.device
+    return FilterCSR(torch.tensor(ptr_l, dtype=torch.int32, device=dev),
+                     torch.tensor(idx_l if idx_l else [0], dtype=torch.int32, device=dev))
+
+
+def filter_csr_from_snapshot(all_triples, num_keys2, rel_predict=0):
+    """Vectorised, device-side equivalent of load_all_answers_for_filter + per-query lookup when the filter set is
+    'every answer among these queries themselves' (time-aware filtering, rgcn/utils.py:286-304: the test snapshot's own
+    triples incl. inverses = exactly `all_triples` of predict()).  key = (h, r) -> answers t (entity prediction) or
+    (h, t) -> answers r (relation prediction)."""
+    h = all_triples[:, 0]
+    k2 = all_triples[:, 2] if rel_predict else all_triples[:, 1]
+    a = all_triples[:, 1] if rel_predict else all_triples[:, 2]
+    key = h * int(num_keys2) + k2
+    # unique (key, answer) pairs sorted by key then answer
+    big = int(a.max().item()) + 1 if a.numel() else 1
+    pair = torch.unique(key * big + a)
+    pkey, pans = pair // big, pair % big
+    ukey, counts = torch.unique_consecutive(pkey, return_counts=True)
+    starts = torch.cumsum(counts, 0) - counts
+    pos = torch.searchsorted(ukey, key)
+    q_start, q_cnt = starts[pos], counts[pos]
+    ptr_t = torch.zeros(key.numel() + 1, dtype=torch.int64, device=key.device)
+    ptr_t[1:] = torch.cumsum(q_cnt, 0)
+    total = int(ptr_t[-1].item())
+    rep = torch.repeat_interleave(torch.arange(key.numel(), device=key.device), q_cnt)
+    within = torch.arange(total, device=key.device) - ptr_t[:-1][rep]
+    idx_t = pans[q_start[rep] + within]
+    return FilterCSR(ptr_t.to(torch.int32), idx_t.to(torch.int32) if total else torch.zeros(1, dtype=torch.int32, device=key.device))
+
+
+# ------------------------------------------------------------------------------ ranking
+def sort_and_rank(score, target):
+    """rgcn/utils.py:21-25: 0-based rank of `target` in each row (count-based, stable-sort tie rule)."""
+    trip = torch.zeros((score.shape[0], 3), dtype=torch.int64, device=score.device)
+    trip[:, 2] = target
+    raw, _, _ = ops.rank_dense(score.contiguous() if score.stride(1) != 1 else score, trip, 2)
+    return raw.long()
+
+
+def get_total_rank(test_triples, score, all_ans, eval_bz, rel_predict=0, filter_csr=None):
+    """rgcn/utils.py:136-166.  Returns (filter_mrr, mrr, rank, filter_rank) with 1-based int64 ranks.
+
+    `all_ans` is the reference's nested dict (or None); pass `filter_csr` to skip the host-side dict walk.
+    Like the reference, the filtered entries of `score` are overwritten with -10000000 in place (utils.py:60,74)."""
+    target_col = {0: 2, 1: 1, 2: 0}[rel_predict]
+    test_triples = test_triples.contiguous()
+    if filter_csr is None and all_ans is not None:
+        filter_csr = filter_csr_from_dict(test_triples, all_ans, rel_predict=1 if rel_predict else 0,
+                                          device=score.device)
+    fp = filter_csr.ptr if filter_csr is not None else None
+    fi = filter_csr.idx if filter_csr is not None else None
+    raw, filt, _ = ops.rank_dense(score, test_triples, target_col, fp, fi)
+    rank, filter_rank = ops.counts_to_ranks(raw, filt)
+    if filter_csr is not None:
+        ops.apply_filter_(score, test_triples, target_col, fp, fi)
+    mrr = torch.mean(1.0 / rank.float())
+    filter_mrr = torch.mean(1.0 / filter_rank.float())
+    return filter_mrr.item(), mrr.item(), rank, filter_rank
+
+
+def stat_ranks(rank_list, method, verbose=True):
+    """rgcn/utils.py:169-178."""
+    total_rank = torch.cat(rank_list)
+    mrr = torch.mean(1.0 / total_rank.float())
+    if verbose:
+        print("MRR ({}): {:.6f}".format(method, mrr.item()))
+        for hit in (1, 3, 10):
+            print("Hits ({}) @ {}: {:.6f}".format(method, hit, torch.mean((total_rank <= hit).float()).item()))
+    return mrr

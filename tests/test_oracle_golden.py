@@ -1,0 +1,94 @@
+"""CPU: the restatement oracle (oracle/restate.py) against the golden fixtures produced by the UNMODIFIED
+reference (oracle/gen_golden.py).  This is what pins the oracle (the reference ships no tests of its own)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import restate, synth
+from tests.helpers import CURV, N_BASES, build_model, close, golden_names, load_golden
+
+
+def _graphs(case):
+    return [restate.build_edges(s, case["num_ents"], case["num_rels"]) for s in case["history"]]
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_edge_index_matches_reference(name):
+    cfg, z = load_golden(name)
+    case = synth.make_case(cfg["shape"], cfg["seed"])
+    R = case["num_rels"]
+    for i, g in enumerate(_graphs(case)):
+        assert np.array_equal(g["src"], z[f"g{i}_src"])
+        assert np.array_equal(g["dst"], z[f"g{i}_dst"])
+        assert np.array_equal(g["etype"], z[f"g{i}_type"])
+        assert np.array_equal(g["norm"], z[f"g{i}_norm"])          # fp32 reciprocal of an int: exact
+        rel_rowptr, rel_ents = restate.r2e(case["history"][i], R)
+        uniq_r, r_len, r_to_e = z[f"g{i}_uniq_r"], z[f"g{i}_r_len"], z[f"g{i}_r_to_e"]
+        present = np.nonzero(np.diff(rel_rowptr))[0]
+        assert np.array_equal(uniq_r, np.concatenate((present, present + R)))
+        for (b, e), r in zip(r_len, uniq_r):
+            mine = rel_ents[rel_rowptr[r % R]:rel_rowptr[r % R + 1]]
+            assert np.array_equal(np.sort(r_to_e[b:e]), mine)        # same *set* (the reference's order is a python set's)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_restatement_matches_reference(name):
+    cfg, z = load_golden(name)
+    case = synth.make_case(cfg["shape"], cfg["seed"])
+    n, r = case["num_ents"], case["num_rels"]
+    _, sd = build_model(cfg, n, r)
+    graphs = _graphs(case)
+    torch.set_num_threads(8)
+    with torch.no_grad():
+        if cfg["kind"] == "regcn":
+            all_t, score, score_rel, hist, h0 = restate.regcn_predict(sd, graphs, r, case["test"],
+                                                                      layer_norm=cfg["layer_norm"])
+        else:
+            all_t, score, score_rel, hist, h0 = restate.hyp_predict(
+                sd, graphs, r, case["test"], c=CURV, decoder=cfg["decoder"], layer_norm=cfg["layer_norm"],
+                encoder=cfg["encoder"], gamma=cfg["gamma"], num_bases=min(N_BASES, 2 * r))
+    assert np.array_equal(all_t, z["all_triples"])
+    ok, worst = close(h0.numpy(), z["h0"])
+    assert ok, f"h0 worst ratio {worst}"
+    if "hist" in z:
+        for i, h in enumerate(hist):
+            ok, worst = close(h.numpy(), z["hist"][i])
+            assert ok, f"hist[{i}] worst ratio {worst}"
+        ok, worst = close(score.numpy(), z["score"], rtol=2e-4)
+        assert ok, f"score worst ratio {worst}"
+        ok, worst = close(score_rel.numpy(), z["score_rel"], rtol=2e-4)
+        assert ok, f"score_rel worst ratio {worst}"
+    else:
+        rows, qrows = z["sub_rows"], z["sub_qrows"]
+        ok, worst = close(hist[-1][rows].numpy(), z["hist_last_rows"])
+        assert ok, f"hist_last worst ratio {worst}"
+        ok, worst = close(hist[0][rows].numpy(), z["hist_first_rows"])
+        assert ok, f"hist_first worst ratio {worst}"
+        ok, worst = close(score[qrows][:, rows].numpy(), z["score_block"], rtol=2e-4)
+        assert ok, f"score block worst ratio {worst}"
+        ok, worst = close(score_rel[qrows].numpy(), z["score_rel_qrows"], rtol=2e-4)
+        assert ok, f"score_rel worst ratio {worst}"
+    # ranks on the oracle's own scores: identical to the reference's except where fp32 noise flips a near-tie
+    all_ans = synth.answers_of(case["test"], r, False)
+    all_ans_r = synth.answers_of(case["test"], r, True)
+    _, _, rank, frank = restate.total_rank(all_t, score.numpy(), all_ans, 0)
+    _, _, rank_r, frank_r = restate.total_rank(all_t, score_rel.numpy(), all_ans_r, 1)
+    for mine, ref, what in ((rank, z["rank"], "rank"), (frank, z["filter_rank"], "filter_rank"),
+                            (rank_r, z["rank_rel"], "rank_rel"), (frank_r, z["filter_rank_rel"], "filter_rank_rel")):
+        flips = np.mean(mine != ref)
+        assert flips <= 0.02, f"{what}: {flips:.3%} of ranks differ from the reference"
+
+
+@pytest.mark.parametrize("name", ["regcn_tiny_s0", "regcn_small_s2", "hyp_lgcn_roth_tiny_s0"])
+def test_rank_restatement_exact_on_reference_scores(name):
+    """Ranks recomputed from the *reference's own* score matrices must be bit-identical to the reference's ranks."""
+    cfg, z = load_golden(name)
+    case = synth.make_case(cfg["shape"], cfg["seed"])
+    r = case["num_rels"]
+    all_ans = synth.answers_of(case["test"], r, False)
+    all_ans_r = synth.answers_of(case["test"], r, True)
+    fm, m, rank, frank = restate.total_rank(z["all_triples"], z["score"], all_ans, 0)
+    fmr, mr, rank_r, frank_r = restate.total_rank(z["all_triples"], z["score_rel"], all_ans_r, 1)
+    assert np.array_equal(rank, z["rank"]) and np.array_equal(frank, z["filter_rank"])
+    assert np.array_equal(rank_r, z["rank_rel"]) and np.array_equal(frank_r, z["filter_rank_rel"])
+    np.testing.assert_allclose([fm, m, fmr, mr], z["mrr"], rtol=1e-6)
