@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""Benchmark of the RE-GCN hot path on B200: one "step" = one evaluated test timestamp of the ICEWS18-shaped
+workload (BASELINE.json configs[2]): evolve L=6 history snapshots, score all B=2914 queries against all
+N=23033 entities, rank raw + time-filtered.
+
+    python bench.py --gpus N --steps K --warmup W                 # our arm (torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K --warmup W  # CPU arm: the oracle port on the host cores
+
+Prints ONE JSON line (rank 0).  `value` is all-entity-ranked queries/s with inputs resident in HBM; `e2e` is the
+same metric through the public API from pinned HOST buffers (H2D of the triples, device edge-index build, predict,
+ranking, D2H of the ranks); `snapshot_steps_per_s` is the other half of BASELINE.json's metric (evolution only).
+N > 1: every rank evaluates its own test timestamps (independent units, weak scaling, no data-path collective);
+the entity-sharded scoring + rank-merge path (NCCL all_reduce of counts) is timed separately and reported under
+"entity_sharded".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "c3"
+H_DIM, N_BASES, N_LAYERS = 200, 100, 2
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=WORKLOAD)
+    ap.add_argument("--model", default="regcn", choices=["regcn", "hyp_lgcn_roth", "hyp_uv_roth"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gemm", default=None, help="override the dense-contraction implementation (simt|tc)")
+    return ap.parse_args()
+
+
+def model_cfg(name):
+    if name == "regcn":
+        return dict(kind="regcn", layer_norm=True)
+    enc = "lgcn" if "lgcn" in name else "hyperbolic_uvrgcn"
+    return dict(kind="hyp", layer_norm=False, encoder=enc, decoder="roth", gamma=0.15)
+
+
+def build_product_model(cfg, n, r, seed):
+    import regcn_b200 as R
+    from regcn_b200 import synth
+    if cfg["kind"] == "regcn":
+        m = R.RecurrentRGCN("convtranse", "uvrgcn", n, r, 0, 0, H_DIM, "sub", 3, num_bases=N_BASES, num_basis=-1,
+                            num_hidden_layers=N_LAYERS, dropout=0.2, self_loop=True, skip_connect=False,
+                            layer_norm=cfg["layer_norm"], input_dropout=0.2, hidden_dropout=0.2, feat_dropout=0.2,
+                            entity_prediction=True, relation_prediction=True, use_cuda=True, gpu=0)
+    else:
+        m = R.HyperbolicRecurrentRGCN(cfg["decoder"], cfg["encoder"], n, r, 0, 0, H_DIM, "sub", 3, num_bases=N_BASES,
+                                      num_hidden_layers=N_LAYERS, dropout=0.2, c=0.01, self_loop=True,
+                                      layer_norm=cfg["layer_norm"], input_dropout=0.2, hidden_dropout=0.2,
+                                      feat_dropout=0.2, entity_prediction=True, relation_prediction=True,
+                                      use_cuda=True, gpu=0, radius_msg_gamma=cfg["gamma"])
+    sd = synth.fill_state_dict(m.state_dict(), seed)
+    m.load_state_dict(sd)
+    return m.eval(), sd
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,utilization.gpu,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for _, r in self.rows]
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_port_step(sd, graphs, r, test, cfg):
+    """One step of the same workload on the host cores through the oracle port (oracle/restate.py)."""
+    from oracle import restate
+    from regcn_b200 import synth
+    import torch
+    with torch.no_grad():
+        if cfg["kind"] == "regcn":
+            all_t, score, _, _, _ = restate.regcn_predict(sd, graphs, r, test, layer_norm=cfg["layer_norm"])
+        else:
+            all_t, score, _, _, _ = restate.hyp_predict(sd, graphs, r, test, c=0.01, decoder=cfg["decoder"],
+                                                        encoder=cfg["encoder"], gamma=cfg["gamma"],
+                                                        num_bases=min(N_BASES, 2 * r))
+    all_ans = synth.answers_of(test, r, False)
+    return restate.total_rank(all_t, score.numpy(), all_ans, 0)
+
+
+def run_cpu_arm(args, steps, warmup, quiet=False):
+    import torch
+    from oracle import restate
+    from regcn_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = model_cfg(args.model)
+    case = synth.make_case(args.workload, 0)
+    n, r = case["num_ents"], case["num_rels"]
+    _, sd = build_product_model(cfg, n, r, 0)
+    graphs = [restate.build_edges(s, n, r) for s in case["history"]]
+    B = 2 * len(case["test"])
+    for _ in range(warmup):
+        cpu_port_step(sd, graphs, r, case["test"], cfg)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_port_step(sd, graphs, r, case["test"], cfg)
+    dt = (time.perf_counter() - t0) / max(1, steps)
+    return {"value": B / dt, "unit": "queries/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} full step(s) of workload {args.workload} (evolve L={len(graphs)} + score {B}x{n} + "
+                      f"raw/filtered rank) after {warmup} warm-up, oracle/restate.py with torch CPU ops on {cores} "
+                      f"threads; scatter-sum is index_add_, not DGL's kernel", "ms_per_step": dt * 1e3}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    metric = "all-entity-ranked queries/sec"
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
+        cb = run_cpu_arm(args, steps, warmup)
+        line = {"impl": "reference", "metric": metric, "value": cb["value"], "unit": "queries/s",
+                "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": cb["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": args.workload, "model": args.model, "note": "steps/warmup capped so the CPU arm "
+                           "finishes in minutes; reference Python cannot travel to the GPU box, so the oracle port runs"},
+                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": cb["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    import regcn_b200 as R
+    from regcn_b200 import _lib, evaluate, ops, synth, utils
+    from regcn_b200 import dist as rdist
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.require_device()
+    if args.gemm:
+        ops.set_gemm_impl(args.gemm)
+
+    cfg = model_cfg(args.model)
+    case = synth.make_case(args.workload, rank)          # every rank owns different test timestamps (weak scaling)
+    n, r = case["num_ents"], case["num_rels"]
+    L, T = len(case["history"]), len(case["history"][0])
+    model, sd = build_product_model(cfg, n, r, 0)
+    model = model.to(dev)
+    glist = [R.build_sub_graph(n, r, s, True, local) for s in case["history"]]
+    test_dev = torch.from_numpy(case["test"]).to(dev)
+    inv = test_dev[:, [2, 1, 0]].clone()
+    inv[:, 1] += r
+    all_t = torch.cat((test_dev, inv)).contiguous()
+    B = all_t.shape[0]
+    fcsr = utils.filter_csr_from_snapshot(all_t, 2 * r, 0)
+    hist_host = [torch.from_numpy(s).pin_memory() for s in case["history"]]
+    test_host = torch.from_numpy(case["test"]).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, timers=False):
+        for _ in range(warmup):
+            fn(None)
+        barrier()
+        pairs, tms = [], []
+        for _ in range(steps):
+            flush.fill_(1.0)                               # L2 flush between timed iterations (untimed)
+            tm = {k: (ev(), ev()) for k in ("evolve", "score", "rank")} if timers else None
+            a, b = ev(), ev()
+            a.record()
+            fn(tm)
+            b.record()
+            pairs.append((a, b))
+            tms.append(tm)
+        barrier()
+        tot = sum(a.elapsed_time(b) for a, b in pairs)
+        parts = {}
+        if timers:
+            for k in ("evolve", "score", "rank"):
+                parts[k] = sum(t[k][0].elapsed_time(t[k][1]) for t in tms) / steps
+        return tot, parts
+
+    def maxr(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident arm ------------------------------------------------------------------
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = _lib.launch_count
+    t_wall0 = time.time()
+    tot_ms, parts = timed(lambda tm: evaluate.evaluate_snapshot(model, glist, all_t, fcsr, tm), args.steps,
+                          args.warmup, timers=True)
+    t_wall1 = time.time()
+    launches = (_lib.launch_count - l0) * args.steps // (args.steps + args.warmup)
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    tot_ms = maxr(tot_ms)
+    ms_per_step = tot_ms / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+    evolve_ms = maxr(parts["evolve"])
+
+    # ---- end-to-end arm: host buffers -> public API -> host results ------------------------------
+    e2e_steps = max(3, min(args.steps, 10))
+    tot_e2e, _ = timed(lambda tm: evaluate.evaluate_from_host(model, hist_host, test_host, n, r, dev), e2e_steps,
+                       min(args.warmup, 3))
+    e2e_ms = maxr(tot_e2e) / e2e_steps
+    h2d = sum(h.numel() for h in hist_host) * 8 + test_host.numel() * 8
+    d2h = 2 * B * 8 + 4 * 4
+
+    # ---- roofline of the dominant kernel (dense contraction), timed live with events on the launch stream ------
+    rec = []
+    real_gemm = ops.gemm
+
+    def gemm_probe(a, b, trans_b=False, **kw):
+        s, e = ev(), ev()
+        s.record()
+        out = real_gemm(a, b, trans_b=trans_b, **kw)
+        e.record()
+        rec.append((s, e, 2.0 * a.shape[0] * a.shape[1] * out.shape[1]))
+        return out
+
+    for mod in (ops,):
+        mod.gemm = gemm_probe
+    probe_steps = 3
+    try:
+        torch.cuda.synchronize()
+        for _ in range(probe_steps):
+            flush.fill_(1.0)
+            evaluate.evaluate_snapshot(model, glist, all_t, fcsr, None)
+        torch.cuda.synchronize()
+    finally:
+        ops.gemm = real_gemm
+    gemm_ms = sum(s.elapsed_time(e) for s, e, _ in rec) / probe_steps
+    gemm_flops = sum(f for _, _, f in rec) / probe_steps
+    n_gemm = len(rec) // probe_steps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    ach_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    roofline = {"kernel": ops.gemm_kernel_name(), "bound": "tensor", "achieved": ach_tf, "peak": peak_tf,
+                "unit": "TFLOP/s", "frac": ach_tf / peak_tf, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks
+                else "fallback 1.4 PFLOP/s (B200_PROFILING.md)",
+                "launches_per_step": n_gemm, "ms_per_step_in_kernel": gemm_ms,
+                "share_of_step": gemm_ms / ms_per_step if ms_per_step > 0 else None,
+                "algorithmic_flops_per_step": gemm_flops}
+
+    # ---- entity-sharded scoring + rank merge (strong scaling of one timestamp), all ranks on the same queries ----
+    sharded = None
+    if world > 1:
+        case0 = synth.make_case(args.workload, 0)
+        g0 = [R.build_sub_graph(n, r, s, True, local) for s in case0["history"]]
+        t0 = torch.from_numpy(case0["test"]).to(dev)
+        inv0 = t0[:, [2, 1, 0]].clone()
+        inv0[:, 1] += r
+        all0 = torch.cat((t0, inv0)).contiguous()
+        f0 = utils.filter_csr_from_snapshot(all0, 2 * r, 0)
+        embs, _, r_emb, _, _ = model.forward(g0, None, True)
+        emb = ops.row_map(embs[-1], ops.ROW_NORMALIZE) if cfg["kind"] == "regcn" else embs[-1]
+        if cfg["kind"] == "regcn":
+            e_all, q = model.decoder_ob.query(emb, r_emb, all0)
+            score_fn = lambda lo, hi: ops.gemm(q, e_all[lo:hi], trans_b=True)
+        else:
+            q, qss = model.decoder_ob.query(emb, r_emb, all0)
+            ess = ops.row_sumsq(emb)
+            sm = model.decoder_ob._scale_margin()
+            score_fn = lambda lo, hi: ops.hyp_score_epilogue_(ops.gemm(q, emb[lo:hi], trans_b=True), qss,
+                                                              ess[lo:hi].contiguous(), None, None, 0.01, sm)
+        out = {}
+
+        def sharded_step(_):
+            out["r"] = rdist.sharded_score_rank(n, all0, 2, f0, score_fn)
+
+        tot_s, _ = timed(sharded_step, args.steps, args.warmup)
+        s_ms = maxr(tot_s) / args.steps
+        full = ops.gemm(q, e_all, trans_b=True) if cfg["kind"] == "regcn" else score_fn(0, n)
+        raw1, filt1, _ = ops.rank_dense(full, all0, 2, f0.ptr, f0.idx)
+        rk1, frk1 = ops.counts_to_ranks(raw1, filt1)
+        same = bool(torch.equal(rk1, out["r"][0]) and torch.equal(frk1, out["r"][1]))
+        sharded = {"queries_per_s": all0.shape[0] / (s_ms * 1e-3), "ms_per_step": s_ms, "scaling": "strong",
+                   "ranks_equal_single_gpu": same, "collectives": "all_reduce(B f32) + all_reduce(2xB i32) over NCCL"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cb = run_cpu_arm(args, 3, 1)
+        cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": metric, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"{args.workload}: ICEWS18-shaped N={n} R={r} T={T}/snapshot L={L} "
+                                       f"B={B} queries/timestamp, d={H_DIM}, 2-layer UnionRGCN + ConvTransE"
+                           if args.model == "regcn" else f"{args.workload} {args.model}",
+                           "model": args.model, "parallelism": f"timestamp-dp{world}",
+                           "l2": "256 MiB buffer written between timed steps (untimed)",
+                           "gemm_impl": ops.gemm_impl()},
+                "snapshot_steps_per_s": world * L / (evolve_ms * 1e-3), "evolve_ms_per_step": evolve_ms,
+                "phase_ms": parts, "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "queries/s",
+                                           "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
+                                           "d2h_bytes_per_step": d2h},
+                "gpu_launches": launches, "roofline": roofline, "clocks": clocks}
+        if cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline
+        if sharded:
+            line["entity_sharded"] = sharded
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

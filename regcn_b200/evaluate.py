@@ -1,0 +1,53 @@
+"""Evaluation step of the hot path as one call: evolve the history, score every entity, rank raw + filtered.
+
+This is the loop body of the reference's test() (src/main.py:67-74, hyperbolic_main.py:100-113) for entity
+prediction, expressed on device-resident inputs so that nothing but kernels runs inside it.
+"""
+import torch
+
+from . import ops, utils
+
+
+@torch.no_grad()
+def evaluate_snapshot(model, glist, all_triples, filter_csr, timers=None):
+    """Returns (rank, filter_rank) int64 (B,) for the 2*T_q queries `all_triples` (forward + inverse).
+
+    timers: optional dict of name -> (start_event, end_event) pairs recorded on the current stream."""
+    def mark(name, which):
+        if timers is not None:
+            timers[name][which].record()
+
+    mark("evolve", 0)
+    evolve_embs, _, r_emb, _, _ = model.forward(glist, None, True)
+    mark("evolve", 1)
+    mark("score", 0)
+    emb = evolve_embs[-1]
+    if model.layer_norm:
+        if hasattr(model, "_c_float"):
+            emb = ops.row_map(emb, ops.ROW_TANGENT_NORMALIZE, c=model._c_float)
+        else:
+            emb = ops.row_map(emb, ops.ROW_NORMALIZE)
+    score = model.decoder_ob.forward(emb, r_emb, all_triples, mode="test")
+    mark("score", 1)
+    mark("rank", 0)
+    raw, filt, _ = ops.rank_dense(score, all_triples, 2, filter_csr.ptr if filter_csr is not None else None,
+                                  filter_csr.idx if filter_csr is not None else None)
+    rank, frank = ops.counts_to_ranks(raw, filt)
+    mark("rank", 1)
+    return rank, frank
+
+
+@torch.no_grad()
+def evaluate_from_host(model, history_host, test_host, num_nodes, num_rels, device):
+    """End-to-end step from HOST buffers (pinned int64 triples): H2D copies, device edge-index build for every
+    history snapshot, predict() (entity + relation decoders, like the reference's test loop), time-aware filtered
+    ranking for both, and the D2H read-back of MRRs and rank vectors.  Returns python floats + host tensors."""
+    from .graph import SnapshotGraph
+    glist = [SnapshotGraph(num_nodes, num_rels, h.to(device, non_blocking=True)) for h in history_host]
+    test = test_host.to(device, non_blocking=True)
+    all_t, score, score_rel = model.predict(glist, num_rels, None, test, True)
+    f_ent = utils.filter_csr_from_snapshot(all_t, 2 * num_rels, 0)
+    f_rel = utils.filter_csr_from_snapshot(all_t, num_nodes, 1)
+    fm_r, m_r, rank_r, frank_r = utils.get_total_rank(all_t, score_rel, None, 1000, rel_predict=1, filter_csr=f_rel)
+    fm, m, rank, frank = utils.get_total_rank(all_t, score, None, 1000, rel_predict=0, filter_csr=f_ent)
+    return (fm, m, fm_r, m_r), rank.cpu(), frank.cpu()

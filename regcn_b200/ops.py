@@ -36,6 +36,21 @@ def _rowmajor(t, name):
 _GEMM_IMPL = {"impl": "simt"}
 
 
+def set_gemm_impl(name):
+    """simt: fp32 CUDA-core kernel (csrc/gemm_simt.cu)."""
+    if name not in ("simt",):
+        raise ValueError(f"unknown gemm implementation {name!r}")
+    _GEMM_IMPL["impl"] = name
+
+
+def gemm_impl():
+    return _GEMM_IMPL["impl"]
+
+
+def gemm_kernel_name():
+    return {"simt": "regcn::gemm_f32_kernel"}[_GEMM_IMPL["impl"]]
+
+
 def gemm(a, b, trans_b=False, bias=None, out=None, accumulate=False, split_k=1):
     """C[M,N] (+)= A[M,K] @ (B[K,N] | B[N,K]^T) (+ bias).  torch.mm / F.linear call sites of the path."""
     a = _rowmajor(a, "a")

@@ -1,0 +1,114 @@
+"""CPU: the C-ABI library loads and exports exactly what include/regcn_b200.h declares; host-side logic."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import restate, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_prototypes():
+    src = open(os.path.join(ROOT, "include", "regcn_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"REGCN_API\s+[\w\s\*]+?\b(regcn_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
+        name, args = m.group(1), m.group(2).strip()
+        protos[name] = 0 if args in ("", "void") else len(args.split(","))
+    return protos
+
+
+def test_library_exports_every_declared_symbol():
+    from regcn_b200 import _lib
+    protos = _header_prototypes()
+    assert len(protos) >= 27
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in protos:
+        assert hasattr(lib, name), f"{name} declared in include/regcn_b200.h but not exported"
+    assert set(_lib.SIGNATURES) == set(protos), set(_lib.SIGNATURES) ^ set(protos)
+    for name, n_args in protos.items():
+        assert len(_lib.SIGNATURES[name][1]) == n_args, f"{name}: ctypes binding has the wrong arity"
+    assert _lib.load().regcn_version() >= 100
+    assert isinstance(_lib.last_error(), str)
+
+
+def test_product_path_refuses_cpu():
+    """No CPU fallback: without a B200 the public API raises instead of computing somewhere else."""
+    import regcn_b200 as R
+    from regcn_b200 import ops
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback|no sm_100"):
+        R.build_sub_graph(10, 2, np.array([[0, 0, 1]]), True, 0)
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        ops.gemm(torch.randn(4, 4), torch.randn(4, 4))
+    with pytest.raises(RuntimeError):
+        R.build_sub_graph(10, 2, np.array([[0, 0, 1]]), False, 0)
+
+
+def test_product_package_never_imports_oracle():
+    pkg = os.path.join(ROOT, "regcn_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            assert "oracle" not in open(os.path.join(pkg, fn)).read().replace("oracle/", ""), fn
+
+
+def test_answer_dicts_and_split_by_time():
+    from regcn_b200 import utils
+    rng = np.random.default_rng(0)
+    quads = np.stack([rng.integers(0, 20, 60), rng.integers(0, 4, 60), rng.integers(0, 20, 60),
+                      np.sort(rng.integers(0, 5, 60)) * 24], 1)
+    snaps = utils.split_by_time(quads)
+    assert sum(len(s) for s in snaps) == 60 and len(snaps) == len(np.unique(quads[:, 3]))
+    for s, t in zip(snaps, np.unique(quads[:, 3])):
+        assert np.array_equal(s, quads[quads[:, 3] == t][:, :3])
+    d = utils.load_all_answers_for_filter(snaps[0], 4, False)
+    assert d == synth.answers_of(snaps[0], 4, False)
+    assert utils.load_all_answers_for_filter(snaps[0], 4, True) == synth.answers_of(snaps[0], 4, True)
+    assert len(utils.load_all_answers_for_time_filter(quads, 4, 20)) == len(snaps)
+
+
+def test_filter_csr_builders_agree_on_cpu():
+    from regcn_b200 import utils
+    case = synth.make_case("small", 8)
+    r = case["num_rels"]
+    all_t = torch.as_tensor(restate.add_inverse(case["test"], r))
+    for rel_p, nk in ((0, 2 * r), (1, case["num_ents"])):
+        d = synth.answers_of(case["test"], r, bool(rel_p))
+        a = utils.filter_csr_from_dict(all_t, d, rel_predict=rel_p)
+        b = utils.filter_csr_from_snapshot(all_t, nk, rel_predict=rel_p)
+        assert torch.equal(a.ptr, b.ptr) and torch.equal(a.idx, b.idx)
+        # every query's own target is in its list; lists are sorted and unique
+        for q in range(0, len(all_t), 17):
+            lst = a.idx[a.ptr[q]:a.ptr[q + 1]].tolist()
+            assert lst == sorted(set(lst)) and int(all_t[q, 1 if rel_p else 2]) in lst
+
+
+def test_state_dict_names_match_reference_listing():
+    """The names the reference's checkpoints carry exist with the right shapes."""
+    import regcn_b200 as R
+    m = R.RecurrentRGCN("convtranse", "uvrgcn", 50, 4, 0, 0, 200, "sub", 3, num_bases=100, num_hidden_layers=2,
+                        dropout=0.2, self_loop=True, skip_connect=True, layer_norm=True)
+    sd = m.state_dict()
+    for k in ("w1", "w2", "emb_rel", "dynamic_emb", "time_gate_weight", "time_gate_bias", "rgcn.rel_emb",
+              "relation_cell_1.weight_ih", "relation_cell_1.bias_hh", "rgcn.layers.0.weight_neighbor",
+              "rgcn.layers.1.loop_weight", "rgcn.layers.1.evolve_loop_weight", "rgcn.layers.1.skip_connect_weight",
+              "rgcn.layers.1.skip_connect_bias", "decoder_ob.conv1.weight", "decoder_ob.bn0.running_mean",
+              "decoder_ob.bn3.weight", "decoder_ob.bn_init.bias", "decoder_ob.fc.weight", "decoder_ob.b", "rdecoder.b"):
+        assert k in sd, k
+    assert "rgcn.layers.0.skip_connect_weight" not in sd
+    assert tuple(sd["decoder_ob.fc.weight"].shape) == (200, 10000) and tuple(sd["rdecoder.b"].shape) == (8,)
+    h = R.HyperbolicRecurrentRGCN("roth", "lgcn", 50, 50, 0, 0, 200, "sub", 3, num_bases=100, num_hidden_layers=2,
+                                  dropout=0.2, self_loop=True)
+    sd = h.state_dict()
+    for k in ("c", "radius_target", "radius_static", "temporal_radius_evolution.radius_mlp.weight",
+              "relation_gru.weight_ih", "rgcn.layers.0.weight", "rgcn.layers.1.evolve_loop_weight",
+              "decoder_ob.rot_proj.weight", "decoder_ob.trans_proj.bias", "decoder_ob.reshape_fc2.weight",
+              "decoder_ob.score_scale_raw", "decoder_ob.score_margin", "rdecoder.global_rot", "rdecoder.rel_bias"):
+        assert k in sd, k
+    assert tuple(sd["rgcn.layers.0.weight"].shape) == (100, 400)
+    assert tuple(sd["decoder_ob.rot_proj.weight"].shape) == (100, 200)

@@ -1,0 +1,466 @@
+"""GPU: every kernel entry point of the C ABI against the CPU oracle (oracle/restate.py) on seeded inputs,
+bit-exact for integer / index work, |a-b| <= 1e-4*max(1,|b|) for fp32, plus size-independent
+properties at sizes the oracle cannot reach."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import restate, synth
+from tests.helpers import close
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _ops():
+    import regcn_b200
+    from regcn_b200 import ops
+    regcn_b200._lib.require_device()
+    return regcn_b200, ops
+
+
+def _t(x, dtype=torch.float32):
+    return torch.as_tensor(np.asarray(x), dtype=dtype).to(DEV)
+
+
+# ----------------------------------------------------------------------------------------- K1
+@pytest.mark.parametrize("shape,zipf", [("tiny", True), ("small", True), ("c1", True), ("c3", False), ("c4d", True)])
+def test_csr_build_bit_exact(shape, zipf):
+    R, _ = _ops()
+    case = synth.make_case(shape, 3, zipf=zipf)
+    n, r = case["num_ents"], case["num_rels"]
+    tri = case["history"][0]
+    g = R.build_sub_graph(n, r, tri, True, 0)
+    o = restate.build_edges(tri, n, r)
+    E = 2 * len(tri)
+    assert g.num_edges == E
+    assert np.array_equal(g.src[:E].cpu().numpy(), o["src"])
+    assert np.array_equal(g.dst[:E].cpu().numpy(), o["dst"])
+    assert np.array_equal(g.etype[:E].cpu().numpy(), o["etype"])
+    assert np.array_equal(g.indeg.cpu().numpy(), o["indeg"])
+    assert np.array_equal(g.norm.cpu().numpy(), o["norm"])
+    rowptr, eperm, src_sorted, etype_sorted = restate.csr_by_dst(o)
+    assert np.array_equal(g.rowptr.cpu().numpy(), rowptr)
+    assert np.array_equal(g.eperm[:E].cpu().numpy(), eperm)
+    assert np.array_equal(g.src_sorted[:E].cpu().numpy(), src_sorted)
+    assert np.array_equal(g.etype_sorted[:E].cpu().numpy(), etype_sorted)
+    rel_rowptr, rel_ents = restate.r2e(tri, r)
+    assert np.array_equal(g.rel_rowptr.cpu().numpy(), rel_rowptr)
+    assert g.n_rel_ents == len(rel_ents)
+    assert np.array_equal(g.rel_ents[:g.n_rel_ents].cpu().numpy(), rel_ents)
+    # virtual rows: chunks of 256 edges per destination, in row order
+    nch = np.maximum(1, -(-o["indeg"] // 256))
+    assert g.n_vrows == int(nch.sum())
+    assert g.n_split_chunks == int(nch[nch > 1].sum())
+    assert np.array_equal(g.vrow_row[:g.n_vrows].cpu().numpy(), np.repeat(np.arange(n), nch))
+    # the DGL-style views the reference's modules read
+    assert g.number_of_nodes() == n and tuple(g.ndata["norm"].shape) == (n, 1)
+    assert np.array_equal(g.edata["type"].cpu().numpy(), o["etype"])
+    present = np.nonzero(np.diff(rel_rowptr))[0]
+    assert np.array_equal(g.uniq_r, np.concatenate((present, present + r)))
+    assert len(g.r_len) == 2 * len(present) and g.r_len[-1][1] == len(g.r_to_e)
+
+
+def test_csr_build_empty_and_duplicates():
+    R, ops = _ops()
+    g = R.build_sub_graph(10, 3, np.zeros((0, 3), dtype=np.int64), True, 0)
+    assert g.num_edges == 0 and g.n_vrows == 10 and g.n_split_chunks == 0 and g.n_rel_ents == 0
+    assert np.array_equal(g.rowptr.cpu().numpy(), np.zeros(11))
+    assert np.array_equal(g.norm.cpu().numpy(), np.ones(10, dtype=np.float32))
+    h = torch.randn(10, 8, device=DEV)
+    rel = torch.randn(6, 8, device=DEV)
+    assert torch.count_nonzero(ops.union_aggregate(h, rel, g)) == 0      # DGL zero-fill for in-degree 0
+    assert torch.count_nonzero(ops.rel_mean_pool(h, g)) == 0
+    tri = np.array([[1, 0, 2], [1, 0, 2], [2, 1, 2]], dtype=np.int64)    # multi-edge + self loop are kept
+    g = R.build_sub_graph(4, 2, tri, True, 0)
+    assert g.indeg.cpu().tolist() == [0, 2, 4, 0]
+
+
+# ----------------------------------------------------------------------------------------- K4 / K2
+@pytest.mark.parametrize("shape,d,radius", [("tiny", 200, False), ("small", 200, True), ("c1", 200, False),
+                                            ("c4d", 200, True), ("small", 64, False), ("c4d", 128, False)])
+def test_union_aggregate_vs_oracle(shape, d, radius):
+    R, ops = _ops()
+    case = synth.make_case(shape, 5)
+    n, r = case["num_ents"], case["num_rels"]
+    tri = case["history"][0]
+    g = R.build_sub_graph(n, r, tri, True, 0)
+    o = restate.build_edges(tri, n, r)
+    rng = np.random.default_rng(1)
+    h = rng.standard_normal((n, d)).astype(np.float32)
+    rel = rng.standard_normal((2 * r, d)).astype(np.float32)
+    rad = rng.uniform(0.5, 3.0, n).astype(np.float32) if radius else None
+    gamma = 0.15
+    out = ops.union_aggregate(_t(h), _t(rel), g, radius=_t(rad) if radius else None, gamma=gamma).cpu().numpy()
+    msg = h[o["src"]].astype(np.float64) + rel[o["etype"]]
+    if radius:
+        w32 = np.exp(-np.float32(gamma) * np.abs(rad[o["src"]] - rad[o["dst"]])).astype(np.float64)
+        msg = msg * w32[:, None]
+    ref = np.zeros((n, d))
+    np.add.at(ref, o["dst"], msg)
+    ref *= o["norm"][:, None]
+    # hub rows sum thousands of O(1) terms in fp32: gate relative to the row's accumulated magnitude
+    mag = np.zeros(n)
+    np.add.at(mag, o["dst"], np.abs(msg).max(axis=1))
+    scale = np.maximum(1.0, (mag * o["norm"])[:, None])
+    assert np.all(np.abs(out - ref) <= 1e-4 * np.maximum(scale, np.abs(ref))), np.abs(out - ref).max()
+    if g.n_split_chunks:
+        assert g.max_hub_degree > 256
+
+
+def test_union_aggregate_large_vs_torch():
+    """Full-size property (oracle-free): 200k entities, 2M edges against torch.index_add_ in fp64 on the GPU."""
+    R, ops = _ops()
+    n, r, t, d = 200_000, 64, 1_000_000, 200
+    rng = np.random.default_rng(0)
+    tri = synth.make_snapshot(rng, n, r, t, zipf=True)
+    g = R.build_sub_graph(n, r, tri, True, 0)
+    h = torch.randn(n, d, device=DEV)
+    rel = torch.randn(2 * r, d, device=DEV)
+    out = ops.union_aggregate(h, rel, g)
+    E = g.num_edges
+    msg = h[g.src[:E].long()].double() + rel[g.etype[:E].long()].double()
+    ref = torch.zeros(n, d, device=DEV, dtype=torch.float64).index_add_(0, g.dst[:E].long(), msg)
+    ref *= g.norm.double().view(-1, 1)
+    err = (out.double() - ref).abs()
+    assert bool((err <= 2e-4 * torch.clamp(ref.abs(), min=1.0)).all()), float(err.max())
+    # linearity in h (size-independent property): agg(h1 + h2, rel) = agg(h1, rel) + agg(h2, 0)
+    h2 = torch.randn(n, d, device=DEV)
+    lhs = ops.union_aggregate(h + h2, rel, g)
+    rhs = out + ops.union_aggregate(h2, torch.zeros_like(rel), g)
+    assert bool(((lhs - rhs).abs() <= 1e-3 * torch.clamp(lhs.abs(), min=1.0)).all())
+
+
+@pytest.mark.parametrize("shape,nsplit", [("tiny", 1), ("c1", 1), ("c4d", 1), ("c4d", 7)])
+def test_rel_mean_pool_vs_oracle(shape, nsplit):
+    R, ops = _ops()
+    case = synth.make_case(shape, 2)
+    n, r = case["num_ents"], case["num_rels"]
+    tri = case["history"][1]
+    g = R.build_sub_graph(n, r, tri, True, 0)
+    h = torch.randn(n, 200, dtype=torch.float64)
+    rel_rowptr, rel_ents = restate.r2e(tri, r)
+    ref = restate.rel_mean_pool(h, rel_rowptr, rel_ents, r).numpy()
+    out = ops.rel_mean_pool(h.float().to(DEV), g, nsplit=nsplit).cpu().numpy()
+    ok, worst = close(out, ref)
+    assert ok, worst
+
+
+# ----------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("M,N,K,trans_b,bias,split_k", [
+    (1, 200, 200, False, False, 1), (513, 200, 200, False, True, 1), (300, 600, 400, True, True, 1),
+    (1000, 23033 // 8, 200, True, False, 1), (257, 200, 10000, True, True, 6), (64, 8, 12, False, False, 1),
+    (130, 131, 204, True, True, 3), (2914, 200, 200, False, False, 1)])
+def test_gemm_f32_vs_fp64(M, N, K, trans_b, bias, split_k):
+    _, ops = _ops()
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N)
+    a = torch.randn(M, K, generator=g)
+    b = torch.randn((N, K) if trans_b else (K, N), generator=g)
+    bv = torch.randn(N, generator=g) if bias else None
+    ref = a.double() @ (b.double().t() if trans_b else b.double())
+    if bias:
+        ref = ref + bv.double()
+    out = ops.gemm(a.to(DEV), b.to(DEV), trans_b=trans_b, bias=bv.to(DEV) if bias else None, split_k=split_k)
+    # fp32 accumulation over K terms of unit variance: error ~ sqrt(K)*eps*|terms|
+    tol = 1e-4 * max(1.0, (K / 200.0) ** 0.5)
+    err = (out.cpu().double() - ref).abs()
+    assert bool((err <= tol * torch.clamp(ref.abs(), min=1.0) * 4).all()), float(err.max())
+    # accumulate into a strided output block
+    big = torch.zeros(M, N + 8, device=DEV)
+    view = big[:, 4:4 + N]
+    view.copy_(torch.ones(M, N))
+    ops.gemm(a.to(DEV), b.to(DEV), trans_b=trans_b, out=view, accumulate=True, split_k=split_k)
+    ref2 = a.double() @ (b.double().t() if trans_b else b.double()) + 1.0
+    err2 = (view.cpu().double() - ref2).abs()
+    assert bool((err2 <= tol * torch.clamp(ref2.abs(), min=1.0) * 4).all())
+    assert float(big[:, :4].abs().sum()) == 0.0 and float(big[:, 4 + N:].abs().sum()) == 0.0
+
+
+def test_gemm_rejects_bad_arguments():
+    _, ops = _ops()
+    a = torch.randn(4, 6, device=DEV)          # K = 6 is not a multiple of 4
+    b = torch.randn(6, 8, device=DEV)
+    with pytest.raises(RuntimeError, match="status -2"):
+        ops.gemm(a, b)
+    with pytest.raises(RuntimeError):
+        ops.gemm(torch.randn(4, 8), torch.randn(8, 8))   # CPU tensors are refused: no fallback
+
+
+# ----------------------------------------------------------------------------------------- row maps
+@pytest.mark.parametrize("d", [200, 64, 256])
+def test_row_maps_vs_oracle(d):
+    _, ops = _ops()
+    c = 0.01
+    g = torch.Generator().manual_seed(d)
+    x = torch.randn(301, d, generator=g) * torch.logspace(-3, 1.2, 301).view(-1, 1)   # tiny to beyond the ball
+    x[7] = 0
+    xd = x.to(DEV)
+    pairs = [
+        (ops.ROW_NORMALIZE, restate.normalize_rows(x)),
+        (ops.ROW_TANH, torch.tanh(x)),
+        (ops.ROW_EXP0, restate.exp0(x, c)),
+        (ops.ROW_PROJECT, restate.project(x, c)),
+    ]
+    ball = restate.project(x * 0.2, c)
+    for mode, ref in pairs:
+        ok, worst = close(ops.row_map(xd, mode, c=c).cpu().numpy(), ref.numpy())
+        assert ok, (mode, worst)
+    bd = ball.to(DEV)
+    t = restate.log0(ball, c)
+    for mode, ref in [(ops.ROW_LOG0, t), (ops.ROW_LEAKY_TANH_LOG0, 0.9 * torch.tanh(t) + 0.1 * t),
+                      (ops.ROW_TANGENT_NORMALIZE, restate.exp0(restate.normalize_rows(t), c))]:
+        out, ss = ops.row_map(bd, mode, c=c, want_sumsq=True)
+        ok, worst = close(out.cpu().numpy(), ref.numpy())
+        assert ok, (mode, worst)
+        ok, worst = close(ss.cpu().numpy(), (ref.double() ** 2).sum(1).numpy())
+        assert ok, (mode, worst)
+    ok, worst = close(ops.row_sumsq(xd).cpu().numpy(), (x.double() ** 2).sum(1).numpy())
+    assert ok, worst
+
+
+def test_gru_gate_vs_oracle():
+    _, ops = _ops()
+    d, M = 200, 460
+    g = torch.Generator().manual_seed(0)
+    x, h = torch.randn(M, 2 * d, generator=g), torch.randn(M, d, generator=g)
+    w_ih, w_hh = torch.randn(3 * d, 2 * d, generator=g) * 0.05, torch.randn(3 * d, d, generator=g) * 0.05
+    b_ih, b_hh = torch.randn(3 * d, generator=g) * 0.1, torch.randn(3 * d, generator=g) * 0.1
+    ref = restate.gru_cell(x.double(), h.double(), w_ih.double(), w_hh.double(), b_ih.double(), b_hh.double())
+    torch_ref = torch.nn.functional.normalize(ref.float())
+    gi = ops.gemm(x.to(DEV), w_ih.to(DEV), trans_b=True, bias=b_ih.to(DEV))
+    gh = ops.gemm(h.to(DEV), w_hh.to(DEV), trans_b=True, bias=b_hh.to(DEV))
+    ok, worst = close(ops.gru_gate(gi, gh, h.to(DEV), False).cpu().numpy(), ref.numpy())
+    assert ok, worst
+    ok, worst = close(ops.gru_gate(gi, gh, h.to(DEV), True).cpu().numpy(), torch_ref.numpy())
+    assert ok, worst
+    # cross-check the restated cell against torch's own GRUCell
+    cell = torch.nn.GRUCell(2 * d, d)
+    with torch.no_grad():
+        cell.weight_ih.copy_(w_ih); cell.weight_hh.copy_(w_hh); cell.bias_ih.copy_(b_ih); cell.bias_hh.copy_(b_hh)
+        ok, worst = close(cell(x, h).numpy(), ref.numpy())
+    assert ok, worst
+
+
+def test_union_combine_and_time_gate_vs_oracle():
+    _, ops = _ops()
+    n, d, c = 777, 200, 0.01
+    g = torch.Generator().manual_seed(4)
+    P = torch.randn(n, d, generator=g) * 6          # exercises the +-10 clamps
+    L = torch.randn(n, 2 * d, generator=g) * 3
+    indeg = (torch.rand(n, generator=g) > 0.4).int()
+    S = torch.randn(n, d, generator=g)
+    sb = torch.randn(d, generator=g) * 0.1
+    prev = torch.randn(n, d, generator=g)
+    loop = torch.where(indeg.view(-1, 1) > 0, L[:, :d], L[:, d:])
+    dev = lambda t: t.to(DEV)
+    # Euclidean
+    out, _, _ = ops.union_combine(dev(P), dev(L), dev(indeg), act=1)
+    ok, worst = close(out.cpu().numpy(), restate.rrelu(P + loop).numpy())
+    assert ok, worst
+    sw = torch.sigmoid(S + sb)
+    out, _, _ = ops.union_combine(dev(P), dev(L), dev(indeg), act=1, skip=dev(S), skip_bias=dev(sb), prev=dev(prev))
+    ok, worst = close(out.cpu().numpy(), restate.rrelu(sw * (P + loop) + (1 - sw) * prev).numpy())
+    assert ok, worst
+    out, _, _ = ops.union_combine(dev(P), None, None, act=0)
+    assert torch.equal(out.cpu(), P)
+    # hyperbolic: clamp, loop, clamp, rrelu, exp_0 (+ tangent / radius of the result)
+    ref_t = restate.rrelu((P.clamp(-10, 10) + loop).clamp(-10, 10))
+    ref_h = restate.exp0(ref_t, c)
+    out, ht, rad = ops.union_combine(dev(P), dev(L), dev(indeg), act=1, hyper=True, c=c, want_tangent=True,
+                                     want_radius=True)
+    ok, worst = close(out.cpu().numpy(), ref_h.numpy())
+    assert ok, worst
+    ok, worst = close(ht.cpu().numpy(), restate.log0(ref_h, c).numpy())
+    assert ok, worst
+    ok, worst = close(rad.cpu().numpy(), restate.get_radius(ref_h).numpy())
+    assert ok, worst
+    # Euclidean time gate
+    G, b, cur, h = torch.randn(n, d, generator=g), torch.randn(d, generator=g), P, prev
+    for ln in (False, True):
+        tw = torch.sigmoid(G + b)
+        ref = tw * (restate.normalize_rows(cur) if ln else cur) + (1 - tw) * h
+        ok, worst = close(ops.time_gate(dev(G), dev(b), dev(cur), dev(h), ln).cpu().numpy(), ref.numpy())
+        assert ok, worst
+
+
+@pytest.mark.parametrize("layer_norm,residual", [(False, True), (True, True), (False, False)])
+def test_hyperbolic_row_kernels_vs_oracle(layer_norm, residual):
+    _, ops = _ops()
+    n, d, c = 513, 200, 0.01
+    rmin, rmax, beta, eps_r = 0.5, 3.0, 0.7, 0.1
+    g = torch.Generator().manual_seed(9)
+    emb = torch.randn(n, d, generator=g)
+    rs_raw = torch.rand(n, generator=g) * 4.0          # some outside [rmin, rmax]
+    rs = restate.static_radius(rs_raw, c, rmin, rmax)
+    init = restate.normalize_rows(emb) if layer_norm else emb
+    ref_h = restate.apply_radius(restate.exp0(init, c), rs, c)
+    h = ops.hyp_init(emb.to(DEV), rs_raw.to(DEV), layer_norm, False, c, rmin, rmax)
+    ok, worst = close(h.cpu().numpy(), ref_h.numpy())
+    assert ok, worst
+    ht, pt, rad = ops.hyp_tangent(h, c)
+    ok, worst = close(ht.cpu().numpy(), restate.log0(ref_h, c).numpy())
+    assert ok, worst
+    ok, worst = close(rad.cpu().numpy(), restate.get_radius(ref_h).numpy())
+    assert ok, worst
+    # time gate + radius evolution
+    h2 = restate.exp0(torch.randn(n, d, generator=g) * 3, c)
+    G = torch.randn(n, d, generator=g)
+    b = torch.randn(d, generator=g) * 0.1
+    w = torch.randn(1, d, generator=g) * 0.05
+    rb = 0.03
+    cur = restate.project(h2, c)
+    if layer_norm:
+        cur = restate.exp0(restate.normalize_rows(restate.log0(cur, c)), c)
+    ct = restate.log0(cur, c).clamp(-10, 10)
+    ptr_ = restate.log0(ref_h, c).clamp(-10, 10)
+    tw = torch.sigmoid(G + b)
+    hn = restate.project(restate.exp0(tw * ct + (1 - tw) * ptr_, c), c)
+    if residual:
+        hn = restate.radius_evolution(hn, rs, w, torch.tensor([rb]), c, beta, eps_r)
+    else:
+        hn = restate.apply_radius(hn, rs, c)
+    out = ops.hyp_time_gate(h2.to(DEV), pt, G.to(DEV), b.to(DEV), rs_raw.to(DEV), w.view(-1).to(DEV), rb, layer_norm,
+                            residual, c, rmin, rmax, beta, eps_r)
+    ok, worst = close(out.cpu().numpy(), hn.numpy(), rtol=2e-4)
+    assert ok, worst
+
+
+# ----------------------------------------------------------------------------------------- K6 / K7
+@pytest.mark.parametrize("nb", [100, 10, 50])
+def test_block_and_lorentz_aggregate_vs_oracle(nb):
+    R, ops = _ops()
+    case = synth.make_case("small_l", 4)
+    n, r, d, c = case["num_ents"], case["num_rels"], 200, 0.01
+    tri = case["history"][2]
+    g = R.build_sub_graph(n, r, tri, True, 0)
+    o = restate.build_edges(tri, n, r)
+    gen = torch.Generator().manual_seed(nb)
+    sb = d // nb
+    W = torch.randn(2 * r, nb * sb * sb, generator=gen) * 0.3
+    rel = torch.randn(2 * r, d, generator=gen) * 0.3
+    h = restate.exp0(torch.randn(n, d, generator=gen), c)
+    # K6 (static-graph layer): rrelu(norm * sum blockdiag(W).h) with the activation done by union_combine
+    ref = restate.block_layer(h.double(), o, W.double(), nb, d)
+    agg = ops.block_aggregate(h.to(DEV), W.to(DEV), g, nb, d)
+    out, _, _ = ops.union_combine(agg, None, None, act=1)
+    ok, worst = close(out.cpu().numpy(), ref.numpy())
+    assert ok, worst
+    # K7: Lorentz centroid aggregate -> full layer output
+    wl, we = torch.randn(d, d, generator=gen) * 0.1, torch.randn(d, d, generator=gen) * 0.1
+    ref_l = restate.lorentz_layer(h, rel, o, W, wl, we, c, nb)
+    ht, _, _ = ops.hyp_tangent(h.to(DEV), c, want_clamped=False, want_radius=False)
+    agg = ops.lorentz_aggregate(ht, W.to(DEV), rel.to(DEV), g, nb, c)
+    L = ops.gemm(ht, torch.cat((wl, we), 1).to(DEV))
+    out, _, _ = ops.union_combine(agg, L, g.indeg, act=1, hyper=True, c=c)
+    ok, worst = close(out.cpu().numpy(), ref_l.numpy(), rtol=2e-4)
+    assert ok, worst
+
+
+# ----------------------------------------------------------------------------------------- decoders
+def test_convtranse_tower_and_hyp_query_vs_oracle():
+    R, ops = _ops()
+    from tests.helpers import build_model
+    cfg = dict(kind="regcn", layer_norm=True, seed=11)
+    n, r, B, d = 300, 20, 77, 200
+    m, sd = build_model(cfg, n, r)
+    m = m.to(DEV)
+    gen = torch.Generator().manual_seed(2)
+    emb = torch.randn(n, d, generator=gen)
+    rel = torch.randn(2 * r, d, generator=gen)
+    tri = torch.stack([torch.randint(0, n, (B,), generator=gen), torch.randint(0, 2 * r, (B,), generator=gen),
+                       torch.randint(0, n, (B,), generator=gen)], 1)
+    P = {k: v.float() for k, v in sd.items() if v.is_floating_point()}
+    ref = restate.convtranse_scores(P, emb, rel, tri.numpy())
+    out = m.decoder_ob(emb.to(DEV), rel.to(DEV), tri.to(DEV), mode="test")
+    ok, worst = close(out.cpu().numpy(), ref.numpy(), rtol=2e-4)
+    assert ok, worst
+    ref = restate.convtransr_scores(P, emb, rel, tri.numpy())
+    out = m.rdecoder(emb.to(DEV), rel.to(DEV), tri.to(DEV), mode="test")
+    ok, worst = close(out.cpu().numpy(), ref.numpy(), rtol=2e-4)
+    assert ok, worst
+    # single-query batch skips bn2 (src/decoder.py:93-94)
+    ref1 = restate.convtranse_scores(P, emb, rel, tri[:1].numpy())
+    out1 = m.decoder_ob(emb.to(DEV), rel.to(DEV), tri[:1].contiguous().to(DEV), mode="test")
+    ok, worst = close(out1.cpu().numpy(), ref1.numpy(), rtol=2e-4)
+    assert ok, worst
+
+
+@pytest.mark.parametrize("decoder", ["roth", "murp", "hyperbolic_convtranse"])
+def test_hyperbolic_decoders_vs_oracle(decoder):
+    R, ops = _ops()
+    from tests.helpers import build_model
+    c = 0.01
+    cfg = dict(kind="hyp", layer_norm=False, seed=5, decoder=decoder, encoder="hyperbolic_uvrgcn", gamma=0.15)
+    n, r, B, d = 400, 25, 90, 200
+    m, sd = build_model(cfg, n, r)
+    m = m.to(DEV)
+    gen = torch.Generator().manual_seed(3)
+    emb = restate.apply_radius(restate.exp0(torch.randn(n, d, generator=gen), c), torch.rand(n, generator=gen) * 2.5 + 0.5, c)
+    rel = torch.randn(2 * r, d, generator=gen) * 0.3
+    tri = torch.stack([torch.randint(0, n, (B,), generator=gen), torch.randint(0, 2 * r, (B,), generator=gen),
+                       torch.randint(0, n, (B,), generator=gen)], 1)
+    P = {k: v.float() for k, v in sd.items() if v.is_floating_point()}
+    fn = {"roth": (restate.roth_scores, restate.rothrel_scores), "murp": (restate.murp_scores, restate.murprel_scores),
+          "hyperbolic_convtranse": (restate.hyp_convtranse_scores, restate.hyp_convtransr_scores)}[decoder]
+    ref = fn[0](P, emb, rel, tri.numpy(), c)
+    ref = ref[0] if isinstance(ref, tuple) else ref
+    out = m.decoder_ob(emb.to(DEV), rel.to(DEV), tri.to(DEV), mode="test")
+    ok, worst = close(out.cpu().numpy(), ref.numpy(), rtol=2e-4)
+    assert ok, worst
+    ref = fn[1](P, emb, rel, tri.numpy(), c)
+    ref = ref[0] if isinstance(ref, tuple) else ref
+    out = m.rdecoder(emb.to(DEV), rel.to(DEV), tri.to(DEV), mode="test")
+    ok, worst = close(out.cpu().numpy(), ref.numpy(), rtol=2e-4)
+    assert ok, worst
+
+
+# ----------------------------------------------------------------------------------------- K14
+@pytest.mark.parametrize("B,N,levels", [(50, 300, 0), (200, 7128, 0), (64, 1000, 7), (1, 5, 2)])
+def test_rank_bit_exact_vs_oracle(B, N, levels):
+    R, ops = _ops()
+    from regcn_b200 import utils
+    rng = np.random.default_rng(B + N)
+    score = rng.standard_normal((B, N)).astype(np.float32)
+    if levels:
+        score = np.round(score * levels) / levels        # heavy ties, including with the target
+    r = 5
+    tri = np.stack([rng.integers(0, 40, B), rng.integers(0, r, B), rng.integers(0, min(N, 40), B)], 1).astype(np.int64)
+    all_ans = {}
+    for h, rr, t in tri:
+        all_ans.setdefault(int(h), {}).setdefault(int(rr), set()).add(int(t))
+    for h in all_ans:                                     # add extra true answers so the filter has work to do
+        for rr in all_ans[h]:
+            all_ans[h][rr].update(int(x) for x in rng.integers(0, N, 4))
+    fm, m, rank, frank = restate.total_rank(tri, score, all_ans, 0)
+    s_dev = _t(score)
+    fm2, m2, rank2, frank2 = utils.get_total_rank(_t(tri, torch.int64), s_dev, all_ans, 1000, rel_predict=0)
+    assert np.array_equal(rank2.cpu().numpy(), rank)
+    assert np.array_equal(frank2.cpu().numpy(), frank)
+    assert abs(fm - fm2) < 1e-6 and abs(m - m2) < 1e-6
+    # the reference's in-place side effect on the score matrix (utils.py:60)
+    assert np.array_equal(s_dev.cpu().numpy(), restate.filter_scores(tri, score, all_ans, 0))
+    # relation-prediction flavour (target = column 1, answers keyed by (h, t))
+    score_r = rng.standard_normal((B, 2 * r)).astype(np.float32)
+    all_ans_r = {}
+    for h, rr, t in tri:
+        all_ans_r.setdefault(int(h), {}).setdefault(int(t), set()).add(int(rr))
+    fm, m, rank, frank = restate.total_rank(tri, score_r, all_ans_r, 1)
+    _, _, rank2, frank2 = utils.get_total_rank(_t(tri, torch.int64), _t(score_r), all_ans_r, 1000, rel_predict=1)
+    assert np.array_equal(rank2.cpu().numpy(), rank) and np.array_equal(frank2.cpu().numpy(), frank)
+    # all_ans=None: filtered == raw
+    _, _, rank3, frank3 = utils.get_total_rank(_t(tri, torch.int64), _t(score), None, 1000, rel_predict=0)
+    assert torch.equal(rank3, frank3)
+
+
+def test_filter_csr_from_snapshot_matches_dict():
+    R, _ = _ops()
+    from regcn_b200 import utils
+    case = synth.make_case("small", 8)
+    r = case["num_rels"]
+    all_t = restate.add_inverse(case["test"], r)
+    for rel_p, nk in ((0, 2 * r), (1, case["num_ents"])):
+        d = synth.answers_of(case["test"], r, bool(rel_p))
+        a = utils.filter_csr_from_dict(torch.as_tensor(all_t), d, rel_predict=rel_p, device=DEV)
+        b = utils.filter_csr_from_snapshot(_t(all_t, torch.int64), nk, rel_predict=rel_p)
+        assert torch.equal(a.ptr, b.ptr) and torch.equal(a.idx, b.idx)

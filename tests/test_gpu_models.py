@@ -1,0 +1,145 @@
+"""GPU: the product modules (reference signatures) end to end against the golden fixtures produced by the
+unmodified reference, and against the fp64 oracle at sizes beyond the fixtures."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import restate, synth
+from tests.helpers import CURV, N_BASES, build_model, close, golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _run(cfg, case):
+    import regcn_b200 as R
+    from regcn_b200 import utils
+    R._lib.require_device()
+    n, r = case["num_ents"], case["num_rels"]
+    model, sd = build_model(cfg, n, r)
+    model = model.to(DEV)
+    glist = [R.build_sub_graph(n, r, s, True, 0) for s in case["history"]]
+    test = torch.from_numpy(case["test"]).to(DEV)
+    all_t, score, score_rel = model.predict(glist, r, None, test, True)
+    hist, _, h0, _, _ = model.forward(glist, None, True)
+    return model, sd, glist, all_t, score, score_rel, hist, h0
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_model_matches_reference_golden(name):
+    from regcn_b200 import utils
+    cfg, z = load_golden(name)
+    case = synth.make_case(cfg["shape"], cfg["seed"])
+    r = case["num_rels"]
+    model, sd, glist, all_t, score, score_rel, hist, h0 = _run(cfg, case)
+    assert np.array_equal(all_t.cpu().numpy(), z["all_triples"])
+    for i, g in enumerate(glist):                                   # bit-exact edge indexing (north_star)
+        E = g.num_edges
+        assert np.array_equal(g.src[:E].cpu().numpy(), z[f"g{i}_src"])
+        assert np.array_equal(g.dst[:E].cpu().numpy(), z[f"g{i}_dst"])
+        assert np.array_equal(g.etype[:E].cpu().numpy(), z[f"g{i}_type"])
+        assert np.array_equal(g.norm.cpu().numpy(), z[f"g{i}_norm"])
+        assert np.array_equal(g.uniq_r, z[f"g{i}_uniq_r"])
+    ok, worst = close(h0.cpu().numpy(), z["h0"])
+    assert ok, f"h0 worst ratio {worst}"
+    # ranks computed by the rank kernels on the reference's OWN scores must equal the reference's ranks exactly
+    all_ans = synth.answers_of(case["test"], r, False)
+    all_ans_r = synth.answers_of(case["test"], r, True)
+    if "hist" in z:
+        for i, h in enumerate(hist):
+            ok, worst = close(h.cpu().numpy(), z["hist"][i])
+            assert ok, f"hist[{i}] worst ratio {worst}"
+        ok, worst = close(score.cpu().numpy(), z["score"], rtol=2e-4)
+        assert ok, f"score worst ratio {worst}"
+        ok, worst = close(score_rel.cpu().numpy(), z["score_rel"], rtol=2e-4)
+        assert ok, f"score_rel worst ratio {worst}"
+        ref_score = torch.from_numpy(z["score"]).to(DEV)
+        fm, m, rank, frank = utils.get_total_rank(all_t, ref_score, all_ans, 1000, rel_predict=0)
+        assert np.array_equal(rank.cpu().numpy(), z["rank"]) and np.array_equal(frank.cpu().numpy(), z["filter_rank"])
+        ref_score_r = torch.from_numpy(z["score_rel"]).to(DEV)
+        fmr, mr, rank_r, frank_r = utils.get_total_rank(all_t, ref_score_r, all_ans_r, 1000, rel_predict=1)
+        assert np.array_equal(rank_r.cpu().numpy(), z["rank_rel"])
+        assert np.array_equal(frank_r.cpu().numpy(), z["filter_rank_rel"])
+        np.testing.assert_allclose([fm, m, fmr, mr], z["mrr"], rtol=1e-5)
+    else:
+        rows, qrows = z["sub_rows"], z["sub_qrows"]
+        ok, worst = close(hist[-1][rows].cpu().numpy(), z["hist_last_rows"])
+        assert ok, f"hist_last worst ratio {worst}"
+        ok, worst = close(hist[0][rows].cpu().numpy(), z["hist_first_rows"])
+        assert ok, f"hist_first worst ratio {worst}"
+        ok, worst = close(score[qrows][:, rows].cpu().numpy(), z["score_block"], rtol=2e-4)
+        assert ok, f"score block worst ratio {worst}"
+        ok, worst = close(score_rel[qrows].cpu().numpy(), z["score_rel_qrows"], rtol=2e-4)
+        assert ok, f"score_rel worst ratio {worst}"
+        ok, worst = close(score.double().sum(1).cpu().numpy(), z["score_rowsum"], rtol=2e-4,
+                          atol_scale=float(np.abs(z["score_absmax"]).max()) * 50)
+        assert ok, f"score row-sum worst ratio {worst}"
+    # end-to-end ranks on our own scores: report-level agreement (fp32 re-association flips near-ties)
+    _, _, rank, frank = utils.get_total_rank(all_t, score, all_ans, 1000, rel_predict=0,
+                                             filter_csr=utils.filter_csr_from_snapshot(all_t, 2 * r, 0))
+    _, _, rank_r, frank_r = utils.get_total_rank(all_t, score_rel, all_ans_r, 1000, rel_predict=1)
+    for mine, ref, what in ((rank, z["rank"], "rank"), (frank, z["filter_rank"], "filter_rank"),
+                            (rank_r, z["rank_rel"], "rank_rel"), (frank_r, z["filter_rank_rel"], "filter_rank_rel")):
+        flips = float(np.mean(mine.cpu().numpy() != ref))
+        assert flips <= 0.02, f"{what}: {flips:.3%} of end-to-end ranks differ from the reference"
+
+
+@pytest.mark.parametrize("kind", ["regcn", "hyp_uv", "hyp_lgcn"])
+def test_kernel_error_vs_fp64_oracle(kind):
+    """SURVEY 8(d) second gate: kernel error against the fp64 oracle <= 2 x the fp32 restatement's own error (+1e-5)."""
+    cfg = {"regcn": dict(kind="regcn", shape="small", seed=21, layer_norm=True),
+           "hyp_uv": dict(kind="hyp", shape="small", seed=22, layer_norm=False, encoder="hyperbolic_uvrgcn",
+                          decoder="roth", gamma=0.15),
+           "hyp_lgcn": dict(kind="hyp", shape="small_l", seed=23, layer_norm=False, encoder="lgcn", decoder="roth",
+                            gamma=0.15)}[kind]
+    case = synth.make_case(cfg["shape"], cfg["seed"])
+    r = case["num_rels"]
+    model, sd, glist, all_t, score, score_rel, hist, h0 = _run(cfg, case)
+    graphs = [restate.build_edges(s, case["num_ents"], r) for s in case["history"]]
+    outs = {}
+    for dt in (torch.float32, torch.float64):
+        if cfg["kind"] == "regcn":
+            o = restate.regcn_predict(sd, graphs, r, case["test"], layer_norm=True, dtype=dt)
+        else:
+            o = restate.hyp_predict(sd, graphs, r, case["test"], c=CURV, decoder="roth", layer_norm=False,
+                                    encoder=cfg["encoder"], gamma=cfg["gamma"], num_bases=min(N_BASES, 2 * r), dtype=dt)
+        outs[dt] = o
+    truth_h, truth_s = outs[torch.float64][3][-1].numpy(), outs[torch.float64][1].numpy()
+    ref_err_h = np.abs(outs[torch.float32][3][-1].numpy() - truth_h).max()
+    ref_err_s = np.abs(outs[torch.float32][1].numpy() - truth_s).max()
+    my_err_h = np.abs(hist[-1].cpu().numpy() - truth_h).max()
+    my_err_s = np.abs(score.cpu().numpy() - truth_s).max()
+    assert my_err_h <= 2 * ref_err_h + 1e-5, (my_err_h, ref_err_h)
+    assert my_err_s <= 2 * ref_err_s + 1e-4, (my_err_s, ref_err_s)
+
+
+def test_layer_signatures_drop_in():
+    """UnionRGCNLayer.forward(g, prev_h, emb_rel) / RGCNBlockLayer.forward(g, prev_h) keep the reference's contract:
+    read g.ndata['h'], write g.ndata['h'], return node_repr (rgcn/layers.py:222-255, :48-91)."""
+    import torch.nn.functional as F
+    import regcn_b200 as R
+    R._lib.require_device()
+    case = synth.make_case("small", 31)
+    n, r, d = case["num_ents"], case["num_rels"], 200
+    g = R.build_sub_graph(n, r, case["history"][0], True, 0)
+    o = restate.build_edges(case["history"][0], n, r)
+    torch.manual_seed(0)
+    layer = R.UnionRGCNLayer(d, d, 2 * r, 100, activation=F.rrelu, self_loop=True, dropout=0.2, skip_connect=True).to(DEV).eval()
+    h, rel, prev = torch.randn(n, d), torch.randn(2 * r, d), torch.randn(n, d)
+    g.ndata['h'] = h.to(DEV)
+    out = layer(g, prev.to(DEV), rel.to(DEV))
+    assert g.ndata['h'] is out
+    P = {k: v.detach().cpu().double() for k, v in layer.state_dict().items()}
+    ref = restate.union_layer(h.double(), rel.double(), o, P["weight_neighbor"], P["loop_weight"],
+                              P["evolve_loop_weight"], skip=(P["skip_connect_weight"], P["skip_connect_bias"]),
+                              prev_h=prev.double())
+    ok, worst = close(out.cpu().numpy(), ref.numpy())
+    assert ok, worst
+    blk = R.RGCNBlockLayer(d, d, 2 * r, 100, activation=F.rrelu, dropout=0.2).to(DEV).eval()
+    g.ndata['h'] = h.to(DEV)
+    out = blk(g, [])
+    ref = restate.block_layer(h.double(), o, blk.weight.detach().cpu().double(), 100, d)
+    ok, worst = close(out.cpu().numpy(), ref.numpy())
+    assert ok, worst
+    with pytest.raises(NotImplementedError):
+        layer.train()(g, [], rel.to(DEV))        # training-mode dropout is refused loudly, never silently skipped
