@@ -84,6 +84,16 @@ REGCN_API int regcn_gemm_f32(const float* A, int lda, const float* B, int ldb, i
                    int N, int K, const float* bias, int accumulate, int split_k, float* workspace,
                    size_t workspace_bytes, void* stream);
 
+/* ---- dense contraction on the tensor cores (tcgen05.mma kind::tf32, TMA-fed, TMEM accumulator) ----
+ * C[M,N] (+)= A[M,K] . B[N,K]^T (+ bias[N]), A and B both K-major.  passes == 3: error-compensated 3xTF32 on the
+ * (hi, lo) splits produced by regcn_split_tf32 (fp32 parity, ~2^-21 operand precision); passes == 1: plain TF32
+ * on a_hi / b_hi only (lo may be NULL).  lda, ldb multiples of 4, pointers 16-byte aligned.                    */
+REGCN_API int regcn_split_tf32(const float* x, float* hi, float* lo, size_t n, void* stream);
+REGCN_API size_t regcn_gemm_tf32_workspace_bytes(int M, int N, int split_k);
+REGCN_API int regcn_gemm_tf32(const float* a_hi, const float* a_lo, int lda, const float* b_hi, const float* b_lo,
+                    int ldb, float* C, int ldc, int M, int N, int K, const float* bias, int accumulate,
+                    int passes, int split_k, float* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- row maps: F.normalize / tanh / log_0 / exp_0 / project (hyperbolic_ops.py:38-116) ---------
  * mode 0 normalize, 1 tanh, 2 0.9 tanh(log_0 x)+0.1 log_0 x, 3 log_0, 4 exp_0, 5 project,
  * 6 exp_0(normalize(log_0 x)), 7 identity; sumsq (optional, M): |out|^2 per row; out may be NULL

@@ -75,6 +75,16 @@ int regcn_gemm_f32(const float* A, int lda, const float* B, int ldb, int transB,
   return gemm_f32(A, lda, B, ldb, transB, C, ldc, M, N, K, bias, accumulate, split_k, workspace, workspace_bytes,
                   ST(stream));
 }
+int regcn_split_tf32(const float* x, float* hi, float* lo, size_t n, void* stream) {
+  return split_tf32(x, hi, lo, n, ST(stream));
+}
+size_t regcn_gemm_tf32_workspace_bytes(int M, int N, int split_k) { return gemm_tf32_workspace_bytes(M, N, split_k); }
+int regcn_gemm_tf32(const float* a_hi, const float* a_lo, int lda, const float* b_hi, const float* b_lo, int ldb,
+                    float* C, int ldc, int M, int N, int K, const float* bias, int accumulate, int passes, int split_k,
+                    float* workspace, size_t workspace_bytes, void* stream) {
+  return gemm_tf32(a_hi, a_lo, lda, b_hi, b_lo, ldb, C, ldc, M, N, K, bias, accumulate, passes, split_k, workspace,
+                   workspace_bytes, ST(stream));
+}
 int regcn_row_map(const float* x, float* out, int M, int d, int mode, double c, float* sumsq, void* stream) {
   return row_map(x, out, M, d, mode, c, sumsq, ST(stream));
 }

@@ -1,0 +1,384 @@
+// Dense contraction on the 5th-generation tensor cores (sm_100a): tcgen05.mma kind::tf32, operands staged in
+// shared memory by TMA (128-byte swizzle), fp32 accumulator in tensor memory, epilogue via tcgen05.ld.
+//
+//   C[M,N] (+)= A[M,K] . B[N,K]^T (+ bias[N])          A and B both K-major (row-major with K contiguous)
+//
+// fp32 parity ("3xTF32"): every operand is split on the fly-side into hi = rna_tf32(x) and lo = rna_tf32(x - hi)
+// (split_tf32_kernel below); the kernel accumulates lo.hi + hi.lo + hi.hi into the same TMEM accumulator,
+// which restores ~2^-21 relative operand precision (the dropped lo.lo term is 2^-22).  With passes == 1 only
+// hi.hi is issued (plain TF32, ~1e-3 relative) -- reported separately, never used for the parity path.
+//
+// Warp roles (192 threads):  warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
+// warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).  One 128 x BLOCK_N output tile per CTA; grid.z = split-K.
+// K is walked in 32-float (128-byte) blocks; TMA zero-fills the K / M / N tails.
+#include "common.cuh"
+#include <cuda.h>
+
+namespace regcn {
+
+namespace tc {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 32;            // fp32 elements = one 128-byte swizzle row
+constexpr int UMMA_K = 8;              // tf32
+constexpr int NUM_THREADS = 192;
+constexpr uint32_t SMEM_BUDGET = 200 * 1024;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_c), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc) : "memory");
+}
+// K-major, 128B-swizzled tile: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO), version 1, layout type 2.
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major), 16 B
+  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset = 1024 B
+  d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct Params {
+  float* C;
+  int ldc;
+  int M, N, K;
+  const float* bias;
+  int accumulate;
+  int block_n;        // multiple of 16, <= 256
+  int tmem_cols;      // power of two >= block_n
+  int stages;
+  int passes;         // 3 = 3xTF32 (fp32 parity), 1 = plain TF32
+  int kb_per_split;   // k-blocks per grid.z slice
+  float* ws;          // split-K partials [gridDim.z][M][N] (NULL when gridDim.z == 1)
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                 const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                 const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[8];
+  __shared__ __align__(8) uint64_t empty_bar[8];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BLOCK_M;
+  const int n0 = blockIdx.x * p.block_n;
+  const int total_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int kb_beg = blockIdx.z * p.kb_per_split;
+  const int kb_end = min(total_kb, kb_beg + p.kb_per_split);
+  const int num_kb = kb_end - kb_beg;
+
+  // dynamic smem carve-up (1024-byte aligned tiles): per stage [A_hi][A_lo?][B_hi][B_lo?]
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t a_bytes = BLOCK_M * BLOCK_K * 4;
+  const uint32_t b_bytes = (uint32_t)p.block_n * BLOCK_K * 4;
+  const bool three = p.passes == 3;
+  const uint32_t stage_bytes = (three ? 2u : 1u) * (a_bytes + b_bytes);
+  const uint32_t smem_base = smem_u32(smem);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(&tmem_full_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_acc = tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0 && num_kb > 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb_beg; kb < kb_end; ++kb) {
+        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+        const uint32_t fb = smem_u32(&full_bar[stage]);
+        mbar_expect_tx(fb, stage_bytes);
+        uint32_t dst = smem_base + stage * stage_bytes;
+        const int k0 = kb * BLOCK_K;
+        tma_load_2d(dst, &tm_a_hi, fb, k0, m0); dst += a_bytes;
+        if (three) { tma_load_2d(dst, &tm_a_lo, fb, k0, m0); dst += a_bytes; }
+        tma_load_2d(dst, &tm_b_hi, fb, k0, n0); dst += b_bytes;
+        if (three) { tma_load_2d(dst, &tm_b_lo, fb, k0, n0); }
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0 && num_kb > 0) {
+      // instruction descriptor: D=f32, A=B=tf32, K-major both, N>>3, M>>4
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.block_n >> 3) << 17) |
+                             ((uint32_t)(BLOCK_M >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t acc = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(smem_u32(&full_bar[stage]), phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa_hi = smem_base + stage * stage_bytes;
+        const uint32_t sa_lo = sa_hi + a_bytes;
+        const uint32_t sb_hi = sa_hi + (three ? 2u : 1u) * a_bytes;
+        const uint32_t sb_lo = sb_hi + b_bytes;
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          const uint32_t koff = k * UMMA_K * 4;   // bytes inside the 128-byte swizzle row
+          if (three) {
+            umma_tf32(tmem_acc, make_desc(sa_lo + koff), make_desc(sb_hi + koff), idesc, acc);
+            acc = 1;
+            umma_tf32(tmem_acc, make_desc(sa_hi + koff), make_desc(sb_lo + koff), idesc, acc);
+          }
+          umma_tf32(tmem_acc, make_desc(sa_hi + koff), make_desc(sb_hi + koff), idesc, acc);
+          acc = 1;
+        }
+        umma_commit(smem_u32(&empty_bar[stage]));      // frees the smem slot once these MMAs retire
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(smem_u32(&tmem_full_bar));           // accumulator complete
+    }
+  } else {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    const int quarter = warp & 3;                      // TMEM lanes [32*quarter, 32*quarter+32)
+    const int row = m0 + quarter * 32 + lane;
+    if (num_kb > 0) {
+      mbar_wait(smem_u32(&tmem_full_bar), 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    const bool split = gridDim.z > 1;
+    float* out = split ? p.ws + (size_t)blockIdx.z * (size_t)p.M * (size_t)p.N : p.C;
+    const int ldo = split ? p.N : p.ldc;
+    const bool vec_ok = ((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+      float v[32];
+      if (num_kb > 0) {
+        tmem_ld32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+      const int gn0 = n0 + c0;
+      if (row < p.M && gn0 < p.N) {
+        float* dst = out + (size_t)row * ldo + gn0;
+        if (!split) {
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (gn0 + j < p.N) v[j] += __ldg(p.bias + gn0 + j);
+          }
+          if (p.accumulate) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (gn0 + j < p.N) v[j] += dst[j];
+          }
+        }
+        if (vec_ok && gn0 + 32 <= p.N && (gn0 & 3) == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) st4(dst + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (gn0 + j < p.N) dst[j] = v[j];
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
+// hi = rna_tf32(x), lo = rna_tf32(x - hi): both exactly representable in tf32, hi + lo == x to 2^-22 relative.
+__global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, size_t n4) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = reinterpret_cast<const float4*>(x)[i];
+  float4 h, l;
+  auto split1 = [](float a, float& hh, float& ll) {
+    uint32_t t;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(a));
+    hh = __uint_as_float(t);
+    const float r = a - hh;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(r));
+    ll = __uint_as_float(t);
+  };
+  split1(v.x, h.x, l.x); split1(v.y, h.y, l.y); split1(v.z, h.z, l.z); split1(v.w, h.w, l.w);
+  reinterpret_cast<float4*>(hi)[i] = h;
+  reinterpret_cast<float4*>(lo)[i] = l;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D fp32 row-major [rows, cols] with leading dimension ld; box = 32 floats x box_rows, 128B swizzle, zero OOB fill.
+static int make_map(CUtensorMap* m, const float* ptr, int rows, int cols, int ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_last_error("gemm_tf32: cuTensorMapEncodeTiled entry point unavailable"); return REGCN_ERR_UNSUPPORTED; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_last_error("gemm_tf32: cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%d", (int)r, rows, cols, ld); return REGCN_ERR_DIM; }
+  return REGCN_OK;
+}
+
+}  // namespace tc
+
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, float* __restrict__ C, int ldc,
+                                     int M, int N, const float* __restrict__ bias, int accumulate);
+
+int split_tf32(const float* x, float* hi, float* lo, size_t n, cudaStream_t st) {
+  if (!x || !hi || !lo) { set_last_error("split_tf32: null pointer"); return REGCN_ERR_NULL; }
+  if (n & 3) { set_last_error("split_tf32: element count must be a multiple of 4"); return REGCN_ERR_DIM; }
+  if (!n) return REGCN_OK;
+  const size_t n4 = n / 4;
+  tc::split_tf32_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(x, hi, lo, n4);
+  return check_launch("split_tf32");
+}
+
+static int pick_block_n(int N) {
+  if (N <= 64) return (N + 15) / 16 * 16;
+  int best = 256, best_waste = 1 << 30;
+  const int cands[4] = {256, 208, 128, 64};
+  for (int i = 0; i < 4; ++i) {
+    const int bn = cands[i];
+    const int waste = (N + bn - 1) / bn * bn - N;
+    if (waste < best_waste) { best = bn; best_waste = waste; }
+  }
+  return best;
+}
+
+size_t gemm_tf32_workspace_bytes(int M, int N, int split_k) {
+  return split_k > 1 ? (size_t)split_k * (size_t)M * (size_t)N * sizeof(float) : 0;
+}
+
+// A_hi/A_lo [M,K] (lda), B_hi/B_lo [N,K] (ldb); passes==1 ignores the lo operands (may be NULL).
+int gemm_tf32(const float* a_hi, const float* a_lo, int lda, const float* b_hi, const float* b_lo, int ldb, float* C,
+              int ldc, int M, int N, int K, const float* bias, int accumulate, int passes, int split_k, float* ws,
+              size_t ws_bytes, cudaStream_t st) {
+  using namespace tc;
+  if (!a_hi || !b_hi || !C || (passes == 3 && (!a_lo || !b_lo))) { set_last_error("gemm_tf32: null pointer"); return REGCN_ERR_NULL; }
+  if (passes != 1 && passes != 3) { set_last_error("gemm_tf32: passes must be 1 or 3"); return REGCN_ERR_DIM; }
+  if (M < 0 || N <= 0 || K <= 0 || (lda & 3) || (ldb & 3) || lda < K || ldb < K || ldc < N ||
+      (((uintptr_t)a_hi | (uintptr_t)b_hi | (uintptr_t)a_lo | (uintptr_t)b_lo) & 15)) {
+    set_last_error("gemm_tf32: bad dims/alignment M=%d N=%d K=%d lda=%d ldb=%d ldc=%d", M, N, K, lda, ldb, ldc);
+    return REGCN_ERR_DIM;
+  }
+  if (M == 0) return REGCN_OK;
+  Params p;
+  p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.bias = bias; p.accumulate = accumulate; p.passes = passes;
+  p.block_n = pick_block_n(N);
+  p.tmem_cols = 32;
+  while (p.tmem_cols < p.block_n) p.tmem_cols <<= 1;
+  const uint32_t stage_bytes = (passes == 3 ? 2u : 1u) * (BLOCK_M * BLOCK_K * 4 + (uint32_t)p.block_n * BLOCK_K * 4);
+  const int total_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  if (split_k < 1) split_k = 1;
+  if (split_k > total_kb) split_k = total_kb;
+  p.kb_per_split = (total_kb + split_k - 1) / split_k;
+  split_k = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
+  p.stages = (int)(SMEM_BUDGET / stage_bytes);
+  if (p.stages > 8) p.stages = 8;
+  if (p.stages > p.kb_per_split) p.stages = p.kb_per_split;
+  if (p.stages < 1) { set_last_error("gemm_tf32: tile does not fit in shared memory"); return REGCN_ERR_UNSUPPORTED; }
+  p.ws = nullptr;
+  if (split_k > 1) {
+    if (!ws || ws_bytes < gemm_tf32_workspace_bytes(M, N, split_k)) { set_last_error("gemm_tf32: split-K workspace too small"); return REGCN_ERR_WORKSPACE; }
+    p.ws = ws;
+  }
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+  int e;
+  if ((e = make_map(&ta_hi, a_hi, M, K, lda, BLOCK_M))) return e;
+  if ((e = make_map(&tb_hi, b_hi, N, K, ldb, p.block_n))) return e;
+  if (passes == 3) {
+    if ((e = make_map(&ta_lo, a_lo, M, K, lda, BLOCK_M))) return e;
+    if ((e = make_map(&tb_lo, b_lo, N, K, ldb, p.block_n))) return e;
+  } else {
+    ta_lo = ta_hi; tb_lo = tb_hi;
+  }
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t ce = cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_BUDGET + 2048));
+    if (ce != cudaSuccess) { set_last_error("gemm_tf32: cudaFuncSetAttribute failed: %s", cudaGetErrorString(ce)); return (int)ce; }
+    attr_set = true;
+  }
+  dim3 grid((N + p.block_n - 1) / p.block_n, (M + BLOCK_M - 1) / BLOCK_M, split_k);
+  gemm_tf32_kernel<<<grid, NUM_THREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+  if (split_k > 1) {
+    const size_t total = (size_t)M * N;
+    splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws, split_k, C, ldc, M, N, bias, accumulate);
+  }
+  return check_launch("gemm_tf32");
+}
+
+}  // namespace regcn

@@ -22,6 +22,11 @@ int lorentz_aggregate(const float* ht, const float* W, const float* rel, const i
 size_t gemm_f32_workspace_bytes(int M, int N, int split_k);
 int gemm_f32(const float* A, int lda, const float* B, int ldb, int transB, float* C, int ldc, int M, int N, int K,
              const float* bias, int accumulate, int split_k, float* ws, size_t ws_bytes, cudaStream_t st);
+int split_tf32(const float* x, float* hi, float* lo, size_t n, cudaStream_t st);
+size_t gemm_tf32_workspace_bytes(int M, int N, int split_k);
+int gemm_tf32(const float* a_hi, const float* a_lo, int lda, const float* b_hi, const float* b_lo, int ldb, float* C,
+              int ldc, int M, int N, int K, const float* bias, int accumulate, int passes, int split_k, float* ws,
+              size_t ws_bytes, cudaStream_t st);
 int row_map(const float* x, float* out, int M, int d, int mode, double c, float* sumsq, cudaStream_t st);
 int gru_gate(const float* gi, const float* gh, const float* hprev, float* out, int M, int d, int normalize, cudaStream_t st);
 int union_combine(const float* P, const float* L, const int* indeg, const float* S, const float* skip_bias,

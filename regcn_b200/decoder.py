@@ -52,7 +52,8 @@ class _ConvTransBase(nn.Module):
         K = feats.shape[1]
         split_k = max(1, min(16, (148 * 2) // max(1, ((B + 127) // 128) * ((self.fc.out_features + 127) // 128))))
         split_k = min(split_k, max(1, K // 512))
-        x = ops.gemm(feats, self.fc.weight.detach(), trans_b=True, bias=self.fc.bias.detach(), split_k=split_k)
+        x = ops.gemm(feats, self.fc.weight.detach(), trans_b=True, bias=self.fc.bias.detach(), split_k=split_k,
+                     b_key=(self.fc.weight, "w"))
         if always_bn2 or B > 1:
             s, t = _fold_bn(self.bn2)
             ops.affine_relu_(x, s, t, relu=True)

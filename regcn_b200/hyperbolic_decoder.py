@@ -44,7 +44,8 @@ class _HypConvBase(nn.Module):
         feats = ops.convtranse_features(ent_act, second, triplets, col0, col1, _fold_bn(self.bn0),
                                         self.conv1.weight.detach(), self.conv1.bias.detach(), _fold_bn(self.bn1))
         split_k = max(1, min(16, (148 * 2) // max(1, ((B + 127) // 128) * ((self.fc.out_features + 127) // 128))))
-        x = ops.gemm(feats, self.fc.weight.detach(), trans_b=True, bias=self.fc.bias.detach(), split_k=split_k)
+        x = ops.gemm(feats, self.fc.weight.detach(), trans_b=True, bias=self.fc.bias.detach(), split_k=split_k,
+                     b_key=(self.fc.weight, "w"))
         if always_bn2 or B > 1:
             s, t = _fold_bn(self.bn2)
             ops.affine_relu_(x, s, t, relu=True)
@@ -149,13 +150,13 @@ class HyperbolicRotH(_HypDistBase):
         """K12: (B,d) query points and their squared norms."""
         self._unsupported_flags()
         s_tan = ops.gather_log0(entity_embedding, triplets, 0, True, self.c)                     # :1066-1070
-        h1 = ops.gemm(s_tan, self.reshape_fc1.weight.detach(), trans_b=True, bias=self.reshape_fc1.bias.detach())
+        h1 = ops.gemm(s_tan, self.reshape_fc1.weight.detach(), trans_b=True, bias=self.reshape_fc1.bias.detach(), b_key=(self.reshape_fc1.weight, "w"))
         ops.affine_relu_(h1, None, None, relu=True)
-        ops.gemm(h1, self.reshape_fc2.weight.detach(), trans_b=True, bias=self.reshape_fc2.bias.detach(),
+        ops.gemm(h1, self.reshape_fc2.weight.detach(), trans_b=True, bias=self.reshape_fc2.bias.detach(), b_key=(self.reshape_fc2.weight, "w"),
                  out=s_tan, accumulate=True)                                                      # x + fc2(relu(fc1 x))
         rel = rel_embedding.contiguous()
-        ang = ops.gemm(rel, self.rot_proj.weight.detach(), trans_b=True, bias=self.rot_proj.bias.detach())      # (2R, d/2)
-        trans = ops.gemm(rel, self.trans_proj.weight.detach(), trans_b=True, bias=self.trans_proj.bias.detach())  # (2R, d)
+        ang = ops.gemm(rel, self.rot_proj.weight.detach(), trans_b=True, bias=self.rot_proj.bias.detach(), b_key=(self.rot_proj.weight, "w"))      # (2R, d/2)
+        trans = ops.gemm(rel, self.trans_proj.weight.detach(), trans_b=True, bias=self.trans_proj.bias.detach(), b_key=(self.trans_proj.weight, "w"))  # (2R, d)
         return ops.hyp_query(s_tan, ang, trans, None, triplets, 0, self.c)
 
     @torch.no_grad()
@@ -205,8 +206,8 @@ class HyperbolicMuRP(_HypDistBase):
         self._unsupported_flags()
         s_tan = ops.gather_log0(entity_embedding, triplets, 0, True, self.c)
         rel = rel_embedding.contiguous()
-        diag = ops.gemm(rel, self.rot_proj.weight.detach(), trans_b=True, bias=self.rot_proj.bias.detach())
-        trans = ops.gemm(rel, self.trans_proj.weight.detach(), trans_b=True, bias=self.trans_proj.bias.detach())
+        diag = ops.gemm(rel, self.rot_proj.weight.detach(), trans_b=True, bias=self.rot_proj.bias.detach(), b_key=(self.rot_proj.weight, "w"))
+        trans = ops.gemm(rel, self.trans_proj.weight.detach(), trans_b=True, bias=self.trans_proj.bias.detach(), b_key=(self.trans_proj.weight, "w"))
         return ops.hyp_query(s_tan, diag, trans, None, triplets, 1, self.c)
 
     @torch.no_grad()
@@ -248,9 +249,9 @@ class HyperbolicRotHRel(_HypDistBase):
         self._unsupported_flags()
         E = entity_embedding.contiguous()
         s_tan = ops.gather_log0(E, triplets, 0, False, self.c)
-        h1 = ops.gemm(s_tan, self.reshape_fc1.weight.detach(), trans_b=True, bias=self.reshape_fc1.bias.detach())
+        h1 = ops.gemm(s_tan, self.reshape_fc1.weight.detach(), trans_b=True, bias=self.reshape_fc1.bias.detach(), b_key=(self.reshape_fc1.weight, "w"))
         ops.affine_relu_(h1, None, None, relu=True)
-        ops.gemm(h1, self.reshape_fc2.weight.detach(), trans_b=True, bias=self.reshape_fc2.bias.detach(), out=s_tan,
+        ops.gemm(h1, self.reshape_fc2.weight.detach(), trans_b=True, bias=self.reshape_fc2.bias.detach(), b_key=(self.reshape_fc2.weight, "w"), out=s_tan,
                  accumulate=True)
         q, qss = ops.hyp_query(s_tan, self.global_rot.detach(), None, E, triplets, 2, self.c)
         rel_hyp, rss = ops.row_map(rel_embedding.contiguous(), ops.ROW_EXP0, c=self.c, want_sumsq=True)
@@ -286,8 +287,8 @@ class HyperbolicMuRPRel(_HypDistBase):
         E = entity_embedding.contiguous()
         s_tan = ops.gather_log0(E, triplets, 0, False, self.c)
         o_tan = ops.gather_log0(E, triplets, 2, False, self.c)
-        q_tan = ops.gemm(s_tan, self.W_s.detach())
-        ops.gemm(o_tan, self.W_o.detach(), out=q_tan, accumulate=True)
+        q_tan = ops.gemm(s_tan, self.W_s.detach(), b_key=(self.W_s, "w"))
+        ops.gemm(o_tan, self.W_o.detach(), out=q_tan, accumulate=True, b_key=(self.W_o, "w"))
         q, qss = ops.row_map(q_tan, ops.ROW_EXP0, c=self.c, want_sumsq=True)
         rel_hyp, rss = ops.row_map(rel_embedding.contiguous(), ops.ROW_EXP0, c=self.c, want_sumsq=True)
         S = ops.gemm(q, rel_hyp, trans_b=True)

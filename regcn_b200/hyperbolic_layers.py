@@ -59,12 +59,13 @@ class HyperbolicUnionRGCNLayer(nn.Module, _LoopMixin):
         if _tangent is None or _radius is None:
             _tangent, _, _radius = ops.hyp_tangent(h_hyper, self.c, want_clamped=False, want_radius=True)
         agg = ops.union_aggregate(_tangent, rel_emb, g, radius=_radius, gamma=self.radius_msg_gamma)
-        P = ops.gemm(agg, self.weight_neighbor)
-        L = ops.gemm(_tangent, self._loop_cat()) if self.self_loop else None
+        P = ops.gemm(agg, self.weight_neighbor, b_key=(self.weight_neighbor, "w"))
+        lc = self._loop_cat() if self.self_loop else None
+        L = ops.gemm(_tangent, lc, b_key=(lc, "w")) if self.self_loop else None
         S = sb = prev_t = None
         if self.skip_connect and prev_h is not None:
             prev_t, _, _ = ops.hyp_tangent(prev_h, self.c, want_clamped=False, want_radius=False)
-            S, sb = ops.gemm(prev_t, self.skip_weight), self.skip_bias
+            S, sb = ops.gemm(prev_t, self.skip_weight, b_key=(self.skip_weight, "w")), self.skip_bias
         out, ht_next, rad_next = ops.union_combine(P, L, g.indeg, act=_act_code(self.activation), hyper=True, c=self.c,
                                                    skip=S, skip_bias=sb, prev=prev_t, want_tangent=_want_next,
                                                    want_radius=_want_next)
@@ -114,11 +115,12 @@ class LorentzRGCNLayer(nn.Module, _LoopMixin):
         if _tangent is None:
             _tangent, _, _ = ops.hyp_tangent(h_hyper, self.c, want_clamped=False, want_radius=False)
         agg = ops.lorentz_aggregate(_tangent, self.weight, rel_emb, g, self.num_bases, self.c)
-        L = ops.gemm(_tangent, self._loop_cat()) if self.self_loop else None
+        lc = self._loop_cat() if self.self_loop else None
+        L = ops.gemm(_tangent, lc, b_key=(lc, "w")) if self.self_loop else None
         S = sb = prev_t = None
         if self.skip_connect and prev_h is not None:
             prev_t, _, _ = ops.hyp_tangent(prev_h, self.c, want_clamped=False, want_radius=False)
-            S, sb = ops.gemm(prev_t, self.skip_weight), self.skip_bias
+            S, sb = ops.gemm(prev_t, self.skip_weight, b_key=(self.skip_weight, "w")), self.skip_bias
         out, ht_next, _ = ops.union_combine(agg, L, g.indeg, act=_act_code(self.activation), hyper=True, c=self.c,
                                             skip=S, skip_bias=sb, prev=prev_t, want_tangent=_want_next)
         if _want_next:

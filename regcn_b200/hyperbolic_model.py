@@ -151,9 +151,11 @@ class HyperbolicRecurrentRGCN(nn.Module):
         cell, d = self.relation_gru, self.h_dim
         x_mean = ops.rel_mean_pool(ht, g)
         w_ih = cell.weight_ih.detach()
-        gi = ops.gemm(self.emb_rel.detach(), w_ih[:, :d], trans_b=True, bias=cell.bias_ih.detach())
-        ops.gemm(x_mean, w_ih[:, d:], trans_b=True, out=gi, accumulate=True)
-        gh = ops.gemm(h0_prev, cell.weight_hh.detach(), trans_b=True, bias=cell.bias_hh.detach())
+        gi = ops.gemm(self.emb_rel.detach(), w_ih[:, :d], trans_b=True, bias=cell.bias_ih.detach(),
+                      b_key=(cell.weight_ih, "left"))
+        ops.gemm(x_mean, w_ih[:, d:], trans_b=True, out=gi, accumulate=True, b_key=(cell.weight_ih, "right"))
+        gh = ops.gemm(h0_prev, cell.weight_hh.detach(), trans_b=True, bias=cell.bias_hh.detach(),
+                      b_key=(cell.weight_hh, "w"))
         return ops.gru_gate(gi, gh, h0_prev, self.layer_norm)
 
     @torch.no_grad()
@@ -184,7 +186,7 @@ class HyperbolicRecurrentRGCN(nn.Module):
             h0_prev = self.emb_rel.detach() if i == 0 else self.h_0
             self.h_0 = self._relation_step(g, ht, h0_prev)
             current_h = self.rgcn.forward(g, self.h, [self.h_0, self.h_0], _tangent=ht, _radius=radius)
-            G = ops.gemm(pt, self.time_gate_weight.detach())
+            G = ops.gemm(pt, self.time_gate_weight.detach(), b_key=(self.time_gate_weight, "w"))
             self.h = ops.hyp_time_gate(current_h, pt, G, self.time_gate_bias.detach(), rs_raw, rw, rb, self.layer_norm,
                                        self.use_residual_evolution, c, self.radius_min, self.radius_max,
                                        tre.anchor_beta, tre.epsilon)

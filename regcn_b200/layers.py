@@ -67,11 +67,13 @@ class UnionRGCNLayer(nn.Module):
         self.rel_emb = emb_rel
         h = g.ndata['h']
         agg = ops.union_aggregate(h, emb_rel, g)                      # K4: (h[src]+rel[type]) summed, norm applied
-        P = ops.gemm(agg, self.weight_neighbor)                       # aggregate-then-transform (linear message)
-        L = ops.gemm(h, self._loop_cat()) if self.self_loop else None
+        P = ops.gemm(agg, self.weight_neighbor, b_key=(self.weight_neighbor, "w"))   # aggregate-then-transform
+        lc = self._loop_cat() if self.self_loop else None
+        L = ops.gemm(h, lc, b_key=(lc, "w")) if self.self_loop else None
         S = sb = prev = None
         if len(prev_h) != 0 and self.skip_connect:
-            S, sb, prev = ops.gemm(prev_h, self.skip_connect_weight), self.skip_connect_bias, prev_h
+            S = ops.gemm(prev_h, self.skip_connect_weight, b_key=(self.skip_connect_weight, "w"))
+            sb, prev = self.skip_connect_bias, prev_h
         out, _, _ = ops.union_combine(P, L, g.indeg, act=_act_code(self.activation), skip=S, skip_bias=sb, prev=prev)
         g.ndata['h'] = out
         return out

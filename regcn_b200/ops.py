@@ -33,12 +33,17 @@ def _rowmajor(t, name):
 
 
 # --------------------------------------------------------------------------- dense contractions
-_GEMM_IMPL = {"impl": "simt"}
+import os
+
+_GEMM_IMPL = {"impl": os.environ.get("REGCN_GEMM", "simt")}
+_IMPLS = {"simt": "regcn::gemm_f32_kernel (fp32 CUDA cores)",
+          "tc": "regcn::tc::gemm_tf32_kernel (tcgen05 kind::tf32, 3xTF32 error-compensated)",
+          "tc1": "regcn::tc::gemm_tf32_kernel (tcgen05 kind::tf32, single pass)"}
 
 
 def set_gemm_impl(name):
-    """simt: fp32 CUDA-core kernel (csrc/gemm_simt.cu)."""
-    if name not in ("simt",):
+    """simt: fp32 CUDA-core kernel (csrc/gemm_simt.cu); tc: tcgen05 3xTF32 (fp32 parity); tc1: tcgen05 plain TF32."""
+    if name not in _IMPLS:
         raise ValueError(f"unknown gemm implementation {name!r}")
     _GEMM_IMPL["impl"] = name
 
@@ -48,11 +53,46 @@ def gemm_impl():
 
 
 def gemm_kernel_name():
-    return {"simt": "regcn::gemm_f32_kernel"}[_GEMM_IMPL["impl"]]
+    return _IMPLS[_GEMM_IMPL["impl"]]
 
 
-def gemm(a, b, trans_b=False, bias=None, out=None, accumulate=False, split_k=1):
-    """C[M,N] (+)= A[M,K] @ (B[K,N] | B[N,K]^T) (+ bias).  torch.mm / F.linear call sites of the path."""
+def cached(owner, key, fn):
+    """Derived static operand of a parameter (transpose / slice / tf32 split), kept on the tensor object itself and
+    recomputed when its version or storage changes.  `owner` must be a long-lived tensor object (the Parameter)."""
+    store = owner.__dict__.setdefault("_regcn_cache", {})
+    stamp = (owner._version, owner.data_ptr())
+    hit = store.get(key)
+    if hit is None or hit[0] != stamp:
+        with torch.no_grad():
+            store[key] = (stamp, fn())
+    return store[key][1]
+
+
+def split_tf32(x):
+    """(hi, lo) TF32 split of a contiguous fp32 tensor (numel % 4 == 0)."""
+    hi = torch.empty_like(x)
+    lo = torch.empty_like(x)
+    call("regcn_split_tf32", ptr(x), ptr(hi), ptr(lo), x.numel())
+    return hi, lo
+
+
+def _tc_operand(m, need_lo):
+    m = m.contiguous()
+    if m.data_ptr() % 16:
+        m = m.clone()
+    if not need_lo:
+        return m, None
+    return split_tf32(m)
+
+
+def gemm(a, b, trans_b=False, bias=None, out=None, accumulate=False, split_k=1, b_key=None):
+    """C[M,N] (+)= A[M,K] @ (B[K,N] | B[N,K]^T) (+ bias).  torch.mm / F.linear call sites of the path.
+
+    b_key=(owner_tensor, name): B is a static weight; its prepared form (K-major transpose, TF32 split) is cached on
+    `owner_tensor` under `name`."""
+    impl = _GEMM_IMPL["impl"]
+    if impl != "simt" and a.shape[1] % 4 == 0:
+        return _gemm_tc(a, b, trans_b, bias, out, accumulate, split_k, b_key, 3 if impl == "tc" else 1)
     a = _rowmajor(a, "a")
     b = _rowmajor(b, "b")
     M, K = a.shape
@@ -73,6 +113,47 @@ def gemm(a, b, trans_b=False, bias=None, out=None, accumulate=False, split_k=1):
         ws = torch.empty(ws_bytes // 4, device=a.device, dtype=F32)
     call("regcn_gemm_f32", a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), int(trans_b), out.data_ptr(), ldc, M, N, K,
          ptr(bias), int(accumulate), split_k, ptr(ws), ws_bytes)
+    return out
+
+
+def _gemm_tc(a, b, trans_b, bias, out, accumulate, split_k, b_key, passes):
+    if not (a.is_cuda and b.is_cuda):
+        raise RuntimeError("regcn_b200: kernels take CUDA tensors only (no CPU fallback)")
+    if a.dtype != F32 or b.dtype != F32:
+        raise TypeError("gemm: operands must be float32")
+    M, K = a.shape
+    N = b.shape[0] if trans_b else b.shape[1]
+    if (b.shape[1] if trans_b else b.shape[0]) != K:
+        raise ValueError(f"gemm: inner dims differ {tuple(a.shape)} x {tuple(b.shape)} trans_b={trans_b}")
+    need_lo = passes == 3
+
+    def prep_b():
+        bd = b.detach()
+        return _tc_operand(bd if trans_b else bd.t(), need_lo)
+
+    if b_key is not None:
+        owner, name = b_key
+        b_hi, b_lo = cached(owner, ("tcB", name, trans_b, passes, tuple(b.shape), b.storage_offset(), tuple(b.stride())),
+                            prep_b)
+    else:
+        b_hi, b_lo = prep_b()
+    a_hi, a_lo = _tc_operand(a.detach(), need_lo)
+    if out is None:
+        if accumulate:
+            raise ValueError("gemm: accumulate needs out")
+        if N % 4:
+            out = torch.empty((M, (N + 3) // 4 * 4), device=a.device, dtype=F32)[:, :N]   # 16-byte aligned rows
+        else:
+            out = torch.empty((M, N), device=a.device, dtype=F32)
+    elif not out.is_cuda or out.dtype != F32 or out.stride(1) != 1:
+        raise ValueError("gemm: out must be a CUDA float32 matrix with unit column stride")
+    ws = None
+    ws_bytes = 0
+    if split_k > 1:
+        ws_bytes = _lib.load().regcn_gemm_tf32_workspace_bytes(M, N, split_k)
+        ws = torch.empty(ws_bytes // 4, device=a.device, dtype=F32)
+    call("regcn_gemm_tf32", ptr(a_hi), ptr(a_lo), K, ptr(b_hi), ptr(b_lo), K, out.data_ptr(), out.stride(0), M, N, K,
+         ptr(bias), int(accumulate), passes, split_k, ptr(ws), ws_bytes)
     return out
 
 

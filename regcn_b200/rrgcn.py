@@ -109,9 +109,11 @@ class RecurrentRGCN(nn.Module):
         d = self.h_dim
         x_mean = ops.rel_mean_pool(h, g)                                       # (2R, d)
         w_ih = cell.weight_ih.detach()                                         # (3d, 2d): [emb_rel | x_mean] halves
-        gi = ops.gemm(self.emb_rel.detach(), w_ih[:, :d], trans_b=True, bias=cell.bias_ih.detach())
-        ops.gemm(x_mean, w_ih[:, d:], trans_b=True, out=gi, accumulate=True)
-        gh = ops.gemm(h0_prev, cell.weight_hh.detach(), trans_b=True, bias=cell.bias_hh.detach())
+        gi = ops.gemm(self.emb_rel.detach(), w_ih[:, :d], trans_b=True, bias=cell.bias_ih.detach(),
+                      b_key=(cell.weight_ih, "left"))
+        ops.gemm(x_mean, w_ih[:, d:], trans_b=True, out=gi, accumulate=True, b_key=(cell.weight_ih, "right"))
+        gh = ops.gemm(h0_prev, cell.weight_hh.detach(), trans_b=True, bias=cell.bias_hh.detach(),
+                      b_key=(cell.weight_hh, "w"))
         return ops.gru_gate(gi, gh, h0_prev, self.layer_norm)
 
     @torch.no_grad()
@@ -135,7 +137,7 @@ class RecurrentRGCN(nn.Module):
             h0_prev = self.emb_rel.detach() if i == 0 else self.h_0
             self.h_0 = self._relation_step(g, self.h, h0_prev)
             current_h = self.rgcn.forward(g, self.h, [self.h_0, self.h_0])
-            G = ops.gemm(self.h, self.time_gate_weight.detach())
+            G = ops.gemm(self.h, self.time_gate_weight.detach(), b_key=(self.time_gate_weight, "w"))
             self.h = ops.time_gate(G, self.time_gate_bias.detach(), current_h, self.h, self.layer_norm)
             history_embs.append(self.h)
         return history_embs, static_emb, self.h_0, gate_list, degree_list

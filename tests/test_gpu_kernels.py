@@ -473,3 +473,58 @@ def test_filter_csr_from_snapshot_matches_dict():
         a = utils.filter_csr_from_dict(torch.as_tensor(all_t), d, rel_predict=rel_p, device=DEV)
         b = utils.filter_csr_from_snapshot(_t(all_t, torch.int64), nk, rel_predict=rel_p)
         assert torch.equal(a.ptr, b.ptr) and torch.equal(a.idx, b.idx)
+
+
+# ----------------------------------------------------------------------------------------- tcgen05 GEMM
+@pytest.mark.parametrize("impl,rtol", [("tc", 1e-4), ("tc1", 4e-3)])
+@pytest.mark.parametrize("M,N,K,trans_b,bias,split_k", [
+    (128, 16, 32, True, False, 1), (1, 200, 200, False, False, 1), (513, 200, 200, False, True, 1),
+    (300, 600, 400, True, True, 1), (1000, 23033 // 8, 200, True, False, 1), (257, 200, 10000, True, True, 6),
+    (64, 8, 12, False, False, 1), (130, 131, 204, True, True, 3), (2914, 400, 200, False, False, 1)])
+def test_gemm_tcgen05_vs_fp64(impl, rtol, M, N, K, trans_b, bias, split_k):
+    """tcgen05 kind::tf32 GEMM: 3xTF32 meets the fp32 parity gate, single-pass TF32 is reported at its own tolerance."""
+    _, ops = _ops()
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N)
+    a = torch.randn(M, K, generator=g)
+    b = torch.randn((N, K) if trans_b else (K, N), generator=g)
+    bv = torch.randn(N, generator=g) if bias else None
+    ref = a.double() @ (b.double().t() if trans_b else b.double())
+    if bias:
+        ref = ref + bv.double()
+    prev = ops.gemm_impl()
+    ops.set_gemm_impl(impl)
+    try:
+        out = ops.gemm(a.to(DEV), b.to(DEV), trans_b=trans_b, bias=bv.to(DEV) if bias else None, split_k=split_k)
+        torch.cuda.synchronize()
+        tol = rtol * max(1.0, (K / 200.0) ** 0.5) * 4
+        err = (out.cpu().double() - ref).abs()
+        scale = torch.clamp(ref.abs(), min=1.0) if impl == "tc" else torch.clamp(ref.abs(), min=float(K) ** 0.5)
+        assert bool((err <= tol * scale).all()), float((err / scale).max())
+        big = torch.zeros(M, N + 8, device=DEV)
+        view = big[:, 4:4 + N]
+        view.copy_(torch.ones(M, N))
+        ops.gemm(a.to(DEV), b.to(DEV), trans_b=trans_b, out=view, accumulate=True, split_k=split_k)
+        ref2 = a.double() @ (b.double().t() if trans_b else b.double()) + 1.0
+        err2 = (view.cpu().double() - ref2).abs()
+        scale2 = torch.clamp(ref2.abs(), min=1.0) if impl == "tc" else torch.clamp(ref2.abs(), min=float(K) ** 0.5)
+        assert bool((err2 <= tol * scale2).all()), float((err2 / scale2).max())
+        assert float(big[:, :4].abs().sum()) == 0.0 and float(big[:, 4 + N:].abs().sum()) == 0.0
+    finally:
+        ops.set_gemm_impl(prev)
+
+
+def test_gemm_tcgen05_static_weight_cache():
+    """A cached (transposed + split) weight is refreshed when the parameter changes in place."""
+    _, ops = _ops()
+    prev = ops.gemm_impl()
+    ops.set_gemm_impl("tc")
+    try:
+        w = torch.nn.Parameter(torch.randn(200, 200, device=DEV))
+        a = torch.randn(77, 200, device=DEV)
+        o1 = ops.gemm(a, w, b_key=(w, "w"))
+        with torch.no_grad():
+            w.mul_(2.0)
+        o2 = ops.gemm(a, w, b_key=(w, "w"))
+        assert torch.allclose(o2, 2 * o1, rtol=1e-5, atol=1e-5)
+    finally:
+        ops.set_gemm_impl(prev)
