@@ -154,6 +154,26 @@ REGCN_API int regcn_counts_to_ranks(const int32_t* raw_count, const int32_t* fil
 REGCN_API int regcn_apply_filter(float* S, int64_t ld, int B, int N, const int64_t* triples, int target_col,
                        const int32_t* filt_ptr, const int32_t* filt_idx, int col_offset, void* stream);
 
+/* ---- whole-recurrence orchestration: RecurrentRGCN.forward, src/rrgcn.py:142-180 (uvrgcn, self_loop, no skip) ---
+ * One call enqueues every kernel of the L-snapshot recurrence on `stream`.  Inputs are pointer / int tables:
+ *   model_ptrs[RM_*]   device pointers to parameters; GEMM weights are passed K-major ([out, in]) and TF32-split
+ *                      (regcn_split_tf32): W_ih[:, d:], W_hh, per layer W_n^T and [W_loop | W_evolve (| W_time)]^T;
+ *                      RM_GI_STATIC = emb_rel . W_ih[:, :d]^T + b_ih  (2R, 3d), constant per model
+ *   model_ints[RMI_*]  N, 2R, d, n_layers, layer_norm, self_loop
+ *   graph_ptrs         L consecutive blocks of RG_NUM_PTRS pointers (outputs of regcn_csr_build)
+ *   graph_ints         L consecutive blocks of RGI_NUM_INTS ints
+ * Outputs: hist (L, N, d) = history_embs, h0_out (2R, d) = evolved relation embeddings.                        */
+enum { RM_DYNAMIC_EMB = 0, RM_EMB_REL, RM_EMB_REL_HI, RM_EMB_REL_LO, RM_GI_STATIC, RM_WIH_R_HI, RM_WIH_R_LO,
+       RM_WHH_HI, RM_WHH_LO, RM_B_HH, RM_GATE_BIAS, RM_LAYER0 /* + 4*l: W_n hi, lo, W_loopcat hi, lo */ };
+enum { RMI_NUM_ENTS = 0, RMI_NUM_RELS2, RMI_DIM, RMI_NUM_LAYERS, RMI_LAYER_NORM, RMI_SELF_LOOP, RMI_NUM_INTS };
+enum { RG_ROWPTR = 0, RG_SRC_SORTED, RG_ETYPE_SORTED, RG_INDEG, RG_NORM, RG_VPTR, RG_SPTR, RG_VROW_ROW,
+       RG_REL_ROWPTR, RG_REL_ENTS, RG_NUM_PTRS };
+enum { RGI_NUM_EDGES = 0, RGI_N_VROWS, RGI_N_SPLIT_CHUNKS, RGI_N_REL_ENTS, RGI_NUM_INTS };
+REGCN_API size_t regcn_regcn_evolve_workspace_bytes(int N, int R2, int d, int max_split_chunks, int rel_nsplit);
+REGCN_API int regcn_regcn_evolve(const void* const* model_ptrs, const int* model_ints, const void* const* graph_ptrs,
+                       const int* graph_ints, int L, float* hist, float* h0_out, int rel_nsplit, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,7 +10,7 @@
 
 namespace regcn {
 
-constexpr int kAggChunk = 256;  // must match graph_build.cu
+constexpr int kAggChunk = 64;  // must match graph_build.cu
 
 // ---------------------------------------------------------------------------
 // K4: agg[v] = norm[v] * sum_{(u,r)->v} w_uv * (h[u] + rel[r]),  w_uv = exp(-gamma*|rad[u]-rad[v]|) or 1.
@@ -22,7 +22,8 @@ __global__ void __launch_bounds__(256) union_aggregate_kernel(
     const float* __restrict__ h, const float* __restrict__ rel, const int* __restrict__ rowptr,
     const int* __restrict__ src_sorted, const int* __restrict__ etype_sorted, const float* __restrict__ norm,
     const int* __restrict__ vptr, const int* __restrict__ sptr, const int* __restrict__ vrow_row, int nv,
-    const float* __restrict__ radius, float gamma, int d, float* __restrict__ out, float* __restrict__ partial) {
+    const float* __restrict__ radius, float gamma, int d, float* __restrict__ out, float* __restrict__ partial,
+    float* __restrict__ out_hi, float* __restrict__ out_lo) {
   const int lane = threadIdx.x & 31;
   const int w = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
   if (w >= nv) return;
@@ -98,7 +99,8 @@ __global__ void __launch_bounds__(256) union_aggregate_kernel(
   }
   if (v1 - v0 == 1) {
     acc.scale(__ldg(norm + row));
-    acc.store(out + (size_t)row * d, nvec, lane);
+    if (out) acc.store(out + (size_t)row * d, nvec, lane);
+    if (out_hi) acc.store_split(out_hi + (size_t)row * d, out_lo + (size_t)row * d, nvec, lane);
   } else {
     acc.store(partial + (size_t)(__ldg(sptr + row) + k) * d, nvec, lane);
   }
@@ -108,7 +110,7 @@ __global__ void __launch_bounds__(256) union_aggregate_kernel(
 template <int RV>
 __global__ void __launch_bounds__(256) aggregate_fixup_kernel(
     const int* __restrict__ vptr, const int* __restrict__ sptr, const float* __restrict__ norm, int N, int d,
-    const float* __restrict__ partial, float* __restrict__ out) {
+    const float* __restrict__ partial, float* __restrict__ out, float* __restrict__ out_hi, float* __restrict__ out_lo) {
   const int lane = threadIdx.x & 31;
   const int row = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
   if (row >= N) return;
@@ -116,22 +118,33 @@ __global__ void __launch_bounds__(256) aggregate_fixup_kernel(
   if (nch <= 1) return;
   const int nvec = d >> 2;
   const int s0 = __ldg(sptr + row);
-  WarpRow<RV> acc, p;
+  WarpRow<RV> acc, p[4];
   acc.zero();
-  for (int k = 0; k < nch; ++k) {
-    p.load_plain(partial + (size_t)(s0 + k) * d, nvec, lane);
+  int k = 0;
+  for (; k + 4 <= nch; k += 4) {   // 4 partial rows in flight; summed in chunk order (deterministic)
 #pragma unroll
-    for (int i = 0; i < RV; ++i) acc.v[i] = f4_add(acc.v[i], p.v[i]);
+    for (int u = 0; u < 4; ++u) p[u].load_plain(partial + (size_t)(s0 + k + u) * d, nvec, lane);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int i = 0; i < RV; ++i) acc.v[i] = f4_add(acc.v[i], p[u].v[i]);
+  }
+  for (; k < nch; ++k) {
+    p[0].load_plain(partial + (size_t)(s0 + k) * d, nvec, lane);
+#pragma unroll
+    for (int i = 0; i < RV; ++i) acc.v[i] = f4_add(acc.v[i], p[0].v[i]);
   }
   acc.scale(__ldg(norm + row));
-  acc.store(out + (size_t)row * d, nvec, lane);
+  if (out) acc.store(out + (size_t)row * d, nvec, lane);
+  if (out_hi) acc.store_split(out_hi + (size_t)row * d, out_lo + (size_t)row * d, nvec, lane);
 }
 
 int union_aggregate(const float* h, const float* rel, const int* rowptr, const int* src_sorted,
                     const int* etype_sorted, const float* norm, const int* vptr, const int* sptr,
                     const int* vrow_row, int nv, int nsplit, const float* radius, float gamma, int N, int d,
-                    float* out, float* partial, cudaStream_t st) {
-  if (!h || !rel || !rowptr || !src_sorted || !etype_sorted || !norm || !vptr || !sptr || !vrow_row || !out) {
+                    float* out, float* partial, float* out_hi, float* out_lo, cudaStream_t st) {
+  if (!h || !rel || !rowptr || !src_sorted || !etype_sorted || !norm || !vptr || !sptr || !vrow_row ||
+      (!out && !out_hi) || (out_hi && !out_lo)) {
     set_last_error("union_aggregate: null pointer"); return REGCN_ERR_NULL;
   }
   if (d <= 0 || (d & 3) || d > 256) { set_last_error("union_aggregate: d=%d unsupported (need d%%4==0, d<=256)", d); return REGCN_ERR_UNSUPPORTED; }
@@ -141,16 +154,16 @@ int union_aggregate(const float* h, const float* rel, const int* rowptr, const i
   const unsigned grid = (unsigned)(((size_t)nv * 32 + TB - 1) / TB);
   const bool small = d <= 128;
   if (radius) {
-    if (small) union_aggregate_kernel<1, true><<<grid, TB, 0, st>>>(h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, radius, gamma, d, out, partial);
-    else union_aggregate_kernel<2, true><<<grid, TB, 0, st>>>(h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, radius, gamma, d, out, partial);
+    if (small) union_aggregate_kernel<1, true><<<grid, TB, 0, st>>>(h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, radius, gamma, d, out, partial, out_hi, out_lo);
+    else union_aggregate_kernel<2, true><<<grid, TB, 0, st>>>(h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, radius, gamma, d, out, partial, out_hi, out_lo);
   } else {
-    if (small) union_aggregate_kernel<1, false><<<grid, TB, 0, st>>>(h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, nullptr, 0.f, d, out, partial);
-    else union_aggregate_kernel<2, false><<<grid, TB, 0, st>>>(h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, nullptr, 0.f, d, out, partial);
+    if (small) union_aggregate_kernel<1, false><<<grid, TB, 0, st>>>(h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, nullptr, 0.f, d, out, partial, out_hi, out_lo);
+    else union_aggregate_kernel<2, false><<<grid, TB, 0, st>>>(h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, nullptr, 0.f, d, out, partial, out_hi, out_lo);
   }
   if (nsplit > 0) {
     const unsigned g2 = (unsigned)(((size_t)N * 32 + TB - 1) / TB);
-    if (small) aggregate_fixup_kernel<1><<<g2, TB, 0, st>>>(vptr, sptr, norm, N, d, partial, out);
-    else aggregate_fixup_kernel<2><<<g2, TB, 0, st>>>(vptr, sptr, norm, N, d, partial, out);
+    if (small) aggregate_fixup_kernel<1><<<g2, TB, 0, st>>>(vptr, sptr, norm, N, d, partial, out, out_hi, out_lo);
+    else aggregate_fixup_kernel<2><<<g2, TB, 0, st>>>(vptr, sptr, norm, N, d, partial, out, out_hi, out_lo);
   }
   return check_launch("union_aggregate");
 }
@@ -301,7 +314,8 @@ int lorentz_aggregate(const float* ht, const float* W, const float* rel, const i
 template <int RV>
 __global__ void __launch_bounds__(256) rel_mean_pool_kernel(
     const float* __restrict__ h, const int* __restrict__ rel_rowptr, const int* __restrict__ rel_ents,
-    int R, int d, int nsplit, float* __restrict__ out, float* __restrict__ partial) {
+    int R, int d, int nsplit, float* __restrict__ out, float* __restrict__ partial,
+    float* __restrict__ out_hi, float* __restrict__ out_lo) {
   __shared__ float4 red[8][RV * 32];
   const int r = blockIdx.x, sp = blockIdx.y;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -330,8 +344,14 @@ __global__ void __launch_bounds__(256) rel_mean_pool_kernel(
         const float fn = (float)n;
         acc.map([=](float a) { return a / fn; });
       }
-      acc.store(out + (size_t)r * d, nvec, lane);
-      acc.store(out + (size_t)(r + R) * d, nvec, lane);
+      if (out) {
+        acc.store(out + (size_t)r * d, nvec, lane);
+        acc.store(out + (size_t)(r + R) * d, nvec, lane);
+      }
+      if (out_hi) {
+        acc.store_split(out_hi + (size_t)r * d, out_lo + (size_t)r * d, nvec, lane);
+        acc.store_split(out_hi + (size_t)(r + R) * d, out_lo + (size_t)(r + R) * d, nvec, lane);
+      }
     } else {
       acc.store(partial + ((size_t)r * nsplit + sp) * d, nvec, lane);
     }
@@ -340,7 +360,8 @@ __global__ void __launch_bounds__(256) rel_mean_pool_kernel(
 
 template <int RV>
 __global__ void rel_mean_finalize_kernel(const float* __restrict__ partial, const int* __restrict__ rel_rowptr,
-                                         int R, int d, int nsplit, float* __restrict__ out) {
+                                         int R, int d, int nsplit, float* __restrict__ out,
+                                         float* __restrict__ out_hi, float* __restrict__ out_lo) {
   const int lane = threadIdx.x & 31;
   const int r = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
   if (r >= R) return;
@@ -357,23 +378,29 @@ __global__ void rel_mean_finalize_kernel(const float* __restrict__ partial, cons
     const float fn = (float)n;
     acc.map([=](float a) { return a / fn; });
   }
-  acc.store(out + (size_t)r * d, nvec, lane);
-  acc.store(out + (size_t)(r + R) * d, nvec, lane);
+  if (out) {
+    acc.store(out + (size_t)r * d, nvec, lane);
+    acc.store(out + (size_t)(r + R) * d, nvec, lane);
+  }
+  if (out_hi) {
+    acc.store_split(out_hi + (size_t)r * d, out_lo + (size_t)r * d, nvec, lane);
+    acc.store_split(out_hi + (size_t)(r + R) * d, out_lo + (size_t)(r + R) * d, nvec, lane);
+  }
 }
 
 int rel_mean_pool(const float* h, const int* rel_rowptr, const int* rel_ents, int R, int d, int nsplit,
-                  float* out, float* partial, cudaStream_t st) {
-  if (!h || !rel_rowptr || !rel_ents || !out) { set_last_error("rel_mean_pool: null pointer"); return REGCN_ERR_NULL; }
+                  float* out, float* partial, float* out_hi, float* out_lo, cudaStream_t st) {
+  if (!h || !rel_rowptr || !rel_ents || (!out && !out_hi) || (out_hi && !out_lo)) { set_last_error("rel_mean_pool: null pointer"); return REGCN_ERR_NULL; }
   if (d <= 0 || (d & 3) || d > 256) { set_last_error("rel_mean_pool: d=%d unsupported", d); return REGCN_ERR_UNSUPPORTED; }
   if (nsplit < 1) nsplit = 1;
   if (nsplit > 1 && !partial) { set_last_error("rel_mean_pool: nsplit>1 needs a partial buffer"); return REGCN_ERR_WORKSPACE; }
   dim3 grid(R, nsplit);
-  if (d <= 128) rel_mean_pool_kernel<1><<<grid, 256, 0, st>>>(h, rel_rowptr, rel_ents, R, d, nsplit, out, partial);
-  else rel_mean_pool_kernel<2><<<grid, 256, 0, st>>>(h, rel_rowptr, rel_ents, R, d, nsplit, out, partial);
+  if (d <= 128) rel_mean_pool_kernel<1><<<grid, 256, 0, st>>>(h, rel_rowptr, rel_ents, R, d, nsplit, out, partial, out_hi, out_lo);
+  else rel_mean_pool_kernel<2><<<grid, 256, 0, st>>>(h, rel_rowptr, rel_ents, R, d, nsplit, out, partial, out_hi, out_lo);
   if (nsplit > 1) {
     const unsigned g2 = (unsigned)(((size_t)R * 32 + 255) / 256);
-    if (d <= 128) rel_mean_finalize_kernel<1><<<g2, 256, 0, st>>>(partial, rel_rowptr, R, d, nsplit, out);
-    else rel_mean_finalize_kernel<2><<<g2, 256, 0, st>>>(partial, rel_rowptr, R, d, nsplit, out);
+    if (d <= 128) rel_mean_finalize_kernel<1><<<g2, 256, 0, st>>>(partial, rel_rowptr, R, d, nsplit, out, out_hi, out_lo);
+    else rel_mean_finalize_kernel<2><<<g2, 256, 0, st>>>(partial, rel_rowptr, R, d, nsplit, out, out_hi, out_lo);
   }
   return check_launch("rel_mean_pool");
 }

@@ -49,14 +49,14 @@ int regcn_csr_build(const int64_t* triples, int T, int N, int R, int32_t* src, i
 }
 int regcn_rel_mean_pool(const float* h, const int32_t* rel_rowptr, const int32_t* rel_ents, int R, int d, int nsplit,
                         float* out, float* partial, void* stream) {
-  return rel_mean_pool(h, rel_rowptr, rel_ents, R, d, nsplit, out, partial, ST(stream));
+  return rel_mean_pool(h, rel_rowptr, rel_ents, R, d, nsplit, out, partial, nullptr, nullptr, ST(stream));
 }
 int regcn_union_aggregate(const float* h, const float* rel, const int32_t* rowptr, const int32_t* src_sorted,
                           const int32_t* etype_sorted, const float* norm, const int32_t* vptr, const int32_t* sptr,
                           const int32_t* vrow_row, int n_vrows, int n_split_chunks, const float* radius, float gamma,
                           int N, int d, float* out, float* partial, void* stream) {
   return union_aggregate(h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, n_vrows, n_split_chunks,
-                         radius, gamma, N, d, out, partial, ST(stream));
+                         radius, gamma, N, d, out, partial, nullptr, nullptr, ST(stream));
 }
 int regcn_block_aggregate(const float* h, const float* W, const int32_t* rowptr, const int32_t* src_sorted,
                           const int32_t* etype_sorted, const float* norm, int N, int d_in, int d_out, int nb, float* out,
@@ -83,23 +83,24 @@ int regcn_gemm_tf32(const float* a_hi, const float* a_lo, int lda, const float* 
                     float* C, int ldc, int M, int N, int K, const float* bias, int accumulate, int passes, int split_k,
                     float* workspace, size_t workspace_bytes, void* stream) {
   return gemm_tf32(a_hi, a_lo, lda, b_hi, b_lo, ldb, C, ldc, M, N, K, bias, accumulate, passes, split_k, workspace,
-                   workspace_bytes, ST(stream));
+                   workspace_bytes, nullptr, 0, ST(stream));
 }
 int regcn_row_map(const float* x, float* out, int M, int d, int mode, double c, float* sumsq, void* stream) {
-  return row_map(x, out, M, d, mode, c, sumsq, ST(stream));
+  return row_map(x, out, M, d, mode, c, sumsq, nullptr, nullptr, ST(stream));
 }
 int regcn_gru_gate(const float* gi, const float* gh, const float* hprev, float* out, int M, int d, int normalize,
                    void* stream) {
-  return gru_gate(gi, gh, hprev, out, M, d, normalize, ST(stream));
+  return gru_gate(gi, gh, hprev, out, M, d, normalize, nullptr, nullptr, ST(stream));
 }
 int regcn_union_combine(const float* P, const float* L, const int32_t* indeg, const float* S, const float* skip_bias,
                         const float* prev, int N, int d, int act, int hyper, double c, float* out, float* ht_next,
                         float* radius_next, void* stream) {
-  return union_combine(P, L, indeg, S, skip_bias, prev, N, d, act, hyper, c, out, ht_next, radius_next, ST(stream));
+  return union_combine(P, L, indeg, S, skip_bias, prev, N, d, act, hyper, c, out, ht_next, radius_next, 0, nullptr,
+                       nullptr, nullptr, nullptr, ST(stream));
 }
 int regcn_time_gate(const float* G, const float* bias, const float* cur, const float* h, float* out, int N, int d,
                     int normalize_cur, void* stream) {
-  return time_gate(G, bias, cur, h, out, N, d, normalize_cur, ST(stream));
+  return time_gate(G, bias, cur, h, out, N, d, normalize_cur, 0, nullptr, nullptr, ST(stream));
 }
 int regcn_hyp_init(const float* emb, const float* radius_static, int N, int d, int normalize, int on_manifold, double c,
                    float radius_min, float radius_max, float* out, void* stream) {

@@ -42,6 +42,15 @@ __device__ __forceinline__ float4 f4_fma(float s, float4 a, float4 acc) {
 __device__ __forceinline__ float4 f4_scale(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
 __device__ __forceinline__ float f4_dot(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
 
+__device__ __forceinline__ void split_tf32_1(float a, float& hi, float& lo) {
+  uint32_t t;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(a));
+  hi = __uint_as_float(t);
+  const float r = a - hi;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(r));
+  lo = __uint_as_float(t);
+}
+
 // ---------------------------------------------------------------------------
 // A row of d floats (d % 4 == 0, d <= 4*32*RV) held by one warp: lane l owns the
 // float4 chunks l, l+32, ...  RV = 2 covers d <= 256 (d = 200 -> 50 chunks).
@@ -72,6 +81,20 @@ struct WarpRow {
     for (int i = 0; i < RV; ++i) {
       int c = lane + i * kWarp;
       if (c < nvec) st4(row + 4 * c, v[i]);
+    }
+  }
+  // TF32 operand split for the tensor-core GEMMs: hi = rna_tf32(x), lo = rna_tf32(x - hi)
+  __device__ __forceinline__ void store_split(float* hi, float* lo, int nvec, int lane) const {
+#pragma unroll
+    for (int i = 0; i < RV; ++i) {
+      int c = lane + i * kWarp;
+      if (c < nvec) {
+        float4 h, l;
+        split_tf32_1(v[i].x, h.x, l.x); split_tf32_1(v[i].y, h.y, l.y);
+        split_tf32_1(v[i].z, h.z, l.z); split_tf32_1(v[i].w, h.w, l.w);
+        st4(hi + 4 * c, h);
+        st4(lo + 4 * c, l);
+      }
     }
   }
   __device__ __forceinline__ float sumsq() const {

@@ -1,0 +1,138 @@
+// Stream-ordered orchestration of one whole history recurrence in a single C-ABI call.
+//
+// The per-snapshot loop of RecurrentRGCN.forward (src/rrgcn.py:159-179) is ~13 kernels on tiny-to-medium
+// operands; driven one launch at a time from Python it is launch-bound.  Here the host side of the loop is C++:
+// every kernel of the L-snapshot recurrence is enqueued back to back on the caller's stream, all intermediates
+// live in one caller-provided workspace, and every producer kernel emits the (hi, lo) TF32 split its consumer
+// GEMM needs, so no stand-alone conversion pass runs inside the loop.
+//
+// Per snapshot (Euclidean RE-GCN, uvrgcn encoder, no skip connection):
+//   K2  rel_mean_pool(h)                       -> x_mean (hi, lo)
+//   GEMM gi = x_mean . W_ih[:, d:]^T + gi_static        gi_static = emb_rel . W_ih[:, :d]^T + b_ih (constant per model)
+//   GEMM gh = h0 . W_hh^T + b_hh
+//   K3  gru_gate                               -> h0 (raw, hi, lo)
+//   per layer l:  K4 aggregate(x, h0)          -> agg (hi, lo)
+//                 GEMM Lm = x . [W_loop | W_evolve (| W_time for l = 0)]
+//                 GEMM P  = agg . W_n
+//                 K5 combine(P, Lm, indeg)     -> x' (raw, hi, lo)
+//   K9  time_gate(Lm0[:, 2d:3d], cur, h)       -> h (raw into hist[i], hi, lo)
+#include "../../include/regcn_b200.h"
+#include "common.cuh"
+#include "internal.h"
+
+namespace regcn {
+
+static inline size_t al(size_t n) { return (n + 63) & ~(size_t)63; }   // 256-byte aligned float counts
+
+struct EvolveWs {
+  size_t xm_hi, xm_lo, gi, gh, h0_hi, h0_lo, agg_hi, agg_lo, Lm, L2, P, set[2][3], h_hi, h_lo, h_init, partial, rel_partial, total;
+};
+
+static EvolveWs plan_evolve(int N, int R2, int d, int max_split_chunks, int rel_nsplit) {
+  EvolveWs w;
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off += al(n); return o; };
+  const size_t nd = (size_t)N * d, rd = (size_t)R2 * d;
+  w.xm_hi = take(rd); w.xm_lo = take(rd);
+  w.gi = take(rd * 3); w.gh = take(rd * 3);
+  w.h0_hi = take(rd); w.h0_lo = take(rd);
+  w.agg_hi = take(nd); w.agg_lo = take(nd);
+  w.Lm = take(nd * 3); w.L2 = take(nd * 2); w.P = take(nd);
+  for (int s = 0; s < 2; ++s) for (int k = 0; k < 3; ++k) w.set[s][k] = take(nd);
+  w.h_hi = take(nd); w.h_lo = take(nd); w.h_init = take(nd);
+  w.partial = take((size_t)(max_split_chunks > 0 ? max_split_chunks : 1) * d);
+  w.rel_partial = take(rel_nsplit > 1 ? (size_t)(R2 / 2) * rel_nsplit * d : 1);
+  w.total = off * sizeof(float);
+  return w;
+}
+
+}  // namespace regcn
+
+using namespace regcn;
+
+extern "C" {
+
+size_t regcn_regcn_evolve_workspace_bytes(int N, int R2, int d, int max_split_chunks, int rel_nsplit) {
+  return plan_evolve(N, R2, d, max_split_chunks, rel_nsplit).total;
+}
+
+int regcn_regcn_evolve(const void* const* mp, const int* mi, const void* const* gp, const int* gi_, int L,
+                       float* hist, float* h0_out, int rel_nsplit, void* workspace, size_t workspace_bytes,
+                       void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!mp || !mi || !gp || !gi_ || !hist || !h0_out || !workspace) { set_last_error("regcn_evolve: null pointer"); return REGCN_ERR_NULL; }
+  const int N = mi[RMI_NUM_ENTS], R2 = mi[RMI_NUM_RELS2], d = mi[RMI_DIM], nl = mi[RMI_NUM_LAYERS];
+  const int layer_norm = mi[RMI_LAYER_NORM], self_loop = mi[RMI_SELF_LOOP];
+  if (N <= 0 || R2 <= 0 || (R2 & 1) || d <= 0 || (d & 3) || d > 256 || nl < 1 || nl > 8 || L < 0) {
+    set_last_error("regcn_evolve: bad model dims N=%d R2=%d d=%d layers=%d", N, R2, d, nl); return REGCN_ERR_DIM;
+  }
+  if (!self_loop) { set_last_error("regcn_evolve: self_loop=False is served by the layer-level path"); return REGCN_ERR_UNSUPPORTED; }
+  int max_split = 0;
+  for (int i = 0; i < L; ++i) max_split = gi_[i * RGI_NUM_INTS + RGI_N_SPLIT_CHUNKS] > max_split ? gi_[i * RGI_NUM_INTS + RGI_N_SPLIT_CHUNKS] : max_split;
+  if (rel_nsplit < 1) rel_nsplit = 1;
+  const EvolveWs w = plan_evolve(N, R2, d, max_split, rel_nsplit);
+  if (workspace_bytes < w.total) { set_last_error("regcn_evolve: workspace %zu < %zu", workspace_bytes, w.total); return REGCN_ERR_WORKSPACE; }
+  float* ws = (float*)workspace;
+  auto F = [&](int k) { return (const float*)mp[k]; };
+  const size_t nd = (size_t)N * d;
+  int e;
+
+  // ---- initial entity state: F.normalize(dynamic_emb) if layer_norm (src/rrgcn.py:154) ----
+  const float* h_raw;
+  if (layer_norm) {
+    if ((e = row_map(F(RM_DYNAMIC_EMB), ws + w.h_init, N, d, 0, 1.0, nullptr, ws + w.h_hi, ws + w.h_lo, st))) return e;
+    h_raw = ws + w.h_init;
+  } else {
+    if ((e = split_tf32(F(RM_DYNAMIC_EMB), ws + w.h_hi, ws + w.h_lo, nd, st))) return e;
+    h_raw = F(RM_DYNAMIC_EMB);
+  }
+  const float* h0_raw = F(RM_EMB_REL);
+  const float* h0_hi = F(RM_EMB_REL_HI);
+  const float* h0_lo = F(RM_EMB_REL_LO);
+
+  for (int i = 0; i < L; ++i) {
+    const void* const* g = gp + (size_t)i * RG_NUM_PTRS;
+    const int* gn = gi_ + (size_t)i * RGI_NUM_INTS;
+    auto GI = [&](int k) { return (const int*)g[k]; };
+    // ---- relation evolution (K2, K3) ----
+    if ((e = rel_mean_pool(h_raw, GI(RG_REL_ROWPTR), GI(RG_REL_ENTS), R2 / 2, d, rel_nsplit, nullptr, ws + w.rel_partial,
+                           ws + w.xm_hi, ws + w.xm_lo, st))) return e;
+    if ((e = gemm_tf32(ws + w.xm_hi, ws + w.xm_lo, d, F(RM_WIH_R_HI), F(RM_WIH_R_LO), d, ws + w.gi, 3 * d, R2, 3 * d, d,
+                       nullptr, 0, 3, 1, nullptr, 0, F(RM_GI_STATIC), 3 * d, st))) return e;
+    if ((e = gemm_tf32(h0_hi, h0_lo, d, F(RM_WHH_HI), F(RM_WHH_LO), d, ws + w.gh, 3 * d, R2, 3 * d, d, F(RM_B_HH), 0, 3, 1,
+                       nullptr, 0, nullptr, 0, st))) return e;
+    if ((e = gru_gate(ws + w.gi, ws + w.gh, h0_raw, h0_out, R2, d, layer_norm, ws + w.h0_hi, ws + w.h0_lo, st))) return e;
+    h0_raw = h0_out; h0_hi = ws + w.h0_hi; h0_lo = ws + w.h0_lo;
+    // ---- entity evolution: n_layers x UnionRGCNLayer (K4, GEMMs, K5) ----
+    const float* x_raw = h_raw;
+    const float* x_hi = ws + w.h_hi;
+    const float* x_lo = ws + w.h_lo;
+    for (int l = 0; l < nl; ++l) {
+      const int base = RM_LAYER0 + 4 * l;
+      const int ncol = (l == 0 ? 3 : 2) * d;           // layer 0 also carries the time-gate weight
+      if ((e = union_aggregate(x_raw, h0_raw, GI(RG_ROWPTR), GI(RG_SRC_SORTED), GI(RG_ETYPE_SORTED), (const float*)g[RG_NORM],
+                               GI(RG_VPTR), GI(RG_SPTR), GI(RG_VROW_ROW), gn[RGI_N_VROWS], gn[RGI_N_SPLIT_CHUNKS], nullptr,
+                               0.f, N, d, nullptr, ws + w.partial, ws + w.agg_hi, ws + w.agg_lo, st))) return e;
+      float* Lbuf = (l == 0) ? ws + w.Lm : ws + w.L2;  // layer 0's result carries the gate columns and must survive
+      if ((e = gemm_tf32(x_hi, x_lo, d, F(base + 2), F(base + 3), d, Lbuf, ncol, N, ncol, d, nullptr, 0, 3, 1, nullptr, 0,
+                         nullptr, 0, st))) return e;
+      if ((e = gemm_tf32(ws + w.agg_hi, ws + w.agg_lo, d, F(base + 0), F(base + 1), d, ws + w.P, d, N, d, d, nullptr, 0, 3,
+                         1, nullptr, 0, nullptr, 0, st))) return e;
+      const bool last = l == nl - 1;
+      float* o_raw = ws + w.set[l & 1][0];
+      float* o_hi = last ? nullptr : ws + w.set[l & 1][1];
+      float* o_lo = last ? nullptr : ws + w.set[l & 1][2];
+      if ((e = union_combine(ws + w.P, Lbuf, GI(RG_INDEG), nullptr, nullptr, nullptr, N, d, 1, 0, 1.0, o_raw, nullptr, nullptr,
+                             ncol, o_hi, o_lo, nullptr, nullptr, st))) return e;
+      x_raw = o_raw; x_hi = o_hi; x_lo = o_lo;
+    }
+    // ---- time gate (K9): h = s(h W_t + b) * [normalize](cur) + (1 - s) * h ----
+    float* h_new = hist + (size_t)i * nd;
+    if ((e = time_gate(ws + w.Lm + 2 * d, F(RM_GATE_BIAS), x_raw, h_raw, h_new, N, d, layer_norm, 3 * d, ws + w.h_hi,
+                       ws + w.h_lo, st))) return e;
+    h_raw = h_new;
+  }
+  return REGCN_OK;
+}
+
+}  // extern "C"

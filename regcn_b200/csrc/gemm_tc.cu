@@ -89,6 +89,8 @@ struct Params {
   int M, N, K;
   const float* bias;
   int accumulate;
+  const float* addend;  // optional [M, N] matrix added in the epilogue (leading dimension ld_add)
+  int ld_add;
   int block_n;        // multiple of 16, <= 256
   int tmem_cols;      // power of two >= block_n
   int stages;
@@ -213,24 +215,30 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
       }
       const int gn0 = n0 + c0;
-      if (row < p.M && gn0 < p.N) {
+      const int ncols = min(32, min(p.block_n - c0, p.N - gn0));   // columns of this chunk owned by this tile
+      if (row < p.M && ncols > 0) {
         float* dst = out + (size_t)row * ldo + gn0;
         if (!split) {
           if (p.bias) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) if (gn0 + j < p.N) v[j] += __ldg(p.bias + gn0 + j);
+            for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += __ldg(p.bias + gn0 + j);
           }
           if (p.accumulate) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) if (gn0 + j < p.N) v[j] += dst[j];
+            for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += dst[j];
+          }
+          if (p.addend) {
+            const float* ad = p.addend + (size_t)row * p.ld_add + gn0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += __ldg(ad + j);
           }
         }
-        if (vec_ok && gn0 + 32 <= p.N && (gn0 & 3) == 0) {
+        if (vec_ok && ncols == 32 && (gn0 & 3) == 0) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) st4(dst + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) if (gn0 + j < p.N) dst[j] = v[j];
+          for (int j = 0; j < 32; ++j) if (j < ncols) dst[j] = v[j];
         }
       }
     }
@@ -325,7 +333,7 @@ size_t gemm_tf32_workspace_bytes(int M, int N, int split_k) {
 // A_hi/A_lo [M,K] (lda), B_hi/B_lo [N,K] (ldb); passes==1 ignores the lo operands (may be NULL).
 int gemm_tf32(const float* a_hi, const float* a_lo, int lda, const float* b_hi, const float* b_lo, int ldb, float* C,
               int ldc, int M, int N, int K, const float* bias, int accumulate, int passes, int split_k, float* ws,
-              size_t ws_bytes, cudaStream_t st) {
+              size_t ws_bytes, const float* addend, int ld_add, cudaStream_t st) {
   using namespace tc;
   if (!a_hi || !b_hi || !C || (passes == 3 && (!a_lo || !b_lo))) { set_last_error("gemm_tf32: null pointer"); return REGCN_ERR_NULL; }
   if (passes != 1 && passes != 3) { set_last_error("gemm_tf32: passes must be 1 or 3"); return REGCN_ERR_DIM; }
@@ -337,6 +345,8 @@ int gemm_tf32(const float* a_hi, const float* a_lo, int lda, const float* b_hi, 
   if (M == 0) return REGCN_OK;
   Params p;
   p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.bias = bias; p.accumulate = accumulate; p.passes = passes;
+  p.addend = addend; p.ld_add = ld_add;
+  if (addend && split_k > 1) { set_last_error("gemm_tf32: addend is not supported together with split-K"); return REGCN_ERR_UNSUPPORTED; }
   p.block_n = pick_block_n(N);
   p.tmem_cols = 32;
   while (p.tmem_cols < p.block_n) p.tmem_cols <<= 1;

@@ -10,10 +10,11 @@ int csr_build(const int64_t* triples, int T, int N, int R, int* src, int* dst, i
               int* rowptr, int* src_sorted, int* etype_sorted, int* eperm, int* vptr, int* sptr, int* vrow_row,
               int* rel_rowptr, int* rel_ents, int* counts, void* ws, size_t ws_bytes, cudaStream_t st);
 int rel_mean_pool(const float* h, const int* rel_rowptr, const int* rel_ents, int R, int d, int nsplit, float* out,
-                  float* partial, cudaStream_t st);
+                  float* partial, float* out_hi, float* out_lo, cudaStream_t st);
 int union_aggregate(const float* h, const float* rel, const int* rowptr, const int* src_sorted, const int* etype_sorted,
                     const float* norm, const int* vptr, const int* sptr, const int* vrow_row, int nv, int nsplit,
-                    const float* radius, float gamma, int N, int d, float* out, float* partial, cudaStream_t st);
+                    const float* radius, float gamma, int N, int d, float* out, float* partial, float* out_hi,
+                    float* out_lo, cudaStream_t st);
 int block_aggregate(const float* h, const float* W, const int* rowptr, const int* src_sorted, const int* etype_sorted,
                     const float* norm, int N, int d_in, int d_out, int nb, float* out, cudaStream_t st);
 int lorentz_aggregate(const float* ht, const float* W, const float* rel, const int* rowptr, const int* src_sorted,
@@ -26,14 +27,17 @@ int split_tf32(const float* x, float* hi, float* lo, size_t n, cudaStream_t st);
 size_t gemm_tf32_workspace_bytes(int M, int N, int split_k);
 int gemm_tf32(const float* a_hi, const float* a_lo, int lda, const float* b_hi, const float* b_lo, int ldb, float* C,
               int ldc, int M, int N, int K, const float* bias, int accumulate, int passes, int split_k, float* ws,
-              size_t ws_bytes, cudaStream_t st);
-int row_map(const float* x, float* out, int M, int d, int mode, double c, float* sumsq, cudaStream_t st);
-int gru_gate(const float* gi, const float* gh, const float* hprev, float* out, int M, int d, int normalize, cudaStream_t st);
+              size_t ws_bytes, const float* addend, int ld_add, cudaStream_t st);
+int row_map(const float* x, float* out, int M, int d, int mode, double c, float* sumsq, float* out_hi, float* out_lo,
+            cudaStream_t st);
+int gru_gate(const float* gi, const float* gh, const float* hprev, float* out, int M, int d, int normalize,
+             float* out_hi, float* out_lo, cudaStream_t st);
 int union_combine(const float* P, const float* L, const int* indeg, const float* S, const float* skip_bias,
                   const float* prev, int N, int d, int act, int hyper, double c, float* out, float* ht_next,
-                  float* radius_next, cudaStream_t st);
+                  float* radius_next, int ldL, float* out_hi, float* out_lo, float* ht_hi, float* ht_lo,
+                  cudaStream_t st);
 int time_gate(const float* G, const float* bias, const float* cur, const float* h, float* out, int N, int d,
-              int normalize_cur, cudaStream_t st);
+              int normalize_cur, int ldg, float* out_hi, float* out_lo, cudaStream_t st);
 int hyp_init(const float* emb, const float* radius_static, int N, int d, int normalize, int on_manifold, double c,
              float rmin, float rmax, float* out, cudaStream_t st);
 int hyp_tangent(const float* h, int N, int d, double c, float* ht, float* pt, float* radius, cudaStream_t st);

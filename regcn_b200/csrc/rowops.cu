@@ -30,7 +30,8 @@ static inline int check_d(const char* who, int d) {
 // sumsq (optional): |out|^2 per row (for the norm/dot form of the hyperbolic scores)
 template <int RV>
 __global__ void __launch_bounds__(256) row_map_kernel(const float* __restrict__ x, float* __restrict__ out, int M, int d,
-                                                      int mode, Curv cv, float* __restrict__ sumsq) {
+                                                      int mode, Curv cv, float* __restrict__ sumsq,
+                                                      float* __restrict__ out_hi, float* __restrict__ out_lo) {
   ROW_KERNEL_PROLOGUE(M)
   WarpRow<RV> r;
   r.load_plain(x + (size_t)row * d, nvec, lane);
@@ -45,20 +46,22 @@ __global__ void __launch_bounds__(256) row_map_kernel(const float* __restrict__ 
     default: break;  // mode 7: identity (row |x|^2 only)
   }
   if (out) r.store(out + (size_t)row * d, nvec, lane);
+  if (out_hi) r.store_split(out_hi + (size_t)row * d, out_lo + (size_t)row * d, nvec, lane);
   if (sumsq) {
     float s = r.sumsq();
     if (lane == 0) sumsq[row] = s;
   }
 }
 
-int row_map(const float* x, float* out, int M, int d, int mode, double c, float* sumsq, cudaStream_t st) {
-  if (!x || (!out && !sumsq)) { set_last_error("row_map: null pointer"); return REGCN_ERR_NULL; }
+int row_map(const float* x, float* out, int M, int d, int mode, double c, float* sumsq, float* out_hi, float* out_lo,
+            cudaStream_t st) {
+  if (!x || (!out && !sumsq && !out_hi) || (out_hi && !out_lo)) { set_last_error("row_map: null pointer"); return REGCN_ERR_NULL; }
   if (int e = check_d("row_map", d)) return e;
   if (mode < 0 || mode > 7) { set_last_error("row_map: bad mode %d", mode); return REGCN_ERR_DIM; }
   if (M <= 0) return REGCN_OK;
   Curv cv = make_curv(c > 0 ? c : 1.0);
-  if (d <= 128) row_map_kernel<1><<<row_grid(M), 256, 0, st>>>(x, out, M, d, mode, cv, sumsq);
-  else row_map_kernel<2><<<row_grid(M), 256, 0, st>>>(x, out, M, d, mode, cv, sumsq);
+  if (d <= 128) row_map_kernel<1><<<row_grid(M), 256, 0, st>>>(x, out, M, d, mode, cv, sumsq, out_hi, out_lo);
+  else row_map_kernel<2><<<row_grid(M), 256, 0, st>>>(x, out, M, d, mode, cv, sumsq, out_hi, out_lo);
   return check_launch("row_map");
 }
 
@@ -68,7 +71,8 @@ int row_map(const float* x, float* out, int M, int d, int mode, double c, float*
 template <int RV>
 __global__ void __launch_bounds__(256) gru_gate_kernel(const float* __restrict__ gi, const float* __restrict__ gh,
                                                        const float* __restrict__ hprev, float* __restrict__ out,
-                                                       int M, int d, int normalize) {
+                                                       int M, int d, int normalize, float* __restrict__ out_hi,
+                                                       float* __restrict__ out_lo) {
   ROW_KERNEL_PROLOGUE(M)
   WarpRow<RV> ir, iz, in_, hr, hz, hn, h;
   const float* gir = gi + (size_t)row * 3 * d;
@@ -85,14 +89,16 @@ __global__ void __launch_bounds__(256) gru_gate_kernel(const float* __restrict__
   h.zip(in_, [](float a, float n) { return a + n; });
   if (normalize) row_l2normalize(h);
   h.store(out + (size_t)row * d, nvec, lane);
+  if (out_hi) h.store_split(out_hi + (size_t)row * d, out_lo + (size_t)row * d, nvec, lane);
 }
 
-int gru_gate(const float* gi, const float* gh, const float* hprev, float* out, int M, int d, int normalize, cudaStream_t st) {
+int gru_gate(const float* gi, const float* gh, const float* hprev, float* out, int M, int d, int normalize,
+             float* out_hi, float* out_lo, cudaStream_t st) {
   if (!gi || !gh || !hprev || !out) { set_last_error("gru_gate: null pointer"); return REGCN_ERR_NULL; }
   if (int e = check_d("gru_gate", d)) return e;
   if (M <= 0) return REGCN_OK;
-  if (d <= 128) gru_gate_kernel<1><<<row_grid(M), 256, 0, st>>>(gi, gh, hprev, out, M, d, normalize);
-  else gru_gate_kernel<2><<<row_grid(M), 256, 0, st>>>(gi, gh, hprev, out, M, d, normalize);
+  if (d <= 128) gru_gate_kernel<1><<<row_grid(M), 256, 0, st>>>(gi, gh, hprev, out, M, d, normalize, out_hi, out_lo);
+  else gru_gate_kernel<2><<<row_grid(M), 256, 0, st>>>(gi, gh, hprev, out, M, d, normalize, out_hi, out_lo);
   return check_launch("gru_gate");
 }
 
@@ -109,14 +115,15 @@ __global__ void __launch_bounds__(256) union_combine_kernel(
     const float* __restrict__ P, const float* __restrict__ L, const int* __restrict__ indeg,
     const float* __restrict__ S, const float* __restrict__ skip_bias, const float* __restrict__ prev,
     int N, int d, int act, int hyper, Curv cv, float* __restrict__ out, float* __restrict__ ht_next,
-    float* __restrict__ radius_next) {
+    float* __restrict__ radius_next, int ldL, float* __restrict__ out_hi, float* __restrict__ out_lo,
+    float* __restrict__ ht_hi, float* __restrict__ ht_lo) {
   ROW_KERNEL_PROLOGUE(N)
   WarpRow<RV> t, u;
   t.load_plain(P + (size_t)row * d, nvec, lane);
   if (hyper) t.map([](float a) { return clampf_(a, -10.f, 10.f); });
   if (L) {
     const int sel = __ldg(indeg + row) > 0 ? 0 : d;
-    u.load_plain(L + (size_t)row * 2 * d + sel, nvec, lane);
+    u.load_plain(L + (size_t)row * ldL + sel, nvec, lane);
     t.zip(u, [](float a, float b) { return a + b; });
   }
   if (S) {
@@ -133,25 +140,28 @@ __global__ void __launch_bounds__(256) union_combine_kernel(
   if (act == 1) t.map([](float a) { return rreluf_(a); });
   if (hyper) row_exp0(t, cv);
   t.store(out + (size_t)row * d, nvec, lane);
-  if (hyper && (ht_next || radius_next)) {
+  if (out_hi) t.store_split(out_hi + (size_t)row * d, out_lo + (size_t)row * d, nvec, lane);
+  if (hyper && (ht_next || radius_next || ht_hi)) {
     float n = fmaxf(sqrtf(t.sumsq()), kEps);
     if (radius_next && lane == 0) radius_next[row] = n;
-    if (ht_next) {
+    if (ht_next || ht_hi) {
       row_log0(t, cv);
-      t.store(ht_next + (size_t)row * d, nvec, lane);
+      if (ht_next) t.store(ht_next + (size_t)row * d, nvec, lane);
+      if (ht_hi) t.store_split(ht_hi + (size_t)row * d, ht_lo + (size_t)row * d, nvec, lane);
     }
   }
 }
 
 int union_combine(const float* P, const float* L, const int* indeg, const float* S, const float* skip_bias,
                   const float* prev, int N, int d, int act, int hyper, double c, float* out, float* ht_next,
-                  float* radius_next, cudaStream_t st) {
+                  float* radius_next, int ldL, float* out_hi, float* out_lo, float* ht_hi, float* ht_lo,
+                  cudaStream_t st) {
   if (!P || !out || (L && !indeg) || (S && (!skip_bias || !prev))) { set_last_error("union_combine: null pointer"); return REGCN_ERR_NULL; }
   if (int e = check_d("union_combine", d)) return e;
   if (N <= 0) return REGCN_OK;
   Curv cv = make_curv(hyper ? c : 1.0);
-  if (d <= 128) union_combine_kernel<1><<<row_grid(N), 256, 0, st>>>(P, L, indeg, S, skip_bias, prev, N, d, act, hyper, cv, out, ht_next, radius_next);
-  else union_combine_kernel<2><<<row_grid(N), 256, 0, st>>>(P, L, indeg, S, skip_bias, prev, N, d, act, hyper, cv, out, ht_next, radius_next);
+  if (d <= 128) union_combine_kernel<1><<<row_grid(N), 256, 0, st>>>(P, L, indeg, S, skip_bias, prev, N, d, act, hyper, cv, out, ht_next, radius_next, ldL > 0 ? ldL : 2 * d, out_hi, out_lo, ht_hi, ht_lo);
+  else union_combine_kernel<2><<<row_grid(N), 256, 0, st>>>(P, L, indeg, S, skip_bias, prev, N, d, act, hyper, cv, out, ht_next, radius_next, ldL > 0 ? ldL : 2 * d, out_hi, out_lo, ht_hi, ht_lo);
   return check_launch("union_combine");
 }
 
@@ -159,10 +169,11 @@ int union_combine(const float* P, const float* L, const int* indeg, const float*
 template <int RV>
 __global__ void __launch_bounds__(256) time_gate_kernel(const float* __restrict__ G, const float* __restrict__ bias,
                                                         const float* __restrict__ cur, const float* __restrict__ h,
-                                                        float* __restrict__ out, int N, int d, int normalize_cur) {
+                                                        float* __restrict__ out, int N, int d, int normalize_cur,
+                                                        int ldg, float* __restrict__ out_hi, float* __restrict__ out_lo) {
   ROW_KERNEL_PROLOGUE(N)
   WarpRow<RV> g, b, c, hh;
-  g.load_plain(G + (size_t)row * d, nvec, lane);
+  g.load_plain(G + (size_t)row * ldg, nvec, lane);
   b.load(bias, nvec, lane);
   c.load_plain(cur + (size_t)row * d, nvec, lane);
   hh.load_plain(h + (size_t)row * d, nvec, lane);
@@ -172,15 +183,16 @@ __global__ void __launch_bounds__(256) time_gate_kernel(const float* __restrict_
   hh.zip(g, [](float a, float s) { return (1.0f - s) * a; });
   c.zip(hh, [](float a, float bb) { return a + bb; });
   c.store(out + (size_t)row * d, nvec, lane);
+  if (out_hi) c.store_split(out_hi + (size_t)row * d, out_lo + (size_t)row * d, nvec, lane);
 }
 
 int time_gate(const float* G, const float* bias, const float* cur, const float* h, float* out, int N, int d,
-              int normalize_cur, cudaStream_t st) {
+              int normalize_cur, int ldg, float* out_hi, float* out_lo, cudaStream_t st) {
   if (!G || !bias || !cur || !h || !out) { set_last_error("time_gate: null pointer"); return REGCN_ERR_NULL; }
   if (int e = check_d("time_gate", d)) return e;
   if (N <= 0) return REGCN_OK;
-  if (d <= 128) time_gate_kernel<1><<<row_grid(N), 256, 0, st>>>(G, bias, cur, h, out, N, d, normalize_cur);
-  else time_gate_kernel<2><<<row_grid(N), 256, 0, st>>>(G, bias, cur, h, out, N, d, normalize_cur);
+  if (d <= 128) time_gate_kernel<1><<<row_grid(N), 256, 0, st>>>(G, bias, cur, h, out, N, d, normalize_cur, ldg > 0 ? ldg : d, out_hi, out_lo);
+  else time_gate_kernel<2><<<row_grid(N), 256, 0, st>>>(G, bias, cur, h, out, N, d, normalize_cur, ldg > 0 ? ldg : d, out_hi, out_lo);
   return check_launch("time_gate");
 }
 

@@ -14,7 +14,7 @@ from . import _lib
 from ._lib import call, ptr
 
 I32 = torch.int32
-AGG_CHUNK = 256  # must match csrc/graph_build.cu kAggChunk
+AGG_CHUNK = 64  # must match csrc/graph_build.cu kAggChunk
 
 
 class _Frame(dict):
@@ -56,6 +56,11 @@ class SnapshotGraph:
         self._ndata = None
         self._edata = None
         self._r2e = None
+        # pointer / int tables consumed by the whole-recurrence entry points (include/regcn_b200.h RG_* / RGI_*)
+        self.ptr_table = np.array([t.data_ptr() for t in (self.rowptr, self.src_sorted, self.etype_sorted, self.indeg,
+                                                          self.norm, self.vptr, self.sptr, self.vrow_row,
+                                                          self.rel_rowptr, self.rel_ents)], dtype=np.uint64)
+        self.int_table = np.array([E, self.n_vrows, self.n_split_chunks, self.n_rel_ents], dtype=np.int32)
 
     # ---- the slice of the DGL surface the reference modules use -----------------
     def number_of_nodes(self):

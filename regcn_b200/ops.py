@@ -35,7 +35,7 @@ def _rowmajor(t, name):
 # --------------------------------------------------------------------------- dense contractions
 import os
 
-_GEMM_IMPL = {"impl": os.environ.get("REGCN_GEMM", "simt")}
+_GEMM_IMPL = {"impl": os.environ.get("REGCN_GEMM", "tc")}
 _IMPLS = {"simt": "regcn::gemm_f32_kernel (fp32 CUDA cores)",
           "tc": "regcn::tc::gemm_tf32_kernel (tcgen05 kind::tf32, 3xTF32 error-compensated)",
           "tc1": "regcn::tc::gemm_tf32_kernel (tcgen05 kind::tf32, single pass)"}
@@ -328,9 +328,11 @@ def rank_dense(score, triples, target_col, filt_ptr=None, filt_idx=None, col_off
     """Counts for a (B, N_shard) dense score block.  Returns (raw_count, filt_count, target_score) int32/int32/f32."""
     B, N = score.shape
     dev = score.device
+    if not score.is_cuda or score.dtype != F32 or score.stride(1) != 1:
+        raise ValueError("rank_dense: score must be a CUDA float32 matrix with unit column stride")
     if target_score is None:
         target_score = torch.zeros(B, device=dev, dtype=F32)
-        call("regcn_gather_target_score", ptr(score), score.stride(0), B, N, ptr(triples), target_col, col_offset,
+        call("regcn_gather_target_score", score.data_ptr(), score.stride(0), B, N, ptr(triples), target_col, col_offset,
              ptr(target_score))
     raw = torch.empty(B, device=dev, dtype=I32)
     filt = torch.empty(B, device=dev, dtype=I32) if filt_ptr is not None else None

@@ -116,9 +116,86 @@ class RecurrentRGCN(nn.Module):
                       b_key=(cell.weight_hh, "w"))
         return ops.gru_gate(gi, gh, h0_prev, self.layer_norm)
 
+    # ------------------------------------------------------------------ whole-recurrence fast path
+    def _engine_ok(self):
+        return (ops.gemm_impl() == "tc" and not self.use_static and self.rgcn.self_loop and not self.rgcn.skip_connect
+                and self.encoder_name == "uvrgcn" and self.h_dim % 4 == 0 and self.h_dim <= 256)
+
+    def _engine_tables(self):
+        """Pointer / int tables of regcn_regcn_evolve (include/regcn_b200.h RM_* / RMI_*), rebuilt when any parameter
+        changes.  GEMM weights are stored K-major and TF32-split once here, never inside the recurrence."""
+        cell = self.relation_cell_1
+        params = [self.dynamic_emb, self.emb_rel, cell.weight_ih, cell.weight_hh, cell.bias_ih, cell.bias_hh,
+                  self.time_gate_weight, self.time_gate_bias]
+        for layer in self.rgcn.layers:
+            params += [layer.weight_neighbor, layer.loop_weight, layer.evolve_loop_weight]
+        stamp = tuple((p._version, p.data_ptr()) for p in params)
+        if getattr(self, "_engine_stamp", None) == stamp:
+            return self._engine_tab
+        import numpy as np
+        d = self.h_dim
+        keep = []
+
+        def split(m):
+            hi, lo = ops.split_tf32(m.detach().contiguous())
+            keep.extend((hi, lo))
+            return hi, lo
+
+        emb_rel = self.emb_rel.detach().contiguous()
+        er_hi, er_lo = split(emb_rel)
+        w_ih = cell.weight_ih.detach()
+        prev = ops.gemm_impl()
+        gi_static = ops.gemm(emb_rel, w_ih[:, :d], trans_b=True, bias=cell.bias_ih.detach())
+        wr_hi, wr_lo = split(w_ih[:, d:])
+        wh_hi, wh_lo = split(cell.weight_hh)
+        b_hh = cell.bias_hh.detach().contiguous()
+        gate_b = self.time_gate_bias.detach().contiguous()
+        dyn = self.dynamic_emb.detach().contiguous()
+        keep += [emb_rel, gi_static, b_hh, gate_b, dyn]
+        ptrs = [dyn, emb_rel, er_hi, er_lo, gi_static, wr_hi, wr_lo, wh_hi, wh_lo, b_hh, gate_b]
+        for l, layer in enumerate(self.rgcn.layers):
+            wn_hi, wn_lo = split(layer.weight_neighbor.detach().t())
+            cat = [layer.loop_weight.detach(), layer.evolve_loop_weight.detach()]
+            if l == 0:
+                cat.append(self.time_gate_weight.detach())
+            wl_hi, wl_lo = split(torch.cat(cat, dim=1).t())
+            ptrs += [wn_hi, wn_lo, wl_hi, wl_lo]
+        ptab = np.array([t.data_ptr() for t in ptrs], dtype=np.uint64)
+        itab = np.array([self.num_ents, 2 * self.num_rels, d, len(self.rgcn.layers), int(bool(self.layer_norm)), 1],
+                        dtype=np.int32)
+        self._engine_tab = (ptab, itab, keep)
+        self._engine_stamp = stamp
+        return self._engine_tab
+
+    def _forward_engine(self, g_list):
+        import numpy as np
+        from . import _lib
+        ptab, itab, _ = self._engine_tables()
+        L = len(g_list)
+        N, R2, d = self.num_ents, 2 * self.num_rels, self.h_dim
+        dev = self.dynamic_emb.device
+        gp = np.concatenate([g.ptr_table for g in g_list]) if L else np.zeros(1, dtype=np.uint64)
+        gi = np.concatenate([g.int_table for g in g_list]) if L else np.zeros(1, dtype=np.int32)
+        max_split = max([g.n_split_chunks for g in g_list], default=0)
+        rel_nsplit = max([max(1, min(64, g.n_rel_ents // (max(1, self.num_rels) * 512))) for g in g_list], default=1)
+        need = _lib.load().regcn_regcn_evolve_workspace_bytes(N, R2, d, max_split, rel_nsplit)
+        ws = getattr(self, "_engine_ws", None)
+        if ws is None or ws.numel() < need or ws.device != dev:
+            ws = torch.empty(need, device=dev, dtype=torch.uint8)
+            self._engine_ws = ws
+        hist = torch.empty((max(L, 1), N, d), device=dev, dtype=torch.float32)
+        h0 = torch.empty((R2, d), device=dev, dtype=torch.float32)
+        _lib.call("regcn_regcn_evolve", ptab.ctypes.data, itab.ctypes.data, gp.ctypes.data, gi.ctypes.data, L,
+                  hist.data_ptr(), h0.data_ptr(), rel_nsplit, ws.data_ptr(), ws.numel())
+        return [hist[i] for i in range(L)], h0
+
     @torch.no_grad()
     def forward(self, g_list, static_graph, use_cuda):
         gate_list, degree_list = [], []
+        if self._engine_ok() and len(g_list) > 0:
+            history_embs, self.h_0 = self._forward_engine(g_list)
+            self.h = history_embs[-1]
+            return history_embs, None, self.h_0, gate_list, degree_list
         if self.use_static:
             static_graph = static_graph.to(self.gpu)
             static_graph.ndata['h'] = torch.cat((self.dynamic_emb, self.words_emb), dim=0).detach()
