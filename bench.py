@@ -264,32 +264,24 @@ def main():
     h2d = sum(h.numel() for h in hist_host) * 8 + test_host.numel() * 8
     d2h = 2 * B * 8 + 4 * 4
 
-    # ---- roofline of the dominant kernel (dense contraction), timed live with events on the launch stream ------
-    rec = []
-    real_gemm = ops.gemm
-
-    def gemm_probe(a, b, trans_b=False, **kw):
-        s, e = ev(), ev()
-        s.record()
-        out = real_gemm(a, b, trans_b=trans_b, **kw)
-        e.record()
-        rec.append((s, e, 2.0 * a.shape[0] * a.shape[1] * out.shape[1]))
-        return out
-
-    for mod in (ops,):
-        mod.gemm = gemm_probe
+    # ---- roofline of the dominant kernel: the library records CUDA events around every launch of the tcgen05 GEMM
+    #      (on the launching stream) while a few extra steps run; flops are the algorithmic 2*M*N*K of each launch ----
+    import ctypes
+    lib = _lib.load()
     probe_steps = 3
-    try:
-        torch.cuda.synchronize()
-        for _ in range(probe_steps):
-            flush.fill_(1.0)
-            evaluate.evaluate_snapshot(model, glist, all_t, fcsr, None)
-        torch.cuda.synchronize()
-    finally:
-        ops.gemm = real_gemm
-    gemm_ms = sum(s.elapsed_time(e) for s, e, _ in rec) / probe_steps
-    gemm_flops = sum(f for _, _, f in rec) / probe_steps
-    n_gemm = len(rec) // probe_steps
+    torch.cuda.synchronize()
+    lib.regcn_prof_enable(1)
+    for _ in range(probe_steps):
+        flush.fill_(1.0)
+        evaluate.evaluate_snapshot(model, glist, all_t, fcsr, None)
+    ms_c, n_c, w_c = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()
+    lib.regcn_prof_read(0, ctypes.byref(ms_c), ctypes.byref(n_c), ctypes.byref(w_c))
+    agg_ms_c, agg_n_c, agg_w_c = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()
+    lib.regcn_prof_read(1, ctypes.byref(agg_ms_c), ctypes.byref(agg_n_c), ctypes.byref(agg_w_c))
+    lib.regcn_prof_enable(0)
+    gemm_ms = ms_c.value / probe_steps
+    gemm_flops = w_c.value / probe_steps
+    n_gemm = n_c.value // probe_steps
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -297,13 +289,26 @@ def main():
         pass
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     ach_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    passes = 3 if ops.gemm_impl() == "tc" else 1
     roofline = {"kernel": ops.gemm_kernel_name(), "bound": "tensor", "achieved": ach_tf, "peak": peak_tf,
                 "unit": "TFLOP/s", "frac": ach_tf / peak_tf, "traffic": None,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks
                 else "fallback 1.4 PFLOP/s (B200_PROFILING.md)",
                 "launches_per_step": n_gemm, "ms_per_step_in_kernel": gemm_ms,
                 "share_of_step": gemm_ms / ms_per_step if ms_per_step > 0 else None,
-                "algorithmic_flops_per_step": gemm_flops}
+                "algorithmic_flops_per_step": gemm_flops,
+                "note": f"fp32-parity mode issues {passes} TF32 MMAs per algorithmic MAC (error-compensated), so executed "
+                        f"tensor work is {passes}x the algorithmic flops; TF32 dense peak is half the bf16 figure"}
+    # edge kernel (HBM-bound) at this workload: algorithmic bytes per launch = 808*E + 808*N + 800*2R
+    agg_launches = max(1, agg_n_c.value // probe_steps)
+    agg_bytes = agg_launches * (808.0 * 2 * T + 808.0 * n + 800.0 * 2 * r)
+    agg_ms = agg_ms_c.value / probe_steps
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    edge = {"kernel": "regcn::union_aggregate_kernel (+fixup)", "bound": "hbm", "launches_per_step": agg_launches,
+            "ms_per_step_in_kernel": agg_ms, "achieved": agg_bytes / (agg_ms * 1e-3) / 1e9 if agg_ms > 0 else 0.0,
+            "peak": hbm, "unit": "GB/s", "note": "latency-bound at this size (E=3082 edges, 18 MB output); see "
+            "profiles/ for the HBM-bound stress sizes"}
+    edge["frac"] = edge["achieved"] / hbm
 
     # ---- entity-sharded scoring + rank merge (strong scaling of one timestamp), all ranks on the same queries ----
     sharded = None
@@ -359,7 +364,7 @@ def main():
                 "phase_ms": parts, "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "queries/s",
                                            "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                                            "d2h_bytes_per_step": d2h},
-                "gpu_launches": launches, "roofline": roofline, "clocks": clocks}
+                "gpu_launches": launches, "roofline": roofline, "edge_kernel": edge, "clocks": clocks}
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
         if sharded:

@@ -94,6 +94,14 @@ REGCN_API int regcn_gemm_tf32(const float* a_hi, const float* a_lo, int lda, con
                     int ldb, float* C, int ldc, int M, int N, int K, const float* bias, int accumulate,
                     int passes, int split_k, float* workspace, size_t workspace_bytes, void* stream);
 
+/* opt-in kernel timing with CUDA events on the launching stream: slot 0 = tcgen05 GEMM (work = 2MNK flops),
+ * slot 1 = union aggregate.  enable(1) clears the records; read() synchronises the device and sums them.       */
+REGCN_API void regcn_prof_enable(int on);
+REGCN_API int regcn_prof_read(int slot, double* total_ms, long long* launches, double* total_work);
+
+/* tuning knob for experiments: force the N tile (multiple of 16, <= 256; 0 = automatic) and cap the pipeline depth */
+REGCN_API void regcn_gemm_tf32_tune(int block_n, int stages);
+
 /* ---- row maps: F.normalize / tanh / log_0 / exp_0 / project (hyperbolic_ops.py:38-116) ---------
  * mode 0 normalize, 1 tanh, 2 0.9 tanh(log_0 x)+0.1 log_0 x, 3 log_0, 4 exp_0, 5 project,
  * 6 exp_0(normalize(log_0 x)), 7 identity; sumsq (optional, M): |out|^2 per row; out may be NULL

@@ -153,6 +153,7 @@ int union_aggregate(const float* h, const float* rel, const int* rowptr, const i
   const int TB = 256;
   const unsigned grid = (unsigned)(((size_t)nv * 32 + TB - 1) / TB);
   const bool small = d <= 128;
+  prof_begin(PROF_AGGREGATE, st);
   if (radius) {
     if (small) union_aggregate_kernel<1, true><<<grid, TB, 0, st>>>(h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, radius, gamma, d, out, partial, out_hi, out_lo);
     else union_aggregate_kernel<2, true><<<grid, TB, 0, st>>>(h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, radius, gamma, d, out, partial, out_hi, out_lo);
@@ -165,6 +166,7 @@ int union_aggregate(const float* h, const float* rel, const int* rowptr, const i
     if (small) aggregate_fixup_kernel<1><<<g2, TB, 0, st>>>(vptr, sptr, norm, N, d, partial, out, out_hi, out_lo);
     else aggregate_fixup_kernel<2><<<g2, TB, 0, st>>>(vptr, sptr, norm, N, d, partial, out, out_hi, out_lo);
   }
+  prof_end(PROF_AGGREGATE, 0.0, st);   // bytes are filled in by the caller-side formula (needs E, R); see bench.py
   return check_launch("union_aggregate");
 }
 

@@ -4,6 +4,7 @@
 #include "internal.h"
 #include <stdarg.h>
 #include <stdio.h>
+#include <vector>
 
 namespace regcn {
 static thread_local char g_err[512] = "";
@@ -23,6 +24,26 @@ int check_launch(const char* what) {
 }
 }  // namespace regcn
 
+namespace regcn {
+struct ProfRec { cudaEvent_t a, b; double work; };
+static bool g_prof = false;
+static std::vector<ProfRec> g_recs[PROF_NUM_SLOTS];
+bool prof_on() { return g_prof; }
+void prof_begin(int slot, cudaStream_t st) {
+  if (!g_prof) return;
+  ProfRec r;
+  cudaEventCreate(&r.a); cudaEventCreate(&r.b); r.work = 0;
+  cudaEventRecord(r.a, st);
+  g_recs[slot].push_back(r);
+}
+void prof_end(int slot, double work, cudaStream_t st) {
+  if (!g_prof || g_recs[slot].empty()) return;
+  ProfRec& r = g_recs[slot].back();
+  r.work = work;
+  cudaEventRecord(r.b, st);
+}
+}  // namespace regcn
+
 using namespace regcn;
 #define ST(s) ((cudaStream_t)(s))
 
@@ -37,6 +58,22 @@ int regcn_device_ok(void) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
   return major == 10 ? 1 : 0;
+}
+
+void regcn_prof_enable(int on) {
+  g_prof = on != 0;
+  if (on) for (int s = 0; s < PROF_NUM_SLOTS; ++s) {
+    for (auto& r : g_recs[s]) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_recs[s].clear();
+  }
+}
+int regcn_prof_read(int slot, double* total_ms, long long* launches, double* total_work) {
+  if (slot < 0 || slot >= PROF_NUM_SLOTS || !total_ms || !launches || !total_work) return REGCN_ERR_DIM;
+  cudaDeviceSynchronize();
+  double ms = 0, work = 0;
+  for (auto& r : g_recs[slot]) { float t = 0; cudaEventElapsedTime(&t, r.a, r.b); ms += t; work += r.work; }
+  *total_ms = ms; *launches = (long long)g_recs[slot].size(); *total_work = work;
+  return REGCN_OK;
 }
 
 size_t regcn_csr_build_workspace_bytes(int T, int N, int R) { return csr_build_workspace_bytes(T, N, R); }
@@ -85,6 +122,7 @@ int regcn_gemm_tf32(const float* a_hi, const float* a_lo, int lda, const float* 
   return gemm_tf32(a_hi, a_lo, lda, b_hi, b_lo, ldb, C, ldc, M, N, K, bias, accumulate, passes, split_k, workspace,
                    workspace_bytes, nullptr, 0, ST(stream));
 }
+void regcn_gemm_tf32_tune(int block_n, int stages) { gemm_tf32_tune(block_n, stages); }
 int regcn_row_map(const float* x, float* out, int M, int d, int mode, double c, float* sumsq, void* stream) {
   return row_map(x, out, M, d, mode, c, sumsq, nullptr, nullptr, ST(stream));
 }

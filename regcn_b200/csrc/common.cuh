@@ -15,6 +15,13 @@ namespace regcn {
 void set_last_error(const char* fmt, ...);
 int check_launch(const char* what);
 
+// Opt-in per-kernel timing with CUDA events on the launching stream (bench.py's roofline numbers).
+// slot 0 = tensor-core GEMM (work = algorithmic flops), slot 1 = union aggregate (work = algorithmic bytes).
+enum { PROF_GEMM_TC = 0, PROF_AGGREGATE = 1, PROF_NUM_SLOTS = 2 };
+bool prof_on();
+void prof_begin(int slot, cudaStream_t st);
+void prof_end(int slot, double work, cudaStream_t st);
+
 constexpr int kWarp = 32;
 constexpr float kEps = 1e-6f;                   // HyperbolicOps.EPS (hyperbolic_ops.py:28)
 constexpr float kRReluSlope = (1.0f / 8.0f + 1.0f / 3.0f) * 0.5f;  // F.rrelu eval slope, 11/48

@@ -314,7 +314,11 @@ int split_tf32(const float* x, float* hi, float* lo, size_t n, cudaStream_t st) 
   return check_launch("split_tf32");
 }
 
+static int g_force_block_n = 0, g_force_stages = 0;
+void gemm_tf32_tune(int block_n, int stages) { g_force_block_n = block_n; g_force_stages = stages; }
+
 static int pick_block_n(int N) {
+  if (g_force_block_n > 0) return g_force_block_n;
   if (N <= 64) return (N + 15) / 16 * 16;
   int best = 256, best_waste = 1 << 30;
   const int cands[4] = {256, 208, 128, 64};
@@ -358,6 +362,7 @@ int gemm_tf32(const float* a_hi, const float* a_lo, int lda, const float* b_hi, 
   split_k = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
   p.stages = (int)(SMEM_BUDGET / stage_bytes);
   if (p.stages > 8) p.stages = 8;
+  if (g_force_stages > 0 && g_force_stages < p.stages) p.stages = g_force_stages;
   if (p.stages > p.kb_per_split) p.stages = p.kb_per_split;
   if (p.stages < 1) { set_last_error("gemm_tf32: tile does not fit in shared memory"); return REGCN_ERR_UNSUPPORTED; }
   p.ws = nullptr;
@@ -383,7 +388,9 @@ int gemm_tf32(const float* a_hi, const float* a_lo, int lda, const float* b_hi, 
     attr_set = true;
   }
   dim3 grid((N + p.block_n - 1) / p.block_n, (M + BLOCK_M - 1) / BLOCK_M, split_k);
+  prof_begin(PROF_GEMM_TC, st);
   gemm_tf32_kernel<<<grid, NUM_THREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+  prof_end(PROF_GEMM_TC, 2.0 * M * (double)N * K, st);
   if (split_k > 1) {
     const size_t total = (size_t)M * N;
     splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws, split_k, C, ldc, M, N, bias, accumulate);

@@ -28,6 +28,7 @@ size_t gemm_tf32_workspace_bytes(int M, int N, int split_k);
 int gemm_tf32(const float* a_hi, const float* a_lo, int lda, const float* b_hi, const float* b_lo, int ldb, float* C,
               int ldc, int M, int N, int K, const float* bias, int accumulate, int passes, int split_k, float* ws,
               size_t ws_bytes, const float* addend, int ld_add, cudaStream_t st);
+void gemm_tf32_tune(int block_n, int stages);
 int row_map(const float* x, float* out, int M, int d, int mode, double c, float* sumsq, float* out_hi, float* out_lo,
             cudaStream_t st);
 int gru_gate(const float* gi, const float* gh, const float* hprev, float* out, int M, int d, int normalize,
