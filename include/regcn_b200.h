@@ -94,6 +94,30 @@ REGCN_API int regcn_gemm_tf32(const float* a_hi, const float* a_lo, int lda, con
                     int ldb, float* C, int ldc, int M, int N, int K, const float* bias, int accumulate,
                     int passes, int split_k, float* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- fused all-entity scoring + rank (K11/K13 + K14), no score matrix: src/decoder.py:96-99 and
+ * hyperbolic_decoder.py:89-179 fused with rgcn/utils.py:21-25,51-75.
+ * regcn_score_count_tf32: the scoring GEMM Q[B,K] . E[N,K]^T with a counting epilogue:
+ *     raw_count[b] += #{n in shard, col_offset+n != target[b] : score(b,n) ranks ahead of tscore[b]}
+ *   score = <q,e> (+col_bias[n]) or, with hyp != 0, scale*(margin - |(-q)(+)_c e|^2) (+col_bias[n]) from x2=|q|^2, y2=|e|^2.
+ * regcn_pair_scores_tf32: out[p] = score(A'[p], B'[p]) for gathered operand rows, through the same tensor-core
+ *   arithmetic (bit-identical to the corresponding element of the scoring GEMM): target and filter-entry scores.
+ * regcn_filter_correct: filt_count[b] = raw_count[b] - (filter entries that beat the target) + (-1e7 entries that do).
+ * regcn_gather_rows2 / regcn_gather_scalars: operand gathers for the pair pass.                                */
+REGCN_API int regcn_score_count_tf32(const float* q_hi, const float* q_lo, const float* e_hi, const float* e_lo, int B,
+                           int N, int K, const float* tscore, const int32_t* target, int32_t* raw_count,
+                           int col_offset, int hyp, const float* x2, const float* y2, const float* col_bias, double c,
+                           const float* scale_margin, int passes, void* stream);
+REGCN_API int regcn_pair_scores_tf32(const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo, int P,
+                           int K, int hyp, const float* x2, const float* y2, const float* col_bias, double c,
+                           const float* scale_margin, float* out, int passes, void* stream);
+REGCN_API int regcn_gather_rows2(const float* src_hi, const float* src_lo, const int32_t* idx, int P, int d,
+                       float* out_hi, float* out_lo, void* stream);
+REGCN_API int regcn_gather_scalars(const float* a, const float* b, const float* c, const int32_t* ia, const int32_t* ib,
+                         int P, float* oa, float* ob, float* oc, void* stream);
+REGCN_API int regcn_filter_correct(int B, const int32_t* filt_ptr, const int32_t* filt_idx, const int32_t* target,
+                         const float* pair_score, const int32_t* raw_count, int col_lo, int col_hi,
+                         int32_t* filt_count, void* stream);
+
 /* opt-in kernel timing with CUDA events on the launching stream: slot 0 = tcgen05 GEMM (work = 2MNK flops),
  * slot 1 = union aggregate.  enable(1) clears the records; read() synchronises the device and sums them.       */
 REGCN_API void regcn_prof_enable(int on);

@@ -123,6 +123,31 @@ int regcn_gemm_tf32(const float* a_hi, const float* a_lo, int lda, const float* 
                    workspace_bytes, nullptr, 0, ST(stream));
 }
 void regcn_gemm_tf32_tune(int block_n, int stages) { gemm_tf32_tune(block_n, stages); }
+int regcn_score_count_tf32(const float* q_hi, const float* q_lo, const float* e_hi, const float* e_lo, int B, int N, int K,
+                           const float* tscore, const int32_t* target, int32_t* raw_count, int col_offset, int hyp,
+                           const float* x2, const float* y2, const float* col_bias, double c,
+                           const float* scale_margin, int passes, void* stream) {
+  return score_count_tf32(q_hi, q_lo, e_hi, e_lo, B, N, K, tscore, target, raw_count, col_offset, hyp, x2, y2, col_bias, c,
+                          scale_margin, passes, ST(stream));
+}
+int regcn_pair_scores_tf32(const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo, int P, int K,
+                           int hyp, const float* x2, const float* y2, const float* col_bias, double c,
+                           const float* scale_margin, float* out, int passes, void* stream) {
+  return pair_scores_tf32(a_hi, a_lo, b_hi, b_lo, P, K, hyp, x2, y2, col_bias, c, scale_margin, out, passes, ST(stream));
+}
+int regcn_gather_rows2(const float* src_hi, const float* src_lo, const int32_t* idx, int P, int d, float* out_hi,
+                       float* out_lo, void* stream) {
+  return gather_rows2(src_hi, src_lo, idx, P, d, out_hi, out_lo, ST(stream));
+}
+int regcn_gather_scalars(const float* a, const float* b, const float* c, const int32_t* ia, const int32_t* ib, int P,
+                         float* oa, float* ob, float* oc, void* stream) {
+  return gather_scalars(a, b, c, ia, ib, P, oa, ob, oc, ST(stream));
+}
+int regcn_filter_correct(int B, const int32_t* filt_ptr, const int32_t* filt_idx, const int32_t* target,
+                         const float* pair_score, const int32_t* raw_count, int col_lo, int col_hi,
+                         int32_t* filt_count, void* stream) {
+  return filter_correct(B, filt_ptr, filt_idx, target, pair_score, raw_count, col_lo, col_hi, filt_count, ST(stream));
+}
 int regcn_row_map(const float* x, float* out, int M, int d, int mode, double c, float* sumsq, void* stream) {
   return row_map(x, out, M, d, mode, c, sumsq, nullptr, nullptr, ST(stream));
 }

@@ -195,4 +195,27 @@ __device__ __forceinline__ void row_l2normalize(WarpRow<RV>& x) {
   x.map([=](float e) { return e / n; });
 }
 
+// K13 score from a dot product, written with explicit IEEE operations (no FMA contraction) so that the dense
+// epilogue kernel, the fused count epilogue and the pair-score pass produce bit-identical values.
+__device__ __forceinline__ float hyp_score_from_dot(float dot, float x_sq, float y_sq, float c, float proj_max,
+                                                    float scale, float margin) {
+  const float xy = -dot;
+  const float two_c_xy = __fmul_rn(__fmul_rn(2.0f, c), xy);
+  const float a = __fadd_rn(__fadd_rn(1.0f, two_c_xy), __fmul_rn(c, y_sq));
+  const float b = __fsub_rn(1.0f, __fmul_rn(c, x_sq));
+  const float t1 = __fmul_rn(__fmul_rn(a, a), x_sq);
+  const float t2 = __fmul_rn(__fmul_rn(__fmul_rn(2.0f, a), b), xy);
+  const float t3 = __fmul_rn(__fmul_rn(b, b), y_sq);
+  const float num_sq = fmaxf(__fadd_rn(__fadd_rn(t1, t2), t3), 0.f);
+  const float den = __fadd_rn(__fadd_rn(__fadd_rn(1.0f, two_c_xy), __fmul_rn(__fmul_rn(__fmul_rn(c, c), x_sq), y_sq)), kEps);
+  float n = __fdiv_rn(__fsqrt_rn(num_sq), fabsf(den));
+  n = fminf(n, proj_max);
+  return __fmul_rn(scale, __fsub_rn(margin, __fmul_rn(n, n)));
+}
+
+// Rank contribution of candidate j (score s) against target t (score st): stable-sort position rule (rank.cu).
+__device__ __forceinline__ int rank_beats(float s, int j, float st, int t) {
+  return (s > st || (s == st && j < t)) ? 1 : 0;
+}
+
 }  // namespace regcn

@@ -197,18 +197,6 @@ int hyp_query(const float* s_tan, const float* ang, const float* trans, const fl
 // with x = -q: x_sq = |q|^2, y_sq = |e|^2, xy = -<q,e>; A = 1+2c*xy+c*y_sq; Bc = 1-c*x_sq;
 // |num|^2 = A^2 x_sq + 2 A Bc xy + Bc^2 y_sq; den = 1+2c*xy+c^2 x_sq y_sq + eps; n = sqrt(|num|^2)/den,
 // clamp_norm -> min(n, proj_max) (for n >= eps).                       hyperbolic_decoder.py:164-172, ops:135-143
-__device__ __forceinline__ float hyp_score_from_dot(float dot, float x_sq, float y_sq, float c, float proj_max,
-                                                    float scale, float margin) {
-  const float xy = -dot;
-  const float a = 1.0f + 2.0f * c * xy + c * y_sq;
-  const float b = 1.0f - c * x_sq;
-  const float num_sq = fmaxf(a * a * x_sq + 2.0f * a * b * xy + b * b * y_sq, 0.f);
-  const float den = 1.0f + 2.0f * c * xy + c * c * x_sq * y_sq + kEps;
-  float n = sqrtf(num_sq) / fabsf(den);
-  n = fminf(n, proj_max);
-  return scale * (margin - n * n);
-}
-
 __global__ void hyp_score_epilogue_kernel(float* __restrict__ S, size_t ld, int B, int N, const float* __restrict__ q_sumsq,
                                           const float* __restrict__ e_sumsq, const float* __restrict__ bias,
                                           const float* __restrict__ qbias, Curv cv, const float* __restrict__ scale_margin) {
@@ -217,8 +205,8 @@ __global__ void hyp_score_epilogue_kernel(float* __restrict__ S, size_t ld, int 
   if (n >= N) return;
   const float scale = scale_margin[0], margin = scale_margin[1];
   float v = hyp_score_from_dot(S[(size_t)b * ld + n], __ldg(q_sumsq + b), __ldg(e_sumsq + n), cv.c, cv.proj_max, scale, margin);
-  if (bias) v += __ldg(bias + n);
-  if (qbias) v += __ldg(qbias + b);
+  if (bias) v = __fadd_rn(v, __ldg(bias + n));
+  if (qbias) v = __fadd_rn(v, __ldg(qbias + b));
   S[(size_t)b * ld + n] = v;
 }
 

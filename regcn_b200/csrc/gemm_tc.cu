@@ -97,7 +97,27 @@ struct Params {
   int passes;         // 3 = 3xTF32 (fp32 parity), 1 = plain TF32
   int kb_per_split;   // k-blocks per grid.z slice
   float* ws;          // split-K partials [gridDim.z][M][N] (NULL when gridDim.z == 1)
+  // ---- fused scoring epilogues (K11/K13 + K14) ----
+  int epi;                    // 0 store C, 1 count candidates beating the target (no C), 2 diagonal (pair scores)
+  const float* tscore;        // epi 1: [M] target score of each query row
+  const int* target;          // epi 1: [M] global candidate id of each query's target
+  int* raw_count;             // epi 1: [M] += #{candidates of this tile beating the target}
+  int col_offset;             // epi 1: global id of candidate row 0 of B (entity shard)
+  int hyp;                    // score = hyp_score_from_dot(dot, x2[row], y2[col]) instead of dot
+  const float* x2;            // [M] |q|^2
+  const float* y2;            // [N] |e|^2   (epi 2: indexed by pair)
+  const float* col_bias;      // [N] candidate bias or NULL (epi 2: indexed by pair)
+  float hc, hproj_max;        // curvature, projection bound
+  const float* scale_margin;  // device [scale, margin]
+  float* diag_out;            // epi 2: [M]
 };
+
+__device__ __forceinline__ float finish_score(const Params& p, float dot, int row, int col, float scale, float margin) {
+  float v = dot;
+  if (p.hyp) v = hyp_score_from_dot(dot, __ldg(p.x2 + row), __ldg(p.y2 + col), p.hc, p.hproj_max, scale, margin);
+  if (p.col_bias) v = __fadd_rn(v, __ldg(p.col_bias + col));
+  return v;
+}
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
@@ -112,7 +132,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * BLOCK_M;
-  const int n0 = blockIdx.x * p.block_n;
+  const int n0 = p.epi == 2 ? m0 : blockIdx.x * p.block_n;   // pair scores: diagonal tiles only
   const int total_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
   const int kb_beg = blockIdx.z * p.kb_per_split;
   const int kb_end = min(total_kb, kb_beg + p.kb_per_split);
@@ -202,45 +222,79 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
       mbar_wait(smem_u32(&tmem_full_bar), 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
-    const bool split = gridDim.z > 1;
-    float* out = split ? p.ws + (size_t)blockIdx.z * (size_t)p.M * (size_t)p.N : p.C;
-    const int ldo = split ? p.N : p.ldc;
-    const bool vec_ok = ((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-    for (int c0 = 0; c0 < p.block_n; c0 += 32) {
-      float v[32];
-      if (num_kb > 0) {
-        tmem_ld32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0.f;
-      }
-      const int gn0 = n0 + c0;
-      const int ncols = min(32, min(p.block_n - c0, p.N - gn0));   // columns of this chunk owned by this tile
-      if (row < p.M && ncols > 0) {
-        float* dst = out + (size_t)row * ldo + gn0;
-        if (!split) {
-          if (p.bias) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += __ldg(p.bias + gn0 + j);
-          }
-          if (p.accumulate) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += dst[j];
-          }
-          if (p.addend) {
-            const float* ad = p.addend + (size_t)row * p.ld_add + gn0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += __ldg(ad + j);
-          }
-        }
-        if (vec_ok && ncols == 32 && (gn0 & 3) == 0) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) st4(dst + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+    if (p.epi == 0) {
+      const bool split = gridDim.z > 1;
+      float* out = split ? p.ws + (size_t)blockIdx.z * (size_t)p.M * (size_t)p.N : p.C;
+      const int ldo = split ? p.N : p.ldc;
+      const bool vec_ok = ((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        float v[32];
+        if (num_kb > 0) {
+          tmem_ld32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) if (j < ncols) dst[j] = v[j];
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+        const int gn0 = n0 + c0;
+        const int ncols = min(32, min(p.block_n - c0, p.N - gn0));   // columns of this chunk owned by this tile
+        if (row < p.M && ncols > 0) {
+          float* dst = out + (size_t)row * ldo + gn0;
+          if (!split) {
+            if (p.bias) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += __ldg(p.bias + gn0 + j);
+            }
+            if (p.accumulate) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += dst[j];
+            }
+            if (p.addend) {
+              const float* ad = p.addend + (size_t)row * p.ld_add + gn0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += __ldg(ad + j);
+            }
+          }
+          if (vec_ok && ncols == 32 && (gn0 & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) st4(dst + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < ncols) dst[j] = v[j];
+          }
         }
       }
+    } else if (p.epi == 1) {
+      // fused K14: count the candidates of this tile that rank ahead of the row's target; nothing is stored
+      const bool rv = row < p.M;
+      const float st_ = rv ? __ldg(p.tscore + row) : 0.f;
+      const int t = rv ? __ldg(p.target + row) - p.col_offset : -1;
+      float scale = 1.f, margin = 0.f;
+      if (p.hyp) { scale = __ldg(p.scale_margin); margin = __ldg(p.scale_margin + 1); }
+      int cnt = 0;
+      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+        const int gn0 = n0 + c0;
+        const int ncols = min(32, min(p.block_n - c0, p.N - gn0));
+        if (rv && ncols > 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = gn0 + j;
+            if (j < ncols && col != t) cnt += rank_beats(finish_score(p, v[j], row, col, scale, margin), col, st_, t);
+          }
+        }
+      }
+      if (rv && cnt) atomicAdd(p.raw_count + row, cnt);
+    } else {
+      // pair scores: the tile is a diagonal block of A' . B'^T (pair p = row), keep acc[r][r]
+      float scale = 1.f, margin = 0.f;
+      if (p.hyp) { scale = __ldg(p.scale_margin); margin = __ldg(p.scale_margin + 1); }
+      float v[32];
+      tmem_ld32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(quarter * 32), v);
+      float dsel = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (j == lane) dsel = v[j];
+      if (row < p.M) p.diag_out[row] = finish_score(p, dsel, row, row, scale, margin);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -334,24 +388,27 @@ size_t gemm_tf32_workspace_bytes(int M, int N, int split_k) {
   return split_k > 1 ? (size_t)split_k * (size_t)M * (size_t)N * sizeof(float) : 0;
 }
 
-// A_hi/A_lo [M,K] (lda), B_hi/B_lo [N,K] (ldb); passes==1 ignores the lo operands (may be NULL).
-int gemm_tf32(const float* a_hi, const float* a_lo, int lda, const float* b_hi, const float* b_lo, int ldb, float* C,
-              int ldc, int M, int N, int K, const float* bias, int accumulate, int passes, int split_k, float* ws,
-              size_t ws_bytes, const float* addend, int ld_add, cudaStream_t st) {
+static void clear_epi(tc::Params& p) {
+  p.epi = 0; p.tscore = nullptr; p.target = nullptr; p.raw_count = nullptr; p.col_offset = 0; p.hyp = 0; p.x2 = nullptr;
+  p.y2 = nullptr; p.col_bias = nullptr; p.hc = 0.f; p.hproj_max = 0.f; p.scale_margin = nullptr; p.diag_out = nullptr;
+  p.addend = nullptr; p.ld_add = 0; p.bias = nullptr; p.accumulate = 0; p.ws = nullptr; p.C = nullptr; p.ldc = 0;
+}
+
+// Common launcher: validates operands, builds the tensor maps, sizes the pipeline, launches.
+static int launch_tc(const float* a_hi, const float* a_lo, int lda, const float* b_hi, const float* b_lo, int ldb,
+                     tc::Params p, int passes, int split_k, int force_block_n, const char* who, cudaStream_t st) {
   using namespace tc;
-  if (!a_hi || !b_hi || !C || (passes == 3 && (!a_lo || !b_lo))) { set_last_error("gemm_tf32: null pointer"); return REGCN_ERR_NULL; }
-  if (passes != 1 && passes != 3) { set_last_error("gemm_tf32: passes must be 1 or 3"); return REGCN_ERR_DIM; }
-  if (M < 0 || N <= 0 || K <= 0 || (lda & 3) || (ldb & 3) || lda < K || ldb < K || ldc < N ||
+  const int M = p.M, N = p.N, K = p.K;
+  if (!a_hi || !b_hi || (passes == 3 && (!a_lo || !b_lo))) { set_last_error("%s: null operand", who); return REGCN_ERR_NULL; }
+  if (passes != 1 && passes != 3) { set_last_error("%s: passes must be 1 or 3", who); return REGCN_ERR_DIM; }
+  if (M < 0 || N <= 0 || K <= 0 || (lda & 3) || (ldb & 3) || lda < K || ldb < K ||
       (((uintptr_t)a_hi | (uintptr_t)b_hi | (uintptr_t)a_lo | (uintptr_t)b_lo) & 15)) {
-    set_last_error("gemm_tf32: bad dims/alignment M=%d N=%d K=%d lda=%d ldb=%d ldc=%d", M, N, K, lda, ldb, ldc);
+    set_last_error("%s: bad dims/alignment M=%d N=%d K=%d lda=%d ldb=%d", who, M, N, K, lda, ldb);
     return REGCN_ERR_DIM;
   }
   if (M == 0) return REGCN_OK;
-  Params p;
-  p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.bias = bias; p.accumulate = accumulate; p.passes = passes;
-  p.addend = addend; p.ld_add = ld_add;
-  if (addend && split_k > 1) { set_last_error("gemm_tf32: addend is not supported together with split-K"); return REGCN_ERR_UNSUPPORTED; }
-  p.block_n = pick_block_n(N);
+  p.passes = passes;
+  p.block_n = force_block_n > 0 ? force_block_n : pick_block_n(N);
   p.tmem_cols = 32;
   while (p.tmem_cols < p.block_n) p.tmem_cols <<= 1;
   const uint32_t stage_bytes = (passes == 3 ? 2u : 1u) * (BLOCK_M * BLOCK_K * 4 + (uint32_t)p.block_n * BLOCK_K * 4);
@@ -364,12 +421,7 @@ int gemm_tf32(const float* a_hi, const float* a_lo, int lda, const float* b_hi, 
   if (p.stages > 8) p.stages = 8;
   if (g_force_stages > 0 && g_force_stages < p.stages) p.stages = g_force_stages;
   if (p.stages > p.kb_per_split) p.stages = p.kb_per_split;
-  if (p.stages < 1) { set_last_error("gemm_tf32: tile does not fit in shared memory"); return REGCN_ERR_UNSUPPORTED; }
-  p.ws = nullptr;
-  if (split_k > 1) {
-    if (!ws || ws_bytes < gemm_tf32_workspace_bytes(M, N, split_k)) { set_last_error("gemm_tf32: split-K workspace too small"); return REGCN_ERR_WORKSPACE; }
-    p.ws = ws;
-  }
+  if (p.stages < 1) { set_last_error("%s: tile does not fit in shared memory", who); return REGCN_ERR_UNSUPPORTED; }
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   int e;
   if ((e = make_map(&ta_hi, a_hi, M, K, lda, BLOCK_M))) return e;
@@ -384,18 +436,116 @@ int gemm_tf32(const float* a_hi, const float* a_lo, int lda, const float* b_hi, 
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t ce = cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_BUDGET + 2048));
-    if (ce != cudaSuccess) { set_last_error("gemm_tf32: cudaFuncSetAttribute failed: %s", cudaGetErrorString(ce)); return (int)ce; }
+    if (ce != cudaSuccess) { set_last_error("%s: cudaFuncSetAttribute failed: %s", who, cudaGetErrorString(ce)); return (int)ce; }
     attr_set = true;
   }
-  dim3 grid((N + p.block_n - 1) / p.block_n, (M + BLOCK_M - 1) / BLOCK_M, split_k);
+  dim3 grid(p.epi == 2 ? 1 : (N + p.block_n - 1) / p.block_n, (M + BLOCK_M - 1) / BLOCK_M, split_k);
   prof_begin(PROF_GEMM_TC, st);
   gemm_tf32_kernel<<<grid, NUM_THREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
-  prof_end(PROF_GEMM_TC, 2.0 * M * (double)N * K, st);
-  if (split_k > 1) {
+  prof_end(PROF_GEMM_TC, p.epi == 2 ? 2.0 * M * (double)K : 2.0 * M * (double)N * K, st);
+  return REGCN_OK;
+}
+
+// A_hi/A_lo [M,K] (lda), B_hi/B_lo [N,K] (ldb); passes==1 ignores the lo operands (may be NULL).
+int gemm_tf32(const float* a_hi, const float* a_lo, int lda, const float* b_hi, const float* b_lo, int ldb, float* C,
+              int ldc, int M, int N, int K, const float* bias, int accumulate, int passes, int split_k, float* ws,
+              size_t ws_bytes, const float* addend, int ld_add, cudaStream_t st) {
+  if (!C) { set_last_error("gemm_tf32: null output"); return REGCN_ERR_NULL; }
+  if (ldc < N) { set_last_error("gemm_tf32: ldc=%d < N=%d", ldc, N); return REGCN_ERR_DIM; }
+  if (addend && split_k > 1) { set_last_error("gemm_tf32: addend is not supported together with split-K"); return REGCN_ERR_UNSUPPORTED; }
+  tc::Params p;
+  clear_epi(p);
+  p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.bias = bias; p.accumulate = accumulate;
+  p.addend = addend; p.ld_add = ld_add;
+  const int total_kb = (K + tc::BLOCK_K - 1) / tc::BLOCK_K;
+  int sk = split_k < 1 ? 1 : (split_k > total_kb ? total_kb : split_k);
+  if (sk > 1) {
+    const int kb_per = (total_kb + sk - 1) / sk;
+    sk = (total_kb + kb_per - 1) / kb_per;
+  }
+  if (sk > 1) {
+    if (!ws || ws_bytes < gemm_tf32_workspace_bytes(M, N, sk)) { set_last_error("gemm_tf32: split-K workspace too small"); return REGCN_ERR_WORKSPACE; }
+    p.ws = ws;
+  }
+  int e = launch_tc(a_hi, a_lo, lda, b_hi, b_lo, ldb, p, passes, sk, 0, "gemm_tf32", st);
+  if (e) return e;
+  if (sk > 1 && M > 0) {
     const size_t total = (size_t)M * N;
-    splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws, split_k, C, ldc, M, N, bias, accumulate);
+    splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws, sk, C, ldc, M, N, bias, accumulate);
   }
   return check_launch("gemm_tf32");
+}
+
+// Fused K11/K13 + K14: raw_count[b] += #{candidate n of this shard, n != target[b] : score(b,n) beats tscore[b]}.
+// Candidates are rows of E (hi/lo, [N,K]); global id of row n is col_offset + n.  Scores are never written.
+int score_count_tf32(const float* q_hi, const float* q_lo, const float* e_hi, const float* e_lo, int B, int N, int K,
+                     const float* tscore, const int* target, int* raw_count, int col_offset, int hyp, const float* x2,
+                     const float* y2, const float* col_bias, double c, const float* scale_margin, int passes,
+                     cudaStream_t st) {
+  if (!tscore || !target || !raw_count || (hyp && (!x2 || !y2 || !scale_margin))) { set_last_error("score_count_tf32: null pointer"); return REGCN_ERR_NULL; }
+  tc::Params p;
+  clear_epi(p);
+  p.M = B; p.N = N; p.K = K; p.epi = 1; p.tscore = tscore; p.target = target; p.raw_count = raw_count;
+  p.col_offset = col_offset; p.hyp = hyp; p.x2 = x2; p.y2 = y2; p.col_bias = col_bias; p.scale_margin = scale_margin;
+  if (hyp) { Curv cv = make_curv(c); p.hc = cv.c; p.hproj_max = cv.proj_max; }
+  int e = launch_tc(q_hi, q_lo, K, e_hi, e_lo, K, p, passes, 1, 0, "score_count_tf32", st);
+  if (e) return e;
+  return check_launch("score_count_tf32");
+}
+
+// Pair scores through the same MMA arithmetic as the scoring GEMM: out[p] = score(A'[p], B'[p]) with A', B' the
+// gathered (hi, lo) operand rows of the P pairs; x2 / y2 / col_bias are gathered per pair as well.
+int pair_scores_tf32(const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo, int P, int K, int hyp,
+                     const float* x2, const float* y2, const float* col_bias, double c, const float* scale_margin,
+                     float* out, int passes, cudaStream_t st) {
+  if (!out || (hyp && (!x2 || !y2 || !scale_margin))) { set_last_error("pair_scores_tf32: null pointer"); return REGCN_ERR_NULL; }
+  tc::Params p;
+  clear_epi(p);
+  p.M = P; p.N = P; p.K = K; p.epi = 2; p.hyp = hyp; p.x2 = x2; p.y2 = y2; p.col_bias = col_bias;
+  p.scale_margin = scale_margin; p.diag_out = out;
+  if (hyp) { Curv cv = make_curv(c); p.hc = cv.c; p.hproj_max = cv.proj_max; }
+  int e = launch_tc(a_hi, a_lo, K, b_hi, b_lo, K, p, passes, 1, 128, "pair_scores_tf32", st);
+  if (e) return e;
+  return check_launch("pair_scores_tf32");
+}
+
+// out_hi/out_lo[p] = src_hi/src_lo[idx[p]]  (operand gather for the pair-score pass)
+__global__ void gather_rows2_kernel(const float* __restrict__ src_hi, const float* __restrict__ src_lo,
+                                    const int* __restrict__ idx, int P, int d, float* __restrict__ out_hi,
+                                    float* __restrict__ out_lo) {
+  const int lane = threadIdx.x & 31;
+  const int row = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+  if (row >= P) return;
+  const size_t s = (size_t)__ldg(idx + row) * d, o = (size_t)row * d;
+  for (int c = lane * 4; c < d; c += 128) {
+    st4(out_hi + o + c, ldg4(src_hi + s + c));
+    if (src_lo) st4(out_lo + o + c, ldg4(src_lo + s + c));
+  }
+}
+__global__ void gather_scalars_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
+                                      const int* __restrict__ ia, const int* __restrict__ ib, int P, float* __restrict__ oa,
+                                      float* __restrict__ ob, float* __restrict__ oc) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  if (a) oa[p] = __ldg(a + __ldg(ia + p));
+  if (b) ob[p] = __ldg(b + __ldg(ib + p));
+  if (c) oc[p] = __ldg(c + __ldg(ib + p));
+}
+
+int gather_rows2(const float* src_hi, const float* src_lo, const int* idx, int P, int d, float* out_hi, float* out_lo,
+                 cudaStream_t st) {
+  if (!src_hi || !idx || !out_hi || (src_lo && !out_lo)) { set_last_error("gather_rows2: null pointer"); return REGCN_ERR_NULL; }
+  if (d & 3) { set_last_error("gather_rows2: d %% 4 != 0"); return REGCN_ERR_DIM; }
+  if (P <= 0) return REGCN_OK;
+  gather_rows2_kernel<<<(unsigned)(((size_t)P * 32 + 255) / 256), 256, 0, st>>>(src_hi, src_lo, idx, P, d, out_hi, out_lo);
+  return check_launch("gather_rows2");
+}
+int gather_scalars(const float* a, const float* b, const float* c, const int* ia, const int* ib, int P, float* oa,
+                   float* ob, float* oc, cudaStream_t st) {
+  if (P <= 0) return REGCN_OK;
+  if (!ia || !ib) { set_last_error("gather_scalars: null index"); return REGCN_ERR_NULL; }
+  gather_scalars_kernel<<<(P + 255) / 256, 256, 0, st>>>(a, b, c, ia, ib, P, oa, ob, oc);
+  return check_launch("gather_scalars");
 }
 
 }  // namespace regcn

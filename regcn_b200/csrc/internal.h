@@ -29,6 +29,19 @@ int gemm_tf32(const float* a_hi, const float* a_lo, int lda, const float* b_hi, 
               int ldc, int M, int N, int K, const float* bias, int accumulate, int passes, int split_k, float* ws,
               size_t ws_bytes, const float* addend, int ld_add, cudaStream_t st);
 void gemm_tf32_tune(int block_n, int stages);
+int score_count_tf32(const float* q_hi, const float* q_lo, const float* e_hi, const float* e_lo, int B, int N, int K,
+                     const float* tscore, const int* target, int* raw_count, int col_offset, int hyp, const float* x2,
+                     const float* y2, const float* col_bias, double c, const float* scale_margin, int passes,
+                     cudaStream_t st);
+int pair_scores_tf32(const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo, int P, int K, int hyp,
+                     const float* x2, const float* y2, const float* col_bias, double c, const float* scale_margin,
+                     float* out, int passes, cudaStream_t st);
+int gather_rows2(const float* src_hi, const float* src_lo, const int* idx, int P, int d, float* out_hi, float* out_lo,
+                 cudaStream_t st);
+int gather_scalars(const float* a, const float* b, const float* c, const int* ia, const int* ib, int P, float* oa,
+                   float* ob, float* oc, cudaStream_t st);
+int filter_correct(int B, const int* filt_ptr, const int* filt_idx, const int* target, const float* pair_score,
+                   const int* raw_count, int col_lo, int col_hi, int* filt_count, cudaStream_t st);
 int row_map(const float* x, float* out, int M, int d, int mode, double c, float* sumsq, float* out_hi, float* out_lo,
             cudaStream_t st);
 int gru_gate(const float* gi, const float* gh, const float* hprev, float* out, int M, int d, int normalize,

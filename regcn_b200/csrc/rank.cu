@@ -12,9 +12,7 @@ namespace regcn {
 
 constexpr float kFilterScore = -10000000.0f;
 
-__device__ __forceinline__ int rank_contrib(float s, int j, float st, int t) {
-  return (s > st || (s == st && j < t)) ? 1 : 0;
-}
+__device__ __forceinline__ int rank_contrib(float s, int j, float st, int t) { return rank_beats(s, j, st, t); }
 
 // One CTA per query row: counts over the dense row, then corrects for the (short, sorted) filter list.
 __global__ void __launch_bounds__(256) rank_rows_kernel(
@@ -86,6 +84,35 @@ __global__ void apply_filter_kernel(float* __restrict__ S, size_t ld, int B, int
     const int j = filt_idx[i] - col_offset;
     if (j >= 0 && j < N && j != t) S[(size_t)b * ld + j] = kFilterScore;
   }
+}
+
+// Filtered counts for the fused (never materialised) scoring path.  pair_score[B + i] is the score of the i-th
+// filter-CSR entry (query b, candidate f = filt_idx[i]) computed by the pair-score pass with the scoring GEMM's own
+// arithmetic, so subtracting its contribution from the raw count is exact.  Only candidates of the shard
+// [col_lo, col_hi) are corrected (entity-sharded scoring sums the shards afterwards).
+__global__ void filter_correct_kernel(int B, const int* __restrict__ filt_ptr, const int* __restrict__ filt_idx,
+                                      const int* __restrict__ target, const float* __restrict__ pair_score,
+                                      const int* __restrict__ raw_count, int col_lo, int col_hi,
+                                      int* __restrict__ filt_count) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float st = pair_score[b];
+  const int t = target[b];
+  int corr = 0;
+  for (int i = filt_ptr[b]; i < filt_ptr[b + 1]; ++i) {
+    const int f = filt_idx[i];
+    if (f == t || f < col_lo || f >= col_hi) continue;
+    corr += rank_contrib(kFilterScore, f, st, t) - rank_contrib(pair_score[B + i], f, st, t);
+  }
+  filt_count[b] = raw_count[b] + corr;
+}
+
+int filter_correct(int B, const int* filt_ptr, const int* filt_idx, const int* target, const float* pair_score,
+                   const int* raw_count, int col_lo, int col_hi, int* filt_count, cudaStream_t st) {
+  if (!filt_ptr || !filt_idx || !target || !pair_score || !raw_count || !filt_count) { set_last_error("filter_correct: null pointer"); return REGCN_ERR_NULL; }
+  if (B <= 0) return REGCN_OK;
+  filter_correct_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, filt_ptr, filt_idx, target, pair_score, raw_count, col_lo, col_hi, filt_count);
+  return check_launch("filter_correct");
 }
 
 int gather_target_score(const float* S, int64_t ld, int B, int N, const int64_t* triples, int target_col, int col_offset,

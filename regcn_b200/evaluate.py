@@ -8,15 +8,38 @@ import torch
 from . import ops, utils
 
 
+def _scoring_operands(model, emb, r_emb, all_triples):
+    """(q, cand, hyp, col_bias) of the entity decoder: everything the scoring GEMM needs except the GEMM itself."""
+    dec = model.decoder_ob
+    name = type(dec).__name__
+    if name == "ConvTransE":
+        e_all, q = dec.query(emb, r_emb, all_triples)
+        return q, e_all, None, None
+    if name == "HyperbolicConvTransE":
+        et = ops.row_map(emb, ops.ROW_LEAKY_TANH_LOG0, c=dec.c)
+        q = dec._tower(et, r_emb.contiguous(), all_triples, 0, 1, always_bn2=False)
+        return q, et, None, dec.b.detach()
+    if name in ("HyperbolicRotH", "HyperbolicMuRP"):
+        q, qss = dec.query(emb, r_emb, all_triples)
+        cand = emb.contiguous()
+        return q, cand, (dec.c, qss, ops.row_sumsq(cand), dec._scale_margin()), None
+    raise NotImplementedError(name)
+
+
 @torch.no_grad()
-def evaluate_snapshot(model, glist, all_triples, filter_csr, timers=None):
+def evaluate_snapshot(model, glist, all_triples, filter_csr, timers=None, fused=None, shard=None):
     """Returns (rank, filter_rank) int64 (B,) for the 2*T_q queries `all_triples` (forward + inverse).
 
+    fused (default: on with the tensor-core GEMM): rank through the counting epilogue of the scoring GEMM, never
+    writing the (B,N) score matrix; otherwise the dense predict()-style path.  shard=(lo,hi) restricts the counted
+    candidates (entity-sharded scoring: the caller all-reduces the counts).
     timers: optional dict of name -> (start_event, end_event) pairs recorded on the current stream."""
     def mark(name, which):
         if timers is not None:
             timers[name][which].record()
 
+    if fused is None:
+        fused = ops.gemm_impl() in ("tc", "tc1") and filter_csr is not None
     mark("evolve", 0)
     evolve_embs, _, r_emb, _, _ = model.forward(glist, None, True)
     mark("evolve", 1)
@@ -27,6 +50,20 @@ def evaluate_snapshot(model, glist, all_triples, filter_csr, timers=None):
             emb = ops.row_map(emb, ops.ROW_TANGENT_NORMALIZE, c=model._c_float)
         else:
             emb = ops.row_map(emb, ops.ROW_NORMALIZE)
+    if fused:
+        q, cand, hyp, col_bias = _scoring_operands(model, emb, r_emb, all_triples)
+        target = all_triples[:, 2].to(torch.int32).contiguous()
+        pa, pe = filter_csr.pairs(target)
+        mark("score", 1)
+        mark("rank", 0)
+        raw, filt, _ = ops.fused_rank_counts(q, cand, target, filter_csr.ptr, filter_csr.idx, pa, pe, hyp=hyp,
+                                             col_bias=col_bias, shard=shard)
+        if shard is not None:
+            mark("rank", 1)
+            return raw, filt
+        rank, frank = ops.counts_to_ranks(raw, filt)
+        mark("rank", 1)
+        return rank, frank
     score = model.decoder_ob.forward(emb, r_emb, all_triples, mode="test")
     mark("score", 1)
     mark("rank", 0)

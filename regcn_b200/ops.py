@@ -354,3 +354,51 @@ def apply_filter_(score, triples, target_col, filt_ptr, filt_idx, col_offset=0):
     call("regcn_apply_filter", score.data_ptr(), score.stride(0), B, N, ptr(triples), target_col, ptr(filt_ptr),
          ptr(filt_idx), col_offset)
     return score
+
+
+# --------------------------------------------------------------------------- fused scoring + rank (no score matrix)
+def fused_rank_counts(q, cand, target, filt_ptr, filt_idx, pair_a, pair_e, hyp=None, col_bias=None, shard=None,
+                      cand_split=None):
+    """Raw / filtered 'beats the target' counts of every query against the candidate rows [lo,hi) of `cand`, computed by
+    the scoring GEMM's counting epilogue (K11/K13 fused with K14); the (B,N) score matrix is never written.
+
+    q (B,d), cand (N,d) fp32; target (B,) int32 global candidate ids; filt_ptr/filt_idx the filter CSR;
+    pair_a/pair_e int32 pair lists: first the B (query, target) pairs, then one pair per filter-CSR entry;
+    hyp = (c, q_sumsq, e_sumsq, scale_margin) selects the hyperbolic score; col_bias (N,) optional candidate bias.
+    Returns (raw_count, filt_count, target_score)."""
+    if _GEMM_IMPL["impl"] not in ("tc", "tc1"):
+        raise RuntimeError("fused_rank_counts needs the tensor-core GEMM (REGCN_GEMM=tc)")
+    passes = 3 if _GEMM_IMPL["impl"] == "tc" else 1
+    B, K = q.shape
+    N = cand.shape[0]
+    dev = q.device
+    q_hi, q_lo = _tc_operand(q.detach(), passes == 3)
+    e_hi, e_lo = cand_split if cand_split is not None else _tc_operand(cand.detach(), passes == 3)
+    P = pair_a.shape[0]
+    a_hi = torch.empty((P, K), device=dev, dtype=F32)
+    b_hi = torch.empty((P, K), device=dev, dtype=F32)
+    a_lo = torch.empty((P, K), device=dev, dtype=F32) if passes == 3 else None
+    b_lo = torch.empty((P, K), device=dev, dtype=F32) if passes == 3 else None
+    call("regcn_gather_rows2", ptr(q_hi), ptr(q_lo), ptr(pair_a), P, K, ptr(a_hi), ptr(a_lo))
+    call("regcn_gather_rows2", ptr(e_hi), ptr(e_lo), ptr(pair_e), P, K, ptr(b_hi), ptr(b_lo))
+    c, x2, y2, sm = (hyp if hyp is not None else (1.0, None, None, None))
+    x2p = y2p = bp = None
+    if hyp is not None or col_bias is not None:
+        x2p = torch.empty(P, device=dev, dtype=F32) if hyp is not None else None
+        y2p = torch.empty(P, device=dev, dtype=F32) if hyp is not None else None
+        bp = torch.empty(P, device=dev, dtype=F32) if col_bias is not None else None
+        call("regcn_gather_scalars", ptr(x2), ptr(y2), ptr(col_bias), ptr(pair_a), ptr(pair_e), P, ptr(x2p), ptr(y2p),
+             ptr(bp))
+    ps = torch.empty(P, device=dev, dtype=F32)
+    call("regcn_pair_scores_tf32", ptr(a_hi), ptr(a_lo), ptr(b_hi), ptr(b_lo), P, K, int(hyp is not None), ptr(x2p),
+         ptr(y2p), ptr(bp), float(c), ptr(sm), ptr(ps), passes)
+    lo, hi = shard if shard is not None else (0, N)
+    raw = torch.zeros(B, device=dev, dtype=I32)
+    if hi > lo:
+        call("regcn_score_count_tf32", ptr(q_hi), ptr(q_lo), e_hi[lo:hi].data_ptr(),
+             e_lo[lo:hi].data_ptr() if e_lo is not None else None, B, hi - lo, K, ptr(ps), ptr(target), ptr(raw), lo,
+             int(hyp is not None), ptr(x2), y2[lo:hi].data_ptr() if y2 is not None else None,
+             col_bias[lo:hi].data_ptr() if col_bias is not None else None, float(c), ptr(sm), passes)
+    filt = torch.empty(B, device=dev, dtype=I32)
+    call("regcn_filter_correct", B, ptr(filt_ptr), ptr(filt_idx), ptr(target), ptr(ps), ptr(raw), lo, hi, ptr(filt))
+    return raw, filt, ps[:B]

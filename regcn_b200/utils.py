@@ -59,6 +59,20 @@ class FilterCSR:
 
     def __init__(self, ptr_t, idx_t):
         self.ptr, self.idx = ptr_t, idx_t
+        self._pairs = None
+
+    def pairs(self, target):
+        """(pair_a, pair_e) int32 lists for the fused rank path: the B (query, target) pairs followed by one
+        (query, candidate) pair per CSR entry."""
+        if self._pairs is None:
+            B = self.ptr.numel() - 1
+            counts = (self.ptr[1:] - self.ptr[:-1]).long()
+            rows = torch.repeat_interleave(torch.arange(B, device=self.ptr.device), counts)
+            n = int(rows.numel())
+            pa = torch.cat((torch.arange(B, device=self.ptr.device), rows)).to(torch.int32)
+            pe = torch.cat((target.to(torch.int32), self.idx[:n])).contiguous()
+            self._pairs = (pa.contiguous(), pe)
+        return self._pairs
 
 
 def filter_csr_from_dict(test_triples, all_ans, rel_predict=0, device=None):

@@ -179,3 +179,47 @@ def test_layer_signatures_drop_in():
     assert ok, worst
     with pytest.raises(NotImplementedError):
         layer.train()(g, [], rel.to(DEV))        # training-mode dropout is refused loudly, never silently skipped
+
+
+@pytest.mark.parametrize("kind", ["regcn", "hyp_uv_roth", "hyp_uv_convtranse", "hyp_lgcn_murp"])
+def test_fused_rank_equals_dense_rank_bit_exact(kind):
+    """The counting epilogue of the scoring GEMM (no score matrix) must give exactly the ranks the rank kernel derives
+    from the materialised score matrix of the same GEMM -- raw and filtered, whole table and entity shards."""
+    import regcn_b200 as R
+    from regcn_b200 import evaluate, ops, utils
+    R._lib.require_device()
+    cfg = {"regcn": dict(kind="regcn", shape="c1", seed=5, layer_norm=True),
+           "hyp_uv_roth": dict(kind="hyp", shape="c1", seed=6, layer_norm=True, encoder="hyperbolic_uvrgcn",
+                               decoder="roth", gamma=0.15),
+           "hyp_uv_convtranse": dict(kind="hyp", shape="small", seed=7, layer_norm=False, encoder="hyperbolic_uvrgcn",
+                                     decoder="hyperbolic_convtranse", gamma=0.15),
+           "hyp_lgcn_murp": dict(kind="hyp", shape="small_l", seed=8, layer_norm=False, encoder="lgcn", decoder="murp",
+                                 gamma=0.15)}[kind]
+    case = synth.make_case(cfg["shape"], cfg["seed"])
+    n, r = case["num_ents"], case["num_rels"]
+    model, _ = build_model(cfg, n, r)
+    model = model.to(DEV)
+    glist = [R.build_sub_graph(n, r, s, True, 0) for s in case["history"]]
+    test = torch.from_numpy(case["test"]).to(DEV)
+    prev = ops.gemm_impl()
+    ops.set_gemm_impl("tc")
+    try:
+        all_t, score, _ = model.predict(glist, r, None, test, True)
+        fcsr = utils.filter_csr_from_snapshot(all_t, 2 * r, 0)
+        rank_d, frank_d = evaluate.evaluate_snapshot(model, glist, all_t, fcsr, fused=False)
+        rank_f, frank_f = evaluate.evaluate_snapshot(model, glist, all_t, fcsr, fused=True)
+        assert torch.equal(rank_d, rank_f), int((rank_d != rank_f).sum())
+        assert torch.equal(frank_d, frank_f), int((frank_d != frank_f).sum())
+        # and both agree with get_total_rank on predict()'s score matrix
+        _, _, rank_p, frank_p = utils.get_total_rank(all_t, score, None, 1000, rel_predict=0, filter_csr=fcsr)
+        assert torch.equal(rank_p, rank_f) and torch.equal(frank_p, frank_f)
+        # entity shards: counts add up to the whole-table counts
+        tot_raw = torch.zeros_like(rank_f)
+        tot_f = torch.zeros_like(rank_f)
+        for lo, hi in ((0, n // 3), (n // 3, n // 3 + 1), (n // 3 + 1, n)):
+            raw, filt = evaluate.evaluate_snapshot(model, glist, all_t, fcsr, fused=True, shard=(lo, hi))
+            tot_raw += raw.long()
+            tot_f += filt.long()
+        assert torch.equal(tot_raw + 1, rank_f) and torch.equal(tot_f + 1, frank_f)
+    finally:
+        ops.set_gemm_impl(prev)
