@@ -322,28 +322,18 @@ def main():
         f0 = utils.filter_csr_from_snapshot(all0, 2 * r, 0)
         embs, _, r_emb, _, _ = model.forward(g0, None, True)
         emb = ops.row_map(embs[-1], ops.ROW_NORMALIZE) if cfg["kind"] == "regcn" else embs[-1]
-        if cfg["kind"] == "regcn":
-            e_all, q = model.decoder_ob.query(emb, r_emb, all0)
-            score_fn = lambda lo, hi: ops.gemm(q, e_all[lo:hi], trans_b=True)
-        else:
-            q, qss = model.decoder_ob.query(emb, r_emb, all0)
-            ess = ops.row_sumsq(emb)
-            sm = model.decoder_ob._scale_margin()
-            score_fn = lambda lo, hi: ops.hyp_score_epilogue_(ops.gemm(q, emb[lo:hi], trans_b=True), qss,
-                                                              ess[lo:hi].contiguous(), None, None, 0.01, sm)
         out = {}
 
         def sharded_step(_):
-            out["r"] = rdist.sharded_score_rank(n, all0, 2, f0, score_fn)
+            out["r"] = evaluate.score_rank_sharded(model, emb, r_emb, all0, f0)
 
         tot_s, _ = timed(sharded_step, args.steps, args.warmup)
         s_ms = maxr(tot_s) / args.steps
-        full = ops.gemm(q, e_all, trans_b=True) if cfg["kind"] == "regcn" else score_fn(0, n)
-        raw1, filt1, _ = ops.rank_dense(full, all0, 2, f0.ptr, f0.idx)
-        rk1, frk1 = ops.counts_to_ranks(raw1, filt1)
+        rk1, frk1 = evaluate.evaluate_snapshot(model, g0, all0, f0, fused=True)
         same = bool(torch.equal(rk1, out["r"][0]) and torch.equal(frk1, out["r"][1]))
         sharded = {"queries_per_s": all0.shape[0] / (s_ms * 1e-3), "ms_per_step": s_ms, "scaling": "strong",
-                   "ranks_equal_single_gpu": same, "collectives": "all_reduce(B f32) + all_reduce(2xB i32) over NCCL"}
+                   "ranks_equal_single_gpu": same, "collectives": "one all_reduce(SUM) of (2,B) int32 counts over NCCL",
+                   "what": "query tower + fused score/count over N/G candidates per GPU + rank merge (evolution excluded)"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

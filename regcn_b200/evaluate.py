@@ -75,6 +75,23 @@ def evaluate_snapshot(model, glist, all_triples, filter_csr, timers=None, fused=
 
 
 @torch.no_grad()
+def score_rank_sharded(model, emb, r_emb, all_triples, filter_csr, group=None):
+    """Entity-partitioned scoring + rank merge: this rank counts over its contiguous slice of the
+    (replicated, already evolved) entity table with the fused kernel; ONE all_reduce(SUM) of the (2,B) int32 counts
+    merges the shards.  Target and filter-entry scores come from the pair pass on the replicated table, so no score
+    exchange is needed.  Returns (rank, filter_rank), identical on every rank."""
+    from . import dist as rdist
+    r, ws = rdist.world()
+    q, cand, hyp, col_bias = _scoring_operands(model, emb, r_emb, all_triples)
+    lo, hi = rdist.shard_bounds(cand.shape[0], r, ws)
+    target = all_triples[:, 2].to(torch.int32).contiguous()
+    pa, pe = filter_csr.pairs(target)
+    raw, filt, _ = ops.fused_rank_counts(q, cand, target, filter_csr.ptr, filter_csr.idx, pa, pe, hyp=hyp,
+                                         col_bias=col_bias, shard=(lo, hi))
+    return rdist.merge_counts(raw, filt, group)
+
+
+@torch.no_grad()
 def evaluate_from_host(model, history_host, test_host, num_nodes, num_rels, device):
     """End-to-end step from HOST buffers (pinned int64 triples): H2D copies, device edge-index build for every
     history snapshot, predict() (entity + relation decoders, like the reference's test loop), time-aware filtered
