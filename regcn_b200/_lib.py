@@ -25,7 +25,7 @@ SIGNATURES = {
     "regcn_last_error_string": (ctypes.c_char_p, []),
     "regcn_device_ok": (_i, []),
     "regcn_csr_build_workspace_bytes": (_sz, [_i, _i, _i]),
-    "regcn_csr_build": (_i, [_p, _i, _i, _i] + [_p] * 15 + [_p, _sz, _p]),
+    "regcn_csr_build": (_i, [_p, _i, _i, _i] + [_p] * 16 + [_p, _sz, _p]),
     "regcn_rel_mean_pool": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p]),
     "regcn_union_aggregate": (_i, [_p] * 9 + [_i, _i, _p, _f, _i, _i, _p, _p, _p]),
     "regcn_block_aggregate": (_i, [_p] * 6 + [_i, _i, _i, _i, _p, _p]),

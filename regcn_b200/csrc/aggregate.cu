@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(256) union_aggregate_kernel(
     const int* __restrict__ src_sorted, const int* __restrict__ etype_sorted, const float* __restrict__ norm,
     const int* __restrict__ vptr, const int* __restrict__ sptr, const int* __restrict__ vrow_row, int nv,
     const float* __restrict__ radius, float gamma, int d, float* __restrict__ out, float* __restrict__ partial,
-    float* __restrict__ out_hi, float* __restrict__ out_lo) {
+    float* __restrict__ out_hi, float* __restrict__ out_lo, const int* __restrict__ active_pos, int ldo) {
   const int lane = threadIdx.x & 31;
   const int w = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
   if (w >= nv) return;
@@ -97,10 +97,18 @@ __global__ void __launch_bounds__(256) union_aggregate_kernel(
       }
     }
   }
+  // compact mode (active_pos != NULL): output row = position among the active destinations, row stride ldo; the
+  // row's own features are copied (TF32-split) into columns [d, 2d) so that [agg | h] is one K = 2d GEMM operand
+  const size_t orow = active_pos ? (size_t)__ldg(active_pos + row) : (size_t)row;
+  if (active_pos && k == 0 && out_hi && ldo >= 2 * d) {
+    WarpRow<RV> self;
+    self.load(h + (size_t)row * d, nvec, lane);
+    self.store_split(out_hi + orow * ldo + d, out_lo + orow * ldo + d, nvec, lane);
+  }
   if (v1 - v0 == 1) {
     acc.scale(__ldg(norm + row));
-    if (out) acc.store(out + (size_t)row * d, nvec, lane);
-    if (out_hi) acc.store_split(out_hi + (size_t)row * d, out_lo + (size_t)row * d, nvec, lane);
+    if (out) acc.store(out + orow * ldo, nvec, lane);
+    if (out_hi) acc.store_split(out_hi + orow * ldo, out_lo + orow * ldo, nvec, lane);
   } else {
     acc.store(partial + (size_t)(__ldg(sptr + row) + k) * d, nvec, lane);
   }
@@ -109,13 +117,16 @@ __global__ void __launch_bounds__(256) union_aggregate_kernel(
 // Rows that were split into several chunks: sum the chunk partials in chunk order, apply norm.
 template <int RV>
 __global__ void __launch_bounds__(256) aggregate_fixup_kernel(
-    const int* __restrict__ vptr, const int* __restrict__ sptr, const float* __restrict__ norm, int N, int d,
-    const float* __restrict__ partial, float* __restrict__ out, float* __restrict__ out_hi, float* __restrict__ out_lo) {
+    const int* __restrict__ vptr, const int* __restrict__ sptr, const int* __restrict__ vrow_row,
+    const float* __restrict__ norm, int nv, int d, const float* __restrict__ partial, float* __restrict__ out,
+    float* __restrict__ out_hi, float* __restrict__ out_lo, const int* __restrict__ active_pos, int ldo) {
   const int lane = threadIdx.x & 31;
-  const int row = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
-  if (row >= N) return;
-  const int nch = __ldg(vptr + row + 1) - __ldg(vptr + row);
-  if (nch <= 1) return;
+  const int w = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+  if (w >= nv) return;
+  const int row = __ldg(vrow_row + w);
+  const int v0 = __ldg(vptr + row);
+  const int nch = __ldg(vptr + row + 1) - v0;
+  if (w != v0 || nch <= 1) return;          // the first chunk's warp folds the row's partials
   const int nvec = d >> 2;
   const int s0 = __ldg(sptr + row);
   WarpRow<RV> acc, p[4];
@@ -135,36 +146,56 @@ __global__ void __launch_bounds__(256) aggregate_fixup_kernel(
     for (int i = 0; i < RV; ++i) acc.v[i] = f4_add(acc.v[i], p[0].v[i]);
   }
   acc.scale(__ldg(norm + row));
-  if (out) acc.store(out + (size_t)row * d, nvec, lane);
-  if (out_hi) acc.store_split(out_hi + (size_t)row * d, out_lo + (size_t)row * d, nvec, lane);
+  const size_t orow = active_pos ? (size_t)__ldg(active_pos + row) : (size_t)row;
+  if (out) acc.store(out + orow * ldo, nvec, lane);
+  if (out_hi) acc.store_split(out_hi + orow * ldo, out_lo + orow * ldo, nvec, lane);
+}
+
+// Dense-output mode: rows without in-edges receive exact zeros (DGL zero fill); one thread per float4.
+__global__ void zero_inactive_rows_kernel(const int* __restrict__ rowptr, int N, int d, float* __restrict__ out,
+                                          float* __restrict__ out_hi, float* __restrict__ out_lo) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const int nvec = d >> 2;
+  const size_t total = (size_t)N * nvec;
+  if (i >= total) return;
+  const int row = (int)(i / nvec);
+  if (__ldg(rowptr + row + 1) != __ldg(rowptr + row)) return;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (out) reinterpret_cast<float4*>(out)[i] = z;
+  if (out_hi) { reinterpret_cast<float4*>(out_hi)[i] = z; reinterpret_cast<float4*>(out_lo)[i] = z; }
 }
 
 int union_aggregate(const float* h, const float* rel, const int* rowptr, const int* src_sorted,
                     const int* etype_sorted, const float* norm, const int* vptr, const int* sptr,
                     const int* vrow_row, int nv, int nsplit, const float* radius, float gamma, int N, int d,
-                    float* out, float* partial, float* out_hi, float* out_lo, cudaStream_t st) {
+                    float* out, float* partial, float* out_hi, float* out_lo, const int* active_pos, int ldo,
+                    cudaStream_t st) {
   if (!h || !rel || !rowptr || !src_sorted || !etype_sorted || !norm || !vptr || !sptr || !vrow_row ||
       (!out && !out_hi) || (out_hi && !out_lo)) {
     set_last_error("union_aggregate: null pointer"); return REGCN_ERR_NULL;
   }
   if (d <= 0 || (d & 3) || d > 256) { set_last_error("union_aggregate: d=%d unsupported (need d%%4==0, d<=256)", d); return REGCN_ERR_UNSUPPORTED; }
   if (nsplit > 0 && !partial) { set_last_error("union_aggregate: split rows need a partial buffer"); return REGCN_ERR_WORKSPACE; }
-  if (nv <= 0) return REGCN_OK;
   const int TB = 256;
+  if (ldo <= 0) ldo = d;
+  prof_begin(PROF_AGGREGATE, st);
+  if (!active_pos) {
+    const size_t total = (size_t)N * (d >> 2);
+    zero_inactive_rows_kernel<<<(unsigned)((total + TB - 1) / TB), TB, 0, st>>>(rowptr, N, d, out, out_hi, out_lo);
+  }
+  if (nv <= 0) { prof_end(PROF_AGGREGATE, 0.0, st); return check_launch("union_aggregate"); }
   const unsigned grid = (unsigned)(((size_t)nv * 32 + TB - 1) / TB);
   const bool small = d <= 128;
-  prof_begin(PROF_AGGREGATE, st);
   if (radius) {
-    if (small) union_aggregate_kernel<1, true><<<grid, TB, 0, st>>>(h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, radius, gamma, d, out, partial, out_hi, out_lo);
-    else union_aggregate_kernel<2, true><<<grid, TB, 0, st>>>(h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, radius, gamma, d, out, partial, out_hi, out_lo);
+    if (small) union_aggregate_kernel<1, true><<<grid, TB, 0, st>>>(h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, radius, gamma, d, out, partial, out_hi, out_lo, active_pos, ldo);
+    else union_aggregate_kernel<2, true><<<grid, TB, 0, st>>>(h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, radius, gamma, d, out, partial, out_hi, out_lo, active_pos, ldo);
   } else {
-    if (small) union_aggregate_kernel<1, false><<<grid, TB, 0, st>>>(h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, nullptr, 0.f, d, out, partial, out_hi, out_lo);
-    else union_aggregate_kernel<2, false><<<grid, TB, 0, st>>>(h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, nullptr, 0.f, d, out, partial, out_hi, out_lo);
+    if (small) union_aggregate_kernel<1, false><<<grid, TB, 0, st>>>(h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, nullptr, 0.f, d, out, partial, out_hi, out_lo, active_pos, ldo);
+    else union_aggregate_kernel<2, false><<<grid, TB, 0, st>>>(h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, nullptr, 0.f, d, out, partial, out_hi, out_lo, active_pos, ldo);
   }
   if (nsplit > 0) {
-    const unsigned g2 = (unsigned)(((size_t)N * 32 + TB - 1) / TB);
-    if (small) aggregate_fixup_kernel<1><<<g2, TB, 0, st>>>(vptr, sptr, norm, N, d, partial, out, out_hi, out_lo);
-    else aggregate_fixup_kernel<2><<<g2, TB, 0, st>>>(vptr, sptr, norm, N, d, partial, out, out_hi, out_lo);
+    if (small) aggregate_fixup_kernel<1><<<grid, TB, 0, st>>>(vptr, sptr, vrow_row, norm, nv, d, partial, out, out_hi, out_lo, active_pos, ldo);
+    else aggregate_fixup_kernel<2><<<grid, TB, 0, st>>>(vptr, sptr, vrow_row, norm, nv, d, partial, out, out_hi, out_lo, active_pos, ldo);
   }
   prof_end(PROF_AGGREGATE, 0.0, st);   // bytes are filled in by the caller-side formula (needs E, R); see bench.py
   return check_launch("union_aggregate");

@@ -79,10 +79,10 @@ int regcn_prof_read(int slot, double* total_ms, long long* launches, double* tot
 size_t regcn_csr_build_workspace_bytes(int T, int N, int R) { return csr_build_workspace_bytes(T, N, R); }
 int regcn_csr_build(const int64_t* triples, int T, int N, int R, int32_t* src, int32_t* dst, int32_t* etype,
                     int32_t* indeg, float* norm, int32_t* rowptr, int32_t* src_sorted, int32_t* etype_sorted,
-                    int32_t* eperm, int32_t* vptr, int32_t* sptr, int32_t* vrow_row, int32_t* rel_rowptr,
-                    int32_t* rel_ents, int32_t* counts, void* workspace, size_t workspace_bytes, void* stream) {
+                    int32_t* eperm, int32_t* vptr, int32_t* sptr, int32_t* vrow_row, int32_t* active_pos,
+                    int32_t* rel_rowptr, int32_t* rel_ents, int32_t* counts, void* workspace, size_t workspace_bytes, void* stream) {
   return csr_build(triples, T, N, R, src, dst, etype, indeg, norm, rowptr, src_sorted, etype_sorted, eperm, vptr, sptr,
-                   vrow_row, rel_rowptr, rel_ents, counts, workspace, workspace_bytes, ST(stream));
+                   vrow_row, active_pos, rel_rowptr, rel_ents, counts, workspace, workspace_bytes, ST(stream));
 }
 int regcn_rel_mean_pool(const float* h, const int32_t* rel_rowptr, const int32_t* rel_ents, int R, int d, int nsplit,
                         float* out, float* partial, void* stream) {
@@ -93,7 +93,7 @@ int regcn_union_aggregate(const float* h, const float* rel, const int32_t* rowpt
                           const int32_t* vrow_row, int n_vrows, int n_split_chunks, const float* radius, float gamma,
                           int N, int d, float* out, float* partial, void* stream) {
   return union_aggregate(h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, n_vrows, n_split_chunks,
-                         radius, gamma, N, d, out, partial, nullptr, nullptr, ST(stream));
+                         radius, gamma, N, d, out, partial, nullptr, nullptr, nullptr, 0, ST(stream));
 }
 int regcn_block_aggregate(const float* h, const float* W, const int32_t* rowptr, const int32_t* src_sorted,
                           const int32_t* etype_sorted, const float* norm, int N, int d_in, int d_out, int nb, float* out,
@@ -159,7 +159,7 @@ int regcn_union_combine(const float* P, const float* L, const int32_t* indeg, co
                         const float* prev, int N, int d, int act, int hyper, double c, float* out, float* ht_next,
                         float* radius_next, void* stream) {
   return union_combine(P, L, indeg, S, skip_bias, prev, N, d, act, hyper, c, out, ht_next, radius_next, 0, nullptr,
-                       nullptr, nullptr, nullptr, ST(stream));
+                       nullptr, nullptr, nullptr, nullptr, ST(stream));
 }
 int regcn_time_gate(const float* G, const float* bias, const float* cur, const float* h, float* out, int N, int d,
                     int normalize_cur, void* stream) {

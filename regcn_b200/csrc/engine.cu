@@ -26,6 +26,7 @@ static inline size_t al(size_t n) { return (n + 63) & ~(size_t)63; }   // 256-by
 
 struct EvolveWs {
   size_t xm_hi, xm_lo, gi, gh, h0_hi, h0_lo, agg_hi, agg_lo, Lm, L2, P, set[2][3], h_hi, h_lo, h_init, partial, rel_partial, total;
+  // agg_hi/agg_lo double as the compact [agg | h] operand of the sparse-snapshot path (n_active <= N/2 rows of 2d)
 };
 
 static EvolveWs plan_evolve(int N, int R2, int d, int max_split_chunks, int rel_nsplit) {
@@ -107,28 +108,54 @@ int regcn_regcn_evolve(const void* const* mp, const int* mi, const void* const* 
     const float* x_raw = h_raw;
     const float* x_hi = ws + w.h_hi;
     const float* x_lo = ws + w.h_lo;
+    // Sparse snapshots (real TKG data: ~10% of the entities have in-edges) use the row-partitioned form
+    //   active rows   : rrelu([agg | x] . [W_n ; W_loop])     one K = 2d GEMM over the n_active compact rows
+    //   inactive rows : rrelu(x . W_evolve)                    one K = d GEMM over all rows (also yields the gate)
+    // dense snapshots keep  rrelu(agg . W_n + where(indeg>0, x.W_loop, x.W_evolve)).
+    const int n_active = gn[RGI_N_ACTIVE];
+    const bool sparse = n_active * 2 <= N;
+    const float* gate_G;
+    int gate_ld;
     for (int l = 0; l < nl; ++l) {
-      const int base = RM_LAYER0 + 4 * l;
-      const int ncol = (l == 0 ? 3 : 2) * d;           // layer 0 also carries the time-gate weight
-      if ((e = union_aggregate(x_raw, h0_raw, GI(RG_ROWPTR), GI(RG_SRC_SORTED), GI(RG_ETYPE_SORTED), (const float*)g[RG_NORM],
-                               GI(RG_VPTR), GI(RG_SPTR), GI(RG_VROW_ROW), gn[RGI_N_VROWS], gn[RGI_N_SPLIT_CHUNKS], nullptr,
-                               0.f, N, d, nullptr, ws + w.partial, ws + w.agg_hi, ws + w.agg_lo, st))) return e;
-      float* Lbuf = (l == 0) ? ws + w.Lm : ws + w.L2;  // layer 0's result carries the gate columns and must survive
-      if ((e = gemm_tf32(x_hi, x_lo, d, F(base + 2), F(base + 3), d, Lbuf, ncol, N, ncol, d, nullptr, 0, 3, 1, nullptr, 0,
-                         nullptr, 0, st))) return e;
-      if ((e = gemm_tf32(ws + w.agg_hi, ws + w.agg_lo, d, F(base + 0), F(base + 1), d, ws + w.P, d, N, d, d, nullptr, 0, 3,
-                         1, nullptr, 0, nullptr, 0, st))) return e;
+      const int base = RM_LAYER0 + RM_LAYER_STRIDE * l;
       const bool last = l == nl - 1;
       float* o_raw = ws + w.set[l & 1][0];
       float* o_hi = last ? nullptr : ws + w.set[l & 1][1];
       float* o_lo = last ? nullptr : ws + w.set[l & 1][2];
-      if ((e = union_combine(ws + w.P, Lbuf, GI(RG_INDEG), nullptr, nullptr, nullptr, N, d, 1, 0, 1.0, o_raw, nullptr, nullptr,
-                             ncol, o_hi, o_lo, nullptr, nullptr, st))) return e;
+      if (sparse) {
+        const int ncol = (l == 0 ? 2 : 1) * d;           // [W_evolve (| W_time)]
+        float* Le = (l == 0) ? ws + w.Lm : ws + w.L2;
+        if ((e = union_aggregate(x_raw, h0_raw, GI(RG_ROWPTR), GI(RG_SRC_SORTED), GI(RG_ETYPE_SORTED), (const float*)g[RG_NORM],
+                                 GI(RG_VPTR), GI(RG_SPTR), GI(RG_VROW_ROW), gn[RGI_N_VROWS], gn[RGI_N_SPLIT_CHUNKS], nullptr,
+                                 0.f, N, d, nullptr, ws + w.partial, ws + w.agg_hi, ws + w.agg_lo, GI(RG_ACTIVE_POS), 2 * d,
+                                 st))) return e;
+        if (n_active > 0 &&
+            (e = gemm_tf32(ws + w.agg_hi, ws + w.agg_lo, 2 * d, F(base + 4), F(base + 5), 2 * d, ws + w.P, d, n_active, d,
+                           2 * d, nullptr, 0, 3, 1, nullptr, 0, nullptr, 0, st))) return e;
+        if ((e = gemm_tf32(x_hi, x_lo, d, F(base + 6), F(base + 7), d, Le, ncol, N, ncol, d, nullptr, 0, 3, 1, nullptr, 0,
+                           nullptr, 0, st))) return e;
+        if ((e = union_combine(ws + w.P, Le, GI(RG_INDEG), nullptr, nullptr, nullptr, N, d, 1, 0, 1.0, o_raw, nullptr, nullptr,
+                               ncol, o_hi, o_lo, nullptr, nullptr, GI(RG_ACTIVE_POS), st))) return e;
+        if (l == 0) { gate_G = Le + d; gate_ld = ncol; }
+      } else {
+        const int ncol = (l == 0 ? 3 : 2) * d;           // [W_loop | W_evolve (| W_time)]
+        float* Lbuf = (l == 0) ? ws + w.Lm : ws + w.L2;  // layer 0's result carries the gate columns and must survive
+        if ((e = union_aggregate(x_raw, h0_raw, GI(RG_ROWPTR), GI(RG_SRC_SORTED), GI(RG_ETYPE_SORTED), (const float*)g[RG_NORM],
+                                 GI(RG_VPTR), GI(RG_SPTR), GI(RG_VROW_ROW), gn[RGI_N_VROWS], gn[RGI_N_SPLIT_CHUNKS], nullptr,
+                                 0.f, N, d, nullptr, ws + w.partial, ws + w.agg_hi, ws + w.agg_lo, nullptr, d, st))) return e;
+        if ((e = gemm_tf32(x_hi, x_lo, d, F(base + 2), F(base + 3), d, Lbuf, ncol, N, ncol, d, nullptr, 0, 3, 1, nullptr, 0,
+                           nullptr, 0, st))) return e;
+        if ((e = gemm_tf32(ws + w.agg_hi, ws + w.agg_lo, d, F(base + 0), F(base + 1), d, ws + w.P, d, N, d, d, nullptr, 0, 3,
+                           1, nullptr, 0, nullptr, 0, st))) return e;
+        if ((e = union_combine(ws + w.P, Lbuf, GI(RG_INDEG), nullptr, nullptr, nullptr, N, d, 1, 0, 1.0, o_raw, nullptr,
+                               nullptr, ncol, o_hi, o_lo, nullptr, nullptr, nullptr, st))) return e;
+        if (l == 0) { gate_G = Lbuf + 2 * d; gate_ld = ncol; }
+      }
       x_raw = o_raw; x_hi = o_hi; x_lo = o_lo;
     }
     // ---- time gate (K9): h = s(h W_t + b) * [normalize](cur) + (1 - s) * h ----
     float* h_new = hist + (size_t)i * nd;
-    if ((e = time_gate(ws + w.Lm + 2 * d, F(RM_GATE_BIAS), x_raw, h_raw, h_new, N, d, layer_norm, 3 * d, ws + w.h_hi,
+    if ((e = time_gate(gate_G, F(RM_GATE_BIAS), x_raw, h_raw, h_new, N, d, layer_norm, gate_ld, ws + w.h_hi,
                        ws + w.h_lo, st))) return e;
     h_raw = h_new;
   }

@@ -28,16 +28,27 @@ __global__ void expand_edges_kernel(const int64_t* __restrict__ triples, int T, 
   rel_keys[T + t] = (unsigned long long)r * (unsigned long long)N + (unsigned long long)o;
 }
 
+// Virtual rows exist only for ACTIVE destinations (in-degree > 0): real snapshots touch ~10% of the entities, and
+// the aggregate kernels walk the active rows only.
 __global__ void norm_chunks_kernel(const int* __restrict__ indeg, int N, float* __restrict__ norm,
-                                   int* __restrict__ nchunk, int* __restrict__ nsplit, int* __restrict__ max_deg) {
+                                   int* __restrict__ nchunk, int* __restrict__ nsplit, int* __restrict__ active_flag,
+                                   int* __restrict__ max_deg) {
   int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= N) return;
   int d = indeg[v];
   norm[v] = 1.0f / (float)(d == 0 ? 1 : d);  // comp_deg_norm, utils.py:110-114
-  int nc = d <= kAggChunk ? 1 : (d + kAggChunk - 1) / kAggChunk;
+  int nc = (d + kAggChunk - 1) / kAggChunk;  // 0 for isolated nodes
   nchunk[v] = nc;
   nsplit[v] = nc > 1 ? nc : 0;
+  active_flag[v] = d > 0 ? 1 : 0;
   if (d > kAggChunk) atomicMax(max_deg, d);
+}
+
+__global__ void active_pos_kernel(const int* __restrict__ indeg, const int* __restrict__ scan, int N,
+                                  int* __restrict__ active_pos) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= N) return;
+  active_pos[v] = indeg[v] > 0 ? scan[v] : -1;
 }
 
 __global__ void gather_sorted_kernel(const int* __restrict__ eperm, const int* __restrict__ src,
@@ -75,18 +86,20 @@ __global__ void rel_compact_kernel(const unsigned long long* __restrict__ keys, 
 
 __global__ void write_counts_kernel(const int* __restrict__ vptr, const int* __restrict__ sptr, int N,
                                     const int* __restrict__ rel_rowptr, int R, const int* __restrict__ max_deg,
-                                    int* __restrict__ rowptr, int E, int* __restrict__ counts) {
+                                    int* __restrict__ rowptr, int E, const int* __restrict__ active_scan,
+                                    int* __restrict__ counts) {
   rowptr[N] = E;
   counts[0] = vptr[N];
   counts[1] = sptr[N];
   counts[2] = rel_rowptr[R];
   counts[3] = *max_deg;
+  counts[4] = active_scan[N];
 }
 
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct BuildWs {
-  size_t eid, eid_alt, dstkey_alt, rel_keys, rel_keys_alt, head, pos, nchunk, nsplit, rel_count, max_deg, cub, total;
+  size_t eid, eid_alt, dstkey_alt, rel_keys, rel_keys_alt, head, pos, nchunk, nsplit, aflag, ascan, rel_count, max_deg, cub, total;
   size_t cub_bytes;
 };
 
@@ -99,6 +112,7 @@ static BuildWs plan_build_ws(int T, int N, int R) {
   w.rel_keys = take(E * 8); w.rel_keys_alt = take(E * 8);
   w.head = take(E * 4); w.pos = take(E * 4);
   w.nchunk = take(((size_t)N + 1) * 4); w.nsplit = take(((size_t)N + 1) * 4);
+  w.aflag = take(((size_t)N + 1) * 4); w.ascan = take(((size_t)N + 1) * 4);
   w.rel_count = take(((size_t)R + 1) * 4); w.max_deg = take(4);
   size_t b1 = 0, b2 = 0, b3 = 0, b4 = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, b1, (const int*)nullptr, (int*)nullptr, (const int*)nullptr, (int*)nullptr, (int)E);
@@ -120,14 +134,14 @@ size_t csr_build_workspace_bytes(int T, int N, int R) { return plan_build_ws(T, 
 int csr_build(const int64_t* triples, int T, int N, int R,
               int* src, int* dst, int* etype, int* indeg, float* norm,
               int* rowptr, int* src_sorted, int* etype_sorted, int* eperm,
-              int* vptr, int* sptr, int* vrow_row,
+              int* vptr, int* sptr, int* vrow_row, int* active_pos,
               int* rel_rowptr, int* rel_ents, int* counts,
               void* ws, size_t ws_bytes, cudaStream_t st) {
   if (T < 0 || N <= 0 || R <= 0) { set_last_error("csr_build: bad dims T=%d N=%d R=%d", T, N, R); return REGCN_ERR_DIM; }
   BuildWs w = plan_build_ws(T, N, R);
   if (ws_bytes < w.total) { set_last_error("csr_build: workspace %zu < %zu", ws_bytes, w.total); return REGCN_ERR_WORKSPACE; }
   if (!src || !dst || !etype || !indeg || !norm || !rowptr || !src_sorted || !etype_sorted || !eperm || !vptr ||
-      !sptr || !vrow_row || !rel_rowptr || !rel_ents || !counts || !ws || (T > 0 && !triples)) {
+      !sptr || !vrow_row || !active_pos || !rel_rowptr || !rel_ents || !counts || !ws || (T > 0 && !triples)) {
     set_last_error("csr_build: null pointer"); return REGCN_ERR_NULL;
   }
   char* base = (char*)ws;
@@ -140,6 +154,8 @@ int csr_build(const int64_t* triples, int T, int N, int R,
   int* pos = (int*)(base + w.pos);
   int* nchunk = (int*)(base + w.nchunk);
   int* nsplit = (int*)(base + w.nsplit);
+  int* aflag = (int*)(base + w.aflag);
+  int* ascan = (int*)(base + w.ascan);
   int* rel_count = (int*)(base + w.rel_count);
   int* max_deg = (int*)(base + w.max_deg);
   void* cubtmp = base + w.cub;
@@ -151,15 +167,18 @@ int csr_build(const int64_t* triples, int T, int N, int R,
   cudaMemsetAsync(max_deg, 0, 4, st);
   cudaMemsetAsync(nchunk + N, 0, 4, st);
   cudaMemsetAsync(nsplit + N, 0, 4, st);
+  cudaMemsetAsync(aflag + N, 0, 4, st);
   if (T > 0) {
     expand_edges_kernel<<<(T + TB - 1) / TB, TB, 0, st>>>(triples, T, R, src, dst, etype, indeg, eid, rk, N);
   }
-  norm_chunks_kernel<<<(N + TB - 1) / TB, TB, 0, st>>>(indeg, N, norm, nchunk, nsplit, max_deg);
+  norm_chunks_kernel<<<(N + TB - 1) / TB, TB, 0, st>>>(indeg, N, norm, nchunk, nsplit, aflag, max_deg);
   // rowptr[0..N-1] = exclusive scan of indeg; rowptr[N] = E is written by write_counts_kernel
   // (every edge has exactly one destination).
   cub::DeviceScan::ExclusiveSum(cubtmp, cb, indeg, rowptr, N, st);
   cub::DeviceScan::ExclusiveSum(cubtmp, cb, nchunk, vptr, N + 1, st);
   cub::DeviceScan::ExclusiveSum(cubtmp, cb, nsplit, sptr, N + 1, st);
+  cub::DeviceScan::ExclusiveSum(cubtmp, cb, aflag, ascan, N + 1, st);
+  active_pos_kernel<<<(N + TB - 1) / TB, TB, 0, st>>>(indeg, ascan, N, active_pos);
   fill_vrows_kernel<<<(N + TB - 1) / TB, TB, 0, st>>>(vptr, N, vrow_row);
   if (T > 0) {
     // stable sort of edge ids by destination: eperm[i] = original edge id of the i-th CSR slot
@@ -174,7 +193,7 @@ int csr_build(const int64_t* triples, int T, int N, int R,
     rel_compact_kernel<<<(E + TB - 1) / TB, TB, 0, st>>>(rk_alt, head, pos, E, N, rel_ents);
   }
   cub::DeviceScan::ExclusiveSum(cubtmp, cb, rel_count, rel_rowptr, R + 1, st);
-  write_counts_kernel<<<1, 1, 0, st>>>(vptr, sptr, N, rel_rowptr, R, max_deg, rowptr, E, counts);
+  write_counts_kernel<<<1, 1, 0, st>>>(vptr, sptr, N, rel_rowptr, R, max_deg, rowptr, E, ascan, counts);
   return check_launch("csr_build");
 }
 

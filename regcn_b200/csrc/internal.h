@@ -8,13 +8,13 @@ namespace regcn {
 size_t csr_build_workspace_bytes(int T, int N, int R);
 int csr_build(const int64_t* triples, int T, int N, int R, int* src, int* dst, int* etype, int* indeg, float* norm,
               int* rowptr, int* src_sorted, int* etype_sorted, int* eperm, int* vptr, int* sptr, int* vrow_row,
-              int* rel_rowptr, int* rel_ents, int* counts, void* ws, size_t ws_bytes, cudaStream_t st);
+              int* active_pos, int* rel_rowptr, int* rel_ents, int* counts, void* ws, size_t ws_bytes, cudaStream_t st);
 int rel_mean_pool(const float* h, const int* rel_rowptr, const int* rel_ents, int R, int d, int nsplit, float* out,
                   float* partial, float* out_hi, float* out_lo, cudaStream_t st);
 int union_aggregate(const float* h, const float* rel, const int* rowptr, const int* src_sorted, const int* etype_sorted,
                     const float* norm, const int* vptr, const int* sptr, const int* vrow_row, int nv, int nsplit,
                     const float* radius, float gamma, int N, int d, float* out, float* partial, float* out_hi,
-                    float* out_lo, cudaStream_t st);
+                    float* out_lo, const int* active_pos, int ldo, cudaStream_t st);
 int block_aggregate(const float* h, const float* W, const int* rowptr, const int* src_sorted, const int* etype_sorted,
                     const float* norm, int N, int d_in, int d_out, int nb, float* out, cudaStream_t st);
 int lorentz_aggregate(const float* ht, const float* W, const float* rel, const int* rowptr, const int* src_sorted,
@@ -49,7 +49,7 @@ int gru_gate(const float* gi, const float* gh, const float* hprev, float* out, i
 int union_combine(const float* P, const float* L, const int* indeg, const float* S, const float* skip_bias,
                   const float* prev, int N, int d, int act, int hyper, double c, float* out, float* ht_next,
                   float* radius_next, int ldL, float* out_hi, float* out_lo, float* ht_hi, float* ht_lo,
-                  cudaStream_t st);
+                  const int* active_pos, cudaStream_t st);
 int time_gate(const float* G, const float* bias, const float* cur, const float* h, float* out, int N, int d,
               int normalize_cur, int ldg, float* out_hi, float* out_lo, cudaStream_t st);
 int hyp_init(const float* emb, const float* radius_static, int N, int d, int normalize, int on_manifold, double c,

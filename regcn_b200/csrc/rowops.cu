@@ -116,12 +116,20 @@ __global__ void __launch_bounds__(256) union_combine_kernel(
     const float* __restrict__ S, const float* __restrict__ skip_bias, const float* __restrict__ prev,
     int N, int d, int act, int hyper, Curv cv, float* __restrict__ out, float* __restrict__ ht_next,
     float* __restrict__ radius_next, int ldL, float* __restrict__ out_hi, float* __restrict__ out_lo,
-    float* __restrict__ ht_hi, float* __restrict__ ht_lo) {
+    float* __restrict__ ht_hi, float* __restrict__ ht_lo, const int* __restrict__ active_pos) {
   ROW_KERNEL_PROLOGUE(N)
   WarpRow<RV> t, u;
-  t.load_plain(P + (size_t)row * d, nvec, lane);
+  if (active_pos) {
+    // sparse-snapshot form: active rows carry the complete pre-activation [agg | h].[W_n ; W_loop] in the compact
+    // matrix P; inactive rows take h.W_evolve from L
+    const int ap = __ldg(active_pos + row);
+    if (ap >= 0) t.load_plain(P + (size_t)ap * d, nvec, lane);
+    else t.load_plain(L + (size_t)row * ldL, nvec, lane);
+  } else {
+    t.load_plain(P + (size_t)row * d, nvec, lane);
+  }
   if (hyper) t.map([](float a) { return clampf_(a, -10.f, 10.f); });
-  if (L) {
+  if (L && !active_pos) {
     const int sel = __ldg(indeg + row) > 0 ? 0 : d;
     u.load_plain(L + (size_t)row * ldL + sel, nvec, lane);
     t.zip(u, [](float a, float b) { return a + b; });
@@ -155,13 +163,13 @@ __global__ void __launch_bounds__(256) union_combine_kernel(
 int union_combine(const float* P, const float* L, const int* indeg, const float* S, const float* skip_bias,
                   const float* prev, int N, int d, int act, int hyper, double c, float* out, float* ht_next,
                   float* radius_next, int ldL, float* out_hi, float* out_lo, float* ht_hi, float* ht_lo,
-                  cudaStream_t st) {
-  if (!P || !out || (L && !indeg) || (S && (!skip_bias || !prev))) { set_last_error("union_combine: null pointer"); return REGCN_ERR_NULL; }
+                  const int* active_pos, cudaStream_t st) {
+  if (!P || !out || (L && !indeg && !active_pos) || (S && (!skip_bias || !prev)) || (active_pos && (hyper || !L))) { set_last_error("union_combine: null pointer"); return REGCN_ERR_NULL; }
   if (int e = check_d("union_combine", d)) return e;
   if (N <= 0) return REGCN_OK;
   Curv cv = make_curv(hyper ? c : 1.0);
-  if (d <= 128) union_combine_kernel<1><<<row_grid(N), 256, 0, st>>>(P, L, indeg, S, skip_bias, prev, N, d, act, hyper, cv, out, ht_next, radius_next, ldL > 0 ? ldL : 2 * d, out_hi, out_lo, ht_hi, ht_lo);
-  else union_combine_kernel<2><<<row_grid(N), 256, 0, st>>>(P, L, indeg, S, skip_bias, prev, N, d, act, hyper, cv, out, ht_next, radius_next, ldL > 0 ? ldL : 2 * d, out_hi, out_lo, ht_hi, ht_lo);
+  if (d <= 128) union_combine_kernel<1><<<row_grid(N), 256, 0, st>>>(P, L, indeg, S, skip_bias, prev, N, d, act, hyper, cv, out, ht_next, radius_next, ldL > 0 ? ldL : 2 * d, out_hi, out_lo, ht_hi, ht_lo, active_pos);
+  else union_combine_kernel<2><<<row_grid(N), 256, 0, st>>>(P, L, indeg, S, skip_bias, prev, N, d, act, hyper, cv, out, ht_next, radius_next, ldL > 0 ? ldL : 2 * d, out_hi, out_lo, ht_hi, ht_lo, active_pos);
   return check_launch("union_combine");
 }
 

@@ -41,26 +41,29 @@ class SnapshotGraph:
         self.rowptr = i32(N + 1)
         self.src_sorted, self.etype_sorted, self.eperm = i32(E), i32(E), i32(E)
         self.vptr, self.sptr = i32(N + 1), i32(N + 1)
-        self.vrow_row = i32(N + E // AGG_CHUNK + 1)
+        self.vrow_row = i32(min(N, E) + E // AGG_CHUNK + 1)
+        self.active_pos = i32(N)
         self.rel_rowptr = i32(R + 1)
         self.rel_ents = i32(E)
-        counts = torch.zeros(4, device=dev, dtype=I32)
+        counts = torch.zeros(8, device=dev, dtype=I32)
         ws_bytes = _lib.load().regcn_csr_build_workspace_bytes(T, N, R)
         ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
         call("regcn_csr_build", ptr(triples_dev), T, N, R, ptr(self.src), ptr(self.dst), ptr(self.etype),
              ptr(self.indeg), ptr(self.norm), ptr(self.rowptr), ptr(self.src_sorted), ptr(self.etype_sorted),
-             ptr(self.eperm), ptr(self.vptr), ptr(self.sptr), ptr(self.vrow_row), ptr(self.rel_rowptr),
+             ptr(self.eperm), ptr(self.vptr), ptr(self.sptr), ptr(self.vrow_row), ptr(self.active_pos),
+             ptr(self.rel_rowptr),
              ptr(self.rel_ents), ptr(counts), ptr(ws), ws_bytes)
         c = counts.tolist()  # the one host sync of graph construction
-        self.n_vrows, self.n_split_chunks, self.n_rel_ents, self.max_hub_degree = c
+        self.n_vrows, self.n_split_chunks, self.n_rel_ents, self.max_hub_degree, self.n_active = c[:5]
         self._ndata = None
         self._edata = None
         self._r2e = None
         # pointer / int tables consumed by the whole-recurrence entry points (include/regcn_b200.h RG_* / RGI_*)
         self.ptr_table = np.array([t.data_ptr() for t in (self.rowptr, self.src_sorted, self.etype_sorted, self.indeg,
                                                           self.norm, self.vptr, self.sptr, self.vrow_row,
-                                                          self.rel_rowptr, self.rel_ents)], dtype=np.uint64)
-        self.int_table = np.array([E, self.n_vrows, self.n_split_chunks, self.n_rel_ents], dtype=np.int32)
+                                                          self.rel_rowptr, self.rel_ents, self.active_pos)],
+                                  dtype=np.uint64)
+        self.int_table = np.array([E, self.n_vrows, self.n_split_chunks, self.n_rel_ents, self.n_active], dtype=np.int32)
 
     # ---- the slice of the DGL surface the reference modules use -----------------
     def number_of_nodes(self):

@@ -154,12 +154,14 @@ class RecurrentRGCN(nn.Module):
         keep += [emb_rel, gi_static, b_hh, gate_b, dyn]
         ptrs = [dyn, emb_rel, er_hi, er_lo, gi_static, wr_hi, wr_lo, wh_hi, wh_lo, b_hh, gate_b]
         for l, layer in enumerate(self.rgcn.layers):
-            wn_hi, wn_lo = split(layer.weight_neighbor.detach().t())
-            cat = [layer.loop_weight.detach(), layer.evolve_loop_weight.detach()]
-            if l == 0:
-                cat.append(self.time_gate_weight.detach())
-            wl_hi, wl_lo = split(torch.cat(cat, dim=1).t())
-            ptrs += [wn_hi, wn_lo, wl_hi, wl_lo]
+            wn, wl, we = (layer.weight_neighbor.detach(), layer.loop_weight.detach(),
+                          layer.evolve_loop_weight.detach())
+            gate = [self.time_gate_weight.detach()] if l == 0 else []
+            wn_hi, wn_lo = split(wn.t())                                        # dense path: agg . W_n
+            wl_hi, wl_lo = split(torch.cat([wl, we] + gate, dim=1).t())         #             x . [W_loop|W_evolve(|W_t)]
+            wc_hi, wc_lo = split(torch.cat([wn, wl], dim=0).t())                # sparse path: [agg|x] . [W_n;W_loop]
+            we_hi, we_lo = split(torch.cat([we] + gate, dim=1).t())             #              x . [W_evolve(|W_t)]
+            ptrs += [wn_hi, wn_lo, wl_hi, wl_lo, wc_hi, wc_lo, we_hi, we_lo]
         ptab = np.array([t.data_ptr() for t in ptrs], dtype=np.uint64)
         itab = np.array([self.num_ents, 2 * self.num_rels, d, len(self.rgcn.layers), int(bool(self.layer_norm)), 1],
                         dtype=np.int32)

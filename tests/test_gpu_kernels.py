@@ -50,10 +50,15 @@ def test_csr_build_bit_exact(shape, zipf):
     assert g.n_rel_ents == len(rel_ents)
     assert np.array_equal(g.rel_ents[:g.n_rel_ents].cpu().numpy(), rel_ents)
     # virtual rows: chunks of 64 edges per destination, in row order
-    nch = np.maximum(1, -(-o["indeg"] // 64))
+    nch = -(-o["indeg"] // 64)                       # isolated destinations get no virtual row
     assert g.n_vrows == int(nch.sum())
     assert g.n_split_chunks == int(nch[nch > 1].sum())
     assert np.array_equal(g.vrow_row[:g.n_vrows].cpu().numpy(), np.repeat(np.arange(n), nch))
+    active = np.nonzero(o["indeg"] > 0)[0]
+    assert g.n_active == len(active)
+    ap = np.full(n, -1, dtype=np.int64)
+    ap[active] = np.arange(len(active))
+    assert np.array_equal(g.active_pos.cpu().numpy(), ap)
     # the DGL-style views the reference's modules read
     assert g.number_of_nodes() == n and tuple(g.ndata["norm"].shape) == (n, 1)
     assert np.array_equal(g.edata["type"].cpu().numpy(), o["etype"])
@@ -65,7 +70,7 @@ def test_csr_build_bit_exact(shape, zipf):
 def test_csr_build_empty_and_duplicates():
     R, ops = _ops()
     g = R.build_sub_graph(10, 3, np.zeros((0, 3), dtype=np.int64), True, 0)
-    assert g.num_edges == 0 and g.n_vrows == 10 and g.n_split_chunks == 0 and g.n_rel_ents == 0
+    assert g.num_edges == 0 and g.n_vrows == 0 and g.n_split_chunks == 0 and g.n_rel_ents == 0 and g.n_active == 0
     assert np.array_equal(g.rowptr.cpu().numpy(), np.zeros(11))
     assert np.array_equal(g.norm.cpu().numpy(), np.ones(10, dtype=np.float32))
     h = torch.randn(10, 8, device=DEV)

@@ -120,19 +120,23 @@ def test_kernel_error_vs_fp64_oracle(kind):
     assert my_err_s <= 2 * ref_err_s + 1e-4, (my_err_s, ref_err_s)
 
 
-def test_engine_path_equals_layer_path():
-    """The single-call recurrence (regcn_regcn_evolve) and the layer-by-layer path run the same kernels: results
-    must agree to fp32 round-off, on a graph with hub rows (split chunks) and absent relations."""
+@pytest.mark.parametrize("shape", ["c4", "c1"])
+def test_engine_path_equals_layer_path(shape):
+    """The single-call recurrence (regcn_regcn_evolve) against the layer-by-layer path, on a dense snapshot (c4: hub rows
+    with split chunks, most entities active -> dense form) and a sparse one (c1: ~5% active -> row-partitioned form)."""
     import regcn_b200 as R
     from regcn_b200 import ops
     R._lib.require_device()
     cfg = dict(kind="regcn", layer_norm=True, seed=77)
-    case = synth.make_case("c4", 77)
+    case = synth.make_case(shape, 77)
     n, r = case["num_ents"], case["num_rels"]
     model, _ = build_model(cfg, n, r)
     model = model.to(DEV)
     glist = [R.build_sub_graph(n, r, s, True, 0) for s in case["history"]]
-    assert max(g.n_split_chunks for g in glist) > 0
+    if shape == "c4":
+        assert max(g.n_split_chunks for g in glist) > 0
+    else:
+        assert all(2 * g.n_active <= n for g in glist)
     prev = ops.gemm_impl()
     try:
         ops.set_gemm_impl("tc")
@@ -143,9 +147,9 @@ def test_engine_path_equals_layer_path():
     finally:
         ops.set_gemm_impl(prev)
     for a, b in zip(h_e, h_l):
-        ok, worst = close(a.cpu().numpy(), b.cpu().numpy(), rtol=2e-5)
+        ok, worst = close(a.cpu().numpy(), b.cpu().numpy(), rtol=5e-5)
         assert ok, worst
-    ok, worst = close(r_e.cpu().numpy(), r_l.cpu().numpy(), rtol=2e-5)
+    ok, worst = close(r_e.cpu().numpy(), r_l.cpu().numpy(), rtol=5e-5)
     assert ok, worst
 
 
