@@ -38,7 +38,7 @@ REGCN_API int regcn_device_ok(void);
 /* ---- K1 edge index: rgcn/utils.py:100-134 (build_sub_graph), :78-97 (r2e) ---------------------
  * triples (T,3) int64 -> E = 2T edges [src;dst]->[dst;src], type [rel;rel+R]; in-degree; norm;
  * CSR by destination (stable in edge id): rowptr (N+1), src_sorted/etype_sorted/eperm (E);
- * virtual rows (chunks of 64 in-edges) of the ACTIVE destinations only: vptr/sptr (N+1), vrow_row (min(N,E)+E/64+1);
+ * virtual rows (chunks of 32 in-edges) of the ACTIVE destinations only: vptr/sptr (N+1), vrow_row (min(N,E)+E/32+1);
  * active_pos (N): position of a destination among the active ones (in-degree > 0), -1 otherwise;
  * relation->entity CSR shared by r and r+R: rel_rowptr (R+1), rel_ents (<= 2T, sorted per relation);
  * counts[8] = {n_virtual_rows, n_split_chunks, n_rel_ents, max_hub_degree, n_active, 0, 0, 0}.   */

@@ -10,7 +10,7 @@
 
 namespace regcn {
 
-constexpr int kAggChunk = 64;  // must match graph_build.cu
+constexpr int kAggChunk = 32;  // must match graph_build.cu
 
 // ---------------------------------------------------------------------------
 // K4: agg[v] = norm[v] * sum_{(u,r)->v} w_uv * (h[u] + rel[r]),  w_uv = exp(-gamma*|rad[u]-rad[v]|) or 1.
@@ -50,18 +50,18 @@ __global__ void __launch_bounds__(256) union_aggregate_kernel(
     }
     const int cnt = min(kWarp, end - base);
     int j = 0;
-    for (; j + 4 <= cnt; j += 4) {  // 4 edges in flight per lane: 8 independent 16-byte row loads
-      int sj[4], tj[4];
-      float wj[4];
+    for (; j + 8 <= cnt; j += 8) {  // 8 edges in flight per lane: 16 independent 16-byte row loads
+      int sj[8], tj[8];
+      float wj[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         sj[u] = __shfl_sync(0xffffffffu, s, j + u);
         tj[u] = __shfl_sync(0xffffffffu, t, j + u);
         wj[u] = RADIUS ? __shfl_sync(0xffffffffu, wgt, j + u) : 1.f;
       }
-      float4 hv[4][RV], rv[4][RV];
+      float4 hv[8][RV], rv[8][RV];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
 #pragma unroll
         for (int i = 0; i < RV; ++i) {
           int c = lane + i * kWarp;
@@ -75,7 +75,40 @@ __global__ void __launch_bounds__(256) union_aggregate_kernel(
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
+#pragma unroll
+        for (int i = 0; i < RV; ++i) {
+          float4 m = f4_add(hv[u][i], rv[u][i]);
+          acc.v[i] = RADIUS ? f4_fma(wj[u], m, acc.v[i]) : f4_add(acc.v[i], m);
+        }
+      }
+    }
+    for (; j + 2 <= cnt; j += 2) {
+      int sj[2], tj[2];
+      float wj[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        sj[u] = __shfl_sync(0xffffffffu, s, j + u);
+        tj[u] = __shfl_sync(0xffffffffu, t, j + u);
+        wj[u] = RADIUS ? __shfl_sync(0xffffffffu, wgt, j + u) : 1.f;
+      }
+      float4 hv[2][RV], rv[2][RV];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+#pragma unroll
+        for (int i = 0; i < RV; ++i) {
+          int c = lane + i * kWarp;
+          if (c < nvec) {
+            hv[u][i] = ldg4(h + (size_t)sj[u] * d + 4 * c);
+            rv[u][i] = ldg4(rel + (size_t)tj[u] * d + 4 * c);
+          } else {
+            hv[u][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            rv[u][i] = hv[u][i];
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
 #pragma unroll
         for (int i = 0; i < RV; ++i) {
           float4 m = f4_add(hv[u][i], rv[u][i]);

@@ -7,7 +7,7 @@
 
 namespace regcn {
 
-constexpr int kAggChunk = 64;  // edges per virtual row (hub rows are split into chunks of this many)
+constexpr int kAggChunk = 32;  // edges per virtual row (hub rows are split into chunks of this many)
 
 // E = 2T edges in the reference's order: [src;dst] -> [dst;src], type [rel; rel+R]  (utils.py:116-118)
 __global__ void expand_edges_kernel(const int64_t* __restrict__ triples, int T, int R,

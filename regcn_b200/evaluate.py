@@ -93,15 +93,40 @@ def score_rank_sharded(model, emb, r_emb, all_triples, filter_csr, group=None):
 
 @torch.no_grad()
 def evaluate_from_host(model, history_host, test_host, num_nodes, num_rels, device):
-    """End-to-end step from HOST buffers (pinned int64 triples): H2D copies, device edge-index build for every
-    history snapshot, predict() (entity + relation decoders, like the reference's test loop), time-aware filtered
-    ranking for both, and the D2H read-back of MRRs and rank vectors.  Returns python floats + host tensors."""
-    from .graph import SnapshotGraph
-    glist = [SnapshotGraph(num_nodes, num_rels, h.to(device, non_blocking=True)) for h in history_host]
+    """End-to-end evaluation of one test timestamp from HOST buffers (pinned int64 triples), the loop body of the
+    reference's test() (src/main.py:67-74): H2D copies, device edge-index build for every history snapshot (one
+    host sync for all of them), evolution, entity ranks through the fused scoring kernel, relation ranks through
+    ConvTransR / RotHRel + the dense rank kernel, time-aware filtering for both, and the D2H read-back of MRRs
+    and rank vectors.  Returns ((filter_mrr, mrr, filter_mrr_rel, mrr_rel), rank_host, filter_rank_host)."""
+    from .graph import build_sub_graphs
+    glist = build_sub_graphs(num_nodes, num_rels, history_host, device)
     test = test_host.to(device, non_blocking=True)
-    all_t, score, score_rel = model.predict(glist, num_rels, None, test, True)
-    f_ent = utils.filter_csr_from_snapshot(all_t, 2 * num_rels, 0)
-    f_rel = utils.filter_csr_from_snapshot(all_t, num_nodes, 1)
-    fm_r, m_r, rank_r, frank_r = utils.get_total_rank(all_t, score_rel, None, 1000, rel_predict=1, filter_csr=f_rel)
-    fm, m, rank, frank = utils.get_total_rank(all_t, score, None, 1000, rel_predict=0, filter_csr=f_ent)
-    return (fm, m, fm_r, m_r), rank.cpu(), frank.cpu()
+    inv = test[:, [2, 1, 0]]
+    inv[:, 1] = inv[:, 1] + num_rels
+    all_t = torch.cat((test, inv)).contiguous()
+    f_ent = utils.filter_csr_from_snapshot(all_t, 2 * num_rels, 0, num_answers=num_nodes)
+    f_rel = utils.filter_csr_from_snapshot(all_t, num_nodes, 1, num_answers=2 * num_rels)
+    evolve_embs, _, r_emb, _, _ = model.forward(glist, None, True)
+    emb = evolve_embs[-1]
+    if model.layer_norm:
+        if hasattr(model, "_c_float"):
+            emb = ops.row_map(emb, ops.ROW_TANGENT_NORMALIZE, c=model._c_float)
+        else:
+            emb = ops.row_map(emb, ops.ROW_NORMALIZE)
+    if ops.gemm_impl() in ("tc", "tc1"):
+        q, cand, hyp, col_bias = _scoring_operands(model, emb, r_emb, all_t)
+        target = all_t[:, 2].to(torch.int32).contiguous()
+        pa, pe = f_ent.pairs(target)
+        raw, filt, _ = ops.fused_rank_counts(q, cand, target, f_ent.ptr, f_ent.idx, pa, pe, hyp=hyp, col_bias=col_bias)
+        rank, frank = ops.counts_to_ranks(raw, filt)
+    else:
+        score = model.decoder_ob.forward(emb, r_emb, all_t, mode="test")
+        _, _, rank, frank = utils.get_total_rank(all_t, score, None, 1000, rel_predict=0, filter_csr=f_ent)
+    score_rel = model.rdecoder.forward(emb, r_emb, all_t, mode="test")
+    raw_r, filt_r, _ = ops.rank_dense(score_rel, all_t, 1, f_rel.ptr, f_rel.idx)
+    rank_r, frank_r = ops.counts_to_ranks(raw_r, filt_r)
+    mrrs = torch.stack([torch.mean(1.0 / frank.float()), torch.mean(1.0 / rank.float()),
+                        torch.mean(1.0 / frank_r.float()), torch.mean(1.0 / rank_r.float())])
+    out = torch.cat((mrrs.double(), rank.double(), frank.double())).cpu()   # one D2H transfer (ranks < 2^53 exactly)
+    B = rank.numel()
+    return tuple(out[:4].tolist()), out[4:4 + B].long(), out[4 + B:].long()

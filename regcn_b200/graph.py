@@ -14,7 +14,7 @@ from . import _lib
 from ._lib import call, ptr
 
 I32 = torch.int32
-AGG_CHUNK = 64  # must match csrc/graph_build.cu kAggChunk
+AGG_CHUNK = 32  # must match csrc/graph_build.cu kAggChunk
 
 
 class _Frame(dict):
@@ -22,7 +22,7 @@ class _Frame(dict):
 
 
 class SnapshotGraph:
-    def __init__(self, num_nodes, num_rels, triples_dev):
+    def __init__(self, num_nodes, num_rels, triples_dev, _defer_counts=False):
         self.num_nodes = int(num_nodes)
         self.num_rels = int(num_rels)
         self.triples = triples_dev  # (T,3) int64 on the device, reference layout
@@ -31,39 +31,40 @@ class SnapshotGraph:
         N, R, E = self.num_nodes, self.num_rels, 2 * T
         self.num_edges = E
         dev = self.device
-
-        def i32(n):
-            return torch.empty(max(int(n), 1), device=dev, dtype=I32)
-
-        self.src, self.dst, self.etype = i32(E), i32(E), i32(E)
-        self.indeg = i32(N)
-        self.norm = torch.empty(N, device=dev, dtype=torch.float32)
-        self.rowptr = i32(N + 1)
-        self.src_sorted, self.etype_sorted, self.eperm = i32(E), i32(E), i32(E)
-        self.vptr, self.sptr = i32(N + 1), i32(N + 1)
-        self.vrow_row = i32(min(N, E) + E // AGG_CHUNK + 1)
-        self.active_pos = i32(N)
-        self.rel_rowptr = i32(R + 1)
-        self.rel_ents = i32(E)
-        counts = torch.zeros(8, device=dev, dtype=I32)
+        # one arena for every int32 array of the index (a single allocation per snapshot)
+        sizes = [E, E, E, N, N + 1, E, E, E, N + 1, N + 1, min(N, E) + E // AGG_CHUNK + 1, N, R + 1, E, 8]
+        offs, tot = [], 0
+        for n in sizes:
+            offs.append(tot)
+            tot += (max(int(n), 1) + 3) // 4 * 4          # keep every view 16-byte aligned
+        arena = torch.empty(tot + N, device=dev, dtype=I32)
+        v = [arena[o:o + max(int(n), 1)] for o, n in zip(offs, sizes)]
+        (self.src, self.dst, self.etype, self.indeg, self.rowptr, self.src_sorted, self.etype_sorted, self.eperm,
+         self.vptr, self.sptr, self.vrow_row, self.active_pos, self.rel_rowptr, self.rel_ents, self._counts) = v
+        self.norm = arena[tot:tot + N].view(torch.float32)
+        self._arena = arena
         ws_bytes = _lib.load().regcn_csr_build_workspace_bytes(T, N, R)
         ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
-        call("regcn_csr_build", ptr(triples_dev), T, N, R, ptr(self.src), ptr(self.dst), ptr(self.etype),
-             ptr(self.indeg), ptr(self.norm), ptr(self.rowptr), ptr(self.src_sorted), ptr(self.etype_sorted),
-             ptr(self.eperm), ptr(self.vptr), ptr(self.sptr), ptr(self.vrow_row), ptr(self.active_pos),
-             ptr(self.rel_rowptr),
-             ptr(self.rel_ents), ptr(counts), ptr(ws), ws_bytes)
-        c = counts.tolist()  # the one host sync of graph construction
-        self.n_vrows, self.n_split_chunks, self.n_rel_ents, self.max_hub_degree, self.n_active = c[:5]
+        call("regcn_csr_build", ptr(triples_dev), T, N, R, self.src.data_ptr(), self.dst.data_ptr(),
+             self.etype.data_ptr(), self.indeg.data_ptr(), self.norm.data_ptr(), self.rowptr.data_ptr(),
+             self.src_sorted.data_ptr(), self.etype_sorted.data_ptr(), self.eperm.data_ptr(), self.vptr.data_ptr(),
+             self.sptr.data_ptr(), self.vrow_row.data_ptr(), self.active_pos.data_ptr(), self.rel_rowptr.data_ptr(),
+             self.rel_ents.data_ptr(), self._counts.data_ptr(), ptr(ws), ws_bytes)
         self._ndata = None
         self._edata = None
         self._r2e = None
-        # pointer / int tables consumed by the whole-recurrence entry points (include/regcn_b200.h RG_* / RGI_*)
         self.ptr_table = np.array([t.data_ptr() for t in (self.rowptr, self.src_sorted, self.etype_sorted, self.indeg,
                                                           self.norm, self.vptr, self.sptr, self.vrow_row,
                                                           self.rel_rowptr, self.rel_ents, self.active_pos)],
                                   dtype=np.uint64)
-        self.int_table = np.array([E, self.n_vrows, self.n_split_chunks, self.n_rel_ents, self.n_active], dtype=np.int32)
+        if not _defer_counts:
+            self._set_counts(self._counts.tolist())          # the one host sync of graph construction
+
+    def _set_counts(self, c):
+        self.n_vrows, self.n_split_chunks, self.n_rel_ents, self.max_hub_degree, self.n_active = c[:5]
+        # pointer / int tables consumed by the whole-recurrence entry points (include/regcn_b200.h RG_* / RGI_*)
+        self.int_table = np.array([self.num_edges, self.n_vrows, self.n_split_chunks, self.n_rel_ents, self.n_active],
+                                  dtype=np.int32)
 
     # ---- the slice of the DGL surface the reference modules use -----------------
     def number_of_nodes(self):
@@ -144,3 +145,17 @@ def build_sub_graph(num_nodes, num_rels, triples, use_cuda=True, gpu=0):
     else:
         t = torch.from_numpy(np.ascontiguousarray(np.asarray(triples, dtype=np.int64)).reshape(-1, 3)).to(dev)
     return SnapshotGraph(num_nodes, num_rels, t.contiguous())
+
+
+def build_sub_graphs(num_nodes, num_rels, triples_list, device):
+    """Build the edge index of several snapshots with ONE host synchronisation: every csr_build is enqueued first,
+    then the per-snapshot size counters come back in a single device->host read.  `triples_list`: (T_i,3) int64
+    tensors (pinned host or device)."""
+    _lib.require_device()
+    gs = [SnapshotGraph(num_nodes, num_rels, t.to(device, non_blocking=True).contiguous(), _defer_counts=True)
+          for t in triples_list]
+    if gs:
+        counts = torch.stack([g._counts for g in gs]).tolist()
+        for g, c in zip(gs, counts):
+            g._set_counts(c)
+    return gs

@@ -89,7 +89,7 @@ def filter_csr_from_dict(test_triples, all_ans, rel_predict=0, device=None):
                      torch.tensor(idx_l if idx_l else [0], dtype=torch.int32, device=dev))
 
 
-def filter_csr_from_snapshot(all_triples, num_keys2, rel_predict=0):
+def filter_csr_from_snapshot(all_triples, num_keys2, rel_predict=0, num_answers=None):
     """Vectorised, device-side equivalent of load_all_answers_for_filter + per-query lookup when the filter set is
     'every answer among these queries themselves' (time-aware filtering, rgcn/utils.py:286-304: the test snapshot's own
     triples incl. inverses = exactly `all_triples` of predict()).  key = (h, r) -> answers t (entity prediction) or
@@ -99,7 +99,8 @@ def filter_csr_from_snapshot(all_triples, num_keys2, rel_predict=0):
     a = all_triples[:, 1] if rel_predict else all_triples[:, 2]
     key = h * int(num_keys2) + k2
     # unique (key, answer) pairs sorted by key then answer
-    big = int(a.max().item()) + 1 if a.numel() else 1
+    # `num_answers` (an upper bound on the answer ids: num_ents, or 2*num_rels for relation prediction) avoids a sync
+    big = int(num_answers) if num_answers is not None else (int(a.max().item()) + 1 if a.numel() else 1)
     pair = torch.unique(key * big + a)
     pkey, pans = pair // big, pair % big
     ukey, counts = torch.unique_consecutive(pkey, return_counts=True)
