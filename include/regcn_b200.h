@@ -202,7 +202,7 @@ enum { RM_DYNAMIC_EMB = 0, RM_EMB_REL, RM_EMB_REL_HI, RM_EMB_REL_LO, RM_GI_STATI
 enum { RMI_NUM_ENTS = 0, RMI_NUM_RELS2, RMI_DIM, RMI_NUM_LAYERS, RMI_LAYER_NORM, RMI_SELF_LOOP, RMI_NUM_INTS };
 enum { RG_ROWPTR = 0, RG_SRC_SORTED, RG_ETYPE_SORTED, RG_INDEG, RG_NORM, RG_VPTR, RG_SPTR, RG_VROW_ROW,
        RG_REL_ROWPTR, RG_REL_ENTS, RG_ACTIVE_POS, RG_NUM_PTRS };
-enum { RGI_NUM_EDGES = 0, RGI_N_VROWS, RGI_N_SPLIT_CHUNKS, RGI_N_REL_ENTS, RGI_N_ACTIVE, RGI_NUM_INTS };
+enum { RGI_NUM_EDGES = 0, RGI_N_VROWS, RGI_N_SPLIT_CHUNKS, RGI_N_REL_ENTS, RGI_N_ACTIVE, RGI_MAX_CHUNKS, RGI_NUM_INTS };
 REGCN_API size_t regcn_regcn_evolve_workspace_bytes(int N, int R2, int d, int max_split_chunks, int rel_nsplit);
 REGCN_API int regcn_regcn_evolve(const void* const* model_ptrs, const int* model_ints, const void* const* graph_ptrs,
                        const int* graph_ints, int L, float* hist, float* h0_out, int rel_nsplit, void* workspace,

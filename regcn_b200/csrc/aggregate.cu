@@ -59,27 +59,33 @@ __global__ void __launch_bounds__(256) union_aggregate_kernel(
         tj[u] = __shfl_sync(0xffffffffu, t, j + u);
         wj[u] = RADIUS ? __shfl_sync(0xffffffffu, wgt, j + u) : 1.f;
       }
-      float4 hv[8][RV], rv[8][RV];
+      float4 hv[8][RV];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
 #pragma unroll
         for (int i = 0; i < RV; ++i) {
           int c = lane + i * kWarp;
-          if (c < nvec) {
-            hv[u][i] = ldg4(h + (size_t)sj[u] * d + 4 * c);
-            rv[u][i] = ldg4(rel + (size_t)tj[u] * d + 4 * c);
-          } else {
-            hv[u][i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            rv[u][i] = hv[u][i];
-          }
+          hv[u][i] = c < nvec ? ldg4(h + (size_t)sj[u] * d + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int half = 0; half < 2; ++half) {      // relation rows come from a cache-resident table: 4 at a time
+        float4 rv[4][RV];
 #pragma unroll
-        for (int i = 0; i < RV; ++i) {
-          float4 m = f4_add(hv[u][i], rv[u][i]);
-          acc.v[i] = RADIUS ? f4_fma(wj[u], m, acc.v[i]) : f4_add(acc.v[i], m);
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+          for (int i = 0; i < RV; ++i) {
+            int c = lane + i * kWarp;
+            rv[u][i] = c < nvec ? ldg4(rel + (size_t)tj[half * 4 + u] * d + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+          for (int i = 0; i < RV; ++i) {
+            float4 m = f4_add(hv[half * 4 + u][i], rv[u][i]);
+            acc.v[i] = RADIUS ? f4_fma(wj[half * 4 + u], m, acc.v[i]) : f4_add(acc.v[i], m);
+          }
         }
       }
     }
@@ -147,41 +153,53 @@ __global__ void __launch_bounds__(256) union_aggregate_kernel(
   }
 }
 
-// Rows that were split into several chunks: sum the chunk partials in chunk order, apply norm.
+// Rows that were split into several chunks: fold the chunk partials with a radix-32 tree, one level per launch.
+// Level with stride s: the warp of chunk k (k % (32 s) == 0) sums partial[k], partial[k+s], ..., partial[k+31 s]
+// (fixed order: deterministic) back into partial[k]; the level that covers the whole row applies the degree norm
+// and writes the output row.  A hub with 350k in-edges (11k chunks) is folded in 3 levels instead of one serial walk.
 template <int RV>
 __global__ void __launch_bounds__(256) aggregate_fixup_kernel(
     const int* __restrict__ vptr, const int* __restrict__ sptr, const int* __restrict__ vrow_row,
-    const float* __restrict__ norm, int nv, int d, const float* __restrict__ partial, float* __restrict__ out,
-    float* __restrict__ out_hi, float* __restrict__ out_lo, const int* __restrict__ active_pos, int ldo) {
+    const float* __restrict__ norm, int nv, int d, float* __restrict__ partial, float* __restrict__ out,
+    float* __restrict__ out_hi, float* __restrict__ out_lo, const int* __restrict__ active_pos, int ldo, int stride) {
   const int lane = threadIdx.x & 31;
   const int w = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
   if (w >= nv) return;
   const int row = __ldg(vrow_row + w);
   const int v0 = __ldg(vptr + row);
   const int nch = __ldg(vptr + row + 1) - v0;
-  if (w != v0 || nch <= 1) return;          // the first chunk's warp folds the row's partials
+  const int k = w - v0;
+  if (nch <= 1 || (k % (32 * stride)) != 0) return;
+  const bool covers_row = (long long)32 * stride >= nch;         // only true for k == 0
+  if (!covers_row && stride > 1 && k + stride >= nch) return;     // a lone slot: nothing to fold at this level
+  if (stride > 1 && (long long)stride >= nch) return;             // row already finished at a lower level
   const int nvec = d >> 2;
   const int s0 = __ldg(sptr + row);
   WarpRow<RV> acc, p[4];
   acc.zero();
-  int k = 0;
-  for (; k + 4 <= nch; k += 4) {   // 4 partial rows in flight; summed in chunk order (deterministic)
+  int j = 0;
+  for (; j + 4 <= 32; j += 4) {
+    if (k + (j + 3) * stride >= nch) break;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) p[u].load_plain(partial + (size_t)(s0 + k + u) * d, nvec, lane);
+    for (int u = 0; u < 4; ++u) p[u].load_plain(partial + (size_t)(s0 + k + (j + u) * stride) * d, nvec, lane);
 #pragma unroll
     for (int u = 0; u < 4; ++u)
 #pragma unroll
       for (int i = 0; i < RV; ++i) acc.v[i] = f4_add(acc.v[i], p[u].v[i]);
   }
-  for (; k < nch; ++k) {
-    p[0].load_plain(partial + (size_t)(s0 + k) * d, nvec, lane);
+  for (; j < 32 && k + j * stride < nch; ++j) {
+    p[0].load_plain(partial + (size_t)(s0 + k + j * stride) * d, nvec, lane);
 #pragma unroll
     for (int i = 0; i < RV; ++i) acc.v[i] = f4_add(acc.v[i], p[0].v[i]);
   }
-  acc.scale(__ldg(norm + row));
-  const size_t orow = active_pos ? (size_t)__ldg(active_pos + row) : (size_t)row;
-  if (out) acc.store(out + orow * ldo, nvec, lane);
-  if (out_hi) acc.store_split(out_hi + orow * ldo, out_lo + orow * ldo, nvec, lane);
+  if (covers_row) {
+    acc.scale(__ldg(norm + row));
+    const size_t orow = active_pos ? (size_t)__ldg(active_pos + row) : (size_t)row;
+    if (out) acc.store(out + orow * ldo, nvec, lane);
+    if (out_hi) acc.store_split(out_hi + orow * ldo, out_lo + orow * ldo, nvec, lane);
+  } else {
+    acc.store(partial + (size_t)(s0 + k) * d, nvec, lane);
+  }
 }
 
 // Dense-output mode: rows without in-edges receive exact zeros (DGL zero fill); one thread per float4.
@@ -202,7 +220,7 @@ int union_aggregate(const float* h, const float* rel, const int* rowptr, const i
                     const int* etype_sorted, const float* norm, const int* vptr, const int* sptr,
                     const int* vrow_row, int nv, int nsplit, const float* radius, float gamma, int N, int d,
                     float* out, float* partial, float* out_hi, float* out_lo, const int* active_pos, int ldo,
-                    cudaStream_t st) {
+                    int max_chunks, cudaStream_t st) {
   if (!h || !rel || !rowptr || !src_sorted || !etype_sorted || !norm || !vptr || !sptr || !vrow_row ||
       (!out && !out_hi) || (out_hi && !out_lo)) {
     set_last_error("union_aggregate: null pointer"); return REGCN_ERR_NULL;
@@ -227,8 +245,12 @@ int union_aggregate(const float* h, const float* rel, const int* rowptr, const i
     else union_aggregate_kernel<2, false><<<grid, TB, 0, st>>>(h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, nullptr, 0.f, d, out, partial, out_hi, out_lo, active_pos, ldo);
   }
   if (nsplit > 0) {
-    if (small) aggregate_fixup_kernel<1><<<grid, TB, 0, st>>>(vptr, sptr, vrow_row, norm, nv, d, partial, out, out_hi, out_lo, active_pos, ldo);
-    else aggregate_fixup_kernel<2><<<grid, TB, 0, st>>>(vptr, sptr, vrow_row, norm, nv, d, partial, out, out_hi, out_lo, active_pos, ldo);
+    // max_chunks = chunk count of the largest hub row (<= nsplit); one launch per radix-32 level
+    if (max_chunks <= 0 || max_chunks > nsplit) max_chunks = nsplit;
+    for (long long stride = 1; stride < (long long)max_chunks; stride *= 32) {
+      if (small) aggregate_fixup_kernel<1><<<grid, TB, 0, st>>>(vptr, sptr, vrow_row, norm, nv, d, partial, out, out_hi, out_lo, active_pos, ldo, (int)stride);
+      else aggregate_fixup_kernel<2><<<grid, TB, 0, st>>>(vptr, sptr, vrow_row, norm, nv, d, partial, out, out_hi, out_lo, active_pos, ldo, (int)stride);
+    }
   }
   prof_end(PROF_AGGREGATE, 0.0, st);   // bytes are filled in by the caller-side formula (needs E, R); see bench.py
   return check_launch("union_aggregate");

@@ -93,7 +93,7 @@ int regcn_union_aggregate(const float* h, const float* rel, const int32_t* rowpt
                           const int32_t* vrow_row, int n_vrows, int n_split_chunks, const float* radius, float gamma,
                           int N, int d, float* out, float* partial, void* stream) {
   return union_aggregate(h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, n_vrows, n_split_chunks,
-                         radius, gamma, N, d, out, partial, nullptr, nullptr, nullptr, 0, ST(stream));
+                         radius, gamma, N, d, out, partial, nullptr, nullptr, nullptr, 0, 0, ST(stream));
 }
 int regcn_block_aggregate(const float* h, const float* W, const int32_t* rowptr, const int32_t* src_sorted,
                           const int32_t* etype_sorted, const float* norm, int N, int d_in, int d_out, int nb, float* out,

@@ -128,7 +128,7 @@ int regcn_regcn_evolve(const void* const* mp, const int* mi, const void* const* 
         if ((e = union_aggregate(x_raw, h0_raw, GI(RG_ROWPTR), GI(RG_SRC_SORTED), GI(RG_ETYPE_SORTED), (const float*)g[RG_NORM],
                                  GI(RG_VPTR), GI(RG_SPTR), GI(RG_VROW_ROW), gn[RGI_N_VROWS], gn[RGI_N_SPLIT_CHUNKS], nullptr,
                                  0.f, N, d, nullptr, ws + w.partial, ws + w.agg_hi, ws + w.agg_lo, GI(RG_ACTIVE_POS), 2 * d,
-                                 st))) return e;
+                                 gn[RGI_MAX_CHUNKS], st))) return e;
         if (n_active > 0 &&
             (e = gemm_tf32(ws + w.agg_hi, ws + w.agg_lo, 2 * d, F(base + 4), F(base + 5), 2 * d, ws + w.P, d, n_active, d,
                            2 * d, nullptr, 0, 3, 1, nullptr, 0, nullptr, 0, st))) return e;
@@ -142,7 +142,8 @@ int regcn_regcn_evolve(const void* const* mp, const int* mi, const void* const* 
         float* Lbuf = (l == 0) ? ws + w.Lm : ws + w.L2;  // layer 0's result carries the gate columns and must survive
         if ((e = union_aggregate(x_raw, h0_raw, GI(RG_ROWPTR), GI(RG_SRC_SORTED), GI(RG_ETYPE_SORTED), (const float*)g[RG_NORM],
                                  GI(RG_VPTR), GI(RG_SPTR), GI(RG_VROW_ROW), gn[RGI_N_VROWS], gn[RGI_N_SPLIT_CHUNKS], nullptr,
-                                 0.f, N, d, nullptr, ws + w.partial, ws + w.agg_hi, ws + w.agg_lo, nullptr, d, st))) return e;
+                                 0.f, N, d, nullptr, ws + w.partial, ws + w.agg_hi, ws + w.agg_lo, nullptr, d,
+                                 gn[RGI_MAX_CHUNKS], st))) return e;
         if ((e = gemm_tf32(x_hi, x_lo, d, F(base + 2), F(base + 3), d, Lbuf, ncol, N, ncol, d, nullptr, 0, 3, 1, nullptr, 0,
                            nullptr, 0, st))) return e;
         if ((e = gemm_tf32(ws + w.agg_hi, ws + w.agg_lo, d, F(base + 0), F(base + 1), d, ws + w.P, d, N, d, d, nullptr, 0, 3,

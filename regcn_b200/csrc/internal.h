@@ -14,7 +14,7 @@ int rel_mean_pool(const float* h, const int* rel_rowptr, const int* rel_ents, in
 int union_aggregate(const float* h, const float* rel, const int* rowptr, const int* src_sorted, const int* etype_sorted,
                     const float* norm, const int* vptr, const int* sptr, const int* vrow_row, int nv, int nsplit,
                     const float* radius, float gamma, int N, int d, float* out, float* partial, float* out_hi,
-                    float* out_lo, const int* active_pos, int ldo, cudaStream_t st);
+                    float* out_lo, const int* active_pos, int ldo, int max_chunks, cudaStream_t st);
 int block_aggregate(const float* h, const float* W, const int* rowptr, const int* src_sorted, const int* etype_sorted,
                     const float* norm, int N, int d_in, int d_out, int nb, float* out, cudaStream_t st);
 int lorentz_aggregate(const float* ht, const float* W, const float* rel, const int* rowptr, const int* src_sorted,

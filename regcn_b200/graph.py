@@ -63,8 +63,9 @@ class SnapshotGraph:
     def _set_counts(self, c):
         self.n_vrows, self.n_split_chunks, self.n_rel_ents, self.max_hub_degree, self.n_active = c[:5]
         # pointer / int tables consumed by the whole-recurrence entry points (include/regcn_b200.h RG_* / RGI_*)
-        self.int_table = np.array([self.num_edges, self.n_vrows, self.n_split_chunks, self.n_rel_ents, self.n_active],
-                                  dtype=np.int32)
+        max_chunks = (self.max_hub_degree + AGG_CHUNK - 1) // AGG_CHUNK
+        self.int_table = np.array([self.num_edges, self.n_vrows, self.n_split_chunks, self.n_rel_ents, self.n_active,
+                                   max_chunks], dtype=np.int32)
 
     # ---- the slice of the DGL surface the reference modules use -----------------
     def number_of_nodes(self):
