@@ -371,15 +371,30 @@ int split_tf32(const float* x, float* hi, float* lo, size_t n, cudaStream_t st) 
 static int g_force_block_n = 0, g_force_stages = 0;
 void gemm_tf32_tune(int block_n, int stages) { g_force_block_n = block_n; g_force_stages = stages; }
 
-static int pick_block_n(int N) {
+// N-tile selection.  Large problems (>= one wave of 128-row tiles): the widest tile with the least padding, i.e.
+// the fewest operand re-reads.  Small problems (relation GRU, compact active-row GEMMs, pair scores): a tile costs
+// ~12 us of pure latency however little it computes, so narrow the tile until the grid covers the machine --
+// every CTA then walks the same K loop on a quarter of the operand bytes and of the MMA work.
+static int pick_block_n(int M, int N, int K, int split_k) {
   if (g_force_block_n > 0) return g_force_block_n;
   if (N <= 64) return (N + 15) / 16 * 16;
+  const int m_tiles = (M + tc::BLOCK_M - 1) / tc::BLOCK_M;
   int best = 256, best_waste = 1 << 30;
   const int cands[4] = {256, 208, 128, 64};
   for (int i = 0; i < 4; ++i) {
     const int bn = cands[i];
     const int waste = (N + bn - 1) / bn * bn - N;
     if (waste < best_waste) { best = bn; best_waste = waste; }
+  }
+  const int kb_per_cta = ((K + tc::BLOCK_K - 1) / tc::BLOCK_K + (split_k > 1 ? split_k : 1) - 1) / (split_k > 1 ? split_k : 1);
+  if (kb_per_cta > 16) return best;                 // long K loops amortise the per-tile latency: keep the wide tile
+  if (m_tiles * ((N + best - 1) / best) >= 148) return best;
+  const int small[3] = {128, 64, 32};
+  for (int i = 0; i < 3; ++i) {
+    const int bn = small[i];
+    if (bn >= best) continue;
+    best = bn;
+    if (m_tiles * ((N + bn - 1) / bn) >= 120) break;
   }
   return best;
 }
@@ -408,7 +423,7 @@ static int launch_tc(const float* a_hi, const float* a_lo, int lda, const float*
   }
   if (M == 0) return REGCN_OK;
   p.passes = passes;
-  p.block_n = force_block_n > 0 ? force_block_n : pick_block_n(N);
+  p.block_n = force_block_n > 0 ? force_block_n : pick_block_n(M, N, K, split_k);
   p.tmem_cols = 32;
   while (p.tmem_cols < p.block_n) p.tmem_cols <<= 1;
   const uint32_t stage_bytes = (passes == 3 ? 2u : 1u) * (BLOCK_M * BLOCK_K * 4 + (uint32_t)p.block_n * BLOCK_K * 4);
