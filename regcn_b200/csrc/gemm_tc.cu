@@ -271,16 +271,31 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
       float scale = 1.f, margin = 0.f;
       if (p.hyp) { scale = __ldg(p.scale_margin); margin = __ldg(p.scale_margin + 1); }
       int cnt = 0;
+      const bool plain = !p.hyp && !p.col_bias;          // hoisted: no per-element uniform branches in the hot loop
       for (int c0 = 0; c0 < p.block_n; c0 += 32) {
         float v[32];
         tmem_ld32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
         const int gn0 = n0 + c0;
         const int ncols = min(32, min(p.block_n - c0, p.N - gn0));
         if (rv && ncols > 0) {
+          if (!plain) {
+            if (p.hyp) {
+              const float x2r = __ldg(p.x2 + row);
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncols) v[j] = hyp_score_from_dot(v[j], x2r, __ldg(p.y2 + gn0 + j), p.hc, p.hproj_max, scale, margin);
+            }
+            if (p.col_bias) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (j < ncols) v[j] = __fadd_rn(v[j], __ldg(p.col_bias + gn0 + j));
+            }
+          }
+          // branch-free stable-rank contribution: (s > st) | (s == st & col < t), masked by validity and col != t
+          const int tj = t - gn0;                         // target position inside this chunk (any int)
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const int col = gn0 + j;
-            if (j < ncols && col != t) cnt += rank_beats(finish_score(p, v[j], row, col, scale, margin), col, st_, t);
+            const int beats = (int)(v[j] > st_) | ((int)(v[j] == st_) & (int)(j < tj));
+            cnt += beats & (int)(j < ncols) & (int)(j != tj);
           }
         }
       }
