@@ -126,6 +126,8 @@ REGCN_API int regcn_prof_read(int slot, double* total_ms, long long* launches, d
 
 /* tuning knob for experiments: force the N tile (multiple of 16, <= 256; 0 = automatic) and cap the pipeline depth */
 REGCN_API void regcn_gemm_tf32_tune(int block_n, int stages);
+/* edge kernel variant: 0 automatic, 1 register-staged gathers, 2 cp.async.bulk gathers staged in shared memory */
+REGCN_API void regcn_aggregate_tune(int impl);
 
 /* ---- row maps: F.normalize / tanh / log_0 / exp_0 / project (hyperbolic_ops.py:38-116) ---------
  * mode 0 normalize, 1 tanh, 2 0.9 tanh(log_0 x)+0.1 log_0 x, 3 log_0, 4 exp_0, 5 project,

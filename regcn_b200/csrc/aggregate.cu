@@ -11,6 +11,8 @@
 namespace regcn {
 
 constexpr int kAggChunk = 32;  // must match graph_build.cu
+static int g_agg_impl = 0;       // 0 auto, 1 register-staged, 2 bulk-copy (shared-memory staged)
+void aggregate_tune(int impl) { g_agg_impl = impl; }
 
 // ---------------------------------------------------------------------------
 // K4: agg[v] = norm[v] * sum_{(u,r)->v} w_uv * (h[u] + rel[r]),  w_uv = exp(-gamma*|rad[u]-rad[v]|) or 1.
@@ -153,6 +155,113 @@ __global__ void __launch_bounds__(256) union_aggregate_kernel(
   }
 }
 
+// ---------------------------------------------------------------------------
+// K4, bulk-copy variant for HBM-bound sizes.  Same math and outputs as union_aggregate_kernel, but the gathered
+// entity rows travel global -> shared memory with cp.async.bulk (one 4*d-byte bulk copy per edge, issued by the
+// lane that owns the edge, completion counted on a per-warp mbarrier), so the bytes in flight per SM are bounded
+// by shared memory (16 warps x 16 rows x 800 B = 205 KB) instead of by the register file.  Persistent: warps
+// stride over the virtual rows.
+// ---------------------------------------------------------------------------
+constexpr int kBulkWarps = 16;
+constexpr int kBulkRows = 16;
+
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int RV, bool RADIUS>
+__global__ void __launch_bounds__(kBulkWarps * 32, 1) union_aggregate_bulk_kernel(
+    const float* __restrict__ h, const float* __restrict__ rel, const int* __restrict__ rowptr,
+    const int* __restrict__ src_sorted, const int* __restrict__ etype_sorted, const float* __restrict__ norm,
+    const int* __restrict__ vptr, const int* __restrict__ sptr, const int* __restrict__ vrow_row, int nv,
+    const float* __restrict__ radius, float gamma, int d, float* __restrict__ out, float* __restrict__ partial,
+    float* __restrict__ out_hi, float* __restrict__ out_lo, const int* __restrict__ active_pos, int ldo) {
+  extern __shared__ __align__(128) unsigned char bulk_smem[];
+  __shared__ __align__(8) unsigned long long bars[kBulkWarps];
+  const int lane = threadIdx.x & 31;
+  const int wid = threadIdx.x >> 5;
+  const int nvec = d >> 2;
+  const uint32_t row_bytes = (uint32_t)d * 4u;
+  float* stage = reinterpret_cast<float*>(bulk_smem) + (size_t)wid * kBulkRows * d;
+  const uint32_t stage_u32 = smem_addr_u32(stage);
+  const uint32_t bar = smem_addr_u32(&bars[wid]);
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  uint32_t phase = 0;
+  const int total_warps = gridDim.x * kBulkWarps;
+  for (int w = blockIdx.x * kBulkWarps + wid; w < nv; w += total_warps) {
+    const int row = __ldg(vrow_row + w);
+    const int v0 = __ldg(vptr + row), v1 = __ldg(vptr + row + 1);
+    const int k = w - v0;
+    const int rbeg = __ldg(rowptr + row), rend = __ldg(rowptr + row + 1);
+    const int beg = rbeg + k * kAggChunk;
+    const int end = min(beg + kAggChunk, rend);
+    float r_dst = 0.f;
+    if (RADIUS) r_dst = __ldg(radius + row);
+    WarpRow<RV> acc;
+    acc.zero();
+    for (int base = beg; base < end; base += kBulkRows) {
+      const int cnt = min(kBulkRows, end - base);
+      int s = 0, t = 0;
+      float wgt = 1.f;
+      if (lane < cnt) {
+        s = __ldg(src_sorted + base + lane);
+        t = __ldg(etype_sorted + base + lane);
+        if (RADIUS) wgt = expf(-gamma * fabsf(__ldg(radius + s) - r_dst));
+      }
+      if (lane == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)cnt * row_bytes) : "memory");
+      }
+      __syncwarp();
+      if (lane < cnt) {
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+            ::"r"(stage_u32 + (uint32_t)lane * row_bytes), "l"(h + (size_t)s * d), "r"(row_bytes), "r"(bar) : "memory");
+      }
+      // relation rows come from a cache-resident table: fetch them while the bulk copies fly
+      uint32_t done = 0;
+      while (!done) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(done) : "r"(bar), "r"(phase) : "memory");
+      }
+      phase ^= 1;
+      for (int j = 0; j < cnt; ++j) {
+        const int tj = __shfl_sync(0xffffffffu, t, j);
+        const float wj = RADIUS ? __shfl_sync(0xffffffffu, wgt, j) : 1.f;
+#pragma unroll
+        for (int i = 0; i < RV; ++i) {
+          const int c = lane + i * kWarp;
+          if (c < nvec) {
+            const float4 hv = *reinterpret_cast<const float4*>(stage + (size_t)j * d + 4 * c);
+            const float4 m = f4_add(hv, ldg4(rel + (size_t)tj * d + 4 * c));
+            acc.v[i] = RADIUS ? f4_fma(wj, m, acc.v[i]) : f4_add(acc.v[i], m);
+          }
+        }
+      }
+      __syncwarp();
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staged rows are dead before the next bulk writes
+    }
+    const size_t orow = active_pos ? (size_t)__ldg(active_pos + row) : (size_t)row;
+    if (active_pos && k == 0 && out_hi && ldo >= 2 * d) {
+      WarpRow<RV> self;
+      self.load(h + (size_t)row * d, nvec, lane);
+      self.store_split(out_hi + orow * ldo + d, out_lo + orow * ldo + d, nvec, lane);
+    }
+    if (v1 - v0 == 1) {
+      acc.scale(__ldg(norm + row));
+      if (out) acc.store(out + orow * ldo, nvec, lane);
+      if (out_hi) acc.store_split(out_hi + orow * ldo, out_lo + orow * ldo, nvec, lane);
+    } else {
+      acc.store(partial + (size_t)(__ldg(sptr + row) + k) * d, nvec, lane);
+    }
+  }
+}
+
 // Rows that were split into several chunks: fold the chunk partials with a radix-32 tree, one level per launch.
 // Level with stride s: the warp of chunk k (k % (32 s) == 0) sums partial[k], partial[k+s], ..., partial[k+31 s]
 // (fixed order: deterministic) back into partial[k]; the level that covers the whole row applies the degree norm
@@ -237,7 +346,29 @@ int union_aggregate(const float* h, const float* rel, const int* rowptr, const i
   if (nv <= 0) { prof_end(PROF_AGGREGATE, 0.0, st); return check_launch("union_aggregate"); }
   const unsigned grid = (unsigned)(((size_t)nv * 32 + TB - 1) / TB);
   const bool small = d <= 128;
-  if (radius) {
+  const int impl = g_agg_impl;
+  const bool bulk = impl == 2 || (impl == 0 && nv >= 65536 && ((size_t)d * 4) % 16 == 0);
+  if (bulk) {
+    const size_t smem = (size_t)kBulkWarps * kBulkRows * d * sizeof(float);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned bgrid = (unsigned)sms;
+#define LAUNCH_BULK(RVV, RAD)                                                                                          \
+    do {                                                                                                               \
+      static bool attr_done = false;                                                                                   \
+      if (!attr_done) {                                                                                                \
+        cudaFuncSetAttribute(union_aggregate_bulk_kernel<RVV, RAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); \
+        attr_done = true;                                                                                              \
+      }                                                                                                                \
+      union_aggregate_bulk_kernel<RVV, RAD><<<bgrid, kBulkWarps * 32, smem, st>>>(                                     \
+          h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, radius, gamma, d, out, partial,   \
+          out_hi, out_lo, active_pos, ldo);                                                                            \
+    } while (0)
+    if (radius) { if (small) LAUNCH_BULK(1, true); else LAUNCH_BULK(2, true); }
+    else { if (small) LAUNCH_BULK(1, false); else LAUNCH_BULK(2, false); }
+#undef LAUNCH_BULK
+  } else if (radius) {
     if (small) union_aggregate_kernel<1, true><<<grid, TB, 0, st>>>(h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, radius, gamma, d, out, partial, out_hi, out_lo, active_pos, ldo);
     else union_aggregate_kernel<2, true><<<grid, TB, 0, st>>>(h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, radius, gamma, d, out, partial, out_hi, out_lo, active_pos, ldo);
   } else {

@@ -123,6 +123,7 @@ int regcn_gemm_tf32(const float* a_hi, const float* a_lo, int lda, const float* 
                    workspace_bytes, nullptr, 0, ST(stream));
 }
 void regcn_gemm_tf32_tune(int block_n, int stages) { gemm_tf32_tune(block_n, stages); }
+void regcn_aggregate_tune(int impl) { aggregate_tune(impl); }
 int regcn_score_count_tf32(const float* q_hi, const float* q_lo, const float* e_hi, const float* e_lo, int B, int N, int K,
                            const float* tscore, const int32_t* target, int32_t* raw_count, int col_offset, int hyp,
                            const float* x2, const float* y2, const float* col_bias, double c,

@@ -29,6 +29,7 @@ int gemm_tf32(const float* a_hi, const float* a_lo, int lda, const float* b_hi, 
               int ldc, int M, int N, int K, const float* bias, int accumulate, int passes, int split_k, float* ws,
               size_t ws_bytes, const float* addend, int ld_add, cudaStream_t st);
 void gemm_tf32_tune(int block_n, int stages);
+void aggregate_tune(int impl);
 int score_count_tf32(const float* q_hi, const float* q_lo, const float* e_hi, const float* e_lo, int B, int N, int K,
                      const float* tscore, const int* target, int* raw_count, int col_offset, int hyp, const float* x2,
                      const float* y2, const float* col_bias, double c, const float* scale_margin, int passes,

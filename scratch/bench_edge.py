@@ -20,10 +20,13 @@ for name,n,r,t,zipf in [("c4d GDELT-dense",7691,240,50000,True),("200k/2M zipf",
     d=200
     h=torch.randn(n,d,device='cuda'); rel=torch.randn(2*r,d,device='cuda')
     o=torch.empty(n,d,device='cuda')
-    ms=timeit(lambda: ops.union_aggregate(h,rel,g,out=o))
     E=2*t
     bytes_=808.0*E+808.0*n+800.0*2*r
-    res=dict(case=name,N=n,E=E,max_deg=g.max_hub_degree,n_vrows=g.n_vrows,n_split=g.n_split_chunks,ms=ms,GBs=bytes_/ms/1e6,frac=bytes_/ms/1e6/peak)
-    print(json.dumps(res)); out.append(res)
+    for impl in (1,2):
+        R._lib.load().regcn_aggregate_tune(impl)
+        ms=timeit(lambda: ops.union_aggregate(h,rel,g,out=o))
+        res=dict(case=name,impl={1:"registers",2:"cp.async.bulk"}[impl],N=n,E=E,max_deg=g.max_hub_degree,n_vrows=g.n_vrows,n_split=g.n_split_chunks,ms=ms,GBs=bytes_/ms/1e6,frac=bytes_/ms/1e6/peak)
+        print(json.dumps(res)); out.append(res)
+    R._lib.load().regcn_aggregate_tune(0)
     del g,h,o
 json.dump(out, open('gpurun_out/edge_stress.json','w'), indent=1)

@@ -83,10 +83,13 @@ def test_csr_build_empty_and_duplicates():
 
 
 # ----------------------------------------------------------------------------------------- K4 / K2
+@pytest.mark.parametrize("impl", [1, 2])
 @pytest.mark.parametrize("shape,d,radius", [("tiny", 200, False), ("small", 200, True), ("c1", 200, False),
                                             ("c4d", 200, True), ("small", 64, False), ("c4d", 128, False)])
-def test_union_aggregate_vs_oracle(shape, d, radius):
+def test_union_aggregate_vs_oracle(shape, d, radius, impl):
+    """impl 1 = register-staged gathers, impl 2 = cp.async.bulk gathers staged in shared memory."""
     R, ops = _ops()
+    R._lib.load().regcn_aggregate_tune(impl)
     case = synth.make_case(shape, 5)
     n, r = case["num_ents"], case["num_rels"]
     tri = case["history"][0]
@@ -109,6 +112,7 @@ def test_union_aggregate_vs_oracle(shape, d, radius):
     mag = np.zeros(n)
     np.add.at(mag, o["dst"], np.abs(msg).max(axis=1))
     scale = np.maximum(1.0, (mag * o["norm"])[:, None])
+    R._lib.load().regcn_aggregate_tune(0)
     assert np.all(np.abs(out - ref) <= 1e-4 * np.maximum(scale, np.abs(ref))), np.abs(out - ref).max()
     if g.n_split_chunks:
         assert g.max_hub_degree > 32
