@@ -347,7 +347,7 @@ int union_aggregate(const float* h, const float* rel, const int* rowptr, const i
   const unsigned grid = (unsigned)(((size_t)nv * 32 + TB - 1) / TB);
   const bool small = d <= 128;
   const int impl = g_agg_impl;
-  const bool bulk = impl == 2 || (impl == 0 && nv >= 65536 && ((size_t)d * 4) % 16 == 0);
+  const bool bulk = impl == 2;   // opt-in: measured within +-10% of the register-staged variant (profiles/README.md)
   if (bulk) {
     const size_t smem = (size_t)kBulkWarps * kBulkRows * d * sizeof(float);
     int dev = 0, sms = 148;

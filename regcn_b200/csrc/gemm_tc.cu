@@ -95,8 +95,9 @@ struct Params {
   int tmem_cols;      // power of two >= block_n
   int stages;
   int passes;         // 3 = 3xTF32 (fp32 parity), 1 = plain TF32
-  int kb_per_split;   // k-blocks per grid.z slice
-  float* ws;          // split-K partials [gridDim.z][M][N] (NULL when gridDim.z == 1)
+  int kb_per_split;   // k-blocks per split-K slice
+  int m_tiles, n_tiles, splits;   // persistent work list: splits x n_tiles x m_tiles items
+  float* ws;          // split-K partials [splits][M][N] (NULL when splits == 1)
   // ---- fused scoring epilogues (K11/K13 + K14) ----
   int epi;                    // 0 store C, 1 count candidates beating the target (no C), 2 diagonal (pair scores)
   const float* tscore;        // epi 1: [M] target score of each query row
@@ -119,6 +120,10 @@ __device__ __forceinline__ float finish_score(const Params& p, float dot, int ro
   return v;
 }
 
+// Persistent kernel: one CTA per SM walks the (split, n-tile, m-tile) work list.  Three pipelines:
+//   smem ring   full[s] / empty[s]          TMA producer  <-> MMA issuer   (continues across tiles)
+//   TMEM slots  tmem_full[a] / tmem_empty[a] MMA issuer   <-> epilogue     (2 accumulators of block_n columns)
+// so the epilogue of tile i (TMEM -> registers -> global / counting) overlaps the main loop of tile i+1.
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                  const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
@@ -126,17 +131,15 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[8];
   __shared__ __align__(8) uint64_t empty_bar[8];
-  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BLOCK_M;
-  const int n0 = p.epi == 2 ? m0 : blockIdx.x * p.block_n;   // pair scores: diagonal tiles only
   const int total_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
-  const int kb_beg = blockIdx.z * p.kb_per_split;
-  const int kb_end = min(total_kb, kb_beg + p.kb_per_split);
-  const int num_kb = kb_end - kb_beg;
+  const int tiles_mn = p.m_tiles * p.n_tiles;
+  const int total_tiles = tiles_mn * p.splits;
 
   // dynamic smem carve-up (1024-byte aligned tiles): per stage [A_hi][A_lo?][B_hi][B_lo?]
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -151,7 +154,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
       mbar_init(smem_u32(&full_bar[s]), 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
-    mbar_init(smem_u32(&tmem_full_bar), 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&tmem_full_bar[a]), 1);
+      mbar_init(smem_u32(&tmem_empty_bar[a]), 128);     // every epilogue thread arrives
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -162,160 +168,189 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_acc = tmem_base_slot;
+  const uint32_t tmem_base = tmem_base_slot;
+
+  // work item -> (split z, n tile, m tile); m fastest so that concurrently running CTAs share the B tile in L2
+  auto decode = [&](int t, int& m0, int& n0, int& kb_beg, int& kb_end) {
+    const int z = t / tiles_mn;
+    const int r = t - z * tiles_mn;
+    const int nt = r / p.m_tiles;
+    const int mt = r - nt * p.m_tiles;
+    m0 = mt * BLOCK_M;
+    n0 = p.epi == 2 ? m0 : nt * p.block_n;   // pair scores: diagonal tiles only
+    kb_beg = z * p.kb_per_split;
+    kb_end = min(total_kb, kb_beg + p.kb_per_split);
+  };
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0 && num_kb > 0) {
+    if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = kb_beg; kb < kb_end; ++kb) {
-        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-        const uint32_t fb = smem_u32(&full_bar[stage]);
-        mbar_expect_tx(fb, stage_bytes);
-        uint32_t dst = smem_base + stage * stage_bytes;
-        const int k0 = kb * BLOCK_K;
-        tma_load_2d(dst, &tm_a_hi, fb, k0, m0); dst += a_bytes;
-        if (three) { tma_load_2d(dst, &tm_a_lo, fb, k0, m0); dst += a_bytes; }
-        tma_load_2d(dst, &tm_b_hi, fb, k0, n0); dst += b_bytes;
-        if (three) { tma_load_2d(dst, &tm_b_lo, fb, k0, n0); }
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int m0, n0, kb_beg, kb_end;
+        decode(t, m0, n0, kb_beg, kb_end);
+        for (int kb = kb_beg; kb < kb_end; ++kb) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          mbar_expect_tx(fb, stage_bytes);
+          uint32_t dst = smem_base + stage * stage_bytes;
+          const int k0 = kb * BLOCK_K;
+          tma_load_2d(dst, &tm_a_hi, fb, k0, m0); dst += a_bytes;
+          if (three) { tma_load_2d(dst, &tm_a_lo, fb, k0, m0); dst += a_bytes; }
+          tma_load_2d(dst, &tm_b_hi, fb, k0, n0); dst += b_bytes;
+          if (three) { tma_load_2d(dst, &tm_b_lo, fb, k0, n0); }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && num_kb > 0) {
+    if (lane == 0) {
       // instruction descriptor: D=f32, A=B=tf32, K-major both, N>>3, M>>4
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.block_n >> 3) << 17) |
                              ((uint32_t)(BLOCK_M >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
-      uint32_t acc = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(smem_u32(&full_bar[stage]), phase);
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        int m0, n0, kb_beg, kb_end;
+        decode(t, m0, n0, kb_beg, kb_end);
+        const int slot = it & 1;
+        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(smem_u32(&tmem_empty_bar[slot]), acc_phase ^ 1);   // epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa_hi = smem_base + stage * stage_bytes;
-        const uint32_t sa_lo = sa_hi + a_bytes;
-        const uint32_t sb_hi = sa_hi + (three ? 2u : 1u) * a_bytes;
-        const uint32_t sb_lo = sb_hi + b_bytes;
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(slot * (p.tmem_cols >> 1));
+        uint32_t acc = 0;
+        for (int kb = kb_beg; kb < kb_end; ++kb) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa_hi = smem_base + stage * stage_bytes;
+          const uint32_t sa_lo = sa_hi + a_bytes;
+          const uint32_t sb_hi = sa_hi + (three ? 2u : 1u) * a_bytes;
+          const uint32_t sb_lo = sb_hi + b_bytes;
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-          const uint32_t koff = k * UMMA_K * 4;   // bytes inside the 128-byte swizzle row
-          if (three) {
-            umma_tf32(tmem_acc, make_desc(sa_lo + koff), make_desc(sb_hi + koff), idesc, acc);
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint32_t koff = k * UMMA_K * 4;   // bytes inside the 128-byte swizzle row
+            if (three) {
+              umma_tf32(tmem_acc, make_desc(sa_lo + koff), make_desc(sb_hi + koff), idesc, acc);
+              acc = 1;
+              umma_tf32(tmem_acc, make_desc(sa_hi + koff), make_desc(sb_lo + koff), idesc, acc);
+            }
+            umma_tf32(tmem_acc, make_desc(sa_hi + koff), make_desc(sb_hi + koff), idesc, acc);
             acc = 1;
-            umma_tf32(tmem_acc, make_desc(sa_hi + koff), make_desc(sb_lo + koff), idesc, acc);
           }
-          umma_tf32(tmem_acc, make_desc(sa_hi + koff), make_desc(sb_hi + koff), idesc, acc);
-          acc = 1;
+          umma_commit(smem_u32(&empty_bar[stage]));      // frees the smem slot once these MMAs retire
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(smem_u32(&empty_bar[stage]));      // frees the smem slot once these MMAs retire
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        umma_commit(smem_u32(&tmem_full_bar[slot]));     // accumulator of this tile complete
       }
-      umma_commit(smem_u32(&tmem_full_bar));           // accumulator complete
     }
   } else {
-    // ===================== epilogue: TMEM -> registers -> global =====================
+    // ===================== epilogue: TMEM -> registers -> global / counts =====================
     const int quarter = warp & 3;                      // TMEM lanes [32*quarter, 32*quarter+32)
-    const int row = m0 + quarter * 32 + lane;
-    if (num_kb > 0) {
-      mbar_wait(smem_u32(&tmem_full_bar), 0);
+    float scale = 1.f, margin = 0.f;
+    if (p.epi != 0 && p.hyp) { scale = __ldg(p.scale_margin); margin = __ldg(p.scale_margin + 1); }
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      int m0, n0, kb_beg, kb_end;
+      decode(t, m0, n0, kb_beg, kb_end);
+      const int slot = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      const int row = m0 + quarter * 32 + lane;
+      mbar_wait(smem_u32(&tmem_full_bar[slot]), acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    }
-    if (p.epi == 0) {
-      const bool split = gridDim.z > 1;
-      float* out = split ? p.ws + (size_t)blockIdx.z * (size_t)p.M * (size_t)p.N : p.C;
-      const int ldo = split ? p.N : p.ldc;
-      const bool vec_ok = ((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(slot * (p.tmem_cols >> 1)) + ((uint32_t)(quarter * 32) << 16);
+      if (p.epi == 0) {
+        const bool split = p.splits > 1;
+        const int z = t / tiles_mn;
+        float* out = split ? p.ws + (size_t)z * (size_t)p.M * (size_t)p.N : p.C;
+        const int ldo = split ? p.N : p.ldc;
+        const bool vec_ok = ((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+        for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+          float v[32];
+          tmem_ld32(tmem_acc + (uint32_t)c0, v);
+          const int gn0 = n0 + c0;
+          const int ncols = min(32, min(p.block_n - c0, p.N - gn0));   // columns of this chunk owned by this tile
+          if (row < p.M && ncols > 0) {
+            float* dst = out + (size_t)row * ldo + gn0;
+            if (!split) {
+              if (p.bias) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += __ldg(p.bias + gn0 + j);
+              }
+              if (p.accumulate) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += dst[j];
+              }
+              if (p.addend) {
+                const float* ad = p.addend + (size_t)row * p.ld_add + gn0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += __ldg(ad + j);
+              }
+            }
+            if (vec_ok && ncols == 32 && (gn0 & 3) == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) st4(dst + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (j < ncols) dst[j] = v[j];
+            }
+          }
+        }
+      } else if (p.epi == 1) {
+        // fused K14: count the candidates of this tile that rank ahead of the row's target; nothing is stored
+        const bool rv = row < p.M;
+        const float st_ = rv ? __ldg(p.tscore + row) : 0.f;
+        const int tg = rv ? __ldg(p.target + row) - p.col_offset : -1;
+        int cnt = 0;
+        const bool plain = !p.hyp && !p.col_bias;          // hoisted: no per-element uniform branches in the hot loop
+        for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+          float v[32];
+          tmem_ld32(tmem_acc + (uint32_t)c0, v);
+          const int gn0 = n0 + c0;
+          const int ncols = min(32, min(p.block_n - c0, p.N - gn0));
+          if (rv && ncols > 0) {
+            if (!plain) {
+              if (p.hyp) {
+                const float x2r = __ldg(p.x2 + row);
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < ncols) v[j] = hyp_score_from_dot(v[j], x2r, __ldg(p.y2 + gn0 + j), p.hc, p.hproj_max, scale, margin);
+              }
+              if (p.col_bias) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (j < ncols) v[j] = __fadd_rn(v[j], __ldg(p.col_bias + gn0 + j));
+              }
+            }
+            // branch-free stable-rank contribution: (s > st) | (s == st & col < t), masked by validity and col != t
+            const int tj = tg - gn0;                        // target position inside this chunk (any int)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int beats = (int)(v[j] > st_) | ((int)(v[j] == st_) & (int)(j < tj));
+              cnt += beats & (int)(j < ncols) & (int)(j != tj);
+            }
+          }
+        }
+        if (rv && cnt) atomicAdd(p.raw_count + row, cnt);
+      } else {
+        // pair scores: the tile is a diagonal block of A' . B'^T (pair p = row), keep acc[r][r]
         float v[32];
-        if (num_kb > 0) {
-          tmem_ld32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
-        } else {
+        tmem_ld32(tmem_acc + (uint32_t)(quarter * 32), v);
+        float dsel = 0.f;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0.f;
-        }
-        const int gn0 = n0 + c0;
-        const int ncols = min(32, min(p.block_n - c0, p.N - gn0));   // columns of this chunk owned by this tile
-        if (row < p.M && ncols > 0) {
-          float* dst = out + (size_t)row * ldo + gn0;
-          if (!split) {
-            if (p.bias) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += __ldg(p.bias + gn0 + j);
-            }
-            if (p.accumulate) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += dst[j];
-            }
-            if (p.addend) {
-              const float* ad = p.addend + (size_t)row * p.ld_add + gn0;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += __ldg(ad + j);
-            }
-          }
-          if (vec_ok && ncols == 32 && (gn0 & 3) == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) st4(dst + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (j < ncols) dst[j] = v[j];
-          }
-        }
+        for (int j = 0; j < 32; ++j) if (j == lane) dsel = v[j];
+        if (row < p.M) p.diag_out[row] = finish_score(p, dsel, row, row, scale, margin);
       }
-    } else if (p.epi == 1) {
-      // fused K14: count the candidates of this tile that rank ahead of the row's target; nothing is stored
-      const bool rv = row < p.M;
-      const float st_ = rv ? __ldg(p.tscore + row) : 0.f;
-      const int t = rv ? __ldg(p.target + row) - p.col_offset : -1;
-      float scale = 1.f, margin = 0.f;
-      if (p.hyp) { scale = __ldg(p.scale_margin); margin = __ldg(p.scale_margin + 1); }
-      int cnt = 0;
-      const bool plain = !p.hyp && !p.col_bias;          // hoisted: no per-element uniform branches in the hot loop
-      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
-        float v[32];
-        tmem_ld32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
-        const int gn0 = n0 + c0;
-        const int ncols = min(32, min(p.block_n - c0, p.N - gn0));
-        if (rv && ncols > 0) {
-          if (!plain) {
-            if (p.hyp) {
-              const float x2r = __ldg(p.x2 + row);
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < ncols) v[j] = hyp_score_from_dot(v[j], x2r, __ldg(p.y2 + gn0 + j), p.hc, p.hproj_max, scale, margin);
-            }
-            if (p.col_bias) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (j < ncols) v[j] = __fadd_rn(v[j], __ldg(p.col_bias + gn0 + j));
-            }
-          }
-          // branch-free stable-rank contribution: (s > st) | (s == st & col < t), masked by validity and col != t
-          const int tj = t - gn0;                         // target position inside this chunk (any int)
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int beats = (int)(v[j] > st_) | ((int)(v[j] == st_) & (int)(j < tj));
-            cnt += beats & (int)(j < ncols) & (int)(j != tj);
-          }
-        }
-      }
-      if (rv && cnt) atomicAdd(p.raw_count + row, cnt);
-    } else {
-      // pair scores: the tile is a diagonal block of A' . B'^T (pair p = row), keep acc[r][r]
-      float scale = 1.f, margin = 0.f;
-      if (p.hyp) { scale = __ldg(p.scale_margin); margin = __ldg(p.scale_margin + 1); }
-      float v[32];
-      tmem_ld32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(quarter * 32), v);
-      float dsel = 0.f;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) if (j == lane) dsel = v[j];
-      if (row < p.M) p.diag_out[row] = finish_score(p, dsel, row, row, scale, margin);
+      // this thread's TMEM reads of the slot are complete (tcgen05.wait::ld inside tmem_ld32): hand it back to the MMA warp
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[slot])) : "memory");
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
   }
 }
 
@@ -440,7 +475,7 @@ static int launch_tc(const float* a_hi, const float* a_lo, int lda, const float*
   p.passes = passes;
   p.block_n = force_block_n > 0 ? force_block_n : pick_block_n(M, N, K, split_k);
   p.tmem_cols = 32;
-  while (p.tmem_cols < p.block_n) p.tmem_cols <<= 1;
+  while (p.tmem_cols < 2 * p.block_n) p.tmem_cols <<= 1;     // two accumulator slots
   const uint32_t stage_bytes = (passes == 3 ? 2u : 1u) * (BLOCK_M * BLOCK_K * 4 + (uint32_t)p.block_n * BLOCK_K * 4);
   const int total_kb = (K + BLOCK_K - 1) / BLOCK_K;
   if (split_k < 1) split_k = 1;
@@ -450,7 +485,6 @@ static int launch_tc(const float* a_hi, const float* a_lo, int lda, const float*
   p.stages = (int)(SMEM_BUDGET / stage_bytes);
   if (p.stages > 8) p.stages = 8;
   if (g_force_stages > 0 && g_force_stages < p.stages) p.stages = g_force_stages;
-  if (p.stages > p.kb_per_split) p.stages = p.kb_per_split;
   if (p.stages < 1) { set_last_error("%s: tile does not fit in shared memory", who); return REGCN_ERR_UNSUPPORTED; }
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   int e;
@@ -469,7 +503,18 @@ static int launch_tc(const float* a_hi, const float* a_lo, int lda, const float*
     if (ce != cudaSuccess) { set_last_error("%s: cudaFuncSetAttribute failed: %s", who, cudaGetErrorString(ce)); return (int)ce; }
     attr_set = true;
   }
-  dim3 grid(p.epi == 2 ? 1 : (N + p.block_n - 1) / p.block_n, (M + BLOCK_M - 1) / BLOCK_M, split_k);
+  p.m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+  p.n_tiles = p.epi == 2 ? 1 : (N + p.block_n - 1) / p.block_n;
+  p.splits = split_k;
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  const long long total_tiles = (long long)p.m_tiles * p.n_tiles * p.splits;
+  dim3 grid((unsigned)(total_tiles < sms ? total_tiles : sms));
   prof_begin(PROF_GEMM_TC, st);
   gemm_tf32_kernel<<<grid, NUM_THREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
   prof_end(PROF_GEMM_TC, p.epi == 2 ? 2.0 * M * (double)K : 2.0 * M * (double)N * K, st);
