@@ -117,7 +117,7 @@ REGCN_API int regcn_gather_scalars(const float* a, const float* b, const float* 
                          int P, float* oa, float* ob, float* oc, void* stream);
 REGCN_API int regcn_filter_correct(int B, const int32_t* filt_ptr, const int32_t* filt_idx, const int32_t* target,
                          const float* pair_score, const int32_t* raw_count, int col_lo, int col_hi,
-                         int32_t* filt_count, void* stream);
+                         int32_t* filt_count, const int32_t* filt_end, void* stream);
 
 /* opt-in kernel timing with CUDA events on the launching stream: slot 0 = tcgen05 GEMM (work = 2MNK flops),
  * slot 1 = union aggregate.  enable(1) clears the records; read() synchronises the device and sums them.       */
@@ -157,11 +157,12 @@ REGCN_API int regcn_hyp_time_gate(const float* h2, const float* pt, const float*
                         int layer_norm, int residual, double c, float radius_min, float radius_max, float beta,
                         float eps_r, float* out, void* stream);
 
-/* ---- K10 ConvTransE/ConvTransR tower: src/decoder.py:29-52,78-95; hyperbolic_decoder.py:376-406 - */
+/* ---- K10 ConvTransE/ConvTransR tower: src/decoder.py:29-52,78-95; hyperbolic_decoder.py:376-406 ---
+ * F (B, C*d) raw features and/or their TF32 split (F_hi, F_lo) for the FC GEMM; either may be NULL.          */
 REGCN_API int regcn_convtranse_features(const float* ent, const float* second, const int64_t* triples, int col0, int col1,
                               int B, int d, int C, int ksz, const float* bn0_scale, const float* bn0_shift,
                               const float* conv_w, const float* conv_b, const float* bn1_scale,
-                              const float* bn1_shift, float* F, void* stream);
+                              const float* bn1_shift, float* F, float* F_hi, float* F_lo, void* stream);
 REGCN_API int regcn_affine_relu(float* x, const float* scale, const float* shift, int M, int d, int relu, void* stream);
 
 /* ---- K12 RotH / MuRP / RotHRel query builder: hyperbolic_decoder.py:744-765,1064-1086,1243-1251 - */
@@ -183,11 +184,19 @@ REGCN_API int regcn_gather_target_score(const float* S, int64_t ld, int B, int N
                               int col_offset, float* target_score, void* stream);
 REGCN_API int regcn_rank_count(const float* S, int64_t ld, int B, int N, const int64_t* triples, int target_col,
                      const int32_t* filt_ptr, const int32_t* filt_idx, int col_offset, const float* target_score,
-                     int32_t* raw_count, int32_t* filt_count, void* stream);
+                     int32_t* raw_count, int32_t* filt_count, const int32_t* filt_end, void* stream);
 REGCN_API int regcn_counts_to_ranks(const int32_t* raw_count, const int32_t* filt_count, int B, int64_t* rank,
                           int64_t* filt_rank, void* stream);
 REGCN_API int regcn_apply_filter(float* S, int64_t ld, int B, int N, const int64_t* triples, int target_col,
-                       const int32_t* filt_ptr, const int32_t* filt_idx, int col_offset, void* stream);
+                       const int32_t* filt_ptr, const int32_t* filt_idx, int col_offset, const int32_t* filt_end,
+                       void* stream);
+/* filter lists of query b are filt_idx[filt_ptr[b] .. filt_end[b]) (filt_end == NULL: .. filt_ptr[b+1]).
+ * regcn_filter_count / regcn_filter_fill build them from the query triples themselves (time-aware filtering,
+ * rgcn/utils.py:264-304): key = (col 0, key_col), answers = ans_col; counts -> exclusive scan (caller) -> fill,
+ * which also emits the (query, candidate) pair lists of the fused rank path (B target pairs first).           */
+REGCN_API int regcn_filter_count(const int64_t* triples, int B, int key_col, int32_t* counts, void* stream);
+REGCN_API int regcn_filter_fill(const int64_t* triples, int B, int key_col, int ans_col, const int32_t* beg, int32_t* idx,
+                      int32_t* end, int32_t* pair_a, int32_t* pair_e, void* stream);
 
 /* ---- whole-recurrence orchestration: RecurrentRGCN.forward, src/rrgcn.py:142-180 (uvrgcn, self_loop, no skip) ---
  * One call enqueues every kernel of the L-snapshot recurrence on `stream`.  Inputs are pointer / int tables:

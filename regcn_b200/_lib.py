@@ -43,7 +43,7 @@ SIGNATURES = {
     "regcn_pair_scores_tf32": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _d, _p, _p, _i, _p]),
     "regcn_gather_rows2": (_i, [_p, _p, _p, _i, _i, _p, _p, _p]),
     "regcn_gather_scalars": (_i, [_p, _p, _p, _p, _p, _i, _p, _p, _p, _p]),
-    "regcn_filter_correct": (_i, [_i, _p, _p, _p, _p, _p, _i, _i, _p, _p]),
+    "regcn_filter_correct": (_i, [_i, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p]),
     "regcn_prof_enable": (None, [_i]),
     "regcn_prof_read": (_i, [_i, _p, _p, _p]),
     "regcn_row_map": (_i, [_p, _p, _i, _i, _i, _d, _p, _p]),
@@ -53,15 +53,17 @@ SIGNATURES = {
     "regcn_hyp_init": (_i, [_p, _p, _i, _i, _i, _i, _d, _f, _f, _p, _p]),
     "regcn_hyp_tangent": (_i, [_p, _i, _i, _d, _p, _p, _p, _p]),
     "regcn_hyp_time_gate": (_i, [_p] * 6 + [_f, _i, _i, _i, _i, _d, _f, _f, _f, _f, _p, _p]),
-    "regcn_convtranse_features": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i] + [_p] * 7 + [_p]),
+    "regcn_convtranse_features": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i] + [_p] * 9 + [_p]),
     "regcn_affine_relu": (_i, [_p, _p, _p, _i, _i, _i, _p]),
     "regcn_gather_log0": (_i, [_p, _p, _i, _i, _i, _i, _d, _p, _p]),
     "regcn_hyp_query": (_i, [_p] * 5 + [_i, _i, _i, _d, _p, _p, _p]),
     "regcn_hyp_score_epilogue": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _d, _p, _p]),
     "regcn_gather_target_score": (_i, [_p, _i64, _i, _i, _p, _i, _i, _p, _p]),
-    "regcn_rank_count": (_i, [_p, _i64, _i, _i, _p, _i, _p, _p, _i, _p, _p, _p, _p]),
+    "regcn_rank_count": (_i, [_p, _i64, _i, _i, _p, _i, _p, _p, _i, _p, _p, _p, _p, _p]),
     "regcn_counts_to_ranks": (_i, [_p, _p, _i, _p, _p, _p]),
-    "regcn_apply_filter": (_i, [_p, _i64, _i, _i, _p, _i, _p, _p, _i, _p]),
+    "regcn_apply_filter": (_i, [_p, _i64, _i, _i, _p, _i, _p, _p, _i, _p, _p]),
+    "regcn_filter_count": (_i, [_p, _i, _i, _p, _p]),
+    "regcn_filter_fill": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
 }
 
 _lib = None

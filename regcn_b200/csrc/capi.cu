@@ -146,8 +146,16 @@ int regcn_gather_scalars(const float* a, const float* b, const float* c, const i
 }
 int regcn_filter_correct(int B, const int32_t* filt_ptr, const int32_t* filt_idx, const int32_t* target,
                          const float* pair_score, const int32_t* raw_count, int col_lo, int col_hi,
-                         int32_t* filt_count, void* stream) {
-  return filter_correct(B, filt_ptr, filt_idx, target, pair_score, raw_count, col_lo, col_hi, filt_count, ST(stream));
+                         int32_t* filt_count, const int32_t* filt_end, void* stream) {
+  return filter_correct(B, filt_ptr, filt_idx, target, pair_score, raw_count, col_lo, col_hi, filt_count, filt_end,
+                        ST(stream));
+}
+int regcn_filter_count(const int64_t* triples, int B, int key_col, int32_t* counts, void* stream) {
+  return filter_count(triples, B, key_col, counts, ST(stream));
+}
+int regcn_filter_fill(const int64_t* triples, int B, int key_col, int ans_col, const int32_t* beg, int32_t* idx,
+                      int32_t* end, int32_t* pair_a, int32_t* pair_e, void* stream) {
+  return filter_fill(triples, B, key_col, ans_col, beg, idx, end, pair_a, pair_e, ST(stream));
 }
 int regcn_row_map(const float* x, float* out, int M, int d, int mode, double c, float* sumsq, void* stream) {
   return row_map(x, out, M, d, mode, c, sumsq, nullptr, nullptr, ST(stream));
@@ -182,9 +190,9 @@ int regcn_hyp_time_gate(const float* h2, const float* pt, const float* G, const 
 int regcn_convtranse_features(const float* ent, const float* second, const int64_t* triples, int col0, int col1, int B,
                               int d, int C, int ksz, const float* bn0_scale, const float* bn0_shift,
                               const float* conv_w, const float* conv_b, const float* bn1_scale, const float* bn1_shift,
-                              float* F, void* stream) {
+                              float* F, float* F_hi, float* F_lo, void* stream) {
   return convtranse_features(ent, second, triples, col0, col1, B, d, C, ksz, bn0_scale, bn0_shift, conv_w, conv_b,
-                             bn1_scale, bn1_shift, F, ST(stream));
+                             bn1_scale, bn1_shift, F, F_hi, F_lo, ST(stream));
 }
 int regcn_affine_relu(float* x, const float* scale, const float* shift, int M, int d, int relu, void* stream) {
   return affine_relu(x, scale, shift, M, d, relu, ST(stream));
@@ -207,17 +215,18 @@ int regcn_gather_target_score(const float* S, int64_t ld, int B, int N, const in
 }
 int regcn_rank_count(const float* S, int64_t ld, int B, int N, const int64_t* triples, int target_col,
                      const int32_t* filt_ptr, const int32_t* filt_idx, int col_offset, const float* target_score,
-                     int32_t* raw_count, int32_t* filt_count, void* stream) {
+                     int32_t* raw_count, int32_t* filt_count, const int32_t* filt_end, void* stream) {
   return rank_count(S, ld, B, N, triples, target_col, filt_ptr, filt_idx, col_offset, target_score, raw_count,
-                    filt_count, ST(stream));
+                    filt_count, filt_end, ST(stream));
 }
 int regcn_counts_to_ranks(const int32_t* raw_count, const int32_t* filt_count, int B, int64_t* rank, int64_t* filt_rank,
                           void* stream) {
   return counts_to_ranks(raw_count, filt_count, B, rank, filt_rank, ST(stream));
 }
 int regcn_apply_filter(float* S, int64_t ld, int B, int N, const int64_t* triples, int target_col,
-                       const int32_t* filt_ptr, const int32_t* filt_idx, int col_offset, void* stream) {
-  return apply_filter(S, ld, B, N, triples, target_col, filt_ptr, filt_idx, col_offset, ST(stream));
+                       const int32_t* filt_ptr, const int32_t* filt_idx, int col_offset, const int32_t* filt_end,
+                       void* stream) {
+  return apply_filter(S, ld, B, N, triples, target_col, filt_ptr, filt_idx, col_offset, filt_end, ST(stream));
 }
 
 }  // extern "C"

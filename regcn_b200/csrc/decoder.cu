@@ -16,7 +16,7 @@ __global__ void __launch_bounds__(256) convtranse_features_kernel(
     const float* __restrict__ bn0_scale, const float* __restrict__ bn0_shift,   // (2)
     const float* __restrict__ conv_w, const float* __restrict__ conv_b,         // (C,2,ksz), (C)
     const float* __restrict__ bn1_scale, const float* __restrict__ bn1_shift,   // (C)
-    float* __restrict__ F) {
+    float* __restrict__ F, float* __restrict__ F_hi, float* __restrict__ F_lo) {
   extern __shared__ float sm[];
   const int pad = ksz / 2;
   const int ld = d + 2 * pad;
@@ -41,30 +41,40 @@ __global__ void __launch_bounds__(256) convtranse_features_kernel(
     wsm[nw + 2 * C + i] = bn1_shift[i];
   }
   __syncthreads();
-  float* Fb = F + (size_t)b * C * d;
-  for (int o = threadIdx.x; o < C * d; o += blockDim.x) {
-    const int c = o / d, i = o - c * d;
-    const float* w = wsm + c * 2 * ksz;
-    float acc = wsm[nw + c];
-    for (int k = 0; k < ksz; ++k) acc = fmaf(w[k], y0[i + k], acc);
-    for (int k = 0; k < ksz; ++k) acc = fmaf(w[ksz + k], y1[i + k], acc);
-    acc = fmaf(acc, wsm[nw + C + c], wsm[nw + 2 * C + c]);
-    Fb[o] = fmaxf(acc, 0.f);
+  // thread <-> position i (fixed), loop over channels: the padded inputs stay in registers, the per-channel
+  // weights are shared-memory broadcasts, stores are coalesced along i; no integer division in the loop
+  const size_t fb = (size_t)b * C * d;
+  for (int i = threadIdx.x; i < d; i += blockDim.x) {
+    float a0[7], a1[7];
+    for (int k = 0; k < ksz && k < 7; ++k) { a0[k] = y0[i + k]; a1[k] = y1[i + k]; }
+    for (int c = 0; c < C; ++c) {
+      const float* w = wsm + c * 2 * ksz;
+      float acc = wsm[nw + c];
+      for (int k = 0; k < ksz; ++k) acc = fmaf(w[k], a0[k], acc);
+      for (int k = 0; k < ksz; ++k) acc = fmaf(w[ksz + k], a1[k], acc);
+      acc = fmaf(acc, wsm[nw + C + c], wsm[nw + 2 * C + c]);
+      acc = fmaxf(acc, 0.f);
+      const size_t o = fb + (size_t)c * d + i;
+      if (F) F[o] = acc;
+      if (F_hi) { float h, l; split_tf32_1(acc, h, l); F_hi[o] = h; F_lo[o] = l; }
+    }
   }
 }
 
 int convtranse_features(const float* ent, const float* second, const int64_t* triples, int col0, int col1, int B,
                         int d, int C, int ksz, const float* bn0_scale, const float* bn0_shift, const float* conv_w,
-                        const float* conv_b, const float* bn1_scale, const float* bn1_shift, float* F, cudaStream_t st) {
-  if (!ent || !second || !triples || !bn0_scale || !bn0_shift || !conv_w || !conv_b || !bn1_scale || !bn1_shift || !F) {
+                        const float* conv_b, const float* bn1_scale, const float* bn1_shift, float* F, float* F_hi,
+                        float* F_lo, cudaStream_t st) {
+  if (!ent || !second || !triples || !bn0_scale || !bn0_shift || !conv_w || !conv_b || !bn1_scale || !bn1_shift ||
+      (!F && !F_hi) || (F_hi && !F_lo)) {
     set_last_error("convtranse_features: null pointer"); return REGCN_ERR_NULL;
   }
   if (B <= 0) return REGCN_OK;
-  if (d <= 0 || C <= 0 || ksz <= 0 || !(ksz & 1)) { set_last_error("convtranse_features: bad dims d=%d C=%d k=%d", d, C, ksz); return REGCN_ERR_DIM; }
+  if (d <= 0 || C <= 0 || ksz <= 0 || !(ksz & 1) || ksz > 7) { set_last_error("convtranse_features: bad dims d=%d C=%d k=%d", d, C, ksz); return REGCN_ERR_DIM; }
   const size_t smem = ((size_t)2 * (d + 2 * (ksz / 2)) + (size_t)C * 2 * ksz + 3 * (size_t)C) * sizeof(float);
   if (smem > 48 * 1024) { set_last_error("convtranse_features: shared memory %zu too large", smem); return REGCN_ERR_UNSUPPORTED; }
   convtranse_features_kernel<<<B, 256, smem, st>>>(ent, second, triples, col0, col1, B, d, C, ksz, bn0_scale, bn0_shift,
-                                                   conv_w, conv_b, bn1_scale, bn1_shift, F);
+                                                   conv_w, conv_b, bn1_scale, bn1_shift, F, F_hi, F_lo);
   return check_launch("convtranse_features");
 }
 

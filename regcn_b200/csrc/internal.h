@@ -42,7 +42,7 @@ int gather_rows2(const float* src_hi, const float* src_lo, const int* idx, int P
 int gather_scalars(const float* a, const float* b, const float* c, const int* ia, const int* ib, int P, float* oa,
                    float* ob, float* oc, cudaStream_t st);
 int filter_correct(int B, const int* filt_ptr, const int* filt_idx, const int* target, const float* pair_score,
-                   const int* raw_count, int col_lo, int col_hi, int* filt_count, cudaStream_t st);
+                   const int* raw_count, int col_lo, int col_hi, int* filt_count, const int* filt_end, cudaStream_t st);
 int row_map(const float* x, float* out, int M, int d, int mode, double c, float* sumsq, float* out_hi, float* out_lo,
             cudaStream_t st);
 int gru_gate(const float* gi, const float* gh, const float* hprev, float* out, int M, int d, int normalize,
@@ -61,7 +61,8 @@ int hyp_time_gate(const float* h2, const float* pt, const float* G, const float*
                   float rmax, float beta, float eps_r, float* out, cudaStream_t st);
 int convtranse_features(const float* ent, const float* second, const int64_t* triples, int col0, int col1, int B,
                         int d, int C, int ksz, const float* bn0_scale, const float* bn0_shift, const float* conv_w,
-                        const float* conv_b, const float* bn1_scale, const float* bn1_shift, float* F, cudaStream_t st);
+                        const float* conv_b, const float* bn1_scale, const float* bn1_shift, float* F, float* F_hi,
+                        float* F_lo, cudaStream_t st);
 int affine_relu(float* x, const float* scale, const float* shift, int M, int d, int relu, cudaStream_t st);
 int gather_log0(const float* E, const int64_t* triples, int col, int B, int d, int project, double c, float* out,
                 cudaStream_t st);
@@ -73,8 +74,11 @@ int gather_target_score(const float* S, int64_t ld, int B, int N, const int64_t*
                         int col_offset, float* target_score, cudaStream_t st);
 int rank_count(const float* S, int64_t ld, int B, int N, const int64_t* triples, int target_col, const int* filt_ptr,
                const int* filt_idx, int col_offset, const float* target_score, int* raw_count, int* filt_count,
-               cudaStream_t st);
+               const int* filt_end, cudaStream_t st);
+int filter_count(const int64_t* triples, int B, int key_col, int* counts, cudaStream_t st);
+int filter_fill(const int64_t* triples, int B, int key_col, int ans_col, const int* beg, int* idx, int* end, int* pair_a,
+                int* pair_e, cudaStream_t st);
 int counts_to_ranks(const int* raw_count, const int* filt_count, int B, int64_t* rank, int64_t* filt_rank, cudaStream_t st);
 int apply_filter(float* S, int64_t ld, int B, int N, const int64_t* triples, int target_col, const int* filt_ptr,
-                 const int* filt_idx, int col_offset, cudaStream_t st);
+                 const int* filt_idx, int col_offset, const int* filt_end, cudaStream_t st);
 }  // namespace regcn

@@ -18,7 +18,8 @@ __device__ __forceinline__ int rank_contrib(float s, int j, float st, int t) { r
 __global__ void __launch_bounds__(256) rank_rows_kernel(
     const float* __restrict__ S, size_t ld, int B, int N, const int64_t* __restrict__ triples, int target_col,
     const int* __restrict__ filt_ptr, const int* __restrict__ filt_idx, int col_offset,
-    int* __restrict__ raw_count, int* __restrict__ filt_count, float* __restrict__ target_score) {
+    int* __restrict__ raw_count, int* __restrict__ filt_count, float* __restrict__ target_score,
+    const int* __restrict__ filt_end) {
   __shared__ int red[8];
   const int b = blockIdx.x;
   const float* row = S + (size_t)b * ld;
@@ -31,7 +32,7 @@ __global__ void __launch_bounds__(256) rank_rows_kernel(
   // filter correction: entries of filt(b) inside this shard, excluding the target itself
   int corr = 0;
   if (filt_ptr) {
-    const int fb = filt_ptr[b], fe = filt_ptr[b + 1];
+    const int fb = filt_ptr[b], fe = filt_end ? filt_end[b] : filt_ptr[b + 1];
     for (int i = fb + threadIdx.x; i < fe; i += blockDim.x) {
       const int j = filt_idx[i] - col_offset;
       if (j < 0 || j >= N || j == t) continue;
@@ -77,10 +78,11 @@ __global__ void counts_to_ranks_kernel(const int* __restrict__ raw_count, const 
 // Optionally reproduce the reference's in-place side effect: score[b][ans \ {t}] = -1e7 (utils.py:60).
 __global__ void apply_filter_kernel(float* __restrict__ S, size_t ld, int B, int N, const int64_t* __restrict__ triples,
                                     int target_col, const int* __restrict__ filt_ptr, const int* __restrict__ filt_idx,
-                                    int col_offset) {
+                                    int col_offset, const int* __restrict__ filt_end) {
   const int b = blockIdx.x;
   const int t = (int)triples[3 * (size_t)b + target_col] - col_offset;
-  for (int i = filt_ptr[b] + threadIdx.x; i < filt_ptr[b + 1]; i += blockDim.x) {
+  const int fe = filt_end ? filt_end[b] : filt_ptr[b + 1];
+  for (int i = filt_ptr[b] + threadIdx.x; i < fe; i += blockDim.x) {
     const int j = filt_idx[i] - col_offset;
     if (j >= 0 && j < N && j != t) S[(size_t)b * ld + j] = kFilterScore;
   }
@@ -93,13 +95,14 @@ __global__ void apply_filter_kernel(float* __restrict__ S, size_t ld, int B, int
 __global__ void filter_correct_kernel(int B, const int* __restrict__ filt_ptr, const int* __restrict__ filt_idx,
                                       const int* __restrict__ target, const float* __restrict__ pair_score,
                                       const int* __restrict__ raw_count, int col_lo, int col_hi,
-                                      int* __restrict__ filt_count) {
+                                      int* __restrict__ filt_count, const int* __restrict__ filt_end) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const float st = pair_score[b];
   const int t = target[b];
   int corr = 0;
-  for (int i = filt_ptr[b]; i < filt_ptr[b + 1]; ++i) {
+  const int fe = filt_end ? filt_end[b] : filt_ptr[b + 1];
+  for (int i = filt_ptr[b]; i < fe; ++i) {
     const int f = filt_idx[i];
     if (f == t || f < col_lo || f >= col_hi) continue;
     corr += rank_contrib(kFilterScore, f, st, t) - rank_contrib(pair_score[B + i], f, st, t);
@@ -108,11 +111,69 @@ __global__ void filter_correct_kernel(int B, const int* __restrict__ filt_ptr, c
 }
 
 int filter_correct(int B, const int* filt_ptr, const int* filt_idx, const int* target, const float* pair_score,
-                   const int* raw_count, int col_lo, int col_hi, int* filt_count, cudaStream_t st) {
+                   const int* raw_count, int col_lo, int col_hi, int* filt_count, const int* filt_end, cudaStream_t st) {
   if (!filt_ptr || !filt_idx || !target || !pair_score || !raw_count || !filt_count) { set_last_error("filter_correct: null pointer"); return REGCN_ERR_NULL; }
   if (B <= 0) return REGCN_OK;
-  filter_correct_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, filt_ptr, filt_idx, target, pair_score, raw_count, col_lo, col_hi, filt_count);
+  filter_correct_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, filt_ptr, filt_idx, target, pair_score, raw_count, col_lo, col_hi, filt_count, filt_end);
   return check_launch("filter_correct");
+}
+
+// ---- time-aware filter lists straight from the query triples (rgcn/utils.py:264-304 on the test snapshot itself) ----
+// Query b = (h, r, t) [all_triples incl. inverses].  Entity prediction: answers of key (h, r) = every t' among the
+// queries with the same (h, r); relation prediction: key (h, t), answers r'.  B is a few thousand, so an all-pairs
+// scan (B^2 comparisons from L1) beats a sort: pass 1 counts the matches, pass 2 (after an exclusive scan) collects
+// them, sorts + uniques each short list in place and emits the (query, candidate) pair lists of the fused rank path.
+__global__ void filter_count_kernel(const int64_t* __restrict__ triples, int B, int key_col, int* __restrict__ counts) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int64_t h = triples[3 * (size_t)b], k2 = triples[3 * (size_t)b + key_col];
+  int c = 0;
+  for (int j = 0; j < B; ++j) c += (triples[3 * (size_t)j] == h && triples[3 * (size_t)j + key_col] == k2) ? 1 : 0;
+  counts[b] = c;
+}
+
+__global__ void filter_fill_kernel(const int64_t* __restrict__ triples, int B, int key_col, int ans_col,
+                                   const int* __restrict__ beg, int* __restrict__ idx, int* __restrict__ end,
+                                   int* __restrict__ pair_a, int* __restrict__ pair_e) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int64_t h = triples[3 * (size_t)b], k2 = triples[3 * (size_t)b + key_col];
+  int* lst = idx + beg[b];
+  int n = 0;
+  for (int j = 0; j < B; ++j) {
+    if (triples[3 * (size_t)j] == h && triples[3 * (size_t)j + key_col] == k2) {
+      const int a = (int)triples[3 * (size_t)j + ans_col];
+      int p = n++;                                   // insertion sort: lists are short
+      while (p > 0 && lst[p - 1] > a) { lst[p] = lst[p - 1]; --p; }
+      lst[p] = a;
+    }
+  }
+  int u = 0;
+  for (int i = 0; i < n; ++i) if (i == 0 || lst[i] != lst[i - 1]) lst[u++] = lst[i];
+  for (int i = u; i < n; ++i) lst[i] = lst[0];       // unused tail slots stay valid candidate ids
+  end[b] = beg[b] + u;
+  if (pair_a) {
+    pair_a[b] = b;
+    pair_e[b] = (int)triples[3 * (size_t)b + ans_col];
+    for (int i = 0; i < n; ++i) { pair_a[B + beg[b] + i] = b; pair_e[B + beg[b] + i] = lst[i]; }
+  }
+}
+
+int filter_count(const int64_t* triples, int B, int key_col, int* counts, cudaStream_t st) {
+  if (!triples || !counts) { set_last_error("filter_count: null pointer"); return REGCN_ERR_NULL; }
+  if (key_col < 1 || key_col > 2) { set_last_error("filter_count: key_col must be 1 or 2"); return REGCN_ERR_DIM; }
+  if (B <= 0) return REGCN_OK;
+  filter_count_kernel<<<(B + 127) / 128, 128, 0, st>>>(triples, B, key_col, counts);
+  return check_launch("filter_count");
+}
+
+int filter_fill(const int64_t* triples, int B, int key_col, int ans_col, const int* beg, int* idx, int* end, int* pair_a,
+                int* pair_e, cudaStream_t st) {
+  if (!triples || !beg || !idx || !end || (pair_a && !pair_e)) { set_last_error("filter_fill: null pointer"); return REGCN_ERR_NULL; }
+  if (key_col < 1 || key_col > 2 || ans_col < 1 || ans_col > 2 || key_col == ans_col) { set_last_error("filter_fill: bad columns"); return REGCN_ERR_DIM; }
+  if (B <= 0) return REGCN_OK;
+  filter_fill_kernel<<<(B + 127) / 128, 128, 0, st>>>(triples, B, key_col, ans_col, beg, idx, end, pair_a, pair_e);
+  return check_launch("filter_fill");
 }
 
 int gather_target_score(const float* S, int64_t ld, int B, int N, const int64_t* triples, int target_col, int col_offset,
@@ -125,12 +186,12 @@ int gather_target_score(const float* S, int64_t ld, int B, int N, const int64_t*
 
 int rank_count(const float* S, int64_t ld, int B, int N, const int64_t* triples, int target_col, const int* filt_ptr,
                const int* filt_idx, int col_offset, const float* target_score, int* raw_count, int* filt_count,
-               cudaStream_t st) {
+               const int* filt_end, cudaStream_t st) {
   if (!S || !triples || !target_score || !raw_count || (filt_ptr && !filt_idx)) { set_last_error("rank_count: null pointer"); return REGCN_ERR_NULL; }
   if (target_col < 0 || target_col > 2 || ld < N) { set_last_error("rank_count: bad target_col=%d or ld", target_col); return REGCN_ERR_DIM; }
   if (B <= 0) return REGCN_OK;
   rank_rows_kernel<<<B, 256, 0, st>>>(S, (size_t)ld, B, N, triples, target_col, filt_ptr, filt_idx, col_offset, raw_count,
-                                      filt_count, const_cast<float*>(target_score));
+                                      filt_count, const_cast<float*>(target_score), filt_end);
   return check_launch("rank_count");
 }
 
@@ -142,10 +203,10 @@ int counts_to_ranks(const int* raw_count, const int* filt_count, int B, int64_t*
 }
 
 int apply_filter(float* S, int64_t ld, int B, int N, const int64_t* triples, int target_col, const int* filt_ptr,
-                 const int* filt_idx, int col_offset, cudaStream_t st) {
+                 const int* filt_idx, int col_offset, const int* filt_end, cudaStream_t st) {
   if (!S || !triples || !filt_ptr || !filt_idx) { set_last_error("apply_filter: null pointer"); return REGCN_ERR_NULL; }
   if (B <= 0) return REGCN_OK;
-  apply_filter_kernel<<<B, 128, 0, st>>>(S, (size_t)ld, B, N, triples, target_col, filt_ptr, filt_idx, col_offset);
+  apply_filter_kernel<<<B, 128, 0, st>>>(S, (size_t)ld, B, N, triples, target_col, filt_ptr, filt_idx, col_offset, filt_end);
   return check_launch("apply_filter");
 }
 

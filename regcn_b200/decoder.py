@@ -14,12 +14,19 @@ from . import ops
 
 
 def _fold_bn(bn):
-    """Eval-mode BatchNorm1d as y = x*scale + shift."""
-    inv = torch.rsqrt(bn.running_var + bn.eps)
-    w = bn.weight if bn.weight is not None else torch.ones_like(inv)
-    b = bn.bias if bn.bias is not None else torch.zeros_like(inv)
-    scale = (w * inv).contiguous()
-    shift = (b - bn.running_mean * w * inv).contiguous()
+    """Eval-mode BatchNorm1d as y = x*scale + shift; cached on the module until one of its tensors changes."""
+    ts = [t for t in (bn.running_var, bn.running_mean, bn.weight, bn.bias) if t is not None]
+    stamp = tuple((t._version, t.data_ptr()) for t in ts)
+    hit = bn.__dict__.get("_regcn_fold")
+    if hit is not None and hit[0] == stamp:
+        return hit[1]
+    with torch.no_grad():
+        inv = torch.rsqrt(bn.running_var + bn.eps)
+        w = bn.weight if bn.weight is not None else torch.ones_like(inv)
+        b = bn.bias if bn.bias is not None else torch.zeros_like(inv)
+        scale = (w * inv).contiguous()
+        shift = (b - bn.running_mean * w * inv).contiguous()
+    bn.__dict__["_regcn_fold"] = (stamp, (scale, shift))
     return scale, shift
 
 
@@ -48,8 +55,9 @@ class _ConvTransBase(nn.Module):
         """K10: bn0 -> conv1d(2->C,k) -> bn1 -> relu -> fc -> bn2 -> relu, returns the (B,d) query matrix."""
         B = len(triplets)
         feats = ops.convtranse_features(ent_act, second, triplets, col0, col1, _fold_bn(self.bn0),
-                                        self.conv1.weight.detach(), self.conv1.bias.detach(), _fold_bn(self.bn1))
-        K = feats.shape[1]
+                                        self.conv1.weight.detach(), self.conv1.bias.detach(), _fold_bn(self.bn1),
+                                        split=ops.gemm_impl() == "tc")
+        K = (feats[0] if isinstance(feats, tuple) else feats).shape[1]
         split_k = max(1, min(16, (148 * 2) // max(1, ((B + 127) // 128) * ((self.fc.out_features + 127) // 128))))
         split_k = min(split_k, max(1, K // 512))
         x = ops.gemm(feats, self.fc.weight.detach(), trans_b=True, bias=self.fc.bias.detach(), split_k=split_k,

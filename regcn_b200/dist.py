@@ -78,7 +78,8 @@ def sharded_score_rank(n_cand, triples, target_col, filter_csr, score_fn, group=
         dist.all_reduce(tscore, op=dist.ReduceOp.SUM, group=group)
     fp = filter_csr.ptr if filter_csr is not None else None
     fi = filter_csr.idx if filter_csr is not None else None
-    raw, filt, _ = ops.rank_dense(block, triples, target_col, fp, fi, col_offset=lo, target_score=tscore)
+    fe = filter_csr.end if filter_csr is not None else None
+    raw, filt, _ = ops.rank_dense(block, triples, target_col, fp, fi, col_offset=lo, target_score=tscore, filt_end=fe)
     if filt is None:
         filt = raw
     return merge_counts(raw, filt, group)

@@ -57,7 +57,7 @@ def evaluate_snapshot(model, glist, all_triples, filter_csr, timers=None, fused=
         mark("score", 1)
         mark("rank", 0)
         raw, filt, _ = ops.fused_rank_counts(q, cand, target, filter_csr.ptr, filter_csr.idx, pa, pe, hyp=hyp,
-                                             col_bias=col_bias, shard=shard)
+                                             col_bias=col_bias, shard=shard, filt_end=filter_csr.end)
         if shard is not None:
             mark("rank", 1)
             return raw, filt
@@ -68,7 +68,8 @@ def evaluate_snapshot(model, glist, all_triples, filter_csr, timers=None, fused=
     mark("score", 1)
     mark("rank", 0)
     raw, filt, _ = ops.rank_dense(score, all_triples, 2, filter_csr.ptr if filter_csr is not None else None,
-                                  filter_csr.idx if filter_csr is not None else None)
+                                  filter_csr.idx if filter_csr is not None else None,
+                                  filt_end=filter_csr.end if filter_csr is not None else None)
     rank, frank = ops.counts_to_ranks(raw, filt)
     mark("rank", 1)
     return rank, frank
@@ -87,7 +88,7 @@ def score_rank_sharded(model, emb, r_emb, all_triples, filter_csr, group=None):
     target = all_triples[:, 2].to(torch.int32).contiguous()
     pa, pe = filter_csr.pairs(target)
     raw, filt, _ = ops.fused_rank_counts(q, cand, target, filter_csr.ptr, filter_csr.idx, pa, pe, hyp=hyp,
-                                         col_bias=col_bias, shard=(lo, hi))
+                                         col_bias=col_bias, shard=(lo, hi), filt_end=filter_csr.end)
     return rdist.merge_counts(raw, filt, group)
 
 
@@ -117,13 +118,14 @@ def evaluate_from_host(model, history_host, test_host, num_nodes, num_rels, devi
         q, cand, hyp, col_bias = _scoring_operands(model, emb, r_emb, all_t)
         target = all_t[:, 2].to(torch.int32).contiguous()
         pa, pe = f_ent.pairs(target)
-        raw, filt, _ = ops.fused_rank_counts(q, cand, target, f_ent.ptr, f_ent.idx, pa, pe, hyp=hyp, col_bias=col_bias)
+        raw, filt, _ = ops.fused_rank_counts(q, cand, target, f_ent.ptr, f_ent.idx, pa, pe, hyp=hyp, col_bias=col_bias,
+                                             filt_end=f_ent.end)
         rank, frank = ops.counts_to_ranks(raw, filt)
     else:
         score = model.decoder_ob.forward(emb, r_emb, all_t, mode="test")
         _, _, rank, frank = utils.get_total_rank(all_t, score, None, 1000, rel_predict=0, filter_csr=f_ent)
     score_rel = model.rdecoder.forward(emb, r_emb, all_t, mode="test")
-    raw_r, filt_r, _ = ops.rank_dense(score_rel, all_t, 1, f_rel.ptr, f_rel.idx)
+    raw_r, filt_r, _ = ops.rank_dense(score_rel, all_t, 1, f_rel.ptr, f_rel.idx, filt_end=f_rel.end)
     rank_r, frank_r = ops.counts_to_ranks(raw_r, filt_r)
     mrrs = torch.stack([torch.mean(1.0 / frank.float()), torch.mean(1.0 / rank.float()),
                         torch.mean(1.0 / frank_r.float()), torch.mean(1.0 / rank_r.float())])

@@ -42,7 +42,8 @@ class _HypConvBase(nn.Module):
             raise NotImplementedError("regcn_b200 decoders: training mode needs the backward kernels; call .eval()")
         B = len(triplets)
         feats = ops.convtranse_features(ent_act, second, triplets, col0, col1, _fold_bn(self.bn0),
-                                        self.conv1.weight.detach(), self.conv1.bias.detach(), _fold_bn(self.bn1))
+                                        self.conv1.weight.detach(), self.conv1.bias.detach(), _fold_bn(self.bn1),
+                                        split=ops.gemm_impl() == "tc")
         split_k = max(1, min(16, (148 * 2) // max(1, ((B + 127) // 128) * ((self.fc.out_features + 127) // 128))))
         x = ops.gemm(feats, self.fc.weight.detach(), trans_b=True, bias=self.fc.bias.detach(), split_k=split_k,
                      b_key=(self.fc.weight, "w"))

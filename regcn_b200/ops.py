@@ -91,7 +91,9 @@ def gemm(a, b, trans_b=False, bias=None, out=None, accumulate=False, split_k=1, 
     b_key=(owner_tensor, name): B is a static weight; its prepared form (K-major transpose, TF32 split) is cached on
     `owner_tensor` under `name`."""
     impl = _GEMM_IMPL["impl"]
-    if impl != "simt" and a.shape[1] % 4 == 0:
+    if isinstance(a, tuple) and impl == "simt":
+        raise ValueError("gemm: a pre-split A operand needs the tensor-core implementation")
+    if impl != "simt" and (isinstance(a, tuple) or a.shape[1] % 4 == 0):
         return _gemm_tc(a, b, trans_b, bias, out, accumulate, split_k, b_key, 3 if impl == "tc" else 1)
     a = _rowmajor(a, "a")
     b = _rowmajor(b, "b")
@@ -117,6 +119,9 @@ def gemm(a, b, trans_b=False, bias=None, out=None, accumulate=False, split_k=1, 
 
 
 def _gemm_tc(a, b, trans_b, bias, out, accumulate, split_k, b_key, passes):
+    a_pre = a if isinstance(a, tuple) else None      # (hi, lo) produced directly by the upstream kernel
+    if a_pre is not None:
+        a = a_pre[0]
     if not (a.is_cuda and b.is_cuda):
         raise RuntimeError("regcn_b200: kernels take CUDA tensors only (no CPU fallback)")
     if a.dtype != F32 or b.dtype != F32:
@@ -137,7 +142,7 @@ def _gemm_tc(a, b, trans_b, bias, out, accumulate, split_k, b_key, passes):
                             prep_b)
     else:
         b_hi, b_lo = prep_b()
-    a_hi, a_lo = _tc_operand(a.detach(), need_lo)
+    a_hi, a_lo = a_pre if a_pre is not None else _tc_operand(a.detach(), need_lo)
     if out is None:
         if accumulate:
             raise ValueError("gemm: accumulate needs out")
@@ -279,14 +284,22 @@ def hyp_time_gate(h2, pt, G, bias, radius_static, radius_w, radius_b, layer_norm
 
 
 # --------------------------------------------------------------------------- decoders
-def convtranse_features(ent, second, triples, col0, col1, bn0, conv_w, conv_b, bn1):
-    """bn0 / bn1 = (scale, shift) folded eval-mode BatchNorm."""
+def convtranse_features(ent, second, triples, col0, col1, bn0, conv_w, conv_b, bn1, split=False):
+    """bn0 / bn1 = (scale, shift) folded eval-mode BatchNorm.  split=True returns the TF32 (hi, lo) pair the FC GEMM
+    consumes instead of the raw feature matrix (no separate conversion pass)."""
     B = triples.shape[0]
     d = ent.shape[1]
     C, _, ksz = conv_w.shape
-    out = torch.empty((B, C * d), device=ent.device, dtype=F32)
+    dev = ent.device
+    if split:
+        hi = torch.empty((B, C * d), device=dev, dtype=F32)
+        lo = torch.empty((B, C * d), device=dev, dtype=F32)
+        call("regcn_convtranse_features", ptr(ent), ptr(second), ptr(triples), col0, col1, B, d, C, ksz, ptr(bn0[0]),
+             ptr(bn0[1]), ptr(conv_w.contiguous()), ptr(conv_b), ptr(bn1[0]), ptr(bn1[1]), None, ptr(hi), ptr(lo))
+        return hi, lo
+    out = torch.empty((B, C * d), device=dev, dtype=F32)
     call("regcn_convtranse_features", ptr(ent), ptr(second), ptr(triples), col0, col1, B, d, C, ksz, ptr(bn0[0]),
-         ptr(bn0[1]), ptr(conv_w.contiguous()), ptr(conv_b), ptr(bn1[0]), ptr(bn1[1]), ptr(out))
+         ptr(bn0[1]), ptr(conv_w.contiguous()), ptr(conv_b), ptr(bn1[0]), ptr(bn1[1]), ptr(out), None, None)
     return out
 
 
@@ -324,7 +337,8 @@ def hyp_score_epilogue_(S, q_sumsq, e_sumsq, bias, qbias, c, scale_margin):
 
 
 # --------------------------------------------------------------------------- ranking
-def rank_dense(score, triples, target_col, filt_ptr=None, filt_idx=None, col_offset=0, target_score=None):
+def rank_dense(score, triples, target_col, filt_ptr=None, filt_idx=None, col_offset=0, target_score=None,
+               filt_end=None):
     """Counts for a (B, N_shard) dense score block.  Returns (raw_count, filt_count, target_score) int32/int32/f32."""
     B, N = score.shape
     dev = score.device
@@ -337,7 +351,7 @@ def rank_dense(score, triples, target_col, filt_ptr=None, filt_idx=None, col_off
     raw = torch.empty(B, device=dev, dtype=I32)
     filt = torch.empty(B, device=dev, dtype=I32) if filt_ptr is not None else None
     call("regcn_rank_count", score.data_ptr(), score.stride(0), B, N, ptr(triples), target_col, ptr(filt_ptr),
-         ptr(filt_idx), col_offset, ptr(target_score), ptr(raw), ptr(filt))
+         ptr(filt_idx), col_offset, ptr(target_score), ptr(raw), ptr(filt), ptr(filt_end))
     return raw, filt, target_score
 
 
@@ -349,16 +363,16 @@ def counts_to_ranks(raw, filt):
     return rank, frank
 
 
-def apply_filter_(score, triples, target_col, filt_ptr, filt_idx, col_offset=0):
+def apply_filter_(score, triples, target_col, filt_ptr, filt_idx, col_offset=0, filt_end=None):
     B, N = score.shape
     call("regcn_apply_filter", score.data_ptr(), score.stride(0), B, N, ptr(triples), target_col, ptr(filt_ptr),
-         ptr(filt_idx), col_offset)
+         ptr(filt_idx), col_offset, ptr(filt_end))
     return score
 
 
 # --------------------------------------------------------------------------- fused scoring + rank (no score matrix)
 def fused_rank_counts(q, cand, target, filt_ptr, filt_idx, pair_a, pair_e, hyp=None, col_bias=None, shard=None,
-                      cand_split=None):
+                      cand_split=None, filt_end=None):
     """Raw / filtered 'beats the target' counts of every query against the candidate rows [lo,hi) of `cand`, computed by
     the scoring GEMM's counting epilogue (K11/K13 fused with K14); the (B,N) score matrix is never written.
 
@@ -400,5 +414,6 @@ def fused_rank_counts(q, cand, target, filt_ptr, filt_idx, pair_a, pair_e, hyp=N
              int(hyp is not None), ptr(x2), y2[lo:hi].data_ptr() if y2 is not None else None,
              col_bias[lo:hi].data_ptr() if col_bias is not None else None, float(c), ptr(sm), passes)
     filt = torch.empty(B, device=dev, dtype=I32)
-    call("regcn_filter_correct", B, ptr(filt_ptr), ptr(filt_idx), ptr(target), ptr(ps), ptr(raw), lo, hi, ptr(filt))
+    call("regcn_filter_correct", B, ptr(filt_ptr), ptr(filt_idx), ptr(target), ptr(ps), ptr(raw), lo, hi, ptr(filt),
+         ptr(filt_end))
     return raw, filt, ps[:B]

@@ -55,15 +55,16 @@ def load_all_answers_for_time_filter(total_data, num_rels, num_nodes, rel_p=Fals
 
 # ------------------------------------------------------------------------------ filter CSR
 class FilterCSR:
-    """Per-query sorted ids of the true answers (the reference's all_ans[h][r] / all_ans[h][t] sets) on the device."""
+    """Per-query sorted ids of the true answers (the reference's all_ans[h][r] / all_ans[h][t] sets) on the device:
+    the list of query b is idx[ptr[b] : end[b]] (end=None means the compact CSR form idx[ptr[b] : ptr[b+1]])."""
 
-    def __init__(self, ptr_t, idx_t):
-        self.ptr, self.idx = ptr_t, idx_t
-        self._pairs = None
+    def __init__(self, ptr_t, idx_t, end_t=None, pairs=None):
+        self.ptr, self.idx, self.end = ptr_t, idx_t, end_t
+        self._pairs = pairs
 
     def pairs(self, target):
         """(pair_a, pair_e) int32 lists for the fused rank path: the B (query, target) pairs followed by one
-        (query, candidate) pair per CSR entry."""
+        (query, candidate) pair per idx slot."""
         if self._pairs is None:
             B = self.ptr.numel() - 1
             counts = (self.ptr[1:] - self.ptr[:-1]).long()
@@ -73,6 +74,33 @@ class FilterCSR:
             pe = torch.cat((target.to(torch.int32), self.idx[:n])).contiguous()
             self._pairs = (pa.contiguous(), pe)
         return self._pairs
+
+    def lists(self):
+        """Host copy as python lists (tests / debugging)."""
+        p, i = self.ptr.cpu().tolist(), self.idx.cpu().tolist()
+        e = self.end.cpu().tolist() if self.end is not None else p[1:]
+        return [i[p[b]:e[b]] for b in range(len(e))]
+
+
+def filter_lists_from_queries(all_triples, rel_predict=0):
+    """Kernel-built time-aware filter lists for the queries themselves (the test snapshot incl. inverses): two
+    launches + one scan + one host read of the slot total; also yields the fused-rank pair lists.  All-pairs scan,
+    meant for the few thousand queries of a timestamp."""
+    from ._lib import call, ptr
+    B = all_triples.shape[0]
+    dev = all_triples.device
+    key_col, ans_col = (2, 1) if rel_predict else (1, 2)
+    counts = torch.empty(B, device=dev, dtype=torch.int32)
+    call("regcn_filter_count", ptr(all_triples), B, key_col, ptr(counts))
+    csum = torch.cumsum(counts, 0, dtype=torch.int32)
+    beg = (csum - counts).contiguous()
+    total = int(csum[-1].item()) if B else 0
+    idx = torch.empty(max(total, 1), device=dev, dtype=torch.int32)
+    end = torch.empty(B, device=dev, dtype=torch.int32)
+    pa = torch.empty(B + total, device=dev, dtype=torch.int32)
+    pe = torch.empty(B + total, device=dev, dtype=torch.int32)
+    call("regcn_filter_fill", ptr(all_triples), B, key_col, ans_col, ptr(beg), ptr(idx), ptr(end), ptr(pa), ptr(pe))
+    return FilterCSR(beg, idx, end, pairs=(pa, pe))
 
 
 def filter_csr_from_dict(test_triples, all_ans, rel_predict=0, device=None):
@@ -89,11 +117,15 @@ def filter_csr_from_dict(test_triples, all_ans, rel_predict=0, device=None):
                      torch.tensor(idx_l if idx_l else [0], dtype=torch.int32, device=dev))
 
 
-def filter_csr_from_snapshot(all_triples, num_keys2, rel_predict=0, num_answers=None):
+def filter_csr_from_snapshot(all_triples, num_keys2, rel_predict=0, num_answers=None, use_kernels=None):
     """Vectorised, device-side equivalent of load_all_answers_for_filter + per-query lookup when the filter set is
     'every answer among these queries themselves' (time-aware filtering, rgcn/utils.py:286-304: the test snapshot's own
     triples incl. inverses = exactly `all_triples` of predict()).  key = (h, r) -> answers t (entity prediction) or
     (h, t) -> answers r (relation prediction)."""
+    if use_kernels is None:
+        use_kernels = all_triples.is_cuda and 0 < all_triples.shape[0] <= 32768
+    if use_kernels:
+        return filter_lists_from_queries(all_triples.contiguous(), rel_predict)
     h = all_triples[:, 0]
     k2 = all_triples[:, 2] if rel_predict else all_triples[:, 1]
     a = all_triples[:, 1] if rel_predict else all_triples[:, 2]
@@ -137,10 +169,11 @@ def get_total_rank(test_triples, score, all_ans, eval_bz, rel_predict=0, filter_
                                           device=score.device)
     fp = filter_csr.ptr if filter_csr is not None else None
     fi = filter_csr.idx if filter_csr is not None else None
-    raw, filt, _ = ops.rank_dense(score, test_triples, target_col, fp, fi)
+    fe = filter_csr.end if filter_csr is not None else None
+    raw, filt, _ = ops.rank_dense(score, test_triples, target_col, fp, fi, filt_end=fe)
     rank, filter_rank = ops.counts_to_ranks(raw, filt)
     if filter_csr is not None:
-        ops.apply_filter_(score, test_triples, target_col, fp, fi)
+        ops.apply_filter_(score, test_triples, target_col, fp, fi, filt_end=fe)
     mrr = torch.mean(1.0 / rank.float())
     filter_mrr = torch.mean(1.0 / filter_rank.float())
     return filter_mrr.item(), mrr.item(), rank, filter_rank

@@ -210,7 +210,12 @@ def test_fused_rank_equals_dense_rank_bit_exact(kind):
     try:
         all_t, score, _ = model.predict(glist, r, None, test, True)
         fcsr = utils.filter_csr_from_snapshot(all_t, 2 * r, 0)
+        assert fcsr.end is not None                                   # kernel-built (beg, end) form
+        fcsr_t = utils.filter_csr_from_snapshot(all_t, 2 * r, 0, use_kernels=False)   # torch-built compact CSR
+        assert fcsr.lists() == fcsr_t.lists()
         rank_d, frank_d = evaluate.evaluate_snapshot(model, glist, all_t, fcsr, fused=False)
+        rank_t, frank_t = evaluate.evaluate_snapshot(model, glist, all_t, fcsr_t, fused=True)
+        assert torch.equal(rank_d, rank_t) and torch.equal(frank_d, frank_t)
         rank_f, frank_f = evaluate.evaluate_snapshot(model, glist, all_t, fcsr, fused=True)
         assert torch.equal(rank_d, rank_f), int((rank_d != rank_f).sum())
         assert torch.equal(frank_d, frank_f), int((frank_d != frank_f).sum())
