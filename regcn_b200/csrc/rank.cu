@@ -123,31 +123,55 @@ int filter_correct(int B, const int* filt_ptr, const int* filt_idx, const int* t
 // queries with the same (h, r); relation prediction: key (h, t), answers r'.  B is a few thousand, so an all-pairs
 // scan (B^2 comparisons from L1) beats a sort: pass 1 counts the matches, pass 2 (after an exclusive scan) collects
 // them, sorts + uniques each short list in place and emits the (query, candidate) pair lists of the fused rank path.
-__global__ void filter_count_kernel(const int64_t* __restrict__ triples, int B, int key_col, int* __restrict__ counts) {
+constexpr int kFiltTile = 256;
+
+__global__ void __launch_bounds__(kFiltTile) filter_count_kernel(const int64_t* __restrict__ triples, int B, int key_col,
+                                                                 int* __restrict__ counts) {
+  __shared__ long long skey[kFiltTile];
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  const int64_t h = triples[3 * (size_t)b], k2 = triples[3 * (size_t)b + key_col];
+  // (h, k2) packed into one 64-bit key: ids are < 2^31
+  const long long mykey = b < B ? (triples[3 * (size_t)b] << 32) | (triples[3 * (size_t)b + key_col] & 0xffffffffLL) : -1;
   int c = 0;
-  for (int j = 0; j < B; ++j) c += (triples[3 * (size_t)j] == h && triples[3 * (size_t)j + key_col] == k2) ? 1 : 0;
-  counts[b] = c;
+  for (int j0 = 0; j0 < B; j0 += kFiltTile) {
+    const int j = j0 + threadIdx.x;
+    skey[threadIdx.x] = j < B ? (triples[3 * (size_t)j] << 32) | (triples[3 * (size_t)j + key_col] & 0xffffffffLL) : -2;
+    __syncthreads();
+    const int lim = min(kFiltTile, B - j0);
+#pragma unroll 8
+    for (int i = 0; i < lim; ++i) c += skey[i] == mykey ? 1 : 0;
+    __syncthreads();
+  }
+  if (b < B) counts[b] = c;
 }
 
-__global__ void filter_fill_kernel(const int64_t* __restrict__ triples, int B, int key_col, int ans_col,
-                                   const int* __restrict__ beg, int* __restrict__ idx, int* __restrict__ end,
-                                   int* __restrict__ pair_a, int* __restrict__ pair_e) {
+__global__ void __launch_bounds__(kFiltTile) filter_fill_kernel(const int64_t* __restrict__ triples, int B, int key_col,
+                                                                int ans_col, const int* __restrict__ beg,
+                                                                int* __restrict__ idx, int* __restrict__ end,
+                                                                int* __restrict__ pair_a, int* __restrict__ pair_e) {
+  __shared__ long long skey[kFiltTile];
+  __shared__ int sans[kFiltTile];
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  const int64_t h = triples[3 * (size_t)b], k2 = triples[3 * (size_t)b + key_col];
-  int* lst = idx + beg[b];
+  const bool valid = b < B;
+  const long long mykey = valid ? (triples[3 * (size_t)b] << 32) | (triples[3 * (size_t)b + key_col] & 0xffffffffLL) : -1;
+  int* lst = valid ? idx + beg[b] : nullptr;
   int n = 0;
-  for (int j = 0; j < B; ++j) {
-    if (triples[3 * (size_t)j] == h && triples[3 * (size_t)j + key_col] == k2) {
-      const int a = (int)triples[3 * (size_t)j + ans_col];
-      int p = n++;                                   // insertion sort: lists are short
-      while (p > 0 && lst[p - 1] > a) { lst[p] = lst[p - 1]; --p; }
-      lst[p] = a;
+  for (int j0 = 0; j0 < B; j0 += kFiltTile) {
+    const int j = j0 + threadIdx.x;
+    skey[threadIdx.x] = j < B ? (triples[3 * (size_t)j] << 32) | (triples[3 * (size_t)j + key_col] & 0xffffffffLL) : -2;
+    sans[threadIdx.x] = j < B ? (int)triples[3 * (size_t)j + ans_col] : 0;
+    __syncthreads();
+    const int lim = min(kFiltTile, B - j0);
+    for (int i = 0; i < lim; ++i) {
+      if (skey[i] == mykey) {
+        const int a = sans[i];
+        int p = n++;                                   // insertion sort: lists are short
+        while (p > 0 && lst[p - 1] > a) { lst[p] = lst[p - 1]; --p; }
+        lst[p] = a;
+      }
     }
+    __syncthreads();
   }
+  if (!valid) return;
   int u = 0;
   for (int i = 0; i < n; ++i) if (i == 0 || lst[i] != lst[i - 1]) lst[u++] = lst[i];
   for (int i = u; i < n; ++i) lst[i] = lst[0];       // unused tail slots stay valid candidate ids
@@ -163,7 +187,7 @@ int filter_count(const int64_t* triples, int B, int key_col, int* counts, cudaSt
   if (!triples || !counts) { set_last_error("filter_count: null pointer"); return REGCN_ERR_NULL; }
   if (key_col < 1 || key_col > 2) { set_last_error("filter_count: key_col must be 1 or 2"); return REGCN_ERR_DIM; }
   if (B <= 0) return REGCN_OK;
-  filter_count_kernel<<<(B + 127) / 128, 128, 0, st>>>(triples, B, key_col, counts);
+  filter_count_kernel<<<(B + kFiltTile - 1) / kFiltTile, kFiltTile, 0, st>>>(triples, B, key_col, counts);
   return check_launch("filter_count");
 }
 
@@ -172,7 +196,7 @@ int filter_fill(const int64_t* triples, int B, int key_col, int ans_col, const i
   if (!triples || !beg || !idx || !end || (pair_a && !pair_e)) { set_last_error("filter_fill: null pointer"); return REGCN_ERR_NULL; }
   if (key_col < 1 || key_col > 2 || ans_col < 1 || ans_col > 2 || key_col == ans_col) { set_last_error("filter_fill: bad columns"); return REGCN_ERR_DIM; }
   if (B <= 0) return REGCN_OK;
-  filter_fill_kernel<<<(B + 127) / 128, 128, 0, st>>>(triples, B, key_col, ans_col, beg, idx, end, pair_a, pair_e);
+  filter_fill_kernel<<<(B + kFiltTile - 1) / kFiltTile, kFiltTile, 0, st>>>(triples, B, key_col, ans_col, beg, idx, end, pair_a, pair_e);
   return check_launch("filter_fill");
 }
 
