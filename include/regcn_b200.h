@@ -219,6 +219,21 @@ REGCN_API int regcn_regcn_evolve(const void* const* model_ptrs, const int* model
                        const int* graph_ints, int L, float* hist, float* h0_out, int rel_nsplit, void* workspace,
                        size_t workspace_bytes, void* stream);
 
+/* ---- whole-recurrence orchestration, hyperbolic: HyperbolicRecurrentRGCN.forward, hyperbolic_model.py:722-890
+ * (encoders hyperbolic_uvrgcn = 0 and lgcn = 1, self_loop, no skip connection, fixed curvature).  Same calling
+ * convention as regcn_regcn_evolve plus a double table for the scalars.                                         */
+enum { HM_DYNAMIC_EMB = 0, HM_RADIUS_STATIC, HM_EMB_REL, HM_EMB_REL_HI, HM_EMB_REL_LO, HM_GI_STATIC, HM_WIH_R_HI,
+       HM_WIH_R_LO, HM_WHH_HI, HM_WHH_LO, HM_B_HH, HM_GATE_W_HI, HM_GATE_W_LO, HM_GATE_BIAS, HM_RADIUS_W, HM_LAYER0,
+       HM_LAYER_STRIDE = 4
+       /* HM_LAYER0 + 4*l: uvrgcn: W_n^T hi, lo | lgcn: block weight (raw), unused ; then [W_loop|W_evolve]^T hi, lo */ };
+enum { HMI_NUM_ENTS = 0, HMI_NUM_RELS2, HMI_DIM, HMI_NUM_LAYERS, HMI_LAYER_NORM, HMI_SELF_LOOP, HMI_ENCODER,
+       HMI_NUM_BASES, HMI_RESIDUAL, HMI_NUM_INTS };
+enum { HMD_C = 0, HMD_GAMMA, HMD_RMIN, HMD_RMAX, HMD_BETA, HMD_EPS_R, HMD_RADIUS_BIAS, HMD_NUM };
+REGCN_API size_t regcn_hyp_evolve_workspace_bytes(int N, int R2, int d, int max_split_chunks, int rel_nsplit);
+REGCN_API int regcn_hyp_evolve(const void* const* model_ptrs, const int* model_ints, const double* model_doubles,
+                     const void* const* graph_ptrs, const int* graph_ints, int L, float* hist, float* h0_out,
+                     int rel_nsplit, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -179,7 +179,7 @@ int regcn_hyp_init(const float* emb, const float* radius_static, int N, int d, i
   return hyp_init(emb, radius_static, N, d, normalize, on_manifold, c, radius_min, radius_max, out, ST(stream));
 }
 int regcn_hyp_tangent(const float* h, int N, int d, double c, float* ht, float* pt, float* radius, void* stream) {
-  return hyp_tangent(h, N, d, c, ht, pt, radius, ST(stream));
+  return hyp_tangent(h, N, d, c, ht, pt, radius, nullptr, nullptr, nullptr, nullptr, ST(stream));
 }
 int regcn_hyp_time_gate(const float* h2, const float* pt, const float* G, const float* bias, const float* radius_static,
                         const float* radius_w, float radius_b, int N, int d, int layer_norm, int residual, double c,

@@ -163,4 +163,121 @@ int regcn_regcn_evolve(const void* const* mp, const int* mi, const void* const* 
   return REGCN_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Hyperbolic recurrence (HyperbolicRecurrentRGCN.forward, hyperbolic_model.py:722-890) in one call.
+// Encoder 0 = hyperbolic_uvrgcn (radius-weighted union aggregate + W_n GEMM), 1 = lgcn (Lorentz centroid).
+// Per snapshot: tangent prep (ht, clamp(ht), |h|, TF32 splits) -> K2 -> GRU GEMMs -> K3 -> per layer
+// {K4 or K7, loop GEMM, [W_n GEMM], K5 with clamps / exp_0 / next tangent} -> gate GEMM -> fused time gate +
+// projection + residual radius evolution (K9 + K8).
+// ---------------------------------------------------------------------------------------------------------
+size_t regcn_hyp_evolve_workspace_bytes(int N, int R2, int d, int max_split_chunks, int rel_nsplit) {
+  return plan_evolve(N, R2, d, max_split_chunks, rel_nsplit).total + (size_t)8 * al((size_t)N * d) * sizeof(float) +
+         al((size_t)2 * N) * sizeof(float) + 1024;
+}
+
+int regcn_hyp_evolve(const void* const* mp, const int* mi, const double* md, const void* const* gp, const int* gi_,
+                     int L, float* hist, float* h0_out, int rel_nsplit, void* workspace, size_t workspace_bytes,
+                     void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!mp || !mi || !md || !gp || !gi_ || !hist || !h0_out || !workspace) { set_last_error("hyp_evolve: null pointer"); return REGCN_ERR_NULL; }
+  const int N = mi[HMI_NUM_ENTS], R2 = mi[HMI_NUM_RELS2], d = mi[HMI_DIM], nl = mi[HMI_NUM_LAYERS];
+  const int layer_norm = mi[HMI_LAYER_NORM], enc = mi[HMI_ENCODER], nb = mi[HMI_NUM_BASES], residual = mi[HMI_RESIDUAL];
+  const double c = md[HMD_C];
+  const float gamma = (float)md[HMD_GAMMA], rmin = (float)md[HMD_RMIN], rmax = (float)md[HMD_RMAX];
+  const float beta = (float)md[HMD_BETA], eps_r = (float)md[HMD_EPS_R], rb = (float)md[HMD_RADIUS_BIAS];
+  if (N <= 0 || R2 <= 0 || (R2 & 1) || d <= 0 || (d & 3) || d > 256 || nl < 1 || nl > 8 || L < 0 || !(c > 0) ||
+      enc < 0 || enc > 1 || !mi[HMI_SELF_LOOP]) {
+    set_last_error("hyp_evolve: bad model configuration N=%d R2=%d d=%d layers=%d enc=%d", N, R2, d, nl, enc); return REGCN_ERR_DIM;
+  }
+  int max_split = 0;
+  for (int i = 0; i < L; ++i) max_split = gi_[i * RGI_NUM_INTS + RGI_N_SPLIT_CHUNKS] > max_split ? gi_[i * RGI_NUM_INTS + RGI_N_SPLIT_CHUNKS] : max_split;
+  if (rel_nsplit < 1) rel_nsplit = 1;
+  const EvolveWs w = plan_evolve(N, R2, d, max_split, rel_nsplit);
+  if (workspace_bytes < regcn_hyp_evolve_workspace_bytes(N, R2, d, max_split, rel_nsplit)) { set_last_error("hyp_evolve: workspace too small"); return REGCN_ERR_WORKSPACE; }
+  float* ws = (float*)workspace;
+  const size_t nd = (size_t)N * d;
+  float* extra = ws + w.total / sizeof(float);
+  float* ht_raw = extra;                  extra += al(nd);
+  float* ht_hi = extra;                   extra += al(nd);
+  float* ht_lo = extra;                   extra += al(nd);
+  float* pt_raw = extra;                  extra += al(nd);
+  float* pt_hi = extra;                   extra += al(nd);
+  float* pt_lo = extra;                   extra += al(nd);
+  float* nx_raw = extra;                  extra += al(nd);   // tangent of a layer output (raw)
+  float* h_init = extra;                  extra += al(nd);
+  float* rad0 = extra;                    extra += al(N);
+  float* rad1 = extra;
+  auto F = [&](int k) { return (const float*)mp[k]; };
+  int e;
+
+  // h = apply_radius(exp_0([normalize](dynamic_emb)), static_radius)          hyperbolic_model.py:773-782
+  if ((e = hyp_init(F(HM_DYNAMIC_EMB), F(HM_RADIUS_STATIC), N, d, layer_norm, 0, c, rmin, rmax, h_init, st))) return e;
+  const float* h_raw = h_init;
+  const float* h0_raw = F(HM_EMB_REL);
+  const float* h0_hi = F(HM_EMB_REL_HI);
+  const float* h0_lo = F(HM_EMB_REL_LO);
+
+  for (int i = 0; i < L; ++i) {
+    const void* const* g = gp + (size_t)i * RG_NUM_PTRS;
+    const int* gn = gi_ + (size_t)i * RGI_NUM_INTS;
+    auto GI = [&](int k) { return (const int*)g[k]; };
+    if ((e = hyp_tangent(h_raw, N, d, c, ht_raw, pt_raw, rad0, ht_hi, ht_lo, pt_hi, pt_lo, st))) return e;
+    // ---- relation evolution on the tangent vectors ----
+    if ((e = rel_mean_pool(ht_raw, GI(RG_REL_ROWPTR), GI(RG_REL_ENTS), R2 / 2, d, rel_nsplit, nullptr, ws + w.rel_partial,
+                           ws + w.xm_hi, ws + w.xm_lo, st))) return e;
+    if ((e = gemm_tf32(ws + w.xm_hi, ws + w.xm_lo, d, F(HM_WIH_R_HI), F(HM_WIH_R_LO), d, ws + w.gi, 3 * d, R2, 3 * d, d,
+                       nullptr, 0, 3, 1, nullptr, 0, F(HM_GI_STATIC), 3 * d, st))) return e;
+    if ((e = gemm_tf32(h0_hi, h0_lo, d, F(HM_WHH_HI), F(HM_WHH_LO), d, ws + w.gh, 3 * d, R2, 3 * d, d, F(HM_B_HH), 0, 3, 1,
+                       nullptr, 0, nullptr, 0, st))) return e;
+    if ((e = gru_gate(ws + w.gi, ws + w.gh, h0_raw, h0_out, R2, d, layer_norm, ws + w.h0_hi, ws + w.h0_lo, st))) return e;
+    h0_raw = h0_out; h0_hi = ws + w.h0_hi; h0_lo = ws + w.h0_lo;
+    // ---- gate pre-activation from the clamped previous tangent (independent of the layers) ----
+    if ((e = gemm_tf32(pt_hi, pt_lo, d, F(HM_GATE_W_HI), F(HM_GATE_W_LO), d, ws + w.Lm, d, N, d, d, nullptr, 0, 3, 1, nullptr,
+                       0, nullptr, 0, st))) return e;
+    // ---- layers ----
+    const float* x_t = ht_raw;     // tangent of the layer input
+    const float* x_hi = ht_hi;
+    const float* x_lo = ht_lo;
+    const float* x_rad = rad0;
+    const float* out_h = nullptr;
+    for (int l = 0; l < nl; ++l) {
+      const int base = HM_LAYER0 + HM_LAYER_STRIDE * l;
+      const bool last = l == nl - 1;
+      float* Lbuf = ws + w.L2;                                     // x_t . [W_loop | W_evolve]
+      if ((e = gemm_tf32(x_hi, x_lo, d, F(base + 2), F(base + 3), d, Lbuf, 2 * d, N, 2 * d, d, nullptr, 0, 3, 1, nullptr, 0,
+                         nullptr, 0, st))) return e;
+      const float* P;
+      if (enc == 0) {
+        if ((e = union_aggregate(x_t, h0_raw, GI(RG_ROWPTR), GI(RG_SRC_SORTED), GI(RG_ETYPE_SORTED), (const float*)g[RG_NORM],
+                                 GI(RG_VPTR), GI(RG_SPTR), GI(RG_VROW_ROW), gn[RGI_N_VROWS], gn[RGI_N_SPLIT_CHUNKS], x_rad,
+                                 gamma, N, d, nullptr, ws + w.partial, ws + w.agg_hi, ws + w.agg_lo, nullptr, d,
+                                 gn[RGI_MAX_CHUNKS], st))) return e;
+        if ((e = gemm_tf32(ws + w.agg_hi, ws + w.agg_lo, d, F(base + 0), F(base + 1), d, ws + w.P, d, N, d, d, nullptr, 0, 3,
+                           1, nullptr, 0, nullptr, 0, st))) return e;
+        P = ws + w.P;
+      } else {
+        if ((e = lorentz_aggregate(x_t, F(base + 0), h0_raw, GI(RG_ROWPTR), GI(RG_SRC_SORTED), GI(RG_ETYPE_SORTED),
+                                   (const float*)g[RG_NORM], N, d, nb, c, ws + w.P, st))) return e;
+        P = ws + w.P;
+      }
+      float* o_raw = ws + w.set[l & 1][0];
+      // next layer consumes the tangent (raw + split) and the radius of this layer's output
+      if ((e = union_combine(P, Lbuf, GI(RG_INDEG), nullptr, nullptr, nullptr, N, d, 1, 1, c, o_raw, last ? nullptr : nx_raw,
+                             last ? nullptr : rad1, 2 * d, nullptr, nullptr, last ? nullptr : ws + w.set[l & 1][1],
+                             last ? nullptr : ws + w.set[l & 1][2], nullptr, st))) return e;
+      out_h = o_raw;
+      if (!last) {
+        // the next layer reads these before its own combine overwrites nx_raw / rad1 (stream order)
+        x_t = nx_raw; x_hi = ws + w.set[l & 1][1]; x_lo = ws + w.set[l & 1][2]; x_rad = rad1;
+      }
+    }
+    // ---- time gate + projection + radius evolution ----
+    float* h_new = hist + (size_t)i * nd;
+    if ((e = hyp_time_gate(out_h, pt_raw, ws + w.Lm, F(HM_GATE_BIAS), F(HM_RADIUS_STATIC), F(HM_RADIUS_W), rb, N, d, layer_norm,
+                           residual, c, rmin, rmax, beta, eps_r, h_new, st))) return e;
+    h_raw = h_new;
+  }
+  return REGCN_OK;
+}
+
 }  // extern "C"

@@ -55,7 +55,8 @@ int time_gate(const float* G, const float* bias, const float* cur, const float* 
               int normalize_cur, int ldg, float* out_hi, float* out_lo, cudaStream_t st);
 int hyp_init(const float* emb, const float* radius_static, int N, int d, int normalize, int on_manifold, double c,
              float rmin, float rmax, float* out, cudaStream_t st);
-int hyp_tangent(const float* h, int N, int d, double c, float* ht, float* pt, float* radius, cudaStream_t st);
+int hyp_tangent(const float* h, int N, int d, double c, float* ht, float* pt, float* radius, float* ht_hi,
+                float* ht_lo, float* pt_hi, float* pt_lo, cudaStream_t st);
 int hyp_time_gate(const float* h2, const float* pt, const float* G, const float* bias, const float* radius_static,
                   const float* rw, float rb, int N, int d, int layer_norm, int residual, double c, float rmin,
                   float rmax, float beta, float eps_r, float* out, cudaStream_t st);

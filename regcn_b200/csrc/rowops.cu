@@ -234,7 +234,9 @@ __global__ void __launch_bounds__(256) hyp_init_kernel(const float* __restrict__
 template <int RV>
 __global__ void __launch_bounds__(256) hyp_tangent_kernel(const float* __restrict__ h, int N, int d, Curv cv,
                                                           float* __restrict__ ht, float* __restrict__ pt,
-                                                          float* __restrict__ radius) {
+                                                          float* __restrict__ radius, float* __restrict__ ht_hi,
+                                                          float* __restrict__ ht_lo, float* __restrict__ pt_hi,
+                                                          float* __restrict__ pt_lo) {
   ROW_KERNEL_PROLOGUE(N)
   WarpRow<RV> r;
   r.load_plain(h + (size_t)row * d, nvec, lane);
@@ -244,9 +246,11 @@ __global__ void __launch_bounds__(256) hyp_tangent_kernel(const float* __restric
   }
   row_log0(r, cv);
   if (ht) r.store(ht + (size_t)row * d, nvec, lane);
-  if (pt) {
+  if (ht_hi) r.store_split(ht_hi + (size_t)row * d, ht_lo + (size_t)row * d, nvec, lane);
+  if (pt || pt_hi) {
     r.map([](float a) { return clampf_(a, -10.f, 10.f); });
-    r.store(pt + (size_t)row * d, nvec, lane);
+    if (pt) r.store(pt + (size_t)row * d, nvec, lane);
+    if (pt_hi) r.store_split(pt_hi + (size_t)row * d, pt_lo + (size_t)row * d, nvec, lane);
   }
 }
 
@@ -308,13 +312,14 @@ int hyp_init(const float* emb, const float* radius_static, int N, int d, int nor
   return check_launch("hyp_init");
 }
 
-int hyp_tangent(const float* h, int N, int d, double c, float* ht, float* pt, float* radius, cudaStream_t st) {
+int hyp_tangent(const float* h, int N, int d, double c, float* ht, float* pt, float* radius, float* ht_hi,
+                float* ht_lo, float* pt_hi, float* pt_lo, cudaStream_t st) {
   if (!h) { set_last_error("hyp_tangent: null pointer"); return REGCN_ERR_NULL; }
   if (int e = check_d("hyp_tangent", d)) return e;
   if (!(c > 0)) { set_last_error("hyp_tangent: curvature must be > 0"); return REGCN_ERR_DIM; }
   Curv cv = make_curv(c);
-  if (d <= 128) hyp_tangent_kernel<1><<<row_grid(N), 256, 0, st>>>(h, N, d, cv, ht, pt, radius);
-  else hyp_tangent_kernel<2><<<row_grid(N), 256, 0, st>>>(h, N, d, cv, ht, pt, radius);
+  if (d <= 128) hyp_tangent_kernel<1><<<row_grid(N), 256, 0, st>>>(h, N, d, cv, ht, pt, radius, ht_hi, ht_lo, pt_hi, pt_lo);
+  else hyp_tangent_kernel<2><<<row_grid(N), 256, 0, st>>>(h, N, d, cv, ht, pt, radius, ht_hi, ht_lo, pt_hi, pt_lo);
   return check_launch("hyp_tangent");
 }
 

@@ -158,9 +158,97 @@ class HyperbolicRecurrentRGCN(nn.Module):
                       b_key=(cell.weight_hh, "w"))
         return ops.gru_gate(gi, gh, h0_prev, self.layer_norm)
 
+    # ------------------------------------------------------------------ whole-recurrence fast path
+    def _engine_ok(self):
+        first = self.rgcn.layers[0]
+        return (ops.gemm_impl() == "tc" and not self.use_static and first.self_loop and not first.skip_connect
+                and self.encoder_name in ("hyperbolic_uvrgcn", "lgcn") and self.h_dim % 4 == 0 and self.h_dim <= 256)
+
+    def _engine_tables(self):
+        """Pointer / int / double tables of regcn_hyp_evolve (include/regcn_b200.h HM_* / HMI_* / HMD_*)."""
+        import numpy as np
+        cell = self.relation_gru
+        tre = self.temporal_radius_evolution
+        params = [self.dynamic_emb, self.emb_rel, self.radius_static, cell.weight_ih, cell.weight_hh, cell.bias_ih,
+                  cell.bias_hh, self.time_gate_weight, self.time_gate_bias, tre.radius_mlp.weight, tre.radius_mlp.bias]
+        for layer in self.rgcn.layers:
+            params += [getattr(layer, "weight_neighbor", None) if self.encoder_name != "lgcn" else layer.weight,
+                       layer.loop_weight, layer.evolve_loop_weight]
+        stamp = tuple((p._version, p.data_ptr()) for p in params)
+        if getattr(self, "_engine_stamp", None) == stamp:
+            return self._engine_tab
+        d = self.h_dim
+        keep = []
+
+        def split(m):
+            hi, lo = ops.split_tf32(m.detach().contiguous())
+            keep.extend((hi, lo))
+            return hi, lo
+
+        emb_rel = self.emb_rel.detach().contiguous()
+        er_hi, er_lo = split(emb_rel)
+        w_ih = cell.weight_ih.detach()
+        gi_static = ops.gemm(emb_rel, w_ih[:, :d], trans_b=True, bias=cell.bias_ih.detach())
+        wr_hi, wr_lo = split(w_ih[:, d:])
+        wh_hi, wh_lo = split(cell.weight_hh)
+        gw_hi, gw_lo = split(self.time_gate_weight.detach().t())
+        b_hh = cell.bias_hh.detach().contiguous()
+        gate_b = self.time_gate_bias.detach().contiguous()
+        dyn = self.dynamic_emb.detach().contiguous()
+        rs = self.radius_static.detach().contiguous()
+        rw = tre.radius_mlp.weight.detach().view(-1).contiguous()
+        keep += [emb_rel, gi_static, b_hh, gate_b, dyn, rs, rw]
+        ptrs = [dyn, rs, emb_rel, er_hi, er_lo, gi_static, wr_hi, wr_lo, wh_hi, wh_lo, b_hh, gw_hi, gw_lo, gate_b, rw]
+        lgcn = self.encoder_name == "lgcn"
+        for layer in self.rgcn.layers:
+            if lgcn:
+                w = layer.weight.detach().contiguous()
+                keep.append(w)
+                first = [w, w]
+            else:
+                first = list(split(layer.weight_neighbor.detach().t()))
+            wl_hi, wl_lo = split(torch.cat([layer.loop_weight.detach(), layer.evolve_loop_weight.detach()], dim=1).t())
+            ptrs += first + [wl_hi, wl_lo]
+        ptab = np.array([t.data_ptr() for t in ptrs], dtype=np.uint64)
+        nb = self.rgcn.layers[0].num_bases if lgcn else 0
+        itab = np.array([self.num_ents, 2 * self.num_rels, d, len(self.rgcn.layers), int(bool(self.layer_norm)), 1,
+                         1 if lgcn else 0, nb, int(bool(self.use_residual_evolution))], dtype=np.int32)
+        dtab = np.array([self._c_float, float(self.radius_msg_gamma), float(self.radius_min), float(self.radius_max),
+                         float(tre.anchor_beta), float(tre.epsilon), float(tre.radius_mlp.bias.detach().item())],
+                        dtype=np.float64)
+        self._engine_tab = (ptab, itab, dtab, keep)
+        self._engine_stamp = stamp
+        return self._engine_tab
+
+    def _forward_engine(self, g_list):
+        import numpy as np
+        from . import _lib
+        ptab, itab, dtab, _ = self._engine_tables()
+        L = len(g_list)
+        N, R2, d = self.num_ents, 2 * self.num_rels, self.h_dim
+        dev = self.dynamic_emb.device
+        gp = np.concatenate([g.ptr_table for g in g_list])
+        gi = np.concatenate([g.int_table for g in g_list])
+        max_split = max(g.n_split_chunks for g in g_list)
+        rel_nsplit = max(max(1, min(64, g.n_rel_ents // (max(1, self.num_rels) * 512))) for g in g_list)
+        need = _lib.load().regcn_hyp_evolve_workspace_bytes(N, R2, d, max_split, rel_nsplit)
+        ws = getattr(self, "_engine_ws", None)
+        if ws is None or ws.numel() < need or ws.device != dev:
+            ws = torch.empty(need, device=dev, dtype=torch.uint8)
+            self._engine_ws = ws
+        hist = torch.empty((L, N, d), device=dev, dtype=torch.float32)
+        h0 = torch.empty((R2, d), device=dev, dtype=torch.float32)
+        _lib.call("regcn_hyp_evolve", ptab.ctypes.data, itab.ctypes.data, dtab.ctypes.data, gp.ctypes.data,
+                  gi.ctypes.data, L, hist.data_ptr(), h0.data_ptr(), rel_nsplit, ws.data_ptr(), ws.numel())
+        return [hist[i] for i in range(L)], h0
+
     @torch.no_grad()
     def forward(self, g_list, static_graph, use_cuda):
         gate_list, degree_list = [], []
+        if self._engine_ok() and len(g_list) > 0:
+            history_embs, self.h_0 = self._forward_engine(g_list)
+            self.h = history_embs[-1]
+            return history_embs, None, self.h_0, gate_list, degree_list
         c = self._c_float
         rs_raw = self.radius_static.detach()
         if self.use_static and static_graph is not None:

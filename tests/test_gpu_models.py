@@ -153,6 +153,35 @@ def test_engine_path_equals_layer_path(shape):
     assert ok, worst
 
 
+@pytest.mark.parametrize("enc,shape,ln", [("hyperbolic_uvrgcn", "c1", True), ("lgcn", "small_l", False),
+                                          ("hyperbolic_uvrgcn", "c4", False)])
+def test_hyperbolic_engine_path_equals_layer_path(enc, shape, ln):
+    """regcn_hyp_evolve (one call) against the layer-by-layer hyperbolic path."""
+    import regcn_b200 as R
+    from regcn_b200 import ops
+    R._lib.require_device()
+    cfg = dict(kind="hyp", layer_norm=ln, seed=91, encoder=enc, decoder="roth", gamma=0.15)
+    case = synth.make_case(shape, 91)
+    n, r = case["num_ents"], case["num_rels"]
+    model, _ = build_model(cfg, n, r)
+    model = model.to(DEV)
+    glist = [R.build_sub_graph(n, r, s, True, 0) for s in case["history"]]
+    prev = ops.gemm_impl()
+    try:
+        ops.set_gemm_impl("tc")
+        assert model._engine_ok()
+        h_e, _, r_e, _, _ = model.forward(glist, None, True)
+        model._engine_ok = lambda: False
+        h_l, _, r_l, _, _ = model.forward(glist, None, True)
+    finally:
+        ops.set_gemm_impl(prev)
+    for a, b in zip(h_e, h_l):
+        ok, worst = close(a.cpu().numpy(), b.cpu().numpy(), rtol=5e-5)
+        assert ok, worst
+    ok, worst = close(r_e.cpu().numpy(), r_l.cpu().numpy(), rtol=5e-5)
+    assert ok, worst
+
+
 def test_layer_signatures_drop_in():
     """UnionRGCNLayer.forward(g, prev_h, emb_rel) / RGCNBlockLayer.forward(g, prev_h) keep the reference's contract:
     read g.ndata['h'], write g.ndata['h'], return node_repr (rgcn/layers.py:222-255, :48-91)."""
