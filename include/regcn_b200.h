@@ -72,10 +72,13 @@ REGCN_API int regcn_block_aggregate(const float* h, const float* W, const int32_
                           float* out, void* stream);
 
 /* ---- K7 Lorentz centroid aggregate: hyperbolic_layers.py:589-625,665-672; hyperbolic_ops.py:477-518,563-581
- * ht tangent input; out = clamp(log_0(to_poincare(centroid)), +-10), zero rows for in-degree 0.  */
+ * ht tangent input; out = clamp(log_0(to_poincare(centroid)), +-10), zero rows for in-degree 0.
+ * partial: n_split_chunks*(d+1) floats for destinations split into several 32-edge chunks (NULL if none). */
 REGCN_API int regcn_lorentz_aggregate(const float* ht, const float* W, const float* rel, const int32_t* rowptr,
-                            const int32_t* src_sorted, const int32_t* etype_sorted, const float* norm, int N,
-                            int d, int nb, double c, float* out, void* stream);
+                            const int32_t* src_sorted, const int32_t* etype_sorted, const float* norm,
+                            const int32_t* vptr, const int32_t* sptr, const int32_t* vrow_row, int n_vrows,
+                            int n_split_chunks, int N, int d, int nb, double c, float* out, float* partial,
+                            void* stream);
 
 /* ---- dense contraction (fp32 CUDA cores): torch.mm / F.linear call sites on the path -----------
  * C[M,N] (+)= A[M,K] . op(B) (+ bias[N]); op(B) = B[K,N] if !transB else B[N,K]^T.

@@ -443,66 +443,49 @@ int block_aggregate(const float* h, const float* W, const int* rowptr, const int
 // indeg 0 -> exact zero row (DGL zero fill; to_poincare(0)=0, log_0(0)=0).
 // Requires si == so == 2 or generic; lanes own float4 chunks of the d-vector like K4.
 // ---------------------------------------------------------------------------
-template <int RV>
-__global__ void __launch_bounds__(256) lorentz_aggregate_kernel(
-    const float* __restrict__ ht, const float* __restrict__ W, const float* __restrict__ rel,
-    const int* __restrict__ rowptr, const int* __restrict__ src_sorted, const int* __restrict__ etype_sorted,
-    const float* __restrict__ norm, int N, int d, int nb, Curv cv, float* __restrict__ out) {
-  const int lane = threadIdx.x & 31;
-  const int row = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
-  if (row >= N) return;
-  const int nvec = d >> 2;
-  const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
-  WarpRow<RV> acc;
-  acc.zero();
-  if (beg == end) { acc.store(out + (size_t)row * d, nvec, lane); return; }
-  const int K = end - beg;
-  const int sb = d / nb;  // square blocks: submat_in == submat_out == sb (in_feat == out_feat)
-  const float nv = __ldg(norm + row);
-  // reduce_func weights (:620): norms / (norms.sum() + 1e-6); torch sums K equal fp32 values
-  float wsum = 0.f;
-  for (int i = 0; i < K; ++i) wsum += nv;
-  const float w0 = nv / (wsum + 1e-6f);
-  // lorentz_centroid (:576): w = weights / (weights.sum() + eps)
-  float w0sum = 0.f;
-  for (int i = 0; i < K; ++i) w0sum += w0;
-  const float wgt = w0 / (w0sum + kEps);
-  float acc0 = 0.f;  // time component of the centroid
-  for (int e = beg; e < end; ++e) {
-    const int s = __ldg(src_sorted + e), t = __ldg(etype_sorted + e);
-    const float* hp = ht + (size_t)s * d;
-    const float* wp = W + (size_t)t * ((size_t)nb * sb * sb);
-    WarpRow<RV> m;
+// Message of one edge for the float4 chunks owned by this lane: m = blockdiag(W[type]) . x[src] + rel[type].
+// SB == 2 (the reference's default: 100 bases of 2x2 at d = 200): a float4 chunk holds exactly two blocks, so the
+// transform is chunk-local -- one float4 of x, two float4 of weights, no index arithmetic.  SB == 0: generic block size.
+template <int RV, int SB>
+__device__ __forceinline__ void lorentz_message(WarpRow<RV>& m, const float* __restrict__ hp, const float* __restrict__ wp,
+                                                const float* __restrict__ rp, int nvec, int lane, int sb) {
 #pragma unroll
-    for (int i = 0; i < RV; ++i) {
-      const int c = lane + i * kWarp;
-      float o4[4] = {0.f, 0.f, 0.f, 0.f};
-      if (c < nvec) {
+  for (int i = 0; i < RV; ++i) {
+    const int c = lane + i * kWarp;
+    if (c < nvec) {
+      float4 r4 = rp ? ldg4(rp + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (SB == 2) {
+        const float4 x = ldg4(hp + 4 * c);
+        const float4 w0 = ldg4(wp + 8 * c);        // block 2c   : [i][o] = (00, 01, 10, 11)
+        const float4 w1 = ldg4(wp + 8 * c + 4);    // block 2c+1
+        m.v[i] = make_float4(fmaf(x.y, w0.z, x.x * w0.x) + r4.x, fmaf(x.y, w0.w, x.x * w0.y) + r4.y,
+                             fmaf(x.w, w1.z, x.z * w1.x) + r4.z, fmaf(x.w, w1.w, x.z * w1.y) + r4.w);
+      } else {
+        float o4[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int j = 4 * c + q;
           const int b = j / sb, o = j - b * sb;
-          float a = 0.f;
-          for (int ii = 0; ii < sb; ++ii) a = fmaf(__ldg(hp + b * sb + ii), __ldg(wp + ((size_t)b * sb + ii) * sb + o), a);
-          o4[q] = a;
+          float acc = 0.f;
+          for (int ii = 0; ii < sb; ++ii) acc = fmaf(__ldg(hp + b * sb + ii), __ldg(wp + ((size_t)b * sb + ii) * sb + o), acc);
+          o4[q] = acc;
         }
-        float4 r4 = rel ? ldg4(rel + (size_t)t * d + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
         m.v[i] = make_float4(o4[0] + r4.x, o4[1] + r4.y, o4[2] + r4.z, o4[3] + r4.w);
-      } else {
-        m.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-    }
-    row_exp0(m, cv);
-    const float nsq = m.sumsq();
-    const float D = fmaxf(1.0f - cv.c * nsq, kEps);
-    const float x0 = (1.0f + cv.c * nsq) / (cv.sqrt_c * D);
-    acc0 = fmaf(wgt, x0, acc0);
-#pragma unroll
-    for (int i = 0; i < RV; ++i) {
-      float4 xi = make_float4(2.0f * m.v[i].x / D, 2.0f * m.v[i].y / D, 2.0f * m.v[i].z / D, 2.0f * m.v[i].w / D);
-      acc.v[i] = f4_fma(wgt, xi, acc.v[i]);
+    } else {
+      m.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
+}
+
+// Centroid tail: cbar = wgt * (sum0, sum) -> normalise to <x,x>_L = -1/c -> to_poincare -> log_0 -> clamp +-10.
+template <int RV>
+__device__ __forceinline__ void lorentz_finish(WarpRow<RV>& acc, float acc0, int K, float nv, const Curv& cv) {
+  // reduce_func weights (:620): norms / (norms.sum() + 1e-6), all K equal; lorentz_centroid (:576): w / (sum w + eps)
+  const float w0 = nv / ((float)K * nv + 1e-6f);
+  const float wgt = w0 / ((float)K * w0 + kEps);
+  acc.scale(wgt);
+  acc0 *= wgt;
   const float ip = -acc0 * acc0 + acc.sumsq();
   const float scale = sqrtf(fmaxf(-ip * cv.c, kEps));
   const float y0 = acc0 / scale;
@@ -510,19 +493,120 @@ __global__ void __launch_bounds__(256) lorentz_aggregate_kernel(
   acc.map([=](float a) { return (a / scale) / den; });
   row_log0(acc, cv);
   acc.map([](float a) { return clampf_(a, -10.f, 10.f); });
+}
+
+// One warp per 32-edge virtual row of an active destination.  Per edge: message (above), exp_0 (one warp reduction;
+// the norm after the projection follows analytically), to_lorentz, accumulate (time, space).  The centroid weights
+// are equal inside a node, so chunks accumulate unweighted sums; single-chunk rows finish in place, hub rows leave
+// (sum, sum0) partials that lorentz_fixup_kernel folds.
+template <int RV, int SB>
+__global__ void __launch_bounds__(256) lorentz_aggregate_kernel(
+    const float* __restrict__ ht, const float* __restrict__ W, const float* __restrict__ rel,
+    const int* __restrict__ rowptr, const int* __restrict__ src_sorted, const int* __restrict__ etype_sorted,
+    const float* __restrict__ norm, const int* __restrict__ vptr, const int* __restrict__ sptr,
+    const int* __restrict__ vrow_row, int nv_rows, int d, int nb, Curv cv, float* __restrict__ out,
+    float* __restrict__ partial, float* __restrict__ partial0) {
+  const int lane = threadIdx.x & 31;
+  const int w = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+  if (w >= nv_rows) return;
+  const int nvec = d >> 2;
+  const int row = __ldg(vrow_row + w);
+  const int v0 = __ldg(vptr + row), v1 = __ldg(vptr + row + 1);
+  const int k = w - v0;
+  const int rbeg = __ldg(rowptr + row), rend = __ldg(rowptr + row + 1);
+  const int beg = rbeg + k * kAggChunk;
+  const int end = min(beg + kAggChunk, rend);
+  const int sb = d / nb;
+  const size_t wstride = (size_t)nb * sb * sb;
+  WarpRow<RV> acc;
+  acc.zero();
+  float acc0 = 0.f;
+  const int e0 = beg + lane;
+  const int s_l = e0 < end ? __ldg(src_sorted + e0) : 0;
+  const int t_l = e0 < end ? __ldg(etype_sorted + e0) : 0;
+  const int cnt = end - beg;
+  for (int j = 0; j < cnt; ++j) {
+    const int s = __shfl_sync(0xffffffffu, s_l, j), t = __shfl_sync(0xffffffffu, t_l, j);
+    WarpRow<RV> m;
+    lorentz_message<RV, SB>(m, ht + (size_t)s * d, W + (size_t)t * wstride, rel ? rel + (size_t)t * d : nullptr, nvec, lane, sb);
+    // exp_0 + projection as one scale factor (hyperbolic_ops.py:91-95, :51-53)
+    const float mn = sqrtf(m.sumsq());
+    const float n = fmaxf(mn, kEps);
+    const float th = tanhf(cv.sqrt_c * n);
+    const float f1 = th / (n * cv.sqrt_c);           // exp_0 scale: p = m * f1
+    const float pn = fmaxf(mn * f1, kEps);
+    const float f2 = fminf(pn, cv.proj_max) / pn;    // projection scale
+    const float f = f1 * f2;
+    const float nsq = (mn * f) * (mn * f);
+    const float D = fmaxf(1.0f - cv.c * nsq, kEps);  // to_lorentz (:492-499)
+    acc0 += (1.0f + cv.c * nsq) / (cv.sqrt_c * D);
+    const float g = 2.0f * f / D;
+#pragma unroll
+    for (int i = 0; i < RV; ++i) acc.v[i] = f4_fma(g, m.v[i], acc.v[i]);
+  }
+  if (v1 - v0 == 1) {
+    lorentz_finish(acc, acc0, rend - rbeg, __ldg(norm + row), cv);
+    acc.store(out + (size_t)row * d, nvec, lane);
+  } else {
+    const size_t slot = (size_t)(__ldg(sptr + row) + k);
+    acc.store(partial + slot * d, nvec, lane);
+    if (lane == 0) partial0[slot] = acc0;
+  }
+}
+
+template <int RV>
+__global__ void __launch_bounds__(256) lorentz_fixup_kernel(
+    const int* __restrict__ rowptr, const int* __restrict__ vptr, const int* __restrict__ sptr,
+    const int* __restrict__ vrow_row, const float* __restrict__ norm, int nv_rows, int d, Curv cv,
+    const float* __restrict__ partial, const float* __restrict__ partial0, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int w = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+  if (w >= nv_rows) return;
+  const int row = __ldg(vrow_row + w);
+  const int v0 = __ldg(vptr + row);
+  const int nch = __ldg(vptr + row + 1) - v0;
+  if (w != v0 || nch <= 1) return;
+  const int nvec = d >> 2;
+  const int s0 = __ldg(sptr + row);
+  WarpRow<RV> acc, p;
+  acc.zero();
+  float acc0 = 0.f;
+  for (int k = 0; k < nch; ++k) {
+    p.load_plain(partial + (size_t)(s0 + k) * d, nvec, lane);
+#pragma unroll
+    for (int i = 0; i < RV; ++i) acc.v[i] = f4_add(acc.v[i], p.v[i]);
+    acc0 += partial0[s0 + k];
+  }
+  lorentz_finish(acc, acc0, __ldg(rowptr + row + 1) - __ldg(rowptr + row), __ldg(norm + row), cv);
   acc.store(out + (size_t)row * d, nvec, lane);
 }
 
 int lorentz_aggregate(const float* ht, const float* W, const float* rel, const int* rowptr,
-                      const int* src_sorted, const int* etype_sorted, const float* norm, int N, int d, int nb,
-                      double c, float* out, cudaStream_t st) {
-  if (!ht || !W || !rowptr || !src_sorted || !etype_sorted || !norm || !out) { set_last_error("lorentz_aggregate: null pointer"); return REGCN_ERR_NULL; }
+                      const int* src_sorted, const int* etype_sorted, const float* norm, const int* vptr,
+                      const int* sptr, const int* vrow_row, int nv_rows, int nsplit, int N, int d, int nb, double c,
+                      float* out, float* partial, cudaStream_t st) {
+  if (!ht || !W || !rowptr || !src_sorted || !etype_sorted || !norm || !vptr || !sptr || !vrow_row || !out) { set_last_error("lorentz_aggregate: null pointer"); return REGCN_ERR_NULL; }
   if (d <= 0 || (d & 3) || d > 256 || nb <= 0 || d % nb) { set_last_error("lorentz_aggregate: d=%d nb=%d unsupported", d, nb); return REGCN_ERR_UNSUPPORTED; }
+  if (nsplit > 0 && !partial) { set_last_error("lorentz_aggregate: split rows need a partial buffer of n_split_chunks*(d+1) floats"); return REGCN_ERR_WORKSPACE; }
   const int TB = 256;
-  const unsigned grid = (unsigned)(((size_t)N * 32 + TB - 1) / TB);
   Curv cv = make_curv(c);
-  if (d <= 128) lorentz_aggregate_kernel<1><<<grid, TB, 0, st>>>(ht, W, rel, rowptr, src_sorted, etype_sorted, norm, N, d, nb, cv, out);
-  else lorentz_aggregate_kernel<2><<<grid, TB, 0, st>>>(ht, W, rel, rowptr, src_sorted, etype_sorted, norm, N, d, nb, cv, out);
+  // isolated destinations: exact zero rows (DGL zero fill; to_poincare(0) = 0, log_0(0) = 0)
+  const size_t total = (size_t)N * (d >> 2);
+  zero_inactive_rows_kernel<<<(unsigned)((total + TB - 1) / TB), TB, 0, st>>>(rowptr, N, d, out, nullptr, nullptr);
+  if (nv_rows > 0) {
+    const unsigned grid = (unsigned)(((size_t)nv_rows * 32 + TB - 1) / TB);
+    float* partial0 = partial ? partial + (size_t)nsplit * d : nullptr;
+    const bool sb2 = (d / nb) == 2;
+    if (d <= 128) {
+      if (sb2) lorentz_aggregate_kernel<1, 2><<<grid, TB, 0, st>>>(ht, W, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv_rows, d, nb, cv, out, partial, partial0);
+      else lorentz_aggregate_kernel<1, 0><<<grid, TB, 0, st>>>(ht, W, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv_rows, d, nb, cv, out, partial, partial0);
+      if (nsplit > 0) lorentz_fixup_kernel<1><<<grid, TB, 0, st>>>(rowptr, vptr, sptr, vrow_row, norm, nv_rows, d, cv, partial, partial0, out);
+    } else {
+      if (sb2) lorentz_aggregate_kernel<2, 2><<<grid, TB, 0, st>>>(ht, W, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv_rows, d, nb, cv, out, partial, partial0);
+      else lorentz_aggregate_kernel<2, 0><<<grid, TB, 0, st>>>(ht, W, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv_rows, d, nb, cv, out, partial, partial0);
+      if (nsplit > 0) lorentz_fixup_kernel<2><<<grid, TB, 0, st>>>(rowptr, vptr, sptr, vrow_row, norm, nv_rows, d, cv, partial, partial0, out);
+    }
+  }
   return check_launch("lorentz_aggregate");
 }
 

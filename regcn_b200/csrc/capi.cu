@@ -101,9 +101,12 @@ int regcn_block_aggregate(const float* h, const float* W, const int32_t* rowptr,
   return block_aggregate(h, W, rowptr, src_sorted, etype_sorted, norm, N, d_in, d_out, nb, out, ST(stream));
 }
 int regcn_lorentz_aggregate(const float* ht, const float* W, const float* rel, const int32_t* rowptr,
-                            const int32_t* src_sorted, const int32_t* etype_sorted, const float* norm, int N, int d,
-                            int nb, double c, float* out, void* stream) {
-  return lorentz_aggregate(ht, W, rel, rowptr, src_sorted, etype_sorted, norm, N, d, nb, c, out, ST(stream));
+                            const int32_t* src_sorted, const int32_t* etype_sorted, const float* norm,
+                            const int32_t* vptr, const int32_t* sptr, const int32_t* vrow_row, int n_vrows,
+                            int n_split_chunks, int N, int d, int nb, double c, float* out, float* partial,
+                            void* stream) {
+  return lorentz_aggregate(ht, W, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, n_vrows,
+                           n_split_chunks, N, d, nb, c, out, partial, ST(stream));
 }
 size_t regcn_gemm_f32_workspace_bytes(int M, int N, int split_k) { return gemm_f32_workspace_bytes(M, N, split_k); }
 int regcn_gemm_f32(const float* A, int lda, const float* B, int ldb, int transB, float* C, int ldc, int M, int N, int K,

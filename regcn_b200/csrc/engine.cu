@@ -41,7 +41,7 @@ static EvolveWs plan_evolve(int N, int R2, int d, int max_split_chunks, int rel_
   w.Lm = take(nd * 3); w.L2 = take(nd * 2); w.P = take(nd);
   for (int s = 0; s < 2; ++s) for (int k = 0; k < 3; ++k) w.set[s][k] = take(nd);
   w.h_hi = take(nd); w.h_lo = take(nd); w.h_init = take(nd);
-  w.partial = take((size_t)(max_split_chunks > 0 ? max_split_chunks : 1) * d);
+  w.partial = take((size_t)(max_split_chunks > 0 ? max_split_chunks : 1) * (d + 1));
   w.rel_partial = take(rel_nsplit > 1 ? (size_t)(R2 / 2) * rel_nsplit * d : 1);
   w.total = off * sizeof(float);
   return w;
@@ -257,7 +257,8 @@ int regcn_hyp_evolve(const void* const* mp, const int* mi, const double* md, con
         P = ws + w.P;
       } else {
         if ((e = lorentz_aggregate(x_t, F(base + 0), h0_raw, GI(RG_ROWPTR), GI(RG_SRC_SORTED), GI(RG_ETYPE_SORTED),
-                                   (const float*)g[RG_NORM], N, d, nb, c, ws + w.P, st))) return e;
+                                   (const float*)g[RG_NORM], GI(RG_VPTR), GI(RG_SPTR), GI(RG_VROW_ROW), gn[RGI_N_VROWS],
+                                   gn[RGI_N_SPLIT_CHUNKS], N, d, nb, c, ws + w.P, ws + w.partial, st))) return e;
         P = ws + w.P;
       }
       float* o_raw = ws + w.set[l & 1][0];

@@ -18,7 +18,8 @@ int union_aggregate(const float* h, const float* rel, const int* rowptr, const i
 int block_aggregate(const float* h, const float* W, const int* rowptr, const int* src_sorted, const int* etype_sorted,
                     const float* norm, int N, int d_in, int d_out, int nb, float* out, cudaStream_t st);
 int lorentz_aggregate(const float* ht, const float* W, const float* rel, const int* rowptr, const int* src_sorted,
-                      const int* etype_sorted, const float* norm, int N, int d, int nb, double c, float* out,
+                      const int* etype_sorted, const float* norm, const int* vptr, const int* sptr, const int* vrow_row,
+                      int nv_rows, int nsplit, int N, int d, int nb, double c, float* out, float* partial,
                       cudaStream_t st);
 size_t gemm_f32_workspace_bytes(int M, int N, int split_k);
 int gemm_f32(const float* A, int lda, const float* B, int ldb, int transB, float* C, int ldc, int M, int N, int K,

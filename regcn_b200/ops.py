@@ -201,8 +201,10 @@ def lorentz_aggregate(ht, weight, rel, g, num_bases, c):
     ht = _f32(ht, "ht")
     N, d = ht.shape
     out = torch.empty((N, d), device=ht.device, dtype=F32)
+    partial = torch.empty(g.n_split_chunks * (d + 1), device=ht.device, dtype=F32) if g.n_split_chunks > 0 else None
     call("regcn_lorentz_aggregate", ptr(ht), ptr(_f32(weight, "weight")), ptr(rel), ptr(g.rowptr), ptr(g.src_sorted),
-         ptr(g.etype_sorted), ptr(g.norm), N, d, num_bases, float(c), ptr(out))
+         ptr(g.etype_sorted), ptr(g.norm), ptr(g.vptr), ptr(g.sptr), ptr(g.vrow_row), g.n_vrows, g.n_split_chunks, N, d,
+         num_bases, float(c), ptr(out), ptr(partial))
     return out
 
 
