@@ -50,6 +50,23 @@ REGCN_API int regcn_csr_build(const int64_t* triples, int T, int N, int R,
                     int32_t* rel_rowptr, int32_t* rel_ents, int32_t* counts,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* Batched form: the index of L history snapshots in one call (the reference rebuilds all L graphs for every
+ * evaluated timestamp, src/main.py:68,233; hyperbolic_main.py:100-113).  `snaps` is a HOST array of L descriptors
+ * holding the same device pointers regcn_csr_build takes.  Snapshots of at most 16384 edges are built by one CTA
+ * each (block radix sorts + fused block scans in shared memory), all L concurrently in one launch; larger ones go
+ * through the regcn_csr_build pipeline on the same stream and need the workspace the query below reports.       */
+typedef struct regcn_csr_arrays {
+  const int64_t* triples;   /* (T,3) int64, device */
+  int32_t T;
+  int32_t* src; int32_t* dst; int32_t* etype; int32_t* indeg; float* norm;
+  int32_t* rowptr; int32_t* src_sorted; int32_t* etype_sorted; int32_t* eperm;
+  int32_t* vptr; int32_t* sptr; int32_t* vrow_row; int32_t* active_pos;
+  int32_t* rel_rowptr; int32_t* rel_ents; int32_t* counts;
+} regcn_csr_arrays;
+REGCN_API size_t regcn_csr_build_batch_workspace_bytes(const int32_t* T, int L, int N, int R);
+REGCN_API int regcn_csr_build_batch(const regcn_csr_arrays* snaps, int L, int N, int R, void* workspace,
+                                    size_t workspace_bytes, void* stream);
+
 /* ---- K2 relation mean-pool: src/rrgcn.py:161-166, hyperbolic_model.py:802-812 -----------------
  * out (2R,d): out[r] = out[r+R] = mean of h rows in ents(r); zero rows for absent relations.
  * nsplit > 1 splits every relation over nsplit CTAs (partial: R*nsplit*d floats).               */

@@ -26,6 +26,8 @@ SIGNATURES = {
     "regcn_device_ok": (_i, []),
     "regcn_csr_build_workspace_bytes": (_sz, [_i, _i, _i]),
     "regcn_csr_build": (_i, [_p, _i, _i, _i] + [_p] * 16 + [_p, _sz, _p]),
+    "regcn_csr_build_batch_workspace_bytes": (_sz, [_p, _i, _i, _i]),
+    "regcn_csr_build_batch": (_i, [_p, _i, _i, _i, _p, _sz, _p]),
     "regcn_rel_mean_pool": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p]),
     "regcn_union_aggregate": (_i, [_p] * 9 + [_i, _i, _p, _f, _i, _i, _p, _p, _p]),
     "regcn_block_aggregate": (_i, [_p] * 6 + [_i, _i, _i, _i, _p, _p]),
@@ -67,6 +69,16 @@ SIGNATURES = {
     "regcn_filter_count": (_i, [_p, _i, _i, _p, _p]),
     "regcn_filter_fill": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
 }
+
+
+
+class CsrArrays(ctypes.Structure):
+    """struct regcn_csr_arrays (include/regcn_b200.h): the device pointers of one snapshot's index."""
+    _fields_ = ([("triples", _p), ("T", ctypes.c_int32)] +
+                [(n, _p) for n in ("src", "dst", "etype", "indeg", "norm", "rowptr", "src_sorted", "etype_sorted",
+                                   "eperm", "vptr", "sptr", "vrow_row", "active_pos", "rel_rowptr", "rel_ents",
+                                   "counts")])
+
 
 _lib = None
 launch_count = 0  # kernels-launching C-ABI calls made by this process (bench.py reports it)

@@ -84,6 +84,13 @@ int regcn_csr_build(const int64_t* triples, int T, int N, int R, int32_t* src, i
   return csr_build(triples, T, N, R, src, dst, etype, indeg, norm, rowptr, src_sorted, etype_sorted, eperm, vptr, sptr,
                    vrow_row, active_pos, rel_rowptr, rel_ents, counts, workspace, workspace_bytes, ST(stream));
 }
+size_t regcn_csr_build_batch_workspace_bytes(const int32_t* T, int L, int N, int R) {
+  return T ? csr_build_batch_workspace_bytes(T, L, N, R) : 0;
+}
+int regcn_csr_build_batch(const regcn_csr_arrays* snaps, int L, int N, int R, void* workspace, size_t workspace_bytes,
+                          void* stream) {
+  return csr_build_batch(snaps, L, N, R, workspace, workspace_bytes, ST(stream));
+}
 int regcn_rel_mean_pool(const float* h, const int32_t* rel_rowptr, const int32_t* rel_ents, int R, int d, int nsplit,
                         float* out, float* partial, void* stream) {
   return rel_mean_pool(h, rel_rowptr, rel_ents, R, d, nsplit, out, partial, nullptr, nullptr, ST(stream));

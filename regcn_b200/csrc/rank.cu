@@ -121,65 +121,98 @@ int filter_correct(int B, const int* filt_ptr, const int* filt_idx, const int* t
 // ---- time-aware filter lists straight from the query triples (rgcn/utils.py:264-304 on the test snapshot itself) ----
 // Query b = (h, r, t) [all_triples incl. inverses].  Entity prediction: answers of key (h, r) = every t' among the
 // queries with the same (h, r); relation prediction: key (h, t), answers r'.  B is a few thousand, so an all-pairs
-// scan (B^2 comparisons from L1) beats a sort: pass 1 counts the matches, pass 2 (after an exclusive scan) collects
-// them, sorts + uniques each short list in place and emits the (query, candidate) pair lists of the fused rank path.
-constexpr int kFiltTile = 256;
+// scan (B^2 key comparisons out of L1) beats a sort.  One WARP per query: the lanes stride over the B keys, matches
+// are compacted with a ballot; pass 1 counts them, pass 2 (after an exclusive scan) collects them, sorts + uniques
+// each short list in registers (rank sort over shuffles) and emits the (query, candidate) pair lists of the fused
+// rank path.
+constexpr int kFiltThreads = 256;
 
-__global__ void __launch_bounds__(kFiltTile) filter_count_kernel(const int64_t* __restrict__ triples, int B, int key_col,
-                                                                 int* __restrict__ counts) {
-  __shared__ long long skey[kFiltTile];
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  // (h, k2) packed into one 64-bit key: ids are < 2^31
-  const long long mykey = b < B ? (triples[3 * (size_t)b] << 32) | (triples[3 * (size_t)b + key_col] & 0xffffffffLL) : -1;
-  int c = 0;
-  for (int j0 = 0; j0 < B; j0 += kFiltTile) {
-    const int j = j0 + threadIdx.x;
-    skey[threadIdx.x] = j < B ? (triples[3 * (size_t)j] << 32) | (triples[3 * (size_t)j + key_col] & 0xffffffffLL) : -2;
-    __syncthreads();
-    const int lim = min(kFiltTile, B - j0);
-#pragma unroll 8
-    for (int i = 0; i < lim; ++i) c += skey[i] == mykey ? 1 : 0;
-    __syncthreads();
-  }
-  if (b < B) counts[b] = c;
+__device__ __forceinline__ long long filt_key(const int64_t* __restrict__ triples, int j, int key_col) {
+  return (long long)((unsigned long long)triples[3 * (size_t)j] << 32) | (triples[3 * (size_t)j + key_col] & 0xffffffffLL);
 }
 
-__global__ void __launch_bounds__(kFiltTile) filter_fill_kernel(const int64_t* __restrict__ triples, int B, int key_col,
-                                                                int ans_col, const int* __restrict__ beg,
-                                                                int* __restrict__ idx, int* __restrict__ end,
-                                                                int* __restrict__ pair_a, int* __restrict__ pair_e) {
-  __shared__ long long skey[kFiltTile];
-  __shared__ int sans[kFiltTile];
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool valid = b < B;
-  const long long mykey = valid ? (triples[3 * (size_t)b] << 32) | (triples[3 * (size_t)b + key_col] & 0xffffffffLL) : -1;
-  int* lst = valid ? idx + beg[b] : nullptr;
+__global__ void __launch_bounds__(kFiltThreads) filter_count_kernel(const int64_t* __restrict__ triples, int B, int key_col,
+                                                                    int* __restrict__ counts) {
+  const int lane = threadIdx.x & 31;
+  const int b = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+  if (b >= B) return;
+  const long long mykey = filt_key(triples, b, key_col);
+  int c = 0;
+  for (int j = lane; j < B; j += 32) c += filt_key(triples, j, key_col) == mykey ? 1 : 0;
+  c = warp_sum_i(c);
+  if (lane == 0) counts[b] = c;
+}
+
+__global__ void __launch_bounds__(kFiltThreads) filter_fill_kernel(const int64_t* __restrict__ triples, int B, int key_col,
+                                                                   int ans_col, const int* __restrict__ beg,
+                                                                   int* __restrict__ idx, int* __restrict__ end,
+                                                                   int* __restrict__ pair_a, int* __restrict__ pair_e) {
+  const int lane = threadIdx.x & 31;
+  const int b = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+  if (b >= B) return;
+  const long long mykey = filt_key(triples, b, key_col);
+  const int b0 = beg[b];
+  int* lst = idx + b0;
+  // collect the answers of the matching queries in query order
   int n = 0;
-  for (int j0 = 0; j0 < B; j0 += kFiltTile) {
-    const int j = j0 + threadIdx.x;
-    skey[threadIdx.x] = j < B ? (triples[3 * (size_t)j] << 32) | (triples[3 * (size_t)j + key_col] & 0xffffffffLL) : -2;
-    sans[threadIdx.x] = j < B ? (int)triples[3 * (size_t)j + ans_col] : 0;
-    __syncthreads();
-    const int lim = min(kFiltTile, B - j0);
-    for (int i = 0; i < lim; ++i) {
-      if (skey[i] == mykey) {
-        const int a = sans[i];
-        int p = n++;                                   // insertion sort: lists are short
+  int mine = 0;                                   // lane i keeps the i-th match (lists of <= 32 stay in registers)
+  for (int j0 = 0; j0 < B; j0 += 32) {
+    const int j = j0 + lane;
+    const bool m = j < B && filt_key(triples, j, key_col) == mykey;
+    const unsigned bal = __ballot_sync(0xffffffffu, m);
+    if (bal) {
+      const int a = m ? (int)triples[3 * (size_t)j + ans_col] : 0;
+      const int pos = n + __popc(bal & ((1u << lane) - 1u));
+      if (m) lst[pos] = a;
+      n += __popc(bal);
+    }
+  }
+  __syncwarp();
+  int u;
+  if (n <= 32) {
+    mine = lane < n ? lst[lane] : 0x7fffffff;
+    // duplicate = an equal value at a smaller lane; unique position = #{distinct values below mine}
+    bool dup = false;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const int o = __shfl_sync(0xffffffffu, mine, k);
+      dup |= (k < lane) & (o == mine);
+    }
+    const bool keep = lane < n && !dup;
+    int upos = 0;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const int o = __shfl_sync(0xffffffffu, mine, k);
+      const int od = __shfl_sync(0xffffffffu, (int)keep, k);
+      upos += od & (int)(o < mine);
+    }
+    u = __popc(__ballot_sync(0xffffffffu, keep));
+    __syncwarp();
+    if (keep) lst[upos] = mine;
+    __syncwarp();
+    const int first = lst[0];
+    if (lane >= u && lane < n) lst[lane] = first;     // unused tail slots stay valid candidate ids
+    __syncwarp();
+  } else {
+    // long list (hub query): insertion sort + unique by one lane, in place
+    u = 0;
+    if (lane == 0) {
+      for (int i = 1; i < n; ++i) {
+        const int a = lst[i];
+        int p = i;
         while (p > 0 && lst[p - 1] > a) { lst[p] = lst[p - 1]; --p; }
         lst[p] = a;
       }
+      for (int i = 0; i < n; ++i) if (i == 0 || lst[i] != lst[i - 1]) lst[u++] = lst[i];
+      for (int i = u; i < n; ++i) lst[i] = lst[0];
     }
-    __syncthreads();
+    u = __shfl_sync(0xffffffffu, u, 0);
+    __syncwarp();
   }
-  if (!valid) return;
-  int u = 0;
-  for (int i = 0; i < n; ++i) if (i == 0 || lst[i] != lst[i - 1]) lst[u++] = lst[i];
-  for (int i = u; i < n; ++i) lst[i] = lst[0];       // unused tail slots stay valid candidate ids
-  end[b] = beg[b] + u;
+  if (lane == 0) end[b] = b0 + u;
   if (pair_a) {
-    pair_a[b] = b;
-    pair_e[b] = (int)triples[3 * (size_t)b + ans_col];
-    for (int i = 0; i < n; ++i) { pair_a[B + beg[b] + i] = b; pair_e[B + beg[b] + i] = lst[i]; }
+    if (lane == 0) { pair_a[b] = b; pair_e[b] = (int)triples[3 * (size_t)b + ans_col]; }
+    for (int i = lane; i < n; i += 32) { pair_a[B + b0 + i] = b; pair_e[B + b0 + i] = lst[i]; }
   }
 }
 
@@ -187,7 +220,7 @@ int filter_count(const int64_t* triples, int B, int key_col, int* counts, cudaSt
   if (!triples || !counts) { set_last_error("filter_count: null pointer"); return REGCN_ERR_NULL; }
   if (key_col < 1 || key_col > 2) { set_last_error("filter_count: key_col must be 1 or 2"); return REGCN_ERR_DIM; }
   if (B <= 0) return REGCN_OK;
-  filter_count_kernel<<<(B + kFiltTile - 1) / kFiltTile, kFiltTile, 0, st>>>(triples, B, key_col, counts);
+  filter_count_kernel<<<(unsigned)(((size_t)B * 32 + kFiltThreads - 1) / kFiltThreads), kFiltThreads, 0, st>>>(triples, B, key_col, counts);
   return check_launch("filter_count");
 }
 
@@ -196,7 +229,7 @@ int filter_fill(const int64_t* triples, int B, int key_col, int ans_col, const i
   if (!triples || !beg || !idx || !end || (pair_a && !pair_e)) { set_last_error("filter_fill: null pointer"); return REGCN_ERR_NULL; }
   if (key_col < 1 || key_col > 2 || ans_col < 1 || ans_col > 2 || key_col == ans_col) { set_last_error("filter_fill: bad columns"); return REGCN_ERR_DIM; }
   if (B <= 0) return REGCN_OK;
-  filter_fill_kernel<<<(B + kFiltTile - 1) / kFiltTile, kFiltTile, 0, st>>>(triples, B, key_col, ans_col, beg, idx, end, pair_a, pair_e);
+  filter_fill_kernel<<<(unsigned)(((size_t)B * 32 + kFiltThreads - 1) / kFiltThreads), kFiltThreads, 0, st>>>(triples, B, key_col, ans_col, beg, idx, end, pair_a, pair_e);
   return check_launch("filter_fill");
 }
 

@@ -99,14 +99,24 @@ def evaluate_from_host(model, history_host, test_host, num_nodes, num_rels, devi
     host sync for all of them), evolution, entity ranks through the fused scoring kernel, relation ranks through
     ConvTransR / RotHRel + the dense rank kernel, time-aware filtering for both, and the D2H read-back of MRRs
     and rank vectors.  Returns ((filter_mrr, mrr, filter_mrr_rel, mrr_rel), rank_host, filter_rank_host)."""
-    from .graph import build_sub_graphs
-    glist = build_sub_graphs(num_nodes, num_rels, history_host, device)
+    from .graph import build_sub_graphs, finish_sub_graphs, pending_counts
+    # every index build is enqueued first (history graphs: one batched launch; filter lists: count pass), then ONE
+    # device->host read returns all the sizes the host needs (per-snapshot counters, filter slot totals)
+    glist = build_sub_graphs(num_nodes, num_rels, history_host, device, sync=False)
     test = test_host.to(device, non_blocking=True)
     inv = test[:, [2, 1, 0]]
     inv[:, 1] = inv[:, 1] + num_rels
     all_t = torch.cat((test, inv)).contiguous()
-    f_ent = utils.filter_csr_from_snapshot(all_t, 2 * num_rels, 0, num_answers=num_nodes)
-    f_rel = utils.filter_csr_from_snapshot(all_t, num_nodes, 1, num_answers=2 * num_rels)
+    if 0 < all_t.shape[0] <= 32768:
+        pf_ent, pf_rel = utils.filter_lists_begin(all_t, 0), utils.filter_lists_begin(all_t, 1)
+        sizes = torch.cat((pending_counts(glist).flatten(), pf_ent.total, pf_rel.total)).tolist()
+        L = len(glist)
+        finish_sub_graphs(glist, [sizes[8 * i:8 * i + 8] for i in range(L)])
+        f_ent, f_rel = pf_ent.finish(sizes[8 * L]), pf_rel.finish(sizes[8 * L + 1])
+    else:
+        finish_sub_graphs(glist)
+        f_ent = utils.filter_csr_from_snapshot(all_t, 2 * num_rels, 0, num_answers=num_nodes)
+        f_rel = utils.filter_csr_from_snapshot(all_t, num_nodes, 1, num_answers=2 * num_rels)
     evolve_embs, _, r_emb, _, _ = model.forward(glist, None, True)
     emb = evolve_embs[-1]
     if model.layer_norm:

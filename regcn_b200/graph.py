@@ -22,7 +22,7 @@ class _Frame(dict):
 
 
 class SnapshotGraph:
-    def __init__(self, num_nodes, num_rels, triples_dev, _defer_counts=False):
+    def __init__(self, num_nodes, num_rels, triples_dev, _defer_counts=False, _defer_build=False):
         self.num_nodes = int(num_nodes)
         self.num_rels = int(num_rels)
         self.triples = triples_dev  # (T,3) int64 on the device, reference layout
@@ -43,13 +43,14 @@ class SnapshotGraph:
          self.vptr, self.sptr, self.vrow_row, self.active_pos, self.rel_rowptr, self.rel_ents, self._counts) = v
         self.norm = arena[tot:tot + N].view(torch.float32)
         self._arena = arena
-        ws_bytes = _lib.load().regcn_csr_build_workspace_bytes(T, N, R)
-        ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
-        call("regcn_csr_build", ptr(triples_dev), T, N, R, self.src.data_ptr(), self.dst.data_ptr(),
-             self.etype.data_ptr(), self.indeg.data_ptr(), self.norm.data_ptr(), self.rowptr.data_ptr(),
-             self.src_sorted.data_ptr(), self.etype_sorted.data_ptr(), self.eperm.data_ptr(), self.vptr.data_ptr(),
-             self.sptr.data_ptr(), self.vrow_row.data_ptr(), self.active_pos.data_ptr(), self.rel_rowptr.data_ptr(),
-             self.rel_ents.data_ptr(), self._counts.data_ptr(), ptr(ws), ws_bytes)
+        if not _defer_build:
+            ws_bytes = _lib.load().regcn_csr_build_workspace_bytes(T, N, R)
+            ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+            call("regcn_csr_build", ptr(triples_dev), T, N, R, self.src.data_ptr(), self.dst.data_ptr(),
+                 self.etype.data_ptr(), self.indeg.data_ptr(), self.norm.data_ptr(), self.rowptr.data_ptr(),
+                 self.src_sorted.data_ptr(), self.etype_sorted.data_ptr(), self.eperm.data_ptr(), self.vptr.data_ptr(),
+                 self.sptr.data_ptr(), self.vrow_row.data_ptr(), self.active_pos.data_ptr(), self.rel_rowptr.data_ptr(),
+                 self.rel_ents.data_ptr(), self._counts.data_ptr(), ptr(ws), ws_bytes)
         self._ndata = None
         self._edata = None
         self._r2e = None
@@ -57,8 +58,17 @@ class SnapshotGraph:
                                                           self.norm, self.vptr, self.sptr, self.vrow_row,
                                                           self.rel_rowptr, self.rel_ents, self.active_pos)],
                                   dtype=np.uint64)
-        if not _defer_counts:
+        if not _defer_counts and not _defer_build:
             self._set_counts(self._counts.tolist())          # the one host sync of graph construction
+
+    def _descriptor(self, desc):
+        """Fill a struct regcn_csr_arrays with this snapshot's pointers (batched build)."""
+        desc.triples = self.triples.data_ptr()
+        desc.T = self.num_edges // 2
+        for name in ("src", "dst", "etype", "indeg", "norm", "rowptr", "src_sorted", "etype_sorted", "eperm", "vptr",
+                     "sptr", "vrow_row", "active_pos", "rel_rowptr", "rel_ents"):
+            setattr(desc, name, getattr(self, name).data_ptr())
+        desc.counts = self._counts.data_ptr()
 
     def _set_counts(self, c):
         self.n_vrows, self.n_split_chunks, self.n_rel_ents, self.max_hub_degree, self.n_active = c[:5]
@@ -148,15 +158,41 @@ def build_sub_graph(num_nodes, num_rels, triples, use_cuda=True, gpu=0):
     return SnapshotGraph(num_nodes, num_rels, t.contiguous())
 
 
-def build_sub_graphs(num_nodes, num_rels, triples_list, device):
-    """Build the edge index of several snapshots with ONE host synchronisation: every csr_build is enqueued first,
-    then the per-snapshot size counters come back in a single device->host read.  `triples_list`: (T_i,3) int64
-    tensors (pinned host or device)."""
+def build_sub_graphs(num_nodes, num_rels, triples_list, device, sync=True):
+    """Build the edge index of several snapshots with ONE C-ABI call (`regcn_csr_build_batch`: one CTA per small
+    snapshot, all of them in one launch) and ONE host synchronisation for the per-snapshot size counters.
+    `triples_list`: (T_i,3) int64 tensors (pinned host or device).  With sync=False the counters are left on the
+    device: call `finish_sub_graphs(gs)` (or pass them through `pending_counts`) before using the graphs."""
+    import ctypes
     _lib.require_device()
-    gs = [SnapshotGraph(num_nodes, num_rels, t.to(device, non_blocking=True).contiguous(), _defer_counts=True)
+    gs = [SnapshotGraph(num_nodes, num_rels, t.to(device, non_blocking=True).contiguous(), _defer_build=True)
           for t in triples_list]
     if gs:
-        counts = torch.stack([g._counts for g in gs]).tolist()
+        L = len(gs)
+        descs = (_lib.CsrArrays * L)()
+        for g, dsc in zip(gs, descs):
+            g._descriptor(dsc)
+        Ts = (ctypes.c_int32 * L)(*[g.num_edges // 2 for g in gs])
+        lib = _lib.load()
+        ws_bytes = lib.regcn_csr_build_batch_workspace_bytes(Ts, L, int(num_nodes), int(num_rels))
+        ws = torch.empty(max(ws_bytes, 1), device=gs[0].device, dtype=torch.uint8)
+        call("regcn_csr_build_batch", ctypes.cast(descs, ctypes.c_void_p), L, int(num_nodes), int(num_rels), ptr(ws),
+             ws_bytes)
+        if sync:
+            finish_sub_graphs(gs)
+    return gs
+
+
+def pending_counts(gs):
+    """Device tensor (L, 8) of the size counters of graphs built with sync=False."""
+    return torch.stack([g._counts for g in gs])
+
+
+def finish_sub_graphs(gs, counts=None):
+    """Read the size counters back (one device->host copy) and finalise the graphs."""
+    if gs:
+        if counts is None:
+            counts = pending_counts(gs).tolist()
         for g, c in zip(gs, counts):
             g._set_counts(c)
     return gs

@@ -82,25 +82,44 @@ class FilterCSR:
         return [i[p[b]:e[b]] for b in range(len(e))]
 
 
+class _PendingFilter:
+    """Phase 1 of the kernel-built filter lists: match counts and list offsets are on the device, the slot total has
+    not been read back yet (so that several index builds can share one host synchronisation)."""
+
+    def __init__(self, all_triples, rel_predict):
+        from ._lib import call, ptr
+        self.triples = all_triples
+        self.B = B = all_triples.shape[0]
+        dev = all_triples.device
+        self.key_col, self.ans_col = (2, 1) if rel_predict else (1, 2)
+        counts = torch.empty(B, device=dev, dtype=torch.int32)
+        call("regcn_filter_count", ptr(all_triples), B, self.key_col, ptr(counts))
+        csum = torch.cumsum(counts, 0, dtype=torch.int32)
+        self.beg = csum - counts
+        self.total = csum[-1:] if B else torch.zeros(1, device=dev, dtype=torch.int32)
+
+    def finish(self, total=None):
+        from ._lib import call, ptr
+        B, dev = self.B, self.triples.device
+        total = int(self.total.item()) if total is None else int(total)
+        idx = torch.empty(max(total, 1), device=dev, dtype=torch.int32)
+        end = torch.empty(B, device=dev, dtype=torch.int32)
+        pa = torch.empty(B + total, device=dev, dtype=torch.int32)
+        pe = torch.empty(B + total, device=dev, dtype=torch.int32)
+        call("regcn_filter_fill", ptr(self.triples), B, self.key_col, self.ans_col, ptr(self.beg), ptr(idx), ptr(end),
+             ptr(pa), ptr(pe))
+        return FilterCSR(self.beg, idx, end, pairs=(pa, pe))
+
+
+def filter_lists_begin(all_triples, rel_predict=0):
+    return _PendingFilter(all_triples.contiguous(), rel_predict)
+
+
 def filter_lists_from_queries(all_triples, rel_predict=0):
     """Kernel-built time-aware filter lists for the queries themselves (the test snapshot incl. inverses): two
-    launches + one scan + one host read of the slot total; also yields the fused-rank pair lists.  All-pairs scan,
-    meant for the few thousand queries of a timestamp."""
-    from ._lib import call, ptr
-    B = all_triples.shape[0]
-    dev = all_triples.device
-    key_col, ans_col = (2, 1) if rel_predict else (1, 2)
-    counts = torch.empty(B, device=dev, dtype=torch.int32)
-    call("regcn_filter_count", ptr(all_triples), B, key_col, ptr(counts))
-    csum = torch.cumsum(counts, 0, dtype=torch.int32)
-    beg = (csum - counts).contiguous()
-    total = int(csum[-1].item()) if B else 0
-    idx = torch.empty(max(total, 1), device=dev, dtype=torch.int32)
-    end = torch.empty(B, device=dev, dtype=torch.int32)
-    pa = torch.empty(B + total, device=dev, dtype=torch.int32)
-    pe = torch.empty(B + total, device=dev, dtype=torch.int32)
-    call("regcn_filter_fill", ptr(all_triples), B, key_col, ans_col, ptr(beg), ptr(idx), ptr(end), ptr(pa), ptr(pe))
-    return FilterCSR(beg, idx, end, pairs=(pa, pe))
+    launches + one scan + one host read of the slot total; also yields the fused-rank pair lists.  All-pairs scan
+    (one warp per query), meant for the few thousand queries of a timestamp."""
+    return _PendingFilter(all_triples.contiguous(), rel_predict).finish()
 
 
 def filter_csr_from_dict(test_triples, all_ans, rel_predict=0, device=None):

@@ -82,6 +82,64 @@ def test_csr_build_empty_and_duplicates():
     assert g.indeg.cpu().tolist() == [0, 2, 4, 0]
 
 
+def _graph_arrays(g):
+    E = g.num_edges
+    out = {k: getattr(g, k)[:E].cpu().numpy() for k in ("src", "dst", "etype", "src_sorted", "etype_sorted", "eperm")}
+    out.update({k: getattr(g, k).cpu().numpy() for k in ("indeg", "norm", "rowptr", "vptr", "sptr", "active_pos",
+                                                         "rel_rowptr")})
+    out["vrow_row"] = g.vrow_row[:g.n_vrows].cpu().numpy()
+    out["rel_ents"] = g.rel_ents[:g.n_rel_ents].cpu().numpy()
+    out["counts"] = np.array([g.n_vrows, g.n_split_chunks, g.n_rel_ents, g.max_hub_degree, g.n_active])
+    return out
+
+
+def test_csr_build_batch_matches_single_builds():
+    """regcn_csr_build_batch (one CTA per small snapshot, every sort width, plus the CUB path for a big one and an
+    empty snapshot in the same call) is bit-identical to regcn_csr_build and to the oracle."""
+    R, _ = _ops()
+    from regcn_b200.graph import build_sub_graphs
+    rng = np.random.default_rng(5)
+    n, r = 3000, 37
+    sizes = [0, 1, 250, 2048, 2049, 3500, 4096, 6000, 8192, 9000]      # E = 2T: widths 4 / 8 / 16 and > 16384 edges
+    snaps = []
+    for i, t in enumerate(sizes):
+        zipf = i % 2 == 0
+        snaps.append(synth.make_snapshot(rng, n, r, t, zipf) if t else np.zeros((0, 3), dtype=np.int64))
+    gs = build_sub_graphs(n, r, [torch.from_numpy(s) for s in snaps], torch.device(DEV))
+    for tri, g in zip(snaps, gs):
+        single = R.build_sub_graph(n, r, tri, True, 0)
+        a, b = _graph_arrays(g), _graph_arrays(single)
+        for k in a:
+            assert np.array_equal(a[k], b[k]), (len(tri), k)
+        o = restate.build_edges(tri, n, r)
+        rowptr, eperm, src_sorted, etype_sorted = restate.csr_by_dst(o)
+        assert np.array_equal(a["rowptr"], rowptr) and np.array_equal(a["eperm"], eperm)
+        assert np.array_equal(a["src_sorted"], src_sorted) and np.array_equal(a["etype_sorted"], etype_sorted)
+        rel_rowptr, rel_ents = restate.r2e(tri, r)
+        assert np.array_equal(a["rel_rowptr"], rel_rowptr) and np.array_equal(a["rel_ents"], rel_ents)
+
+
+def test_csr_build_batch_many_snapshots_and_big_ids():
+    """More snapshots than one launch holds (16), and entity / relation counts near the packed-key limit."""
+    R, _ = _ops()
+    from regcn_b200.graph import build_sub_graphs
+    rng = np.random.default_rng(6)
+    n, r = 23033, 256
+    snaps = [synth.make_snapshot(rng, n, r, 100 + 37 * i, True) for i in range(19)]
+    gs = build_sub_graphs(n, r, [torch.from_numpy(s) for s in snaps], torch.device(DEV))
+    for tri, g in zip(snaps, gs):
+        a, b = _graph_arrays(g), _graph_arrays(R.build_sub_graph(n, r, tri, True, 0))
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
+    n, r = 262_144, 8191                                               # largest N / R the one-CTA path takes
+    tri = np.stack((rng.integers(0, n, 500), rng.integers(0, r, 500), rng.integers(0, n, 500)), 1).astype(np.int64)
+    tri[:8] = [[n - 1, r - 1, n - 1]] * 4 + [[0, 0, n - 1]] * 4
+    g = build_sub_graphs(n, r, [torch.from_numpy(tri)], torch.device(DEV))[0]
+    a, b = _graph_arrays(g), _graph_arrays(R.build_sub_graph(n, r, tri, True, 0))
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+
+
 # ----------------------------------------------------------------------------------------- K4 / K2
 @pytest.mark.parametrize("impl", [1, 2])
 @pytest.mark.parametrize("shape,d,radius", [("tiny", 200, False), ("small", 200, True), ("c1", 200, False),
@@ -482,6 +540,36 @@ def test_filter_csr_from_snapshot_matches_dict():
         a = utils.filter_csr_from_dict(torch.as_tensor(all_t), d, rel_predict=rel_p, device=DEV)
         b = utils.filter_csr_from_snapshot(_t(all_t, torch.int64), nk, rel_predict=rel_p)
         assert a.lists() == b.lists()
+
+
+def test_filter_lists_hub_queries_and_duplicates():
+    """Warp-per-query filter kernels: lists longer than a warp (hub subject with > 32 answers), duplicate triples,
+    a single query, and the pair lists of the fused rank path."""
+    R, _ = _ops()
+    from regcn_b200 import utils
+    rng = np.random.default_rng(11)
+    n, r = 500, 7
+    hub = np.stack((np.full(90, 3), np.full(90, 2), rng.integers(0, n, 90)), 1)        # 90 answers, some repeated
+    dup = np.array([[5, 1, 9]] * 4 + [[5, 1, 8]] * 2)
+    rest = np.stack((rng.integers(0, n, 300), rng.integers(0, r, 300), rng.integers(0, n, 300)), 1)
+    for test in (np.concatenate((hub, dup, rest)).astype(np.int64), np.array([[1, 0, 2]], dtype=np.int64)):
+        all_t = restate.add_inverse(test, r)
+        for rel_p in (0, 1):
+            d = synth.answers_of(test, r, bool(rel_p))
+            a = utils.filter_csr_from_dict(torch.as_tensor(all_t), d, rel_predict=rel_p, device=DEV)
+            b = utils.filter_lists_from_queries(_t(all_t, torch.int64), rel_p)
+            assert a.lists() == b.lists()
+            B = all_t.shape[0]
+            pa, pe = b.pairs(None)
+            assert pa[:B].cpu().tolist() == list(range(B))
+            assert pe[:B].cpu().tolist() == all_t[:, 1 if rel_p else 2].tolist()
+            beg = b.ptr.cpu().numpy()
+            rows = pa[B:].cpu().numpy()
+            cand = pe[B:].cpu().numpy()
+            lists = b.lists()
+            for q in rng.integers(0, B, 20):
+                sl = slice(beg[q], beg[q] + int((rows == q).sum()))
+                assert (rows[sl] == q).all() and set(cand[sl].tolist()) == set(lists[q])
 
 
 # ----------------------------------------------------------------------------------------- tcgen05 GEMM
