@@ -119,7 +119,9 @@ REGCN_API int regcn_gemm_tf32(const float* a_hi, const float* a_lo, int lda, con
  * hyperbolic_decoder.py:89-179 fused with rgcn/utils.py:21-25,51-75.
  * regcn_score_count_tf32: the scoring GEMM Q[B,K] . E[N,K]^T with a counting epilogue:
  *     raw_count[b] += #{n in shard, col_offset+n != target[b] : score(b,n) ranks ahead of tscore[b]}
- *   score = <q,e> (+col_bias[n]) or, with hyp != 0, scale*(margin - |(-q)(+)_c e|^2) (+col_bias[n]) from x2=|q|^2, y2=|e|^2.
+ *   score = <q,e> (+col_bias[n]) or, with hyp != 0, scale*(margin - |(-q)(+)_c e|^2) (+col_bias[n]) from x2=|q|^2, y2=|e|^2;
+ *   row_c != NULL (needs hyp != 0) selects the true-distance branch with a per-query curvature (hyperbolic_decoder.py:145-163):
+ *   scale*(margin - 2/sqrt(c_q) * artanh(sqrt(c_q) |(-q)(+)_{c_q} e|)), c_q = row_c[b] (regcn_pair_scores_tf32: row_c[p]).
  * regcn_pair_scores_tf32: out[p] = score(A'[p], B'[p]) for gathered operand rows, through the same tensor-core
  *   arithmetic (bit-identical to the corresponding element of the scoring GEMM): target and filter-entry scores.
  * regcn_filter_correct: filt_count[b] = raw_count[b] - (filter entries that beat the target) + (-1e7 entries that do).
@@ -127,10 +129,10 @@ REGCN_API int regcn_gemm_tf32(const float* a_hi, const float* a_lo, int lda, con
 REGCN_API int regcn_score_count_tf32(const float* q_hi, const float* q_lo, const float* e_hi, const float* e_lo, int B,
                            int N, int K, const float* tscore, const int32_t* target, int32_t* raw_count,
                            int col_offset, int hyp, const float* x2, const float* y2, const float* col_bias, double c,
-                           const float* scale_margin, int passes, void* stream);
+                           const float* scale_margin, const float* row_c, int passes, void* stream);
 REGCN_API int regcn_pair_scores_tf32(const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo, int P,
                            int K, int hyp, const float* x2, const float* y2, const float* col_bias, double c,
-                           const float* scale_margin, float* out, int passes, void* stream);
+                           const float* scale_margin, const float* row_c, float* out, int passes, void* stream);
 REGCN_API int regcn_gather_rows2(const float* src_hi, const float* src_lo, const int32_t* idx, int P, int d,
                        float* out_hi, float* out_lo, void* stream);
 REGCN_API int regcn_gather_scalars(const float* a, const float* b, const float* c, const int32_t* ia, const int32_t* ib,
@@ -192,10 +194,16 @@ REGCN_API int regcn_hyp_query(const float* s_tan, const float* ang, const float*
                     const int64_t* triples, int B, int d, int kind, double c, float* Q, float* q_sumsq,
                     void* stream);
 
-/* ---- K13 hyperbolic score epilogue on a dense <q,e> matrix: hyperbolic_decoder.py:89-179 -------- */
+/* ---- K13 hyperbolic score epilogue on a dense <q,e> matrix: hyperbolic_decoder.py:89-179 --------
+ * bias (N) candidate bias, qbias (B) per-query bias (entity_bias[subject], :1097-1098), row_c (B) per-query
+ * curvature selecting the artanh true-distance branch (:145-163); each may be NULL.                 */
 REGCN_API int regcn_hyp_score_epilogue(float* S, int ld, int B, int N, const float* q_sumsq, const float* e_sumsq,
                              const float* bias, const float* qbias, double c, const float* scale_margin,
-                             void* stream);
+                             const float* row_c, void* stream);
+/* per-query curvature c_q[b] = max(1e-5, min(softplus(raw[r_b mod R]), 0.999 c, cmax)): hyperbolic_decoder.py:66-86,1020-1026
+ * (cmax <= 0: no warm-up bound) */
+REGCN_API int regcn_rel_curvature(const float* raw, const int64_t* triples, int B, int R, double c, double cmax,
+                                  float* out, void* stream);
 
 /* ---- K14 rank / filter: rgcn/utils.py:21-25,51-75,136-166 --------------------------------------
  * S (B, ld) scores of a shard of N candidate columns starting at global column col_offset.

@@ -45,6 +45,12 @@ CASES = {
                                    layer_norm=False, gamma=0.15),
     "hyp_lgcn_roth_c1_s0": dict(kind="hyp", shape="c1", seed=0, encoder="lgcn", decoder="roth", layer_norm=False,
                                 gamma=0.15, sub=96),
+    "hyp_uv_roth_tiny_flags_s3": dict(kind="hyp", shape="tiny", seed=3, encoder="hyperbolic_uvrgcn", decoder="roth",
+                                      layer_norm=False, gamma=0.15, entity_bias=True, rel_curvature=True),
+    "hyp_uv_murp_tiny_flags_s4": dict(kind="hyp", shape="tiny", seed=4, encoder="hyperbolic_uvrgcn", decoder="murp",
+                                      layer_norm=True, gamma=0.15, entity_bias=True, rel_curvature=True),
+    "hyp_lgcn_roth_tiny_bias_s5": dict(kind="hyp", shape="tiny_l", seed=5, encoder="lgcn", decoder="roth",
+                                       layer_norm=False, gamma=0.15, entity_bias=True),
     "hyp_uv_roth_c1_s1": dict(kind="hyp", shape="c1", seed=1, encoder="hyperbolic_uvrgcn", decoder="roth",
                               layer_norm=True, gamma=0.15, sub=96),
 }
@@ -79,7 +85,9 @@ def build_reference_model(cfg, n, r, RecurrentRGCN, HyperbolicRecurrentRGCN):
                                     skip_connect=False, layer_norm=cfg["layer_norm"], input_dropout=0.2,
                                     hidden_dropout=0.2, feat_dropout=0.2, entity_prediction=True,
                                     relation_prediction=True, use_cuda=False, gpu="cpu",
-                                    radius_msg_gamma=cfg["gamma"], hyp_init_scale=1e-3)
+                                    radius_msg_gamma=cfg["gamma"], hyp_init_scale=1e-3,
+                                    use_entity_euclidean_bias=cfg.get("entity_bias", False),
+                                    use_relation_specific_curvature=cfg.get("rel_curvature", False))
     m.load_state_dict(synth.fill_state_dict(m.state_dict(), cfg["seed"]))
     m.eval()
     return m

@@ -464,21 +464,60 @@ def hyp_forward(p, graphs, num_rels, c=0.01, encoder="hyperbolic_uvrgcn", layer_
 # =====================================================================================
 # Hyperbolic decoders (hyperbolic_decoder.py)
 # =====================================================================================
-def hyp_dist_scores(query, cand, bias, c, scale, margin, chunk=4096):
-    """hyperbolic_decoder.py:89-179, proxy-distance branch (use_hyperbolic_distance=False):
-    scale * (margin - |(-q) (+)_c e|^2) + bias, evaluated pair by pair (chunked over queries only)."""
+def hyp_dist_scores(query, cand, bias, c, scale, margin, chunk=4096, query_curvature=None):
+    """hyperbolic_decoder.py:89-179.  Proxy-distance branch (use_hyperbolic_distance=False, :164-167):
+    scale * (margin - |(-q) (+)_c e|^2) + bias; with `query_curvature` (B,) the true-distance branch with a
+    per-query curvature (:145-163): scale * (margin - 2/sqrt(c_q) atanh(sqrt(c_q) |(-q) (+)_{c_q} e|)) + bias.
+    Evaluated pair by pair in d dimensions (chunked over queries only)."""
     out = torch.empty(query.shape[0], cand.shape[0], dtype=query.dtype)
     step = max(1, min(64, chunk // max(1, cand.shape[0] // 64)))
     for b0 in range(0, query.shape[0], step):
         q = query[b0:b0 + step]
         qe = q.unsqueeze(1).expand(-1, cand.shape[0], -1)
         ce = cand.unsqueeze(0).expand(q.shape[0], -1, -1)
-        diff = mobius_add(-qe, ce, c)
-        blk = scale * (margin - (diff ** 2).sum(-1))
+        if query_curvature is None:
+            diff = mobius_add(-qe, ce, c)
+            blk = scale * (margin - (diff ** 2).sum(-1))
+        else:
+            c_eff = query_curvature[b0:b0 + step].reshape(-1, 1, 1).to(query.dtype)
+            sqrt_c = torch.sqrt(c_eff + EPS)
+            x_sq = (qe * qe).sum(-1, keepdim=True)
+            y_sq = (ce * ce).sum(-1, keepdim=True)
+            xy = (qe * ce).sum(-1, keepdim=True)
+            num = (1 - 2 * c_eff * xy + c_eff * y_sq) * (-qe) + (1 - c_eff * x_sq) * ce
+            denom = 1 - 2 * c_eff * xy + (c_eff ** 2) * x_sq * y_sq
+            diff = num / (denom + EPS)
+            dn = torch.norm(diff, p=2, dim=-1, keepdim=True).clamp(min=EPS)
+            dn = torch.min(dn, 1.0 / (sqrt_c + EPS) - EPS)
+            dist = (2.0 / (sqrt_c + EPS)) * torch.atanh((sqrt_c * dn).clamp(max=1.0 - EPS))
+            blk = scale * (margin - dist.squeeze(-1))
         if bias is not None:
             blk = blk + bias.unsqueeze(0)
         out[b0:b0 + step] = blk
     return out
+
+
+def relation_curvature(P, pre, r_idx, c, cmax=None):
+    """hyperbolic_decoder.py:66-86,1020-1026: c_q = max(1e-5, min(softplus(raw[r mod R]), 0.999 c, cmax)); None
+    when the decoder has no rel_curvature_raw."""
+    raw = P.get(pre + "rel_curvature_raw")
+    if raw is None:
+        return None
+    rel_c = _softplus(raw[torch.remainder(r_idx, raw.shape[0])])
+    upper = raw.new_tensor(0.999 * float(c))
+    if cmax is not None:
+        upper = torch.min(upper, raw.new_tensor(float(cmax)))
+    return torch.max(torch.min(rel_c, upper), raw.new_tensor(1e-5))
+
+
+def _flagged_scores(P, pre, q, emb, t, c, scale):
+    """Shared tail of RotH / MuRP (:1087-1099, :767-779): candidate bias, per-query curvature, subject bias."""
+    eb = P.get(pre + "entity_bias")
+    rel_c = relation_curvature(P, pre, t[:, 1], c, cmax=c)
+    s = hyp_dist_scores(q, emb, eb, c, scale, P[pre + "score_margin"], query_curvature=rel_c)
+    if eb is not None:
+        s = s + eb[t[:, 0]].unsqueeze(1)
+    return s
 
 
 def givens(x, ang):
@@ -493,7 +532,7 @@ def _softplus(x):
 
 
 def roth_scores(P, emb, rel, triples, c, pre="decoder_ob."):
-    """hyperbolic_decoder.py:1053-1099 (HyperbolicRotH.forward, eval, no entity bias / relation curvature)."""
+    """hyperbolic_decoder.py:1053-1099 (HyperbolicRotH.forward, eval; optional entity bias / relation curvature)."""
     t = torch.as_tensor(triples)
     r_idx = t[:, 1]
     s_tan = log0(project(emb[t[:, 0]], c), c)
@@ -505,7 +544,7 @@ def roth_scores(P, emb, rel, triples, c, pre="decoder_ob."):
     t_r = project(exp0(v_r, c), c)
     q = mobius_add(rot_s, t_r, c)
     scale = _softplus(P[pre + "score_scale_raw"]) + 1e-6
-    return hyp_dist_scores(q, emb, None, c, scale, P[pre + "score_margin"]), q
+    return _flagged_scores(P, pre, q, emb, t, c, scale), q
 
 
 def murp_scores(P, emb, rel, triples, c, pre="decoder_ob."):
@@ -519,7 +558,7 @@ def murp_scores(P, emb, rel, triples, c, pre="decoder_ob."):
     t_r = project(exp0(v_r, c), c)
     q = mobius_add(rot_s, t_r, c)
     scale = _softplus(P[pre + "score_scale_raw"]) + 1e-6
-    return hyp_dist_scores(q, emb, None, c, scale, P[pre + "score_margin"]), q
+    return _flagged_scores(P, pre, q, emb, t, c, scale), q
 
 
 def rothrel_scores(P, emb, rel, triples, c, pre="rdecoder."):

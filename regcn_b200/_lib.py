@@ -41,8 +41,8 @@ SIGNATURES = {
     "regcn_regcn_evolve": (_i, [_p, _p, _p, _p, _i, _p, _p, _i, _p, _sz, _p]),
     "regcn_gemm_tf32_tune": (None, [_i, _i]),
     "regcn_aggregate_tune": (None, [_i]),
-    "regcn_score_count_tf32": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _i, _i, _p, _p, _p, _d, _p, _i, _p]),
-    "regcn_pair_scores_tf32": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _d, _p, _p, _i, _p]),
+    "regcn_score_count_tf32": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _i, _i, _p, _p, _p, _d, _p, _p, _i, _p]),
+    "regcn_pair_scores_tf32": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _d, _p, _p, _p, _i, _p]),
     "regcn_gather_rows2": (_i, [_p, _p, _p, _i, _i, _p, _p, _p]),
     "regcn_gather_scalars": (_i, [_p, _p, _p, _p, _p, _i, _p, _p, _p, _p]),
     "regcn_filter_correct": (_i, [_i, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p]),
@@ -61,7 +61,8 @@ SIGNATURES = {
     "regcn_affine_relu": (_i, [_p, _p, _p, _i, _i, _i, _p]),
     "regcn_gather_log0": (_i, [_p, _p, _i, _i, _i, _i, _d, _p, _p]),
     "regcn_hyp_query": (_i, [_p] * 5 + [_i, _i, _i, _d, _p, _p, _p]),
-    "regcn_hyp_score_epilogue": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _d, _p, _p]),
+    "regcn_hyp_score_epilogue": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _d, _p, _p, _p]),
+    "regcn_rel_curvature": (_i, [_p, _p, _i, _i, _d, _d, _p, _p]),
     "regcn_gather_target_score": (_i, [_p, _i64, _i, _i, _p, _i, _i, _p, _p]),
     "regcn_rank_count": (_i, [_p, _i64, _i, _i, _p, _i, _p, _p, _i, _p, _p, _p, _p, _p]),
     "regcn_counts_to_ranks": (_i, [_p, _p, _i, _p, _p, _p]),

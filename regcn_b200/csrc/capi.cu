@@ -137,14 +137,15 @@ void regcn_aggregate_tune(int impl) { aggregate_tune(impl); }
 int regcn_score_count_tf32(const float* q_hi, const float* q_lo, const float* e_hi, const float* e_lo, int B, int N, int K,
                            const float* tscore, const int32_t* target, int32_t* raw_count, int col_offset, int hyp,
                            const float* x2, const float* y2, const float* col_bias, double c,
-                           const float* scale_margin, int passes, void* stream) {
+                           const float* scale_margin, const float* row_c, int passes, void* stream) {
   return score_count_tf32(q_hi, q_lo, e_hi, e_lo, B, N, K, tscore, target, raw_count, col_offset, hyp, x2, y2, col_bias, c,
-                          scale_margin, passes, ST(stream));
+                          scale_margin, row_c, passes, ST(stream));
 }
 int regcn_pair_scores_tf32(const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo, int P, int K,
                            int hyp, const float* x2, const float* y2, const float* col_bias, double c,
-                           const float* scale_margin, float* out, int passes, void* stream) {
-  return pair_scores_tf32(a_hi, a_lo, b_hi, b_lo, P, K, hyp, x2, y2, col_bias, c, scale_margin, out, passes, ST(stream));
+                           const float* scale_margin, const float* row_c, float* out, int passes, void* stream) {
+  return pair_scores_tf32(a_hi, a_lo, b_hi, b_lo, P, K, hyp, x2, y2, col_bias, c, scale_margin, row_c, out, passes,
+                          ST(stream));
 }
 int regcn_gather_rows2(const float* src_hi, const float* src_lo, const int32_t* idx, int P, int d, float* out_hi,
                        float* out_lo, void* stream) {
@@ -216,8 +217,13 @@ int regcn_hyp_query(const float* s_tan, const float* ang, const float* trans, co
   return hyp_query(s_tan, ang, trans, E, triples, B, d, kind, c, Q, q_sumsq, ST(stream));
 }
 int regcn_hyp_score_epilogue(float* S, int ld, int B, int N, const float* q_sumsq, const float* e_sumsq,
-                             const float* bias, const float* qbias, double c, const float* scale_margin, void* stream) {
-  return hyp_score_epilogue(S, ld, B, N, q_sumsq, e_sumsq, bias, qbias, c, scale_margin, ST(stream));
+                             const float* bias, const float* qbias, double c, const float* scale_margin,
+                             const float* row_c, void* stream) {
+  return hyp_score_epilogue(S, ld, B, N, q_sumsq, e_sumsq, bias, qbias, c, scale_margin, row_c, ST(stream));
+}
+int regcn_rel_curvature(const float* raw, const int64_t* triples, int B, int R, double c, double cmax, float* out,
+                        void* stream) {
+  return rel_curvature(raw, triples, B, R, c, cmax, out, ST(stream));
 }
 int regcn_gather_target_score(const float* S, int64_t ld, int B, int N, const int64_t* triples, int target_col,
                               int col_offset, float* target_score, void* stream) {

@@ -213,6 +213,29 @@ __device__ __forceinline__ float hyp_score_from_dot(float dot, float x_sq, float
   return __fmul_rn(scale, __fsub_rn(margin, __fmul_rn(n, n)));
 }
 
+// K13, true-distance branch (hyperbolic_decoder.py:145-163: use_hyperbolic_distance with a per-query curvature c_q):
+//   score = scale * (margin - 2/(sqrt(c_q)+eps) * atanh(min(sqrt(c_q) * n, 1-eps))),   n = |(-q) (+)_{c_q} e|
+// from the same three scalars <q,e>, |q|^2, |e|^2.  sqrt(c_q) is sqrt(c_q + eps) like the reference (:148).
+__device__ __forceinline__ float hyp_dist_score_from_dot(float dot, float x_sq, float y_sq, float cq, float scale,
+                                                         float margin) {
+  const float sqrt_c = __fsqrt_rn(__fadd_rn(cq, kEps));
+  const float two_c_xy = __fmul_rn(__fmul_rn(2.0f, cq), dot);
+  const float a = __fadd_rn(__fsub_rn(1.0f, two_c_xy), __fmul_rn(cq, y_sq));
+  const float b = __fsub_rn(1.0f, __fmul_rn(cq, x_sq));
+  // |a*(-q) + b*e|^2 = a^2 x_sq - 2ab<q,e> + b^2 y_sq
+  const float t1 = __fmul_rn(__fmul_rn(a, a), x_sq);
+  const float t2 = __fmul_rn(__fmul_rn(__fmul_rn(2.0f, a), b), dot);
+  const float t3 = __fmul_rn(__fmul_rn(b, b), y_sq);
+  const float num_sq = fmaxf(__fadd_rn(__fsub_rn(t1, t2), t3), 0.f);
+  const float den = __fadd_rn(__fadd_rn(__fsub_rn(1.0f, two_c_xy), __fmul_rn(__fmul_rn(__fmul_rn(cq, cq), x_sq), y_sq)), kEps);
+  float n = fmaxf(__fdiv_rn(__fsqrt_rn(num_sq), fabsf(den)), kEps);
+  const float inv = __fadd_rn(sqrt_c, kEps);
+  n = fminf(n, __fsub_rn(__fdiv_rn(1.0f, inv), kEps));
+  const float arg = fminf(__fmul_rn(sqrt_c, n), 0.999999f);
+  const float dist = __fmul_rn(__fdiv_rn(2.0f, inv), atanhf(arg));
+  return __fmul_rn(scale, __fsub_rn(margin, dist));
+}
+
 // Rank contribution of candidate j (score s) against target t (score st): stable-sort position rule (rank.cu).
 __device__ __forceinline__ int rank_beats(float s, int j, float st, int t) {
   return (s > st || (s == st && j < t)) ? 1 : 0;

@@ -209,26 +209,54 @@ int hyp_query(const float* s_tan, const float* ang, const float* trans, const fl
 // clamp_norm -> min(n, proj_max) (for n >= eps).                       hyperbolic_decoder.py:164-172, ops:135-143
 __global__ void hyp_score_epilogue_kernel(float* __restrict__ S, size_t ld, int B, int N, const float* __restrict__ q_sumsq,
                                           const float* __restrict__ e_sumsq, const float* __restrict__ bias,
-                                          const float* __restrict__ qbias, Curv cv, const float* __restrict__ scale_margin) {
+                                          const float* __restrict__ qbias, Curv cv, const float* __restrict__ scale_margin,
+                                          const float* __restrict__ row_c) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   if (n >= N) return;
   const float scale = scale_margin[0], margin = scale_margin[1];
-  float v = hyp_score_from_dot(S[(size_t)b * ld + n], __ldg(q_sumsq + b), __ldg(e_sumsq + n), cv.c, cv.proj_max, scale, margin);
+  const float dot = S[(size_t)b * ld + n];
+  float v = row_c ? hyp_dist_score_from_dot(dot, __ldg(q_sumsq + b), __ldg(e_sumsq + n), __ldg(row_c + b), scale, margin)
+                  : hyp_score_from_dot(dot, __ldg(q_sumsq + b), __ldg(e_sumsq + n), cv.c, cv.proj_max, scale, margin);
   if (bias) v = __fadd_rn(v, __ldg(bias + n));
   if (qbias) v = __fadd_rn(v, __ldg(qbias + b));
   S[(size_t)b * ld + n] = v;
 }
 
 int hyp_score_epilogue(float* S, int ld, int B, int N, const float* q_sumsq, const float* e_sumsq, const float* bias,
-                       const float* qbias, double c, const float* scale_margin, cudaStream_t st) {
+                       const float* qbias, double c, const float* scale_margin, const float* row_c, cudaStream_t st) {
   if (!S || !q_sumsq || !e_sumsq || !scale_margin) { set_last_error("hyp_score_epilogue: null pointer"); return REGCN_ERR_NULL; }
   if (B <= 0 || N <= 0) return REGCN_OK;
   if (B > 65535) { set_last_error("hyp_score_epilogue: B=%d > 65535 (chunk the queries)", B); return REGCN_ERR_DIM; }
   Curv cv = make_curv(c);
   dim3 grid((N + 255) / 256, B);
-  hyp_score_epilogue_kernel<<<grid, 256, 0, st>>>(S, (size_t)ld, B, N, q_sumsq, e_sumsq, bias, qbias, cv, scale_margin);
+  hyp_score_epilogue_kernel<<<grid, 256, 0, st>>>(S, (size_t)ld, B, N, q_sumsq, e_sumsq, bias, qbias, cv, scale_margin, row_c);
   return check_launch("hyp_score_epilogue");
+}
+
+
+// Per-query curvature of the relation-specific-curvature decoders (hyperbolic_decoder.py:66-86,1020-1026):
+// c_q = max(1e-5, min(softplus(raw[r mod R]), 0.999 * c, cmax)).
+__global__ void rel_curvature_kernel(const float* __restrict__ raw, const int64_t* __restrict__ triples, int B, int R,
+                                     float upper, float* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int r = (int)(triples[3 * (size_t)b + 1] % R);
+  const float x = __ldg(raw + r);
+  const float sp = x > 20.f ? x : log1pf(expf(x));       // F.softplus (beta 1, threshold 20)
+  out[b] = fmaxf(fminf(sp, upper), 1e-5f);
+}
+
+int rel_curvature(const float* raw, const int64_t* triples, int B, int R, double c, double cmax, float* out,
+                  cudaStream_t st) {
+  if (!raw || !triples || !out) { set_last_error("rel_curvature: null pointer"); return REGCN_ERR_NULL; }
+  if (R <= 0) { set_last_error("rel_curvature: R=%d", R); return REGCN_ERR_DIM; }
+  if (B <= 0) return REGCN_OK;
+  // upper = min(0.999 * c, cmax) formed in fp32 like the reference's tensors (new_tensor(float(...)))
+  float upper = 0.999f * (float)c;
+  if (cmax > 0 && (float)cmax < upper) upper = (float)cmax;
+  rel_curvature_kernel<<<(B + 255) / 256, 256, 0, st>>>(raw, triples, B, R, upper, out);
+  return check_launch("rel_curvature");
 }
 
 }  // namespace regcn

@@ -110,12 +110,14 @@ struct Params {
   const float* col_bias;      // [N] candidate bias or NULL (epi 2: indexed by pair)
   float hc, hproj_max;        // curvature, projection bound
   const float* scale_margin;  // device [scale, margin]
+  const float* row_c;         // hyp == 2: [M] per-query curvature (true-distance branch); epi 2: indexed by pair
   float* diag_out;            // epi 2: [M]
 };
 
 __device__ __forceinline__ float finish_score(const Params& p, float dot, int row, int col, float scale, float margin) {
   float v = dot;
-  if (p.hyp) v = hyp_score_from_dot(dot, __ldg(p.x2 + row), __ldg(p.y2 + col), p.hc, p.hproj_max, scale, margin);
+  if (p.hyp == 2) v = hyp_dist_score_from_dot(dot, __ldg(p.x2 + row), __ldg(p.y2 + col), __ldg(p.row_c + row), scale, margin);
+  else if (p.hyp) v = hyp_score_from_dot(dot, __ldg(p.x2 + row), __ldg(p.y2 + col), p.hc, p.hproj_max, scale, margin);
   if (p.col_bias) v = __fadd_rn(v, __ldg(p.col_bias + col));
   return v;
 }
@@ -312,7 +314,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
           const int ncols = min(32, min(p.block_n - c0, p.N - gn0));
           if (rv && ncols > 0) {
             if (!plain) {
-              if (p.hyp) {
+              if (p.hyp == 2) {
+                const float x2r = __ldg(p.x2 + row), cq = __ldg(p.row_c + row);
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < ncols) v[j] = hyp_dist_score_from_dot(v[j], x2r, __ldg(p.y2 + gn0 + j), cq, scale, margin);
+              } else if (p.hyp) {
                 const float x2r = __ldg(p.x2 + row);
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
@@ -455,7 +462,7 @@ size_t gemm_tf32_workspace_bytes(int M, int N, int split_k) {
 
 static void clear_epi(tc::Params& p) {
   p.epi = 0; p.tscore = nullptr; p.target = nullptr; p.raw_count = nullptr; p.col_offset = 0; p.hyp = 0; p.x2 = nullptr;
-  p.y2 = nullptr; p.col_bias = nullptr; p.hc = 0.f; p.hproj_max = 0.f; p.scale_margin = nullptr; p.diag_out = nullptr;
+  p.y2 = nullptr; p.row_c = nullptr; p.col_bias = nullptr; p.hc = 0.f; p.hproj_max = 0.f; p.scale_margin = nullptr; p.diag_out = nullptr;
   p.addend = nullptr; p.ld_add = 0; p.bias = nullptr; p.accumulate = 0; p.ws = nullptr; p.C = nullptr; p.ldc = 0;
 }
 
@@ -555,13 +562,15 @@ int gemm_tf32(const float* a_hi, const float* a_lo, int lda, const float* b_hi, 
 // Candidates are rows of E (hi/lo, [N,K]); global id of row n is col_offset + n.  Scores are never written.
 int score_count_tf32(const float* q_hi, const float* q_lo, const float* e_hi, const float* e_lo, int B, int N, int K,
                      const float* tscore, const int* target, int* raw_count, int col_offset, int hyp, const float* x2,
-                     const float* y2, const float* col_bias, double c, const float* scale_margin, int passes,
-                     cudaStream_t st) {
+                     const float* y2, const float* col_bias, double c, const float* scale_margin, const float* row_c,
+                     int passes, cudaStream_t st) {
   if (!tscore || !target || !raw_count || (hyp && (!x2 || !y2 || !scale_margin))) { set_last_error("score_count_tf32: null pointer"); return REGCN_ERR_NULL; }
+  if (row_c && !hyp) { set_last_error("score_count_tf32: row_c needs hyp != 0"); return REGCN_ERR_DIM; }
   tc::Params p;
   clear_epi(p);
   p.M = B; p.N = N; p.K = K; p.epi = 1; p.tscore = tscore; p.target = target; p.raw_count = raw_count;
-  p.col_offset = col_offset; p.hyp = hyp; p.x2 = x2; p.y2 = y2; p.col_bias = col_bias; p.scale_margin = scale_margin;
+  p.col_offset = col_offset; p.hyp = hyp ? (row_c ? 2 : 1) : 0; p.x2 = x2; p.y2 = y2; p.col_bias = col_bias;
+  p.scale_margin = scale_margin; p.row_c = row_c;
   if (hyp) { Curv cv = make_curv(c); p.hc = cv.c; p.hproj_max = cv.proj_max; }
   int e = launch_tc(q_hi, q_lo, K, e_hi, e_lo, K, p, passes, 1, 0, "score_count_tf32", st);
   if (e) return e;
@@ -572,12 +581,13 @@ int score_count_tf32(const float* q_hi, const float* q_lo, const float* e_hi, co
 // gathered (hi, lo) operand rows of the P pairs; x2 / y2 / col_bias are gathered per pair as well.
 int pair_scores_tf32(const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo, int P, int K, int hyp,
                      const float* x2, const float* y2, const float* col_bias, double c, const float* scale_margin,
-                     float* out, int passes, cudaStream_t st) {
+                     const float* row_c, float* out, int passes, cudaStream_t st) {
   if (!out || (hyp && (!x2 || !y2 || !scale_margin))) { set_last_error("pair_scores_tf32: null pointer"); return REGCN_ERR_NULL; }
+  if (row_c && !hyp) { set_last_error("pair_scores_tf32: row_c needs hyp != 0"); return REGCN_ERR_DIM; }
   tc::Params p;
   clear_epi(p);
-  p.M = P; p.N = P; p.K = K; p.epi = 2; p.hyp = hyp; p.x2 = x2; p.y2 = y2; p.col_bias = col_bias;
-  p.scale_margin = scale_margin; p.diag_out = out;
+  p.M = P; p.N = P; p.K = K; p.epi = 2; p.hyp = hyp ? (row_c ? 2 : 1) : 0; p.x2 = x2; p.y2 = y2; p.col_bias = col_bias;
+  p.scale_margin = scale_margin; p.diag_out = out; p.row_c = row_c;
   if (hyp) { Curv cv = make_curv(c); p.hc = cv.c; p.hproj_max = cv.proj_max; }
   int e = launch_tc(a_hi, a_lo, K, b_hi, b_lo, K, p, passes, 1, 128, "pair_scores_tf32", st);
   if (e) return e;

@@ -36,11 +36,11 @@ void gemm_tf32_tune(int block_n, int stages);
 void aggregate_tune(int impl);
 int score_count_tf32(const float* q_hi, const float* q_lo, const float* e_hi, const float* e_lo, int B, int N, int K,
                      const float* tscore, const int* target, int* raw_count, int col_offset, int hyp, const float* x2,
-                     const float* y2, const float* col_bias, double c, const float* scale_margin, int passes,
-                     cudaStream_t st);
+                     const float* y2, const float* col_bias, double c, const float* scale_margin, const float* row_c,
+                     int passes, cudaStream_t st);
 int pair_scores_tf32(const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo, int P, int K, int hyp,
                      const float* x2, const float* y2, const float* col_bias, double c, const float* scale_margin,
-                     float* out, int passes, cudaStream_t st);
+                     const float* row_c, float* out, int passes, cudaStream_t st);
 int gather_rows2(const float* src_hi, const float* src_lo, const int* idx, int P, int d, float* out_hi, float* out_lo,
                  cudaStream_t st);
 int gather_scalars(const float* a, const float* b, const float* c, const int* ia, const int* ib, int P, float* oa,
@@ -74,7 +74,9 @@ int gather_log0(const float* E, const int64_t* triples, int col, int B, int d, i
 int hyp_query(const float* s_tan, const float* ang, const float* trans, const float* E, const int64_t* triples, int B,
               int d, int kind, double c, float* Q, float* q_sumsq, cudaStream_t st);
 int hyp_score_epilogue(float* S, int ld, int B, int N, const float* q_sumsq, const float* e_sumsq, const float* bias,
-                       const float* qbias, double c, const float* scale_margin, cudaStream_t st);
+                       const float* qbias, double c, const float* scale_margin, const float* row_c, cudaStream_t st);
+int rel_curvature(const float* raw, const int64_t* triples, int B, int R, double c, double cmax, float* out,
+                  cudaStream_t st);
 int gather_target_score(const float* S, int64_t ld, int B, int N, const int64_t* triples, int target_col,
                         int col_offset, float* target_score, cudaStream_t st);
 int rank_count(const float* S, int64_t ld, int B, int N, const int64_t* triples, int target_col, const int* filt_ptr,

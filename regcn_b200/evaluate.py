@@ -22,7 +22,8 @@ def _scoring_operands(model, emb, r_emb, all_triples):
     if name in ("HyperbolicRotH", "HyperbolicMuRP"):
         q, qss = dec.query(emb, r_emb, all_triples)
         cand = emb.contiguous()
-        return q, cand, (dec.c, qss, ops.row_sumsq(cand), dec._scale_margin()), None
+        # entity_bias[subject] shifts a whole row and cannot change a rank: only the candidate bias is needed here
+        return q, cand, dec.hyp_operands(qss, cand, all_triples), dec._entity_bias(all_triples)[0]
     raise NotImplementedError(name)
 
 

@@ -5,8 +5,9 @@ HyperbolicRotH (:931-1138) and HyperbolicRotHRel (:1141-1280).
 The all-entity hyperbolic score (:89-179, proxy-distance branch) is evaluated in norm/dot form: one dense
 contraction <q_b, e_n> followed by an epilogue that needs only |q_b|^2 and |e_n|^2, instead of
 the reference's B*N*d Mobius-add temporaries.
-Not implemented in this round (raise): entity Euclidean bias, relation-specific curvature (both default off,
-hyperbolic_main.py:803-810), the streaming-CE `loss` heads (training), AttH / MuRPRel.
+Entity Euclidean bias (candidate bias + entity_bias[subject], :1097-1098) and relation-specific curvature (per-query
+c_q, true-distance artanh branch, :145-163) are served by the same kernels (`col_bias` / `qbias` / `row_c`).
+Not implemented in this round (raise): the streaming-CE `loss` heads (training), AttH.
 """
 import math
 
@@ -19,6 +20,14 @@ from . import ops
 from .decoder import _fold_bn
 
 SCORE_SCALE_EPSILON = 1e-6
+REL_CURVATURE_EPSILON = 1e-5
+REL_CURVATURE_INIT_RATIO = 0.95
+
+
+def _relation_curvature_theta_init(global_c):
+    """hyperbolic_decoder.py:38-63: softplus(theta) = 0.95 * c."""
+    target = max(float(global_c) * REL_CURVATURE_INIT_RATIO, REL_CURVATURE_EPSILON)
+    return math.log(max(math.expm1(target), 1e-12))
 
 
 class _HypConvBase(nn.Module):
@@ -97,16 +106,42 @@ class _HypDistBase(nn.Module):
         return torch.stack((self._score_scale().detach(), self.score_margin.detach())).float().contiguous()
 
     def _unsupported_flags(self):
-        if getattr(self, "use_entity_euclidean_bias", False) or getattr(self, "use_relation_specific_curvature", False):
-            raise NotImplementedError("entity Euclidean bias / relation-specific curvature are not implemented yet "
-                                      "(default-off flags, SURVEY.md 8f-3)")
         if self.training and self.dropout.p > 0:
             raise NotImplementedError("regcn_b200 decoders: training mode needs the backward kernels; call .eval()")
 
-    def _dist_scores(self, query, q_sumsq, cand, bias):
+    def _relation_curvature(self, triplets):
+        """(B,) per-query curvature or None (hyperbolic_decoder.py:1020-1026); inverse relations share c_r."""
+        if getattr(self, "rel_curvature_raw", None) is None:
+            return None
+        return ops.rel_curvature(self.rel_curvature_raw, triplets, self.num_relations, self.c, self.rel_curvature_max)
+
+    def set_relation_curvature_bounds(self, curvature_max=None):
+        if curvature_max is not None:
+            self.rel_curvature_max = float(curvature_max)
+
+    def _entity_bias(self, triplets):
+        """(candidate bias (N,), per-query bias entity_bias[subject] (B,)) or (None, None)."""
+        eb = getattr(self, "entity_bias", None)
+        if eb is None:
+            return None, None
+        eb = eb.detach().contiguous()
+        return eb, eb[triplets[:, 0]].contiguous()
+
+    def hyp_operands(self, q_sumsq, cand, triplets):
+        """The `hyp` tuple of ops.fused_rank_counts for this decoder's score."""
+        rc = self._relation_curvature(triplets)
+        base = (self.c, q_sumsq, ops.row_sumsq(cand), self._scale_margin())
+        return base if rc is None else base + (rc,)
+
+    def _dist_scores(self, query, q_sumsq, cand, bias, triplets=None):
         e_sumsq = ops.row_sumsq(cand)
         S = ops.gemm(query, cand, trans_b=True)                                  # <q_b, e_n>
-        return ops.hyp_score_epilogue_(S, q_sumsq, e_sumsq, bias, None, self.c, self._scale_margin())
+        qbias = row_c = None
+        if triplets is not None:
+            cb, qbias = self._entity_bias(triplets)
+            bias = cb if cb is not None else bias
+            row_c = self._relation_curvature(triplets)
+        return ops.hyp_score_epilogue_(S, q_sumsq, e_sumsq, bias, qbias, self.c, self._scale_margin(), row_c)
 
 
 class HyperbolicRotH(_HypDistBase):
@@ -138,7 +173,7 @@ class HyperbolicRotH(_HypDistBase):
         else:
             self.register_parameter("entity_bias", None)
         if use_relation_specific_curvature:
-            self.rel_curvature_raw = nn.Parameter(torch.zeros(num_relations))
+            self.rel_curvature_raw = nn.Parameter(torch.full((num_relations,), _relation_curvature_theta_init(c)))
         else:
             self.register_parameter("rel_curvature_raw", None)
         self.rel_curvature_max = float(c) if use_relation_specific_curvature else None
@@ -163,7 +198,7 @@ class HyperbolicRotH(_HypDistBase):
     @torch.no_grad()
     def forward(self, entity_embedding, rel_embedding, triplets, mode="train"):
         q, qss = self.query(entity_embedding, rel_embedding, triplets)
-        return self._dist_scores(q, qss, entity_embedding.contiguous(), None)
+        return self._dist_scores(q, qss, entity_embedding.contiguous(), None, triplets)
 
     def loss(self, *a, **k):
         raise NotImplementedError("streaming-CE training head is SURVEY.md 8f rank 1 (next)")
@@ -194,7 +229,7 @@ class HyperbolicMuRP(_HypDistBase):
         else:
             self.register_parameter("entity_bias", None)
         if use_relation_specific_curvature:
-            self.rel_curvature_raw = nn.Parameter(torch.zeros(num_relations))
+            self.rel_curvature_raw = nn.Parameter(torch.full((num_relations,), _relation_curvature_theta_init(c)))
         else:
             self.register_parameter("rel_curvature_raw", None)
         self.rel_curvature_max = float(c) if use_relation_specific_curvature else None
@@ -214,7 +249,7 @@ class HyperbolicMuRP(_HypDistBase):
     @torch.no_grad()
     def forward(self, entity_embedding, rel_embedding, triplets, mode="train"):
         q, qss = self.query(entity_embedding, rel_embedding, triplets)
-        return self._dist_scores(q, qss, entity_embedding.contiguous(), None)
+        return self._dist_scores(q, qss, entity_embedding.contiguous(), None, triplets)
 
     def loss(self, *a, **k):
         raise NotImplementedError("streaming-CE training head is SURVEY.md 8f rank 1 (next)")

@@ -328,13 +328,23 @@ def hyp_query(s_tan, ang, trans, E, triples, kind, c):
     return Q, qss
 
 
-def hyp_score_epilogue_(S, q_sumsq, e_sumsq, bias, qbias, c, scale_margin):
+def rel_curvature(raw, triples, num_relations, c, cmax):
+    """Per-query curvature of the relation-specific-curvature decoders (hyperbolic_decoder.py:66-86,1020-1026)."""
+    B = triples.shape[0]
+    out = torch.empty(B, device=triples.device, dtype=F32)
+    call("regcn_rel_curvature", ptr(raw.detach().contiguous()), ptr(triples), B, int(num_relations), float(c),
+         float(cmax) if cmax is not None else 0.0, ptr(out))
+    return out
+
+
+def hyp_score_epilogue_(S, q_sumsq, e_sumsq, bias, qbias, c, scale_margin, row_c=None):
     B, N = S.shape
     step = 65535
     for b0 in range(0, B, step):
         b1 = min(B, b0 + step)
         call("regcn_hyp_score_epilogue", S[b0:b1].data_ptr(), S.stride(0), b1 - b0, N, q_sumsq[b0:b1].data_ptr(),
-             ptr(e_sumsq), ptr(bias), None if qbias is None else qbias[b0:b1].data_ptr(), float(c), ptr(scale_margin))
+             ptr(e_sumsq), ptr(bias), None if qbias is None else qbias[b0:b1].data_ptr(), float(c), ptr(scale_margin),
+             None if row_c is None else row_c[b0:b1].data_ptr())
     return S
 
 
@@ -380,7 +390,8 @@ def fused_rank_counts(q, cand, target, filt_ptr, filt_idx, pair_a, pair_e, hyp=N
 
     q (B,d), cand (N,d) fp32; target (B,) int32 global candidate ids; filt_ptr/filt_idx the filter CSR;
     pair_a/pair_e int32 pair lists: first the B (query, target) pairs, then one pair per filter-CSR entry;
-    hyp = (c, q_sumsq, e_sumsq, scale_margin) selects the hyperbolic score; col_bias (N,) optional candidate bias.
+    hyp = (c, q_sumsq, e_sumsq, scale_margin[, row_c]) selects the hyperbolic score (row_c (B,): per-query curvature,
+    true-distance artanh branch); col_bias (N,) optional candidate bias.
     Returns (raw_count, filt_count, target_score)."""
     if _GEMM_IMPL["impl"] not in ("tc", "tc1"):
         raise RuntimeError("fused_rank_counts needs the tensor-core GEMM (REGCN_GEMM=tc)")
@@ -397,24 +408,28 @@ def fused_rank_counts(q, cand, target, filt_ptr, filt_idx, pair_a, pair_e, hyp=N
     b_lo = torch.empty((P, K), device=dev, dtype=F32) if passes == 3 else None
     call("regcn_gather_rows2", ptr(q_hi), ptr(q_lo), ptr(pair_a), P, K, ptr(a_hi), ptr(a_lo))
     call("regcn_gather_rows2", ptr(e_hi), ptr(e_lo), ptr(pair_e), P, K, ptr(b_hi), ptr(b_lo))
-    c, x2, y2, sm = (hyp if hyp is not None else (1.0, None, None, None))
-    x2p = y2p = bp = None
+    c, x2, y2, sm = (hyp[:4] if hyp is not None else (1.0, None, None, None))
+    row_c = hyp[4] if hyp is not None and len(hyp) > 4 else None
+    x2p = y2p = bp = rcp = None
     if hyp is not None or col_bias is not None:
         x2p = torch.empty(P, device=dev, dtype=F32) if hyp is not None else None
         y2p = torch.empty(P, device=dev, dtype=F32) if hyp is not None else None
         bp = torch.empty(P, device=dev, dtype=F32) if col_bias is not None else None
         call("regcn_gather_scalars", ptr(x2), ptr(y2), ptr(col_bias), ptr(pair_a), ptr(pair_e), P, ptr(x2p), ptr(y2p),
              ptr(bp))
+        if row_c is not None:
+            rcp = torch.empty(P, device=dev, dtype=F32)
+            call("regcn_gather_scalars", ptr(row_c), None, None, ptr(pair_a), ptr(pair_e), P, ptr(rcp), None, None)
     ps = torch.empty(P, device=dev, dtype=F32)
     call("regcn_pair_scores_tf32", ptr(a_hi), ptr(a_lo), ptr(b_hi), ptr(b_lo), P, K, int(hyp is not None), ptr(x2p),
-         ptr(y2p), ptr(bp), float(c), ptr(sm), ptr(ps), passes)
+         ptr(y2p), ptr(bp), float(c), ptr(sm), ptr(rcp), ptr(ps), passes)
     lo, hi = shard if shard is not None else (0, N)
     raw = torch.zeros(B, device=dev, dtype=I32)
     if hi > lo:
         call("regcn_score_count_tf32", ptr(q_hi), ptr(q_lo), e_hi[lo:hi].data_ptr(),
              e_lo[lo:hi].data_ptr() if e_lo is not None else None, B, hi - lo, K, ptr(ps), ptr(target), ptr(raw), lo,
              int(hyp is not None), ptr(x2), y2[lo:hi].data_ptr() if y2 is not None else None,
-             col_bias[lo:hi].data_ptr() if col_bias is not None else None, float(c), ptr(sm), passes)
+             col_bias[lo:hi].data_ptr() if col_bias is not None else None, float(c), ptr(sm), ptr(row_c), passes)
     filt = torch.empty(B, device=dev, dtype=I32)
     call("regcn_filter_correct", B, ptr(filt_ptr), ptr(filt_idx), ptr(target), ptr(ps), ptr(raw), lo, hi, ptr(filt),
          ptr(filt_end))

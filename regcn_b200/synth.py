@@ -61,6 +61,8 @@ def _scale_for(name, shape):
         return "radius"
     if leaf in ("score_scale_raw", "score_margin"):
         return "one"
+    if leaf == "rel_curvature_raw":
+        return "relcurv"
     if ".bn" in name and leaf == "weight":
         return "bnw"
     if leaf in ("bias", "b", "time_gate_bias", "skip_connect_bias", "skip_bias", "rel_bias", "entity_bias",
@@ -96,6 +98,8 @@ def fill_state_dict(state_dict, seed):
             v = rng.uniform(0.8, 1.2, size=shape)
         elif kind == "radius":
             v = rng.uniform(0.6, 2.9, size=shape)
+        elif kind == "relcurv":
+            v = -4.65 + 0.5 * rng.standard_normal(size=shape)     # softplus ~ 0.006 .. 0.016 around 0.95 c (c = 0.01)
         elif kind == "one":
             v = np.full(shape, 1.0) + rng.uniform(-0.2, 0.2, size=shape)
         else:

@@ -36,7 +36,9 @@ def build_model(cfg, n, r, h_dim=H_DIM):
                                       skip_connect=False, layer_norm=cfg["layer_norm"], input_dropout=0.2,
                                       hidden_dropout=0.2, feat_dropout=0.2, entity_prediction=True,
                                       relation_prediction=True, use_cuda=True, gpu=0,
-                                      radius_msg_gamma=cfg["gamma"], hyp_init_scale=1e-3)
+                                      radius_msg_gamma=cfg["gamma"], hyp_init_scale=1e-3,
+                                      use_entity_euclidean_bias=cfg.get("entity_bias", False),
+                                      use_relation_specific_curvature=cfg.get("rel_curvature", False))
     sd = synth.fill_state_dict(m.state_dict(), cfg["seed"])
     m.load_state_dict(sd)
     m.eval()

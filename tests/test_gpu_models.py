@@ -214,7 +214,8 @@ def test_layer_signatures_drop_in():
         layer.train()(g, [], rel.to(DEV))        # training-mode dropout is refused loudly, never silently skipped
 
 
-@pytest.mark.parametrize("kind", ["regcn", "hyp_uv_roth", "hyp_uv_convtranse", "hyp_lgcn_murp"])
+@pytest.mark.parametrize("kind", ["regcn", "hyp_uv_roth", "hyp_uv_convtranse", "hyp_lgcn_murp", "hyp_uv_roth_flags",
+                                  "hyp_lgcn_murp_flags"])
 def test_fused_rank_equals_dense_rank_bit_exact(kind):
     """The counting epilogue of the scoring GEMM (no score matrix) must give exactly the ranks the rank kernel derives
     from the materialised score matrix of the same GEMM -- raw and filtered, whole table and entity shards."""
@@ -227,7 +228,12 @@ def test_fused_rank_equals_dense_rank_bit_exact(kind):
            "hyp_uv_convtranse": dict(kind="hyp", shape="small", seed=7, layer_norm=False, encoder="hyperbolic_uvrgcn",
                                      decoder="hyperbolic_convtranse", gamma=0.15),
            "hyp_lgcn_murp": dict(kind="hyp", shape="small_l", seed=8, layer_norm=False, encoder="lgcn", decoder="murp",
-                                 gamma=0.15)}[kind]
+                                 gamma=0.15),
+           # entity Euclidean bias + relation-specific curvature: artanh true-distance epilogue, per-query c_q
+           "hyp_uv_roth_flags": dict(kind="hyp", shape="c1", seed=9, layer_norm=False, encoder="hyperbolic_uvrgcn",
+                                     decoder="roth", gamma=0.15, entity_bias=True, rel_curvature=True),
+           "hyp_lgcn_murp_flags": dict(kind="hyp", shape="small_l", seed=10, layer_norm=False, encoder="lgcn",
+                                       decoder="murp", gamma=0.15, entity_bias=True, rel_curvature=True)}[kind]
     case = synth.make_case(cfg["shape"], cfg["seed"])
     n, r = case["num_ents"], case["num_rels"]
     model, _ = build_model(cfg, n, r)
