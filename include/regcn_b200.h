@@ -40,13 +40,14 @@ REGCN_API int regcn_device_ok(void);
  * CSR by destination (stable in edge id): rowptr (N+1), src_sorted/etype_sorted/eperm (E);
  * virtual rows (chunks of 32 in-edges) of the ACTIVE destinations only: vptr/sptr (N+1), vrow_row (min(N,E)+E/32+1);
  * active_pos (N): position of a destination among the active ones (in-degree > 0), -1 otherwise;
+ * active_rows (min(N,E)): the inverse map, the sorted ids of the active destinations;
  * relation->entity CSR shared by r and r+R: rel_rowptr (R+1), rel_ents (<= 2T, sorted per relation);
  * counts[8] = {n_virtual_rows, n_split_chunks, n_rel_ents, max_hub_degree, n_active, 0, 0, 0}.   */
 REGCN_API size_t regcn_csr_build_workspace_bytes(int T, int N, int R);
 REGCN_API int regcn_csr_build(const int64_t* triples, int T, int N, int R,
                     int32_t* src, int32_t* dst, int32_t* etype, int32_t* indeg, float* norm,
                     int32_t* rowptr, int32_t* src_sorted, int32_t* etype_sorted, int32_t* eperm,
-                    int32_t* vptr, int32_t* sptr, int32_t* vrow_row, int32_t* active_pos,
+                    int32_t* vptr, int32_t* sptr, int32_t* vrow_row, int32_t* active_pos, int32_t* active_rows,
                     int32_t* rel_rowptr, int32_t* rel_ents, int32_t* counts,
                     void* workspace, size_t workspace_bytes, void* stream);
 
@@ -60,7 +61,7 @@ typedef struct regcn_csr_arrays {
   int32_t T;
   int32_t* src; int32_t* dst; int32_t* etype; int32_t* indeg; float* norm;
   int32_t* rowptr; int32_t* src_sorted; int32_t* etype_sorted; int32_t* eperm;
-  int32_t* vptr; int32_t* sptr; int32_t* vrow_row; int32_t* active_pos;
+  int32_t* vptr; int32_t* sptr; int32_t* vrow_row; int32_t* active_pos; int32_t* active_rows;
   int32_t* rel_rowptr; int32_t* rel_ents; int32_t* counts;
 } regcn_csr_arrays;
 REGCN_API size_t regcn_csr_build_batch_workspace_bytes(const int32_t* T, int L, int N, int R);
@@ -240,7 +241,7 @@ enum { RM_DYNAMIC_EMB = 0, RM_EMB_REL, RM_EMB_REL_HI, RM_EMB_REL_LO, RM_GI_STATI
        /* RM_LAYER0 + 8*l: W_n^T hi,lo | [W_loop|W_evolve(|W_time)]^T hi,lo | [W_n;W_loop]^T hi,lo | [W_evolve(|W_time)]^T hi,lo */ };
 enum { RMI_NUM_ENTS = 0, RMI_NUM_RELS2, RMI_DIM, RMI_NUM_LAYERS, RMI_LAYER_NORM, RMI_SELF_LOOP, RMI_NUM_INTS };
 enum { RG_ROWPTR = 0, RG_SRC_SORTED, RG_ETYPE_SORTED, RG_INDEG, RG_NORM, RG_VPTR, RG_SPTR, RG_VROW_ROW,
-       RG_REL_ROWPTR, RG_REL_ENTS, RG_ACTIVE_POS, RG_NUM_PTRS };
+       RG_REL_ROWPTR, RG_REL_ENTS, RG_ACTIVE_POS, RG_ACTIVE_ROWS, RG_NUM_PTRS };
 enum { RGI_NUM_EDGES = 0, RGI_N_VROWS, RGI_N_SPLIT_CHUNKS, RGI_N_REL_ENTS, RGI_N_ACTIVE, RGI_MAX_CHUNKS, RGI_NUM_INTS };
 REGCN_API size_t regcn_regcn_evolve_workspace_bytes(int N, int R2, int d, int max_split_chunks, int rel_nsplit);
 REGCN_API int regcn_regcn_evolve(const void* const* model_ptrs, const int* model_ints, const void* const* graph_ptrs,

@@ -25,7 +25,7 @@ SIGNATURES = {
     "regcn_last_error_string": (ctypes.c_char_p, []),
     "regcn_device_ok": (_i, []),
     "regcn_csr_build_workspace_bytes": (_sz, [_i, _i, _i]),
-    "regcn_csr_build": (_i, [_p, _i, _i, _i] + [_p] * 16 + [_p, _sz, _p]),
+    "regcn_csr_build": (_i, [_p, _i, _i, _i] + [_p] * 17 + [_p, _sz, _p]),
     "regcn_csr_build_batch_workspace_bytes": (_sz, [_p, _i, _i, _i]),
     "regcn_csr_build_batch": (_i, [_p, _i, _i, _i, _p, _sz, _p]),
     "regcn_rel_mean_pool": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p]),
@@ -77,7 +77,8 @@ class CsrArrays(ctypes.Structure):
     """struct regcn_csr_arrays (include/regcn_b200.h): the device pointers of one snapshot's index."""
     _fields_ = ([("triples", _p), ("T", ctypes.c_int32)] +
                 [(n, _p) for n in ("src", "dst", "etype", "indeg", "norm", "rowptr", "src_sorted", "etype_sorted",
-                                   "eperm", "vptr", "sptr", "vrow_row", "active_pos", "rel_rowptr", "rel_ents",
+                                   "eperm", "vptr", "sptr", "vrow_row", "active_pos", "active_rows", "rel_rowptr",
+                                   "rel_ents",
                                    "counts")])
 
 

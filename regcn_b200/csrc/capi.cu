@@ -80,9 +80,10 @@ size_t regcn_csr_build_workspace_bytes(int T, int N, int R) { return csr_build_w
 int regcn_csr_build(const int64_t* triples, int T, int N, int R, int32_t* src, int32_t* dst, int32_t* etype,
                     int32_t* indeg, float* norm, int32_t* rowptr, int32_t* src_sorted, int32_t* etype_sorted,
                     int32_t* eperm, int32_t* vptr, int32_t* sptr, int32_t* vrow_row, int32_t* active_pos,
-                    int32_t* rel_rowptr, int32_t* rel_ents, int32_t* counts, void* workspace, size_t workspace_bytes, void* stream) {
+                    int32_t* active_rows, int32_t* rel_rowptr, int32_t* rel_ents, int32_t* counts, void* workspace,
+                    size_t workspace_bytes, void* stream) {
   return csr_build(triples, T, N, R, src, dst, etype, indeg, norm, rowptr, src_sorted, etype_sorted, eperm, vptr, sptr,
-                   vrow_row, active_pos, rel_rowptr, rel_ents, counts, workspace, workspace_bytes, ST(stream));
+                   vrow_row, active_pos, active_rows, rel_rowptr, rel_ents, counts, workspace, workspace_bytes, ST(stream));
 }
 size_t regcn_csr_build_batch_workspace_bytes(const int32_t* T, int L, int N, int R) {
   return T ? csr_build_batch_workspace_bytes(T, L, N, R) : 0;

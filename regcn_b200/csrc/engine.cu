@@ -114,15 +114,48 @@ int regcn_regcn_evolve(const void* const* mp, const int* mi, const void* const* 
     // dense snapshots keep  rrelu(agg . W_n + where(indeg>0, x.W_loop, x.W_evolve)).
     const int n_active = gn[RGI_N_ACTIVE];
     const bool sparse = n_active * 2 <= N;
-    const float* gate_G;
-    int gate_ld;
+    const float* gate_G = nullptr;
+    int gate_ld = 0;
+    bool gate_done = false;
     for (int l = 0; l < nl; ++l) {
       const int base = RM_LAYER0 + RM_LAYER_STRIDE * l;
       const bool last = l == nl - 1;
       float* o_raw = ws + w.set[l & 1][0];
       float* o_hi = last ? nullptr : ws + w.set[l & 1][1];
       float* o_lo = last ? nullptr : ws + w.set[l & 1][2];
-      if (sparse) {
+      if (sparse && nl >= 2) {
+        // Row-partitioned layer with the elementwise tail fused into the GEMM epilogues (gemm_tf32_layer):
+        //   inactive rows : x' = rrelu(x . W_evolve) written as the TF32 split only (nobody reads their fp32 rows: every
+        //                   edge source is also a destination, so the next aggregate gathers active rows only);
+        //                   layer 0 also emits the gate pre-activations x . W_time, the last layer applies the time gate
+        //   active rows   : x' = rrelu([agg | x] . [W_n ; W_loop]) scattered back through active_rows
+        const int ncol = (l == 0 ? 2 : 1) * d;           // [W_evolve (| W_time)]
+        const int* arows = GI(RG_ACTIVE_ROWS);
+        if ((e = union_aggregate(x_raw, h0_raw, GI(RG_ROWPTR), GI(RG_SRC_SORTED), GI(RG_ETYPE_SORTED), (const float*)g[RG_NORM],
+                                 GI(RG_VPTR), GI(RG_SPTR), GI(RG_VROW_ROW), gn[RGI_N_VROWS], gn[RGI_N_SPLIT_CHUNKS], nullptr,
+                                 0.f, N, d, nullptr, ws + w.partial, ws + w.agg_hi, ws + w.agg_lo, GI(RG_ACTIVE_POS), 2 * d,
+                                 gn[RGI_MAX_CHUNKS], st))) return e;
+        if (!last) {
+          if ((e = gemm_tf32_layer(x_hi, x_lo, d, F(base + 6), F(base + 7), d, N, ncol, d, d, nullptr, o_hi, o_lo,
+                                   l == 0 ? ws + w.Lm : nullptr, d, nullptr, GI(RG_ACTIVE_POS), nullptr, 0, nullptr, nullptr,
+                                   0, st))) return e;
+          if (n_active > 0 &&
+              (e = gemm_tf32_layer(ws + w.agg_hi, ws + w.agg_lo, 2 * d, F(base + 4), F(base + 5), 2 * d, n_active, d, 2 * d, d,
+                                   o_raw, o_hi, o_lo, nullptr, 0, arows, nullptr, nullptr, 0, nullptr, nullptr, 0, st))) return e;
+        } else {
+          float* h_new = hist + (size_t)i * nd;
+          if (n_active > 0 &&
+              (e = gemm_tf32(ws + w.agg_hi, ws + w.agg_lo, 2 * d, F(base + 4), F(base + 5), 2 * d, ws + w.P, d, n_active, d,
+                             2 * d, nullptr, 0, 3, 1, nullptr, 0, nullptr, 0, st))) return e;
+          if ((e = gemm_tf32_layer(x_hi, x_lo, d, F(base + 6), F(base + 7), d, N, d, d, d, h_new, ws + w.h_hi, ws + w.h_lo,
+                                   nullptr, 0, nullptr, GI(RG_ACTIVE_POS), ws + w.Lm, d, F(RM_GATE_BIAS), h_raw, layer_norm,
+                                   st))) return e;
+          if (n_active > 0 &&
+              (e = time_gate(ws + w.Lm, F(RM_GATE_BIAS), ws + w.P, h_raw, h_new, n_active, d, layer_norm, d, ws + w.h_hi,
+                             ws + w.h_lo, st, arows, 1))) return e;
+          gate_done = true;
+        }
+      } else if (sparse) {
         const int ncol = (l == 0 ? 2 : 1) * d;           // [W_evolve (| W_time)]
         float* Le = (l == 0) ? ws + w.Lm : ws + w.L2;
         if ((e = union_aggregate(x_raw, h0_raw, GI(RG_ROWPTR), GI(RG_SRC_SORTED), GI(RG_ETYPE_SORTED), (const float*)g[RG_NORM],
@@ -156,7 +189,8 @@ int regcn_regcn_evolve(const void* const* mp, const int* mi, const void* const* 
     }
     // ---- time gate (K9): h = s(h W_t + b) * [normalize](cur) + (1 - s) * h ----
     float* h_new = hist + (size_t)i * nd;
-    if ((e = time_gate(gate_G, F(RM_GATE_BIAS), x_raw, h_raw, h_new, N, d, layer_norm, gate_ld, ws + w.h_hi,
+    if (!gate_done &&
+        (e = time_gate(gate_G, F(RM_GATE_BIAS), x_raw, h_raw, h_new, N, d, layer_norm, gate_ld, ws + w.h_hi,
                        ws + w.h_lo, st))) return e;
     h_raw = h_new;
   }

@@ -8,8 +8,10 @@
 // which restores ~2^-21 relative operand precision (the dropped lo.lo term is 2^-22).  With passes == 1 only
 // hi.hi is issued (plain TF32, ~1e-3 relative) -- reported separately, never used for the parity path.
 //
-// Warp roles (192 threads):  warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
-// warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).  One 128 x BLOCK_N output tile per CTA; grid.z = split-K.
+// Warp roles (320 threads):  warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
+// warps 2..9 = epilogue (TMEM lane quarter = warp_id % 4, two warps per quarter splitting the 32-column chunks: one
+// warp per scheduler cannot hide the ALU / memory latency of a non-trivial epilogue).  Persistent: each CTA walks a
+// list of 128 x BLOCK_N output tiles (x split-K slices).
 // K is walked in 32-float (128-byte) blocks; TMA zero-fills the K / M / N tails.
 #include "common.cuh"
 #include <cuda.h>
@@ -21,8 +23,14 @@ namespace tc {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 32;            // fp32 elements = one 128-byte swizzle row
 constexpr int UMMA_K = 8;              // tf32
-constexpr int NUM_THREADS = 192;
-constexpr uint32_t SMEM_BUDGET = 200 * 1024;
+constexpr int EPI_WARPS = 8;           // epilogue warps: 2 per TMEM lane quarter, each takes every other 32-column chunk
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
+constexpr uint32_t SMEM_BUDGET = 192 * 1024;   // operand ring; + 32 KB of epilogue staging + alignment slack <= 227 KB
+constexpr int kStagePitch = 32;                                      // floats per row of an epilogue staging tile (XOR-swizzled)
+constexpr uint32_t STAGING_BYTES = EPI_WARPS * 32 * kStagePitch * 4; // one 32 x 32 fp32 tile per epilogue warp
+// staging tile addressing: float4 block q of row r lives at block (q ^ (r & 7)) -- conflict-free for the row-per-thread
+// writes (a quarter-warp writes 8 different blocks) and for the transposed reads (8 lanes read the 8 blocks of one row)
+__device__ __forceinline__ int stage_off(int r, int q) { return r * kStagePitch + 4 * (q ^ (r & 7)); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -112,7 +120,24 @@ struct Params {
   const float* scale_margin;  // device [scale, margin]
   const float* row_c;         // hyp == 2: [M] per-query curvature (true-distance branch); epi 2: indexed by pair
   float* diag_out;            // epi 2: [M]
+  // ---- fused layer epilogue (epi 3): UnionRGCNLayer apply (rgcn/layers.py:247-255) and, for the last layer, the
+  //      time gate (src/rrgcn.py:176-178) straight out of the accumulator ----
+  int lay_d;                  // hidden size: columns [0, lay_d) are layer outputs rrelu(acc); columns >= lay_d are stored
+                              // unchanged to C[row, col - lay_d] (gate pre-activations x.W_time riding in the same GEMM)
+  float* lay_raw;             // [*, lay_d] fp32 output rows (NULL: not needed)
+  float* lay_hi;              // [*, lay_d] TF32 split of the output for the consumer GEMM (NULL: not needed)
+  float* lay_lo;
+  const int* row_idx;         // tile row r writes output row row_idx[r] (compact active-row GEMM); NULL = identity
+  const int* skip_rows;       // rows with skip_rows[row] >= 0 are left alone (they belong to the compact GEMM)
+  const float* gate_G;        // time gate: pre-activation [*, gate_ld] (NULL = no gate); needs N == lay_d <= block_n
+  int gate_ld;
+  const float* gate_bias;     // [lay_d]
+  const float* gate_h;        // [*, lay_d] previous entity state
+  int gate_norm;              // F.normalize the layer output first (layer_norm)
 };
+
+// sigmoid on the SFU (ex2.approx + rcp.approx, ~2 ulp): the epilogue warps have no spare issue slots for the IEEE path
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 __device__ __forceinline__ float finish_score(const Params& p, float dot, int row, int col, float scale, float margin) {
   float v = dot;
@@ -126,6 +151,7 @@ __device__ __forceinline__ float finish_score(const Params& p, float dot, int ro
 //   smem ring   full[s] / empty[s]          TMA producer  <-> MMA issuer   (continues across tiles)
 //   TMEM slots  tmem_full[a] / tmem_empty[a] MMA issuer   <-> epilogue     (2 accumulators of block_n columns)
 // so the epilogue of tile i (TMEM -> registers -> global / counting) overlaps the main loop of tile i+1.
+template <int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                  const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
@@ -158,7 +184,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&tmem_full_bar[a]), 1);
-      mbar_init(smem_u32(&tmem_empty_bar[a]), 128);     // every epilogue thread arrives
+      mbar_init(smem_u32(&tmem_empty_bar[a]), 32 * EPI_WARPS);     // every epilogue thread arrives
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -179,7 +205,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     const int nt = r / p.m_tiles;
     const int mt = r - nt * p.m_tiles;
     m0 = mt * BLOCK_M;
-    n0 = p.epi == 2 ? m0 : nt * p.block_n;   // pair scores: diagonal tiles only
+    n0 = EPI == 2 ? m0 : nt * p.block_n;   // pair scores: diagonal tiles only
     kb_beg = z * p.kb_per_split;
     kb_end = min(total_kb, kb_beg + p.kb_per_split);
   };
@@ -251,8 +277,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
   } else {
     // ===================== epilogue: TMEM -> registers -> global / counts =====================
     const int quarter = warp & 3;                      // TMEM lanes [32*quarter, 32*quarter+32)
+    const int part = (warp - 2) >> 2;                  // which share of the 32-column chunks this warp takes
+    constexpr int kParts = EPI_WARPS / 4;
+    float* stage = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes) + (warp - 2) * (32 * kStagePitch);
     float scale = 1.f, margin = 0.f;
-    if (p.epi != 0 && p.hyp) { scale = __ldg(p.scale_margin); margin = __ldg(p.scale_margin + 1); }
+    if (EPI != 0 && EPI != 3 && p.hyp) { scale = __ldg(p.scale_margin); margin = __ldg(p.scale_margin + 1); }
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       int m0, n0, kb_beg, kb_end;
@@ -263,51 +292,77 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
       mbar_wait(smem_u32(&tmem_full_bar[slot]), acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tmem_acc = tmem_base + (uint32_t)(slot * (p.tmem_cols >> 1)) + ((uint32_t)(quarter * 32) << 16);
-      if (p.epi == 0) {
+      if constexpr (EPI == 0) {
+        // Store epilogue.  The accumulator arrives one ROW per thread (TMEM lane = row); written like that, every
+        // store instruction would touch 32 rows x 16 bytes.  Each warp therefore transposes its 32 x 32 chunk through a
+        // private shared-memory tile (pitch 36 floats: conflict-free float4 writes and reads) so that a store
+        // instruction covers 4 rows x 128 contiguous bytes -- full sectors, full lines.
         const bool split = p.splits > 1;
         const int z = t / tiles_mn;
         float* out = split ? p.ws + (size_t)z * (size_t)p.M * (size_t)p.N : p.C;
         const int ldo = split ? p.N : p.ldc;
-        const bool vec_ok = ((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-        for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        const bool vec_ok = ((ldo & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
+                            (!p.addend || (((p.ld_add & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.addend) & 15) == 0)));
+        const int sub_r = lane >> 3, sub_q = lane & 7, sub_c = sub_q * 4;
+        for (int c0 = 32 * part; c0 < p.block_n; c0 += 32 * kParts) {
           float v[32];
           tmem_ld32(tmem_acc + (uint32_t)c0, v);
           const int gn0 = n0 + c0;
           const int ncols = min(32, min(p.block_n - c0, p.N - gn0));   // columns of this chunk owned by this tile
-          if (row < p.M && ncols > 0) {
-            float* dst = out + (size_t)row * ldo + gn0;
-            if (!split) {
-              if (p.bias) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += __ldg(p.bias + gn0 + j);
-              }
-              if (p.accumulate) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += dst[j];
-              }
-              if (p.addend) {
-                const float* ad = p.addend + (size_t)row * p.ld_add + gn0;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += __ldg(ad + j);
-              }
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(stage + stage_off(lane, q)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          __syncwarp();
+          if (ncols > 0) {
+            const int col = gn0 + sub_c;
+            const int nc = min(4, ncols - sub_c);              // valid columns of this lane's float4 (<= 0: none)
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!split && p.bias && nc > 0) {
+              b4.x = __ldg(p.bias + col);
+              if (nc > 1) b4.y = __ldg(p.bias + col + 1);
+              if (nc > 2) b4.z = __ldg(p.bias + col + 2);
+              if (nc > 3) b4.w = __ldg(p.bias + col + 3);
             }
-            if (vec_ok && ncols == 32 && (gn0 & 3) == 0) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) st4(dst + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (j < ncols) dst[j] = v[j];
+            for (int i = 0; i < 8; ++i) {
+              const int r = 4 * i + sub_r;
+              const int grow = m0 + quarter * 32 + r;
+              if (grow < p.M && nc > 0) {
+                float4 a = *reinterpret_cast<const float4*>(stage + stage_off(r, sub_q));
+                float* dst = out + (size_t)grow * ldo + col;
+                if (vec_ok && nc == 4) {
+                  if (!split) {
+                    a = f4_add(a, b4);
+                    if (p.accumulate) a = f4_add(a, *reinterpret_cast<const float4*>(dst));
+                    if (p.addend) a = f4_add(a, *reinterpret_cast<const float4*>(p.addend + (size_t)grow * p.ld_add + col));
+                  }
+                  st4(dst, a);
+                } else {
+                  float e[4] = {a.x, a.y, a.z, a.w};
+                  const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+                  for (int j = 0; j < nc; ++j) {
+                    float x = e[j];
+                    if (!split) {
+                      x += bb[j];
+                      if (p.accumulate) x += dst[j];
+                      if (p.addend) x += p.addend[(size_t)grow * p.ld_add + col + j];
+                    }
+                    dst[j] = x;
+                  }
+                }
+              }
             }
           }
+          __syncwarp();
         }
-      } else if (p.epi == 1) {
+      } else if constexpr (EPI == 1) {
         // fused K14: count the candidates of this tile that rank ahead of the row's target; nothing is stored
         const bool rv = row < p.M;
         const float st_ = rv ? __ldg(p.tscore + row) : 0.f;
         const int tg = rv ? __ldg(p.target + row) - p.col_offset : -1;
         int cnt = 0;
         const bool plain = !p.hyp && !p.col_bias;          // hoisted: no per-element uniform branches in the hot loop
-        for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        for (int c0 = 32 * part; c0 < p.block_n; c0 += 32 * kParts) {
           float v[32];
           tmem_ld32(tmem_acc + (uint32_t)c0, v);
           const int gn0 = n0 + c0;
@@ -340,6 +395,98 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
           }
         }
         if (rv && cnt) atomicAdd(p.raw_count + row, cnt);
+      } else if constexpr (EPI == 3) {
+        // Fused layer epilogue, same transposed staging as the store epilogue: per-row quantities (output row, skip
+        // flag, row norm) are computed by the thread that owns the row in TMEM and fetched by shuffle afterwards.
+        const bool rv = row < p.M;
+        int my_orow = rv ? row : 0;
+        int my_skip = rv ? 0 : 1;
+        if (rv && p.row_idx) my_orow = __ldg(p.row_idx + row);
+        if (rv && p.skip_rows && __ldg(p.skip_rows + row) >= 0) my_skip = 1;
+        float my_nrm = 1.f;
+        const bool gate = p.gate_G != nullptr;
+        if (gate && p.gate_norm) {
+          // pass 1 over the accumulator: |rrelu(acc)| of the whole row (the tile spans all lay_d columns)
+          float ss = 0.f;
+          for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+            float v[32];
+            tmem_ld32(tmem_acc + (uint32_t)c0, v);
+            const int ncols = min(32, p.lay_d - c0);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float r = rreluf_(v[j]);
+              ss = j < ncols ? fmaf(r, r, ss) : ss;
+            }
+          }
+          my_nrm = 1.0f / fmaxf(sqrtf(ss), 1e-12f);     // F.normalize: x / max(|x|, 1e-12), applied as a multiply
+        }
+        const int sub_r = lane >> 3, sub_q = lane & 7, sub_c = sub_q * 4;
+        for (int c0 = 32 * part; c0 < p.block_n; c0 += 32 * kParts) {
+          float v[32];
+          tmem_ld32(tmem_acc + (uint32_t)c0, v);
+          const int gn0 = n0 + c0;
+          const int ncols = min(32, min(p.block_n - c0, p.N - gn0));
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(stage + stage_off(lane, q)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          __syncwarp();
+          const int col = gn0 + sub_c;
+          const bool cvalid = sub_c < ncols;                 // N and lay_d are multiples of 4: whole float4 or nothing
+          const bool is_out = col < p.lay_d;
+          // batch every global load of the chunk first (16 independent float4 loads in flight per thread), then compute
+          float4 g4[8], h4[8];
+          int orow_[8];
+          float nrm_[8];
+          bool wr_[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = 4 * i + sub_r;
+            const int orow = __shfl_sync(0xffffffffu, my_orow, r);
+            const int skip = __shfl_sync(0xffffffffu, my_skip, r);
+            nrm_[i] = __shfl_sync(0xffffffffu, my_nrm, r);
+            const bool rowv = (m0 + quarter * 32 + r) < p.M;
+            orow_[i] = orow;
+            // skip_rows only masks the layer-output columns: the gate pre-activations are needed for every row
+            wr_[i] = rowv && cvalid && (is_out ? !skip : true);
+            if (gate && wr_[i] && is_out) {
+              g4[i] = *reinterpret_cast<const float4*>(p.gate_G + (size_t)orow * p.gate_ld + col);
+              h4[i] = *reinterpret_cast<const float4*>(p.gate_h + (size_t)orow * p.lay_d + col);
+            }
+          }
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (gate && cvalid && is_out) b4 = ldg4(p.gate_bias + col);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (!wr_[i]) continue;
+            const int r = 4 * i + sub_r;
+            float4 a = *reinterpret_cast<const float4*>(stage + stage_off(r, sub_q));
+            if (is_out) {
+              a.x = rreluf_(a.x); a.y = rreluf_(a.y); a.z = rreluf_(a.z); a.w = rreluf_(a.w);
+              const size_t o = (size_t)orow_[i] * p.lay_d + col;
+              if (gate) {
+                if (p.gate_norm) {
+                  const float nrm = nrm_[i];
+                  a.x = a.x * nrm; a.y = a.y * nrm; a.z = a.z * nrm; a.w = a.w * nrm;
+                }
+                const float sx = fast_sigmoid(g4[i].x + b4.x), sy = fast_sigmoid(g4[i].y + b4.y);
+                const float sz = fast_sigmoid(g4[i].z + b4.z), sw = fast_sigmoid(g4[i].w + b4.w);
+                a.x = sx * a.x + (1.0f - sx) * h4[i].x; a.y = sy * a.y + (1.0f - sy) * h4[i].y;
+                a.z = sz * a.z + (1.0f - sz) * h4[i].z; a.w = sw * a.w + (1.0f - sw) * h4[i].w;
+              }
+              if (p.lay_raw) st4(p.lay_raw + o, a);
+              if (p.lay_hi) {
+                float4 h, l;
+                split_tf32_1(a.x, h.x, l.x); split_tf32_1(a.y, h.y, l.y);
+                split_tf32_1(a.z, h.z, l.z); split_tf32_1(a.w, h.w, l.w);
+                st4(p.lay_hi + o, h);
+                st4(p.lay_lo + o, l);
+              }
+            } else {
+              st4(p.C + (size_t)orow_[i] * p.ldc + (col - p.lay_d), a);
+            }
+          }
+          __syncwarp();
+        }
       } else {
         // pair scores: the tile is a diagonal block of A' . B'^T (pair p = row), keep acc[r][r]
         float v[32];
@@ -347,7 +494,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         float dsel = 0.f;
 #pragma unroll
         for (int j = 0; j < 32; ++j) if (j == lane) dsel = v[j];
-        if (row < p.M) p.diag_out[row] = finish_score(p, dsel, row, row, scale, margin);
+        if (row < p.M && part == 0) p.diag_out[row] = finish_score(p, dsel, row, row, scale, margin);
       }
       // this thread's TMEM reads of the slot are complete (tcgen05.wait::ld inside tmem_ld32): hand it back to the MMA warp
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -464,6 +611,8 @@ static void clear_epi(tc::Params& p) {
   p.epi = 0; p.tscore = nullptr; p.target = nullptr; p.raw_count = nullptr; p.col_offset = 0; p.hyp = 0; p.x2 = nullptr;
   p.y2 = nullptr; p.row_c = nullptr; p.col_bias = nullptr; p.hc = 0.f; p.hproj_max = 0.f; p.scale_margin = nullptr; p.diag_out = nullptr;
   p.addend = nullptr; p.ld_add = 0; p.bias = nullptr; p.accumulate = 0; p.ws = nullptr; p.C = nullptr; p.ldc = 0;
+  p.lay_d = 0; p.lay_raw = nullptr; p.lay_hi = nullptr; p.lay_lo = nullptr; p.row_idx = nullptr; p.skip_rows = nullptr;
+  p.gate_G = nullptr; p.gate_ld = 0; p.gate_bias = nullptr; p.gate_h = nullptr; p.gate_norm = 0;
 }
 
 // Common launcher: validates operands, builds the tensor maps, sizes the pipeline, launches.
@@ -503,10 +652,14 @@ static int launch_tc(const float* a_hi, const float* a_lo, int lda, const float*
   } else {
     ta_lo = ta_hi; tb_lo = tb_hi;
   }
-  const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024 + STAGING_BYTES;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t ce = cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_BUDGET + 2048));
+    const int mx = (int)(SMEM_BUDGET + 2048 + STAGING_BYTES);
+    cudaError_t ce = cudaFuncSetAttribute(gemm_tf32_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(gemm_tf32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(gemm_tf32_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(gemm_tf32_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     if (ce != cudaSuccess) { set_last_error("%s: cudaFuncSetAttribute failed: %s", who, cudaGetErrorString(ce)); return (int)ce; }
     attr_set = true;
   }
@@ -523,7 +676,12 @@ static int launch_tc(const float* a_hi, const float* a_lo, int lda, const float*
   const long long total_tiles = (long long)p.m_tiles * p.n_tiles * p.splits;
   dim3 grid((unsigned)(total_tiles < sms ? total_tiles : sms));
   prof_begin(PROF_GEMM_TC, st);
-  gemm_tf32_kernel<<<grid, NUM_THREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+  switch (p.epi) {
+    case 0: gemm_tf32_kernel<0><<<grid, NUM_THREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p); break;
+    case 1: gemm_tf32_kernel<1><<<grid, NUM_THREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p); break;
+    case 2: gemm_tf32_kernel<2><<<grid, NUM_THREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p); break;
+    default: gemm_tf32_kernel<3><<<grid, NUM_THREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p); break;
+  }
   prof_end(PROF_GEMM_TC, p.epi == 2 ? 2.0 * M * (double)K : 2.0 * M * (double)N * K, st);
   return REGCN_OK;
 }
@@ -556,6 +714,29 @@ int gemm_tf32(const float* a_hi, const float* a_lo, int lda, const float* b_hi, 
     splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws, sk, C, ldc, M, N, bias, accumulate);
   }
   return check_launch("gemm_tf32");
+}
+
+// GEMM with the fused layer epilogue (see Params): out rows = rrelu(A . B^T)[:, :d] (+ time gate), gate columns -> C.
+int gemm_tf32_layer(const float* a_hi, const float* a_lo, int lda, const float* b_hi, const float* b_lo, int ldb, int M,
+                    int N, int K, int d, float* out_raw, float* out_hi, float* out_lo, float* gate_out, int ld_gate_out,
+                    const int* row_idx, const int* skip_rows, const float* gate_G, int gate_ld, const float* gate_bias,
+                    const float* gate_h, int gate_norm, cudaStream_t st) {
+  if ((!out_raw && !out_hi) || (out_hi && !out_lo)) { set_last_error("gemm_tf32_layer: no output"); return REGCN_ERR_NULL; }
+  if (d <= 0 || (d & 3) || (N & 3) || N < d || (N > d && (!gate_out || ld_gate_out < N - d || (ld_gate_out & 3)))) {
+    set_last_error("gemm_tf32_layer: bad dims N=%d d=%d", N, d); return REGCN_ERR_DIM;
+  }
+  if (gate_G && (N != d || d > 256 || !gate_bias || !gate_h || (gate_ld & 3))) {
+    set_last_error("gemm_tf32_layer: the fused time gate needs N == d <= 256"); return REGCN_ERR_DIM;
+  }
+  tc::Params p;
+  clear_epi(p);
+  p.M = M; p.N = N; p.K = K; p.epi = 3; p.lay_d = d; p.lay_raw = out_raw; p.lay_hi = out_hi; p.lay_lo = out_lo;
+  p.C = gate_out; p.ldc = ld_gate_out; p.row_idx = row_idx; p.skip_rows = skip_rows;
+  p.gate_G = gate_G; p.gate_ld = gate_ld; p.gate_bias = gate_bias; p.gate_h = gate_h; p.gate_norm = gate_norm;
+  const int force_bn = gate_G ? (d + 15) / 16 * 16 : 0;      // one tile must span the whole row for the norm
+  int e = launch_tc(a_hi, a_lo, lda, b_hi, b_lo, ldb, p, 3, 1, force_bn, "gemm_tf32_layer", st);
+  if (e) return e;
+  return check_launch("gemm_tf32_layer");
 }
 
 // Fused K11/K13 + K14: raw_count[b] += #{candidate n of this shard, n != target[b] : score(b,n) beats tscore[b]}.

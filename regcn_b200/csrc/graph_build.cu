@@ -47,10 +47,12 @@ __global__ void norm_chunks_kernel(const int* __restrict__ indeg, int N, float* 
 }
 
 __global__ void active_pos_kernel(const int* __restrict__ indeg, const int* __restrict__ scan, int N,
-                                  int* __restrict__ active_pos) {
+                                  int* __restrict__ active_pos, int* __restrict__ active_rows) {
   int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= N) return;
-  active_pos[v] = indeg[v] > 0 ? scan[v] : -1;
+  const bool act = indeg[v] > 0;
+  active_pos[v] = act ? scan[v] : -1;
+  if (act) active_rows[scan[v]] = v;            // inverse map: the sorted list of active destinations
 }
 
 __global__ void gather_sorted_kernel(const int* __restrict__ eperm, const int* __restrict__ src,
@@ -136,14 +138,14 @@ size_t csr_build_workspace_bytes(int T, int N, int R) { return plan_build_ws(T, 
 int csr_build(const int64_t* triples, int T, int N, int R,
               int* src, int* dst, int* etype, int* indeg, float* norm,
               int* rowptr, int* src_sorted, int* etype_sorted, int* eperm,
-              int* vptr, int* sptr, int* vrow_row, int* active_pos,
+              int* vptr, int* sptr, int* vrow_row, int* active_pos, int* active_rows,
               int* rel_rowptr, int* rel_ents, int* counts,
               void* ws, size_t ws_bytes, cudaStream_t st) {
   if (T < 0 || N <= 0 || R <= 0) { set_last_error("csr_build: bad dims T=%d N=%d R=%d", T, N, R); return REGCN_ERR_DIM; }
   BuildWs w = plan_build_ws(T, N, R);
   if (ws_bytes < w.total) { set_last_error("csr_build: workspace %zu < %zu", ws_bytes, w.total); return REGCN_ERR_WORKSPACE; }
   if (!src || !dst || !etype || !indeg || !norm || !rowptr || !src_sorted || !etype_sorted || !eperm || !vptr ||
-      !sptr || !vrow_row || !active_pos || !rel_rowptr || !rel_ents || !counts || !ws || (T > 0 && !triples)) {
+      !sptr || !vrow_row || !active_pos || !active_rows || !rel_rowptr || !rel_ents || !counts || !ws || (T > 0 && !triples)) {
     set_last_error("csr_build: null pointer"); return REGCN_ERR_NULL;
   }
   char* base = (char*)ws;
@@ -180,7 +182,7 @@ int csr_build(const int64_t* triples, int T, int N, int R,
   cub::DeviceScan::ExclusiveSum(cubtmp, cb, nchunk, vptr, N + 1, st);
   cub::DeviceScan::ExclusiveSum(cubtmp, cb, nsplit, sptr, N + 1, st);
   cub::DeviceScan::ExclusiveSum(cubtmp, cb, aflag, ascan, N + 1, st);
-  active_pos_kernel<<<(N + TB - 1) / TB, TB, 0, st>>>(indeg, ascan, N, active_pos);
+  active_pos_kernel<<<(N + TB - 1) / TB, TB, 0, st>>>(indeg, ascan, N, active_pos, active_rows);
   fill_vrows_kernel<<<(N + TB - 1) / TB, TB, 0, st>>>(vptr, N, vrow_row);
   if (T > 0) {
     // stable sort of edge ids by destination: eperm[i] = original edge id of the i-th CSR slot
@@ -209,13 +211,13 @@ int csr_build(const int64_t* triples, int T, int N, int R,
 // Same outputs, bit for bit, as csr_build (tests compare the two).
 // =====================================================================================================================
 constexpr int kSmallThreads = 1024;
-constexpr int kSmallBatch = 16;          // snapshots per launch (kernel-parameter space: 16 x 168 bytes)
+constexpr int kSmallBatch = 16;          // snapshots per launch (kernel-parameter space: 16 x 176 bytes)
 constexpr int kSmallMaxRels = 8191;      // rel_count lives in shared memory
 
 struct SmallSnap {
   const int64_t* triples;
   int* src; int* dst; int* etype; int* indeg; float* norm; int* rowptr; int* src_sorted; int* etype_sorted; int* eperm;
-  int* vptr; int* sptr; int* vrow_row; int* active_pos; int* rel_rowptr; int* rel_ents; int* counts;
+  int* vptr; int* sptr; int* vrow_row; int* active_pos; int* active_rows; int* rel_rowptr; int* rel_ents; int* counts;
   int T;
 };
 struct SmallBatch { SmallSnap g[kSmallBatch]; };
@@ -305,6 +307,7 @@ csr_build_small_kernel(const __grid_constant__ SmallBatch batch, int N, int R) {
         g.vptr[v] = vb;
         g.sptr[v] = pre.c + out[i].c;
         g.active_pos[v] = d > 0 ? pre.d + out[i].d : -1;
+        if (d > 0) g.active_rows[pre.d + out[i].d] = v;
         for (int k = 0; k < in[i].b; ++k) g.vrow_row[vb + k] = v;
       }
     }
@@ -449,7 +452,7 @@ int csr_build_batch(const regcn_csr_arrays* snaps, int L, int N, int R, void* ws
     const regcn_csr_arrays& a = snaps[i];
     if (a.T < 0) { set_last_error("csr_build_batch: snapshot %d has T=%d", i, a.T); return REGCN_ERR_DIM; }
     if (!a.src || !a.dst || !a.etype || !a.indeg || !a.norm || !a.rowptr || !a.src_sorted || !a.etype_sorted || !a.eperm ||
-        !a.vptr || !a.sptr || !a.vrow_row || !a.active_pos || !a.rel_rowptr || !a.rel_ents || !a.counts || (a.T > 0 && !a.triples)) {
+        !a.vptr || !a.sptr || !a.vrow_row || !a.active_pos || !a.active_rows || !a.rel_rowptr || !a.rel_ents || !a.counts || (a.T > 0 && !a.triples)) {
       set_last_error("csr_build_batch: null pointer in snapshot %d", i); return REGCN_ERR_NULL;
     }
   }
@@ -471,7 +474,7 @@ int csr_build_batch(const regcn_csr_arrays* snaps, int L, int N, int R, void* ws
         SmallSnap& s = b.g[n++];
         s.triples = a.triples; s.src = a.src; s.dst = a.dst; s.etype = a.etype; s.indeg = a.indeg; s.norm = a.norm;
         s.rowptr = a.rowptr; s.src_sorted = a.src_sorted; s.etype_sorted = a.etype_sorted; s.eperm = a.eperm;
-        s.vptr = a.vptr; s.sptr = a.sptr; s.vrow_row = a.vrow_row; s.active_pos = a.active_pos;
+        s.vptr = a.vptr; s.sptr = a.sptr; s.vrow_row = a.vrow_row; s.active_pos = a.active_pos; s.active_rows = a.active_rows;
         s.rel_rowptr = a.rel_rowptr; s.rel_ents = a.rel_ents; s.counts = a.counts; s.T = a.T;
       }
       if (n == kSmallBatch || (i == L && n > 0)) {
@@ -485,7 +488,8 @@ int csr_build_batch(const regcn_csr_arrays* snaps, int L, int N, int R, void* ws
     const regcn_csr_arrays& a = snaps[i];
     if (small_ok(a.T, N, R)) continue;
     int e = csr_build(a.triples, a.T, N, R, a.src, a.dst, a.etype, a.indeg, a.norm, a.rowptr, a.src_sorted, a.etype_sorted,
-                      a.eperm, a.vptr, a.sptr, a.vrow_row, a.active_pos, a.rel_rowptr, a.rel_ents, a.counts, ws, ws_bytes, st);
+                      a.eperm, a.vptr, a.sptr, a.vrow_row, a.active_pos, a.active_rows, a.rel_rowptr, a.rel_ents, a.counts, ws,
+                      ws_bytes, st);
     if (e) return e;
   }
   return REGCN_OK;

@@ -9,7 +9,7 @@ namespace regcn {
 size_t csr_build_workspace_bytes(int T, int N, int R);
 int csr_build(const int64_t* triples, int T, int N, int R, int* src, int* dst, int* etype, int* indeg, float* norm,
               int* rowptr, int* src_sorted, int* etype_sorted, int* eperm, int* vptr, int* sptr, int* vrow_row,
-              int* active_pos, int* rel_rowptr, int* rel_ents, int* counts, void* ws, size_t ws_bytes, cudaStream_t st);
+              int* active_pos, int* active_rows, int* rel_rowptr, int* rel_ents, int* counts, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t csr_build_batch_workspace_bytes(const int* T, int L, int N, int R);
 int csr_build_batch(const regcn_csr_arrays* snaps, int L, int N, int R, void* ws, size_t ws_bytes, cudaStream_t st);
 int rel_mean_pool(const float* h, const int* rel_rowptr, const int* rel_ents, int R, int d, int nsplit, float* out,
@@ -32,6 +32,10 @@ size_t gemm_tf32_workspace_bytes(int M, int N, int split_k);
 int gemm_tf32(const float* a_hi, const float* a_lo, int lda, const float* b_hi, const float* b_lo, int ldb, float* C,
               int ldc, int M, int N, int K, const float* bias, int accumulate, int passes, int split_k, float* ws,
               size_t ws_bytes, const float* addend, int ld_add, cudaStream_t st);
+int gemm_tf32_layer(const float* a_hi, const float* a_lo, int lda, const float* b_hi, const float* b_lo, int ldb, int M,
+                    int N, int K, int d, float* out_raw, float* out_hi, float* out_lo, float* gate_out, int ld_gate_out,
+                    const int* row_idx, const int* skip_rows, const float* gate_G, int gate_ld, const float* gate_bias,
+                    const float* gate_h, int gate_norm, cudaStream_t st);
 void gemm_tf32_tune(int block_n, int stages);
 void aggregate_tune(int impl);
 int score_count_tf32(const float* q_hi, const float* q_lo, const float* e_hi, const float* e_lo, int B, int N, int K,
@@ -56,7 +60,8 @@ int union_combine(const float* P, const float* L, const int* indeg, const float*
                   float* radius_next, int ldL, float* out_hi, float* out_lo, float* ht_hi, float* ht_lo,
                   const int* active_pos, cudaStream_t st);
 int time_gate(const float* G, const float* bias, const float* cur, const float* h, float* out, int N, int d,
-              int normalize_cur, int ldg, float* out_hi, float* out_lo, cudaStream_t st);
+              int normalize_cur, int ldg, float* out_hi, float* out_lo, cudaStream_t st, const int* row_idx = nullptr,
+              int act = 0);
 int hyp_init(const float* emb, const float* radius_static, int N, int d, int normalize, int on_manifold, double c,
              float rmin, float rmax, float* out, cudaStream_t st);
 int hyp_tangent(const float* h, int N, int d, double c, float* ht, float* pt, float* radius, float* ht_hi,

@@ -178,29 +178,33 @@ template <int RV>
 __global__ void __launch_bounds__(256) time_gate_kernel(const float* __restrict__ G, const float* __restrict__ bias,
                                                         const float* __restrict__ cur, const float* __restrict__ h,
                                                         float* __restrict__ out, int N, int d, int normalize_cur,
-                                                        int ldg, float* __restrict__ out_hi, float* __restrict__ out_lo) {
+                                                        int ldg, float* __restrict__ out_hi, float* __restrict__ out_lo,
+                                                        const int* __restrict__ row_idx, int act) {
   ROW_KERNEL_PROLOGUE(N)
   WarpRow<RV> g, b, c, hh;
-  g.load_plain(G + (size_t)row * ldg, nvec, lane);
+  // row_idx: `cur` is a compact matrix (one row per listed entity), everything else is indexed by the entity id
+  const int erow = row_idx ? __ldg(row_idx + row) : row;
+  g.load_plain(G + (size_t)erow * ldg, nvec, lane);
   b.load(bias, nvec, lane);
   c.load_plain(cur + (size_t)row * d, nvec, lane);
-  hh.load_plain(h + (size_t)row * d, nvec, lane);
+  hh.load_plain(h + (size_t)erow * d, nvec, lane);
+  if (act == 1) c.map([](float a) { return rreluf_(a); });
   if (normalize_cur) row_l2normalize(c);
   g.zip(b, [](float a, float bb) { return sigmoidf_(a + bb); });
   c.zip(g, [](float a, float s) { return s * a; });
   hh.zip(g, [](float a, float s) { return (1.0f - s) * a; });
   c.zip(hh, [](float a, float bb) { return a + bb; });
-  c.store(out + (size_t)row * d, nvec, lane);
-  if (out_hi) c.store_split(out_hi + (size_t)row * d, out_lo + (size_t)row * d, nvec, lane);
+  c.store(out + (size_t)erow * d, nvec, lane);
+  if (out_hi) c.store_split(out_hi + (size_t)erow * d, out_lo + (size_t)erow * d, nvec, lane);
 }
 
 int time_gate(const float* G, const float* bias, const float* cur, const float* h, float* out, int N, int d,
-              int normalize_cur, int ldg, float* out_hi, float* out_lo, cudaStream_t st) {
+              int normalize_cur, int ldg, float* out_hi, float* out_lo, cudaStream_t st, const int* row_idx, int act) {
   if (!G || !bias || !cur || !h || !out) { set_last_error("time_gate: null pointer"); return REGCN_ERR_NULL; }
   if (int e = check_d("time_gate", d)) return e;
   if (N <= 0) return REGCN_OK;
-  if (d <= 128) time_gate_kernel<1><<<row_grid(N), 256, 0, st>>>(G, bias, cur, h, out, N, d, normalize_cur, ldg > 0 ? ldg : d, out_hi, out_lo);
-  else time_gate_kernel<2><<<row_grid(N), 256, 0, st>>>(G, bias, cur, h, out, N, d, normalize_cur, ldg > 0 ? ldg : d, out_hi, out_lo);
+  if (d <= 128) time_gate_kernel<1><<<row_grid(N), 256, 0, st>>>(G, bias, cur, h, out, N, d, normalize_cur, ldg > 0 ? ldg : d, out_hi, out_lo, row_idx, act);
+  else time_gate_kernel<2><<<row_grid(N), 256, 0, st>>>(G, bias, cur, h, out, N, d, normalize_cur, ldg > 0 ? ldg : d, out_hi, out_lo, row_idx, act);
   return check_launch("time_gate");
 }
 

@@ -32,7 +32,7 @@ class SnapshotGraph:
         self.num_edges = E
         dev = self.device
         # one arena for every int32 array of the index (a single allocation per snapshot)
-        sizes = [E, E, E, N, N + 1, E, E, E, N + 1, N + 1, min(N, E) + E // AGG_CHUNK + 1, N, R + 1, E, 8]
+        sizes = [E, E, E, N, N + 1, E, E, E, N + 1, N + 1, min(N, E) + E // AGG_CHUNK + 1, N, R + 1, E, 8, min(N, E)]
         offs, tot = [], 0
         for n in sizes:
             offs.append(tot)
@@ -40,7 +40,8 @@ class SnapshotGraph:
         arena = torch.empty(tot + N, device=dev, dtype=I32)
         v = [arena[o:o + max(int(n), 1)] for o, n in zip(offs, sizes)]
         (self.src, self.dst, self.etype, self.indeg, self.rowptr, self.src_sorted, self.etype_sorted, self.eperm,
-         self.vptr, self.sptr, self.vrow_row, self.active_pos, self.rel_rowptr, self.rel_ents, self._counts) = v
+         self.vptr, self.sptr, self.vrow_row, self.active_pos, self.rel_rowptr, self.rel_ents, self._counts,
+         self.active_rows) = v
         self.norm = arena[tot:tot + N].view(torch.float32)
         self._arena = arena
         if not _defer_build:
@@ -49,14 +50,16 @@ class SnapshotGraph:
             call("regcn_csr_build", ptr(triples_dev), T, N, R, self.src.data_ptr(), self.dst.data_ptr(),
                  self.etype.data_ptr(), self.indeg.data_ptr(), self.norm.data_ptr(), self.rowptr.data_ptr(),
                  self.src_sorted.data_ptr(), self.etype_sorted.data_ptr(), self.eperm.data_ptr(), self.vptr.data_ptr(),
-                 self.sptr.data_ptr(), self.vrow_row.data_ptr(), self.active_pos.data_ptr(), self.rel_rowptr.data_ptr(),
+                 self.sptr.data_ptr(), self.vrow_row.data_ptr(), self.active_pos.data_ptr(), self.active_rows.data_ptr(),
+                 self.rel_rowptr.data_ptr(),
                  self.rel_ents.data_ptr(), self._counts.data_ptr(), ptr(ws), ws_bytes)
         self._ndata = None
         self._edata = None
         self._r2e = None
         self.ptr_table = np.array([t.data_ptr() for t in (self.rowptr, self.src_sorted, self.etype_sorted, self.indeg,
                                                           self.norm, self.vptr, self.sptr, self.vrow_row,
-                                                          self.rel_rowptr, self.rel_ents, self.active_pos)],
+                                                          self.rel_rowptr, self.rel_ents, self.active_pos,
+                                                          self.active_rows)],
                                   dtype=np.uint64)
         if not _defer_counts and not _defer_build:
             self._set_counts(self._counts.tolist())          # the one host sync of graph construction
@@ -66,7 +69,7 @@ class SnapshotGraph:
         desc.triples = self.triples.data_ptr()
         desc.T = self.num_edges // 2
         for name in ("src", "dst", "etype", "indeg", "norm", "rowptr", "src_sorted", "etype_sorted", "eperm", "vptr",
-                     "sptr", "vrow_row", "active_pos", "rel_rowptr", "rel_ents"):
+                     "sptr", "vrow_row", "active_pos", "active_rows", "rel_rowptr", "rel_ents"):
             setattr(desc, name, getattr(self, name).data_ptr())
         desc.counts = self._counts.data_ptr()
 

@@ -59,6 +59,7 @@ def test_csr_build_bit_exact(shape, zipf):
     ap = np.full(n, -1, dtype=np.int64)
     ap[active] = np.arange(len(active))
     assert np.array_equal(g.active_pos.cpu().numpy(), ap)
+    assert np.array_equal(g.active_rows[:g.n_active].cpu().numpy(), active)
     # the DGL-style views the reference's modules read
     assert g.number_of_nodes() == n and tuple(g.ndata["norm"].shape) == (n, 1)
     assert np.array_equal(g.edata["type"].cpu().numpy(), o["etype"])
@@ -89,6 +90,7 @@ def _graph_arrays(g):
                                                          "rel_rowptr")})
     out["vrow_row"] = g.vrow_row[:g.n_vrows].cpu().numpy()
     out["rel_ents"] = g.rel_ents[:g.n_rel_ents].cpu().numpy()
+    out["active_rows"] = g.active_rows[:g.n_active].cpu().numpy()
     out["counts"] = np.array([g.n_vrows, g.n_split_chunks, g.n_rel_ents, g.max_hub_degree, g.n_active])
     return out
 
