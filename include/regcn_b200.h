@@ -127,6 +127,10 @@ REGCN_API int regcn_gemm_tf32(const float* a_hi, const float* a_lo, int lda, con
  *   arithmetic (bit-identical to the corresponding element of the scoring GEMM): target and filter-entry scores.
  * regcn_filter_correct: filt_count[b] = raw_count[b] - (filter entries that beat the target) + (-1e7 entries that do).
  * regcn_gather_rows2 / regcn_gather_scalars: operand gathers for the pair pass.                                */
+/* bf16 scoring mode (reported separately from the fp32-parity mode): passes == 0 in regcn_score_count_tf32 /
+ * regcn_pair_scores_tf32 means the "hi" operand pointers address bf16 rows of K elements (K % 8 == 0) produced by
+ * regcn_to_bf16, the "lo" pointers are ignored, and the contraction runs as tcgen05.mma kind::f16 (fp32 accumulate). */
+REGCN_API int regcn_to_bf16(const float* x, void* out_bf16, size_t n, void* stream);
 REGCN_API int regcn_score_count_tf32(const float* q_hi, const float* q_lo, const float* e_hi, const float* e_lo, int B,
                            int N, int K, const float* tscore, const int32_t* target, int32_t* raw_count,
                            int col_offset, int hyp, const float* x2, const float* y2, const float* col_bias, double c,
@@ -147,6 +151,9 @@ REGCN_API int regcn_filter_correct(int B, const int32_t* filt_ptr, const int32_t
 REGCN_API void regcn_prof_enable(int on);
 REGCN_API int regcn_prof_read(int slot, double* total_ms, long long* launches, double* total_work);
 
+/* programmatic dependent launch between the kernels of the path (default on; REGCN_PDL=0 in the environment or
+ * regcn_pdl_enable(0) falls back to plain stream-ordered launches) */
+REGCN_API void regcn_pdl_enable(int on);
 /* tuning knob for experiments: force the N tile (multiple of 16, <= 256; 0 = automatic) and cap the pipeline depth */
 REGCN_API void regcn_gemm_tf32_tune(int block_n, int stages);
 /* edge kernel variant: 0 automatic, 1 register-staged gathers, 2 cp.async.bulk gathers staged in shared memory */

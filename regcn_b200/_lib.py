@@ -35,11 +35,13 @@ SIGNATURES = {
     "regcn_gemm_f32_workspace_bytes": (_sz, [_i, _i, _i]),
     "regcn_gemm_f32": (_i, [_p, _i, _p, _i, _i, _p, _i, _i, _i, _i, _p, _i, _i, _p, _sz, _p]),
     "regcn_split_tf32": (_i, [_p, _p, _p, _sz, _p]),
+    "regcn_to_bf16": (_i, [_p, _p, _sz, _p]),
     "regcn_gemm_tf32_workspace_bytes": (_sz, [_i, _i, _i]),
     "regcn_gemm_tf32": (_i, [_p, _p, _i, _p, _p, _i, _p, _i, _i, _i, _i, _p, _i, _i, _i, _p, _sz, _p]),
     "regcn_regcn_evolve_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "regcn_regcn_evolve": (_i, [_p, _p, _p, _p, _i, _p, _p, _i, _p, _sz, _p]),
     "regcn_gemm_tf32_tune": (None, [_i, _i]),
+    "regcn_pdl_enable": (None, [_i]),
     "regcn_aggregate_tune": (None, [_i]),
     "regcn_score_count_tf32": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _i, _i, _p, _p, _p, _d, _p, _p, _i, _p]),
     "regcn_pair_scores_tf32": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _d, _p, _p, _p, _i, _p]),

@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(256) union_aggregate_kernel(
     const int* __restrict__ vptr, const int* __restrict__ sptr, const int* __restrict__ vrow_row, int nv,
     const float* __restrict__ radius, float gamma, int d, float* __restrict__ out, float* __restrict__ partial,
     float* __restrict__ out_hi, float* __restrict__ out_lo, const int* __restrict__ active_pos, int ldo) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const int w = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
   if (w >= nv) return;
@@ -174,6 +175,7 @@ __global__ void __launch_bounds__(kBulkWarps * 32, 1) union_aggregate_bulk_kerne
     const int* __restrict__ vptr, const int* __restrict__ sptr, const int* __restrict__ vrow_row, int nv,
     const float* __restrict__ radius, float gamma, int d, float* __restrict__ out, float* __restrict__ partial,
     float* __restrict__ out_hi, float* __restrict__ out_lo, const int* __restrict__ active_pos, int ldo) {
+  pdl_grid_sync();
   extern __shared__ __align__(128) unsigned char bulk_smem[];
   __shared__ __align__(8) unsigned long long bars[kBulkWarps];
   const int lane = threadIdx.x & 31;
@@ -271,6 +273,7 @@ __global__ void __launch_bounds__(256) aggregate_fixup_kernel(
     const int* __restrict__ vptr, const int* __restrict__ sptr, const int* __restrict__ vrow_row,
     const float* __restrict__ norm, int nv, int d, float* __restrict__ partial, float* __restrict__ out,
     float* __restrict__ out_hi, float* __restrict__ out_lo, const int* __restrict__ active_pos, int ldo, int stride) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const int w = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
   if (w >= nv) return;
@@ -314,6 +317,7 @@ __global__ void __launch_bounds__(256) aggregate_fixup_kernel(
 // Dense-output mode: rows without in-edges receive exact zeros (DGL zero fill); one thread per float4.
 __global__ void zero_inactive_rows_kernel(const int* __restrict__ rowptr, int N, int d, float* __restrict__ out,
                                           float* __restrict__ out_hi, float* __restrict__ out_lo) {
+  pdl_grid_sync();
   const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   const int nvec = d >> 2;
   const size_t total = (size_t)N * nvec;
@@ -341,7 +345,7 @@ int union_aggregate(const float* h, const float* rel, const int* rowptr, const i
   prof_begin(PROF_AGGREGATE, st);
   if (!active_pos) {
     const size_t total = (size_t)N * (d >> 2);
-    zero_inactive_rows_kernel<<<(unsigned)((total + TB - 1) / TB), TB, 0, st>>>(rowptr, N, d, out, out_hi, out_lo);
+    launch_k(zero_inactive_rows_kernel, (unsigned)((total + TB - 1) / TB), TB, 0, st, rowptr, N, d, out, out_hi, out_lo);
   }
   if (nv <= 0) { prof_end(PROF_AGGREGATE, 0.0, st); return check_launch("union_aggregate"); }
   const unsigned grid = (unsigned)(((size_t)nv * 32 + TB - 1) / TB);
@@ -361,7 +365,7 @@ int union_aggregate(const float* h, const float* rel, const int* rowptr, const i
         cudaFuncSetAttribute(union_aggregate_bulk_kernel<RVV, RAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); \
         attr_done = true;                                                                                              \
       }                                                                                                                \
-      union_aggregate_bulk_kernel<RVV, RAD><<<bgrid, kBulkWarps * 32, smem, st>>>(                                     \
+      launch_k(union_aggregate_bulk_kernel<RVV, RAD>, bgrid, kBulkWarps * 32, smem, st,                                      \
           h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, radius, gamma, d, out, partial,   \
           out_hi, out_lo, active_pos, ldo);                                                                            \
     } while (0)
@@ -369,18 +373,18 @@ int union_aggregate(const float* h, const float* rel, const int* rowptr, const i
     else { if (small) LAUNCH_BULK(1, false); else LAUNCH_BULK(2, false); }
 #undef LAUNCH_BULK
   } else if (radius) {
-    if (small) union_aggregate_kernel<1, true><<<grid, TB, 0, st>>>(h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, radius, gamma, d, out, partial, out_hi, out_lo, active_pos, ldo);
-    else union_aggregate_kernel<2, true><<<grid, TB, 0, st>>>(h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, radius, gamma, d, out, partial, out_hi, out_lo, active_pos, ldo);
+    if (small) launch_k(union_aggregate_kernel<1, true>, grid, TB, 0, st, h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, radius, gamma, d, out, partial, out_hi, out_lo, active_pos, ldo);
+    else launch_k(union_aggregate_kernel<2, true>, grid, TB, 0, st, h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, radius, gamma, d, out, partial, out_hi, out_lo, active_pos, ldo);
   } else {
-    if (small) union_aggregate_kernel<1, false><<<grid, TB, 0, st>>>(h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, nullptr, 0.f, d, out, partial, out_hi, out_lo, active_pos, ldo);
-    else union_aggregate_kernel<2, false><<<grid, TB, 0, st>>>(h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, nullptr, 0.f, d, out, partial, out_hi, out_lo, active_pos, ldo);
+    if (small) launch_k(union_aggregate_kernel<1, false>, grid, TB, 0, st, h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, nullptr, 0.f, d, out, partial, out_hi, out_lo, active_pos, ldo);
+    else launch_k(union_aggregate_kernel<2, false>, grid, TB, 0, st, h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, nullptr, 0.f, d, out, partial, out_hi, out_lo, active_pos, ldo);
   }
   if (nsplit > 0) {
     // max_chunks = chunk count of the largest hub row (<= nsplit); one launch per radix-32 level
     if (max_chunks <= 0 || max_chunks > nsplit) max_chunks = nsplit;
     for (long long stride = 1; stride < (long long)max_chunks; stride *= 32) {
-      if (small) aggregate_fixup_kernel<1><<<grid, TB, 0, st>>>(vptr, sptr, vrow_row, norm, nv, d, partial, out, out_hi, out_lo, active_pos, ldo, (int)stride);
-      else aggregate_fixup_kernel<2><<<grid, TB, 0, st>>>(vptr, sptr, vrow_row, norm, nv, d, partial, out, out_hi, out_lo, active_pos, ldo, (int)stride);
+      if (small) launch_k(aggregate_fixup_kernel<1>, grid, TB, 0, st, vptr, sptr, vrow_row, norm, nv, d, partial, out, out_hi, out_lo, active_pos, ldo, (int)stride);
+      else launch_k(aggregate_fixup_kernel<2>, grid, TB, 0, st, vptr, sptr, vrow_row, norm, nv, d, partial, out, out_hi, out_lo, active_pos, ldo, (int)stride);
     }
   }
   prof_end(PROF_AGGREGATE, 0.0, st);   // bytes are filled in by the caller-side formula (needs E, R); see bench.py
@@ -396,6 +400,7 @@ __global__ void __launch_bounds__(256) block_aggregate_kernel(
     const float* __restrict__ h, const float* __restrict__ W, const float* __restrict__ rel_add,
     const int* __restrict__ rowptr, const int* __restrict__ src_sorted, const int* __restrict__ etype_sorted,
     const float* __restrict__ norm, int N, int d_in, int d_out, int nb, float* __restrict__ out) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const int row = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
   if (row >= N) return;
@@ -428,7 +433,7 @@ int block_aggregate(const float* h, const float* W, const int* rowptr, const int
   if (nb <= 0 || d_in % nb || d_out % nb) { set_last_error("block_aggregate: num_bases=%d must divide d_in=%d and d_out=%d", nb, d_in, d_out); return REGCN_ERR_UNSUPPORTED; }
   const int TB = 256;
   const unsigned grid = (unsigned)(((size_t)N * 32 + TB - 1) / TB);
-  block_aggregate_kernel<<<grid, TB, 0, st>>>(h, W, nullptr, rowptr, src_sorted, etype_sorted, norm, N, d_in, d_out, nb, out);
+  launch_k(block_aggregate_kernel, grid, TB, 0, st, h, W, nullptr, rowptr, src_sorted, etype_sorted, norm, N, d_in, d_out, nb, out);
   return check_launch("block_aggregate");
 }
 
@@ -506,6 +511,7 @@ __global__ void __launch_bounds__(256) lorentz_aggregate_kernel(
     const float* __restrict__ norm, const int* __restrict__ vptr, const int* __restrict__ sptr,
     const int* __restrict__ vrow_row, int nv_rows, int d, int nb, Curv cv, float* __restrict__ out,
     float* __restrict__ partial, float* __restrict__ partial0) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const int w = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
   if (w >= nv_rows) return;
@@ -559,6 +565,7 @@ __global__ void __launch_bounds__(256) lorentz_fixup_kernel(
     const int* __restrict__ rowptr, const int* __restrict__ vptr, const int* __restrict__ sptr,
     const int* __restrict__ vrow_row, const float* __restrict__ norm, int nv_rows, int d, Curv cv,
     const float* __restrict__ partial, const float* __restrict__ partial0, float* __restrict__ out) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const int w = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
   if (w >= nv_rows) return;
@@ -592,19 +599,19 @@ int lorentz_aggregate(const float* ht, const float* W, const float* rel, const i
   Curv cv = make_curv(c);
   // isolated destinations: exact zero rows (DGL zero fill; to_poincare(0) = 0, log_0(0) = 0)
   const size_t total = (size_t)N * (d >> 2);
-  zero_inactive_rows_kernel<<<(unsigned)((total + TB - 1) / TB), TB, 0, st>>>(rowptr, N, d, out, nullptr, nullptr);
+  launch_k(zero_inactive_rows_kernel, (unsigned)((total + TB - 1) / TB), TB, 0, st, rowptr, N, d, out, nullptr, nullptr);
   if (nv_rows > 0) {
     const unsigned grid = (unsigned)(((size_t)nv_rows * 32 + TB - 1) / TB);
     float* partial0 = partial ? partial + (size_t)nsplit * d : nullptr;
     const bool sb2 = (d / nb) == 2;
     if (d <= 128) {
-      if (sb2) lorentz_aggregate_kernel<1, 2><<<grid, TB, 0, st>>>(ht, W, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv_rows, d, nb, cv, out, partial, partial0);
-      else lorentz_aggregate_kernel<1, 0><<<grid, TB, 0, st>>>(ht, W, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv_rows, d, nb, cv, out, partial, partial0);
-      if (nsplit > 0) lorentz_fixup_kernel<1><<<grid, TB, 0, st>>>(rowptr, vptr, sptr, vrow_row, norm, nv_rows, d, cv, partial, partial0, out);
+      if (sb2) launch_k(lorentz_aggregate_kernel<1, 2>, grid, TB, 0, st, ht, W, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv_rows, d, nb, cv, out, partial, partial0);
+      else launch_k(lorentz_aggregate_kernel<1, 0>, grid, TB, 0, st, ht, W, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv_rows, d, nb, cv, out, partial, partial0);
+      if (nsplit > 0) launch_k(lorentz_fixup_kernel<1>, grid, TB, 0, st, rowptr, vptr, sptr, vrow_row, norm, nv_rows, d, cv, partial, partial0, out);
     } else {
-      if (sb2) lorentz_aggregate_kernel<2, 2><<<grid, TB, 0, st>>>(ht, W, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv_rows, d, nb, cv, out, partial, partial0);
-      else lorentz_aggregate_kernel<2, 0><<<grid, TB, 0, st>>>(ht, W, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv_rows, d, nb, cv, out, partial, partial0);
-      if (nsplit > 0) lorentz_fixup_kernel<2><<<grid, TB, 0, st>>>(rowptr, vptr, sptr, vrow_row, norm, nv_rows, d, cv, partial, partial0, out);
+      if (sb2) launch_k(lorentz_aggregate_kernel<2, 2>, grid, TB, 0, st, ht, W, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv_rows, d, nb, cv, out, partial, partial0);
+      else launch_k(lorentz_aggregate_kernel<2, 0>, grid, TB, 0, st, ht, W, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv_rows, d, nb, cv, out, partial, partial0);
+      if (nsplit > 0) launch_k(lorentz_fixup_kernel<2>, grid, TB, 0, st, rowptr, vptr, sptr, vrow_row, norm, nv_rows, d, cv, partial, partial0, out);
     }
   }
   return check_launch("lorentz_aggregate");
@@ -619,6 +626,7 @@ __global__ void __launch_bounds__(256) rel_mean_pool_kernel(
     const float* __restrict__ h, const int* __restrict__ rel_rowptr, const int* __restrict__ rel_ents,
     int R, int d, int nsplit, float* __restrict__ out, float* __restrict__ partial,
     float* __restrict__ out_hi, float* __restrict__ out_lo) {
+  pdl_grid_sync();
   __shared__ float4 red[8][RV * 32];
   const int r = blockIdx.x, sp = blockIdx.y;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -665,6 +673,7 @@ template <int RV>
 __global__ void rel_mean_finalize_kernel(const float* __restrict__ partial, const int* __restrict__ rel_rowptr,
                                          int R, int d, int nsplit, float* __restrict__ out,
                                          float* __restrict__ out_hi, float* __restrict__ out_lo) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const int r = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
   if (r >= R) return;
@@ -698,12 +707,12 @@ int rel_mean_pool(const float* h, const int* rel_rowptr, const int* rel_ents, in
   if (nsplit < 1) nsplit = 1;
   if (nsplit > 1 && !partial) { set_last_error("rel_mean_pool: nsplit>1 needs a partial buffer"); return REGCN_ERR_WORKSPACE; }
   dim3 grid(R, nsplit);
-  if (d <= 128) rel_mean_pool_kernel<1><<<grid, 256, 0, st>>>(h, rel_rowptr, rel_ents, R, d, nsplit, out, partial, out_hi, out_lo);
-  else rel_mean_pool_kernel<2><<<grid, 256, 0, st>>>(h, rel_rowptr, rel_ents, R, d, nsplit, out, partial, out_hi, out_lo);
+  if (d <= 128) launch_k(rel_mean_pool_kernel<1>, grid, 256, 0, st, h, rel_rowptr, rel_ents, R, d, nsplit, out, partial, out_hi, out_lo);
+  else launch_k(rel_mean_pool_kernel<2>, grid, 256, 0, st, h, rel_rowptr, rel_ents, R, d, nsplit, out, partial, out_hi, out_lo);
   if (nsplit > 1) {
     const unsigned g2 = (unsigned)(((size_t)R * 32 + 255) / 256);
-    if (d <= 128) rel_mean_finalize_kernel<1><<<g2, 256, 0, st>>>(partial, rel_rowptr, R, d, nsplit, out, out_hi, out_lo);
-    else rel_mean_finalize_kernel<2><<<g2, 256, 0, st>>>(partial, rel_rowptr, R, d, nsplit, out, out_hi, out_lo);
+    if (d <= 128) launch_k(rel_mean_finalize_kernel<1>, g2, 256, 0, st, partial, rel_rowptr, R, d, nsplit, out, out_hi, out_lo);
+    else launch_k(rel_mean_finalize_kernel<2>, g2, 256, 0, st, partial, rel_rowptr, R, d, nsplit, out, out_hi, out_lo);
   }
   return check_launch("rel_mean_pool");
 }

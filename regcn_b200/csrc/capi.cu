@@ -4,6 +4,7 @@
 #include "internal.h"
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <vector>
 
 namespace regcn {
@@ -22,6 +23,18 @@ int check_launch(const char* what) {
   }
   return REGCN_OK;
 }
+}  // namespace regcn
+
+namespace regcn {
+static int g_pdl = -1;
+bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("REGCN_PDL");
+    g_pdl = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_pdl != 0;
+}
+void pdl_set(int on) { g_pdl = on ? 1 : 0; }
 }  // namespace regcn
 
 namespace regcn {
@@ -126,6 +139,7 @@ int regcn_gemm_f32(const float* A, int lda, const float* B, int ldb, int transB,
 int regcn_split_tf32(const float* x, float* hi, float* lo, size_t n, void* stream) {
   return split_tf32(x, hi, lo, n, ST(stream));
 }
+int regcn_to_bf16(const float* x, void* out, size_t n, void* stream) { return to_bf16(x, out, n, ST(stream)); }
 size_t regcn_gemm_tf32_workspace_bytes(int M, int N, int split_k) { return gemm_tf32_workspace_bytes(M, N, split_k); }
 int regcn_gemm_tf32(const float* a_hi, const float* a_lo, int lda, const float* b_hi, const float* b_lo, int ldb,
                     float* C, int ldc, int M, int N, int K, const float* bias, int accumulate, int passes, int split_k,
@@ -133,6 +147,7 @@ int regcn_gemm_tf32(const float* a_hi, const float* a_lo, int lda, const float* 
   return gemm_tf32(a_hi, a_lo, lda, b_hi, b_lo, ldb, C, ldc, M, N, K, bias, accumulate, passes, split_k, workspace,
                    workspace_bytes, nullptr, 0, ST(stream));
 }
+void regcn_pdl_enable(int on) { regcn::pdl_set(on); }
 void regcn_gemm_tf32_tune(int block_n, int stages) { gemm_tf32_tune(block_n, stages); }
 void regcn_aggregate_tune(int impl) { aggregate_tune(impl); }
 int regcn_score_count_tf32(const float* q_hi, const float* q_lo, const float* e_hi, const float* e_lo, int B, int N, int K,

@@ -22,6 +22,32 @@ bool prof_on();
 void prof_begin(int slot, cudaStream_t st);
 void prof_end(int slot, double work, cudaStream_t st);
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------------
+// The hot path is a chain of ~100 short kernels per evaluated timestamp; a plain stream serialises them with a
+// ~2 us launch gap each.  Every kernel here starts with pdl_grid_sync(): it first lets the NEXT kernel of the stream
+// be scheduled (its CTAs become resident as ours retire and park at their own wait), then waits until the PREVIOUS
+// kernel has completed and flushed its memory.  Kernels are launched through launch_k() with the
+// programmatic-stream-serialization attribute; correctness never depends on the overlap (the wait is a full grid
+// dependency), only the launch latency is hidden.
+__device__ __forceinline__ void pdl_grid_sync() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled();
+template <typename... P, typename... A>
+inline void launch_k(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+}
+
 constexpr int kWarp = 32;
 constexpr float kEps = 1e-6f;                   // HyperbolicOps.EPS (hyperbolic_ops.py:28)
 constexpr float kRReluSlope = (1.0f / 8.0f + 1.0f / 3.0f) * 0.5f;  // F.rrelu eval slope, 11/48

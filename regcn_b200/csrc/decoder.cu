@@ -17,6 +17,7 @@ __global__ void __launch_bounds__(256) convtranse_features_kernel(
     const float* __restrict__ conv_w, const float* __restrict__ conv_b,         // (C,2,ksz), (C)
     const float* __restrict__ bn1_scale, const float* __restrict__ bn1_shift,   // (C)
     float* __restrict__ F, float* __restrict__ F_hi, float* __restrict__ F_lo) {
+  pdl_grid_sync();
   extern __shared__ float sm[];
   const int pad = ksz / 2;
   const int ld = d + 2 * pad;
@@ -73,7 +74,7 @@ int convtranse_features(const float* ent, const float* second, const int64_t* tr
   if (d <= 0 || C <= 0 || ksz <= 0 || !(ksz & 1) || ksz > 7) { set_last_error("convtranse_features: bad dims d=%d C=%d k=%d", d, C, ksz); return REGCN_ERR_DIM; }
   const size_t smem = ((size_t)2 * (d + 2 * (ksz / 2)) + (size_t)C * 2 * ksz + 3 * (size_t)C) * sizeof(float);
   if (smem > 48 * 1024) { set_last_error("convtranse_features: shared memory %zu too large", smem); return REGCN_ERR_UNSUPPORTED; }
-  convtranse_features_kernel<<<B, 256, smem, st>>>(ent, second, triples, col0, col1, B, d, C, ksz, bn0_scale, bn0_shift,
+  launch_k(convtranse_features_kernel, B, 256, smem, st, ent, second, triples, col0, col1, B, d, C, ksz, bn0_scale, bn0_shift,
                                                    conv_w, conv_b, bn1_scale, bn1_shift, F, F_hi, F_lo);
   return check_launch("convtranse_features");
 }
@@ -81,6 +82,7 @@ int convtranse_features(const float* ent, const float* second, const int64_t* tr
 // ---- K10b: x = relu(x*scale + shift) per feature (bn2 folded; scale==null -> plain relu, the B==1 case) ----
 __global__ void affine_relu_kernel(float* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
                                    size_t total, int d, int relu) {
+  pdl_grid_sync();
   const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int j = (int)(i % d);
@@ -93,7 +95,7 @@ int affine_relu(float* x, const float* scale, const float* shift, int M, int d, 
   if (!x || (scale && !shift)) { set_last_error("affine_relu: null pointer"); return REGCN_ERR_NULL; }
   const size_t total = (size_t)M * d;
   if (!total) return REGCN_OK;
-  affine_relu_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, scale, shift, total, d, relu);
+  launch_k(affine_relu_kernel, (unsigned)((total + 255) / 256), 256, 0, st, x, scale, shift, total, d, relu);
   return check_launch("affine_relu");
 }
 
@@ -101,6 +103,7 @@ int affine_relu(float* x, const float* scale, const float* shift, int M, int d, 
 template <int RV>
 __global__ void __launch_bounds__(256) gather_log0_kernel(const float* __restrict__ E, const int64_t* __restrict__ triples,
                                                           int col, int B, int d, int project, Curv cv, float* __restrict__ out) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const int row = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
   if (row >= B) return;
@@ -118,8 +121,8 @@ int gather_log0(const float* E, const int64_t* triples, int col, int B, int d, i
   if (B <= 0) return REGCN_OK;
   Curv cv = make_curv(c);
   const unsigned grid = (unsigned)(((size_t)B * 32 + 255) / 256);
-  if (d <= 128) gather_log0_kernel<1><<<grid, 256, 0, st>>>(E, triples, col, B, d, project, cv, out);
-  else gather_log0_kernel<2><<<grid, 256, 0, st>>>(E, triples, col, B, d, project, cv, out);
+  if (d <= 128) launch_k(gather_log0_kernel<1>, grid, 256, 0, st, E, triples, col, B, d, project, cv, out);
+  else launch_k(gather_log0_kernel<2>, grid, 256, 0, st, E, triples, col, B, d, project, cv, out);
   return check_launch("gather_log0");
 }
 
@@ -152,6 +155,7 @@ __global__ void __launch_bounds__(256) hyp_query_kernel(
     const float* __restrict__ s_tan, const float* __restrict__ ang, const float* __restrict__ trans,
     const float* __restrict__ E, const int64_t* __restrict__ triples, int B, int d, int kind, Curv cv,
     float* __restrict__ Q, float* __restrict__ q_sumsq) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const int row = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
   if (row >= B) return;
@@ -197,8 +201,8 @@ int hyp_query(const float* s_tan, const float* ang, const float* trans, const fl
   if (B <= 0) return REGCN_OK;
   Curv cv = make_curv(c);
   const unsigned grid = (unsigned)(((size_t)B * 32 + 255) / 256);
-  if (d <= 128) hyp_query_kernel<1><<<grid, 256, 0, st>>>(s_tan, ang, trans, E, triples, B, d, kind, cv, Q, q_sumsq);
-  else hyp_query_kernel<2><<<grid, 256, 0, st>>>(s_tan, ang, trans, E, triples, B, d, kind, cv, Q, q_sumsq);
+  if (d <= 128) launch_k(hyp_query_kernel<1>, grid, 256, 0, st, s_tan, ang, trans, E, triples, B, d, kind, cv, Q, q_sumsq);
+  else launch_k(hyp_query_kernel<2>, grid, 256, 0, st, s_tan, ang, trans, E, triples, B, d, kind, cv, Q, q_sumsq);
   return check_launch("hyp_query");
 }
 
@@ -211,6 +215,7 @@ __global__ void hyp_score_epilogue_kernel(float* __restrict__ S, size_t ld, int 
                                           const float* __restrict__ e_sumsq, const float* __restrict__ bias,
                                           const float* __restrict__ qbias, Curv cv, const float* __restrict__ scale_margin,
                                           const float* __restrict__ row_c) {
+  pdl_grid_sync();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   if (n >= N) return;
@@ -230,7 +235,7 @@ int hyp_score_epilogue(float* S, int ld, int B, int N, const float* q_sumsq, con
   if (B > 65535) { set_last_error("hyp_score_epilogue: B=%d > 65535 (chunk the queries)", B); return REGCN_ERR_DIM; }
   Curv cv = make_curv(c);
   dim3 grid((N + 255) / 256, B);
-  hyp_score_epilogue_kernel<<<grid, 256, 0, st>>>(S, (size_t)ld, B, N, q_sumsq, e_sumsq, bias, qbias, cv, scale_margin, row_c);
+  launch_k(hyp_score_epilogue_kernel, grid, 256, 0, st, S, (size_t)ld, B, N, q_sumsq, e_sumsq, bias, qbias, cv, scale_margin, row_c);
   return check_launch("hyp_score_epilogue");
 }
 
@@ -239,6 +244,7 @@ int hyp_score_epilogue(float* S, int ld, int B, int N, const float* q_sumsq, con
 // c_q = max(1e-5, min(softplus(raw[r mod R]), 0.999 * c, cmax)).
 __global__ void rel_curvature_kernel(const float* __restrict__ raw, const int64_t* __restrict__ triples, int B, int R,
                                      float upper, float* __restrict__ out) {
+  pdl_grid_sync();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const int r = (int)(triples[3 * (size_t)b + 1] % R);
@@ -255,7 +261,7 @@ int rel_curvature(const float* raw, const int64_t* triples, int B, int R, double
   // upper = min(0.999 * c, cmax) formed in fp32 like the reference's tensors (new_tensor(float(...)))
   float upper = 0.999f * (float)c;
   if (cmax > 0 && (float)cmax < upper) upper = (float)cmax;
-  rel_curvature_kernel<<<(B + 255) / 256, 256, 0, st>>>(raw, triples, B, R, upper, out);
+  launch_k(rel_curvature_kernel, (B + 255) / 256, 256, 0, st, raw, triples, B, R, upper, out);
   return check_launch("rel_curvature");
 }
 

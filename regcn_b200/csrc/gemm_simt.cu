@@ -13,6 +13,7 @@ template <bool TRANSB>
 __global__ void __launch_bounds__(TBG) gemm_f32_kernel(
     const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
     int M, int N, int K, const float* __restrict__ bias, int accumulate, int k_per_split, float* __restrict__ ws) {
+  pdl_grid_sync();
   __shared__ __align__(16) float As[2][BK][BM];
   __shared__ __align__(16) float Bs[2][BK][BN];
   const int tid = threadIdx.x;
@@ -118,6 +119,7 @@ __global__ void __launch_bounds__(TBG) gemm_f32_kernel(
 
 __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, float* __restrict__ C, int ldc,
                                      int M, int N, const float* __restrict__ bias, int accumulate) {
+  pdl_grid_sync();
   const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   const size_t total = (size_t)M * N;
   if (idx >= total) return;
@@ -149,11 +151,11 @@ int gemm_f32(const float* A, int lda, const float* B, int ldb, int transB, float
     set_last_error("gemm_f32: split-K workspace too small"); return REGCN_ERR_WORKSPACE;
   }
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, split_k);
-  if (transB) gemm_f32_kernel<true><<<grid, TBG, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, bias, accumulate, k_per, ws);
-  else gemm_f32_kernel<false><<<grid, TBG, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, bias, accumulate, k_per, ws);
+  if (transB) launch_k(gemm_f32_kernel<true>, grid, TBG, 0, st, A, lda, B, ldb, C, ldc, M, N, K, bias, accumulate, k_per, ws);
+  else launch_k(gemm_f32_kernel<false>, grid, TBG, 0, st, A, lda, B, ldb, C, ldc, M, N, K, bias, accumulate, k_per, ws);
   if (split_k > 1) {
     const size_t total = (size_t)M * N;
-    splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws, split_k, C, ldc, M, N, bias, accumulate);
+    launch_k(splitk_reduce_kernel, (unsigned)((total + 255) / 256), 256, 0, st, ws, split_k, C, ldc, M, N, bias, accumulate);
   }
   return check_launch("gemm_f32");
 }

@@ -67,6 +67,14 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t desc_a, uint
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_c), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc) : "memory");
 }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_c), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc) : "memory");
+}
 // K-major, 128B-swizzled tile: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO), version 1, layout type 2.
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -102,7 +110,8 @@ struct Params {
   int block_n;        // multiple of 16, <= 256
   int tmem_cols;      // power of two >= block_n
   int stages;
-  int passes;         // 3 = 3xTF32 (fp32 parity), 1 = plain TF32
+  int passes;         // 3 = 3xTF32 (fp32 parity), 1 = plain TF32 (or bf16)
+  int bf16;           // operands are bf16 (kind::f16 MMA, 64-element k-blocks); passes == 1
   int kb_per_split;   // k-blocks per split-K slice
   int m_tiles, n_tiles, splits;   // persistent work list: splits x n_tiles x m_tiles items
   float* ws;          // split-K partials [splits][M][N] (NULL when splits == 1)
@@ -156,6 +165,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                  const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                  const Params p) {
+  pdl_trigger();          // the next kernel may be scheduled; its own wait keeps it off our outputs
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[8];
   __shared__ __align__(8) uint64_t empty_bar[8];
@@ -165,7 +175,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int block_k = p.bf16 ? 2 * BLOCK_K : BLOCK_K;      // elements per 128-byte k-block row
+  const int total_kb = (p.K + block_k - 1) / block_k;
   const int tiles_mn = p.m_tiles * p.n_tiles;
   const int total_tiles = tiles_mn * p.splits;
 
@@ -197,6 +208,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_slot;
+  pdl_wait();             // barrier init and the TMEM allocation above overlap the tail of the previous kernel
 
   // work item -> (split z, n tile, m tile); m fastest so that concurrently running CTAs share the B tile in L2
   auto decode = [&](int t, int& m0, int& n0, int& kb_beg, int& kb_end) {
@@ -223,7 +235,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
           const uint32_t fb = smem_u32(&full_bar[stage]);
           mbar_expect_tx(fb, stage_bytes);
           uint32_t dst = smem_base + stage * stage_bytes;
-          const int k0 = kb * BLOCK_K;
+          const int k0 = kb * block_k;
           tma_load_2d(dst, &tm_a_hi, fb, k0, m0); dst += a_bytes;
           if (three) { tma_load_2d(dst, &tm_a_lo, fb, k0, m0); dst += a_bytes; }
           tma_load_2d(dst, &tm_b_hi, fb, k0, n0); dst += b_bytes;
@@ -236,7 +248,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     // ===================== MMA issuer =====================
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=tf32, K-major both, N>>3, M>>4
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.block_n >> 3) << 17) |
+      // (kind::f16 with bf16 operands: format code 1 for A and B, same layout of the other fields)
+      const uint32_t fmt = p.bf16 ? 1u : 2u;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.block_n >> 3) << 17) |
                              ((uint32_t)(BLOCK_M >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
@@ -265,7 +279,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
               acc = 1;
               umma_tf32(tmem_acc, make_desc(sa_hi + koff), make_desc(sb_lo + koff), idesc, acc);
             }
-            umma_tf32(tmem_acc, make_desc(sa_hi + koff), make_desc(sb_hi + koff), idesc, acc);
+            if (p.bf16) umma_f16(tmem_acc, make_desc(sa_hi + koff), make_desc(sb_hi + koff), idesc, acc);   // 16 bf16 = 32 bytes per step
+            else umma_tf32(tmem_acc, make_desc(sa_hi + koff), make_desc(sb_hi + koff), idesc, acc);
             acc = 1;
           }
           umma_commit(smem_u32(&empty_bar[stage]));      // frees the smem slot once these MMAs retire
@@ -510,6 +525,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
 
 // hi = rna_tf32(x), lo = rna_tf32(x - hi): both exactly representable in tf32, hi + lo == x to 2^-22 relative.
 __global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, size_t n4) {
+  pdl_grid_sync();
   const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= n4) return;
   const float4 v = reinterpret_cast<const float4*>(x)[i];
@@ -525,6 +541,22 @@ __global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict
   split1(v.x, h.x, l.x); split1(v.y, h.y, l.y); split1(v.z, h.z, l.z); split1(v.w, h.w, l.w);
   reinterpret_cast<float4*>(hi)[i] = h;
   reinterpret_cast<float4*>(lo)[i] = l;
+}
+
+// fp32 -> bf16 (round to nearest even), 8 elements per thread; the bf16 scoring mode's operand conversion
+__global__ void to_bf16_kernel(const float* __restrict__ x, uint16_t* __restrict__ out, size_t n8) {
+  pdl_grid_sync();
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const float4 a = reinterpret_cast<const float4*>(x)[2 * i], b = reinterpret_cast<const float4*>(x)[2 * i + 1];
+  auto pack = [](float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+  };
+  uint4 o;
+  o.x = pack(a.x, a.y); o.y = pack(a.z, a.w); o.z = pack(b.x, b.y); o.w = pack(b.z, b.w);
+  reinterpret_cast<uint4*>(out)[i] = o;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -544,14 +576,14 @@ static EncodeTiledFn get_encode() {
 }
 
 // 2-D fp32 row-major [rows, cols] with leading dimension ld; box = 32 floats x box_rows, 128B swizzle, zero OOB fill.
-static int make_map(CUtensorMap* m, const float* ptr, int rows, int cols, int ld, int box_rows) {
+static int make_map(CUtensorMap* m, const void* ptr, int rows, int cols, int ld, int box_rows, bool bf16 = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_last_error("gemm_tf32: cuTensorMapEncodeTiled entry point unavailable"); return REGCN_ERR_UNSUPPORTED; }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * (bf16 ? 2 : 4)};
+  cuuint32_t box[2] = {(cuuint32_t)(bf16 ? 2 * BLOCK_K : BLOCK_K), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+  CUresult r = enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_last_error("gemm_tf32: cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%d", (int)r, rows, cols, ld); return REGCN_ERR_DIM; }
@@ -568,8 +600,17 @@ int split_tf32(const float* x, float* hi, float* lo, size_t n, cudaStream_t st) 
   if (n & 3) { set_last_error("split_tf32: element count must be a multiple of 4"); return REGCN_ERR_DIM; }
   if (!n) return REGCN_OK;
   const size_t n4 = n / 4;
-  tc::split_tf32_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(x, hi, lo, n4);
+  launch_k(tc::split_tf32_kernel, (unsigned)((n4 + 255) / 256), 256, 0, st, x, hi, lo, n4);
   return check_launch("split_tf32");
+}
+
+int to_bf16(const float* x, void* out, size_t n, cudaStream_t st) {
+  if (!x || !out) { set_last_error("to_bf16: null pointer"); return REGCN_ERR_NULL; }
+  if (n & 7) { set_last_error("to_bf16: element count must be a multiple of 8"); return REGCN_ERR_DIM; }
+  if (!n) return REGCN_OK;
+  const size_t n8 = n / 8;
+  launch_k(tc::to_bf16_kernel, (unsigned)((n8 + 255) / 256), 256, 0, st, x, (uint16_t*)out, n8);
+  return check_launch("to_bf16");
 }
 
 static int g_force_block_n = 0, g_force_stages = 0;
@@ -613,6 +654,7 @@ static void clear_epi(tc::Params& p) {
   p.addend = nullptr; p.ld_add = 0; p.bias = nullptr; p.accumulate = 0; p.ws = nullptr; p.C = nullptr; p.ldc = 0;
   p.lay_d = 0; p.lay_raw = nullptr; p.lay_hi = nullptr; p.lay_lo = nullptr; p.row_idx = nullptr; p.skip_rows = nullptr;
   p.gate_G = nullptr; p.gate_ld = 0; p.gate_bias = nullptr; p.gate_h = nullptr; p.gate_norm = 0;
+  p.bf16 = 0;
 }
 
 // Common launcher: validates operands, builds the tensor maps, sizes the pipeline, launches.
@@ -622,7 +664,9 @@ static int launch_tc(const float* a_hi, const float* a_lo, int lda, const float*
   const int M = p.M, N = p.N, K = p.K;
   if (!a_hi || !b_hi || (passes == 3 && (!a_lo || !b_lo))) { set_last_error("%s: null operand", who); return REGCN_ERR_NULL; }
   if (passes != 1 && passes != 3) { set_last_error("%s: passes must be 1 or 3", who); return REGCN_ERR_DIM; }
-  if (M < 0 || N <= 0 || K <= 0 || (lda & 3) || (ldb & 3) || lda < K || ldb < K ||
+  const int ld_mask = p.bf16 ? 7 : 3;                 // row pitch must be a multiple of 16 bytes
+  if (p.bf16 && passes != 1) { set_last_error("%s: bf16 operands take one pass", who); return REGCN_ERR_DIM; }
+  if (M < 0 || N <= 0 || K <= 0 || (lda & ld_mask) || (ldb & ld_mask) || lda < K || ldb < K ||
       (((uintptr_t)a_hi | (uintptr_t)b_hi | (uintptr_t)a_lo | (uintptr_t)b_lo) & 15)) {
     set_last_error("%s: bad dims/alignment M=%d N=%d K=%d lda=%d ldb=%d", who, M, N, K, lda, ldb);
     return REGCN_ERR_DIM;
@@ -633,7 +677,8 @@ static int launch_tc(const float* a_hi, const float* a_lo, int lda, const float*
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * p.block_n) p.tmem_cols <<= 1;     // two accumulator slots
   const uint32_t stage_bytes = (passes == 3 ? 2u : 1u) * (BLOCK_M * BLOCK_K * 4 + (uint32_t)p.block_n * BLOCK_K * 4);
-  const int total_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  const int block_k = p.bf16 ? 2 * BLOCK_K : BLOCK_K;
+  const int total_kb = (K + block_k - 1) / block_k;
   if (split_k < 1) split_k = 1;
   if (split_k > total_kb) split_k = total_kb;
   p.kb_per_split = (total_kb + split_k - 1) / split_k;
@@ -644,8 +689,8 @@ static int launch_tc(const float* a_hi, const float* a_lo, int lda, const float*
   if (p.stages < 1) { set_last_error("%s: tile does not fit in shared memory", who); return REGCN_ERR_UNSUPPORTED; }
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   int e;
-  if ((e = make_map(&ta_hi, a_hi, M, K, lda, BLOCK_M))) return e;
-  if ((e = make_map(&tb_hi, b_hi, N, K, ldb, p.block_n))) return e;
+  if ((e = make_map(&ta_hi, a_hi, M, K, lda, BLOCK_M, p.bf16 != 0))) return e;
+  if ((e = make_map(&tb_hi, b_hi, N, K, ldb, p.block_n, p.bf16 != 0))) return e;
   if (passes == 3) {
     if ((e = make_map(&ta_lo, a_lo, M, K, lda, BLOCK_M))) return e;
     if ((e = make_map(&tb_lo, b_lo, N, K, ldb, p.block_n))) return e;
@@ -677,10 +722,10 @@ static int launch_tc(const float* a_hi, const float* a_lo, int lda, const float*
   dim3 grid((unsigned)(total_tiles < sms ? total_tiles : sms));
   prof_begin(PROF_GEMM_TC, st);
   switch (p.epi) {
-    case 0: gemm_tf32_kernel<0><<<grid, NUM_THREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p); break;
-    case 1: gemm_tf32_kernel<1><<<grid, NUM_THREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p); break;
-    case 2: gemm_tf32_kernel<2><<<grid, NUM_THREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p); break;
-    default: gemm_tf32_kernel<3><<<grid, NUM_THREADS, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, p); break;
+    case 0: launch_k(gemm_tf32_kernel<0>, grid, NUM_THREADS, smem, st, ta_hi, ta_lo, tb_hi, tb_lo, p); break;
+    case 1: launch_k(gemm_tf32_kernel<1>, grid, NUM_THREADS, smem, st, ta_hi, ta_lo, tb_hi, tb_lo, p); break;
+    case 2: launch_k(gemm_tf32_kernel<2>, grid, NUM_THREADS, smem, st, ta_hi, ta_lo, tb_hi, tb_lo, p); break;
+    default: launch_k(gemm_tf32_kernel<3>, grid, NUM_THREADS, smem, st, ta_hi, ta_lo, tb_hi, tb_lo, p); break;
   }
   prof_end(PROF_GEMM_TC, p.epi == 2 ? 2.0 * M * (double)K : 2.0 * M * (double)N * K, st);
   return REGCN_OK;
@@ -711,7 +756,7 @@ int gemm_tf32(const float* a_hi, const float* a_lo, int lda, const float* b_hi, 
   if (e) return e;
   if (sk > 1 && M > 0) {
     const size_t total = (size_t)M * N;
-    splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws, sk, C, ldc, M, N, bias, accumulate);
+    launch_k(splitk_reduce_kernel, (unsigned)((total + 255) / 256), 256, 0, st, ws, sk, C, ldc, M, N, bias, accumulate);
   }
   return check_launch("gemm_tf32");
 }
@@ -753,6 +798,7 @@ int score_count_tf32(const float* q_hi, const float* q_lo, const float* e_hi, co
   p.col_offset = col_offset; p.hyp = hyp ? (row_c ? 2 : 1) : 0; p.x2 = x2; p.y2 = y2; p.col_bias = col_bias;
   p.scale_margin = scale_margin; p.row_c = row_c;
   if (hyp) { Curv cv = make_curv(c); p.hc = cv.c; p.hproj_max = cv.proj_max; }
+  if (passes == 0) { p.bf16 = 1; passes = 1; }       // bf16 operands (q_hi / e_hi point at bf16 rows of K elements)
   int e = launch_tc(q_hi, q_lo, K, e_hi, e_lo, K, p, passes, 1, 0, "score_count_tf32", st);
   if (e) return e;
   return check_launch("score_count_tf32");
@@ -770,6 +816,7 @@ int pair_scores_tf32(const float* a_hi, const float* a_lo, const float* b_hi, co
   p.M = P; p.N = P; p.K = K; p.epi = 2; p.hyp = hyp ? (row_c ? 2 : 1) : 0; p.x2 = x2; p.y2 = y2; p.col_bias = col_bias;
   p.scale_margin = scale_margin; p.diag_out = out; p.row_c = row_c;
   if (hyp) { Curv cv = make_curv(c); p.hc = cv.c; p.hproj_max = cv.proj_max; }
+  if (passes == 0) { p.bf16 = 1; passes = 1; }
   int e = launch_tc(a_hi, a_lo, K, b_hi, b_lo, K, p, passes, 1, 128, "pair_scores_tf32", st);
   if (e) return e;
   return check_launch("pair_scores_tf32");
@@ -779,6 +826,7 @@ int pair_scores_tf32(const float* a_hi, const float* a_lo, const float* b_hi, co
 __global__ void gather_rows2_kernel(const float* __restrict__ src_hi, const float* __restrict__ src_lo,
                                     const int* __restrict__ idx, int P, int d, float* __restrict__ out_hi,
                                     float* __restrict__ out_lo) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const int row = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
   if (row >= P) return;
@@ -791,6 +839,7 @@ __global__ void gather_rows2_kernel(const float* __restrict__ src_hi, const floa
 __global__ void gather_scalars_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
                                       const int* __restrict__ ia, const int* __restrict__ ib, int P, float* __restrict__ oa,
                                       float* __restrict__ ob, float* __restrict__ oc) {
+  pdl_grid_sync();
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
   if (a) oa[p] = __ldg(a + __ldg(ia + p));
@@ -803,14 +852,14 @@ int gather_rows2(const float* src_hi, const float* src_lo, const int* idx, int P
   if (!src_hi || !idx || !out_hi || (src_lo && !out_lo)) { set_last_error("gather_rows2: null pointer"); return REGCN_ERR_NULL; }
   if (d & 3) { set_last_error("gather_rows2: d %% 4 != 0"); return REGCN_ERR_DIM; }
   if (P <= 0) return REGCN_OK;
-  gather_rows2_kernel<<<(unsigned)(((size_t)P * 32 + 255) / 256), 256, 0, st>>>(src_hi, src_lo, idx, P, d, out_hi, out_lo);
+  launch_k(gather_rows2_kernel, (unsigned)(((size_t)P * 32 + 255) / 256), 256, 0, st, src_hi, src_lo, idx, P, d, out_hi, out_lo);
   return check_launch("gather_rows2");
 }
 int gather_scalars(const float* a, const float* b, const float* c, const int* ia, const int* ib, int P, float* oa,
                    float* ob, float* oc, cudaStream_t st) {
   if (P <= 0) return REGCN_OK;
   if (!ia || !ib) { set_last_error("gather_scalars: null index"); return REGCN_ERR_NULL; }
-  gather_scalars_kernel<<<(P + 255) / 256, 256, 0, st>>>(a, b, c, ia, ib, P, oa, ob, oc);
+  launch_k(gather_scalars_kernel, (P + 255) / 256, 256, 0, st, a, b, c, ia, ib, P, oa, ob, oc);
   return check_launch("gather_scalars");
 }
 

@@ -28,6 +28,7 @@ size_t gemm_f32_workspace_bytes(int M, int N, int split_k);
 int gemm_f32(const float* A, int lda, const float* B, int ldb, int transB, float* C, int ldc, int M, int N, int K,
              const float* bias, int accumulate, int split_k, float* ws, size_t ws_bytes, cudaStream_t st);
 int split_tf32(const float* x, float* hi, float* lo, size_t n, cudaStream_t st);
+int to_bf16(const float* x, void* out, size_t n, cudaStream_t st);
 size_t gemm_tf32_workspace_bytes(int M, int N, int split_k);
 int gemm_tf32(const float* a_hi, const float* a_lo, int lda, const float* b_hi, const float* b_lo, int ldb, float* C,
               int ldc, int M, int N, int K, const float* bias, int accumulate, int passes, int split_k, float* ws,
@@ -36,6 +37,7 @@ int gemm_tf32_layer(const float* a_hi, const float* a_lo, int lda, const float* 
                     int N, int K, int d, float* out_raw, float* out_hi, float* out_lo, float* gate_out, int ld_gate_out,
                     const int* row_idx, const int* skip_rows, const float* gate_G, int gate_ld, const float* gate_bias,
                     const float* gate_h, int gate_norm, cudaStream_t st);
+void pdl_set(int on);
 void gemm_tf32_tune(int block_n, int stages);
 void aggregate_tune(int impl);
 int score_count_tf32(const float* q_hi, const float* q_lo, const float* e_hi, const float* e_lo, int B, int N, int K,

@@ -20,6 +20,7 @@ __global__ void __launch_bounds__(256) rank_rows_kernel(
     const int* __restrict__ filt_ptr, const int* __restrict__ filt_idx, int col_offset,
     int* __restrict__ raw_count, int* __restrict__ filt_count, float* __restrict__ target_score,
     const int* __restrict__ filt_end) {
+  pdl_grid_sync();
   __shared__ int red[8];
   const int b = blockIdx.x;
   const float* row = S + (size_t)b * ld;
@@ -61,6 +62,7 @@ __global__ void __launch_bounds__(256) rank_rows_kernel(
 __global__ void gather_target_score_kernel(const float* __restrict__ S, size_t ld, int B, int N,
                                            const int64_t* __restrict__ triples, int target_col, int col_offset,
                                            float* __restrict__ target_score) {
+  pdl_grid_sync();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const int t = (int)triples[3 * (size_t)b + target_col] - col_offset;
@@ -69,6 +71,7 @@ __global__ void gather_target_score_kernel(const float* __restrict__ S, size_t l
 
 __global__ void counts_to_ranks_kernel(const int* __restrict__ raw_count, const int* __restrict__ filt_count, int B,
                                        int64_t* __restrict__ rank, int64_t* __restrict__ filt_rank) {
+  pdl_grid_sync();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   rank[b] = (int64_t)raw_count[b] + 1;
@@ -79,6 +82,7 @@ __global__ void counts_to_ranks_kernel(const int* __restrict__ raw_count, const 
 __global__ void apply_filter_kernel(float* __restrict__ S, size_t ld, int B, int N, const int64_t* __restrict__ triples,
                                     int target_col, const int* __restrict__ filt_ptr, const int* __restrict__ filt_idx,
                                     int col_offset, const int* __restrict__ filt_end) {
+  pdl_grid_sync();
   const int b = blockIdx.x;
   const int t = (int)triples[3 * (size_t)b + target_col] - col_offset;
   const int fe = filt_end ? filt_end[b] : filt_ptr[b + 1];
@@ -96,6 +100,7 @@ __global__ void filter_correct_kernel(int B, const int* __restrict__ filt_ptr, c
                                       const int* __restrict__ target, const float* __restrict__ pair_score,
                                       const int* __restrict__ raw_count, int col_lo, int col_hi,
                                       int* __restrict__ filt_count, const int* __restrict__ filt_end) {
+  pdl_grid_sync();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const float st = pair_score[b];
@@ -114,7 +119,7 @@ int filter_correct(int B, const int* filt_ptr, const int* filt_idx, const int* t
                    const int* raw_count, int col_lo, int col_hi, int* filt_count, const int* filt_end, cudaStream_t st) {
   if (!filt_ptr || !filt_idx || !target || !pair_score || !raw_count || !filt_count) { set_last_error("filter_correct: null pointer"); return REGCN_ERR_NULL; }
   if (B <= 0) return REGCN_OK;
-  filter_correct_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, filt_ptr, filt_idx, target, pair_score, raw_count, col_lo, col_hi, filt_count, filt_end);
+  launch_k(filter_correct_kernel, (B + 127) / 128, 128, 0, st, B, filt_ptr, filt_idx, target, pair_score, raw_count, col_lo, col_hi, filt_count, filt_end);
   return check_launch("filter_correct");
 }
 
@@ -133,6 +138,7 @@ __device__ __forceinline__ long long filt_key(const int64_t* __restrict__ triple
 
 __global__ void __launch_bounds__(kFiltThreads) filter_count_kernel(const int64_t* __restrict__ triples, int B, int key_col,
                                                                     int* __restrict__ counts) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const int b = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
   if (b >= B) return;
@@ -147,6 +153,7 @@ __global__ void __launch_bounds__(kFiltThreads) filter_fill_kernel(const int64_t
                                                                    int ans_col, const int* __restrict__ beg,
                                                                    int* __restrict__ idx, int* __restrict__ end,
                                                                    int* __restrict__ pair_a, int* __restrict__ pair_e) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const int b = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
   if (b >= B) return;
@@ -220,7 +227,7 @@ int filter_count(const int64_t* triples, int B, int key_col, int* counts, cudaSt
   if (!triples || !counts) { set_last_error("filter_count: null pointer"); return REGCN_ERR_NULL; }
   if (key_col < 1 || key_col > 2) { set_last_error("filter_count: key_col must be 1 or 2"); return REGCN_ERR_DIM; }
   if (B <= 0) return REGCN_OK;
-  filter_count_kernel<<<(unsigned)(((size_t)B * 32 + kFiltThreads - 1) / kFiltThreads), kFiltThreads, 0, st>>>(triples, B, key_col, counts);
+  launch_k(filter_count_kernel, (unsigned)(((size_t)B * 32 + kFiltThreads - 1) / kFiltThreads), kFiltThreads, 0, st, triples, B, key_col, counts);
   return check_launch("filter_count");
 }
 
@@ -229,7 +236,7 @@ int filter_fill(const int64_t* triples, int B, int key_col, int ans_col, const i
   if (!triples || !beg || !idx || !end || (pair_a && !pair_e)) { set_last_error("filter_fill: null pointer"); return REGCN_ERR_NULL; }
   if (key_col < 1 || key_col > 2 || ans_col < 1 || ans_col > 2 || key_col == ans_col) { set_last_error("filter_fill: bad columns"); return REGCN_ERR_DIM; }
   if (B <= 0) return REGCN_OK;
-  filter_fill_kernel<<<(unsigned)(((size_t)B * 32 + kFiltThreads - 1) / kFiltThreads), kFiltThreads, 0, st>>>(triples, B, key_col, ans_col, beg, idx, end, pair_a, pair_e);
+  launch_k(filter_fill_kernel, (unsigned)(((size_t)B * 32 + kFiltThreads - 1) / kFiltThreads), kFiltThreads, 0, st, triples, B, key_col, ans_col, beg, idx, end, pair_a, pair_e);
   return check_launch("filter_fill");
 }
 
@@ -237,7 +244,7 @@ int gather_target_score(const float* S, int64_t ld, int B, int N, const int64_t*
                         float* target_score, cudaStream_t st) {
   if (!S || !triples || !target_score) { set_last_error("gather_target_score: null pointer"); return REGCN_ERR_NULL; }
   if (B <= 0) return REGCN_OK;
-  gather_target_score_kernel<<<(B + 255) / 256, 256, 0, st>>>(S, (size_t)ld, B, N, triples, target_col, col_offset, target_score);
+  launch_k(gather_target_score_kernel, (B + 255) / 256, 256, 0, st, S, (size_t)ld, B, N, triples, target_col, col_offset, target_score);
   return check_launch("gather_target_score");
 }
 
@@ -247,7 +254,7 @@ int rank_count(const float* S, int64_t ld, int B, int N, const int64_t* triples,
   if (!S || !triples || !target_score || !raw_count || (filt_ptr && !filt_idx)) { set_last_error("rank_count: null pointer"); return REGCN_ERR_NULL; }
   if (target_col < 0 || target_col > 2 || ld < N) { set_last_error("rank_count: bad target_col=%d or ld", target_col); return REGCN_ERR_DIM; }
   if (B <= 0) return REGCN_OK;
-  rank_rows_kernel<<<B, 256, 0, st>>>(S, (size_t)ld, B, N, triples, target_col, filt_ptr, filt_idx, col_offset, raw_count,
+  launch_k(rank_rows_kernel, B, 256, 0, st, S, (size_t)ld, B, N, triples, target_col, filt_ptr, filt_idx, col_offset, raw_count,
                                       filt_count, const_cast<float*>(target_score), filt_end);
   return check_launch("rank_count");
 }
@@ -255,7 +262,7 @@ int rank_count(const float* S, int64_t ld, int B, int N, const int64_t* triples,
 int counts_to_ranks(const int* raw_count, const int* filt_count, int B, int64_t* rank, int64_t* filt_rank, cudaStream_t st) {
   if (!raw_count || !rank) { set_last_error("counts_to_ranks: null pointer"); return REGCN_ERR_NULL; }
   if (B <= 0) return REGCN_OK;
-  counts_to_ranks_kernel<<<(B + 255) / 256, 256, 0, st>>>(raw_count, filt_count, B, rank, filt_rank);
+  launch_k(counts_to_ranks_kernel, (B + 255) / 256, 256, 0, st, raw_count, filt_count, B, rank, filt_rank);
   return check_launch("counts_to_ranks");
 }
 
@@ -263,7 +270,7 @@ int apply_filter(float* S, int64_t ld, int B, int N, const int64_t* triples, int
                  const int* filt_idx, int col_offset, const int* filt_end, cudaStream_t st) {
   if (!S || !triples || !filt_ptr || !filt_idx) { set_last_error("apply_filter: null pointer"); return REGCN_ERR_NULL; }
   if (B <= 0) return REGCN_OK;
-  apply_filter_kernel<<<B, 128, 0, st>>>(S, (size_t)ld, B, N, triples, target_col, filt_ptr, filt_idx, col_offset, filt_end);
+  launch_k(apply_filter_kernel, B, 128, 0, st, S, (size_t)ld, B, N, triples, target_col, filt_ptr, filt_idx, col_offset, filt_end);
   return check_launch("apply_filter");
 }
 

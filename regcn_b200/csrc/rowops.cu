@@ -32,6 +32,7 @@ template <int RV>
 __global__ void __launch_bounds__(256) row_map_kernel(const float* __restrict__ x, float* __restrict__ out, int M, int d,
                                                       int mode, Curv cv, float* __restrict__ sumsq,
                                                       float* __restrict__ out_hi, float* __restrict__ out_lo) {
+  pdl_grid_sync();
   ROW_KERNEL_PROLOGUE(M)
   WarpRow<RV> r;
   r.load_plain(x + (size_t)row * d, nvec, lane);
@@ -60,8 +61,8 @@ int row_map(const float* x, float* out, int M, int d, int mode, double c, float*
   if (mode < 0 || mode > 7) { set_last_error("row_map: bad mode %d", mode); return REGCN_ERR_DIM; }
   if (M <= 0) return REGCN_OK;
   Curv cv = make_curv(c > 0 ? c : 1.0);
-  if (d <= 128) row_map_kernel<1><<<row_grid(M), 256, 0, st>>>(x, out, M, d, mode, cv, sumsq, out_hi, out_lo);
-  else row_map_kernel<2><<<row_grid(M), 256, 0, st>>>(x, out, M, d, mode, cv, sumsq, out_hi, out_lo);
+  if (d <= 128) launch_k(row_map_kernel<1>, row_grid(M), 256, 0, st, x, out, M, d, mode, cv, sumsq, out_hi, out_lo);
+  else launch_k(row_map_kernel<2>, row_grid(M), 256, 0, st, x, out, M, d, mode, cv, sumsq, out_hi, out_lo);
   return check_launch("row_map");
 }
 
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(256) gru_gate_kernel(const float* __restrict__
                                                        const float* __restrict__ hprev, float* __restrict__ out,
                                                        int M, int d, int normalize, float* __restrict__ out_hi,
                                                        float* __restrict__ out_lo) {
+  pdl_grid_sync();
   ROW_KERNEL_PROLOGUE(M)
   WarpRow<RV> ir, iz, in_, hr, hz, hn, h;
   const float* gir = gi + (size_t)row * 3 * d;
@@ -97,8 +99,8 @@ int gru_gate(const float* gi, const float* gh, const float* hprev, float* out, i
   if (!gi || !gh || !hprev || !out) { set_last_error("gru_gate: null pointer"); return REGCN_ERR_NULL; }
   if (int e = check_d("gru_gate", d)) return e;
   if (M <= 0) return REGCN_OK;
-  if (d <= 128) gru_gate_kernel<1><<<row_grid(M), 256, 0, st>>>(gi, gh, hprev, out, M, d, normalize, out_hi, out_lo);
-  else gru_gate_kernel<2><<<row_grid(M), 256, 0, st>>>(gi, gh, hprev, out, M, d, normalize, out_hi, out_lo);
+  if (d <= 128) launch_k(gru_gate_kernel<1>, row_grid(M), 256, 0, st, gi, gh, hprev, out, M, d, normalize, out_hi, out_lo);
+  else launch_k(gru_gate_kernel<2>, row_grid(M), 256, 0, st, gi, gh, hprev, out, M, d, normalize, out_hi, out_lo);
   return check_launch("gru_gate");
 }
 
@@ -117,6 +119,7 @@ __global__ void __launch_bounds__(256) union_combine_kernel(
     int N, int d, int act, int hyper, Curv cv, float* __restrict__ out, float* __restrict__ ht_next,
     float* __restrict__ radius_next, int ldL, float* __restrict__ out_hi, float* __restrict__ out_lo,
     float* __restrict__ ht_hi, float* __restrict__ ht_lo, const int* __restrict__ active_pos) {
+  pdl_grid_sync();
   ROW_KERNEL_PROLOGUE(N)
   WarpRow<RV> t, u;
   if (active_pos) {
@@ -168,8 +171,8 @@ int union_combine(const float* P, const float* L, const int* indeg, const float*
   if (int e = check_d("union_combine", d)) return e;
   if (N <= 0) return REGCN_OK;
   Curv cv = make_curv(hyper ? c : 1.0);
-  if (d <= 128) union_combine_kernel<1><<<row_grid(N), 256, 0, st>>>(P, L, indeg, S, skip_bias, prev, N, d, act, hyper, cv, out, ht_next, radius_next, ldL > 0 ? ldL : 2 * d, out_hi, out_lo, ht_hi, ht_lo, active_pos);
-  else union_combine_kernel<2><<<row_grid(N), 256, 0, st>>>(P, L, indeg, S, skip_bias, prev, N, d, act, hyper, cv, out, ht_next, radius_next, ldL > 0 ? ldL : 2 * d, out_hi, out_lo, ht_hi, ht_lo, active_pos);
+  if (d <= 128) launch_k(union_combine_kernel<1>, row_grid(N), 256, 0, st, P, L, indeg, S, skip_bias, prev, N, d, act, hyper, cv, out, ht_next, radius_next, ldL > 0 ? ldL : 2 * d, out_hi, out_lo, ht_hi, ht_lo, active_pos);
+  else launch_k(union_combine_kernel<2>, row_grid(N), 256, 0, st, P, L, indeg, S, skip_bias, prev, N, d, act, hyper, cv, out, ht_next, radius_next, ldL > 0 ? ldL : 2 * d, out_hi, out_lo, ht_hi, ht_lo, active_pos);
   return check_launch("union_combine");
 }
 
@@ -180,6 +183,7 @@ __global__ void __launch_bounds__(256) time_gate_kernel(const float* __restrict_
                                                         float* __restrict__ out, int N, int d, int normalize_cur,
                                                         int ldg, float* __restrict__ out_hi, float* __restrict__ out_lo,
                                                         const int* __restrict__ row_idx, int act) {
+  pdl_grid_sync();
   ROW_KERNEL_PROLOGUE(N)
   WarpRow<RV> g, b, c, hh;
   // row_idx: `cur` is a compact matrix (one row per listed entity), everything else is indexed by the entity id
@@ -203,8 +207,8 @@ int time_gate(const float* G, const float* bias, const float* cur, const float* 
   if (!G || !bias || !cur || !h || !out) { set_last_error("time_gate: null pointer"); return REGCN_ERR_NULL; }
   if (int e = check_d("time_gate", d)) return e;
   if (N <= 0) return REGCN_OK;
-  if (d <= 128) time_gate_kernel<1><<<row_grid(N), 256, 0, st>>>(G, bias, cur, h, out, N, d, normalize_cur, ldg > 0 ? ldg : d, out_hi, out_lo, row_idx, act);
-  else time_gate_kernel<2><<<row_grid(N), 256, 0, st>>>(G, bias, cur, h, out, N, d, normalize_cur, ldg > 0 ? ldg : d, out_hi, out_lo, row_idx, act);
+  if (d <= 128) launch_k(time_gate_kernel<1>, row_grid(N), 256, 0, st, G, bias, cur, h, out, N, d, normalize_cur, ldg > 0 ? ldg : d, out_hi, out_lo, row_idx, act);
+  else launch_k(time_gate_kernel<2>, row_grid(N), 256, 0, st, G, bias, cur, h, out, N, d, normalize_cur, ldg > 0 ? ldg : d, out_hi, out_lo, row_idx, act);
   return check_launch("time_gate");
 }
 
@@ -222,6 +226,7 @@ template <int RV>
 __global__ void __launch_bounds__(256) hyp_init_kernel(const float* __restrict__ emb, const float* __restrict__ radius_static,
                                                        int N, int d, int normalize, int on_manifold, Curv cv, RadiusCfg rc,
                                                        float* __restrict__ out) {
+  pdl_grid_sync();
   ROW_KERNEL_PROLOGUE(N)
   WarpRow<RV> r;
   r.load_plain(emb + (size_t)row * d, nvec, lane);
@@ -241,6 +246,7 @@ __global__ void __launch_bounds__(256) hyp_tangent_kernel(const float* __restric
                                                           float* __restrict__ radius, float* __restrict__ ht_hi,
                                                           float* __restrict__ ht_lo, float* __restrict__ pt_hi,
                                                           float* __restrict__ pt_lo) {
+  pdl_grid_sync();
   ROW_KERNEL_PROLOGUE(N)
   WarpRow<RV> r;
   r.load_plain(h + (size_t)row * d, nvec, lane);
@@ -266,6 +272,7 @@ __global__ void __launch_bounds__(256) hyp_time_gate_kernel(
     const float* __restrict__ h2, const float* __restrict__ pt, const float* __restrict__ G,
     const float* __restrict__ bias, const float* __restrict__ radius_static, const float* __restrict__ rw,
     float rb, int N, int d, int layer_norm, int residual, Curv cv, RadiusCfg rc, float* __restrict__ out) {
+  pdl_grid_sync();
   ROW_KERNEL_PROLOGUE(N)
   WarpRow<RV> cur, p, g, b;
   cur.load_plain(h2 + (size_t)row * d, nvec, lane);
@@ -311,8 +318,8 @@ int hyp_init(const float* emb, const float* radius_static, int N, int d, int nor
   if (!(c > 0)) { set_last_error("hyp_init: curvature must be > 0"); return REGCN_ERR_DIM; }
   Curv cv = make_curv(c);
   RadiusCfg rc = make_rc(c, rmin, rmax, 1.f, 0.f);
-  if (d <= 128) hyp_init_kernel<1><<<row_grid(N), 256, 0, st>>>(emb, radius_static, N, d, normalize, on_manifold, cv, rc, out);
-  else hyp_init_kernel<2><<<row_grid(N), 256, 0, st>>>(emb, radius_static, N, d, normalize, on_manifold, cv, rc, out);
+  if (d <= 128) launch_k(hyp_init_kernel<1>, row_grid(N), 256, 0, st, emb, radius_static, N, d, normalize, on_manifold, cv, rc, out);
+  else launch_k(hyp_init_kernel<2>, row_grid(N), 256, 0, st, emb, radius_static, N, d, normalize, on_manifold, cv, rc, out);
   return check_launch("hyp_init");
 }
 
@@ -322,8 +329,8 @@ int hyp_tangent(const float* h, int N, int d, double c, float* ht, float* pt, fl
   if (int e = check_d("hyp_tangent", d)) return e;
   if (!(c > 0)) { set_last_error("hyp_tangent: curvature must be > 0"); return REGCN_ERR_DIM; }
   Curv cv = make_curv(c);
-  if (d <= 128) hyp_tangent_kernel<1><<<row_grid(N), 256, 0, st>>>(h, N, d, cv, ht, pt, radius, ht_hi, ht_lo, pt_hi, pt_lo);
-  else hyp_tangent_kernel<2><<<row_grid(N), 256, 0, st>>>(h, N, d, cv, ht, pt, radius, ht_hi, ht_lo, pt_hi, pt_lo);
+  if (d <= 128) launch_k(hyp_tangent_kernel<1>, row_grid(N), 256, 0, st, h, N, d, cv, ht, pt, radius, ht_hi, ht_lo, pt_hi, pt_lo);
+  else launch_k(hyp_tangent_kernel<2>, row_grid(N), 256, 0, st, h, N, d, cv, ht, pt, radius, ht_hi, ht_lo, pt_hi, pt_lo);
   return check_launch("hyp_tangent");
 }
 
@@ -335,8 +342,8 @@ int hyp_time_gate(const float* h2, const float* pt, const float* G, const float*
   if (!(c > 0)) { set_last_error("hyp_time_gate: curvature must be > 0"); return REGCN_ERR_DIM; }
   Curv cv = make_curv(c);
   RadiusCfg rc = make_rc(c, rmin, rmax, beta, eps_r);
-  if (d <= 128) hyp_time_gate_kernel<1><<<row_grid(N), 256, 0, st>>>(h2, pt, G, bias, radius_static, rw, rb, N, d, layer_norm, residual, cv, rc, out);
-  else hyp_time_gate_kernel<2><<<row_grid(N), 256, 0, st>>>(h2, pt, G, bias, radius_static, rw, rb, N, d, layer_norm, residual, cv, rc, out);
+  if (d <= 128) launch_k(hyp_time_gate_kernel<1>, row_grid(N), 256, 0, st, h2, pt, G, bias, radius_static, rw, rb, N, d, layer_norm, residual, cv, rc, out);
+  else launch_k(hyp_time_gate_kernel<2>, row_grid(N), 256, 0, st, h2, pt, G, bias, radius_static, rw, rb, N, d, layer_norm, residual, cv, rc, out);
   return check_launch("hyp_time_gate");
 }
 

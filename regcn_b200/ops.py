@@ -52,6 +52,31 @@ def gemm_impl():
     return _GEMM_IMPL["impl"]
 
 
+# all-entity scoring precision: "fp32" = 3xTF32 error-compensated (the parity mode), "bf16" = tcgen05 kind::f16 on
+# bf16-rounded operands with fp32 accumulation (reported separately: ranks may move where scores are within ~1e-2)
+_SCORE_DTYPE = {"dtype": os.environ.get("REGCN_SCORE_DTYPE", "fp32")}
+
+
+def set_score_dtype(name):
+    if name not in ("fp32", "bf16"):
+        raise ValueError(f"unknown scoring dtype {name!r}")
+    _SCORE_DTYPE["dtype"] = name
+
+
+def score_dtype():
+    return _SCORE_DTYPE["dtype"]
+
+
+def to_bf16(x):
+    """(M, K) fp32 -> bf16 rows (K % 8 == 0), round to nearest even."""
+    M, K = x.shape
+    if K % 8:
+        raise ValueError("to_bf16: K must be a multiple of 8")
+    out = torch.empty((M, K), device=x.device, dtype=torch.bfloat16)
+    call("regcn_to_bf16", ptr(x.contiguous()), ptr(out), M * K)
+    return out
+
+
 def gemm_kernel_name():
     return _IMPLS[_GEMM_IMPL["impl"]]
 
@@ -399,15 +424,28 @@ def fused_rank_counts(q, cand, target, filt_ptr, filt_idx, pair_a, pair_e, hyp=N
     B, K = q.shape
     N = cand.shape[0]
     dev = q.device
-    q_hi, q_lo = _tc_operand(q.detach(), passes == 3)
-    e_hi, e_lo = cand_split if cand_split is not None else _tc_operand(cand.detach(), passes == 3)
     P = pair_a.shape[0]
-    a_hi = torch.empty((P, K), device=dev, dtype=F32)
-    b_hi = torch.empty((P, K), device=dev, dtype=F32)
-    a_lo = torch.empty((P, K), device=dev, dtype=F32) if passes == 3 else None
-    b_lo = torch.empty((P, K), device=dev, dtype=F32) if passes == 3 else None
-    call("regcn_gather_rows2", ptr(q_hi), ptr(q_lo), ptr(pair_a), P, K, ptr(a_hi), ptr(a_lo))
-    call("regcn_gather_rows2", ptr(e_hi), ptr(e_lo), ptr(pair_e), P, K, ptr(b_hi), ptr(b_lo))
+    bf16 = _SCORE_DTYPE["dtype"] == "bf16"
+    if bf16:
+        # bf16 mode: one kind::f16 pass on bf16-rounded operands; the pair pass uses the same operands and the same
+        # MMA arithmetic, so target / filter-entry scores stay bit-identical to the counted scores
+        passes = 0
+        q_hi, q_lo = to_bf16(q.detach()), None
+        e_hi, e_lo = (cand_split if cand_split is not None else (to_bf16(cand.detach()), None))
+        a_hi = torch.empty((P, K), device=dev, dtype=torch.bfloat16)
+        b_hi = torch.empty((P, K), device=dev, dtype=torch.bfloat16)
+        a_lo = b_lo = None
+        call("regcn_gather_rows2", ptr(q_hi), None, ptr(pair_a), P, K // 2, ptr(a_hi), None)     # a bf16 row = K/2 words
+        call("regcn_gather_rows2", ptr(e_hi), None, ptr(pair_e), P, K // 2, ptr(b_hi), None)
+    else:
+        q_hi, q_lo = _tc_operand(q.detach(), passes == 3)
+        e_hi, e_lo = cand_split if cand_split is not None else _tc_operand(cand.detach(), passes == 3)
+        a_hi = torch.empty((P, K), device=dev, dtype=F32)
+        b_hi = torch.empty((P, K), device=dev, dtype=F32)
+        a_lo = torch.empty((P, K), device=dev, dtype=F32) if passes == 3 else None
+        b_lo = torch.empty((P, K), device=dev, dtype=F32) if passes == 3 else None
+        call("regcn_gather_rows2", ptr(q_hi), ptr(q_lo), ptr(pair_a), P, K, ptr(a_hi), ptr(a_lo))
+        call("regcn_gather_rows2", ptr(e_hi), ptr(e_lo), ptr(pair_e), P, K, ptr(b_hi), ptr(b_lo))
     c, x2, y2, sm = (hyp[:4] if hyp is not None else (1.0, None, None, None))
     row_c = hyp[4] if hyp is not None and len(hyp) > 4 else None
     x2p = y2p = bp = rcp = None

@@ -16,11 +16,13 @@ for name,B,N in [("c3",2914,23033),("c5 shard 1/8",8192,125000),("c5 full",8192,
     target=torch.randint(0,N,(B,),device='cuda',dtype=torch.int32)
     tscore=torch.zeros(B,device='cuda'); raw=torch.zeros(B,device='cuda',dtype=torch.int32)
     qh,ql=ops.split_tf32(q); eh,el=ops.split_tf32(e)
-    for passes in (3,1):
-        def f(): _lib.call("regcn_score_count_tf32", qh.data_ptr(), ql.data_ptr(), eh.data_ptr(), el.data_ptr(), B,N,d, tscore.data_ptr(), target.data_ptr(), raw.data_ptr(), 0, 0, None,None,None, 1.0, None, passes)
+    qb,eb=ops.to_bf16(q),ops.to_bf16(e)
+    for passes in (3,1,0):
+        a_,b_=(qb,eb) if passes==0 else (qh,eh)
+        def f(): _lib.call("regcn_score_count_tf32", a_.data_ptr(), ql.data_ptr(), b_.data_ptr(), el.data_ptr(), B,N,d, tscore.data_ptr(), target.data_ptr(), raw.data_ptr(), 0, 0, None,None,None, 1.0, None, None, passes)
         ms=timeit(f)
         alg=2.0*B*N*d/ms/1e9
-        r=dict(shape=name,B=B,N=N,passes=passes,ms=ms,algorithmic_TFLOPs=alg,executed_TFLOPs=alg*passes,frac_tf32_peak_executed=alg*passes/(1369.2/2),frac_bf16_peak_algorithmic=alg/1369.2)
+        r=dict(shape=name,B=B,N=N,mode={3:'3xTF32',1:'TF32',0:'bf16'}[passes],ms=ms,algorithmic_TFLOPs=alg,executed_TFLOPs=alg*max(passes,1),frac_of_mode_peak_executed=alg*max(passes,1)/(1369.2 if passes==0 else 1369.2/2),frac_bf16_peak_algorithmic=alg/1369.2)
         print(json.dumps(r)); res.append(r)
-    del q,e,qh,ql,eh,el
+    del q,e,qh,ql,eh,el,qb,eb
 json.dump(res,open('gpurun_out/score_kernel.json','w'),indent=1)

@@ -627,3 +627,55 @@ def test_gemm_tcgen05_static_weight_cache():
         assert torch.allclose(o2, 2 * o1, rtol=1e-5, atol=1e-5)
     finally:
         ops.set_gemm_impl(prev)
+
+
+# ----------------------------------------------------------------------------------------- bf16 scoring mode
+@pytest.mark.parametrize("hyp", [False, True])
+def test_bf16_scoring_counts_bracketed_by_fp64_on_rounded_operands(hyp):
+    """bf16 scoring mode (tcgen05 kind::f16): the counts must be the exact 'beats the target' counts of SOME score
+    matrix within 2e-5 (relative to the row scale) of the fp64 scores of the bf16-ROUNDED operands -- i.e. the only
+    freedom is the fp32 accumulation order.  Stated separately from the fp32-parity mode (north_star)."""
+    R, ops = _ops()
+    rng = np.random.default_rng(21)
+    B, N, d = 300, 5000, 200
+    q = torch.from_numpy(rng.standard_normal((B, d)).astype(np.float32) * 0.3).to(DEV)
+    e = torch.from_numpy(rng.standard_normal((N, d)).astype(np.float32) * 0.3).to(DEV)
+    target = torch.from_numpy(rng.integers(0, N, B).astype(np.int32)).to(DEV)
+    ptr_t = torch.arange(B + 1, device=DEV, dtype=torch.int32) * 0
+    idx_t = torch.zeros(1, device=DEV, dtype=torch.int32)
+    pa = torch.arange(B, device=DEV, dtype=torch.int32)
+    hyp_t = None
+    if hyp:
+        c = 0.01
+        sm = torch.tensor([1.3, 0.7], device=DEV)
+        hyp_t = (c, ops.row_sumsq(q), ops.row_sumsq(e), sm)
+    prev = ops.score_dtype()
+    ops.set_score_dtype("bf16")
+    try:
+        raw, filt, ts = ops.fused_rank_counts(q, e, target, ptr_t, idx_t, pa, target, hyp=hyp_t)
+    finally:
+        ops.set_score_dtype(prev)
+    assert torch.equal(raw, filt)
+    qb, eb = q.bfloat16().double().cpu(), e.bfloat16().double().cpu()
+    dot = qb @ eb.T
+    if hyp:
+        x2 = (q.double().cpu() ** 2).sum(1, keepdim=True)
+        y2 = (e.double().cpu() ** 2).sum(1).unsqueeze(0)
+        xy = -dot
+        a = 1 + 2 * c * xy + c * y2
+        b = 1 - c * x2
+        num = (a * a * x2 + 2 * a * b * xy + b * b * y2).clamp(min=0)
+        den = 1 + 2 * c * xy + c * c * x2 * y2 + 1e-6
+        n = torch.minimum(num.sqrt() / den.abs(), torch.tensor(1 / np.sqrt(c) - 2e-6, dtype=torch.float64))
+        S = 1.3 * (0.7 - n * n)
+    else:
+        S = dot
+    t = target.long().cpu()
+    st = S[torch.arange(B), t].unsqueeze(1)
+    eps = 2e-5 * S.abs().max(1, keepdim=True).values.clamp(min=1.0)
+    lo = (S > st + eps).sum(1)
+    hi = (S > st - eps).sum(1) - 1                         # the target itself is never counted
+    r = raw.long().cpu()
+    assert bool(((r >= lo) & (r <= hi)).all()), int(((r < lo) | (r > hi)).sum())
+    ok, worst = close(ts.cpu().numpy(), st.squeeze(1).numpy(), rtol=2e-5, atol_scale=float(S.abs().max()))
+    assert ok, worst
