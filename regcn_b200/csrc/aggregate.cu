@@ -11,7 +11,7 @@
 namespace regcn {
 
 constexpr int kAggChunk = 32;  // must match graph_build.cu
-static int g_agg_impl = 0;       // 0 auto, 1 register-staged, 2 bulk-copy (shared-memory staged)
+static int g_agg_impl = 0;       // 0 auto, 1 register-staged, 2 bulk-copy per row, 3 streaming bulk-copy ring
 void aggregate_tune(int impl) { g_agg_impl = impl; }
 
 // ---------------------------------------------------------------------------
@@ -264,6 +264,226 @@ __global__ void __launch_bounds__(kBulkWarps * 32, 1) union_aggregate_bulk_kerne
   }
 }
 
+// ---------------------------------------------------------------------------
+// K4, streaming variant for HBM-bound sizes (impl 3).  The per-row variants above issue a batch of gathers, wait for
+// it, and then walk the index chain of the NEXT row (vrow_row -> vptr/rowptr -> src ids) with nothing in flight:
+// on a 10-edges-per-row graph the gathers are outstanding a third of the time (ncu: DRAM 42 % busy, L2 31 %,
+// long-scoreboard stalls).  Here a warp owns BLOCKS of 32 consecutive virtual rows, whose edges are one contiguous
+// CSR range, and treats them as an edge STREAM:
+//   * the row metadata of a block is loaded 32 rows at a time (one lane per row), one block ahead;
+//   * gathers are issued in windows of 8 edges (cp.async.bulk, one 4*d-byte copy per edge, mbarrier completion)
+//     into a two-slot ring, so a window is always in flight while the previous one is being summed;
+//   * relation rows of a window are fetched into registers before the wait;
+//   * row boundaries are handled while consuming (flush = scale by the degree norm, store, zero).
+// Same outputs (bit for bit: same summation order inside a virtual row) as the other variants.
+// ---------------------------------------------------------------------------
+constexpr int kStreamWarps = 16;
+constexpr int kStreamWin = 8;
+
+template <int RV, bool RADIUS>
+__global__ void __launch_bounds__(kStreamWarps * 32, 1) union_aggregate_stream_kernel(
+    const float* __restrict__ h, const float* __restrict__ rel, const int* __restrict__ rowptr,
+    const int* __restrict__ src_sorted, const int* __restrict__ etype_sorted, const float* __restrict__ norm,
+    const int* __restrict__ vptr, const int* __restrict__ sptr, const int* __restrict__ vrow_row, int nv,
+    const float* __restrict__ radius, float gamma, int d, float* __restrict__ out, float* __restrict__ partial,
+    float* __restrict__ out_hi, float* __restrict__ out_lo, const int* __restrict__ active_pos, int ldo) {
+  pdl_grid_sync();
+  extern __shared__ __align__(128) unsigned char stream_smem[];
+  __shared__ __align__(8) unsigned long long bars[kStreamWarps][2];
+  __shared__ int meta_t[kStreamWarps][2][kStreamWin];
+  __shared__ float meta_rs[kStreamWarps][2][kStreamWin];
+  const int lane = threadIdx.x & 31;
+  const int wid = threadIdx.x >> 5;
+  const int nvec = d >> 2;
+  const uint32_t row_bytes = (uint32_t)d * 4u;
+  float* stage = reinterpret_cast<float*>(stream_smem) + (size_t)wid * 2 * kStreamWin * d;
+  const uint32_t stage_u32 = smem_addr_u32(stage);
+  const uint32_t bar0 = smem_addr_u32(&bars[wid][0]);
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0), "r"(1));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+
+  const int G = gridDim.x * kStreamWarps;                 // warps in the grid
+  const int nblk = (nv + 31) >> 5;
+  // per-lane metadata of one block: lane i describes virtual row 32*blk + i
+  struct Meta { int row, beg, end, part, k0; float nrm, rdst; int orow; };
+  auto load_meta = [&](int blk) {
+    Meta m;
+    m.row = 0; m.beg = 0; m.end = 0; m.part = -1; m.k0 = 0; m.nrm = 0.f; m.rdst = 0.f; m.orow = 0;
+    const int w = blk * 32 + lane;
+    if (blk < nblk && w < nv) {
+      const int row = __ldg(vrow_row + w);
+      const int v0 = __ldg(vptr + row), v1 = __ldg(vptr + row + 1);
+      const int rb = __ldg(rowptr + row), re = __ldg(rowptr + row + 1);
+      const int k = w - v0;
+      m.row = row;
+      m.beg = rb + k * kAggChunk;
+      m.end = min(m.beg + kAggChunk, re);
+      m.part = (v1 - v0 == 1) ? -1 : __ldg(sptr + row) + k;
+      m.k0 = k == 0;
+      m.nrm = __ldg(norm + row);
+      m.orow = active_pos ? __ldg(active_pos + row) : row;
+      if (RADIUS) m.rdst = __ldg(radius + row);
+    }
+    return m;
+  };
+  auto block_rows = [&](int blk) { return min(32, nv - blk * 32); };
+
+  int cblk = blockIdx.x * kStreamWarps + wid;             // consumer's block; blocks cblk, cblk + G, ... belong to this warp
+  if (cblk >= nblk) return;
+  Meta cur = load_meta(cblk);
+  Meta nxt = load_meta(cblk + G);
+  // producer cursor: edge range [pe, p_hi) of block pblk
+  int pblk = cblk;
+  int pe = __shfl_sync(0xffffffffu, cur.beg, 0);
+  int p_hi = __shfl_sync(0xffffffffu, cur.end, block_rows(cblk) - 1);
+  // consumer cursor
+  int ce = pe, c_hi = p_hi;
+  int cv = 0;                                             // current virtual row inside the consumer's block
+  int cv_end = __shfl_sync(0xffffffffu, cur.end, 0);
+  float cv_rdst = RADIUS ? __shfl_sync(0xffffffffu, cur.rdst, 0) : 0.f;
+  uint32_t prod_j = 0, cons_j = 0;
+  uint32_t phase_bits = 0;                                // bit s = phase of ring slot s
+
+  auto produce = [&]() {
+    // one window of the producer's block into ring slot prod_j & 1 (the slot was drained two windows ago)
+    const int cnt = min(kStreamWin, p_hi - pe);
+    const int slot = (int)(prod_j & 1u);
+    const uint32_t bar = bar0 + 8u * (uint32_t)slot;
+    int s = 0, t = 0;
+    if (lane < cnt) {
+      s = __ldg(src_sorted + pe + lane);
+      t = __ldg(etype_sorted + pe + lane);
+    }
+    if (lane == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)cnt * row_bytes) : "memory");
+    }
+    __syncwarp();
+    if (lane < cnt) {
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+          ::"r"(stage_u32 + (uint32_t)(slot * kStreamWin + lane) * row_bytes), "l"(h + (size_t)s * d), "r"(row_bytes), "r"(bar) : "memory");
+      meta_t[wid][slot][lane] = t;
+      if (RADIUS) meta_rs[wid][slot][lane] = __ldg(radius + s);
+    }
+    __syncwarp();
+    pe += cnt;
+    ++prod_j;
+    if (pe == p_hi) {                                     // producer moves on to this warp's next block
+      pblk += G;
+      if (pblk < nblk) {
+        // the producer is never more than two windows (16 edges) ahead and every block but the very last holds
+        // >= 32 edges, so the next block is always the one described by `nxt`
+        pe = __shfl_sync(0xffffffffu, nxt.beg, 0);
+        p_hi = __shfl_sync(0xffffffffu, nxt.end, block_rows(pblk) - 1);
+      }
+    }
+  };
+
+  WarpRow<RV> acc;
+  acc.zero();
+  auto flush = [&]() {
+    // virtual row cv of the consumer's block is complete
+    const int row = __shfl_sync(0xffffffffu, cur.row, cv);
+    const int part = __shfl_sync(0xffffffffu, cur.part, cv);
+    const int k0 = __shfl_sync(0xffffffffu, cur.k0, cv);
+    const float nrm = __shfl_sync(0xffffffffu, cur.nrm, cv);
+    const size_t orow = (size_t)__shfl_sync(0xffffffffu, cur.orow, cv);
+    if (active_pos && k0 && out_hi && ldo >= 2 * d) {
+      WarpRow<RV> self;
+      self.load(h + (size_t)row * d, nvec, lane);
+      self.store_split(out_hi + orow * ldo + d, out_lo + orow * ldo + d, nvec, lane);
+    }
+    if (part < 0) {
+      acc.scale(nrm);
+      if (out) acc.store(out + orow * ldo, nvec, lane);
+      if (out_hi) acc.store_split(out_hi + orow * ldo, out_lo + orow * ldo, nvec, lane);
+    } else {
+      acc.store(partial + (size_t)part * d, nvec, lane);
+    }
+    acc.zero();
+  };
+
+  produce();
+  while (true) {
+    if (pblk < nblk) produce();                           // keep one window in flight behind the one being consumed
+    // ---- consume window cons_j ----
+    const int cnt = min(kStreamWin, c_hi - ce);
+    const int slot = (int)(cons_j & 1u);
+    const uint32_t bar = bar0 + 8u * (uint32_t)slot;
+    // relation rows of the window (cache-resident table) travel while the bulk copies land
+    float4 rv[kStreamWin][RV];
+    float wj[kStreamWin];
+#pragma unroll
+    for (int i = 0; i < kStreamWin; ++i) {
+      wj[i] = 1.f;
+      if (i < cnt) {
+        const int t = meta_t[wid][slot][i];
+#pragma unroll
+        for (int q = 0; q < RV; ++q) {
+          const int c = lane + q * kWarp;
+          rv[i][q] = c < nvec ? ldg4(rel + (size_t)t * d + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    }
+    {
+      const uint32_t ph = (phase_bits >> slot) & 1u;
+      uint32_t done = 0;
+      while (!done) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(done) : "r"(bar), "r"(ph) : "memory");
+      }
+      phase_bits ^= 1u << slot;
+    }
+    const float* srow = stage + (size_t)slot * kStreamWin * d;
+#pragma unroll
+    for (int i = 0; i < kStreamWin; ++i) {
+      if (i < cnt) {
+        const int e = ce + i;
+        if (e >= cv_end) {                                // first edge of the next virtual row
+          flush();
+          ++cv;
+          cv_end = __shfl_sync(0xffffffffu, cur.end, cv);
+          if (RADIUS) cv_rdst = __shfl_sync(0xffffffffu, cur.rdst, cv);
+        }
+        if (RADIUS) wj[i] = expf(-gamma * fabsf(meta_rs[wid][slot][i] - cv_rdst));
+#pragma unroll
+        for (int q = 0; q < RV; ++q) {
+          const int c = lane + q * kWarp;
+          if (c < nvec) {
+            const float4 hv = *reinterpret_cast<const float4*>(srow + (size_t)i * d + 4 * c);
+            const float4 m = f4_add(hv, rv[i][q]);
+            acc.v[q] = RADIUS ? f4_fma(wj[i], m, acc.v[q]) : f4_add(acc.v[q], m);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the slot's rows are dead before the next bulk writes
+    ce += cnt;
+    ++cons_j;
+    if (ce == c_hi) {                                     // block finished: flush its last row, move to the next block
+      flush();
+      cblk += G;
+      if (cblk >= nblk) break;
+      cur = nxt;
+      nxt = load_meta(cblk + G);
+      ce = __shfl_sync(0xffffffffu, cur.beg, 0);
+      c_hi = __shfl_sync(0xffffffffu, cur.end, block_rows(cblk) - 1);
+      cv = 0;
+      cv_end = __shfl_sync(0xffffffffu, cur.end, 0);
+      if (RADIUS) cv_rdst = __shfl_sync(0xffffffffu, cur.rdst, 0);
+    }
+  }
+}
+
 // Rows that were split into several chunks: fold the chunk partials with a radix-32 tree, one level per launch.
 // Level with stride s: the warp of chunk k (k % (32 s) == 0) sums partial[k], partial[k+s], ..., partial[k+31 s]
 // (fixed order: deterministic) back into partial[k]; the level that covers the whole row applies the degree norm
@@ -352,7 +572,32 @@ int union_aggregate(const float* h, const float* rel, const int* rowptr, const i
   const bool small = d <= 128;
   const int impl = g_agg_impl;
   const bool bulk = impl == 2;   // opt-in: measured within +-10% of the register-staged variant (profiles/README.md)
-  if (bulk) {
+  // streaming variant: automatic for HBM-bound sizes (the gathered rows no longer fit in L2), opt-in otherwise
+  // (hub-heavy graphs stay on the register variant: their hot source rows hit in L1, which bulk copies bypass --
+  //  measured on B200, N = 1M, E = 10M: uniform endpoints 2.14 ms stream vs 2.89 ms registers, Zipf 3.58 vs 2.91)
+  const bool stream = impl == 3 || (impl == 0 && (size_t)nv >= 65536 && (size_t)N * d * 4 > (size_t)96 * 1024 * 1024 &&
+                                    (size_t)nsplit * 8 < (size_t)nv);
+  if (stream) {
+    const size_t smem = (size_t)kStreamWarps * 2 * kStreamWin * d * sizeof(float);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned sgrid = (unsigned)sms;
+#define LAUNCH_STREAM(RVV, RAD)                                                                                        \
+    do {                                                                                                               \
+      static bool attr_done = false;                                                                                   \
+      if (!attr_done) {                                                                                                \
+        cudaFuncSetAttribute(union_aggregate_stream_kernel<RVV, RAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); \
+        attr_done = true;                                                                                              \
+      }                                                                                                                \
+      launch_k(union_aggregate_stream_kernel<RVV, RAD>, sgrid, kStreamWarps * 32, smem, st,                            \
+          h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, radius, gamma, d, out, partial,   \
+          out_hi, out_lo, active_pos, ldo);                                                                            \
+    } while (0)
+    if (radius) { if (small) LAUNCH_STREAM(1, true); else LAUNCH_STREAM(2, true); }
+    else { if (small) LAUNCH_STREAM(1, false); else LAUNCH_STREAM(2, false); }
+#undef LAUNCH_STREAM
+  } else if (bulk) {
     const size_t smem = (size_t)kBulkWarps * kBulkRows * d * sizeof(float);
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);

@@ -22,10 +22,10 @@ for name,n,r,t,zipf in [("c4d GDELT-dense",7691,240,50000,True),("200k/2M zipf",
     o=torch.empty(n,d,device='cuda')
     E=2*t
     bytes_=808.0*E+808.0*n+800.0*2*r
-    for impl in (1,2):
+    for impl in (1,2,3):
         R._lib.load().regcn_aggregate_tune(impl)
         ms=timeit(lambda: ops.union_aggregate(h,rel,g,out=o))
-        res=dict(case=name,impl={1:"registers",2:"cp.async.bulk"}[impl],N=n,E=E,max_deg=g.max_hub_degree,n_vrows=g.n_vrows,n_split=g.n_split_chunks,ms=ms,GBs=bytes_/ms/1e6,frac=bytes_/ms/1e6/peak)
+        res=dict(case=name,impl={1:"registers",2:"cp.async.bulk",3:"stream"}[impl],N=n,E=E,max_deg=g.max_hub_degree,n_vrows=g.n_vrows,n_split=g.n_split_chunks,ms=ms,GBs=bytes_/ms/1e6,frac=bytes_/ms/1e6/peak)
         print(json.dumps(res)); out.append(res)
     R._lib.load().regcn_aggregate_tune(0)
     del g,h,o

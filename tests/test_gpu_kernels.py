@@ -143,7 +143,7 @@ def test_csr_build_batch_many_snapshots_and_big_ids():
 
 
 # ----------------------------------------------------------------------------------------- K4 / K2
-@pytest.mark.parametrize("impl", [1, 2])
+@pytest.mark.parametrize("impl", [1, 2, 3])
 @pytest.mark.parametrize("shape,d,radius", [("tiny", 200, False), ("small", 200, True), ("c1", 200, False),
                                             ("c4d", 200, True), ("small", 64, False), ("c4d", 128, False)])
 def test_union_aggregate_vs_oracle(shape, d, radius, impl):
