@@ -138,6 +138,23 @@ REGCN_API int regcn_score_count_tf32(const float* q_hi, const float* q_lo, const
 REGCN_API int regcn_pair_scores_tf32(const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo, int P,
                            int K, int hyp, const float* x2, const float* y2, const float* col_bias, double c,
                            const float* scale_margin, const float* row_c, float* out, int passes, void* stream);
+/* ---- loss heads (forward): CrossEntropy over ALL candidates without the (B,N) logits -- src/rrgcn.py:205-223
+ * (loss_e / loss_r), hyperbolic_decoder.py:182-307 (_chunked_hyperbolic_ce_loss).
+ * regcn_score_lse_tf32: the scoring GEMM with a streaming log-sum-exp epilogue; every (256-candidate tile, warp share)
+ *   writes max and sum-of-exp of its slice of each row into part_max / part_sum, regcn_score_lse_num_parts(N) slices of
+ *   B floats each.  Score arguments as regcn_score_count_tf32.
+ * regcn_ce_from_lse: ce[b] = logsumexp_n score(b,n) - tscore[b] (tscore from regcn_pair_scores_tf32: same arithmetic),
+ *   loss[0] = mean(ce) when loss != NULL.  Deterministic (fixed slice order, single-CTA mean).                       */
+REGCN_API int regcn_score_lse_num_parts(int N);
+REGCN_API int regcn_score_lse_tf32(const float* q_hi, const float* q_lo, const float* e_hi, const float* e_lo, int B, int N,
+                         int K, int hyp, const float* x2, const float* y2, const float* col_bias, double c,
+                         const float* scale_margin, const float* row_c, int passes, float* part_max, float* part_sum,
+                         void* stream);
+REGCN_API int regcn_ce_from_lse(const float* part_max, const float* part_sum, int nparts, int B, const float* tscore,
+                      float* ce, float* loss, void* stream);
+/* dense variant for small candidate sets (relation prediction, N = 2R): ce[b] = logsumexp(S[b,:]) - S[b, triples[b,target_col]] */
+REGCN_API int regcn_ce_rows(const float* S, int64_t ld, int B, int N, const int64_t* triples, int target_col, float* ce,
+                  float* loss, void* stream);
 REGCN_API int regcn_gather_rows2(const float* src_hi, const float* src_lo, const int32_t* idx, int P, int d,
                        float* out_hi, float* out_lo, void* stream);
 REGCN_API int regcn_gather_scalars(const float* a, const float* b, const float* c, const int32_t* ia, const int32_t* ib,

@@ -141,9 +141,29 @@ def run_case(name, cfg, ref_utils, RecurrentRGCN, HyperbolicRecurrentRGCN):
           f"mrr(filter/raw)={fm:.4f}/{m:.4f}")
 
 
+def run_losses(ref_utils, RecurrentRGCN, HyperbolicRecurrentRGCN):
+    """tests/golden/losses.json: the reference's get_loss() (src/rrgcn.py:197-248, hyperbolic_model.py:941-1088) on
+    every golden case, eval mode (dropout off, rrelu at its eval slope) under no_grad, with the test snapshot as the
+    training triples.  Values: [loss_ent, loss_rel, loss_static(, loss_radius)]."""
+    out = {}
+    for name, cfg in CASES.items():
+        case = synth.make_case(cfg["shape"], cfg["seed"])
+        n, r = case["num_ents"], case["num_rels"]
+        model = build_reference_model(cfg, n, r, RecurrentRGCN, HyperbolicRecurrentRGCN)
+        glist = [ref_utils.build_sub_graph(n, r, snap, False, "cpu") for snap in case["history"]]
+        with torch.no_grad():
+            losses = model.get_loss(glist, torch.from_numpy(case["test"]), None, False)
+        out[name] = [float(x.reshape(-1)[0]) for x in losses]
+        print(name, out[name])
+    with open(os.path.join(GOLDEN, "losses.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+
+
 def main(argv):
     ref_utils, RecurrentRGCN, HyperbolicRecurrentRGCN = _import_reference()
     torch.set_num_threads(os.cpu_count() or 1)
+    if len(argv) > 1 and argv[1] == "--losses":
+        return run_losses(ref_utils, RecurrentRGCN, HyperbolicRecurrentRGCN)
     names = argv[1:] or list(CASES)
     for name in names:
         run_case(name, CASES[name], ref_utils, RecurrentRGCN, HyperbolicRecurrentRGCN)

@@ -623,3 +623,32 @@ def hyp_predict(p, graphs, num_rels, test_triples, c=0.01, decoder="roth", layer
     else:
         raise NotImplementedError(decoder)
     return all_triples, score, score_rel, hist, h0
+
+
+# =====================================================================================
+# Loss heads (eval-mode forward): src/rrgcn.py:197-223, hyperbolic_model.py:941-1036,1066-1073
+# =====================================================================================
+def cross_entropy(score, target):
+    """nn.CrossEntropyLoss (mean): logsumexp(row) - row[target]; the hyperbolic decoders' streaming `loss`
+    (hyperbolic_decoder.py:182-307) is the same quantity computed chunk by chunk."""
+    t = torch.as_tensor(np.asarray(target), dtype=torch.long)
+    return (torch.logsumexp(score, dim=1) - score[torch.arange(score.shape[0]), t]).mean()
+
+
+def regcn_loss(p, graphs, num_rels, triples, layer_norm=True, dtype=torch.float32, **kw):
+    """RecurrentRGCN.get_loss without the static-graph term: (loss_ent, loss_rel, 0)."""
+    all_t, score, score_rel, _, _ = regcn_predict(p, graphs, num_rels, triples, layer_norm=layer_norm, dtype=dtype, **kw)
+    return (float(cross_entropy(score, all_t[:, 2])), float(cross_entropy(score_rel, all_t[:, 1])), 0.0)
+
+
+def hyp_loss(p, graphs, num_rels, triples, c=0.01, decoder="roth", layer_norm=False, radius_lambda=0.02, rmin=0.5,
+             rmax=3.0, dtype=torch.float32, **kw):
+    """HyperbolicRecurrentRGCN.get_loss: (loss_ent, loss_rel, 0, loss_radius); the per-query entity bias cancels in CE
+    (hyperbolic_decoder.py:205-206) and radius supervision is an MSE over the entities of the batch (:1066-1073)."""
+    all_t, score, score_rel, _, _ = hyp_predict(p, graphs, num_rels, triples, c=c, decoder=decoder,
+                                                layer_norm=layer_norm, dtype=dtype, **kw)
+    ids = torch.unique(torch.as_tensor(all_t[:, [0, 2]].reshape(-1)))
+    rs = static_radius(p["radius_static"].to(dtype), c, rmin, rmax)[ids]
+    rt = p["radius_target"].to(dtype)[ids]
+    return (float(cross_entropy(score, all_t[:, 2])), float(cross_entropy(score_rel, all_t[:, 1])), 0.0,
+            float(radius_lambda * torch.mean((rs - rt) ** 2)))

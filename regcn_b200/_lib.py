@@ -45,6 +45,10 @@ SIGNATURES = {
     "regcn_aggregate_tune": (None, [_i]),
     "regcn_score_count_tf32": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _i, _i, _p, _p, _p, _d, _p, _p, _i, _p]),
     "regcn_pair_scores_tf32": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _d, _p, _p, _p, _i, _p]),
+    "regcn_score_lse_num_parts": (_i, [_i]),
+    "regcn_score_lse_tf32": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _d, _p, _p, _i, _p, _p, _p]),
+    "regcn_ce_from_lse": (_i, [_p, _p, _i, _i, _p, _p, _p, _p]),
+    "regcn_ce_rows": (_i, [_p, _i64, _i, _i, _p, _i, _p, _p, _p]),
     "regcn_gather_rows2": (_i, [_p, _p, _p, _i, _i, _p, _p, _p]),
     "regcn_gather_scalars": (_i, [_p, _p, _p, _p, _p, _i, _p, _p, _p, _p]),
     "regcn_filter_correct": (_i, [_i, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p]),

@@ -163,6 +163,18 @@ int regcn_pair_scores_tf32(const float* a_hi, const float* a_lo, const float* b_
   return pair_scores_tf32(a_hi, a_lo, b_hi, b_lo, P, K, hyp, x2, y2, col_bias, c, scale_margin, row_c, out, passes,
                           ST(stream));
 }
+int regcn_score_lse_num_parts(int N) { return score_lse_num_parts(N); }
+int regcn_score_lse_tf32(const float* q_hi, const float* q_lo, const float* e_hi, const float* e_lo, int B, int N, int K,
+                         int hyp, const float* x2, const float* y2, const float* col_bias, double c,
+                         const float* scale_margin, const float* row_c, int passes, float* part_max, float* part_sum,
+                         void* stream) {
+  return score_lse_tf32(q_hi, q_lo, e_hi, e_lo, B, N, K, hyp, x2, y2, col_bias, c, scale_margin, row_c, passes, part_max,
+                        part_sum, ST(stream));
+}
+int regcn_ce_from_lse(const float* part_max, const float* part_sum, int nparts, int B, const float* tscore, float* ce,
+                      float* loss, void* stream) {
+  return ce_from_lse(part_max, part_sum, nparts, B, tscore, ce, loss, ST(stream));
+}
 int regcn_gather_rows2(const float* src_hi, const float* src_lo, const int32_t* idx, int P, int d, float* out_hi,
                        float* out_lo, void* stream) {
   return gather_rows2(src_hi, src_lo, idx, P, d, out_hi, out_lo, ST(stream));
@@ -250,6 +262,12 @@ int regcn_rank_count(const float* S, int64_t ld, int B, int N, const int64_t* tr
                      int32_t* raw_count, int32_t* filt_count, const int32_t* filt_end, void* stream) {
   return rank_count(S, ld, B, N, triples, target_col, filt_ptr, filt_idx, col_offset, target_score, raw_count,
                     filt_count, filt_end, ST(stream));
+}
+int regcn_ce_rows(const float* S, int64_t ld, int B, int N, const int64_t* triples, int target_col, float* ce,
+                  float* loss, void* stream) {
+  int e = ce_rows(S, ld, B, N, triples, target_col, ce, ST(stream));
+  if (e || !loss || B <= 0) return e;
+  return mean_f32(ce, B, loss, ST(stream));
 }
 int regcn_counts_to_ranks(const int32_t* raw_count, const int32_t* filt_count, int B, int64_t* rank, int64_t* filt_rank,
                           void* stream) {

@@ -129,6 +129,8 @@ struct Params {
   const float* scale_margin;  // device [scale, margin]
   const float* row_c;         // hyp == 2: [M] per-query curvature (true-distance branch); epi 2: indexed by pair
   float* diag_out;            // epi 2: [M]
+  float* lse_max;             // epi 4: [n_tiles * EPI_WARPS/4][M] running maximum of this (tile, warp share) slice
+  float* lse_sum;             // epi 4: same shape, sum of exp(score - max) over the slice
   // ---- fused layer epilogue (epi 3): UnionRGCNLayer apply (rgcn/layers.py:247-255) and, for the last layer, the
   //      time gate (src/rrgcn.py:176-178) straight out of the accumulator ----
   int lay_d;                  // hidden size: columns [0, lay_d) are layer outputs rrelu(acc); columns >= lay_d are stored
@@ -502,6 +504,47 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
           }
           __syncwarp();
         }
+      } else if constexpr (EPI == 4) {
+        // Streaming log-sum-exp of the score row (the training loss heads: CrossEntropy over all entities without the
+        // (B,N) logits, src/rrgcn.py:217-218, hyperbolic_decoder.py:182-307).  Each (n-tile, warp share) emits the
+        // maximum and the sum of exp(score - max) of its slice of the row; ce_from_lse folds the slices.
+        const bool rv = row < p.M;
+        float m_run = -INFINITY, s_run = 0.f;
+        for (int c0 = 32 * part; c0 < p.block_n; c0 += 32 * kParts) {
+          float v[32];
+          tmem_ld32(tmem_acc + (uint32_t)c0, v);
+          const int gn0 = n0 + c0;
+          const int ncols = min(32, min(p.block_n - c0, p.N - gn0));
+          if (rv && ncols > 0) {
+            if (p.hyp == 2) {
+              const float x2r = __ldg(p.x2 + row), cq = __ldg(p.row_c + row);
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncols) v[j] = hyp_dist_score_from_dot(v[j], x2r, __ldg(p.y2 + gn0 + j), cq, scale, margin);
+            } else if (p.hyp) {
+              const float x2r = __ldg(p.x2 + row);
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncols) v[j] = hyp_score_from_dot(v[j], x2r, __ldg(p.y2 + gn0 + j), p.hc, p.hproj_max, scale, margin);
+            }
+            if (p.col_bias) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (j < ncols) v[j] = __fadd_rn(v[j], __ldg(p.col_bias + gn0 + j));
+            }
+            float cm = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) cm = j < ncols ? fmaxf(cm, v[j]) : cm;
+            if (cm > m_run) { s_run *= expf(m_run - cm); m_run = cm; }     // exp(-inf) = 0 on the first chunk
+#pragma unroll
+            for (int j = 0; j < 32; ++j) s_run += j < ncols ? expf(v[j] - m_run) : 0.f;
+          }
+        }
+        if (rv) {
+          const int nt = n0 / p.block_n;
+          const size_t slot = ((size_t)(nt * kParts + part)) * (size_t)p.M + row;
+          p.lse_max[slot] = m_run;
+          p.lse_sum[slot] = s_run;
+        }
       } else {
         // pair scores: the tile is a diagonal block of A' . B'^T (pair p = row), keep acc[r][r]
         float v[32];
@@ -652,6 +695,7 @@ static void clear_epi(tc::Params& p) {
   p.epi = 0; p.tscore = nullptr; p.target = nullptr; p.raw_count = nullptr; p.col_offset = 0; p.hyp = 0; p.x2 = nullptr;
   p.y2 = nullptr; p.row_c = nullptr; p.col_bias = nullptr; p.hc = 0.f; p.hproj_max = 0.f; p.scale_margin = nullptr; p.diag_out = nullptr;
   p.addend = nullptr; p.ld_add = 0; p.bias = nullptr; p.accumulate = 0; p.ws = nullptr; p.C = nullptr; p.ldc = 0;
+  p.lse_max = nullptr; p.lse_sum = nullptr;
   p.lay_d = 0; p.lay_raw = nullptr; p.lay_hi = nullptr; p.lay_lo = nullptr; p.row_idx = nullptr; p.skip_rows = nullptr;
   p.gate_G = nullptr; p.gate_ld = 0; p.gate_bias = nullptr; p.gate_h = nullptr; p.gate_norm = 0;
   p.bf16 = 0;
@@ -705,6 +749,7 @@ static int launch_tc(const float* a_hi, const float* a_lo, int lda, const float*
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(gemm_tf32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(gemm_tf32_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(gemm_tf32_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(gemm_tf32_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     if (ce != cudaSuccess) { set_last_error("%s: cudaFuncSetAttribute failed: %s", who, cudaGetErrorString(ce)); return (int)ce; }
     attr_set = true;
   }
@@ -725,7 +770,8 @@ static int launch_tc(const float* a_hi, const float* a_lo, int lda, const float*
     case 0: launch_k(gemm_tf32_kernel<0>, grid, NUM_THREADS, smem, st, ta_hi, ta_lo, tb_hi, tb_lo, p); break;
     case 1: launch_k(gemm_tf32_kernel<1>, grid, NUM_THREADS, smem, st, ta_hi, ta_lo, tb_hi, tb_lo, p); break;
     case 2: launch_k(gemm_tf32_kernel<2>, grid, NUM_THREADS, smem, st, ta_hi, ta_lo, tb_hi, tb_lo, p); break;
-    default: launch_k(gemm_tf32_kernel<3>, grid, NUM_THREADS, smem, st, ta_hi, ta_lo, tb_hi, tb_lo, p); break;
+    case 3: launch_k(gemm_tf32_kernel<3>, grid, NUM_THREADS, smem, st, ta_hi, ta_lo, tb_hi, tb_lo, p); break;
+    default: launch_k(gemm_tf32_kernel<4>, grid, NUM_THREADS, smem, st, ta_hi, ta_lo, tb_hi, tb_lo, p); break;
   }
   prof_end(PROF_GEMM_TC, p.epi == 2 ? 2.0 * M * (double)K : 2.0 * M * (double)N * K, st);
   return REGCN_OK;
@@ -802,6 +848,71 @@ int score_count_tf32(const float* q_hi, const float* q_lo, const float* e_hi, co
   int e = launch_tc(q_hi, q_lo, K, e_hi, e_lo, K, p, passes, 1, 0, "score_count_tf32", st);
   if (e) return e;
   return check_launch("score_count_tf32");
+}
+
+// Fused K11/K13 + loss head: per-row streaming log-sum-exp over all candidates (no (B,N) logits).  The N tile is fixed
+// at 256 so that the caller can size the slice buffers: score_lse_num_parts(N) slices of B floats each.
+constexpr int kLseBlockN = 256;
+int score_lse_num_parts(int N) { return ((N + kLseBlockN - 1) / kLseBlockN) * (tc::EPI_WARPS / 4); }
+
+int score_lse_tf32(const float* q_hi, const float* q_lo, const float* e_hi, const float* e_lo, int B, int N, int K, int hyp,
+                   const float* x2, const float* y2, const float* col_bias, double c, const float* scale_margin,
+                   const float* row_c, int passes, float* part_max, float* part_sum, cudaStream_t st) {
+  if (!part_max || !part_sum || (hyp && (!x2 || !y2 || !scale_margin))) { set_last_error("score_lse_tf32: null pointer"); return REGCN_ERR_NULL; }
+  if (row_c && !hyp) { set_last_error("score_lse_tf32: row_c needs hyp != 0"); return REGCN_ERR_DIM; }
+  tc::Params p;
+  clear_epi(p);
+  p.M = B; p.N = N; p.K = K; p.epi = 4; p.hyp = hyp ? (row_c ? 2 : 1) : 0; p.x2 = x2; p.y2 = y2; p.col_bias = col_bias;
+  p.scale_margin = scale_margin; p.row_c = row_c; p.lse_max = part_max; p.lse_sum = part_sum;
+  if (hyp) { Curv cv = make_curv(c); p.hc = cv.c; p.hproj_max = cv.proj_max; }
+  if (passes == 0) { p.bf16 = 1; passes = 1; }
+  int e = launch_tc(q_hi, q_lo, K, e_hi, e_lo, K, p, passes, 1, kLseBlockN, "score_lse_tf32", st);
+  if (e) return e;
+  return check_launch("score_lse_tf32");
+}
+
+// ce[b] = logsumexp_n score(b,n) - tscore[b] from the slices of score_lse_tf32 (fixed slice order: deterministic)
+__global__ void ce_from_lse_kernel(const float* __restrict__ part_max, const float* __restrict__ part_sum, int nparts,
+                                   int B, const float* __restrict__ tscore, float* __restrict__ ce) {
+  pdl_grid_sync();
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float m = -INFINITY;
+  for (int t = 0; t < nparts; ++t) m = fmaxf(m, part_max[(size_t)t * B + b]);
+  float s = 0.f;
+  for (int t = 0; t < nparts; ++t) {
+    const float pm = part_max[(size_t)t * B + b];
+    if (pm > -INFINITY) s += part_sum[(size_t)t * B + b] * expf(pm - m);
+  }
+  ce[b] = (m + logf(s)) - tscore[b];
+}
+// loss = mean(ce): one CTA, fixed reduction tree (deterministic)
+__global__ void __launch_bounds__(1024) mean_kernel(const float* __restrict__ x, int n, float* __restrict__ out) {
+  pdl_grid_sync();
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += x[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) out[0] = t / (float)n;
+  }
+}
+int mean_f32(const float* x, int n, float* out, cudaStream_t st) {
+  if (!x || !out || n <= 0) { set_last_error("mean_f32: bad arguments"); return REGCN_ERR_NULL; }
+  launch_k(mean_kernel, 1, 1024, 0, st, x, n, out);
+  return check_launch("mean_f32");
+}
+int ce_from_lse(const float* part_max, const float* part_sum, int nparts, int B, const float* tscore, float* ce,
+                float* loss, cudaStream_t st) {
+  if (!part_max || !part_sum || !tscore || !ce) { set_last_error("ce_from_lse: null pointer"); return REGCN_ERR_NULL; }
+  if (B <= 0 || nparts <= 0) { set_last_error("ce_from_lse: empty batch"); return REGCN_ERR_DIM; }
+  launch_k(ce_from_lse_kernel, (unsigned)((B + 127) / 128), 128, 0, st, part_max, part_sum, nparts, B, tscore, ce);
+  if (loss) launch_k(mean_kernel, 1, 1024, 0, st, (const float*)ce, B, loss);
+  return check_launch("ce_from_lse");
 }
 
 // Pair scores through the same MMA arithmetic as the scoring GEMM: out[p] = score(A'[p], B'[p]) with A', B' the

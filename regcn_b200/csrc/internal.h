@@ -47,6 +47,12 @@ int score_count_tf32(const float* q_hi, const float* q_lo, const float* e_hi, co
 int pair_scores_tf32(const float* a_hi, const float* a_lo, const float* b_hi, const float* b_lo, int P, int K, int hyp,
                      const float* x2, const float* y2, const float* col_bias, double c, const float* scale_margin,
                      const float* row_c, float* out, int passes, cudaStream_t st);
+int score_lse_num_parts(int N);
+int score_lse_tf32(const float* q_hi, const float* q_lo, const float* e_hi, const float* e_lo, int B, int N, int K, int hyp,
+                   const float* x2, const float* y2, const float* col_bias, double c, const float* scale_margin,
+                   const float* row_c, int passes, float* part_max, float* part_sum, cudaStream_t st);
+int ce_from_lse(const float* part_max, const float* part_sum, int nparts, int B, const float* tscore, float* ce,
+                float* loss, cudaStream_t st);
 int gather_rows2(const float* src_hi, const float* src_lo, const int* idx, int P, int d, float* out_hi, float* out_lo,
                  cudaStream_t st);
 int gather_scalars(const float* a, const float* b, const float* c, const int* ia, const int* ib, int P, float* oa,
@@ -92,6 +98,8 @@ int rank_count(const float* S, int64_t ld, int B, int N, const int64_t* triples,
 int filter_count(const int64_t* triples, int B, int key_col, int* counts, cudaStream_t st);
 int filter_fill(const int64_t* triples, int B, int key_col, int ans_col, const int* beg, int* idx, int* end, int* pair_a,
                 int* pair_e, cudaStream_t st);
+int mean_f32(const float* x, int n, float* out, cudaStream_t st);
+int ce_rows(const float* S, int64_t ld, int B, int N, const int64_t* triples, int target_col, float* ce, cudaStream_t st);
 int counts_to_ranks(const int* raw_count, const int* filt_count, int B, int64_t* rank, int64_t* filt_rank, cudaStream_t st);
 int apply_filter(float* S, int64_t ld, int B, int N, const int64_t* triples, int target_col, const int* filt_ptr,
                  const int* filt_idx, int col_offset, const int* filt_end, cudaStream_t st);

@@ -274,4 +274,33 @@ int apply_filter(float* S, int64_t ld, int B, int N, const int64_t* triples, int
   return check_launch("apply_filter");
 }
 
+
+// Cross entropy of a dense (B, N) score matrix against column triples[:, target_col] (the relation-prediction loss
+// head, src/rrgcn.py:220-222: N = 2R is small enough to materialise).  One warp per row, fixed lane order.
+__global__ void __launch_bounds__(256) ce_rows_kernel(const float* __restrict__ S, size_t ld, int B, int N,
+                                                      const int64_t* __restrict__ triples, int target_col,
+                                                      float* __restrict__ ce) {
+  pdl_grid_sync();
+  const int lane = threadIdx.x & 31;
+  const int b = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+  if (b >= B) return;
+  const float* row = S + (size_t)b * ld;
+  float m = -INFINITY;
+  for (int j = lane; j < N; j += 32) m = fmaxf(m, row[j]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float s = 0.f;
+  for (int j = lane; j < N; j += 32) s += expf(row[j] - m);
+  s = warp_sum(s);
+  if (lane == 0) ce[b] = (m + logf(s)) - row[(int)triples[3 * (size_t)b + target_col]];
+}
+
+int ce_rows(const float* S, int64_t ld, int B, int N, const int64_t* triples, int target_col, float* ce, cudaStream_t st) {
+  if (!S || !triples || !ce) { set_last_error("ce_rows: null pointer"); return REGCN_ERR_NULL; }
+  if (target_col < 0 || target_col > 2 || ld < N || N <= 0) { set_last_error("ce_rows: bad dims"); return REGCN_ERR_DIM; }
+  if (B <= 0) return REGCN_OK;
+  launch_k(ce_rows_kernel, (unsigned)(((size_t)B * 32 + 255) / 256), 256, 0, st, S, (size_t)ld, B, N, triples, target_col, ce);
+  return check_launch("ce_rows");
+}
+
 }  // namespace regcn

@@ -301,7 +301,41 @@ class HyperbolicRecurrentRGCN(nn.Module):
             del self._rb_cache
         return out
 
+    @torch.no_grad()
     def get_loss(self, glist, triples, static_graph, use_cuda, query_time=None):
-        raise NotImplementedError(
-            "regcn_b200.HyperbolicRecurrentRGCN.get_loss: the training step (backward kernels, SURVEY.md 8f rank 1) "
-            "is not part of this round's hot path; forward()/predict() are")
+        """hyperbolic_model.py:941-1088, forward values: (loss_ent, loss_rel, loss_static, loss_radius).
+
+        Entity head: the decoders' streaming CE (hyperbolic_decoder.py:182-307) as the scoring GEMM's log-sum-exp
+        epilogue; relation head on its (B,2R) score matrix; radius supervision as in :1066-1073.  Evaluation-mode
+        forward only: training mode raises until the backward kernels exist."""
+        from . import evaluate
+        if self.training:
+            raise NotImplementedError("regcn_b200.HyperbolicRecurrentRGCN.get_loss: training mode needs the backward "
+                                      "kernels (SURVEY.md 8f rank 1); the forward loss is available after .eval()")
+        if getattr(self, "use_static", False):
+            raise NotImplementedError("static-graph constraint loss is SURVEY.md 8f rank 3")
+        dev = self.dynamic_emb.device
+        triples = torch.as_tensor(triples).to(dev)
+        inverse_triples = triples[:, [2, 1, 0]]
+        inverse_triples[:, 1] = inverse_triples[:, 1] + self.num_rels
+        all_triples = torch.cat([triples, inverse_triples]).contiguous()
+        evolve_embs, _, r_emb, _, _ = self.forward(glist, static_graph, use_cuda)
+        pre_emb = evolve_embs[-1]
+        if self.layer_norm:
+            pre_emb = ops.row_map(pre_emb, ops.ROW_TANGENT_NORMALIZE, c=self._c_float)
+        loss_ent = torch.zeros(1, device=dev)
+        loss_rel = torch.zeros(1, device=dev)
+        loss_static = torch.zeros(1, device=dev)
+        if self.entity_prediction:
+            q, cand, hyp, col_bias = evaluate._scoring_operands(self, pre_emb, r_emb, all_triples)
+            _, loss_ent = ops.fused_ce(q, cand, all_triples[:, 2], hyp=hyp, col_bias=col_bias)
+        if self.relation_prediction:
+            score_rel = self.rdecoder.forward(pre_emb, r_emb, all_triples, mode="train")
+            _, loss_rel = ops.ce_dense(score_rel, all_triples, 1)
+        # radius supervision on the entities of the batch (tiny: a few thousand scalars)
+        ids = torch.unique(all_triples[:, [0, 2]].reshape(-1))
+        rs = torch.clamp(self.radius_static.detach(), min=self.radius_min, max=self.radius_max)
+        rs = torch.clamp(rs, max=1.0 / (self._c_float ** 0.5) - 1e-6).index_select(0, ids)
+        rt = self.radius_target.index_select(0, ids)
+        loss_radius = (self.radius_lambda * torch.mean((rs - rt) ** 2)).reshape(1)
+        return loss_ent, loss_rel, loss_static, loss_radius

@@ -472,3 +472,50 @@ def fused_rank_counts(q, cand, target, filt_ptr, filt_idx, pair_a, pair_e, hyp=N
     call("regcn_filter_correct", B, ptr(filt_ptr), ptr(filt_idx), ptr(target), ptr(ps), ptr(raw), lo, hi, ptr(filt),
          ptr(filt_end))
     return raw, filt, ps[:B]
+
+
+# --------------------------------------------------------------------------- loss heads (forward)
+def fused_ce(q, cand, target, hyp=None, col_bias=None):
+    """Cross entropy of every query row against ALL candidates without the (B,N) logits: the scoring GEMM runs with a
+    streaming log-sum-exp epilogue, the target logit comes from the pair-score pass (same arithmetic).
+    Returns (ce (B,), loss (1,) = mean(ce)).  Arguments as fused_rank_counts."""
+    if _GEMM_IMPL["impl"] not in ("tc", "tc1"):
+        raise RuntimeError("fused_ce needs the tensor-core GEMM (REGCN_GEMM=tc)")
+    passes = 3 if _GEMM_IMPL["impl"] == "tc" else 1
+    B, K = q.shape
+    N = cand.shape[0]
+    dev = q.device
+    target = target.to(torch.int32).contiguous()
+    q_hi, q_lo = _tc_operand(q.detach(), passes == 3)
+    e_hi, e_lo = _tc_operand(cand.detach(), passes == 3)
+    b_hi = torch.empty((B, K), device=dev, dtype=F32)
+    b_lo = torch.empty((B, K), device=dev, dtype=F32) if passes == 3 else None
+    call("regcn_gather_rows2", ptr(e_hi), ptr(e_lo), ptr(target), B, K, ptr(b_hi), ptr(b_lo))
+    c, x2, y2, sm = (hyp[:4] if hyp is not None else (1.0, None, None, None))
+    row_c = hyp[4] if hyp is not None and len(hyp) > 4 else None
+    y2p = bp = None
+    if hyp is not None or col_bias is not None:
+        y2p = torch.empty(B, device=dev, dtype=F32) if hyp is not None else None
+        bp = torch.empty(B, device=dev, dtype=F32) if col_bias is not None else None
+        call("regcn_gather_scalars", None, ptr(y2), ptr(col_bias), ptr(target), ptr(target), B, None, ptr(y2p), ptr(bp))
+    ts = torch.empty(B, device=dev, dtype=F32)
+    call("regcn_pair_scores_tf32", ptr(q_hi), ptr(q_lo), ptr(b_hi), ptr(b_lo), B, K, int(hyp is not None), ptr(x2),
+         ptr(y2p), ptr(bp), float(c), ptr(sm), ptr(row_c), ptr(ts), passes)
+    nparts = _lib.load().regcn_score_lse_num_parts(N)
+    pm = torch.empty(nparts * B, device=dev, dtype=F32)
+    psum = torch.empty(nparts * B, device=dev, dtype=F32)
+    call("regcn_score_lse_tf32", ptr(q_hi), ptr(q_lo), ptr(e_hi), ptr(e_lo), B, N, K, int(hyp is not None), ptr(x2),
+         ptr(y2), ptr(col_bias), float(c), ptr(sm), ptr(row_c), passes, ptr(pm), ptr(psum))
+    ce = torch.empty(B, device=dev, dtype=F32)
+    loss = torch.empty(1, device=dev, dtype=F32)
+    call("regcn_ce_from_lse", ptr(pm), ptr(psum), nparts, B, ptr(ts), ptr(ce), ptr(loss))
+    return ce, loss
+
+
+def ce_dense(score, triples, target_col):
+    """(ce (B,), loss (1,)) of a materialised (B,N) score matrix (small candidate sets: relation prediction)."""
+    B, N = score.shape
+    ce = torch.empty(B, device=score.device, dtype=F32)
+    loss = torch.empty(1, device=score.device, dtype=F32)
+    call("regcn_ce_rows", score.data_ptr(), score.stride(0), B, N, ptr(triples), target_col, ptr(ce), ptr(loss))
+    return ce, loss

@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 import torch
 
+import regcn_b200 as R
 from oracle import restate, synth
 from tests.helpers import CURV, N_BASES, build_model, close, golden_names, load_golden
 
@@ -267,3 +268,50 @@ def test_fused_rank_equals_dense_rank_bit_exact(kind):
         assert torch.equal(tot_raw + 1, rank_f) and torch.equal(tot_f + 1, frank_f)
     finally:
         ops.set_gemm_impl(prev)
+
+
+# ----------------------------------------------------------------------------------------- loss heads (a21)
+@pytest.mark.parametrize("name", golden_names())
+def test_get_loss_matches_reference(name):
+    """get_loss() forward values (fused log-sum-exp epilogue of the scoring GEMM, no (B,N) logits) against the
+    reference's own get_loss() outputs (tests/golden/losses.json, eval mode) -- 1e-4 relative."""
+    import json
+    import os
+    from tests.helpers import GOLDEN
+    ref = json.load(open(os.path.join(GOLDEN, "losses.json")))[name]
+    cfg, _ = load_golden(name)
+    case = synth.make_case(cfg["shape"], cfg["seed"])
+    n, r = case["num_ents"], case["num_rels"]
+    model, _ = build_model(cfg, n, r)
+    model = model.to(DEV)
+    glist = [R.build_sub_graph(n, r, s, True, 0) for s in case["history"]]
+    losses = model.get_loss(glist, torch.from_numpy(case["test"]).to(DEV), None, True)
+    mine = [float(x.reshape(-1)[0]) for x in losses]
+    assert len(mine) == len(ref)
+    np.testing.assert_allclose(mine, ref, rtol=1e-4, atol=1e-6)
+    with pytest.raises(NotImplementedError):
+        model.train().get_loss(glist, torch.from_numpy(case["test"]).to(DEV), None, True)
+
+
+def test_fused_ce_equals_dense_ce():
+    """The streaming log-sum-exp epilogue against torch.logsumexp on the materialised scores of the same GEMM, and the
+    dense CE kernel against torch, incl. a candidate count that is not a multiple of the tile."""
+    from regcn_b200 import ops
+    R._lib.require_device()
+    g = torch.Generator(device="cpu").manual_seed(3)
+    for B, N in ((300, 5000), (129, 257), (1, 40)):
+        q = (torch.randn(B, 200, generator=g) * 0.4).to(DEV)
+        e = (torch.randn(N, 200, generator=g) * 0.4).to(DEV)
+        bias = (torch.randn(N, generator=g) * 0.1).to(DEV)
+        tgt = torch.randint(0, N, (B,), generator=g).to(DEV)
+        S = ops.gemm(q, e, trans_b=True, bias=bias)
+        ref = torch.logsumexp(S.double(), 1) - S.double()[torch.arange(B, device=DEV), tgt]
+        ce, loss = ops.fused_ce(q, e, tgt, col_bias=bias)
+        ok, worst = close(ce.cpu().numpy(), ref.cpu().numpy(), rtol=2e-5)
+        assert ok, worst
+        assert abs(float(loss) - float(ref.mean())) <= 2e-5 * max(1.0, abs(float(ref.mean())))
+        trip = torch.zeros((B, 3), dtype=torch.int64, device=DEV)
+        trip[:, 1] = tgt
+        ce2, loss2 = ops.ce_dense(S, trip, 1)
+        ok, worst = close(ce2.cpu().numpy(), ref.cpu().numpy(), rtol=2e-5)
+        assert ok, worst

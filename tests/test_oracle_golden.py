@@ -92,3 +92,25 @@ def test_rank_restatement_exact_on_reference_scores(name):
     assert np.array_equal(rank, z["rank"]) and np.array_equal(frank, z["filter_rank"])
     assert np.array_equal(rank_r, z["rank_rel"]) and np.array_equal(frank_r, z["filter_rank_rel"])
     np.testing.assert_allclose([fm, m, fmr, mr], z["mrr"], rtol=1e-6)
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if "c3" not in n and "c1" not in n])
+def test_loss_restatement_matches_reference(name):
+    """restate.regcn_loss / hyp_loss against the reference's get_loss() outputs (tests/golden/losses.json)."""
+    import json
+    import os
+    from tests.helpers import GOLDEN
+    ref = json.load(open(os.path.join(GOLDEN, "losses.json")))[name]
+    cfg, _ = load_golden(name)
+    case = synth.make_case(cfg["shape"], cfg["seed"])
+    n, r = case["num_ents"], case["num_rels"]
+    _, sd = build_model(cfg, n, r)
+    graphs = _graphs(case)
+    with torch.no_grad():
+        if cfg["kind"] == "regcn":
+            mine = restate.regcn_loss(sd, graphs, r, case["test"], layer_norm=cfg["layer_norm"])
+        else:
+            mine = restate.hyp_loss(sd, graphs, r, case["test"], c=CURV, decoder=cfg["decoder"],
+                                    layer_norm=cfg["layer_norm"], encoder=cfg["encoder"], gamma=cfg["gamma"],
+                                    num_bases=min(N_BASES, 2 * r))
+    np.testing.assert_allclose(mine, ref, rtol=1e-4, atol=1e-6)
