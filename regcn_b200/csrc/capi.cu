@@ -35,6 +35,9 @@ bool pdl_enabled() {
   return g_pdl != 0;
 }
 void pdl_set(int on) { g_pdl = on ? 1 : 0; }
+static thread_local bool g_pdl_suppress = false;
+void pdl_suppress(bool on) { g_pdl_suppress = on; }
+bool pdl_suppressed() { return g_pdl_suppress; }
 }  // namespace regcn
 
 namespace regcn {

@@ -36,6 +36,10 @@ __device__ __forceinline__ void pdl_grid_sync() {
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 bool pdl_enabled();
+// per-thread opt-out for the next launches: a persistent kernel launched early parks one CTA per SM at its wait and
+// would take the SMs the two-stream schedule leaves free for the side stream
+void pdl_suppress(bool on);
+bool pdl_suppressed();
 template <typename... P, typename... A>
 inline void launch_k(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
   cudaLaunchConfig_t cfg = {};
@@ -44,7 +48,7 @@ inline void launch_k(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, c
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = (pdl_enabled() && !pdl_suppressed()) ? 1 : 0;
   cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
 }
 

@@ -19,10 +19,52 @@
 #include "../../include/regcn_b200.h"
 #include "common.cuh"
 #include "internal.h"
+#include <stdlib.h>
 
 namespace regcn {
 
 static inline size_t al(size_t n) { return (n + 63) & ~(size_t)63; }   // 256-byte aligned float counts
+
+// Side stream of the two-stream evolve schedule (library-owned, one per device, created on first use).  The caller's
+// stream carries the large all-entity GEMMs of a snapshot; the side stream carries the chain of small kernels
+// (relation GRU, aggregates, active-row GEMMs) that would otherwise sit between them, each costing a launch ramp
+// and a memory-latency chain on an otherwise idle machine.
+struct AuxStream { cudaStream_t sb = nullptr; cudaEvent_t fork = nullptr, a_done = nullptr, b_done = nullptr; bool ok = false; };
+static AuxStream* aux_stream() {
+  static AuxStream aux[16];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  AuxStream& a = aux[dev];
+  if (!a.ok) {
+    if (cudaStreamCreateWithFlags(&a.sb, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&a.a_done, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&a.b_done, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    a.ok = true;
+  }
+  return &a;
+}
+// SMs a persistent all-entity GEMM of `ncol` output columns leaves free (see the balanced grid in gemm_tc.cu)
+static int side_hint(int N, int d, int ncol, int sms) {
+  (void)d;
+  const long long t = (long long)((N + 127) / 128) * ((ncol + 207) / 208);
+  const long long rounds = (t + sms - 1) / sms;
+  const int grid_a = (int)((t + rounds - 1) / (rounds > 0 ? rounds : 1));
+  return sms - grid_a >= 16 ? sms - grid_a : 16;
+}
+static bool side_pdl_keep() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("REGCN_SIDE_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+static int g_two_stream = -1;
+static bool two_stream_enabled() {
+  if (g_two_stream < 0) {
+    const char* e = getenv("REGCN_TWO_STREAM");
+    g_two_stream = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_two_stream != 0;
+}
 
 struct EvolveWs {
   size_t xm_hi, xm_lo, gi, gh, h0_hi, h0_lo, agg_hi, agg_lo, Lm, L2, P, set[2][3], h_hi, h_lo, h_init, partial, rel_partial, total;
@@ -90,19 +132,45 @@ int regcn_regcn_evolve(const void* const* mp, const int* mi, const void* const* 
   const float* h0_raw = F(RM_EMB_REL);
   const float* h0_hi = F(RM_EMB_REL_HI);
   const float* h0_lo = F(RM_EMB_REL_LO);
+  AuxStream* aux = two_stream_enabled() ? aux_stream() : nullptr;
+  int sm_count = 148;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (sm_count <= 0) sm_count = 148;
+  }
 
   for (int i = 0; i < L; ++i) {
     const void* const* g = gp + (size_t)i * RG_NUM_PTRS;
     const int* gn = gi_ + (size_t)i * RGI_NUM_INTS;
     auto GI = [&](int k) { return (const int*)g[k]; };
+    // ---- schedule of this snapshot ----
+    // Two-stream form (sparse snapshot, >= 2 layers, a table large enough for the all-entity GEMMs to matter): the
+    // caller's stream runs the all-entity GEMMs  x . [W_evolve | W_time]  of every layer back to back -- they depend
+    // on nothing but the previous snapshot -- while the side stream runs the chain they do not depend on: relation
+    // mean-pool -> GRU GEMMs -> gate -> per layer {aggregate, fix-up, active-row GEMM}.  The persistent GEMMs leave
+    // whole SMs free (balanced grids), which is where the side stream's kernels run.
+    bool side_pdl_off = false;
+    const int n_active_ = gn[RGI_N_ACTIVE];
+    const bool two = aux && n_active_ * 2 <= N && nl >= 2 && N >= 4096;
+    cudaStream_t sB = two ? aux->sb : st;
+    if (two) {
+      side_pdl_off = !side_pdl_keep();
+      cudaEventRecord(aux->fork, st);              // everything the side stream reads (h of the previous snapshot) is ordered before this
+      cudaStreamWaitEvent(sB, aux->fork, 0);
+      gemm_tf32_sm_hint(side_hint(N, d, 2 * d, sm_count));
+      // kernels launched early park their CTAs on the SMs the other stream needs: the side stream stays plainly ordered
+      pdl_suppress(side_pdl_off);
+    }
     // ---- relation evolution (K2, K3) ----
     if ((e = rel_mean_pool(h_raw, GI(RG_REL_ROWPTR), GI(RG_REL_ENTS), R2 / 2, d, rel_nsplit, nullptr, ws + w.rel_partial,
-                           ws + w.xm_hi, ws + w.xm_lo, st))) return e;
+                           ws + w.xm_hi, ws + w.xm_lo, sB))) return e;
     if ((e = gemm_tf32(ws + w.xm_hi, ws + w.xm_lo, d, F(RM_WIH_R_HI), F(RM_WIH_R_LO), d, ws + w.gi, 3 * d, R2, 3 * d, d,
-                       nullptr, 0, 3, 1, nullptr, 0, F(RM_GI_STATIC), 3 * d, st))) return e;
+                       nullptr, 0, 3, 1, nullptr, 0, F(RM_GI_STATIC), 3 * d, sB))) return e;
     if ((e = gemm_tf32(h0_hi, h0_lo, d, F(RM_WHH_HI), F(RM_WHH_LO), d, ws + w.gh, 3 * d, R2, 3 * d, d, F(RM_B_HH), 0, 3, 1,
-                       nullptr, 0, nullptr, 0, st))) return e;
-    if ((e = gru_gate(ws + w.gi, ws + w.gh, h0_raw, h0_out, R2, d, layer_norm, ws + w.h0_hi, ws + w.h0_lo, st))) return e;
+                       nullptr, 0, nullptr, 0, sB))) return e;
+    if ((e = gru_gate(ws + w.gi, ws + w.gh, h0_raw, h0_out, R2, d, layer_norm, ws + w.h0_hi, ws + w.h0_lo, sB))) return e;
     h0_raw = h0_out; h0_hi = ws + w.h0_hi; h0_lo = ws + w.h0_lo;
     // ---- entity evolution: n_layers x UnionRGCNLayer (K4, GEMMs, K5) ----
     const float* x_raw = h_raw;
@@ -134,22 +202,32 @@ int regcn_regcn_evolve(const void* const* mp, const int* mi, const void* const* 
         if ((e = union_aggregate(x_raw, h0_raw, GI(RG_ROWPTR), GI(RG_SRC_SORTED), GI(RG_ETYPE_SORTED), (const float*)g[RG_NORM],
                                  GI(RG_VPTR), GI(RG_SPTR), GI(RG_VROW_ROW), gn[RGI_N_VROWS], gn[RGI_N_SPLIT_CHUNKS], nullptr,
                                  0.f, N, d, nullptr, ws + w.partial, ws + w.agg_hi, ws + w.agg_lo, GI(RG_ACTIVE_POS), 2 * d,
-                                 gn[RGI_MAX_CHUNKS], st))) return e;
+                                 gn[RGI_MAX_CHUNKS], sB))) return e;
         if (!last) {
-          if ((e = gemm_tf32_layer(x_hi, x_lo, d, F(base + 6), F(base + 7), d, N, ncol, d, d, nullptr, o_hi, o_lo,
-                                   l == 0 ? ws + w.Lm : nullptr, d, nullptr, GI(RG_ACTIVE_POS), nullptr, 0, nullptr, nullptr,
-                                   0, st))) return e;
+          if (two) { gemm_tf32_sm_hint(0); pdl_suppress(l > 0); }   // later layers must not park CTAs on the free SMs early
+          e = gemm_tf32_layer(x_hi, x_lo, d, F(base + 6), F(base + 7), d, N, ncol, d, d, nullptr, o_hi, o_lo,
+                              l == 0 ? ws + w.Lm : nullptr, d, nullptr, GI(RG_ACTIVE_POS), nullptr, 0, nullptr, nullptr, 0, st);
+          pdl_suppress(two && side_pdl_off);
+          if (e) return e;
+          if (two) gemm_tf32_sm_hint(side_hint(N, d, ncol, sm_count));
           if (n_active > 0 &&
               (e = gemm_tf32_layer(ws + w.agg_hi, ws + w.agg_lo, 2 * d, F(base + 4), F(base + 5), 2 * d, n_active, d, 2 * d, d,
-                                   o_raw, o_hi, o_lo, nullptr, 0, arows, nullptr, nullptr, 0, nullptr, nullptr, 0, st))) return e;
+                                   o_raw, o_hi, o_lo, nullptr, 0, arows, nullptr, nullptr, 0, nullptr, nullptr, 0, sB))) return e;
         } else {
           float* h_new = hist + (size_t)i * nd;
+          if (two) gemm_tf32_sm_hint(side_hint(N, d, d, sm_count));
           if (n_active > 0 &&
               (e = gemm_tf32(ws + w.agg_hi, ws + w.agg_lo, 2 * d, F(base + 4), F(base + 5), 2 * d, ws + w.P, d, n_active, d,
-                             2 * d, nullptr, 0, 3, 1, nullptr, 0, nullptr, 0, st))) return e;
-          if ((e = gemm_tf32_layer(x_hi, x_lo, d, F(base + 6), F(base + 7), d, N, d, d, d, h_new, ws + w.h_hi, ws + w.h_lo,
-                                   nullptr, 0, nullptr, GI(RG_ACTIVE_POS), ws + w.Lm, d, F(RM_GATE_BIAS), h_raw, layer_norm,
-                                   st))) return e;
+                             2 * d, nullptr, 0, 3, 1, nullptr, 0, nullptr, 0, sB))) return e;
+          if (two) { gemm_tf32_sm_hint(0); pdl_suppress(true); }
+          e = gemm_tf32_layer(x_hi, x_lo, d, F(base + 6), F(base + 7), d, N, d, d, d, h_new, ws + w.h_hi, ws + w.h_lo,
+                              nullptr, 0, nullptr, GI(RG_ACTIVE_POS), ws + w.Lm, d, F(RM_GATE_BIAS), h_raw, layer_norm, st);
+          pdl_suppress(false);
+          if (e) return e;
+          if (two) {                                   // join: the active rows need the gate columns (caller's stream) and P (side stream)
+            cudaEventRecord(aux->b_done, sB);
+            cudaStreamWaitEvent(st, aux->b_done, 0);
+          }
           if (n_active > 0 &&
               (e = time_gate(ws + w.Lm, F(RM_GATE_BIAS), ws + w.P, h_raw, h_new, n_active, d, layer_norm, d, ws + w.h_hi,
                              ws + w.h_lo, st, arows, 1))) return e;
@@ -188,6 +266,8 @@ int regcn_regcn_evolve(const void* const* mp, const int* mi, const void* const* 
       x_raw = o_raw; x_hi = o_hi; x_lo = o_lo;
     }
     // ---- time gate (K9): h = s(h W_t + b) * [normalize](cur) + (1 - s) * h ----
+    gemm_tf32_sm_hint(0);
+    pdl_suppress(false);
     float* h_new = hist + (size_t)i * nd;
     if (!gate_done &&
         (e = time_gate(gate_G, F(RM_GATE_BIAS), x_raw, h_raw, h_new, N, d, layer_norm, gate_ld, ws + w.h_hi,

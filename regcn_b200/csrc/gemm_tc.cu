@@ -663,10 +663,21 @@ void gemm_tf32_tune(int block_n, int stages) { g_force_block_n = block_n; g_forc
 // the fewest operand re-reads.  Small problems (relation GRU, compact active-row GEMMs, pair scores): a tile costs
 // ~12 us of pure latency however little it computes, so narrow the tile until the grid covers the machine --
 // every CTA then walks the same K loop on a quarter of the operand bytes and of the MMA work.
+// SM hint: the evolve engine runs the small relation / active-row GEMMs on a side stream next to a large GEMM that
+// owns most of the machine; they then pick the narrowest tile whose grid still fits the SMs that are left (one wave)
+static thread_local int g_sm_hint = 0;
+void gemm_tf32_sm_hint(int sms) { g_sm_hint = sms; }
+
 static int pick_block_n(int M, int N, int K, int split_k) {
   if (g_force_block_n > 0) return g_force_block_n;
   if (N <= 64) return (N + 15) / 16 * 16;
   const int m_tiles = (M + tc::BLOCK_M - 1) / tc::BLOCK_M;
+  if (g_sm_hint > 0) {
+    const int opts[5] = {32, 64, 128, 208, 256};
+    for (int i = 0; i < 5; ++i)
+      if (m_tiles * ((N + opts[i] - 1) / opts[i]) <= g_sm_hint) return opts[i];
+    return N <= 208 ? 208 : 256;
+  }
   int best = 256, best_waste = 1 << 30;
   const int cands[4] = {256, 208, 128, 64};
   for (int i = 0; i < 4; ++i) {
@@ -764,7 +775,10 @@ static int launch_tc(const float* a_hi, const float* a_lo, int lda, const float*
     if (sms <= 0) sms = 148;
   }
   const long long total_tiles = (long long)p.m_tiles * p.n_tiles * p.splits;
-  dim3 grid((unsigned)(total_tiles < sms ? total_tiles : sms));
+  // balanced persistent grid: the smallest grid that needs no more rounds than the whole machine would (360 tiles on
+  // 148 SMs take 3 rounds; so do 120 CTAs -- and 28 SMs stay free for whatever runs next to this kernel)
+  const long long rounds = (total_tiles + sms - 1) / sms;
+  dim3 grid((unsigned)((total_tiles + rounds - 1) / (rounds > 0 ? rounds : 1)));
   prof_begin(PROF_GEMM_TC, st);
   switch (p.epi) {
     case 0: launch_k(gemm_tf32_kernel<0>, grid, NUM_THREADS, smem, st, ta_hi, ta_lo, tb_hi, tb_lo, p); break;

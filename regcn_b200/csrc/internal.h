@@ -39,6 +39,7 @@ int gemm_tf32_layer(const float* a_hi, const float* a_lo, int lda, const float* 
                     const float* gate_h, int gate_norm, cudaStream_t st);
 void pdl_set(int on);
 void gemm_tf32_tune(int block_n, int stages);
+void gemm_tf32_sm_hint(int sms);
 void aggregate_tune(int impl);
 int score_count_tf32(const float* q_hi, const float* q_lo, const float* e_hi, const float* e_lo, int B, int N, int K,
                      const float* tscore, const int* target, int* raw_count, int col_offset, int hyp, const float* x2,
