@@ -37,6 +37,7 @@ def parse():
     ap.add_argument("--workload", default=WORKLOAD)
     ap.add_argument("--model", default="regcn", choices=["regcn", "hyp_lgcn_roth", "hyp_uv_roth"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stress", action="store_true", help="skip the HBM-bound edge-kernel and the scoring-kernel sections")
     ap.add_argument("--gemm", default=None, help="override the dense-contraction implementation (simt|tc)")
     return ap.parse_args()
 
@@ -151,6 +152,72 @@ def run_cpu_arm(args, steps, warmup, quiet=False):
                       f"threads; scatter-sum is index_add_, not DGL's kernel", "ms_per_step": dt * 1e3}
 
 
+def run_stress(dev, hbm_peak, tf_peak):
+    """(1) K4 union aggregate at BASELINE configs[4] size (N = 1M entities, E = 10M edges, d = 200): algorithmic bytes
+    808*E + 808*N + 800*2R over the CUDA-event time, uniform and Zipf endpoints.  (2) The fused
+    scoring + count GEMM alone at the C3 shape and at one C5 entity shard, fp32-parity (3xTF32) and bf16 modes."""
+    import numpy as np
+    import torch
+    import regcn_b200 as R
+    from regcn_b200 import _lib, ops, synth
+
+    def med(fn, n=7):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(n):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ts.sort()
+        return ts[len(ts) // 2]
+
+    out = {}
+    n, r, t, d = 1_000_000, 512, 5_000_000, 200
+    h = torch.randn(n, d, device=dev)
+    rel = torch.randn(2 * r, d, device=dev)
+    o = torch.empty(n, d, device=dev)
+    edge = {"kernel": "regcn::union_aggregate_{stream,}kernel (+ radix-32 fix-up for hub rows)", "bound": "hbm",
+            "peak": hbm_peak, "unit": "GB/s", "shape": f"N={n} E={2 * t} d={d} 2R={2 * r} (BASELINE configs[4])",
+            "algorithmic_bytes_per_launch": 808.0 * 2 * t + 808.0 * n + 800.0 * 2 * r}
+    for name, zipf in (("uniform", False), ("zipf", True)):
+        tri = synth.make_snapshot(np.random.default_rng(0), n, r, t, zipf=zipf)
+        g = R.build_sub_graph(n, r, tri, True, dev.index or 0)
+        ms = med(lambda: ops.union_aggregate(h, rel, g, out=o))
+        gbs = edge["algorithmic_bytes_per_launch"] / ms / 1e6
+        edge[name] = {"ms": ms, "achieved": gbs, "frac": gbs / hbm_peak, "split_chunks": g.n_split_chunks}
+        del g
+    edge["achieved"], edge["frac"] = edge["uniform"]["achieved"], edge["uniform"]["frac"]
+    out["edge_kernel_hbm_bound"] = edge
+    del h, o
+    score = {"kernel": "regcn::tc::gemm_tf32_kernel<1> (counting epilogue, no score matrix)", "bound": "tensor",
+             "peak": tf_peak, "unit": "TFLOP/s", "cases": []}
+    for shape, B, N in (("c3", 2914, 23033), ("c5 shard 1/8", 8192, 125000)):
+        q = torch.randn(B, d, device=dev)
+        e = torch.randn(N, d, device=dev) * 0.5
+        target = torch.randint(0, N, (B,), device=dev, dtype=torch.int32)
+        tscore = torch.zeros(B, device=dev)
+        raw = torch.zeros(B, device=dev, dtype=torch.int32)
+        qh, ql = ops.split_tf32(q)
+        eh, el = ops.split_tf32(e)
+        qb, eb = ops.to_bf16(q), ops.to_bf16(e)
+        for mode, passes in (("3xTF32 (fp32 parity)", 3), ("bf16", 0)):
+            a_, b_ = (qb, eb) if passes == 0 else (qh, eh)
+            ms = med(lambda: _lib.call("regcn_score_count_tf32", a_.data_ptr(), ql.data_ptr(), b_.data_ptr(),
+                                       el.data_ptr(), B, N, d, tscore.data_ptr(), target.data_ptr(), raw.data_ptr(), 0, 0,
+                                       None, None, None, 1.0, None, None, passes))
+            alg = 2.0 * B * N * d / ms / 1e9
+            ex = alg * max(passes, 1)
+            mode_peak = tf_peak if passes == 0 else tf_peak / 2      # TF32 dense peak = half the bf16 figure
+            score["cases"].append({"shape": shape, "B": B, "N": N, "mode": mode, "ms": ms, "algorithmic": alg,
+                                   "executed": ex, "frac_of_mode_peak_executed": ex / mode_peak,
+                                   "frac_of_bf16_peak_algorithmic": alg / tf_peak})
+        del q, e, qh, ql, eh, el, qb, eb
+    out["scoring_kernel"] = score
+    return out
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -244,12 +311,19 @@ def main():
 
     # ---- device-resident arm ------------------------------------------------------------------
     sampler = ClockSampler(local) if rank == 0 else None
-    l0 = _lib.launch_count
+    lib0 = _lib.load()
+    l0 = None
     t_wall0 = time.time()
     tot_ms, parts = timed(lambda tm: evaluate.evaluate_snapshot(model, glist, all_t, fcsr, tm), args.steps,
                           args.warmup, timers=True)
     t_wall1 = time.time()
-    launches = (_lib.launch_count - l0) * args.steps // (args.steps + args.warmup)
+    # kernels launched by libregcn_b200.so in ONE device-resident step (counted inside the library's launcher)
+    torch.cuda.synchronize()
+    l0 = lib0.regcn_kernel_launches()
+    evaluate.evaluate_snapshot(model, glist, all_t, fcsr, None)
+    torch.cuda.synchronize()
+    launches_per_step = int(lib0.regcn_kernel_launches() - l0)
+    launches = launches_per_step * args.steps
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     tot_ms = maxr(tot_ms)
     ms_per_step = tot_ms / args.steps
@@ -270,15 +344,28 @@ def main():
     lib = _lib.load()
     probe_steps = 3
     torch.cuda.synchronize()
+    # per-kernel timing brackets every launch with CUDA events on its stream: the probe steps run single-stream and
+    # without programmatic dependent launch, so that a kernel's time is its own (the timed region above keeps both on)
+    lib.regcn_two_stream_enable(0)
+    lib.regcn_pdl_enable(0)
     lib.regcn_prof_enable(1)
+    pa, pb = ev(), ev()
+    probe_ms = 0.0
     for _ in range(probe_steps):
         flush.fill_(1.0)
+        pa.record()
         evaluate.evaluate_snapshot(model, glist, all_t, fcsr, None)
+        pb.record()
+        torch.cuda.synchronize()
+        probe_ms += pa.elapsed_time(pb)
+    probe_ms /= probe_steps
     ms_c, n_c, w_c = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()
     lib.regcn_prof_read(0, ctypes.byref(ms_c), ctypes.byref(n_c), ctypes.byref(w_c))
     agg_ms_c, agg_n_c, agg_w_c = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()
     lib.regcn_prof_read(1, ctypes.byref(agg_ms_c), ctypes.byref(agg_n_c), ctypes.byref(agg_w_c))
     lib.regcn_prof_enable(0)
+    lib.regcn_two_stream_enable(1)
+    lib.regcn_pdl_enable(1)
     gemm_ms = ms_c.value / probe_steps
     gemm_flops = w_c.value / probe_steps
     n_gemm = n_c.value // probe_steps
@@ -288,17 +375,29 @@ def main():
     except Exception:
         pass
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    traffic = None
+    try:
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch of the GEMM kernel over one step, from the committed
+        # `ncu --set full` capture of this same workload (profiles/README.md)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get("gemm_tf32_kernel_bytes_per_launch")
+    except Exception:
+        pass
     ach_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     passes = 3 if ops.gemm_impl() == "tc" else 1
     roofline = {"kernel": ops.gemm_kernel_name(), "bound": "tensor", "achieved": ach_tf, "peak": peak_tf,
-                "unit": "TFLOP/s", "frac": ach_tf / peak_tf, "traffic": None,
+                "unit": "TFLOP/s", "frac": ach_tf / peak_tf, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks
                 else "fallback 1.4 PFLOP/s (B200_PROFILING.md)",
                 "launches_per_step": n_gemm, "ms_per_step_in_kernel": gemm_ms,
-                "share_of_step": gemm_ms / ms_per_step if ms_per_step > 0 else None,
+                "share_of_step": gemm_ms / probe_ms if probe_ms > 0 else None,
+                "probe_step_ms": probe_ms,
+                "executed_frac_of_tf32_peak": passes * ach_tf / (peak_tf / 2),
                 "algorithmic_flops_per_step": gemm_flops,
-                "note": f"fp32-parity mode issues {passes} TF32 MMAs per algorithmic MAC (error-compensated), so executed "
-                        f"tensor work is {passes}x the algorithmic flops; TF32 dense peak is half the bf16 figure"}
+                "note": f"average over the {n_gemm} GEMM launches of a step, most of them latency-bound at this size (N=23033 "
+                        f"rows x 200..400 columns, relation GRU 512 rows); fp32-parity mode issues {passes} TF32 MMAs per "
+                        f"algorithmic MAC, so executed tensor work is {passes}x the algorithmic flops and the TF32 dense peak is "
+                        f"half the bf16 figure; probe steps run single-stream (see scoring_kernel for the kernel at a size "
+                        f"where the tensor roofline binds)"}
     # edge kernel (HBM-bound) at this workload: algorithmic bytes per launch = 808*E + 808*N + 800*2R
     agg_launches = max(1, agg_n_c.value // probe_steps)
     agg_bytes = agg_launches * (808.0 * 2 * T + 808.0 * n + 800.0 * 2 * r)
@@ -309,6 +408,11 @@ def main():
             "peak": hbm, "unit": "GB/s", "note": "latency-bound at this size (E=3082 edges, 18 MB output); see "
             "profiles/ for the HBM-bound stress sizes"}
     edge["frac"] = edge["achieved"] / hbm
+
+    # ---- the two kernels north_star sets targets for, at sizes where their rooflines bind (rank 0, N = 1 only) ----
+    stress = None
+    if rank == 0 and world == 1 and not args.no_stress:
+        stress = run_stress(dev, hbm, peak_tf)
 
     # ---- entity-sharded scoring + rank merge (strong scaling of one timestamp), all ranks on the same queries ----
     sharded = None
@@ -355,6 +459,9 @@ def main():
                                            "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                                            "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "roofline": roofline, "edge_kernel": edge, "clocks": clocks}
+        line["gpu_launches_per_step"] = launches_per_step
+        if stress:
+            line.update(stress)
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
         if sharded:

@@ -171,6 +171,12 @@ REGCN_API int regcn_prof_read(int slot, double* total_ms, long long* launches, d
 /* programmatic dependent launch between the kernels of the path (default on; REGCN_PDL=0 in the environment or
  * regcn_pdl_enable(0) falls back to plain stream-ordered launches) */
 REGCN_API void regcn_pdl_enable(int on);
+/* two-stream schedule of the evolve engines (default on; REGCN_TWO_STREAM=0 or regcn_two_stream_enable(0): every kernel
+ * on the caller's stream, which is also how the per-kernel timings of bench.py's roofline block are taken) */
+REGCN_API void regcn_two_stream_enable(int on);
+/* number of kernels this library has launched in the calling process (the snapshot-index build adds ~8 CUB launches per
+ * large snapshot that are not counted) */
+REGCN_API long long regcn_kernel_launches(void);
 /* tuning knob for experiments: force the N tile (multiple of 16, <= 256; 0 = automatic) and cap the pipeline depth */
 REGCN_API void regcn_gemm_tf32_tune(int block_n, int stages);
 /* edge kernel variant: 0 automatic, 1 register-staged gathers, 2 cp.async.bulk gathers staged in shared memory */

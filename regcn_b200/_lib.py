@@ -42,6 +42,8 @@ SIGNATURES = {
     "regcn_regcn_evolve": (_i, [_p, _p, _p, _p, _i, _p, _p, _i, _p, _sz, _p]),
     "regcn_gemm_tf32_tune": (None, [_i, _i]),
     "regcn_pdl_enable": (None, [_i]),
+    "regcn_two_stream_enable": (None, [_i]),
+    "regcn_kernel_launches": (ctypes.c_longlong, []),
     "regcn_aggregate_tune": (None, [_i]),
     "regcn_score_count_tf32": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _i, _i, _p, _p, _p, _d, _p, _p, _i, _p]),
     "regcn_pair_scores_tf32": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _d, _p, _p, _p, _i, _p]),

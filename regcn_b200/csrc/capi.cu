@@ -35,6 +35,8 @@ bool pdl_enabled() {
   return g_pdl != 0;
 }
 void pdl_set(int on) { g_pdl = on ? 1 : 0; }
+static long long g_kernel_launches = 0;
+void count_kernel_launch() { __atomic_fetch_add(&g_kernel_launches, 1, __ATOMIC_RELAXED); }
 static thread_local bool g_pdl_suppress = false;
 void pdl_suppress(bool on) { g_pdl_suppress = on; }
 bool pdl_suppressed() { return g_pdl_suppress; }
@@ -151,6 +153,8 @@ int regcn_gemm_tf32(const float* a_hi, const float* a_lo, int lda, const float* 
                    workspace_bytes, nullptr, 0, ST(stream));
 }
 void regcn_pdl_enable(int on) { regcn::pdl_set(on); }
+void regcn_two_stream_enable(int on) { regcn::two_stream_set(on); }
+long long regcn_kernel_launches(void) { return __atomic_load_n(&regcn::g_kernel_launches, __ATOMIC_RELAXED); }
 void regcn_gemm_tf32_tune(int block_n, int stages) { gemm_tf32_tune(block_n, stages); }
 void regcn_aggregate_tune(int impl) { aggregate_tune(impl); }
 int regcn_score_count_tf32(const float* q_hi, const float* q_lo, const float* e_hi, const float* e_lo, int B, int N, int K,

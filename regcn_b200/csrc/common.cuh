@@ -40,6 +40,7 @@ bool pdl_enabled();
 // would take the SMs the two-stream schedule leaves free for the side stream
 void pdl_suppress(bool on);
 bool pdl_suppressed();
+void count_kernel_launch();     // feeds regcn_kernel_launches() (bench.py reports it as gpu_launches)
 template <typename... P, typename... A>
 inline void launch_k(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
   cudaLaunchConfig_t cfg = {};
@@ -49,6 +50,7 @@ inline void launch_k(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, c
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = (pdl_enabled() && !pdl_suppressed()) ? 1 : 0;
+  count_kernel_launch();
   cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
 }
 

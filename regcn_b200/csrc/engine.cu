@@ -58,6 +58,7 @@ static bool side_pdl_keep() {
   return v != 0;
 }
 static int g_two_stream = -1;
+void two_stream_set(int on) { g_two_stream = on ? 1 : 0; }
 static bool two_stream_enabled() {
   if (g_two_stream < 0) {
     const char* e = getenv("REGCN_TWO_STREAM");

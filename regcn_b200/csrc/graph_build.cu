@@ -426,6 +426,7 @@ static int launch_small(const SmallBatch& b, int n, int N, int R, cudaStream_t s
     if (ce != cudaSuccess) { set_last_error("csr_build_batch: cudaFuncSetAttribute failed: %s", cudaGetErrorString(ce)); return (int)ce; }
     attr = true;
   }
+  count_kernel_launch();
   csr_build_small_kernel<ITEMS><<<n, kSmallThreads, SmallTypes<ITEMS>::smem_bytes, st>>>(b, N, R);
   return check_launch("csr_build_batch");
 }

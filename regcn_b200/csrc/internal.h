@@ -38,6 +38,7 @@ int gemm_tf32_layer(const float* a_hi, const float* a_lo, int lda, const float* 
                     const int* row_idx, const int* skip_rows, const float* gate_G, int gate_ld, const float* gate_bias,
                     const float* gate_h, int gate_norm, cudaStream_t st);
 void pdl_set(int on);
+void two_stream_set(int on);
 void gemm_tf32_tune(int block_n, int stages);
 void gemm_tf32_sm_hint(int sms);
 void aggregate_tune(int impl);
