@@ -4,7 +4,7 @@ scoring path behind the reference's own module signatures.  See DESIGN.md for th
 The kernels live in libregcn_b200.so (C ABI: include/regcn_b200.h); there is no CPU or eager fallback.
 """
 from . import _lib  # noqa: F401
-from .graph import SnapshotGraph, build_sub_graph  # noqa: F401
+from .graph import SnapshotCache, SnapshotGraph, build_sub_graph, build_sub_graphs  # noqa: F401
 from .layers import RGCNBlockLayer, UnionRGCNLayer  # noqa: F401
 from .rrgcn import RecurrentRGCN, RGCNCell  # noqa: F401
 from .decoder import ConvTransE, ConvTransR  # noqa: F401
@@ -14,5 +14,6 @@ from .hyperbolic_decoder import (HyperbolicConvTransE, HyperbolicConvTransR, Hyp
                                  HyperbolicMuRPRel, HyperbolicRotH, HyperbolicRotHRel)
 from .hyperbolic_model import HyperbolicRecurrentRGCN  # noqa: F401
 from . import utils  # noqa: F401
+from .evaluate import test  # noqa: F401  (the reference's evaluation loop, src/main.py:33)
 
 __version__ = "0.1.0"

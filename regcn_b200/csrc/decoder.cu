@@ -42,9 +42,48 @@ __global__ void __launch_bounds__(256) convtranse_features_kernel(
     wsm[nw + 2 * C + i] = bn1_shift[i];
   }
   __syncthreads();
-  // thread <-> position i (fixed), loop over channels: the padded inputs stay in registers, the per-channel
-  // weights are shared-memory broadcasts, stores are coalesced along i; no integer division in the loop
   const size_t fb = (size_t)b * C * d;
+  if ((d & 3) == 0 && ksz <= 5) {
+    // thread <-> (4 consecutive positions, a slice of the channels): the padded inputs of the 4 positions stay in
+    // registers, per-channel weights are shared-memory broadcasts, and every store is a 16-byte vector, coalesced along i
+    const int ngrp = d >> 2;                                   // position groups per channel row
+    const int nslice = max(1, (int)blockDim.x / ngrp);         // channel slices handled concurrently
+    const int pg = threadIdx.x % ngrp, cs = threadIdx.x / ngrp;
+    if (cs < nslice) {
+      float a0[8], a1[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const bool ok = k < ksz + 3;
+        a0[k] = ok ? y0[4 * pg + k] : 0.f;
+        a1[k] = ok ? y1[4 * pg + k] : 0.f;
+      }
+      for (int c = cs; c < C; c += nslice) {
+        const float* w = wsm + c * 2 * ksz;
+        const float cb = wsm[nw + c], bs = wsm[nw + C + c], bt = wsm[nw + 2 * C + c];
+        float o4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float acc = cb;
+#pragma unroll
+          for (int k = 0; k < 5; ++k) if (k < ksz) acc = fmaf(w[k], a0[u + k], acc);
+#pragma unroll
+          for (int k = 0; k < 5; ++k) if (k < ksz) acc = fmaf(w[ksz + k], a1[u + k], acc);
+          o4[u] = fmaxf(fmaf(acc, bs, bt), 0.f);
+        }
+        const size_t o = fb + (size_t)c * d + 4 * pg;
+        if (F) st4(F + o, make_float4(o4[0], o4[1], o4[2], o4[3]));
+        if (F_hi) {
+          float4 h, l;
+          split_tf32_1(o4[0], h.x, l.x); split_tf32_1(o4[1], h.y, l.y);
+          split_tf32_1(o4[2], h.z, l.z); split_tf32_1(o4[3], h.w, l.w);
+          st4(F_hi + o, h);
+          st4(F_lo + o, l);
+        }
+      }
+    }
+    return;
+  }
+  // generic shape: thread <-> position i (fixed), loop over channels
   for (int i = threadIdx.x; i < d; i += blockDim.x) {
     float a0[7], a1[7];
     for (int k = 0; k < ksz && k < 7; ++k) { a0[k] = y0[i + k]; a1[k] = y1[i + k]; }

@@ -199,3 +199,39 @@ def finish_sub_graphs(gs, counts=None):
         for g, c in zip(gs, counts):
             g._set_counts(c)
     return gs
+
+
+class SnapshotCache:
+    """Device-resident index cache: the reference rebuilds the DGL graph of every history snapshot for every evaluated
+    timestamp (src/main.py:68, hyperbolic_main.py:100-113 -- L graphs per step, of which L-1 were built the step before);
+    here a snapshot's index is built once, kept in HBM (a few hundred KB per snapshot) and reused while it stays in the
+    history window.  Keyed by the identity of the triple array (the reference's sliding `input_list` holds the same
+    array objects from step to step); entries leave in insertion order once `capacity` is exceeded."""
+
+    def __init__(self, num_nodes, num_rels, device, capacity=64):
+        self.num_nodes, self.num_rels, self.device, self.capacity = int(num_nodes), int(num_rels), device, int(capacity)
+        self._graphs = {}          # id(array) -> (array (kept alive), SnapshotGraph)
+
+    def ensure(self, snapshots):
+        """Graphs of `snapshots` (list of (T,3) int64 numpy arrays / tensors), building the missing ones in one batched
+        call WITHOUT reading their size counters back.  Returns (graphs, new_graphs): call finish_sub_graphs(new_graphs,
+        counts) (or let `finish` do it) before the graphs are used."""
+        missing = [s for s in snapshots if id(s) not in self._graphs]
+        new = []
+        if missing:
+            uniq, seen = [], set()
+            for s in missing:
+                if id(s) not in seen:
+                    seen.add(id(s))
+                    uniq.append(s)
+            tens = [s if isinstance(s, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(s, dtype=np.int64))
+                    for s in uniq]
+            new = build_sub_graphs(self.num_nodes, self.num_rels, tens, self.device, sync=False)
+            for s, g in zip(uniq, new):
+                self._graphs[id(s)] = (s, g)
+            while len(self._graphs) > self.capacity:
+                self._graphs.pop(next(iter(self._graphs)))
+        return [self._graphs[id(s)][1] for s in snapshots], new
+
+    def __len__(self):
+        return len(self._graphs)

@@ -283,7 +283,7 @@ class HyperbolicRecurrentRGCN(nn.Module):
 
     @torch.no_grad()
     def predict(self, test_graph, num_rels, static_graph, test_triplets, use_cuda):
-        inverse_test_triplets = test_triplets[:, [2, 1, 0]]
+        inverse_test_triplets = test_triplets.flip(1)
         inverse_test_triplets[:, 1] = inverse_test_triplets[:, 1] + num_rels
         all_triples = torch.cat((test_triplets, inverse_test_triplets)).contiguous()
         evolve_embs, _, r_emb, _, _ = self.forward(test_graph, static_graph, use_cuda)
@@ -316,7 +316,7 @@ class HyperbolicRecurrentRGCN(nn.Module):
             raise NotImplementedError("static-graph constraint loss is SURVEY.md 8f rank 3")
         dev = self.dynamic_emb.device
         triples = torch.as_tensor(triples).to(dev)
-        inverse_triples = triples[:, [2, 1, 0]]
+        inverse_triples = triples.flip(1)
         inverse_triples[:, 1] = inverse_triples[:, 1] + self.num_rels
         all_triples = torch.cat([triples, inverse_triples]).contiguous()
         evolve_embs, _, r_emb, _, _ = self.forward(glist, static_graph, use_cuda)

@@ -49,6 +49,17 @@ def make_case(shape="tiny", seed=0, zipf=True):
     return {"num_ents": n, "num_rels": r, "history": history, "test": test}
 
 
+def make_stream(shape="tiny", seed=0, n_test=4, zipf=True):
+    """A sliding-window evaluation stream for the reference's test() loop (src/main.py:33-123): `hist` history
+    snapshots of `t` triples, then `n_test` test snapshots of `tq` triples; every evaluated snapshot joins the history
+    window afterwards.  Same generator / seeding as make_case (the first hist + 1 snapshots are identical to it)."""
+    n, r, t, hist, tq = SHAPES[shape] if isinstance(shape, str) else shape
+    rng = np.random.default_rng(seed)
+    history = [make_snapshot(rng, n, r, t, zipf) for _ in range(hist)]
+    tests = [make_snapshot(rng, n, r, tq, zipf) for _ in range(n_test)]
+    return {"num_ents": n, "num_rels": r, "history": history, "tests": tests}
+
+
 def _scale_for(name, shape):
     leaf = name.split(".")[-1]
     if leaf in ("running_var",):

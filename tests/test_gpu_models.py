@@ -315,3 +315,34 @@ def test_fused_ce_equals_dense_ce():
         ce2, loss2 = ops.ce_dense(S, trip, 1)
         ok, worst = close(ce2.cpu().numpy(), ref.cpu().numpy(), rtol=2e-5)
         assert ok, worst
+
+
+# ----------------------------------------------------------------------------------------- test() loop (src/main.py:33)
+@pytest.mark.parametrize("kind", ["regcn", "hyp_lgcn_roth"])
+def test_evaluation_loop_matches_stepwise_reference_style_loop(kind):
+    """regcn_b200.test() (snapshot cache + software pipeline + fused ranks) against the plain loop the reference runs:
+    rebuild every history graph, predict(), get_total_rank() with the reference's answer dicts -- identical ranks."""
+    from regcn_b200 import utils
+    cfg = (dict(kind="regcn", shape="small", seed=3, layer_norm=True) if kind == "regcn" else
+           dict(kind="hyp", shape="small_l", seed=4, layer_norm=False, encoder="lgcn", decoder="roth", gamma=0.15))
+    st = synth.make_stream(cfg["shape"], cfg["seed"], n_test=4)
+    n, r = st["num_ents"], st["num_rels"]
+    model, _ = build_model(cfg, n, r)
+    model = model.to(DEV)
+    L = len(st["history"])
+    mrrs, ranks = R.test(model, st["history"], st["tests"], r, n, True, None, None, None, None, "eval",
+                         test_history_len=L, return_ranks=True)
+    window = list(st["history"])
+    for k, snap in enumerate(st["tests"]):
+        glist = [R.build_sub_graph(n, r, s, True, 0) for s in window]
+        all_t, score, score_rel = model.predict(glist, r, None, torch.from_numpy(snap).to(DEV), True)
+        _, _, rank, frank = utils.get_total_rank(all_t, score, synth.answers_of(snap, r, False), 1000, rel_predict=0)
+        _, _, rank_r, frank_r = utils.get_total_rank(all_t, score_rel, synth.answers_of(snap, r, True), 1000, rel_predict=1)
+        assert torch.equal(ranks[0][k], rank.cpu()) and torch.equal(ranks[1][k], frank.cpu())
+        assert torch.equal(ranks[2][k], rank_r.cpu()) and torch.equal(ranks[3][k], frank_r.cpu())
+        window.pop(0)
+        window.append(snap)
+    ref_mrr = float(torch.mean(1.0 / torch.cat(ranks[1]).float()))
+    assert abs(mrrs[1] - ref_mrr) < 1e-7
+    with pytest.raises(NotImplementedError):
+        R.test(model, st["history"], st["tests"], r, n, True, None, None, None, None, "eval", multi_step=True)
