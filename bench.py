@@ -341,10 +341,15 @@ def main():
     # entities and relations (raw + time-filtered) and copies the four rank vectors device->host.
     e2e_steps = max(3, min(args.steps, 12))
     e2e_warm = max(L + 1, min(args.warmup, 3))       # the window must have turned over once (steady-state cache)
-    stream = synth.make_stream(args.workload, 1000 + rank, n_test=e2e_warm + e2e_steps)
+    stream = synth.make_stream(args.workload, 1000 + rank, n_test=e2e_warm + 2 * e2e_steps)
     s_hist = [torch.from_numpy(s).pin_memory() for s in stream["history"]]
     s_tests = [torch.from_numpy(s).pin_memory() for s in stream["tests"]]
+    # warm-up: turn the window over, then one untimed call of exactly the timed call's shape (the pinned staging areas
+    # and the caching allocators then hold blocks of the right sizes)
     R.test(model, s_hist, s_tests[:e2e_warm], r, n, True, test_history_len=L)
+    R.test(model, (s_hist + s_tests[:e2e_warm])[-L:], s_tests[e2e_warm:e2e_warm + e2e_steps], r, n, True,
+           test_history_len=L)
+    e2e_warm += e2e_steps
     win = (s_hist + s_tests[:e2e_warm])[-L:]
     barrier()
     ea, eb = ev(), ev()
