@@ -293,6 +293,102 @@ REGCN_API int regcn_hyp_evolve(const void* const* model_ptrs, const int* model_i
                      const void* const* graph_ptrs, const int* graph_ints, int L, float* hist, float* h0_out,
                      int rel_nsplit, void* workspace, size_t workspace_bytes, void* stream);
 
+/* =================================================================================================================
+ * Training step: RecurrentRGCN.get_loss in train mode, src/rrgcn.py:197-223, and the
+ * optimisation step of src/main.py:235-246 (backward, clip_grad_norm_(1.0), Adam(lr, weight_decay)).
+ * All reductions are fixed-order (no float atomics): a training step is bit-reproducible.
+ * ================================================================================================================= */
+
+/* CSR gather-sum: out[row] (+)= row_w[row] * sum_{j in row} col_w[col_j] * (X[col_j] (+ X[col_j + col2_off])).
+ * The backward of every gather on the path: UnionRGCNLayer message (rgcn/layers.py:257-279; the snapshot graph holds
+ * each edge with its inverse, so the forward CSR-by-destination is also the CSR-by-source), the relation table
+ * gather (same lines), the relation mean-pool (src/rrgcn.py:161-166, col2_off = R) and the decoder's E[s] / rel[r]
+ * gathers (src/decoder.py:81-82).  col_w / row_w may be NULL (= 1).                                              */
+REGCN_API int regcn_csr_gather_sum(const float* X, int ldx, const float* col_w, const float* row_w, const int32_t* rowptr,
+                         const int32_t* col, int nrows, int d, int col2_off, float* out, int ldo, int accumulate,
+                         void* stream);
+/* Stable grouping of n int32 keys in [0,nkeys): rowptr (nkeys+1), perm (n) original positions grouped by key,
+ * vals_out[i] = vals[perm[i]] (vals may be NULL).  Builds the transposed indices the gathers above run on.      */
+REGCN_API size_t regcn_group_by_key_workspace_bytes(int n);
+REGCN_API int regcn_group_by_key(const int32_t* keys, int n, int nkeys, const int32_t* vals, int32_t* rowptr, int32_t* perm,
+                       int32_t* vals_out, void* workspace, size_t workspace_bytes, void* stream);
+/* rowid[i] = CSR row of position i (nnz entries); inv_len[r] = 1/len(row r) or 0 (either output may be NULL).   */
+REGCN_API int regcn_expand_rowptr(const int32_t* rowptr, int nrows, int nnz, int32_t* rowid, float* inv_len, void* stream);
+
+/* F.normalize backward (src/rrgcn.py:154,170,176,206): dx = (dy - y <y,dy>) / max(|x|,1e-12).                   */
+REGCN_API int regcn_normalize_bwd(const float* x, const float* dy, float* dx, int M, int d, void* stream);
+/* nn.GRUCell backward from the saved pre-activations gi, gh (M,3d) (src/rrgcn.py:133,168-174), optional F.normalize
+ * of the output folded in: dgi, dgh (M,3d), dhprev (M,d).                                                        */
+REGCN_API int regcn_gru_gate_bwd(const float* gi, const float* gh, const float* hprev, const float* dout, int M, int d,
+                       int normalize, float* dgi, float* dgh, float* dhprev, void* stream);
+/* UnionRGCNLayer apply-step backward (rgcn/layers.py:241-253): out = dropout_p(rrelu(P + where(indeg>0, L0, L1)));
+ * masks recovered from `out`.  dP (N,d); dL (N,2d) = [indeg>0 ? dP : 0 | indeg>0 ? 0 : dP] (may be NULL).         */
+REGCN_API int regcn_union_combine_bwd(const float* out, const float* dout, const int32_t* indeg, int N, int d, float p,
+                            float* dP, float* dL, void* stream);
+/* time gate backward (src/rrgcn.py:176-178): dG (pre-sigmoid), dcur (through the optional F.normalize), dh (direct). */
+REGCN_API int regcn_time_gate_bwd(const float* G, const float* bias, const float* cur, const float* h, const float* dout,
+                        int N, int d, int normalize_cur, float* dG, float* dcur, float* dh, void* stream);
+/* dx = dy * (1 - y^2), y = tanh(x)  (src/decoder.py:30,79); n % 4 == 0                                           */
+REGCN_API int regcn_tanh_bwd(const float* y, const float* dy, float* dx, size_t n, void* stream);
+/* in-place nn.Dropout(p) in train mode (counter-based mask: element i of call `seed`)                            */
+REGCN_API int regcn_dropout(float* x, size_t n, float p, uint32_t seed, void* stream);
+
+/* BatchNorm1d, train mode (src/decoder.py:20-22,68-70): X viewed as (B,C,L).  Two fixed-order stages (row slabs, then
+ * channels in double).  workspace: regcn_col_reduce_workspace_bytes(B, C*L).                                      */
+REGCN_API size_t regcn_col_reduce_workspace_bytes(int rows, int cols);
+REGCN_API int regcn_bn_stats(const float* X, int B, int C, int L, float eps, float momentum, float* mean, float* invstd,
+                   float* running_mean, float* running_var, float* workspace, size_t workspace_bytes, void* stream);
+/* sums of the BatchNorm backward: sum_dy (C) = dbeta, sum_dy_xhat (C) = dgamma; dy = mask(dZ; Z): mask_mode 0 none,
+ * 1 Z>0 (relu + dropout), 2 Z!=0 (dropout), times mask_scale.  Y = the BatchNorm input.                           */
+REGCN_API int regcn_bn_bwd_stats(const float* dZ, const float* Z, const float* Y, int B, int C, int L, int mask_mode,
+                       float mask_scale, const float* mean, const float* invstd, float* sum_dy, float* sum_dy_xhat,
+                       float* workspace, size_t workspace_bytes, void* stream);
+/* out (cols) (+)= column sums of X (rows, cols; pitch ld): bias gradients                                        */
+REGCN_API int regcn_col_sum(const float* X, int ld, int rows, int cols, float* out, int accumulate, float* workspace,
+                  size_t workspace_bytes, void* stream);
+/* out = dropout_p(relu?(gamma (x-mean) invstd + beta)); mean == NULL skips the normalisation                    */
+REGCN_API int regcn_bn_act_drop(const float* X, int B, int C, int L, const float* mean, const float* invstd,
+                      const float* gamma, const float* beta, int relu, float p, uint32_t seed, float* out, void* stream);
+/* dX = gamma invstd (dy - sum_dy/n - xhat sum_dy_xhat/n) with dy = mask(dZ; Z); then mask(.; out_src) of the dropout
+ * that precedes the BatchNorm input.  mean == NULL: masks only.                                                   */
+REGCN_API int regcn_bn_bwd_apply(const float* dZ, const float* Z, const float* Y, int B, int C, int L, int mask_mode,
+                       float mask_scale, const float* mean, const float* invstd, const float* gamma,
+                       const float* sum_dy, const float* sum_dy_xhat, const float* out_src, int out_mode,
+                       float out_scale, float* dX, void* stream);
+
+/* ConvTransE / ConvTransR tower in train mode (src/decoder.py:29-52, 78-100): stacked inputs, bn0 + input dropout +
+ * Conv1d(2,C,3,pad 1) with the dropped input kept, and the three convolution gradients.                          */
+REGCN_API int regcn_dec_gather_stack(const float* first, const float* second, const int64_t* triples, int col0, int col1,
+                           int B, int d, float* X0, void* stream);
+REGCN_API int regcn_dec_conv_fwd(const float* X0, int B, int d, int C, int ksz, const float* mean0, const float* invstd0,
+                       const float* gamma0, const float* beta0, float p, uint32_t seed, const float* W,
+                       const float* bias, float* X1, float* Y, void* stream);
+REGCN_API int regcn_dec_conv_bwd_input(const float* dY, const float* X1, int B, int d, int C, int ksz, const float* W,
+                             float p, float* dX1, void* stream);
+REGCN_API size_t regcn_dec_conv_bwd_weight_workspace_bytes(int B, int C);
+/* dW_db: C*2*3 weight gradients followed by C bias gradients                                                     */
+REGCN_API int regcn_dec_conv_bwd_weight(const float* dY, const float* X1, int B, int d, int C, int ksz, float* dW_db,
+                              float* workspace, size_t workspace_bytes, void* stream);
+
+/* nn.CrossEntropyLoss over materialised logits (src/rrgcn.py:87-88,218-223): ce (B), lse (B), loss (1) = mean(ce);
+ * and its gradient in place: S <- (softmax(S) - onehot) * (*gscale) / B, pitch padding zeroed.                   */
+REGCN_API int regcn_ce_lse_rows(const float* S, int64_t ld, int B, int N, const int64_t* triples, int target_col,
+                      float* ce, float* lse, float* loss, void* stream);
+REGCN_API int regcn_softmax_grad_rows(float* S, int64_t ld, int B, int N, const int64_t* triples, int target_col,
+                            const float* lse, const float* gscale, void* stream);
+/* out[c][r] = X[r][c] for r < rows, 0 for rows <= r < ldo (a K-major GEMM operand with K = ldo); plain and/or TF32
+ * (hi, lo) outputs: the weight-gradient GEMMs dW = x^T dy                                                        */
+REGCN_API int regcn_transpose_split(const float* X, int rows, int cols, int ldx, float* out, float* out_hi, float* out_lo,
+                          int ldo, void* stream);
+
+/* clip_grad_norm_ + torch.optim.Adam over one flat fp32 buffer (src/main.py:194,243-246).  total_norm: device float.
+ * step counts from 1.  max_norm <= 0 or total_norm == NULL: no clipping.                                          */
+REGCN_API size_t regcn_adam_workspace_bytes(void);
+REGCN_API int regcn_grad_norm(const float* g, size_t n, float* total_norm, void* workspace, size_t workspace_bytes,
+                    void* stream);
+REGCN_API int regcn_adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2,
+                    float eps, float weight_decay, int step, float max_norm, const float* total_norm, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -159,11 +159,87 @@ def run_losses(ref_utils, RecurrentRGCN, HyperbolicRecurrentRGCN):
         json.dump(out, f, indent=1, sort_keys=True)
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# training golden: the reference's optimisation step (src/main.py:235-246) executed here, dropout 0
+# ---------------------------------------------------------------------------------------------------------------
+TRAIN_CASES = {
+    "regcn_tiny_s0": dict(kind="regcn", shape="tiny", seed=0, layer_norm=True),
+    "regcn_tiny_s1_noln": dict(kind="regcn", shape="tiny", seed=1, layer_norm=False),
+    "regcn_small_s2": dict(kind="regcn", shape="small", seed=2, layer_norm=True),
+}
+TRAIN_STEPS = 2
+TASK_WEIGHT, GRAD_NORM, LR, WEIGHT_DECAY = 0.7, 1.0, 1e-3, 1e-5     # src/main.py:325,367,365,194
+SAMPLE = 1024
+
+
+def sample_of(x):
+    """Fixture-sized view of a tensor: a fixed-stride sample of at most SAMPLE values (the whole tensor if smaller)."""
+    flat = np.asarray(x, dtype=np.float32).reshape(-1)
+    step = max(1, flat.size // SAMPLE)
+    return flat[::step][:SAMPLE].copy()
+
+
+def run_train(ref_utils, RecurrentRGCN):
+    """tests/golden/train_regcn.npz: TRAIN_STEPS optimisation steps of the UNMODIFIED reference (get_loss in train()
+    mode with every dropout probability 0 -- torch's dropout generator cannot be reproduced by another implementation --
+    backward, clip_grad_norm_, Adam) on the same history / triples.  Stored per case and step: the three losses, the
+    clipped-from gradient norm, and per parameter the gradient norm + a strided sample of the gradient and of the
+    updated value; after the last step the BatchNorm running statistics."""
+    out = {}
+    for name, cfg in TRAIN_CASES.items():
+        case = synth.make_case(cfg["shape"], cfg["seed"])
+        n, r = case["num_ents"], case["num_rels"]
+        m = RecurrentRGCN("convtranse", "uvrgcn", n, r, 0, 0, H_DIM, "sub", 3, num_bases=N_BASES, num_basis=-1,
+                          num_hidden_layers=N_LAYERS, dropout=0.0, self_loop=True, skip_connect=False,
+                          layer_norm=cfg["layer_norm"], input_dropout=0.0, hidden_dropout=0.0, feat_dropout=0.0,
+                          entity_prediction=True, relation_prediction=True, use_cuda=False, gpu="cpu")
+        m.load_state_dict(synth.fill_state_dict(m.state_dict(), cfg["seed"]))
+        m.train()
+        m.gpu = "cpu"
+        # get_loss creates its accumulators as leaves and adds in place (src/rrgcn.py:205-207,219): that only works on
+        # the use_cuda path, where .cuda() returns a (non-leaf) copy.  Mimic exactly that: .cuda() of a leaf that
+        # requires grad is a differentiable copy, of anything else the identity (CPU stand-in for the device copy).
+        torch.Tensor.cuda = lambda self, *a, **k: (self.clone() if (self.requires_grad and self.is_leaf) else self)
+        opt = torch.optim.Adam(m.parameters(), lr=LR, weight_decay=WEIGHT_DECAY)
+        glist = [ref_utils.build_sub_graph(n, r, snap, False, "cpu") for snap in case["history"]]
+        triples = torch.from_numpy(case["test"])
+        for step in range(TRAIN_STEPS):
+            le, lr_, ls = m.get_loss(glist, triples.clone(), None, True)
+            loss = TASK_WEIGHT * le + (1 - TASK_WEIGHT) * lr_ + ls
+            loss.backward()
+            tn = torch.nn.utils.clip_grad_norm_(m.parameters(), GRAD_NORM)
+            grads = {k: (None if p.grad is None else p.grad.detach().clone()) for k, p in m.named_parameters()}
+            # clip_grad_norm_ scaled .grad in place: undo to store the raw gradient
+            coef = min(1.0, GRAD_NORM / (float(tn) + 1e-6))
+            opt.step()
+            opt.zero_grad()
+            out[f"{name}.s{step}.losses"] = np.array([float(le), float(lr_), float(ls)], dtype=np.float64)
+            out[f"{name}.s{step}.grad_norm"] = np.array(float(tn), dtype=np.float64)
+            for k, p in m.named_parameters():
+                if grads[k] is None:
+                    continue
+                g = grads[k].numpy() / coef
+                out[f"{name}.s{step}.gn.{k}"] = np.array(np.linalg.norm(g.astype(np.float64)))
+                out[f"{name}.s{step}.g.{k}"] = sample_of(g)
+                out[f"{name}.s{step}.p.{k}"] = sample_of(p.detach().numpy())
+            print(name, step, [float(le), float(lr_)], "grad norm", float(tn))
+        for k, v in m.state_dict().items():
+            if "running_" in k and (".bn0." in k or ".bn1." in k or ".bn2." in k):
+                out[f"{name}.bn.{k}"] = v.numpy().astype(np.float32)
+        out[f"{name}.no_grad"] = np.array(json.dumps(sorted(k for k, p in m.named_parameters() if k not in
+                                                              [kk for kk, g in grads.items() if g is not None])))
+    path = os.path.join(GOLDEN, "train_regcn.npz")
+    np.savez_compressed(path, **out)
+    print("->", path, os.path.getsize(path) / 1e6, "MB")
+
+
 def main(argv):
     ref_utils, RecurrentRGCN, HyperbolicRecurrentRGCN = _import_reference()
     torch.set_num_threads(os.cpu_count() or 1)
     if len(argv) > 1 and argv[1] == "--losses":
         return run_losses(ref_utils, RecurrentRGCN, HyperbolicRecurrentRGCN)
+    if len(argv) > 1 and argv[1] == "--train":
+        return run_train(ref_utils, RecurrentRGCN)
     names = argv[1:] or list(CASES)
     for name in names:
         run_case(name, CASES[name], ref_utils, RecurrentRGCN, HyperbolicRecurrentRGCN)

@@ -652,3 +652,86 @@ def hyp_loss(p, graphs, num_rels, triples, c=0.01, decoder="roth", layer_norm=Fa
     rt = p["radius_target"].to(dtype)[ids]
     return (float(cross_entropy(score, all_t[:, 2])), float(cross_entropy(score_rel, all_t[:, 1])), 0.0,
             float(radius_lambda * torch.mean((rs - rt) ** 2)))
+
+
+# =====================================================================================
+# Training step (src/rrgcn.py:197-223 in train() mode + src/main.py:235-246), dropout 0.
+# Gradients come from torch autograd over the restated forward (CPU); BatchNorm uses batch statistics
+# and updates its running ones like nn.BatchNorm1d (momentum 0.1, unbiased variance).
+# =====================================================================================
+def _bn_train(x, P, pre, stats, eps=1e-5, momentum=0.1):
+    dims = [0] + list(range(2, x.dim()))
+    shape = [1, -1] + [1] * (x.dim() - 2)
+    mean = x.mean(dims)
+    var = x.var(dims, unbiased=False)
+    n = x.numel() // x.shape[1]
+    rm = stats.get(pre + "running_mean", P[pre + "running_mean"])
+    rv = stats.get(pre + "running_var", P[pre + "running_var"])
+    stats[pre + "running_mean"] = ((1 - momentum) * rm + momentum * mean).detach()
+    stats[pre + "running_var"] = ((1 - momentum) * rv + momentum * var * n / max(n - 1, 1)).detach()
+    return (x - mean.view(shape)) / torch.sqrt(var.view(shape) + eps) * P[pre + "weight"].view(shape) + P[pre + "bias"].view(shape)
+
+
+def conv_tower_train(first, second, P, pre, stats):
+    """src/decoder.py:35-50 / 83-95 in train() mode with every dropout probability 0."""
+    x = torch.stack([first, second], dim=1)
+    x = _bn_train(x, P, pre + "bn0.", stats)
+    x = _conv1d_same(x, P[pre + "conv1.weight"], P[pre + "conv1.bias"])
+    x = torch.relu(_bn_train(x, P, pre + "bn1.", stats))
+    x = x.reshape(x.shape[0], -1)
+    x = x @ P[pre + "fc.weight"].t() + P[pre + "fc.bias"]
+    x = _bn_train(x, P, pre + "bn2.", stats)
+    return torch.relu(x)
+
+
+def regcn_train_losses(P, graphs, num_rels, triples, layer_norm, stats, n_layers=2):
+    """(loss_ent, loss_rel) with the autograd tape on; P holds leaf tensors (parameters) and buffers."""
+    all_t = torch.as_tensor(add_inverse(triples, num_rels))
+    hist, h0 = regcn_forward(P, graphs, num_rels, layer_norm=layer_norm, n_layers=n_layers, dtype=P["emb_rel"].dtype)
+    emb = normalize_rows(hist[-1]) if layer_norm else hist[-1]
+    e_all = torch.tanh(emb)
+    q = conv_tower_train(e_all[all_t[:, 0]], h0[all_t[:, 1]], P, "decoder_ob.", stats)
+    loss_e = cross_entropy(q @ e_all.t(), all_t[:, 2])
+    q = conv_tower_train(e_all[all_t[:, 0]], e_all[all_t[:, 2]], P, "rdecoder.", stats)
+    loss_r = cross_entropy(q @ h0.t(), all_t[:, 1])
+    return loss_e, loss_r
+
+
+def regcn_train_steps(sd, graphs, num_rels, triples, layer_norm=True, steps=1, task_weight=0.7, grad_norm=1.0,
+                      lr=1e-3, weight_decay=1e-5, betas=(0.9, 0.999), eps=1e-8, dtype=torch.float32):
+    """`steps` optimisation steps (loss.backward, clip_grad_norm_, torch.optim.Adam with L2 weight decay) on the same
+    batch.  Returns a list of per-step dicts {losses, grad_norm, grads{name}, params{name}} and the final buffers."""
+    P = {}
+    for k, v in sd.items():
+        if not v.is_floating_point() or k == "rgcn.rel_emb":
+            continue
+        t = v.detach().clone().to(dtype)
+        if "running_" not in k:
+            t.requires_grad_(True)
+        P[k] = t
+    m = {k: torch.zeros_like(v) for k, v in P.items() if v.requires_grad}
+    vv = {k: torch.zeros_like(v) for k, v in P.items() if v.requires_grad}
+    log = []
+    for step in range(1, steps + 1):
+        stats = {}
+        loss_e, loss_r = regcn_train_losses(P, graphs, num_rels, triples, layer_norm, stats)
+        loss = task_weight * loss_e + (1 - task_weight) * loss_r
+        names = [k for k, v in P.items() if v.requires_grad]
+        gs = torch.autograd.grad(loss, [P[k] for k in names], allow_unused=True)
+        grads = {k: g for k, g in zip(names, gs) if g is not None}
+        total = torch.sqrt(sum((g.double() ** 2).sum() for g in grads.values()))
+        coef = min(1.0, grad_norm / (float(total) + 1e-6))
+        with torch.no_grad():
+            for k, g in grads.items():
+                p = P[k]
+                gg = g * coef + weight_decay * p
+                m[k] = betas[0] * m[k] + (1 - betas[0]) * gg
+                vv[k] = betas[1] * vv[k] + (1 - betas[1]) * gg * gg
+                denom = vv[k].sqrt() / math.sqrt(1 - betas[1] ** step) + eps
+                p -= (lr / (1 - betas[0] ** step)) * m[k] / denom
+            for k, s in stats.items():
+                P[k] = s
+        log.append({"losses": (float(loss_e), float(loss_r)), "grad_norm": float(total),
+                    "grads": {k: g.detach().clone() for k, g in grads.items()},
+                    "params": {k: P[k].detach().clone() for k in grads}})
+    return log, {k: v.detach() for k, v in P.items() if "running_" in k}

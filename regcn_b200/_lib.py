@@ -18,6 +18,7 @@ _i64 = ctypes.c_int64
 _f = ctypes.c_float
 _d = ctypes.c_double
 _sz = ctypes.c_size_t
+_u32 = ctypes.c_uint32
 
 # name -> (restype, argtypes); must list every symbol of include/regcn_b200.h (tests check this)
 SIGNATURES = {
@@ -77,6 +78,34 @@ SIGNATURES = {
     "regcn_apply_filter": (_i, [_p, _i64, _i, _i, _p, _i, _p, _p, _i, _p, _p]),
     "regcn_filter_count": (_i, [_p, _i, _i, _p, _p]),
     "regcn_filter_fill": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
+    # ---- training (csrc/backward.cu)
+    "regcn_csr_gather_sum": (_i, [_p, _i, _p, _p, _p, _p, _i, _i, _i, _p, _i, _i, _p]),
+    "regcn_group_by_key_workspace_bytes": (_sz, [_i]),
+    "regcn_group_by_key": (_i, [_p, _i, _i, _p, _p, _p, _p, _p, _sz, _p]),
+    "regcn_expand_rowptr": (_i, [_p, _i, _i, _p, _p, _p]),
+    "regcn_normalize_bwd": (_i, [_p, _p, _p, _i, _i, _p]),
+    "regcn_gru_gate_bwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p]),
+    "regcn_union_combine_bwd": (_i, [_p, _p, _p, _i, _i, _f, _p, _p, _p]),
+    "regcn_time_gate_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p]),
+    "regcn_tanh_bwd": (_i, [_p, _p, _p, _sz, _p]),
+    "regcn_dropout": (_i, [_p, _sz, _f, _u32, _p]),
+    "regcn_col_reduce_workspace_bytes": (_sz, [_i, _i]),
+    "regcn_bn_stats": (_i, [_p, _i, _i, _i, _f, _f, _p, _p, _p, _p, _p, _sz, _p]),
+    "regcn_bn_bwd_stats": (_i, [_p, _p, _p, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _sz, _p]),
+    "regcn_col_sum": (_i, [_p, _i, _i, _i, _p, _i, _p, _sz, _p]),
+    "regcn_bn_act_drop": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _i, _f, _u32, _p, _p]),
+    "regcn_bn_bwd_apply": (_i, [_p, _p, _p, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _p, _i, _f, _p, _p]),
+    "regcn_dec_gather_stack": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p]),
+    "regcn_dec_conv_fwd": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, _f, _u32, _p, _p, _p, _p, _p]),
+    "regcn_dec_conv_bwd_input": (_i, [_p, _p, _i, _i, _i, _i, _p, _f, _p, _p]),
+    "regcn_dec_conv_bwd_weight_workspace_bytes": (_sz, [_i, _i]),
+    "regcn_dec_conv_bwd_weight": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _sz, _p]),
+    "regcn_ce_lse_rows": (_i, [_p, _i64, _i, _i, _p, _i, _p, _p, _p, _p]),
+    "regcn_softmax_grad_rows": (_i, [_p, _i64, _i, _i, _p, _i, _p, _p, _p]),
+    "regcn_transpose_split": (_i, [_p, _i, _i, _i, _p, _p, _p, _i, _p]),
+    "regcn_adam_workspace_bytes": (_sz, []),
+    "regcn_grad_norm": (_i, [_p, _sz, _p, _p, _sz, _p]),
+    "regcn_adam_step": (_i, [_p, _p, _p, _p, _sz, _f, _f, _f, _f, _f, _i, _f, _p, _p]),
 }
 
 

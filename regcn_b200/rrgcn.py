@@ -234,34 +234,41 @@ class RecurrentRGCN(nn.Module):
         score_rel = self.rdecoder.forward(embedding, r_emb, all_triples, mode="test")
         return all_triples, score, score_rel
 
-    @torch.no_grad()
     def get_loss(self, glist, triples, static_graph, use_cuda):
-        """src/rrgcn.py:197-248, forward values: (loss_ent, loss_rel, loss_static), each of shape (1,).
+        """src/rrgcn.py:197-248: (loss_ent, loss_rel, loss_static), each of shape (1,).
 
-        The entity head is CrossEntropy over all entities computed by the scoring GEMM's streaming log-sum-exp epilogue
-        (no (B,N) logits); the relation head materialises its (B,2R) scores.  This is the evaluation-mode forward of the
-        loss (dropout off, rrelu at its eval slope, BatchNorm running statistics): the backward kernels / optimizer
-        step are SURVEY.md 8f rank 1, so training mode raises instead of silently returning a loss without gradients."""
+        Training mode (`model.train()`): the losses carry gradients -- the evolution, the train-mode ConvTransE/R
+        towers (batch-statistics BatchNorm, dropout) and the cross entropies run as autograd nodes whose forward and
+        backward are kernels (regcn_b200/train.py); `loss.backward()` then `regcn_b200.optim.Adam.step()` is the
+        reference's optimisation step (src/main.py:235-246).
+
+        Evaluation mode: forward values only.  The entity head is CrossEntropy over all entities computed by the
+        scoring GEMM's streaming log-sum-exp epilogue (no (B,N) logits); the relation head materialises its (B,2R)
+        scores (dropout off, BatchNorm running statistics)."""
         from . import evaluate
-        if self.training:
-            raise NotImplementedError("regcn_b200.RecurrentRGCN.get_loss: training mode needs the backward kernels "
-                                      "(SURVEY.md 8f rank 1); the forward loss is available after .eval()")
         if self.use_static:
             raise NotImplementedError("static-graph constraint loss (src/rrgcn.py:225-247) is SURVEY.md 8f rank 3")
-        dev = self.dynamic_emb.device
-        triples = torch.as_tensor(triples).to(dev)
-        inverse_triples = triples.flip(1)
-        inverse_triples[:, 1] = inverse_triples[:, 1] + self.num_rels
-        all_triples = torch.cat([triples, inverse_triples]).contiguous()
-        evolve_embs, _, r_emb, _, _ = self.forward(glist, static_graph, use_cuda)
-        pre_emb = ops.row_map(evolve_embs[-1], ops.ROW_NORMALIZE) if self.layer_norm else evolve_embs[-1]
-        loss_ent = torch.zeros(1, device=dev)
-        loss_rel = torch.zeros(1, device=dev)
-        loss_static = torch.zeros(1, device=dev)
-        if self.entity_prediction:
-            q, cand, hyp, col_bias = evaluate._scoring_operands(self, pre_emb, r_emb, all_triples)
-            _, loss_ent = ops.fused_ce(q, cand, all_triples[:, 2], hyp=hyp, col_bias=col_bias)
-        if self.relation_prediction:
-            score_rel = self.rdecoder.forward(pre_emb, r_emb, all_triples, mode="train")
-            _, loss_rel = ops.ce_dense(score_rel, all_triples, 1)
-        return loss_ent, loss_rel, loss_static
+        if not use_cuda:
+            raise RuntimeError("regcn_b200: kernels take CUDA tensors only (no CPU fallback)")
+        if self.training:
+            from . import train
+            with torch.enable_grad():
+                return train.regcn_get_loss(self, glist, triples)
+        with torch.no_grad():
+            dev = self.dynamic_emb.device
+            triples = torch.as_tensor(triples).to(dev)
+            inverse_triples = triples.flip(1)
+            inverse_triples[:, 1] = inverse_triples[:, 1] + self.num_rels
+            all_triples = torch.cat([triples, inverse_triples]).contiguous()
+            evolve_embs, _, r_emb, _, _ = self.forward(glist, static_graph, use_cuda)
+            pre_emb = ops.row_map(evolve_embs[-1], ops.ROW_NORMALIZE) if self.layer_norm else evolve_embs[-1]
+            loss_ent = torch.zeros(1, device=dev)
+            loss_rel = torch.zeros(1, device=dev)
+            loss_static = torch.zeros(1, device=dev)
+            if self.entity_prediction:
+                q, cand, hyp, col_bias = evaluate._scoring_operands(self, pre_emb, r_emb, all_triples)
+                _, loss_ent = ops.fused_ce(q, cand, all_triples[:, 2], hyp=hyp, col_bias=col_bias)
+            if self.relation_prediction:
+                score_rel = self.rdecoder.forward(pre_emb, r_emb, all_triples, mode="train")
+                _, loss_rel = ops.ce_dense(score_rel, all_triples, 1)
+            return loss_ent, loss_rel, loss_static

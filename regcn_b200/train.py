@@ -1,0 +1,543 @@
+"""Training-mode path of RecurrentRGCN: `get_loss` with gradients, src/rrgcn.py:197-223,
+for the optimisation step of src/main.py:235-246.
+
+torch.autograd is used as the tape only: every node below is a `torch.autograd.Function` whose forward AND backward
+are C-ABI kernel calls (csrc/backward.cu + the forward kernels); no torch arithmetic runs on the path apart from
+autograd's own gradient accumulation for tensors with several consumers.  Dense contractions (forward, dX and dW)
+go through the tcgen05 3xTF32 GEMM; the dW = x^T dy products get their K-major operands from a fused
+transpose + TF32-split kernel.  Dropout masks come from a counter-based generator (`manual_seed`), so they cannot
+match torch's generator element for element -- parity tests run with dropout 0, statistics tests with dropout on.
+"""
+import torch
+
+from . import _lib, ops
+from ._lib import call, ptr
+
+F32 = torch.float32
+I32 = torch.int32
+
+_rng = {"seed": 0x5EED1234, "ctr": 0}
+
+
+def manual_seed(seed):
+    """Seed of the dropout masks (the kernels hash (seed, call counter, element index))."""
+    _rng["seed"] = int(seed) & 0xFFFFFFFF
+    _rng["ctr"] = 0
+
+
+def _next_seed():
+    _rng["ctr"] += 1
+    return (_rng["seed"] * 0x9E3779B1 + _rng["ctr"] * 0x85EBCA6B) & 0xFFFFFFFF
+
+
+def _pad4(n):
+    return (int(n) + 3) // 4 * 4
+
+
+_ws_cache = {}
+
+
+def _ws(dev, nbytes, slot=0):
+    """Grow-only scratch buffer per (device, slot); kernels on one stream use it one after the other."""
+    key = (dev, slot)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), device=dev, dtype=torch.uint8)
+        _ws_cache[key] = buf
+    return buf
+
+
+# ------------------------------------------------------------------------------------------------ dense helpers
+def _split(x):
+    """(hi, lo) TF32 split of a contiguous (M, K) matrix, K % 4 == 0."""
+    return ops.split_tf32(x.contiguous())
+
+
+def _tsplit(x):
+    """x (rows, cols) -> (hi, lo) of x^T as (cols, pad4(rows)), zero padded: a K-major operand with K = pad4(rows)."""
+    rows, cols = x.shape
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    ldo = _pad4(rows)
+    hi = torch.empty((cols, ldo), device=x.device, dtype=F32)
+    lo = torch.empty((cols, ldo), device=x.device, dtype=F32)
+    call("regcn_transpose_split", x.data_ptr(), rows, cols, x.stride(0), None, ptr(hi), ptr(lo), ldo)
+    return hi, lo
+
+
+def _auto_split_k(M, N, K):
+    tiles = ((M + 127) // 128) * ((N + 127) // 128)
+    if K < 1024 or tiles >= 120:
+        return 1
+    return max(1, min(32, 148 // tiles, K // 256))
+
+
+def _mm_nt(a, b, M, N, K, bias=None, out=None, ldc=None):
+    """C (M, N) = A (M, K) . B (N, K)^T; a, b = (hi, lo) pairs whose row pitch is K (zero padded)."""
+    dev = a[0].device
+    if out is None:
+        ldc = _pad4(N)
+        out = torch.empty((M, ldc), device=dev, dtype=F32)
+        out = out[:, :N] if ldc != N else out
+    elif ldc is None:
+        ldc = out.stride(0)
+    split_k = _auto_split_k(M, N, K)
+    ws, ws_bytes = None, 0
+    if split_k > 1:
+        ws_bytes = _lib.load().regcn_gemm_tf32_workspace_bytes(M, N, split_k)
+        ws = _ws(dev, ws_bytes, slot=1)
+    call("regcn_gemm_tf32", ptr(a[0]), ptr(a[1]), K, ptr(b[0]), ptr(b[1]), K, out.data_ptr(), ldc, M, N, K, ptr(bias),
+         0, 3, split_k, ptr(ws), ws_bytes)
+    return out
+
+
+def _col_sum(x):
+    rows, cols = x.shape
+    x = x.contiguous()
+    out = torch.empty(cols, device=x.device, dtype=F32)
+    nb = _lib.load().regcn_col_reduce_workspace_bytes(rows, cols)
+    ws = _ws(x.device, nb)
+    call("regcn_col_sum", ptr(x), cols, rows, cols, ptr(out), 0, ptr(ws), nb)
+    return out
+
+
+class _Linear(torch.autograd.Function):
+    """y = x W (+ b) with W (K, N)  [w_kn=True: torch.mm(x, W)]  or  y = x W^T (+ b) with W (N, K) [F.linear]."""
+
+    @staticmethod
+    def forward(ctx, x, W, bias, w_kn):
+        x = x.contiguous()
+        W = W.contiguous()
+        M, K = x.shape
+        N = W.shape[1] if w_kn else W.shape[0]
+        if K % 4:
+            raise ValueError("regcn_b200.train: inner dimension must be a multiple of 4")
+        b_op = _tsplit(W) if w_kn else _split(W)
+        y = _mm_nt(_split(x), b_op, M, N, K, bias=None if bias is None else bias.contiguous())
+        ctx.save_for_backward(x, W)
+        ctx.w_kn = w_kn
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W = ctx.saved_tensors
+        dy = dy.contiguous()
+        M, K = x.shape
+        N = dy.shape[1]
+        dx = dW = db = None
+        if N % 4:
+            raise ValueError("regcn_b200.train: output dimension must be a multiple of 4")
+        if ctx.needs_input_grad[0]:
+            # dx (M,K) = dy (M,N) . Wop (K,N)^T
+            w_op = _split(W) if ctx.w_kn else _tsplit(W)
+            dx = _mm_nt(_split(dy), w_op, M, K, N)
+        if ctx.needs_input_grad[1]:
+            xt, dyt = _tsplit(x), _tsplit(dy)                    # (K, pad4(M)), (N, pad4(M))
+            Mp = _pad4(M)
+            dW = _mm_nt(xt, dyt, K, N, Mp) if ctx.w_kn else _mm_nt(dyt, xt, N, K, Mp)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = _col_sum(dy)
+        return dx, dW, db, None
+
+
+def linear(x, W, bias=None, w_kn=False):
+    return _Linear.apply(x, W, bias, w_kn)
+
+
+# ------------------------------------------------------------------------------------------------ graph transposes
+def _group(keys, nkeys, vals=None):
+    n = int(keys.shape[0])
+    dev = keys.device
+    rowptr = torch.empty(nkeys + 1, device=dev, dtype=I32)
+    perm = torch.empty(max(n, 1), device=dev, dtype=I32)
+    vout = torch.empty(max(n, 1), device=dev, dtype=I32) if vals is not None else None
+    nb = _lib.load().regcn_group_by_key_workspace_bytes(n)
+    ws = _ws(dev, nb)
+    call("regcn_group_by_key", ptr(keys), n, nkeys, ptr(vals), ptr(rowptr), ptr(perm), ptr(vout), ptr(ws), nb)
+    return rowptr, perm, vout
+
+
+def _train_index(g):
+    """Transposed indices of one snapshot for the backward gathers (cached on the graph object):
+    edges grouped by relation type (-> destination ids) and relation memberships grouped by entity."""
+    idx = getattr(g, "_train_idx", None)
+    if idx is None:
+        E, R, N = g.num_edges, g.num_rels, g.num_nodes
+        type_rowptr, _, type_dst = _group(g.etype[:E].contiguous(), 2 * R, g.dst[:E].contiguous())
+        nnz = int(g.n_rel_ents)
+        rowid = torch.empty(max(nnz, 1), device=g.device, dtype=I32)
+        inv_len = torch.empty(R, device=g.device, dtype=F32)
+        call("regcn_expand_rowptr", ptr(g.rel_rowptr), R, nnz, ptr(rowid), ptr(inv_len))
+        ent_rowptr, _, ent_rel = _group(g.rel_ents[:nnz].contiguous(), N, rowid[:nnz].contiguous())
+        idx = g._train_idx = dict(type_rowptr=type_rowptr, type_dst=type_dst, ent_rowptr=ent_rowptr, ent_rel=ent_rel,
+                                  inv_len=inv_len)
+    return idx
+
+
+def _gather_sum(X, ldx, col_w, rowptr, col, nrows, d, col2_off=0, x_ptr=None):
+    out = torch.empty((nrows, d), device=X.device, dtype=F32)
+    call("regcn_csr_gather_sum", X.data_ptr() if x_ptr is None else x_ptr, ldx, ptr(col_w), None, ptr(rowptr), ptr(col),
+         nrows, d, col2_off, ptr(out), d, 0)
+    return out
+
+
+class _RelMeanPool(torch.autograd.Function):
+    """src/rrgcn.py:161-166."""
+
+    @staticmethod
+    def forward(ctx, h, g):
+        ctx.g = g
+        return ops.rel_mean_pool(h, g)
+
+    @staticmethod
+    def backward(ctx, gx):
+        g = ctx.g
+        ti = _train_index(g)
+        gx = gx.contiguous()
+        d = gx.shape[1]
+        dh = _gather_sum(gx, d, ti["inv_len"], ti["ent_rowptr"], ti["ent_rel"], g.num_nodes, d, col2_off=g.num_rels)
+        return dh, None
+
+
+class _UnionAggregate(torch.autograd.Function):
+    """agg[v] = norm[v] sum_{(u,r)->v} (h[u] + rel[r])   (rgcn/layers.py:257-279 before the W_n product)."""
+
+    @staticmethod
+    def forward(ctx, h, rel, g):
+        ctx.g = g
+        return ops.union_aggregate(h.contiguous(), rel.contiguous(), g)
+
+    @staticmethod
+    def backward(ctx, dagg):
+        g = ctx.g
+        ti = _train_index(g)
+        dagg = dagg.contiguous()
+        d = dagg.shape[1]
+        dh = _gather_sum(dagg, d, g.norm, g.rowptr, g.src_sorted, g.num_nodes, d)
+        drel = _gather_sum(dagg, d, g.norm, ti["type_rowptr"], ti["type_dst"], 2 * g.num_rels, d)
+        return dh, drel, None
+
+
+class _UnionCombine(torch.autograd.Function):
+    """out = dropout_p(rrelu(P + where(indeg>0, L[:, :d], L[:, d:])))   (rgcn/layers.py:241-253)."""
+
+    @staticmethod
+    def forward(ctx, P, L, g, p):
+        out, _, _ = ops.union_combine(P.contiguous(), L.contiguous(), g.indeg, act=1)
+        if p > 0:
+            call("regcn_dropout", ptr(out), out.numel(), float(p), _next_seed())
+        ctx.g, ctx.p = g, float(p)
+        ctx.save_for_backward(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (out,) = ctx.saved_tensors
+        N, d = out.shape
+        dP = torch.empty((N, d), device=out.device, dtype=F32)
+        dL = torch.empty((N, 2 * d), device=out.device, dtype=F32)
+        call("regcn_union_combine_bwd", ptr(out), ptr(dout.contiguous()), ptr(ctx.g.indeg), N, d, ctx.p, ptr(dP), ptr(dL))
+        return dP, dL, None, None
+
+
+class _TimeGate(torch.autograd.Function):
+    """h' = s(G+b) [normalize](cur) + (1 - s(G+b)) h   (src/rrgcn.py:176-178)."""
+
+    @staticmethod
+    def forward(ctx, G, bias, cur, h, normalize):
+        G, bias, cur, h = G.contiguous(), bias.contiguous(), cur.contiguous(), h.contiguous()
+        ctx.save_for_backward(G, bias, cur, h)
+        ctx.normalize = bool(normalize)
+        return ops.time_gate(G, bias, cur, h, normalize)
+
+    @staticmethod
+    def backward(ctx, dout):
+        G, bias, cur, h = ctx.saved_tensors
+        N, d = h.shape
+        dG, dcur, dh = (torch.empty((N, d), device=h.device, dtype=F32) for _ in range(3))
+        call("regcn_time_gate_bwd", ptr(G), ptr(bias), ptr(cur), ptr(h), ptr(dout.contiguous()), N, d,
+             int(ctx.normalize), ptr(dG), ptr(dcur), ptr(dh))
+        return dG, _col_sum(dG), dcur, dh, None
+
+
+class _GRUGate(torch.autograd.Function):
+    """nn.GRUCell gates (+ F.normalize) from gi, gh   (src/rrgcn.py:168-174)."""
+
+    @staticmethod
+    def forward(ctx, gi, gh, hprev, normalize):
+        gi, gh, hprev = gi.contiguous(), gh.contiguous(), hprev.contiguous()
+        ctx.save_for_backward(gi, gh, hprev)
+        ctx.normalize = bool(normalize)
+        return ops.gru_gate(gi, gh, hprev, normalize)
+
+    @staticmethod
+    def backward(ctx, dout):
+        gi, gh, hprev = ctx.saved_tensors
+        M, d = hprev.shape
+        dgi = torch.empty((M, 3 * d), device=gi.device, dtype=F32)
+        dgh = torch.empty((M, 3 * d), device=gi.device, dtype=F32)
+        dh = torch.empty((M, d), device=gi.device, dtype=F32)
+        call("regcn_gru_gate_bwd", ptr(gi), ptr(gh), ptr(hprev), ptr(dout.contiguous()), M, d, int(ctx.normalize),
+             ptr(dgi), ptr(dgh), ptr(dh))
+        return dgi, dgh, dh, None
+
+
+class _Normalize(torch.autograd.Function):
+    """F.normalize rows   (src/rrgcn.py:154,206)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        ctx.save_for_backward(x)
+        return ops.row_map(x, ops.ROW_NORMALIZE)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dx = torch.empty_like(x)
+        call("regcn_normalize_bwd", ptr(x), ptr(dy.contiguous()), ptr(dx), x.shape[0], x.shape[1])
+        return dx
+
+
+class _Tanh(torch.autograd.Function):
+    """tanh of the entity table   (src/decoder.py:30,79)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        y = ops.row_map(x.contiguous(), ops.ROW_TANH)
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        dx = torch.empty_like(y)
+        call("regcn_tanh_bwd", ptr(y), ptr(dy.contiguous()), ptr(dx), y.numel())
+        return dx
+
+
+# ------------------------------------------------------------------------------------------------ decoder tower
+def _bn_stats(x, B, C, L, bn):
+    dev = x.device
+    mean = torch.empty(C, device=dev, dtype=F32)
+    invstd = torch.empty(C, device=dev, dtype=F32)
+    nb = _lib.load().regcn_col_reduce_workspace_bytes(B, C * L)
+    ws = _ws(dev, nb)
+    mom = 0.1 if bn.momentum is None else float(bn.momentum)
+    track = bn.track_running_stats and bn.running_mean is not None
+    call("regcn_bn_stats", ptr(x), B, C, L, float(bn.eps), mom, ptr(mean), ptr(invstd),
+         ptr(bn.running_mean) if track else None, ptr(bn.running_var) if track else None, ptr(ws), nb)
+    if track and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked += 1
+    return mean, invstd
+
+
+def _bn_bwd(dZ, Z, Y, B, C, L, mask_mode, mask_scale, mean, invstd, gamma, out_src=None, out_mode=0, out_scale=1.0):
+    dev = dZ.device
+    sdy = torch.empty(C, device=dev, dtype=F32)
+    sdyx = torch.empty(C, device=dev, dtype=F32)
+    nb = _lib.load().regcn_col_reduce_workspace_bytes(B, C * L)
+    ws = _ws(dev, nb)
+    call("regcn_bn_bwd_stats", ptr(dZ), ptr(Z), ptr(Y), B, C, L, mask_mode, float(mask_scale), ptr(mean), ptr(invstd),
+         ptr(sdy), ptr(sdyx), ptr(ws), nb)
+    dX = torch.empty_like(Y)
+    call("regcn_bn_bwd_apply", ptr(dZ), ptr(Z), ptr(Y), B, C, L, mask_mode, float(mask_scale), ptr(mean), ptr(invstd),
+         ptr(gamma), ptr(sdy), ptr(sdyx), ptr(out_src), out_mode, float(out_scale), ptr(dX))
+    return dX, sdyx, sdy          # dX, dgamma, dbeta
+
+
+class _ConvTower(torch.autograd.Function):
+    """The ConvTransE / ConvTransR query tower in train mode (src/decoder.py:35-50, 83-95): stacked gathers -> bn0 ->
+    input dropout -> Conv1d(2,C,3) -> bn1 -> relu -> feature dropout -> fc -> hidden dropout -> bn2 -> relu.
+    BatchNorm uses batch statistics and updates the running ones (momentum 0.1, unbiased variance)."""
+
+    @staticmethod
+    def forward(ctx, first, second, g0, b0, wc, bc, g1, b1, wf, bf, g2, b2, triples, col0, col1, mod):
+        dev = first.device
+        first, second = first.contiguous(), second.contiguous()
+        B = int(triples.shape[0])
+        d = first.shape[1]
+        C, _, ksz = wc.shape
+        if B < 2:
+            raise ValueError("regcn_b200.train: BatchNorm in train mode needs more than one query")
+        p_in, p_feat, p_hid = float(mod.inp_drop.p), float(mod.feature_map_drop.p), float(mod.hidden_drop.p)
+        X0 = torch.empty((B, 2, d), device=dev, dtype=F32)
+        call("regcn_dec_gather_stack", ptr(first), ptr(second), ptr(triples), col0, col1, B, d, ptr(X0))
+        m0, is0 = _bn_stats(X0, B, 2, d, mod.bn0)
+        X1 = torch.empty((B, 2, d), device=dev, dtype=F32)
+        Y = torch.empty((B, C, d), device=dev, dtype=F32)
+        wc_c, bc_c = wc.contiguous(), bc.contiguous()
+        call("regcn_dec_conv_fwd", ptr(X0), B, d, C, ksz, ptr(m0), ptr(is0), ptr(g0.contiguous()), ptr(b0.contiguous()),
+             p_in, _next_seed(), ptr(wc_c), ptr(bc_c), ptr(X1), ptr(Y))
+        m1, is1 = _bn_stats(Y, B, C, d, mod.bn1)
+        Z = torch.empty((B, C * d), device=dev, dtype=F32)
+        call("regcn_bn_act_drop", ptr(Y), B, C, d, ptr(m1), ptr(is1), ptr(g1.contiguous()), ptr(b1.contiguous()), 1,
+             p_feat, _next_seed(), ptr(Z))
+        wf_c = wf.contiguous()
+        Fq = _mm_nt(_split(Z), _split(wf_c), B, d, C * d, bias=bf.contiguous())
+        Fq = Fq.contiguous()
+        if p_hid > 0:
+            call("regcn_dropout", ptr(Fq), Fq.numel(), p_hid, _next_seed())
+        m2, is2 = _bn_stats(Fq, B, d, 1, mod.bn2)
+        Q = torch.empty((B, d), device=dev, dtype=F32)
+        call("regcn_bn_act_drop", ptr(Fq), B, d, 1, ptr(m2), ptr(is2), ptr(g2.contiguous()), ptr(b2.contiguous()), 1,
+             0.0, 0, ptr(Q))
+        ctx.save_for_backward(X0, X1, Y, Z, Fq, Q, m0, is0, m1, is1, m2, is2, g0, wc_c, g1, wf_c, g2, triples)
+        ctx.dims = (B, d, C, ksz, col0, col1, first.shape[0], second.shape[0], p_in, p_feat, p_hid)
+        return Q
+
+    @staticmethod
+    def backward(ctx, dQ):
+        X0, X1, Y, Z, Fq, Q, m0, is0, m1, is1, m2, is2, g0, wc, g1, wf, g2, triples = ctx.saved_tensors
+        B, d, C, ksz, col0, col1, n_first, n_second, p_in, p_feat, p_hid = ctx.dims
+        dev = dQ.device
+        dQ = dQ.contiguous()
+        # bn2 + relu (mask Q > 0), then the hidden dropout in front of it (mask Fq != 0)
+        dF, dg2, db2 = _bn_bwd(dQ, Q, Fq, B, d, 1, 1, 1.0, m2, is2, g2.contiguous(), out_src=Fq,
+                               out_mode=2 if p_hid > 0 else 0, out_scale=1.0 / (1.0 - p_hid) if p_hid > 0 else 1.0)
+        dbf = _col_sum(dF)
+        Bp = _pad4(B)
+        dwf = _mm_nt(_tsplit(dF), _tsplit(Z), d, C * d, Bp)                    # (d, C d) = dF^T Z
+        dZ = _mm_nt(_split(dF), _tsplit(wf), B, C * d, d)                      # (B, C d) = dF W_fc
+        dZ = dZ.contiguous()
+        # bn1 + relu + feature dropout (mask Z > 0, scale 1/(1-p))
+        dY, dg1, db1 = _bn_bwd(dZ, Z, Y, B, C, d, 1, 1.0 / (1.0 - p_feat) if p_feat > 0 else 1.0, m1, is1,
+                               g1.contiguous())
+        nb = _lib.load().regcn_dec_conv_bwd_weight_workspace_bytes(B, C)
+        ws = _ws(dev, nb)
+        dwb = torch.empty(C * 2 * ksz + C, device=dev, dtype=F32)
+        call("regcn_dec_conv_bwd_weight", ptr(dY), ptr(X1), B, d, C, ksz, ptr(dwb), ptr(ws), nb)
+        dwc = dwb[: C * 2 * ksz].view(C, 2, ksz)
+        dbc = dwb[C * 2 * ksz:]
+        dX1 = torch.empty((B, 2, d), device=dev, dtype=F32)
+        call("regcn_dec_conv_bwd_input", ptr(dY), ptr(X1), B, d, C, ksz, ptr(wc), p_in, ptr(dX1))
+        dX0, dg0, db0 = _bn_bwd(dX1, None, X0, B, 2, d, 0, 1.0, m0, is0, g0.contiguous())
+        # scatter back to the table rows: queries grouped by the gathered id
+        t32 = triples.to(I32)
+        dfirst = dsecond = None
+        if ctx.needs_input_grad[0]:
+            rp, perm, _ = _group(t32[:, col0].contiguous(), n_first)
+            dfirst = _gather_sum(dX0, 2 * d, None, rp, perm, n_first, d)
+        if ctx.needs_input_grad[1]:
+            rp, perm, _ = _group(t32[:, col1].contiguous(), n_second)
+            dsecond = _gather_sum(dX0, 2 * d, None, rp, perm, n_second, d, x_ptr=dX0.data_ptr() + 4 * d)
+        return (dfirst, dsecond, dg0, db0, dwc, dbc, dg1, db1, dwf, dbf, dg2, db2, None, None, None, None)
+
+
+def conv_tower(mod, first, second, triples, col0, col1):
+    return _ConvTower.apply(first, second, mod.bn0.weight, mod.bn0.bias, mod.conv1.weight, mod.conv1.bias,
+                            mod.bn1.weight, mod.bn1.bias, mod.fc.weight, mod.fc.bias, mod.bn2.weight, mod.bn2.bias,
+                            triples, col0, col1, mod)
+
+
+class _ScoreCE(torch.autograd.Function):
+    """loss = mean_b CrossEntropy(q_b . cand^T, target_b)   (src/rrgcn.py:218-223; decoder :96-99 / :51).
+    The logits are materialised once (pitch padded to 4), turned into their own gradient in place in the backward,
+    and contracted twice: dq = dS cand, dcand = dS^T q."""
+
+    @staticmethod
+    def forward(ctx, q, cand, triples, target_col):
+        q, cand = q.contiguous(), cand.contiguous()
+        B, d = q.shape
+        N = cand.shape[0]
+        Np = _pad4(N)
+        dev = q.device
+        S = torch.empty((B, Np), device=dev, dtype=F32)
+        _mm_nt(_split(q), _split(cand), B, N, d, out=S, ldc=Np)
+        ce = torch.empty(B, device=dev, dtype=F32)
+        lse = torch.empty(B, device=dev, dtype=F32)
+        loss = torch.empty(1, device=dev, dtype=F32)
+        call("regcn_ce_lse_rows", ptr(S), Np, B, N, ptr(triples), target_col, ptr(ce), ptr(lse), ptr(loss))
+        ctx.save_for_backward(q, cand, triples, lse)
+        ctx.S = S
+        ctx.target_col = target_col
+        return loss
+
+    @staticmethod
+    def backward(ctx, gloss):
+        q, cand, triples, lse = ctx.saved_tensors
+        S = ctx.S
+        ctx.S = None
+        if S is None:
+            raise RuntimeError("regcn_b200.train: the loss graph can be back-propagated once")
+        B, d = q.shape
+        N = cand.shape[0]
+        Np = S.shape[1]
+        call("regcn_softmax_grad_rows", ptr(S), Np, B, N, ptr(triples), ctx.target_col, ptr(lse),
+             ptr(gloss.contiguous().view(-1)))
+        dq = dcand = None
+        if ctx.needs_input_grad[0]:
+            dq = _mm_nt(_split(S), _tsplit(cand), B, d, Np)                       # cand^T: (d, pad4(N)) == (d, Np)
+        if ctx.needs_input_grad[1]:
+            Bp = _pad4(B)
+            dcand = _mm_nt(_tsplit(S[:, :N]), _tsplit(q), N, d, Bp)               # (N, Bp) . (d, Bp)^T
+        return dq, dcand, None, None
+
+
+def score_ce(q, cand, triples, target_col):
+    return _ScoreCE.apply(q, cand, triples, target_col)
+
+
+rel_mean_pool = _RelMeanPool.apply
+union_aggregate = _UnionAggregate.apply
+union_combine = _UnionCombine.apply
+time_gate = _TimeGate.apply
+gru_gate = _GRUGate.apply
+normalize = _Normalize.apply
+tanh = _Tanh.apply
+
+
+# ------------------------------------------------------------------------------------------------ model-level glue
+def regcn_evolve(model, g_list):
+    """RecurrentRGCN.forward with the tape on (src/rrgcn.py:142-180; uvrgcn, self_loop, no skip connection, no static
+    graph).  Returns (history_embs, h_0)."""
+    if model.use_static or model.rgcn.skip_connect or not model.rgcn.self_loop or model.encoder_name != "uvrgcn":
+        raise NotImplementedError("regcn_b200.train: uvrgcn + self_loop without skip_connect / static graph only")
+    cell = model.relation_cell_1
+    h = normalize(model.dynamic_emb) if model.layer_norm else model.dynamic_emb
+    h0 = None
+    hist = []
+    for i, g in enumerate(g_list):
+        x_mean = rel_mean_pool(h, g)
+        x_cat = torch.cat((model.emb_rel, x_mean), dim=1)
+        gi = linear(x_cat, cell.weight_ih, cell.bias_ih)
+        hprev = model.emb_rel if i == 0 else h0
+        gh = linear(hprev, cell.weight_hh, cell.bias_hh)
+        h0 = gru_gate(gi, gh, hprev, model.layer_norm)
+        cur = h
+        for layer in model.rgcn.layers:
+            p = float(layer.dropout.p) if (layer.dropout is not None and model.training) else 0.0
+            agg = union_aggregate(cur, h0, g)
+            P = linear(agg, layer.weight_neighbor, None, True)
+            L = linear(cur, torch.cat((layer.loop_weight, layer.evolve_loop_weight), dim=1), None, True)
+            cur = union_combine(P, L, g, p)
+        G = linear(h, model.time_gate_weight, None, True)
+        h = time_gate(G, model.time_gate_bias, cur, h, model.layer_norm)
+        hist.append(h)
+    return hist, h0
+
+
+def regcn_get_loss(model, glist, triples):
+    """src/rrgcn.py:197-223 with gradients: (loss_ent, loss_rel, loss_static), each of shape (1,)."""
+    _lib.require_device()
+    if ops.gemm_impl() != "tc":
+        raise RuntimeError("regcn_b200.train needs the tensor-core GEMM (REGCN_GEMM=tc)")
+    dev = model.dynamic_emb.device
+    triples = torch.as_tensor(triples).to(dev)
+    inverse = triples.flip(1)
+    inverse[:, 1] = inverse[:, 1] + model.num_rels
+    all_triples = torch.cat([triples, inverse]).contiguous()
+    hist, r_emb = regcn_evolve(model, glist)
+    pre = normalize(hist[-1]) if model.layer_norm else hist[-1]
+    e_all = tanh(pre)
+    loss_ent = torch.zeros(1, device=dev)
+    loss_rel = torch.zeros(1, device=dev)
+    loss_static = torch.zeros(1, device=dev)
+    if model.entity_prediction:
+        q = conv_tower(model.decoder_ob, e_all, r_emb, all_triples, 0, 1)
+        loss_ent = score_ce(q, e_all, all_triples, 2)
+    if model.relation_prediction:
+        q = conv_tower(model.rdecoder, e_all, e_all, all_triples, 0, 2)
+        loss_rel = score_ce(q, r_emb, all_triples, 1)
+    return loss_ent, loss_rel, loss_static

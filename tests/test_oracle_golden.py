@@ -114,3 +114,43 @@ def test_loss_restatement_matches_reference(name):
                                     layer_norm=cfg["layer_norm"], encoder=cfg["encoder"], gamma=cfg["gamma"],
                                     num_bases=min(N_BASES, 2 * r))
     np.testing.assert_allclose(mine, ref, rtol=1e-4, atol=1e-6)
+
+
+# ----------------------------------------------------------------------------------------- training step (8f-1)
+def _train_golden():
+    import os
+    from tests.helpers import GOLDEN
+    return np.load(os.path.join(GOLDEN, "train_regcn.npz"))
+
+
+from tests.helpers import compare_train_step  # noqa: E402
+
+
+TRAIN_CASES = {"regcn_tiny_s0": ("tiny", 0, True), "regcn_tiny_s1_noln": ("tiny", 1, False),
+               "regcn_small_s2": ("small", 2, True)}
+
+
+@pytest.mark.parametrize("name", sorted(TRAIN_CASES))
+def test_oracle_train_step_matches_reference(name):
+    """restate.regcn_train_steps (autograd over the restated forward + clip + Adam) against two optimisation steps of
+    the UNMODIFIED reference (tests/golden/train_regcn.npz, oracle/gen_golden.py --train): losses, gradient norm,
+    per-parameter gradients and updated values."""
+    import regcn_b200 as R
+    shape, seed, ln = TRAIN_CASES[name]
+    z = _train_golden()
+    case = synth.make_case(shape, seed)
+    n, r = case["num_ents"], case["num_rels"]
+    m = R.RecurrentRGCN("convtranse", "uvrgcn", n, r, 0, 0, 200, "sub", 3, num_bases=100, num_basis=-1,
+                        num_hidden_layers=2, dropout=0.0, self_loop=True, skip_connect=False, layer_norm=ln,
+                        input_dropout=0.0, hidden_dropout=0.0, feat_dropout=0.0, entity_prediction=True,
+                        relation_prediction=True, use_cuda=True, gpu=0)
+    sd = synth.fill_state_dict(m.state_dict(), seed)
+    graphs = [restate.build_edges(s, n, r) for s in case["history"]]
+    log, bufs = restate.regcn_train_steps(sd, graphs, r, case["test"], layer_norm=ln, steps=2)
+    for s, rec in enumerate(log):
+        compare_train_step(z, name, s, rec["losses"], rec["grad_norm"], {k: v.numpy() for k, v in rec["grads"].items()},
+                           {k: v.numpy() for k, v in rec["params"].items()})
+    for k, v in bufs.items():
+        if f"{name}.bn.{k}" not in z.files:
+            continue                                                     # bn3 / bn_init are never used (src/decoder.py:73-76)
+        np.testing.assert_allclose(v.numpy(), z[f"{name}.bn.{k}"], rtol=2e-3, atol=1e-5)   # after the 2nd step
