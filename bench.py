@@ -224,6 +224,31 @@ def run_stress(dev, hbm_peak, tf_peak):
     return out
 
 
+def run_cpu_train_arm(args, steps=1, warmup=1):
+    """The reference's optimisation step (src/main.py:233-246: get_loss in train() mode, backward, clip_grad_norm_,
+    Adam) through the oracle port (torch autograd over oracle/restate.py) on the host cores; dropout 0 (mask draws are
+    negligible next to the GEMMs)."""
+    import torch
+    from oracle import restate
+    from regcn_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = model_cfg(args.model)
+    case = synth.make_case(args.workload, 0)
+    n, r = case["num_ents"], case["num_rels"]
+    _, sd = build_product_model(cfg, n, r, 0)
+    graphs = [restate.build_edges(s, n, r) for s in case["history"]]
+    restate.regcn_train_steps(sd, graphs, r, case["test"], layer_norm=cfg["layer_norm"], steps=warmup)
+    t0 = time.perf_counter()
+    restate.regcn_train_steps(sd, graphs, r, case["test"], layer_norm=cfg["layer_norm"], steps=steps)
+    dt = (time.perf_counter() - t0) / steps
+    L = len(graphs)
+    return {"value": L / dt, "unit": "train snapshot-steps/s", "ms_per_step": dt * 1e3, "cores": cores, "kind": "port",
+            "sample": f"{steps} optimisation step(s) on workload {args.workload} (evolve L={L} snapshots, ConvTransE + "
+                      f"ConvTransR heads over all candidates, backward, clip, Adam) after {warmup} warm-up; torch autograd "
+                      f"over oracle/restate.py on {cores} threads"}
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -463,10 +488,47 @@ def main():
                    "ranks_equal_single_gpu": same, "collectives": "one all_reduce(SUM) of (2,B) int32 counts over NCCL",
                    "what": "query tower + fused score/count over N/G candidates per GPU + rank merge (evolution excluded)"}
 
+    # ---- training step: get_loss in train() mode -> backward -> clip_grad_norm_(1.0) -> Adam, the
+    #      reference's src/main.py:233-246 with its default dropout 0.2; every rank trains its own replica (no
+    #      collective: the reference takes one optimiser step per snapshot, SURVEY 8e "replicas only") ----
+    train_line = None
+    if cfg["kind"] == "regcn":
+        from regcn_b200 import optim as roptim
+        tmodel, _ = build_product_model(cfg, n, r, 0)
+        tmodel = tmodel.to(dev).train()
+        topt = roptim.Adam(tmodel.parameters(), lr=1e-3, weight_decay=1e-5)
+        out_t = {}
+
+        def train_step(_):
+            le, lr_, ls = tmodel.get_loss(glist, test_dev, None, True)
+            (0.7 * le + 0.3 * lr_ + ls).backward()
+            roptim.clip_grad_norm_(topt, 1.0)
+            topt.step()
+            topt.zero_grad()
+            out_t["loss"] = le
+
+        t_steps = max(3, min(args.steps, 10))
+        tot_t, _ = timed(train_step, t_steps, 3)
+        train_ms = maxr(tot_t) / t_steps
+        torch.cuda.synchronize()
+        l0 = lib0.regcn_kernel_launches()
+        train_step(None)
+        torch.cuda.synchronize()
+        train_line = {"ms_per_step": train_ms, "train_snapshot_steps_per_s": world * L / (train_ms * 1e-3),
+                      "optimisation_steps_per_s": world / (train_ms * 1e-3), "steps": t_steps,
+                      "gpu_launches_per_step": int(lib0.regcn_kernel_launches() - l0),
+                      "loss_ent_after": float(out_t["loss"]),
+                      "what": "RecurrentRGCN.get_loss (train mode, dropout 0.2, batch-stat BatchNorm) + backward + "
+                              "clip_grad_norm_(1.0) + Adam(lr 1e-3, wd 1e-5); 3xTF32 tcgen05 GEMMs for forward, dX and dW"}
+        del tmodel, topt
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb = run_cpu_arm(args, 3, 1)
         cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        if train_line is not None:
+            ct = run_cpu_train_arm(args, 1, 1)
+            train_line["cpu_baseline"] = ct
 
     if rank == 0:
         line = {"metric": metric, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
@@ -493,6 +555,8 @@ def main():
             line["cpu_baseline"] = cpu_baseline
         if sharded:
             line["entity_sharded"] = sharded
+        if train_line:
+            line["train"] = train_line
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

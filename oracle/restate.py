@@ -731,7 +731,7 @@ def regcn_train_steps(sd, graphs, num_rels, triples, layer_norm=True, steps=1, t
                 p -= (lr / (1 - betas[0] ** step)) * m[k] / denom
             for k, s in stats.items():
                 P[k] = s
-        log.append({"losses": (float(loss_e), float(loss_r)), "grad_norm": float(total),
+        log.append({"losses": (float(loss_e.detach()), float(loss_r.detach())), "grad_norm": float(total),
                     "grads": {k: g.detach().clone() for k, g in grads.items()},
                     "params": {k: P[k].detach().clone() for k in grads}})
     return log, {k: v.detach() for k, v in P.items() if "running_" in k}

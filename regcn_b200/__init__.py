@@ -14,6 +14,7 @@ from .hyperbolic_decoder import (HyperbolicConvTransE, HyperbolicConvTransR, Hyp
                                  HyperbolicMuRPRel, HyperbolicRotH, HyperbolicRotHRel)
 from .hyperbolic_model import HyperbolicRecurrentRGCN  # noqa: F401
 from . import utils  # noqa: F401
+from . import knowledge_graph  # noqa: F401  (on-disk TKG format reader)
 from . import optim, train  # noqa: F401  (training step: get_loss with gradients + clipped Adam)
 from .evaluate import test  # noqa: F401  (the reference's evaluation loop, src/main.py:33)
 

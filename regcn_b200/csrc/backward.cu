@@ -57,19 +57,15 @@ __device__ __forceinline__ float masked(float g, const float* Z, size_t i, int m
 //   * relation mean-pool backward (src/rrgcn.py:161-166): rows = entities, columns = relations, col2_off = R;
 //   * decoder gathers E[s], rel[r] backward (src/decoder.py:81-82): rows = table rows, columns = query ids.
 // =====================================================================================================
+// Long rows (hub entities of a Zipf-shaped snapshot, popular relations) are finished by the whole CTA: every warp first
+// sums the leading kGatherHead columns of its own row; the tails of the CTA's 8 rows are then split 32 columns at a
+// time over the 8 warps and folded through shared memory in warp order -- still a fixed summation order.
+constexpr int kGatherHead = 64;
 template <int RV>
-__global__ void __launch_bounds__(256) csr_gather_sum_kernel(const float* __restrict__ X, int ldx,
-                                                             const float* __restrict__ col_w,
-                                                             const float* __restrict__ row_w,
-                                                             const int* __restrict__ rowptr, const int* __restrict__ col,
-                                                             int nrows, int d, int col2_off, float* __restrict__ out,
-                                                             int ldo, int accumulate) {
-  pdl_grid_sync();
-  ROW_PROLOGUE(nrows)
-  WarpRow<RV> acc;
-  acc.zero();
-  const int b = __ldg(rowptr + row), e = __ldg(rowptr + row + 1);
-  for (int j0 = b; j0 < e; j0 += 32) {
+__device__ __forceinline__ void gather_span(WarpRow<RV>& acc, const float* __restrict__ X, int ldx,
+                                            const float* __restrict__ col_w, const int* __restrict__ col, int j0, int e,
+                                            int stride, int nvec, int lane, int col2_off) {
+  for (; j0 < e; j0 += stride) {
     const int n = min(32, e - j0);
     int c = 0;
     float w = 0.f;
@@ -92,6 +88,46 @@ __global__ void __launch_bounds__(256) csr_gather_sum_kernel(const float* __rest
       }
     }
   }
+}
+
+template <int RV>
+__global__ void __launch_bounds__(256) csr_gather_sum_kernel(const float* __restrict__ X, int ldx,
+                                                             const float* __restrict__ col_w,
+                                                             const float* __restrict__ row_w,
+                                                             const int* __restrict__ rowptr, const int* __restrict__ col,
+                                                             int nrows, int d, int col2_off, float* __restrict__ out,
+                                                             int ldo, int accumulate) {
+  pdl_grid_sync();
+  __shared__ float4 part[8][32 * RV];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int row0 = blockIdx.x * 8;
+  const int row = row0 + wid;
+  const int nvec = d >> 2;
+  WarpRow<RV> acc;
+  acc.zero();
+  if (row < nrows) {
+    const int b = __ldg(rowptr + row), e = __ldg(rowptr + row + 1);
+    gather_span(acc, X, ldx, col_w, col, b, min(e, b + kGatherHead), 32, nvec, lane, col2_off);
+  }
+  for (int rr = 0; rr < 8; ++rr) {                        // block-uniform loop: the tails of this CTA's rows
+    if (row0 + rr >= nrows) break;
+    const int b2 = __ldg(rowptr + row0 + rr) + kGatherHead, e2 = __ldg(rowptr + row0 + rr + 1);
+    if (e2 <= b2) continue;
+    WarpRow<RV> p;
+    p.zero();
+    gather_span(p, X, ldx, col_w, col, b2 + 32 * wid, e2, 32 * 8, nvec, lane, col2_off);
+#pragma unroll
+    for (int i = 0; i < RV; ++i) part[wid][lane + i * kWarp] = p.v[i];
+    __syncthreads();
+    if (wid == rr) {
+#pragma unroll
+      for (int w = 0; w < 8; ++w)
+#pragma unroll
+        for (int i = 0; i < RV; ++i) acc.v[i] = f4_add(acc.v[i], part[w][lane + i * kWarp]);
+    }
+    __syncthreads();
+  }
+  if (row >= nrows) return;
   if (row_w) acc.scale(__ldg(row_w + row));
   float* o = out + (size_t)row * ldo;
   if (accumulate) {

@@ -48,6 +48,12 @@ def split_by_time(data):
     return snapshot_list
 
 
+def load_data(dataset, data_dir="../data"):
+    """rgcn/utils.py:356-365 (temporal datasets)."""
+    from . import knowledge_graph as knwlgrh
+    return knwlgrh.load_data(dataset, data_dir)
+
+
 def load_all_answers_for_time_filter(total_data, num_rels, num_nodes, rel_p=False):
     """rgcn/utils.py:286-304."""
     return [load_all_answers_for_filter(snap, num_rels, rel_p) for snap in split_by_time(total_data)]

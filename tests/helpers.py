@@ -55,13 +55,16 @@ def close(a, b, rtol=1e-4, atol_scale=1.0):
     return bool(np.all(ratio <= 1.0)), float(ratio.max()) if ratio.size else 0.0
 
 
-def grad_close(g, g_ref, total_norm, rtol=2e-4):
+def grad_close(g, g_ref, total_norm, rtol=2e-4, kink_floor=0.0):
     """Gradient parity gate: |g - g_ref| <= rtol * max(max|g_ref|, 1e-3 * total gradient norm) elementwise.  The floor
     covers gradients that are analytically zero (e.g. a bias in front of a BatchNorm) and differ only by rounding noise.
     Returns (ok, worst ratio)."""
     g = np.asarray(g, dtype=np.float64).reshape(-1)
     g_ref = np.asarray(g_ref, dtype=np.float64).reshape(-1)
     tol = rtol * max(float(np.max(np.abs(g_ref))) if g_ref.size else 0.0, 1e-3 * float(total_norm))
+    # kink_floor (whole-model steps only): a ReLU input within rounding of zero flips its mask between two correct fp32
+    # implementations and moves a per-channel sum (BatchNorm / conv parameter gradients) by one whole term
+    tol = max(tol, kink_floor * float(total_norm))
     worst = float(np.max(np.abs(g - g_ref)) / tol) if g.size else 0.0
     return worst <= 1.0, worst
 
@@ -73,7 +76,8 @@ def sample_of(x, n=1024):
     return flat[::step][:n]
 
 
-def compare_train_step(z, name, step, losses, grad_norm, grads, params, lr=1e-3, loss_rtol=2e-5, rtol=2e-4):
+def compare_train_step(z, name, step, losses, grad_norm, grads, params, lr=1e-3, loss_rtol=2e-5, rtol=2e-4,
+                       kink_floor=2e-5):
     """One optimisation step against tests/golden/train_regcn.npz (the UNMODIFIED reference, oracle/gen_golden.py
     --train).  grads / params: {parameter name: full numpy array} (raw, un-clipped gradients; values after the update).
 
@@ -96,7 +100,7 @@ def compare_train_step(z, name, step, losses, grad_norm, grads, params, lr=1e-3,
         gn_ref = float(z[f"{name}.s{step}.gn.{k}"])
         gn = float(np.linalg.norm(np.asarray(grads[k], dtype=np.float64)))
         if step == 0:
-            ok, worst = grad_close(g, g_ref, tn, rtol)
+            ok, worst = grad_close(g, g_ref, tn, rtol, kink_floor)
             worst_all = max(worst_all, worst)
             assert ok, (k, "gradient", worst)
             assert abs(gn - gn_ref) <= 5e-4 * gn_ref + 1e-6 * tn, (k, gn, gn_ref)

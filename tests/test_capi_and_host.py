@@ -113,3 +113,49 @@ def test_state_dict_names_match_reference_listing():
         assert k in sd, k
     assert tuple(sd["rgcn.layers.0.weight"].shape) == (100, 400)
     assert tuple(sd["decoder_ob.rot_proj.weight"].shape) == (100, 200)
+
+
+def test_dataset_reader_round_trip(tmp_path):
+    """The reference's on-disk format (rgcn/knowledge_graph.py:189-206,526-555): write a tiny dataset, read it back
+    through load_data, cut it with split_by_time; compared with the reference's own reader when it is present."""
+    from regcn_b200 import knowledge_graph, utils
+    rng = np.random.default_rng(3)
+    root = tmp_path / "data"
+    d = root / "SMALL"
+    d.mkdir(parents=True)
+    (d / "entity2id.txt").write_text("".join(f"ent {i}\t{i}\n" for i in range(30)))
+    (d / "relation2id.txt").write_text("".join(f"rel_{i}\t{i}\n" for i in range(5)))
+    quads = {}
+    t0 = 0
+    for split, n in (("train", 80), ("valid", 20), ("test", 25)):
+        q = np.stack([rng.integers(0, 30, n), rng.integers(0, 5, n), rng.integers(0, 30, n),
+                      t0 + np.sort(rng.integers(0, 4, n)) * 24, np.zeros(n, dtype=np.int64)], 1)
+        t0 = int(q[-1, 3]) + 24
+        quads[split] = q
+        (d / f"{split}.txt").write_text("".join("\t".join(str(int(v)) for v in row) + "\n" for row in q))
+    data = utils.load_data("SMALL", str(root))
+    assert (data.num_nodes, data.num_rels) == (30, 5)
+    assert data.entity_dict[7] == "ent 7" and data.relation_dict[4] == "rel_4"
+    for split in ("train", "valid", "test"):
+        got = getattr(data, split)
+        assert got.dtype == np.int64 and np.array_equal(got, quads[split][:, :4])
+    snaps = utils.split_by_time(data.train)
+    assert sum(len(s) for s in snaps) == 80
+    with pytest.raises(ValueError):
+        utils.load_data("FB15k", str(root))
+    with pytest.raises(ValueError):
+        knowledge_graph.RGCNLinkDataset("SMALL")
+    ref_root = os.environ.get("REGCN_REFERENCE", "/root/reference")
+    if os.path.isdir(ref_root):                      # build container only: the reference's own reader on the same files
+        import sys
+        from oracle import fake_dgl
+        fake_dgl.install()
+        sys.path.insert(0, ref_root)
+        try:
+            from rgcn import knowledge_graph as ref_kg
+            ref = ref_kg.load_from_local(str(root), "SMALL")
+        finally:
+            sys.path.remove(ref_root)
+        assert (ref.num_nodes, ref.num_rels) == (data.num_nodes, data.num_rels)
+        for split in ("train", "valid", "test"):
+            assert np.array_equal(np.asarray(getattr(ref, split)), getattr(data, split))

@@ -279,7 +279,8 @@ def test_train_steps_match_reference(name, shape, seed, ln):
         params = {k: p.detach().cpu().numpy().copy() for k, p in named.items()}
         opt.zero_grad()
         # single nodes hold 2e-4 (tests above); the whole chain (~45 3xTF32 GEMMs deep, un-normalised in the noln case)
-        # is gated at 5e-4 of each gradient's largest element -- measured worst on B200: 3.3e-4
+        # is gated at 5e-4 of each gradient's largest element (measured against the fp64 oracle on B200: <= 5e-4 where
+        # no ReLU mask flips; see helpers.grad_close for the kink floor of 2e-5 of the total gradient norm)
         compare_train_step(z, name, step, (float(le), float(lr_)), float(opt.total_norm), grads, params, rtol=5e-4)
     sd = m.state_dict()
     for k in z.files:
