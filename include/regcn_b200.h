@@ -389,6 +389,20 @@ REGCN_API int regcn_grad_norm(const float* g, size_t n, float* total_norm, void*
 REGCN_API int regcn_adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2,
                     float eps, float weight_decay, int step, float max_norm, const float* total_norm, void* stream);
 
+/* Static-graph constraint in training (src/rrgcn.py:101-106,146-152,225-247): RGCNBlockLayer backward (dh over the
+ * forward CSR with inverse relation types; dW over edges grouped by type: type_rowptr (R2+1), type_src / type_dst) and
+ * the angle loss: term[row] = weight * max(cos_step - sim(row), 0) per history step, and its gradient.            */
+REGCN_API size_t regcn_block_aggregate_bwd_workspace_bytes(int R2, int d_in, int d_out, int num_bases);
+REGCN_API int regcn_block_aggregate_bwd(const float* h, const float* dAgg, const float* W, const int32_t* rowptr,
+                              const int32_t* src_sorted, const int32_t* etype_sorted, const float* norm,
+                              const int32_t* type_rowptr, const int32_t* type_src, const int32_t* type_dst, int N, int R2,
+                              int d_in, int d_out, int num_bases, float* dh, float* dW, float* workspace,
+                              size_t workspace_bytes, void* stream);
+REGCN_API int regcn_static_angle_fwd(const float* S, const float* E, int N, int d, float cos_step, float weight,
+                           int layer_norm, float* term, void* stream);
+REGCN_API int regcn_static_angle_bwd(const float* S, const float* E, int N, int d, float cos_step, float weight,
+                           int layer_norm, const float* gscale, float* dS, int accumulate_dS, float* dE, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -233,11 +233,81 @@ def run_train(ref_utils, RecurrentRGCN):
     print("->", path, os.path.getsize(path) / 1e6, "MB")
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# static-graph constraint golden (src/rrgcn.py:101-106,146-152,225-247): predict + eval losses + one training step
+# ---------------------------------------------------------------------------------------------------------------
+STATIC_CASES = {
+    "static_tiny_s0": dict(shape="tiny", seed=0, layer_norm=True, discount=1, angle=10, weight=0.5),
+    "static_tiny_s1_noln": dict(shape="tiny", seed=1, layer_norm=False, discount=0, angle=10, weight=1.0),
+    "static_small_s2": dict(shape="small", seed=2, layer_norm=True, discount=1, angle=10, weight=0.5),
+}
+
+
+def build_static_reference_model(cfg, n, r, n_srel, n_words, RecurrentRGCN, dropout=0.0):
+    m = RecurrentRGCN("convtranse", "uvrgcn", n, r, n_srel, n_words, H_DIM, "sub", 3, num_bases=N_BASES, num_basis=-1,
+                      num_hidden_layers=N_LAYERS, dropout=dropout, self_loop=True, skip_connect=False,
+                      layer_norm=cfg["layer_norm"], input_dropout=dropout, hidden_dropout=dropout, feat_dropout=dropout,
+                      weight=cfg["weight"], discount=cfg["discount"], angle=cfg["angle"], use_static=True,
+                      entity_prediction=True, relation_prediction=True, use_cuda=False, gpu="cpu")
+    m.load_state_dict(synth.fill_state_dict(m.state_dict(), cfg["seed"]))
+    return m
+
+
+def run_static(ref_utils, RecurrentRGCN):
+    """tests/golden/train_static_regcn.npz: the UNMODIFIED reference with --add-static-graph semantics."""
+    out = {}
+    for name, cfg in STATIC_CASES.items():
+        case = synth.make_case(cfg["shape"], cfg["seed"])
+        n, r = case["num_ents"], case["num_rels"]
+        st, n_srel, n_words = synth.make_static(n, cfg["seed"])
+        m = build_static_reference_model(cfg, n, r, n_srel, n_words, RecurrentRGCN)
+        m.gpu = "cpu"
+        sg = ref_utils.build_sub_graph(n + n_words, n_srel, st, False, "cpu")
+        glist = [ref_utils.build_sub_graph(n, r, snap, False, "cpu") for snap in case["history"]]
+        triples = torch.from_numpy(case["test"])
+        m.eval()
+        with torch.no_grad():
+            all_t, score, score_rel = m.predict(glist, r, sg, triples, False)
+            hist, static_emb, h0, _, _ = m.forward(glist, sg, False)
+            losses = m.get_loss(glist, triples.clone(), sg, False)
+        out[f"{name}.score"] = score.numpy()
+        out[f"{name}.score_rel"] = score_rel.numpy()
+        out[f"{name}.static_emb"] = static_emb.numpy()
+        out[f"{name}.hist_last"] = hist[-1].numpy()
+        out[f"{name}.eval_losses"] = np.array([float(x.reshape(-1)[0]) for x in losses], dtype=np.float64)
+        # one optimisation step (dropout 0), as in run_train
+        m.train()
+        torch.Tensor.cuda = lambda self, *a, **k: (self.clone() if (self.requires_grad and self.is_leaf) else self)
+        opt = torch.optim.Adam(m.parameters(), lr=LR, weight_decay=WEIGHT_DECAY)
+        le, lr_, ls = m.get_loss(glist, triples.clone(), sg, True)
+        loss = TASK_WEIGHT * le + (1 - TASK_WEIGHT) * lr_ + ls
+        loss.backward()
+        tn = torch.nn.utils.clip_grad_norm_(m.parameters(), GRAD_NORM)
+        coef = min(1.0, GRAD_NORM / (float(tn) + 1e-6))
+        grads = {k: (None if p.grad is None else p.grad.detach().clone()) for k, p in m.named_parameters()}
+        opt.step()
+        out[f"{name}.s0.losses"] = np.array([float(le.detach()), float(lr_.detach()), float(ls.detach())], dtype=np.float64)
+        out[f"{name}.s0.grad_norm"] = np.array(float(tn), dtype=np.float64)
+        for k, p in m.named_parameters():
+            if grads[k] is None:
+                continue
+            g = grads[k].numpy() / coef
+            out[f"{name}.s0.gn.{k}"] = np.array(np.linalg.norm(g.astype(np.float64)))
+            out[f"{name}.s0.g.{k}"] = sample_of(g)
+            out[f"{name}.s0.p.{k}"] = sample_of(p.detach().numpy())
+        print(name, "eval losses", out[f"{name}.eval_losses"], "train losses", out[f"{name}.s0.losses"], "grad norm", float(tn))
+    path = os.path.join(GOLDEN, "train_static_regcn.npz")
+    np.savez_compressed(path, **out)
+    print("->", path, os.path.getsize(path) / 1e6, "MB")
+
+
 def main(argv):
     ref_utils, RecurrentRGCN, HyperbolicRecurrentRGCN = _import_reference()
     torch.set_num_threads(os.cpu_count() or 1)
     if len(argv) > 1 and argv[1] == "--losses":
         return run_losses(ref_utils, RecurrentRGCN, HyperbolicRecurrentRGCN)
+    if len(argv) > 1 and argv[1] == "--static":
+        return run_static(ref_utils, RecurrentRGCN)
     if len(argv) > 1 and argv[1] == "--train":
         return run_train(ref_utils, RecurrentRGCN)
     names = argv[1:] or list(CASES)

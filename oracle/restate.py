@@ -136,12 +136,36 @@ def block_layer(h, g, weight, num_bases, out_feat):
     return rrelu(agg)
 
 
+def regcn_static_emb(P, sg, num_ents, num_bases, layer_norm):
+    """src/rrgcn.py:146-152: RGCNBlockLayer over the entity-word graph on cat(dynamic_emb, words_emb), entity rows,
+    F.normalize when layer_norm.  (No dropout on this layer: RGCNLayer only drops the self-loop message, :52-53.)"""
+    x = torch.cat((P["dynamic_emb"], P["words_emb"]), dim=0)
+    out = block_layer(x, sg, P["statci_rgcn_layer.weight"], num_bases, x.shape[1])[:num_ents]
+    return normalize_rows(out) if layer_norm else out
+
+
+def static_angle_loss(static_emb, hist, layer_norm, angle, discount, weight):
+    """src/rrgcn.py:225-247."""
+    loss = static_emb.new_zeros(())
+    for t, e in enumerate(hist):
+        step = (angle * math.pi / 180) * ((t + 1) if discount == 1 else 1)
+        if layer_norm:
+            sim = (static_emb * normalize_rows(e)).sum(dim=1)
+        else:
+            sim = (static_emb * e).sum(dim=1) / (static_emb.norm(dim=1) * e.norm(dim=1))
+        v = math.cos(step) - sim
+        loss = loss + weight * v[v > 0].sum()
+    return loss
+
+
 def regcn_forward(p, graphs, num_rels, layer_norm=True, n_layers=2, self_loop=True, dtype=torch.float32,
-                  trace=None):
+                  trace=None, h_init=None):
     """src/rrgcn.py:142-180 (RecurrentRGCN.forward, use_static=False).  p: state dict (reference names).
     Returns (history_embs, h_0).  `trace` (dict) collects intermediates for per-kernel parity tests."""
     P = {k: v.to(dtype) for k, v in p.items() if v.is_floating_point()}
     h = normalize_rows(P["dynamic_emb"]) if layer_norm else P["dynamic_emb"]
+    if h_init is not None:
+        h = h_init                                  # use_static: the static embedding replaces it (src/rrgcn.py:152)
     emb_rel = P["emb_rel"]
     h0 = None
     hist = []
@@ -684,21 +708,29 @@ def conv_tower_train(first, second, P, pre, stats):
     return torch.relu(x)
 
 
-def regcn_train_losses(P, graphs, num_rels, triples, layer_norm, stats, n_layers=2):
-    """(loss_ent, loss_rel) with the autograd tape on; P holds leaf tensors (parameters) and buffers."""
+def regcn_train_losses(P, graphs, num_rels, triples, layer_norm, stats, n_layers=2, static=None):
+    """(loss_ent, loss_rel[, loss_static]) with the autograd tape on; P holds leaf tensors (parameters) and buffers.
+    static = dict(graph, num_ents, num_bases, angle, discount, weight) switches the static-graph constraint on."""
     all_t = torch.as_tensor(add_inverse(triples, num_rels))
-    hist, h0 = regcn_forward(P, graphs, num_rels, layer_norm=layer_norm, n_layers=n_layers, dtype=P["emb_rel"].dtype)
+    s_emb = None
+    if static is not None:
+        s_emb = regcn_static_emb(P, static["graph"], static["num_ents"], static["num_bases"], layer_norm)
+    hist, h0 = regcn_forward(P, graphs, num_rels, layer_norm=layer_norm, n_layers=n_layers, dtype=P["emb_rel"].dtype,
+                             h_init=s_emb)
     emb = normalize_rows(hist[-1]) if layer_norm else hist[-1]
     e_all = torch.tanh(emb)
     q = conv_tower_train(e_all[all_t[:, 0]], h0[all_t[:, 1]], P, "decoder_ob.", stats)
     loss_e = cross_entropy(q @ e_all.t(), all_t[:, 2])
     q = conv_tower_train(e_all[all_t[:, 0]], e_all[all_t[:, 2]], P, "rdecoder.", stats)
     loss_r = cross_entropy(q @ h0.t(), all_t[:, 1])
+    if static is not None:
+        return loss_e, loss_r, static_angle_loss(s_emb, hist, layer_norm, static["angle"], static["discount"],
+                                                 static["weight"])
     return loss_e, loss_r
 
 
 def regcn_train_steps(sd, graphs, num_rels, triples, layer_norm=True, steps=1, task_weight=0.7, grad_norm=1.0,
-                      lr=1e-3, weight_decay=1e-5, betas=(0.9, 0.999), eps=1e-8, dtype=torch.float32):
+                      lr=1e-3, weight_decay=1e-5, betas=(0.9, 0.999), eps=1e-8, dtype=torch.float32, static=None):
     """`steps` optimisation steps (loss.backward, clip_grad_norm_, torch.optim.Adam with L2 weight decay) on the same
     batch.  Returns a list of per-step dicts {losses, grad_norm, grads{name}, params{name}} and the final buffers."""
     P = {}
@@ -714,8 +746,11 @@ def regcn_train_steps(sd, graphs, num_rels, triples, layer_norm=True, steps=1, t
     log = []
     for step in range(1, steps + 1):
         stats = {}
-        loss_e, loss_r = regcn_train_losses(P, graphs, num_rels, triples, layer_norm, stats)
+        ls = regcn_train_losses(P, graphs, num_rels, triples, layer_norm, stats, static=static)
+        loss_e, loss_r = ls[0], ls[1]
         loss = task_weight * loss_e + (1 - task_weight) * loss_r
+        if static is not None:
+            loss = loss + ls[2]
         names = [k for k, v in P.items() if v.requires_grad]
         gs = torch.autograd.grad(loss, [P[k] for k in names], allow_unused=True)
         grads = {k: g for k, g in zip(names, gs) if g is not None}
@@ -731,7 +766,7 @@ def regcn_train_steps(sd, graphs, num_rels, triples, layer_norm=True, steps=1, t
                 p -= (lr / (1 - betas[0] ** step)) * m[k] / denom
             for k, s in stats.items():
                 P[k] = s
-        log.append({"losses": (float(loss_e.detach()), float(loss_r.detach())), "grad_norm": float(total),
+        log.append({"losses": tuple(float(x.detach()) for x in ls), "grad_norm": float(total),
                     "grads": {k: g.detach().clone() for k, g in grads.items()},
                     "params": {k: P[k].detach().clone() for k in grads}})
     return log, {k: v.detach() for k, v in P.items() if "running_" in k}

@@ -106,6 +106,10 @@ SIGNATURES = {
     "regcn_adam_workspace_bytes": (_sz, []),
     "regcn_grad_norm": (_i, [_p, _sz, _p, _p, _sz, _p]),
     "regcn_adam_step": (_i, [_p, _p, _p, _p, _sz, _f, _f, _f, _f, _f, _i, _f, _p, _p]),
+    "regcn_block_aggregate_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "regcn_block_aggregate_bwd": (_i, [_p] * 10 + [_i, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),
+    "regcn_static_angle_fwd": (_i, [_p, _p, _i, _i, _f, _f, _i, _p, _p]),
+    "regcn_static_angle_bwd": (_i, [_p, _p, _i, _i, _f, _f, _i, _p, _p, _i, _p, _p]),
 }
 
 

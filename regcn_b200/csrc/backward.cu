@@ -1006,6 +1006,171 @@ int adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, 
   return check_launch("adam_step");
 }
 
+// =====================================================================================================
+// Static-graph constraint: RGCNBlockLayer backward (rgcn/layers.py:147-179 through
+// RGCNLayer.forward :48-91, static configuration of src/rrgcn.py:101-106,146-152) and the angle loss (:225-247).
+// =====================================================================================================
+// dh[u] = sum_{in-edges (w->u, r')} norm[w] * dAgg[w]_b . W[inv(r')]_b^T : every edge (u->v, r) of the snapshot graph has
+// its inverse (v->u, r +- R) as an in-edge of u, so the forward CSR-by-destination serves again.
+__global__ void __launch_bounds__(256) block_aggregate_bwd_h_kernel(
+    const float* __restrict__ dAgg, const float* __restrict__ W, const int* __restrict__ rowptr,
+    const int* __restrict__ src_sorted, const int* __restrict__ etype_sorted, const float* __restrict__ norm, int N,
+    int d_in, int d_out, int nb, int R, float* __restrict__ dh) {
+  pdl_grid_sync();
+  const int lane = threadIdx.x & 31;
+  const int row = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+  if (row >= N) return;
+  const int si = d_in / nb, so = d_out / nb;
+  const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+  for (int j0 = 0; j0 < d_in; j0 += kWarp) {
+    const int j = j0 + lane;
+    if (j >= d_in) continue;
+    const int b = j / si, i = j - b * si;
+    float acc = 0.f;
+    for (int e = beg; e < end; ++e) {
+      const int w = __ldg(src_sorted + e), t = __ldg(etype_sorted + e);
+      const int ti = t < R ? t + R : t - R;
+      const float* gp = dAgg + (size_t)w * d_out + b * so;
+      const float* wp = W + (size_t)ti * ((size_t)nb * si * so) + ((size_t)b * si + i) * so;
+      float m = 0.f;
+      for (int o = 0; o < so; ++o) m = fmaf(gp[o], __ldg(wp + o), m);
+      acc = fmaf(__ldg(norm + w), m, acc);
+    }
+    dh[(size_t)row * d_in + j] = acc;
+  }
+}
+// dW[r]_b[i][o] = sum_{e: type r} norm[dst] h[src]_{b,i} dAgg[dst]_{b,o}; CTA = (relation, split of its edge list),
+// partial (nsplit, R2*wsz) summed afterwards by col_sum (fixed order).
+__global__ void __launch_bounds__(256) block_aggregate_bwd_w_kernel(
+    const float* __restrict__ h, const float* __restrict__ dAgg, const int* __restrict__ type_rowptr,
+    const int* __restrict__ type_src, const int* __restrict__ type_dst, const float* __restrict__ norm, int d_in,
+    int d_out, int nb, int nsplit, int R2, float* __restrict__ partial) {
+  pdl_grid_sync();
+  const int r = blockIdx.x, sp = blockIdx.y;
+  const int si = d_in / nb, so = d_out / nb;
+  const int wsz = nb * si * so;
+  const int tb = __ldg(type_rowptr + r), te = __ldg(type_rowptr + r + 1);
+  const int per = (te - tb + nsplit - 1) / nsplit;
+  const int e0 = tb + sp * per, e1 = min(te, e0 + per);
+  for (int idx = threadIdx.x; idx < wsz; idx += blockDim.x) {
+    const int b = idx / (si * so), rem = idx - b * si * so;
+    const int i = rem / so, o = rem - i * so;
+    float acc = 0.f;
+    for (int e = e0; e < e1; ++e) {
+      const int sr = __ldg(type_src + e), ds = __ldg(type_dst + e);
+      acc = fmaf(__ldg(norm + ds) * h[(size_t)sr * d_in + b * si + i], dAgg[(size_t)ds * d_out + b * so + o], acc);
+    }
+    partial[((size_t)sp * R2 + r) * wsz + idx] = acc;
+  }
+}
+constexpr int kBlockWSplit = 16;
+size_t block_aggregate_bwd_w_workspace_bytes(int R2, int d_in, int d_out, int nb) {
+  const size_t wsz = (size_t)nb * (d_in / nb) * (d_out / nb);
+  return (size_t)kBlockWSplit * R2 * wsz * sizeof(float) + col_reduce_workspace_bytes(kBlockWSplit, (int)(R2 * wsz));
+}
+int block_aggregate_bwd(const float* h, const float* dAgg, const float* W, const int* rowptr, const int* src_sorted,
+                        const int* etype_sorted, const float* norm, const int* type_rowptr, const int* type_src,
+                        const int* type_dst, int N, int R2, int d_in, int d_out, int nb, float* dh, float* dW, float* ws,
+                        size_t ws_bytes, cudaStream_t st) {
+  if (!h || !dAgg || !W || !rowptr || !src_sorted || !etype_sorted || !norm) { set_last_error("block_aggregate_bwd: null pointer"); return REGCN_ERR_NULL; }
+  if (nb <= 0 || d_in % nb || d_out % nb || (R2 & 1)) { set_last_error("block_aggregate_bwd: bad num_bases / relation count"); return REGCN_ERR_UNSUPPORTED; }
+  if (N <= 0) return REGCN_OK;
+  if (dh) launch_k(block_aggregate_bwd_h_kernel, rgrid(N), 256, 0, st, dAgg, W, rowptr, src_sorted, etype_sorted, norm, N, d_in, d_out, nb, R2 / 2, dh);
+  if (dW) {
+    if (!type_rowptr || !type_src || !type_dst || !ws) { set_last_error("block_aggregate_bwd: null pointer"); return REGCN_ERR_NULL; }
+    if (ws_bytes < block_aggregate_bwd_w_workspace_bytes(R2, d_in, d_out, nb)) { set_last_error("block_aggregate_bwd: workspace too small"); return REGCN_ERR_WORKSPACE; }
+    const int wsz = nb * (d_in / nb) * (d_out / nb);
+    float* partial = ws;
+    float* ws2 = ws + (size_t)kBlockWSplit * R2 * wsz;
+    dim3 grid((unsigned)R2, (unsigned)kBlockWSplit);
+    launch_k(block_aggregate_bwd_w_kernel, grid, 256, 0, st, h, dAgg, type_rowptr, type_src, type_dst, norm, d_in, d_out, nb, (int)kBlockWSplit, R2, partial);
+    return col_sum(partial, R2 * wsz, kBlockWSplit, R2 * wsz, 1, dW, 0, ws2, ws_bytes - (size_t)kBlockWSplit * R2 * wsz * sizeof(float), st);
+  }
+  return check_launch("block_aggregate_bwd");
+}
+
+// Angle loss term of one history step (src/rrgcn.py:225-247): sim = <s, e/|e|> (layer_norm) or <s,e>/(|s||e|);
+// term[row] = weight * max(cos_step - sim, 0).  The caller sums the (L*N) terms with col_sum.
+template <int RV>
+__global__ void __launch_bounds__(256) static_angle_fwd_kernel(const float* __restrict__ S, const float* __restrict__ E,
+                                                               int N, int d, float cos_step, float weight,
+                                                               int layer_norm, float* __restrict__ term) {
+  pdl_grid_sync();
+  ROW_PROLOGUE(N)
+  WarpRow<RV> s, e;
+  s.load_plain(S + (size_t)row * d, nvec, lane);
+  e.load_plain(E + (size_t)row * d, nvec, lane);
+  float sim;
+  if (layer_norm) {
+    row_l2normalize(e);
+    sim = s.dot(e);
+  } else {
+    const float c = sqrtf(s.sumsq()) * sqrtf(e.sumsq());
+    sim = s.dot(e) / c;
+  }
+  const float v = cos_step - sim;
+  if (lane == 0) term[row] = v > 0.f ? weight * v : 0.f;
+}
+// dS (+)= -w m ehat (through normalize(s) when not layer_norm), dE = normalize_bwd(e, -w m shat); m = [cos - sim > 0]
+template <int RV>
+__global__ void __launch_bounds__(256) static_angle_bwd_kernel(const float* __restrict__ S, const float* __restrict__ E,
+                                                               int N, int d, float cos_step, float weight,
+                                                               int layer_norm, const float* __restrict__ gscale,
+                                                               float* __restrict__ dS, int accumulate_dS,
+                                                               float* __restrict__ dE) {
+  pdl_grid_sync();
+  ROW_PROLOGUE(N)
+  WarpRow<RV> s, e;
+  s.load_plain(S + (size_t)row * d, nvec, lane);
+  e.load_plain(E + (size_t)row * d, nvec, lane);
+  WarpRow<RV> eh = e, sh = s;
+  row_l2normalize(eh);
+  float sim;
+  if (layer_norm) sim = s.dot(eh);
+  else { sh.scale(1.0f / sqrtf(s.sumsq())); eh = e; eh.scale(1.0f / sqrtf(e.sumsq())); sim = sh.dot(eh); }
+  const float g = (cos_step - sim > 0.f) ? -weight * (gscale ? *gscale : 1.0f) : 0.f;
+  WarpRow<RV> gs = eh, ge = sh;                // d sim / d s(hat) = ehat, d sim / d ehat = s(hat)
+  gs.scale(g);
+  ge.scale(g);
+  if (!layer_norm) {                            // s enters through s/|s| (no clamp in the reference: plain division)
+    const float n = sqrtf(s.sumsq());
+    const float dotv = sh.dot(gs);
+    gs.zip(sh, [=](float a, float y) { return (a - y * dotv) / n; });
+    const float ne = sqrtf(e.sumsq());
+    const float dote = eh.dot(ge);
+    ge.zip(eh, [=](float a, float y) { return (a - y * dote) / ne; });
+  } else {
+    row_normalize_bwd(e, ge);
+    ge = e;
+  }
+  float* ds = dS + (size_t)row * d;
+  if (accumulate_dS) {
+    WarpRow<RV> prev;
+    prev.load_plain(ds, nvec, lane);
+    gs.zip(prev, [](float a, float p) { return a + p; });
+  }
+  gs.store(ds, nvec, lane);
+  ge.store(dE + (size_t)row * d, nvec, lane);
+}
+int static_angle_fwd(const float* S, const float* E, int N, int d, float cos_step, float weight, int layer_norm,
+                     float* term, cudaStream_t st) {
+  if (!S || !E || !term) { set_last_error("static_angle_fwd: null pointer"); return REGCN_ERR_NULL; }
+  if (int e = chk_d("static_angle_fwd", d)) return e;
+  if (N <= 0) return REGCN_OK;
+  if (d <= 128) launch_k(static_angle_fwd_kernel<1>, rgrid(N), 256, 0, st, S, E, N, d, cos_step, weight, layer_norm, term);
+  else launch_k(static_angle_fwd_kernel<2>, rgrid(N), 256, 0, st, S, E, N, d, cos_step, weight, layer_norm, term);
+  return check_launch("static_angle_fwd");
+}
+int static_angle_bwd(const float* S, const float* E, int N, int d, float cos_step, float weight, int layer_norm,
+                     const float* gscale, float* dS, int accumulate_dS, float* dE, cudaStream_t st) {
+  if (!S || !E || !dS || !dE) { set_last_error("static_angle_bwd: null pointer"); return REGCN_ERR_NULL; }
+  if (int e = chk_d("static_angle_bwd", d)) return e;
+  if (N <= 0) return REGCN_OK;
+  if (d <= 128) launch_k(static_angle_bwd_kernel<1>, rgrid(N), 256, 0, st, S, E, N, d, cos_step, weight, layer_norm, gscale, dS, accumulate_dS, dE);
+  else launch_k(static_angle_bwd_kernel<2>, rgrid(N), 256, 0, st, S, E, N, d, cos_step, weight, layer_norm, gscale, dS, accumulate_dS, dE);
+  return check_launch("static_angle_bwd");
+}
+
 }  // namespace regcn
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1111,5 +1276,24 @@ int regcn_grad_norm(const float* g, size_t n, float* total_norm, void* workspace
 int regcn_adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps,
                     float weight_decay, int step, float max_norm, const float* total_norm, void* stream) {
   return adam_step(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, max_norm, total_norm, ST(stream));
+}
+size_t regcn_block_aggregate_bwd_workspace_bytes(int R2, int d_in, int d_out, int num_bases) {
+  return block_aggregate_bwd_w_workspace_bytes(R2, d_in, d_out, num_bases);
+}
+int regcn_block_aggregate_bwd(const float* h, const float* dAgg, const float* W, const int32_t* rowptr,
+                              const int32_t* src_sorted, const int32_t* etype_sorted, const float* norm,
+                              const int32_t* type_rowptr, const int32_t* type_src, const int32_t* type_dst, int N, int R2,
+                              int d_in, int d_out, int num_bases, float* dh, float* dW, float* workspace,
+                              size_t workspace_bytes, void* stream) {
+  return block_aggregate_bwd(h, dAgg, W, rowptr, src_sorted, etype_sorted, norm, type_rowptr, type_src, type_dst, N, R2,
+                             d_in, d_out, num_bases, dh, dW, workspace, workspace_bytes, ST(stream));
+}
+int regcn_static_angle_fwd(const float* S, const float* E, int N, int d, float cos_step, float weight, int layer_norm,
+                           float* term, void* stream) {
+  return static_angle_fwd(S, E, N, d, cos_step, weight, layer_norm, term, ST(stream));
+}
+int regcn_static_angle_bwd(const float* S, const float* E, int N, int d, float cos_step, float weight, int layer_norm,
+                           const float* gscale, float* dS, int accumulate_dS, float* dE, void* stream) {
+  return static_angle_bwd(S, E, N, d, cos_step, weight, layer_norm, gscale, dS, accumulate_dS, dE, ST(stream));
 }
 }  // extern "C"

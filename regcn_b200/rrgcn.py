@@ -118,18 +118,20 @@ class RecurrentRGCN(nn.Module):
 
     # ------------------------------------------------------------------ whole-recurrence fast path
     def _engine_ok(self):
-        return (ops.gemm_impl() == "tc" and not self.use_static and self.rgcn.self_loop and not self.rgcn.skip_connect
+        return (ops.gemm_impl() == "tc" and self.rgcn.self_loop and not self.rgcn.skip_connect
                 and self.encoder_name == "uvrgcn" and self.h_dim % 4 == 0 and self.h_dim <= 256)
 
-    def _engine_tables(self):
+    def _engine_tables(self, h_init=None):
         """Pointer / int tables of regcn_regcn_evolve (include/regcn_b200.h RM_* / RMI_*), rebuilt when any parameter
-        changes.  GEMM weights are stored K-major and TF32-split once here, never inside the recurrence."""
+        changes.  GEMM weights are stored K-major and TF32-split once here, never inside the recurrence.
+        h_init: persistent buffer holding the initial entity table instead of dynamic_emb (use_static)."""
         cell = self.relation_cell_1
-        params = [self.dynamic_emb, self.emb_rel, cell.weight_ih, cell.weight_hh, cell.bias_ih, cell.bias_hh,
+        params = [self.dynamic_emb if h_init is None else h_init, self.emb_rel, cell.weight_ih, cell.weight_hh, cell.bias_ih, cell.bias_hh,
                   self.time_gate_weight, self.time_gate_bias]
         for layer in self.rgcn.layers:
             params += [layer.weight_neighbor, layer.loop_weight, layer.evolve_loop_weight]
-        stamp = tuple((p._version, p.data_ptr()) for p in params)
+        # (the static buffer is rewritten before every call: only its address identifies it)
+        stamp = tuple((p._version if (i or h_init is None) else -1, p.data_ptr()) for i, p in enumerate(params))
         if getattr(self, "_engine_stamp", None) == stamp:
             return self._engine_tab
         import numpy as np
@@ -150,7 +152,7 @@ class RecurrentRGCN(nn.Module):
         wh_hi, wh_lo = split(cell.weight_hh)
         b_hh = cell.bias_hh.detach().contiguous()
         gate_b = self.time_gate_bias.detach().contiguous()
-        dyn = self.dynamic_emb.detach().contiguous()
+        dyn = self.dynamic_emb.detach().contiguous() if h_init is None else h_init
         keep += [emb_rel, gi_static, b_hh, gate_b, dyn]
         ptrs = [dyn, emb_rel, er_hi, er_lo, gi_static, wr_hi, wr_lo, wh_hi, wh_lo, b_hh, gate_b]
         for l, layer in enumerate(self.rgcn.layers):
@@ -169,10 +171,10 @@ class RecurrentRGCN(nn.Module):
         self._engine_stamp = stamp
         return self._engine_tab
 
-    def _forward_engine(self, g_list):
+    def _forward_engine(self, g_list, h_init=None):
         import numpy as np
         from . import _lib
-        ptab, itab, _ = self._engine_tables()
+        ptab, itab, _ = self._engine_tables(h_init)
         L = len(g_list)
         N, R2, d = self.num_ents, 2 * self.num_rels, self.h_dim
         dev = self.dynamic_emb.device
@@ -194,16 +196,27 @@ class RecurrentRGCN(nn.Module):
     @torch.no_grad()
     def forward(self, g_list, static_graph, use_cuda):
         gate_list, degree_list = [], []
-        if self._engine_ok() and len(g_list) > 0:
-            history_embs, self.h_0 = self._forward_engine(g_list)
-            self.h = history_embs[-1]
-            return history_embs, None, self.h_0, gate_list, degree_list
+        static_emb = None
         if self.use_static:
             static_graph = static_graph.to(self.gpu)
             static_graph.ndata['h'] = torch.cat((self.dynamic_emb, self.words_emb), dim=0).detach()
             self.statci_rgcn_layer(static_graph, [])
             static_emb = static_graph.ndata.pop('h')[:self.num_ents, :].contiguous()
             static_emb = ops.row_map(static_emb, ops.ROW_NORMALIZE) if self.layer_norm else static_emb
+        if self._engine_ok() and len(g_list) > 0:
+            h_init = None
+            if static_emb is not None:
+                # the engine reads its initial table through a fixed pointer: keep the static embedding in a persistent
+                # buffer (its row normalisation inside the engine is then idempotent, src/rrgcn.py:150-152)
+                buf = getattr(self, "_static_h", None)
+                if buf is None or buf.shape != static_emb.shape or buf.device != static_emb.device:
+                    buf = self._static_h = torch.empty_like(static_emb)
+                buf.copy_(static_emb)
+                h_init = buf
+            history_embs, self.h_0 = self._forward_engine(g_list, h_init)
+            self.h = history_embs[-1]
+            return history_embs, static_emb, self.h_0, gate_list, degree_list
+        if self.use_static:
             self.h = static_emb
         else:
             dyn = self.dynamic_emb.detach()
@@ -246,21 +259,19 @@ class RecurrentRGCN(nn.Module):
         scoring GEMM's streaming log-sum-exp epilogue (no (B,N) logits); the relation head materialises its (B,2R)
         scores (dropout off, BatchNorm running statistics)."""
         from . import evaluate
-        if self.use_static:
-            raise NotImplementedError("static-graph constraint loss (src/rrgcn.py:225-247) is SURVEY.md 8f rank 3")
         if not use_cuda:
             raise RuntimeError("regcn_b200: kernels take CUDA tensors only (no CPU fallback)")
         if self.training:
             from . import train
             with torch.enable_grad():
-                return train.regcn_get_loss(self, glist, triples)
+                return train.regcn_get_loss(self, glist, triples, static_graph)
         with torch.no_grad():
             dev = self.dynamic_emb.device
             triples = torch.as_tensor(triples).to(dev)
             inverse_triples = triples.flip(1)
             inverse_triples[:, 1] = inverse_triples[:, 1] + self.num_rels
             all_triples = torch.cat([triples, inverse_triples]).contiguous()
-            evolve_embs, _, r_emb, _, _ = self.forward(glist, static_graph, use_cuda)
+            evolve_embs, static_emb, r_emb, _, _ = self.forward(glist, static_graph, use_cuda)
             pre_emb = ops.row_map(evolve_embs[-1], ops.ROW_NORMALIZE) if self.layer_norm else evolve_embs[-1]
             loss_ent = torch.zeros(1, device=dev)
             loss_rel = torch.zeros(1, device=dev)
@@ -271,4 +282,8 @@ class RecurrentRGCN(nn.Module):
             if self.relation_prediction:
                 score_rel = self.rdecoder.forward(pre_emb, r_emb, all_triples, mode="train")
                 _, loss_rel = ops.ce_dense(score_rel, all_triples, 1)
+            if self.use_static and self.discount in (0, 1):
+                from . import train
+                loss_static, _ = train.static_angle_terms(static_emb, list(evolve_embs), self.layer_norm, self.angle,
+                                                          self.discount, self.weight)
             return loss_ent, loss_rel, loss_static

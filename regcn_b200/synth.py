@@ -60,6 +60,19 @@ def make_stream(shape="tiny", seed=0, n_test=4, zipf=True):
     return {"num_ents": n, "num_rels": r, "history": history, "tests": tests}
 
 
+def make_static(num_ents, seed=0, num_static_rels=3, num_words=20, per_entity=2):
+    """Synthetic entity-word graph in the layout of the reference's e-w-graph.txt after src/main.py:146-150: (T,3) int64
+    triples (entity, static relation, num_ents + word); every word and every static relation occurs at least once.
+    Returns (static_triples, num_static_rels, num_words)."""
+    rng = np.random.default_rng(50_000 + seed)
+    ents = np.repeat(np.arange(num_ents, dtype=np.int64), per_entity)
+    rels = rng.integers(0, num_static_rels, size=ents.size, dtype=np.int64)
+    words = rng.integers(0, num_words, size=ents.size, dtype=np.int64)
+    rels[:num_static_rels] = np.arange(num_static_rels)
+    words[:num_words] = np.arange(num_words)
+    return np.stack([ents, rels, words + num_ents], axis=1), num_static_rels, num_words
+
+
 def _scale_for(name, shape):
     leaf = name.split(".")[-1]
     if leaf in ("running_var",):

@@ -479,6 +479,121 @@ def score_ce(q, cand, triples, target_col):
     return _ScoreCE.apply(q, cand, triples, target_col)
 
 
+# ------------------------------------------------------------------------------------------------ static-graph constraint
+def _block_index(g):
+    """Edges of a graph grouped by relation type with their endpoints (the dW gather of the block layer)."""
+    idx = getattr(g, "_block_idx", None)
+    if idx is None:
+        E, R2 = g.num_edges, 2 * g.num_rels
+        et = g.etype[:E].contiguous()
+        type_rowptr, _, type_src = _group(et, R2, g.src[:E].contiguous())
+        _, _, type_dst = _group(et, R2, g.dst[:E].contiguous())
+        idx = g._block_idx = (type_rowptr, type_src, type_dst)
+    return idx
+
+
+class _BlockAggregate(torch.autograd.Function):
+    """agg[v] = norm[v] sum_{(u,r)->v} blockdiag(W[r]) h[u]   (rgcn/layers.py:167-179)."""
+
+    @staticmethod
+    def forward(ctx, h, weight, g, num_bases, d_out):
+        h, weight = h.contiguous(), weight.contiguous()
+        ctx.save_for_backward(h, weight)
+        ctx.g, ctx.nb, ctx.d_out = g, int(num_bases), int(d_out)
+        return ops.block_aggregate(h, weight, g, num_bases, d_out)
+
+    @staticmethod
+    def backward(ctx, dagg):
+        h, weight = ctx.saved_tensors
+        g = ctx.g
+        N, d_in = h.shape
+        R2 = 2 * g.num_rels
+        type_rowptr, type_src, type_dst = _block_index(g)
+        dh = torch.empty_like(h) if ctx.needs_input_grad[0] else None
+        dW = torch.empty_like(weight) if ctx.needs_input_grad[1] else None
+        nb = _lib.load().regcn_block_aggregate_bwd_workspace_bytes(R2, d_in, ctx.d_out, ctx.nb)
+        ws = _ws(h.device, nb)
+        call("regcn_block_aggregate_bwd", ptr(h), ptr(dagg.contiguous()), ptr(weight), ptr(g.rowptr), ptr(g.src_sorted),
+             ptr(g.etype_sorted), ptr(g.norm), ptr(type_rowptr), ptr(type_src), ptr(type_dst), N, R2, d_in, ctx.d_out,
+             ctx.nb, ptr(dh), ptr(dW), ptr(ws), nb)
+        return dh, dW, None, None, None
+
+
+class _RReluDrop(torch.autograd.Function):
+    """out = dropout_p(rrelu(x))  -- the activation of a layer without self-loop (rgcn/layers.py:84-87)."""
+
+    @staticmethod
+    def forward(ctx, x, p):
+        out, _, _ = ops.union_combine(x.contiguous(), None, None, act=1)
+        if p > 0:
+            call("regcn_dropout", ptr(out), out.numel(), float(p), _next_seed())
+        ctx.p = float(p)
+        ctx.save_for_backward(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (out,) = ctx.saved_tensors
+        N, d = out.shape
+        dx = torch.empty_like(out)
+        call("regcn_union_combine_bwd", ptr(out), ptr(dout.contiguous()), None, N, d, ctx.p, ptr(dx), None)
+        return dx, None
+
+
+def static_angle_terms(static_emb, hist, layer_norm, angle, discount, weight):
+    """src/rrgcn.py:225-247 forward: (loss (1,), cosines) -- one row kernel per history step + one fixed-order sum."""
+    import math
+    N, d = static_emb.shape
+    L = len(hist)
+    dev = static_emb.device
+    terms = torch.empty((max(L, 1) * N, 1), device=dev, dtype=F32)
+    coss = []
+    for t, e in enumerate(hist):
+        step = (angle * math.pi / 180) * ((t + 1) if discount == 1 else 1)
+        coss.append(math.cos(step))
+        call("regcn_static_angle_fwd", ptr(static_emb), ptr(e.contiguous()), N, d, coss[-1], float(weight),
+             int(bool(layer_norm)), terms[t * N:(t + 1) * N].data_ptr())
+    if L == 0:
+        return torch.zeros(1, device=dev), coss
+    return _col_sum(terms), coss
+
+
+class _StaticAngle(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, static_emb, layer_norm, angle, discount, weight, *hist):
+        static_emb = static_emb.contiguous()
+        hist = [e.contiguous() for e in hist]
+        loss, coss = static_angle_terms(static_emb, hist, layer_norm, angle, discount, weight)
+        ctx.save_for_backward(static_emb, *hist)
+        ctx.cfg = (bool(layer_norm), float(weight), coss)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gloss):
+        static_emb, *hist = ctx.saved_tensors
+        layer_norm, weight, coss = ctx.cfg
+        N, d = static_emb.shape
+        dS = torch.zeros_like(static_emb)
+        dEs = []
+        g = gloss.contiguous().view(-1)
+        for t, e in enumerate(hist):
+            dE = torch.empty_like(e)
+            call("regcn_static_angle_bwd", ptr(static_emb), ptr(e), N, d, coss[t], weight, int(layer_norm), ptr(g),
+                 ptr(dS), 1, ptr(dE))
+            dEs.append(dE)
+        return (dS, None, None, None, None, *dEs)
+
+
+def static_embedding(model, static_graph):
+    """src/rrgcn.py:146-152 with the tape on: block layer over cat(dynamic_emb, words_emb), entity rows, F.normalize."""
+    layer = model.statci_rgcn_layer
+    x = torch.cat((model.dynamic_emb, model.words_emb), dim=0)
+    agg = _BlockAggregate.apply(x, layer.weight, static_graph, layer.num_bases, layer.out_feat)
+    out = _RReluDrop.apply(agg, 0.0)              # RGCNLayer drops only the self-loop message (:52-53); none here
+    s_emb = out[:model.num_ents]
+    return normalize(s_emb) if model.layer_norm else s_emb.contiguous()
+
+
 rel_mean_pool = _RelMeanPool.apply
 union_aggregate = _UnionAggregate.apply
 union_combine = _UnionCombine.apply
@@ -489,13 +604,18 @@ tanh = _Tanh.apply
 
 
 # ------------------------------------------------------------------------------------------------ model-level glue
-def regcn_evolve(model, g_list):
-    """RecurrentRGCN.forward with the tape on (src/rrgcn.py:142-180; uvrgcn, self_loop, no skip connection, no static
-    graph).  Returns (history_embs, h_0)."""
-    if model.use_static or model.rgcn.skip_connect or not model.rgcn.self_loop or model.encoder_name != "uvrgcn":
-        raise NotImplementedError("regcn_b200.train: uvrgcn + self_loop without skip_connect / static graph only")
+def regcn_evolve(model, g_list, static_graph=None):
+    """RecurrentRGCN.forward with the tape on (src/rrgcn.py:142-180; uvrgcn, self_loop, no skip connection).
+    Returns (history_embs, h_0, static_emb)."""
+    if model.rgcn.skip_connect or not model.rgcn.self_loop or model.encoder_name != "uvrgcn":
+        raise NotImplementedError("regcn_b200.train: uvrgcn + self_loop without skip_connect only")
     cell = model.relation_cell_1
-    h = normalize(model.dynamic_emb) if model.layer_norm else model.dynamic_emb
+    static_emb = None
+    if model.use_static:
+        static_emb = static_embedding(model, static_graph)
+        h = static_emb
+    else:
+        h = normalize(model.dynamic_emb) if model.layer_norm else model.dynamic_emb
     h0 = None
     hist = []
     for i, g in enumerate(g_list):
@@ -515,10 +635,10 @@ def regcn_evolve(model, g_list):
         G = linear(h, model.time_gate_weight, None, True)
         h = time_gate(G, model.time_gate_bias, cur, h, model.layer_norm)
         hist.append(h)
-    return hist, h0
+    return hist, h0, static_emb
 
 
-def regcn_get_loss(model, glist, triples):
+def regcn_get_loss(model, glist, triples, static_graph=None):
     """src/rrgcn.py:197-223 with gradients: (loss_ent, loss_rel, loss_static), each of shape (1,)."""
     _lib.require_device()
     if ops.gemm_impl() != "tc":
@@ -528,7 +648,7 @@ def regcn_get_loss(model, glist, triples):
     inverse = triples.flip(1)
     inverse[:, 1] = inverse[:, 1] + model.num_rels
     all_triples = torch.cat([triples, inverse]).contiguous()
-    hist, r_emb = regcn_evolve(model, glist)
+    hist, r_emb, static_emb = regcn_evolve(model, glist, static_graph)
     pre = normalize(hist[-1]) if model.layer_norm else hist[-1]
     e_all = tanh(pre)
     loss_ent = torch.zeros(1, device=dev)
@@ -540,4 +660,6 @@ def regcn_get_loss(model, glist, triples):
     if model.relation_prediction:
         q = conv_tower(model.rdecoder, e_all, e_all, all_triples, 0, 2)
         loss_rel = score_ce(q, r_emb, all_triples, 1)
+    if model.use_static and model.discount in (0, 1):
+        loss_static = _StaticAngle.apply(static_emb, model.layer_norm, model.angle, model.discount, model.weight, *hist)
     return loss_ent, loss_rel, loss_static

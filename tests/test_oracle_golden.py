@@ -154,3 +154,34 @@ def test_oracle_train_step_matches_reference(name):
         if f"{name}.bn.{k}" not in z.files:
             continue                                                     # bn3 / bn_init are never used (src/decoder.py:73-76)
         np.testing.assert_allclose(v.numpy(), z[f"{name}.bn.{k}"], rtol=2e-3, atol=1e-5)   # after the 2nd step
+
+
+@pytest.mark.parametrize("name", sorted(__import__("tests.helpers", fromlist=["STATIC_CASES"]).STATIC_CASES))
+def test_oracle_static_graph_matches_reference(name):
+    """Static-graph constraint (src/rrgcn.py:101-106,146-152,225-247): the restated static embedding, scores, eval
+    losses and one optimisation step against the UNMODIFIED reference (tests/golden/train_static_regcn.npz)."""
+    import os
+    from tests.helpers import GOLDEN, STATIC_CASES, build_static_model
+    z = np.load(os.path.join(GOLDEN, "train_static_regcn.npz"))
+    cfg = STATIC_CASES[name]
+    case = synth.make_case(cfg["shape"], cfg["seed"])
+    n, r = case["num_ents"], case["num_rels"]
+    st, n_srel, n_words = synth.make_static(n, cfg["seed"])
+    _, sd = build_static_model(cfg, n, r, n_srel, n_words)
+    graphs = [restate.build_edges(s, n, r) for s in case["history"]]
+    sg = restate.build_edges(st, n + n_words, n_srel)
+    ln = cfg["layer_norm"]
+    P = {k: v for k, v in sd.items() if v.is_floating_point()}
+    with torch.no_grad():
+        s_emb = restate.regcn_static_emb(P, sg, n, 100, ln)
+        all_t, score, score_rel, hist, h0 = restate.regcn_predict(sd, graphs, r, case["test"], layer_norm=ln, h_init=s_emb)
+        l_static = restate.static_angle_loss(s_emb, hist, ln, cfg["angle"], cfg["discount"], cfg["weight"])
+    for mine, key in ((s_emb, "static_emb"), (hist[-1], "hist_last"), (score, "score"), (score_rel, "score_rel")):
+        ok, worst = close(mine.numpy(), z[f"{name}.{key}"], rtol=2e-4 if "score" in key else 1e-4)
+        assert ok, (key, worst)
+    np.testing.assert_allclose(float(l_static), z[f"{name}.eval_losses"][2], rtol=1e-4)
+    static = dict(graph=sg, num_ents=n, num_bases=100, angle=cfg["angle"], discount=cfg["discount"], weight=cfg["weight"])
+    log, _ = restate.regcn_train_steps(sd, graphs, r, case["test"], layer_norm=ln, steps=1, static=static)
+    rec = log[0]
+    compare_train_step(z, name, 0, rec["losses"], rec["grad_norm"], {k: v.numpy() for k, v in rec["grads"].items()},
+                       {k: v.numpy() for k, v in rec["params"].items()})
