@@ -753,11 +753,10 @@ int dec_conv_bwd_input(const float* dY, const float* X1, int B, int d, int C, in
 // CTA = (slab of kConvSlab queries) x (group of kConvCG channels); thread j owns position j and keeps the 7 partial sums
 // of each channel of the group in registers; block tree at the end -> partial[slab][C*7].
 constexpr int kConvCG = 10;
-constexpr int kConvSlab = 32;
+constexpr int kConvSlab = 16;
 __global__ void __launch_bounds__(256) dec_conv_bwd_weight_kernel(const float* __restrict__ dY, const float* __restrict__ X1,
                                                                   int B, int d, int C, float* __restrict__ partial) {
   pdl_grid_sync();
-  __shared__ float xs[2][kConvMaxD + 2];
   __shared__ float red[8][kConvCG * 7];
   const int c0 = blockIdx.y * kConvCG;
   const int b0 = blockIdx.x * kConvSlab, b1 = min(B, b0 + kConvSlab);
@@ -767,21 +766,20 @@ __global__ void __launch_bounds__(256) dec_conv_bwd_weight_kernel(const float* _
   for (int c = 0; c < kConvCG; ++c)
 #pragma unroll
     for (int q = 0; q < 7; ++q) acc[c][q] = 0.f;
-  for (int b = b0; b < b1; ++b) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < 2 * (d + 2); i += blockDim.x) {
-      const int ch = i / (d + 2), jj = i - ch * (d + 2) - 1;
-      xs[ch][jj + 1] = (jj >= 0 && jj < d) ? X1[((size_t)b * 2 + ch) * d + jj] : 0.f;
-    }
-    __syncthreads();
-    if (j < d) {
+  if (j < d) {
+    // no staging, no barriers in the loop: the three taps of both input rows come straight from L1 (neighbouring
+    // threads share them), the dY loads are coalesced over j, and consecutive queries overlap freely
+#pragma unroll 2
+    for (int b = b0; b < b1; ++b) {
+      const float* xr = X1 + (size_t)b * 2 * d;
       float x[6];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) { x[k] = xs[0][j + k]; x[3 + k] = xs[1][j + k]; }
+      x[0] = j > 0 ? xr[j - 1] : 0.f;         x[1] = xr[j];         x[2] = j + 1 < d ? xr[j + 1] : 0.f;
+      x[3] = j > 0 ? xr[d + j - 1] : 0.f;     x[4] = xr[d + j];     x[5] = j + 1 < d ? xr[d + j + 1] : 0.f;
+      const float* gy = dY + ((size_t)b * C + c0) * d + j;
 #pragma unroll
       for (int c = 0; c < kConvCG; ++c) {
         if (c0 + c < C) {
-          const float g = dY[((size_t)b * C + c0 + c) * d + j];
+          const float g = gy[(size_t)c * d];
 #pragma unroll
           for (int q = 0; q < 6; ++q) acc[c][q] = fmaf(g, x[q], acc[c][q]);
           acc[c][6] += g;
