@@ -403,6 +403,12 @@ REGCN_API int regcn_static_angle_fwd(const float* S, const float* E, int N, int 
 REGCN_API int regcn_static_angle_bwd(const float* S, const float* E, int N, int d, float cos_step, float weight,
                            int layer_norm, const float* gscale, float* dS, int accumulate_dS, float* dE, void* stream);
 
+/* Multi-step inference (src/main.py:90-97; construct_snap / construct_snap_r, rgcn/utils.py:367-405): top_idx (B,K) =
+ * the K best candidates of every score row in descending order, ties by ascending id (a stable descending sort);
+ * out (B*K,3) int64 = the predicted snapshot (may be NULL).  rel_mode 0: entity scores, 1: relation scores.        */
+REGCN_API int regcn_topk_construct_snap(const float* S, int64_t ld, int B, int N, int K, const int64_t* triples, int R,
+                              int rel_mode, int32_t* top_idx, int64_t* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

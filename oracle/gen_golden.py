@@ -301,11 +301,29 @@ def run_static(ref_utils, RecurrentRGCN):
     print("->", path, os.path.getsize(path) / 1e6, "MB")
 
 
+def run_construct_snap(ref_utils):
+    """tests/golden/aux_construct_snap.npz: the reference's construct_snap / construct_snap_r (rgcn/utils.py:367-405)
+    on seeded score matrices without ties."""
+    rng = np.random.default_rng(99)
+    out = {}
+    for name, (B, N, R, K) in {"ent": (40, 300, 7, 10), "rel": (40, 14, 7, 5)}.items():
+        score = rng.permutation(B * N).reshape(B, N).astype(np.float32) / 7.0      # all distinct
+        trip = np.stack([rng.integers(0, 300, B), rng.integers(0, 2 * R, B), rng.integers(0, 300, B)], 1).astype(np.int64)
+        fn = ref_utils.construct_snap if name == "ent" else ref_utils.construct_snap_r
+        res = fn(torch.from_numpy(trip), 300, R, torch.from_numpy(score), K)
+        out[f"{name}.score"], out[f"{name}.triples"], out[f"{name}.out"] = score, trip, np.asarray(res, dtype=np.int64)
+        out[f"{name}.cfg"] = np.array([B, N, R, K])
+    np.savez_compressed(os.path.join(GOLDEN, "aux_construct_snap.npz"), **out)
+    print("-> aux_construct_snap.npz")
+
+
 def main(argv):
     ref_utils, RecurrentRGCN, HyperbolicRecurrentRGCN = _import_reference()
     torch.set_num_threads(os.cpu_count() or 1)
     if len(argv) > 1 and argv[1] == "--losses":
         return run_losses(ref_utils, RecurrentRGCN, HyperbolicRecurrentRGCN)
+    if len(argv) > 1 and argv[1] == "--construct-snap":
+        return run_construct_snap(ref_utils)
     if len(argv) > 1 and argv[1] == "--static":
         return run_static(ref_utils, RecurrentRGCN)
     if len(argv) > 1 and argv[1] == "--train":

@@ -678,6 +678,21 @@ def hyp_loss(p, graphs, num_rels, triples, c=0.01, decoder="roth", layer_norm=Fa
             float(radius_lambda * torch.mean((rs - rt) ** 2)))
 
 
+def construct_snap(all_triples, num_rels, score, topk, rel_mode=0):
+    """rgcn/utils.py:367-405 (construct_snap / construct_snap_r): top-k of every row in descending order (ties by
+    ascending id: the order of a stable sort; torch.sort leaves it unspecified), turned into predicted triples."""
+    score = np.asarray(score)
+    top = np.argsort(-score, axis=1, kind="stable")[:, :topk]
+    out = []
+    for q, (h, r, t) in enumerate(np.asarray(all_triples)):
+        for idx in top[q]:
+            if not rel_mode:
+                out.append([h, r, idx] if r < num_rels else [idx, r - num_rels, h])
+            else:
+                out.append([h, idx, t] if idx < num_rels else [t, idx - num_rels, h])
+    return np.asarray(out, dtype=np.int64).reshape(-1, 3)
+
+
 # =====================================================================================
 # Training step (src/rrgcn.py:197-223 in train() mode + src/main.py:235-246), dropout 0.
 # Gradients come from torch autograd over the restated forward (CPU); BatchNorm uses batch statistics

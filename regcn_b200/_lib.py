@@ -109,6 +109,7 @@ SIGNATURES = {
     "regcn_block_aggregate_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "regcn_block_aggregate_bwd": (_i, [_p] * 10 + [_i, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),
     "regcn_static_angle_fwd": (_i, [_p, _p, _i, _i, _f, _f, _i, _p, _p]),
+    "regcn_topk_construct_snap": (_i, [_p, _i64, _i, _i, _i, _p, _i, _i, _p, _p, _p]),
     "regcn_static_angle_bwd": (_i, [_p, _p, _i, _i, _f, _f, _i, _p, _p, _i, _p, _p]),
 }
 

@@ -286,4 +286,8 @@ int regcn_apply_filter(float* S, int64_t ld, int B, int N, const int64_t* triple
   return apply_filter(S, ld, B, N, triples, target_col, filt_ptr, filt_idx, col_offset, filt_end, ST(stream));
 }
 
+int regcn_topk_construct_snap(const float* S, int64_t ld, int B, int N, int K, const int64_t* triples, int R,
+                              int rel_mode, int32_t* top_idx, int64_t* out, void* stream) {
+  return topk_construct_snap(S, ld, B, N, K, triples, R, rel_mode, top_idx, out, ST(stream));
+}
 }  // extern "C"

@@ -105,6 +105,8 @@ int ce_rows(const float* S, int64_t ld, int B, int N, const int64_t* triples, in
 int counts_to_ranks(const int* raw_count, const int* filt_count, int B, int64_t* rank, int64_t* filt_rank, cudaStream_t st);
 int apply_filter(float* S, int64_t ld, int B, int N, const int64_t* triples, int target_col, const int* filt_ptr,
                  const int* filt_idx, int col_offset, const int* filt_end, cudaStream_t st);
+int topk_construct_snap(const float* S, int64_t ld, int B, int N, int K, const int64_t* triples, int R, int rel_mode,
+                        int* top_idx, int64_t* out, cudaStream_t st);
 // training (backward.cu)
 int csr_gather_sum(const float* X, int ldx, const float* col_w, const float* row_w, const int* rowptr, const int* col,
                    int nrows, int d, int col2_off, float* out, int ldo, int accumulate, cudaStream_t st);

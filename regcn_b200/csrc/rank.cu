@@ -303,4 +303,78 @@ int ce_rows(const float* S, int64_t ld, int B, int N, const int64_t* triples, in
   return check_launch("ce_rows");
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Multi-step inference (src/main.py:90-97, rgcn/utils.py:367-405): the K best candidates of every score row, in
+// descending order with ties by ascending id (the order of a stable descending sort), turned into the predicted
+// snapshot's triples.  One CTA per row, K selection passes over the row (it stays in L1/L2): pass p takes the
+// greatest (score, -id) strictly below the pass p-1 winner; the score matrix is not modified.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) topk_rows_kernel(const float* __restrict__ S, int64_t ld, int B, int N, int K,
+                                                        int* __restrict__ top_idx) {
+  pdl_grid_sync();
+  __shared__ float sv[8];
+  __shared__ int si[8];
+  __shared__ float last_v_s;
+  __shared__ int last_i_s;
+  const int b = blockIdx.x;
+  const float* s = S + (size_t)b * ld;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float last_v = INFINITY;
+  int last_i = -1;
+  for (int p = 0; p < K; ++p) {
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+      const float v = s[j];
+      const bool below = p == 0 || v < last_v || (v == last_v && j > last_i);
+      if (below && (v > bv || (v == bv && j < bi))) { bv = v; bi = j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { sv[wid] = bv; si[wid] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float v = sv[0];
+      int i = si[0];
+      for (int w = 1; w < 8; ++w)
+        if (sv[w] > v || (sv[w] == v && si[w] < i)) { v = sv[w]; i = si[w]; }
+      last_v_s = v; last_i_s = i;
+      top_idx[(size_t)b * K + p] = i == 0x7fffffff ? -1 : i;
+    }
+    __syncthreads();
+    last_v = last_v_s; last_i = last_i_s;
+  }
+}
+// rel_mode 0 (construct_snap): query (s, r, .) -> r < R ? (s, r, idx) : (idx, r-R, s)
+// rel_mode 1 (construct_snap_r): query (h, ., t) -> idx < R ? (h, idx, t) : (t, idx-R, h)
+__global__ void construct_snap_kernel(const int64_t* __restrict__ triples, const int* __restrict__ top_idx, int B, int K,
+                                      int R, int rel_mode, int64_t* __restrict__ out) {
+  pdl_grid_sync();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * K) return;
+  const int b = i / K;
+  const int64_t idx = top_idx[i];
+  const int64_t h = triples[(size_t)b * 3], r = triples[(size_t)b * 3 + 1], t = triples[(size_t)b * 3 + 2];
+  int64_t o0, o1, o2;
+  if (!rel_mode) {
+    if (r < R) { o0 = h; o1 = r; o2 = idx; } else { o0 = idx; o1 = r - R; o2 = h; }
+  } else {
+    if (idx < R) { o0 = h; o1 = idx; o2 = t; } else { o0 = t; o1 = idx - R; o2 = h; }
+  }
+  out[(size_t)i * 3] = o0; out[(size_t)i * 3 + 1] = o1; out[(size_t)i * 3 + 2] = o2;
+}
+int topk_construct_snap(const float* S, int64_t ld, int B, int N, int K, const int64_t* triples, int R, int rel_mode,
+                        int* top_idx, int64_t* out, cudaStream_t st) {
+  if (!S || !top_idx || (out && !triples)) { set_last_error("topk_construct_snap: null pointer"); return REGCN_ERR_NULL; }
+  if (K <= 0 || K > N) { set_last_error("topk_construct_snap: need 0 < K <= N (K=%d, N=%d)", K, N); return REGCN_ERR_DIM; }
+  if (B <= 0) return REGCN_OK;
+  launch_k(topk_rows_kernel, (unsigned)B, 256, 0, st, S, ld, B, N, K, top_idx);
+  if (out) launch_k(construct_snap_kernel, (unsigned)(((size_t)B * K + 255) / 256), 256, 0, st, triples, (const int*)top_idx, B, K, R, rel_mode, out);
+  return check_launch("topk_construct_snap");
+}
 }  // namespace regcn

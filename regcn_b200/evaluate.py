@@ -192,9 +192,40 @@ def _finish_prepare(p):
 
 
 @torch.no_grad()
+def _test_multi_step(model, input_list, test_list, num_rels, num_nodes, static_graph, dev, topk, relation_evaluation,
+                     return_ranks):
+    """src/main.py:66-100 with args.multi_step: predict, rank, then replace the oldest history snapshot by the predicted
+    one (top-k entities -- or relations with --relation-evaluation -- of every query)."""
+    from .graph import build_sub_graph
+    ranks = [[], [], [], []]
+    gpu = dev.index if dev.index is not None else 0
+    for snap in test_list:
+        glist = [build_sub_graph(num_nodes, num_rels, g, True, gpu) for g in input_list]
+        triples = torch.as_tensor(snap).to(dev)
+        all_t, score, score_rel = model.predict(glist, num_rels, static_graph, triples, True)
+        f_rel = utils.filter_csr_from_snapshot(all_t, num_nodes, 1)
+        f_ent = utils.filter_csr_from_snapshot(all_t, 2 * num_rels, 0)
+        _, _, rank_r, frank_r = utils.get_total_rank(all_t, score_rel, None, 1000, rel_predict=1, filter_csr=f_rel)
+        _, _, rank, frank = utils.get_total_rank(all_t, score, None, 1000, rel_predict=0, filter_csr=f_ent)
+        for lst, v in zip(ranks, (rank, frank, rank_r, frank_r)):
+            lst.append(v.cpu())
+        if relation_evaluation:
+            predicted = utils.construct_snap_r(all_t, num_nodes, num_rels, score_rel, topk)
+        else:
+            predicted = utils.construct_snap(all_t, num_nodes, num_rels, score, topk)
+        if len(predicted):
+            input_list.pop(0)
+            input_list.append(predicted)
+
+    def mrr(lst):
+        return float(torch.mean(1.0 / torch.cat(lst).float())) if lst else float("nan")
+    out = (mrr(ranks[0]), mrr(ranks[1]), mrr(ranks[2]), mrr(ranks[3]))
+    return (out, ranks) if return_ranks else out
+
+
 def test(model, history_list, test_list, num_rels, num_nodes, use_cuda=True, all_ans_list=None, all_ans_r_list=None,
          model_name=None, static_graph=None, mode="eval", test_history_len=None, multi_step=False, device=None,
-         return_ranks=False):
+         return_ranks=False, topk=10, relation_evaluation=False):
     """Drop-in for the reference's evaluation loop `test()` (src/main.py:33-123, hyperbolic_main.py:60-170): slide a
     window of `test_history_len` snapshots over `test_list`, predict every entity / relation for each test snapshot,
     rank raw + time-filtered, return (mrr_raw, mrr_filter, mrr_raw_r, mrr_filter_r).
@@ -208,14 +239,13 @@ def test(model, history_list, test_list, num_rels, num_nodes, use_cuda=True, all
       * the loop is software-pipelined: while the GPU works on timestamp k, the host prepares timestamp k+1 (H2D copy,
         index build of the snapshot that just entered the window, filter-list counting) and only then waits for the few
         integers it needs to size step k+1's buffers; ranks travel back through pinned buffers, one copy per timestamp.
-    `mode="test"` with `model_name` loads the checkpoint first like the reference.  Multi-step inference (feeding
-    predictions back, src/main.py:90-97) is SURVEY.md 8f rank 4 and raises."""
+    `mode="test"` with `model_name` loads the checkpoint first like the reference.  `multi_step=True` feeds the model's
+    own top-`topk` predictions back as the next history snapshot (src/main.py:90-97, --multi-step / --topk /
+    --relation-evaluation); that recurrence is sequential, so it runs the plain (un-pipelined) loop on dense scores."""
     import os
     import time
     if not use_cuda:
         raise RuntimeError("regcn_b200.test: use_cuda=False is not supported (no CPU path)")
-    if multi_step:
-        raise NotImplementedError("multi-step inference (construct_snap top-k feedback) is SURVEY.md 8f rank 4")
     from . import _lib
     from .graph import SnapshotCache
     _lib.require_device()
@@ -226,6 +256,9 @@ def test(model, history_list, test_list, num_rels, num_nodes, use_cuda=True, all
     dev = device if device is not None else next(model.parameters()).device
     L = test_history_len if test_history_len is not None else getattr(model, "sequence_len", len(history_list))
     input_list = [snap for snap in history_list[-L:]]
+    if multi_step:
+        return _test_multi_step(model, input_list, test_list, num_rels, num_nodes, static_graph, dev, topk,
+                                relation_evaluation, return_ranks)
     cache = SnapshotCache(num_nodes, num_rels, dev, capacity=max(2 * L + 2, 8))
     fused_ok = ops.gemm_impl() in ("tc", "tc1")
     K = len(test_list)

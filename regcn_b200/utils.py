@@ -213,3 +213,33 @@ def stat_ranks(rank_list, method, verbose=True):
         for hit in (1, 3, 10):
             print("Hits ({}) @ {}: {:.6f}".format(method, hit, torch.mean((total_rank <= hit).float()).item()))
     return mrr
+
+
+# ------------------------------------------------------------------------------ multi-step inference
+def _construct(test_triples, num_rels, final_score, topK, rel_mode):
+    from . import _lib
+    from ._lib import call, ptr
+    _lib.require_device()
+    if not final_score.is_cuda:
+        raise RuntimeError("regcn_b200: kernels take CUDA tensors only (no CPU fallback)")
+    B, N = final_score.shape
+    K = int(topK)
+    test_triples = test_triples.to(final_score.device).contiguous()
+    if final_score.stride(1) != 1:
+        final_score = final_score.contiguous()
+    top = torch.empty((B, K), device=final_score.device, dtype=torch.int32)
+    out = torch.empty((B * K, 3), device=final_score.device, dtype=torch.int64)
+    call("regcn_topk_construct_snap", final_score.data_ptr(), final_score.stride(0), B, N, K, ptr(test_triples),
+         int(num_rels), rel_mode, ptr(top), ptr(out))
+    return out
+
+
+def construct_snap(test_triples, num_nodes, num_rels, final_score, topK):
+    """rgcn/utils.py:367-381: the predicted snapshot from the top-K entities of every query (a device int64 (B*K,3)
+    tensor where the reference returns a numpy array; `build_sub_graph` takes either).  Ties: ascending id."""
+    return _construct(test_triples, num_rels, final_score, topK, 0)
+
+
+def construct_snap_r(test_triples, num_nodes, num_rels, final_score, topK):
+    """rgcn/utils.py:383-405: the same from the top-K relations."""
+    return _construct(test_triples, num_rels, final_score, topK, 1)

@@ -14,7 +14,7 @@ H_DIM, N_BASES, N_LAYERS, CURV = 200, 100, 2, 0.01
 
 def golden_names(prefix=""):
     return sorted(f[:-4] for f in os.listdir(GOLDEN)
-                  if f.endswith(".npz") and f.startswith(prefix) and not f.startswith("train_"))
+                  if f.endswith(".npz") and f.startswith(prefix) and not f.startswith(("train_", "aux_")))
 
 
 def load_golden(name):

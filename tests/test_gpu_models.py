@@ -345,8 +345,54 @@ def test_evaluation_loop_matches_stepwise_reference_style_loop(kind):
         window.append(snap)
     ref_mrr = float(torch.mean(1.0 / torch.cat(ranks[1]).float()))
     assert abs(mrrs[1] - ref_mrr) < 1e-7
-    with pytest.raises(NotImplementedError):
-        R.test(model, st["history"], st["tests"], r, n, True, None, None, None, None, "eval", multi_step=True)
+
+
+def test_construct_snap_kernels_bit_exact():
+    """Top-k + predicted-snapshot kernels (multi-step inference) against the reference's outputs and, with ties and a
+    non-multiple-of-anything width, against the oracle's stable order."""
+    import os
+    from regcn_b200 import utils
+    from tests.helpers import GOLDEN
+    R._lib.require_device()
+    z = np.load(os.path.join(GOLDEN, "aux_construct_snap.npz"))
+    for name, fn in (("ent", utils.construct_snap), ("rel", utils.construct_snap_r)):
+        B, N, Rr, K = (int(v) for v in z[f"{name}.cfg"])
+        got = fn(torch.from_numpy(z[f"{name}.triples"]).to(DEV), 300, Rr, torch.from_numpy(z[f"{name}.score"]).to(DEV), K)
+        assert got.dtype == torch.int64 and np.array_equal(got.cpu().numpy(), z[f"{name}.out"])
+    rng = np.random.default_rng(5)
+    B, N, Rr, K = 70, 1237, 9, 10
+    score = rng.integers(0, 40, size=(B, N)).astype(np.float32)            # heavy ties
+    trip = np.stack([rng.integers(0, N, B), rng.integers(0, 2 * Rr, B), rng.integers(0, N, B)], 1).astype(np.int64)
+    got = utils.construct_snap(torch.from_numpy(trip).to(DEV), N, Rr, torch.from_numpy(score).to(DEV), K)
+    assert np.array_equal(got.cpu().numpy(), restate.construct_snap(trip, Rr, score, K, 0))
+
+
+@pytest.mark.parametrize("rel_eval", [False, True])
+def test_multi_step_loop_equals_reference_style_loop(rel_eval):
+    """test(multi_step=True) (src/main.py:90-97): ranks identical to a hand-written loop that feeds the ORACLE's
+    construct_snap of the same (filtered, like the reference's in-place filter_score) scores back into the window."""
+    from regcn_b200 import utils
+    R._lib.require_device()
+    cfg = dict(kind="regcn", shape="small", seed=3, layer_norm=True)
+    st = synth.make_stream(cfg["shape"], cfg["seed"], n_test=3)
+    n, r = st["num_ents"], st["num_rels"]
+    model, _ = build_model(cfg, n, r)
+    model = model.to(DEV)
+    L = len(st["history"])
+    _, ranks = R.test(model, st["history"], st["tests"], r, n, True, None, None, None, None, "eval", test_history_len=L,
+                      multi_step=True, topk=5, relation_evaluation=rel_eval, return_ranks=True)
+    window = list(st["history"])
+    for k, snap in enumerate(st["tests"]):
+        glist = [R.build_sub_graph(n, r, s, True, 0) for s in window]
+        all_t, score, score_rel = model.predict(glist, r, None, torch.from_numpy(snap).to(DEV), True)
+        _, _, rank_r, frank_r = utils.get_total_rank(all_t, score_rel, synth.answers_of(snap, r, True), 1000, rel_predict=1)
+        _, _, rank, frank = utils.get_total_rank(all_t, score, synth.answers_of(snap, r, False), 1000, rel_predict=0)
+        assert torch.equal(ranks[0][k], rank.cpu()) and torch.equal(ranks[1][k], frank.cpu())
+        assert torch.equal(ranks[2][k], rank_r.cpu()) and torch.equal(ranks[3][k], frank_r.cpu())
+        pred = restate.construct_snap(all_t.cpu().numpy(), r, (score_rel if rel_eval else score).cpu().numpy(), 5,
+                                      int(rel_eval))
+        window.pop(0)
+        window.append(pred)
 
 
 # ----------------------------------------------------------------------------------------- engine variants

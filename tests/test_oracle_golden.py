@@ -185,3 +185,14 @@ def test_oracle_static_graph_matches_reference(name):
     rec = log[0]
     compare_train_step(z, name, 0, rec["losses"], rec["grad_norm"], {k: v.numpy() for k, v in rec["grads"].items()},
                        {k: v.numpy() for k, v in rec["params"].items()})
+
+
+def test_oracle_construct_snap_matches_reference():
+    """Multi-step feedback (rgcn/utils.py:367-405) against the reference's own outputs (aux_construct_snap.npz)."""
+    import os
+    from tests.helpers import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "aux_construct_snap.npz"))
+    for name, mode in (("ent", 0), ("rel", 1)):
+        B, N, Rr, K = (int(v) for v in z[f"{name}.cfg"])
+        got = restate.construct_snap(z[f"{name}.triples"], Rr, z[f"{name}.score"], K, mode)
+        assert np.array_equal(got, z[f"{name}.out"])
