@@ -409,6 +409,14 @@ REGCN_API int regcn_static_angle_bwd(const float* S, const float* E, int N, int 
 REGCN_API int regcn_topk_construct_snap(const float* S, int64_t ld, int B, int N, int K, const int64_t* triples, int R,
                               int rel_mode, int32_t* top_idx, int64_t* out, void* stream);
 
+/* AttH / AttHRel query builders (hyperbolic_decoder.py:1403-1480, 1593-1640): attention-weighted mix of a Givens
+ * rotation and a Givens reflection of the subject's tangent vector.  mode 0: per-relation tables rot, ref (2R,d/2),
+ * attn (2R,2d), rel (2R,d), trans (2R,d), query = project(exp_0(mix)) (+)_c project(exp_0(trans[r]));
+ * mode 1: global rot, ref (d/2), attn (2d), query = (-exp_0(mix)) (+)_c E[o].  Q (B,d), q_sumsq (B) optional.        */
+REGCN_API int regcn_atth_query(const float* s_tan, const float* rot, const float* ref, const float* attn, const float* rel,
+                     const float* trans, const float* E, const int64_t* triples, int B, int d, int mode, double c,
+                     float* Q, float* q_sumsq, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

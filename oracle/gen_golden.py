@@ -51,6 +51,10 @@ CASES = {
                                       layer_norm=True, gamma=0.15, entity_bias=True, rel_curvature=True),
     "hyp_lgcn_roth_tiny_bias_s5": dict(kind="hyp", shape="tiny_l", seed=5, encoder="lgcn", decoder="roth",
                                        layer_norm=False, gamma=0.15, entity_bias=True),
+    "hyp_uv_atth_tiny_s6": dict(kind="hyp", shape="tiny", seed=6, encoder="hyperbolic_uvrgcn", decoder="atth",
+                                layer_norm=False, gamma=0.15),
+    "hyp_lgcn_atth_small_flags_s7": dict(kind="hyp", shape="small_l", seed=7, encoder="lgcn", decoder="atth",
+                                         layer_norm=False, gamma=0.15, entity_bias=True, rel_curvature=True),
     "hyp_uv_roth_c1_s1": dict(kind="hyp", shape="c1", seed=1, encoder="hyperbolic_uvrgcn", decoder="roth",
                               layer_norm=True, gamma=0.15, sub=96),
 }

@@ -571,6 +571,43 @@ def roth_scores(P, emb, rel, triples, c, pre="decoder_ob."):
     return _flagged_scores(P, pre, q, emb, t, c, scale), q
 
 
+def givens_reflection(x, ang):
+    """hyperbolic_decoder.py:1391-1401: pairs -> (cos a x1 + sin a x2, sin a x1 - cos a x2)."""
+    x1, x2 = x[:, 0::2], x[:, 1::2]
+    ca, sa = torch.cos(ang), torch.sin(ang)
+    return torch.stack([ca * x1 + sa * x2, sa * x1 - ca * x2], dim=2).reshape(x.shape)
+
+
+def atth_scores(P, emb, rel, triples, c, pre="decoder_ob."):
+    """hyperbolic_decoder.py:1403-1480 (HyperbolicAttH.forward, eval)."""
+    t = torch.as_tensor(triples)
+    r = rel[t[:, 1]]
+    s_tan = log0(project(emb[t[:, 0]], c), c)
+    lin = lambda n, x: x @ P[pre + n + ".weight"].t() + P[pre + n + ".bias"]
+    rot_s = givens(s_tan, lin("rot_proj", r))
+    ref_s = givens_reflection(s_tan, lin("ref_proj", r))
+    a = torch.sigmoid((lin("attn_proj", r) * torch.cat([s_tan, r], dim=-1)).sum(dim=-1, keepdim=True))
+    mixed = project(exp0(a * rot_s + (1.0 - a) * ref_s, c), c)
+    t_r = project(exp0(lin("trans_proj", r), c), c)
+    q = mobius_add(mixed, t_r, c)
+    scale = _softplus(P[pre + "score_scale_raw"]) + 1e-6
+    return _flagged_scores(P, pre, q, emb, t, c, scale), q
+
+
+def atthrel_scores(P, emb, rel, triples, c, pre="rdecoder."):
+    """hyperbolic_decoder.py:1593-1640 (HyperbolicAttHRel.forward)."""
+    t = torch.as_tensor(triples)
+    o_emb = emb[t[:, 2]]
+    s_tan, o_tan = log0(emb[t[:, 0]], c), log0(o_emb, c)
+    n = s_tan.shape[0]
+    rot_s = givens(s_tan, P[pre + "global_rot"].unsqueeze(0).expand(n, -1))
+    ref_s = givens_reflection(s_tan, P[pre + "global_ref"].unsqueeze(0).expand(n, -1))
+    a = torch.sigmoid(torch.cat([s_tan, o_tan], dim=-1) @ P[pre + "attn_weight"]).unsqueeze(1)
+    q = mobius_add(-exp0(a * rot_s + (1.0 - a) * ref_s, c), o_emb, c)
+    scale = _softplus(P[pre + "score_scale_raw"]) + 1e-6
+    return hyp_dist_scores(q, exp0(rel, c), P[pre + "rel_bias"], c, scale, P[pre + "score_margin"]), q
+
+
 def murp_scores(P, emb, rel, triples, c, pre="decoder_ob."):
     """hyperbolic_decoder.py:733-779 (HyperbolicMuRP.forward)."""
     t = torch.as_tensor(triples)
@@ -644,6 +681,9 @@ def hyp_predict(p, graphs, num_rels, test_triples, c=0.01, decoder="roth", layer
     elif decoder == "murp":
         score = murp_scores(P, emb, h0, all_triples, c)[0]
         score_rel = murprel_scores(P, emb, h0, all_triples, c)[0]
+    elif decoder == "atth":
+        score = atth_scores(P, emb, h0, all_triples, c)[0]
+        score_rel = atthrel_scores(P, emb, h0, all_triples, c)[0]
     else:
         raise NotImplementedError(decoder)
     return all_triples, score, score_rel, hist, h0

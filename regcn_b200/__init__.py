@@ -10,8 +10,9 @@ from .rrgcn import RecurrentRGCN, RGCNCell  # noqa: F401
 from .decoder import ConvTransE, ConvTransR  # noqa: F401
 from .hyperbolic_layers import (HyperbolicRGCNCell, HyperbolicUnionRGCNLayer, LorentzRGCNCell,  # noqa: F401
                                 LorentzRGCNLayer)
-from .hyperbolic_decoder import (HyperbolicConvTransE, HyperbolicConvTransR, HyperbolicMuRP,  # noqa: F401
-                                 HyperbolicMuRPRel, HyperbolicRotH, HyperbolicRotHRel)
+from .hyperbolic_decoder import (HyperbolicAttH, HyperbolicAttHRel, HyperbolicConvTransE,  # noqa: F401
+                                 HyperbolicConvTransR, HyperbolicMuRP, HyperbolicMuRPRel, HyperbolicRotH,
+                                 HyperbolicRotHRel)
 from .hyperbolic_model import HyperbolicRecurrentRGCN  # noqa: F401
 from . import utils  # noqa: F401
 from . import knowledge_graph  # noqa: F401  (on-disk TKG format reader)

@@ -290,4 +290,9 @@ int regcn_topk_construct_snap(const float* S, int64_t ld, int B, int N, int K, c
                               int rel_mode, int32_t* top_idx, int64_t* out, void* stream) {
   return topk_construct_snap(S, ld, B, N, K, triples, R, rel_mode, top_idx, out, ST(stream));
 }
+int regcn_atth_query(const float* s_tan, const float* rot, const float* ref, const float* attn, const float* rel,
+                     const float* trans, const float* E, const int64_t* triples, int B, int d, int mode, double c,
+                     float* Q, float* q_sumsq, void* stream) {
+  return atth_query(s_tan, rot, ref, attn, rel, trans, E, triples, B, d, mode, c, Q, q_sumsq, ST(stream));
+}
 }  // extern "C"

@@ -304,4 +304,83 @@ int rel_curvature(const float* raw, const int64_t* triples, int B, int R, double
   return check_launch("rel_curvature");
 }
 
+
+// ---- AttH / AttHRel query builder (hyperbolic_decoder.py:1283-1512, 1515-1700) ------------------------------------
+// mode 0 (HyperbolicAttH.forward :1403-1480): per-relation tables rot, ref (2R, d/2), attn (2R, 2d), rel (2R, d), trans (2R, d)
+//   a = s(<attn[r,:d], x> + <attn[r,d:], rel[r]>);  m = a Rot(x) + (1-a) Ref(x);  q = project(exp_0(m)) (+) project(exp_0(trans[r]))
+// mode 1 (HyperbolicAttHRel.forward :1593-1640): global rot, ref (d/2), attn (2d); o = E[o_b]
+//   a = s(<attn[:d], x> + <attn[d:], log_0(o)>);  q = (-exp_0(m)) (+) o
+__device__ __forceinline__ float4 givens_ref4(float4 x, float a0, float a1) {
+  float s0, c0, s1, c1;
+  sincosf(a0, &s0, &c0);
+  sincosf(a1, &s1, &c1);
+  return make_float4(c0 * x.x + s0 * x.y, s0 * x.x - c0 * x.y, c1 * x.z + s1 * x.w, s1 * x.z - c1 * x.w);
+}
+template <int RV>
+__global__ void __launch_bounds__(256) atth_query_kernel(
+    const float* __restrict__ s_tan, const float* __restrict__ rot, const float* __restrict__ ref,
+    const float* __restrict__ attn, const float* __restrict__ rel, const float* __restrict__ trans,
+    const float* __restrict__ E, const int64_t* __restrict__ triples, int B, int d, int mode, Curv cv,
+    float* __restrict__ Q, float* __restrict__ q_sumsq) {
+  pdl_grid_sync();
+  const int lane = threadIdx.x & 31;
+  const int row = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+  if (row >= B) return;
+  const int nvec = d >> 2;
+  const int64_t r = triples[3 * (size_t)row + 1];
+  WarpRow<RV> x, y, w, u;
+  x.load_plain(s_tan + (size_t)row * d, nvec, lane);
+  const float* aw = mode == 0 ? attn + (size_t)r * 2 * d : attn;
+  w.load(aw, nvec, lane);
+  float logit = x.dot(w);
+  if (mode == 0) {
+    u.load(rel + (size_t)r * d, nvec, lane);
+  } else {
+    y.load(E + (size_t)triples[3 * (size_t)row + 2] * d, nvec, lane);
+    u = y;
+    row_log0(u, cv);
+  }
+  w.load(aw + d, nvec, lane);
+  logit += u.dot(w);
+  const float a = sigmoidf_(logit);
+  const float* rp = mode == 0 ? rot + (size_t)r * (d / 2) : rot;
+  const float* fp = mode == 0 ? ref + (size_t)r * (d / 2) : ref;
+#pragma unroll
+  for (int i = 0; i < RV; ++i) {
+    const int cidx = lane + i * kWarp;
+    if (cidx < nvec) {
+      const float4 ro = givens4(x.v[i], __ldg(rp + 2 * cidx), __ldg(rp + 2 * cidx + 1));
+      const float4 re = givens_ref4(x.v[i], __ldg(fp + 2 * cidx), __ldg(fp + 2 * cidx + 1));
+      const float b1 = 1.0f - a;
+      x.v[i] = make_float4(a * ro.x + b1 * re.x, a * ro.y + b1 * re.y, a * ro.z + b1 * re.z, a * ro.w + b1 * re.w);
+    }
+  }
+  row_exp0(x, cv);
+  if (mode == 0) {
+    row_project(x, cv);
+    y.load(trans + (size_t)r * d, nvec, lane);
+    row_exp0(y, cv);
+    row_project(y, cv);
+  } else {
+    x.map([](float v) { return -v; });
+  }
+  row_mobius_add(x, y, cv);
+  x.store(Q + (size_t)row * d, nvec, lane);
+  if (q_sumsq) {
+    const float s = x.sumsq();
+    if (lane == 0) q_sumsq[row] = s;
+  }
+}
+int atth_query(const float* s_tan, const float* rot, const float* ref, const float* attn, const float* rel,
+               const float* trans, const float* E, const int64_t* triples, int B, int d, int mode, double c, float* Q,
+               float* q_sumsq, cudaStream_t st) {
+  if (!s_tan || !rot || !ref || !attn || !triples || !Q || (mode == 0 && (!rel || !trans)) || (mode == 1 && !E)) { set_last_error("atth_query: null pointer"); return REGCN_ERR_NULL; }
+  if (d <= 0 || (d & 3) || d > 256 || mode < 0 || mode > 1) { set_last_error("atth_query: d=%d mode=%d unsupported", d, mode); return REGCN_ERR_UNSUPPORTED; }
+  if (B <= 0) return REGCN_OK;
+  Curv cv = make_curv(c);
+  const unsigned grid = (unsigned)(((size_t)B * 32 + 255) / 256);
+  if (d <= 128) launch_k(atth_query_kernel<1>, grid, 256, 0, st, s_tan, rot, ref, attn, rel, trans, E, triples, B, d, mode, cv, Q, q_sumsq);
+  else launch_k(atth_query_kernel<2>, grid, 256, 0, st, s_tan, rot, ref, attn, rel, trans, E, triples, B, d, mode, cv, Q, q_sumsq);
+  return check_launch("atth_query");
+}
 }  // namespace regcn

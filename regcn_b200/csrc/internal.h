@@ -107,6 +107,9 @@ int apply_filter(float* S, int64_t ld, int B, int N, const int64_t* triples, int
                  const int* filt_idx, int col_offset, const int* filt_end, cudaStream_t st);
 int topk_construct_snap(const float* S, int64_t ld, int B, int N, int K, const int64_t* triples, int R, int rel_mode,
                         int* top_idx, int64_t* out, cudaStream_t st);
+int atth_query(const float* s_tan, const float* rot, const float* ref, const float* attn, const float* rel,
+               const float* trans, const float* E, const int64_t* triples, int B, int d, int mode, double c, float* Q,
+               float* q_sumsq, cudaStream_t st);
 // training (backward.cu)
 int csr_gather_sum(const float* X, int ldx, const float* col_w, const float* row_w, const int* rowptr, const int* col,
                    int nrows, int d, int col2_off, float* out, int ldo, int accumulate, cudaStream_t st);

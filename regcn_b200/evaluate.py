@@ -19,7 +19,7 @@ def _scoring_operands(model, emb, r_emb, all_triples):
         et = ops.row_map(emb, ops.ROW_LEAKY_TANH_LOG0, c=dec.c)
         q = dec._tower(et, r_emb.contiguous(), all_triples, 0, 1, always_bn2=False)
         return q, et, None, dec.b.detach()
-    if name in ("HyperbolicRotH", "HyperbolicMuRP"):
+    if name in ("HyperbolicRotH", "HyperbolicMuRP", "HyperbolicAttH"):
         q, qss = dec.query(emb, r_emb, all_triples)
         cand = emb.contiguous()
         # entity_bias[subject] shifts a whole row and cannot change a rank: only the candidate bias is needed here

@@ -17,6 +17,7 @@ import torch.nn.functional as F
 from torch.nn.parameter import Parameter
 
 from . import ops
+from ._lib import call as _call, ptr as _ptr
 from .decoder import _fold_bn
 
 SCORE_SCALE_EPSILON = 1e-6
@@ -333,3 +334,112 @@ class HyperbolicMuRPRel(_HypDistBase):
 
     def loss(self, *a, **k):
         raise NotImplementedError("streaming-CE training head is SURVEY.md 8f rank 1 (next)")
+
+
+class HyperbolicAttH(_HypDistBase):
+    """hyperbolic_decoder.py:1283-1512: query = exp_0(a Rot_r(log_0 s) + (1-a) Ref_r(log_0 s)) (+)_c exp_0(trans_proj(rel_r)),
+    a = sigmoid(<attn_proj(rel_r), [log_0 s ; rel_r]>); scored like RotH."""
+
+    def __init__(self, num_entities, num_relations, embedding_dim, c=0.01, dropout=0.0, query_chunk_size=128,
+                 candidate_chunk_size=256, init_scale=1e-3, score_scale_init=1.0, score_margin_init=1.0,
+                 use_entity_euclidean_bias=False, use_relation_specific_curvature=False):
+        super().__init__()
+        assert embedding_dim % 2 == 0, "embedding_dim must be even"
+        self.num_entities = num_entities
+        self.embedding_dim = embedding_dim
+        self.half_dim = embedding_dim // 2
+        self.c = c
+        self.query_chunk_size = query_chunk_size
+        self.candidate_chunk_size = candidate_chunk_size
+        self.num_relations = num_relations
+        self.use_entity_euclidean_bias = use_entity_euclidean_bias
+        self.use_relation_specific_curvature = use_relation_specific_curvature
+        self.rot_proj = nn.Linear(embedding_dim, self.half_dim)
+        self.ref_proj = nn.Linear(embedding_dim, self.half_dim)
+        self.trans_proj = nn.Linear(embedding_dim, embedding_dim)
+        self.attn_proj = nn.Linear(embedding_dim, 2 * embedding_dim)
+        for lin in (self.rot_proj, self.ref_proj, self.trans_proj, self.attn_proj):
+            nn.init.uniform_(lin.weight, -init_scale, init_scale)
+            nn.init.zeros_(lin.bias)
+        if use_entity_euclidean_bias:
+            self.entity_bias = nn.Parameter(torch.zeros(num_entities))
+        else:
+            self.register_parameter("entity_bias", None)
+        if use_relation_specific_curvature:
+            self.rel_curvature_raw = nn.Parameter(torch.full((num_relations,), _relation_curvature_theta_init(c)))
+        else:
+            self.register_parameter("rel_curvature_raw", None)
+        self.rel_curvature_max = float(c) if use_relation_specific_curvature else None
+        self.score_scale_raw = nn.Parameter(torch.tensor(float(score_scale_init)))
+        self.score_margin = nn.Parameter(torch.tensor(float(score_margin_init)))
+        self.dropout = nn.Dropout(dropout)
+
+    @torch.no_grad()
+    def query(self, entity_embedding, rel_embedding, triplets):
+        self._unsupported_flags()
+        s_tan = ops.gather_log0(entity_embedding, triplets, 0, True, self.c)                     # :1417-1421
+        rel = rel_embedding.contiguous()
+
+        def table(lin):                                                                           # per-relation projections
+            return ops.gemm(rel, lin.weight.detach(), trans_b=True, bias=lin.bias.detach(), b_key=(lin.weight, "w"))
+
+        rot, ref, trans, attn = table(self.rot_proj), table(self.ref_proj), table(self.trans_proj), table(self.attn_proj)
+        B, d = s_tan.shape
+        Q = torch.empty((B, d), device=s_tan.device, dtype=torch.float32)
+        qss = torch.empty(B, device=s_tan.device, dtype=torch.float32)
+        _call("regcn_atth_query", _ptr(s_tan), _ptr(rot.contiguous()), _ptr(ref.contiguous()), _ptr(attn.contiguous()),
+              _ptr(rel), _ptr(trans.contiguous()), None, _ptr(triplets.contiguous()), B, d, 0, float(self.c), _ptr(Q),
+              _ptr(qss))
+        return Q, qss
+
+    @torch.no_grad()
+    def forward(self, entity_embedding, rel_embedding, triplets, mode="train"):
+        q, qss = self.query(entity_embedding, rel_embedding, triplets)
+        return self._dist_scores(q, qss, entity_embedding.contiguous(), None, triplets)
+
+    def loss(self, *a, **k):
+        raise NotImplementedError("streaming-CE training head of the hyperbolic decoders is SURVEY.md 8f rank 1 (next)")
+
+
+class HyperbolicAttHRel(_HypDistBase):
+    """hyperbolic_decoder.py:1515-1700: global rotation / reflection mixed by a(s, o), query = (-exp_0(mix)) (+)_c h_o,
+    scored against exp_0(rel)."""
+
+    def __init__(self, num_relations, embedding_dim, c=0.01, dropout=0.0, query_chunk_size=128,
+                 candidate_chunk_size=256, init_scale=1e-3, score_scale_init=1.0, score_margin_init=1.0):
+        super().__init__()
+        assert embedding_dim % 2 == 0, "embedding_dim must be even"
+        self.num_relations = num_relations
+        self.embedding_dim = embedding_dim
+        self.half_dim = embedding_dim // 2
+        self.c = c
+        self.query_chunk_size = query_chunk_size
+        self.candidate_chunk_size = candidate_chunk_size
+        self.global_rot = nn.Parameter(torch.Tensor(self.half_dim))
+        nn.init.uniform_(self.global_rot, -math.pi, math.pi)
+        self.global_ref = nn.Parameter(torch.Tensor(self.half_dim))
+        nn.init.uniform_(self.global_ref, -math.pi, math.pi)
+        self.attn_weight = nn.Parameter(torch.Tensor(2 * embedding_dim))
+        nn.init.uniform_(self.attn_weight, -init_scale, init_scale)
+        self.rel_bias = nn.Parameter(torch.zeros(num_relations * 2))
+        self.score_scale_raw = nn.Parameter(torch.tensor(float(score_scale_init)))
+        self.score_margin = nn.Parameter(torch.tensor(float(score_margin_init)))
+        self.dropout = nn.Dropout(dropout)
+
+    @torch.no_grad()
+    def forward(self, entity_embedding, rel_embedding, triplets, mode="train"):
+        self._unsupported_flags()
+        E = entity_embedding.contiguous()
+        s_tan = ops.gather_log0(E, triplets, 0, False, self.c)
+        B, d = s_tan.shape
+        q = torch.empty((B, d), device=E.device, dtype=torch.float32)
+        qss = torch.empty(B, device=E.device, dtype=torch.float32)
+        _call("regcn_atth_query", _ptr(s_tan), _ptr(self.global_rot.detach().contiguous()),
+              _ptr(self.global_ref.detach().contiguous()), _ptr(self.attn_weight.detach().contiguous()), None, None,
+              _ptr(E), _ptr(triplets.contiguous()), B, d, 1, float(self.c), _ptr(q), _ptr(qss))
+        rel_hyp, rss = ops.row_map(rel_embedding.contiguous(), ops.ROW_EXP0, c=self.c, want_sumsq=True)
+        S = ops.gemm(q, rel_hyp, trans_b=True)
+        return ops.hyp_score_epilogue_(S, qss, rss, self.rel_bias.detach(), None, self.c, self._scale_margin())
+
+    def loss(self, *a, **k):
+        raise NotImplementedError("streaming-CE training head of the hyperbolic decoders is SURVEY.md 8f rank 1 (next)")

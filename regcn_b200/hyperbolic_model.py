@@ -16,8 +16,8 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
-from .hyperbolic_decoder import (HyperbolicConvTransE, HyperbolicConvTransR, HyperbolicMuRP, HyperbolicMuRPRel,
-                                 HyperbolicRotH, HyperbolicRotHRel)
+from .hyperbolic_decoder import (HyperbolicAttH, HyperbolicAttHRel, HyperbolicConvTransE, HyperbolicConvTransR,
+                                 HyperbolicMuRP, HyperbolicMuRPRel, HyperbolicRotH, HyperbolicRotHRel)
 from .hyperbolic_layers import HyperbolicRGCNCell, LorentzRGCNCell
 from .layers import RGCNBlockLayer
 
@@ -134,8 +134,14 @@ class HyperbolicRecurrentRGCN(nn.Module):
             self.rdecoder = HyperbolicRotHRel(num_rels, h_dim, **dist_kw, init_scale=hyp_init_scale,
                                               score_scale_init=hyp_score_scale_init,
                                               score_margin_init=hyp_score_margin_init)
+        elif decoder_name == "atth":
+            self.decoder_ob = HyperbolicAttH(num_ents, num_rels * 2, h_dim, **dist_kw, **ent_kw)
+            self.rdecoder = HyperbolicAttHRel(num_rels, h_dim, **dist_kw, init_scale=hyp_init_scale,
+                                              score_scale_init=hyp_score_scale_init,
+                                              score_margin_init=hyp_score_margin_init)
         else:
-            raise NotImplementedError(f"Decoder '{decoder_name}' not implemented here (hyperbolic_convtranse, murp, roth)")
+            raise NotImplementedError(f"Decoder '{decoder_name}' not implemented. Choose from: hyperbolic_convtranse, "
+                                      "murp, roth, atth")
 
         if radius_target is None:
             target = torch.full((num_ents,), 0.5 * (radius_min + radius_max))
