@@ -281,6 +281,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", device_id=dev)
     _lib.require_device()
     if args.gemm:
@@ -517,7 +519,7 @@ def main():
         train_line = {"ms_per_step": train_ms, "train_snapshot_steps_per_s": world * L / (train_ms * 1e-3),
                       "optimisation_steps_per_s": world / (train_ms * 1e-3), "steps": t_steps,
                       "gpu_launches_per_step": int(lib0.regcn_kernel_launches() - l0),
-                      "loss_ent_after": float(out_t["loss"]),
+                      "loss_ent_after": float(out_t["loss"].detach()),
                       "what": "RecurrentRGCN.get_loss (train mode, dropout 0.2, batch-stat BatchNorm) + backward + "
                               "clip_grad_norm_(1.0) + Adam(lr 1e-3, wd 1e-5); 3xTF32 tcgen05 GEMMs for forward, dX and dW"}
         del tmodel, topt
