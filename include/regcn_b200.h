@@ -417,6 +417,16 @@ REGCN_API int regcn_atth_query(const float* s_tan, const float* rot, const float
                      const float* trans, const float* E, const int64_t* triples, int B, int d, int mode, double c,
                      float* Q, float* q_sumsq, void* stream);
 
+/* regcn_gemm_tf32 with operands in their natural row-major layouts, fed to tcgen05 as MN-major tiles (no transposes):
+ *   a_mn = 1: A is passed as X (K,M), the product uses X^T;   b_mn = 1: B is passed as Y (K,N), the product uses Y
+ *   (b_mn = 0 keeps regcn_gemm_tf32's B (N,K), i.e. B^T).  So (a_mn, b_mn) = (1,1): C = X^T Y, the weight gradient
+ *   dW = x^T dy of every torch.mm / F.linear on the path (src/rrgcn.py:168-178, rgcn/layers.py:229-233,257-276,
+ *   src/decoder.py:90);  (0,1): C = A Y, i.e. torch.mm(x, W) and dX = dY W without transposing W.
+ * TF32 (hi, lo) pairs (lo NULL with passes == 1); split-K workspace: regcn_gemm_tf32_workspace_bytes(M, N, split_k). */
+REGCN_API int regcn_gemm_tf32_mn(const float* a_hi, const float* a_lo, int lda, const float* b_hi, const float* b_lo, int ldb,
+                       float* C, int ldc, int M, int N, int K, int a_mn, int b_mn, const float* bias, int accumulate,
+                       int passes, int split_k, float* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

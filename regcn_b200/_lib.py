@@ -111,6 +111,7 @@ SIGNATURES = {
     "regcn_static_angle_fwd": (_i, [_p, _p, _i, _i, _f, _f, _i, _p, _p]),
     "regcn_topk_construct_snap": (_i, [_p, _i64, _i, _i, _i, _p, _i, _i, _p, _p, _p]),
     "regcn_atth_query": (_i, [_p] * 8 + [_i, _i, _i, _d, _p, _p, _p]),
+    "regcn_gemm_tf32_mn": (_i, [_p, _p, _i, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _i, _p, _sz, _p]),
     "regcn_static_angle_bwd": (_i, [_p, _p, _i, _i, _f, _f, _i, _p, _p, _i, _p, _p]),
 }
 

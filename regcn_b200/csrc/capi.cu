@@ -295,4 +295,10 @@ int regcn_atth_query(const float* s_tan, const float* rot, const float* ref, con
                      float* Q, float* q_sumsq, void* stream) {
   return atth_query(s_tan, rot, ref, attn, rel, trans, E, triples, B, d, mode, c, Q, q_sumsq, ST(stream));
 }
+int regcn_gemm_tf32_mn(const float* a_hi, const float* a_lo, int lda, const float* b_hi, const float* b_lo, int ldb,
+                       float* C, int ldc, int M, int N, int K, int a_mn, int b_mn, const float* bias, int accumulate,
+                       int passes, int split_k, float* workspace, size_t workspace_bytes, void* stream) {
+  return gemm_tf32_mn(a_hi, a_lo, lda, b_hi, b_lo, ldb, C, ldc, M, N, K, a_mn, b_mn, bias, accumulate, passes, split_k,
+                      workspace, workspace_bytes, ST(stream));
+}
 }  // extern "C"

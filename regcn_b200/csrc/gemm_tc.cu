@@ -85,6 +85,20 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
   return d;
 }
+// MN-major tf32 tile.  For 32-bit operands tcgen05 accepts exactly one MN-major shared-memory layout: 128-byte rows
+// swizzled in 32-byte chunks (layout type SWIZZLE_128B_BASE32B; TMA mode CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B), atom =
+// 32 MN elements (one 128-byte row) x 4 K rows.  As written by TMA boxes of 32 floats (MN) x 32 rows (K): 4-row groups
+// follow each other along K every 512 bytes (SBO), the next 32 MN elements start a new 4096-byte box (LBO).  One tf32
+// MMA (K = 8) consumes two groups, so the K step is +1024 bytes.
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)(4096 >> 4) << 16;          // leading byte offset: stride between MN atoms (boxes)
+  d |= (uint64_t)(512 >> 4) << 32;           // stride byte offset: stride between 4-row K groups
+  d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
+  d |= (uint64_t)1 << 61;                    // SWIZZLE_128B_BASE32B
+  return d;
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
   asm volatile(
@@ -112,6 +126,8 @@ struct Params {
   int stages;
   int passes;         // 3 = 3xTF32 (fp32 parity), 1 = plain TF32 (or bf16)
   int bf16;           // operands are bf16 (kind::f16 MMA, 64-element k-blocks); passes == 1
+  int a_mn, b_mn;     // operand is MN-major: A given as X (K, M) row-major (A = X^T) / B given as Y (K, N) row-major
+                      // (B^T = Y, i.e. C = A Y): dW = x^T dy and y = x W straight from the natural layouts
   int kb_per_split;   // k-blocks per split-K slice
   int m_tiles, n_tiles, splits;   // persistent work list: splits x n_tiles x m_tiles items
   float* ws;          // split-K partials [splits][M][N] (NULL when splits == 1)
@@ -238,10 +254,17 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
           mbar_expect_tx(fb, stage_bytes);
           uint32_t dst = smem_base + stage * stage_bytes;
           const int k0 = kb * block_k;
-          tma_load_2d(dst, &tm_a_hi, fb, k0, m0); dst += a_bytes;
-          if (three) { tma_load_2d(dst, &tm_a_lo, fb, k0, m0); dst += a_bytes; }
-          tma_load_2d(dst, &tm_b_hi, fb, k0, n0); dst += b_bytes;
-          if (three) { tma_load_2d(dst, &tm_b_lo, fb, k0, n0); }
+          // K-major operand: one box of 32 k-floats x rows; MN-major operand: boxes of 32 MN-elements x 32 reduction
+          // rows, 4096 bytes each (inner coordinate = MN offset)
+          auto load_op = [&](const CUtensorMap* tm, int mn, int r0, int nrows, uint32_t bytes) {
+            if (mn) { for (int j = 0; j < nrows / 32; ++j) tma_load_2d(dst + j * 4096, tm, fb, r0 + 32 * j, k0); }
+            else tma_load_2d(dst, tm, fb, k0, r0);
+            dst += bytes;
+          };
+          load_op(&tm_a_hi, p.a_mn, m0, BLOCK_M, a_bytes);
+          if (three) load_op(&tm_a_lo, p.a_mn, m0, BLOCK_M, a_bytes);
+          load_op(&tm_b_hi, p.b_mn, n0, p.block_n, b_bytes);
+          if (three) load_op(&tm_b_lo, p.b_mn, n0, p.block_n, b_bytes);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -253,7 +276,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
       // (kind::f16 with bf16 operands: format code 1 for A and B, same layout of the other fields)
       const uint32_t fmt = p.bf16 ? 1u : 2u;
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.block_n >> 3) << 17) |
-                             ((uint32_t)(BLOCK_M >> 4) << 24);
+                             ((uint32_t)(BLOCK_M >> 4) << 24) | (p.a_mn ? (1u << 15) : 0u) | (p.b_mn ? (1u << 16) : 0u);   // a_major / b_major
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -273,6 +296,22 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
           const uint32_t sa_lo = sa_hi + a_bytes;
           const uint32_t sb_hi = sa_hi + (three ? 2u : 1u) * a_bytes;
           const uint32_t sb_lo = sb_hi + b_bytes;
+          if (p.a_mn | p.b_mn) {
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              // K step: one 8-row group (1024 B) of an MN-major tile, 32 B inside the swizzle row of a K-major one
+              const uint32_t ka = p.a_mn ? k * 1024 : k * UMMA_K * 4, kbo = p.b_mn ? k * 1024 : k * UMMA_K * 4;
+              auto da = [&](uint32_t base) { return p.a_mn ? make_desc_mn(base + ka) : make_desc(base + ka); };
+              auto db = [&](uint32_t base) { return p.b_mn ? make_desc_mn(base + kbo) : make_desc(base + kbo); };
+              if (three) {
+                umma_tf32(tmem_acc, da(sa_lo), db(sb_hi), idesc, acc);
+                acc = 1;
+                umma_tf32(tmem_acc, da(sa_hi), db(sb_lo), idesc, acc);
+              }
+              umma_tf32(tmem_acc, da(sa_hi), db(sb_hi), idesc, acc);
+              acc = 1;
+            }
+          } else
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint32_t koff = k * UMMA_K * 4;   // bytes inside the 128-byte swizzle row
@@ -619,7 +658,8 @@ static EncodeTiledFn get_encode() {
 }
 
 // 2-D fp32 row-major [rows, cols] with leading dimension ld; box = 32 floats x box_rows, 128B swizzle, zero OOB fill.
-static int make_map(CUtensorMap* m, const void* ptr, int rows, int cols, int ld, int box_rows, bool bf16 = false) {
+static int make_map(CUtensorMap* m, const void* ptr, int rows, int cols, int ld, int box_rows, bool bf16 = false,
+                    bool atom32 = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_last_error("gemm_tf32: cuTensorMapEncodeTiled entry point unavailable"); return REGCN_ERR_UNSUPPORTED; }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -627,7 +667,8 @@ static int make_map(CUtensorMap* m, const void* ptr, int rows, int cols, int ld,
   cuuint32_t box[2] = {(cuuint32_t)(bf16 ? 2 * BLOCK_K : BLOCK_K), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_last_error("gemm_tf32: cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%d", (int)r, rows, cols, ld); return REGCN_ERR_DIM; }
   return REGCN_OK;
@@ -709,7 +750,7 @@ static void clear_epi(tc::Params& p) {
   p.lse_max = nullptr; p.lse_sum = nullptr;
   p.lay_d = 0; p.lay_raw = nullptr; p.lay_hi = nullptr; p.lay_lo = nullptr; p.row_idx = nullptr; p.skip_rows = nullptr;
   p.gate_G = nullptr; p.gate_ld = 0; p.gate_bias = nullptr; p.gate_h = nullptr; p.gate_norm = 0;
-  p.bf16 = 0;
+  p.bf16 = 0; p.a_mn = 0; p.b_mn = 0;
 }
 
 // Common launcher: validates operands, builds the tensor maps, sizes the pipeline, launches.
@@ -721,7 +762,7 @@ static int launch_tc(const float* a_hi, const float* a_lo, int lda, const float*
   if (passes != 1 && passes != 3) { set_last_error("%s: passes must be 1 or 3", who); return REGCN_ERR_DIM; }
   const int ld_mask = p.bf16 ? 7 : 3;                 // row pitch must be a multiple of 16 bytes
   if (p.bf16 && passes != 1) { set_last_error("%s: bf16 operands take one pass", who); return REGCN_ERR_DIM; }
-  if (M < 0 || N <= 0 || K <= 0 || (lda & ld_mask) || (ldb & ld_mask) || lda < K || ldb < K ||
+  if (M < 0 || N <= 0 || K <= 0 || (lda & ld_mask) || (ldb & ld_mask) || lda < (p.a_mn ? M : K) || ldb < (p.b_mn ? N : K) ||
       (((uintptr_t)a_hi | (uintptr_t)b_hi | (uintptr_t)a_lo | (uintptr_t)b_lo) & 15)) {
     set_last_error("%s: bad dims/alignment M=%d N=%d K=%d lda=%d ldb=%d", who, M, N, K, lda, ldb);
     return REGCN_ERR_DIM;
@@ -729,6 +770,13 @@ static int launch_tc(const float* a_hi, const float* a_lo, int lda, const float*
   if (M == 0) return REGCN_OK;
   p.passes = passes;
   p.block_n = force_block_n > 0 ? force_block_n : pick_block_n(M, N, K, split_k);
+  if (p.a_mn || p.b_mn) {
+    if (p.bf16 || p.epi != 0) { set_last_error("%s: MN-major operands take fp32 data and the store epilogue", who); return REGCN_ERR_UNSUPPORTED; }
+  }
+  if (p.b_mn) {                                         // MN-major B tiles are whole 32-element atoms
+    const int nt = (N + 255) / 256;
+    p.block_n = ((N + nt - 1) / nt + 31) / 32 * 32;
+  }
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * p.block_n) p.tmem_cols <<= 1;     // two accumulator slots
   const uint32_t stage_bytes = (passes == 3 ? 2u : 1u) * (BLOCK_M * BLOCK_K * 4 + (uint32_t)p.block_n * BLOCK_K * 4);
@@ -744,11 +792,12 @@ static int launch_tc(const float* a_hi, const float* a_lo, int lda, const float*
   if (p.stages < 1) { set_last_error("%s: tile does not fit in shared memory", who); return REGCN_ERR_UNSUPPORTED; }
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   int e;
-  if ((e = make_map(&ta_hi, a_hi, M, K, lda, BLOCK_M, p.bf16 != 0))) return e;
-  if ((e = make_map(&tb_hi, b_hi, N, K, ldb, p.block_n, p.bf16 != 0))) return e;
+  // K-major operand (rows, K): box of 32 k-floats x tile rows; MN-major operand (K, rows): boxes of 32 columns x 32 rows
+  if ((e = p.a_mn ? make_map(&ta_hi, a_hi, K, M, lda, BLOCK_K, false, true) : make_map(&ta_hi, a_hi, M, K, lda, BLOCK_M, p.bf16 != 0))) return e;
+  if ((e = p.b_mn ? make_map(&tb_hi, b_hi, K, N, ldb, BLOCK_K, false, true) : make_map(&tb_hi, b_hi, N, K, ldb, p.block_n, p.bf16 != 0))) return e;
   if (passes == 3) {
-    if ((e = make_map(&ta_lo, a_lo, M, K, lda, BLOCK_M))) return e;
-    if ((e = make_map(&tb_lo, b_lo, N, K, ldb, p.block_n))) return e;
+    if ((e = p.a_mn ? make_map(&ta_lo, a_lo, K, M, lda, BLOCK_K, false, true) : make_map(&ta_lo, a_lo, M, K, lda, BLOCK_M))) return e;
+    if ((e = p.b_mn ? make_map(&tb_lo, b_lo, K, N, ldb, BLOCK_K, false, true) : make_map(&tb_lo, b_lo, N, K, ldb, p.block_n))) return e;
   } else {
     ta_lo = ta_hi; tb_lo = tb_hi;
   }
@@ -819,6 +868,36 @@ int gemm_tf32(const float* a_hi, const float* a_lo, int lda, const float* b_hi, 
     launch_k(splitk_reduce_kernel, (unsigned)((total + 255) / 256), 256, 0, st, ws, sk, C, ldc, M, N, bias, accumulate);
   }
   return check_launch("gemm_tf32");
+}
+
+// C (M, N) = op(A) op(B) with either operand given in its natural row-major layout as an MN-major tcgen05 operand:
+//   a_mn: A passed as X (K, M) (C = X^T ...), else A (M, K);  b_mn: B passed as Y (K, N) (C = ... Y), else B (N, K) (C = ... B^T)
+int gemm_tf32_mn(const float* x_hi, const float* x_lo, int ldx, const float* y_hi, const float* y_lo, int ldy, float* C,
+                 int ldc, int M, int N, int K, int a_mn, int b_mn, const float* bias, int accumulate, int passes,
+                 int split_k, float* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!C) { set_last_error("gemm_tf32_mn: null output"); return REGCN_ERR_NULL; }
+  if (ldc < N) { set_last_error("gemm_tf32_mn: ldc=%d < N=%d", ldc, N); return REGCN_ERR_DIM; }
+  tc::Params p;
+  clear_epi(p);
+  p.a_mn = a_mn != 0; p.b_mn = b_mn != 0;
+  p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.accumulate = accumulate; p.bias = bias;
+  const int total_kb = (K + tc::BLOCK_K - 1) / tc::BLOCK_K;
+  int sk = split_k < 1 ? 1 : (split_k > total_kb ? total_kb : split_k);
+  if (sk > 1) {
+    const int kb_per = (total_kb + sk - 1) / sk;
+    sk = (total_kb + kb_per - 1) / kb_per;
+  }
+  if (sk > 1) {
+    if (!ws || ws_bytes < gemm_tf32_workspace_bytes(M, N, sk)) { set_last_error("gemm_tf32_mn: split-K workspace too small"); return REGCN_ERR_WORKSPACE; }
+    p.ws = ws;
+  }
+  int e = launch_tc(x_hi, x_lo, ldx, y_hi, y_lo, ldy, p, passes, sk, 0, "gemm_tf32_mn", st);
+  if (e) return e;
+  if (sk > 1 && M > 0) {
+    const size_t total = (size_t)M * N;
+    launch_k(splitk_reduce_kernel, (unsigned)((total + 255) / 256), 256, 0, st, ws, sk, C, ldc, M, N, bias, accumulate);
+  }
+  return check_launch("gemm_tf32_mn");
 }
 
 // GEMM with the fused layer epilogue (see Params): out rows = rrelu(A . B^T)[:, :d] (+ time gate), gate columns -> C.

