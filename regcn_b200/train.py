@@ -53,18 +53,6 @@ def _split(x):
     return ops.split_tf32(x.contiguous())
 
 
-def _tsplit(x):
-    """x (rows, cols) -> (hi, lo) of x^T as (cols, pad4(rows)), zero padded: a K-major operand with K = pad4(rows)."""
-    rows, cols = x.shape
-    if x.stride(1) != 1:
-        x = x.contiguous()
-    ldo = _pad4(rows)
-    hi = torch.empty((cols, ldo), device=x.device, dtype=F32)
-    lo = torch.empty((cols, ldo), device=x.device, dtype=F32)
-    call("regcn_transpose_split", x.data_ptr(), rows, cols, x.stride(0), None, ptr(hi), ptr(lo), ldo)
-    return hi, lo
-
-
 def _auto_split_k(M, N, K):
     tiles = ((M + 127) // 128) * ((N + 127) // 128)
     if K < 1024 or tiles >= 120:
@@ -72,8 +60,11 @@ def _auto_split_k(M, N, K):
     return max(1, min(32, 148 // tiles, K // 256))
 
 
-def _mm_nt(a, b, M, N, K, bias=None, out=None, ldc=None):
-    """C (M, N) = A (M, K) . B (N, K)^T; a, b = (hi, lo) pairs whose row pitch is K (zero padded)."""
+def _mm(a, b, M, N, K, a_mn=False, b_mn=False, bias=None, out=None, ldc=None, lda=None, ldb=None):
+    """C (M, N) = op(A) op(B) on the 3xTF32 tcgen05 GEMM; a, b = (hi, lo) pairs in their natural row-major layout:
+       a_mn=False: A is (M, K);  a_mn=True: A is given as X (K, M) and the product uses X^T   (dW = x^T dy)
+       b_mn=False: B is (N, K) and the product uses B^T;  b_mn=True: B is given as Y (K, N)    (y = x W, dX = dY W)
+    MN-major operands go to the tensor core as they lie in memory (csrc/gemm_tc.cu): no transposes anywhere."""
     dev = a[0].device
     if out is None:
         ldc = _pad4(N)
@@ -81,13 +72,15 @@ def _mm_nt(a, b, M, N, K, bias=None, out=None, ldc=None):
         out = out[:, :N] if ldc != N else out
     elif ldc is None:
         ldc = out.stride(0)
+    lda = a[0].stride(0) if lda is None else lda
+    ldb = b[0].stride(0) if ldb is None else ldb
     split_k = _auto_split_k(M, N, K)
     ws, ws_bytes = None, 0
     if split_k > 1:
         ws_bytes = _lib.load().regcn_gemm_tf32_workspace_bytes(M, N, split_k)
         ws = _ws(dev, ws_bytes, slot=1)
-    call("regcn_gemm_tf32", ptr(a[0]), ptr(a[1]), K, ptr(b[0]), ptr(b[1]), K, out.data_ptr(), ldc, M, N, K, ptr(bias),
-         0, 3, split_k, ptr(ws), ws_bytes)
+    call("regcn_gemm_tf32_mn", a[0].data_ptr(), a[1].data_ptr(), lda, b[0].data_ptr(), b[1].data_ptr(), ldb,
+         out.data_ptr(), ldc, M, N, K, int(a_mn), int(b_mn), ptr(bias), 0, 3, split_k, ptr(ws), ws_bytes)
     return out
 
 
@@ -110,11 +103,12 @@ class _Linear(torch.autograd.Function):
         W = W.contiguous()
         M, K = x.shape
         N = W.shape[1] if w_kn else W.shape[0]
-        if K % 4:
-            raise ValueError("regcn_b200.train: inner dimension must be a multiple of 4")
-        b_op = _tsplit(W) if w_kn else _split(W)
-        y = _mm_nt(_split(x), b_op, M, N, K, bias=None if bias is None else bias.contiguous())
+        if K % 4 or N % 4:
+            raise ValueError("regcn_b200.train: matrix dimensions must be multiples of 4")
+        xs = _split(x)
+        y = _mm(xs, _split(W), M, N, K, b_mn=w_kn, bias=None if bias is None else bias.contiguous())
         ctx.save_for_backward(x, W)
+        ctx.xs = xs                                   # the TF32 split of x is the A operand of dW again
         ctx.w_kn = w_kn
         ctx.has_bias = bias is not None
         return y
@@ -122,20 +116,18 @@ class _Linear(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         x, W = ctx.saved_tensors
+        xs, ctx.xs = ctx.xs, None
         dy = dy.contiguous()
         M, K = x.shape
         N = dy.shape[1]
         dx = dW = db = None
-        if N % 4:
-            raise ValueError("regcn_b200.train: output dimension must be a multiple of 4")
+        dys = _split(dy)
         if ctx.needs_input_grad[0]:
-            # dx (M,K) = dy (M,N) . Wop (K,N)^T
-            w_op = _split(W) if ctx.w_kn else _tsplit(W)
-            dx = _mm_nt(_split(dy), w_op, M, K, N)
+            # w_kn: dx = dy W^T, W (K, N) is already the K-major B operand;  F.linear: dx = dy W with W (N, K) as Y
+            dx = _mm(dys, _split(W), M, K, N, b_mn=not ctx.w_kn)
         if ctx.needs_input_grad[1]:
-            xt, dyt = _tsplit(x), _tsplit(dy)                    # (K, pad4(M)), (N, pad4(M))
-            Mp = _pad4(M)
-            dW = _mm_nt(xt, dyt, K, N, Mp) if ctx.w_kn else _mm_nt(dyt, xt, N, K, Mp)
+            # dW = x^T dy (K, N)  /  dy^T x (N, K): both operands MN-major, reduction over the M rows
+            dW = _mm(xs, dys, K, N, M, a_mn=True, b_mn=True) if ctx.w_kn else _mm(dys, xs, N, K, M, a_mn=True, b_mn=True)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = _col_sum(dy)
         return dx, dW, db, None
@@ -375,7 +367,8 @@ class _ConvTower(torch.autograd.Function):
         call("regcn_bn_act_drop", ptr(Y), B, C, d, ptr(m1), ptr(is1), ptr(g1.contiguous()), ptr(b1.contiguous()), 1,
              p_feat, _next_seed(), ptr(Z))
         wf_c = wf.contiguous()
-        Fq = _mm_nt(_split(Z), _split(wf_c), B, d, C * d, bias=bf.contiguous())
+        Zs = _split(Z)
+        Fq = _mm(Zs, _split(wf_c), B, d, C * d, bias=bf.contiguous())
         Fq = Fq.contiguous()
         if p_hid > 0:
             call("regcn_dropout", ptr(Fq), Fq.numel(), p_hid, _next_seed())
@@ -385,6 +378,7 @@ class _ConvTower(torch.autograd.Function):
              0.0, 0, ptr(Q))
         ctx.save_for_backward(X0, X1, Y, Z, Fq, Q, m0, is0, m1, is1, m2, is2, g0, wc_c, g1, wf_c, g2, triples)
         ctx.dims = (B, d, C, ksz, col0, col1, first.shape[0], second.shape[0], p_in, p_feat, p_hid)
+        ctx.Zs = Zs
         return Q
 
     @staticmethod
@@ -397,9 +391,11 @@ class _ConvTower(torch.autograd.Function):
         dF, dg2, db2 = _bn_bwd(dQ, Q, Fq, B, d, 1, 1, 1.0, m2, is2, g2.contiguous(), out_src=Fq,
                                out_mode=2 if p_hid > 0 else 0, out_scale=1.0 / (1.0 - p_hid) if p_hid > 0 else 1.0)
         dbf = _col_sum(dF)
-        Bp = _pad4(B)
-        dwf = _mm_nt(_tsplit(dF), _tsplit(Z), d, C * d, Bp)                    # (d, C d) = dF^T Z
-        dZ = _mm_nt(_split(dF), _tsplit(wf), B, C * d, d)                      # (B, C d) = dF W_fc
+        Zs, ctx.Zs = ctx.Zs, None
+        dFs = _split(dF)
+        dwf = _mm(dFs, Zs, d, C * d, B, a_mn=True, b_mn=True)                  # (d, C d) = dF^T Z
+        dZ = _mm(dFs, _split(wf), B, C * d, d, b_mn=True)                      # (B, C d) = dF W_fc
+        del Zs
         dZ = dZ.contiguous()
         # bn1 + relu + feature dropout (mask Z > 0, scale 1/(1-p))
         dY, dg1, db1 = _bn_bwd(dZ, Z, Y, B, C, d, 1, 1.0 / (1.0 - p_feat) if p_feat > 0 else 1.0, m1, is1,
@@ -444,7 +440,7 @@ class _ScoreCE(torch.autograd.Function):
         Np = _pad4(N)
         dev = q.device
         S = torch.empty((B, Np), device=dev, dtype=F32)
-        _mm_nt(_split(q), _split(cand), B, N, d, out=S, ldc=Np)
+        _mm(_split(q), _split(cand), B, N, d, out=S, ldc=Np)
         ce = torch.empty(B, device=dev, dtype=F32)
         lse = torch.empty(B, device=dev, dtype=F32)
         loss = torch.empty(1, device=dev, dtype=F32)
@@ -467,11 +463,11 @@ class _ScoreCE(torch.autograd.Function):
         call("regcn_softmax_grad_rows", ptr(S), Np, B, N, ptr(triples), ctx.target_col, ptr(lse),
              ptr(gloss.contiguous().view(-1)))
         dq = dcand = None
+        Ss = _split(S)                                                            # (B, Np) pitch, padding columns zero
         if ctx.needs_input_grad[0]:
-            dq = _mm_nt(_split(S), _tsplit(cand), B, d, Np)                       # cand^T: (d, pad4(N)) == (d, Np)
+            dq = _mm(Ss, _split(cand), B, d, N, b_mn=True)                        # dS cand: cand (N, d) as Y
         if ctx.needs_input_grad[1]:
-            Bp = _pad4(B)
-            dcand = _mm_nt(_tsplit(S[:, :N]), _tsplit(q), N, d, Bp)               # (N, Bp) . (d, Bp)^T
+            dcand = _mm(Ss, _split(q), N, d, B, a_mn=True, b_mn=True)             # dS^T q
         return dq, dcand, None, None
 
 
