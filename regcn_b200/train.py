@@ -4,8 +4,8 @@ for the optimisation step of src/main.py:235-246.
 torch.autograd is used as the tape only: every node below is a `torch.autograd.Function` whose forward AND backward
 are C-ABI kernel calls (csrc/backward.cu + the forward kernels); no torch arithmetic runs on the path apart from
 autograd's own gradient accumulation for tensors with several consumers.  Dense contractions (forward, dX and dW)
-go through the tcgen05 3xTF32 GEMM; the dW = x^T dy products get their K-major operands from a fused
-transpose + TF32-split kernel.  Dropout masks come from a counter-based generator (`manual_seed`), so they cannot
+go through the tcgen05 3xTF32 GEMM; dW = x^T dy, y = x W and dX = dY W hand their operands to the tensor core in the
+natural row-major layout (MN-major tiles, `regcn_gemm_tf32_mn`), so nothing is transposed.  Dropout masks come from a counter-based generator (`manual_seed`), so they cannot
 match torch's generator element for element -- parity tests run with dropout 0, statistics tests with dropout on.
 """
 import torch
