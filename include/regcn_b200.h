@@ -427,6 +427,23 @@ REGCN_API int regcn_gemm_tf32_mn(const float* a_hi, const float* a_lo, int lda, 
                        float* C, int ldc, int M, int N, int K, int a_mn, int b_mn, const float* bias, int accumulate,
                        int passes, int split_k, float* workspace, size_t workspace_bytes, void* stream);
 
+/* One-call decode + rank of an evaluated timestamp for the ConvTransE / ConvTransR pair (src/rrgcn.py:190-193,
+ * src/decoder.py:29-52,78-100, rgcn/utils.py:136-166 as called from src/main.py:71-74): [F.normalize] -> tanh(E) ->
+ * entity tower -> fused score/count over all N entities + filter correction -> relation tower -> (B,2R) scores ->
+ * raw/filtered relation ranks.  packed (4*B int32) = [rank | filter_rank | rank_rel | filter_rank_rel], 1-based.
+ * tower_ent / tower_rel: HOST arrays of 11 device pointers {bn0 scale, bn0 shift, conv weight (C,2,k), conv bias,
+ * bn1 scale, bn1 shift, fc weight hi, fc weight lo (d, C*d), fc bias, bn2 scale, bn2 shift} (eval-mode BatchNorm folded
+ * to scale/shift).  fe_* / fr_*: the entity / relation filter lists (ptr, idx, end as built by regcn_filter_count /
+ * regcn_filter_fill); pair_a / pair_e (P >= B): the (query, candidate) pairs regcn_filter_fill emits.
+ * Same kernels and arithmetic as the per-op entry points, so ranks are bit-identical to calling those in sequence. */
+REGCN_API size_t regcn_convtrans_decode_rank_workspace_bytes(int N, int R2, int d, int B, int C, int P);
+REGCN_API int regcn_convtrans_decode_rank(const float* emb, const float* r_emb, const int64_t* triples,
+                                const void* const* tower_ent, const void* const* tower_rel, const int32_t* fe_ptr,
+                                const int32_t* fe_idx, const int32_t* fe_end, const int32_t* pair_a,
+                                const int32_t* pair_e, int P, const int32_t* fr_ptr, const int32_t* fr_idx,
+                                const int32_t* fr_end, int N, int R2, int d, int B, int C, int ksz, int layer_norm,
+                                int32_t* packed, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -112,6 +112,8 @@ SIGNATURES = {
     "regcn_topk_construct_snap": (_i, [_p, _i64, _i, _i, _i, _p, _i, _i, _p, _p, _p]),
     "regcn_atth_query": (_i, [_p] * 8 + [_i, _i, _i, _d, _p, _p, _p]),
     "regcn_gemm_tf32_mn": (_i, [_p, _p, _i, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _i, _p, _sz, _p]),
+    "regcn_convtrans_decode_rank_workspace_bytes": (_sz, [_i] * 6),
+    "regcn_convtrans_decode_rank": (_i, [_p] * 10 + [_i, _p, _p, _p] + [_i] * 7 + [_p, _p, _sz, _p]),
     "regcn_static_angle_bwd": (_i, [_p, _p, _i, _i, _f, _f, _i, _p, _p, _i, _p, _p]),
 }
 

@@ -27,6 +27,60 @@ def _scoring_operands(model, emb, r_emb, all_triples):
     raise NotImplementedError(name)
 
 
+def _tower_table(dec):
+    """Host array of the 11 device pointers regcn_convtrans_decode_rank takes per decoder (include/regcn_b200.h), rebuilt
+    when any of the module's tensors changes (version / storage)."""
+    import numpy as np
+    from .decoder import _fold_bn
+    srcs = [dec.conv1.weight, dec.conv1.bias, dec.fc.weight, dec.fc.bias]
+    for bn in (dec.bn0, dec.bn1, dec.bn2):
+        srcs += [bn.weight, bn.bias, bn.running_mean, bn.running_var]
+    stamp = tuple((t._version, t.data_ptr()) for t in srcs)
+    hit = dec.__dict__.get("_regcn_tower_tab")
+    if hit is not None and hit[0] == stamp:
+        return hit[1]
+    with torch.no_grad():
+        s0, b0 = _fold_bn(dec.bn0)
+        s1, b1 = _fold_bn(dec.bn1)
+        s2, b2 = _fold_bn(dec.bn2)
+        cw = dec.conv1.weight.detach().contiguous()
+        cb = dec.conv1.bias.detach().contiguous()
+        fw_hi, fw_lo = ops.split_tf32(dec.fc.weight.detach().contiguous())
+        fb = dec.fc.bias.detach().contiguous()
+    keep = [s0, b0, cw, cb, s1, b1, fw_hi, fw_lo, fb, s2, b2]
+    tab = np.array([t.data_ptr() for t in keep], dtype=np.uint64)
+    dec.__dict__["_regcn_tower_tab"] = (stamp, (tab, keep))
+    return tab, keep
+
+
+def convtrans_decode_rank(model, emb, r_emb, all_t, f_ent, f_rel):
+    """The decode + rank half of one evaluated timestamp (src/main.py:71-74 after the evolution) in ONE C-ABI call
+    (`regcn_convtrans_decode_rank`).  emb: the evolved entity table BEFORE the predict-time F.normalize.  Returns the
+    packed int32 ranks [rank | filter_rank | rank_rel | filter_rank_rel] (4B,) on the device."""
+    from . import _lib
+    dec, rdec = model.decoder_ob, model.rdecoder
+    emb, r_emb = emb.contiguous(), r_emb.contiguous()
+    N, d = emb.shape
+    R2, B = r_emb.shape[0], all_t.shape[0]
+    C, _, ksz = dec.conv1.weight.shape
+    pa, pe = f_ent.pairs(None if f_ent._pairs is not None else all_t[:, 2].to(torch.int32).contiguous())
+    P = int(pa.shape[0])
+    tab_e, _keep_e = _tower_table(dec)
+    tab_r, _keep_r = _tower_table(rdec)
+    need = _lib.load().regcn_convtrans_decode_rank_workspace_bytes(N, R2, d, B, C, P)
+    ws = model.__dict__.get("_regcn_decode_ws")
+    if ws is None or ws.numel() < need or ws.device != emb.device:
+        ws = torch.empty(int(need * 1.25), device=emb.device, dtype=torch.uint8)
+        model.__dict__["_regcn_decode_ws"] = ws
+    packed = torch.empty(4 * B, device=emb.device, dtype=torch.int32)
+    _lib.call("regcn_convtrans_decode_rank", emb.data_ptr(), r_emb.data_ptr(), all_t.data_ptr(), tab_e.ctypes.data,
+              tab_r.ctypes.data, f_ent.ptr.data_ptr(), f_ent.idx.data_ptr(),
+              None if f_ent.end is None else f_ent.end.data_ptr(), pa.data_ptr(), pe.data_ptr(), P, f_rel.ptr.data_ptr(),
+              f_rel.idx.data_ptr(), None if f_rel.end is None else f_rel.end.data_ptr(), N, R2, d, B, C, ksz,
+              int(bool(model.layer_norm)), packed.data_ptr(), ws.data_ptr(), ws.numel())
+    return packed
+
+
 @torch.no_grad()
 def evaluate_snapshot(model, glist, all_triples, filter_csr, timers=None, fused=None, shard=None):
     """Returns (rank, filter_rank) int64 (B,) for the 2*T_q queries `all_triples` (forward + inverse).
@@ -261,6 +315,10 @@ def test(model, history_list, test_list, num_rels, num_nodes, use_cuda=True, all
                                 relation_evaluation, return_ranks)
     cache = SnapshotCache(num_nodes, num_rels, dev, capacity=max(2 * L + 2, 8))
     fused_ok = ops.gemm_impl() in ("tc", "tc1")
+    # ConvTransE / ConvTransR in fp32-parity mode: decode + rank of a timestamp is one C call (same kernels, same ranks)
+    one_call = (ops.gemm_impl() == "tc" and ops.score_dtype() == "fp32" and os.environ.get("REGCN_DECODE_ENGINE", "1") != "0"
+                and type(model.decoder_ob).__name__ == "ConvTransE" and type(model.rdecoder).__name__ == "ConvTransR"
+                and model.h_dim % 4 == 0 and model.h_dim <= 256)
     K = len(test_list)
     # pinned staging, allocated once: two size slots (ping-pong between the step being run and the one being prepared)
     # and one result area holding [rank | frank | rank_r | frank_r] of every timestamp
@@ -295,25 +353,28 @@ def test(model, history_list, test_list, num_rels, num_nodes, use_cuda=True, all
         evolve_embs, _, r_emb, _, _ = model.forward(cur.glist, static_graph, True)
         _t3 = time.perf_counter()
         emb = evolve_embs[-1]
-        if model.layer_norm:
-            if hasattr(model, "_c_float"):
-                emb = ops.row_map(emb, ops.ROW_TANGENT_NORMALIZE, c=model._c_float)
-            else:
-                emb = ops.row_map(emb, ops.ROW_NORMALIZE)
-        if fused_ok:
-            q, cand, hyp, col_bias = _scoring_operands(model, emb, r_emb, all_t)
-            target = all_t[:, 2].to(torch.int32).contiguous()
-            pa, pe = f_ent.pairs(target)
-            raw, filt, _ = ops.fused_rank_counts(q, cand, target, f_ent.ptr, f_ent.idx, pa, pe, hyp=hyp,
-                                                 col_bias=col_bias, filt_end=f_ent.end)
-            rank, frank = ops.counts_to_ranks(raw, filt)
+        if one_call:
+            packed = convtrans_decode_rank(model, emb, r_emb, all_t, f_ent, f_rel)
         else:
-            score = model.decoder_ob.forward(emb, r_emb, all_t, mode="test")
-            _, _, rank, frank = utils.get_total_rank(all_t, score, None, 1000, rel_predict=0, filter_csr=f_ent)
-        score_rel = model.rdecoder.forward(emb, r_emb, all_t, mode="test")
-        raw_r, filt_r, _ = ops.rank_dense(score_rel, all_t, 1, f_rel.ptr, f_rel.idx, filt_end=f_rel.end)
-        rank_r, frank_r = ops.counts_to_ranks(raw_r, filt_r)
-        packed = torch.cat((rank, frank, rank_r, frank_r)).to(torch.int32)
+            if model.layer_norm:
+                if hasattr(model, "_c_float"):
+                    emb = ops.row_map(emb, ops.ROW_TANGENT_NORMALIZE, c=model._c_float)
+                else:
+                    emb = ops.row_map(emb, ops.ROW_NORMALIZE)
+            if fused_ok:
+                q, cand, hyp, col_bias = _scoring_operands(model, emb, r_emb, all_t)
+                target = all_t[:, 2].to(torch.int32).contiguous()
+                pa, pe = f_ent.pairs(target)
+                raw, filt, _ = ops.fused_rank_counts(q, cand, target, f_ent.ptr, f_ent.idx, pa, pe, hyp=hyp,
+                                                     col_bias=col_bias, filt_end=f_ent.end)
+                rank, frank = ops.counts_to_ranks(raw, filt)
+            else:
+                score = model.decoder_ob.forward(emb, r_emb, all_t, mode="test")
+                _, _, rank, frank = utils.get_total_rank(all_t, score, None, 1000, rel_predict=0, filter_csr=f_ent)
+            score_rel = model.rdecoder.forward(emb, r_emb, all_t, mode="test")
+            raw_r, filt_r, _ = ops.rank_dense(score_rel, all_t, 1, f_rel.ptr, f_rel.idx, filt_end=f_rel.end)
+            rank_r, frank_r = ops.counts_to_ranks(raw_r, filt_r)
+            packed = torch.cat((rank, frank, rank_r, frank_r)).to(torch.int32)
         host = result_host[offs[k]:offs[k + 1]]
         host.copy_(packed, non_blocking=True)                      # this timestamp's result, device -> host
         results.append(host)

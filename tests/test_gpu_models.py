@@ -347,6 +347,27 @@ def test_evaluation_loop_matches_stepwise_reference_style_loop(kind):
     assert abs(mrrs[1] - ref_mrr) < 1e-7
 
 
+def test_one_call_decode_rank_equals_per_op_path(monkeypatch):
+    """regcn_convtrans_decode_rank (decode + rank of a timestamp in one C call) against the per-op path of test():
+    the same kernels in the same order -> identical ranks, entity and relation, raw and filtered."""
+    R._lib.require_device()
+    cfg = dict(kind="regcn", shape="c1", seed=4, layer_norm=True)
+    st = synth.make_stream(cfg["shape"], cfg["seed"], n_test=3)
+    n, r = st["num_ents"], st["num_rels"]
+    model, _ = build_model(cfg, n, r)
+    model = model.to(DEV)
+    L = len(st["history"])
+    out = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("REGCN_DECODE_ENGINE", flag)
+        out.append(R.test(model, st["history"], st["tests"], r, n, True, None, None, None, None, "eval",
+                          test_history_len=L, return_ranks=True))
+    assert out[0][0] == out[1][0]
+    for a, b in zip(out[0][1], out[1][1]):
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
+
+
 def test_construct_snap_kernels_bit_exact():
     """Top-k + predicted-snapshot kernels (multi-step inference) against the reference's outputs and, with ties and a
     non-multiple-of-anything width, against the oracle's stable order."""
