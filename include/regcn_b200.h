@@ -303,10 +303,12 @@ REGCN_API int regcn_hyp_evolve(const void* const* model_ptrs, const int* model_i
  * The backward of every gather on the path: UnionRGCNLayer message (rgcn/layers.py:257-279; the snapshot graph holds
  * each edge with its inverse, so the forward CSR-by-destination is also the CSR-by-source), the relation table
  * gather (same lines), the relation mean-pool (src/rrgcn.py:161-166, col2_off = R) and the decoder's E[s] / rel[r]
- * gathers (src/decoder.py:81-82).  col_w / row_w may be NULL (= 1).                                              */
+ * gathers (src/decoder.py:81-82).  col_w / row_w may be NULL (= 1).  rho != NULL multiplies every term by the
+ * radius-difference edge weight exp(-gamma |rho[col_j] - rho[other]|) of the hyperbolic layers
+ * (hyperbolic_layers.py:232-234), other = partner[j] (per CSR position) or the row itself when partner is NULL.  */
 REGCN_API int regcn_csr_gather_sum(const float* X, int ldx, const float* col_w, const float* row_w, const int32_t* rowptr,
                          const int32_t* col, int nrows, int d, int col2_off, float* out, int ldo, int accumulate,
-                         void* stream);
+                         const float* rho, float gamma, const int32_t* partner, void* stream);
 /* Stable grouping of n int32 keys in [0,nkeys): rowptr (nkeys+1), perm (n) original positions grouped by key,
  * vals_out[i] = vals[perm[i]] (vals may be NULL).  Builds the transposed indices the gathers above run on.      */
 REGCN_API size_t regcn_group_by_key_workspace_bytes(int n);
@@ -322,7 +324,8 @@ REGCN_API int regcn_normalize_bwd(const float* x, const float* dy, float* dx, in
 REGCN_API int regcn_gru_gate_bwd(const float* gi, const float* gh, const float* hprev, const float* dout, int M, int d,
                        int normalize, float* dgi, float* dgh, float* dhprev, void* stream);
 /* UnionRGCNLayer apply-step backward (rgcn/layers.py:241-253): out = dropout_p(rrelu(P + where(indeg>0, L0, L1)));
- * masks recovered from `out`.  dP (N,d); dL (N,2d) = [indeg>0 ? dP : 0 | indeg>0 ? 0 : dP] (may be NULL).         */
+ * masks recovered from `out` (out == NULL: no activation / dropout, dP = dout).  dP (N,d); dL (N,2d) =
+ * [indeg>0 ? dP : 0 | indeg>0 ? 0 : dP] (may be NULL).                                                              */
 REGCN_API int regcn_union_combine_bwd(const float* out, const float* dout, const int32_t* indeg, int N, int d, float p,
                             float* dP, float* dL, void* stream);
 /* time gate backward (src/rrgcn.py:176-178): dG (pre-sigmoid), dcur (through the optional F.normalize), dh (direct). */
@@ -443,6 +446,47 @@ REGCN_API int regcn_convtrans_decode_rank(const float* emb, const float* r_emb, 
                                 const int32_t* pair_e, int P, const int32_t* fr_ptr, const int32_t* fr_idx,
                                 const int32_t* fr_end, int N, int R2, int d, int B, int C, int ksz, int layer_norm,
                                 int32_t* packed, void* workspace, size_t workspace_bytes, void* stream);
+
+/* =================================================================================================================
+ * Hyperbolic training step: HyperbolicRecurrentRGCN.get_loss in train mode, hyperbolic_uvrgcn encoder +
+ * hyperbolic_convtranse decoder (hyperbolic_model.py:722-890,941-1088; hyperbolic_layers.py:222-323;
+ * hyperbolic_ops.py:38-233,395-435; hyperbolic_decoder.py:360-413).
+ * ================================================================================================================= */
+/* Backward of the radial Poincare row maps y = s(|x|) x: mode 0 log_0, 1 exp_0 (with its projection), 2 project_to_ball,
+ * 3 exp_0(F.normalize(log_0 x)).  dx = s dy + s'(n)/n <x,dy> x with the reference's norm clamps (s' = 0 where active). */
+REGCN_API int regcn_radial_bwd(const float* x, const float* dy, float* dx, int M, int d, int mode, double c, void* stream);
+/* get_radius (hyperbolic_ops.py:206) and apply_radius (:222-233), forward and backward                             */
+REGCN_API int regcn_row_radius(const float* x, int M, int d, float* rho, void* stream);
+REGCN_API int regcn_row_radius_bwd(const float* x, const float* drho, int M, int d, float* dx, void* stream);
+REGCN_API int regcn_apply_radius(const float* x, const float* r, int M, int d, double c, float* y, void* stream);
+REGCN_API int regcn_apply_radius_bwd(const float* x, const float* r, const float* dy, int M, int d, double c, float* dx,
+                           float* dr, void* stream);
+/* elementwise op 0: clamp(x, -lim, lim) (the +-10 tangent clamps); op 1: 0.9 tanh(x) + 0.1 x (hyperbolic_decoder.py:378) */
+REGCN_API int regcn_eltwise_fwd(const float* x, float* y, size_t n, int op, float lim, void* stream);
+REGCN_API int regcn_eltwise_bwd(const float* x, const float* dy, float* dx, size_t n, int op, float lim, void* stream);
+/* _static_radius (hyperbolic_model.py:715-720) + TemporalRadiusEvolution's scalar part (hyperbolic_ops.py:408-424):
+ * out = beta rs + (1-beta) dyn + clamp(delta, +-eps_r), rs = min(clamp(raw, rmin, rmax), 1/sqrt(c) - 1e-6); dyn = delta =
+ * NULL gives out = rs.  Backward: draw, ddyn, ddelta.                                                               */
+REGCN_API int regcn_radius_combine(const float* raw, const float* dyn, const float* delta, int M, float rmin, float rmax,
+                         double c, float beta, float eps_r, float* out, void* stream);
+REGCN_API int regcn_radius_combine_bwd(const float* raw, const float* delta, const float* g, int M, float rmin, float rmax,
+                             double c, float beta, float eps_r, float* draw, float* ddyn, float* ddelta, void* stream);
+/* radius_mlp = Linear(d,1): out[n] = <t[n], w> + b[0] (b: device scalar, may be NULL); backward: dt and the rows dout[n] t[n] (their column sum is dw)   */
+REGCN_API int regcn_row_dot(const float* t, const float* w, const float* b, int M, int d, float* out, void* stream);
+REGCN_API int regcn_row_dot_bwd(const float* t, const float* w, const float* dout, int M, int d, float* dt, float* scaled,
+                      void* stream);
+/* gradient of the radius-difference edge weights w.r.t. the radii: s_edge (per CSR position) and drho_dst (N);
+ * regcn_edge_scalar_gather sums s_edge per source through a grouping of src_sorted (regcn_group_by_key)            */
+REGCN_API int regcn_edge_radius_grad(const float* ht, const float* rel, const float* dagg, const int32_t* rowptr,
+                           const int32_t* src_sorted, const int32_t* etype_sorted, const float* norm, const float* rho,
+                           float gamma, int N, int d, float* s_edge, float* drho_dst, void* stream);
+REGCN_API int regcn_edge_scalar_gather(const float* vals, const int32_t* rowptr, const int32_t* perm, int nrows, float* out,
+                             int accumulate, void* stream);
+/* loss_radius (hyperbolic_model.py:1066-1073): term[j] = lambda/n (rs[ids[j]] - target[ids[j]])^2 and d/d radius_static */
+REGCN_API int regcn_radius_mse(const float* raw, const float* target, const int64_t* ids, int n, float rmin, float rmax,
+                     double c, float lambda, float* term, void* stream);
+REGCN_API int regcn_radius_mse_bwd(const float* raw, const float* target, const int64_t* ids, int n, float rmin, float rmax,
+                         double c, float lambda, const float* gscale, float* draw, void* stream);
 
 #ifdef __cplusplus
 }

@@ -321,11 +321,64 @@ def run_construct_snap(ref_utils):
     print("-> aux_construct_snap.npz")
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# hyperbolic training golden (hyperbolic_main.py:585-628, hyperbolic_model.py:941-1088), dropout 0
+# ---------------------------------------------------------------------------------------------------------------
+HYP_TRAIN_CASES = {
+    "hyptrain_tiny_s0": dict(kind="hyp", shape="tiny", seed=0, encoder="hyperbolic_uvrgcn", decoder="hyperbolic_convtranse",
+                             layer_norm=False, gamma=0.15),
+    "hyptrain_tiny_s1_ln": dict(kind="hyp", shape="tiny", seed=1, encoder="hyperbolic_uvrgcn",
+                                decoder="hyperbolic_convtranse", layer_norm=True, gamma=1.0),
+    "hyptrain_small_s2_ln": dict(kind="hyp", shape="small", seed=2, encoder="hyperbolic_uvrgcn",
+                                 decoder="hyperbolic_convtranse", layer_norm=True, gamma=0.15),
+}
+
+
+def run_hyp_train(ref_utils, HyperbolicRecurrentRGCN):
+    """tests/golden/train_hyp.npz: one optimisation step of the UNMODIFIED hyperbolic reference (get_loss in train() mode
+    with every dropout 0, loss = 0.7 l_e + 0.3 l_r + l_static + l_radius, clip_grad_norm_(1.0), Adam)."""
+    out = {}
+    for name, cfg in HYP_TRAIN_CASES.items():
+        case = synth.make_case(cfg["shape"], cfg["seed"])
+        n, r = case["num_ents"], case["num_rels"]
+        m = HyperbolicRecurrentRGCN(cfg["decoder"], cfg["encoder"], n, r, 0, 0, H_DIM, "sub", 3, num_bases=N_BASES,
+                                    num_hidden_layers=N_LAYERS, dropout=0.0, c=CURV, self_loop=True, skip_connect=False,
+                                    layer_norm=cfg["layer_norm"], input_dropout=0.0, hidden_dropout=0.0, feat_dropout=0.0,
+                                    entity_prediction=True, relation_prediction=True, use_cuda=False, gpu="cpu",
+                                    radius_msg_gamma=cfg["gamma"], hyp_init_scale=1e-3)
+        m.load_state_dict(synth.fill_state_dict(m.state_dict(), cfg["seed"]))
+        m.train()
+        opt = torch.optim.Adam(m.parameters(), lr=LR, weight_decay=WEIGHT_DECAY)
+        glist = [ref_utils.build_sub_graph(n, r, snap, False, "cpu") for snap in case["history"]]
+        le, lr_, ls, lrad = m.get_loss(glist, torch.from_numpy(case["test"]), None, False)
+        loss = TASK_WEIGHT * le + (1 - TASK_WEIGHT) * lr_ + ls + lrad
+        loss.backward()
+        tn = torch.nn.utils.clip_grad_norm_(m.parameters(), GRAD_NORM)
+        coef = min(1.0, GRAD_NORM / (float(tn) + 1e-6))
+        grads = {k: (None if p.grad is None else p.grad.detach().clone()) for k, p in m.named_parameters()}
+        opt.step()
+        out[f"{name}.s0.losses"] = np.array([float(x.detach().reshape(-1)[0]) for x in (le, lr_, ls, lrad)], dtype=np.float64)
+        out[f"{name}.s0.grad_norm"] = np.array(float(tn), dtype=np.float64)
+        for k, p in m.named_parameters():
+            if grads[k] is None:
+                continue
+            g = grads[k].numpy() / coef
+            out[f"{name}.s0.gn.{k}"] = np.array(np.linalg.norm(g.astype(np.float64)))
+            out[f"{name}.s0.g.{k}"] = sample_of(g)
+            out[f"{name}.s0.p.{k}"] = sample_of(p.detach().numpy())
+        print(name, out[f"{name}.s0.losses"], "grad norm", float(tn), "params with grad", sum(g is not None for g in grads.values()))
+    path = os.path.join(GOLDEN, "train_hyp.npz")
+    np.savez_compressed(path, **out)
+    print("->", path, os.path.getsize(path) / 1e6, "MB")
+
+
 def main(argv):
     ref_utils, RecurrentRGCN, HyperbolicRecurrentRGCN = _import_reference()
     torch.set_num_threads(os.cpu_count() or 1)
     if len(argv) > 1 and argv[1] == "--losses":
         return run_losses(ref_utils, RecurrentRGCN, HyperbolicRecurrentRGCN)
+    if len(argv) > 1 and argv[1] == "--hyp-train":
+        return run_hyp_train(ref_utils, HyperbolicRecurrentRGCN)
     if len(argv) > 1 and argv[1] == "--construct-snap":
         return run_construct_snap(ref_utils)
     if len(argv) > 1 and argv[1] == "--static":

@@ -825,3 +825,66 @@ def regcn_train_steps(sd, graphs, num_rels, triples, layer_norm=True, steps=1, t
                     "grads": {k: g.detach().clone() for k, g in grads.items()},
                     "params": {k: P[k].detach().clone() for k in grads}})
     return log, {k: v.detach() for k, v in P.items() if "running_" in k}
+
+
+# =====================================================================================
+# Hyperbolic training step (hyperbolic_model.py:941-1088 in train() mode + hyperbolic_main.py:585-628), dropout 0,
+# hyperbolic_uvrgcn encoder + hyperbolic_convtranse decoder.
+# =====================================================================================
+def hyp_train_losses(P, graphs, num_rels, triples, c, layer_norm, gamma, stats, rmin=0.5, rmax=3.0, beta=1.0, eps_r=0.1,
+                     radius_lambda=0.02):
+    all_t = torch.as_tensor(add_inverse(triples, num_rels))
+    hist, h0 = hyp_forward(P, graphs, num_rels, c=c, encoder="hyperbolic_uvrgcn", layer_norm=layer_norm, gamma=gamma,
+                           rmin=rmin, rmax=rmax, beta=beta, eps_r=eps_r, dtype=P["emb_rel"].dtype)
+    emb = hist[-1]
+    if layer_norm:
+        emb = exp0(normalize_rows(log0(emb, c)), c)
+    et = log0(emb, c)
+    et = 0.9 * torch.tanh(et) + 0.1 * et
+    q = conv_tower_train(et[all_t[:, 0]], h0[all_t[:, 1]], P, "decoder_ob.", stats)
+    loss_e = cross_entropy(q @ et.t() + P["decoder_ob.b"], all_t[:, 2])
+    q = conv_tower_train(et[all_t[:, 0]], et[all_t[:, 2]], P, "rdecoder.", stats)
+    loss_r = cross_entropy(q @ h0.t() + P["rdecoder.b"], all_t[:, 1])
+    ids = torch.unique(all_t[:, [0, 2]].reshape(-1))
+    rs = static_radius(P["radius_static"], c, rmin, rmax)[ids]
+    loss_rad = radius_lambda * torch.mean((rs - P["radius_target"][ids]) ** 2)
+    return loss_e, loss_r, loss_rad
+
+
+def hyp_train_steps(sd, graphs, num_rels, triples, c=0.01, layer_norm=False, gamma=0.15, steps=1, task_weight=0.7,
+                    grad_norm=1.0, lr=1e-3, weight_decay=1e-5, betas=(0.9, 0.999), eps=1e-8, dtype=torch.float32):
+    """Like regcn_train_steps for the hyperbolic model.  Returns per-step dicts {losses (e, r, static, radius),
+    grad_norm, grads, params}."""
+    P = {}
+    for k, v in sd.items():
+        if not v.is_floating_point() or k == "rgcn.rel_emb":
+            continue
+        t = v.detach().clone().to(dtype)
+        if "running_" not in k and k not in ("c", "log_c", "radius_target"):
+            t.requires_grad_(True)
+        P[k] = t
+    m = {k: torch.zeros_like(v) for k, v in P.items() if v.requires_grad}
+    vv = {k: torch.zeros_like(v) for k, v in P.items() if v.requires_grad}
+    log = []
+    for step in range(1, steps + 1):
+        stats = {}
+        le, lrel, lrad = hyp_train_losses(P, graphs, num_rels, triples, c, layer_norm, gamma, stats)
+        loss = task_weight * le + (1 - task_weight) * lrel + lrad
+        names = [k for k, v in P.items() if v.requires_grad]
+        gs = torch.autograd.grad(loss, [P[k] for k in names], allow_unused=True)
+        grads = {k: g for k, g in zip(names, gs) if g is not None}
+        total = torch.sqrt(sum((g.double() ** 2).sum() for g in grads.values()))
+        coef = min(1.0, grad_norm / (float(total) + 1e-6))
+        with torch.no_grad():
+            for k, g in grads.items():
+                p = P[k]
+                gg = g * coef + weight_decay * p
+                m[k] = betas[0] * m[k] + (1 - betas[0]) * gg
+                vv[k] = betas[1] * vv[k] + (1 - betas[1]) * gg * gg
+                p -= (lr / (1 - betas[0] ** step)) * m[k] / (vv[k].sqrt() / math.sqrt(1 - betas[1] ** step) + eps)
+            for k, s in stats.items():
+                P[k] = s
+        log.append({"losses": (float(le.detach()), float(lrel.detach()), 0.0, float(lrad.detach())),
+                    "grad_norm": float(total), "grads": {k: g.detach().clone() for k, g in grads.items()},
+                    "params": {k: P[k].detach().clone() for k in grads}})
+    return log

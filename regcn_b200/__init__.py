@@ -16,7 +16,7 @@ from .hyperbolic_decoder import (HyperbolicAttH, HyperbolicAttHRel, HyperbolicCo
 from .hyperbolic_model import HyperbolicRecurrentRGCN  # noqa: F401
 from . import utils  # noqa: F401
 from . import knowledge_graph  # noqa: F401  (on-disk TKG format reader)
-from . import optim, train  # noqa: F401  (training step: get_loss with gradients + clipped Adam)
+from . import optim, train, train_hyp  # noqa: F401  (training step: get_loss with gradients + clipped Adam)
 from .evaluate import test  # noqa: F401  (the reference's evaluation loop, src/main.py:33)
 
 __version__ = "0.1.0"

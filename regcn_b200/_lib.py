@@ -79,7 +79,7 @@ SIGNATURES = {
     "regcn_filter_count": (_i, [_p, _i, _i, _p, _p]),
     "regcn_filter_fill": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
     # ---- training (csrc/backward.cu)
-    "regcn_csr_gather_sum": (_i, [_p, _i, _p, _p, _p, _p, _i, _i, _i, _p, _i, _i, _p]),
+    "regcn_csr_gather_sum": (_i, [_p, _i, _p, _p, _p, _p, _i, _i, _i, _p, _i, _i, _p, _f, _p, _p]),
     "regcn_group_by_key_workspace_bytes": (_sz, [_i]),
     "regcn_group_by_key": (_i, [_p, _i, _i, _p, _p, _p, _p, _p, _sz, _p]),
     "regcn_expand_rowptr": (_i, [_p, _i, _i, _p, _p, _p]),
@@ -114,6 +114,21 @@ SIGNATURES = {
     "regcn_gemm_tf32_mn": (_i, [_p, _p, _i, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _i, _p, _sz, _p]),
     "regcn_convtrans_decode_rank_workspace_bytes": (_sz, [_i] * 6),
     "regcn_convtrans_decode_rank": (_i, [_p] * 10 + [_i, _p, _p, _p] + [_i] * 7 + [_p, _p, _sz, _p]),
+    "regcn_radial_bwd": (_i, [_p, _p, _p, _i, _i, _i, _d, _p]),
+    "regcn_row_radius": (_i, [_p, _i, _i, _p, _p]),
+    "regcn_row_radius_bwd": (_i, [_p, _p, _i, _i, _p, _p]),
+    "regcn_apply_radius": (_i, [_p, _p, _i, _i, _d, _p, _p]),
+    "regcn_apply_radius_bwd": (_i, [_p, _p, _p, _i, _i, _d, _p, _p, _p]),
+    "regcn_eltwise_fwd": (_i, [_p, _p, _sz, _i, _f, _p]),
+    "regcn_eltwise_bwd": (_i, [_p, _p, _p, _sz, _i, _f, _p]),
+    "regcn_radius_combine": (_i, [_p, _p, _p, _i, _f, _f, _d, _f, _f, _p, _p]),
+    "regcn_radius_combine_bwd": (_i, [_p, _p, _p, _i, _f, _f, _d, _f, _f, _p, _p, _p, _p]),
+    "regcn_row_dot": (_i, [_p, _p, _p, _i, _i, _p, _p]),
+    "regcn_row_dot_bwd": (_i, [_p, _p, _p, _i, _i, _p, _p, _p]),
+    "regcn_edge_radius_grad": (_i, [_p] * 8 + [_f, _i, _i, _p, _p, _p]),
+    "regcn_edge_scalar_gather": (_i, [_p, _p, _p, _i, _p, _i, _p]),
+    "regcn_radius_mse": (_i, [_p, _p, _p, _i, _f, _f, _d, _f, _p, _p]),
+    "regcn_radius_mse_bwd": (_i, [_p, _p, _p, _i, _f, _f, _d, _f, _p, _p, _p]),
     "regcn_static_angle_bwd": (_i, [_p, _p, _i, _i, _f, _f, _i, _p, _p, _i, _p, _p]),
 }
 

@@ -64,7 +64,9 @@ constexpr int kGatherHead = 64;
 template <int RV>
 __device__ __forceinline__ void gather_span(WarpRow<RV>& acc, const float* __restrict__ X, int ldx,
                                             const float* __restrict__ col_w, const int* __restrict__ col, int j0, int e,
-                                            int stride, int nvec, int lane, int col2_off) {
+                                            int stride, int nvec, int lane, int col2_off,
+                                            const float* __restrict__ rho = nullptr, float gamma = 0.f,
+                                            const int* __restrict__ partner = nullptr, int row = 0) {
   for (; j0 < e; j0 += stride) {
     const int n = min(32, e - j0);
     int c = 0;
@@ -72,6 +74,10 @@ __device__ __forceinline__ void gather_span(WarpRow<RV>& acc, const float* __res
     if (lane < n) {
       c = __ldg(col + j0 + lane);
       w = col_w ? __ldg(col_w + c) : 1.f;
+      if (rho) {   // radius-difference edge weight exp(-gamma |rho_a - rho_b|), hyperbolic_layers.py:232-234
+        const int other = partner ? __ldg(partner + j0 + lane) : row;
+        w *= expf(-gamma * fabsf(__ldg(rho + c) - __ldg(rho + other)));
+      }
     }
     for (int k = 0; k < n; ++k) {
       const int ck = __shfl_sync(0xffffffffu, c, k);
@@ -96,7 +102,8 @@ __global__ void __launch_bounds__(256) csr_gather_sum_kernel(const float* __rest
                                                              const float* __restrict__ row_w,
                                                              const int* __restrict__ rowptr, const int* __restrict__ col,
                                                              int nrows, int d, int col2_off, float* __restrict__ out,
-                                                             int ldo, int accumulate) {
+                                                             int ldo, int accumulate, const float* __restrict__ rho,
+                                                             float gamma, const int* __restrict__ partner) {
   pdl_grid_sync();
   __shared__ float4 part[8][32 * RV];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -107,7 +114,7 @@ __global__ void __launch_bounds__(256) csr_gather_sum_kernel(const float* __rest
   acc.zero();
   if (row < nrows) {
     const int b = __ldg(rowptr + row), e = __ldg(rowptr + row + 1);
-    gather_span(acc, X, ldx, col_w, col, b, min(e, b + kGatherHead), 32, nvec, lane, col2_off);
+    gather_span(acc, X, ldx, col_w, col, b, min(e, b + kGatherHead), 32, nvec, lane, col2_off, rho, gamma, partner, row);
   }
   for (int rr = 0; rr < 8; ++rr) {                        // block-uniform loop: the tails of this CTA's rows
     if (row0 + rr >= nrows) break;
@@ -115,7 +122,7 @@ __global__ void __launch_bounds__(256) csr_gather_sum_kernel(const float* __rest
     if (e2 <= b2) continue;
     WarpRow<RV> p;
     p.zero();
-    gather_span(p, X, ldx, col_w, col, b2 + 32 * wid, e2, 32 * 8, nvec, lane, col2_off);
+    gather_span(p, X, ldx, col_w, col, b2 + 32 * wid, e2, 32 * 8, nvec, lane, col2_off, rho, gamma, partner, row0 + rr);
 #pragma unroll
     for (int i = 0; i < RV; ++i) part[wid][lane + i * kWarp] = p.v[i];
     __syncthreads();
@@ -139,13 +146,14 @@ __global__ void __launch_bounds__(256) csr_gather_sum_kernel(const float* __rest
 }
 
 int csr_gather_sum(const float* X, int ldx, const float* col_w, const float* row_w, const int* rowptr, const int* col,
-                   int nrows, int d, int col2_off, float* out, int ldo, int accumulate, cudaStream_t st) {
+                   int nrows, int d, int col2_off, float* out, int ldo, int accumulate, cudaStream_t st, const float* rho,
+                   float gamma, const int* partner) {
   if (!X || !rowptr || !col || !out) { set_last_error("csr_gather_sum: null pointer"); return REGCN_ERR_NULL; }
   if (int e = chk_d("csr_gather_sum", d)) return e;
   if ((ldx & 3) || (ldo & 3) || ldx < d || ldo < d) { set_last_error("csr_gather_sum: bad pitch"); return REGCN_ERR_DIM; }
   if (nrows <= 0) return REGCN_OK;
-  if (d <= 128) launch_k(csr_gather_sum_kernel<1>, rgrid(nrows), 256, 0, st, X, ldx, col_w, row_w, rowptr, col, nrows, d, col2_off, out, ldo, accumulate);
-  else launch_k(csr_gather_sum_kernel<2>, rgrid(nrows), 256, 0, st, X, ldx, col_w, row_w, rowptr, col, nrows, d, col2_off, out, ldo, accumulate);
+  if (d <= 128) launch_k(csr_gather_sum_kernel<1>, rgrid(nrows), 256, 0, st, X, ldx, col_w, row_w, rowptr, col, nrows, d, col2_off, out, ldo, accumulate, rho, gamma, partner);
+  else launch_k(csr_gather_sum_kernel<2>, rgrid(nrows), 256, 0, st, X, ldx, col_w, row_w, rowptr, col, nrows, d, col2_off, out, ldo, accumulate, rho, gamma, partner);
   return check_launch("csr_gather_sum");
 }
 
@@ -336,11 +344,13 @@ __global__ void __launch_bounds__(256) union_combine_bwd_kernel(const float* __r
   pdl_grid_sync();
   ROW_PROLOGUE(N)
   WarpRow<RV> o, g;
-  o.load_plain(out + (size_t)row * d, nvec, lane);
   g.load_plain(dout + (size_t)row * d, nvec, lane);
-  const float inv_keep = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
-  const float zero_f = p > 0.f ? 0.f : kRReluSlope;
-  g.zip(o, [=](float gg, float oo) { return gg * (oo > 0.f ? inv_keep : (oo < 0.f ? kRReluSlope * inv_keep : zero_f)); });
+  if (out) {
+    o.load_plain(out + (size_t)row * d, nvec, lane);
+    const float inv_keep = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;
+    const float zero_f = p > 0.f ? 0.f : kRReluSlope;
+    g.zip(o, [=](float gg, float oo) { return gg * (oo > 0.f ? inv_keep : (oo < 0.f ? kRReluSlope * inv_keep : zero_f)); });
+  }
   g.store(dP + (size_t)row * d, nvec, lane);
   if (dL) {
     WarpRow<RV> zr;
@@ -353,7 +363,7 @@ __global__ void __launch_bounds__(256) union_combine_bwd_kernel(const float* __r
 }
 int union_combine_bwd(const float* out, const float* dout, const int* indeg, int N, int d, float p, float* dP, float* dL,
                       cudaStream_t st) {
-  if (!out || !dout || !dP || (dL && !indeg)) { set_last_error("union_combine_bwd: null pointer"); return REGCN_ERR_NULL; }
+  if (!dout || !dP || (dL && !indeg)) { set_last_error("union_combine_bwd: null pointer"); return REGCN_ERR_NULL; }
   if (int e = chk_d("union_combine_bwd", d)) return e;
   if (N <= 0) return REGCN_OK;
   if (d <= 128) launch_k(union_combine_bwd_kernel<1>, rgrid(N), 256, 0, st, out, dout, indeg, N, d, p, dP, dL);
@@ -1179,8 +1189,9 @@ using namespace regcn;
 extern "C" {
 int regcn_csr_gather_sum(const float* X, int ldx, const float* col_w, const float* row_w, const int32_t* rowptr,
                          const int32_t* col, int nrows, int d, int col2_off, float* out, int ldo, int accumulate,
-                         void* stream) {
-  return csr_gather_sum(X, ldx, col_w, row_w, rowptr, col, nrows, d, col2_off, out, ldo, accumulate, ST(stream));
+                         const float* rho, float gamma, const int32_t* partner, void* stream) {
+  return csr_gather_sum(X, ldx, col_w, row_w, rowptr, col, nrows, d, col2_off, out, ldo, accumulate, ST(stream), rho, gamma,
+                        partner);
 }
 size_t regcn_group_by_key_workspace_bytes(int n) { return group_by_key_workspace_bytes(n); }
 int regcn_group_by_key(const int32_t* keys, int n, int nkeys, const int32_t* vals, int32_t* rowptr, int32_t* perm,

@@ -1,0 +1,456 @@
+// Backward kernels of the hyperbolic evolution step (second half): HyperbolicRecurrentRGCN.get_loss
+// in train mode for the hyperbolic_uvrgcn encoder + hyperbolic_convtranse decoder (hyperbolic_model.py:722-890,941-1088,
+// hyperbolic_layers.py:222-323, hyperbolic_ops.py:38-233,395-435, hyperbolic_decoder.py:360-413).
+//
+// Every Poincare row map on the path is RADIAL: y = s(n) x with n = max(|x|, eps) -- exp_0 (with its projection),
+// log_0, project_to_ball, F.normalize, the tangent normalisation exp_0(normalize(log_0 x)) -- so one backward kernel
+// serves them all:  dx = s dy + (s'(n)/n) <x,dy> x   (s' = 0 where the norm clamp is active).
+#include "common.cuh"
+#include "internal.h"
+
+namespace regcn {
+
+#define ROWP(M_)                                                                       \
+  const int lane = threadIdx.x & 31;                                                   \
+  const int row = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);         \
+  if (row >= (M_)) return;                                                             \
+  const int nvec = d >> 2;
+static inline unsigned rg(int M) { return (unsigned)(((size_t)M * 32 + 255) / 256); }
+static inline int chk(const char* who, int d) {
+  if (d <= 0 || (d & 3) || d > 256) { set_last_error("%s: d=%d unsupported (need d%%4==0, d<=256)", who, d); return REGCN_ERR_UNSUPPORTED; }
+  return REGCN_OK;
+}
+
+// mode 0 log_0, 1 exp_0 (+ projection), 2 project_to_ball, 3 exp_0(F.normalize(log_0 x))   -> (s, s')
+__device__ __forceinline__ void radial_coeff(int mode, float nraw, const Curv& k, float& s, float& sp) {
+  const float n = fmaxf(nraw, kEps);
+  const bool free_n = nraw > kEps;                 // below eps the norm clamp holds n constant
+  const float sc = k.sqrt_c;
+  if (mode == 0) {
+    const float u = sc * n;
+    const bool clamped = u >= 1.0f - kEps;
+    const float a = atanhf(fminf(u, 1.0f - kEps));
+    s = a / (sc * n);
+    sp = (clamped ? 0.f : 1.0f / (n * (1.0f - k.c * n * n))) - a / (sc * n * n);
+  } else if (mode == 1) {
+    const float t = tanhf(sc * n);
+    const float m = t / sc;                        // |exp_0(v)| before the projection
+    if (m > k.proj_max) { s = k.proj_max / n; sp = -k.proj_max / (n * n); }
+    else { s = t / (sc * n); sp = (1.0f - t * t) / n - t / (sc * n * n); }
+  } else if (mode == 2) {
+    if (n > k.proj_max) { s = k.proj_max / n; sp = -k.proj_max / (n * n); }
+    else { s = 1.0f; sp = 0.f; }
+  } else {
+    const float K = fminf(tanhf(sc) / sc, k.proj_max);   // |exp_0(unit vector)|, projected
+    s = K / n; sp = -K / (n * n);
+  }
+  if (!free_n) sp = 0.f;
+}
+
+template <int RV>
+__global__ void __launch_bounds__(256) radial_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                         float* __restrict__ dx, int M, int d, int mode, Curv cv) {
+  pdl_grid_sync();
+  ROWP(M)
+  WarpRow<RV> a, g;
+  a.load_plain(x + (size_t)row * d, nvec, lane);
+  g.load_plain(dy + (size_t)row * d, nvec, lane);
+  const float nraw = sqrtf(a.sumsq());
+  float s, sp;
+  radial_coeff(mode, nraw, cv, s, sp);
+  const float n = fmaxf(nraw, kEps);
+  const float coef = sp / n * a.dot(g);
+  g.zip(a, [=](float gg, float xx) { return s * gg + coef * xx; });
+  g.store(dx + (size_t)row * d, nvec, lane);
+}
+int radial_bwd(const float* x, const float* dy, float* dx, int M, int d, int mode, double c, cudaStream_t st) {
+  if (!x || !dy || !dx) { set_last_error("radial_bwd: null pointer"); return REGCN_ERR_NULL; }
+  if (int e = chk("radial_bwd", d)) return e;
+  if (mode < 0 || mode > 3 || !(c > 0)) { set_last_error("radial_bwd: bad mode / curvature"); return REGCN_ERR_DIM; }
+  if (M <= 0) return REGCN_OK;
+  Curv cv = make_curv(c);
+  if (d <= 128) launch_k(radial_bwd_kernel<1>, rg(M), 256, 0, st, x, dy, dx, M, d, mode, cv);
+  else launch_k(radial_bwd_kernel<2>, rg(M), 256, 0, st, x, dy, dx, M, d, mode, cv);
+  return check_launch("radial_bwd");
+}
+
+// radius (hyperbolic_ops.py:206): rho = max(|x|, eps);   apply_radius (:222-233): y = x / max(|x|,eps) * clamp(r, eps, rmax)
+template <int RV>
+__global__ void __launch_bounds__(256) row_radius_kernel(const float* __restrict__ x, int M, int d, float* __restrict__ rho) {
+  pdl_grid_sync();
+  ROWP(M)
+  WarpRow<RV> a;
+  a.load_plain(x + (size_t)row * d, nvec, lane);
+  const float n = fmaxf(sqrtf(a.sumsq()), kEps);
+  if (lane == 0) rho[row] = n;
+}
+// dx (+)= drho * x / |x|
+template <int RV>
+__global__ void __launch_bounds__(256) row_radius_bwd_kernel(const float* __restrict__ x, const float* __restrict__ drho,
+                                                             int M, int d, float* __restrict__ dx) {
+  pdl_grid_sync();
+  ROWP(M)
+  WarpRow<RV> a;
+  a.load_plain(x + (size_t)row * d, nvec, lane);
+  const float nraw = sqrtf(a.sumsq());
+  const float f = nraw > kEps ? __ldg(drho + row) / nraw : 0.f;
+  a.scale(f);
+  a.store(dx + (size_t)row * d, nvec, lane);
+}
+template <int RV>
+__global__ void __launch_bounds__(256) apply_radius_kernel(const float* __restrict__ x, const float* __restrict__ r, int M,
+                                                           int d, Curv cv, float* __restrict__ y) {
+  pdl_grid_sync();
+  ROWP(M)
+  WarpRow<RV> a;
+  a.load_plain(x + (size_t)row * d, nvec, lane);
+  row_apply_radius(a, __ldg(r + row), cv);
+  a.store(y + (size_t)row * d, nvec, lane);
+}
+template <int RV>
+__global__ void __launch_bounds__(256) apply_radius_bwd_kernel(const float* __restrict__ x, const float* __restrict__ r,
+                                                               const float* __restrict__ dy, int M, int d, Curv cv,
+                                                               float* __restrict__ dx, float* __restrict__ dr) {
+  pdl_grid_sync();
+  ROWP(M)
+  WarpRow<RV> a, g;
+  a.load_plain(x + (size_t)row * d, nvec, lane);
+  g.load_plain(dy + (size_t)row * d, nvec, lane);
+  const float nraw = sqrtf(a.sumsq());
+  const float n = fmaxf(nraw, kEps);
+  const float rv = __ldg(r + row);
+  const float rr = clampf_(rv, kEps, cv.radius_max);
+  a.scale(1.0f / n);                                     // unit direction
+  const float dotv = a.dot(g);
+  if (lane == 0) dr[row] = (rv > kEps && rv < cv.radius_max) ? dotv : 0.f;
+  const bool free_n = nraw > kEps;
+  const float f = rr / n;
+  g.zip(a, [=](float gg, float u) { return f * (gg - (free_n ? u * dotv : 0.f)); });
+  g.store(dx + (size_t)row * d, nvec, lane);
+}
+int row_radius(const float* x, int M, int d, float* rho, cudaStream_t st) {
+  if (!x || !rho) { set_last_error("row_radius: null pointer"); return REGCN_ERR_NULL; }
+  if (int e = chk("row_radius", d)) return e;
+  if (M <= 0) return REGCN_OK;
+  if (d <= 128) launch_k(row_radius_kernel<1>, rg(M), 256, 0, st, x, M, d, rho);
+  else launch_k(row_radius_kernel<2>, rg(M), 256, 0, st, x, M, d, rho);
+  return check_launch("row_radius");
+}
+int row_radius_bwd(const float* x, const float* drho, int M, int d, float* dx, cudaStream_t st) {
+  if (!x || !drho || !dx) { set_last_error("row_radius_bwd: null pointer"); return REGCN_ERR_NULL; }
+  if (int e = chk("row_radius_bwd", d)) return e;
+  if (M <= 0) return REGCN_OK;
+  if (d <= 128) launch_k(row_radius_bwd_kernel<1>, rg(M), 256, 0, st, x, drho, M, d, dx);
+  else launch_k(row_radius_bwd_kernel<2>, rg(M), 256, 0, st, x, drho, M, d, dx);
+  return check_launch("row_radius_bwd");
+}
+int apply_radius_fwd(const float* x, const float* r, int M, int d, double c, float* y, cudaStream_t st) {
+  if (!x || !r || !y) { set_last_error("apply_radius: null pointer"); return REGCN_ERR_NULL; }
+  if (int e = chk("apply_radius", d)) return e;
+  if (M <= 0) return REGCN_OK;
+  Curv cv = make_curv(c);
+  if (d <= 128) launch_k(apply_radius_kernel<1>, rg(M), 256, 0, st, x, r, M, d, cv, y);
+  else launch_k(apply_radius_kernel<2>, rg(M), 256, 0, st, x, r, M, d, cv, y);
+  return check_launch("apply_radius");
+}
+int apply_radius_bwd(const float* x, const float* r, const float* dy, int M, int d, double c, float* dx, float* dr,
+                     cudaStream_t st) {
+  if (!x || !r || !dy || !dx || !dr) { set_last_error("apply_radius_bwd: null pointer"); return REGCN_ERR_NULL; }
+  if (int e = chk("apply_radius_bwd", d)) return e;
+  if (M <= 0) return REGCN_OK;
+  Curv cv = make_curv(c);
+  if (d <= 128) launch_k(apply_radius_bwd_kernel<1>, rg(M), 256, 0, st, x, r, dy, M, d, cv, dx, dr);
+  else launch_k(apply_radius_bwd_kernel<2>, rg(M), 256, 0, st, x, r, dy, M, d, cv, dx, dr);
+  return check_launch("apply_radius_bwd");
+}
+
+// Elementwise pieces.  op 0: y = clamp(x, -lim, lim)  (torch.clamp: gradient 1 inside the closed interval)
+//                      op 1: y = 0.9 tanh(x) + 0.1 x  (HyperbolicConvTransE entity activation, hyperbolic_decoder.py:378)
+__global__ void __launch_bounds__(256) eltwise_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n,
+                                                          int op, float lim) {
+  pdl_grid_sync();
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = x[i];
+  y[i] = op == 0 ? clampf_(v, -lim, lim) : 0.9f * tanhf(v) + 0.1f * v;
+}
+__global__ void __launch_bounds__(256) eltwise_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                          float* __restrict__ dx, size_t n, int op, float lim) {
+  pdl_grid_sync();
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = x[i];
+  float f;
+  if (op == 0) f = (v >= -lim && v <= lim) ? 1.f : 0.f;
+  else { const float t = tanhf(v); f = 0.9f * (1.0f - t * t) + 0.1f; }
+  dx[i] = dy[i] * f;
+}
+int eltwise_fwd(const float* x, float* y, size_t n, int op, float lim, cudaStream_t st) {
+  if (!x || !y) { set_last_error("eltwise_fwd: null pointer"); return REGCN_ERR_NULL; }
+  if (n == 0) return REGCN_OK;
+  launch_k(eltwise_fwd_kernel, (unsigned)((n + 255) / 256), 256, 0, st, x, y, n, op, lim);
+  return check_launch("eltwise_fwd");
+}
+int eltwise_bwd(const float* x, const float* dy, float* dx, size_t n, int op, float lim, cudaStream_t st) {
+  if (!x || !dy || !dx) { set_last_error("eltwise_bwd: null pointer"); return REGCN_ERR_NULL; }
+  if (n == 0) return REGCN_OK;
+  launch_k(eltwise_bwd_kernel, (unsigned)((n + 255) / 256), 256, 0, st, x, dy, dx, n, op, lim);
+  return check_launch("eltwise_bwd");
+}
+
+// TemporalRadiusEvolution scalars (hyperbolic_ops.py:406-425) and _static_radius (hyperbolic_model.py:715-720):
+//   rs = min(clamp(raw, rmin, rmax), cap);  new_r = beta rs + (1-beta) dyn + clamp(delta, -eps_r, eps_r)
+// dyn / delta NULL: new_r = rs (the plain static radius).
+__global__ void radius_combine_kernel(const float* __restrict__ raw, const float* __restrict__ dyn,
+                                      const float* __restrict__ delta, int M, float rmin, float rmax, float cap, float beta,
+                                      float eps_r, float* __restrict__ out) {
+  pdl_grid_sync();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  const float rs = fminf(clampf_(raw[i], rmin, rmax), cap);
+  out[i] = dyn ? beta * rs + (1.0f - beta) * dyn[i] + clampf_(delta[i], -eps_r, eps_r) : rs;
+}
+__global__ void radius_combine_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ delta,
+                                          const float* __restrict__ g, int M, float rmin, float rmax, float cap, float beta,
+                                          float eps_r, int has_dyn, float* __restrict__ draw, float* __restrict__ ddyn,
+                                          float* __restrict__ ddelta) {
+  pdl_grid_sync();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  const float r = raw[i], gi = g[i];
+  const float cl = clampf_(r, rmin, rmax);
+  const float pass = (r >= rmin && r <= rmax && cl <= cap) ? 1.f : 0.f;      // torch.clamp / torch.min gradients
+  draw[i] = gi * pass * (has_dyn ? beta : 1.0f);
+  if (has_dyn) {
+    ddyn[i] = gi * (1.0f - beta);
+    const float dl = delta[i];
+    ddelta[i] = (dl >= -eps_r && dl <= eps_r) ? gi : 0.f;
+  }
+}
+int radius_combine(const float* raw, const float* dyn, const float* delta, int M, float rmin, float rmax, double c,
+                   float beta, float eps_r, float* out, cudaStream_t st) {
+  if (!raw || !out || ((dyn != nullptr) != (delta != nullptr))) { set_last_error("radius_combine: null pointer"); return REGCN_ERR_NULL; }
+  if (M <= 0) return REGCN_OK;
+  const float cap = (float)(1.0 / sqrt(c) - 1e-6);
+  launch_k(radius_combine_kernel, (unsigned)((M + 255) / 256), 256, 0, st, raw, dyn, delta, M, rmin, rmax, cap, beta, eps_r, out);
+  return check_launch("radius_combine");
+}
+int radius_combine_bwd(const float* raw, const float* delta, const float* g, int M, float rmin, float rmax, double c,
+                       float beta, float eps_r, float* draw, float* ddyn, float* ddelta, cudaStream_t st) {
+  if (!raw || !g || !draw || ((ddyn != nullptr) != (ddelta != nullptr)) || (ddyn && !delta)) { set_last_error("radius_combine_bwd: null pointer"); return REGCN_ERR_NULL; }
+  if (M <= 0) return REGCN_OK;
+  const float cap = (float)(1.0 / sqrt(c) - 1e-6);
+  launch_k(radius_combine_bwd_kernel, (unsigned)((M + 255) / 256), 256, 0, st, raw, delta, g, M, rmin, rmax, cap, beta, eps_r,
+           ddyn ? 1 : 0, draw, ddyn, ddelta);
+  return check_launch("radius_combine_bwd");
+}
+
+// radius_mlp = Linear(d, 1) (hyperbolic_ops.py:390-392,407): delta[n] = <t[n], w> + b;  backward: dt = ddelta (x) w and the
+// scaled rows ddelta[n] t[n] whose column sums are dw (col_sum); db = sum ddelta.
+template <int RV>
+__global__ void __launch_bounds__(256) row_dot_kernel(const float* __restrict__ t, const float* __restrict__ w,
+                                                      const float* __restrict__ b, int M, int d, float* __restrict__ out) {
+  pdl_grid_sync();
+  ROWP(M)
+  WarpRow<RV> a, ww;
+  a.load_plain(t + (size_t)row * d, nvec, lane);
+  ww.load(w, nvec, lane);
+  const float v = a.dot(ww) + (b ? __ldg(b) : 0.f);
+  if (lane == 0) out[row] = v;
+}
+template <int RV>
+__global__ void __launch_bounds__(256) row_dot_bwd_kernel(const float* __restrict__ t, const float* __restrict__ w,
+                                                          const float* __restrict__ dout, int M, int d,
+                                                          float* __restrict__ dt, float* __restrict__ scaled) {
+  pdl_grid_sync();
+  ROWP(M)
+  WarpRow<RV> a, ww;
+  a.load_plain(t + (size_t)row * d, nvec, lane);
+  ww.load(w, nvec, lane);
+  const float g = __ldg(dout + row);
+  ww.scale(g);
+  ww.store(dt + (size_t)row * d, nvec, lane);
+  a.scale(g);
+  a.store(scaled + (size_t)row * d, nvec, lane);
+}
+int row_dot(const float* t, const float* w, const float* b, int M, int d, float* out, cudaStream_t st) {
+  if (!t || !w || !out) { set_last_error("row_dot: null pointer"); return REGCN_ERR_NULL; }
+  if (int e = chk("row_dot", d)) return e;
+  if (M <= 0) return REGCN_OK;
+  if (d <= 128) launch_k(row_dot_kernel<1>, rg(M), 256, 0, st, t, w, b, M, d, out);
+  else launch_k(row_dot_kernel<2>, rg(M), 256, 0, st, t, w, b, M, d, out);
+  return check_launch("row_dot");
+}
+int row_dot_bwd(const float* t, const float* w, const float* dout, int M, int d, float* dt, float* scaled, cudaStream_t st) {
+  if (!t || !w || !dout || !dt || !scaled) { set_last_error("row_dot_bwd: null pointer"); return REGCN_ERR_NULL; }
+  if (int e = chk("row_dot_bwd", d)) return e;
+  if (M <= 0) return REGCN_OK;
+  if (d <= 128) launch_k(row_dot_bwd_kernel<1>, rg(M), 256, 0, st, t, w, dout, M, d, dt, scaled);
+  else launch_k(row_dot_bwd_kernel<2>, rg(M), 256, 0, st, t, w, dout, M, d, dt, scaled);
+  return check_launch("row_dot_bwd");
+}
+
+// Radius-difference edge weights (hyperbolic_layers.py:232-234): w_e = exp(-gamma |rho_src - rho_dst|) multiplies the message
+// of edge e.  Gradient w.r.t. the radii: with m_e = h_tan[src] + rel[type] and v = dst,
+//   s_e = -gamma sign(rho_src - rho_dst) norm[v] w_e <dAgg[v], m_e>;   drho[src] += s_e,  drho[dst] -= s_e.
+// One warp per destination row: the 200-wide dot per in-edge, its own -sum written directly, s_e stored per CSR position
+// for the by-source pass (edge_scalar_gather).
+template <int RV>
+__global__ void __launch_bounds__(256) edge_radius_grad_kernel(
+    const float* __restrict__ ht, const float* __restrict__ rel, const float* __restrict__ dagg,
+    const int* __restrict__ rowptr, const int* __restrict__ src_sorted, const int* __restrict__ etype_sorted,
+    const float* __restrict__ norm, const float* __restrict__ rho, float gamma, int N, int d,
+    float* __restrict__ s_edge, float* __restrict__ drho_dst) {
+  pdl_grid_sync();
+  ROWP(N)
+  const int b = __ldg(rowptr + row), e = __ldg(rowptr + row + 1);
+  WarpRow<RV> g;
+  g.load_plain(dagg + (size_t)row * d, nvec, lane);
+  const float nv = __ldg(norm + row), rv = __ldg(rho + row);
+  float acc = 0.f;
+  for (int p = b; p < e; ++p) {
+    const int u = __ldg(src_sorted + p), t = __ldg(etype_sorted + p);
+    WarpRow<RV> m, r;
+    m.load_plain(ht + (size_t)u * d, nvec, lane);
+    r.load(rel + (size_t)t * d, nvec, lane);
+    m.zip(r, [](float a, float bb) { return a + bb; });
+    const float dotv = g.dot(m);
+    const float diff = __ldg(rho + u) - rv;
+    const float w = expf(-gamma * fabsf(diff));
+    const float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+    const float s = -gamma * sgn * nv * w * dotv;
+    if (lane == 0) s_edge[p] = s;
+    acc += s;
+  }
+  if (lane == 0) drho_dst[row] = -acc;
+}
+// out[row] (+)= sum_{j in row} vals[perm[j]]  (per-source sums of the per-edge scalars; fixed order)
+__global__ void edge_scalar_gather_kernel(const float* __restrict__ vals, const int* __restrict__ rowptr,
+                                          const int* __restrict__ perm, int nrows, float* __restrict__ out, int accumulate) {
+  pdl_grid_sync();
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= nrows) return;
+  float a = 0.f;
+  for (int j = rowptr[row]; j < rowptr[row + 1]; ++j) a += vals[perm[j]];
+  out[row] = (accumulate ? out[row] : 0.f) + a;
+}
+int edge_radius_grad(const float* ht, const float* rel, const float* dagg, const int* rowptr, const int* src_sorted,
+                     const int* etype_sorted, const float* norm, const float* rho, float gamma, int N, int d,
+                     float* s_edge, float* drho_dst, cudaStream_t st) {
+  if (!ht || !rel || !dagg || !rowptr || !src_sorted || !etype_sorted || !norm || !rho || !s_edge || !drho_dst) { set_last_error("edge_radius_grad: null pointer"); return REGCN_ERR_NULL; }
+  if (int e = chk("edge_radius_grad", d)) return e;
+  if (N <= 0) return REGCN_OK;
+  if (d <= 128) launch_k(edge_radius_grad_kernel<1>, rg(N), 256, 0, st, ht, rel, dagg, rowptr, src_sorted, etype_sorted, norm, rho, gamma, N, d, s_edge, drho_dst);
+  else launch_k(edge_radius_grad_kernel<2>, rg(N), 256, 0, st, ht, rel, dagg, rowptr, src_sorted, etype_sorted, norm, rho, gamma, N, d, s_edge, drho_dst);
+  return check_launch("edge_radius_grad");
+}
+int edge_scalar_gather(const float* vals, const int* rowptr, const int* perm, int nrows, float* out, int accumulate,
+                       cudaStream_t st) {
+  if (!vals || !rowptr || !perm || !out) { set_last_error("edge_scalar_gather: null pointer"); return REGCN_ERR_NULL; }
+  if (nrows <= 0) return REGCN_OK;
+  launch_k(edge_scalar_gather_kernel, (unsigned)((nrows + 255) / 256), 256, 0, st, vals, rowptr, perm, nrows, out, accumulate);
+  return check_launch("edge_scalar_gather");
+}
+
+// loss_radius (hyperbolic_model.py:1066-1073): lambda * mean_{i in ids} (rs[i] - target[i])^2 over the entities of the batch;
+// term[j] per id (summed by col_sum) and the gradient w.r.t. radius_static (through _static_radius' clamps).
+__global__ void radius_mse_kernel(const float* __restrict__ raw, const float* __restrict__ target,
+                                  const int64_t* __restrict__ ids, int n, float rmin, float rmax, float cap, float scale,
+                                  float* __restrict__ term) {
+  pdl_grid_sync();
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int64_t i = ids[j];
+  const float rs = fminf(clampf_(raw[i], rmin, rmax), cap);
+  const float df = rs - target[i];
+  term[j] = scale * df * df;
+}
+__global__ void radius_mse_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ target,
+                                      const int64_t* __restrict__ ids, int n, float rmin, float rmax, float cap, float scale,
+                                      const float* __restrict__ gscale, float* __restrict__ draw) {
+  pdl_grid_sync();
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int64_t i = ids[j];                              // ids are unique: no write conflicts
+  const float r = raw[i];
+  const float cl = clampf_(r, rmin, rmax);
+  const float rs = fminf(cl, cap);
+  const float pass = (r >= rmin && r <= rmax && cl <= cap) ? 1.f : 0.f;
+  draw[i] = 2.0f * scale * (rs - target[i]) * pass * (gscale ? *gscale : 1.0f);
+}
+int radius_mse(const float* raw, const float* target, const int64_t* ids, int n, float rmin, float rmax, double c,
+               float lambda, float* term, cudaStream_t st) {
+  if (!raw || !target || !ids || !term) { set_last_error("radius_mse: null pointer"); return REGCN_ERR_NULL; }
+  if (n <= 0) return REGCN_OK;
+  launch_k(radius_mse_kernel, (unsigned)((n + 255) / 256), 256, 0, st, raw, target, ids, n, rmin, rmax,
+           (float)(1.0 / sqrt(c) - 1e-6), lambda / (float)n, term);
+  return check_launch("radius_mse");
+}
+int radius_mse_bwd(const float* raw, const float* target, const int64_t* ids, int n, float rmin, float rmax, double c,
+                   float lambda, const float* gscale, float* draw, cudaStream_t st) {
+  if (!raw || !target || !ids || !draw) { set_last_error("radius_mse_bwd: null pointer"); return REGCN_ERR_NULL; }
+  if (n <= 0) return REGCN_OK;
+  launch_k(radius_mse_bwd_kernel, (unsigned)((n + 255) / 256), 256, 0, st, raw, target, ids, n, rmin, rmax,
+           (float)(1.0 / sqrt(c) - 1e-6), lambda / (float)n, gscale, draw);
+  return check_launch("radius_mse_bwd");
+}
+
+}  // namespace regcn
+
+using namespace regcn;
+#define ST(s) ((cudaStream_t)(s))
+extern "C" {
+int regcn_radial_bwd(const float* x, const float* dy, float* dx, int M, int d, int mode, double c, void* stream) {
+  return radial_bwd(x, dy, dx, M, d, mode, c, ST(stream));
+}
+int regcn_row_radius(const float* x, int M, int d, float* rho, void* stream) { return row_radius(x, M, d, rho, ST(stream)); }
+int regcn_row_radius_bwd(const float* x, const float* drho, int M, int d, float* dx, void* stream) {
+  return row_radius_bwd(x, drho, M, d, dx, ST(stream));
+}
+int regcn_apply_radius(const float* x, const float* r, int M, int d, double c, float* y, void* stream) {
+  return apply_radius_fwd(x, r, M, d, c, y, ST(stream));
+}
+int regcn_apply_radius_bwd(const float* x, const float* r, const float* dy, int M, int d, double c, float* dx, float* dr,
+                           void* stream) {
+  return apply_radius_bwd(x, r, dy, M, d, c, dx, dr, ST(stream));
+}
+int regcn_eltwise_fwd(const float* x, float* y, size_t n, int op, float lim, void* stream) {
+  return eltwise_fwd(x, y, n, op, lim, ST(stream));
+}
+int regcn_eltwise_bwd(const float* x, const float* dy, float* dx, size_t n, int op, float lim, void* stream) {
+  return eltwise_bwd(x, dy, dx, n, op, lim, ST(stream));
+}
+int regcn_radius_combine(const float* raw, const float* dyn, const float* delta, int M, float rmin, float rmax, double c,
+                         float beta, float eps_r, float* out, void* stream) {
+  return radius_combine(raw, dyn, delta, M, rmin, rmax, c, beta, eps_r, out, ST(stream));
+}
+int regcn_radius_combine_bwd(const float* raw, const float* delta, const float* g, int M, float rmin, float rmax, double c,
+                             float beta, float eps_r, float* draw, float* ddyn, float* ddelta, void* stream) {
+  return radius_combine_bwd(raw, delta, g, M, rmin, rmax, c, beta, eps_r, draw, ddyn, ddelta, ST(stream));
+}
+int regcn_row_dot(const float* t, const float* w, const float* b, int M, int d, float* out, void* stream) {
+  return row_dot(t, w, b, M, d, out, ST(stream));
+}
+int regcn_row_dot_bwd(const float* t, const float* w, const float* dout, int M, int d, float* dt, float* scaled,
+                      void* stream) {
+  return row_dot_bwd(t, w, dout, M, d, dt, scaled, ST(stream));
+}
+int regcn_edge_radius_grad(const float* ht, const float* rel, const float* dagg, const int32_t* rowptr,
+                           const int32_t* src_sorted, const int32_t* etype_sorted, const float* norm, const float* rho,
+                           float gamma, int N, int d, float* s_edge, float* drho_dst, void* stream) {
+  return edge_radius_grad(ht, rel, dagg, rowptr, src_sorted, etype_sorted, norm, rho, gamma, N, d, s_edge, drho_dst,
+                          ST(stream));
+}
+int regcn_edge_scalar_gather(const float* vals, const int32_t* rowptr, const int32_t* perm, int nrows, float* out,
+                             int accumulate, void* stream) {
+  return edge_scalar_gather(vals, rowptr, perm, nrows, out, accumulate, ST(stream));
+}
+int regcn_radius_mse(const float* raw, const float* target, const int64_t* ids, int n, float rmin, float rmax, double c,
+                     float lambda, float* term, void* stream) {
+  return radius_mse(raw, target, ids, n, rmin, rmax, c, lambda, term, ST(stream));
+}
+int regcn_radius_mse_bwd(const float* raw, const float* target, const int64_t* ids, int n, float rmin, float rmax, double c,
+                         float lambda, const float* gscale, float* draw, void* stream) {
+  return radius_mse_bwd(raw, target, ids, n, rmin, rmax, c, lambda, gscale, draw, ST(stream));
+}
+}

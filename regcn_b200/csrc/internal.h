@@ -115,7 +115,8 @@ int gemm_tf32_mn(const float* x_hi, const float* x_lo, int ldx, const float* y_h
                  int split_k, float* ws, size_t ws_bytes, cudaStream_t st);
 // training (backward.cu)
 int csr_gather_sum(const float* X, int ldx, const float* col_w, const float* row_w, const int* rowptr, const int* col,
-                   int nrows, int d, int col2_off, float* out, int ldo, int accumulate, cudaStream_t st);
+                   int nrows, int d, int col2_off, float* out, int ldo, int accumulate, cudaStream_t st,
+                   const float* rho = nullptr, float gamma = 0.f, const int* partner = nullptr);
 int col_sum(const float* X, int ld, int rows, int cols, int L, float* out, int accumulate, float* ws, size_t ws_bytes,
             cudaStream_t st);
 }  // namespace regcn

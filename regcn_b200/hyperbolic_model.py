@@ -307,17 +307,24 @@ class HyperbolicRecurrentRGCN(nn.Module):
             del self._rb_cache
         return out
 
-    @torch.no_grad()
     def get_loss(self, glist, triples, static_graph, use_cuda, query_time=None):
-        """hyperbolic_model.py:941-1088, forward values: (loss_ent, loss_rel, loss_static, loss_radius).
+        """hyperbolic_model.py:941-1088: (loss_ent, loss_rel, loss_static, loss_radius).
 
-        Entity head: the decoders' streaming CE (hyperbolic_decoder.py:182-307) as the scoring GEMM's log-sum-exp
-        epilogue; relation head on its (B,2R) score matrix; radius supervision as in :1066-1073.  Evaluation-mode
-        forward only: training mode raises until the backward kernels exist."""
-        from . import evaluate
+        Training mode (`model.train()`): losses with gradients for the hyperbolic_uvrgcn encoder + hyperbolic_convtranse
+        decoder (regcn_b200/train_hyp.py: kernels as autograd nodes); other encoders / decoders raise there.
+        Evaluation mode: forward values.  Entity head: the decoders' streaming CE (hyperbolic_decoder.py:182-307) as the
+        scoring GEMM's log-sum-exp epilogue; relation head on its (B,2R) score matrix; radius supervision :1066-1073."""
         if self.training:
-            raise NotImplementedError("regcn_b200.HyperbolicRecurrentRGCN.get_loss: training mode needs the backward "
-                                      "kernels (SURVEY.md 8f rank 1); the forward loss is available after .eval()")
+            if getattr(self, "use_static", False):
+                raise NotImplementedError("static-graph constraint in hyperbolic training is not implemented")
+            from . import train_hyp
+            with torch.enable_grad():
+                return train_hyp.hyp_get_loss(self, glist, triples)
+        with torch.no_grad():
+            return self._get_loss_eval(glist, triples, static_graph, use_cuda)
+
+    def _get_loss_eval(self, glist, triples, static_graph, use_cuda):
+        from . import evaluate
         if getattr(self, "use_static", False):
             raise NotImplementedError("static-graph constraint loss is SURVEY.md 8f rank 3")
         dev = self.dynamic_emb.device

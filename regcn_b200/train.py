@@ -86,11 +86,12 @@ def _mm(a, b, M, N, K, a_mn=False, b_mn=False, bias=None, out=None, ldc=None, ld
 
 def _col_sum(x):
     rows, cols = x.shape
-    x = x.contiguous()
+    if x.stride(1) != 1:
+        x = x.contiguous()
     out = torch.empty(cols, device=x.device, dtype=F32)
     nb = _lib.load().regcn_col_reduce_workspace_bytes(rows, cols)
     ws = _ws(x.device, nb)
-    call("regcn_col_sum", ptr(x), cols, rows, cols, ptr(out), 0, ptr(ws), nb)
+    call("regcn_col_sum", x.data_ptr(), x.stride(0), rows, cols, ptr(out), 0, ptr(ws), nb)
     return out
 
 
@@ -167,10 +168,10 @@ def _train_index(g):
     return idx
 
 
-def _gather_sum(X, ldx, col_w, rowptr, col, nrows, d, col2_off=0, x_ptr=None):
+def _gather_sum(X, ldx, col_w, rowptr, col, nrows, d, col2_off=0, x_ptr=None, rho=None, gamma=0.0, partner=None):
     out = torch.empty((nrows, d), device=X.device, dtype=F32)
     call("regcn_csr_gather_sum", X.data_ptr() if x_ptr is None else x_ptr, ldx, ptr(col_w), None, ptr(rowptr), ptr(col),
-         nrows, d, col2_off, ptr(out), d, 0)
+         nrows, d, col2_off, ptr(out), d, 0, ptr(rho), float(gamma), ptr(partner))
     return out
 
 
@@ -433,14 +434,15 @@ class _ScoreCE(torch.autograd.Function):
     and contracted twice: dq = dS cand, dcand = dS^T q."""
 
     @staticmethod
-    def forward(ctx, q, cand, triples, target_col):
+    def forward(ctx, q, cand, triples, target_col, col_bias=None):
         q, cand = q.contiguous(), cand.contiguous()
         B, d = q.shape
         N = cand.shape[0]
         Np = _pad4(N)
         dev = q.device
         S = torch.empty((B, Np), device=dev, dtype=F32)
-        _mm(_split(q), _split(cand), B, N, d, out=S, ldc=Np)
+        _mm(_split(q), _split(cand), B, N, d, out=S, ldc=Np, bias=None if col_bias is None else col_bias.contiguous())
+        ctx.has_bias = col_bias is not None
         ce = torch.empty(B, device=dev, dtype=F32)
         lse = torch.empty(B, device=dev, dtype=F32)
         loss = torch.empty(1, device=dev, dtype=F32)
@@ -468,11 +470,12 @@ class _ScoreCE(torch.autograd.Function):
             dq = _mm(Ss, _split(cand), B, d, N, b_mn=True)                        # dS cand: cand (N, d) as Y
         if ctx.needs_input_grad[1]:
             dcand = _mm(Ss, _split(q), N, d, B, a_mn=True, b_mn=True)             # dS^T q
-        return dq, dcand, None, None
+        db = _col_sum(S[:, :N]) if ctx.has_bias else None                         # scores + b  (hyperbolic_decoder.py:411)
+        return dq, dcand, None, None, db
 
 
-def score_ce(q, cand, triples, target_col):
-    return _ScoreCE.apply(q, cand, triples, target_col)
+def score_ce(q, cand, triples, target_col, col_bias=None):
+    return _ScoreCE.apply(q, cand, triples, target_col, col_bias)
 
 
 # ------------------------------------------------------------------------------------------------ static-graph constraint

@@ -1,0 +1,327 @@
+"""Training-mode path of HyperbolicRecurrentRGCN (second half): `get_loss` with gradients for the
+hyperbolic_uvrgcn encoder + hyperbolic_convtranse decoder (hyperbolic_model.py:722-890, 941-1088) -- the configuration of
+the reference's only published run (hyperbolic_src/train.log).
+
+Same construction as regcn_b200/train.py: torch.autograd is the tape, every node's forward and backward is a kernel.
+The Poincare row maps (exp_0 with its projection, log_0, project_to_ball, the tangent normalisation) are radial maps
+y = s(|x|) x and share one backward kernel (`regcn_radial_bwd`); the radius-difference edge weights
+exp(-gamma |rho_u - rho_v|) (hyperbolic_layers.py:232-234) are differentiated w.r.t. the messages AND the radii."""
+import torch
+
+from . import _lib, ops
+from ._lib import call, ptr
+from . import train as T
+
+F32 = torch.float32
+LOG0, EXP0, PROJECT, TNORM = 0, 1, 2, 3
+_ROWMAP = {LOG0: ops.ROW_LOG0, EXP0: ops.ROW_EXP0, PROJECT: ops.ROW_PROJECT, TNORM: ops.ROW_TANGENT_NORMALIZE}
+
+
+class _Radial(torch.autograd.Function):
+    """log_0 / exp_0 / project_to_ball / exp_0(normalize(log_0 .))   (hyperbolic_ops.py:38-116)."""
+
+    @staticmethod
+    def forward(ctx, x, mode, c):
+        x = x.contiguous()
+        ctx.save_for_backward(x)
+        ctx.mode, ctx.c = mode, float(c)
+        return ops.row_map(x, _ROWMAP[mode], c=c)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dx = torch.empty_like(x)
+        call("regcn_radial_bwd", ptr(x), ptr(dy.contiguous()), ptr(dx), x.shape[0], x.shape[1], ctx.mode, ctx.c)
+        return dx, None, None
+
+
+class _Radius(torch.autograd.Function):
+    """get_radius (hyperbolic_ops.py:206)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        ctx.save_for_backward(x)
+        rho = torch.empty(x.shape[0], device=x.device, dtype=F32)
+        call("regcn_row_radius", ptr(x), x.shape[0], x.shape[1], ptr(rho))
+        return rho
+
+    @staticmethod
+    def backward(ctx, drho):
+        (x,) = ctx.saved_tensors
+        dx = torch.empty_like(x)
+        call("regcn_row_radius_bwd", ptr(x), ptr(drho.contiguous()), x.shape[0], x.shape[1], ptr(dx))
+        return dx
+
+
+class _ApplyRadius(torch.autograd.Function):
+    """apply_radius (hyperbolic_ops.py:222-233)."""
+
+    @staticmethod
+    def forward(ctx, x, r, c):
+        x, r = x.contiguous(), r.contiguous()
+        ctx.save_for_backward(x, r)
+        ctx.c = float(c)
+        y = torch.empty_like(x)
+        call("regcn_apply_radius", ptr(x), ptr(r), x.shape[0], x.shape[1], ctx.c, ptr(y))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, r = ctx.saved_tensors
+        dx = torch.empty_like(x)
+        dr = torch.empty_like(r)
+        call("regcn_apply_radius_bwd", ptr(x), ptr(r), ptr(dy.contiguous()), x.shape[0], x.shape[1], ctx.c, ptr(dx), ptr(dr))
+        return dx, dr, None
+
+
+class _Eltwise(torch.autograd.Function):
+    """op 0: clamp(x, -lim, lim); op 1: 0.9 tanh(x) + 0.1 x."""
+
+    @staticmethod
+    def forward(ctx, x, op, lim):
+        x = x.contiguous()
+        ctx.save_for_backward(x)
+        ctx.op, ctx.lim = int(op), float(lim)
+        y = torch.empty_like(x)
+        call("regcn_eltwise_fwd", ptr(x), ptr(y), x.numel(), ctx.op, ctx.lim)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dx = torch.empty_like(x)
+        call("regcn_eltwise_bwd", ptr(x), ptr(dy.contiguous()), ptr(dx), x.numel(), ctx.op, ctx.lim)
+        return dx, None, None
+
+
+class _RadiusCombine(torch.autograd.Function):
+    """_static_radius (hyperbolic_model.py:715-720) [+ the scalar part of TemporalRadiusEvolution, ops:408-424]."""
+
+    @staticmethod
+    def forward(ctx, raw, dyn, delta, rmin, rmax, c, beta, eps_r):
+        raw = raw.contiguous()
+        has = dyn is not None
+        dyn = dyn.contiguous() if has else None
+        delta = delta.contiguous() if has else None
+        ctx.save_for_backward(raw, delta if has else raw)
+        ctx.cfg = (float(rmin), float(rmax), float(c), float(beta), float(eps_r), has)
+        out = torch.empty_like(raw)
+        call("regcn_radius_combine", ptr(raw), ptr(dyn), ptr(delta), raw.shape[0], float(rmin), float(rmax), float(c),
+             float(beta), float(eps_r), ptr(out))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        raw, delta = ctx.saved_tensors
+        rmin, rmax, c, beta, eps_r, has = ctx.cfg
+        draw = torch.empty_like(raw)
+        ddyn = torch.empty_like(raw) if has else None
+        ddelta = torch.empty_like(raw) if has else None
+        call("regcn_radius_combine_bwd", ptr(raw), ptr(delta) if has else None, ptr(g.contiguous()), raw.shape[0], rmin, rmax,
+             c, beta, eps_r, ptr(draw), ptr(ddyn), ptr(ddelta))
+        return draw, ddyn, ddelta, None, None, None, None, None
+
+
+class _RowDot(torch.autograd.Function):
+    """radius_mlp = nn.Linear(d, 1) (hyperbolic_ops.py:390-392,407): delta[n] = <t[n], w> + b."""
+
+    @staticmethod
+    def forward(ctx, t, w, b):
+        t, w, b = t.contiguous(), w.contiguous(), b.contiguous()
+        ctx.save_for_backward(t, w)
+        out = torch.empty(t.shape[0], device=t.device, dtype=F32)
+        call("regcn_row_dot", ptr(t), ptr(w), ptr(b), t.shape[0], t.shape[1], ptr(out))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        t, w = ctx.saved_tensors
+        dout = dout.contiguous()
+        dt = torch.empty_like(t)
+        scaled = torch.empty_like(t)
+        call("regcn_row_dot_bwd", ptr(t), ptr(w), ptr(dout), t.shape[0], t.shape[1], ptr(dt), ptr(scaled))
+        dw = T._col_sum(scaled).view_as(w)
+        db = T._col_sum(dout.view(-1, 1)).view(1)
+        return dt, dw, db
+
+
+def _src_index(g):
+    """CSR positions grouped by their source entity (the by-source pass of the radius gradient)."""
+    idx = getattr(g, "_src_idx", None)
+    if idx is None:
+        rp, perm, _ = T._group(g.src_sorted[:g.num_edges].contiguous(), g.num_nodes)
+        idx = g._src_idx = (rp, perm)
+    return idx
+
+
+class _HypAggregate(torch.autograd.Function):
+    """agg[v] = norm[v] sum_{(u,r)->v} exp(-gamma |rho_u - rho_v|) (ht[u] + rel[r])   (hyperbolic_layers.py:222-240)."""
+
+    @staticmethod
+    def forward(ctx, ht, rel, rho, g, gamma):
+        ht, rel, rho = ht.contiguous(), rel.contiguous(), rho.contiguous()
+        ctx.save_for_backward(ht, rel, rho)
+        ctx.g, ctx.gamma = g, float(gamma)
+        return ops.union_aggregate(ht, rel, g, radius=rho, gamma=gamma)
+
+    @staticmethod
+    def backward(ctx, dagg):
+        ht, rel, rho = ctx.saved_tensors
+        g, gamma = ctx.g, ctx.gamma
+        dagg = dagg.contiguous()
+        N, d = ht.shape
+        type_rowptr, type_src, type_dst = T._block_index(g)
+        dht = T._gather_sum(dagg, d, g.norm, g.rowptr, g.src_sorted, N, d, rho=rho, gamma=gamma)
+        drel = T._gather_sum(dagg, d, g.norm, type_rowptr, type_dst, 2 * g.num_rels, d, rho=rho, gamma=gamma,
+                             partner=type_src)
+        s_edge = torch.empty(max(g.num_edges, 1), device=ht.device, dtype=F32)
+        drho = torch.empty(N, device=ht.device, dtype=F32)
+        call("regcn_edge_radius_grad", ptr(ht), ptr(rel), ptr(dagg), ptr(g.rowptr), ptr(g.src_sorted), ptr(g.etype_sorted),
+             ptr(g.norm), ptr(rho), gamma, N, d, ptr(s_edge), ptr(drho))
+        rp, perm = _src_index(g)
+        call("regcn_edge_scalar_gather", ptr(s_edge), ptr(rp), ptr(perm), N, ptr(drho), 1)
+        return dht, drel, drho, None, None
+
+
+class _SelectAdd(torch.autograd.Function):
+    """P + where(indeg > 0, L[:, :d], L[:, d:])   (hyperbolic_layers.py:273-283, 302-308)."""
+
+    @staticmethod
+    def forward(ctx, P, L, g):
+        ctx.g = g
+        out, _, _ = ops.union_combine(P.contiguous(), L.contiguous(), g.indeg, act=0)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dout = dout.contiguous()
+        N, d = dout.shape
+        dP = torch.empty_like(dout)
+        dL = torch.empty((N, 2 * d), device=dout.device, dtype=F32)
+        call("regcn_union_combine_bwd", None, ptr(dout), ptr(ctx.g.indeg), N, d, 0.0, ptr(dP), ptr(dL))
+        return dP, dL, None
+
+
+radial = _Radial.apply
+radius = _Radius.apply
+apply_radius = _ApplyRadius.apply
+eltwise = _Eltwise.apply
+row_dot = _RowDot.apply
+
+
+def static_radius(model):
+    return _RadiusCombine.apply(model.radius_static, None, None, model.radius_min, model.radius_max, model._c_float, 1.0, 0.0)
+
+
+def hyp_union_layer(layer, g, h_in, h0, c, training):
+    """HyperbolicUnionRGCNLayer.forward (hyperbolic_layers.py:262-323; self_loop, no skip connection)."""
+    p = float(layer.dropout.p) if (layer.dropout is not None and training) else 0.0
+    ht = radial(h_in, LOG0, c)
+    rho = radius(h_in)
+    agg = _HypAggregate.apply(ht, h0, rho, g, float(layer.radius_msg_gamma))
+    P = eltwise(T.linear(agg, layer.weight_neighbor, None, True), 0, 10.0)
+    L = T.linear(ht, torch.cat((layer.loop_weight, layer.evolve_loop_weight), dim=1), None, True)
+    t = eltwise(_SelectAdd.apply(P, L, g), 0, 10.0)
+    t = T._RReluDrop.apply(t, p)
+    return radial(t, EXP0, c)
+
+
+def hyp_evolve(model, g_list):
+    """HyperbolicRecurrentRGCN.forward with the tape on (hyperbolic_model.py:773-890)."""
+    if (model.encoder_name != "hyperbolic_uvrgcn" or getattr(model, "use_static", False)
+            or any(l.skip_connect or not l.self_loop for l in model.rgcn.layers)):
+        raise NotImplementedError("regcn_b200.train_hyp: hyperbolic_uvrgcn + self_loop without skip_connect / static graph")
+    c = model._c_float
+    cell = model.relation_gru
+    init = T.normalize(model.dynamic_emb) if model.layer_norm else model.dynamic_emb
+    h = radial(init, EXP0, c)
+    rs = static_radius(model)
+    h = apply_radius(h, rs, c)
+    tre = model.temporal_radius_evolution
+    h0 = None
+    hist = []
+    for i, g in enumerate(g_list):
+        ht = radial(h, LOG0, c)
+        x_mean = T.rel_mean_pool(ht, g)
+        x_cat = torch.cat((model.emb_rel, x_mean), dim=1)
+        hprev = model.emb_rel if i == 0 else h0
+        gi = T.linear(x_cat, cell.weight_ih, cell.bias_ih)
+        gh = T.linear(hprev, cell.weight_hh, cell.bias_hh)
+        h0 = T.gru_gate(gi, gh, hprev, model.layer_norm)
+        cur = h
+        for layer in model.rgcn.layers:
+            cur = hyp_union_layer(layer, g, cur, h0, c, model.training)
+        cur = radial(cur, PROJECT, c)
+        if model.layer_norm:
+            cur = radial(cur, TNORM, c)
+        ct = eltwise(radial(cur, LOG0, c), 0, 10.0)
+        pt = eltwise(radial(h, LOG0, c), 0, 10.0)
+        G = T.linear(pt, model.time_gate_weight, None, True)
+        nt = T.time_gate(G, model.time_gate_bias, ct, pt, False)
+        h = radial(radial(nt, EXP0, c), PROJECT, c)
+        if model.use_residual_evolution:
+            t = radial(h, LOG0, c)
+            delta = row_dot(t, tre.radius_mlp.weight, tre.radius_mlp.bias)
+            r_new = _RadiusCombine.apply(model.radius_static, radius(h), delta, model.radius_min, model.radius_max, c,
+                                         float(tre.anchor_beta), float(tre.epsilon))
+            h = apply_radius(h, r_new, c)
+        else:
+            h = apply_radius(h, rs, c)
+        hist.append(h)
+    return hist, h0
+
+
+class _RadiusLoss(torch.autograd.Function):
+    """loss_radius = lambda * mse(static_radius[ids], radius_target[ids])   (hyperbolic_model.py:1066-1073)."""
+
+    @staticmethod
+    def forward(ctx, raw, target, ids, rmin, rmax, c, lam):
+        raw, target, ids = raw.contiguous(), target.contiguous(), ids.contiguous()
+        n = int(ids.shape[0])
+        term = torch.empty((max(n, 1), 1), device=raw.device, dtype=F32)
+        call("regcn_radius_mse", ptr(raw), ptr(target), ptr(ids), n, float(rmin), float(rmax), float(c), float(lam), ptr(term))
+        ctx.save_for_backward(raw, target, ids)
+        ctx.cfg = (float(rmin), float(rmax), float(c), float(lam))
+        return T._col_sum(term) if n else torch.zeros(1, device=raw.device)
+
+    @staticmethod
+    def backward(ctx, g):
+        raw, target, ids = ctx.saved_tensors
+        rmin, rmax, c, lam = ctx.cfg
+        draw = torch.zeros_like(raw)
+        call("regcn_radius_mse_bwd", ptr(raw), ptr(target), ptr(ids), int(ids.shape[0]), rmin, rmax, c, lam,
+             ptr(g.contiguous().view(-1)), ptr(draw))
+        return draw, None, None, None, None, None, None
+
+
+def hyp_get_loss(model, glist, triples):
+    """hyperbolic_model.py:941-1088 with gradients: (loss_ent, loss_rel, loss_static, loss_radius), each (1,)."""
+    _lib.require_device()
+    if ops.gemm_impl() != "tc":
+        raise RuntimeError("regcn_b200.train_hyp needs the tensor-core GEMM (REGCN_GEMM=tc)")
+    if model.decoder_name != "hyperbolic_convtranse":
+        raise NotImplementedError("regcn_b200.train_hyp: training mode is implemented for --decoder hyperbolic_convtranse "
+                                  "(the reference's default); the distance decoders' streaming-CE heads are next")
+    dev = model.dynamic_emb.device
+    c = model._c_float
+    triples = torch.as_tensor(triples).to(dev)
+    inverse = triples.flip(1)
+    inverse[:, 1] = inverse[:, 1] + model.num_rels
+    all_triples = torch.cat([triples, inverse]).contiguous()
+    hist, r_emb = hyp_evolve(model, glist)
+    pre = radial(hist[-1], TNORM, c) if model.layer_norm else hist[-1]
+    et = eltwise(radial(pre, LOG0, c), 1, 0.0)                      # 0.9 tanh(log_0 E) + 0.1 log_0 E  (:377-379)
+    loss_ent = torch.zeros(1, device=dev)
+    loss_rel = torch.zeros(1, device=dev)
+    loss_static = torch.zeros(1, device=dev)
+    if model.entity_prediction:
+        q = T.conv_tower(model.decoder_ob, et, r_emb, all_triples, 0, 1)
+        loss_ent = T.score_ce(q, et, all_triples, 2, model.decoder_ob.b)
+    if model.relation_prediction:
+        q = T.conv_tower(model.rdecoder, et, et, all_triples, 0, 2)
+        loss_rel = T.score_ce(q, r_emb, all_triples, 1, model.rdecoder.b)
+    ids = torch.unique(all_triples[:, [0, 2]].reshape(-1))
+    loss_radius = _RadiusLoss.apply(model.radius_static, model.radius_target, ids, model.radius_min, model.radius_max, c,
+                                    float(model.radius_lambda))
+    return loss_ent, loss_rel, loss_static, loss_radius

@@ -133,3 +133,25 @@ def build_static_model(cfg, n, r, n_srel, n_words, dropout=0.0):
     sd = synth.fill_state_dict(m.state_dict(), cfg["seed"])
     m.load_state_dict(sd)
     return m, sd
+
+
+HYP_TRAIN_CASES = {
+    "hyptrain_tiny_s0": dict(kind="hyp", shape="tiny", seed=0, encoder="hyperbolic_uvrgcn", decoder="hyperbolic_convtranse",
+                             layer_norm=False, gamma=0.15),
+    "hyptrain_tiny_s1_ln": dict(kind="hyp", shape="tiny", seed=1, encoder="hyperbolic_uvrgcn",
+                                decoder="hyperbolic_convtranse", layer_norm=True, gamma=1.0),
+    "hyptrain_small_s2_ln": dict(kind="hyp", shape="small", seed=2, encoder="hyperbolic_uvrgcn",
+                                 decoder="hyperbolic_convtranse", layer_norm=True, gamma=0.15),
+}
+
+
+def build_hyp_train_model(cfg, n, r, dropout=0.0):
+    import regcn_b200 as R
+    m = R.HyperbolicRecurrentRGCN(cfg["decoder"], cfg["encoder"], n, r, 0, 0, H_DIM, "sub", 3, num_bases=N_BASES,
+                                  num_hidden_layers=N_LAYERS, dropout=dropout, c=CURV, self_loop=True, skip_connect=False,
+                                  layer_norm=cfg["layer_norm"], input_dropout=dropout, hidden_dropout=dropout,
+                                  feat_dropout=dropout, entity_prediction=True, relation_prediction=True, use_cuda=True,
+                                  gpu=0, radius_msg_gamma=cfg["gamma"], hyp_init_scale=1e-3)
+    sd = synth.fill_state_dict(m.state_dict(), cfg["seed"])
+    m.load_state_dict(sd)
+    return m, sd

@@ -1,0 +1,151 @@
+"""GPU parity of the hyperbolic training step (hyperbolic_uvrgcn + hyperbolic_convtranse): every autograd node of
+regcn_b200/train_hyp.py against torch autograd over the CPU oracle, the whole optimisation step against the UNMODIFIED
+hyperbolic reference (tests/golden/train_hyp.npz).  Tolerances as in test_gpu_train.py."""
+import numpy as np
+import pytest
+import torch
+
+import regcn_b200 as R
+from oracle import restate, synth
+from regcn_b200 import optim, train, train_hyp
+from tests.helpers import CURV, HYP_TRAIN_CASES, build_hyp_train_model, close, compare_train_step, grad_close
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+C = 0.01
+
+
+def _leaf(a):
+    return torch.as_tensor(np.asarray(a, dtype=np.float32)).to(DEV).requires_grad_(True)
+
+
+def _cmp(mine, ref, names, rtol=2e-4):
+    tn = float(np.sqrt(sum(float((r.double() ** 2).sum()) for r in ref)))
+    for m, r, n in zip(mine, ref, names):
+        ok, worst = grad_close(m.detach().cpu().numpy(), r.detach().numpy(), tn, rtol)
+        assert ok, (n, worst)
+
+
+def test_radial_row_maps_backward():
+    """log_0 / exp_0 / project / tangent-normalise, radius, apply_radius, clamp, leaky tanh, radius_combine, row_dot."""
+    R._lib.require_device()
+    rng = np.random.default_rng(3)
+    n, d = 300, 200
+    # rows inside the ball (|x| < 10), some near the boundary, some tiny; tangent rows large enough to hit the projection
+    x = rng.standard_normal((n, d)) * rng.uniform(0.01, 0.45, size=(n, 1))   # |x| up to ~6.5 of the radius-10 ball
+    x[:5] *= 1e-9
+    v = rng.standard_normal((n, d)) * rng.uniform(0.01, 3.0, size=(n, 1))
+    go = rng.standard_normal((n, d))
+    got = torch.as_tensor(go, dtype=torch.float32, device=DEV)
+    for mode, inp, ref_fn in ((train_hyp.LOG0, x, lambda t: restate.log0(t, C)), (train_hyp.EXP0, v, lambda t: restate.exp0(t, C)),
+                              (train_hyp.PROJECT, v * 8, lambda t: restate.project(t, C)),
+                              (train_hyp.TNORM, x, lambda t: restate.exp0(restate.normalize_rows(restate.log0(t, C)), C))):
+        xd = _leaf(inp)
+        y = train_hyp.radial(xd, mode, C)
+        y.backward(got)
+        xc = torch.tensor(inp, dtype=torch.float64, requires_grad=True)
+        yc = ref_fn(xc)
+        yc.backward(torch.as_tensor(go))
+        ok, worst = close(y.detach().cpu().numpy(), yc.detach().numpy())
+        assert ok, (mode, worst)
+        _cmp([xd.grad], [xc.grad], [f"radial mode {mode}"])
+    # radius / apply_radius
+    r = rng.uniform(0.2, 12.0, size=n)                      # some beyond 1/sqrt(c): clamped
+    xd, rd = _leaf(x), _leaf(r)
+    y = train_hyp.apply_radius(xd, rd, C)
+    rho = train_hyp.radius(xd)
+    (y * got).sum().backward(retain_graph=True)
+    (rho * torch.arange(n, device=DEV)).sum().backward()
+    xc = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+    rc = torch.tensor(r, dtype=torch.float64, requires_grad=True)
+    yc = restate.apply_radius(xc, rc, C)
+    ((yc * torch.as_tensor(go)).sum() + (restate.get_radius(xc) * torch.arange(n)).sum()).backward()
+    ok, worst = close(y.detach().cpu().numpy(), yc.detach().numpy())
+    assert ok, worst
+    _cmp([xd.grad, rd.grad], [xc.grad, rc.grad], ["apply_radius dx (+ radius)", "apply_radius dr"])
+    # elementwise
+    for op, ref_fn in ((0, lambda t: t.clamp(-1.5, 1.5)), (1, lambda t: 0.9 * torch.tanh(t) + 0.1 * t)):
+        xd = _leaf(v)
+        train_hyp.eltwise(xd, op, 1.5).backward(got)
+        xc = torch.tensor(v, dtype=torch.float64, requires_grad=True)
+        ref_fn(xc).backward(torch.as_tensor(go))
+        _cmp([xd.grad], [xc.grad], [f"eltwise {op}"])
+    # radius_combine + row_dot (TemporalRadiusEvolution scalars)
+    raw = rng.uniform(0.2, 3.5, size=n)
+    w, b = rng.standard_normal((1, d)) * 0.05, rng.standard_normal(1) * 0.05
+    gv = rng.standard_normal(n)
+    rawd, xd, wd, bd = _leaf(raw), _leaf(x), _leaf(w), _leaf(b)
+    t = train_hyp.radial(xd, train_hyp.LOG0, C)
+    delta = train_hyp.row_dot(t, wd, bd)
+    out = train_hyp._RadiusCombine.apply(rawd, train_hyp.radius(xd), delta, 0.5, 3.0, C, 0.7, 0.1)
+    out.backward(torch.as_tensor(gv, dtype=torch.float32, device=DEV))
+    rawc, xc, wc, bc = (torch.tensor(a, dtype=torch.float64, requires_grad=True) for a in (raw, x, w, b))
+    tc = restate.log0(xc, C)
+    dc = (tc @ wc.t()).squeeze(-1) + bc
+    rs = restate.static_radius(rawc, C, 0.5, 3.0)
+    outc = 0.7 * rs + 0.3 * restate.get_radius(xc) + dc.clamp(-0.1, 0.1)
+    outc.backward(torch.as_tensor(gv))
+    ok, worst = close(out.detach().cpu().numpy(), outc.detach().numpy())
+    assert ok, worst
+    _cmp([rawd.grad, xd.grad, wd.grad, bd.grad], [rawc.grad, xc.grad, wc.grad, bc.grad], ["draw", "dx", "dw", "db"])
+
+
+def test_hyperbolic_union_layer_backward():
+    """One HyperbolicUnionRGCNLayer (radius-weighted aggregate incl. the gradient w.r.t. the radii) against the oracle."""
+    R._lib.require_device()
+    case = synth.make_case("small", 6)
+    n, r = case["num_ents"], case["num_rels"]
+    g = R.build_sub_graph(n, r, case["history"][0], True, 0)
+    og = restate.build_edges(case["history"][0], n, r)
+    rng = np.random.default_rng(8)
+    d = 200
+    h = rng.standard_normal((n, d)) * rng.uniform(0.02, 0.25, size=(n, 1))
+    rel = rng.standard_normal((2 * r, d)) * 0.2
+    W = [rng.standard_normal((d, d)) * 0.1 for _ in range(3)]
+    go = rng.standard_normal((n, d))
+    layer = R.HyperbolicUnionRGCNLayer(d, d, 2 * r, c=C, activation=torch.nn.functional.rrelu, self_loop=True,
+                                       dropout=0.0, radius_msg_gamma=0.6).to(DEV)
+    with torch.no_grad():
+        for p, w in zip((layer.weight_neighbor, layer.loop_weight, layer.evolve_loop_weight), W):
+            p.copy_(torch.as_tensor(w, dtype=torch.float32))
+    hd, rd = _leaf(h), _leaf(rel)
+    out = train_hyp.hyp_union_layer(layer, g, hd, rd, C, True)
+    out.backward(torch.as_tensor(go, dtype=torch.float32, device=DEV))
+    hc, rc = (torch.tensor(a, dtype=torch.float64, requires_grad=True) for a in (h, rel))
+    Wc = [torch.tensor(w, dtype=torch.float64, requires_grad=True) for w in W]
+    outc = restate.hyp_union_layer(hc, rc, og, Wc[0], Wc[1], Wc[2], C, 0.6)
+    outc.backward(torch.as_tensor(go))
+    ok, worst = close(out.detach().cpu().numpy(), outc.detach().numpy())
+    assert ok, worst
+    _cmp([hd.grad, rd.grad, layer.weight_neighbor.grad, layer.loop_weight.grad, layer.evolve_loop_weight.grad],
+         [hc.grad, rc.grad] + [w.grad for w in Wc], ["dh", "drel", "dW_n", "dW_loop", "dW_evolve"])
+
+
+@pytest.mark.parametrize("name", sorted(HYP_TRAIN_CASES))
+def test_hyperbolic_train_step_matches_reference(name):
+    """One optimisation step of HyperbolicRecurrentRGCN (get_loss in train() mode -> backward -> clip -> Adam) against the
+    UNMODIFIED reference: four losses, gradient norm, all 39 parameter gradients, updated values."""
+    import os
+    from tests.helpers import GOLDEN
+    R._lib.require_device()
+    z = np.load(os.path.join(GOLDEN, "train_hyp.npz"))
+    cfg = HYP_TRAIN_CASES[name]
+    case = synth.make_case(cfg["shape"], cfg["seed"])
+    n, r = case["num_ents"], case["num_rels"]
+    m, _ = build_hyp_train_model(cfg, n, r)
+    m = m.to(DEV).train()
+    opt = optim.Adam(m.parameters(), lr=1e-3, weight_decay=1e-5)
+    glist = [R.build_sub_graph(n, r, s, True, 0) for s in case["history"]]
+    le, lr_, ls, lrad = m.get_loss(glist, torch.from_numpy(case["test"]).to(DEV), None, True)
+    (0.7 * le + 0.3 * lr_ + ls + lrad).backward()
+    named = {k: p for k, p in m.named_parameters() if p.grad is not None}
+    grads = {k: p.grad.detach().cpu().numpy().copy() for k, p in named.items()}
+    optim.clip_grad_norm_(opt, 1.0)
+    opt.step()
+    params = {k: p.detach().cpu().numpy().copy() for k, p in named.items()}
+    losses = tuple(float(x.detach().reshape(-1)[0]) for x in (le, lr_, ls, lrad))
+    compare_train_step(z, name, 0, losses, float(opt.total_norm), grads, params, rtol=1.5e-3)
+    # and the trained model still evaluates (operand caches follow the version counters)
+    m.eval()
+    _, score, _ = m.predict(glist, r, None, torch.from_numpy(case["test"]).to(DEV), True)
+    assert torch.isfinite(score).all()

@@ -196,3 +196,21 @@ def test_oracle_construct_snap_matches_reference():
         B, N, Rr, K = (int(v) for v in z[f"{name}.cfg"])
         got = restate.construct_snap(z[f"{name}.triples"], Rr, z[f"{name}.score"], K, mode)
         assert np.array_equal(got, z[f"{name}.out"])
+
+
+@pytest.mark.parametrize("name", sorted(__import__("tests.helpers", fromlist=["HYP_TRAIN_CASES"]).HYP_TRAIN_CASES))
+def test_oracle_hyperbolic_train_step_matches_reference(name):
+    """restate.hyp_train_steps against one optimisation step of the UNMODIFIED hyperbolic reference
+    (tests/golden/train_hyp.npz, oracle/gen_golden.py --hyp-train)."""
+    import os
+    from tests.helpers import GOLDEN, HYP_TRAIN_CASES, build_hyp_train_model
+    z = np.load(os.path.join(GOLDEN, "train_hyp.npz"))
+    cfg = HYP_TRAIN_CASES[name]
+    case = synth.make_case(cfg["shape"], cfg["seed"])
+    n, r = case["num_ents"], case["num_rels"]
+    _, sd = build_hyp_train_model(cfg, n, r)
+    graphs = [restate.build_edges(s, n, r) for s in case["history"]]
+    log = restate.hyp_train_steps(sd, graphs, r, case["test"], c=CURV, layer_norm=cfg["layer_norm"], gamma=cfg["gamma"])
+    rec = log[0]
+    compare_train_step(z, name, 0, rec["losses"], rec["grad_norm"], {k: v.numpy() for k, v in rec["grads"].items()},
+                       {k: v.numpy() for k, v in rec["params"].items()})
