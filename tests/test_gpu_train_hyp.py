@@ -39,13 +39,15 @@ def test_radial_row_maps_backward():
     got = torch.as_tensor(go, dtype=torch.float32, device=DEV)
     for mode, inp, ref_fn in ((train_hyp.LOG0, x, lambda t: restate.log0(t, C)), (train_hyp.EXP0, v, lambda t: restate.exp0(t, C)),
                               (train_hyp.PROJECT, v * 8, lambda t: restate.project(t, C)),
-                              (train_hyp.TNORM, x, lambda t: restate.exp0(restate.normalize_rows(restate.log0(t, C)), C))):
+                              # (rows below eps = 1e-6 are outside the tangent normalisation's domain: F.normalize
+                              #  divides by the true norm there while log_0 clamps it; entities sit at radius >= 0.5)
+                              (train_hyp.TNORM, x[5:], lambda t: restate.exp0(restate.normalize_rows(restate.log0(t, C)), C))):
         xd = _leaf(inp)
         y = train_hyp.radial(xd, mode, C)
-        y.backward(got)
+        y.backward(got[:len(inp)])
         xc = torch.tensor(inp, dtype=torch.float64, requires_grad=True)
         yc = ref_fn(xc)
-        yc.backward(torch.as_tensor(go))
+        yc.backward(torch.as_tensor(go[:len(inp)]))
         ok, worst = close(y.detach().cpu().numpy(), yc.detach().numpy())
         assert ok, (mode, worst)
         _cmp([xd.grad], [xc.grad], [f"radial mode {mode}"])
