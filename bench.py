@@ -524,6 +524,43 @@ def main():
                               "clip_grad_norm_(1.0) + Adam(lr 1e-3, wd 1e-5); 3xTF32 tcgen05 GEMMs for forward, dX and dW"}
         del tmodel, topt
 
+    # ---- the reference's only published number (hyperbolic_src/train.log: hyperbolic_uvrgcn + hyperbolic_convtranse,
+    #      ICEWS14s, layer_norm, history 3: 61.9-69.2 s per epoch of 303 snapshot steps = 4.9 optimisation steps/s on an
+    #      unnamed GPU): the same configuration on the ICEWS14s-shaped synthetic workload c1 ----
+    train_hyp_line = None
+    if rank == 0 and world == 1 and not args.no_stress:
+        from regcn_b200 import optim as roptim
+        hcase = synth.make_case("c1", 0)
+        hn, hr = hcase["num_ents"], hcase["num_rels"]
+        hm = R.HyperbolicRecurrentRGCN("hyperbolic_convtranse", "hyperbolic_uvrgcn", hn, hr, 0, 0, H_DIM, "sub", 3,
+                                       num_bases=N_BASES, num_hidden_layers=N_LAYERS, dropout=0.2, c=0.01, self_loop=True,
+                                       layer_norm=True, input_dropout=0.2, hidden_dropout=0.2, feat_dropout=0.2,
+                                       entity_prediction=True, relation_prediction=True, use_cuda=True, gpu=0)
+        hm.load_state_dict(synth.fill_state_dict(hm.state_dict(), 0))
+        hm = hm.to(dev).train()
+        hopt = roptim.Adam(hm.parameters(), lr=1e-3, weight_decay=1e-5)
+        hg = [R.build_sub_graph(hn, hr, s, True, local) for s in hcase["history"]]
+        ht = torch.from_numpy(hcase["test"]).to(dev)
+
+        def hyp_train_step(_):
+            le, lr_, ls, lrad = hm.get_loss(hg, ht, None, True)
+            (0.7 * le + 0.3 * lr_ + ls + lrad).backward()
+            roptim.clip_grad_norm_(hopt, 1.0)
+            hopt.step()
+            hopt.zero_grad()
+
+        h_steps = max(3, min(args.steps, 10))
+        tot_h, _ = timed(hyp_train_step, h_steps, 3)
+        h_ms = tot_h / h_steps
+        train_hyp_line = {"workload": "c1 (ICEWS14s-shaped: N=7128 R=230 T=250/snapshot, history 3), hyperbolic_uvrgcn + "
+                                      "hyperbolic_convtranse, layer_norm, dropout 0.2, whole snapshot per step",
+                          "ms_per_step": h_ms, "optimisation_steps_per_s": 1e3 / h_ms,
+                          "train_snapshot_steps_per_s": len(hg) * 1e3 / h_ms,
+                          "reference_published_steps_per_s": 4.9,
+                          "reference_source": "hyperbolic_src/train.log:36-44 (unnamed GPU, real ICEWS14s, fwd+bwd+Adam)",
+                          "ratio_to_published": (1e3 / h_ms) / 4.9}
+        del hm, hopt
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb = run_cpu_arm(args, 3, 1)
@@ -559,6 +596,8 @@ def main():
             line["entity_sharded"] = sharded
         if train_line:
             line["train"] = train_line
+        if train_hyp_line:
+            line["train_hyperbolic"] = train_hyp_line
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
