@@ -524,6 +524,69 @@ def main():
                               "clip_grad_norm_(1.0) + Adam(lr 1e-3, wd 1e-5); 3xTF32 tcgen05 GEMMs for forward, dX and dW"}
         del tmodel, topt
 
+    # ---- entity-sharded scoring at BASELINE configs[4] size (1M entities, 8192 queries, RotH-form hyperbolic score):
+    #      each rank counts over its N/G candidate rows with the fused kernel, ONE all_reduce(SUM) of the (B,) counts;
+    #      rank 0 also times the whole table on one GPU, so the line carries its own strong-scaling figure ----
+    sharded_c5 = None
+    if world > 1:
+        Bq5, N5, d5 = 8192, 1_000_000, H_DIM
+        lo5, hi5 = rdist.shard_bounds(N5, rank, world)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(1234)
+        q5 = torch.randn(Bq5, d5, device=dev, generator=gen) * 0.05
+        gen.manual_seed(99 + rank)
+        e5 = torch.randn(hi5 - lo5, d5, device=dev, generator=gen) * 0.05
+        qh5, ql5 = ops.split_tf32(q5)
+        eh5, el5 = ops.split_tf32(e5)
+        x2_5, y2_5 = ops.row_sumsq(q5), ops.row_sumsq(e5)
+        sm5 = torch.tensor([1.0, 1.0], device=dev)
+        tgt5 = torch.randint(0, N5, (Bq5,), device=dev, dtype=torch.int32, generator=gen)
+        ts5 = torch.zeros(Bq5, device=dev)
+        raw5 = torch.zeros(Bq5, device=dev, dtype=torch.int32)
+
+        def sharded5(_):
+            raw5.zero_()
+            _lib.call("regcn_score_count_tf32", qh5.data_ptr(), ql5.data_ptr(), eh5.data_ptr(), el5.data_ptr(), Bq5,
+                      hi5 - lo5, d5, ts5.data_ptr(), tgt5.data_ptr(), raw5.data_ptr(), lo5, 1, x2_5.data_ptr(),
+                      y2_5.data_ptr(), None, 0.01, sm5.data_ptr(), None, 3)
+            dist.all_reduce(raw5)
+
+        n5 = max(3, min(args.steps, 10))
+        tot5, _ = timed(sharded5, n5, 3)
+        ms5 = maxr(tot5) / n5
+        single_ms = None
+        if rank == 0:
+            gen.manual_seed(7)
+            eF = torch.randn(N5, d5, device=dev, generator=gen) * 0.05
+            eFh, eFl = ops.split_tf32(eF)
+            y2F = ops.row_sumsq(eF)
+            del eF
+
+            def full5():
+                raw5.zero_()
+                _lib.call("regcn_score_count_tf32", qh5.data_ptr(), ql5.data_ptr(), eFh.data_ptr(), eFl.data_ptr(), Bq5,
+                          N5, d5, ts5.data_ptr(), tgt5.data_ptr(), raw5.data_ptr(), 0, 1, x2_5.data_ptr(), y2F.data_ptr(),
+                          None, 0.01, sm5.data_ptr(), None, 3)
+
+            for _ in range(2):
+                full5()
+            torch.cuda.synchronize()
+            fa, fb = ev(), ev()
+            fa.record()
+            for _ in range(3):
+                full5()
+            fb.record()
+            torch.cuda.synchronize()
+            single_ms = fa.elapsed_time(fb) / 3
+            del eFh, eFl, y2F
+        barrier()
+        sharded_c5 = {"shape": f"B={Bq5} queries x N={N5} entities, d={d5}, hyperbolic (RotH-form) score, 3xTF32",
+                      "ms_per_step": ms5, "queries_per_s": Bq5 / (ms5 * 1e-3), "single_gpu_full_table_ms": single_ms,
+                      "speedup_vs_one_gpu": (single_ms / ms5) if single_ms else None,
+                      "strong_scaling_efficiency": (single_ms / ms5 / world) if single_ms else None,
+                      "collectives": "one all_reduce(SUM) of (B,) int32 counts over NCCL"}
+        del q5, e5, qh5, ql5, eh5, el5
+
     # ---- the reference's only published number (hyperbolic_src/train.log: hyperbolic_uvrgcn + hyperbolic_convtranse,
     #      ICEWS14s, layer_norm, history 3: 61.9-69.2 s per epoch of 303 snapshot steps = 4.9 optimisation steps/s on an
     #      unnamed GPU): the same configuration on the ICEWS14s-shaped synthetic workload c1 ----
@@ -594,6 +657,8 @@ def main():
             line["cpu_baseline"] = cpu_baseline
         if sharded:
             line["entity_sharded"] = sharded
+        if sharded_c5:
+            line["entity_sharded_c5"] = sharded_c5
         if train_line:
             line["train"] = train_line
         if train_hyp_line:
