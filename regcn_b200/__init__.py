@@ -18,5 +18,6 @@ from . import utils  # noqa: F401
 from . import knowledge_graph  # noqa: F401  (on-disk TKG format reader)
 from . import optim, train, train_hyp  # noqa: F401  (training step: get_loss with gradients + clipped Adam)
 from .evaluate import test  # noqa: F401  (the reference's evaluation loop, src/main.py:33)
+from .fit import fit_epoch  # noqa: F401  (the reference's training epoch, src/main.py:213-246)
 
 __version__ = "0.1.0"
