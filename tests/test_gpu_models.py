@@ -482,3 +482,45 @@ def test_schedule_switches_do_not_change_results():
         lib.regcn_pdl_enable(1)
     for h, r0 in outs[1:]:
         assert torch.equal(h, outs[0][0]) and torch.equal(r0, outs[0][1])
+
+
+def test_edge_cases_empty_and_single_snapshots():
+    """Ragged inputs: an EMPTY history snapshot (no edges: every entity takes the evolve-loop path, absent relations
+    pool to zero), a single-triple test snapshot (B = 2 queries, BatchNorm eval), a one-snapshot history -- against the
+    oracle where it defines a value, finite and well-formed otherwise; and the same inputs through a training step."""
+    from regcn_b200 import optim
+    R._lib.require_device()
+    cfg = dict(kind="regcn", shape="tiny", seed=0, layer_norm=True)
+    case = synth.make_case("tiny", 0)
+    n, r = case["num_ents"], case["num_rels"]
+    model, sd = build_model(cfg, n, r)
+    model = model.to(DEV)
+    empty = np.zeros((0, 3), dtype=np.int64)
+    hist = [case["history"][0], empty, case["history"][2]]
+    glist = [R.build_sub_graph(n, r, s, True, 0) for s in hist]
+    assert glist[1].num_edges == 0 and int(glist[1].in_degrees().sum()) == 0
+    all_t, score, score_rel = model.predict(glist, r, None, torch.from_numpy(case["test"]).to(DEV), True)
+    graphs = [restate.build_edges(s, n, r) for s in hist]
+    o_t, o_score, o_rel, _, _ = restate.regcn_predict(sd, graphs, r, case["test"], layer_norm=True)
+    ok, worst = close(score.cpu().numpy(), o_score.numpy(), rtol=2e-4)
+    assert ok, worst
+    ok, worst = close(score_rel.cpu().numpy(), o_rel.numpy(), rtol=2e-4)
+    assert ok, worst
+    one = case["test"][:1]
+    _, s1, _ = model.predict(glist, r, None, torch.from_numpy(one).to(DEV), True)
+    _, o1, _, _, _ = restate.regcn_predict(sd, graphs, r, one, layer_norm=True)
+    ok, worst = close(s1.cpu().numpy(), o1.numpy(), rtol=2e-4)
+    assert ok and s1.shape == (2, n), worst
+    mrrs = R.test(model, hist, [one, case["test"]], r, n, True, test_history_len=3)
+    assert all(np.isfinite(v) and 0 < v <= 1 for v in mrrs)
+    model.train()
+    opt = optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-5)
+    for g, tr in ((glist, case["test"]), (glist[:1], case["test"]), (glist, one)):
+        le, lr_, ls = model.get_loss(g, torch.from_numpy(tr).to(DEV), None, True)
+        (0.7 * le + 0.3 * lr_ + ls).backward()
+        optim.clip_grad_norm_(opt, 1.0)
+        opt.step()
+        opt.zero_grad()
+        assert np.isfinite(float(le.detach())) and np.isfinite(float(opt.total_norm))
+    res = R.fit_epoch(model, opt, [hist[0], empty, hist[2], case["test"]], r, n, 3, shuffle=False)
+    assert res["steps"] == 2 and np.isfinite(res["loss"])          # t = 0 is skipped, t = 1 has no triples
