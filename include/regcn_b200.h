@@ -488,6 +488,19 @@ REGCN_API int regcn_radius_mse(const float* raw, const float* target, const int6
 REGCN_API int regcn_radius_mse_bwd(const float* raw, const float* target, const int64_t* ids, int n, float rmin, float rmax,
                          double c, float lambda, const float* gscale, float* draw, void* stream);
 
+/* Distance decoders in training (HyperbolicMuRP / MuRPRel .loss, hyperbolic_decoder.py:647-928): mobius_add without its
+ * projection, forward and backward (hyperbolic_ops.py:135-142); z = x*y; out[r] += alpha s[r] x[r]; and the gradient of
+ * the proxy-distance score through its three scalars (dot, |q|^2, |e|^2): in place D <- dS dS/dD, H <- dS dS/d|e|^2,
+ * per query gx = sum dS dS/d|q|^2, gs = sum dS (margin - n^2) (d scale), gm = sum dS scale (d margin).              */
+REGCN_API int regcn_mobius_fwd(const float* x, const float* y, int M, int d, double c, float* z, void* stream);
+REGCN_API int regcn_mobius_bwd(const float* x, const float* y, const float* dz, int M, int d, double c, float* dx, float* dy,
+                     void* stream);
+REGCN_API int regcn_eltwise_mul(const float* x, const float* y, float* z, size_t n, void* stream);
+REGCN_API int regcn_row_axpy(const float* x, const float* s, float alpha, int M, int d, float* out, void* stream);
+REGCN_API int regcn_hyp_dist_grad(float* D, const float* dS, float* H, int64_t ld, int B, int N, const float* x2,
+                        const float* y2, double c, const float* scale_margin, float* gx, float* gs, float* gm,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -331,6 +331,10 @@ HYP_TRAIN_CASES = {
                                 decoder="hyperbolic_convtranse", layer_norm=True, gamma=1.0),
     "hyptrain_small_s2_ln": dict(kind="hyp", shape="small", seed=2, encoder="hyperbolic_uvrgcn",
                                  decoder="hyperbolic_convtranse", layer_norm=True, gamma=0.15),
+    "hyptrain_murp_tiny_s3": dict(kind="hyp", shape="tiny", seed=3, encoder="hyperbolic_uvrgcn", decoder="murp",
+                                  layer_norm=False, gamma=0.15),
+    "hyptrain_murp_small_s4_bias": dict(kind="hyp", shape="small", seed=4, encoder="hyperbolic_uvrgcn", decoder="murp",
+                                        layer_norm=True, gamma=0.15, entity_bias=True),
 }
 
 
@@ -345,7 +349,8 @@ def run_hyp_train(ref_utils, HyperbolicRecurrentRGCN):
                                     num_hidden_layers=N_LAYERS, dropout=0.0, c=CURV, self_loop=True, skip_connect=False,
                                     layer_norm=cfg["layer_norm"], input_dropout=0.0, hidden_dropout=0.0, feat_dropout=0.0,
                                     entity_prediction=True, relation_prediction=True, use_cuda=False, gpu="cpu",
-                                    radius_msg_gamma=cfg["gamma"], hyp_init_scale=1e-3)
+                                    radius_msg_gamma=cfg["gamma"], hyp_init_scale=1e-3,
+                                    use_entity_euclidean_bias=cfg.get("entity_bias", False))
         m.load_state_dict(synth.fill_state_dict(m.state_dict(), cfg["seed"]))
         m.train()
         opt = torch.optim.Adam(m.parameters(), lr=LR, weight_decay=WEIGHT_DECAY)

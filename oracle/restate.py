@@ -832,19 +832,28 @@ def regcn_train_steps(sd, graphs, num_rels, triples, layer_norm=True, steps=1, t
 # hyperbolic_uvrgcn encoder + hyperbolic_convtranse decoder.
 # =====================================================================================
 def hyp_train_losses(P, graphs, num_rels, triples, c, layer_norm, gamma, stats, rmin=0.5, rmax=3.0, beta=1.0, eps_r=0.1,
-                     radius_lambda=0.02):
+                     radius_lambda=0.02, decoder="hyperbolic_convtranse"):
     all_t = torch.as_tensor(add_inverse(triples, num_rels))
     hist, h0 = hyp_forward(P, graphs, num_rels, c=c, encoder="hyperbolic_uvrgcn", layer_norm=layer_norm, gamma=gamma,
                            rmin=rmin, rmax=rmax, beta=beta, eps_r=eps_r, dtype=P["emb_rel"].dtype)
     emb = hist[-1]
     if layer_norm:
         emb = exp0(normalize_rows(log0(emb, c)), c)
-    et = log0(emb, c)
-    et = 0.9 * torch.tanh(et) + 0.1 * et
-    q = conv_tower_train(et[all_t[:, 0]], h0[all_t[:, 1]], P, "decoder_ob.", stats)
-    loss_e = cross_entropy(q @ et.t() + P["decoder_ob.b"], all_t[:, 2])
-    q = conv_tower_train(et[all_t[:, 0]], et[all_t[:, 2]], P, "rdecoder.", stats)
-    loss_r = cross_entropy(q @ h0.t() + P["rdecoder.b"], all_t[:, 1])
+    if decoder == "murp":
+        # HyperbolicMuRP.loss / MuRPRel.loss (hyperbolic_decoder.py:781-817, 897-928): CE over the forward scores; the
+        # per-query subject bias of forward() is not part of loss() (and would cancel in the CE anyway)
+        sc = murp_scores(P, emb, h0, all_t.numpy(), c)[0]
+        if "decoder_ob.entity_bias" in P:
+            sc = sc - P["decoder_ob.entity_bias"][all_t[:, 0]].unsqueeze(1)
+        loss_e = cross_entropy(sc, all_t[:, 2])
+        loss_r = cross_entropy(murprel_scores(P, emb, h0, all_t.numpy(), c)[0], all_t[:, 1])
+    else:
+        et = log0(emb, c)
+        et = 0.9 * torch.tanh(et) + 0.1 * et
+        q = conv_tower_train(et[all_t[:, 0]], h0[all_t[:, 1]], P, "decoder_ob.", stats)
+        loss_e = cross_entropy(q @ et.t() + P["decoder_ob.b"], all_t[:, 2])
+        q = conv_tower_train(et[all_t[:, 0]], et[all_t[:, 2]], P, "rdecoder.", stats)
+        loss_r = cross_entropy(q @ h0.t() + P["rdecoder.b"], all_t[:, 1])
     ids = torch.unique(all_t[:, [0, 2]].reshape(-1))
     rs = static_radius(P["radius_static"], c, rmin, rmax)[ids]
     loss_rad = radius_lambda * torch.mean((rs - P["radius_target"][ids]) ** 2)
@@ -852,7 +861,8 @@ def hyp_train_losses(P, graphs, num_rels, triples, c, layer_norm, gamma, stats, 
 
 
 def hyp_train_steps(sd, graphs, num_rels, triples, c=0.01, layer_norm=False, gamma=0.15, steps=1, task_weight=0.7,
-                    grad_norm=1.0, lr=1e-3, weight_decay=1e-5, betas=(0.9, 0.999), eps=1e-8, dtype=torch.float32):
+                    grad_norm=1.0, lr=1e-3, weight_decay=1e-5, betas=(0.9, 0.999), eps=1e-8, dtype=torch.float32,
+                    decoder="hyperbolic_convtranse"):
     """Like regcn_train_steps for the hyperbolic model.  Returns per-step dicts {losses (e, r, static, radius),
     grad_norm, grads, params}."""
     P = {}
@@ -868,7 +878,7 @@ def hyp_train_steps(sd, graphs, num_rels, triples, c=0.01, layer_norm=False, gam
     log = []
     for step in range(1, steps + 1):
         stats = {}
-        le, lrel, lrad = hyp_train_losses(P, graphs, num_rels, triples, c, layer_norm, gamma, stats)
+        le, lrel, lrad = hyp_train_losses(P, graphs, num_rels, triples, c, layer_norm, gamma, stats, decoder=decoder)
         loss = task_weight * le + (1 - task_weight) * lrel + lrad
         names = [k for k, v in P.items() if v.requires_grad]
         gs = torch.autograd.grad(loss, [P[k] for k in names], allow_unused=True)

@@ -129,6 +129,11 @@ SIGNATURES = {
     "regcn_edge_scalar_gather": (_i, [_p, _p, _p, _i, _p, _i, _p]),
     "regcn_radius_mse": (_i, [_p, _p, _p, _i, _f, _f, _d, _f, _p, _p]),
     "regcn_radius_mse_bwd": (_i, [_p, _p, _p, _i, _f, _f, _d, _f, _p, _p, _p]),
+    "regcn_mobius_fwd": (_i, [_p, _p, _i, _i, _d, _p, _p]),
+    "regcn_mobius_bwd": (_i, [_p, _p, _p, _i, _i, _d, _p, _p, _p]),
+    "regcn_eltwise_mul": (_i, [_p, _p, _p, _sz, _p]),
+    "regcn_row_axpy": (_i, [_p, _p, _f, _i, _i, _p, _p]),
+    "regcn_hyp_dist_grad": (_i, [_p, _p, _p, _i64, _i, _i, _p, _p, _d, _p, _p, _p, _p, _p]),
     "regcn_static_angle_bwd": (_i, [_p, _p, _i, _i, _f, _f, _i, _p, _p, _i, _p, _p]),
 }
 

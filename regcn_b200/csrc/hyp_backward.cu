@@ -454,3 +454,201 @@ int regcn_radius_mse_bwd(const float* raw, const float* target, const int64_t* i
   return radius_mse_bwd(raw, target, ids, n, rmin, rmax, c, lambda, gscale, draw, ST(stream));
 }
 }
+
+// =====================================================================================================================
+// Distance decoders in training (HyperbolicMuRP / MuRPRel .loss, hyperbolic_decoder.py:647-928; the scoring core
+// _chunked_hyperbolic_ce_loss :182-307 in the <q,e>, |q|^2, |e|^2 form of a18).
+// =====================================================================================================================
+namespace regcn {
+
+// mobius_add without its final projection (a separate radial node): z = (a x + b y) / den,
+//   a = 1 + 2c<x,y> + c|y|^2, b = 1 - c|x|^2, den = 1 + 2c<x,y> + c^2|x|^2|y|^2 + eps      (hyperbolic_ops.py:135-142)
+template <int RV>
+__global__ void __launch_bounds__(256) mobius_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, int M,
+                                                         int d, float c, float* __restrict__ z) {
+  pdl_grid_sync();
+  ROWP(M)
+  WarpRow<RV> a, b;
+  a.load_plain(x + (size_t)row * d, nvec, lane);
+  b.load_plain(y + (size_t)row * d, nvec, lane);
+  const float X = a.sumsq(), Y = b.sumsq(), xy = a.dot(b);
+  const float ca = 1.0f + 2.0f * c * xy + c * Y, cb = 1.0f - c * X;
+  const float den = 1.0f + 2.0f * c * xy + c * c * X * Y + kEps;
+  a.zip(b, [=](float xx, float yy) { return (ca * xx + cb * yy) / den; });
+  a.store(z + (size_t)row * d, nvec, lane);
+}
+template <int RV>
+__global__ void __launch_bounds__(256) mobius_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                         const float* __restrict__ dz, int M, int d, float c,
+                                                         float* __restrict__ dx, float* __restrict__ dy) {
+  pdl_grid_sync();
+  ROWP(M)
+  WarpRow<RV> a, b, g;
+  a.load_plain(x + (size_t)row * d, nvec, lane);
+  b.load_plain(y + (size_t)row * d, nvec, lane);
+  g.load_plain(dz + (size_t)row * d, nvec, lane);
+  const float X = a.sumsq(), Y = b.sumsq(), xy = a.dot(b);
+  const float ca = 1.0f + 2.0f * c * xy + c * Y, cb = 1.0f - c * X;
+  const float den = 1.0f + 2.0f * c * xy + c * c * X * Y + kEps;
+  const float gx = g.dot(a), gy = g.dot(b);
+  const float gz = (ca * gx + cb * gy) / den;                  // <g, z>
+  const float inv = 1.0f / den;
+  // dx = (a/den) g + (2c gx/den) y - (2c gy/den) x - (gz/den)(2c y + 2c^2 Y x)
+  const float kx_g = ca * inv, kx_y = 2.0f * c * gx * inv - gz * inv * 2.0f * c,
+              kx_x = -2.0f * c * gy * inv - gz * inv * 2.0f * c * c * Y;
+  // dy = (b/den) g + (gx/den)(2c x + 2c y) - (gz/den)(2c x + 2c^2 X y)
+  const float ky_g = cb * inv, ky_x = 2.0f * c * gx * inv - gz * inv * 2.0f * c,
+              ky_y = 2.0f * c * gx * inv - gz * inv * 2.0f * c * c * X;
+  WarpRow<RV> ox, oy;
+#pragma unroll
+  for (int i = 0; i < RV; ++i) {
+    ox.v[i] = make_float4(kx_g * g.v[i].x + kx_y * b.v[i].x + kx_x * a.v[i].x, kx_g * g.v[i].y + kx_y * b.v[i].y + kx_x * a.v[i].y,
+                          kx_g * g.v[i].z + kx_y * b.v[i].z + kx_x * a.v[i].z, kx_g * g.v[i].w + kx_y * b.v[i].w + kx_x * a.v[i].w);
+    oy.v[i] = make_float4(ky_g * g.v[i].x + ky_x * a.v[i].x + ky_y * b.v[i].x, ky_g * g.v[i].y + ky_x * a.v[i].y + ky_y * b.v[i].y,
+                          ky_g * g.v[i].z + ky_x * a.v[i].z + ky_y * b.v[i].z, ky_g * g.v[i].w + ky_x * a.v[i].w + ky_y * b.v[i].w);
+  }
+  ox.store(dx + (size_t)row * d, nvec, lane);
+  oy.store(dy + (size_t)row * d, nvec, lane);
+}
+int mobius_fwd(const float* x, const float* y, int M, int d, double c, float* z, cudaStream_t st) {
+  if (!x || !y || !z) { set_last_error("mobius_fwd: null pointer"); return REGCN_ERR_NULL; }
+  if (int e = chk("mobius_fwd", d)) return e;
+  if (M <= 0) return REGCN_OK;
+  if (d <= 128) launch_k(mobius_fwd_kernel<1>, rg(M), 256, 0, st, x, y, M, d, (float)c, z);
+  else launch_k(mobius_fwd_kernel<2>, rg(M), 256, 0, st, x, y, M, d, (float)c, z);
+  return check_launch("mobius_fwd");
+}
+int mobius_bwd(const float* x, const float* y, const float* dz, int M, int d, double c, float* dx, float* dy, cudaStream_t st) {
+  if (!x || !y || !dz || !dx || !dy) { set_last_error("mobius_bwd: null pointer"); return REGCN_ERR_NULL; }
+  if (int e = chk("mobius_bwd", d)) return e;
+  if (M <= 0) return REGCN_OK;
+  if (d <= 128) launch_k(mobius_bwd_kernel<1>, rg(M), 256, 0, st, x, y, dz, M, d, (float)c, dx, dy);
+  else launch_k(mobius_bwd_kernel<2>, rg(M), 256, 0, st, x, y, dz, M, d, (float)c, dx, dy);
+  return check_launch("mobius_bwd");
+}
+
+// z = x * y elementwise (MuRP's diagonal relation map, :748-752); the backward is the same kernel twice.
+__global__ void __launch_bounds__(256) eltwise_mul_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                          float* __restrict__ z, size_t n) {
+  pdl_grid_sync();
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) z[i] = x[i] * y[i];
+}
+int eltwise_mul(const float* x, const float* y, float* z, size_t n, cudaStream_t st) {
+  if (!x || !y || !z) { set_last_error("eltwise_mul: null pointer"); return REGCN_ERR_NULL; }
+  if (n == 0) return REGCN_OK;
+  launch_k(eltwise_mul_kernel, (unsigned)((n + 255) / 256), 256, 0, st, x, y, z, n);
+  return check_launch("eltwise_mul");
+}
+
+// out[r] += alpha * s[r] * x[r]   (the |q|^2 / |e|^2 terms of the distance-score gradient)
+template <int RV>
+__global__ void __launch_bounds__(256) row_axpy_kernel(const float* __restrict__ x, const float* __restrict__ s, float alpha,
+                                                       int M, int d, float* __restrict__ out) {
+  pdl_grid_sync();
+  ROWP(M)
+  WarpRow<RV> a, o;
+  a.load_plain(x + (size_t)row * d, nvec, lane);
+  o.load_plain(out + (size_t)row * d, nvec, lane);
+  const float f = alpha * __ldg(s + row);
+  o.zip(a, [=](float oo, float xx) { return fmaf(f, xx, oo); });
+  o.store(out + (size_t)row * d, nvec, lane);
+}
+int row_axpy(const float* x, const float* s, float alpha, int M, int d, float* out, cudaStream_t st) {
+  if (!x || !s || !out) { set_last_error("row_axpy: null pointer"); return REGCN_ERR_NULL; }
+  if (int e = chk("row_axpy", d)) return e;
+  if (M <= 0) return REGCN_OK;
+  if (d <= 128) launch_k(row_axpy_kernel<1>, rg(M), 256, 0, st, x, s, alpha, M, d, out);
+  else launch_k(row_axpy_kernel<2>, rg(M), 256, 0, st, x, s, alpha, M, d, out);
+  return check_launch("row_axpy");
+}
+
+// Gradient of the proxy-distance score S = scale (margin - n^2) + bias, n = min(|(-q)(+)e|, proj_max), through its three
+// scalars per (query, candidate): dot D, x2 = |q|^2, y2 = |e|^2 (a18's form; hyperbolic_decoder.py:164-172).
+// In place: D[b,n] <- dS * dS/dD; H[b,n] <- dS * dS/dy2; per row: gx[b] = sum_n dS * dS/dx2, gs[b] = sum_n dS (margin - n^2),
+// gm[b] = sum_n dS * scale.  One CTA per query row.
+__global__ void __launch_bounds__(256) hyp_dist_grad_kernel(float* __restrict__ D, const float* __restrict__ dS,
+                                                            float* __restrict__ H, int64_t ld, int B, int N,
+                                                            const float* __restrict__ x2, const float* __restrict__ y2,
+                                                            float c, float pm, const float* __restrict__ scale_margin,
+                                                            float* __restrict__ gx, float* __restrict__ gs,
+                                                            float* __restrict__ gm) {
+  pdl_grid_sync();
+  __shared__ float sh[3][8];
+  const int b = blockIdx.x;
+  const float scale = scale_margin[0], margin = scale_margin[1];
+  const float X = x2[b];
+  float ax = 0.f, as = 0.f, am = 0.f;
+  for (int j = threadIdx.x; j < (int)ld; j += blockDim.x) {
+    const size_t i = (size_t)b * ld + j;
+    float g1 = 0.f, h = 0.f;
+    if (j < N) {
+      const float g = dS[i];
+      const float u = -D[i], Y = y2[j];
+      const float A = 1.0f + 2.0f * c * u + c * Y, Bc = 1.0f - c * X;
+      const float num = fmaxf(A * A * X + 2.0f * A * Bc * u + Bc * Bc * Y, 0.f);
+      const float den = 1.0f + 2.0f * c * u + c * c * X * Y + kEps;
+      const float n2 = num / (den * den);
+      const bool clamped = sqrtf(num) / fabsf(den) > pm;
+      const float n2c = clamped ? pm * pm : n2;
+      as += g * (margin - n2c);
+      am += g * scale;
+      if (!clamped) {
+        const float inv2 = 1.0f / (den * den), k3 = 2.0f * num * inv2 / den;
+        const float dnum_u = 4.0f * c * A * X + 4.0f * c * Bc * u + 2.0f * A * Bc;
+        const float dnum_X = A * A - 2.0f * c * A * u - 2.0f * c * Bc * Y;
+        const float dnum_Y = 2.0f * c * A * X + 2.0f * c * Bc * u + Bc * Bc;
+        const float dn2_u = dnum_u * inv2 - k3 * (2.0f * c);
+        const float dn2_X = dnum_X * inv2 - k3 * (c * c * Y);
+        const float dn2_Y = dnum_Y * inv2 - k3 * (c * c * X);
+        g1 = g * scale * dn2_u;                     // dS/dD = scale dn2/du   (u = -D, S = -scale n^2)
+        ax += g * (-scale) * dn2_X;
+        h = g * (-scale) * dn2_Y;
+      }
+    }
+    D[i] = g1;
+    H[i] = h;
+  }
+  float v[3] = {ax, as, am};
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    const float s = warp_sum(v[q]);
+    if ((threadIdx.x & 31) == 0) sh[q][threadIdx.x >> 5] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += sh[threadIdx.x][w];
+    (threadIdx.x == 0 ? gx : threadIdx.x == 1 ? gs : gm)[b] = s;
+  }
+}
+int hyp_dist_grad(float* D, const float* dS, float* H, int64_t ld, int B, int N, const float* x2, const float* y2, double c,
+                  const float* scale_margin, float* gx, float* gs, float* gm, cudaStream_t st) {
+  if (!D || !dS || !H || !x2 || !y2 || !scale_margin || !gx || !gs || !gm) { set_last_error("hyp_dist_grad: null pointer"); return REGCN_ERR_NULL; }
+  if (B <= 0 || N <= 0) return REGCN_OK;
+  const Curv cv = make_curv(c);
+  launch_k(hyp_dist_grad_kernel, (unsigned)B, 256, 0, st, D, dS, H, ld, B, N, x2, y2, cv.c, cv.proj_max, scale_margin, gx, gs, gm);
+  return check_launch("hyp_dist_grad");
+}
+
+}  // namespace regcn
+
+extern "C" {
+int regcn_mobius_fwd(const float* x, const float* y, int M, int d, double c, float* z, void* stream) {
+  return regcn::mobius_fwd(x, y, M, d, c, z, (cudaStream_t)stream);
+}
+int regcn_mobius_bwd(const float* x, const float* y, const float* dz, int M, int d, double c, float* dx, float* dy,
+                     void* stream) {
+  return regcn::mobius_bwd(x, y, dz, M, d, c, dx, dy, (cudaStream_t)stream);
+}
+int regcn_eltwise_mul(const float* x, const float* y, float* z, size_t n, void* stream) {
+  return regcn::eltwise_mul(x, y, z, n, (cudaStream_t)stream);
+}
+int regcn_row_axpy(const float* x, const float* s, float alpha, int M, int d, float* out, void* stream) {
+  return regcn::row_axpy(x, s, alpha, M, d, out, (cudaStream_t)stream);
+}
+int regcn_hyp_dist_grad(float* D, const float* dS, float* H, int64_t ld, int B, int N, const float* x2, const float* y2,
+                        double c, const float* scale_margin, float* gx, float* gs, float* gm, void* stream) {
+  return regcn::hyp_dist_grad(D, dS, H, ld, B, N, x2, y2, c, scale_margin, gx, gs, gm, (cudaStream_t)stream);
+}
+}

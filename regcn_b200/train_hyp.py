@@ -295,14 +295,185 @@ class _RadiusLoss(torch.autograd.Function):
         return draw, None, None, None, None, None, None
 
 
+# ------------------------------------------------------------------------------------------------ distance decoders
+class _GatherRows(torch.autograd.Function):
+    """out[b] = table[idx[b]]   (entity / relation lookups of the decoders, hyperbolic_decoder.py:744-746)."""
+
+    @staticmethod
+    def forward(ctx, table, idx32):
+        table, idx32 = table.contiguous(), idx32.contiguous()
+        P, d = int(idx32.shape[0]), table.shape[1]
+        out = torch.empty((P, d), device=table.device, dtype=F32)
+        call("regcn_gather_rows2", ptr(table), None, ptr(idx32), P, d, ptr(out), None)
+        ctx.save_for_backward(idx32)
+        ctx.nrows = table.shape[0]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (idx32,) = ctx.saved_tensors
+        dout = dout.contiguous()
+        rp, perm, _ = T._group(idx32, ctx.nrows)
+        return T._gather_sum(dout, dout.shape[1], None, rp, perm, ctx.nrows, dout.shape[1]), None
+
+
+class _Mul(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y):
+        x, y = x.contiguous(), y.contiguous()
+        ctx.save_for_backward(x, y)
+        z = torch.empty_like(x)
+        call("regcn_eltwise_mul", ptr(x), ptr(y), ptr(z), x.numel())
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        x, y = ctx.saved_tensors
+        dz = dz.contiguous()
+        dx, dy = torch.empty_like(x), torch.empty_like(x)
+        call("regcn_eltwise_mul", ptr(dz), ptr(y), ptr(dx), x.numel())
+        call("regcn_eltwise_mul", ptr(dz), ptr(x), ptr(dy), x.numel())
+        return dx, dy
+
+
+class _Mobius(torch.autograd.Function):
+    """mobius_add before its projection (hyperbolic_ops.py:135-142); follow with radial(., PROJECT)."""
+
+    @staticmethod
+    def forward(ctx, x, y, c):
+        x, y = x.contiguous(), y.contiguous()
+        ctx.save_for_backward(x, y)
+        ctx.c = float(c)
+        z = torch.empty_like(x)
+        call("regcn_mobius_fwd", ptr(x), ptr(y), x.shape[0], x.shape[1], ctx.c, ptr(z))
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        x, y = ctx.saved_tensors
+        dx, dy = torch.empty_like(x), torch.empty_like(x)
+        call("regcn_mobius_bwd", ptr(x), ptr(y), ptr(dz.contiguous()), x.shape[0], x.shape[1], ctx.c, ptr(dx), ptr(dy))
+        return dx, dy, None
+
+
+class _Dropout(torch.autograd.Function):
+    """nn.Dropout in train mode (mask recovered from the output)."""
+
+    @staticmethod
+    def forward(ctx, x, p):
+        out = x.contiguous().clone()
+        call("regcn_dropout", ptr(out), out.numel(), float(p), T._next_seed())
+        ctx.p = float(p)
+        ctx.save_for_backward(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (out,) = ctx.saved_tensors
+        M, d = out.shape
+        dx = torch.empty_like(out)
+        call("regcn_bn_bwd_apply", ptr(dout.contiguous()), ptr(out), None, M, 1, d, 2, 1.0 / (1.0 - ctx.p), None, None, None,
+             None, None, None, 0, 1.0, ptr(dx))
+        return dx, None
+
+
+def dropout(x, p, training):
+    return _Dropout.apply(x, p) if (training and p > 0) else x
+
+
+class _HypDistCE(torch.autograd.Function):
+    """mean_b CrossEntropy over scale (margin - |(-q_b)(+)_c e_n|^2) + bias_n   (_chunked_hyperbolic_ce_loss,
+    hyperbolic_decoder.py:182-307, proxy-distance branch) in the <q,e>, |q|^2, |e|^2 form: one GEMM for the dots, the
+    score epilogue in place, and in the backward the three partial derivatives per (query, candidate) feed two GEMMs."""
+
+    @staticmethod
+    def forward(ctx, q, cand, bias, scale, margin, triples, target_col, c):
+        q, cand = q.contiguous(), cand.contiguous()
+        B, d = q.shape
+        N = cand.shape[0]
+        Np = T._pad4(N)
+        dev = q.device
+        sm = torch.stack((scale.detach().reshape(()), margin.detach().reshape(()))).float().contiguous()
+        x2, y2 = ops.row_sumsq(q), ops.row_sumsq(cand)
+        S = torch.empty((B, Np), device=dev, dtype=F32)
+        T._mm(T._split(q), T._split(cand), B, N, d, out=S, ldc=Np)
+        call("regcn_hyp_score_epilogue", ptr(S), Np, B, N, ptr(x2), ptr(y2), ptr(bias.contiguous()) if bias is not None else None,
+             None, float(c), ptr(sm), None)
+        ce = torch.empty(B, device=dev, dtype=F32)
+        lse = torch.empty(B, device=dev, dtype=F32)
+        loss = torch.empty(1, device=dev, dtype=F32)
+        call("regcn_ce_lse_rows", ptr(S), Np, B, N, ptr(triples), target_col, ptr(ce), ptr(lse), ptr(loss))
+        ctx.save_for_backward(q, cand, triples, lse, x2, y2, sm)
+        ctx.S, ctx.target_col, ctx.c, ctx.has_bias = S, target_col, float(c), bias is not None
+        return loss
+
+    @staticmethod
+    def backward(ctx, gloss):
+        q, cand, triples, lse, x2, y2, sm = ctx.saved_tensors
+        S, ctx.S = ctx.S, None
+        B, d = q.shape
+        N, Np = cand.shape[0], S.shape[1]
+        dev = q.device
+        call("regcn_softmax_grad_rows", ptr(S), Np, B, N, ptr(triples), ctx.target_col, ptr(lse),
+             ptr(gloss.contiguous().view(-1)))                                    # S <- dS
+        qs, cs = T._split(q), T._split(cand)
+        D = torch.empty((B, Np), device=dev, dtype=F32)
+        T._mm(qs, cs, B, N, d, out=D, ldc=Np)                                   # the dots again (cheaper than keeping them)
+        H = torch.empty((B, Np), device=dev, dtype=F32)
+        gx, gs, gm = (torch.empty(B, device=dev, dtype=F32) for _ in range(3))
+        call("regcn_hyp_dist_grad", ptr(D), ptr(S), ptr(H), Np, B, N, ptr(x2), ptr(y2), ctx.c, ptr(sm), ptr(gx), ptr(gs), ptr(gm))
+        Ds = T._split(D)
+        dq = T._mm(Ds, cs, B, d, N, b_mn=True).contiguous()
+        call("regcn_row_axpy", ptr(q), ptr(gx), 2.0, B, d, ptr(dq))
+        dcand = T._mm(Ds, qs, N, d, B, a_mn=True, b_mn=True).contiguous()
+        gy = T._col_sum(H[:, :N])
+        call("regcn_row_axpy", ptr(cand), ptr(gy), 2.0, N, d, ptr(dcand))
+        dbias = T._col_sum(S[:, :N]) if ctx.has_bias else None
+        dscale = T._col_sum(gs.view(B, 1)).view(())
+        dmargin = T._col_sum(gm.view(B, 1)).view(())
+        return dq, dcand, dbias, dscale, dmargin, None, None, None
+
+
+def murp_losses(model, pre, r_emb, all_t):
+    """HyperbolicMuRP.loss / HyperbolicMuRPRel.loss (hyperbolic_decoder.py:781-817, 897-928)."""
+    c = model._c_float
+    dec, rdec = model.decoder_ob, model.rdecoder
+    if getattr(dec, "rel_curvature_raw", None) is not None:
+        raise NotImplementedError("regcn_b200.train_hyp: relation-specific curvature in training is not implemented")
+    s32 = all_t[:, 0].to(torch.int32).contiguous()
+    r32 = all_t[:, 1].to(torch.int32).contiguous()
+    o32 = all_t[:, 2].to(torch.int32).contiguous()
+    loss_ent = torch.zeros(1, device=pre.device)
+    loss_rel = torch.zeros(1, device=pre.device)
+    if model.entity_prediction:
+        s_emb = radial(_GatherRows.apply(pre, s32), PROJECT, c)
+        rot = _GatherRows.apply(T.linear(r_emb, dec.rot_proj.weight, dec.rot_proj.bias), r32)
+        st = dropout(radial(s_emb, LOG0, c), float(dec.dropout.p), model.training)
+        rs = radial(radial(_Mul.apply(rot, st), EXP0, c), PROJECT, c)
+        tr = _GatherRows.apply(T.linear(r_emb, dec.trans_proj.weight, dec.trans_proj.bias), r32)
+        tr = radial(radial(tr, EXP0, c), PROJECT, c)
+        q = radial(_Mobius.apply(rs, tr, c), PROJECT, c)
+        scale = torch.nn.functional.softplus(dec.score_scale_raw) + 1e-6          # two scalars: host-side glue
+        loss_ent = _HypDistCE.apply(q, pre, dec.entity_bias, scale, dec.score_margin, all_t, 2, c)
+    if model.relation_prediction:
+        p = float(rdec.dropout.p)
+        st = dropout(radial(_GatherRows.apply(pre, s32), LOG0, c), p, model.training)
+        ot = dropout(radial(_GatherRows.apply(pre, o32), LOG0, c), p, model.training)
+        q_tan = T.linear(torch.cat((st, ot), dim=1), torch.cat((rdec.W_s, rdec.W_o), dim=0), None, True)
+        q = radial(q_tan, EXP0, c)
+        one = torch.ones((), device=pre.device)
+        loss_rel = _HypDistCE.apply(q, radial(r_emb, EXP0, c), rdec.rel_bias, one, one * 0.0, all_t, 1, c)
+    return loss_ent, loss_rel
+
+
 def hyp_get_loss(model, glist, triples):
     """hyperbolic_model.py:941-1088 with gradients: (loss_ent, loss_rel, loss_static, loss_radius), each (1,)."""
     _lib.require_device()
     if ops.gemm_impl() != "tc":
         raise RuntimeError("regcn_b200.train_hyp needs the tensor-core GEMM (REGCN_GEMM=tc)")
-    if model.decoder_name != "hyperbolic_convtranse":
+    if model.decoder_name not in ("hyperbolic_convtranse", "murp"):
         raise NotImplementedError("regcn_b200.train_hyp: training mode is implemented for --decoder hyperbolic_convtranse "
-                                  "(the reference's default); the distance decoders' streaming-CE heads are next")
+                                  "(the reference's default) and murp; the roth / atth query builders are next")
     dev = model.dynamic_emb.device
     c = model._c_float
     triples = torch.as_tensor(triples).to(dev)
@@ -311,17 +482,20 @@ def hyp_get_loss(model, glist, triples):
     all_triples = torch.cat([triples, inverse]).contiguous()
     hist, r_emb = hyp_evolve(model, glist)
     pre = radial(hist[-1], TNORM, c) if model.layer_norm else hist[-1]
-    et = eltwise(radial(pre, LOG0, c), 1, 0.0)                      # 0.9 tanh(log_0 E) + 0.1 log_0 E  (:377-379)
     loss_ent = torch.zeros(1, device=dev)
     loss_rel = torch.zeros(1, device=dev)
     loss_static = torch.zeros(1, device=dev)
+    ids = torch.unique(all_triples[:, [0, 2]].reshape(-1))
+    loss_radius = _RadiusLoss.apply(model.radius_static, model.radius_target, ids, model.radius_min, model.radius_max, c,
+                                    float(model.radius_lambda))
+    if model.decoder_name == "murp":
+        loss_ent, loss_rel = murp_losses(model, pre, r_emb, all_triples)
+        return loss_ent, loss_rel, loss_static, loss_radius
+    et = eltwise(radial(pre, LOG0, c), 1, 0.0)                      # 0.9 tanh(log_0 E) + 0.1 log_0 E  (:377-379)
     if model.entity_prediction:
         q = T.conv_tower(model.decoder_ob, et, r_emb, all_triples, 0, 1)
         loss_ent = T.score_ce(q, et, all_triples, 2, model.decoder_ob.b)
     if model.relation_prediction:
         q = T.conv_tower(model.rdecoder, et, et, all_triples, 0, 2)
         loss_rel = T.score_ce(q, r_emb, all_triples, 1, model.rdecoder.b)
-    ids = torch.unique(all_triples[:, [0, 2]].reshape(-1))
-    loss_radius = _RadiusLoss.apply(model.radius_static, model.radius_target, ids, model.radius_min, model.radius_max, c,
-                                    float(model.radius_lambda))
     return loss_ent, loss_rel, loss_static, loss_radius

@@ -142,6 +142,10 @@ HYP_TRAIN_CASES = {
                                 decoder="hyperbolic_convtranse", layer_norm=True, gamma=1.0),
     "hyptrain_small_s2_ln": dict(kind="hyp", shape="small", seed=2, encoder="hyperbolic_uvrgcn",
                                  decoder="hyperbolic_convtranse", layer_norm=True, gamma=0.15),
+    "hyptrain_murp_tiny_s3": dict(kind="hyp", shape="tiny", seed=3, encoder="hyperbolic_uvrgcn", decoder="murp",
+                                  layer_norm=False, gamma=0.15),
+    "hyptrain_murp_small_s4_bias": dict(kind="hyp", shape="small", seed=4, encoder="hyperbolic_uvrgcn", decoder="murp",
+                                        layer_norm=True, gamma=0.15, entity_bias=True),
 }
 
 
@@ -151,7 +155,8 @@ def build_hyp_train_model(cfg, n, r, dropout=0.0):
                                   num_hidden_layers=N_LAYERS, dropout=dropout, c=CURV, self_loop=True, skip_connect=False,
                                   layer_norm=cfg["layer_norm"], input_dropout=dropout, hidden_dropout=dropout,
                                   feat_dropout=dropout, entity_prediction=True, relation_prediction=True, use_cuda=True,
-                                  gpu=0, radius_msg_gamma=cfg["gamma"], hyp_init_scale=1e-3)
+                                  gpu=0, radius_msg_gamma=cfg["gamma"], hyp_init_scale=1e-3,
+                                  use_entity_euclidean_bias=cfg.get("entity_bias", False))
     sd = synth.fill_state_dict(m.state_dict(), cfg["seed"])
     m.load_state_dict(sd)
     return m, sd

@@ -151,3 +151,41 @@ def test_hyperbolic_train_step_matches_reference(name):
     m.eval()
     _, score, _ = m.predict(glist, r, None, torch.from_numpy(case["test"]).to(DEV), True)
     assert torch.isfinite(score).all()
+
+
+def test_distance_decoder_nodes_backward():
+    """mobius_add, gather, elementwise product and the all-candidate hyperbolic-distance cross entropy (dq, dE, dbias,
+    dscale, dmargin through the <q,e>, |q|^2, |e|^2 form) against autograd on the oracle."""
+    R._lib.require_device()
+    rng = np.random.default_rng(21)
+    B, N, d = 96, 301, 200
+    q = rng.standard_normal((B, d)) * rng.uniform(0.02, 0.3, size=(B, 1))
+    E = rng.standard_normal((N, d)) * rng.uniform(0.02, 0.3, size=(N, 1))
+    bias = rng.standard_normal(N) * 0.1
+    trip = np.stack([rng.integers(0, N, B), rng.integers(0, 5, B), rng.integers(0, N, B)], 1).astype(np.int64)
+    qd, Ed, bd = _leaf(q), _leaf(E), _leaf(bias)
+    sc, mg = _leaf(np.array(1.3)), _leaf(np.array(0.8))
+    loss = train_hyp._HypDistCE.apply(qd, Ed, bd, sc, mg, torch.from_numpy(trip).to(DEV), 2, C)
+    (loss * 1.5).backward()
+    qc, Ec, bc = (torch.tensor(a, dtype=torch.float64, requires_grad=True) for a in (q, E, bias))
+    scc, mgc = torch.tensor(1.3, dtype=torch.float64, requires_grad=True), torch.tensor(0.8, dtype=torch.float64, requires_grad=True)
+    S = restate.hyp_dist_scores(qc, Ec, bc, C, scc, mgc)
+    lc = restate.cross_entropy(S, trip[:, 2])
+    (lc * 1.5).backward()
+    assert abs(float(loss.detach()) - float(lc.detach())) <= 1e-4 * max(1.0, abs(float(lc.detach())))
+    _cmp([qd.grad, Ed.grad, bd.grad, sc.grad.view(1), mg.grad.view(1)], [qc.grad, Ec.grad, bc.grad, scc.grad.view(1), mgc.grad.view(1)],
+         ["dq", "dE", "dbias", "dscale", "dmargin"])
+    # mobius + product + gather
+    x, y = q, rng.standard_normal((B, d)) * 0.1
+    go = rng.standard_normal((B, d))
+    idx = rng.integers(0, N, B).astype(np.int32)
+    xd, yd, Ed = _leaf(x), _leaf(y), _leaf(E)
+    z = train_hyp._Mobius.apply(train_hyp._Mul.apply(xd, train_hyp._GatherRows.apply(Ed, torch.from_numpy(idx).to(DEV))), yd, C)
+    z = train_hyp.radial(z, train_hyp.PROJECT, C)
+    z.backward(torch.as_tensor(go, dtype=torch.float32, device=DEV))
+    xc, yc, Ec = (torch.tensor(a, dtype=torch.float64, requires_grad=True) for a in (x, y, E))
+    zc = restate.mobius_add(xc * Ec[torch.as_tensor(idx, dtype=torch.long)], yc, C)
+    zc.backward(torch.as_tensor(go))
+    ok, worst = close(z.detach().cpu().numpy(), zc.detach().numpy())
+    assert ok, worst
+    _cmp([xd.grad, yd.grad, Ed.grad], [xc.grad, yc.grad, Ec.grad], ["mobius dx", "mobius dy", "gather dE"])
