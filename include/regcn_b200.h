@@ -461,7 +461,8 @@ REGCN_API int regcn_row_radius_bwd(const float* x, const float* drho, int M, int
 REGCN_API int regcn_apply_radius(const float* x, const float* r, int M, int d, double c, float* y, void* stream);
 REGCN_API int regcn_apply_radius_bwd(const float* x, const float* r, const float* dy, int M, int d, double c, float* dx,
                            float* dr, void* stream);
-/* elementwise op 0: clamp(x, -lim, lim) (the +-10 tangent clamps); op 1: 0.9 tanh(x) + 0.1 x (hyperbolic_decoder.py:378) */
+/* elementwise op 0: clamp(x, -lim, lim) (the +-10 tangent clamps); op 1: 0.9 tanh(x) + 0.1 x (hyperbolic_decoder.py:378);
+ * op 2: -x; op 3: relu(x)                                                                                          */
 REGCN_API int regcn_eltwise_fwd(const float* x, float* y, size_t n, int op, float lim, void* stream);
 REGCN_API int regcn_eltwise_bwd(const float* x, const float* dy, float* dx, size_t n, int op, float lim, void* stream);
 /* _static_radius (hyperbolic_model.py:715-720) + TemporalRadiusEvolution's scalar part (hyperbolic_ops.py:408-424):
@@ -500,6 +501,14 @@ REGCN_API int regcn_row_axpy(const float* x, const float* s, float alpha, int M,
 REGCN_API int regcn_hyp_dist_grad(float* D, const float* dS, float* H, int64_t ld, int B, int N, const float* x2,
                         const float* y2, double c, const float* scale_margin, float* gx, float* gs, float* gm,
                         void* stream);
+
+/* Givens rotation (mode 0) / reflection (mode 1) of the tangent pairs (hyperbolic_decoder.py:1033-1051,1380-1401) and its
+ * backward w.r.t. the vector and the angles; ang (B,d/2), or one (d/2) vector for all rows with ang_bcast (dang stays
+ * per row: its column sum is the gradient of the shared angles).                                                    */
+REGCN_API int regcn_givens_fwd(const float* x, const float* ang, int ang_bcast, int B, int d, int mode, float* y,
+                     void* stream);
+REGCN_API int regcn_givens_bwd(const float* x, const float* ang, const float* dy, int ang_bcast, int B, int d, int mode,
+                     float* dx, float* dang, void* stream);
 
 #ifdef __cplusplus
 }

@@ -335,6 +335,10 @@ HYP_TRAIN_CASES = {
                                   layer_norm=False, gamma=0.15),
     "hyptrain_murp_small_s4_bias": dict(kind="hyp", shape="small", seed=4, encoder="hyperbolic_uvrgcn", decoder="murp",
                                         layer_norm=True, gamma=0.15, entity_bias=True),
+    "hyptrain_roth_tiny_s5": dict(kind="hyp", shape="tiny", seed=5, encoder="hyperbolic_uvrgcn", decoder="roth",
+                                  layer_norm=False, gamma=0.15),
+    "hyptrain_roth_small_s6_bias": dict(kind="hyp", shape="small", seed=6, encoder="hyperbolic_uvrgcn", decoder="roth",
+                                        layer_norm=True, gamma=0.15, entity_bias=True),
 }
 
 

@@ -839,14 +839,15 @@ def hyp_train_losses(P, graphs, num_rels, triples, c, layer_norm, gamma, stats, 
     emb = hist[-1]
     if layer_norm:
         emb = exp0(normalize_rows(log0(emb, c)), c)
-    if decoder == "murp":
-        # HyperbolicMuRP.loss / MuRPRel.loss (hyperbolic_decoder.py:781-817, 897-928): CE over the forward scores; the
-        # per-query subject bias of forward() is not part of loss() (and would cancel in the CE anyway)
-        sc = murp_scores(P, emb, h0, all_t.numpy(), c)[0]
+    if decoder in ("murp", "roth"):
+        # Hyperbolic{MuRP,RotH}.loss / {MuRP,RotH}Rel.loss (hyperbolic_decoder.py:781-817, 897-928, 1101-1138, 1264-1280):
+        # CE over the forward scores; the per-query subject bias of forward() is not part of loss() (and cancels in CE)
+        ent_fn, rel_fn = (murp_scores, murprel_scores) if decoder == "murp" else (roth_scores, rothrel_scores)
+        sc = ent_fn(P, emb, h0, all_t.numpy(), c)[0]
         if "decoder_ob.entity_bias" in P:
             sc = sc - P["decoder_ob.entity_bias"][all_t[:, 0]].unsqueeze(1)
         loss_e = cross_entropy(sc, all_t[:, 2])
-        loss_r = cross_entropy(murprel_scores(P, emb, h0, all_t.numpy(), c)[0], all_t[:, 1])
+        loss_r = cross_entropy(rel_fn(P, emb, h0, all_t.numpy(), c)[0], all_t[:, 1])
     else:
         et = log0(emb, c)
         et = 0.9 * torch.tanh(et) + 0.1 * et

@@ -134,6 +134,8 @@ SIGNATURES = {
     "regcn_eltwise_mul": (_i, [_p, _p, _p, _sz, _p]),
     "regcn_row_axpy": (_i, [_p, _p, _f, _i, _i, _p, _p]),
     "regcn_hyp_dist_grad": (_i, [_p, _p, _p, _i64, _i, _i, _p, _p, _d, _p, _p, _p, _p, _p]),
+    "regcn_givens_fwd": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
+    "regcn_givens_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "regcn_static_angle_bwd": (_i, [_p, _p, _i, _i, _f, _f, _i, _p, _p, _i, _p, _p]),
 }
 

@@ -166,13 +166,14 @@ int apply_radius_bwd(const float* x, const float* r, const float* dy, int M, int
 
 // Elementwise pieces.  op 0: y = clamp(x, -lim, lim)  (torch.clamp: gradient 1 inside the closed interval)
 //                      op 1: y = 0.9 tanh(x) + 0.1 x  (HyperbolicConvTransE entity activation, hyperbolic_decoder.py:378)
+//                      op 2: y = -x;  op 3: y = relu(x)  (RotH's residual tangent MLP, :1028-1030)
 __global__ void __launch_bounds__(256) eltwise_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n,
                                                           int op, float lim) {
   pdl_grid_sync();
   const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float v = x[i];
-  y[i] = op == 0 ? clampf_(v, -lim, lim) : 0.9f * tanhf(v) + 0.1f * v;
+  y[i] = op == 0 ? clampf_(v, -lim, lim) : op == 1 ? 0.9f * tanhf(v) + 0.1f * v : op == 2 ? -v : fmaxf(v, 0.f);
 }
 __global__ void __launch_bounds__(256) eltwise_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                           float* __restrict__ dx, size_t n, int op, float lim) {
@@ -182,7 +183,9 @@ __global__ void __launch_bounds__(256) eltwise_bwd_kernel(const float* __restric
   const float v = x[i];
   float f;
   if (op == 0) f = (v >= -lim && v <= lim) ? 1.f : 0.f;
-  else { const float t = tanhf(v); f = 0.9f * (1.0f - t * t) + 0.1f; }
+  else if (op == 1) { const float t = tanhf(v); f = 0.9f * (1.0f - t * t) + 0.1f; }
+  else if (op == 2) f = -1.f;
+  else f = v > 0.f ? 1.f : 0.f;
   dx[i] = dy[i] * f;
 }
 int eltwise_fwd(const float* x, float* y, size_t n, int op, float lim, cudaStream_t st) {
@@ -650,5 +653,73 @@ int regcn_row_axpy(const float* x, const float* s, float alpha, int M, int d, fl
 int regcn_hyp_dist_grad(float* D, const float* dS, float* H, int64_t ld, int B, int N, const float* x2, const float* y2,
                         double c, const float* scale_margin, float* gx, float* gs, float* gm, void* stream) {
   return regcn::hyp_dist_grad(D, dS, H, ld, B, N, x2, y2, c, scale_margin, gx, gs, gm, (cudaStream_t)stream);
+}
+}
+
+// =====================================================================================================================
+// RotH / RotHRel / AttH in training: Givens rotation / reflection of the tangent pairs (hyperbolic_decoder.py:1033-1051,
+// 1380-1401), forward and backward w.r.t. the vector and the angles.
+// =====================================================================================================================
+namespace regcn {
+// mode 0 rotation: (c x1 - s x2, s x1 + c x2);  mode 1 reflection: (c x1 + s x2, s x1 - c x2).
+// ang: (B, d/2) or, with ang_bcast, one (d/2) vector shared by all rows.
+__global__ void __launch_bounds__(256) givens_fwd_kernel(const float* __restrict__ x, const float* __restrict__ ang,
+                                                         int ang_bcast, size_t npairs, int half, int mode,
+                                                         float* __restrict__ y) {
+  pdl_grid_sync();
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= npairs) return;
+  const float a = ang[ang_bcast ? i % half : i];
+  float s, c;
+  sincosf(a, &s, &c);
+  const float2 v = reinterpret_cast<const float2*>(x)[i];
+  reinterpret_cast<float2*>(y)[i] = mode == 0 ? make_float2(c * v.x - s * v.y, s * v.x + c * v.y)
+                                              : make_float2(c * v.x + s * v.y, s * v.x - c * v.y);
+}
+__global__ void __launch_bounds__(256) givens_bwd_kernel(const float* __restrict__ x, const float* __restrict__ ang,
+                                                         const float* __restrict__ dy, int ang_bcast, size_t npairs,
+                                                         int half, int mode, float* __restrict__ dx,
+                                                         float* __restrict__ dang) {
+  pdl_grid_sync();
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= npairs) return;
+  const float a = ang[ang_bcast ? i % half : i];
+  float s, c;
+  sincosf(a, &s, &c);
+  const float2 v = reinterpret_cast<const float2*>(x)[i];
+  const float2 g = reinterpret_cast<const float2*>(dy)[i];
+  if (mode == 0) {
+    reinterpret_cast<float2*>(dx)[i] = make_float2(c * g.x + s * g.y, -s * g.x + c * g.y);
+    dang[i] = g.x * (-s * v.x - c * v.y) + g.y * (c * v.x - s * v.y);
+  } else {
+    reinterpret_cast<float2*>(dx)[i] = make_float2(c * g.x + s * g.y, s * g.x - c * g.y);
+    dang[i] = g.x * (-s * v.x + c * v.y) + g.y * (c * v.x + s * v.y);
+  }
+}
+int givens_fwd(const float* x, const float* ang, int ang_bcast, int B, int d, int mode, float* y, cudaStream_t st) {
+  if (!x || !ang || !y) { set_last_error("givens_fwd: null pointer"); return REGCN_ERR_NULL; }
+  if (d <= 0 || (d & 1) || mode < 0 || mode > 1) { set_last_error("givens_fwd: bad d / mode"); return REGCN_ERR_DIM; }
+  const size_t np = (size_t)B * (d / 2);
+  if (np == 0) return REGCN_OK;
+  launch_k(givens_fwd_kernel, (unsigned)((np + 255) / 256), 256, 0, st, x, ang, ang_bcast, np, d / 2, mode, y);
+  return check_launch("givens_fwd");
+}
+int givens_bwd(const float* x, const float* ang, const float* dy, int ang_bcast, int B, int d, int mode, float* dx,
+               float* dang, cudaStream_t st) {
+  if (!x || !ang || !dy || !dx || !dang) { set_last_error("givens_bwd: null pointer"); return REGCN_ERR_NULL; }
+  if (d <= 0 || (d & 1) || mode < 0 || mode > 1) { set_last_error("givens_bwd: bad d / mode"); return REGCN_ERR_DIM; }
+  const size_t np = (size_t)B * (d / 2);
+  if (np == 0) return REGCN_OK;
+  launch_k(givens_bwd_kernel, (unsigned)((np + 255) / 256), 256, 0, st, x, ang, dy, ang_bcast, np, d / 2, mode, dx, dang);
+  return check_launch("givens_bwd");
+}
+}  // namespace regcn
+extern "C" {
+int regcn_givens_fwd(const float* x, const float* ang, int ang_bcast, int B, int d, int mode, float* y, void* stream) {
+  return regcn::givens_fwd(x, ang, ang_bcast, B, d, mode, y, (cudaStream_t)stream);
+}
+int regcn_givens_bwd(const float* x, const float* ang, const float* dy, int ang_bcast, int B, int d, int mode, float* dx,
+                     float* dang, void* stream) {
+  return regcn::givens_bwd(x, ang, dy, ang_bcast, B, d, mode, dx, dang, (cudaStream_t)stream);
 }
 }

@@ -466,14 +466,90 @@ def murp_losses(model, pre, r_emb, all_t):
     return loss_ent, loss_rel
 
 
+class _Givens(torch.autograd.Function):
+    """Givens rotation (mode 0) / reflection (mode 1); ang (B, d/2) or a shared (d/2,) vector."""
+
+    @staticmethod
+    def forward(ctx, x, ang, mode):
+        x, ang = x.contiguous(), ang.contiguous()
+        B, d = x.shape
+        ctx.bcast = int(ang.dim() == 1)
+        ctx.mode = int(mode)
+        ctx.save_for_backward(x, ang)
+        y = torch.empty_like(x)
+        call("regcn_givens_fwd", ptr(x), ptr(ang), ctx.bcast, B, d, ctx.mode, ptr(y))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, ang = ctx.saved_tensors
+        B, d = x.shape
+        dx = torch.empty_like(x)
+        dang = torch.empty((B, d // 2), device=x.device, dtype=F32)
+        call("regcn_givens_bwd", ptr(x), ptr(ang), ptr(dy.contiguous()), ctx.bcast, B, d, ctx.mode, ptr(dx), ptr(dang))
+        return dx, (T._col_sum(dang) if ctx.bcast else dang), None
+
+
+class _Add(torch.autograd.Function):
+    """a + b (the residual of RotH's tangent MLP) on the row-axpy kernel."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        out = b.contiguous().clone()
+        ones = torch.ones(a.shape[0], device=a.device, dtype=F32)
+        call("regcn_row_axpy", ptr(a.contiguous()), ptr(ones), 1.0, a.shape[0], a.shape[1], ptr(out))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g
+
+
+def _reshape_tangent(dec, x):
+    """x + fc2(relu(fc1(x)))   (hyperbolic_decoder.py:1028-1030)."""
+    h1 = eltwise(T.linear(x, dec.reshape_fc1.weight, dec.reshape_fc1.bias), 3, 0.0)
+    return _Add.apply(x, T.linear(h1, dec.reshape_fc2.weight, dec.reshape_fc2.bias))
+
+
+def roth_losses(model, pre, r_emb, all_t):
+    """HyperbolicRotH.loss / HyperbolicRotHRel.loss (hyperbolic_decoder.py:1101-1138, 1264-1280)."""
+    c = model._c_float
+    dec, rdec = model.decoder_ob, model.rdecoder
+    if getattr(dec, "rel_curvature_raw", None) is not None:
+        raise NotImplementedError("regcn_b200.train_hyp: relation-specific curvature in training is not implemented")
+    s32 = all_t[:, 0].to(torch.int32).contiguous()
+    r32 = all_t[:, 1].to(torch.int32).contiguous()
+    o32 = all_t[:, 2].to(torch.int32).contiguous()
+    loss_ent = torch.zeros(1, device=pre.device)
+    loss_rel = torch.zeros(1, device=pre.device)
+    sp = torch.nn.functional.softplus
+    if model.entity_prediction:
+        st = radial(radial(_GatherRows.apply(pre, s32), PROJECT, c), LOG0, c)
+        st = _reshape_tangent(dec, dropout(st, float(dec.dropout.p), model.training))
+        ang = _GatherRows.apply(T.linear(r_emb, dec.rot_proj.weight, dec.rot_proj.bias), r32)
+        rs = radial(radial(_Givens.apply(st, ang, 0), EXP0, c), PROJECT, c)
+        tr = _GatherRows.apply(T.linear(r_emb, dec.trans_proj.weight, dec.trans_proj.bias), r32)
+        tr = radial(radial(tr, EXP0, c), PROJECT, c)
+        q = radial(_Mobius.apply(rs, tr, c), PROJECT, c)
+        loss_ent = _HypDistCE.apply(q, pre, dec.entity_bias, sp(dec.score_scale_raw) + 1e-6, dec.score_margin, all_t, 2, c)
+    if model.relation_prediction:
+        st = radial(_GatherRows.apply(pre, s32), LOG0, c)
+        st = _reshape_tangent(rdec, dropout(st, float(rdec.dropout.p), model.training))
+        rs = eltwise(radial(_Givens.apply(st, rdec.global_rot, 0), EXP0, c), 2, 0.0)          # -exp_0(rot)
+        q = radial(_Mobius.apply(rs, _GatherRows.apply(pre, o32), c), PROJECT, c)
+        loss_rel = _HypDistCE.apply(q, radial(r_emb, EXP0, c), rdec.rel_bias, sp(rdec.score_scale_raw) + 1e-6,
+                                    rdec.score_margin, all_t, 1, c)
+    return loss_ent, loss_rel
+
+
 def hyp_get_loss(model, glist, triples):
     """hyperbolic_model.py:941-1088 with gradients: (loss_ent, loss_rel, loss_static, loss_radius), each (1,)."""
     _lib.require_device()
     if ops.gemm_impl() != "tc":
         raise RuntimeError("regcn_b200.train_hyp needs the tensor-core GEMM (REGCN_GEMM=tc)")
-    if model.decoder_name not in ("hyperbolic_convtranse", "murp"):
+    if model.decoder_name not in ("hyperbolic_convtranse", "murp", "roth"):
         raise NotImplementedError("regcn_b200.train_hyp: training mode is implemented for --decoder hyperbolic_convtranse "
-                                  "(the reference's default) and murp; the roth / atth query builders are next")
+                                  "(the reference's default), murp and roth; the atth query builder is next")
     dev = model.dynamic_emb.device
     c = model._c_float
     triples = torch.as_tensor(triples).to(dev)
@@ -488,8 +564,9 @@ def hyp_get_loss(model, glist, triples):
     ids = torch.unique(all_triples[:, [0, 2]].reshape(-1))
     loss_radius = _RadiusLoss.apply(model.radius_static, model.radius_target, ids, model.radius_min, model.radius_max, c,
                                     float(model.radius_lambda))
-    if model.decoder_name == "murp":
-        loss_ent, loss_rel = murp_losses(model, pre, r_emb, all_triples)
+    if model.decoder_name in ("murp", "roth"):
+        fn = murp_losses if model.decoder_name == "murp" else roth_losses
+        loss_ent, loss_rel = fn(model, pre, r_emb, all_triples)
         return loss_ent, loss_rel, loss_static, loss_radius
     et = eltwise(radial(pre, LOG0, c), 1, 0.0)                      # 0.9 tanh(log_0 E) + 0.1 log_0 E  (:377-379)
     if model.entity_prediction:

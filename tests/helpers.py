@@ -108,7 +108,8 @@ def compare_train_step(z, name, step, losses, grad_norm, grads, params, lr=1e-3,
                 assert l2 <= 5e-3, (k, "gradient", worst, l2)
             worst_all = max(worst_all, worst)
             assert abs(gn - gn_ref) <= max(10 * rtol * gn_ref, 4 * kink_floor * tn) + 1e-6 * tn, (k, gn, gn_ref)
-            floor = 1e-3 * max(float(np.max(np.abs(g_ref))), 1e-3 * tn)
+            # an element whose reference gradient is within the gradient gate of zero may carry either sign
+            floor = max(max(rtol, 1e-3) * max(float(np.max(np.abs(g_ref))), 1e-3 * tn), kink_floor * tn)
             atol = np.where(np.abs(g_ref) < floor, 2.1 * lr, 2e-5)
             assert np.all(np.abs(p - p_ref) <= atol + 1e-4 * np.abs(p_ref)), (k, "value", float(np.max(np.abs(p - p_ref))))
         else:
@@ -145,6 +146,10 @@ HYP_TRAIN_CASES = {
     "hyptrain_murp_tiny_s3": dict(kind="hyp", shape="tiny", seed=3, encoder="hyperbolic_uvrgcn", decoder="murp",
                                   layer_norm=False, gamma=0.15),
     "hyptrain_murp_small_s4_bias": dict(kind="hyp", shape="small", seed=4, encoder="hyperbolic_uvrgcn", decoder="murp",
+                                        layer_norm=True, gamma=0.15, entity_bias=True),
+    "hyptrain_roth_tiny_s5": dict(kind="hyp", shape="tiny", seed=5, encoder="hyperbolic_uvrgcn", decoder="roth",
+                                  layer_norm=False, gamma=0.15),
+    "hyptrain_roth_small_s6_bias": dict(kind="hyp", shape="small", seed=6, encoder="hyperbolic_uvrgcn", decoder="roth",
                                         layer_norm=True, gamma=0.15, entity_bias=True),
 }
 
