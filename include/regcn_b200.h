@@ -510,6 +510,15 @@ REGCN_API int regcn_givens_fwd(const float* x, const float* ang, int ang_bcast, 
 REGCN_API int regcn_givens_bwd(const float* x, const float* ang, const float* dy, int ang_bcast, int B, int d, int mode,
                      float* dx, float* dang, void* stream);
 
+/* AttH / AttHRel attention mix in training (hyperbolic_decoder.py:1434-1445, 1617-1625): a[b] = sigmoid(<w[b], u[b]>) over
+ * 2d features (w (B,2d), or one shared (2d) vector with w_bcast), mixed = a rot + (1-a) ref; and its backward (dw stays
+ * per row: its column sum is the gradient of a shared w).                                                          */
+REGCN_API int regcn_attn_mix_fwd(const float* w, int w_bcast, const float* u, const float* rot, const float* ref, int B, int d,
+                       float* a, float* mixed, void* stream);
+REGCN_API int regcn_attn_mix_bwd(const float* w, int w_bcast, const float* u, const float* rot, const float* ref,
+                       const float* a, const float* g, int B, int d, float* dw, float* du, float* drot, float* dref,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -339,6 +339,10 @@ HYP_TRAIN_CASES = {
                                   layer_norm=False, gamma=0.15),
     "hyptrain_roth_small_s6_bias": dict(kind="hyp", shape="small", seed=6, encoder="hyperbolic_uvrgcn", decoder="roth",
                                         layer_norm=True, gamma=0.15, entity_bias=True),
+    "hyptrain_atth_tiny_s7": dict(kind="hyp", shape="tiny", seed=7, encoder="hyperbolic_uvrgcn", decoder="atth",
+                                  layer_norm=False, gamma=0.15),
+    "hyptrain_atth_small_s8_bias": dict(kind="hyp", shape="small", seed=8, encoder="hyperbolic_uvrgcn", decoder="atth",
+                                        layer_norm=True, gamma=0.15, entity_bias=True),
 }
 
 

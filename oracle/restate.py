@@ -839,10 +839,12 @@ def hyp_train_losses(P, graphs, num_rels, triples, c, layer_norm, gamma, stats, 
     emb = hist[-1]
     if layer_norm:
         emb = exp0(normalize_rows(log0(emb, c)), c)
-    if decoder in ("murp", "roth"):
-        # Hyperbolic{MuRP,RotH}.loss / {MuRP,RotH}Rel.loss (hyperbolic_decoder.py:781-817, 897-928, 1101-1138, 1264-1280):
+    if decoder in ("murp", "roth", "atth"):
+        # Hyperbolic{MuRP,RotH,AttH}.loss / ...Rel.loss (hyperbolic_decoder.py:781-817, 897-928, 1101-1138, 1264-1280,
+        # 1482-1512, 1642-1700):
         # CE over the forward scores; the per-query subject bias of forward() is not part of loss() (and cancels in CE)
-        ent_fn, rel_fn = (murp_scores, murprel_scores) if decoder == "murp" else (roth_scores, rothrel_scores)
+        ent_fn, rel_fn = {"murp": (murp_scores, murprel_scores), "roth": (roth_scores, rothrel_scores),
+                          "atth": (atth_scores, atthrel_scores)}[decoder]
         sc = ent_fn(P, emb, h0, all_t.numpy(), c)[0]
         if "decoder_ob.entity_bias" in P:
             sc = sc - P["decoder_ob.entity_bias"][all_t[:, 0]].unsqueeze(1)

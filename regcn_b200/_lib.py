@@ -136,6 +136,8 @@ SIGNATURES = {
     "regcn_hyp_dist_grad": (_i, [_p, _p, _p, _i64, _i, _i, _p, _p, _d, _p, _p, _p, _p, _p]),
     "regcn_givens_fwd": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
     "regcn_givens_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
+    "regcn_attn_mix_fwd": (_i, [_p, _i, _p, _p, _p, _i, _i, _p, _p, _p]),
+    "regcn_attn_mix_bwd": (_i, [_p, _i, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p]),
     "regcn_static_angle_bwd": (_i, [_p, _p, _i, _i, _f, _f, _i, _p, _p, _i, _p, _p]),
 }
 

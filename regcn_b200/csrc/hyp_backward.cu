@@ -723,3 +723,79 @@ int regcn_givens_bwd(const float* x, const float* ang, const float* dy, int ang_
   return regcn::givens_bwd(x, ang, dy, ang_bcast, B, d, mode, dx, dang, (cudaStream_t)stream);
 }
 }
+
+// =====================================================================================================================
+// AttH / AttHRel attention mix (hyperbolic_decoder.py:1434-1445, 1617-1625): a = sigmoid(<w, u>) over 2d features,
+// mixed = a rot + (1 - a) ref.  One warp per query row.
+// =====================================================================================================================
+namespace regcn {
+__global__ void __launch_bounds__(256) attn_mix_fwd_kernel(const float* __restrict__ w, int w_bcast, const float* __restrict__ u,
+                                                           const float* __restrict__ rot, const float* __restrict__ ref,
+                                                           int B, int d, float* __restrict__ a_out, float* __restrict__ mixed) {
+  pdl_grid_sync();
+  const int lane = threadIdx.x & 31;
+  const int row = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+  if (row >= B) return;
+  const float* wr = w_bcast ? w : w + (size_t)row * 2 * d;
+  const float* ur = u + (size_t)row * 2 * d;
+  float acc = 0.f;
+  for (int j = lane; j < 2 * d; j += 32) acc = fmaf(wr[j], ur[j], acc);
+  const float a = sigmoidf_(warp_sum(acc));
+  if (lane == 0) a_out[row] = a;
+  for (int j = lane; j < d; j += 32) {
+    const size_t i = (size_t)row * d + j;
+    mixed[i] = a * rot[i] + (1.0f - a) * ref[i];
+  }
+}
+__global__ void __launch_bounds__(256) attn_mix_bwd_kernel(const float* __restrict__ w, int w_bcast, const float* __restrict__ u,
+                                                           const float* __restrict__ rot, const float* __restrict__ ref,
+                                                           const float* __restrict__ a_in, const float* __restrict__ g, int B,
+                                                           int d, float* __restrict__ dw, float* __restrict__ du,
+                                                           float* __restrict__ drot, float* __restrict__ dref) {
+  pdl_grid_sync();
+  const int lane = threadIdx.x & 31;
+  const int row = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+  if (row >= B) return;
+  const float a = a_in[row];
+  float acc = 0.f;
+  for (int j = lane; j < d; j += 32) {
+    const size_t i = (size_t)row * d + j;
+    const float gg = g[i];
+    acc = fmaf(gg, rot[i] - ref[i], acc);
+    drot[i] = a * gg;
+    dref[i] = (1.0f - a) * gg;
+  }
+  const float dlogit = warp_sum(acc) * a * (1.0f - a);
+  const float* wr = w_bcast ? w : w + (size_t)row * 2 * d;
+  const float* ur = u + (size_t)row * 2 * d;
+  for (int j = lane; j < 2 * d; j += 32) {
+    const size_t i = (size_t)row * 2 * d + j;
+    dw[i] = dlogit * ur[j];
+    du[i] = dlogit * wr[j];
+  }
+}
+int attn_mix_fwd(const float* w, int w_bcast, const float* u, const float* rot, const float* ref, int B, int d, float* a,
+                 float* mixed, cudaStream_t st) {
+  if (!w || !u || !rot || !ref || !a || !mixed) { set_last_error("attn_mix_fwd: null pointer"); return REGCN_ERR_NULL; }
+  if (B <= 0 || d <= 0) return REGCN_OK;
+  launch_k(attn_mix_fwd_kernel, rg(B), 256, 0, st, w, w_bcast, u, rot, ref, B, d, a, mixed);
+  return check_launch("attn_mix_fwd");
+}
+int attn_mix_bwd(const float* w, int w_bcast, const float* u, const float* rot, const float* ref, const float* a,
+                 const float* g, int B, int d, float* dw, float* du, float* drot, float* dref, cudaStream_t st) {
+  if (!w || !u || !rot || !ref || !a || !g || !dw || !du || !drot || !dref) { set_last_error("attn_mix_bwd: null pointer"); return REGCN_ERR_NULL; }
+  if (B <= 0 || d <= 0) return REGCN_OK;
+  launch_k(attn_mix_bwd_kernel, rg(B), 256, 0, st, w, w_bcast, u, rot, ref, a, g, B, d, dw, du, drot, dref);
+  return check_launch("attn_mix_bwd");
+}
+}  // namespace regcn
+extern "C" {
+int regcn_attn_mix_fwd(const float* w, int w_bcast, const float* u, const float* rot, const float* ref, int B, int d,
+                       float* a, float* mixed, void* stream) {
+  return regcn::attn_mix_fwd(w, w_bcast, u, rot, ref, B, d, a, mixed, (cudaStream_t)stream);
+}
+int regcn_attn_mix_bwd(const float* w, int w_bcast, const float* u, const float* rot, const float* ref, const float* a,
+                       const float* g, int B, int d, float* dw, float* du, float* drot, float* dref, void* stream) {
+  return regcn::attn_mix_bwd(w, w_bcast, u, rot, ref, a, g, B, d, dw, du, drot, dref, (cudaStream_t)stream);
+}
+}

@@ -314,7 +314,18 @@ class _GatherRows(torch.autograd.Function):
         (idx32,) = ctx.saved_tensors
         dout = dout.contiguous()
         rp, perm, _ = T._group(idx32, ctx.nrows)
-        return T._gather_sum(dout, dout.shape[1], None, rp, perm, ctx.nrows, dout.shape[1]), None
+        d = dout.shape[1]
+        if d <= 256:
+            return T._gather_sum(dout, d, None, rp, perm, ctx.nrows, d), None
+        # wider rows (AttH's (2R, 2d) attention table): column blocks of at most 256 through the same kernel
+        out = torch.empty((ctx.nrows, d), device=dout.device, dtype=F32)
+        nblk = (d + 255) // 256
+        step = ((d + nblk - 1) // nblk + 3) // 4 * 4
+        for c0 in range(0, d, step):
+            w = min(step, d - c0)
+            call("regcn_csr_gather_sum", dout.data_ptr() + 4 * c0, d, None, None, ptr(rp), ptr(perm), ctx.nrows, w, 0,
+                 out.data_ptr() + 4 * c0, d, 0, None, 0.0, None)
+        return out, None
 
 
 class _Mul(torch.autograd.Function):
@@ -542,14 +553,79 @@ def roth_losses(model, pre, r_emb, all_t):
     return loss_ent, loss_rel
 
 
+class _AttnMix(torch.autograd.Function):
+    """a = sigmoid(<w, u>), mixed = a rot + (1-a) ref   (hyperbolic_decoder.py:1434-1445, 1617-1625)."""
+
+    @staticmethod
+    def forward(ctx, w, u, rot, ref):
+        w, u, rot, ref = w.contiguous(), u.contiguous(), rot.contiguous(), ref.contiguous()
+        B, d = rot.shape
+        ctx.bcast = int(w.dim() == 1)
+        a = torch.empty(B, device=rot.device, dtype=F32)
+        mixed = torch.empty_like(rot)
+        call("regcn_attn_mix_fwd", ptr(w), ctx.bcast, ptr(u), ptr(rot), ptr(ref), B, d, ptr(a), ptr(mixed))
+        ctx.save_for_backward(w, u, rot, ref, a)
+        return mixed
+
+    @staticmethod
+    def backward(ctx, g):
+        w, u, rot, ref, a = ctx.saved_tensors
+        B, d = rot.shape
+        dw = torch.empty((B, 2 * d), device=rot.device, dtype=F32)
+        du = torch.empty_like(dw)
+        drot, dref = torch.empty_like(rot), torch.empty_like(rot)
+        call("regcn_attn_mix_bwd", ptr(w), ctx.bcast, ptr(u), ptr(rot), ptr(ref), ptr(a), ptr(g.contiguous()), B, d, ptr(dw),
+             ptr(du), ptr(drot), ptr(dref))
+        return (T._col_sum(dw) if ctx.bcast else dw), du, drot, dref
+
+
+def atth_losses(model, pre, r_emb, all_t):
+    """HyperbolicAttH.loss / HyperbolicAttHRel.loss (hyperbolic_decoder.py:1482-1512, 1642-1700)."""
+    c = model._c_float
+    dec, rdec = model.decoder_ob, model.rdecoder
+    if getattr(dec, "rel_curvature_raw", None) is not None:
+        raise NotImplementedError("regcn_b200.train_hyp: relation-specific curvature in training is not implemented")
+    s32 = all_t[:, 0].to(torch.int32).contiguous()
+    r32 = all_t[:, 1].to(torch.int32).contiguous()
+    o32 = all_t[:, 2].to(torch.int32).contiguous()
+    loss_ent = torch.zeros(1, device=pre.device)
+    loss_rel = torch.zeros(1, device=pre.device)
+    sp = torch.nn.functional.softplus
+
+    def table(lin):
+        return _GatherRows.apply(T.linear(r_emb, lin.weight, lin.bias), r32)
+
+    if model.entity_prediction:
+        st = dropout(radial(radial(_GatherRows.apply(pre, s32), PROJECT, c), LOG0, c), float(dec.dropout.p), model.training)
+        rel_r = _GatherRows.apply(r_emb, r32)
+        rot = _Givens.apply(st, table(dec.rot_proj), 0)
+        ref = _Givens.apply(st, table(dec.ref_proj), 1)
+        mixed = _AttnMix.apply(table(dec.attn_proj), torch.cat((st, rel_r), dim=1), rot, ref)
+        mh = radial(radial(mixed, EXP0, c), PROJECT, c)
+        tr = radial(radial(table(dec.trans_proj), EXP0, c), PROJECT, c)
+        q = radial(_Mobius.apply(mh, tr, c), PROJECT, c)
+        loss_ent = _HypDistCE.apply(q, pre, dec.entity_bias, sp(dec.score_scale_raw) + 1e-6, dec.score_margin, all_t, 2, c)
+    if model.relation_prediction:
+        o_emb = _GatherRows.apply(pre, o32)
+        st = dropout(radial(_GatherRows.apply(pre, s32), LOG0, c), float(rdec.dropout.p), model.training)
+        ot = radial(o_emb, LOG0, c)
+        rot = _Givens.apply(st, rdec.global_rot, 0)
+        ref = _Givens.apply(st, rdec.global_ref, 1)
+        mixed = _AttnMix.apply(rdec.attn_weight, torch.cat((st, ot), dim=1), rot, ref)
+        mh = eltwise(radial(mixed, EXP0, c), 2, 0.0)
+        q = radial(_Mobius.apply(mh, o_emb, c), PROJECT, c)
+        loss_rel = _HypDistCE.apply(q, radial(r_emb, EXP0, c), rdec.rel_bias, sp(rdec.score_scale_raw) + 1e-6,
+                                    rdec.score_margin, all_t, 1, c)
+    return loss_ent, loss_rel
+
+
 def hyp_get_loss(model, glist, triples):
     """hyperbolic_model.py:941-1088 with gradients: (loss_ent, loss_rel, loss_static, loss_radius), each (1,)."""
     _lib.require_device()
     if ops.gemm_impl() != "tc":
         raise RuntimeError("regcn_b200.train_hyp needs the tensor-core GEMM (REGCN_GEMM=tc)")
-    if model.decoder_name not in ("hyperbolic_convtranse", "murp", "roth"):
-        raise NotImplementedError("regcn_b200.train_hyp: training mode is implemented for --decoder hyperbolic_convtranse "
-                                  "(the reference's default), murp and roth; the atth query builder is next")
+    if model.decoder_name not in ("hyperbolic_convtranse", "murp", "roth", "atth"):
+        raise NotImplementedError(f"regcn_b200.train_hyp: unknown decoder {model.decoder_name!r}")
     dev = model.dynamic_emb.device
     c = model._c_float
     triples = torch.as_tensor(triples).to(dev)
@@ -564,8 +640,8 @@ def hyp_get_loss(model, glist, triples):
     ids = torch.unique(all_triples[:, [0, 2]].reshape(-1))
     loss_radius = _RadiusLoss.apply(model.radius_static, model.radius_target, ids, model.radius_min, model.radius_max, c,
                                     float(model.radius_lambda))
-    if model.decoder_name in ("murp", "roth"):
-        fn = murp_losses if model.decoder_name == "murp" else roth_losses
+    if model.decoder_name in ("murp", "roth", "atth"):
+        fn = {"murp": murp_losses, "roth": roth_losses, "atth": atth_losses}[model.decoder_name]
         loss_ent, loss_rel = fn(model, pre, r_emb, all_triples)
         return loss_ent, loss_rel, loss_static, loss_radius
     et = eltwise(radial(pre, LOG0, c), 1, 0.0)                      # 0.9 tanh(log_0 E) + 0.1 log_0 E  (:377-379)
