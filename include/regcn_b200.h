@@ -519,6 +519,19 @@ REGCN_API int regcn_attn_mix_bwd(const float* w, int w_bcast, const float* u, co
                        const float* a, const float* g, int B, int d, float* dw, float* du, float* drot, float* dref,
                        void* stream);
 
+/* LorentzRGCNLayer aggregate backward (lgcn encoder in training; hyperbolic_layers.py:589-625, hyperbolic_ops.py:492-518,
+ * 563-581), 2x2 relation blocks (num_bases = d/2).  gout (N,d) = dL/d(aggregate output).  dht (N,d); part_rel
+ * (S, R2, d) and part_w (S, R2, 2d) with S = regcn_lorentz_bwd_splits(): per-split partial sums of drel / dW, to be
+ * summed over S (regcn_col_sum).  type_* : edges grouped by relation type (regcn_group_by_key).
+ * workspace: regcn_lorentz_aggregate_bwd_workspace_bytes(N, R2, d).                                                */
+REGCN_API size_t regcn_lorentz_aggregate_bwd_workspace_bytes(int N, int R2, int d);
+REGCN_API int regcn_lorentz_bwd_splits(void);
+REGCN_API int regcn_lorentz_aggregate_bwd(const float* ht, const float* W, const float* rel, const float* gout,
+                                const int32_t* rowptr, const int32_t* src_sorted, const int32_t* etype_sorted,
+                                const float* norm, const int32_t* type_rowptr, const int32_t* type_src,
+                                const int32_t* type_dst, int N, int R2, int d, int num_bases, double c, float* dht,
+                                float* part_rel, float* part_w, float* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

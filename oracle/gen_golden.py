@@ -343,6 +343,10 @@ HYP_TRAIN_CASES = {
                                   layer_norm=False, gamma=0.15),
     "hyptrain_atth_small_s8_bias": dict(kind="hyp", shape="small", seed=8, encoder="hyperbolic_uvrgcn", decoder="atth",
                                         layer_norm=True, gamma=0.15, entity_bias=True),
+    "hyptrain_lgcn_roth_small_s9": dict(kind="hyp", shape="small_l", seed=9, encoder="lgcn", decoder="roth",
+                                        layer_norm=False, gamma=0.15),
+    "hyptrain_lgcn_convtranse_small_s10_ln": dict(kind="hyp", shape="small_l", seed=10, encoder="lgcn",
+                                                  decoder="hyperbolic_convtranse", layer_norm=True, gamma=0.15),
 }
 
 

@@ -832,10 +832,10 @@ def regcn_train_steps(sd, graphs, num_rels, triples, layer_norm=True, steps=1, t
 # hyperbolic_uvrgcn encoder + hyperbolic_convtranse decoder.
 # =====================================================================================
 def hyp_train_losses(P, graphs, num_rels, triples, c, layer_norm, gamma, stats, rmin=0.5, rmax=3.0, beta=1.0, eps_r=0.1,
-                     radius_lambda=0.02, decoder="hyperbolic_convtranse"):
+                     radius_lambda=0.02, decoder="hyperbolic_convtranse", encoder="hyperbolic_uvrgcn", num_bases=100):
     all_t = torch.as_tensor(add_inverse(triples, num_rels))
-    hist, h0 = hyp_forward(P, graphs, num_rels, c=c, encoder="hyperbolic_uvrgcn", layer_norm=layer_norm, gamma=gamma,
-                           rmin=rmin, rmax=rmax, beta=beta, eps_r=eps_r, dtype=P["emb_rel"].dtype)
+    hist, h0 = hyp_forward(P, graphs, num_rels, c=c, encoder=encoder, layer_norm=layer_norm, gamma=gamma,
+                           num_bases=num_bases, rmin=rmin, rmax=rmax, beta=beta, eps_r=eps_r, dtype=P["emb_rel"].dtype)
     emb = hist[-1]
     if layer_norm:
         emb = exp0(normalize_rows(log0(emb, c)), c)
@@ -865,7 +865,7 @@ def hyp_train_losses(P, graphs, num_rels, triples, c, layer_norm, gamma, stats, 
 
 def hyp_train_steps(sd, graphs, num_rels, triples, c=0.01, layer_norm=False, gamma=0.15, steps=1, task_weight=0.7,
                     grad_norm=1.0, lr=1e-3, weight_decay=1e-5, betas=(0.9, 0.999), eps=1e-8, dtype=torch.float32,
-                    decoder="hyperbolic_convtranse"):
+                    decoder="hyperbolic_convtranse", encoder="hyperbolic_uvrgcn", num_bases=100):
     """Like regcn_train_steps for the hyperbolic model.  Returns per-step dicts {losses (e, r, static, radius),
     grad_norm, grads, params}."""
     P = {}
@@ -881,7 +881,8 @@ def hyp_train_steps(sd, graphs, num_rels, triples, c=0.01, layer_norm=False, gam
     log = []
     for step in range(1, steps + 1):
         stats = {}
-        le, lrel, lrad = hyp_train_losses(P, graphs, num_rels, triples, c, layer_norm, gamma, stats, decoder=decoder)
+        le, lrel, lrad = hyp_train_losses(P, graphs, num_rels, triples, c, layer_norm, gamma, stats, decoder=decoder,
+                                          encoder=encoder, num_bases=num_bases)
         loss = task_weight * le + (1 - task_weight) * lrel + lrad
         names = [k for k, v in P.items() if v.requires_grad]
         gs = torch.autograd.grad(loss, [P[k] for k in names], allow_unused=True)

@@ -962,4 +962,255 @@ int rel_mean_pool(const float* h, const int* rel_rowptr, const int* rel_ents, in
   return check_launch("rel_mean_pool");
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K7 backward (lgcn encoder in training; hyperbolic_layers.py:589-625, ops:492-518,563-581).  The centroid weights are
+// equal inside a node, so d(out_v)/d(mL_e) is ONE (d+1)-vector G_v per destination: a node kernel produces it, the edge
+// kernels recompute every message and push G through to_lorentz and exp_0.  num_bases blocks of 2x2 only (the
+// reference's 100 bases at d = 200).
+// ---------------------------------------------------------------------------------------------------------------------
+template <int RV>
+__device__ __forceinline__ void lorentz_edge_forward(const WarpRow<RV>& m, const Curv& cv, float& f, float& D, float& mn) {
+  mn = sqrtf(m.sumsq());
+  const float n = fmaxf(mn, kEps);
+  const float th = tanhf(cv.sqrt_c * n);
+  const float f1 = th / (n * cv.sqrt_c);
+  const float pn = fmaxf(mn * f1, kEps);
+  const float f2 = fminf(pn, cv.proj_max) / pn;
+  f = f1 * f2;
+  const float nsq = (mn * f) * (mn * f);
+  D = fmaxf(1.0f - cv.c * nsq, kEps);
+}
+// gradient of the loss w.r.t. the message m_e given G = dL/d(mL_e) = (g0, g):  p = f m;
+//   dp = (4 sqrt_c g0 / D^2) p + 2 g / D + (4 c <p,g> / D^2) p;   dm = s dp + (s'/n) <m,dp> m   (exp_0 with projection)
+template <int RV>
+__device__ __forceinline__ void lorentz_message_grad(WarpRow<RV>& m, float g0, const WarpRow<RV>& g, const Curv& cv) {
+  float f, D, mn;
+  lorentz_edge_forward(m, cv, f, D, mn);
+  const float pg = f * m.dot(g);
+  const float kp = (4.0f * cv.sqrt_c * g0 + 4.0f * cv.c * pg) / (D * D) * f;     // coefficient of m in dp
+  const float kg = 2.0f / D;
+  WarpRow<RV> dp = m;
+  dp.zip(g, [=](float mm, float gg) { return kp * mm + kg * gg; });
+  // radial backward of exp_0 (+ projection) at m
+  const float n = fmaxf(mn, kEps);
+  const float t = tanhf(cv.sqrt_c * n);
+  float s, sp;
+  if (t / cv.sqrt_c > cv.proj_max) { s = cv.proj_max / n; sp = -cv.proj_max / (n * n); }
+  else { s = t / (cv.sqrt_c * n); sp = (1.0f - t * t) / n - t / (cv.sqrt_c * n * n); }
+  if (!(mn > kEps)) sp = 0.f;
+  const float coef = sp / n * m.dot(dp);
+  m.zip(dp, [=](float mm, float dd) { return s * dd + coef * mm; });
+}
+
+template <int RV>
+__global__ void __launch_bounds__(256) lorentz_node_grad_kernel(
+    const float* __restrict__ ht, const float* __restrict__ W, const float* __restrict__ rel,
+    const int* __restrict__ rowptr, const int* __restrict__ src_sorted, const int* __restrict__ etype_sorted,
+    const float* __restrict__ norm, const float* __restrict__ gout, int N, int d, int nb, Curv cv,
+    float* __restrict__ G0, float* __restrict__ G) {
+  pdl_grid_sync();
+  const int lane = threadIdx.x & 31;
+  const int row = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+  if (row >= N) return;
+  const int nvec = d >> 2;
+  const int b = __ldg(rowptr + row), e = __ldg(rowptr + row + 1);
+  WarpRow<RV> acc;
+  acc.zero();
+  if (e == b) {
+    acc.store(G + (size_t)row * d, nvec, lane);
+    if (lane == 0) G0[row] = 0.f;
+    return;
+  }
+  const size_t wstride = (size_t)nb * 4;
+  float acc0 = 0.f;
+  for (int p = b; p < e; ++p) {
+    const int s = __ldg(src_sorted + p), t = __ldg(etype_sorted + p);
+    WarpRow<RV> m;
+    lorentz_message<RV, 2>(m, ht + (size_t)s * d, W + (size_t)t * wstride, rel + (size_t)t * d, nvec, lane, 2);
+    float f, D, mn;
+    lorentz_edge_forward(m, cv, f, D, mn);
+    const float nsq = (mn * f) * (mn * f);
+    acc0 += (1.0f + cv.c * nsq) / (cv.sqrt_c * D);
+    const float g = 2.0f * f / D;
+#pragma unroll
+    for (int i = 0; i < RV; ++i) acc.v[i] = f4_fma(g, m.v[i], acc.v[i]);
+  }
+  // forward tail (lorentz_finish) with its intermediates
+  const int K = e - b;
+  const float nv = __ldg(norm + row);
+  const float w0 = nv / ((float)K * nv + 1e-6f);
+  const float wgt = w0 / ((float)K * w0 + kEps);
+  acc.scale(wgt);                                        // a
+  const float a0 = acc0 * wgt;
+  const float ip = -a0 * a0 + acc.sumsq();
+  const bool sc_free = -ip * cv.c > kEps;
+  const float sc = sqrtf(fmaxf(-ip * cv.c, kEps));
+  const float Q = sc + cv.sqrt_c * a0;                   // sc * (1 + sqrt_c a0 / sc)
+  const bool q_free = Q / sc > kEps;
+  const float Qc = q_free ? Q : kEps * sc;
+  WarpRow<RV> y = acc;
+  y.scale(1.0f / Qc);
+  // log_0 and the +-10 clamp, backward
+  WarpRow<RV> t = y;
+  row_log0(t, cv);
+  WarpRow<RV> g;
+  g.load_plain(gout + (size_t)row * d, nvec, lane);
+  g.zip(t, [](float gg, float tt) { return (tt >= -10.f && tt <= 10.f) ? gg : 0.f; });
+  {
+    const float nraw = sqrtf(y.sumsq());
+    const float n = fmaxf(nraw, kEps);
+    const float u = cv.sqrt_c * n;
+    const bool clamped = u >= 1.0f - kEps;
+    const float a = atanhf(fminf(u, 1.0f - kEps));
+    const float s = a / (cv.sqrt_c * n);
+    float sp = (clamped ? 0.f : 1.0f / (n * (1.0f - cv.c * n * n))) - a / (cv.sqrt_c * n * n);
+    if (!(nraw > kEps)) sp = 0.f;
+    const float coef = sp / n * y.dot(g);
+    g.zip(y, [=](float gg, float yy) { return s * gg + coef * yy; });       // g = dL/dy
+  }
+  // y = a / Q
+  const float dQ = q_free ? -g.dot(acc) / (Qc * Qc) : 0.f;
+  float da0 = cv.sqrt_c * dQ;
+  const float dip = sc_free ? dQ * (-cv.c / (2.0f * sc)) : 0.f;
+  da0 += dip * (-2.0f * a0);
+  const float k1 = 1.0f / Qc, k2 = 2.0f * dip;
+  g.zip(acc, [=](float gg, float aa) { return (k1 * gg + k2 * aa) * wgt; });
+  g.store(G + (size_t)row * d, nvec, lane);
+  if (lane == 0) G0[row] = da0 * wgt;
+}
+
+// dht[u] = sum over the in-edges (w -> u, r') of row u of W[inv r']^T dm(u -> w, inv r')   (the graph holds every edge with
+// its inverse, so the forward CSR enumerates u's out-edges too)
+template <int RV>
+__global__ void __launch_bounds__(256) lorentz_grad_src_kernel(
+    const float* __restrict__ ht, const float* __restrict__ W, const float* __restrict__ rel,
+    const int* __restrict__ rowptr, const int* __restrict__ src_sorted, const int* __restrict__ etype_sorted,
+    const float* __restrict__ G0, const float* __restrict__ G, int N, int d, int nb, int R, Curv cv,
+    float* __restrict__ dht) {
+  pdl_grid_sync();
+  const int lane = threadIdx.x & 31;
+  const int row = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+  if (row >= N) return;
+  const int nvec = d >> 2;
+  const int b = __ldg(rowptr + row), e = __ldg(rowptr + row + 1);
+  const size_t wstride = (size_t)nb * 4;
+  WarpRow<RV> acc;
+  acc.zero();
+  for (int p = b; p < e; ++p) {
+    const int w = __ldg(src_sorted + p), t = __ldg(etype_sorted + p);
+    const int ti = t < R ? t + R : t - R;
+    const float* wp = W + (size_t)ti * wstride;
+    WarpRow<RV> m, g;
+    lorentz_message<RV, 2>(m, ht + (size_t)row * d, wp, rel + (size_t)ti * d, nvec, lane, 2);
+    g.load_plain(G + (size_t)w * d, nvec, lane);
+    lorentz_message_grad(m, __ldg(G0 + w), g, cv);         // m <- dm
+#pragma unroll
+    for (int i = 0; i < RV; ++i) {
+      const int c = lane + i * kWarp;
+      if (c < nvec) {
+        const float4 w0 = ldg4(wp + 8 * c), w1 = ldg4(wp + 8 * c + 4);
+        const float4 dm = m.v[i];
+        acc.v[i].x += w0.x * dm.x + w0.y * dm.y;
+        acc.v[i].y += w0.z * dm.x + w0.w * dm.y;
+        acc.v[i].z += w1.x * dm.z + w1.y * dm.w;
+        acc.v[i].w += w1.z * dm.z + w1.w * dm.w;
+      }
+    }
+  }
+  acc.store(dht + (size_t)row * d, nvec, lane);
+}
+
+// per relation type (edges grouped by type: type_src, type_dst): drel[r] = sum dm, dW[r] = sum ht[src] (x) dm per 2x2 block.
+// CTA = (type, split); its 8 warps stride over the edges, partial sums folded through shared memory in warp order.
+constexpr int kLorentzSplit = 8;
+template <int RV>
+__global__ void __launch_bounds__(256) lorentz_grad_type_kernel(
+    const float* __restrict__ ht, const float* __restrict__ W, const float* __restrict__ rel,
+    const int* __restrict__ type_rowptr, const int* __restrict__ type_src, const int* __restrict__ type_dst,
+    const float* __restrict__ G0, const float* __restrict__ G, int d, int nb, int R2, Curv cv,
+    float* __restrict__ part_rel, float* __restrict__ part_w) {
+  pdl_grid_sync();
+  extern __shared__ float4 lsm[];                 // [8 warps][3][32*RV]
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int r = blockIdx.x, sp = blockIdx.y;
+  const int nvec = d >> 2;
+  const int tb = __ldg(type_rowptr + r), te = __ldg(type_rowptr + r + 1);
+  const int per = (te - tb + kLorentzSplit - 1) / kLorentzSplit;
+  const int e0 = tb + sp * per, e1 = min(te, e0 + per);
+  const float* wp = W + (size_t)r * nb * 4;
+  WarpRow<RV> ar, aw0, aw1;
+  ar.zero(); aw0.zero(); aw1.zero();
+  for (int e = e0 + wid; e < e1; e += 8) {
+    const int u = __ldg(type_src + e), v = __ldg(type_dst + e);
+    WarpRow<RV> m, g, x;
+    x.load_plain(ht + (size_t)u * d, nvec, lane);
+    lorentz_message<RV, 2>(m, ht + (size_t)u * d, wp, rel + (size_t)r * d, nvec, lane, 2);
+    g.load_plain(G + (size_t)v * d, nvec, lane);
+    lorentz_message_grad(m, __ldg(G0 + v), g, cv);
+#pragma unroll
+    for (int i = 0; i < RV; ++i) {
+      const float4 dm = m.v[i], xx = x.v[i];
+      ar.v[i] = f4_add(ar.v[i], dm);
+      aw0.v[i].x += xx.x * dm.x; aw0.v[i].y += xx.x * dm.y; aw0.v[i].z += xx.y * dm.x; aw0.v[i].w += xx.y * dm.y;
+      aw1.v[i].x += xx.z * dm.z; aw1.v[i].y += xx.z * dm.w; aw1.v[i].z += xx.w * dm.z; aw1.v[i].w += xx.w * dm.w;
+    }
+  }
+  const int W3 = 32 * RV;
+#pragma unroll
+  for (int i = 0; i < RV; ++i) {
+    lsm[(wid * 3 + 0) * W3 + lane + i * kWarp] = ar.v[i];
+    lsm[(wid * 3 + 1) * W3 + lane + i * kWarp] = aw0.v[i];
+    lsm[(wid * 3 + 2) * W3 + lane + i * kWarp] = aw1.v[i];
+  }
+  __syncthreads();
+  if (wid == 0) {
+#pragma unroll
+    for (int i = 0; i < RV; ++i) {
+      const int c = lane + i * kWarp;
+      if (c < nvec) {
+        float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, s2 = s0;
+        for (int w = 0; w < 8; ++w) {
+          s0 = f4_add(s0, lsm[(w * 3 + 0) * W3 + c]);
+          s1 = f4_add(s1, lsm[(w * 3 + 1) * W3 + c]);
+          s2 = f4_add(s2, lsm[(w * 3 + 2) * W3 + c]);
+        }
+        const size_t pr = (size_t)sp * R2 + r;
+        st4(part_rel + pr * d + 4 * c, s0);
+        st4(part_w + pr * (size_t)nb * 4 + 8 * c, s1);
+        st4(part_w + pr * (size_t)nb * 4 + 8 * c + 4, s2);
+      }
+    }
+  }
+}
+
+size_t lorentz_aggregate_bwd_workspace_bytes(int N, int R2, int d) {
+  return ((size_t)N * (d + 1) + (size_t)kLorentzSplit * R2 * 3 * d) * sizeof(float) + 1024;
+}
+int lorentz_aggregate_bwd(const float* ht, const float* W, const float* rel, const float* gout, const int* rowptr,
+                          const int* src_sorted, const int* etype_sorted, const float* norm, const int* type_rowptr,
+                          const int* type_src, const int* type_dst, int N, int R2, int d, int nb, double c, float* dht,
+                          float* part_rel, float* part_w, float* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!ht || !W || !rel || !gout || !rowptr || !src_sorted || !etype_sorted || !norm || !type_rowptr || !type_src ||
+      !type_dst || !dht || !part_rel || !part_w || !ws) { set_last_error("lorentz_aggregate_bwd: null pointer"); return REGCN_ERR_NULL; }
+  if (d <= 0 || (d & 3) || d > 256 || nb * 2 != d || (R2 & 1)) { set_last_error("lorentz_aggregate_bwd: needs 2x2 blocks (num_bases = d/2), d%%4==0, d<=256"); return REGCN_ERR_UNSUPPORTED; }
+  if (ws_bytes < (size_t)N * (d + 1) * sizeof(float)) { set_last_error("lorentz_aggregate_bwd: workspace too small"); return REGCN_ERR_WORKSPACE; }
+  if (N <= 0) return REGCN_OK;
+  Curv cv = make_curv(c);
+  float* G = ws;
+  float* G0 = ws + (size_t)N * d;
+  const unsigned grid = (unsigned)(((size_t)N * 32 + 255) / 256);
+  dim3 tgrid((unsigned)R2, (unsigned)kLorentzSplit);
+  if (d <= 128) {
+    launch_k(lorentz_node_grad_kernel<1>, grid, 256, 0, st, ht, W, rel, rowptr, src_sorted, etype_sorted, norm, gout, N, d, nb, cv, G0, G);
+    launch_k(lorentz_grad_src_kernel<1>, grid, 256, 0, st, ht, W, rel, rowptr, src_sorted, etype_sorted, (const float*)G0, (const float*)G, N, d, nb, R2 / 2, cv, dht);
+    launch_k(lorentz_grad_type_kernel<1>, tgrid, 256, (size_t)8 * 3 * 32 * sizeof(float4), st, ht, W, rel, type_rowptr, type_src, type_dst, (const float*)G0, (const float*)G, d, nb, R2, cv, part_rel, part_w);
+  } else {
+    launch_k(lorentz_node_grad_kernel<2>, grid, 256, 0, st, ht, W, rel, rowptr, src_sorted, etype_sorted, norm, gout, N, d, nb, cv, G0, G);
+    launch_k(lorentz_grad_src_kernel<2>, grid, 256, 0, st, ht, W, rel, rowptr, src_sorted, etype_sorted, (const float*)G0, (const float*)G, N, d, nb, R2 / 2, cv, dht);
+    launch_k(lorentz_grad_type_kernel<2>, tgrid, 256, (size_t)8 * 3 * 64 * sizeof(float4), st, ht, W, rel, type_rowptr, type_src, type_dst, (const float*)G0, (const float*)G, d, nb, R2, cv, part_rel, part_w);
+  }
+  return check_launch("lorentz_aggregate_bwd");
+}
+int lorentz_bwd_splits() { return kLorentzSplit; }
 }  // namespace regcn

@@ -301,4 +301,14 @@ int regcn_gemm_tf32_mn(const float* a_hi, const float* a_lo, int lda, const floa
   return gemm_tf32_mn(a_hi, a_lo, lda, b_hi, b_lo, ldb, C, ldc, M, N, K, a_mn, b_mn, bias, accumulate, passes, split_k,
                       workspace, workspace_bytes, ST(stream));
 }
+size_t regcn_lorentz_aggregate_bwd_workspace_bytes(int N, int R2, int d) { return lorentz_aggregate_bwd_workspace_bytes(N, R2, d); }
+int regcn_lorentz_bwd_splits(void) { return lorentz_bwd_splits(); }
+int regcn_lorentz_aggregate_bwd(const float* ht, const float* W, const float* rel, const float* gout, const int32_t* rowptr,
+                                const int32_t* src_sorted, const int32_t* etype_sorted, const float* norm,
+                                const int32_t* type_rowptr, const int32_t* type_src, const int32_t* type_dst, int N, int R2,
+                                int d, int num_bases, double c, float* dht, float* part_rel, float* part_w, float* workspace,
+                                size_t workspace_bytes, void* stream) {
+  return lorentz_aggregate_bwd(ht, W, rel, gout, rowptr, src_sorted, etype_sorted, norm, type_rowptr, type_src, type_dst, N,
+                               R2, d, num_bases, c, dht, part_rel, part_w, workspace, workspace_bytes, ST(stream));
+}
 }  // extern "C"

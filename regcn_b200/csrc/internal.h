@@ -113,6 +113,12 @@ int atth_query(const float* s_tan, const float* rot, const float* ref, const flo
 int gemm_tf32_mn(const float* x_hi, const float* x_lo, int ldx, const float* y_hi, const float* y_lo, int ldy, float* C,
                  int ldc, int M, int N, int K, int a_mn, int b_mn, const float* bias, int accumulate, int passes,
                  int split_k, float* ws, size_t ws_bytes, cudaStream_t st);
+size_t lorentz_aggregate_bwd_workspace_bytes(int N, int R2, int d);
+int lorentz_aggregate_bwd(const float* ht, const float* W, const float* rel, const float* gout, const int* rowptr,
+                          const int* src_sorted, const int* etype_sorted, const float* norm, const int* type_rowptr,
+                          const int* type_src, const int* type_dst, int N, int R2, int d, int nb, double c, float* dht,
+                          float* part_rel, float* part_w, float* ws, size_t ws_bytes, cudaStream_t st);
+int lorentz_bwd_splits();
 // training (backward.cu)
 int csr_gather_sum(const float* X, int ldx, const float* col_w, const float* row_w, const int* rowptr, const int* col,
                    int nrows, int d, int col2_off, float* out, int ldo, int accumulate, cudaStream_t st,

@@ -227,11 +227,60 @@ def hyp_union_layer(layer, g, h_in, h0, c, training):
     return radial(t, EXP0, c)
 
 
+class _LorentzAggregate(torch.autograd.Function):
+    """LorentzRGCNLayer message passing (hyperbolic_layers.py:589-625, 665-672): per-edge blockdiag(W[r]) ht[u] + rel[r]
+    -> exp_0 -> to_lorentz, per-node Lorentz centroid -> to_poincare -> log_0 -> clamp.  2x2 relation blocks in training."""
+
+    @staticmethod
+    def forward(ctx, ht, weight, rel, g, num_bases, c):
+        ht, weight, rel = ht.contiguous(), weight.contiguous(), rel.contiguous()
+        ctx.save_for_backward(ht, weight, rel)
+        ctx.g, ctx.nb, ctx.c = g, int(num_bases), float(c)
+        return ops.lorentz_aggregate(ht, weight, rel, g, num_bases, c)
+
+    @staticmethod
+    def backward(ctx, gout):
+        ht, weight, rel = ctx.saved_tensors
+        g = ctx.g
+        N, d = ht.shape
+        R2 = 2 * g.num_rels
+        dev = ht.device
+        lib = _lib.load()
+        S = lib.regcn_lorentz_bwd_splits()
+        type_rowptr, type_src, type_dst = T._block_index(g)
+        dht = torch.empty_like(ht)
+        part_rel = torch.empty((S, R2 * d), device=dev, dtype=F32)
+        part_w = torch.empty((S, R2 * 2 * d), device=dev, dtype=F32)
+        nb = lib.regcn_lorentz_aggregate_bwd_workspace_bytes(N, R2, d)
+        ws = T._ws(dev, nb, slot=2)
+        call("regcn_lorentz_aggregate_bwd", ptr(ht), ptr(weight), ptr(rel), ptr(gout.contiguous()), ptr(g.rowptr),
+             ptr(g.src_sorted), ptr(g.etype_sorted), ptr(g.norm), ptr(type_rowptr), ptr(type_src), ptr(type_dst), N, R2, d,
+             ctx.nb, ctx.c, ptr(dht), ptr(part_rel), ptr(part_w), ptr(ws), nb)
+        drel = T._col_sum(part_rel).view(R2, d)
+        dW = T._col_sum(part_w).view_as(weight)
+        return dht, dW, drel, None, None, None
+
+
+def lorentz_layer(layer, g, h_in, h0, c, training):
+    """LorentzRGCNLayer.forward (hyperbolic_layers.py:627-694; self_loop, no skip connection)."""
+    p = float(layer.dropout.p) if (layer.dropout is not None and training) else 0.0
+    ht = radial(h_in, LOG0, c)
+    agg = _LorentzAggregate.apply(ht, layer.weight, h0, g, layer.num_bases, c)
+    L = T.linear(ht, torch.cat((layer.loop_weight, layer.evolve_loop_weight), dim=1), None, True)
+    t = eltwise(_SelectAdd.apply(agg, L, g), 0, 10.0)
+    t = T._RReluDrop.apply(t, p)
+    return radial(t, EXP0, c)
+
+
 def hyp_evolve(model, g_list):
     """HyperbolicRecurrentRGCN.forward with the tape on (hyperbolic_model.py:773-890)."""
-    if (model.encoder_name != "hyperbolic_uvrgcn" or getattr(model, "use_static", False)
+    if (model.encoder_name not in ("hyperbolic_uvrgcn", "lgcn") or getattr(model, "use_static", False)
             or any(l.skip_connect or not l.self_loop for l in model.rgcn.layers)):
-        raise NotImplementedError("regcn_b200.train_hyp: hyperbolic_uvrgcn + self_loop without skip_connect / static graph")
+        raise NotImplementedError("regcn_b200.train_hyp: hyperbolic_uvrgcn / lgcn + self_loop without skip_connect / static graph")
+    if model.encoder_name == "lgcn" and any(2 * l.num_bases != model.h_dim for l in model.rgcn.layers):
+        raise NotImplementedError("regcn_b200.train_hyp: the lgcn encoder trains with 2x2 relation blocks (num_bases = h_dim/2, "
+                                  "the reference's 100 bases at h_dim 200)")
+    layer_fn = hyp_union_layer if model.encoder_name == "hyperbolic_uvrgcn" else lorentz_layer
     c = model._c_float
     cell = model.relation_gru
     init = T.normalize(model.dynamic_emb) if model.layer_norm else model.dynamic_emb
@@ -251,7 +300,7 @@ def hyp_evolve(model, g_list):
         h0 = T.gru_gate(gi, gh, hprev, model.layer_norm)
         cur = h
         for layer in model.rgcn.layers:
-            cur = hyp_union_layer(layer, g, cur, h0, c, model.training)
+            cur = layer_fn(layer, g, cur, h0, c, model.training)
         cur = radial(cur, PROJECT, c)
         if model.layer_norm:
             cur = radial(cur, TNORM, c)

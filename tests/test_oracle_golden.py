@@ -211,7 +211,7 @@ def test_oracle_hyperbolic_train_step_matches_reference(name):
     _, sd = build_hyp_train_model(cfg, n, r)
     graphs = [restate.build_edges(s, n, r) for s in case["history"]]
     log = restate.hyp_train_steps(sd, graphs, r, case["test"], c=CURV, layer_norm=cfg["layer_norm"], gamma=cfg["gamma"],
-                                  decoder=cfg["decoder"])
+                                  decoder=cfg["decoder"], encoder=cfg["encoder"], num_bases=min(N_BASES, 2 * r))
     rec = log[0]
     compare_train_step(z, name, 0, rec["losses"], rec["grad_norm"], {k: v.numpy() for k, v in rec["grads"].items()},
                        {k: v.numpy() for k, v in rec["params"].items()})
