@@ -1,5 +1,5 @@
 """Workload of the hyperbolic training-step capture: optimisation steps of HyperbolicRecurrentRGCN (hyperbolic_uvrgcn +
-<decoder>, layer_norm, dropout 0.2) at the C1 (ICEWS14s) shape.  `python profiles/prof_train_hyp.py [decoder] [steps]`."""
+<decoder>, layer_norm, dropout 0.2) at the C1 (ICEWS14s) shape.  `python profiles/prof_train_hyp.py [decoder] [steps] [encoder]`."""
 import os
 import sys
 import time
@@ -13,7 +13,8 @@ from tests.helpers import build_hyp_train_model
 
 decoder = sys.argv[1] if len(sys.argv) > 1 else "hyperbolic_convtranse"
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-cfg = dict(kind="hyp", shape="c1", seed=0, encoder="hyperbolic_uvrgcn", decoder=decoder, layer_norm=True, gamma=0.15)
+encoder = sys.argv[3] if len(sys.argv) > 3 else "hyperbolic_uvrgcn"
+cfg = dict(kind="hyp", shape="c1", seed=0, encoder=encoder, decoder=decoder, layer_norm=True, gamma=0.15)
 case = synth.make_case("c1", 0)
 n, r = case["num_ents"], case["num_rels"]
 m, _ = build_hyp_train_model(cfg, n, r, dropout=0.2)
@@ -31,5 +32,5 @@ for i in range(steps):
     opt.zero_grad()
     t1 = time.perf_counter()
     torch.cuda.synchronize()
-    print(f"{decoder} step {i}: host enqueue {1e3 * (t1 - t0):.2f} ms, to completion {1e3 * (time.perf_counter() - t0):.2f} ms "
+    print(f"{encoder}+{decoder} step {i}: host enqueue {1e3 * (t1 - t0):.2f} ms, to completion {1e3 * (time.perf_counter() - t0):.2f} ms "
           f"loss_e {float(le.detach()):.4f}", flush=True)
