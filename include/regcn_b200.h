@@ -532,6 +532,16 @@ REGCN_API int regcn_lorentz_aggregate_bwd(const float* ht, const float* W, const
                                 const int32_t* type_dst, int N, int R2, int d, int num_bases, double c, float* dht,
                                 float* part_rel, float* part_w, float* workspace, size_t workspace_bytes, void* stream);
 
+/* --plus-relation-specific-curvature in training (hyperbolic_decoder.py:66-86,145-163): gradient of the true-distance
+ * score with per-query curvature row_c (as regcn_hyp_dist_grad, plus gc[b] = sum_n dS dS/dc_q), and the per-query
+ * gradient w.r.t. rel_curvature_raw through softplus and the two clamps (draw_q (B), base_rel (B) = r mod R for the
+ * per-relation sum).                                                                                                */
+REGCN_API int regcn_hyp_truedist_grad(float* D, const float* dS, float* H, int64_t ld, int B, int N, const float* x2,
+                            const float* y2, const float* row_c, const float* scale_margin, float* gx, float* gs,
+                            float* gm, float* gc, void* stream);
+REGCN_API int regcn_rel_curvature_bwd(const float* raw, const int64_t* triples, int B, int R, double c, double cmax,
+                            const float* dcq, float* draw_q, int32_t* base_rel, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -141,6 +141,8 @@ SIGNATURES = {
     "regcn_lorentz_aggregate_bwd_workspace_bytes": (_sz, [_i, _i, _i]),
     "regcn_lorentz_bwd_splits": (_i, []),
     "regcn_lorentz_aggregate_bwd": (_i, [_p] * 11 + [_i, _i, _i, _i, _d, _p, _p, _p, _p, _sz, _p]),
+    "regcn_hyp_truedist_grad": (_i, [_p, _p, _p, _i64, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "regcn_rel_curvature_bwd": (_i, [_p, _p, _i, _i, _d, _d, _p, _p, _p, _p]),
     "regcn_static_angle_bwd": (_i, [_p, _p, _i, _i, _f, _f, _i, _p, _p, _i, _p, _p]),
 }
 

@@ -799,3 +799,126 @@ int regcn_attn_mix_bwd(const float* w, int w_bcast, const float* u, const float*
   return regcn::attn_mix_bwd(w, w_bcast, u, rot, ref, a, g, B, d, dw, du, drot, dref, (cudaStream_t)stream);
 }
 }
+
+// =====================================================================================================================
+// Relation-specific curvature in training (--plus-relation-specific-curvature, hyperbolic_decoder.py:66-86,145-163): the
+// true-distance score S = scale (margin - 2/(sqrt(c_q+eps)+eps) atanh(min(sqrt(c_q+eps) n, 1-1e-6))) with a per-query
+// curvature, differentiated w.r.t. the dot, the two squared norms and c_q.
+// =====================================================================================================================
+namespace regcn {
+__global__ void __launch_bounds__(256) hyp_truedist_grad_kernel(float* __restrict__ D, const float* __restrict__ dS,
+                                                                float* __restrict__ H, int64_t ld, int B, int N,
+                                                                const float* __restrict__ x2, const float* __restrict__ y2,
+                                                                const float* __restrict__ row_c,
+                                                                const float* __restrict__ scale_margin,
+                                                                float* __restrict__ gx, float* __restrict__ gs,
+                                                                float* __restrict__ gm, float* __restrict__ gc) {
+  pdl_grid_sync();
+  __shared__ float sh[4][8];
+  const int b = blockIdx.x;
+  const float scale = scale_margin[0], margin = scale_margin[1];
+  const float X = x2[b], c = row_c[b];
+  const float sc = sqrtf(c + kEps), inv = sc + kEps;
+  const float dsc = 0.5f / sc;                          // d sqrt(c+eps)/dc = d inv/dc
+  const float nmax = 1.0f / inv - kEps;
+  float ax = 0.f, as = 0.f, am = 0.f, ac = 0.f;
+  for (int j = threadIdx.x; j < (int)ld; j += blockDim.x) {
+    const size_t i = (size_t)b * ld + j;
+    float g1 = 0.f, h = 0.f;
+    if (j < N) {
+      const float g = dS[i];
+      const float Dv = D[i], Y = y2[j];
+      const float a = 1.0f - 2.0f * c * Dv + c * Y, bb = 1.0f - c * X;
+      const float num = fmaxf(a * a * X - 2.0f * a * bb * Dv + bb * bb * Y, 0.f);
+      const float den = 1.0f - 2.0f * c * Dv + c * c * X * Y + kEps;
+      const float nraw = sqrtf(num) / fabsf(den);
+      const bool lo = nraw < kEps, hi = nraw > nmax;
+      const float n = lo ? kEps : (hi ? nmax : nraw);
+      const float argr = sc * n;
+      const bool aclamp = argr >= 0.999999f;
+      const float arg = fminf(argr, 0.999999f);
+      const float at = atanhf(arg);
+      const float dist = 2.0f / inv * at;
+      as += g * (margin - dist);
+      am += g * scale;
+      const float ddist_dn = aclamp ? 0.f : (2.0f / inv) * sc / (1.0f - arg * arg);
+      // d dist / d c with n held fixed, plus the moving upper bound of n
+      float ddist_dc = -2.0f / (inv * inv) * dsc * at + (aclamp ? 0.f : (2.0f / inv) * dsc * n / (1.0f - arg * arg));
+      if (hi) ddist_dc += ddist_dn * (-dsc / (inv * inv));
+      if (!lo && !hi && num > 0.f) {
+        const float q = Y - 2.0f * Dv;
+        const float dnum_D = -4.0f * c * a * X - 2.0f * a * bb + 4.0f * bb * c * Dv;
+        const float dnum_X = a * a + 2.0f * a * c * Dv - 2.0f * bb * c * Y;
+        const float dnum_Y = 2.0f * a * c * X - 2.0f * bb * c * Dv + bb * bb;
+        const float dnum_c = 2.0f * a * X * q - 2.0f * bb * Dv * q + 2.0f * a * Dv * X - 2.0f * bb * X * Y;
+        const float i2n = 0.5f / num, iden = 1.0f / den;
+        const float dn_D = n * (dnum_D * i2n - (-2.0f * c) * iden);
+        const float dn_X = n * (dnum_X * i2n - (c * c * Y) * iden);
+        const float dn_Y = n * (dnum_Y * i2n - (c * c * X) * iden);
+        const float dn_c = n * (dnum_c * i2n - (-2.0f * Dv + 2.0f * c * X * Y) * iden);
+        g1 = g * (-scale) * ddist_dn * dn_D;
+        ax += g * (-scale) * ddist_dn * dn_X;
+        h = g * (-scale) * ddist_dn * dn_Y;
+        ddist_dc += ddist_dn * dn_c;
+      }
+      ac += g * (-scale) * ddist_dc;
+    }
+    D[i] = g1;
+    H[i] = h;
+  }
+  float v[4] = {ax, as, am, ac};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float s = warp_sum(v[q]);
+    if ((threadIdx.x & 31) == 0) sh[q][threadIdx.x >> 5] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += sh[threadIdx.x][w];
+    (threadIdx.x == 0 ? gx : threadIdx.x == 1 ? gs : threadIdx.x == 2 ? gm : gc)[b] = s;
+  }
+}
+// c_q = max(1e-5, min(softplus(raw[r mod R]), upper)): per-query d raw = dc_q * sigmoid(raw) where neither clamp is active
+__global__ void rel_curvature_bwd_kernel(const float* __restrict__ raw, const int64_t* __restrict__ triples, int B, int R,
+                                         float upper, const float* __restrict__ dcq, float* __restrict__ draw_q,
+                                         int* __restrict__ base_rel) {
+  pdl_grid_sync();
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int r = (int)(triples[3 * (size_t)b + 1] % R);
+  const float x = raw[r];
+  const float sp = x > 20.f ? x : log1pf(expf(x));
+  const float sg = x > 20.f ? 1.f : 1.0f / (1.0f + expf(-x));
+  draw_q[b] = (sp <= upper && sp >= 1e-5f) ? dcq[b] * sg : 0.f;
+  base_rel[b] = r;
+}
+int hyp_truedist_grad(float* D, const float* dS, float* H, int64_t ld, int B, int N, const float* x2, const float* y2,
+                      const float* row_c, const float* scale_margin, float* gx, float* gs, float* gm, float* gc,
+                      cudaStream_t st) {
+  if (!D || !dS || !H || !x2 || !y2 || !row_c || !scale_margin || !gx || !gs || !gm || !gc) { set_last_error("hyp_truedist_grad: null pointer"); return REGCN_ERR_NULL; }
+  if (B <= 0 || N <= 0) return REGCN_OK;
+  launch_k(hyp_truedist_grad_kernel, (unsigned)B, 256, 0, st, D, dS, H, ld, B, N, x2, y2, row_c, scale_margin, gx, gs, gm, gc);
+  return check_launch("hyp_truedist_grad");
+}
+int rel_curvature_bwd(const float* raw, const int64_t* triples, int B, int R, double c, double cmax, const float* dcq,
+                      float* draw_q, int* base_rel, cudaStream_t st) {
+  if (!raw || !triples || !dcq || !draw_q || !base_rel) { set_last_error("rel_curvature_bwd: null pointer"); return REGCN_ERR_NULL; }
+  if (B <= 0) return REGCN_OK;
+  float upper = 0.999f * (float)c;
+  if (cmax > 0 && (float)cmax < upper) upper = (float)cmax;
+  launch_k(rel_curvature_bwd_kernel, (unsigned)((B + 255) / 256), 256, 0, st, raw, triples, B, R, upper, dcq, draw_q, base_rel);
+  return check_launch("rel_curvature_bwd");
+}
+}  // namespace regcn
+extern "C" {
+int regcn_hyp_truedist_grad(float* D, const float* dS, float* H, int64_t ld, int B, int N, const float* x2, const float* y2,
+                            const float* row_c, const float* scale_margin, float* gx, float* gs, float* gm, float* gc,
+                            void* stream) {
+  return regcn::hyp_truedist_grad(D, dS, H, ld, B, N, x2, y2, row_c, scale_margin, gx, gs, gm, gc, (cudaStream_t)stream);
+}
+int regcn_rel_curvature_bwd(const float* raw, const int64_t* triples, int B, int R, double c, double cmax, const float* dcq,
+                            float* draw_q, int32_t* base_rel, void* stream) {
+  return regcn::rel_curvature_bwd(raw, triples, B, R, c, cmax, dcq, draw_q, base_rel, (cudaStream_t)stream);
+}
+}

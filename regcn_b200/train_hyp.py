@@ -447,7 +447,7 @@ class _HypDistCE(torch.autograd.Function):
     score epilogue in place, and in the backward the three partial derivatives per (query, candidate) feed two GEMMs."""
 
     @staticmethod
-    def forward(ctx, q, cand, bias, scale, margin, triples, target_col, c):
+    def forward(ctx, q, cand, bias, scale, margin, triples, target_col, c, curv_raw=None, curv_cfg=None):
         q, cand = q.contiguous(), cand.contiguous()
         B, d = q.shape
         N = cand.shape[0]
@@ -457,8 +457,15 @@ class _HypDistCE(torch.autograd.Function):
         x2, y2 = ops.row_sumsq(q), ops.row_sumsq(cand)
         S = torch.empty((B, Np), device=dev, dtype=F32)
         T._mm(T._split(q), T._split(cand), B, N, d, out=S, ldc=Np)
+        # per-query curvature (--plus-relation-specific-curvature): true-distance branch of the score
+        row_c = None
+        if curv_raw is not None:
+            num_rel, cmax = curv_cfg
+            row_c = ops.rel_curvature(curv_raw, triples, num_rel, c, cmax)
+        ctx.row_c, ctx.curv_cfg = row_c, curv_cfg
+        ctx.curv_raw = curv_raw.detach().contiguous() if curv_raw is not None else None
         call("regcn_hyp_score_epilogue", ptr(S), Np, B, N, ptr(x2), ptr(y2), ptr(bias.contiguous()) if bias is not None else None,
-             None, float(c), ptr(sm), None)
+             None, float(c), ptr(sm), ptr(row_c))
         ce = torch.empty(B, device=dev, dtype=F32)
         lse = torch.empty(B, device=dev, dtype=F32)
         loss = torch.empty(1, device=dev, dtype=F32)
@@ -481,7 +488,22 @@ class _HypDistCE(torch.autograd.Function):
         T._mm(qs, cs, B, N, d, out=D, ldc=Np)                                   # the dots again (cheaper than keeping them)
         H = torch.empty((B, Np), device=dev, dtype=F32)
         gx, gs, gm = (torch.empty(B, device=dev, dtype=F32) for _ in range(3))
-        call("regcn_hyp_dist_grad", ptr(D), ptr(S), ptr(H), Np, B, N, ptr(x2), ptr(y2), ctx.c, ptr(sm), ptr(gx), ptr(gs), ptr(gm))
+        draw = None
+        if ctx.row_c is not None:
+            gc = torch.empty(B, device=dev, dtype=F32)
+            call("regcn_hyp_truedist_grad", ptr(D), ptr(S), ptr(H), Np, B, N, ptr(x2), ptr(y2), ptr(ctx.row_c), ptr(sm), ptr(gx),
+                 ptr(gs), ptr(gm), ptr(gc))
+            num_rel, cmax = ctx.curv_cfg
+            draw_q = torch.empty(B, device=dev, dtype=F32)
+            base = torch.empty(B, device=dev, dtype=torch.int32)
+            call("regcn_rel_curvature_bwd", ptr(ctx.curv_raw), ptr(triples), B, int(num_rel), ctx.c,
+                 float(cmax) if cmax is not None else 0.0, ptr(gc), ptr(draw_q), ptr(base))
+            rp, perm, _ = T._group(base, int(ctx.curv_raw.shape[0]))
+            draw = torch.empty_like(ctx.curv_raw)
+            call("regcn_edge_scalar_gather", ptr(draw_q), ptr(rp), ptr(perm), int(draw.shape[0]), ptr(draw), 0)
+        else:
+            call("regcn_hyp_dist_grad", ptr(D), ptr(S), ptr(H), Np, B, N, ptr(x2), ptr(y2), ctx.c, ptr(sm), ptr(gx), ptr(gs),
+                 ptr(gm))
         Ds = T._split(D)
         dq = T._mm(Ds, cs, B, d, N, b_mn=True).contiguous()
         call("regcn_row_axpy", ptr(q), ptr(gx), 2.0, B, d, ptr(dq))
@@ -491,15 +513,19 @@ class _HypDistCE(torch.autograd.Function):
         dbias = T._col_sum(S[:, :N]) if ctx.has_bias else None
         dscale = T._col_sum(gs.view(B, 1)).view(())
         dmargin = T._col_sum(gm.view(B, 1)).view(())
-        return dq, dcand, dbias, dscale, dmargin, None, None, None
+        return dq, dcand, dbias, dscale, dmargin, None, None, None, draw, None
+
+
+def _curv_args(dec):
+    """(rel_curvature_raw, (num_relations, rel_curvature_max)) or (None, None)."""
+    raw = getattr(dec, "rel_curvature_raw", None)
+    return (raw, (dec.num_relations, dec.rel_curvature_max)) if raw is not None else (None, None)
 
 
 def murp_losses(model, pre, r_emb, all_t):
     """HyperbolicMuRP.loss / HyperbolicMuRPRel.loss (hyperbolic_decoder.py:781-817, 897-928)."""
     c = model._c_float
     dec, rdec = model.decoder_ob, model.rdecoder
-    if getattr(dec, "rel_curvature_raw", None) is not None:
-        raise NotImplementedError("regcn_b200.train_hyp: relation-specific curvature in training is not implemented")
     s32 = all_t[:, 0].to(torch.int32).contiguous()
     r32 = all_t[:, 1].to(torch.int32).contiguous()
     o32 = all_t[:, 2].to(torch.int32).contiguous()
@@ -514,7 +540,7 @@ def murp_losses(model, pre, r_emb, all_t):
         tr = radial(radial(tr, EXP0, c), PROJECT, c)
         q = radial(_Mobius.apply(rs, tr, c), PROJECT, c)
         scale = torch.nn.functional.softplus(dec.score_scale_raw) + 1e-6          # two scalars: host-side glue
-        loss_ent = _HypDistCE.apply(q, pre, dec.entity_bias, scale, dec.score_margin, all_t, 2, c)
+        loss_ent = _HypDistCE.apply(q, pre, dec.entity_bias, scale, dec.score_margin, all_t, 2, c, *_curv_args(dec))
     if model.relation_prediction:
         p = float(rdec.dropout.p)
         st = dropout(radial(_GatherRows.apply(pre, s32), LOG0, c), p, model.training)
@@ -575,8 +601,6 @@ def roth_losses(model, pre, r_emb, all_t):
     """HyperbolicRotH.loss / HyperbolicRotHRel.loss (hyperbolic_decoder.py:1101-1138, 1264-1280)."""
     c = model._c_float
     dec, rdec = model.decoder_ob, model.rdecoder
-    if getattr(dec, "rel_curvature_raw", None) is not None:
-        raise NotImplementedError("regcn_b200.train_hyp: relation-specific curvature in training is not implemented")
     s32 = all_t[:, 0].to(torch.int32).contiguous()
     r32 = all_t[:, 1].to(torch.int32).contiguous()
     o32 = all_t[:, 2].to(torch.int32).contiguous()
@@ -591,7 +615,8 @@ def roth_losses(model, pre, r_emb, all_t):
         tr = _GatherRows.apply(T.linear(r_emb, dec.trans_proj.weight, dec.trans_proj.bias), r32)
         tr = radial(radial(tr, EXP0, c), PROJECT, c)
         q = radial(_Mobius.apply(rs, tr, c), PROJECT, c)
-        loss_ent = _HypDistCE.apply(q, pre, dec.entity_bias, sp(dec.score_scale_raw) + 1e-6, dec.score_margin, all_t, 2, c)
+        loss_ent = _HypDistCE.apply(q, pre, dec.entity_bias, sp(dec.score_scale_raw) + 1e-6, dec.score_margin, all_t, 2, c,
+                                    *_curv_args(dec))
     if model.relation_prediction:
         st = radial(_GatherRows.apply(pre, s32), LOG0, c)
         st = _reshape_tangent(rdec, dropout(st, float(rdec.dropout.p), model.training))
@@ -632,8 +657,6 @@ def atth_losses(model, pre, r_emb, all_t):
     """HyperbolicAttH.loss / HyperbolicAttHRel.loss (hyperbolic_decoder.py:1482-1512, 1642-1700)."""
     c = model._c_float
     dec, rdec = model.decoder_ob, model.rdecoder
-    if getattr(dec, "rel_curvature_raw", None) is not None:
-        raise NotImplementedError("regcn_b200.train_hyp: relation-specific curvature in training is not implemented")
     s32 = all_t[:, 0].to(torch.int32).contiguous()
     r32 = all_t[:, 1].to(torch.int32).contiguous()
     o32 = all_t[:, 2].to(torch.int32).contiguous()
@@ -653,7 +676,8 @@ def atth_losses(model, pre, r_emb, all_t):
         mh = radial(radial(mixed, EXP0, c), PROJECT, c)
         tr = radial(radial(table(dec.trans_proj), EXP0, c), PROJECT, c)
         q = radial(_Mobius.apply(mh, tr, c), PROJECT, c)
-        loss_ent = _HypDistCE.apply(q, pre, dec.entity_bias, sp(dec.score_scale_raw) + 1e-6, dec.score_margin, all_t, 2, c)
+        loss_ent = _HypDistCE.apply(q, pre, dec.entity_bias, sp(dec.score_scale_raw) + 1e-6, dec.score_margin, all_t, 2, c,
+                                    *_curv_args(dec))
     if model.relation_prediction:
         o_emb = _GatherRows.apply(pre, o32)
         st = dropout(radial(_GatherRows.apply(pre, s32), LOG0, c), float(rdec.dropout.p), model.training)

@@ -155,6 +155,10 @@ HYP_TRAIN_CASES = {
                                   layer_norm=False, gamma=0.15),
     "hyptrain_atth_small_s8_bias": dict(kind="hyp", shape="small", seed=8, encoder="hyperbolic_uvrgcn", decoder="atth",
                                         layer_norm=True, gamma=0.15, entity_bias=True),
+    "hyptrain_roth_small_s11_curv": dict(kind="hyp", shape="small", seed=11, encoder="hyperbolic_uvrgcn", decoder="roth",
+                                         layer_norm=False, gamma=0.15, entity_bias=True, rel_curvature=True),
+    "hyptrain_murp_tiny_s12_curv": dict(kind="hyp", shape="tiny", seed=12, encoder="hyperbolic_uvrgcn", decoder="murp",
+                                        layer_norm=True, gamma=0.15, rel_curvature=True),
     "hyptrain_lgcn_roth_small_s9": dict(kind="hyp", shape="small_l", seed=9, encoder="lgcn", decoder="roth",
                                         layer_norm=False, gamma=0.15),
     "hyptrain_lgcn_convtranse_small_s10_ln": dict(kind="hyp", shape="small_l", seed=10, encoder="lgcn",
@@ -169,7 +173,8 @@ def build_hyp_train_model(cfg, n, r, dropout=0.0):
                                   layer_norm=cfg["layer_norm"], input_dropout=dropout, hidden_dropout=dropout,
                                   feat_dropout=dropout, entity_prediction=True, relation_prediction=True, use_cuda=True,
                                   gpu=0, radius_msg_gamma=cfg["gamma"], hyp_init_scale=1e-3,
-                                  use_entity_euclidean_bias=cfg.get("entity_bias", False))
+                                  use_entity_euclidean_bias=cfg.get("entity_bias", False),
+                                  use_relation_specific_curvature=cfg.get("rel_curvature", False))
     sd = synth.fill_state_dict(m.state_dict(), cfg["seed"])
     m.load_state_dict(sd)
     return m, sd

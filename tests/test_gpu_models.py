@@ -290,9 +290,9 @@ def test_get_loss_matches_reference(name):
     assert len(mine) == len(ref)
     np.testing.assert_allclose(mine, ref, rtol=1e-4, atol=1e-6)
     if cfg["kind"] != "regcn":
-        # training mode: both encoders train with every decoder (tests/test_gpu_train_hyp.py); lgcn blocks other than
-        # 2x2 and the relation-specific-curvature branch refuse loudly instead of returning a loss without gradients
-        if (cfg["encoder"] == "lgcn" and cfg["shape"] == "tiny_l") or cfg.get("rel_curvature"):   # 20x20 blocks / c_r
+        # training mode: both encoders train with every decoder and flag (tests/test_gpu_train_hyp.py); lgcn blocks other
+        # than 2x2 refuse loudly instead of returning a loss without gradients
+        if cfg["encoder"] == "lgcn" and cfg["shape"] == "tiny_l":                                   # 20x20 relation blocks
             with pytest.raises(NotImplementedError):
                 model.train().get_loss(glist, torch.from_numpy(case["test"]).to(DEV), None, True)
         else:
