@@ -249,6 +249,16 @@ def run_cpu_train_arm(args, steps=1, warmup=1):
                       f"over oracle/restate.py on {cores} threads"}
 
 
+def workload_string(args):
+    """The same `config.workload` text for both arms."""
+    from regcn_b200 import synth
+    n, r, t, hist, tq = synth.SHAPES[args.workload]
+    if args.model == "regcn":
+        return (f"{args.workload}: ICEWS18-shaped N={n} R={r} T={t}/snapshot L={hist} B={2 * tq} queries/timestamp, "
+                f"d={H_DIM}, 2-layer UnionRGCN + ConvTransE")
+    return f"{args.workload} {args.model}"
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -264,7 +274,7 @@ def main():
         line = {"impl": "reference", "metric": metric, "value": cb["value"], "unit": "queries/s",
                 "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": cb["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": args.workload, "model": args.model, "note": "steps/warmup capped so the CPU arm "
+                "config": {"workload": workload_string(args), "variant": args.model, "note": "steps/warmup capped so the CPU arm "
                            "finishes in minutes; reference Python cannot travel to the GPU box, so the oracle port runs"},
                 "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": cb["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -636,10 +646,8 @@ def main():
         line = {"metric": metric, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"{args.workload}: ICEWS18-shaped N={n} R={r} T={T}/snapshot L={L} "
-                                       f"B={B} queries/timestamp, d={H_DIM}, 2-layer UnionRGCN + ConvTransE"
-                           if args.model == "regcn" else f"{args.workload} {args.model}",
-                           "model": args.model, "parallelism": f"timestamp-dp{world}",
+                "config": {"workload": workload_string(args),
+                           "variant": args.model, "parallelism": f"timestamp-dp{world}",
                            "l2": "256 MiB buffer written between timed steps (untimed)",
                            "gemm_impl": ops.gemm_impl()},
                 "snapshot_steps_per_s": world * L / (evolve_ms * 1e-3), "evolve_ms_per_step": evolve_ms,
