@@ -347,6 +347,11 @@ HYP_TRAIN_CASES = {
                                          layer_norm=False, gamma=0.15, entity_bias=True, rel_curvature=True),
     "hyptrain_murp_tiny_s12_curv": dict(kind="hyp", shape="tiny", seed=12, encoder="hyperbolic_uvrgcn", decoder="murp",
                                         layer_norm=True, gamma=0.15, rel_curvature=True),
+    "hyptrain_static_tiny_s13": dict(kind="hyp", shape="tiny", seed=13, encoder="hyperbolic_uvrgcn",
+                                     decoder="hyperbolic_convtranse", layer_norm=True, gamma=0.15,
+                                     static=dict(discount=1, angle=10, weight=0.5)),
+    "hyptrain_static_small_s14_roth": dict(kind="hyp", shape="small", seed=14, encoder="hyperbolic_uvrgcn", decoder="roth",
+                                           layer_norm=False, gamma=0.15, static=dict(discount=0, angle=10, weight=1.0)),
     "hyptrain_lgcn_roth_small_s9": dict(kind="hyp", shape="small_l", seed=9, encoder="lgcn", decoder="roth",
                                         layer_norm=False, gamma=0.15),
     "hyptrain_lgcn_convtranse_small_s10_ln": dict(kind="hyp", shape="small_l", seed=10, encoder="lgcn",
@@ -361,18 +366,33 @@ def run_hyp_train(ref_utils, HyperbolicRecurrentRGCN):
     for name, cfg in HYP_TRAIN_CASES.items():
         case = synth.make_case(cfg["shape"], cfg["seed"])
         n, r = case["num_ents"], case["num_rels"]
-        m = HyperbolicRecurrentRGCN(cfg["decoder"], cfg["encoder"], n, r, 0, 0, H_DIM, "sub", 3, num_bases=N_BASES,
+        st_cfg, sg, n_srel, n_words = cfg.get("static"), None, 0, 0
+        if st_cfg:
+            st, n_srel, n_words = synth.make_static(n, cfg["seed"])
+            sg = ref_utils.build_sub_graph(n + n_words, n_srel, st, False, "cpu")
+        m = HyperbolicRecurrentRGCN(cfg["decoder"], cfg["encoder"], n, r, n_srel, n_words, H_DIM, "sub", 3,
+                                    num_bases=N_BASES,
                                     num_hidden_layers=N_LAYERS, dropout=0.0, c=CURV, self_loop=True, skip_connect=False,
                                     layer_norm=cfg["layer_norm"], input_dropout=0.0, hidden_dropout=0.0, feat_dropout=0.0,
                                     entity_prediction=True, relation_prediction=True, use_cuda=False, gpu="cpu",
+                                    use_static=bool(st_cfg), **(st_cfg or {}),
                                     radius_msg_gamma=cfg["gamma"], hyp_init_scale=1e-3,
                                     use_entity_euclidean_bias=cfg.get("entity_bias", False),
                                     use_relation_specific_curvature=cfg.get("rel_curvature", False))
         m.load_state_dict(synth.fill_state_dict(m.state_dict(), cfg["seed"]))
+        glist = [ref_utils.build_sub_graph(n, r, snap, False, "cpu") for snap in case["history"]]
+        if st_cfg:
+            m.eval()
+            with torch.no_grad():
+                _, score, score_rel = m.predict(glist, r, sg, torch.from_numpy(case["test"]), False)
+                hist, static_emb, _, _, _ = m.forward(glist, sg, False)
+                ev = m.get_loss(glist, torch.from_numpy(case["test"]).clone(), sg, False)
+            out[f"{name}.score"], out[f"{name}.score_rel"] = score.numpy(), score_rel.numpy()
+            out[f"{name}.static_emb"], out[f"{name}.hist_last"] = static_emb.numpy(), hist[-1].numpy()
+            out[f"{name}.eval_losses"] = np.array([float(x.reshape(-1)[0]) for x in ev], dtype=np.float64)
         m.train()
         opt = torch.optim.Adam(m.parameters(), lr=LR, weight_decay=WEIGHT_DECAY)
-        glist = [ref_utils.build_sub_graph(n, r, snap, False, "cpu") for snap in case["history"]]
-        le, lr_, ls, lrad = m.get_loss(glist, torch.from_numpy(case["test"]), None, False)
+        le, lr_, ls, lrad = m.get_loss(glist, torch.from_numpy(case["test"]), sg, False)
         loss = TASK_WEIGHT * le + (1 - TASK_WEIGHT) * lr_ + ls + lrad
         loss.backward()
         tn = torch.nn.utils.clip_grad_norm_(m.parameters(), GRAD_NORM)

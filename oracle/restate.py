@@ -436,10 +436,13 @@ def lorentz_layer(h_hyper, rel, g, weight, w_loop, w_evolve, c, num_bases):
 
 def hyp_forward(p, graphs, num_rels, c=0.01, encoder="hyperbolic_uvrgcn", layer_norm=False, n_layers=2,
                 self_loop=True, gamma=1.0, num_bases=100, rmin=0.5, rmax=3.0, beta=1.0, eps_r=0.1, residual=True,
-                dtype=torch.float32, trace=None):
-    """hyperbolic_model.py:722-890 (HyperbolicRecurrentRGCN.forward; no static graph, no geoopt, no EST)."""
+                dtype=torch.float32, trace=None, static_init=None):
+    """hyperbolic_model.py:722-890 (HyperbolicRecurrentRGCN.forward; no geoopt, no EST).  static_init: the (already
+    normalised) static embedding that replaces the initial table with --add-static-graph (:762-771)."""
     P = {k: v.to(dtype) for k, v in p.items() if v.is_floating_point()}
     init = normalize_rows(P["dynamic_emb"]) if layer_norm else P["dynamic_emb"]
+    if static_init is not None:
+        init = static_init
     h = exp0(init, c)                                                            # :779-780
     rs = static_radius(P["radius_static"], c, rmin, rmax)
     h = apply_radius(h, rs, c)                                                   # :782
@@ -831,11 +834,23 @@ def regcn_train_steps(sd, graphs, num_rels, triples, layer_norm=True, steps=1, t
 # Hyperbolic training step (hyperbolic_model.py:941-1088 in train() mode + hyperbolic_main.py:585-628), dropout 0,
 # hyperbolic_uvrgcn encoder + hyperbolic_convtranse decoder.
 # =====================================================================================
+def hyp_static_emb(P, sg, num_ents, num_bases, layer_norm):
+    """hyperbolic_model.py:762-770: the block layer is called `static_rgcn_layer` here."""
+    x = torch.cat((P["dynamic_emb"], P["words_emb"]), dim=0)
+    out = block_layer(x, sg, P["static_rgcn_layer.weight"], num_bases, x.shape[1])[:num_ents]
+    return normalize_rows(out) if layer_norm else out
+
+
 def hyp_train_losses(P, graphs, num_rels, triples, c, layer_norm, gamma, stats, rmin=0.5, rmax=3.0, beta=1.0, eps_r=0.1,
-                     radius_lambda=0.02, decoder="hyperbolic_convtranse", encoder="hyperbolic_uvrgcn", num_bases=100):
+                     radius_lambda=0.02, decoder="hyperbolic_convtranse", encoder="hyperbolic_uvrgcn", num_bases=100,
+                     static=None):
     all_t = torch.as_tensor(add_inverse(triples, num_rels))
+    s_emb = None
+    if static is not None:
+        s_emb = hyp_static_emb(P, static["graph"], static["num_ents"], static["num_bases"], layer_norm)
     hist, h0 = hyp_forward(P, graphs, num_rels, c=c, encoder=encoder, layer_norm=layer_norm, gamma=gamma,
-                           num_bases=num_bases, rmin=rmin, rmax=rmax, beta=beta, eps_r=eps_r, dtype=P["emb_rel"].dtype)
+                           num_bases=num_bases, rmin=rmin, rmax=rmax, beta=beta, eps_r=eps_r, dtype=P["emb_rel"].dtype,
+                           static_init=s_emb)
     emb = hist[-1]
     if layer_norm:
         emb = exp0(normalize_rows(log0(emb, c)), c)
@@ -860,12 +875,17 @@ def hyp_train_losses(P, graphs, num_rels, triples, c, layer_norm, gamma, stats, 
     ids = torch.unique(all_t[:, [0, 2]].reshape(-1))
     rs = static_radius(P["radius_static"], c, rmin, rmax)[ids]
     loss_rad = radius_lambda * torch.mean((rs - P["radius_target"][ids]) ** 2)
+    if static is not None:
+        # hyperbolic_model.py:1039-1064: the angle loss against the TANGENT vectors log_0(evolve_emb)
+        loss_st = static_angle_loss(s_emb, [log0(e, c) for e in hist], layer_norm, static["angle"], static["discount"],
+                                    static["weight"])
+        return loss_e, loss_r, loss_rad, loss_st
     return loss_e, loss_r, loss_rad
 
 
 def hyp_train_steps(sd, graphs, num_rels, triples, c=0.01, layer_norm=False, gamma=0.15, steps=1, task_weight=0.7,
                     grad_norm=1.0, lr=1e-3, weight_decay=1e-5, betas=(0.9, 0.999), eps=1e-8, dtype=torch.float32,
-                    decoder="hyperbolic_convtranse", encoder="hyperbolic_uvrgcn", num_bases=100):
+                    decoder="hyperbolic_convtranse", encoder="hyperbolic_uvrgcn", num_bases=100, static=None):
     """Like regcn_train_steps for the hyperbolic model.  Returns per-step dicts {losses (e, r, static, radius),
     grad_norm, grads, params}."""
     P = {}
@@ -881,9 +901,11 @@ def hyp_train_steps(sd, graphs, num_rels, triples, c=0.01, layer_norm=False, gam
     log = []
     for step in range(1, steps + 1):
         stats = {}
-        le, lrel, lrad = hyp_train_losses(P, graphs, num_rels, triples, c, layer_norm, gamma, stats, decoder=decoder,
-                                          encoder=encoder, num_bases=num_bases)
-        loss = task_weight * le + (1 - task_weight) * lrel + lrad
+        ls = hyp_train_losses(P, graphs, num_rels, triples, c, layer_norm, gamma, stats, decoder=decoder,
+                              encoder=encoder, num_bases=num_bases, static=static)
+        le, lrel, lrad = ls[:3]
+        lst = ls[3] if static is not None else torch.zeros(())
+        loss = task_weight * le + (1 - task_weight) * lrel + lrad + lst
         names = [k for k, v in P.items() if v.requires_grad]
         gs = torch.autograd.grad(loss, [P[k] for k in names], allow_unused=True)
         grads = {k: g for k, g in zip(names, gs) if g is not None}
@@ -898,7 +920,7 @@ def hyp_train_steps(sd, graphs, num_rels, triples, c=0.01, layer_norm=False, gam
                 p -= (lr / (1 - betas[0] ** step)) * m[k] / (vv[k].sqrt() / math.sqrt(1 - betas[1] ** step) + eps)
             for k, s in stats.items():
                 P[k] = s
-        log.append({"losses": (float(le.detach()), float(lrel.detach()), 0.0, float(lrad.detach())),
+        log.append({"losses": (float(le.detach()), float(lrel.detach()), float(lst.detach()), float(lrad.detach())),
                     "grad_norm": float(total), "grads": {k: g.detach().clone() for k, g in grads.items()},
                     "params": {k: P[k].detach().clone() for k in grads}})
     return log

@@ -271,8 +271,10 @@ class HyperbolicRecurrentRGCN(nn.Module):
 
         tre = self.temporal_radius_evolution
         rw = tre.radius_mlp.weight.detach().view(-1).contiguous()
-        rb = float(tre.radius_mlp.bias.detach().item()) if not hasattr(self, "_rb_cache") else self._rb_cache
-        self._rb_cache = rb
+        bias = tre.radius_mlp.bias
+        if getattr(self, "_rb_cache", (None, None))[0] != bias._version:    # one D2H sync per optimiser step, not per call
+            self._rb_cache = (bias._version, float(bias.detach().item()))
+        rb = self._rb_cache[1]
         history_embs = []
         for i, g in enumerate(g_list):
             g = g.to(self.gpu)
@@ -315,30 +317,32 @@ class HyperbolicRecurrentRGCN(nn.Module):
         Evaluation mode: forward values.  Entity head: the decoders' streaming CE (hyperbolic_decoder.py:182-307) as the
         scoring GEMM's log-sum-exp epilogue; relation head on its (B,2R) score matrix; radius supervision :1066-1073."""
         if self.training:
-            if getattr(self, "use_static", False):
-                raise NotImplementedError("static-graph constraint in hyperbolic training is not implemented")
             from . import train_hyp
             with torch.enable_grad():
-                return train_hyp.hyp_get_loss(self, glist, triples)
+                return train_hyp.hyp_get_loss(self, glist, triples, static_graph)
         with torch.no_grad():
             return self._get_loss_eval(glist, triples, static_graph, use_cuda)
 
     def _get_loss_eval(self, glist, triples, static_graph, use_cuda):
         from . import evaluate
-        if getattr(self, "use_static", False):
-            raise NotImplementedError("static-graph constraint loss is SURVEY.md 8f rank 3")
         dev = self.dynamic_emb.device
         triples = torch.as_tensor(triples).to(dev)
         inverse_triples = triples.flip(1)
         inverse_triples[:, 1] = inverse_triples[:, 1] + self.num_rels
         all_triples = torch.cat([triples, inverse_triples]).contiguous()
-        evolve_embs, _, r_emb, _, _ = self.forward(glist, static_graph, use_cuda)
+        evolve_embs, static_emb, r_emb, _, _ = self.forward(glist, static_graph, use_cuda)
         pre_emb = evolve_embs[-1]
         if self.layer_norm:
             pre_emb = ops.row_map(pre_emb, ops.ROW_TANGENT_NORMALIZE, c=self._c_float)
         loss_ent = torch.zeros(1, device=dev)
         loss_rel = torch.zeros(1, device=dev)
         loss_static = torch.zeros(1, device=dev)
+        if getattr(self, "use_static", False) and static_emb is not None and self.discount in (0, 1):
+            # hyperbolic_src/hyperbolic_model.py:1039-1064: angle loss against the tangent vectors log_0(evolve_emb)
+            from . import train
+            tangent = [ops.row_map(e, ops.ROW_LOG0, c=self._c_float) for e in evolve_embs]
+            loss_static, _ = train.static_angle_terms(static_emb.contiguous(), tangent, self.layer_norm, self.angle,
+                                                      self.discount, self.weight)
         if self.entity_prediction:
             q, cand, hyp, col_bias = evaluate._scoring_operands(self, pre_emb, r_emb, all_triples)
             _, loss_ent = ops.fused_ce(q, cand, all_triples[:, 2], hyp=hyp, col_bias=col_bias)

@@ -584,8 +584,9 @@ class _StaticAngle(torch.autograd.Function):
 
 
 def static_embedding(model, static_graph):
-    """src/rrgcn.py:146-152 with the tape on: block layer over cat(dynamic_emb, words_emb), entity rows, F.normalize."""
-    layer = model.statci_rgcn_layer
+    """src/rrgcn.py:146-152 (hyperbolic_model.py:762-770) with the tape on: block layer over cat(dynamic_emb, words_emb),
+    entity rows, F.normalize."""
+    layer = model.statci_rgcn_layer if hasattr(model, "statci_rgcn_layer") else model.static_rgcn_layer
     x = torch.cat((model.dynamic_emb, model.words_emb), dim=0)
     agg = _BlockAggregate.apply(x, layer.weight, static_graph, layer.num_bases, layer.out_feat)
     out = _RReluDrop.apply(agg, 0.0)              # RGCNLayer drops only the self-loop message (:52-53); none here

@@ -272,18 +272,22 @@ def lorentz_layer(layer, g, h_in, h0, c, training):
     return radial(t, EXP0, c)
 
 
-def hyp_evolve(model, g_list):
-    """HyperbolicRecurrentRGCN.forward with the tape on (hyperbolic_model.py:773-890)."""
-    if (model.encoder_name not in ("hyperbolic_uvrgcn", "lgcn") or getattr(model, "use_static", False)
+def hyp_evolve(model, g_list, static_graph=None):
+    """HyperbolicRecurrentRGCN.forward with the tape on (hyperbolic_model.py:762-890).  Returns (hist, h_0, static_emb)."""
+    if (model.encoder_name not in ("hyperbolic_uvrgcn", "lgcn")
             or any(l.skip_connect or not l.self_loop for l in model.rgcn.layers)):
-        raise NotImplementedError("regcn_b200.train_hyp: hyperbolic_uvrgcn / lgcn + self_loop without skip_connect / static graph")
+        raise NotImplementedError("regcn_b200.train_hyp: hyperbolic_uvrgcn / lgcn + self_loop without skip_connect")
     if model.encoder_name == "lgcn" and any(2 * l.num_bases != model.h_dim for l in model.rgcn.layers):
         raise NotImplementedError("regcn_b200.train_hyp: the lgcn encoder trains with 2x2 relation blocks (num_bases = h_dim/2, "
                                   "the reference's 100 bases at h_dim 200)")
     layer_fn = hyp_union_layer if model.encoder_name == "hyperbolic_uvrgcn" else lorentz_layer
     c = model._c_float
     cell = model.relation_gru
-    init = T.normalize(model.dynamic_emb) if model.layer_norm else model.dynamic_emb
+    static_emb = None
+    if getattr(model, "use_static", False) and static_graph is not None:
+        static_emb = init = T.static_embedding(model, static_graph)
+    else:
+        init = T.normalize(model.dynamic_emb) if model.layer_norm else model.dynamic_emb
     h = radial(init, EXP0, c)
     rs = static_radius(model)
     h = apply_radius(h, rs, c)
@@ -318,7 +322,7 @@ def hyp_evolve(model, g_list):
         else:
             h = apply_radius(h, rs, c)
         hist.append(h)
-    return hist, h0
+    return hist, h0, static_emb
 
 
 class _RadiusLoss(torch.autograd.Function):
@@ -692,7 +696,7 @@ def atth_losses(model, pre, r_emb, all_t):
     return loss_ent, loss_rel
 
 
-def hyp_get_loss(model, glist, triples):
+def hyp_get_loss(model, glist, triples, static_graph=None):
     """hyperbolic_model.py:941-1088 with gradients: (loss_ent, loss_rel, loss_static, loss_radius), each (1,)."""
     _lib.require_device()
     if ops.gemm_impl() != "tc":
@@ -705,11 +709,15 @@ def hyp_get_loss(model, glist, triples):
     inverse = triples.flip(1)
     inverse[:, 1] = inverse[:, 1] + model.num_rels
     all_triples = torch.cat([triples, inverse]).contiguous()
-    hist, r_emb = hyp_evolve(model, glist)
+    hist, r_emb, static_emb = hyp_evolve(model, glist, static_graph)
     pre = radial(hist[-1], TNORM, c) if model.layer_norm else hist[-1]
     loss_ent = torch.zeros(1, device=dev)
     loss_rel = torch.zeros(1, device=dev)
     loss_static = torch.zeros(1, device=dev)
+    if static_emb is not None and model.discount in (0, 1):
+        # hyperbolic_model.py:1039-1064: angle loss between the static embedding and the TANGENT vectors log_0(evolve_emb)
+        loss_static = T._StaticAngle.apply(static_emb, model.layer_norm, model.angle, model.discount, model.weight,
+                                           *[radial(e, LOG0, c) for e in hist])
     ids = torch.unique(all_triples[:, [0, 2]].reshape(-1))
     loss_radius = _RadiusLoss.apply(model.radius_static, model.radius_target, ids, model.radius_min, model.radius_max, c,
                                     float(model.radius_lambda))

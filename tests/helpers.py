@@ -159,6 +159,11 @@ HYP_TRAIN_CASES = {
                                          layer_norm=False, gamma=0.15, entity_bias=True, rel_curvature=True),
     "hyptrain_murp_tiny_s12_curv": dict(kind="hyp", shape="tiny", seed=12, encoder="hyperbolic_uvrgcn", decoder="murp",
                                         layer_norm=True, gamma=0.15, rel_curvature=True),
+    "hyptrain_static_tiny_s13": dict(kind="hyp", shape="tiny", seed=13, encoder="hyperbolic_uvrgcn",
+                                     decoder="hyperbolic_convtranse", layer_norm=True, gamma=0.15,
+                                     static=dict(discount=1, angle=10, weight=0.5)),
+    "hyptrain_static_small_s14_roth": dict(kind="hyp", shape="small", seed=14, encoder="hyperbolic_uvrgcn", decoder="roth",
+                                           layer_norm=False, gamma=0.15, static=dict(discount=0, angle=10, weight=1.0)),
     "hyptrain_lgcn_roth_small_s9": dict(kind="hyp", shape="small_l", seed=9, encoder="lgcn", decoder="roth",
                                         layer_norm=False, gamma=0.15),
     "hyptrain_lgcn_convtranse_small_s10_ln": dict(kind="hyp", shape="small_l", seed=10, encoder="lgcn",
@@ -168,7 +173,11 @@ HYP_TRAIN_CASES = {
 
 def build_hyp_train_model(cfg, n, r, dropout=0.0):
     import regcn_b200 as R
-    m = R.HyperbolicRecurrentRGCN(cfg["decoder"], cfg["encoder"], n, r, 0, 0, H_DIM, "sub", 3, num_bases=N_BASES,
+    st_cfg, n_srel, n_words = cfg.get("static"), 0, 0
+    if st_cfg:
+        _, n_srel, n_words = synth.make_static(n, cfg["seed"])
+    m = R.HyperbolicRecurrentRGCN(cfg["decoder"], cfg["encoder"], n, r, n_srel, n_words, H_DIM, "sub", 3,
+                                  use_static=bool(st_cfg), **(st_cfg or {}), num_bases=N_BASES,
                                   num_hidden_layers=N_LAYERS, dropout=dropout, c=CURV, self_loop=True, skip_connect=False,
                                   layer_norm=cfg["layer_norm"], input_dropout=dropout, hidden_dropout=dropout,
                                   feat_dropout=dropout, entity_prediction=True, relation_prediction=True, use_cuda=True,

@@ -135,10 +135,24 @@ def test_hyperbolic_train_step_matches_reference(name):
     case = synth.make_case(cfg["shape"], cfg["seed"])
     n, r = case["num_ents"], case["num_rels"]
     m, _ = build_hyp_train_model(cfg, n, r)
+    glist = [R.build_sub_graph(n, r, s, True, 0) for s in case["history"]]
+    sg = None
+    if cfg.get("static"):
+        # --add-static-graph (hyperbolic_src/hyperbolic_model.py:762-771,1039-1064): eval outputs first
+        st, n_srel, n_words = synth.make_static(n, cfg["seed"])
+        sg = R.build_sub_graph(n + n_words, n_srel, st, True, 0)
+        m = m.to(DEV).eval()
+        triples = torch.from_numpy(case["test"]).to(DEV)
+        _, score, score_rel = m.predict(glist, r, sg, triples, True)
+        hist, static_emb, _, _, _ = m.forward(glist, sg, True)
+        for mine, key in ((static_emb, "static_emb"), (hist[-1], "hist_last"), (score, "score"), (score_rel, "score_rel")):
+            ok, worst = close(mine.cpu().numpy(), z[f"{name}.{key}"], rtol=2e-4 if "score" in key else 1e-4)
+            assert ok, (key, worst)
+        ev = m.get_loss(glist, triples, sg, True)
+        np.testing.assert_allclose([float(x.reshape(-1)[0]) for x in ev], z[f"{name}.eval_losses"], rtol=1e-4)
     m = m.to(DEV).train()
     opt = optim.Adam(m.parameters(), lr=1e-3, weight_decay=1e-5)
-    glist = [R.build_sub_graph(n, r, s, True, 0) for s in case["history"]]
-    le, lr_, ls, lrad = m.get_loss(glist, torch.from_numpy(case["test"]).to(DEV), None, True)
+    le, lr_, ls, lrad = m.get_loss(glist, torch.from_numpy(case["test"]).to(DEV), sg, True)
     (0.7 * le + 0.3 * lr_ + ls + lrad).backward()
     named = {k: p for k, p in m.named_parameters() if p.grad is not None}
     grads = {k: p.grad.detach().cpu().numpy().copy() for k, p in named.items()}
@@ -149,7 +163,7 @@ def test_hyperbolic_train_step_matches_reference(name):
     compare_train_step(z, name, 0, losses, float(opt.total_norm), grads, params, rtol=1.5e-3)
     # and the trained model still evaluates (operand caches follow the version counters)
     m.eval()
-    _, score, _ = m.predict(glist, r, None, torch.from_numpy(case["test"]).to(DEV), True)
+    _, score, _ = m.predict(glist, r, sg, torch.from_numpy(case["test"]).to(DEV), True)
     assert torch.isfinite(score).all()
 
 

@@ -210,8 +210,21 @@ def test_oracle_hyperbolic_train_step_matches_reference(name):
     n, r = case["num_ents"], case["num_rels"]
     _, sd = build_hyp_train_model(cfg, n, r)
     graphs = [restate.build_edges(s, n, r) for s in case["history"]]
+    static = None
+    if cfg.get("static"):
+        # --add-static-graph (hyperbolic_src/hyperbolic_model.py:762-771,1039-1064)
+        st, n_srel, n_words = synth.make_static(n, cfg["seed"])
+        static = dict(graph=restate.build_edges(st, n + n_words, n_srel), num_ents=n, num_bases=N_BASES, **cfg["static"])
+        P = {k: v for k, v in sd.items() if v.is_floating_point()}
+        with torch.no_grad():
+            s_emb = restate.hyp_static_emb(P, static["graph"], n, N_BASES, cfg["layer_norm"])
+            ls = restate.hyp_train_losses(P, graphs, r, case["test"], CURV, cfg["layer_norm"], cfg["gamma"], {},
+                                          decoder=cfg["decoder"], encoder=cfg["encoder"],
+                                          num_bases=min(N_BASES, 2 * r), static=static)
+        np.testing.assert_allclose(s_emb.numpy(), z[f"{name}.static_emb"], rtol=1e-4, atol=1e-6)
     log = restate.hyp_train_steps(sd, graphs, r, case["test"], c=CURV, layer_norm=cfg["layer_norm"], gamma=cfg["gamma"],
-                                  decoder=cfg["decoder"], encoder=cfg["encoder"], num_bases=min(N_BASES, 2 * r))
+                                  decoder=cfg["decoder"], encoder=cfg["encoder"], num_bases=min(N_BASES, 2 * r),
+                                  static=static)
     rec = log[0]
     compare_train_step(z, name, 0, rec["losses"], rec["grad_norm"], {k: v.numpy() for k, v in rec["grads"].items()},
                        {k: v.numpy() for k, v in rec["params"].items()})
