@@ -170,6 +170,9 @@ TRAIN_CASES = {
     "regcn_tiny_s0": dict(kind="regcn", shape="tiny", seed=0, layer_norm=True),
     "regcn_tiny_s1_noln": dict(kind="regcn", shape="tiny", seed=1, layer_norm=False),
     "regcn_small_s2": dict(kind="regcn", shape="small", seed=2, layer_norm=True),
+    # --skip-connect: the uvrgcn cell calls every layer with prev_h=[] (src/rrgcn.py:37-38), so the gate weights exist,
+    # are never used and never receive a gradient
+    "regcn_tiny_s3_skip": dict(kind="regcn", shape="tiny", seed=3, layer_norm=True, skip_connect=True),
 }
 TRAIN_STEPS = 2
 TASK_WEIGHT, GRAD_NORM, LR, WEIGHT_DECAY = 0.7, 1.0, 1e-3, 1e-5     # src/main.py:325,367,365,194
@@ -194,7 +197,8 @@ def run_train(ref_utils, RecurrentRGCN):
         case = synth.make_case(cfg["shape"], cfg["seed"])
         n, r = case["num_ents"], case["num_rels"]
         m = RecurrentRGCN("convtranse", "uvrgcn", n, r, 0, 0, H_DIM, "sub", 3, num_bases=N_BASES, num_basis=-1,
-                          num_hidden_layers=N_LAYERS, dropout=0.0, self_loop=True, skip_connect=False,
+                          num_hidden_layers=N_LAYERS, dropout=0.0, self_loop=True,
+                          skip_connect=cfg.get("skip_connect", False),
                           layer_norm=cfg["layer_norm"], input_dropout=0.0, hidden_dropout=0.0, feat_dropout=0.0,
                           entity_prediction=True, relation_prediction=True, use_cuda=False, gpu="cpu")
         m.load_state_dict(synth.fill_state_dict(m.state_dict(), cfg["seed"]))
@@ -352,6 +356,8 @@ HYP_TRAIN_CASES = {
                                      static=dict(discount=1, angle=10, weight=0.5)),
     "hyptrain_static_small_s14_roth": dict(kind="hyp", shape="small", seed=14, encoder="hyperbolic_uvrgcn", decoder="roth",
                                            layer_norm=False, gamma=0.15, static=dict(discount=0, angle=10, weight=1.0)),
+    "hyptrain_skip_tiny_s15": dict(kind="hyp", shape="tiny", seed=15, encoder="hyperbolic_uvrgcn",
+                                   decoder="hyperbolic_convtranse", layer_norm=True, gamma=0.15, skip_connect=True),
     "hyptrain_lgcn_roth_small_s9": dict(kind="hyp", shape="small_l", seed=9, encoder="lgcn", decoder="roth",
                                         layer_norm=False, gamma=0.15),
     "hyptrain_lgcn_convtranse_small_s10_ln": dict(kind="hyp", shape="small_l", seed=10, encoder="lgcn",
@@ -372,7 +378,8 @@ def run_hyp_train(ref_utils, HyperbolicRecurrentRGCN):
             sg = ref_utils.build_sub_graph(n + n_words, n_srel, st, False, "cpu")
         m = HyperbolicRecurrentRGCN(cfg["decoder"], cfg["encoder"], n, r, n_srel, n_words, H_DIM, "sub", 3,
                                     num_bases=N_BASES,
-                                    num_hidden_layers=N_LAYERS, dropout=0.0, c=CURV, self_loop=True, skip_connect=False,
+                                    num_hidden_layers=N_LAYERS, dropout=0.0, c=CURV, self_loop=True,
+                                    skip_connect=cfg.get("skip_connect", False),
                                     layer_norm=cfg["layer_norm"], input_dropout=0.0, hidden_dropout=0.0, feat_dropout=0.0,
                                     entity_prediction=True, relation_prediction=True, use_cuda=False, gpu="cpu",
                                     use_static=bool(st_cfg), **(st_cfg or {}),

@@ -167,7 +167,11 @@ class HyperbolicRecurrentRGCN(nn.Module):
     # ------------------------------------------------------------------ whole-recurrence fast path
     def _engine_ok(self):
         first = self.rgcn.layers[0]
-        return (ops.gemm_impl() == "tc" and not self.use_static and first.self_loop and not first.skip_connect
+        # --skip-connect is inert for hyperbolic_uvrgcn (its cell never passes prev_h, hyperbolic_src/hyperbolic_model.py:152)
+        # and live from the second Lorentz layer on (hyperbolic_src/hyperbolic_layers.py:737-740): that one takes the
+        # per-layer path
+        live_skip = self.encoder_name == "lgcn" and any(l.skip_connect for l in self.rgcn.layers)
+        return (ops.gemm_impl() == "tc" and not self.use_static and first.self_loop and not live_skip
                 and self.encoder_name in ("hyperbolic_uvrgcn", "lgcn") and self.h_dim % 4 == 0 and self.h_dim <= 256)
 
     def _engine_tables(self):

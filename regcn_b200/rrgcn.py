@@ -118,7 +118,8 @@ class RecurrentRGCN(nn.Module):
 
     # ------------------------------------------------------------------ whole-recurrence fast path
     def _engine_ok(self):
-        return (ops.gemm_impl() == "tc" and self.rgcn.self_loop and not self.rgcn.skip_connect
+        # skip_connect is not a condition: the uvrgcn cell passes prev_h=[] to every layer (src/rrgcn.py:37-38)
+        return (ops.gemm_impl() == "tc" and self.rgcn.self_loop
                 and self.encoder_name == "uvrgcn" and self.h_dim % 4 == 0 and self.h_dim <= 256)
 
     def _engine_tables(self, h_init=None):

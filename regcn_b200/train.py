@@ -605,10 +605,11 @@ tanh = _Tanh.apply
 
 # ------------------------------------------------------------------------------------------------ model-level glue
 def regcn_evolve(model, g_list, static_graph=None):
-    """RecurrentRGCN.forward with the tape on (src/rrgcn.py:142-180; uvrgcn, self_loop, no skip connection).
-    Returns (history_embs, h_0, static_emb)."""
-    if model.rgcn.skip_connect or not model.rgcn.self_loop or model.encoder_name != "uvrgcn":
-        raise NotImplementedError("regcn_b200.train: uvrgcn + self_loop without skip_connect only")
+    """RecurrentRGCN.forward with the tape on (src/rrgcn.py:142-180; uvrgcn, self_loop).  --skip-connect changes
+    nothing here: RGCNCell calls every layer with prev_h=[] (src/rrgcn.py:37-38), so the gate of rgcn/layers.py:234-245
+    is never taken and its weights never receive a gradient.  Returns (history_embs, h_0, static_emb)."""
+    if not model.rgcn.self_loop or model.encoder_name != "uvrgcn":
+        raise NotImplementedError("regcn_b200.train: uvrgcn + self_loop only")
     cell = model.relation_cell_1
     static_emb = None
     if model.use_static:

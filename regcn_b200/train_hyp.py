@@ -274,9 +274,11 @@ def lorentz_layer(layer, g, h_in, h0, c, training):
 
 def hyp_evolve(model, g_list, static_graph=None):
     """HyperbolicRecurrentRGCN.forward with the tape on (hyperbolic_model.py:762-890).  Returns (hist, h_0, static_emb)."""
-    if (model.encoder_name not in ("hyperbolic_uvrgcn", "lgcn")
-            or any(l.skip_connect or not l.self_loop for l in model.rgcn.layers)):
-        raise NotImplementedError("regcn_b200.train_hyp: hyperbolic_uvrgcn / lgcn + self_loop without skip_connect")
+    # --skip-connect: HyperbolicRGCNCell never passes prev_h (hyperbolic_src/hyperbolic_model.py:152), so the flag is
+    # inert for hyperbolic_uvrgcn; LorentzRGCNCell does (hyperbolic_src/hyperbolic_layers.py:737-740)
+    if (model.encoder_name not in ("hyperbolic_uvrgcn", "lgcn") or any(not l.self_loop for l in model.rgcn.layers)
+            or (model.encoder_name == "lgcn" and any(l.skip_connect for l in model.rgcn.layers))):
+        raise NotImplementedError("regcn_b200.train_hyp: hyperbolic_uvrgcn / lgcn (without skip_connect) + self_loop")
     if model.encoder_name == "lgcn" and any(2 * l.num_bases != model.h_dim for l in model.rgcn.layers):
         raise NotImplementedError("regcn_b200.train_hyp: the lgcn encoder trains with 2x2 relation blocks (num_bases = h_dim/2, "
                                   "the reference's 100 bases at h_dim 200)")

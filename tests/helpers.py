@@ -164,6 +164,8 @@ HYP_TRAIN_CASES = {
                                      static=dict(discount=1, angle=10, weight=0.5)),
     "hyptrain_static_small_s14_roth": dict(kind="hyp", shape="small", seed=14, encoder="hyperbolic_uvrgcn", decoder="roth",
                                            layer_norm=False, gamma=0.15, static=dict(discount=0, angle=10, weight=1.0)),
+    "hyptrain_skip_tiny_s15": dict(kind="hyp", shape="tiny", seed=15, encoder="hyperbolic_uvrgcn",
+                                   decoder="hyperbolic_convtranse", layer_norm=True, gamma=0.15, skip_connect=True),
     "hyptrain_lgcn_roth_small_s9": dict(kind="hyp", shape="small_l", seed=9, encoder="lgcn", decoder="roth",
                                         layer_norm=False, gamma=0.15),
     "hyptrain_lgcn_convtranse_small_s10_ln": dict(kind="hyp", shape="small_l", seed=10, encoder="lgcn",
@@ -178,7 +180,8 @@ def build_hyp_train_model(cfg, n, r, dropout=0.0):
         _, n_srel, n_words = synth.make_static(n, cfg["seed"])
     m = R.HyperbolicRecurrentRGCN(cfg["decoder"], cfg["encoder"], n, r, n_srel, n_words, H_DIM, "sub", 3,
                                   use_static=bool(st_cfg), **(st_cfg or {}), num_bases=N_BASES,
-                                  num_hidden_layers=N_LAYERS, dropout=dropout, c=CURV, self_loop=True, skip_connect=False,
+                                  num_hidden_layers=N_LAYERS, dropout=dropout, c=CURV, self_loop=True,
+                                  skip_connect=cfg.get("skip_connect", False),
                                   layer_norm=cfg["layer_norm"], input_dropout=dropout, hidden_dropout=dropout,
                                   feat_dropout=dropout, entity_prediction=True, relation_prediction=True, use_cuda=True,
                                   gpu=0, radius_msg_gamma=cfg["gamma"], hyp_init_scale=1e-3,

@@ -248,7 +248,8 @@ def test_adam_matches_torch():
 
 
 @pytest.mark.parametrize("name,shape,seed,ln", [("regcn_tiny_s0", "tiny", 0, True), ("regcn_tiny_s1_noln", "tiny", 1, False),
-                                                ("regcn_small_s2", "small", 2, True)])
+                                                ("regcn_small_s2", "small", 2, True),
+                                                ("regcn_tiny_s3_skip", "tiny", 3, True)])
 def test_train_steps_match_reference(name, shape, seed, ln):
     """Two optimisation steps (get_loss in train() mode -> backward -> clip_grad_norm_(1.0) -> Adam) against the
     UNMODIFIED reference's (tests/golden/train_regcn.npz): losses, gradient norm, every gradient, every updated value,
@@ -260,14 +261,15 @@ def test_train_steps_match_reference(name, shape, seed, ln):
     case = synth.make_case(shape, seed)
     n, r = case["num_ents"], case["num_rels"]
     m = R.RecurrentRGCN("convtranse", "uvrgcn", n, r, 0, 0, 200, "sub", 3, num_bases=100, num_basis=-1,
-                        num_hidden_layers=2, dropout=0.0, self_loop=True, skip_connect=False, layer_norm=ln,
-                        input_dropout=0.0, hidden_dropout=0.0, feat_dropout=0.0, entity_prediction=True,
+                        num_hidden_layers=2, dropout=0.0, self_loop=True, skip_connect=name.endswith("_skip"),
+                        layer_norm=ln, input_dropout=0.0, hidden_dropout=0.0, feat_dropout=0.0, entity_prediction=True,
                         relation_prediction=True, use_cuda=True, gpu=0)
     m.load_state_dict(synth.fill_state_dict(m.state_dict(), seed))
     m = m.to(DEV).train()
     opt = optim.Adam(m.parameters(), lr=1e-3, weight_decay=1e-5)
     glist = [R.build_sub_graph(n, r, s, True, 0) for s in case["history"]]
     triples = torch.from_numpy(case["test"]).to(DEV)
+    assert m._engine_ok()            # --skip-connect is dead for uvrgcn (prev_h=[], src/rrgcn.py:37-38): engine path too
     for step in range(2):
         le, lr_, ls = m.get_loss(glist, triples, None, True)
         loss = 0.7 * le + 0.3 * lr_ + ls
@@ -448,3 +450,34 @@ def test_fit_epoch_equals_hand_written_loop_and_learns():
     for _ in range(2):
         b = R.fit_epoch(mh, oh, train_list, r, n, L, order=order, triple_batch_size=64)
     assert a["steps"] == 7 and "loss_radius" in a and np.isfinite(b["loss"]) and b["loss"] < a["loss"]
+
+
+def test_skip_connect_flag_is_inert_for_uvrgcn():
+    """--skip-connect with the uvrgcn encoder: the cell hands prev_h=[] to every layer (src/rrgcn.py:37-38), so scores
+    equal those of the same weights without the flag, on the engine path too, and the gate weights get no gradient."""
+    R._lib.require_device()
+    case = synth.make_case("tiny", 5)
+    n, r = case["num_ents"], case["num_rels"]
+    models = []
+    for skip in (True, False):
+        m = R.RecurrentRGCN("convtranse", "uvrgcn", n, r, 0, 0, 200, "sub", 3, num_bases=100, num_basis=-1,
+                            num_hidden_layers=2, dropout=0.0, self_loop=True, skip_connect=skip, layer_norm=True,
+                            input_dropout=0.0, hidden_dropout=0.0, feat_dropout=0.0, entity_prediction=True,
+                            relation_prediction=True, use_cuda=True, gpu=0)
+        models.append(m)
+    sd = synth.fill_state_dict(models[0].state_dict(), 5)
+    models[0].load_state_dict(sd)
+    models[1].load_state_dict({k: v for k, v in sd.items() if "skip_connect" not in k})
+    glist = [R.build_sub_graph(n, r, s, True, 0) for s in case["history"]]
+    triples = torch.from_numpy(case["test"]).to(DEV)
+    scores = []
+    for m in models:
+        m = m.to(DEV).eval()
+        assert m._engine_ok()
+        _, score, score_rel = m.predict(glist, r, None, triples, True)
+        scores.append((score.clone(), score_rel.clone()))
+    assert torch.equal(scores[0][0], scores[1][0]) and torch.equal(scores[0][1], scores[1][1])
+    m = models[0].train()
+    le, lr_, ls = m.get_loss(glist, triples, None, True)
+    (0.7 * le + 0.3 * lr_ + ls).backward()
+    assert m.rgcn.layers[1].skip_connect_weight.grad is None and m.rgcn.layers[1].skip_connect_bias.grad is None

@@ -127,7 +127,7 @@ from tests.helpers import compare_train_step  # noqa: E402
 
 
 TRAIN_CASES = {"regcn_tiny_s0": ("tiny", 0, True), "regcn_tiny_s1_noln": ("tiny", 1, False),
-               "regcn_small_s2": ("small", 2, True)}
+               "regcn_small_s2": ("small", 2, True), "regcn_tiny_s3_skip": ("tiny", 3, True)}
 
 
 @pytest.mark.parametrize("name", sorted(TRAIN_CASES))
@@ -141,8 +141,8 @@ def test_oracle_train_step_matches_reference(name):
     case = synth.make_case(shape, seed)
     n, r = case["num_ents"], case["num_rels"]
     m = R.RecurrentRGCN("convtranse", "uvrgcn", n, r, 0, 0, 200, "sub", 3, num_bases=100, num_basis=-1,
-                        num_hidden_layers=2, dropout=0.0, self_loop=True, skip_connect=False, layer_norm=ln,
-                        input_dropout=0.0, hidden_dropout=0.0, feat_dropout=0.0, entity_prediction=True,
+                        num_hidden_layers=2, dropout=0.0, self_loop=True, skip_connect=name.endswith("_skip"),
+                        layer_norm=ln, input_dropout=0.0, hidden_dropout=0.0, feat_dropout=0.0, entity_prediction=True,
                         relation_prediction=True, use_cuda=True, gpu=0)
     sd = synth.fill_state_dict(m.state_dict(), seed)
     graphs = [restate.build_edges(s, n, r) for s in case["history"]]
