@@ -171,20 +171,22 @@ class HyperbolicRecurrentRGCN(nn.Module):
         # and live from the second Lorentz layer on (hyperbolic_src/hyperbolic_layers.py:737-740): that one takes the
         # per-layer path
         live_skip = self.encoder_name == "lgcn" and any(l.skip_connect for l in self.rgcn.layers)
-        return (ops.gemm_impl() == "tc" and not self.use_static and first.self_loop and not live_skip
+        return (ops.gemm_impl() == "tc" and first.self_loop and not live_skip
                 and self.encoder_name in ("hyperbolic_uvrgcn", "lgcn") and self.h_dim % 4 == 0 and self.h_dim <= 256)
 
-    def _engine_tables(self):
-        """Pointer / int / double tables of regcn_hyp_evolve (include/regcn_b200.h HM_* / HMI_* / HMD_*)."""
+    def _engine_tables(self, h_init=None):
+        """Pointer / int / double tables of regcn_hyp_evolve (include/regcn_b200.h HM_* / HMI_* / HMD_*).
+        h_init: persistent buffer holding the initial tangent table instead of dynamic_emb (use_static)."""
         import numpy as np
         cell = self.relation_gru
         tre = self.temporal_radius_evolution
-        params = [self.dynamic_emb, self.emb_rel, self.radius_static, cell.weight_ih, cell.weight_hh, cell.bias_ih,
+        params = [self.dynamic_emb if h_init is None else h_init, self.emb_rel, self.radius_static, cell.weight_ih, cell.weight_hh, cell.bias_ih,
                   cell.bias_hh, self.time_gate_weight, self.time_gate_bias, tre.radius_mlp.weight, tre.radius_mlp.bias]
         for layer in self.rgcn.layers:
             params += [getattr(layer, "weight_neighbor", None) if self.encoder_name != "lgcn" else layer.weight,
                        layer.loop_weight, layer.evolve_loop_weight]
-        stamp = tuple((p._version, p.data_ptr()) for p in params)
+        # the static buffer is rewritten in place before every call: its version is not part of the stamp
+        stamp = tuple((p._version if (i or h_init is None) else -1, p.data_ptr()) for i, p in enumerate(params))
         if getattr(self, "_engine_stamp", None) == stamp:
             return self._engine_tab
         d = self.h_dim
@@ -204,7 +206,7 @@ class HyperbolicRecurrentRGCN(nn.Module):
         gw_hi, gw_lo = split(self.time_gate_weight.detach().t())
         b_hh = cell.bias_hh.detach().contiguous()
         gate_b = self.time_gate_bias.detach().contiguous()
-        dyn = self.dynamic_emb.detach().contiguous()
+        dyn = self.dynamic_emb.detach().contiguous() if h_init is None else h_init
         rs = self.radius_static.detach().contiguous()
         rw = tre.radius_mlp.weight.detach().view(-1).contiguous()
         keep += [emb_rel, gi_static, b_hh, gate_b, dyn, rs, rw]
@@ -230,10 +232,10 @@ class HyperbolicRecurrentRGCN(nn.Module):
         self._engine_stamp = stamp
         return self._engine_tab
 
-    def _forward_engine(self, g_list):
+    def _forward_engine(self, g_list, h_init=None):
         import numpy as np
         from . import _lib
-        ptab, itab, dtab, _ = self._engine_tables()
+        ptab, itab, dtab, _ = self._engine_tables(h_init)
         L = len(g_list)
         N, R2, d = self.num_ents, 2 * self.num_rels, self.h_dim
         dev = self.dynamic_emb.device
@@ -255,23 +257,33 @@ class HyperbolicRecurrentRGCN(nn.Module):
     @torch.no_grad()
     def forward(self, g_list, static_graph, use_cuda):
         gate_list, degree_list = [], []
-        if self._engine_ok() and len(g_list) > 0:
-            history_embs, self.h_0 = self._forward_engine(g_list)
-            self.h = history_embs[-1]
-            return history_embs, None, self.h_0, gate_list, degree_list
-        c = self._c_float
-        rs_raw = self.radius_static.detach()
+        static_emb = None
         if self.use_static and static_graph is not None:
             static_graph = static_graph.to(self.gpu)
             static_graph.ndata['h'] = torch.cat((self.dynamic_emb, self.words_emb), dim=0).detach()
             self.static_rgcn_layer(static_graph, [])
             static_emb = static_graph.ndata.pop('h')[:self.num_ents, :].contiguous()
             static_emb = ops.row_map(static_emb, ops.ROW_NORMALIZE) if self.layer_norm else static_emb
+        if self._engine_ok() and len(g_list) > 0:
+            h_init = None
+            if static_emb is not None:
+                # fixed-pointer initial table, as in RecurrentRGCN.forward: the engine's row normalisation of the already
+                # normalised static embedding is idempotent (hyperbolic_src/hyperbolic_model.py:769-771)
+                buf = getattr(self, "_static_h", None)
+                if buf is None or buf.shape != static_emb.shape or buf.device != static_emb.device:
+                    buf = self._static_h = torch.empty_like(static_emb)
+                buf.copy_(static_emb)
+                h_init = buf
+            history_embs, self.h_0 = self._forward_engine(g_list, h_init)
+            self.h = history_embs[-1]
+            return history_embs, static_emb, self.h_0, gate_list, degree_list
+        c = self._c_float
+        rs_raw = self.radius_static.detach()
+        if static_emb is not None:
             self.h = ops.hyp_init(static_emb, rs_raw, False, False, c, self.radius_min, self.radius_max)
         else:
             self.h = ops.hyp_init(self.dynamic_emb.detach(), rs_raw, self.layer_norm, False, c, self.radius_min,
                                   self.radius_max)
-            static_emb = None
 
         tre = self.temporal_radius_evolution
         rw = tre.radius_mlp.weight.detach().view(-1).contiguous()

@@ -143,6 +143,7 @@ def test_hyperbolic_train_step_matches_reference(name):
         sg = R.build_sub_graph(n + n_words, n_srel, st, True, 0)
         m = m.to(DEV).eval()
         triples = torch.from_numpy(case["test"]).to(DEV)
+        assert m._engine_ok()            # static initial table through the one-call evolve engine
         _, score, score_rel = m.predict(glist, r, sg, triples, True)
         hist, static_emb, _, _, _ = m.forward(glist, sg, True)
         for mine, key in ((static_emb, "static_emb"), (hist[-1], "hist_last"), (score, "score"), (score_rel, "score_rel")):
