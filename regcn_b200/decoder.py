@@ -86,9 +86,21 @@ class ConvTransE(_ConvTransBase):
         q = self._tower(e_all, emb_rel.contiguous(), triplets, 0, 1, always_bn2=False)
         return e_all, q
 
+    def _forward_train(self, embedding, emb_rel, triplets, partial_embeding=None):
+        """train() mode (batch-statistics BatchNorm, dropout, running-stat updates) with gradients: the kernel-backed
+        autograd nodes of regcn_b200.train; the (B,N) scores are materialised because the caller asked for them."""
+        from . import train as T
+        with torch.enable_grad():
+            t = torch.as_tensor(triplets).to(embedding.device).contiguous()
+            e_all = T.tanh(embedding)
+            q = T.conv_tower(self, e_all, emb_rel, t, 0, 1)
+            return T.linear(q, e_all if partial_embeding is None else partial_embeding)
+
     @torch.no_grad()
     def forward(self, embedding, emb_rel, triplets, nodes_id=None, mode="train", negative_rate=0,
                 partial_embeding=None):
+        if self.training:
+            return self._forward_train(embedding, emb_rel, triplets, partial_embeding)
         e_all, q = self.query(embedding, emb_rel, triplets)
         cand = e_all if partial_embeding is None else partial_embeding.contiguous()
         return ops.gemm(q, cand, trans_b=True)   # K11 (note: the reference registers `b` but never adds it, :72,:96-99)
@@ -104,7 +116,12 @@ class ConvTransR(_ConvTransBase):
 
     @torch.no_grad()
     def forward(self, embedding, emb_rel, triplets, nodes_id=None, mode="train", negative_rate=0):
-        self._check_eval()
+        if self.training:
+            from . import train as T
+            with torch.enable_grad():
+                t = torch.as_tensor(triplets).to(embedding.device).contiguous()
+                e_all = T.tanh(embedding)
+                return T.linear(T.conv_tower(self, e_all, e_all, t, 0, 2), emb_rel)
         e_all = ops.row_map(embedding, ops.ROW_TANH)
         q = self._tower(e_all, e_all, triplets, 0, 2, always_bn2=True)
         return ops.gemm(q, emb_rel.contiguous(), trans_b=True)

@@ -65,6 +65,21 @@ class _HypConvBase(nn.Module):
         return x
 
 
+def _hyp_conv_forward_train(self, entity_embedding, rel_embedding, triplets, relation_head):
+    """train() mode of the two ConvTrans heads with gradients (kernel-backed autograd nodes of regcn_b200.train /
+    train_hyp); the scores are materialised because the caller asked for them."""
+    from . import train as T, train_hyp as TH
+    with torch.enable_grad():
+        t = torch.as_tensor(triplets).to(entity_embedding.device).contiguous()
+        et = TH.eltwise(TH.radial(entity_embedding, TH.LOG0, float(self.c)), 1, 0.0)      # 0.9 tanh(log_0 E) + 0.1 log_0 E
+        if relation_head:
+            return T.linear(T.conv_tower(self, et, et, t, 0, 2), rel_embedding, self.b)
+        return T.linear(T.conv_tower(self, et, rel_embedding, t, 0, 1), et, self.b)
+
+
+_HypConvBase._forward_train = _hyp_conv_forward_train
+
+
 class HyperbolicConvTransE(_HypConvBase):
     """hyperbolic_decoder.py:310-413."""
 
@@ -76,6 +91,8 @@ class HyperbolicConvTransE(_HypConvBase):
 
     @torch.no_grad()
     def forward(self, entity_embedding, rel_embedding, triplets, mode="train"):
+        if self.training:
+            return self._forward_train(entity_embedding, rel_embedding, triplets, False)
         et = ops.row_map(entity_embedding, ops.ROW_LEAKY_TANH_LOG0, c=self.c)
         q = self._tower(et, rel_embedding.contiguous(), triplets, 0, 1, always_bn2=False)
         return ops.gemm(q, et, trans_b=True, bias=self.b.detach())
@@ -92,6 +109,8 @@ class HyperbolicConvTransR(_HypConvBase):
 
     @torch.no_grad()
     def forward(self, entity_embedding, rel_embedding, triplets, mode="train"):
+        if self.training:
+            return self._forward_train(entity_embedding, rel_embedding, triplets, True)
         et = ops.row_map(entity_embedding, ops.ROW_LEAKY_TANH_LOG0, c=self.c)
         q = self._tower(et, et, triplets, 0, 2, always_bn2=True)
         return ops.gemm(q, rel_embedding.contiguous(), trans_b=True, bias=self.b.detach())
@@ -99,6 +118,14 @@ class HyperbolicConvTransR(_HypConvBase):
 
 class _HypDistBase(nn.Module):
     """Shared scoring tail of the distance decoders: scale*(margin - |(-q)(+)e|^2) + bias  (:164-172)."""
+
+    def _train_loss(self, builder, entity_embedding, rel_embedding, triplets):
+        """The decoder's own training head: regcn_b200.train_hyp builds it from kernel-backed autograd nodes."""
+        from . import train_hyp
+        with torch.enable_grad():
+            t = torch.as_tensor(triplets).to(entity_embedding.device).contiguous()
+            return getattr(train_hyp, builder)(self, entity_embedding, rel_embedding, t, float(self.c),
+                                               self.training).reshape(())
 
     def _score_scale(self):
         return F.softplus(self.score_scale_raw) + SCORE_SCALE_EPSILON
@@ -201,8 +228,9 @@ class HyperbolicRotH(_HypDistBase):
         q, qss = self.query(entity_embedding, rel_embedding, triplets)
         return self._dist_scores(q, qss, entity_embedding.contiguous(), None, triplets)
 
-    def loss(self, *a, **k):
-        raise NotImplementedError("streaming-CE training head is SURVEY.md 8f rank 1 (next)")
+    def loss(self, entity_embedding, rel_embedding, triplets):
+        """hyperbolic_decoder.py:1101-1138: scalar cross entropy over all candidates, with gradients (no (B,N) logits)."""
+        return self._train_loss("roth_ent_loss", entity_embedding, rel_embedding, triplets)
 
 
 class HyperbolicMuRP(_HypDistBase):
@@ -252,8 +280,9 @@ class HyperbolicMuRP(_HypDistBase):
         q, qss = self.query(entity_embedding, rel_embedding, triplets)
         return self._dist_scores(q, qss, entity_embedding.contiguous(), None, triplets)
 
-    def loss(self, *a, **k):
-        raise NotImplementedError("streaming-CE training head is SURVEY.md 8f rank 1 (next)")
+    def loss(self, entity_embedding, rel_embedding, triplets):
+        """hyperbolic_decoder.py:781-817: scalar cross entropy over all candidates, with gradients (no (B,N) logits)."""
+        return self._train_loss("murp_ent_loss", entity_embedding, rel_embedding, triplets)
 
 
 class HyperbolicRotHRel(_HypDistBase):
@@ -295,8 +324,9 @@ class HyperbolicRotHRel(_HypDistBase):
         S = ops.gemm(q, rel_hyp, trans_b=True)
         return ops.hyp_score_epilogue_(S, qss, rss, self.rel_bias.detach(), None, self.c, self._scale_margin())
 
-    def loss(self, *a, **k):
-        raise NotImplementedError("streaming-CE training head is SURVEY.md 8f rank 1 (next)")
+    def loss(self, entity_embedding, rel_embedding, triplets):
+        """hyperbolic_decoder.py:1249-1280: scalar cross entropy over all candidates, with gradients (no (B,N) logits)."""
+        return self._train_loss("roth_rel_loss", entity_embedding, rel_embedding, triplets)
 
 
 class HyperbolicMuRPRel(_HypDistBase):
@@ -332,8 +362,9 @@ class HyperbolicMuRPRel(_HypDistBase):
         sm = torch.tensor([1.0, 0.0], device=S.device, dtype=torch.float32)
         return ops.hyp_score_epilogue_(S, qss, rss, self.rel_bias.detach(), None, self.c, sm)
 
-    def loss(self, *a, **k):
-        raise NotImplementedError("streaming-CE training head is SURVEY.md 8f rank 1 (next)")
+    def loss(self, entity_embedding, rel_embedding, triplets):
+        """hyperbolic_decoder.py:897-928: scalar cross entropy over all candidates, with gradients (no (B,N) logits)."""
+        return self._train_loss("murp_rel_loss", entity_embedding, rel_embedding, triplets)
 
 
 class HyperbolicAttH(_HypDistBase):
@@ -397,8 +428,9 @@ class HyperbolicAttH(_HypDistBase):
         q, qss = self.query(entity_embedding, rel_embedding, triplets)
         return self._dist_scores(q, qss, entity_embedding.contiguous(), None, triplets)
 
-    def loss(self, *a, **k):
-        raise NotImplementedError("streaming-CE training head of the hyperbolic decoders is SURVEY.md 8f rank 1 (next)")
+    def loss(self, entity_embedding, rel_embedding, triplets):
+        """hyperbolic_decoder.py:1464-1512: scalar cross entropy over all candidates, with gradients (no (B,N) logits)."""
+        return self._train_loss("atth_ent_loss", entity_embedding, rel_embedding, triplets)
 
 
 class HyperbolicAttHRel(_HypDistBase):
@@ -441,5 +473,6 @@ class HyperbolicAttHRel(_HypDistBase):
         S = ops.gemm(q, rel_hyp, trans_b=True)
         return ops.hyp_score_epilogue_(S, qss, rss, self.rel_bias.detach(), None, self.c, self._scale_margin())
 
-    def loss(self, *a, **k):
-        raise NotImplementedError("streaming-CE training head of the hyperbolic decoders is SURVEY.md 8f rank 1 (next)")
+    def loss(self, entity_embedding, rel_embedding, triplets):
+        """hyperbolic_decoder.py:1641-1700: scalar cross entropy over all candidates, with gradients (no (B,N) logits)."""
+        return self._train_loss("atth_rel_loss", entity_embedding, rel_embedding, triplets)

@@ -528,34 +528,42 @@ def _curv_args(dec):
     return (raw, (dec.num_relations, dec.rel_curvature_max)) if raw is not None else (None, None)
 
 
-def murp_losses(model, pre, r_emb, all_t):
-    """HyperbolicMuRP.loss / HyperbolicMuRPRel.loss (hyperbolic_decoder.py:781-817, 897-928)."""
-    c = model._c_float
-    dec, rdec = model.decoder_ob, model.rdecoder
+def murp_ent_loss(dec, pre, r_emb, all_t, c, training):
+    """HyperbolicMuRP.loss (hyperbolic_decoder.py:781-817)."""
     s32 = all_t[:, 0].to(torch.int32).contiguous()
     r32 = all_t[:, 1].to(torch.int32).contiguous()
     o32 = all_t[:, 2].to(torch.int32).contiguous()
-    loss_ent = torch.zeros(1, device=pre.device)
-    loss_rel = torch.zeros(1, device=pre.device)
-    if model.entity_prediction:
-        s_emb = radial(_GatherRows.apply(pre, s32), PROJECT, c)
-        rot = _GatherRows.apply(T.linear(r_emb, dec.rot_proj.weight, dec.rot_proj.bias), r32)
-        st = dropout(radial(s_emb, LOG0, c), float(dec.dropout.p), model.training)
-        rs = radial(radial(_Mul.apply(rot, st), EXP0, c), PROJECT, c)
-        tr = _GatherRows.apply(T.linear(r_emb, dec.trans_proj.weight, dec.trans_proj.bias), r32)
-        tr = radial(radial(tr, EXP0, c), PROJECT, c)
-        q = radial(_Mobius.apply(rs, tr, c), PROJECT, c)
-        scale = torch.nn.functional.softplus(dec.score_scale_raw) + 1e-6          # two scalars: host-side glue
-        loss_ent = _HypDistCE.apply(q, pre, dec.entity_bias, scale, dec.score_margin, all_t, 2, c, *_curv_args(dec))
-    if model.relation_prediction:
-        p = float(rdec.dropout.p)
-        st = dropout(radial(_GatherRows.apply(pre, s32), LOG0, c), p, model.training)
-        ot = dropout(radial(_GatherRows.apply(pre, o32), LOG0, c), p, model.training)
-        q_tan = T.linear(torch.cat((st, ot), dim=1), torch.cat((rdec.W_s, rdec.W_o), dim=0), None, True)
-        q = radial(q_tan, EXP0, c)
-        one = torch.ones((), device=pre.device)
-        loss_rel = _HypDistCE.apply(q, radial(r_emb, EXP0, c), rdec.rel_bias, one, one * 0.0, all_t, 1, c)
-    return loss_ent, loss_rel
+    s_emb = radial(_GatherRows.apply(pre, s32), PROJECT, c)
+    rot = _GatherRows.apply(T.linear(r_emb, dec.rot_proj.weight, dec.rot_proj.bias), r32)
+    st = dropout(radial(s_emb, LOG0, c), float(dec.dropout.p), training)
+    rs = radial(radial(_Mul.apply(rot, st), EXP0, c), PROJECT, c)
+    tr = _GatherRows.apply(T.linear(r_emb, dec.trans_proj.weight, dec.trans_proj.bias), r32)
+    tr = radial(radial(tr, EXP0, c), PROJECT, c)
+    q = radial(_Mobius.apply(rs, tr, c), PROJECT, c)
+    scale = torch.nn.functional.softplus(dec.score_scale_raw) + 1e-6          # two scalars: host-side glue
+    return _HypDistCE.apply(q, pre, dec.entity_bias, scale, dec.score_margin, all_t, 2, c, *_curv_args(dec))
+
+
+def murp_rel_loss(rdec, pre, r_emb, all_t, c, training):
+    """HyperbolicMuRPRel.loss (hyperbolic_decoder.py:897-928)."""
+    s32 = all_t[:, 0].to(torch.int32).contiguous()
+    r32 = all_t[:, 1].to(torch.int32).contiguous()
+    o32 = all_t[:, 2].to(torch.int32).contiguous()
+    p = float(rdec.dropout.p)
+    st = dropout(radial(_GatherRows.apply(pre, s32), LOG0, c), p, training)
+    ot = dropout(radial(_GatherRows.apply(pre, o32), LOG0, c), p, training)
+    q_tan = T.linear(torch.cat((st, ot), dim=1), torch.cat((rdec.W_s, rdec.W_o), dim=0), None, True)
+    q = radial(q_tan, EXP0, c)
+    one = torch.ones((), device=pre.device)
+    return _HypDistCE.apply(q, radial(r_emb, EXP0, c), rdec.rel_bias, one, one * 0.0, all_t, 1, c)
+
+
+def murp_losses(model, pre, r_emb, all_t):
+    """HyperbolicMuRP.loss / HyperbolicMuRPRel.loss (hyperbolic_decoder.py:781-817, 897-928)."""
+    zero = torch.zeros(1, device=pre.device)
+    c = model._c_float
+    return (murp_ent_loss(model.decoder_ob, pre, r_emb, all_t, c, model.training) if model.entity_prediction else zero,
+            murp_rel_loss(model.rdecoder, pre, r_emb, all_t, c, model.training) if model.relation_prediction else zero)
 
 
 class _Givens(torch.autograd.Function):
@@ -603,34 +611,43 @@ def _reshape_tangent(dec, x):
     return _Add.apply(x, T.linear(h1, dec.reshape_fc2.weight, dec.reshape_fc2.bias))
 
 
-def roth_losses(model, pre, r_emb, all_t):
-    """HyperbolicRotH.loss / HyperbolicRotHRel.loss (hyperbolic_decoder.py:1101-1138, 1264-1280)."""
-    c = model._c_float
-    dec, rdec = model.decoder_ob, model.rdecoder
+def roth_ent_loss(dec, pre, r_emb, all_t, c, training):
+    """HyperbolicRotH.loss (hyperbolic_decoder.py:1101-1138)."""
     s32 = all_t[:, 0].to(torch.int32).contiguous()
     r32 = all_t[:, 1].to(torch.int32).contiguous()
     o32 = all_t[:, 2].to(torch.int32).contiguous()
-    loss_ent = torch.zeros(1, device=pre.device)
-    loss_rel = torch.zeros(1, device=pre.device)
     sp = torch.nn.functional.softplus
-    if model.entity_prediction:
-        st = radial(radial(_GatherRows.apply(pre, s32), PROJECT, c), LOG0, c)
-        st = _reshape_tangent(dec, dropout(st, float(dec.dropout.p), model.training))
-        ang = _GatherRows.apply(T.linear(r_emb, dec.rot_proj.weight, dec.rot_proj.bias), r32)
-        rs = radial(radial(_Givens.apply(st, ang, 0), EXP0, c), PROJECT, c)
-        tr = _GatherRows.apply(T.linear(r_emb, dec.trans_proj.weight, dec.trans_proj.bias), r32)
-        tr = radial(radial(tr, EXP0, c), PROJECT, c)
-        q = radial(_Mobius.apply(rs, tr, c), PROJECT, c)
-        loss_ent = _HypDistCE.apply(q, pre, dec.entity_bias, sp(dec.score_scale_raw) + 1e-6, dec.score_margin, all_t, 2, c,
-                                    *_curv_args(dec))
-    if model.relation_prediction:
-        st = radial(_GatherRows.apply(pre, s32), LOG0, c)
-        st = _reshape_tangent(rdec, dropout(st, float(rdec.dropout.p), model.training))
-        rs = eltwise(radial(_Givens.apply(st, rdec.global_rot, 0), EXP0, c), 2, 0.0)          # -exp_0(rot)
-        q = radial(_Mobius.apply(rs, _GatherRows.apply(pre, o32), c), PROJECT, c)
-        loss_rel = _HypDistCE.apply(q, radial(r_emb, EXP0, c), rdec.rel_bias, sp(rdec.score_scale_raw) + 1e-6,
-                                    rdec.score_margin, all_t, 1, c)
-    return loss_ent, loss_rel
+    st = radial(radial(_GatherRows.apply(pre, s32), PROJECT, c), LOG0, c)
+    st = _reshape_tangent(dec, dropout(st, float(dec.dropout.p), training))
+    ang = _GatherRows.apply(T.linear(r_emb, dec.rot_proj.weight, dec.rot_proj.bias), r32)
+    rs = radial(radial(_Givens.apply(st, ang, 0), EXP0, c), PROJECT, c)
+    tr = _GatherRows.apply(T.linear(r_emb, dec.trans_proj.weight, dec.trans_proj.bias), r32)
+    tr = radial(radial(tr, EXP0, c), PROJECT, c)
+    q = radial(_Mobius.apply(rs, tr, c), PROJECT, c)
+    return _HypDistCE.apply(q, pre, dec.entity_bias, sp(dec.score_scale_raw) + 1e-6, dec.score_margin, all_t, 2, c,
+                                *_curv_args(dec))
+
+
+def roth_rel_loss(rdec, pre, r_emb, all_t, c, training):
+    """HyperbolicRotHRel.loss (hyperbolic_decoder.py:1249-1280)."""
+    s32 = all_t[:, 0].to(torch.int32).contiguous()
+    r32 = all_t[:, 1].to(torch.int32).contiguous()
+    o32 = all_t[:, 2].to(torch.int32).contiguous()
+    sp = torch.nn.functional.softplus
+    st = radial(_GatherRows.apply(pre, s32), LOG0, c)
+    st = _reshape_tangent(rdec, dropout(st, float(rdec.dropout.p), training))
+    rs = eltwise(radial(_Givens.apply(st, rdec.global_rot, 0), EXP0, c), 2, 0.0)          # -exp_0(rot)
+    q = radial(_Mobius.apply(rs, _GatherRows.apply(pre, o32), c), PROJECT, c)
+    return _HypDistCE.apply(q, radial(r_emb, EXP0, c), rdec.rel_bias, sp(rdec.score_scale_raw) + 1e-6,
+                                rdec.score_margin, all_t, 1, c)
+
+
+def roth_losses(model, pre, r_emb, all_t):
+    """HyperbolicRotH.loss / HyperbolicRotHRel.loss (hyperbolic_decoder.py:1101-1138, 1264-1280)."""
+    zero = torch.zeros(1, device=pre.device)
+    c = model._c_float
+    return (roth_ent_loss(model.decoder_ob, pre, r_emb, all_t, c, model.training) if model.entity_prediction else zero,
+            roth_rel_loss(model.rdecoder, pre, r_emb, all_t, c, model.training) if model.relation_prediction else zero)
 
 
 class _AttnMix(torch.autograd.Function):
@@ -659,43 +676,56 @@ class _AttnMix(torch.autograd.Function):
         return (T._col_sum(dw) if ctx.bcast else dw), du, drot, dref
 
 
-def atth_losses(model, pre, r_emb, all_t):
-    """HyperbolicAttH.loss / HyperbolicAttHRel.loss (hyperbolic_decoder.py:1482-1512, 1642-1700)."""
-    c = model._c_float
-    dec, rdec = model.decoder_ob, model.rdecoder
+def atth_ent_loss(dec, pre, r_emb, all_t, c, training):
+    """HyperbolicAttH.loss (hyperbolic_decoder.py:1464-1512)."""
     s32 = all_t[:, 0].to(torch.int32).contiguous()
     r32 = all_t[:, 1].to(torch.int32).contiguous()
     o32 = all_t[:, 2].to(torch.int32).contiguous()
-    loss_ent = torch.zeros(1, device=pre.device)
-    loss_rel = torch.zeros(1, device=pre.device)
     sp = torch.nn.functional.softplus
 
     def table(lin):
         return _GatherRows.apply(T.linear(r_emb, lin.weight, lin.bias), r32)
 
-    if model.entity_prediction:
-        st = dropout(radial(radial(_GatherRows.apply(pre, s32), PROJECT, c), LOG0, c), float(dec.dropout.p), model.training)
-        rel_r = _GatherRows.apply(r_emb, r32)
-        rot = _Givens.apply(st, table(dec.rot_proj), 0)
-        ref = _Givens.apply(st, table(dec.ref_proj), 1)
-        mixed = _AttnMix.apply(table(dec.attn_proj), torch.cat((st, rel_r), dim=1), rot, ref)
-        mh = radial(radial(mixed, EXP0, c), PROJECT, c)
-        tr = radial(radial(table(dec.trans_proj), EXP0, c), PROJECT, c)
-        q = radial(_Mobius.apply(mh, tr, c), PROJECT, c)
-        loss_ent = _HypDistCE.apply(q, pre, dec.entity_bias, sp(dec.score_scale_raw) + 1e-6, dec.score_margin, all_t, 2, c,
-                                    *_curv_args(dec))
-    if model.relation_prediction:
-        o_emb = _GatherRows.apply(pre, o32)
-        st = dropout(radial(_GatherRows.apply(pre, s32), LOG0, c), float(rdec.dropout.p), model.training)
-        ot = radial(o_emb, LOG0, c)
-        rot = _Givens.apply(st, rdec.global_rot, 0)
-        ref = _Givens.apply(st, rdec.global_ref, 1)
-        mixed = _AttnMix.apply(rdec.attn_weight, torch.cat((st, ot), dim=1), rot, ref)
-        mh = eltwise(radial(mixed, EXP0, c), 2, 0.0)
-        q = radial(_Mobius.apply(mh, o_emb, c), PROJECT, c)
-        loss_rel = _HypDistCE.apply(q, radial(r_emb, EXP0, c), rdec.rel_bias, sp(rdec.score_scale_raw) + 1e-6,
-                                    rdec.score_margin, all_t, 1, c)
-    return loss_ent, loss_rel
+    st = dropout(radial(radial(_GatherRows.apply(pre, s32), PROJECT, c), LOG0, c), float(dec.dropout.p), training)
+    rel_r = _GatherRows.apply(r_emb, r32)
+    rot = _Givens.apply(st, table(dec.rot_proj), 0)
+    ref = _Givens.apply(st, table(dec.ref_proj), 1)
+    mixed = _AttnMix.apply(table(dec.attn_proj), torch.cat((st, rel_r), dim=1), rot, ref)
+    mh = radial(radial(mixed, EXP0, c), PROJECT, c)
+    tr = radial(radial(table(dec.trans_proj), EXP0, c), PROJECT, c)
+    q = radial(_Mobius.apply(mh, tr, c), PROJECT, c)
+    return _HypDistCE.apply(q, pre, dec.entity_bias, sp(dec.score_scale_raw) + 1e-6, dec.score_margin, all_t, 2, c,
+                                *_curv_args(dec))
+
+
+def atth_rel_loss(rdec, pre, r_emb, all_t, c, training):
+    """HyperbolicAttHRel.loss (hyperbolic_decoder.py:1641-1700)."""
+    s32 = all_t[:, 0].to(torch.int32).contiguous()
+    r32 = all_t[:, 1].to(torch.int32).contiguous()
+    o32 = all_t[:, 2].to(torch.int32).contiguous()
+    sp = torch.nn.functional.softplus
+
+    def table(lin):
+        return _GatherRows.apply(T.linear(r_emb, lin.weight, lin.bias), r32)
+
+    o_emb = _GatherRows.apply(pre, o32)
+    st = dropout(radial(_GatherRows.apply(pre, s32), LOG0, c), float(rdec.dropout.p), training)
+    ot = radial(o_emb, LOG0, c)
+    rot = _Givens.apply(st, rdec.global_rot, 0)
+    ref = _Givens.apply(st, rdec.global_ref, 1)
+    mixed = _AttnMix.apply(rdec.attn_weight, torch.cat((st, ot), dim=1), rot, ref)
+    mh = eltwise(radial(mixed, EXP0, c), 2, 0.0)
+    q = radial(_Mobius.apply(mh, o_emb, c), PROJECT, c)
+    return _HypDistCE.apply(q, radial(r_emb, EXP0, c), rdec.rel_bias, sp(rdec.score_scale_raw) + 1e-6,
+                                rdec.score_margin, all_t, 1, c)
+
+
+def atth_losses(model, pre, r_emb, all_t):
+    """HyperbolicAttH.loss / HyperbolicAttHRel.loss (hyperbolic_decoder.py:1482-1512, 1642-1700)."""
+    zero = torch.zeros(1, device=pre.device)
+    c = model._c_float
+    return (atth_ent_loss(model.decoder_ob, pre, r_emb, all_t, c, model.training) if model.entity_prediction else zero,
+            atth_rel_loss(model.rdecoder, pre, r_emb, all_t, c, model.training) if model.relation_prediction else zero)
 
 
 def hyp_get_loss(model, glist, triples, static_graph=None):

@@ -481,3 +481,43 @@ def test_skip_connect_flag_is_inert_for_uvrgcn():
     le, lr_, ls = m.get_loss(glist, triples, None, True)
     (0.7 * le + 0.3 * lr_ + ls).backward()
     assert m.rgcn.layers[1].skip_connect_weight.grad is None and m.rgcn.layers[1].skip_connect_bias.grad is None
+
+
+@pytest.mark.parametrize("which", ["decoder_ob", "rdecoder"])
+def test_decoder_forward_in_train_mode_carries_gradients(which):
+    """ConvTransE / ConvTransR called directly in train() mode (src/decoder.py:78-100, 29-52 with batch-statistics
+    BatchNorm): the (B, N) / (B, 2R) score matrix and the gradients a caller's own loss sends through it."""
+    R._lib.require_device()
+    case = synth.make_case("tiny", 6)
+    n, r = case["num_ents"], case["num_rels"]
+    m, sd = _decoder_pair(n, r, 6)
+    mod = getattr(m, which).train()
+    rng = np.random.default_rng(8)
+    d = 200
+    emb = rng.standard_normal((n, d))
+    rel = rng.standard_normal((2 * r, d)) * 0.3
+    all_t = restate.add_inverse(case["test"], r)
+    ed, rd = _leaf(emb), _leaf(rel)
+    score = mod(ed, rd, torch.from_numpy(all_t).to(DEV), mode="train")
+    assert score.requires_grad and score.shape == (len(all_t), n if which == "decoder_ob" else 2 * r)
+    w = rng.standard_normal(tuple(score.shape))
+    (score * torch.as_tensor(w, dtype=torch.float32, device=DEV)).sum().backward()
+    P = {k: v.clone().double() for k, v in sd.items() if v.is_floating_point()}
+    names = [k for k in P if k.startswith(which + ".") and "running" not in k and ".bn3." not in k and ".bn_init." not in k
+             and not k.endswith(".b")]
+    for k in names:
+        P[k].requires_grad_(True)
+    ec = torch.tensor(emb, dtype=torch.float64, requires_grad=True)
+    rc = torch.tensor(rel, dtype=torch.float64, requires_grad=True)
+    tt = torch.as_tensor(all_t)
+    ea = torch.tanh(ec)
+    if which == "decoder_ob":
+        sc = restate.conv_tower_train(ea[tt[:, 0]], rc[tt[:, 1]], P, which + ".", {}) @ ea.t()
+    else:
+        sc = restate.conv_tower_train(ea[tt[:, 0]], ea[tt[:, 2]], P, which + ".", {}) @ rc.t()
+    (sc * torch.as_tensor(w)).sum().backward()
+    ok, worst = close(score.detach().cpu().numpy(), sc.detach().numpy(), rtol=2e-4)
+    assert ok, worst
+    mine = [ed.grad, rd.grad] + [dict(m.named_parameters())[k].grad for k in names]
+    assert all(g is not None for g in mine)
+    _cmp_grads(mine, [ec.grad, rc.grad] + [P[k].grad for k in names], ["d emb", "d rel"] + names)

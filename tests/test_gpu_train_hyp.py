@@ -204,3 +204,90 @@ def test_distance_decoder_nodes_backward():
     ok, worst = close(z.detach().cpu().numpy(), zc.detach().numpy())
     assert ok, worst
     _cmp([xd.grad, yd.grad, Ed.grad], [xc.grad, yc.grad, Ec.grad], ["mobius dx", "mobius dy", "gather dE"])
+
+
+@pytest.mark.parametrize("decoder", ["murp", "roth", "atth"])
+def test_decoder_loss_methods_match_oracle(decoder):
+    """The decoders' own training heads -- Hyperbolic{MuRP,RotH,AttH}.loss and ...Rel.loss
+    (hyperbolic_src/hyperbolic_decoder.py:781,897,1101,1249,1464,1641) -- called directly on an entity / relation table:
+    the scalar and its gradients w.r.t. the entity table and every decoder parameter against autograd on the oracle."""
+    R._lib.require_device()
+    cfg = dict(kind="hyp", shape="tiny", seed=31, encoder="hyperbolic_uvrgcn", decoder=decoder, layer_norm=False,
+               gamma=0.15, entity_bias=True)
+    case = synth.make_case(cfg["shape"], cfg["seed"])
+    n, r = case["num_ents"], case["num_rels"]
+    m, sd = build_hyp_train_model(cfg, n, r)
+    m = m.to(DEV).train()
+    rng = np.random.default_rng(5)
+    emb = rng.standard_normal((n, 200)) * rng.uniform(0.05, 0.4, size=(n, 1))
+    rel = rng.standard_normal((2 * r, 200)) * 0.3
+    t = case["test"]
+    inv = t[:, ::-1].copy()
+    inv[:, 1] += r
+    all_t = np.concatenate([t, inv]).astype(np.int64)
+    ed, rd = _leaf(emb), _leaf(rel)
+    le = m.decoder_ob.loss(ed, rd, torch.from_numpy(all_t).to(DEV))
+    lr_ = m.rdecoder.loss(ed, rd, torch.from_numpy(all_t).to(DEV))
+    assert le.dim() == 0 and lr_.dim() == 0
+    (le + 0.5 * lr_).backward()
+    P = {k: v.detach().double().requires_grad_(True) for k, v in sd.items() if v.is_floating_point()}
+    ec = torch.tensor(emb, dtype=torch.float64, requires_grad=True)
+    rc = torch.tensor(rel, dtype=torch.float64, requires_grad=True)
+    ent_fn, rel_fn = {"murp": (restate.murp_scores, restate.murprel_scores),
+                      "roth": (restate.roth_scores, restate.rothrel_scores),
+                      "atth": (restate.atth_scores, restate.atthrel_scores)}[decoder]
+    tt = torch.from_numpy(all_t)
+    sc = ent_fn(P, ec, rc, all_t, CURV)[0] - P["decoder_ob.entity_bias"][tt[:, 0]].unsqueeze(1)
+    lec = restate.cross_entropy(sc, tt[:, 2])
+    lrc = restate.cross_entropy(rel_fn(P, ec, rc, all_t, CURV)[0], tt[:, 1])
+    (lec + 0.5 * lrc).backward()
+    for mine, ref in ((le, lec), (lr_, lrc)):
+        assert abs(float(mine.detach()) - float(ref.detach())) <= 1e-4 * max(1.0, abs(float(ref.detach())))
+    names = [k for k, p in m.named_parameters() if k.startswith(("decoder_ob.", "rdecoder.")) and p.grad is not None]
+    assert names and all(P[k].grad is not None for k in names)
+    params = dict(m.named_parameters())
+    _cmp([ed.grad, rd.grad] + [params[k].grad.reshape(P[k].shape) for k in names],
+         [ec.grad, rc.grad] + [P[k].grad for k in names], ["dE", "drel"] + names)
+
+
+@pytest.mark.parametrize("which", ["decoder_ob", "rdecoder"])
+def test_hyperbolic_convtrans_forward_in_train_mode(which):
+    """HyperbolicConvTransE / ConvTransR called directly in train() mode (hyperbolic_src/hyperbolic_decoder.py:360-413,
+    464-510): scores with the candidate bias, and the gradients of a caller's loss through them."""
+    R._lib.require_device()
+    cfg = dict(kind="hyp", shape="tiny", seed=33, encoder="hyperbolic_uvrgcn", decoder="hyperbolic_convtranse",
+               layer_norm=False, gamma=0.15)
+    case = synth.make_case(cfg["shape"], cfg["seed"])
+    n, r = case["num_ents"], case["num_rels"]
+    m, sd = build_hyp_train_model(cfg, n, r)
+    m = m.to(DEV).train()
+    mod = getattr(m, which)
+    rng = np.random.default_rng(9)
+    emb = rng.standard_normal((n, 200)) * rng.uniform(0.05, 0.4, size=(n, 1))
+    rel = rng.standard_normal((2 * r, 200)) * 0.3
+    all_t = restate.add_inverse(case["test"], r)
+    ed, rd = _leaf(emb), _leaf(rel)
+    score = mod(ed, rd, torch.from_numpy(all_t).to(DEV), mode="train")
+    assert score.requires_grad
+    w = rng.standard_normal(tuple(score.shape))
+    (score * torch.as_tensor(w, dtype=torch.float32, device=DEV)).sum().backward()
+    P = {k: v.clone().double() for k, v in sd.items() if v.is_floating_point()}
+    names = [k for k in P if k.startswith(which + ".") and "running" not in k and ".bn3." not in k and ".bn_init." not in k]
+    for k in names:
+        P[k].requires_grad_(True)
+    ec = torch.tensor(emb, dtype=torch.float64, requires_grad=True)
+    rc = torch.tensor(rel, dtype=torch.float64, requires_grad=True)
+    tt = torch.as_tensor(all_t)
+    et = restate.log0(ec, CURV)
+    et = 0.9 * torch.tanh(et) + 0.1 * et
+    if which == "decoder_ob":
+        sc = restate.conv_tower_train(et[tt[:, 0]], rc[tt[:, 1]], P, which + ".", {}) @ et.t() + P[which + ".b"]
+    else:
+        sc = restate.conv_tower_train(et[tt[:, 0]], et[tt[:, 2]], P, which + ".", {}) @ rc.t() + P[which + ".b"]
+    (sc * torch.as_tensor(w)).sum().backward()
+    ok, worst = close(score.detach().cpu().numpy(), sc.detach().numpy(), rtol=2e-4)
+    assert ok, worst
+    params = dict(m.named_parameters())
+    mine = [ed.grad, rd.grad] + [params[k].grad for k in names]
+    assert all(g is not None for g in mine), [k for k, g in zip(["dE", "drel"] + names, mine) if g is None]
+    _cmp(mine, [ec.grad, rc.grad] + [P[k].grad for k in names], ["dE", "drel"] + names)
