@@ -61,8 +61,25 @@ class UnionRGCNLayer(nn.Module):
             self._loop_cat_key = key
         return self._loop_cat_val
 
+    def _forward_train(self, g, emb_rel):
+        """train() mode with gradients and dropout: the kernel-backed autograd nodes RecurrentRGCN's training path uses
+        (regcn_b200/train.py), for a caller that drives the layer itself (rgcn/layers.py:222-255)."""
+        from . import train as T
+        with torch.enable_grad():
+            h = g.ndata['h']
+            p = float(self.dropout.p) if self.dropout is not None else 0.0
+            P = T.linear(T.union_aggregate(h, emb_rel, g), self.weight_neighbor, None, True)
+            L = T.linear(h, torch.cat((self.loop_weight, self.evolve_loop_weight), dim=1), None, True)
+            out = T.union_combine(P, L, g, p)
+        g.ndata['h'] = out
+        return out
+
     @torch.no_grad()
     def forward(self, g, prev_h, emb_rel):
+        if (self.training and self.self_loop and self.activation is F.rrelu
+                and not (len(prev_h) != 0 and self.skip_connect)):
+            self.rel_emb = emb_rel
+            return self._forward_train(g, emb_rel)
         _no_train_dropout(self)
         self.rel_emb = emb_rel
         h = g.ndata['h']

@@ -211,8 +211,23 @@ def test_layer_signatures_drop_in():
     ref = restate.block_layer(h.double(), o, blk.weight.detach().cpu().double(), 100, d)
     ok, worst = close(out.cpu().numpy(), ref.numpy())
     assert ok, worst
+    # train() mode: the layer runs on the kernel-backed autograd nodes (dropout 0.2 applied, gradients flow); with a LIVE
+    # skip gate (prev_h given) it refuses loudly instead of silently skipping the dropout
+    hd = h.to(DEV).requires_grad_(True)
+    g.ndata['h'] = hd
+    out_t = layer.train()(g, [], rel.to(DEV))
+    assert out_t.requires_grad and g.ndata['h'] is out_t
+    zeros = float((out_t == 0).float().mean())
+    assert 0.15 < zeros < 0.25, zeros
+    kept = out_t != 0
+    g.ndata['h'] = h.to(DEV)
+    out_e = layer.eval()(g, [], rel.to(DEV))
+    assert torch.allclose(out_t.detach()[kept], out_e[kept] / 0.8, rtol=1e-5, atol=1e-6)
+    out_t.sum().backward()
+    assert hd.grad is not None and layer.weight_neighbor.grad is not None and layer.loop_weight.grad is not None
+    g.ndata['h'] = h.to(DEV)
     with pytest.raises(NotImplementedError):
-        layer.train()(g, [], rel.to(DEV))        # training-mode dropout is refused loudly, never silently skipped
+        layer.train()(g, prev.to(DEV), rel.to(DEV))
 
 
 @pytest.mark.parametrize("kind", ["regcn", "hyp_uv_roth", "hyp_uv_convtranse", "hyp_lgcn_murp", "hyp_uv_roth_flags",
