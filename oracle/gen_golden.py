@@ -358,6 +358,8 @@ HYP_TRAIN_CASES = {
                                            layer_norm=False, gamma=0.15, static=dict(discount=0, angle=10, weight=1.0)),
     "hyptrain_skip_tiny_s15": dict(kind="hyp", shape="tiny", seed=15, encoder="hyperbolic_uvrgcn",
                                    decoder="hyperbolic_convtranse", layer_norm=True, gamma=0.15, skip_connect=True),
+    "hyptrain_lgcn_skip_small_s16": dict(kind="hyp", shape="small_l", seed=16, encoder="lgcn", decoder="roth",
+                                         layer_norm=True, gamma=0.15, skip_connect=True),
     "hyptrain_lgcn_roth_small_s9": dict(kind="hyp", shape="small_l", seed=9, encoder="lgcn", decoder="roth",
                                         layer_norm=False, gamma=0.15),
     "hyptrain_lgcn_convtranse_small_s10_ln": dict(kind="hyp", shape="small_l", seed=10, encoder="lgcn",
@@ -388,14 +390,16 @@ def run_hyp_train(ref_utils, HyperbolicRecurrentRGCN):
                                     use_relation_specific_curvature=cfg.get("rel_curvature", False))
         m.load_state_dict(synth.fill_state_dict(m.state_dict(), cfg["seed"]))
         glist = [ref_utils.build_sub_graph(n, r, snap, False, "cpu") for snap in case["history"]]
-        if st_cfg:
+        if st_cfg or cfg.get("skip_connect"):
             m.eval()
             with torch.no_grad():
                 _, score, score_rel = m.predict(glist, r, sg, torch.from_numpy(case["test"]), False)
                 hist, static_emb, _, _, _ = m.forward(glist, sg, False)
                 ev = m.get_loss(glist, torch.from_numpy(case["test"]).clone(), sg, False)
             out[f"{name}.score"], out[f"{name}.score_rel"] = score.numpy(), score_rel.numpy()
-            out[f"{name}.static_emb"], out[f"{name}.hist_last"] = static_emb.numpy(), hist[-1].numpy()
+            out[f"{name}.hist_last"] = hist[-1].numpy()
+            if static_emb is not None:
+                out[f"{name}.static_emb"] = static_emb.numpy()
             out[f"{name}.eval_losses"] = np.array([float(x.reshape(-1)[0]) for x in ev], dtype=np.float64)
         m.train()
         opt = torch.optim.Adam(m.parameters(), lr=LR, weight_decay=WEIGHT_DECAY)

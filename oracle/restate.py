@@ -403,8 +403,9 @@ def hyp_union_layer(h_hyper, rel, g, w_n, w_loop, w_evolve, c, gamma):
     return exp0(h_new, c)                                                        # :321
 
 
-def lorentz_layer(h_hyper, rel, g, weight, w_loop, w_evolve, c, num_bases):
-    """hyperbolic_layers.py:589-694 (LorentzRGCNLayer, no skip connection, rrelu, eval)."""
+def lorentz_layer(h_hyper, rel, g, weight, w_loop, w_evolve, c, num_bases, skip=None, prev_h=None):
+    """hyperbolic_layers.py:589-694 (LorentzRGCNLayer, rrelu, eval).  skip = (skip_weight, skip_bias) with prev_h = the
+    previous layer's INPUT (hyperbolic_layers.py:657-662, 675-678, cell :737-740)."""
     n, d = h_hyper.shape
     nb = num_bases
     sb = d // nb
@@ -430,6 +431,10 @@ def lorentz_layer(h_hyper, rel, g, weight, w_loop, w_evolve, c, num_bases):
     if w_loop is not None:
         has_in = torch.as_tensor(g["indeg"] > 0).view(-1, 1)
         h_new = h_new + torch.where(has_in, ht @ w_loop, ht @ w_evolve)          # :649-655, :681
+    if skip is not None and prev_h is not None:
+        pt = log0(prev_h, c)
+        gate = torch.sigmoid(pt @ skip[0] + skip[1])
+        h_new = gate * h_new + (1 - gate) * pt                                   # :678
     h_new = rrelu(h_new.clamp(-10.0, 10.0))                                      # :683-687
     return exp0(h_new, c)                                                        # :694
 
@@ -458,6 +463,7 @@ def hyp_forward(p, graphs, num_rels, c=0.01, encoder="hyperbolic_uvrgcn", layer_
                       P["relation_gru.bias_ih"], P["relation_gru.bias_hh"])      # :815-824
         h0 = normalize_rows(h0) if layer_norm else h0
         cur = h
+        prev_in = None
         for l in range(n_layers):
             pre = f"rgcn.layers.{l}."
             wl = P.get(pre + "loop_weight") if self_loop else None
@@ -465,7 +471,8 @@ def hyp_forward(p, graphs, num_rels, c=0.01, encoder="hyperbolic_uvrgcn", layer_
             if encoder == "hyperbolic_uvrgcn":
                 cur = hyp_union_layer(cur, h0, g, P[pre + "weight_neighbor"], wl, we, c, gamma)
             elif encoder == "lgcn":
-                cur = lorentz_layer(cur, h0, g, P[pre + "weight"], wl, we, c, num_bases)
+                skip = (P[pre + "skip_weight"], P[pre + "skip_bias"]) if pre + "skip_weight" in P else None
+                cur, prev_in = lorentz_layer(cur, h0, g, P[pre + "weight"], wl, we, c, num_bases, skip, prev_in), cur
             else:
                 raise NotImplementedError(encoder)
             if trace is not None:

@@ -261,13 +261,19 @@ class _LorentzAggregate(torch.autograd.Function):
         return dht, dW, drel, None, None, None
 
 
-def lorentz_layer(layer, g, h_in, h0, c, training):
-    """LorentzRGCNLayer.forward (hyperbolic_layers.py:627-694; self_loop, no skip connection)."""
+def lorentz_layer(layer, g, h_in, h0, c, training, prev_h=None):
+    """LorentzRGCNLayer.forward (hyperbolic_layers.py:627-694; self_loop; skip gate when the cell hands over the
+    previous layer's input, :657-662,675-678)."""
     p = float(layer.dropout.p) if (layer.dropout is not None and training) else 0.0
     ht = radial(h_in, LOG0, c)
     agg = _LorentzAggregate.apply(ht, layer.weight, h0, g, layer.num_bases, c)
     L = T.linear(ht, torch.cat((layer.loop_weight, layer.evolve_loop_weight), dim=1), None, True)
-    t = eltwise(_SelectAdd.apply(agg, L, g), 0, 10.0)
+    t = _SelectAdd.apply(agg, L, g)
+    if layer.skip_connect and prev_h is not None:
+        pt = radial(prev_h, LOG0, c)
+        # sigmoid(pt W_s + b) * t + (1 - sigmoid) * pt: the time-gate node without its normalisation
+        t = T.time_gate(T.linear(pt, layer.skip_weight, None, True), layer.skip_bias, t, pt, False)
+    t = eltwise(t, 0, 10.0)
     t = T._RReluDrop.apply(t, p)
     return radial(t, EXP0, c)
 
@@ -276,9 +282,8 @@ def hyp_evolve(model, g_list, static_graph=None):
     """HyperbolicRecurrentRGCN.forward with the tape on (hyperbolic_model.py:762-890).  Returns (hist, h_0, static_emb)."""
     # --skip-connect: HyperbolicRGCNCell never passes prev_h (hyperbolic_src/hyperbolic_model.py:152), so the flag is
     # inert for hyperbolic_uvrgcn; LorentzRGCNCell does (hyperbolic_src/hyperbolic_layers.py:737-740)
-    if (model.encoder_name not in ("hyperbolic_uvrgcn", "lgcn") or any(not l.self_loop for l in model.rgcn.layers)
-            or (model.encoder_name == "lgcn" and any(l.skip_connect for l in model.rgcn.layers))):
-        raise NotImplementedError("regcn_b200.train_hyp: hyperbolic_uvrgcn / lgcn (without skip_connect) + self_loop")
+    if model.encoder_name not in ("hyperbolic_uvrgcn", "lgcn") or any(not l.self_loop for l in model.rgcn.layers):
+        raise NotImplementedError("regcn_b200.train_hyp: hyperbolic_uvrgcn / lgcn with self_loop")
     if model.encoder_name == "lgcn" and any(2 * l.num_bases != model.h_dim for l in model.rgcn.layers):
         raise NotImplementedError("regcn_b200.train_hyp: the lgcn encoder trains with 2x2 relation blocks (num_bases = h_dim/2, "
                                   "the reference's 100 bases at h_dim 200)")
@@ -305,8 +310,12 @@ def hyp_evolve(model, g_list, static_graph=None):
         gh = T.linear(hprev, cell.weight_hh, cell.bias_hh)
         h0 = T.gru_gate(gi, gh, hprev, model.layer_norm)
         cur = h
+        prev_in = None
         for layer in model.rgcn.layers:
-            cur = layer_fn(layer, g, cur, h0, c, model.training)
+            if model.encoder_name == "lgcn":
+                cur, prev_in = lorentz_layer(layer, g, cur, h0, c, model.training, prev_in), cur
+            else:
+                cur = layer_fn(layer, g, cur, h0, c, model.training)
         cur = radial(cur, PROJECT, c)
         if model.layer_norm:
             cur = radial(cur, TNORM, c)

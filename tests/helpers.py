@@ -166,6 +166,8 @@ HYP_TRAIN_CASES = {
                                            layer_norm=False, gamma=0.15, static=dict(discount=0, angle=10, weight=1.0)),
     "hyptrain_skip_tiny_s15": dict(kind="hyp", shape="tiny", seed=15, encoder="hyperbolic_uvrgcn",
                                    decoder="hyperbolic_convtranse", layer_norm=True, gamma=0.15, skip_connect=True),
+    "hyptrain_lgcn_skip_small_s16": dict(kind="hyp", shape="small_l", seed=16, encoder="lgcn", decoder="roth",
+                                         layer_norm=True, gamma=0.15, skip_connect=True),
     "hyptrain_lgcn_roth_small_s9": dict(kind="hyp", shape="small_l", seed=9, encoder="lgcn", decoder="roth",
                                         layer_norm=False, gamma=0.15),
     "hyptrain_lgcn_convtranse_small_s10_ln": dict(kind="hyp", shape="small_l", seed=10, encoder="lgcn",

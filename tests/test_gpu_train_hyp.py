@@ -137,16 +137,20 @@ def test_hyperbolic_train_step_matches_reference(name):
     m, _ = build_hyp_train_model(cfg, n, r)
     glist = [R.build_sub_graph(n, r, s, True, 0) for s in case["history"]]
     sg = None
-    if cfg.get("static"):
-        # --add-static-graph (hyperbolic_src/hyperbolic_model.py:762-771,1039-1064): eval outputs first
-        st, n_srel, n_words = synth.make_static(n, cfg["seed"])
-        sg = R.build_sub_graph(n + n_words, n_srel, st, True, 0)
+    if cfg.get("static") or cfg.get("skip_connect"):
+        # --add-static-graph (hyperbolic_src/hyperbolic_model.py:762-771,1039-1064) / --skip-connect: eval outputs first
+        if cfg.get("static"):
+            st, n_srel, n_words = synth.make_static(n, cfg["seed"])
+            sg = R.build_sub_graph(n + n_words, n_srel, st, True, 0)
         m = m.to(DEV).eval()
         triples = torch.from_numpy(case["test"]).to(DEV)
-        assert m._engine_ok()            # static initial table through the one-call evolve engine
+        # static initial table / inert skip flag through the one-call evolve engine; the live Lorentz skip gate
+        # (hyperbolic_src/hyperbolic_layers.py:657-678) on the per-layer path
+        assert m._engine_ok() == (not (cfg["encoder"] == "lgcn" and cfg.get("skip_connect")))
         _, score, score_rel = m.predict(glist, r, sg, triples, True)
         hist, static_emb, _, _, _ = m.forward(glist, sg, True)
-        for mine, key in ((static_emb, "static_emb"), (hist[-1], "hist_last"), (score, "score"), (score_rel, "score_rel")):
+        pairs = [(hist[-1], "hist_last"), (score, "score"), (score_rel, "score_rel")]
+        for mine, key in pairs + ([(static_emb, "static_emb")] if sg is not None else []):
             ok, worst = close(mine.cpu().numpy(), z[f"{name}.{key}"], rtol=2e-4 if "score" in key else 1e-4)
             assert ok, (key, worst)
         ev = m.get_loss(glist, triples, sg, True)
