@@ -53,6 +53,37 @@ def _split(x):
     return ops.split_tf32(x.contiguous())
 
 
+_wsplit_cache = {}
+
+
+def _split_w(W):
+    """TF32 split of a WEIGHT operand, shared by every use inside one optimisation step: the same matrix is the B
+    operand of L snapshots' forward GEMMs and of their dX GEMMs.  Keyed on (storage pointer, version, shape); the entry
+    keeps the tensor alive so the pointer cannot be recycled; `begin_step()` drops the table."""
+    key = (W.data_ptr(), W._version, tuple(W.shape), W.stride(0))
+    hit = _wsplit_cache.get(key)
+    if hit is None:
+        if len(_wsplit_cache) > 256:          # a caller that never reaches begin_step() (decoder.loss() on its own)
+            _wsplit_cache.clear()
+        hit = _wsplit_cache[key] = (W, _split(W))
+    return hit[1]
+
+
+def begin_step():
+    """Called by the get_loss entry points: weight splits of the previous step are stale after the optimiser update."""
+    _wsplit_cache.clear()
+
+
+def loop_cat(layer):
+    """[W_loop | W_evolve] (d, 2d) once per layer and step: one autograd node (and one TF32 split) shared by all
+    snapshots.  Only for callers that ran begin_step() (the get_loss entry points)."""
+    key = ("loop_cat", id(layer), layer.loop_weight._version, layer.evolve_loop_weight._version)
+    hit = _wsplit_cache.get(key)
+    if hit is None or hit[0] is not layer.loop_weight:          # the entry pins the parameter: ids cannot be recycled
+        hit = _wsplit_cache[key] = (layer.loop_weight, torch.cat((layer.loop_weight, layer.evolve_loop_weight), dim=1))
+    return hit[1]
+
+
 def _auto_split_k(M, N, K):
     tiles = ((M + 127) // 128) * ((N + 127) // 128)
     if K < 1024 or tiles >= 120:
@@ -107,7 +138,7 @@ class _Linear(torch.autograd.Function):
         if K % 4 or N % 4:
             raise ValueError("regcn_b200.train: matrix dimensions must be multiples of 4")
         xs = _split(x)
-        y = _mm(xs, _split(W), M, N, K, b_mn=w_kn, bias=None if bias is None else bias.contiguous())
+        y = _mm(xs, _split_w(W), M, N, K, b_mn=w_kn, bias=None if bias is None else bias.contiguous())
         ctx.save_for_backward(x, W)
         ctx.xs = xs                                   # the TF32 split of x is the A operand of dW again
         ctx.w_kn = w_kn
@@ -125,7 +156,7 @@ class _Linear(torch.autograd.Function):
         dys = _split(dy)
         if ctx.needs_input_grad[0]:
             # w_kn: dx = dy W^T, W (K, N) is already the K-major B operand;  F.linear: dx = dy W with W (N, K) as Y
-            dx = _mm(dys, _split(W), M, K, N, b_mn=not ctx.w_kn)
+            dx = _mm(dys, _split_w(W), M, K, N, b_mn=not ctx.w_kn)
         if ctx.needs_input_grad[1]:
             # dW = x^T dy (K, N)  /  dy^T x (N, K): both operands MN-major, reduction over the M rows
             dW = _mm(xs, dys, K, N, M, a_mn=True, b_mn=True) if ctx.w_kn else _mm(dys, xs, N, K, M, a_mn=True, b_mn=True)
@@ -619,6 +650,7 @@ def regcn_evolve(model, g_list, static_graph=None):
         h = normalize(model.dynamic_emb) if model.layer_norm else model.dynamic_emb
     h0 = None
     hist = []
+    loop_cats = [loop_cat(layer) for layer in model.rgcn.layers]
     for i, g in enumerate(g_list):
         x_mean = rel_mean_pool(h, g)
         x_cat = torch.cat((model.emb_rel, x_mean), dim=1)
@@ -627,11 +659,11 @@ def regcn_evolve(model, g_list, static_graph=None):
         gh = linear(hprev, cell.weight_hh, cell.bias_hh)
         h0 = gru_gate(gi, gh, hprev, model.layer_norm)
         cur = h
-        for layer in model.rgcn.layers:
+        for layer, lw in zip(model.rgcn.layers, loop_cats):
             p = float(layer.dropout.p) if (layer.dropout is not None and model.training) else 0.0
             agg = union_aggregate(cur, h0, g)
             P = linear(agg, layer.weight_neighbor, None, True)
-            L = linear(cur, torch.cat((layer.loop_weight, layer.evolve_loop_weight), dim=1), None, True)
+            L = linear(cur, lw, None, True)
             cur = union_combine(P, L, g, p)
         G = linear(h, model.time_gate_weight, None, True)
         h = time_gate(G, model.time_gate_bias, cur, h, model.layer_norm)
@@ -642,6 +674,7 @@ def regcn_evolve(model, g_list, static_graph=None):
 def regcn_get_loss(model, glist, triples, static_graph=None):
     """src/rrgcn.py:197-223 with gradients: (loss_ent, loss_rel, loss_static), each of shape (1,)."""
     _lib.require_device()
+    begin_step()
     if ops.gemm_impl() != "tc":
         raise RuntimeError("regcn_b200.train needs the tensor-core GEMM (REGCN_GEMM=tc)")
     dev = model.dynamic_emb.device

@@ -221,7 +221,7 @@ def hyp_union_layer(layer, g, h_in, h0, c, training):
     rho = radius(h_in)
     agg = _HypAggregate.apply(ht, h0, rho, g, float(layer.radius_msg_gamma))
     P = eltwise(T.linear(agg, layer.weight_neighbor, None, True), 0, 10.0)
-    L = T.linear(ht, torch.cat((layer.loop_weight, layer.evolve_loop_weight), dim=1), None, True)
+    L = T.linear(ht, T.loop_cat(layer), None, True)
     t = eltwise(_SelectAdd.apply(P, L, g), 0, 10.0)
     t = T._RReluDrop.apply(t, p)
     return radial(t, EXP0, c)
@@ -267,7 +267,7 @@ def lorentz_layer(layer, g, h_in, h0, c, training, prev_h=None):
     p = float(layer.dropout.p) if (layer.dropout is not None and training) else 0.0
     ht = radial(h_in, LOG0, c)
     agg = _LorentzAggregate.apply(ht, layer.weight, h0, g, layer.num_bases, c)
-    L = T.linear(ht, torch.cat((layer.loop_weight, layer.evolve_loop_weight), dim=1), None, True)
+    L = T.linear(ht, T.loop_cat(layer), None, True)
     t = _SelectAdd.apply(agg, L, g)
     if layer.skip_connect and prev_h is not None:
         pt = radial(prev_h, LOG0, c)
@@ -740,6 +740,7 @@ def atth_losses(model, pre, r_emb, all_t):
 def hyp_get_loss(model, glist, triples, static_graph=None):
     """hyperbolic_model.py:941-1088 with gradients: (loss_ent, loss_rel, loss_static, loss_radius), each (1,)."""
     _lib.require_device()
+    T.begin_step()
     if ops.gemm_impl() != "tc":
         raise RuntimeError("regcn_b200.train_hyp needs the tensor-core GEMM (REGCN_GEMM=tc)")
     if model.decoder_name not in ("hyperbolic_convtranse", "murp", "roth", "atth"):
