@@ -79,17 +79,33 @@ __device__ __forceinline__ void gather_span(WarpRow<RV>& acc, const float* __res
         w *= expf(-gamma * fabsf(__ldg(rho + c) - __ldg(rho + other)));
       }
     }
-    for (int k = 0; k < n; ++k) {
-      const int ck = __shfl_sync(0xffffffffu, c, k);
-      const float wk = __shfl_sync(0xffffffffu, w, k);
-      const float* xr = X + (size_t)ck * ldx;
+    // four gathered rows in flight per step: the loads of columns k..k+3 are issued before the first FMA (a row is
+    // an 800-byte L2/HBM access, so one load per iteration leaves the warp waiting a full memory latency per edge);
+    // the FMAs still run in CSR order, so the sum is bit-identical to the one-at-a-time loop
+    for (int k = 0; k < n; k += 4) {
+      float4 v[4][RV];
+      float wk[4];
 #pragma unroll
-      for (int i = 0; i < RV; ++i) {
-        const int cc = lane + i * kWarp;
-        if (cc < nvec) {
-          float4 v = *reinterpret_cast<const float4*>(xr + 4 * cc);
-          if (col2_off) v = f4_add(v, *reinterpret_cast<const float4*>(xr + (size_t)col2_off * ldx + 4 * cc));
-          acc.v[i] = f4_fma(wk, v, acc.v[i]);
+      for (int u = 0; u < 4; ++u) {
+        const int kk = min(k + u, n - 1);
+        const int ck = __shfl_sync(0xffffffffu, c, kk);
+        wk[u] = __shfl_sync(0xffffffffu, w, kk);
+        const float* xr = X + (size_t)ck * ldx;
+#pragma unroll
+        for (int i = 0; i < RV; ++i) {
+          const int cc = lane + i * kWarp;
+          v[u][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (cc < nvec) {
+            v[u][i] = *reinterpret_cast<const float4*>(xr + 4 * cc);
+            if (col2_off) v[u][i] = f4_add(v[u][i], *reinterpret_cast<const float4*>(xr + (size_t)col2_off * ldx + 4 * cc));
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (k + u < n) {
+#pragma unroll
+          for (int i = 0; i < RV; ++i) acc.v[i] = f4_fma(wk[u], v[u][i], acc.v[i]);
         }
       }
     }
