@@ -259,8 +259,30 @@ def workload_string(args):
     return f"{args.workload} {args.model}"
 
 
+_JSON_FD = None
+
+
+def _quiet_stdout():
+    """stdout carries exactly ONE JSON line: libraries that write to fd 1 (NCCL prints its version there at WARN/VERSION
+    level) are pointed at stderr for the whole run; emit() writes the line on the saved descriptor."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_JSON_FD, data)
+
+
 def main():
     args = parse()
+    _quiet_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -279,7 +301,7 @@ def main():
                 "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": cb["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch
@@ -291,8 +313,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (NCCL prints its version there)
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ.pop("NCCL_DEBUG")                # NCCL prints its version on stdout at VERSION and WARN level
         dist.init_process_group("nccl", device_id=dev)
     _lib.require_device()
     if args.gemm:
@@ -671,7 +693,7 @@ def main():
             line["train"] = train_line
         if train_hyp_line:
             line["train_hyperbolic"] = train_hyp_line
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
