@@ -179,6 +179,39 @@ REGCN_API void regcn_two_stream_enable(int on);
 REGCN_API long long regcn_kernel_launches(void);
 /* tuning knob for experiments: force the N tile (multiple of 16, <= 256; 0 = automatic) and cap the pipeline depth */
 REGCN_API void regcn_gemm_tf32_tune(int block_n, int stages);
+/* fp32-A variants of regcn_gemm_tf32 / regcn_gemm_tf32_layer: the A operand is ONE fp32 copy in memory,
+ *   A[m, :] = [ a0[rows0 ? rows0[m] : m, 0:k0] | a1[rows1 ? rows1[m] : m, 0:k1] ]      (k1 = 0: one segment)
+ * and is split into the TF32 (hi, lo) pair inside shared memory by converter warps of the GEMM kernel, bit-identically
+ * to regcn_split_tf32.  B stays a pre-split weight (N, k0 + k1), K-major.  k0, k1, lda0, lda1 multiples of 4, 16-byte
+ * aligned bases.  This is what the evolve engines use: activations exist once, as fp32 (torch.mm call sites of
+ * rgcn/layers.py:222-255, src/rrgcn.py:168-178). */
+REGCN_API int regcn_gemm_tf32_a32(const float* a0, int lda0, int k0, const int32_t* rows0, const float* a1, int lda1, int k1,
+                                  const int32_t* rows1, const float* b_hi, const float* b_lo, int ldb, float* C, int ldc,
+                                  int M, int N, const float* bias, int accumulate, int passes, int split_k, float* workspace,
+                                  size_t workspace_bytes, const float* addend, int ld_add, void* stream);
+REGCN_API int regcn_gemm_tf32_layer_a32(const float* a0, int lda0, int k0, const int32_t* rows0, const float* a1, int lda1,
+                                        int k1, const int32_t* rows1, const float* b_hi, const float* b_lo, int ldb, int M,
+                                        int N, int d, float* out_raw, float* out_hi, float* out_lo, float* gate_out,
+                                        int ld_gate_out, const int32_t* row_idx, const int32_t* skip_rows,
+                                        const float* gate_G, int gate_ld, const float* gate_bias, const float* gate_h,
+                                        int gate_norm, void* stream);
+/* in-kernel timeline of the tcgen05 GEMM (profiles/gemm_trace.py): while a device buffer of
+ * gridDim.x * regcn_gemm_tf32_trace_slots() uint64 is attached, one thread per warp role stamps %globaltimer at the
+ * pipeline hand-over points of its CTA (entry, dependency wait, per tile: loads issued, first operands landed, MMAs
+ * issued, accumulator complete, epilogue done).  NULL detaches.  Not thread-safe; a measurement aid only. */
+REGCN_API void regcn_gemm_tf32_trace(void* dev_buf);
+REGCN_API int regcn_gemm_tf32_trace_slots(void);
+/* the layer GEMM of the evolve engine on its own (UnionRGCNLayer apply step, rgcn/layers.py:247-255, and for the last
+ * layer the time gate, src/rrgcn.py:176-178, straight out of the accumulator):
+ *   acc = A[M,K] . B[N,K]^T (3xTF32);  columns [0,d): out row (row_idx ? row_idx[m] : m) = rrelu(acc) unless
+ *   skip_rows[m] >= 0, written as fp32 (out_raw) and / or as the TF32 split (out_hi, out_lo); columns [d,N) are stored
+ *   unchanged to gate_out[:, col-d].  gate_G != NULL (needs N == d): out = s * [normalize](rrelu(acc)) + (1-s) * gate_h,
+ *   s = sigmoid(gate_G + gate_bias). */
+REGCN_API int regcn_gemm_tf32_layer(const float* a_hi, const float* a_lo, int lda, const float* b_hi, const float* b_lo,
+                                    int ldb, int M, int N, int K, int d, float* out_raw, float* out_hi, float* out_lo,
+                                    float* gate_out, int ld_gate_out, const int32_t* row_idx, const int32_t* skip_rows,
+                                    const float* gate_G, int gate_ld, const float* gate_bias, const float* gate_h,
+                                    int gate_norm, void* stream);
 /* edge kernel variant: 0 automatic, 1 register-staged gathers, 2 cp.async.bulk gathers staged in shared memory */
 REGCN_API void regcn_aggregate_tune(int impl);
 

@@ -931,3 +931,23 @@ def hyp_train_steps(sd, graphs, num_rels, triples, c=0.01, layer_norm=False, gam
                     "grad_norm": float(total), "grads": {k: g.detach().clone() for k, g in grads.items()},
                     "params": {k: P[k].detach().clone() for k in grads}})
     return log
+
+
+# --------------------------------------------------------------------------------------------------------------
+# TF32 operand split of the tensor-core contractions (not a reference function: the 3xTF32 GEMMs feed every fp32
+# operand x as hi + lo with hi = rna_tf32(x), lo = rna_tf32(x - hi); PTX cvt.rna.tf32.f32 = round to nearest, ties away
+# from zero, to 11 significant bits).  Written with frexp / floor in float64 -- independently of the bit trick the
+# kernels use -- and valid for normal fp32 values.
+# --------------------------------------------------------------------------------------------------------------
+def rna_tf32(x):
+    x = np.asarray(x, dtype=np.float32).astype(np.float64)
+    m, e = np.frexp(np.abs(x))                      # |x| = m * 2^e, m in [0.5, 1)
+    q = np.floor(m * 2048.0 + 0.5) / 2048.0         # 11 significant bits, ties away from zero
+    return (np.sign(x) * np.ldexp(q, e)).astype(np.float32)
+
+
+def split_tf32(x):
+    x = np.asarray(x, dtype=np.float32)
+    hi = rna_tf32(x)
+    lo = rna_tf32((x.astype(np.float32) - hi).astype(np.float32))
+    return hi, lo

@@ -1,0 +1,102 @@
+"""Kernel timeline of the hot path WITHOUT serialisation: torch.profiler (CUPTI activity records) around a few
+device-resident steps, so the two streams, programmatic dependent launch and warm caches are all as in the timed
+region of bench.py.  Writes gpurun_out/timeline_<tag>.json = [{name, stream, t_us (from the step's first kernel),
+dur_us}] for the LAST profiled step and prints a per-kernel summary plus the critical-path view per stream.
+
+    python profiles/timeline.py [c3|c1hyp|c4|score5] [steps]
+"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from torch.profiler import ProfilerActivity, profile
+
+import regcn_b200 as R
+from regcn_b200 import _lib, evaluate, synth, utils
+from bench import build_product_model, model_cfg
+
+
+def short(name):
+    name = name.replace("regcn::", "").replace("void ", "")
+    cut = name.find("(")
+    return name[:cut] if cut > 0 else name
+
+
+def run(tag, fn, steps):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda")
+    marks = []
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        for _ in range(steps):
+            flush.fill_(1.0)
+            torch.cuda.synchronize()
+            fn()
+            torch.cuda.synchronize()
+    path = os.path.join(ROOT, "gpurun_out", f"trace_{tag}.json")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    prof.export_chrome_trace(path)
+    ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") == "kernel"]
+    os.remove(path)
+    ev.sort(key=lambda e: e["ts"])
+    # split into steps at the L2-flush fill kernels
+    groups, cur = [], []
+    for e in ev:
+        if "fill" in e["name"].lower() and e["dur"] > 20:
+            if cur:
+                groups.append(cur)
+            cur = []
+        else:
+            cur.append(e)
+    if cur:
+        groups.append(cur)
+    last = groups[-1]
+    t0 = last[0]["ts"]
+    rows = [{"name": short(e["name"]), "stream": e["args"].get("stream"), "t_us": round(e["ts"] - t0, 2),
+             "dur_us": round(e["dur"], 2), "grid": e["args"].get("grid"), "block": e["args"].get("block")}
+            for e in last]
+    span = max(r["t_us"] + r["dur_us"] for r in rows)
+    json.dump({"tag": tag, "span_us": span, "kernels": rows}, open(os.path.join(ROOT, "gpurun_out", f"timeline_{tag}.json"), "w"))
+    print(f"== {tag}: {len(rows)} kernels, span {span:.1f} us (steps profiled {len(groups)}; spans "
+          f"{[round(max(e['ts'] + e['dur'] for e in g) - g[0]['ts'], 1) for g in groups]})")
+    agg = {}
+    for r in rows:
+        a = agg.setdefault((r["name"], r["stream"]), [0, 0.0])
+        a[0] += 1
+        a[1] += r["dur_us"]
+    for (nm, s), (c, d) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"  {d:9.1f} us  x{c:<3d} stream {s}  {nm[:100]}")
+    print("  -- first 40 kernels --")
+    for r in rows[:40]:
+        print(f"  t={r['t_us']:8.1f}  dur={r['dur_us']:7.1f}  s={r['stream']}  grid={r['grid']}  {r['name'][:90]}")
+
+
+def main():
+    what = sys.argv[1] if len(sys.argv) > 1 else "c3"
+    steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+    _lib.require_device()
+    dev = torch.device("cuda", 0)
+    if what in ("c3", "c1", "c4", "c1hyp", "c3hyp"):
+        shape = what.replace("hyp", "")
+        cfg = model_cfg("hyp_lgcn_roth" if what.endswith("hyp") else "regcn")
+        case = synth.make_case(shape, 0)
+        n, r = case["num_ents"], case["num_rels"]
+        model, _ = build_product_model(cfg, n, r, 0)
+        model = model.to(dev)
+        gl = [R.build_sub_graph(n, r, s, True, 0) for s in case["history"]]
+        test = torch.from_numpy(case["test"]).to(dev)
+        inv = test[:, [2, 1, 0]].clone()
+        inv[:, 1] += r
+        all_t = torch.cat((test, inv)).contiguous()
+        f = utils.filter_csr_from_snapshot(all_t, 2 * r, 0)
+        run(what, lambda: evaluate.evaluate_snapshot(model, gl, all_t, f), steps)
+    else:
+        raise SystemExit("unknown workload " + what)
+
+
+if __name__ == "__main__":
+    main()

@@ -42,6 +42,12 @@ SIGNATURES = {
     "regcn_regcn_evolve_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "regcn_regcn_evolve": (_i, [_p, _p, _p, _p, _i, _p, _p, _i, _p, _sz, _p]),
     "regcn_gemm_tf32_tune": (None, [_i, _i]),
+    "regcn_gemm_tf32_a32": (_i, [_p, _i, _i, _p, _p, _i, _i, _p, _p, _p, _i, _p, _i, _i, _i, _p, _i, _i, _i, _p, _sz, _p, _i, _p]),
+    "regcn_gemm_tf32_layer_a32": (_i, [_p, _i, _i, _p, _p, _i, _i, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p,
+                                       _p, _i, _p, _p, _i, _p]),
+    "regcn_gemm_tf32_trace": (None, [_p]),
+    "regcn_gemm_tf32_trace_slots": (_i, []),
+    "regcn_gemm_tf32_layer": (_i, [_p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p, _i, _p, _p, _i, _p]),
     "regcn_pdl_enable": (None, [_i]),
     "regcn_two_stream_enable": (None, [_i]),
     "regcn_kernel_launches": (ctypes.c_longlong, []),

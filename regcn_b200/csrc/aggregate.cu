@@ -25,7 +25,8 @@ __global__ void __launch_bounds__(256) union_aggregate_kernel(
     const int* __restrict__ src_sorted, const int* __restrict__ etype_sorted, const float* __restrict__ norm,
     const int* __restrict__ vptr, const int* __restrict__ sptr, const int* __restrict__ vrow_row, int nv,
     const float* __restrict__ radius, float gamma, int d, float* __restrict__ out, float* __restrict__ partial,
-    float* __restrict__ out_hi, float* __restrict__ out_lo, const int* __restrict__ active_pos, int ldo) {
+    float* __restrict__ out_hi, float* __restrict__ out_lo, const int* __restrict__ active_pos, int ldo,
+    int* __restrict__ fold_count) {
   pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const int w = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
@@ -152,7 +153,49 @@ __global__ void __launch_bounds__(256) union_aggregate_kernel(
     if (out) acc.store(out + orow * ldo, nvec, lane);
     if (out_hi) acc.store_split(out_hi + orow * ldo, out_lo + orow * ldo, nvec, lane);
   } else {
-    acc.store(partial + (size_t)(__ldg(sptr + row) + k) * d, nvec, lane);
+    const int s0 = __ldg(sptr + row);
+    acc.store(partial + (size_t)(s0 + k) * d, nvec, lane);
+    if (fold_count) {
+      // In-kernel fold of a row split into <= 32 chunks (the launcher only passes fold_count then): the chunk warp that
+      // arrives LAST sums the partials in chunk order -- the arithmetic of aggregate_fixup_kernel at stride 1, so the
+      // result does not depend on which warp that is -- and re-arms the counter for the next launch.
+      const int nch = v1 - v0;
+      __threadfence();
+      int prev = 0;
+      if (lane == 0) prev = atomicAdd(fold_count + s0, 1);
+      prev = __shfl_sync(0xffffffffu, prev, 0);
+      if (prev == nch - 1) {
+        __threadfence();
+        WarpRow<RV> sum, p[4];
+        sum.zero();
+        int j = 0;
+        for (; j + 4 <= nch; j += 4) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int i = 0; i < RV; ++i) {
+              const int c = lane + i * kWarp;
+              p[u].v[i] = c < nvec ? __ldcg(reinterpret_cast<const float4*>(partial + (size_t)(s0 + j + u) * d) + c)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int i = 0; i < RV; ++i) sum.v[i] = f4_add(sum.v[i], p[u].v[i]);
+        }
+        for (; j < nch; ++j) {
+#pragma unroll
+          for (int i = 0; i < RV; ++i) {
+            const int c = lane + i * kWarp;
+            if (c < nvec) sum.v[i] = f4_add(sum.v[i], __ldcg(reinterpret_cast<const float4*>(partial + (size_t)(s0 + j) * d) + c));
+          }
+        }
+        sum.scale(__ldg(norm + row));
+        if (out) sum.store(out + orow * ldo, nvec, lane);
+        if (out_hi) sum.store_split(out_hi + orow * ldo, out_lo + orow * ldo, nvec, lane);
+        if (lane == 0) fold_count[s0] = 0;
+      }
+    }
   }
 }
 
@@ -553,7 +596,7 @@ int union_aggregate(const float* h, const float* rel, const int* rowptr, const i
                     const int* etype_sorted, const float* norm, const int* vptr, const int* sptr,
                     const int* vrow_row, int nv, int nsplit, const float* radius, float gamma, int N, int d,
                     float* out, float* partial, float* out_hi, float* out_lo, const int* active_pos, int ldo,
-                    int max_chunks, cudaStream_t st) {
+                    int max_chunks, cudaStream_t st, int* fold_count) {
   if (!h || !rel || !rowptr || !src_sorted || !etype_sorted || !norm || !vptr || !sptr || !vrow_row ||
       (!out && !out_hi) || (out_hi && !out_lo)) {
     set_last_error("union_aggregate: null pointer"); return REGCN_ERR_NULL;
@@ -575,8 +618,13 @@ int union_aggregate(const float* h, const float* rel, const int* rowptr, const i
   // streaming variant: automatic for HBM-bound sizes (the gathered rows no longer fit in L2), opt-in otherwise
   // (hub-heavy graphs stay on the register variant: their hot source rows hit in L1, which bulk copies bypass --
   //  measured on B200, N = 1M, E = 10M: uniform endpoints 2.14 ms stream vs 2.89 ms registers, Zipf 3.58 vs 2.91)
+  // split rows of at most 32 chunks (1024 in-edges) are folded by the last chunk warp of the register kernel itself when
+  // the caller provides zeroed arrival counters (one per partial slot): no fix-up launch
+  if (max_chunks <= 0 || max_chunks > nsplit) max_chunks = nsplit;
+  int* fold = (fold_count && nsplit > 0 && max_chunks <= 32) ? fold_count : nullptr;
   const bool stream = impl == 3 || (impl == 0 && (size_t)nv >= 65536 && (size_t)N * d * 4 > (size_t)96 * 1024 * 1024 &&
                                     (size_t)nsplit * 8 < (size_t)nv);
+  if (stream || bulk) fold = nullptr;          // only the register kernel folds in place
   if (stream) {
     const size_t smem = (size_t)kStreamWarps * 2 * kStreamWin * d * sizeof(float);
     int dev = 0, sms = 148;
@@ -618,15 +666,14 @@ int union_aggregate(const float* h, const float* rel, const int* rowptr, const i
     else { if (small) LAUNCH_BULK(1, false); else LAUNCH_BULK(2, false); }
 #undef LAUNCH_BULK
   } else if (radius) {
-    if (small) launch_k(union_aggregate_kernel<1, true>, grid, TB, 0, st, h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, radius, gamma, d, out, partial, out_hi, out_lo, active_pos, ldo);
-    else launch_k(union_aggregate_kernel<2, true>, grid, TB, 0, st, h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, radius, gamma, d, out, partial, out_hi, out_lo, active_pos, ldo);
+    if (small) launch_k(union_aggregate_kernel<1, true>, grid, TB, 0, st, h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, radius, gamma, d, out, partial, out_hi, out_lo, active_pos, ldo, fold);
+    else launch_k(union_aggregate_kernel<2, true>, grid, TB, 0, st, h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, radius, gamma, d, out, partial, out_hi, out_lo, active_pos, ldo, fold);
   } else {
-    if (small) launch_k(union_aggregate_kernel<1, false>, grid, TB, 0, st, h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, nullptr, 0.f, d, out, partial, out_hi, out_lo, active_pos, ldo);
-    else launch_k(union_aggregate_kernel<2, false>, grid, TB, 0, st, h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, nullptr, 0.f, d, out, partial, out_hi, out_lo, active_pos, ldo);
+    if (small) launch_k(union_aggregate_kernel<1, false>, grid, TB, 0, st, h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, nullptr, 0.f, d, out, partial, out_hi, out_lo, active_pos, ldo, fold);
+    else launch_k(union_aggregate_kernel<2, false>, grid, TB, 0, st, h, rel, rowptr, src_sorted, etype_sorted, norm, vptr, sptr, vrow_row, nv, nullptr, 0.f, d, out, partial, out_hi, out_lo, active_pos, ldo, fold);
   }
-  if (nsplit > 0) {
+  if (nsplit > 0 && !fold) {
     // max_chunks = chunk count of the largest hub row (<= nsplit); one launch per radix-32 level
-    if (max_chunks <= 0 || max_chunks > nsplit) max_chunks = nsplit;
     for (long long stride = 1; stride < (long long)max_chunks; stride *= 32) {
       if (small) launch_k(aggregate_fixup_kernel<1>, grid, TB, 0, st, vptr, sptr, vrow_row, norm, nv, d, partial, out, out_hi, out_lo, active_pos, ldo, (int)stride);
       else launch_k(aggregate_fixup_kernel<2>, grid, TB, 0, st, vptr, sptr, vrow_row, norm, nv, d, partial, out, out_hi, out_lo, active_pos, ldo, (int)stride);

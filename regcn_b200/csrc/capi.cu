@@ -157,6 +157,31 @@ void regcn_two_stream_enable(int on) { regcn::two_stream_set(on); }
 long long regcn_kernel_launches(void) { return __atomic_load_n(&regcn::g_kernel_launches, __ATOMIC_RELAXED); }
 void regcn_gemm_tf32_tune(int block_n, int stages) { gemm_tf32_tune(block_n, stages); }
 void regcn_aggregate_tune(int impl) { aggregate_tune(impl); }
+int regcn_gemm_tf32_a32(const float* a0, int lda0, int k0, const int32_t* rows0, const float* a1, int lda1, int k1,
+                        const int32_t* rows1, const float* b_hi, const float* b_lo, int ldb, float* C, int ldc, int M, int N,
+                        const float* bias, int accumulate, int passes, int split_k, float* workspace, size_t workspace_bytes,
+                        const float* addend, int ld_add, void* stream) {
+  return gemm_tf32_a32(a0, lda0, k0, rows0, a1, lda1, k1, rows1, b_hi, b_lo, ldb, C, ldc, M, N, bias, accumulate, passes,
+                       split_k, workspace, workspace_bytes, addend, ld_add, ST(stream));
+}
+int regcn_gemm_tf32_layer_a32(const float* a0, int lda0, int k0, const int32_t* rows0, const float* a1, int lda1, int k1,
+                              const int32_t* rows1, const float* b_hi, const float* b_lo, int ldb, int M, int N, int d,
+                              float* out_raw, float* out_hi, float* out_lo, float* gate_out, int ld_gate_out,
+                              const int32_t* row_idx, const int32_t* skip_rows, const float* gate_G, int gate_ld,
+                              const float* gate_bias, const float* gate_h, int gate_norm, void* stream) {
+  return gemm_tf32_layer_a32(a0, lda0, k0, rows0, a1, lda1, k1, rows1, b_hi, b_lo, ldb, M, N, d, out_raw, out_hi, out_lo,
+                             gate_out, ld_gate_out, row_idx, skip_rows, gate_G, gate_ld, gate_bias, gate_h, gate_norm,
+                             ST(stream));
+}
+void regcn_gemm_tf32_trace(void* dev_buf) { gemm_tf32_trace(dev_buf); }
+int regcn_gemm_tf32_trace_slots(void) { return gemm_tf32_trace_slots(); }
+int regcn_gemm_tf32_layer(const float* a_hi, const float* a_lo, int lda, const float* b_hi, const float* b_lo, int ldb,
+                          int M, int N, int K, int d, float* out_raw, float* out_hi, float* out_lo, float* gate_out,
+                          int ld_gate_out, const int32_t* row_idx, const int32_t* skip_rows, const float* gate_G,
+                          int gate_ld, const float* gate_bias, const float* gate_h, int gate_norm, void* stream) {
+  return gemm_tf32_layer(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, d, out_raw, out_hi, out_lo, gate_out, ld_gate_out,
+                         row_idx, skip_rows, gate_G, gate_ld, gate_bias, gate_h, gate_norm, ST(stream));
+}
 int regcn_score_count_tf32(const float* q_hi, const float* q_lo, const float* e_hi, const float* e_lo, int B, int N, int K,
                            const float* tscore, const int32_t* target, int32_t* raw_count, int col_offset, int hyp,
                            const float* x2, const float* y2, const float* col_bias, double c,

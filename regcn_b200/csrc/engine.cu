@@ -20,30 +20,65 @@
 #include "common.cuh"
 #include "internal.h"
 #include <stdlib.h>
+#include <mutex>
 
 namespace regcn {
 
 static inline size_t al(size_t n) { return (n + 63) & ~(size_t)63; }   // 256-byte aligned float counts
 
-// Side stream of the two-stream evolve schedule (library-owned, one per device, created on first use).  The caller's
-// stream carries the large all-entity GEMMs of a snapshot; the side stream carries the chain of small kernels
-// (relation GRU, aggregates, active-row GEMMs) that would otherwise sit between them, each costing a launch ramp
-// and a memory-latency chain on an otherwise idle machine.
-struct AuxStream { cudaStream_t sb = nullptr; cudaEvent_t fork = nullptr, a_done = nullptr, b_done = nullptr; bool ok = false; };
+// Side streams of the evolve schedule (library-owned, per device, created on first use).  The caller's stream carries
+// the large all-entity GEMMs of a snapshot; side stream B carries the chain of small kernels (relation mean-pool, GRU,
+// aggregates, active-row GEMMs) that would otherwise sit between them, each costing a launch ramp and a memory-latency
+// chain on an otherwise idle machine; side stream C runs the one GEMM of that chain that only depends on the PREVIOUS
+// snapshot (gh = h0 . W_hh^T) ahead of time.
+// The streams and their events are shared by every call on the device, so an evolve call holds the device's mutex
+// from its first fork to its last join: two host threads (or two caller streams) cannot interleave their event
+// records.  StreamScope joins whatever is still outstanding on the side streams back into the caller's stream on
+// EVERY exit path, and puts the thread-local launch knobs (PDL suppression, SM hint) back.
+struct AuxStream {
+  cudaStream_t sb = nullptr, sc = nullptr;
+  cudaEvent_t fork = nullptr, b_done = nullptr, c_done = nullptr, h0_ready = nullptr;
+  bool ok = false, failed = false;
+  std::mutex mu;
+};
 static AuxStream* aux_stream() {
   static AuxStream aux[16];
+  static std::mutex init_mu;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
   AuxStream& a = aux[dev];
-  if (!a.ok) {
-    if (cudaStreamCreateWithFlags(&a.sb, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&a.a_done, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    if (cudaEventCreateWithFlags(&a.b_done, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    a.ok = true;
+  std::lock_guard<std::mutex> g(init_mu);
+  if (!a.ok && !a.failed) {
+    bool good = cudaStreamCreateWithFlags(&a.sb, cudaStreamNonBlocking) == cudaSuccess &&
+                cudaStreamCreateWithFlags(&a.sc, cudaStreamNonBlocking) == cudaSuccess;
+    cudaEvent_t* evs[4] = {&a.fork, &a.b_done, &a.c_done, &a.h0_ready};
+    for (int i = 0; good && i < 4; ++i) good = cudaEventCreateWithFlags(evs[i], cudaEventDisableTiming) == cudaSuccess;
+    if (good) a.ok = true; else { a.failed = true; cudaGetLastError(); }
   }
-  return &a;
+  return a.ok ? &a : nullptr;
 }
+// orders `waiter` after everything enqueued on `src` so far; false (and a cleared error) when the event API fails
+static bool stream_after(cudaStream_t waiter, cudaStream_t src, cudaEvent_t ev) {
+  if (cudaEventRecord(ev, src) != cudaSuccess || cudaStreamWaitEvent(waiter, ev, 0) != cudaSuccess) { cudaGetLastError(); return false; }
+  return true;
+}
+void gemm_tf32_sm_hint(int sms);
+struct StreamScope {
+  AuxStream* aux;
+  cudaStream_t st;
+  bool b_open = false, c_open = false;     // work enqueued on a side stream that the caller's stream has not waited for
+  StreamScope(AuxStream* a, cudaStream_t s) : aux(a), st(s) { if (aux) aux->mu.lock(); }
+  void join() {
+    if (aux && b_open) { if (!stream_after(st, aux->sb, aux->b_done)) cudaStreamSynchronize(aux->sb); b_open = false; }
+    if (aux && c_open) { if (!stream_after(st, aux->sc, aux->c_done)) cudaStreamSynchronize(aux->sc); c_open = false; }
+  }
+  ~StreamScope() {
+    join();
+    pdl_suppress(false);
+    gemm_tf32_sm_hint(0);
+    if (aux) aux->mu.unlock();
+  }
+};
 // SMs a persistent all-entity GEMM of `ncol` output columns leaves free (see the balanced grid in gemm_tc.cu)
 static int side_hint(int N, int d, int ncol, int sms) {
   (void)d;
@@ -52,9 +87,13 @@ static int side_hint(int N, int d, int ncol, int sms) {
   const int grid_a = (int)((t + rounds - 1) / (rounds > 0 ? rounds : 1));
   return sms - grid_a >= 16 ? sms - grid_a : 16;
 }
+// Programmatic dependent launch on side stream B: off by default.  A side kernel launched early parks its CTAs (the
+// aggregates: ~200 CTAs, one or two per SM) at their dependency wait on exactly the SMs the next all-entity GEMM of the
+// caller's stream needs -- a 384-thread GEMM CTA takes a whole SM's registers -- and that GEMM then runs its tiles in
+// two waves (measured at C3, B200: 1.13 ms per step with plain stream order on the side stream, 1.18 ms with PDL).
 static bool side_pdl_keep() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("REGCN_SIDE_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  if (v < 0) { const char* e = getenv("REGCN_SIDE_PDL"); v = (e && e[0] == '1') ? 1 : 0; }
   return v != 0;
 }
 static int g_two_stream = -1;
@@ -68,7 +107,7 @@ static bool two_stream_enabled() {
 }
 
 struct EvolveWs {
-  size_t xm_hi, xm_lo, gi, gh, h0_hi, h0_lo, agg_hi, agg_lo, Lm, L2, P, set[2][3], h_hi, h_lo, h_init, partial, rel_partial, total;
+  size_t xm_hi, xm_lo, gi, gh, h0_hi, h0_lo, agg_hi, agg_lo, Lm, L2, P, set[2][3], h_hi, h_lo, h_init, partial, rel_partial, fold, fold_n, total;
   // agg_hi/agg_lo double as the compact [agg | h] operand of the sparse-snapshot path (n_active <= N/2 rows of 2d)
 };
 
@@ -86,6 +125,8 @@ static EvolveWs plan_evolve(int N, int R2, int d, int max_split_chunks, int rel_
   w.h_hi = take(nd); w.h_lo = take(nd); w.h_init = take(nd);
   w.partial = take((size_t)(max_split_chunks > 0 ? max_split_chunks : 1) * (d + 1));
   w.rel_partial = take(rel_nsplit > 1 ? (size_t)(R2 / 2) * rel_nsplit * d : 1);
+  w.fold_n = (size_t)(max_split_chunks > 0 ? max_split_chunks : 1);      // arrival counters of the in-kernel fold (int32)
+  w.fold = take(w.fold_n);
   w.total = off * sizeof(float);
   return w;
 }
@@ -133,7 +174,12 @@ int regcn_regcn_evolve(const void* const* mp, const int* mi, const void* const* 
   const float* h0_raw = F(RM_EMB_REL);
   const float* h0_hi = F(RM_EMB_REL_HI);
   const float* h0_lo = F(RM_EMB_REL_LO);
-  AuxStream* aux = two_stream_enabled() ? aux_stream() : nullptr;
+  int* fold = reinterpret_cast<int*>(ws + w.fold);
+  if (max_split > 0 && cudaMemsetAsync(fold, 0, w.fold_n * sizeof(int), st) != cudaSuccess) { cudaGetLastError(); fold = nullptr; }
+  if (max_split <= 0) fold = nullptr;
+  StreamScope scope(two_stream_enabled() ? aux_stream() : nullptr, st);
+  AuxStream* aux = scope.aux;
+  bool gh_ahead = false;        // gh of the current snapshot was already enqueued on side stream C
   int sm_count = 148;
   {
     int dev = 0;
@@ -154,25 +200,51 @@ int regcn_regcn_evolve(const void* const* mp, const int* mi, const void* const* 
     // whole SMs free (balanced grids), which is where the side stream's kernels run.
     bool side_pdl_off = false;
     const int n_active_ = gn[RGI_N_ACTIVE];
-    const bool two = aux && n_active_ * 2 <= N && nl >= 2 && N >= 4096;
+    bool two = aux && n_active_ * 2 <= N && nl >= 2 && N >= 4096;
+    if (two) {
+      // everything the side streams read (h of the previous snapshot) is ordered before this fork
+      two = stream_after(aux->sb, st, aux->fork);
+      if (!two) scope.join();
+    }
     cudaStream_t sB = two ? aux->sb : st;
     if (two) {
+      scope.b_open = true;
       side_pdl_off = !side_pdl_keep();
-      cudaEventRecord(aux->fork, st);              // everything the side stream reads (h of the previous snapshot) is ordered before this
-      cudaStreamWaitEvent(sB, aux->fork, 0);
       gemm_tf32_sm_hint(side_hint(N, d, 2 * d, sm_count));
       // kernels launched early park their CTAs on the SMs the other stream needs: the side stream stays plainly ordered
       pdl_suppress(side_pdl_off);
     }
     // ---- relation evolution (K2, K3) ----
+    // gh = h0 . W_hh^T + b_hh depends on the previous snapshot only: in the two-stream schedule it was enqueued on
+    // side stream C right after the previous snapshot's GRU gate (below) and is joined in front of this one's
+    if (!gh_ahead) {
+      cudaStream_t sG = sB;
+      if (two && cudaStreamWaitEvent(aux->sc, aux->fork, 0) == cudaSuccess) { sG = aux->sc; scope.c_open = true; }
+      if ((e = gemm_tf32(h0_hi, h0_lo, d, F(RM_WHH_HI), F(RM_WHH_LO), d, ws + w.gh, 3 * d, R2, 3 * d, d, F(RM_B_HH), 0, 3, 1,
+                         nullptr, 0, nullptr, 0, sG))) return e;
+      gh_ahead = sG != sB;
+    }
     if ((e = rel_mean_pool(h_raw, GI(RG_REL_ROWPTR), GI(RG_REL_ENTS), R2 / 2, d, rel_nsplit, nullptr, ws + w.rel_partial,
                            ws + w.xm_hi, ws + w.xm_lo, sB))) return e;
     if ((e = gemm_tf32(ws + w.xm_hi, ws + w.xm_lo, d, F(RM_WIH_R_HI), F(RM_WIH_R_LO), d, ws + w.gi, 3 * d, R2, 3 * d, d,
                        nullptr, 0, 3, 1, nullptr, 0, F(RM_GI_STATIC), 3 * d, sB))) return e;
-    if ((e = gemm_tf32(h0_hi, h0_lo, d, F(RM_WHH_HI), F(RM_WHH_LO), d, ws + w.gh, 3 * d, R2, 3 * d, d, F(RM_B_HH), 0, 3, 1,
-                       nullptr, 0, nullptr, 0, sB))) return e;
+    if (gh_ahead) {
+      if (!stream_after(sB, aux->sc, aux->c_done)) cudaStreamSynchronize(aux->sc);
+      scope.c_open = false;
+      gh_ahead = false;
+    }
     if ((e = gru_gate(ws + w.gi, ws + w.gh, h0_raw, h0_out, R2, d, layer_norm, ws + w.h0_hi, ws + w.h0_lo, sB))) return e;
     h0_raw = h0_out; h0_hi = ws + w.h0_hi; h0_lo = ws + w.h0_lo;
+    if (two && i + 1 < L) {
+      // next snapshot's gh: needs nothing but the relation state just written
+      const int n_next = gi_[(size_t)(i + 1) * RGI_NUM_INTS + RGI_N_ACTIVE];
+      if (n_next * 2 <= N && stream_after(aux->sc, sB, aux->h0_ready)) {
+        scope.c_open = true;
+        if ((e = gemm_tf32(h0_hi, h0_lo, d, F(RM_WHH_HI), F(RM_WHH_LO), d, ws + w.gh, 3 * d, R2, 3 * d, d, F(RM_B_HH), 0, 3,
+                           1, nullptr, 0, nullptr, 0, aux->sc))) return e;
+        gh_ahead = true;
+      }
+    }
     // ---- entity evolution: n_layers x UnionRGCNLayer (K4, GEMMs, K5) ----
     const float* x_raw = h_raw;
     const float* x_hi = ws + w.h_hi;
@@ -203,7 +275,7 @@ int regcn_regcn_evolve(const void* const* mp, const int* mi, const void* const* 
         if ((e = union_aggregate(x_raw, h0_raw, GI(RG_ROWPTR), GI(RG_SRC_SORTED), GI(RG_ETYPE_SORTED), (const float*)g[RG_NORM],
                                  GI(RG_VPTR), GI(RG_SPTR), GI(RG_VROW_ROW), gn[RGI_N_VROWS], gn[RGI_N_SPLIT_CHUNKS], nullptr,
                                  0.f, N, d, nullptr, ws + w.partial, ws + w.agg_hi, ws + w.agg_lo, GI(RG_ACTIVE_POS), 2 * d,
-                                 gn[RGI_MAX_CHUNKS], sB))) return e;
+                                 gn[RGI_MAX_CHUNKS], sB, fold))) return e;
         if (!last) {
           if (two) { gemm_tf32_sm_hint(0); pdl_suppress(l > 0); }   // later layers must not park CTAs on the free SMs early
           e = gemm_tf32_layer(x_hi, x_lo, d, F(base + 6), F(base + 7), d, N, ncol, d, d, nullptr, o_hi, o_lo,
@@ -226,8 +298,8 @@ int regcn_regcn_evolve(const void* const* mp, const int* mi, const void* const* 
           pdl_suppress(false);
           if (e) return e;
           if (two) {                                   // join: the active rows need the gate columns (caller's stream) and P (side stream)
-            cudaEventRecord(aux->b_done, sB);
-            cudaStreamWaitEvent(st, aux->b_done, 0);
+            if (!stream_after(st, sB, aux->b_done)) cudaStreamSynchronize(sB);
+            scope.b_open = false;
           }
           if (n_active > 0 &&
               (e = time_gate(ws + w.Lm, F(RM_GATE_BIAS), ws + w.P, h_raw, h_new, n_active, d, layer_norm, d, ws + w.h_hi,
@@ -240,7 +312,7 @@ int regcn_regcn_evolve(const void* const* mp, const int* mi, const void* const* 
         if ((e = union_aggregate(x_raw, h0_raw, GI(RG_ROWPTR), GI(RG_SRC_SORTED), GI(RG_ETYPE_SORTED), (const float*)g[RG_NORM],
                                  GI(RG_VPTR), GI(RG_SPTR), GI(RG_VROW_ROW), gn[RGI_N_VROWS], gn[RGI_N_SPLIT_CHUNKS], nullptr,
                                  0.f, N, d, nullptr, ws + w.partial, ws + w.agg_hi, ws + w.agg_lo, GI(RG_ACTIVE_POS), 2 * d,
-                                 gn[RGI_MAX_CHUNKS], st))) return e;
+                                 gn[RGI_MAX_CHUNKS], st, fold))) return e;
         if (n_active > 0 &&
             (e = gemm_tf32(ws + w.agg_hi, ws + w.agg_lo, 2 * d, F(base + 4), F(base + 5), 2 * d, ws + w.P, d, n_active, d,
                            2 * d, nullptr, 0, 3, 1, nullptr, 0, nullptr, 0, st))) return e;

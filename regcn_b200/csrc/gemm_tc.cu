@@ -8,11 +8,18 @@
 // which restores ~2^-21 relative operand precision (the dropped lo.lo term is 2^-22).  With passes == 1 only
 // hi.hi is issued (plain TF32, ~1e-3 relative) -- reported separately, never used for the parity path.
 //
-// Warp roles (320 threads):  warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
-// warps 2..9 = epilogue (TMEM lane quarter = warp_id % 4, two warps per quarter splitting the 32-column chunks: one
-// warp per scheduler cannot hide the ALU / memory latency of a non-trivial epilogue).  Persistent: each CTA walks a
-// list of 128 x BLOCK_N output tiles (x split-K slices).
+// Warp roles (384 threads):  warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
+// warps 2..3 = A-operand converters (fp32-A mode, below), warps 4..11 = epilogue (TMEM lane quarter = warp_id % 4, two
+// warps per quarter splitting the 32-column chunks: one warp per scheduler cannot hide the ALU / memory latency of a
+// non-trivial epilogue).  Persistent: each CTA walks a list of 128 x BLOCK_N output tiles (x split-K slices).
 // K is walked in 32-float (128-byte) blocks; TMA zero-fills the K / M / N tails.
+//
+// fp32-A mode (Params::a_f32): the A operand stays ONE fp32 copy in global memory.  The two converter warps read the
+// 128 x 32 k-block of the tile with coalesced 16-byte loads (optionally gathering rows through an index list, optionally
+// from two K segments -- the compact [agg | x] operand of the active rows never exists in memory), split every value into
+// hi / lo in registers and write both halves straight into the 128-byte-swizzled K-major stage buffers the tensor core
+// reads (same bytes TMA would have written from pre-split copies), then fence.proxy.async + mbarrier arrive.  Producers
+// of activations therefore write fp32 only, and a layer GEMM moves half the A bytes through L2.
 #include "common.cuh"
 #include <cuda.h>
 
@@ -24,7 +31,9 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 32;            // fp32 elements = one 128-byte swizzle row
 constexpr int UMMA_K = 8;              // tf32
 constexpr int EPI_WARPS = 8;           // epilogue warps: 2 per TMEM lane quarter, each takes every other 32-column chunk
-constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
+constexpr int CVT_WARPS = 2;           // A-operand converter warps (fp32-A mode)
+constexpr int EPI_WARP0 = 2 + CVT_WARPS;   // first epilogue warp; a multiple of 4 so that warp % 4 is the TMEM lane quarter
+constexpr int NUM_THREADS = 32 * (EPI_WARP0 + EPI_WARPS);
 constexpr uint32_t SMEM_BUDGET = 192 * 1024;   // operand ring; + 32 KB of epilogue staging + alignment slack <= 227 KB
 constexpr int kStagePitch = 32;                                      // floats per row of an epilogue staging tile (XOR-swizzled)
 constexpr uint32_t STAGING_BYTES = EPI_WARPS * 32 * kStagePitch * 4; // one 32 x 32 fp32 tile per epilogue warp
@@ -161,7 +170,23 @@ struct Params {
   const float* gate_bias;     // [lay_d]
   const float* gate_h;        // [*, lay_d] previous entity state
   int gate_norm;              // F.normalize the layer output first (layer_norm)
+  // ---- fp32-A mode: A = [seg0 | seg1] along K, each segment an fp32 row-major matrix, rows optionally gathered ----
+  int a_f32;                  // 1: the tensor maps of A are unused, converter warps build the hi / lo tiles
+  const float* a_ptr[2];      // segment base pointers (seg1 NULL when a_k[1] == 0)
+  int a_ld[2];                // leading dimensions (floats, multiples of 4)
+  int a_k[2];                 // segment lengths along K (multiples of 4); p.K = k-block-padded total
+  const int* a_rows[2];       // tile row m reads source row a_rows[s][m] (NULL: m)
+  int a_kb0;                  // k-blocks of segment 0 = ceil(a_k[0] / 32)
+  unsigned long long* trace;  // optional in-kernel timeline: [gridDim.x][kTraceSlots] %globaltimer stamps (NULL = off)
 };
+constexpr int kTraceSlots = 48;
+__device__ __forceinline__ void trace_stamp(const Params& p, int slot) {
+  if (p.trace) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.trace[(size_t)blockIdx.x * kTraceSlots + slot] = t;
+  }
+}
 
 // sigmoid on the SFU (ex2.approx + rcp.approx, ~2 ulp): the epilogue warps have no spare issue slots for the IEEE path
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
@@ -184,12 +209,14 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                  const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                  const Params p) {
   pdl_trigger();          // the next kernel may be scheduled; its own wait keeps it off our outputs
+  if (threadIdx.x == 0) trace_stamp(p, 0);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[8];
   __shared__ __align__(8) uint64_t empty_bar[8];
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
+  __shared__ float norm_xchg[EPI_WARPS / 4][BLOCK_M];      // EPI 3: row-norm partial sums of the two warps of a lane quarter
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -208,7 +235,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&full_bar[s]), p.a_f32 ? 1 + CVT_WARPS : 1);   // TMA (expect_tx) + one arrival per converter warp
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -227,6 +254,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_slot;
   pdl_wait();             // barrier init and the TMEM allocation above overlap the tail of the previous kernel
+  if (threadIdx.x == 0) trace_stamp(p, 1);
 
   // work item -> (split z, n tile, m tile); m fastest so that concurrently running CTAs share the B tile in L2
   auto decode = [&](int t, int& m0, int& n0, int& kb_beg, int& kb_end) {
@@ -245,15 +273,19 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int pit = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++pit) {
         int m0, n0, kb_beg, kb_end;
         decode(t, m0, n0, kb_beg, kb_end);
+        if (pit < 4) trace_stamp(p, 2 + pit);          // producer starts issuing tile pit
         for (int kb = kb_beg; kb < kb_end; ++kb) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
           const uint32_t fb = smem_u32(&full_bar[stage]);
-          mbar_expect_tx(fb, stage_bytes);
+          mbar_expect_tx(fb, p.a_f32 ? (three ? 2u : 1u) * b_bytes : stage_bytes);
           uint32_t dst = smem_base + stage * stage_bytes;
-          const int k0 = kb * block_k;
+          // fp32-A mode with two K segments: k-blocks never straddle a segment, so the weight columns of segment 1
+          // start at a_k[0] (the zero-filled A tail of segment 0 cancels the columns its last k-block overlaps)
+          const int k0 = (p.a_f32 && kb >= p.a_kb0) ? p.a_k[0] + (kb - p.a_kb0) * BLOCK_K : kb * block_k;
           // K-major operand: one box of 32 k-floats x rows; MN-major operand: boxes of 32 MN-elements x 32 reduction
           // rows, 4096 bytes each (inner coordinate = MN offset)
           auto load_op = [&](const CUtensorMap* tm, int mn, int r0, int nrows, uint32_t bytes) {
@@ -261,12 +293,16 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
             else tma_load_2d(dst, tm, fb, k0, r0);
             dst += bytes;
           };
-          load_op(&tm_a_hi, p.a_mn, m0, BLOCK_M, a_bytes);
-          if (three) load_op(&tm_a_lo, p.a_mn, m0, BLOCK_M, a_bytes);
+          if (p.a_f32) dst += (three ? 2u : 1u) * a_bytes;        // the converter warps fill the A half of the stage
+          else {
+            load_op(&tm_a_hi, p.a_mn, m0, BLOCK_M, a_bytes);
+            if (three) load_op(&tm_a_lo, p.a_mn, m0, BLOCK_M, a_bytes);
+          }
           load_op(&tm_b_hi, p.b_mn, n0, p.block_n, b_bytes);
           if (three) load_op(&tm_b_lo, p.b_mn, n0, p.block_n, b_bytes);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
+        if (pit < 4) trace_stamp(p, 6 + pit);          // all loads of tile pit issued
       }
     }
   } else if (warp == 1) {
@@ -289,8 +325,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tmem_acc = tmem_base + (uint32_t)(slot * (p.tmem_cols >> 1));
         uint32_t acc = 0;
+        if (it < 6) trace_stamp(p, 10 + 3 * it);       // accumulator slot free, waiting for operands
         for (int kb = kb_beg; kb < kb_end; ++kb) {
           mbar_wait(smem_u32(&full_bar[stage]), phase);
+          if (kb == kb_beg && it < 6) trace_stamp(p, 11 + 3 * it);   // first operands landed
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sa_hi = smem_base + stage * stage_bytes;
           const uint32_t sa_lo = sa_hi + a_bytes;
@@ -328,14 +366,90 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(smem_u32(&tmem_full_bar[slot]));     // accumulator of this tile complete
+        if (it < 6) trace_stamp(p, 12 + 3 * it);       // all MMAs of the tile issued
+      }
+    }
+  } else if (warp < EPI_WARP0) {
+    // ===================== A-operand converters (fp32-A mode) =====================
+    // Each warp owns 64 rows of the 128-row tile; a lane owns ONE 16-byte chunk column (c16) of 16 rows, so a warp-wide
+    // load instruction reads 4 rows x 128 contiguous bytes.  The raw fp32 chunks of k-block kb+1 are loaded into
+    // registers BEFORE the warp waits for the stage of k-block kb to drain: a stage turns around in the time of the
+    // split + 32 shared-memory stores, not in a global-memory round trip.  hi = rna_tf32(x) and lo = rna_tf32(x - hi) go
+    // to the swizzled places TMA would have written them to; fence.proxy.async publishes them to the tensor core.
+    if (p.a_f32) {
+      const int cw = warp - 2;
+      const int c16 = lane & 7, rsub = lane >> 3;
+      constexpr int RPL = BLOCK_M / CVT_WARPS / 4;        // rows per lane (16)
+      int ti = blockIdx.x, mi0 = 0, ni0 = 0, kbi = 0, kbi_end = 0;      // load cursor
+      int tc_ = blockIdx.x, mc0 = 0, nc0 = 0, kbc = 0, kbc_end = 0;     // store cursor (same sequence, one k-block behind)
+      int stage_c = 0;
+      uint32_t phase_c = 0;
+      if (ti < total_tiles) { decode(ti, mi0, ni0, kbi, kbi_end); decode(tc_, mc0, nc0, kbc, kbc_end); }
+      auto load_kb = [&](float4 (&v)[RPL]) {
+        const int s = kbi >= p.a_kb0 ? 1 : 0;
+        const int* rows = p.a_rows[s];
+        const int kloc = (kbi - (s ? p.a_kb0 : 0)) * BLOCK_K + 4 * c16;
+        const bool kval = kloc < p.a_k[s];
+        const float* base = p.a_ptr[s] + kloc;
+        const size_t ld = (size_t)p.a_ld[s];
+        int src[RPL];
+#pragma unroll
+        for (int j = 0; j < RPL; ++j) {
+          const int m = mi0 + cw * (BLOCK_M / CVT_WARPS) + 4 * j + rsub;
+          src[j] = (kval && m < p.M) ? (rows ? __ldg(rows + m) : m) : -1;
+        }
+#pragma unroll
+        for (int j = 0; j < RPL; ++j)
+          v[j] = src[j] >= 0 ? __ldg(reinterpret_cast<const float4*>(base + (size_t)src[j] * ld)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (++kbi == kbi_end) {
+          ti += gridDim.x;
+          if (ti < total_tiles) decode(ti, mi0, ni0, kbi, kbi_end);
+        }
+      };
+      // rna_tf32 on the bit pattern: add half an ulp of the 10-bit mantissa to the magnitude, drop the low 13 bits.
+      // Bit-identical to cvt.rna.tf32.f32 for every finite value (the PTX instruction costs 4 SASS instructions for its
+      // Inf/NaN handling, 12 per element for the split; this is 5).
+      auto rna = [](float a) { return rna_tf32(a); };
+      auto store_kb = [&](const float4 (&v)[RPL]) {
+        mbar_wait(smem_u32(&empty_bar[stage_c]), phase_c ^ 1);
+        const uint32_t a_hi = smem_base + stage_c * stage_bytes;
+#pragma unroll
+        for (int j = 0; j < RPL; ++j) {
+          const int r = cw * (BLOCK_M / CVT_WARPS) + 4 * j + rsub;
+          const uint32_t ph = a_hi + r * 128 + ((c16 ^ (r & 7)) << 4);
+          float4 h, l;
+          h.x = rna(v[j].x); h.y = rna(v[j].y); h.z = rna(v[j].z); h.w = rna(v[j].w);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ph), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+          if (three) {
+            l.x = rna(v[j].x - h.x); l.y = rna(v[j].y - h.y); l.z = rna(v[j].z - h.z); l.w = rna(v[j].w - h.w);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ph + a_bytes), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_bar[stage_c])) : "memory");
+        if (++stage_c == p.stages) { stage_c = 0; phase_c ^= 1; }
+        if (++kbc == kbc_end) {
+          tc_ += gridDim.x;
+          if (tc_ < total_tiles) decode(tc_, mc0, nc0, kbc, kbc_end);
+        }
+      };
+      float4 b0[RPL], b1[RPL];
+      if (ti < total_tiles) load_kb(b0);
+      while (tc_ < total_tiles) {
+        if (ti < total_tiles) load_kb(b1);
+        store_kb(b0);
+        if (tc_ >= total_tiles) break;
+        if (ti < total_tiles) load_kb(b0);
+        store_kb(b1);
       }
     }
   } else {
     // ===================== epilogue: TMEM -> registers -> global / counts =====================
     const int quarter = warp & 3;                      // TMEM lanes [32*quarter, 32*quarter+32)
-    const int part = (warp - 2) >> 2;                  // which share of the 32-column chunks this warp takes
+    const int part = (warp - EPI_WARP0) >> 2;                  // which share of the 32-column chunks this warp takes
     constexpr int kParts = EPI_WARPS / 4;
-    float* stage = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes) + (warp - 2) * (32 * kStagePitch);
+    float* stage = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes) + (warp - EPI_WARP0) * (32 * kStagePitch);
     float scale = 1.f, margin = 0.f;
     if (EPI != 0 && EPI != 3 && p.hyp) { scale = __ldg(p.scale_margin); margin = __ldg(p.scale_margin + 1); }
     int it = 0;
@@ -346,6 +460,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       const int row = m0 + quarter * 32 + lane;
       mbar_wait(smem_u32(&tmem_full_bar[slot]), acc_phase);
+      if (warp == EPI_WARP0 && lane == 0 && it < 6) trace_stamp(p, 28 + 2 * it);     // accumulator complete
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tmem_acc = tmem_base + (uint32_t)(slot * (p.tmem_cols >> 1)) + ((uint32_t)(quarter * 32) << 16);
       if constexpr (EPI == 0) {
@@ -379,6 +494,21 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
               if (nc > 2) b4.z = __ldg(p.bias + col + 2);
               if (nc > 3) b4.w = __ldg(p.bias + col + 3);
             }
+            // every global read of the chunk (accumulate / addend rows) is issued before the first store: the stores
+            // may alias them as far as the compiler knows, and one exposed L2 round trip per row group is 8 per chunk
+            float4 acc4[8], add4[8];
+            const bool fast = vec_ok && nc == 4 && !split;
+            if (fast && (p.accumulate || p.addend)) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int grow = m0 + quarter * 32 + 4 * i + sub_r;
+                acc4[i] = add4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (grow < p.M) {
+                  if (p.accumulate) acc4[i] = *reinterpret_cast<const float4*>(out + (size_t)grow * ldo + col);
+                  if (p.addend) add4[i] = *reinterpret_cast<const float4*>(p.addend + (size_t)grow * p.ld_add + col);
+                }
+              }
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int r = 4 * i + sub_r;
@@ -389,8 +519,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                 if (vec_ok && nc == 4) {
                   if (!split) {
                     a = f4_add(a, b4);
-                    if (p.accumulate) a = f4_add(a, *reinterpret_cast<const float4*>(dst));
-                    if (p.addend) a = f4_add(a, *reinterpret_cast<const float4*>(p.addend + (size_t)grow * p.ld_add + col));
+                    if (p.accumulate) a = f4_add(a, acc4[i]);
+                    if (p.addend) a = f4_add(a, add4[i]);
                   }
                   st4(dst, a);
                 } else {
@@ -462,9 +592,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         float my_nrm = 1.f;
         const bool gate = p.gate_G != nullptr;
         if (gate && p.gate_norm) {
-          // pass 1 over the accumulator: |rrelu(acc)| of the whole row (the tile spans all lay_d columns)
+          // pass 1 over the accumulator: |rrelu(acc)|^2 of the whole row (the tile spans all lay_d columns).  The two
+          // warps of a TMEM lane quarter each sum their own 32-column chunks and swap the partial sums through shared
+          // memory (named barrier of the pair, a second one frees the slots); both add them in the same order.
           float ss = 0.f;
-          for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+          for (int c0 = 32 * part; c0 < p.block_n; c0 += 32 * kParts) {
             float v[32];
             tmem_ld32(tmem_acc + (uint32_t)c0, v);
             const int ncols = min(32, p.lay_d - c0);
@@ -474,7 +606,14 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
               ss = j < ncols ? fmaf(r, r, ss) : ss;
             }
           }
-          my_nrm = 1.0f / fmaxf(sqrtf(ss), 1e-12f);     // F.normalize: x / max(|x|, 1e-12), applied as a multiply
+          float* slot = &norm_xchg[0][0];
+          slot[part * BLOCK_M + quarter * 32 + lane] = ss;
+          asm volatile("bar.sync %0, %1;" ::"r"(1 + quarter), "r"(32 * kParts) : "memory");
+          float tot = 0.f;
+#pragma unroll
+          for (int q = 0; q < kParts; ++q) tot += slot[q * BLOCK_M + quarter * 32 + lane];
+          asm volatile("bar.sync %0, %1;" ::"r"(1 + quarter), "r"(32 * kParts) : "memory");   // slots free for the next tile
+          my_nrm = 1.0f / fmaxf(sqrtf(tot), 1e-12f);    // F.normalize: x / max(|x|, 1e-12), applied as a multiply
         }
         const int sub_r = lane >> 3, sub_q = lane & 7, sub_c = sub_q * 4;
         for (int c0 = 32 * part; c0 < p.block_n; c0 += 32 * kParts) {
@@ -596,10 +735,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
       // this thread's TMEM reads of the slot are complete (tcgen05.wait::ld inside tmem_ld32): hand it back to the MMA warp
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[slot])) : "memory");
+      if (warp == EPI_WARP0 && lane == 0 && it < 6) trace_stamp(p, 29 + 2 * it);     // epilogue of the tile done (this warp)
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (threadIdx.x == 0) trace_stamp(p, 40);
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
   }
@@ -612,14 +753,7 @@ __global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict
   if (i >= n4) return;
   const float4 v = reinterpret_cast<const float4*>(x)[i];
   float4 h, l;
-  auto split1 = [](float a, float& hh, float& ll) {
-    uint32_t t;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(a));
-    hh = __uint_as_float(t);
-    const float r = a - hh;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(r));
-    ll = __uint_as_float(t);
-  };
+  auto split1 = [](float a, float& hh, float& ll) { split_tf32_1(a, hh, ll); };
   split1(v.x, h.x, l.x); split1(v.y, h.y, l.y); split1(v.z, h.z, l.z); split1(v.w, h.w, l.w);
   reinterpret_cast<float4*>(hi)[i] = h;
   reinterpret_cast<float4*>(lo)[i] = l;
@@ -699,6 +833,9 @@ int to_bf16(const float* x, void* out, size_t n, cudaStream_t st) {
 
 static int g_force_block_n = 0, g_force_stages = 0;
 void gemm_tf32_tune(int block_n, int stages) { g_force_block_n = block_n; g_force_stages = stages; }
+static unsigned long long* g_trace = nullptr;
+void gemm_tf32_trace(void* dev_buf) { g_trace = (unsigned long long*)dev_buf; }
+int gemm_tf32_trace_slots() { return tc::kTraceSlots; }
 
 // N-tile selection.  Large problems (>= one wave of 128-row tiles): the widest tile with the least padding, i.e.
 // the fewest operand re-reads.  Small problems (relation GRU, compact active-row GEMMs, pair scores): a tile costs
@@ -751,18 +888,45 @@ static void clear_epi(tc::Params& p) {
   p.lay_d = 0; p.lay_raw = nullptr; p.lay_hi = nullptr; p.lay_lo = nullptr; p.row_idx = nullptr; p.skip_rows = nullptr;
   p.gate_G = nullptr; p.gate_ld = 0; p.gate_bias = nullptr; p.gate_h = nullptr; p.gate_norm = 0;
   p.bf16 = 0; p.a_mn = 0; p.b_mn = 0;
+  p.a_f32 = 0; p.a_ptr[0] = p.a_ptr[1] = nullptr; p.a_ld[0] = p.a_ld[1] = 0; p.a_k[0] = p.a_k[1] = 0;
+  p.a_rows[0] = p.a_rows[1] = nullptr; p.a_kb0 = 0;
+  p.trace = g_trace;
+}
+
+// fp32-A operand description (see the header comment): up to two K segments, rows optionally gathered.
+static int set_a_f32(tc::Params& p, const float* a0, int lda0, int k0, const int* rows0, const float* a1, int lda1, int k1,
+                     const int* rows1, const char* who) {
+  if (!a0 || k0 <= 0 || (k0 & 3) || (lda0 & 3) || lda0 < k0 || ((uintptr_t)a0 & 15) ||
+      (k1 > 0 && (!a1 || (k1 & 3) || (lda1 & 3) || lda1 < k1 || ((uintptr_t)a1 & 15))) || k1 < 0) {
+    set_last_error("%s: bad fp32 A operand (k0=%d lda0=%d k1=%d lda1=%d; 16-byte alignment, multiples of 4)", who, k0, lda0, k1, lda1);
+    return REGCN_ERR_DIM;
+  }
+  p.a_f32 = 1;
+  p.a_ptr[0] = a0; p.a_ld[0] = lda0; p.a_k[0] = k0; p.a_rows[0] = rows0;
+  p.a_ptr[1] = k1 > 0 ? a1 : nullptr; p.a_ld[1] = lda1; p.a_k[1] = k1; p.a_rows[1] = rows1;
+  p.a_kb0 = (k0 + tc::BLOCK_K - 1) / tc::BLOCK_K;
+  return REGCN_OK;
 }
 
 // Common launcher: validates operands, builds the tensor maps, sizes the pipeline, launches.
 static int launch_tc(const float* a_hi, const float* a_lo, int lda, const float* b_hi, const float* b_lo, int ldb,
                      tc::Params p, int passes, int split_k, int force_block_n, const char* who, cudaStream_t st) {
   using namespace tc;
-  const int M = p.M, N = p.N, K = p.K;
+  const int M = p.M, N = p.N;
+  const int Ktrue = p.K;                 // reduction length of B (the weights); fp32-A mode pads every segment to k-blocks
+  if (p.a_f32) {
+    if (p.a_k[0] + p.a_k[1] != Ktrue) { set_last_error("%s: fp32 A segments %d + %d != K = %d", who, p.a_k[0], p.a_k[1], Ktrue); return REGCN_ERR_DIM; }
+    if (p.bf16 || p.a_mn || p.b_mn) { set_last_error("%s: fp32 A takes K-major tf32 operands", who); return REGCN_ERR_UNSUPPORTED; }
+    p.K = BLOCK_K * (p.a_kb0 + (p.a_k[1] + BLOCK_K - 1) / BLOCK_K);
+    a_hi = a_lo = b_hi;                  // placeholders for the checks / unused tensor maps below
+    lda = ldb;
+  }
+  const int K = p.K;
   if (!a_hi || !b_hi || (passes == 3 && (!a_lo || !b_lo))) { set_last_error("%s: null operand", who); return REGCN_ERR_NULL; }
   if (passes != 1 && passes != 3) { set_last_error("%s: passes must be 1 or 3", who); return REGCN_ERR_DIM; }
   const int ld_mask = p.bf16 ? 7 : 3;                 // row pitch must be a multiple of 16 bytes
   if (p.bf16 && passes != 1) { set_last_error("%s: bf16 operands take one pass", who); return REGCN_ERR_DIM; }
-  if (M < 0 || N <= 0 || K <= 0 || (lda & ld_mask) || (ldb & ld_mask) || lda < (p.a_mn ? M : K) || ldb < (p.b_mn ? N : K) ||
+  if (M < 0 || N <= 0 || K <= 0 || (lda & ld_mask) || (ldb & ld_mask) || (!p.a_f32 && lda < (p.a_mn ? M : K)) || ldb < (p.b_mn ? N : Ktrue) ||
       (((uintptr_t)a_hi | (uintptr_t)b_hi | (uintptr_t)a_lo | (uintptr_t)b_lo) & 15)) {
     set_last_error("%s: bad dims/alignment M=%d N=%d K=%d lda=%d ldb=%d", who, M, N, K, lda, ldb);
     return REGCN_ERR_DIM;
@@ -789,22 +953,24 @@ static int launch_tc(const float* a_hi, const float* a_lo, int lda, const float*
   p.stages = (int)(SMEM_BUDGET / stage_bytes);
   if (p.stages > 8) p.stages = 8;
   if (g_force_stages > 0 && g_force_stages < p.stages) p.stages = g_force_stages;
-  if (p.stages < 1) { set_last_error("%s: tile does not fit in shared memory", who); return REGCN_ERR_UNSUPPORTED; }
+  if (p.stages < (p.a_f32 ? 2 : 1)) { set_last_error("%s: tile does not fit in shared memory", who); return REGCN_ERR_UNSUPPORTED; }
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   int e;
   // K-major operand (rows, K): box of 32 k-floats x tile rows; MN-major operand (K, rows): boxes of 32 columns x 32 rows
-  if ((e = p.a_mn ? make_map(&ta_hi, a_hi, K, M, lda, BLOCK_K, false, true) : make_map(&ta_hi, a_hi, M, K, lda, BLOCK_M, p.bf16 != 0))) return e;
-  if ((e = p.b_mn ? make_map(&tb_hi, b_hi, K, N, ldb, BLOCK_K, false, true) : make_map(&tb_hi, b_hi, N, K, ldb, p.block_n, p.bf16 != 0))) return e;
+  if ((e = p.b_mn ? make_map(&tb_hi, b_hi, K, N, ldb, BLOCK_K, false, true) : make_map(&tb_hi, b_hi, N, Ktrue, ldb, p.block_n, p.bf16 != 0))) return e;
+  if (p.a_f32) ta_hi = tb_hi;           // never dereferenced: the converter warps build the A tiles
+  else if ((e = p.a_mn ? make_map(&ta_hi, a_hi, K, M, lda, BLOCK_K, false, true) : make_map(&ta_hi, a_hi, M, K, lda, BLOCK_M, p.bf16 != 0))) return e;
   if (passes == 3) {
-    if ((e = p.a_mn ? make_map(&ta_lo, a_lo, K, M, lda, BLOCK_K, false, true) : make_map(&ta_lo, a_lo, M, K, lda, BLOCK_M))) return e;
-    if ((e = p.b_mn ? make_map(&tb_lo, b_lo, K, N, ldb, BLOCK_K, false, true) : make_map(&tb_lo, b_lo, N, K, ldb, p.block_n))) return e;
+    if (p.a_f32) ta_lo = tb_hi;
+    else if ((e = p.a_mn ? make_map(&ta_lo, a_lo, K, M, lda, BLOCK_K, false, true) : make_map(&ta_lo, a_lo, M, K, lda, BLOCK_M))) return e;
+    if ((e = p.b_mn ? make_map(&tb_lo, b_lo, K, N, ldb, BLOCK_K, false, true) : make_map(&tb_lo, b_lo, N, Ktrue, ldb, p.block_n))) return e;
   } else {
     ta_lo = ta_hi; tb_lo = tb_hi;
   }
   const size_t smem = (size_t)p.stages * stage_bytes + 1024 + STAGING_BYTES;
   static bool attr_set = false;
   if (!attr_set) {
-    const int mx = (int)(SMEM_BUDGET + 2048 + STAGING_BYTES);
+    const int mx = (int)(SMEM_BUDGET + 1024 + STAGING_BYTES);   // + 2 KB of static shared memory = the 227 KB limit
     cudaError_t ce = cudaFuncSetAttribute(gemm_tf32_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(gemm_tf32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(gemm_tf32_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
@@ -836,7 +1002,7 @@ static int launch_tc(const float* a_hi, const float* a_lo, int lda, const float*
     case 3: launch_k(gemm_tf32_kernel<3>, grid, NUM_THREADS, smem, st, ta_hi, ta_lo, tb_hi, tb_lo, p); break;
     default: launch_k(gemm_tf32_kernel<4>, grid, NUM_THREADS, smem, st, ta_hi, ta_lo, tb_hi, tb_lo, p); break;
   }
-  prof_end(PROF_GEMM_TC, p.epi == 2 ? 2.0 * M * (double)K : 2.0 * M * (double)N * K, st);
+  prof_end(PROF_GEMM_TC, p.epi == 2 ? 2.0 * M * (double)Ktrue : 2.0 * M * (double)N * Ktrue, st);
   return REGCN_OK;
 }
 
@@ -921,6 +1087,65 @@ int gemm_tf32_layer(const float* a_hi, const float* a_lo, int lda, const float* 
   int e = launch_tc(a_hi, a_lo, lda, b_hi, b_lo, ldb, p, 3, 1, force_bn, "gemm_tf32_layer", st);
   if (e) return e;
   return check_launch("gemm_tf32_layer");
+}
+
+// ---- fp32-A variants: the A operand is one fp32 copy (two K segments, optional row gather), split to TF32 on chip ----
+int gemm_tf32_a32(const float* a0, int lda0, int k0, const int* rows0, const float* a1, int lda1, int k1, const int* rows1,
+                  const float* b_hi, const float* b_lo, int ldb, float* C, int ldc, int M, int N, const float* bias,
+                  int accumulate, int passes, int split_k, float* ws, size_t ws_bytes, const float* addend, int ld_add,
+                  cudaStream_t st) {
+  if (!C) { set_last_error("gemm_tf32_a32: null output"); return REGCN_ERR_NULL; }
+  if (ldc < N) { set_last_error("gemm_tf32_a32: ldc=%d < N=%d", ldc, N); return REGCN_ERR_DIM; }
+  if (addend && split_k > 1) { set_last_error("gemm_tf32_a32: addend is not supported together with split-K"); return REGCN_ERR_UNSUPPORTED; }
+  tc::Params p;
+  clear_epi(p);
+  int e = set_a_f32(p, a0, lda0, k0, rows0, a1, lda1, k1, rows1, "gemm_tf32_a32");
+  if (e) return e;
+  const int K = k0 + (k1 > 0 ? k1 : 0);
+  p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.bias = bias; p.accumulate = accumulate;
+  p.addend = addend; p.ld_add = ld_add;
+  const int total_kb = p.a_kb0 + (p.a_k[1] + tc::BLOCK_K - 1) / tc::BLOCK_K;
+  int sk = split_k < 1 ? 1 : (split_k > total_kb ? total_kb : split_k);
+  if (sk > 1) {
+    const int kb_per = (total_kb + sk - 1) / sk;
+    sk = (total_kb + kb_per - 1) / kb_per;
+  }
+  if (sk > 1) {
+    if (!ws || ws_bytes < gemm_tf32_workspace_bytes(M, N, sk)) { set_last_error("gemm_tf32_a32: split-K workspace too small"); return REGCN_ERR_WORKSPACE; }
+    p.ws = ws;
+  }
+  e = launch_tc(nullptr, nullptr, 0, b_hi, b_lo, ldb, p, passes, sk, 0, "gemm_tf32_a32", st);
+  if (e) return e;
+  if (sk > 1 && M > 0) {
+    const size_t total = (size_t)M * N;
+    launch_k(splitk_reduce_kernel, (unsigned)((total + 255) / 256), 256, 0, st, ws, sk, C, ldc, M, N, bias, accumulate);
+  }
+  return check_launch("gemm_tf32_a32");
+}
+
+int gemm_tf32_layer_a32(const float* a0, int lda0, int k0, const int* rows0, const float* a1, int lda1, int k1,
+                        const int* rows1, const float* b_hi, const float* b_lo, int ldb, int M, int N, int d,
+                        float* out_raw, float* out_hi, float* out_lo, float* gate_out, int ld_gate_out, const int* row_idx,
+                        const int* skip_rows, const float* gate_G, int gate_ld, const float* gate_bias, const float* gate_h,
+                        int gate_norm, cudaStream_t st) {
+  if ((!out_raw && !out_hi) || (out_hi && !out_lo)) { set_last_error("gemm_tf32_layer_a32: no output"); return REGCN_ERR_NULL; }
+  if (d <= 0 || (d & 3) || (N & 3) || N < d || (N > d && (!gate_out || ld_gate_out < N - d || (ld_gate_out & 3)))) {
+    set_last_error("gemm_tf32_layer_a32: bad dims N=%d d=%d", N, d); return REGCN_ERR_DIM;
+  }
+  if (gate_G && (N != d || d > 256 || !gate_bias || !gate_h || (gate_ld & 3))) {
+    set_last_error("gemm_tf32_layer_a32: the fused time gate needs N == d <= 256"); return REGCN_ERR_DIM;
+  }
+  tc::Params p;
+  clear_epi(p);
+  int e = set_a_f32(p, a0, lda0, k0, rows0, a1, lda1, k1, rows1, "gemm_tf32_layer_a32");
+  if (e) return e;
+  p.M = M; p.N = N; p.K = k0 + (k1 > 0 ? k1 : 0); p.epi = 3; p.lay_d = d; p.lay_raw = out_raw; p.lay_hi = out_hi; p.lay_lo = out_lo;
+  p.C = gate_out; p.ldc = ld_gate_out; p.row_idx = row_idx; p.skip_rows = skip_rows;
+  p.gate_G = gate_G; p.gate_ld = gate_ld; p.gate_bias = gate_bias; p.gate_h = gate_h; p.gate_norm = gate_norm;
+  const int force_bn = gate_G ? (d + 15) / 16 * 16 : 0;
+  e = launch_tc(nullptr, nullptr, 0, b_hi, b_lo, ldb, p, 3, 1, force_bn, "gemm_tf32_layer_a32", st);
+  if (e) return e;
+  return check_launch("gemm_tf32_layer_a32");
 }
 
 // Fused K11/K13 + K14: raw_count[b] += #{candidate n of this shard, n != target[b] : score(b,n) beats tscore[b]}.

@@ -17,7 +17,8 @@ int rel_mean_pool(const float* h, const int* rel_rowptr, const int* rel_ents, in
 int union_aggregate(const float* h, const float* rel, const int* rowptr, const int* src_sorted, const int* etype_sorted,
                     const float* norm, const int* vptr, const int* sptr, const int* vrow_row, int nv, int nsplit,
                     const float* radius, float gamma, int N, int d, float* out, float* partial, float* out_hi,
-                    float* out_lo, const int* active_pos, int ldo, int max_chunks, cudaStream_t st);
+                    float* out_lo, const int* active_pos, int ldo, int max_chunks, cudaStream_t st,
+                    int* fold_count = nullptr);
 int block_aggregate(const float* h, const float* W, const int* rowptr, const int* src_sorted, const int* etype_sorted,
                     const float* norm, int N, int d_in, int d_out, int nb, float* out, cudaStream_t st);
 int lorentz_aggregate(const float* ht, const float* W, const float* rel, const int* rowptr, const int* src_sorted,
@@ -37,9 +38,20 @@ int gemm_tf32_layer(const float* a_hi, const float* a_lo, int lda, const float* 
                     int N, int K, int d, float* out_raw, float* out_hi, float* out_lo, float* gate_out, int ld_gate_out,
                     const int* row_idx, const int* skip_rows, const float* gate_G, int gate_ld, const float* gate_bias,
                     const float* gate_h, int gate_norm, cudaStream_t st);
+int gemm_tf32_a32(const float* a0, int lda0, int k0, const int* rows0, const float* a1, int lda1, int k1, const int* rows1,
+                  const float* b_hi, const float* b_lo, int ldb, float* C, int ldc, int M, int N, const float* bias,
+                  int accumulate, int passes, int split_k, float* ws, size_t ws_bytes, const float* addend, int ld_add,
+                  cudaStream_t st);
+int gemm_tf32_layer_a32(const float* a0, int lda0, int k0, const int* rows0, const float* a1, int lda1, int k1,
+                        const int* rows1, const float* b_hi, const float* b_lo, int ldb, int M, int N, int d,
+                        float* out_raw, float* out_hi, float* out_lo, float* gate_out, int ld_gate_out, const int* row_idx,
+                        const int* skip_rows, const float* gate_G, int gate_ld, const float* gate_bias, const float* gate_h,
+                        int gate_norm, cudaStream_t st);
 void pdl_set(int on);
 void two_stream_set(int on);
 void gemm_tf32_tune(int block_n, int stages);
+void gemm_tf32_trace(void* dev_buf);
+int gemm_tf32_trace_slots();
 void gemm_tf32_sm_hint(int sms);
 void aggregate_tune(int impl);
 int score_count_tf32(const float* q_hi, const float* q_lo, const float* e_hi, const float* e_lo, int B, int N, int K,

@@ -729,3 +729,114 @@ def test_gemm_mn_major_operands(a_mn, b_mn, M, N, K, split_k):
     same = torch.equal(C[:, :N], C2[:, :N])
     assert same or float((C[:, :N] - C2[:, :N]).abs().max()) <= 1e-6 * max(1.0, float(C2[:, :N].abs().max())), \
         float((C[:, :N] - C2[:, :N]).abs().max())
+
+
+# ----------------------------------------------------------------------------------------- fp32-A GEMM (on-chip TF32 split)
+@pytest.mark.parametrize("M,N,k0,k1,gather,split_k", [
+    (300, 200, 200, 0, False, 1), (23033, 400, 200, 0, False, 1), (1560, 200, 200, 200, True, 1),
+    (129, 64, 36, 8, True, 1), (2914, 200, 1000, 0, False, 3), (5, 16, 4, 0, False, 1)])
+def test_gemm_fp32_a_bit_identical_to_presplit(M, N, k0, k1, gather, split_k):
+    """regcn_gemm_tf32_a32 (A split into TF32 hi/lo inside shared memory by converter warps, optional row gather, two K
+    segments) must equal regcn_gemm_tf32 on the pre-split, pre-gathered, concatenated operand BIT FOR BIT."""
+    R, ops = _ops()
+    from regcn_b200 import _lib
+    g = torch.Generator(device=DEV)
+    g.manual_seed(M * 7 + N)
+    src_rows = M + 77 if gather else M
+    a0 = torch.randn(src_rows, k0 + 4, device=DEV, generator=g)[:, :k0]          # lda > k
+    a1 = torch.randn(src_rows, max(k1, 4), device=DEV, generator=g)
+    rows0 = torch.randperm(src_rows, device=DEV, generator=g)[:M].to(torch.int32) if gather else None
+    rows1 = torch.randperm(src_rows, device=DEV, generator=g)[:M].to(torch.int32) if gather and k1 else None
+    K = k0 + k1
+    w = torch.randn(N, K, device=DEV, generator=g)
+    bias = torch.randn(N, device=DEV, generator=g)
+    parts = [a0[rows0.long()] if gather else a0]
+    if k1:
+        parts.append((a1[rows1.long()] if rows1 is not None else a1[:M])[:, :k1])
+    a_cat = torch.cat(parts, dim=1).contiguous()
+    ah, al = ops.split_tf32(a_cat) if K % 4 == 0 else (None, None)
+    wh, wl = ops.split_tf32(w)
+    ref = torch.empty(M, N, device=DEV)
+    ws = torch.empty(max(1, split_k * M * N), device=DEV)
+    _lib.call("regcn_gemm_tf32", ah.data_ptr(), al.data_ptr(), K, wh.data_ptr(), wl.data_ptr(), K, ref.data_ptr(), N, M, N, K,
+              bias.data_ptr(), 0, 3, split_k, ws.data_ptr(), ws.numel() * 4)
+    out = torch.full((M, N), float("nan"), device=DEV)
+    _lib.call("regcn_gemm_tf32_a32", a0.data_ptr(), a0.stride(0), k0, None if rows0 is None else rows0.data_ptr(),
+              a1.data_ptr() if k1 else None, a1.stride(0), k1, None if rows1 is None else rows1.data_ptr(), wh.data_ptr(),
+              wl.data_ptr(), K, out.data_ptr(), N, M, N, bias.data_ptr(), 0, 3, split_k, ws.data_ptr(), ws.numel() * 4, None, 0)
+    torch.cuda.synchronize()
+    if k0 % 32 == 0 or k1 == 0:
+        assert torch.equal(out, ref), f"max |diff| {(out - ref).abs().max().item()}"
+    else:
+        # two segments with a ragged first segment: k-blocks are padded per segment, so products are accumulated in a
+        # different k-block grouping than on the concatenated operand -- same values to fp32 rounding
+        ok, worst = close(out.cpu().numpy(), ref.cpu().numpy(), rtol=1e-5)
+        assert ok, worst
+
+
+def test_gemm_layer_fp32_a_matches_presplit_layer():
+    """Layer epilogue (rrelu, gate columns, row scatter / skip, fused normalise + time gate) through the fp32-A path equals
+    the pre-split path bit for bit."""
+    R, ops = _ops()
+    from regcn_b200 import _lib
+    g = torch.Generator(device=DEV)
+    g.manual_seed(5)
+    N, d = 3000, 200
+    x = torch.randn(N, d, device=DEV, generator=g) * 0.3
+    w = torch.randn(2 * d, d, device=DEV, generator=g) * 0.1
+    xh, xl = ops.split_tf32(x)
+    wh, wl = ops.split_tf32(w)
+    skip = torch.full((N,), -1, device=DEV, dtype=torch.int32)
+    skip[::7] = 1
+    outs = []
+    for a32 in (False, True):
+        o_raw = torch.zeros(N, d, device=DEV)
+        gate = torch.zeros(N, d, device=DEV)
+        if a32:
+            _lib.call("regcn_gemm_tf32_layer_a32", x.data_ptr(), d, d, None, None, 0, 0, None, wh.data_ptr(), wl.data_ptr(), d,
+                      N, 2 * d, d, o_raw.data_ptr(), None, None, gate.data_ptr(), d, None, skip.data_ptr(), None, 0, None,
+                      None, 0)
+        else:
+            _lib.call("regcn_gemm_tf32_layer", xh.data_ptr(), xl.data_ptr(), d, wh.data_ptr(), wl.data_ptr(), d, N, 2 * d, d,
+                      d, o_raw.data_ptr(), None, None, gate.data_ptr(), d, None, skip.data_ptr(), None, 0, None, None, 0)
+        # last layer: normalise + time gate on the layer-0 gate columns
+        h_new = torch.zeros(N, d, device=DEV)
+        b = torch.randn(d, device=DEV, generator=torch.Generator(device=DEV).manual_seed(9)) * 0.1
+        w1 = torch.randn(d, d, device=DEV, generator=torch.Generator(device=DEV).manual_seed(11)) * 0.1
+        w1h, w1l = ops.split_tf32(w1)
+        if a32:
+            _lib.call("regcn_gemm_tf32_layer_a32", o_raw.data_ptr(), d, d, None, None, 0, 0, None, w1h.data_ptr(),
+                      w1l.data_ptr(), d, N, d, d, h_new.data_ptr(), None, None, None, 0, None, skip.data_ptr(),
+                      gate.data_ptr(), d, b.data_ptr(), x.data_ptr(), 1)
+        else:
+            oh, ol = ops.split_tf32(o_raw)
+            _lib.call("regcn_gemm_tf32_layer", oh.data_ptr(), ol.data_ptr(), d, w1h.data_ptr(), w1l.data_ptr(), d, N, d, d, d,
+                      h_new.data_ptr(), None, None, None, 0, None, skip.data_ptr(), gate.data_ptr(), d, b.data_ptr(),
+                      x.data_ptr(), 1)
+        torch.cuda.synchronize()
+        outs.append((o_raw, gate, h_new))
+    for a, b_ in zip(*outs):
+        assert torch.equal(a, b_), (a - b_).abs().max().item()
+    # and against torch in fp64
+    ref1 = torch.nn.functional.rrelu((x.double() @ w[:d].double().t()), training=False)
+    act = skip.cpu().numpy() < 0
+    ok, worst = close(outs[1][0].cpu().numpy()[act], ref1.float().cpu().numpy()[act], rtol=1e-4)
+    assert ok, worst
+
+
+def test_split_tf32_matches_rna_restatement():
+    """regcn_split_tf32 (bit-pattern rna) == the frexp/floor restatement of cvt.rna.tf32.f32 on normal values, ties and
+    signs included; hi and lo have their 13 low mantissa bits clear and hi + lo reproduces x to 2^-21."""
+    R, ops = _ops()
+    rng = np.random.default_rng(3)
+    x = np.concatenate([rng.standard_normal(40000).astype(np.float32) * s for s in (1e-20, 1e-3, 1.0, 3e4, 1e20)])
+    ties = (np.arange(1, 4097, dtype=np.uint32) << 13 | 0x1000 | 0x3f800000).view(np.float32)   # exactly half-way cases
+    x = np.concatenate([x, ties, -ties, np.array([0.0, -0.0, 1.0, -1.0, 0.1, 1e-30], dtype=np.float32)]).astype(np.float32)
+    x = np.resize(x, (x.size + 3) // 4 * 4)
+    hi, lo = ops.split_tf32(_t(x))
+    hi, lo = hi.cpu().numpy(), lo.cpu().numpy()
+    r_hi, r_lo = restate.split_tf32(x)
+    assert np.array_equal(hi, r_hi)
+    assert np.array_equal(lo, r_lo)
+    assert not (hi.view(np.uint32) & 0x1fff).any() and not (lo.view(np.uint32) & 0x1fff).any()
+    assert np.all(np.abs(hi.astype(np.float64) + lo - x) <= 2.0 ** -21 * np.abs(x))

@@ -228,3 +228,16 @@ def test_oracle_hyperbolic_train_step_matches_reference(name):
     rec = log[0]
     compare_train_step(z, name, 0, rec["losses"], rec["grad_norm"], {k: v.numpy() for k, v in rec["grads"].items()},
                        {k: v.numpy() for k, v in rec["params"].items()})
+
+
+def test_rna_tf32_restatement_matches_bit_pattern_rule():
+    """oracle.restate.rna_tf32 (frexp / floor in float64) == add-half-ulp-and-mask on the bit pattern (what the kernels
+    compute) on normal fp32 values incl. exact ties."""
+    import numpy as np
+    from oracle import restate
+    rng = np.random.default_rng(0)
+    x = (rng.standard_normal(100000) * np.exp(rng.uniform(-40, 40, 100000))).astype(np.float32)
+    ties = (np.arange(1, 4097, dtype=np.uint32) << 13 | 0x1000 | 0x3f800000).view(np.float32)
+    x = np.concatenate([x, ties, -ties])
+    bits = ((x.view(np.uint32) + np.uint32(0x1000)) & np.uint32(0xffffe000)).view(np.float32)
+    assert np.array_equal(bits, restate.rna_tf32(x))
