@@ -200,6 +200,11 @@ REGCN_API int regcn_gemm_tf32_layer_a32(const float* a0, int lda0, int k0, const
  * pipeline hand-over points of its CTA (entry, dependency wait, per tile: loads issued, first operands landed, MMAs
  * issued, accumulator complete, epilogue done).  NULL detaches.  Not thread-safe; a measurement aid only. */
 REGCN_API void regcn_gemm_tf32_trace(void* dev_buf);
+/* regcn_score_count_tf32 with a hyperbolic (RotH / MuRP form) score and no candidate bias decides "beats the target"
+ * with a division- and sqrt-free polynomial threshold test per candidate and evaluates the IEEE score
+ * (hyperbolic_decoder.py:89-179) only inside its rounding band; counts are identical either way.  0 switches the test
+ * off (every candidate takes the IEEE score): the yardstick of tests and bench.py. Default 1. */
+REGCN_API void regcn_score_count_poly(int on);
 REGCN_API int regcn_gemm_tf32_trace_slots(void);
 /* the layer GEMM of the evolve engine on its own (UnionRGCNLayer apply step, rgcn/layers.py:247-255, and for the last
  * layer the time gate, src/rrgcn.py:176-178, straight out of the accumulator):

@@ -46,6 +46,7 @@ SIGNATURES = {
     "regcn_gemm_tf32_layer_a32": (_i, [_p, _i, _i, _p, _p, _i, _i, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p,
                                        _p, _i, _p, _p, _i, _p]),
     "regcn_gemm_tf32_trace": (None, [_p]),
+    "regcn_score_count_poly": (None, [_i]),
     "regcn_gemm_tf32_trace_slots": (_i, []),
     "regcn_gemm_tf32_layer": (_i, [_p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p, _i, _p, _p, _i, _p]),
     "regcn_pdl_enable": (None, [_i]),

@@ -122,6 +122,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld1(uint32_t taddr, float& v) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  v = __uint_as_float(r);
+}
+
 struct Params {
   float* C;
   int ldc;
@@ -151,6 +158,7 @@ struct Params {
   const float* y2;            // [N] |e|^2   (epi 2: indexed by pair)
   const float* col_bias;      // [N] candidate bias or NULL (epi 2: indexed by pair)
   float hc, hproj_max;        // curvature, projection bound
+  float hyp_ymax;             // epi 1 polynomial test: bound on |e|^2 (and |q|^2) its rounding band is valid for
   const float* scale_margin;  // device [scale, margin]
   const float* row_c;         // hyp == 2: [M] per-query curvature (true-distance branch); epi 2: indexed by pair
   float* diag_out;            // epi 2: [M]
@@ -548,23 +556,110 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         const int tg = rv ? __ldg(p.target + row) - p.col_offset : -1;
         int cnt = 0;
         const bool plain = !p.hyp && !p.col_bias;          // hoisted: no per-element uniform branches in the hot loop
+        // ---- hyperbolic (RotH / MuRP form) score without a bias: threshold test instead of the score -------------------
+        // score(dot) > st  <=>  |(-q) (+) e|^2 < T,  T = margin - st / scale  (scale > 0, below the projection clamp)
+        //                  <=>  num - T den^2 < 0  with the Moebius numerator / denominator of hyp_score_from_dot.
+        // For a fixed query row, num - T den^2 is a quadratic polynomial in (dot, y = |e|^2):
+        //   diff = dot (k1 dot + k2 y + k4) + (y (k3 y + k5) + k6)                         5 FMAs, no division, no sqrt
+        // with six per-row coefficients formed in double.  The sign of diff decides the comparison whenever |diff| exceeds
+        // `band`, a bound on the rounding of BOTH evaluations (this polynomial and the IEEE sequence of
+        // hyp_score_from_dot), evaluated per 32-candidate chunk from the largest |e|^2 of the chunk; candidates inside
+        // the band -- ties included -- and rows whose target sits at the projection clamp take the exact score, so every
+        // count equals the dense path's bit for bit.
+        const bool poly = p.hyp == 1 && !p.col_bias && p.hyp_ymax > 0.f;
+        // band_on: 0 = every candidate beats (target below the clamped minimum; k6 = -1), 1 = polynomial, 2 = exact only
+        float k1 = 0.f, k2 = 0.f, k3 = 0.f, k4 = 0.f, k5 = 0.f, k6 = -1.f, x2r = 0.f, sx = 0.f, e0 = 0.f;
+        int band_on = rv ? 2 : 0;
+        if (poly && rv) {
+          x2r = __ldg(p.x2 + row);
+          const double c = (double)p.hc, x2 = (double)x2r, pm2 = (double)p.hproj_max * (double)p.hproj_max;
+          const double T = (double)margin - (double)st_ / (double)scale;
+          if (scale > 0.f && x2 >= 0.0 && c * x2 <= 1.0 && T == T && fabs(T) < 1e30) {
+            if (T > pm2 * (1.0 + 1e-5)) {
+              band_on = 0;
+            } else if (T < pm2 * (1.0 - 1e-5)) {
+              const double b = 1.0 - c * x2, kap = c * c * x2, del = 1.0 + (double)kEps;
+              // s = -dot:  num = x2 a^2 + 2 a b s + b^2 y,  a = 1 + 2 c s + c y;  den = del + 2 c s + kap y
+              const double q1 = 4.0 * c * c * x2 + 4.0 * b * c - 4.0 * c * c * T;          // s^2
+              const double q2 = 4.0 * c * c * x2 + 2.0 * b * c - 4.0 * c * kap * T;        // s y
+              const double q3 = c * c * x2 - kap * kap * T;                                // y^2
+              const double q4 = 4.0 * c * x2 + 2.0 * b - 4.0 * c * del * T;                // s
+              const double q5 = 2.0 * c * x2 + b * b - 2.0 * del * kap * T;                // y
+              const double q6 = x2 - del * del * T;                                        // 1
+              k1 = (float)q1; k2 = (float)-q2; k3 = (float)q3; k4 = (float)-q4; k5 = (float)q5; k6 = (float)q6;
+              sx = (float)(sqrt(x2) * 1.0001);
+              // weight of a^2 / den^2 in the magnitudes the IEEE sequence rounds: |q|^2 and |T|, |margin|, |st / scale|
+              e0 = (float)((x2 + fabs(T) + fabs((double)margin) + fabs((double)st_ / (double)scale)) * 1.0001);
+              band_on = 1;
+            }
+          }
+        }
         for (int c0 = 32 * part; c0 < p.block_n; c0 += 32 * kParts) {
           float v[32];
           tmem_ld32(tmem_acc + (uint32_t)c0, v);
           const int gn0 = n0 + c0;
           const int ncols = min(32, min(p.block_n - c0, p.N - gn0));
+          if (poly) {
+            if (ncols > 0) {                                 // uniform across the warp
+              const float ycol = lane < ncols ? __ldg(p.y2 + gn0 + lane) : 0.f;      // lane j holds |e_j|^2 of the chunk
+              float ymx = ycol;
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) ymx = fmaxf(ymx, __shfl_xor_sync(0xffffffffu, ymx, o));
+              // rounding band of this (row, chunk): 64 ulp of the summed magnitudes of every monomial either evaluation
+              // rounds, with |dot| <= u = |q| sqrt(ymax) (Cauchy-Schwarz) and |e|^2 <= ymax, a, den <= A = 1 + 2cu + c ymax
+              float bnd = INFINITY;
+              if (band_on == 0) bnd = 0.f;
+              else if (band_on == 1 && ymx >= 0.f && p.hc * ymx <= 1.0001f) {
+                const float u = sx * (sqrtf(ymx) * 1.0001f);
+                const float A = fmaf(2.0f * p.hc, u, fmaf(p.hc, ymx, 1.0001f));
+                float mag = fmaf(fabsf(k1), u * u, fmaf(fabsf(k2), u * ymx, fmaf(fabsf(k3), ymx * ymx,
+                            fmaf(fabsf(k4), u, fmaf(fabsf(k5), ymx, fabsf(k6))))));
+                mag += fmaf(A * A, e0, fmaf(2.0f * A, u, ymx));
+                bnd = mag * (64.0f * 5.9604644775390625e-08f * 1.01f);
+              }
+              const int tj = tg - gn0;
+              // pass 1, branch-free: decide every candidate outside its band, remember the others in a bit mask
+              uint32_t amb = 0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float y = __shfl_sync(0xffffffffu, ycol, j);
+                const float dotv = v[j];
+                const float diff = fmaf(dotv, fmaf(k1, dotv, fmaf(k2, y, k4)), fmaf(y, fmaf(k3, y, k5), k6));
+                const int inband = (int)!(fabsf(diff) > bnd);          // inside the rounding band, or NaN
+                const int valid = (int)(j < ncols) & (int)(j != tj) & (int)rv;
+                amb |= (uint32_t)(inband & valid) << j;
+                cnt += (int)(diff < 0.f) & (inband ^ 1) & valid;
+              }
+              // pass 2, rare: the exact IEEE score for the in-band candidates.  One rolled loop over the columns any lane
+              // needs (the accumulator column is re-read from TMEM, warp-uniformly), so the division / sqrt sequence
+              // exists once in the instruction stream instead of 32 times inside the hot loop
+              uint32_t any = __reduce_or_sync(0xffffffffu, amb);
+              while (any) {
+                const int j = __ffs(any) - 1;
+                any &= any - 1;
+                float dotv;
+                tmem_ld1(tmem_acc + (uint32_t)(c0 + j), dotv);
+                const float y = __shfl_sync(0xffffffffu, ycol, j);
+                if ((amb >> j) & 1u) {
+                  const float sc = hyp_score_from_dot(dotv, x2r, y, p.hc, p.hproj_max, scale, margin);
+                  cnt += (int)(sc > st_) | ((int)(sc == st_) & (int)(j < tj));
+                }
+              }
+            }
+            continue;
+          }
           if (rv && ncols > 0) {
             if (!plain) {
               if (p.hyp == 2) {
-                const float x2r = __ldg(p.x2 + row), cq = __ldg(p.row_c + row);
+                const float x2q = __ldg(p.x2 + row), cq = __ldg(p.row_c + row);
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
-                  if (j < ncols) v[j] = hyp_dist_score_from_dot(v[j], x2r, __ldg(p.y2 + gn0 + j), cq, scale, margin);
+                  if (j < ncols) v[j] = hyp_dist_score_from_dot(v[j], x2q, __ldg(p.y2 + gn0 + j), cq, scale, margin);
               } else if (p.hyp) {
-                const float x2r = __ldg(p.x2 + row);
+                const float x2q = __ldg(p.x2 + row);
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
-                  if (j < ncols) v[j] = hyp_score_from_dot(v[j], x2r, __ldg(p.y2 + gn0 + j), p.hc, p.hproj_max, scale, margin);
+                  if (j < ncols) v[j] = hyp_score_from_dot(v[j], x2q, __ldg(p.y2 + gn0 + j), p.hc, p.hproj_max, scale, margin);
               }
               if (p.col_bias) {
 #pragma unroll
@@ -832,6 +927,8 @@ int to_bf16(const float* x, void* out, size_t n, cudaStream_t st) {
 }
 
 static int g_force_block_n = 0, g_force_stages = 0;
+static int g_hyp_poly = 1;      // 0: the counting epilogue evaluates the IEEE score of every candidate (yardstick / tests)
+void score_count_poly(int on) { g_hyp_poly = on ? 1 : 0; }
 void gemm_tf32_tune(int block_n, int stages) { g_force_block_n = block_n; g_force_stages = stages; }
 static unsigned long long* g_trace = nullptr;
 void gemm_tf32_trace(void* dev_buf) { g_trace = (unsigned long long*)dev_buf; }
@@ -882,7 +979,7 @@ size_t gemm_tf32_workspace_bytes(int M, int N, int split_k) {
 
 static void clear_epi(tc::Params& p) {
   p.epi = 0; p.tscore = nullptr; p.target = nullptr; p.raw_count = nullptr; p.col_offset = 0; p.hyp = 0; p.x2 = nullptr;
-  p.y2 = nullptr; p.row_c = nullptr; p.col_bias = nullptr; p.hc = 0.f; p.hproj_max = 0.f; p.scale_margin = nullptr; p.diag_out = nullptr;
+  p.y2 = nullptr; p.row_c = nullptr; p.col_bias = nullptr; p.hc = 0.f; p.hproj_max = 0.f; p.hyp_ymax = 0.f; p.scale_margin = nullptr; p.diag_out = nullptr;
   p.addend = nullptr; p.ld_add = 0; p.bias = nullptr; p.accumulate = 0; p.ws = nullptr; p.C = nullptr; p.ldc = 0;
   p.lse_max = nullptr; p.lse_sum = nullptr;
   p.lay_d = 0; p.lay_raw = nullptr; p.lay_hi = nullptr; p.lay_lo = nullptr; p.row_idx = nullptr; p.skip_rows = nullptr;
@@ -1161,7 +1258,12 @@ int score_count_tf32(const float* q_hi, const float* q_lo, const float* e_hi, co
   p.M = B; p.N = N; p.K = K; p.epi = 1; p.tscore = tscore; p.target = target; p.raw_count = raw_count;
   p.col_offset = col_offset; p.hyp = hyp ? (row_c ? 2 : 1) : 0; p.x2 = x2; p.y2 = y2; p.col_bias = col_bias;
   p.scale_margin = scale_margin; p.row_c = row_c;
-  if (hyp) { Curv cv = make_curv(c); p.hc = cv.c; p.hproj_max = cv.proj_max; }
+  if (hyp) {
+    Curv cv = make_curv(c); p.hc = cv.c; p.hproj_max = cv.proj_max;
+    // points of the ball satisfy |e|^2 <= proj_max^2; the polynomial threshold test (EPI 1) bounds its rounding over
+    // that range and sends anything outside it to the exact score
+    p.hyp_ymax = g_hyp_poly ? (float)((double)cv.proj_max * (double)cv.proj_max * 1.0001) : -1.f;
+  }
   if (passes == 0) { p.bf16 = 1; passes = 1; }       // bf16 operands (q_hi / e_hi point at bf16 rows of K elements)
   int e = launch_tc(q_hi, q_lo, K, e_hi, e_lo, K, p, passes, 1, 0, "score_count_tf32", st);
   if (e) return e;

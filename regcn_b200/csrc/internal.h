@@ -51,6 +51,7 @@ void pdl_set(int on);
 void two_stream_set(int on);
 void gemm_tf32_tune(int block_n, int stages);
 void gemm_tf32_trace(void* dev_buf);
+void score_count_poly(int on);
 int gemm_tf32_trace_slots();
 void gemm_tf32_sm_hint(int sms);
 void aggregate_tune(int impl);

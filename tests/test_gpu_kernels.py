@@ -840,3 +840,64 @@ def test_split_tf32_matches_rna_restatement():
     assert np.array_equal(lo, r_lo)
     assert not (hi.view(np.uint32) & 0x1fff).any() and not (lo.view(np.uint32) & 0x1fff).any()
     assert np.all(np.abs(hi.astype(np.float64) + lo - x) <= 2.0 ** -21 * np.abs(x))
+
+
+@pytest.mark.parametrize("B,N,scale,margin,rmax", [(300, 5000, 1.0, 1.0, 3.0), (129, 2049, 0.37, 4.0, 9.9),
+                                                  (64, 777, 2.5, 0.0, 0.3), (8192, 20000, 1.0, 1.0, 3.0)])
+def test_hyp_count_threshold_polynomial_equals_exact_scores(B, N, scale, margin, rmax):
+    """The division-free polynomial threshold test of the hyperbolic counting epilogue (regcn_score_count_poly(1)) gives
+    exactly the counts of the IEEE score evaluated for every candidate (regcn_score_count_poly(0)) -- on random points of
+    the ball, on exact ties (duplicated target rows), near-ties (rows one ulp away) and targets at the projection clamp."""
+    R, ops = _ops()
+    from regcn_b200 import _lib
+    lib = _lib.load()
+    d, c = 200, 0.01
+    g = torch.Generator(device=DEV)
+    g.manual_seed(B + N)
+
+    def ball(n):
+        x = torch.randn(n, d, device=DEV, generator=g)
+        r = torch.rand(n, 1, device=DEV, generator=g) * rmax
+        return x / x.norm(dim=1, keepdim=True) * r
+
+    q, e = ball(B), ball(N)
+    target = torch.randint(0, N, (B,), device=DEV, dtype=torch.int32, generator=g)
+    # exact ties and near ties of the target row; a few candidates at / beyond the ball's boundary
+    for k in range(0, B, 3):
+        t = int(target[k])
+        e[(t + 17) % N] = e[t]
+        e[(t + 31) % N] = e[t] * (1.0 + 1.2e-7)
+        e[(t + 47) % N] = torch.nextafter(e[t], torch.full_like(e[t], 100.0))
+    e[5] = e[5] / e[5].norm() * 9.999995
+    e[6] = e[6] / e[6].norm() * 10.5
+    q[1] = q[1] / q[1].norm() * 9.9999
+    target[2] = 5
+    target[3] = 6
+    qh, ql = ops.split_tf32(q.contiguous())
+    eh, el = ops.split_tf32(e.contiguous())
+    x2, y2 = ops.row_sumsq(q), ops.row_sumsq(e)
+    sm = torch.tensor([scale, margin], device=DEV)
+    # target scores through the pair kernel (the arithmetic of the counted scores), like ops.fused_rank_counts
+    idx_a = torch.arange(B, device=DEV, dtype=torch.int32)
+    ah, al = torch.empty(B, d, device=DEV), torch.empty(B, d, device=DEV)
+    bh, bl = torch.empty(B, d, device=DEV), torch.empty(B, d, device=DEV)
+    _lib.call("regcn_gather_rows2", qh.data_ptr(), ql.data_ptr(), idx_a.data_ptr(), B, d, ah.data_ptr(), al.data_ptr())
+    _lib.call("regcn_gather_rows2", eh.data_ptr(), el.data_ptr(), target.data_ptr(), B, d, bh.data_ptr(), bl.data_ptr())
+    y2p = y2[target.long()].contiguous()
+    ts = torch.empty(B, device=DEV)
+    _lib.call("regcn_pair_scores_tf32", ah.data_ptr(), al.data_ptr(), bh.data_ptr(), bl.data_ptr(), B, d, 1, x2.data_ptr(),
+              y2p.data_ptr(), None, c, sm.data_ptr(), None, ts.data_ptr(), 3)
+    counts = []
+    try:
+        for on in (0, 1):
+            lib.regcn_score_count_poly(on)
+            raw = torch.zeros(B, device=DEV, dtype=torch.int32)
+            _lib.call("regcn_score_count_tf32", qh.data_ptr(), ql.data_ptr(), eh.data_ptr(), el.data_ptr(), B, N, d,
+                      ts.data_ptr(), target.data_ptr(), raw.data_ptr(), 0, 1, x2.data_ptr(), y2.data_ptr(), None, c,
+                      sm.data_ptr(), None, 3)
+            torch.cuda.synchronize()
+            counts.append(raw.cpu().numpy())
+    finally:
+        lib.regcn_score_count_poly(1)
+    assert np.array_equal(counts[0], counts[1]), np.nonzero(counts[0] != counts[1])[0][:10]
+    assert counts[0].max() > 0
