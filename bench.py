@@ -38,7 +38,7 @@ def parse():
     ap.add_argument("--model", default="regcn", choices=["regcn", "hyp_lgcn_roth", "hyp_uv_roth"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stress", action="store_true", help="skip the HBM-bound edge-kernel and the scoring-kernel sections")
-    ap.add_argument("--gemm", default=None, help="override the dense-contraction implementation (simt|tc)")
+    ap.add_argument("--gemm", default=None, help="tc (3xTF32, default) | tc1 (single TF32 pass, reported separately)")
     return ap.parse_args()
 
 

@@ -88,6 +88,11 @@ REGCN_API int regcn_union_aggregate(const float* h, const float* rel, const int3
 REGCN_API int regcn_block_aggregate(const float* h, const float* W, const int32_t* rowptr, const int32_t* src_sorted,
                           const int32_t* etype_sorted, const float* norm, int N, int d_in, int d_out, int nb,
                           float* out, void* stream);
+/* HyperbolicRGCNLayer message (hyperbolic_layers.py:87-109): the block-diagonal transform of the source's tangent vector
+ * weighted by exp(-gamma |radius[src] - radius[dst]|), summed per destination, times norm. */
+REGCN_API int regcn_block_aggregate_radius(const float* h, const float* W, const float* radius, float gamma,
+                                           const int32_t* rowptr, const int32_t* src_sorted, const int32_t* etype_sorted,
+                                           const float* norm, int N, int d_in, int d_out, int nb, float* out, void* stream);
 
 /* ---- K7 Lorentz centroid aggregate: hyperbolic_layers.py:589-625,665-672; hyperbolic_ops.py:477-518,563-581
  * ht tangent input; out = clamp(log_0(to_poincare(centroid)), +-10), zero rows for in-degree 0.
@@ -222,7 +227,7 @@ REGCN_API void regcn_aggregate_tune(int impl);
 
 /* ---- row maps: F.normalize / tanh / log_0 / exp_0 / project (hyperbolic_ops.py:38-116) ---------
  * mode 0 normalize, 1 tanh, 2 0.9 tanh(log_0 x)+0.1 log_0 x, 3 log_0, 4 exp_0, 5 project,
- * 6 exp_0(normalize(log_0 x)), 7 identity; sumsq (optional, M): |out|^2 per row; out may be NULL
+ * 6 exp_0(normalize(log_0 x)), 7 identity, 8 exp_0(rrelu(x)); sumsq (optional, M): |out|^2 per row; out may be NULL
  * when only sumsq is wanted.                                                                    */
 REGCN_API int regcn_row_map(const float* x, float* out, int M, int d, int mode, double c, float* sumsq, void* stream);
 

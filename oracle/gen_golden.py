@@ -57,6 +57,11 @@ CASES = {
                                          layer_norm=False, gamma=0.15, entity_bias=True, rel_curvature=True),
     "hyp_uv_roth_c1_s1": dict(kind="hyp", shape="c1", seed=1, encoder="hyperbolic_uvrgcn", decoder="roth",
                               layer_norm=True, gamma=0.15, sub=96),
+    # GDELT shape with dense snapshots (BASELINE configs[3]: 5000 triples per snapshot, hub rows of ~900 in-edges)
+    "regcn_c4_s0": dict(kind="regcn", shape="c4", seed=0, layer_norm=True, sub=96),
+    # the hyperbolic model of BASELINE configs[1] at the ICEWS18 shape of configs[2]
+    "hyp_lgcn_roth_c3_s2": dict(kind="hyp", shape="c3", seed=2, encoder="lgcn", decoder="roth", layer_norm=False,
+                                gamma=0.15, sub=64),
 }
 H_DIM = 200
 N_BASES = 100
@@ -136,6 +141,9 @@ def run_case(name, cfg, ref_utils, RecurrentRGCN, HyperbolicRecurrentRGCN):
                    hist_first_rows=hist[0][rows].numpy(), score_block=score[qrows][:, rows].numpy(),
                    score_rel_qrows=score_rel[qrows].numpy(),
                    score_rowsum=score.double().sum(1).numpy(), score_absmax=score.abs().max(1).values.numpy())
+        # complete score rows (every candidate) of 16 seeded queries: the gate on scores covers whole rows, not a block
+        frows = np.sort(rng.choice(score.shape[0], size=min(16, score.shape[0]), replace=False))
+        out.update(full_qrows=frows, score_full_rows=score[frows].numpy())
     else:
         out.update(hist=np.stack([h.numpy() for h in hist]), score=score.numpy(), score_rel=score_rel.numpy())
     os.makedirs(GOLDEN, exist_ok=True)
@@ -425,8 +433,43 @@ def run_hyp_train(ref_utils, HyperbolicRecurrentRGCN):
     print("->", path, os.path.getsize(path) / 1e6, "MB")
 
 
+def run_layers(ref_utils):
+    """HyperbolicRGCNLayer (hyperbolic_src/hyperbolic_layers.py:21-161) on its own: the reference layer on seeded
+    points of the ball, every structural variant (block sizes, self loop, skip gate, activation)."""
+    import torch.nn.functional as F
+    from hyperbolic_src.hyperbolic_layers import HyperbolicRGCNLayer
+    out = {}
+    variants = [dict(shape="tiny", nb=4, self_loop=True, skip=False, act=True, gamma=0.15),
+                dict(shape="tiny_l", nb=10, self_loop=True, skip=True, act=True, gamma=1.0),
+                dict(shape="small", nb=20, self_loop=False, skip=False, act=False, gamma=0.0),
+                dict(shape="small_l", nb=100, self_loop=True, skip=True, act=True, gamma=0.15)]
+    for k, v in enumerate(variants):
+        case = synth.make_case(v["shape"], 40 + k)
+        n, r = case["num_ents"], case["num_rels"]
+        g = ref_utils.build_sub_graph(n, r, case["history"][0], False, "cpu")
+        layer = HyperbolicRGCNLayer(H_DIM, H_DIM, 2 * r, v["nb"], c=CURV, activation=F.rrelu if v["act"] else None,
+                                    self_loop=v["self_loop"], dropout=0.0, skip_connect=v["skip"],
+                                    radius_msg_gamma=v["gamma"])
+        layer.load_state_dict(synth.fill_state_dict(layer.state_dict(), 60 + k))
+        layer.eval()
+        rng = np.random.default_rng(900 + k)
+        h = rng.standard_normal((n, H_DIM)).astype(np.float32)
+        h = h / np.linalg.norm(h, axis=1, keepdims=True) * rng.uniform(0.2, 6.0, size=(n, 1)).astype(np.float32)
+        prev = rng.standard_normal((n, H_DIM)).astype(np.float32)
+        prev = prev / np.linalg.norm(prev, axis=1, keepdims=True) * rng.uniform(0.2, 6.0, size=(n, 1)).astype(np.float32)
+        with torch.no_grad():
+            y = layer(g, torch.from_numpy(h), None, torch.from_numpy(prev) if v["skip"] else None)
+        out[f"v{k}_config"] = np.array(json.dumps(v))
+        out[f"v{k}_out"] = y.numpy()
+    path = os.path.join(GOLDEN, "aux_layer_hyp_rgcn.npz")
+    np.savez_compressed(path, **out)
+    print("->", path, os.path.getsize(path) / 1e6, "MB")
+
+
 def main(argv):
     ref_utils, RecurrentRGCN, HyperbolicRecurrentRGCN = _import_reference()
+    if len(argv) > 1 and argv[1] == "--layers":
+        return run_layers(ref_utils)
     torch.set_num_threads(os.cpu_count() or 1)
     if len(argv) > 1 and argv[1] == "--losses":
         return run_losses(ref_utils, RecurrentRGCN, HyperbolicRecurrentRGCN)

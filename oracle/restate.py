@@ -403,6 +403,30 @@ def hyp_union_layer(h_hyper, rel, g, w_n, w_loop, w_evolve, c, gamma):
     return exp0(h_new, c)                                                        # :321
 
 
+def hyp_rgcn_layer(h_hyper, g, weight, num_bases, c, gamma, w_loop=None, skip=None, prev_h=None, act=True):
+    """hyperbolic_layers.py:87-161 (HyperbolicRGCNLayer.msg_func / apply_func / forward, eval): block-diagonal relation
+    transform of log_0(h[src]) weighted by exp(-gamma |r_src - r_dst|), sum, degree norm, + self loop, skip gate on
+    log_0(prev_h), activation, exp_0.  skip = (skip_weight, skip_bias)."""
+    ht = log0(h_hyper, c)
+    radius = get_radius(h_hyper).unsqueeze(-1)
+    out_feat = ht.shape[1]
+    si, so = ht.shape[1] // num_bases, out_feat // num_bases
+    src, dst, etype = (torch.as_tensor(g[k]) for k in ("src", "dst", "etype"))
+    w = weight[etype].view(-1, si, so)                                            # :90-91
+    msg = torch.bmm(ht[src].reshape(-1, 1, si), w).view(-1, out_feat)             # :94-98
+    msg = msg * torch.exp(-gamma * (radius[src] - radius[dst]).abs())             # :99-101
+    h_new = scatter_sum(msg, g["dst"], g["num_nodes"]) * torch.as_tensor(g["norm"]).to(ht.dtype).view(-1, 1)   # :107-109
+    if w_loop is not None:
+        h_new = h_new + ht @ w_loop                                               # :138-140
+    if skip is not None and prev_h is not None:
+        pt = log0(prev_h, c)
+        gate = torch.sigmoid(pt @ skip[0] + skip[1])                              # :143-146
+        h_new = gate * h_new + (1 - gate) * pt
+    if act:
+        h_new = rrelu(h_new)                                                      # :149-150
+    return exp0(h_new, c)                                                         # :157
+
+
 def lorentz_layer(h_hyper, rel, g, weight, w_loop, w_evolve, c, num_bases, skip=None, prev_h=None):
     """hyperbolic_layers.py:589-694 (LorentzRGCNLayer, rrelu, eval).  skip = (skip_weight, skip_bias) with prev_h = the
     previous layer's INPUT (hyperbolic_layers.py:657-662, 675-678, cell :737-740)."""

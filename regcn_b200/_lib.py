@@ -32,6 +32,7 @@ SIGNATURES = {
     "regcn_rel_mean_pool": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p]),
     "regcn_union_aggregate": (_i, [_p] * 9 + [_i, _i, _p, _f, _i, _i, _p, _p, _p]),
     "regcn_block_aggregate": (_i, [_p] * 6 + [_i, _i, _i, _i, _p, _p]),
+    "regcn_block_aggregate_radius": (_i, [_p, _p, _p, _f] + [_p] * 4 + [_i, _i, _i, _i, _p, _p]),
     "regcn_lorentz_aggregate": (_i, [_p] * 10 + [_i, _i, _i, _i, _i, _d, _p, _p, _p]),
     "regcn_gemm_f32_workspace_bytes": (_sz, [_i, _i, _i]),
     "regcn_gemm_f32": (_i, [_p, _i, _p, _i, _i, _p, _i, _i, _i, _i, _p, _i, _i, _p, _sz, _p]),

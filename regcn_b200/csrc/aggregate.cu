@@ -691,7 +691,8 @@ int union_aggregate(const float* h, const float* rel, const int* rowptr, const i
 __global__ void __launch_bounds__(256) block_aggregate_kernel(
     const float* __restrict__ h, const float* __restrict__ W, const float* __restrict__ rel_add,
     const int* __restrict__ rowptr, const int* __restrict__ src_sorted, const int* __restrict__ etype_sorted,
-    const float* __restrict__ norm, int N, int d_in, int d_out, int nb, float* __restrict__ out) {
+    const float* __restrict__ norm, int N, int d_in, int d_out, int nb, float* __restrict__ out,
+    const float* __restrict__ radius, float gamma) {
   pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const int row = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
@@ -699,6 +700,7 @@ __global__ void __launch_bounds__(256) block_aggregate_kernel(
   const int si = d_in / nb, so = d_out / nb;
   const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
   const float nrm = __ldg(norm + row);
+  const float r_dst = radius ? __ldg(radius + row) : 0.f;
   for (int j0 = 0; j0 < d_out; j0 += kWarp) {
     const int j = j0 + lane;
     float acc = 0.f;
@@ -711,6 +713,8 @@ __global__ void __launch_bounds__(256) block_aggregate_kernel(
         float m = 0.f;
         for (int i = 0; i < si; ++i) m = fmaf(__ldg(hp + i), __ldg(wp + i * so), m);
         if (rel_add) m += __ldg(rel_add + (size_t)t * d_out + j);
+        // radius-difference message weight exp(-gamma |r_src - r_dst|)   (hyperbolic_layers.py:100-103)
+        if (radius) m *= expf(-gamma * fabsf(__ldg(radius + s) - r_dst));
         acc += m;
       }
       out[(size_t)row * d_out + j] = acc * nrm;
@@ -720,12 +724,13 @@ __global__ void __launch_bounds__(256) block_aggregate_kernel(
 
 int block_aggregate(const float* h, const float* W, const int* rowptr, const int* src_sorted,
                     const int* etype_sorted, const float* norm, int N, int d_in, int d_out, int nb,
-                    float* out, cudaStream_t st) {
+                    float* out, cudaStream_t st, const float* radius, float gamma) {
   if (!h || !W || !rowptr || !src_sorted || !etype_sorted || !norm || !out) { set_last_error("block_aggregate: null pointer"); return REGCN_ERR_NULL; }
   if (nb <= 0 || d_in % nb || d_out % nb) { set_last_error("block_aggregate: num_bases=%d must divide d_in=%d and d_out=%d", nb, d_in, d_out); return REGCN_ERR_UNSUPPORTED; }
   const int TB = 256;
   const unsigned grid = (unsigned)(((size_t)N * 32 + TB - 1) / TB);
-  launch_k(block_aggregate_kernel, grid, TB, 0, st, h, W, nullptr, rowptr, src_sorted, etype_sorted, norm, N, d_in, d_out, nb, out);
+  launch_k(block_aggregate_kernel, grid, TB, 0, st, h, W, nullptr, rowptr, src_sorted, etype_sorted, norm, N, d_in, d_out, nb, out,
+           radius, gamma);
   return check_launch("block_aggregate");
 }
 

@@ -126,6 +126,12 @@ int regcn_block_aggregate(const float* h, const float* W, const int32_t* rowptr,
                           void* stream) {
   return block_aggregate(h, W, rowptr, src_sorted, etype_sorted, norm, N, d_in, d_out, nb, out, ST(stream));
 }
+int regcn_block_aggregate_radius(const float* h, const float* W, const float* radius, float gamma, const int32_t* rowptr,
+                                 const int32_t* src_sorted, const int32_t* etype_sorted, const float* norm, int N, int d_in,
+                                 int d_out, int nb, float* out, void* stream) {
+  if (!radius) { set_last_error("block_aggregate_radius: null radius"); return REGCN_ERR_NULL; }
+  return block_aggregate(h, W, rowptr, src_sorted, etype_sorted, norm, N, d_in, d_out, nb, out, ST(stream), radius, gamma);
+}
 int regcn_lorentz_aggregate(const float* ht, const float* W, const float* rel, const int32_t* rowptr,
                             const int32_t* src_sorted, const int32_t* etype_sorted, const float* norm,
                             const int32_t* vptr, const int32_t* sptr, const int32_t* vrow_row, int n_vrows,

@@ -20,7 +20,8 @@ int union_aggregate(const float* h, const float* rel, const int* rowptr, const i
                     float* out_lo, const int* active_pos, int ldo, int max_chunks, cudaStream_t st,
                     int* fold_count = nullptr);
 int block_aggregate(const float* h, const float* W, const int* rowptr, const int* src_sorted, const int* etype_sorted,
-                    const float* norm, int N, int d_in, int d_out, int nb, float* out, cudaStream_t st);
+                    const float* norm, int N, int d_in, int d_out, int nb, float* out, cudaStream_t st,
+                    const float* radius = nullptr, float gamma = 0.f);
 int lorentz_aggregate(const float* ht, const float* W, const float* rel, const int* rowptr, const int* src_sorted,
                       const int* etype_sorted, const float* norm, const int* vptr, const int* sptr, const int* vrow_row,
                       int nv_rows, int nsplit, int N, int d, int nb, double c, float* out, float* partial,

@@ -49,7 +49,7 @@ class _ConvTransBase(nn.Module):
 
     def _check_eval(self):
         if self.training:
-            raise NotImplementedError("regcn_b200 decoders: training-mode BatchNorm/dropout need the backward kernels; call .eval()")
+            raise NotImplementedError("regcn_b200 decoders: the standalone forward() is the inference path (folded BatchNorm, no dropout); batch-statistics BatchNorm, dropout and gradients run through the model's get_loss() (regcn_b200/train.py, train_hyp.py)")
 
     def _tower(self, ent_act, second, triplets, col0, col1, always_bn2):
         """K10: bn0 -> conv1d(2->C,k) -> bn1 -> relu -> fc -> bn2 -> relu, returns the (B,d) query matrix."""

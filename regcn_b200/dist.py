@@ -14,9 +14,11 @@ import torch
 import torch.distributed as dist
 
 
-def world():
+def world(group=None):
+    """(rank, world size) INSIDE `group` (None = the default group): shard bounds and the collectives that merge them
+    must be taken from the same group, or the shards do not tile [0, N)."""
     if dist.is_available() and dist.is_initialized():
-        return dist.get_rank(), dist.get_world_size()
+        return dist.get_rank(group), dist.get_world_size(group)
     return 0, 1
 
 
@@ -67,7 +69,7 @@ def sharded_score_rank(n_cand, triples, target_col, filter_csr, score_fn, group=
     Returns (rank, filter_rank), identical on all ranks."""
     from . import ops
     from ._lib import call, ptr
-    r, ws = world()
+    r, ws = world(group)
     lo, hi = shard_bounds(n_cand, r, ws)
     block = score_fn(lo, hi)
     B = block.shape[0]

@@ -137,7 +137,7 @@ def score_rank_sharded(model, emb, r_emb, all_triples, filter_csr, group=None):
     merges the shards.  Target and filter-entry scores come from the pair pass on the replicated table, so no score
     exchange is needed.  Returns (rank, filter_rank), identical on every rank."""
     from . import dist as rdist
-    r, ws = rdist.world()
+    r, ws = rdist.world(group)
     q, cand, hyp, col_bias = _scoring_operands(model, emb, r_emb, all_triples)
     lo, hi = rdist.shard_bounds(cand.shape[0], r, ws)
     target = all_triples[:, 2].to(torch.int32).contiguous()
@@ -277,6 +277,26 @@ def _test_multi_step(model, input_list, test_list, num_rels, num_nodes, static_g
     return (out, ranks) if return_ranks else out
 
 
+def _check_time_aware_filters(test_list, num_rels, all_ans_list, all_ans_r_list):
+    """test() filters with the test snapshot's own answers (what the reference's main passes: rgcn/utils.py:286-304).
+    Filter dicts handed in must describe exactly those sets -- anything else (static / global filtering) would silently
+    be ignored, so it is refused here; utils.get_total_rank(..., all_ans) takes arbitrary dicts."""
+    for name, lst, rel_p in (("all_ans_list", all_ans_list, False), ("all_ans_r_list", all_ans_r_list, True)):
+        if lst is None:
+            continue
+        if len(lst) != len(test_list):
+            raise ValueError(f"regcn_b200.test: {name} has {len(lst)} entries for {len(test_list)} test snapshots")
+        for k, (snap, given) in enumerate(zip(test_list, lst)):
+            arr = snap.cpu().numpy() if torch.is_tensor(snap) else snap
+            own = utils.load_all_answers_for_filter(arr, num_rels, rel_p)
+            same = own.keys() == given.keys() and all(
+                own[a].keys() == given[a].keys() and all(set(own[a][b]) == set(given[a][b]) for b in own[a]) for a in own)
+            if not same:
+                raise ValueError(f"regcn_b200.test: {name}[{k}] is not the time-aware answer set of test snapshot {k}; "
+                                 "test() builds its filter lists from the snapshot itself (the reference's main does the "
+                                 "same) -- rank with utils.get_total_rank(test_triples, score, all_ans, ...) for other filters")
+
+
 def test(model, history_list, test_list, num_rels, num_nodes, use_cuda=True, all_ans_list=None, all_ans_r_list=None,
          model_name=None, static_graph=None, mode="eval", test_history_len=None, multi_step=False, device=None,
          return_ranks=False, topk=10, relation_evaluation=False):
@@ -307,6 +327,7 @@ def test(model, history_list, test_list, num_rels, num_nodes, use_cuda=True, all
         ck = torch.load(model_name, map_location="cpu")
         model.load_state_dict(ck["state_dict"] if "state_dict" in ck else ck)
     model.eval()
+    _check_time_aware_filters(test_list, num_rels, all_ans_list, all_ans_r_list)
     dev = device if device is not None else next(model.parameters()).device
     L = test_history_len if test_history_len is not None else getattr(model, "sequence_len", len(history_list))
     input_list = [snap for snap in history_list[-L:]]

@@ -49,7 +49,7 @@ class _HypConvBase(nn.Module):
 
     def _tower(self, ent_act, second, triplets, col0, col1, always_bn2):
         if self.training:
-            raise NotImplementedError("regcn_b200 decoders: training mode needs the backward kernels; call .eval()")
+            raise NotImplementedError("regcn_b200 decoders: the standalone forward() is the inference path (folded BatchNorm, no dropout); batch-statistics BatchNorm, dropout and gradients run through the model's get_loss() (regcn_b200/train.py, train_hyp.py)")
         B = len(triplets)
         feats = ops.convtranse_features(ent_act, second, triplets, col0, col1, _fold_bn(self.bn0),
                                         self.conv1.weight.detach(), self.conv1.bias.detach(), _fold_bn(self.bn1),
@@ -135,7 +135,7 @@ class _HypDistBase(nn.Module):
 
     def _unsupported_flags(self):
         if self.training and self.dropout.p > 0:
-            raise NotImplementedError("regcn_b200 decoders: training mode needs the backward kernels; call .eval()")
+            raise NotImplementedError("regcn_b200 decoders: the standalone forward() is the inference path (folded BatchNorm, no dropout); batch-statistics BatchNorm, dropout and gradients run through the model's get_loss() (regcn_b200/train.py, train_hyp.py)")
 
     def _relation_curvature(self, triplets):
         """(B,) per-query curvature or None (hyperbolic_decoder.py:1020-1026); inverse relations share c_r."""

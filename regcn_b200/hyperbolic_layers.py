@@ -1,5 +1,5 @@
 """Hyperbolic encoder layers with the reference's signatures and parameter names
-(hyperbolic_src/hyperbolic_layers.py:164-323 HyperbolicUnionRGCNLayer, :524-743 LorentzRGCNLayer/Cell;
+(hyperbolic_src/hyperbolic_layers.py:21-161 HyperbolicRGCNLayer, :164-323 HyperbolicUnionRGCNLayer, :524-743 LorentzRGCNLayer/Cell;
 hyperbolic_src/hyperbolic_model.py:114-154 HyperbolicRGCNCell) on the sm_100a kernels.
 
 Layer inputs/outputs are points on the Poincare ball like the reference.  Internally each layer works on the
@@ -24,6 +24,58 @@ class _LoopMixin:
             self._loop_cat_val = torch.cat((self.loop_weight.detach(), self.evolve_loop_weight.detach()), dim=1).contiguous()
             self._loop_cat_key = key
         return self._loop_cat_val
+
+
+class HyperbolicRGCNLayer(nn.Module):
+    """hyperbolic_layers.py:21-161: RGCN message passing in tangent space with block-diagonal relation transforms.
+
+        t = log_0(h);  agg[v] = norm[v] * sum_{(u,r)->v} exp(-gamma |rad_u - rad_v|) * blockdiag(W[r]) t[u]     (K6)
+        x = agg (+ t W_loop) -> optional skip gate with log_0(prev_h) -> activation -> exp_0
+
+    Same constructor, parameter names (`weight`, `loop_weight`, `skip_weight`, `skip_bias`) and forward signature as the
+    reference.  Unlike the union layers it has no evolve-loop weight and no +-10 tangent clamps."""
+
+    def __init__(self, in_feat, out_feat, num_rels, num_bases=-1, c=0.01, activation=None, self_loop=False,
+                 dropout=0.0, skip_connect=False, radius_msg_gamma=1.0):
+        super().__init__()
+        self.in_feat, self.out_feat, self.num_rels = in_feat, out_feat, num_rels
+        self.num_bases = num_bases if num_bases > 0 else num_rels
+        if self.num_bases > self.num_rels:
+            self.num_bases = self.num_rels
+        self.c = c
+        self.activation = activation
+        self.self_loop = self_loop
+        self.skip_connect = skip_connect
+        self.radius_msg_gamma = radius_msg_gamma
+        self.submat_in = in_feat // self.num_bases
+        self.submat_out = out_feat // self.num_bases
+        self.weight = nn.Parameter(torch.Tensor(self.num_rels, self.num_bases * self.submat_in * self.submat_out))
+        nn.init.xavier_uniform_(self.weight, gain=_RELU_GAIN)
+        if self.self_loop:
+            self.loop_weight = nn.Parameter(torch.Tensor(in_feat, out_feat))
+            nn.init.xavier_uniform_(self.loop_weight, gain=_RELU_GAIN)
+        if self.skip_connect:
+            self.skip_weight = nn.Parameter(torch.Tensor(out_feat, out_feat))
+            nn.init.xavier_uniform_(self.skip_weight, gain=_RELU_GAIN)
+            self.skip_bias = nn.Parameter(torch.zeros(out_feat))
+        self.dropout = nn.Dropout(dropout) if dropout > 0 else None
+
+    @torch.no_grad()
+    def forward(self, g, h_hyper, rel_emb=None, prev_h=None):
+        _no_train_dropout(self)
+        if self.in_feat % self.num_bases or self.out_feat % self.num_bases:
+            raise NotImplementedError("HyperbolicRGCNLayer: num_bases must divide in_feat and out_feat")
+        act = _act_code(self.activation)
+        ht, _, rad = ops.hyp_tangent(h_hyper, self.c, want_clamped=False, want_radius=True)
+        x = ops.block_aggregate(ht, self.weight.detach(), g, self.num_bases, self.out_feat, radius=rad,
+                                gamma=self.radius_msg_gamma)
+        if self.self_loop:
+            ops.gemm(ht, self.loop_weight, b_key=(self.loop_weight, "w"), out=x, accumulate=True)
+        if self.skip_connect and prev_h is not None:
+            prev_t, _, _ = ops.hyp_tangent(prev_h, self.c, want_clamped=False, want_radius=False)
+            G = ops.gemm(prev_t, self.skip_weight, b_key=(self.skip_weight, "w"))
+            x = ops.time_gate(G, self.skip_bias.detach(), x, prev_t, False)      # sigmoid(G + b) * x + (1 - sigmoid) * prev_t
+        return ops.row_map(x, ops.ROW_RRELU_EXP0 if act else ops.ROW_EXP0, c=self.c)
 
 
 class HyperbolicUnionRGCNLayer(nn.Module, _LoopMixin):

@@ -22,7 +22,7 @@ def _act_code(activation):
 
 def _no_train_dropout(mod):
     if mod.training and getattr(mod, "dropout", None) is not None and mod.dropout.p > 0:
-        raise NotImplementedError("regcn_b200: training-mode dropout needs the backward kernels (SURVEY 8f-1); call .eval()")
+        raise NotImplementedError("regcn_b200: a layer's standalone forward() is the inference path (kernels under no_grad); training-mode dropout and gradients run through the model's get_loss() (regcn_b200/train.py, train_hyp.py)")
 
 
 class UnionRGCNLayer(nn.Module):

@@ -35,16 +35,19 @@ def _rowmajor(t, name):
 # --------------------------------------------------------------------------- dense contractions
 import os
 
-_GEMM_IMPL = {"impl": os.environ.get("REGCN_GEMM", "tc")}
-_IMPLS = {"simt": "regcn::gemm_f32_kernel (fp32 CUDA cores)",
-          "tc": "regcn::tc::gemm_tf32_kernel (tcgen05 kind::tf32, 3xTF32 error-compensated)",
+# ONE dense-contraction backend on the product path: the tcgen05 kernel (csrc/gemm_tc.cu).  "tc" = 3xTF32
+# error-compensated (fp32 parity, the default), "tc1" = single TF32 pass (reported separately, never the parity path).
+# The fp32 CUDA-core kernel (csrc/gemm_simt.cu) is NOT selectable here: it is the yardstick tests/ compare against
+# through gemm_f32_yardstick() below.
+_GEMM_IMPL = {"impl": "tc"}
+_IMPLS = {"tc": "regcn::tc::gemm_tf32_kernel (tcgen05 kind::tf32, 3xTF32 error-compensated)",
           "tc1": "regcn::tc::gemm_tf32_kernel (tcgen05 kind::tf32, single pass)"}
 
 
 def set_gemm_impl(name):
-    """simt: fp32 CUDA-core kernel (csrc/gemm_simt.cu); tc: tcgen05 3xTF32 (fp32 parity); tc1: tcgen05 plain TF32."""
+    """tc: tcgen05 3xTF32 (fp32 parity); tc1: tcgen05 plain TF32 (one pass)."""
     if name not in _IMPLS:
-        raise ValueError(f"unknown gemm implementation {name!r}")
+        raise ValueError(f"unknown gemm implementation {name!r} (the product path has one backend: tc | tc1)")
     _GEMM_IMPL["impl"] = name
 
 
@@ -111,15 +114,22 @@ def _tc_operand(m, need_lo):
 
 
 def gemm(a, b, trans_b=False, bias=None, out=None, accumulate=False, split_k=1, b_key=None):
-    """C[M,N] (+)= A[M,K] @ (B[K,N] | B[N,K]^T) (+ bias).  torch.mm / F.linear call sites of the path.
+    """C[M,N] (+)= A[M,K] @ (B[K,N] | B[N,K]^T) (+ bias) on the tcgen05 kernel.  torch.mm / F.linear call sites of the path.
 
     b_key=(owner_tensor, name): B is a static weight; its prepared form (K-major transpose, TF32 split) is cached on
-    `owner_tensor` under `name`."""
+    `owner_tensor` under `name`.  K must be a multiple of 4 (16-byte operand rows for TMA): every contraction of the
+    path has K = h_dim, 2 h_dim or 50 h_dim; anything else raises -- there is no second backend to fall to."""
     impl = _GEMM_IMPL["impl"]
-    if isinstance(a, tuple) and impl == "simt":
-        raise ValueError("gemm: a pre-split A operand needs the tensor-core implementation")
-    if impl != "simt" and (isinstance(a, tuple) or a.shape[1] % 4 == 0):
-        return _gemm_tc(a, b, trans_b, bias, out, accumulate, split_k, b_key, 3 if impl == "tc" else 1)
+    K = (a[0] if isinstance(a, tuple) else a).shape[1]
+    if K % 4:
+        raise ValueError(f"gemm: reduction length K={K} must be a multiple of 4 (TMA needs 16-byte operand rows); pad the "
+                         "operands with zero columns")
+    return _gemm_tc(a, b, trans_b, bias, out, accumulate, split_k, b_key, 3 if impl == "tc" else 1)
+
+
+def gemm_f32_yardstick(a, b, trans_b=False, bias=None, out=None, accumulate=False, split_k=1):
+    """Plain fp32 CUDA-core GEMM (csrc/gemm_simt.cu, regcn_gemm_f32).  TEST / MEASUREMENT YARDSTICK ONLY: nothing in
+    regcn_b200/ calls it; tests compare the tensor-core path against it and against fp64."""
     a = _rowmajor(a, "a")
     b = _rowmajor(b, "b")
     M, K = a.shape
@@ -212,13 +222,18 @@ def union_aggregate(h, rel, g, radius=None, gamma=0.0, out=None):
     return out
 
 
-def block_aggregate(h, weight, g, num_bases, d_out):
+def block_aggregate(h, weight, g, num_bases, d_out, radius=None, gamma=0.0):
+    """K6; radius (N,) + gamma: messages weighted by exp(-gamma |radius[src] - radius[dst]|) (HyperbolicRGCNLayer)."""
     h = _f32(h, "h")
     weight = _f32(weight, "weight")
     N, d_in = h.shape
     out = torch.empty((N, d_out), device=h.device, dtype=F32)
-    call("regcn_block_aggregate", ptr(h), ptr(weight), ptr(g.rowptr), ptr(g.src_sorted), ptr(g.etype_sorted),
-         ptr(g.norm), N, d_in, d_out, num_bases, ptr(out))
+    if radius is not None:
+        call("regcn_block_aggregate_radius", ptr(h), ptr(weight), ptr(_f32(radius, "radius")), float(gamma), ptr(g.rowptr),
+             ptr(g.src_sorted), ptr(g.etype_sorted), ptr(g.norm), N, d_in, d_out, num_bases, ptr(out))
+    else:
+        call("regcn_block_aggregate", ptr(h), ptr(weight), ptr(g.rowptr), ptr(g.src_sorted), ptr(g.etype_sorted),
+             ptr(g.norm), N, d_in, d_out, num_bases, ptr(out))
     return out
 
 
@@ -234,7 +249,8 @@ def lorentz_aggregate(ht, weight, rel, g, num_bases, c):
 
 
 # --------------------------------------------------------------------------- row maps
-ROW_NORMALIZE, ROW_TANH, ROW_LEAKY_TANH_LOG0, ROW_LOG0, ROW_EXP0, ROW_PROJECT, ROW_TANGENT_NORMALIZE, ROW_IDENTITY = range(8)
+ROW_NORMALIZE, ROW_TANH, ROW_LEAKY_TANH_LOG0, ROW_LOG0, ROW_EXP0, ROW_PROJECT, ROW_TANGENT_NORMALIZE, ROW_IDENTITY, \
+    ROW_RRELU_EXP0 = range(9)
 
 
 def row_sumsq(x):

@@ -65,13 +65,20 @@ class Adam:
                 views_g.append(vg)
         nb = _lib.load().regcn_adam_workspace_bytes()
         self._flat = dict(p=flat_p, g=flat_g, m=torch.zeros_like(flat_p), v=torch.zeros_like(flat_p), act=act,
-                          views_g=views_g, n=tot, ws=torch.empty((nb + 7) // 8, device=dev, dtype=torch.float64),
+                          views_g=views_g, ids={id(p) for p in act}, n=tot, ws=torch.empty((nb + 7) // 8, device=dev, dtype=torch.float64),
                           ws_bytes=nb)
         self.total_norm = torch.zeros(1, device=dev, dtype=F32)
 
     def _sync_grads(self):
         """Gradients must live in the flat buffer; re-attach the views if something replaced or dropped p.grad."""
         f = self._flat
+        late = [p for p in self.params if p.grad is not None and id(p) not in f["ids"]]
+        if late:
+            # torch.optim.Adam would start these parameters' moments and step count now; the fused kernel keeps ONE step
+            # count for the flat buffer, so silently skipping them (or sharing the count) would diverge from the reference
+            raise RuntimeError(f"regcn_b200.optim.Adam: {len(late)} parameter(s) received their first gradient after the first "
+                               "step() (e.g. a loss head switched on later); build the optimizer after the first backward of "
+                               "the full loss, or create a new optimizer")
         with torch.no_grad():
             for p, vg in zip(f["act"], f["views_g"]):
                 if p.grad is None:

@@ -11,27 +11,32 @@ import torch.nn.functional as F
 from . import ops
 from .decoder import ConvTransE, ConvTransR
 from .layers import RGCNBlockLayer, UnionRGCNLayer
-from .model import BaseRGCN
 
 
-class RGCNCell(BaseRGCN):
-    """src/rrgcn.py:14-54."""
+class RGCNCell(nn.Module):
+    """The entity encoder `rgcn` of RecurrentRGCN (src/rrgcn.py:14-54): a ModuleList `layers` of UnionRGCNLayer and the
+    `rel_emb` handle (the reference registers emb_rel a second time as `rgcn.rel_emb`; state dicts carry both names).
+    Constructor arguments as the reference passes them (src/rrgcn.py:108-121)."""
 
-    def build_hidden_layer(self, idx):
-        act = F.rrelu
-        if idx:
-            self.num_basis = 0
-        sc = bool(self.skip_connect and idx != 0)
-        if self.encoder_name == "uvrgcn":
-            return UnionRGCNLayer(self.h_dim, self.h_dim, self.num_rels, self.num_bases, activation=act,
-                                  dropout=self.dropout, self_loop=self.self_loop, skip_connect=sc,
-                                  rel_emb=self.rel_emb)
-        raise NotImplementedError
+    def __init__(self, num_nodes, h_dim, out_dim, num_rels, num_bases=-1, num_basis=-1, num_hidden_layers=1, dropout=0,
+                 self_loop=False, skip_connect=False, encoder_name="", opn="sub", rel_emb=None, use_cuda=False,
+                 analysis=False):
+        super().__init__()
+        if encoder_name != "uvrgcn":
+            raise NotImplementedError(f"encoder {encoder_name!r}: RecurrentRGCN evolves with 'uvrgcn' (src/rrgcn.py:17-27)")
+        self.num_nodes, self.h_dim, self.out_dim, self.num_rels = num_nodes, h_dim, out_dim, num_rels
+        self.num_bases, self.num_basis, self.num_hidden_layers = num_bases, num_basis, num_hidden_layers
+        self.dropout, self.self_loop, self.skip_connect = dropout, self_loop, skip_connect
+        self.encoder_name, self.opn, self.use_cuda, self.run_analysis = encoder_name, opn, use_cuda, analysis
+        self.rel_emb = rel_emb
+        self.layers = nn.ModuleList(
+            UnionRGCNLayer(h_dim, h_dim, num_rels, num_bases, activation=F.rrelu, dropout=dropout, self_loop=self_loop,
+                           skip_connect=bool(skip_connect and idx != 0), rel_emb=rel_emb)
+            for idx in range(num_hidden_layers))
 
     def forward(self, g, init_ent_emb, init_rel_emb):
-        if self.encoder_name != "uvrgcn":
-            raise NotImplementedError
-        # ndata['id'] is arange(N) (rgcn/utils.py:122), so init_ent_emb[node_id] is the identity gather
+        # ndata['id'] is arange(N) (rgcn/utils.py:122), so init_ent_emb[node_id] is the identity gather; the cell never
+        # passes prev_h (src/rrgcn.py:37-38), so a configured skip connection stays inert exactly like the reference's
         g.ndata['h'] = init_ent_emb
         for i, layer in enumerate(self.layers):
             layer(g, [], init_rel_emb[i])

@@ -352,8 +352,13 @@ def _bn_stats(x, B, C, L, bn):
     track = bn.track_running_stats and bn.running_mean is not None
     call("regcn_bn_stats", ptr(x), B, C, L, float(bn.eps), mom, ptr(mean), ptr(invstd),
          ptr(bn.running_mean) if track else None, ptr(bn.running_var) if track else None, ptr(ws), nb)
-    if track and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked += 1
+    if track:
+        # the kernel wrote the running statistics through raw pointers: bump their version counters, the folded-BatchNorm
+        # caches of the inference path (decoder._fold_bn, evaluate._tower_table) key on them
+        torch.autograd.graph.increment_version(bn.running_mean)
+        torch.autograd.graph.increment_version(bn.running_var)
+        if bn.num_batches_tracked is not None:
+            bn.num_batches_tracked += 1
     return mean, invstd
 
 

@@ -192,3 +192,22 @@ def build_hyp_train_model(cfg, n, r, dropout=0.0):
     sd = synth.fill_state_dict(m.state_dict(), cfg["seed"])
     m.load_state_dict(sd)
     return m, sd
+
+
+def hyp_rgcn_layer_cases():
+    """Inputs of tests/golden/aux_layer_hyp_rgcn.npz (oracle/gen_golden.py --layers): yields (k, variant, case, h, prev, sd)."""
+    import json
+    from oracle import synth
+    z = np.load(os.path.join(GOLDEN, "aux_layer_hyp_rgcn.npz"))
+    k = 0
+    while f"v{k}_config" in z.files:
+        v = json.loads(str(z[f"v{k}_config"]))
+        case = synth.make_case(v["shape"], 40 + k)
+        n = case["num_ents"]
+        rng = np.random.default_rng(900 + k)
+        h = rng.standard_normal((n, 200)).astype(np.float32)
+        h = h / np.linalg.norm(h, axis=1, keepdims=True) * rng.uniform(0.2, 6.0, size=(n, 1)).astype(np.float32)
+        prev = rng.standard_normal((n, 200)).astype(np.float32)
+        prev = prev / np.linalg.norm(prev, axis=1, keepdims=True) * rng.uniform(0.2, 6.0, size=(n, 1)).astype(np.float32)
+        yield k, v, case, h, prev, z[f"v{k}_out"]
+        k += 1

@@ -246,12 +246,26 @@ def test_gemm_f32_vs_fp64(M, N, K, trans_b, bias, split_k):
     assert float(big[:, :4].abs().sum()) == 0.0 and float(big[:, 4 + N:].abs().sum()) == 0.0
 
 
+def test_gemm_f32_yardstick_vs_fp64():
+    """regcn_gemm_f32 (fp32 CUDA cores): kept as the yardstick the tensor-core path is compared with."""
+    _, ops = _ops()
+    g = torch.Generator(device="cpu").manual_seed(11)
+    a, b = torch.randn(130, 204, generator=g), torch.randn(131, 204, generator=g)
+    out = ops.gemm_f32_yardstick(a.to(DEV), b.to(DEV), trans_b=True, split_k=3)
+    ref = a.double() @ b.double().t()
+    assert float((out.cpu().double() - ref).abs().max()) <= 4e-4
+    tc = ops.gemm(a.to(DEV), b.to(DEV), trans_b=True)
+    assert float((tc - out).abs().max()) <= 4e-4
+
+
 def test_gemm_rejects_bad_arguments():
     _, ops = _ops()
     a = torch.randn(4, 6, device=DEV)          # K = 6 is not a multiple of 4
     b = torch.randn(6, 8, device=DEV)
-    with pytest.raises(RuntimeError, match="status -2"):
-        ops.gemm(a, b)
+    with pytest.raises(ValueError, match="multiple of 4"):
+        ops.gemm(a, b)                          # one backend: no silent route to the CUDA-core kernel
+    with pytest.raises(ValueError):
+        ops.set_gemm_impl("simt")               # the fp32 CUDA-core kernel is a test yardstick, not a product backend
     with pytest.raises(RuntimeError):
         ops.gemm(torch.randn(4, 8), torch.randn(8, 8))   # CPU tensors are refused: no fallback
 

@@ -75,6 +75,9 @@ def test_model_matches_reference_golden(name):
         ok, worst = close(score.double().sum(1).cpu().numpy(), z["score_rowsum"], rtol=2e-4,
                           atol_scale=float(np.abs(z["score_absmax"]).max()) * 50)
         assert ok, f"score row-sum worst ratio {worst}"
+        if "score_full_rows" in z.files:                     # complete score rows of 16 queries (every candidate)
+            ok, worst = close(score[torch.as_tensor(z["full_qrows"]).to(DEV)].cpu().numpy(), z["score_full_rows"], rtol=2e-4)
+            assert ok, f"full score rows worst ratio {worst}"
     # end-to-end ranks on our own scores: report-level agreement (fp32 re-association flips near-ties)
     _, _, rank, frank = utils.get_total_rank(all_t, score, all_ans, 1000, rel_predict=0,
                                              filter_csr=utils.filter_csr_from_snapshot(all_t, 2 * r, 0))
@@ -545,3 +548,22 @@ def test_edge_cases_empty_and_single_snapshots():
         assert np.isfinite(float(le.detach())) and np.isfinite(float(opt.total_norm))
     res = R.fit_epoch(model, opt, [hist[0], empty, hist[2], case["test"]], r, n, 3, shuffle=False)
     assert res["steps"] == 2 and np.isfinite(res["loss"])          # t = 0 is skipped, t = 1 has no triples
+
+
+def test_hyperbolic_rgcn_layer_matches_reference_golden():
+    """HyperbolicRGCNLayer (hyperbolic_layers.py:21-161) on the K6 block-diagonal kernel with radius-difference message
+    weights vs the reference's own outputs (tests/golden/aux_layer_hyp_rgcn.npz)."""
+    import torch.nn.functional as F
+    import regcn_b200 as R
+    from regcn_b200.hyperbolic_layers import HyperbolicRGCNLayer
+    from tests.helpers import hyp_rgcn_layer_cases
+    for k, v, case, h, prev, want in hyp_rgcn_layer_cases():
+        n, r = case["num_ents"], case["num_rels"]
+        layer = HyperbolicRGCNLayer(200, 200, 2 * r, v["nb"], c=0.01, activation=F.rrelu if v["act"] else None,
+                                    self_loop=v["self_loop"], skip_connect=v["skip"], radius_msg_gamma=v["gamma"])
+        layer.load_state_dict(synth.fill_state_dict(layer.state_dict(), 60 + k))
+        layer = layer.cuda().eval()
+        g = R.build_sub_graph(n, r, case["history"][0], True, 0)
+        got = layer(g, torch.from_numpy(h).cuda(), None, torch.from_numpy(prev).cuda() if v["skip"] else None)
+        ok, worst = close(got.cpu().numpy(), want, rtol=1e-4)
+        assert ok, (k, worst)

@@ -68,6 +68,9 @@ def test_restatement_matches_reference(name):
         assert ok, f"score block worst ratio {worst}"
         ok, worst = close(score_rel[qrows].numpy(), z["score_rel_qrows"], rtol=2e-4)
         assert ok, f"score_rel worst ratio {worst}"
+        if "score_full_rows" in z.files:                     # complete score rows of 16 queries (every candidate)
+            ok, worst = close(score[z["full_qrows"]].numpy(), z["score_full_rows"], rtol=2e-4)
+            assert ok, f"full score rows worst ratio {worst}"
     # ranks on the oracle's own scores: identical to the reference's except where fp32 noise flips a near-tie
     all_ans = synth.answers_of(case["test"], r, False)
     all_ans_r = synth.answers_of(case["test"], r, True)
@@ -241,3 +244,26 @@ def test_rna_tf32_restatement_matches_bit_pattern_rule():
     x = np.concatenate([x, ties, -ties])
     bits = ((x.view(np.uint32) + np.uint32(0x1000)) & np.uint32(0xffffe000)).view(np.float32)
     assert np.array_equal(bits, restate.rna_tf32(x))
+
+
+def test_hyp_rgcn_layer_restatement_matches_reference():
+    """restate.hyp_rgcn_layer == the reference's HyperbolicRGCNLayer (hyperbolic_layers.py:21-161) on every structural
+    variant of tests/golden/aux_layer_hyp_rgcn.npz (block sizes, self loop, skip gate, activation)."""
+    import regcn_b200.hyperbolic_layers as HL
+    import torch.nn.functional as F
+    from tests.helpers import hyp_rgcn_layer_cases
+    n_cases = 0
+    for k, v, case, h, prev, want in hyp_rgcn_layer_cases():
+        n, r = case["num_ents"], case["num_rels"]
+        layer = HL.HyperbolicRGCNLayer(200, 200, 2 * r, v["nb"], c=CURV, activation=F.rrelu if v["act"] else None,
+                                       self_loop=v["self_loop"], skip_connect=v["skip"], radius_msg_gamma=v["gamma"])
+        sd = synth.fill_state_dict(layer.state_dict(), 60 + k)
+        g = restate.build_edges(case["history"][0], n, r)
+        got = restate.hyp_rgcn_layer(torch.from_numpy(h), g, sd["weight"], layer.num_bases, CURV, v["gamma"],
+                                     w_loop=sd.get("loop_weight"),
+                                     skip=(sd["skip_weight"], sd["skip_bias"]) if v["skip"] else None,
+                                     prev_h=torch.from_numpy(prev) if v["skip"] else None, act=v["act"])
+        ok, worst = close(got.numpy(), want, rtol=1e-5)
+        assert ok, (k, worst)
+        n_cases += 1
+    assert n_cases == 4
