@@ -4,7 +4,9 @@ workload (BASELINE.json configs[2]): evolve L=6 history snapshots, score all B=2
 N=23033 entities, rank raw + time-filtered.
 
     python bench.py --gpus N --steps K --warmup W                 # our arm (torchrun for N > 1)
-    python bench.py --impl reference --gpus N --steps K --warmup W  # CPU arm: the oracle port on the host cores
+    python bench.py --impl reference --gpus N --steps K --warmup W  # CPU arm: the UNMODIFIED reference's own test() loop
+                                                                    # (oracle/_ref, staged by oracle/build_ref.py) under
+                                                                    # the DGL stand-in, on the box's host cores
 
 Prints ONE JSON line (rank 0).  `value` is all-entity-ranked queries/s with inputs resident in HBM; `e2e` is the
 same metric through the public API from pinned HOST buffers (H2D of the triples, device edge-index build, predict,
@@ -129,7 +131,7 @@ def cpu_port_step(sd, graphs, r, test, cfg):
 
 
 def run_cpu_arm(args, steps, warmup, quiet=False):
-    """The reference's evaluation loop (src/main.py:33-123) through the oracle port on the host cores: per step rebuild
+    """The reference's evaluation loop (src/main.py:33-123) through the oracle PORT on the host cores: per step rebuild
     the L history graphs, predict, rank entities raw + filtered; the window slides like the GPU arm's."""
     import torch
     from oracle import restate
@@ -142,7 +144,7 @@ def run_cpu_arm(args, steps, warmup, quiet=False):
     _, sd = build_product_model(cfg, n, r, 0)
     window = list(stream["history"])
     B = 2 * len(stream["tests"][0])
-    t0 = None
+    t0 = time.perf_counter()
     for k, snap in enumerate(stream["tests"]):
         if k == warmup:
             t0 = time.perf_counter()
@@ -153,12 +155,132 @@ def run_cpu_arm(args, steps, warmup, quiet=False):
     dt = (time.perf_counter() - t0) / max(1, steps)
     return {"value": B / dt, "unit": "queries/s", "cores": cores, "kind": "port",
             "sample": f"{steps} step(s) of the sliding-window evaluation loop on workload {args.workload} (per step: "
-                      f"rebuild L={len(window)} graphs, evolve, score {B}x{n}, raw/filtered rank) after {warmup} warm-up, "
-                      f"oracle/restate.py with torch CPU ops on {cores} threads; scatter-sum is index_add_, not DGL's kernel",
+                      f"rebuild L={len(window)} graphs, evolve, score {B}x{n}, raw/filtered entity rank) after {warmup} "
+                      f"warm-up, oracle/restate.py with torch CPU ops on {cores} threads; scatter-sum is index_add_, not "
+                      f"DGL's kernel",
             "ms_per_step": dt * 1e3}
 
 
-def run_stress(dev, hbm_peak, tf_peak):
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def reference_available():
+    return os.path.isfile(os.path.join(REF_DIR, "src", "main.py"))
+
+
+def run_reference_arm(args, steps, warmup):
+    """The UNMODIFIED reference on the host cores: its own evaluation loop `test()` (src/main.py:33-123, or
+    hyperbolic_src/hyperbolic_main.py:60-170) imported from oracle/_ref (byte copies staged by oracle/build_ref.py; not in
+    the git history, shipped like the built .so) and run on CPU tensors under the DGL stand-in oracle/fake_dgl.py.  Per
+    test snapshot the reference rebuilds its L history graphs, predicts, and ranks entities AND relations raw + filtered
+    with its python filter loop -- the same work the GPU arm's e2e number covers.  The model takes the same seeded
+    parameters as the GPU arm (state-dict names are identical)."""
+    import argparse as _ap
+    import logging
+    import torch
+    from oracle import fake_dgl
+    from regcn_b200 import synth
+    fake_dgl.install()
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    logging.disable(logging.CRITICAL)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = model_cfg(args.model)
+    stream = synth.make_stream(args.workload, 1000, n_test=warmup + steps)
+    n, r = stream["num_ents"], stream["num_rels"]
+    L = len(stream["history"])
+    _, sd = build_product_model(cfg, n, r, 0)
+    from rgcn import utils as ref_utils
+    if cfg["kind"] == "regcn":
+        import src.main as ref_main
+        from src.rrgcn import RecurrentRGCN
+        model = RecurrentRGCN("convtranse", "uvrgcn", n, r, 0, 0, H_DIM, "sub", 3, num_bases=N_BASES, num_basis=-1,
+                              num_hidden_layers=N_LAYERS, dropout=0.2, self_loop=True, skip_connect=False,
+                              layer_norm=cfg["layer_norm"], input_dropout=0.2, hidden_dropout=0.2, feat_dropout=0.2,
+                              entity_prediction=True, relation_prediction=True, use_cuda=False, gpu="cpu")
+        ref_main.args = _ap.Namespace(gpu="cpu", run_analysis=False, test_history_len=L, multi_step=False,
+                                      relation_evaluation=False, topk=10)
+
+        def loop(hist, tests, ae, ar):
+            return ref_main.test(model, hist, tests, r, n, False, ae, ar, None, None, "eval")
+    else:
+        import hyperbolic_src.hyperbolic_main as ref_main
+        from hyperbolic_src.hyperbolic_model import HyperbolicRecurrentRGCN
+        model = HyperbolicRecurrentRGCN(cfg["decoder"], cfg["encoder"], n, r, 0, 0, H_DIM, "sub", 3, num_bases=N_BASES,
+                                        num_hidden_layers=N_LAYERS, dropout=0.2, c=0.01, self_loop=True,
+                                        layer_norm=cfg["layer_norm"], input_dropout=0.2, hidden_dropout=0.2,
+                                        feat_dropout=0.2, entity_prediction=True, relation_prediction=True,
+                                        use_cuda=False, gpu="cpu", radius_msg_gamma=cfg["gamma"])
+        hargs = _ap.Namespace(gpu="cpu", run_analysis=False, test_history_len=L, multi_step=False,
+                              relation_evaluation=False, topk=10, verbose=False)
+
+        def loop(hist, tests, ae, ar):
+            return ref_main.test(model, hist, tests, r, n, False, ae, ar, None, None, "eval", hargs)
+    model.load_state_dict(sd)
+    model.eval()
+    tests = stream["tests"]
+    ans_e = [ref_utils.load_all_answers_for_filter(s, r, False) for s in tests]
+    ans_r = [ref_utils.load_all_answers_for_filter(s, r, True) for s in tests]
+    hist = list(stream["history"])
+    B = 2 * len(tests[0])
+    # the reference hard-codes one `.cuda()` (rgcn/layers.py:230) even with use_cuda=False; on a box WITH a GPU that call
+    # would really move the mask, so it is neutralised for the duration of the CPU run (and only then)
+    orig_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        with torch.no_grad():
+            if warmup:
+                loop(hist, tests[:warmup], ans_e[:warmup], ans_r[:warmup])
+            window = (hist + tests[:warmup])[-L:]
+            t0 = time.perf_counter()
+            loop(window, tests[warmup:], ans_e[warmup:], ans_r[warmup:])
+            dt = (time.perf_counter() - t0) / max(1, steps)
+    finally:
+        torch.Tensor.cuda = orig_cuda
+    return {"value": B / dt, "unit": "queries/s", "cores": cores, "kind": "reference",
+            "sample": f"{steps} step(s) of the reference's own test() loop (oracle/_ref/{'src/main.py' if cfg['kind'] == 'regcn' else 'hyperbolic_src/hyperbolic_main.py'}, "
+                      f"unmodified) on workload {args.workload} after {warmup} warm-up step(s): per step build_sub_graph x L={L}, "
+                      f"model.predict, get_total_rank for entities and relations (raw + filtered), {B} queries x {n} entities; "
+                      f"torch CPU ops on {cores} threads; DGL is not installable here, its scatter-sum is the stand-in's "
+                      f"index_add_ (oracle/fake_dgl.py), every other instruction is the reference's",
+            "ms_per_step": dt * 1e3}
+
+
+def measure_tf32_peak(dev, seconds=2.0):
+    """cuBLAS TF32 dense peak measured the way MEASURED_PEAKS.json measures bf16: torch.matmul on 8192^3 fp32 operands with
+    TF32 tensor cores allowed; best of 10 (burst) and back to back for `seconds` (sustained).  TFLOP/s."""
+    import torch
+    n = 8192
+    a = torch.randn(n, n, device=dev)
+    b = torch.randn(n, n, device=dev)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        for _ in range(3):
+            torch.matmul(a, b)
+        torch.cuda.synchronize()
+        best = 1e30
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch.matmul(a, b); e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        reps = max(5, int(seconds * 1e3 / best))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            torch.matmul(a, b)
+        e1.record(); torch.cuda.synchronize()
+        sus = e0.elapsed_time(e1) / reps
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    fl = 2.0 * n ** 3
+    return {"burst": fl / best / 1e9, "sustained": fl / sus / 1e9,
+            "how": "torch.matmul fp32 8192^3 with torch.backends.cuda.matmul.allow_tf32 (cuBLAS TF32): best of 10 and "
+                   f"{reps} back to back"}
+
+
+def run_stress(dev, hbm_peak, tf_peak, tf32_peak=None):
     """(1) K4 union aggregate at BASELINE configs[4] size (N = 1M entities, E = 10M edges, d = 200): algorithmic bytes
     808*E + 808*N + 800*2R over the CUDA-event time, uniform and Zipf endpoints.  (2) The fused
     scoring + count GEMM alone at the C3 shape and at one C5 entity shard, fp32-parity (3xTF32) and bf16 modes."""
@@ -184,7 +306,7 @@ def run_stress(dev, hbm_peak, tf_peak):
     h = torch.randn(n, d, device=dev)
     rel = torch.randn(2 * r, d, device=dev)
     o = torch.empty(n, d, device=dev)
-    edge = {"kernel": "regcn::union_aggregate_{stream,}kernel (+ radix-32 fix-up for hub rows)", "bound": "hbm",
+    edge = {"kernel": "regcn::union_aggregate_{stream,}kernel (+ radix-32 fix-up for hub rows of > 1024 in-edges)", "bound": "hbm",
             "peak": hbm_peak, "unit": "GB/s", "shape": f"N={n} E={2 * t} d={d} 2R={2 * r} (BASELINE configs[4])",
             "algorithmic_bytes_per_launch": 808.0 * 2 * t + 808.0 * n + 800.0 * 2 * r}
     for name, zipf in (("uniform", False), ("zipf", True)):
@@ -197,27 +319,55 @@ def run_stress(dev, hbm_peak, tf_peak):
     edge["achieved"], edge["frac"] = edge["uniform"]["achieved"], edge["uniform"]["frac"]
     out["edge_kernel_hbm_bound"] = edge
     del h, o
+    # GDELT-dense stress (BASELINE configs[3], 50 000 triples per snapshot: hub rows of ~9 000 in-edges)
+    cn, cr, ct = synth.SHAPES["c4d"][:3]
+    tri = synth.make_snapshot(np.random.default_rng(0), cn, cr, ct, zipf=True)
+    g = R.build_sub_graph(cn, cr, tri, True, dev.index or 0)
+    h4, rel4 = torch.randn(cn, d, device=dev), torch.randn(2 * cr, d, device=dev)
+    o4 = torch.empty(cn, d, device=dev)
+    ms = med(lambda: ops.union_aggregate(h4, rel4, g, out=o4))
+    b4 = 808.0 * 2 * ct + 808.0 * cn + 800.0 * 2 * cr
+    out["edge_kernel_c4_dense"] = {"shape": f"N={cn} E={2 * ct} d={d} 2R={2 * cr} Zipf endpoints (BASELINE configs[3], dense stress)",
+                                   "ms": ms, "algorithmic_bytes_per_launch": b4, "achieved": b4 / ms / 1e6,
+                                   "frac": b4 / ms / 1e6 / hbm_peak, "split_chunks": g.n_split_chunks,
+                                   "note": "the whole working set (6 MB table + 1 MB index) is L2-resident: the launch is "
+                                           "latency-bound, the HBM fraction is reported for the record"}
+    del g, h4, o4
+    tf32 = tf32_peak["burst"] if tf32_peak else tf_peak / 2
     score = {"kernel": "regcn::tc::gemm_tf32_kernel<1> (counting epilogue, no score matrix)", "bound": "tensor",
-             "peak": tf_peak, "unit": "TFLOP/s", "cases": []}
+             "peak": tf_peak, "unit": "TFLOP/s", "tf32_peak_measured_burst": tf32 if tf32_peak else None, "cases": []}
+    lib = _lib.load()
     for shape, B, N in (("c3", 2914, 23033), ("c5 shard 1/8", 8192, 125000)):
-        q = torch.randn(B, d, device=dev)
-        e = torch.randn(N, d, device=dev) * 0.5
-        target = torch.randint(0, N, (B,), device=dev, dtype=torch.int32)
+        gq = torch.Generator(device=dev)
+        gq.manual_seed(1)
+        q = torch.randn(B, d, device=dev, generator=gq) * 0.05
+        e = torch.randn(N, d, device=dev, generator=gq) * 0.05
+        target = torch.randint(0, N, (B,), device=dev, dtype=torch.int32, generator=gq)
         tscore = torch.zeros(B, device=dev)
         raw = torch.zeros(B, device=dev, dtype=torch.int32)
         qh, ql = ops.split_tf32(q)
         eh, el = ops.split_tf32(e)
         qb, eb = ops.to_bf16(q), ops.to_bf16(e)
-        for mode, passes in (("3xTF32 (fp32 parity)", 3), ("bf16", 0)):
+        x2, y2 = ops.row_sumsq(q), ops.row_sumsq(e)
+        sm = torch.tensor([1.0, 1.0], device=dev)
+        for mode, passes, hyp, poly in (("dot, 3xTF32 (fp32 parity)", 3, 0, 1), ("dot, bf16", 0, 0, 1),
+                                        ("hyperbolic RotH-form, 3xTF32, polynomial threshold test", 3, 1, 1),
+                                        ("hyperbolic RotH-form, 3xTF32, IEEE score per candidate (round-1 epilogue)", 3, 1, 0)):
             a_, b_ = (qb, eb) if passes == 0 else (qh, eh)
+            lib.regcn_score_count_poly(poly)
             ms = med(lambda: _lib.call("regcn_score_count_tf32", a_.data_ptr(), ql.data_ptr(), b_.data_ptr(),
-                                       el.data_ptr(), B, N, d, tscore.data_ptr(), target.data_ptr(), raw.data_ptr(), 0, 0,
-                                       None, None, None, 1.0, None, None, passes))
+                                       el.data_ptr(), B, N, d, tscore.data_ptr(), target.data_ptr(), raw.data_ptr(), 0, hyp,
+                                       x2.data_ptr() if hyp else None, y2.data_ptr() if hyp else None, None, 0.01,
+                                       sm.data_ptr() if hyp else None, None, passes))
+            lib.regcn_score_count_poly(1)
             alg = 2.0 * B * N * d / ms / 1e9
             ex = alg * max(passes, 1)
-            mode_peak = tf_peak if passes == 0 else tf_peak / 2      # TF32 dense peak = half the bf16 figure
+            mode_peak = tf_peak if passes == 0 else tf32
             score["cases"].append({"shape": shape, "B": B, "N": N, "mode": mode, "ms": ms, "algorithmic": alg,
                                    "executed": ex, "frac_of_mode_peak_executed": ex / mode_peak,
+                                   "mode_peak": mode_peak,
+                                   "mode_peak_source": "MEASURED_PEAKS bf16 sustained" if passes == 0 else
+                                   ("cuBLAS TF32 8192^3 burst measured in this run" if tf32_peak else "bf16 / 2 (assumed)"),
                                    "frac_of_bf16_peak_algorithmic": alg / tf_peak})
         del q, e, qh, ql, eh, el, qb, eb
     out["scoring_kernel"] = score
@@ -249,6 +399,153 @@ def run_cpu_train_arm(args, steps=1, warmup=1):
                       f"over oracle/restate.py on {cores} threads"}
 
 
+def parity_record(model, sd, case, cfg, dev):
+    """Scores and ranks of the GPU path against the fp32 oracle port on the SAME inputs (the bench's own model and
+    snapshot): max |dscore| relative to max(1, |score|), and the fraction of raw / time-filtered entity ranks that differ
+    (random-weight models score thousands of candidates within 1e-5 of each other, so a few ranks move by +-1..2 under
+    any fp32 re-association; MRR is what the metric is built from)."""
+    import numpy as np
+    import torch
+    from oracle import restate
+    from regcn_b200 import evaluate, synth, utils
+    import regcn_b200 as R
+    n, r = case["num_ents"], case["num_rels"]
+    graphs = [restate.build_edges(s, n, r) for s in case["history"]]
+    with torch.no_grad():
+        if cfg["kind"] == "regcn":
+            o_t, o_score, _, _, _ = restate.regcn_predict(sd, graphs, r, case["test"], layer_norm=cfg["layer_norm"])
+        else:
+            o_t, o_score, _, _, _ = restate.hyp_predict(sd, graphs, r, case["test"], c=0.01, decoder=cfg["decoder"],
+                                                        encoder=cfg["encoder"], gamma=cfg["gamma"],
+                                                        num_bases=min(N_BASES, 2 * r))
+    glist = [R.build_sub_graph(n, r, s, True, dev.index or 0) for s in case["history"]]
+    all_t, score, _ = model.predict(glist, r, None, torch.from_numpy(case["test"]).to(dev), True)
+    mine = score.cpu().numpy()
+    ref = o_score.numpy()
+    rel = np.abs(mine - ref) / np.maximum(1.0, np.abs(ref))
+    all_ans = synth.answers_of(case["test"], r, False)
+    _, _, rank_o, frank_o = restate.total_rank(o_t, ref, all_ans, 0)
+    fcsr = utils.filter_csr_from_snapshot(all_t, 2 * r, 0)
+    rk, frk = evaluate.evaluate_snapshot(model, glist, all_t, fcsr)
+    rk, frk = rk.cpu().numpy(), frk.cpu().numpy()
+    return {"against": "oracle/restate.py (fp32 CPU restatement pinned to the reference's outputs) on this run's own inputs",
+            "max_rel_dscore": float(rel.max()), "gate": 1e-4,
+            "rank_flip_rate_raw": float(np.mean(rk != rank_o)), "rank_flip_rate_filtered": float(np.mean(frk != frank_o)),
+            "max_abs_drank": int(np.abs(rk - rank_o).max()),
+            "mrr_raw": [float(np.mean(1.0 / rk)), float(np.mean(1.0 / rank_o))],
+            "mrr_filtered": [float(np.mean(1.0 / frk)), float(np.mean(1.0 / frank_o))],
+            "note": "ranks of the fused counting epilogue (3xTF32) vs ranks of the oracle's fp32 scores; [ours, oracle]"}
+
+
+def run_other_configs(dev, flush, hbm_peak):
+    """BASELINE configs [1], [3], [4] as short sub-records (<= 5 timed steps each, L2 flushed between steps)."""
+    import numpy as np
+    import torch
+    import regcn_b200 as R
+    from regcn_b200 import _lib, evaluate, synth, utils
+    lib = _lib.load()
+
+    def step_time(model, glist, all_t, fcsr, steps=5, warm=3):
+        for _ in range(warm):
+            evaluate.evaluate_snapshot(model, glist, all_t, fcsr)
+        torch.cuda.synchronize()
+        tot, parts = 0.0, {"evolve": 0.0, "score": 0.0, "rank": 0.0}
+        for _ in range(steps):
+            flush.fill_(1.0)
+            tm = {k: (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for k in parts}
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            evaluate.evaluate_snapshot(model, glist, all_t, fcsr, tm)
+            b.record()
+            torch.cuda.synchronize()
+            tot += a.elapsed_time(b)
+            for k in parts:
+                parts[k] += tm[k][0].elapsed_time(tm[k][1])
+        l0 = lib.regcn_kernel_launches()
+        evaluate.evaluate_snapshot(model, glist, all_t, fcsr)
+        torch.cuda.synchronize()
+        return tot / steps, {k: v / steps for k, v in parts.items()}, int(lib.regcn_kernel_launches() - l0)
+
+    def prepare(case, cfg, seed=0):
+        n, r = case["num_ents"], case["num_rels"]
+        model, _ = build_product_model(cfg, n, r, seed)
+        model = model.to(dev)
+        glist = [R.build_sub_graph(n, r, s, True, dev.index or 0) for s in case["history"]]
+        t = torch.from_numpy(case["test"]).to(dev)
+        inv = t[:, [2, 1, 0]].clone()
+        inv[:, 1] += r
+        all_t = torch.cat((t, inv)).contiguous()
+        return model, glist, all_t, utils.filter_csr_from_snapshot(all_t, 2 * r, 0)
+
+    out = {}
+    # configs[1]: Hyperbolic RE-GCN, lgcn encoder + RotH decoder, c = 0.01, ICEWS14s shape, history 3
+    try:
+        case = synth.make_case("c1", 0)
+        model, glist, all_t, fcsr = prepare(case, model_cfg("hyp_lgcn_roth"))
+        ms, parts, nl = step_time(model, glist, all_t, fcsr)
+        out["configs[1] hyperbolic lgcn+roth, ICEWS14s shape"] = {
+            "ms_per_step": ms, "queries_per_s": all_t.shape[0] / (ms * 1e-3), "phase_ms": parts,
+            "snapshot_steps_per_s": len(glist) / (parts["evolve"] * 1e-3), "gpu_launches_per_step": nl,
+            "shape": "N=7128 R=230 T=250/snapshot L=3 B=500"}
+        del model, glist
+    except Exception as e:  # noqa: BLE001
+        out["configs[1] hyperbolic lgcn+roth, ICEWS14s shape"] = {"error": repr(e)[:300]}
+    # configs[3]: RE-GCN, GDELT shape, dense snapshots (5 000 and 50 000 triples per snapshot), history 3
+    for shp in ("c4", "c4d"):
+        key = f"configs[3] RE-GCN GDELT shape, {synth.SHAPES[shp][2]} triples/snapshot"
+        try:
+            case = synth.make_case(shp, 0)
+            model, glist, all_t, fcsr = prepare(case, model_cfg("regcn"))
+            ms, parts, nl = step_time(model, glist, all_t, fcsr)
+            E = 2 * len(case["history"][0])
+            n, r = case["num_ents"], case["num_rels"]
+            out[key] = {"ms_per_step": ms, "queries_per_s": all_t.shape[0] / (ms * 1e-3), "phase_ms": parts,
+                        "snapshot_steps_per_s": len(glist) / (parts["evolve"] * 1e-3), "gpu_launches_per_step": nl,
+                        "edges_per_s_through_the_aggregate": 2 * len(glist) * E / (parts["evolve"] * 1e-3),
+                        "shape": f"N={n} R={r} E={E}/snapshot L={len(glist)} B={all_t.shape[0]}"}
+            del model, glist
+        except Exception as e:  # noqa: BLE001
+            out[key] = {"error": repr(e)[:300]}
+    # configs[4]: synthetic TKG, 1M entities, 512 relations, 10M edges / snapshot, d = 200, history 3, RotH scoring
+    key = "configs[4] 1M entities, 10M edges/snapshot, RotH scoring (one GPU, whole table)"
+    try:
+        n, r, t, L5, tq = 1_000_000, 512, 5_000_000, 3, 4096
+        rng = np.random.default_rng(5)
+        hist = [synth.make_snapshot(rng, n, r, t, zipf=False) for _ in range(L5)]
+        test = synth.make_snapshot(rng, n, r, tq, zipf=False)
+        m5 = R.HyperbolicRecurrentRGCN("roth", "hyperbolic_uvrgcn", n, r, 0, 0, H_DIM, "sub", 3, num_bases=N_BASES,
+                                        num_hidden_layers=N_LAYERS, dropout=0.2, c=0.01, self_loop=True, layer_norm=False,
+                                        input_dropout=0.2, hidden_dropout=0.2, feat_dropout=0.2, entity_prediction=True,
+                                        relation_prediction=True, use_cuda=True, gpu=0, radius_msg_gamma=0.15)
+        with torch.no_grad():
+            g5 = torch.Generator().manual_seed(5)           # the reference's own initialisers everywhere else
+            m5.dynamic_emb.copy_(torch.randn(n, H_DIM, generator=g5) * 0.5)
+        m5 = m5.to(dev).eval()
+        glist = [R.build_sub_graph(n, r, s, True, dev.index or 0) for s in hist]
+        tt = torch.from_numpy(test).to(dev)
+        inv = tt[:, [2, 1, 0]].clone()
+        inv[:, 1] += r
+        all_t = torch.cat((tt, inv)).contiguous()
+        fcsr = utils.filter_csr_from_snapshot(all_t, 2 * r, 0)
+        ms, parts, nl = step_time(m5, glist, all_t, fcsr, steps=3, warm=2)
+        E = 2 * t
+        edge_bytes = 2 * L5 * (812.0 * E + 812.0 * n + 800.0 * 2 * r)
+        gemm_flops = L5 * (2 * 3 + 1) * 2.0 * n * H_DIM * H_DIM + 2.0 * all_t.shape[0] * n * H_DIM
+        out[key] = {"ms_per_step": ms, "queries_per_s": all_t.shape[0] / (ms * 1e-3), "phase_ms": parts,
+                    "snapshot_steps_per_s": L5 / (parts["evolve"] * 1e-3), "gpu_launches_per_step": nl,
+                    "shape": f"N={n} R={r} E={E}/snapshot L={L5} B={all_t.shape[0]}, hyperbolic_uvrgcn encoder (radius-weighted "
+                             f"union aggregate) + RotH decoder, uniform endpoints",
+                    "algorithmic_edge_bytes_per_step": edge_bytes, "algorithmic_dense_flops_per_step": gemm_flops,
+                    "evolve_lower_bound_ms": {"edge path at measured HBM peak": edge_bytes / hbm_peak / 1e6},
+                    "note": "evolution replicated, scoring over the whole 1M-entity table on one GPU; the 8-GPU line "
+                            "(entity_sharded_c5) shards the scoring"}
+        del m5, glist
+    except Exception as e:  # noqa: BLE001
+        out[key] = {"error": repr(e)[:300]}
+    torch.cuda.empty_cache()
+    return out
+
+
 def workload_string(args):
     """The same `config.workload` text for both arms."""
     from regcn_b200 import synth
@@ -257,6 +554,13 @@ def workload_string(args):
         return (f"{args.workload}: ICEWS18-shaped N={n} R={r} T={t}/snapshot L={hist} B={2 * tq} queries/timestamp, "
                 f"d={H_DIM}, 2-layer UnionRGCN + ConvTransE")
     return f"{args.workload} {args.model}"
+
+
+def config_dict(args):
+    """`config` of the JSON line -- the same dict in both arms (the driver compares them)."""
+    return {"workload": workload_string(args), "variant": args.model,
+            "step": "one evaluated test timestamp: evolve the L history snapshots, score every query against every "
+                    "entity, rank raw + time-filtered"}
 
 
 _JSON_FD = None
@@ -291,13 +595,13 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
-        cb = run_cpu_arm(args, steps, warmup)
+        # honours --steps / --warmup: one step = one test snapshot of the workload through the reference's own loop
+        steps, warmup = max(1, args.steps), max(0, args.warmup)
+        cb = run_reference_arm(args, steps, warmup) if reference_available() else run_cpu_arm(args, steps, warmup)
         line = {"impl": "reference", "metric": metric, "value": cb["value"], "unit": "queries/s",
                 "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": cb["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload_string(args), "variant": args.model, "note": "steps/warmup capped so the CPU arm "
-                           "finishes in minutes; reference Python cannot travel to the GPU box, so the oracle port runs"},
+                "config": config_dict(args),
                 "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": cb["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -313,8 +617,6 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ.pop("NCCL_DEBUG")                # NCCL prints its version on stdout at VERSION and WARN level
         dist.init_process_group("nccl", device_id=dev)
     _lib.require_device()
     if args.gemm:
@@ -400,7 +702,8 @@ def main():
     # entities and relations (raw + time-filtered) and copies the four rank vectors device->host.
     e2e_steps = max(3, min(args.steps, 12))
     e2e_warm = max(L + 1, min(args.warmup, 3))       # the window must have turned over once (steady-state cache)
-    stream = synth.make_stream(args.workload, 1000 + rank, n_test=e2e_warm + 2 * e2e_steps)
+    e2e_reps = 3                                     # the loop is timed three times over fresh snapshots: median
+    stream = synth.make_stream(args.workload, 1000 + rank, n_test=e2e_warm + (1 + e2e_reps) * e2e_steps)
     s_hist = [torch.from_numpy(s).pin_memory() for s in stream["history"]]
     s_tests = [torch.from_numpy(s).pin_memory() for s in stream["tests"]]
     # warm-up: turn the window over, then one untimed call of exactly the timed call's shape (the pinned staging areas
@@ -408,30 +711,43 @@ def main():
     R.test(model, s_hist, s_tests[:e2e_warm], r, n, True, test_history_len=L)
     R.test(model, (s_hist + s_tests[:e2e_warm])[-L:], s_tests[e2e_warm:e2e_warm + e2e_steps], r, n, True,
            test_history_len=L)
-    e2e_warm += e2e_steps
-    win = (s_hist + s_tests[:e2e_warm])[-L:]
-    barrier()
-    ea, eb = ev(), ev()
-    ea.record()
-    R.test(model, win, s_tests[e2e_warm:], r, n, True, test_history_len=L)
-    eb.record()
-    barrier()
-    e2e_ms = maxr(ea.elapsed_time(eb)) / e2e_steps
+    pos = e2e_warm + e2e_steps
+    e2e_all = []
+    for _ in range(e2e_reps):
+        win = (s_hist + s_tests[:pos])[-L:]
+        barrier()
+        ea, eb = ev(), ev()
+        ea.record()
+        R.test(model, win, s_tests[pos:pos + e2e_steps], r, n, True, test_history_len=L)
+        eb.record()
+        barrier()
+        e2e_all.append(maxr(ea.elapsed_time(eb)) / e2e_steps)
+        pos += e2e_steps
+    e2e_ms = sorted(e2e_all)[len(e2e_all) // 2]
     Bq = 2 * s_tests[0].shape[0]
     h2d = s_tests[0].numel() * 8
     d2h = 4 * Bq * 4 + 2 * 4 + 8 * 4
 
-    # ---- roofline of the dominant kernel: the library records CUDA events around every launch of the tcgen05 GEMM
-    #      (on the launching stream) while a few extra steps run; flops are the algorithmic 2*M*N*K of each launch ----
+    # ---- roofline of the dominant kernel (the tcgen05 GEMM): every launch of a few extra steps stamps %globaltimer
+    #      INSIDE the kernel (regcn_gemm_tf32_trace_begin: per CTA, past the dependency wait ... exit), so the durations are
+    #      taken with both streams, programmatic dependent launch and warm caches exactly as in the timed region above.
+    #      frac = sum(algorithmic flops) / sum(durations) / peak;  per-instance rows say where the time goes ----
     import ctypes
+    import numpy as np
     lib = _lib.load()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     probe_steps = 3
+    slots = lib.regcn_gemm_tf32_trace_slots()
+    rec_words = 148 * slots
+    cap = (launches_per_step + 8) * probe_steps
+    tbuf = torch.zeros(cap * rec_words, device=dev, dtype=torch.int64)
     torch.cuda.synchronize()
-    # per-kernel timing brackets every launch with CUDA events on its stream: the probe steps run single-stream and
-    # without programmatic dependent launch, so that a kernel's time is its own (the timed region above keeps both on)
-    lib.regcn_two_stream_enable(0)
-    lib.regcn_pdl_enable(0)
-    lib.regcn_prof_enable(1)
+    lib.regcn_gemm_tf32_trace_begin(tbuf.data_ptr(), tbuf.numel() * 8)
     pa, pb = ev(), ev()
     probe_ms = 0.0
     for _ in range(probe_steps):
@@ -442,60 +758,96 @@ def main():
         torch.cuda.synchronize()
         probe_ms += pa.elapsed_time(pb)
     probe_ms /= probe_steps
-    ms_c, n_c, w_c = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()
-    lib.regcn_prof_read(0, ctypes.byref(ms_c), ctypes.byref(n_c), ctypes.byref(w_c))
+    n_rec = lib.regcn_gemm_tf32_trace_count()
+    tr = tbuf.cpu().numpy().reshape(cap, 148, slots)
+    inst = {}
+    tot_ns, tot_fl = 0.0, 0.0
+    names = {0: "store", 1: "score+count", 2: "pair scores", 3: "layer / time-gate", 4: "log-sum-exp"}
+    for i in range(n_rec):
+        e_, m_, n_, k_, g_, p_ = (ctypes.c_int() for _ in range(6))
+        fl_ = ctypes.c_double()
+        lib.regcn_gemm_tf32_trace_read(i, ctypes.byref(e_), ctypes.byref(m_), ctypes.byref(n_), ctypes.byref(k_),
+                                       ctypes.byref(g_), ctypes.byref(p_), ctypes.byref(fl_))
+        rec = tr[i, :g_.value]
+        t_in, t_out = rec[:, 1], rec[:, 40]
+        if (t_in <= 0).any() or (t_out <= 0).any():
+            continue
+        ns = float(t_out.max() - t_in.min())
+        tot_ns += ns
+        tot_fl += fl_.value
+        key = f"{names.get(e_.value, e_.value)} {m_.value}x{n_.value}x{k_.value}"
+        d_ = inst.setdefault(key, {"launches": 0, "us": 0.0, "flops": 0.0, "grid": g_.value})
+        d_["launches"] += 1
+        d_["us"] += ns / 1e3
+        d_["flops"] += fl_.value
+    lib.regcn_gemm_tf32_trace_begin(None, 0)
+    del tbuf
+    gemm_ms = tot_ns / 1e6 / probe_steps
+    gemm_flops = tot_fl / probe_steps
+    n_gemm = n_rec // probe_steps
+    tf32_peak = measure_tf32_peak(dev) if rank == 0 else None
+    passes = 3 if ops.gemm_impl() == "tc" else 1
+    ach_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    per_instance = []
+    for key, d_ in sorted(inst.items(), key=lambda kv: -kv[1]["us"]):
+        us = d_["us"] / d_["launches"]
+        alg = d_["flops"] / d_["launches"] / (us * 1e-6) / 1e12
+        per_instance.append({"gemm": key, "grid": d_["grid"], "launches_per_step": d_["launches"] / probe_steps, "us": us,
+                             "algorithmic_tflops": alg, "frac": alg / peak_tf})
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+    except Exception:
+        pass
+    roofline = {"kernel": ops.gemm_kernel_name(), "bound": "tensor", "achieved": ach_tf, "peak": peak_tf,
+                "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
+                "traffic": traffic.get("gemm_tf32_kernel_bytes_per_launch") if traffic else None,
+                "traffic_source": ("committed `ncu --set full` capture of this workload, not a measurement of this run: "
+                                   + traffic.get("source", "profiles/")) if traffic else None,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks
+                else "fallback 1.4 PFLOP/s (B200_PROFILING.md)",
+                "how": "in-kernel %globaltimer stamps of every GEMM launch of 3 untimed probe steps run exactly like the "
+                       "timed steps (two streams, programmatic dependent launch): frac = sum(2MNK) / sum(kernel durations) / "
+                       "peak; durations of launches that overlap on different streams are each counted in full",
+                "launches_per_step": n_gemm, "ms_per_step_in_kernel": gemm_ms,
+                "probe_step_ms": probe_ms,
+                "tf32_peak_measured": tf32_peak,
+                "executed_tflops": passes * ach_tf,
+                "executed_frac_of_tf32_peak_measured": (passes * ach_tf / tf32_peak["sustained"]) if tf32_peak else None,
+                "algorithmic_flops_per_step": gemm_flops,
+                "per_instance": per_instance,
+                "note": f"fp32-parity mode issues {passes} TF32 MMAs per algorithmic MAC (lo.hi + hi.lo + hi.hi), so the "
+                        f"algorithmic fraction of the bf16 peak cannot exceed 1/(2*{passes}) = {1.0 / (2 * passes):.3f}; most "
+                        f"launches at this size (23033 rows x 200..400 columns, relation GRU 512 rows) are latency- and "
+                        f"L2-operand-bound, see per_instance and scoring_kernel"}
+    # edge kernel (HBM-bound) at this workload: CUDA events around the aggregate launches of single-stream probe steps
+    lib.regcn_two_stream_enable(0)
+    lib.regcn_pdl_enable(0)
+    lib.regcn_prof_enable(1)
+    for _ in range(probe_steps):
+        flush.fill_(1.0)
+        evaluate.evaluate_snapshot(model, glist, all_t, fcsr, None)
+    torch.cuda.synchronize()
     agg_ms_c, agg_n_c, agg_w_c = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()
     lib.regcn_prof_read(1, ctypes.byref(agg_ms_c), ctypes.byref(agg_n_c), ctypes.byref(agg_w_c))
     lib.regcn_prof_enable(0)
     lib.regcn_two_stream_enable(1)
     lib.regcn_pdl_enable(1)
-    gemm_ms = ms_c.value / probe_steps
-    gemm_flops = w_c.value / probe_steps
-    n_gemm = n_c.value // probe_steps
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
-    traffic = None
-    try:
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch of the GEMM kernel over one step, from the committed
-        # `ncu --set full` capture of this same workload (profiles/README.md)
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get("gemm_tf32_kernel_bytes_per_launch")
-    except Exception:
-        pass
-    ach_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-    passes = 3 if ops.gemm_impl() == "tc" else 1
-    roofline = {"kernel": ops.gemm_kernel_name(), "bound": "tensor", "achieved": ach_tf, "peak": peak_tf,
-                "unit": "TFLOP/s", "frac": ach_tf / peak_tf, "traffic": traffic,
-                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks
-                else "fallback 1.4 PFLOP/s (B200_PROFILING.md)",
-                "launches_per_step": n_gemm, "ms_per_step_in_kernel": gemm_ms,
-                "share_of_step": gemm_ms / probe_ms if probe_ms > 0 else None,
-                "probe_step_ms": probe_ms,
-                "executed_frac_of_tf32_peak": passes * ach_tf / (peak_tf / 2),
-                "algorithmic_flops_per_step": gemm_flops,
-                "note": f"average over the {n_gemm} GEMM launches of a step, most of them latency-bound at this size (N=23033 "
-                        f"rows x 200..400 columns, relation GRU 512 rows); fp32-parity mode issues {passes} TF32 MMAs per "
-                        f"algorithmic MAC, so executed tensor work is {passes}x the algorithmic flops and the TF32 dense peak is "
-                        f"half the bf16 figure; probe steps run single-stream (see scoring_kernel for the kernel at a size "
-                        f"where the tensor roofline binds)"}
-    # edge kernel (HBM-bound) at this workload: algorithmic bytes per launch = 808*E + 808*N + 800*2R
     agg_launches = max(1, agg_n_c.value // probe_steps)
     agg_bytes = agg_launches * (808.0 * 2 * T + 808.0 * n + 800.0 * 2 * r)
     agg_ms = agg_ms_c.value / probe_steps
     hbm = float(peaks.get("hbm_gbs", 6650.0))
-    edge = {"kernel": "regcn::union_aggregate_kernel (+fixup)", "bound": "hbm", "launches_per_step": agg_launches,
+    edge = {"kernel": "regcn::union_aggregate_kernel (split rows folded in-kernel)", "bound": "hbm",
+            "launches_per_step": agg_launches,
             "ms_per_step_in_kernel": agg_ms, "achieved": agg_bytes / (agg_ms * 1e-3) / 1e9 if agg_ms > 0 else 0.0,
             "peak": hbm, "unit": "GB/s", "note": "latency-bound at this size (E=3082 edges, 18 MB output); see "
-            "profiles/ for the HBM-bound stress sizes"}
+            "edge_kernel_hbm_bound for the HBM-bound stress sizes"}
     edge["frac"] = edge["achieved"] / hbm
 
     # ---- the two kernels north_star sets targets for, at sizes where their rooflines bind (rank 0, N = 1 only) ----
     stress = None
     if rank == 0 and world == 1 and not args.no_stress:
-        stress = run_stress(dev, hbm, peak_tf)
+        stress = run_stress(dev, hbm, peak_tf, tf32_peak)
 
     # ---- entity-sharded scoring + rank merge (strong scaling of one timestamp), all ranks on the same queries ----
     sharded = None
@@ -656,10 +1008,19 @@ def main():
                           "ratio_to_published": (1e3 / h_ms) / 4.9}
         del hm, hopt
 
-    cpu_baseline = None
+    other = None
+    if rank == 0 and world == 1 and not args.no_stress:
+        other = run_other_configs(dev, flush, hbm)
+
+    cpu_baseline = cpu_port = parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cb = run_cpu_arm(args, 3, 1)
+        # bounded sample (about 10-30 s of host work): the UNMODIFIED reference's test() loop when oracle/_ref is staged,
+        # and the oracle port beside it
+        cp = run_cpu_arm(args, 3, 1)
+        cpu_port = {k: cp[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cb = run_reference_arm(args, 3, 1) if reference_available() else cp
         cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        parity = parity_record(model, sd, case, cfg, dev)
         if train_line is not None:
             ct = run_cpu_train_arm(args, 1, 1)
             train_line["cpu_baseline"] = ct
@@ -668,14 +1029,15 @@ def main():
         line = {"metric": metric, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload_string(args),
-                           "variant": args.model, "parallelism": f"timestamp-dp{world}",
-                           "l2": "256 MiB buffer written between timed steps (untimed)",
-                           "gemm_impl": ops.gemm_impl()},
+                "config": config_dict(args),
+                "run": {"parallelism": f"timestamp-dp{world}", "l2": "256 MiB buffer written between timed steps (untimed)",
+                        "gemm_impl": ops.gemm_impl(), "reference_arm": "oracle/_ref staged" if reference_available()
+                        else "oracle/_ref missing: the CPU arm falls back to the oracle port"},
                 "snapshot_steps_per_s": world * L / (evolve_ms * 1e-3), "evolve_ms_per_step": evolve_ms,
                 "phase_ms": parts, "e2e": {"value": world * Bq / (e2e_ms * 1e-3), "unit": "queries/s",
                                            "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                                            "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                                           "ms_per_step_of_each_repeat": e2e_all,
                                            "api": "regcn_b200.test(): sliding-window loop of src/main.py:33-123 over "
                                                   "pinned host snapshots (entity + relation ranks, raw + filtered); "
                                                   "per-step working set ~480 MB > L2"},
@@ -685,6 +1047,11 @@ def main():
             line.update(stress)
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
+            line["cpu_baseline_port"] = cpu_port
+        if parity:
+            line["parity"] = parity
+        if other:
+            line["other_configs"] = other
         if sharded:
             line["entity_sharded"] = sharded
         if sharded_c5:

@@ -82,7 +82,6 @@ REGCN_API int regcn_union_aggregate(const float* h, const float* rel, const int3
                           const int32_t* sptr, const int32_t* vrow_row, int n_vrows, int n_split_chunks,
                           const float* radius, float gamma, int N, int d, float* out, float* partial,
                           void* stream);
-
 /* ---- K6 block-diagonal aggregate: rgcn/layers.py:167-179; hyperbolic_layers.py:87-109 ----------
  * out[v] = norm[v] * sum_in blockdiag(W[type]) . h[src];  W (num_rels, nb*(d_in/nb)*(d_out/nb)). */
 REGCN_API int regcn_block_aggregate(const float* h, const float* W, const int32_t* rowptr, const int32_t* src_sorted,
@@ -211,6 +210,14 @@ REGCN_API void regcn_gemm_tf32_trace(void* dev_buf);
  * off (every candidate takes the IEEE score): the yardstick of tests and bench.py. Default 1. */
 REGCN_API void regcn_score_count_poly(int on);
 REGCN_API int regcn_gemm_tf32_trace_slots(void);
+/* multi-launch session (bench.py's roofline): record r of the buffer = 148 CTAs x regcn_gemm_tf32_trace_slots() uint64;
+ * launch i of the session stamps into record i (launches beyond bytes / record size are not recorded) and the library
+ * remembers what it computed.  Per launch: duration = max over CTAs of slot 40 (exit) - min over CTAs of slot 1 (past
+ * the dependency wait), both %globaltimer nanoseconds -- measured inside the kernel, so streams, programmatic dependent
+ * launch and warm caches are those of the timed region.  regcn_gemm_tf32_trace_begin(NULL, 0) ends the session. */
+REGCN_API void regcn_gemm_tf32_trace_begin(void* dev_buf, size_t bytes);
+REGCN_API int regcn_gemm_tf32_trace_count(void);
+REGCN_API int regcn_gemm_tf32_trace_read(int i, int* epi, int* M, int* N, int* K, int* grid, int* passes, double* flops);
 /* the layer GEMM of the evolve engine on its own (UnionRGCNLayer apply step, rgcn/layers.py:247-255, and for the last
  * layer the time gate, src/rrgcn.py:176-178, straight out of the accumulator):
  *   acc = A[M,K] . B[N,K]^T (3xTF32);  columns [0,d): out row (row_idx ? row_idx[m] : m) = rrelu(acc) unless

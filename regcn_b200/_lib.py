@@ -49,6 +49,9 @@ SIGNATURES = {
     "regcn_gemm_tf32_trace": (None, [_p]),
     "regcn_score_count_poly": (None, [_i]),
     "regcn_gemm_tf32_trace_slots": (_i, []),
+    "regcn_gemm_tf32_trace_begin": (None, [_p, _sz]),
+    "regcn_gemm_tf32_trace_count": (_i, []),
+    "regcn_gemm_tf32_trace_read": (_i, [_i, _p, _p, _p, _p, _p, _p, _p]),
     "regcn_gemm_tf32_layer": (_i, [_p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p, _i, _p, _p, _i, _p]),
     "regcn_pdl_enable": (None, [_i]),
     "regcn_two_stream_enable": (None, [_i]),

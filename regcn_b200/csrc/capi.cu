@@ -180,6 +180,11 @@ int regcn_gemm_tf32_layer_a32(const float* a0, int lda0, int k0, const int32_t* 
                              ST(stream));
 }
 void regcn_gemm_tf32_trace(void* dev_buf) { gemm_tf32_trace(dev_buf); }
+void regcn_gemm_tf32_trace_begin(void* dev_buf, size_t bytes) { gemm_tf32_trace_begin(dev_buf, bytes); }
+int regcn_gemm_tf32_trace_count(void) { return gemm_tf32_trace_count(); }
+int regcn_gemm_tf32_trace_read(int i, int* epi, int* M, int* N, int* K, int* grid, int* passes, double* flops) {
+  return gemm_tf32_trace_read(i, epi, M, N, K, grid, passes, flops);
+}
 void regcn_score_count_poly(int on) { score_count_poly(on); }
 int regcn_gemm_tf32_trace_slots(void) { return gemm_tf32_trace_slots(); }
 int regcn_gemm_tf32_layer(const float* a_hi, const float* a_lo, int lda, const float* b_hi, const float* b_lo, int ldb,

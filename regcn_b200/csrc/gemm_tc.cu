@@ -22,6 +22,8 @@
 // of activations therefore write fp32 only, and a layer GEMM moves half the A bytes through L2.
 #include "common.cuh"
 #include <cuda.h>
+#include <mutex>
+#include <vector>
 
 namespace regcn {
 
@@ -191,7 +193,7 @@ constexpr int kTraceSlots = 48;
 __device__ __forceinline__ void trace_stamp(const Params& p, int slot) {
   if (p.trace) {
     unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory");   // "memory": stays on its side of barriers
     p.trace[(size_t)blockIdx.x * kTraceSlots + slot] = t;
   }
 }
@@ -930,8 +932,34 @@ static int g_force_block_n = 0, g_force_stages = 0;
 static int g_hyp_poly = 1;      // 0: the counting epilogue evaluates the IEEE score of every candidate (yardstick / tests)
 void score_count_poly(int on) { g_hyp_poly = on ? 1 : 0; }
 void gemm_tf32_tune(int block_n, int stages) { g_force_block_n = block_n; g_force_stages = stages; }
+// In-kernel timeline: launch i of an attached session stamps into record (i % capacity) of the device buffer; the host
+// keeps what each recorded launch computed (epilogue kind, shape, grid, algorithmic flops).
+struct TraceRec { int epi, M, N, K, grid, passes; double flops; };
 static unsigned long long* g_trace = nullptr;
-void gemm_tf32_trace(void* dev_buf) { g_trace = (unsigned long long*)dev_buf; }
+static size_t g_trace_cap = 0;
+static std::vector<TraceRec> g_trace_recs;
+static std::mutex g_trace_mu;
+constexpr int kTraceCtas = 148;
+void gemm_tf32_trace(void* dev_buf) {                   // single-record session (profiles/gemm_trace.py)
+  std::lock_guard<std::mutex> g(g_trace_mu);
+  g_trace = (unsigned long long*)dev_buf; g_trace_cap = dev_buf ? 1 : 0; g_trace_recs.clear();
+}
+void gemm_tf32_trace_begin(void* dev_buf, size_t bytes) {
+  std::lock_guard<std::mutex> g(g_trace_mu);
+  g_trace = (unsigned long long*)dev_buf;
+  g_trace_cap = dev_buf ? bytes / ((size_t)kTraceCtas * tc::kTraceSlots * sizeof(unsigned long long)) : 0;
+  if (!g_trace_cap) g_trace = nullptr;
+  g_trace_recs.clear();
+}
+int gemm_tf32_trace_count() { std::lock_guard<std::mutex> g(g_trace_mu); return (int)g_trace_recs.size(); }
+int gemm_tf32_trace_read(int i, int* epi, int* M, int* N, int* K, int* grid, int* passes, double* flops) {
+  std::lock_guard<std::mutex> g(g_trace_mu);
+  if (i < 0 || i >= (int)g_trace_recs.size()) return REGCN_ERR_DIM;
+  const TraceRec& r = g_trace_recs[i];
+  if (epi) *epi = r.epi; if (M) *M = r.M; if (N) *N = r.N; if (K) *K = r.K; if (grid) *grid = r.grid;
+  if (passes) *passes = r.passes; if (flops) *flops = r.flops;
+  return REGCN_OK;
+}
 int gemm_tf32_trace_slots() { return tc::kTraceSlots; }
 
 // N-tile selection.  Large problems (>= one wave of 128-row tiles): the widest tile with the least padding, i.e.
@@ -987,7 +1015,7 @@ static void clear_epi(tc::Params& p) {
   p.bf16 = 0; p.a_mn = 0; p.b_mn = 0;
   p.a_f32 = 0; p.a_ptr[0] = p.a_ptr[1] = nullptr; p.a_ld[0] = p.a_ld[1] = 0; p.a_k[0] = p.a_k[1] = 0;
   p.a_rows[0] = p.a_rows[1] = nullptr; p.a_kb0 = 0;
-  p.trace = g_trace;
+  p.trace = nullptr;
 }
 
 // fp32-A operand description (see the header comment): up to two K segments, rows optionally gathered.
@@ -1091,6 +1119,20 @@ static int launch_tc(const float* a_hi, const float* a_lo, int lda, const float*
   // 148 SMs take 3 rounds; so do 120 CTAs -- and 28 SMs stay free for whatever runs next to this kernel)
   const long long rounds = (total_tiles + sms - 1) / sms;
   dim3 grid((unsigned)((total_tiles + rounds - 1) / (rounds > 0 ? rounds : 1)));
+  const double alg_flops = p.epi == 2 ? 2.0 * M * (double)Ktrue : 2.0 * M * (double)N * Ktrue;
+  if (g_trace) {
+    std::lock_guard<std::mutex> g(g_trace_mu);
+    if (g_trace && grid.x <= (unsigned)kTraceCtas) {
+      const size_t rec = g_trace_recs.size() % g_trace_cap;
+      p.trace = g_trace + rec * (size_t)kTraceCtas * kTraceSlots;
+      if (g_trace_recs.size() < g_trace_cap || g_trace_cap == 1) {
+        if (g_trace_cap == 1) g_trace_recs.clear();
+        g_trace_recs.push_back(TraceRec{p.epi, M, N, Ktrue, (int)grid.x, passes, alg_flops});
+      } else {
+        p.trace = nullptr;                               // session full: later launches are not recorded
+      }
+    }
+  }
   prof_begin(PROF_GEMM_TC, st);
   switch (p.epi) {
     case 0: launch_k(gemm_tf32_kernel<0>, grid, NUM_THREADS, smem, st, ta_hi, ta_lo, tb_hi, tb_lo, p); break;
@@ -1099,7 +1141,7 @@ static int launch_tc(const float* a_hi, const float* a_lo, int lda, const float*
     case 3: launch_k(gemm_tf32_kernel<3>, grid, NUM_THREADS, smem, st, ta_hi, ta_lo, tb_hi, tb_lo, p); break;
     default: launch_k(gemm_tf32_kernel<4>, grid, NUM_THREADS, smem, st, ta_hi, ta_lo, tb_hi, tb_lo, p); break;
   }
-  prof_end(PROF_GEMM_TC, p.epi == 2 ? 2.0 * M * (double)Ktrue : 2.0 * M * (double)N * Ktrue, st);
+  prof_end(PROF_GEMM_TC, alg_flops, st);
   return REGCN_OK;
 }
 

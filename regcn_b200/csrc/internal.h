@@ -52,6 +52,9 @@ void pdl_set(int on);
 void two_stream_set(int on);
 void gemm_tf32_tune(int block_n, int stages);
 void gemm_tf32_trace(void* dev_buf);
+void gemm_tf32_trace_begin(void* dev_buf, size_t bytes);
+int gemm_tf32_trace_count();
+int gemm_tf32_trace_read(int i, int* epi, int* M, int* N, int* K, int* grid, int* passes, double* flops);
 void score_count_poly(int on);
 int gemm_tf32_trace_slots();
 void gemm_tf32_sm_hint(int sms);
