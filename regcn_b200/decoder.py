@@ -51,9 +51,12 @@ class _ConvTransBase(nn.Module):
         if self.training:
             raise NotImplementedError("regcn_b200 decoders: the standalone forward() is the inference path (folded BatchNorm, no dropout); batch-statistics BatchNorm, dropout and gradients run through the model's get_loss() (regcn_b200/train.py, train_hyp.py)")
 
-    def _tower(self, ent_act, second, triplets, col0, col1, always_bn2):
-        """K10: bn0 -> conv1d(2->C,k) -> bn1 -> relu -> fc -> bn2 -> relu, returns the (B,d) query matrix."""
-        B = len(triplets)
+    def _tower(self, ent_act, second, triplets, col0, col1, always_bn2, batch_total=None):
+        """K10: bn0 -> conv1d(2->C,k) -> bn1 -> relu -> fc -> bn2 -> relu, returns the (B,d) query matrix.
+        batch_total: size of the whole query batch when `triplets` is one rank's slice of it (query-sharded tower): the
+        split-K factor of the FC and the B == 1 rule of bn2 then follow the whole batch, so a row's value does not depend
+        on how the batch was cut."""
+        B = len(triplets) if batch_total is None else int(batch_total)
         feats = ops.convtranse_features(ent_act, second, triplets, col0, col1, _fold_bn(self.bn0),
                                         self.conv1.weight.detach(), self.conv1.bias.detach(), _fold_bn(self.bn1),
                                         split=ops.gemm_impl() == "tc")
@@ -79,11 +82,11 @@ class ConvTransE(_ConvTransBase):
                          kernel_size)
 
     @torch.no_grad()
-    def query(self, embedding, emb_rel, triplets):
+    def query(self, embedding, emb_rel, triplets, batch_total=None):
         """Returns (tanh(E), Q): the activated entity table and the (B,d) query matrix of the dot scoring."""
         self._check_eval()
         e_all = ops.row_map(embedding, ops.ROW_TANH)
-        q = self._tower(e_all, emb_rel.contiguous(), triplets, 0, 1, always_bn2=False)
+        q = self._tower(e_all, emb_rel.contiguous(), triplets, 0, 1, always_bn2=False, batch_total=batch_total)
         return e_all, q
 
     def _forward_train(self, embedding, emb_rel, triplets, partial_embeding=None):

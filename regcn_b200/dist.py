@@ -5,6 +5,9 @@ torch.distributed (NCCL over NVLink on the B200 box, gloo in the CPU tests).
    contiguously over ranks; every rank scores all B queries against its shard and counts, per query, the
    candidates that beat the target (raw and time-filtered); ONE all_reduce(SUM) of a (2,B) int32 tensor merges the
    shards (rank = 1 + total count), after an all_reduce(SUM) of the (B,) target scores published by the owner shards.
+   The query tower is sharded the other way round: every rank builds the queries of its B/G slice and one all_gather
+   of the (B,d) query matrix (gather_rows) precedes the count -- at the ICEWS18 size the tower is half of a timestamp's
+   decode time, so leaving it replicated caps the speed-up at ~1.
 2. Query-timestamp data parallelism for evaluation: test timestamps are independent units (src/main.py:98-100,
    non multi-step); ranks take contiguous slices and one all_gather of the rank vectors closes the job.
 
@@ -57,6 +60,26 @@ def gather_ranks(local_ranks, group=None):
     bufs = [torch.zeros_like(pad) for _ in range(ws)]
     dist.all_gather(bufs, pad, group=group)
     return torch.cat([b[:s] for b, s in zip(bufs, sizes)])
+
+
+def gather_rows(local_rows, n_total, group=None):
+    """all_gather the row blocks of a matrix that was computed in contiguous row shards (shard_bounds(n_total, rank, ws)):
+    returns the full (n_total, d) matrix on every rank.  Shards are padded to the largest size for the collective (sizes
+    differ by at most one row) and the padding rows are dropped afterwards."""
+    r, ws = world(group)
+    if ws == 1:
+        return local_rows
+    d = local_rows.shape[1]
+    per = -(-int(n_total) // ws)
+    pad = local_rows
+    if local_rows.shape[0] != per:
+        pad = torch.zeros((per, d), device=local_rows.device, dtype=local_rows.dtype)
+        pad[: local_rows.shape[0]] = local_rows
+    bufs = [torch.empty_like(pad) for _ in range(ws)]
+    dist.all_gather(bufs, pad.contiguous(), group=group)
+    if n_total % ws == 0:
+        return torch.cat(bufs)
+    return torch.cat([b[: shard_bounds(n_total, i, ws)[1] - shard_bounds(n_total, i, ws)[0]] for i, b in enumerate(bufs)])
 
 
 def sharded_score_rank(n_cand, triples, target_col, filter_csr, score_fn, group=None):

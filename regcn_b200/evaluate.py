@@ -138,7 +138,16 @@ def score_rank_sharded(model, emb, r_emb, all_triples, filter_csr, group=None):
     exchange is needed.  Returns (rank, filter_rank), identical on every rank."""
     from . import dist as rdist
     r, ws = rdist.world(group)
-    q, cand, hyp, col_bias = _scoring_operands(model, emb, r_emb, all_triples)
+    B = all_triples.shape[0]
+    if ws > 1 and type(model.decoder_ob).__name__ == "ConvTransE" and B >= ws:
+        # query-sharded tower: this rank builds the queries of its B/G slice (conv features + split-K FC: half of a
+        # timestamp's decode time at the ICEWS18 size), one all_gather of the (B,d) matrix over NVLink
+        b0, b1 = rdist.shard_bounds(B, r, ws)
+        cand, q_loc = model.decoder_ob.query(emb, r_emb, all_triples[b0:b1].contiguous(), batch_total=B)
+        q = rdist.gather_rows(q_loc, B, group).contiguous()
+        hyp = col_bias = None
+    else:
+        q, cand, hyp, col_bias = _scoring_operands(model, emb, r_emb, all_triples)
     lo, hi = rdist.shard_bounds(cand.shape[0], r, ws)
     target = all_triples[:, 2].to(torch.int32).contiguous()
     pa, pe = filter_csr.pairs(target)

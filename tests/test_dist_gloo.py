@@ -57,6 +57,15 @@ def _worker(rank, ws, port, q):
         local = torch.arange(lo_t, hi_t, dtype=torch.int64) * 10
         allr = rd.gather_ranks(local)
         ok = ok and torch.equal(allr, torch.arange(7, dtype=torch.int64) * 10)
+        # query-sharded tower: row shards of a (B, d) matrix gathered back in order, ragged (37 = 19 + 18) and even sizes
+        for rows in (37, 36, 1):
+            full = torch.arange(rows * 5, dtype=torch.float32).view(rows, 5)
+            b0, b1 = rd.shard_bounds(rows, rank, ws)
+            ok = ok and torch.equal(rd.gather_rows(full[b0:b1].clone(), rows), full)
+        # shard bounds follow the GROUP the collectives run on (a sub-group of one rank owns every candidate)
+        g0, g1 = dist.new_group([0]), dist.new_group([1])
+        mine = g0 if rank == 0 else g1
+        ok = ok and rd.world(mine) == (0, 1) and rd.shard_bounds(N, *rd.world(mine)) == (0, N)
         q.put((rank, bool(ok), (lo, hi)))
     finally:
         dist.destroy_process_group()
