@@ -75,6 +75,14 @@ def gather_rows(local_rows, n_total, group=None):
     if local_rows.shape[0] != per:
         pad = torch.zeros((per, d), device=local_rows.device, dtype=local_rows.dtype)
         pad[: local_rows.shape[0]] = local_rows
+    if local_rows.is_cuda:
+        out = torch.empty((ws * per, d), device=local_rows.device, dtype=local_rows.dtype)
+        dist.all_gather_into_tensor(out, pad.contiguous(), group=group)          # one NCCL all-gather, no staging copies
+        if n_total % ws == 0:
+            return out
+        keep = torch.cat([torch.arange(i * per, i * per + shard_bounds(n_total, i, ws)[1] - shard_bounds(n_total, i, ws)[0],
+                                       device=out.device) for i in range(ws)])
+        return out.index_select(0, keep)
     bufs = [torch.empty_like(pad) for _ in range(ws)]
     dist.all_gather(bufs, pad.contiguous(), group=group)
     if n_total % ws == 0:

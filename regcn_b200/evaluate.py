@@ -130,6 +130,9 @@ def evaluate_snapshot(model, glist, all_triples, filter_csr, timers=None, fused=
     return rank, frank
 
 
+QUERY_SHARD_MIN = 16384      # smallest query batch whose tower is cut across ranks (see score_rank_sharded)
+
+
 @torch.no_grad()
 def score_rank_sharded(model, emb, r_emb, all_triples, filter_csr, group=None):
     """Entity-partitioned scoring + rank merge: this rank counts over its contiguous slice of the
@@ -139,9 +142,12 @@ def score_rank_sharded(model, emb, r_emb, all_triples, filter_csr, group=None):
     from . import dist as rdist
     r, ws = rdist.world(group)
     B = all_triples.shape[0]
-    if ws > 1 and type(model.decoder_ob).__name__ == "ConvTransE" and B >= ws:
-        # query-sharded tower: this rank builds the queries of its B/G slice (conv features + split-K FC: half of a
-        # timestamp's decode time at the ICEWS18 size), one all_gather of the (B,d) matrix over NVLink
+    if ws > 1 and type(model.decoder_ob).__name__ == "ConvTransE" and B >= QUERY_SHARD_MIN:
+        # query-sharded tower: this rank builds the queries of its B/G slice (conv features + split-K FC), one all_gather
+        # of the (B,d) matrix over NVLink.  Only for large query batches: measured on 2 B200s at the ICEWS18 size
+        # (B = 2914) the FC of a half batch takes as long as the whole one (73 vs 78 us: 313 k-blocks of latency, the
+        # split-K factor is pinned to the whole batch so that a row's value does not depend on the cut) and the extra
+        # collective costs more than the 30 us the feature kernel saves (profiles/README.md, round 2)
         b0, b1 = rdist.shard_bounds(B, r, ws)
         cand, q_loc = model.decoder_ob.query(emb, r_emb, all_triples[b0:b1].contiguous(), batch_total=B)
         q = rdist.gather_rows(q_loc, B, group).contiguous()
