@@ -835,9 +835,15 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
       if (warp == EPI_WARP0 && lane == 0 && it < 6) trace_stamp(p, 29 + 2 * it);     // epilogue of the tile done (this warp)
     }
   }
+  // exit stamp of the CTA = the latest of its epilogue warps (the producer / MMA lanes reach the barrier below long
+  // before the last accumulator has been drained, so a stamp by thread 0 would not mean "done")
+  if (p.trace && warp >= EPI_WARP0 && lane == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory");
+    atomicMax(p.trace + (size_t)blockIdx.x * kTraceSlots + 40, t);
+  }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (threadIdx.x == 0) trace_stamp(p, 40);
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
   }
