@@ -220,7 +220,7 @@ class _Prepared:
     __slots__ = ("glist", "new_graphs", "all_t", "pf_ent", "pf_rel", "sizes_host", "event")
 
 
-def _prepare(cache, input_list, test_snap, num_rels, device, sizes_slot, prep_stream, main_stream):
+def _prepare(cache, input_list, test_snap, num_rels, device, sizes_slot, prep_stream, main_stream, ahead=()):
     """Enqueue the device-side preparation of one timestamp on `prep_stream` (so that it runs next to, not behind, the
     previous timestamp's kernels) and start the copy of its sizes into `sizes_slot`, a pinned int32 buffer allocated once
     per test() call (page-locking memory per step would cost more than the step).  Every tensor created here is handed
@@ -229,7 +229,10 @@ def _prepare(cache, input_list, test_snap, num_rels, device, sizes_slot, prep_st
     p = _Prepared()
     import contextlib
     with (torch.cuda.stream(prep_stream) if prep_stream is not main_stream else contextlib.nullcontext()):
-        p.glist, p.new_graphs = cache.ensure(input_list)
+        # `ahead`: snapshots that will enter the window during the next steps; their indices are built in the same batched
+        # launch (one CTA per snapshot, all concurrent) as whatever is missing now
+        glist, p.new_graphs = cache.ensure(list(input_list) + list(ahead))
+        p.glist = glist[:len(input_list)]
         t = test_snap if isinstance(test_snap, torch.Tensor) else torch.from_numpy(test_snap)
         test = t.to(device, non_blocking=True)
         inv = test.flip(1)
@@ -349,7 +352,7 @@ def test(model, history_list, test_list, num_rels, num_nodes, use_cuda=True, all
     if multi_step:
         return _test_multi_step(model, input_list, test_list, num_rels, num_nodes, static_graph, dev, topk,
                                 relation_evaluation, return_ranks)
-    cache = SnapshotCache(num_nodes, num_rels, dev, capacity=max(2 * L + 2, 8))
+    cache = SnapshotCache(num_nodes, num_rels, dev, capacity=max(2 * L + 4, 10) + 8)
     fused_ok = ops.gemm_impl() in ("tc", "tc1")
     # ConvTransE / ConvTransR in fp32-parity mode: decode + rank of a timestamp is one C call (same kernels, same ranks)
     one_call = (ops.gemm_impl() == "tc" and ops.score_dtype() == "fp32" and os.environ.get("REGCN_DECODE_ENGINE", "1") != "0"
@@ -358,26 +361,43 @@ def test(model, history_list, test_list, num_rels, num_nodes, use_cuda=True, all
     K = len(test_list)
     # pinned staging, allocated once: two size slots (ping-pong between the step being run and the one being prepared)
     # and one result area holding [rank | frank | rank_r | frank_r] of every timestamp
-    size_slots = torch.empty((2, 2 + 8 * (L + 2)), dtype=torch.int32, pin_memory=True)
+    PREP_DEPTH = 2      # timestamps whose device-side preparation is in flight ahead of the one being evaluated
+    AHEAD = 8           # test snapshots whose edge index is built per batched launch (one CTA each, concurrently): the
+                        # one-CTA build of a single snapshot is 86 us of latency at the ICEWS18 size, eight cost the same
+    size_slots = torch.empty((PREP_DEPTH + 1, 2 + 8 * (L + AHEAD + 2)), dtype=torch.int32, pin_memory=True)
     offs = [0]
     for snap in test_list:
         offs.append(offs[-1] + 8 * int(snap.shape[0]))
     result_host = torch.empty(max(offs[-1], 1), dtype=torch.int32, pin_memory=True)
     results = []
-    # The preparation of timestamp k+1 is enqueued on the SAME stream behind timestamp k's kernels: measured on B200 /
-    # C3, a separate preparation stream removes the ~0.2 ms the host waits for the sizes but costs more than that in
-    # stream switching and allocator bookkeeping on the host, which is the side that limits the loop (REGCN_PREP_STREAM=1
-    # selects it anyway).
+    # The preparation of a timestamp (H2D copy, index build of the snapshot entering the window, filter-list counting, D2H
+    # of the sizes) is enqueued on the SAME stream, TWO timestamps ahead: when the host is about to enqueue timestamp k+1
+    # the sizes it needs were produced in front of timestamp k's kernels and have long arrived, so the host never blocks on
+    # the GPU and the GPU never waits for the host (with a depth of one the GPU idled ~0.2 ms per step while the host
+    # fetched the sizes and enqueued the next evolution).  A separate preparation stream would also overlap those small
+    # kernels with the evolution, but makes the caching allocator fall back to fresh allocations for every cross-stream
+    # tensor (measured: 2.7-4.7 ms per step); REGCN_PREP_STREAM=1 selects it anyway.
+    # Non multi-step evaluation feeds ground-truth history (src/main.py:98-100), so every window is known up front.
     main_stream = torch.cuda.current_stream()
     prep_stream = main_stream
     if os.environ.get("REGCN_PREP_STREAM") == "1":
         prep_stream = torch.cuda.Stream(device=dev)
         prep_stream.wait_stream(main_stream)
-    nxt = _prepare(cache, input_list, test_list[0], num_rels, dev, size_slots[0], prep_stream, main_stream) if K else None
+    base = list(input_list)
+
+    def window(k):
+        return (base + list(test_list[:k]))[-len(base):] if len(base) else []
+
+    def ahead(j):
+        # test snapshot i joins the window at step i + 1; every AHEAD-th step builds the next AHEAD of them at once
+        return list(test_list[j:min(j + AHEAD, K - 1)]) if (j % AHEAD == 0 and len(base)) else []
+
+    queue = [_prepare(cache, window(j), test_list[j], num_rels, dev, size_slots[j % (PREP_DEPTH + 1)], prep_stream,
+                      main_stream, ahead(j)) for j in range(min(PREP_DEPTH, K))]
     _tm = os.environ.get("REGCN_TEST_TIMING") == "1"
     _acc = [0.0] * 6
     for k in range(K):
-        cur = nxt
+        cur = queue.pop(0)
         _t0 = time.perf_counter()
         cur.event.synchronize()
         if prep_stream is not main_stream:
@@ -415,12 +435,11 @@ def test(model, history_list, test_list, num_rels, num_nodes, use_cuda=True, all
         host.copy_(packed, non_blocking=True)                      # this timestamp's result, device -> host
         results.append(host)
         _t4 = time.perf_counter()
-        # slide the window (src/main.py:98-100) and prepare the next timestamp while the GPU is busy with this one
-        input_list.pop(0)
-        input_list.append(test_list[k])
-        if k + 1 < K:
-            nxt = _prepare(cache, input_list, test_list[k + 1], num_rels, dev, size_slots[(k + 1) & 1], prep_stream,
-                           main_stream)
+        # the window slides (src/main.py:98-100); prepare the timestamp PREP_DEPTH ahead while the GPU is busy
+        j = k + PREP_DEPTH
+        if j < K:
+            queue.append(_prepare(cache, window(j), test_list[j], num_rels, dev, size_slots[j % (PREP_DEPTH + 1)],
+                                  prep_stream, main_stream, ahead(j)))
         _t5 = time.perf_counter()
         for _i, _d in enumerate((_t1 - _t0, _t2 - _t1, _t3 - _t2, _t4 - _t3, _t5 - _t4)):
             _acc[_i] += _d
