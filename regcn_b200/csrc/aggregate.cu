@@ -537,59 +537,103 @@ __global__ void __launch_bounds__(256) aggregate_fixup_kernel(
     const float* __restrict__ norm, int nv, int d, float* __restrict__ partial, float* __restrict__ out,
     float* __restrict__ out_hi, float* __restrict__ out_lo, const int* __restrict__ active_pos, int ldo, int stride) {
   pdl_grid_sync();
+  // Persistent grid: every lane tests one virtual row per sweep (three dependent index loads), the warp then folds the
+  // few that have work at this level one after the other.  A launch over all ~10^6 virtual rows of a 10 M-edge graph with
+  // a warp per row cost 155-215 us per level just to start and retire 128 k CTAs that had nothing to do.
   const int lane = threadIdx.x & 31;
-  const int w = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
-  if (w >= nv) return;
-  const int row = __ldg(vrow_row + w);
-  const int v0 = __ldg(vptr + row);
-  const int nch = __ldg(vptr + row + 1) - v0;
-  const int k = w - v0;
-  if (nch <= 1 || (k % (32 * stride)) != 0) return;
-  const bool covers_row = (long long)32 * stride >= nch;         // only true for k == 0
-  if (!covers_row && stride > 1 && k + stride >= nch) return;     // a lone slot: nothing to fold at this level
-  if (stride > 1 && (long long)stride >= nch) return;             // row already finished at a lower level
   const int nvec = d >> 2;
-  const int s0 = __ldg(sptr + row);
-  WarpRow<RV> acc, p[4];
-  acc.zero();
-  int j = 0;
-  for (; j + 4 <= 32; j += 4) {
-    if (k + (j + 3) * stride >= nch) break;
+  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long base = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; base < nv; base += warps * 32) {
+    const long long wl = base + lane;
+    int row = 0, nch = 0, k = 0;
+    bool work = false;
+    if (wl < nv) {
+      row = __ldg(vrow_row + wl);
+      const int v0 = __ldg(vptr + row);
+      nch = __ldg(vptr + row + 1) - v0;
+      k = (int)wl - v0;
+      work = nch > 1 && (k % (32 * stride)) == 0;
+      const bool covers = (long long)32 * stride >= nch;
+      if (work && !covers && stride > 1 && k + stride >= nch) work = false;   // a lone slot: nothing to fold at this level
+      if (work && stride > 1 && (long long)stride >= nch) work = false;       // row already finished at a lower level
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, work);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int r_ = __shfl_sync(0xffffffffu, row, src);
+      const int n_ = __shfl_sync(0xffffffffu, nch, src);
+      const int k_ = __shfl_sync(0xffffffffu, k, src);
+      const bool covers_row = (long long)32 * stride >= n_;                   // only true for k == 0
+      const int s0 = __ldg(sptr + r_);
+      WarpRow<RV> acc, p[4];
+      acc.zero();
+      int j = 0;
+      for (; j + 4 <= 32; j += 4) {
+        if (k_ + (j + 3) * stride >= n_) break;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) p[u].load_plain(partial + (size_t)(s0 + k + (j + u) * stride) * d, nvec, lane);
+        for (int u = 0; u < 4; ++u) p[u].load_plain(partial + (size_t)(s0 + k_ + (j + u) * stride) * d, nvec, lane);
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < 4; ++u)
 #pragma unroll
-      for (int i = 0; i < RV; ++i) acc.v[i] = f4_add(acc.v[i], p[u].v[i]);
-  }
-  for (; j < 32 && k + j * stride < nch; ++j) {
-    p[0].load_plain(partial + (size_t)(s0 + k + j * stride) * d, nvec, lane);
+          for (int i = 0; i < RV; ++i) acc.v[i] = f4_add(acc.v[i], p[u].v[i]);
+      }
+      for (; j < 32 && k_ + j * stride < n_; ++j) {
+        p[0].load_plain(partial + (size_t)(s0 + k_ + j * stride) * d, nvec, lane);
 #pragma unroll
-    for (int i = 0; i < RV; ++i) acc.v[i] = f4_add(acc.v[i], p[0].v[i]);
-  }
-  if (covers_row) {
-    acc.scale(__ldg(norm + row));
-    const size_t orow = active_pos ? (size_t)__ldg(active_pos + row) : (size_t)row;
-    if (out) acc.store(out + orow * ldo, nvec, lane);
-    if (out_hi) acc.store_split(out_hi + orow * ldo, out_lo + orow * ldo, nvec, lane);
-  } else {
-    acc.store(partial + (size_t)(s0 + k) * d, nvec, lane);
+        for (int i = 0; i < RV; ++i) acc.v[i] = f4_add(acc.v[i], p[0].v[i]);
+      }
+      if (covers_row) {
+        acc.scale(__ldg(norm + r_));
+        const size_t orow = active_pos ? (size_t)__ldg(active_pos + r_) : (size_t)r_;
+        if (out) acc.store(out + orow * ldo, nvec, lane);
+        if (out_hi) acc.store_split(out_hi + orow * ldo, out_lo + orow * ldo, nvec, lane);
+      } else {
+        acc.store(partial + (size_t)(s0 + k_) * d, nvec, lane);
+      }
+    }
   }
 }
 
-// Dense-output mode: rows without in-edges receive exact zeros (DGL zero fill); one thread per float4.
-__global__ void zero_inactive_rows_kernel(const int* __restrict__ rowptr, int N, int d, float* __restrict__ out,
-                                          float* __restrict__ out_hi, float* __restrict__ out_lo) {
+// Dense-output mode: rows without in-edges receive exact zeros (DGL zero fill).  Persistent grid: a lane tests one row per
+// sweep, the warp writes the rows that need it (a thread per float4 of the whole table spent 0.2 ms at N = 1M finding out that
+// nothing had to be written).
+__global__ void __launch_bounds__(256) zero_inactive_rows_kernel(const int* __restrict__ rowptr, int N, int d,
+                                                                 float* __restrict__ out, float* __restrict__ out_hi,
+                                                                 float* __restrict__ out_lo) {
   pdl_grid_sync();
-  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
   const int nvec = d >> 2;
-  const size_t total = (size_t)N * nvec;
-  if (i >= total) return;
-  const int row = (int)(i / nvec);
-  if (__ldg(rowptr + row + 1) != __ldg(rowptr + row)) return;
+  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (out) reinterpret_cast<float4*>(out)[i] = z;
-  if (out_hi) { reinterpret_cast<float4*>(out_hi)[i] = z; reinterpret_cast<float4*>(out_lo)[i] = z; }
+  for (long long base = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; base < N; base += warps * 32) {
+    const long long r = base + lane;
+    const bool empty = r < N && __ldg(rowptr + r + 1) == __ldg(rowptr + r);
+    unsigned todo = __ballot_sync(0xffffffffu, empty);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const size_t o = (size_t)(base + src) * d;
+      for (int c = lane; c < nvec; c += 32) {
+        if (out) reinterpret_cast<float4*>(out + o)[c] = z;
+        if (out_hi) { reinterpret_cast<float4*>(out_hi + o)[c] = z; reinterpret_cast<float4*>(out_lo + o)[c] = z; }
+      }
+    }
+  }
+}
+
+// grid of the two persistent index-sweep kernels above: enough warps to keep every SM busy, never more than the work
+static unsigned sweep_grid(long long items) {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  const long long need = (items + 255) / 256;            // one lane per item, 8 warps per CTA
+  const long long cap = (long long)sms * 8;
+  return (unsigned)(need < 1 ? 1 : (need < cap ? need : cap));
 }
 
 int union_aggregate(const float* h, const float* rel, const int* rowptr, const int* src_sorted,
@@ -608,7 +652,8 @@ int union_aggregate(const float* h, const float* rel, const int* rowptr, const i
   prof_begin(PROF_AGGREGATE, st);
   if (!active_pos) {
     const size_t total = (size_t)N * (d >> 2);
-    launch_k(zero_inactive_rows_kernel, (unsigned)((total + TB - 1) / TB), TB, 0, st, rowptr, N, d, out, out_hi, out_lo);
+    (void)total;
+    launch_k(zero_inactive_rows_kernel, sweep_grid(N), TB, 0, st, rowptr, N, d, out, out_hi, out_lo);
   }
   if (nv <= 0) { prof_end(PROF_AGGREGATE, 0.0, st); return check_launch("union_aggregate"); }
   const unsigned grid = (unsigned)(((size_t)nv * 32 + TB - 1) / TB);
@@ -675,8 +720,8 @@ int union_aggregate(const float* h, const float* rel, const int* rowptr, const i
   if (nsplit > 0 && !fold) {
     // max_chunks = chunk count of the largest hub row (<= nsplit); one launch per radix-32 level
     for (long long stride = 1; stride < (long long)max_chunks; stride *= 32) {
-      if (small) launch_k(aggregate_fixup_kernel<1>, grid, TB, 0, st, vptr, sptr, vrow_row, norm, nv, d, partial, out, out_hi, out_lo, active_pos, ldo, (int)stride);
-      else launch_k(aggregate_fixup_kernel<2>, grid, TB, 0, st, vptr, sptr, vrow_row, norm, nv, d, partial, out, out_hi, out_lo, active_pos, ldo, (int)stride);
+      if (small) launch_k(aggregate_fixup_kernel<1>, sweep_grid(nv), TB, 0, st, vptr, sptr, vrow_row, norm, nv, d, partial, out, out_hi, out_lo, active_pos, ldo, (int)stride);
+      else launch_k(aggregate_fixup_kernel<2>, sweep_grid(nv), TB, 0, st, vptr, sptr, vrow_row, norm, nv, d, partial, out, out_hi, out_lo, active_pos, ldo, (int)stride);
     }
   }
   prof_end(PROF_AGGREGATE, 0.0, st);   // bytes are filled in by the caller-side formula (needs E, R); see bench.py
@@ -896,7 +941,8 @@ int lorentz_aggregate(const float* ht, const float* W, const float* rel, const i
   Curv cv = make_curv(c);
   // isolated destinations: exact zero rows (DGL zero fill; to_poincare(0) = 0, log_0(0) = 0)
   const size_t total = (size_t)N * (d >> 2);
-  launch_k(zero_inactive_rows_kernel, (unsigned)((total + TB - 1) / TB), TB, 0, st, rowptr, N, d, out, nullptr, nullptr);
+  (void)total;
+  launch_k(zero_inactive_rows_kernel, sweep_grid(N), TB, 0, st, rowptr, N, d, out, nullptr, nullptr);
   if (nv_rows > 0) {
     const unsigned grid = (unsigned)(((size_t)nv_rows * 32 + TB - 1) / TB);
     float* partial0 = partial ? partial + (size_t)nsplit * d : nullptr;
