@@ -26,7 +26,7 @@ def short(name):
 
 
 def run(tag, fn, steps):
-    for _ in range(3):
+    for _ in range(2 if tag == "c5" else 3):
         fn()
     torch.cuda.synchronize()
     flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda")
@@ -71,7 +71,7 @@ def run(tag, fn, steps):
     for (nm, s), (c, d) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print(f"  {d:9.1f} us  x{c:<3d} stream {s}  {nm[:100]}")
     print("  -- first 40 kernels --")
-    for r in rows[:40]:
+    for r in rows[:(80 if tag == "c5" else 40)]:
         print(f"  t={r['t_us']:8.1f}  dur={r['dur_us']:7.1f}  s={r['stream']}  grid={r['grid']}  {r['name'][:90]}")
 
 
@@ -94,6 +94,27 @@ def main():
         all_t = torch.cat((test, inv)).contiguous()
         f = utils.filter_csr_from_snapshot(all_t, 2 * r, 0)
         run(what, lambda: evaluate.evaluate_snapshot(model, gl, all_t, f), steps)
+    elif what == "c5":
+        # BASELINE configs[4]: 1 M entities, 512 relations, 10 M edges per snapshot, L = 3, hyperbolic_uvrgcn + RotH
+        import numpy as np
+        n, r, t, L5, tq = 1_000_000, 512, 5_000_000, 3, 4096
+        rng = np.random.default_rng(5)
+        hist = [synth.make_snapshot(rng, n, r, t, zipf=False) for _ in range(L5)]
+        test = synth.make_snapshot(rng, n, r, tq, zipf=False)
+        m5 = R.HyperbolicRecurrentRGCN("roth", "hyperbolic_uvrgcn", n, r, 0, 0, 200, "sub", 3, num_bases=100,
+                                       num_hidden_layers=2, dropout=0.2, c=0.01, self_loop=True, layer_norm=False,
+                                       input_dropout=0.2, hidden_dropout=0.2, feat_dropout=0.2, entity_prediction=True,
+                                       relation_prediction=True, use_cuda=True, gpu=0, radius_msg_gamma=0.15)
+        with torch.no_grad():
+            m5.dynamic_emb.copy_(torch.randn(n, 200, generator=torch.Generator().manual_seed(5)) * 0.5)
+        m5 = m5.to(dev).eval()
+        gl = [R.build_sub_graph(n, r, s_, True, 0) for s_ in hist]
+        tt = torch.from_numpy(test).to(dev)
+        inv = tt[:, [2, 1, 0]].clone()
+        inv[:, 1] += r
+        all_t = torch.cat((tt, inv)).contiguous()
+        f = utils.filter_csr_from_snapshot(all_t, 2 * r, 0)
+        run(what, lambda: evaluate.evaluate_snapshot(m5, gl, all_t, f), min(steps, 2))
     else:
         raise SystemExit("unknown workload " + what)
 

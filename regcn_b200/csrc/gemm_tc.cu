@@ -987,12 +987,19 @@ static int pick_block_n(int M, int N, int K, int split_k) {
       if (m_tiles * ((N + opts[i] - 1) / opts[i]) <= g_sm_hint) return opts[i];
     return N <= 208 ? 208 : 256;
   }
+  // Wide N (scoring against a large candidate table): the widest tile -- the padding of the last tile is noise next to
+  // the A-operand re-reads of a narrow one (N = 1 000 000 is a multiple of 64: "least padding" picked 64-column tiles and
+  // the counting GEMM ran 2.35x slower per output than at N = 125 000).  Narrow N: least padding among the wide tiles.
   int best = 256, best_waste = 1 << 30;
-  const int cands[4] = {256, 208, 128, 64};
-  for (int i = 0; i < 4; ++i) {
-    const int bn = cands[i];
-    const int waste = (N + bn - 1) / bn * bn - N;
-    if (waste < best_waste) { best = bn; best_waste = waste; }
+  if (N < 8 * 256) {
+    const int cands[4] = {256, 208, 128, 64};
+    for (int i = 0; i < 4; ++i) {
+      const int bn = cands[i];
+      const int waste = (N + bn - 1) / bn * bn - N;
+      if (waste < best_waste) { best = bn; best_waste = waste; }
+    }
+  } else if ((N + 207) / 208 * 208 - N < ((N + 255) / 256 * 256 - N) / 4 && (N + 207) / 208 * 208 - N < N / 256) {
+    best = 208;
   }
   const int kb_per_cta = ((K + tc::BLOCK_K - 1) / tc::BLOCK_K + (split_k > 1 ? split_k : 1) - 1) / (split_k > 1 ? split_k : 1);
   if (kb_per_cta > 16) return best;                 // long K loops amortise the per-tile latency: keep the wide tile
