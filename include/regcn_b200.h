@@ -68,6 +68,17 @@ REGCN_API size_t regcn_csr_build_batch_workspace_bytes(const int32_t* T, int L, 
 REGCN_API int regcn_csr_build_batch(const regcn_csr_arrays* snaps, int L, int N, int R, void* workspace,
                                     size_t workspace_bytes, void* stream);
 
+/* Block-diagonal union of G (<= 16) snapshot indices, each over N entities / R relations, as ONE index over G*N entities
+ * and G*R relations: the graph one step of a recurrence batched over G independent history windows runs on.  The
+ * reference evaluates test timestamps one after the other, each over its own window (src/main.py:60-90,
+ * hyperbolic_main.py:100-113); they do not depend on each other, so G windows are evolved by the same kernels at G times
+ * the rows per launch.  Member g's entity v -> g*N + v, relation r < R -> g*R + r, inverse relation R + r ->
+ * G*R + g*R + r.  member_sizes: (G,4) HOST int32 = counts[0], counts[1], counts[2], counts[4] of every member as
+ * regcn_csr_build reported them; `out` must provide arrays for G*N entities, G*R relations and the summed edge counts
+ * (out->triples / out->T are not read).  out->counts receives the combined counters.                              */
+REGCN_API int regcn_csr_concat(const regcn_csr_arrays* members, const int32_t* member_sizes, int G, int N, int R,
+                               const regcn_csr_arrays* out, void* stream);
+
 /* ---- K2 relation mean-pool: src/rrgcn.py:161-166, hyperbolic_model.py:802-812 -----------------
  * out (2R,d): out[r] = out[r+R] = mean of h rows in ents(r); zero rows for absent relations.
  * nsplit > 1 splits every relation over nsplit CTAs (partial: R*nsplit*d floats).               */

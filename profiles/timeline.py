@@ -11,6 +11,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "profiles"))
 import torch
 from torch.profiler import ProfilerActivity, profile
 
@@ -94,6 +95,27 @@ def main():
         all_t = torch.cat((test, inv)).contiguous()
         f = utils.filter_csr_from_snapshot(all_t, 2 * r, 0)
         run(what, lambda: evaluate.evaluate_snapshot(model, gl, all_t, f), steps)
+    elif what.startswith("c3x"):
+        # G test timestamps evolved as one block-diagonal graph (profiles/prof_batched_evolve.py)
+        import numpy as np
+        from prof_batched_evolve import batched_model
+        G = int(what[3:])
+        n, r, t, L, tq = synth.SHAPES["c3"]
+        rng = np.random.default_rng(0)
+        snaps = [synth.make_snapshot(rng, n, r, t, True) for _ in range(L + G - 1)]
+        m, sd = build_product_model(model_cfg("regcn"), n, r, 0)
+        mG = batched_model(m, sd, n, r, G, dev)
+        comb = []
+        for i in range(L):
+            parts = []
+            for g in range(G):
+                s_ = snaps[g + i].copy()
+                s_[:, 0] += g * n
+                s_[:, 2] += g * n
+                s_[:, 1] += g * r
+                parts.append(s_)
+            comb.append(R.build_sub_graph(G * n, G * r, np.concatenate(parts), True, 0))
+        run(what, lambda: mG.forward(comb, None, True), steps)
     elif what == "c5":
         # BASELINE configs[4]: 1 M entities, 512 relations, 10 M edges per snapshot, L = 3, hyperbolic_uvrgcn + RotH
         import numpy as np

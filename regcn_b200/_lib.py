@@ -29,6 +29,7 @@ SIGNATURES = {
     "regcn_csr_build": (_i, [_p, _i, _i, _i] + [_p] * 17 + [_p, _sz, _p]),
     "regcn_csr_build_batch_workspace_bytes": (_sz, [_p, _i, _i, _i]),
     "regcn_csr_build_batch": (_i, [_p, _i, _i, _i, _p, _sz, _p]),
+    "regcn_csr_concat": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "regcn_rel_mean_pool": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p]),
     "regcn_union_aggregate": (_i, [_p] * 9 + [_i, _i, _p, _f, _i, _i, _p, _p, _p]),
     "regcn_block_aggregate": (_i, [_p] * 6 + [_i, _i, _i, _i, _p, _p]),

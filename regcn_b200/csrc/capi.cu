@@ -110,6 +110,10 @@ int regcn_csr_build_batch(const regcn_csr_arrays* snaps, int L, int N, int R, vo
                           void* stream) {
   return csr_build_batch(snaps, L, N, R, workspace, workspace_bytes, ST(stream));
 }
+int regcn_csr_concat(const regcn_csr_arrays* members, const int32_t* member_sizes, int G, int N, int R,
+                     const regcn_csr_arrays* out, void* stream) {
+  return csr_concat(members, member_sizes, G, N, R, out, ST(stream));
+}
 int regcn_rel_mean_pool(const float* h, const int32_t* rel_rowptr, const int32_t* rel_ents, int R, int d, int nsplit,
                         float* out, float* partial, void* stream) {
   return rel_mean_pool(h, rel_rowptr, rel_ents, R, d, nsplit, out, partial, nullptr, nullptr, ST(stream));

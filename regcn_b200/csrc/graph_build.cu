@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "internal.h"
 #include <cub/cub.cuh>
+#include <algorithm>
 
 namespace regcn {
 
@@ -494,6 +495,114 @@ int csr_build_batch(const regcn_csr_arrays* snaps, int L, int N, int R, void* ws
     if (e) return e;
   }
   return REGCN_OK;
+}
+
+// =====================================================================================================================
+// Index concatenation: the indices of G snapshots over (N entities, R relations) become ONE index over G*N entities and
+// G*R relations -- the block-diagonal union graph.  The windows of consecutive test timestamps are independent
+// (src/main.py:60-90: every timestamp re-runs the recurrence over its own history), so G of them can be evolved by the
+// same kernels with G times the rows per launch; step i of that batched recurrence needs the union of G snapshots, and
+// every one of them is already indexed (SnapshotCache).  Member g's entity v becomes g*N + v, its relation r < R becomes
+// g*R + r and the inverse relation R + r becomes G*R + g*R + r; CSR slots, virtual rows, split chunks, active rows and
+// relation->entity lists keep their member-local order and are shifted by the totals of the members before them.
+// One launch; pure copies with offsets (a few hundred KB per member).
+// =====================================================================================================================
+constexpr int kConcatMax = 16;
+
+struct ConcatMember {
+  const int* src; const int* dst; const int* etype; const int* indeg; const float* norm; const int* rowptr;
+  const int* src_sorted; const int* etype_sorted; const int* eperm; const int* vptr; const int* sptr; const int* vrow_row;
+  const int* active_pos; const int* active_rows; const int* rel_rowptr; const int* rel_ents; const int* counts;
+  int E, n_vrows, n_split, n_rel_ents, n_active;          // member sizes
+  int eoff, voff, soff, roff, aoff;                       // totals of the members before this one
+};
+struct ConcatArgs {
+  ConcatMember m[kConcatMax];
+  int* src; int* dst; int* etype; int* indeg; float* norm; int* rowptr; int* src_sorted; int* etype_sorted; int* eperm;
+  int* vptr; int* sptr; int* vrow_row; int* active_pos; int* active_rows; int* rel_rowptr; int* rel_ents; int* counts;
+  int G, N, R;
+};
+
+__global__ void __launch_bounds__(256) csr_concat_kernel(const __grid_constant__ ConcatArgs a) {
+  pdl_grid_sync();
+  const int g = blockIdx.y;
+  const ConcatMember& m = a.m[g];
+  const int N = a.N, R = a.R, G = a.G;
+  const int noff = g * N, reloff = g * R, GR = G * R;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  const bool last = g == G - 1;
+  for (int v = tid; v < N + (last ? 1 : 0); v += nth) {          // per-entity arrays (+ the closing pointer entries)
+    a.rowptr[noff + v] = m.rowptr[v] + m.eoff;
+    a.vptr[noff + v] = m.vptr[v] + m.voff;
+    a.sptr[noff + v] = m.sptr[v] + m.soff;
+    if (v < N) {
+      a.indeg[noff + v] = m.indeg[v];
+      a.norm[noff + v] = m.norm[v];
+      const int ap = m.active_pos[v];
+      a.active_pos[noff + v] = ap < 0 ? -1 : ap + m.aoff;
+    }
+  }
+  for (int j = tid; j < m.E; j += nth) {                          // per-edge arrays
+    const int o = m.eoff + j;
+    const int t0 = m.etype[j], t1 = m.etype_sorted[j];
+    a.src[o] = m.src[j] + noff;
+    a.dst[o] = m.dst[j] + noff;
+    a.etype[o] = t0 < R ? t0 + reloff : t0 - R + GR + reloff;
+    a.src_sorted[o] = m.src_sorted[j] + noff;
+    a.etype_sorted[o] = t1 < R ? t1 + reloff : t1 - R + GR + reloff;
+    a.eperm[o] = m.eperm[j] + m.eoff;
+  }
+  for (int k = tid; k < m.n_vrows; k += nth) a.vrow_row[m.voff + k] = m.vrow_row[k] + noff;
+  for (int k = tid; k < m.n_active; k += nth) a.active_rows[m.aoff + k] = m.active_rows[k] + noff;
+  for (int r = tid; r < R + (last ? 1 : 0); r += nth) a.rel_rowptr[reloff + r] = m.rel_rowptr[r] + m.roff;
+  for (int k = tid; k < m.n_rel_ents; k += nth) a.rel_ents[m.roff + k] = m.rel_ents[k] + noff;
+  if (g == 0 && tid == 0) {
+    int maxdeg = 0;
+    for (int i = 0; i < G; ++i) maxdeg = max(maxdeg, a.m[i].counts[3]);
+    const ConcatMember& z = a.m[G - 1];
+    a.counts[0] = z.voff + z.n_vrows; a.counts[1] = z.soff + z.n_split; a.counts[2] = z.roff + z.n_rel_ents;
+    a.counts[3] = maxdeg; a.counts[4] = z.aoff + z.n_active; a.counts[5] = 0; a.counts[6] = 0; a.counts[7] = 0;
+  }
+}
+
+// sizes: (G,4) host ints per member: n_vrows, n_split_chunks, n_rel_ents, n_active (the counters regcn_csr_build reports)
+int csr_concat(const regcn_csr_arrays* members, const int* sizes, int G, int N, int R, const regcn_csr_arrays* out,
+               cudaStream_t st) {
+  if (G <= 0 || G > kConcatMax || N <= 0 || R <= 0) { set_last_error("csr_concat: bad dims G=%d (max %d) N=%d R=%d", G, kConcatMax, N, R); return REGCN_ERR_DIM; }
+  if (!members || !sizes || !out) { set_last_error("csr_concat: null pointer"); return REGCN_ERR_NULL; }
+  if ((long long)G * N > 0x7fffffffLL || (long long)G * R * 2 > 0x7fffffffLL) { set_last_error("csr_concat: G*N overflows int32"); return REGCN_ERR_DIM; }
+  ConcatArgs a;
+  long long eo = 0, vo = 0, so = 0, ro = 0, ao = 0;
+  for (int g = 0; g < G; ++g) {
+    const regcn_csr_arrays& s = members[g];
+    if (s.T < 0 || !s.src || !s.dst || !s.etype || !s.indeg || !s.norm || !s.rowptr || !s.src_sorted || !s.etype_sorted || !s.eperm ||
+        !s.vptr || !s.sptr || !s.vrow_row || !s.active_pos || !s.active_rows || !s.rel_rowptr || !s.rel_ents || !s.counts) {
+      set_last_error("csr_concat: null pointer / bad T in member %d", g); return REGCN_ERR_NULL;
+    }
+    ConcatMember& m = a.m[g];
+    m.src = s.src; m.dst = s.dst; m.etype = s.etype; m.indeg = s.indeg; m.norm = s.norm; m.rowptr = s.rowptr;
+    m.src_sorted = s.src_sorted; m.etype_sorted = s.etype_sorted; m.eperm = s.eperm; m.vptr = s.vptr; m.sptr = s.sptr;
+    m.vrow_row = s.vrow_row; m.active_pos = s.active_pos; m.active_rows = s.active_rows; m.rel_rowptr = s.rel_rowptr;
+    m.rel_ents = s.rel_ents; m.counts = s.counts;
+    m.E = 2 * s.T; m.n_vrows = sizes[4 * g]; m.n_split = sizes[4 * g + 1]; m.n_rel_ents = sizes[4 * g + 2]; m.n_active = sizes[4 * g + 3];
+    if (m.n_vrows < 0 || m.n_split < 0 || m.n_rel_ents < 0 || m.n_active < 0 || m.n_active > N) { set_last_error("csr_concat: bad sizes of member %d", g); return REGCN_ERR_DIM; }
+    m.eoff = (int)eo; m.voff = (int)vo; m.soff = (int)so; m.roff = (int)ro; m.aoff = (int)ao;
+    eo += m.E; vo += m.n_vrows; so += m.n_split; ro += m.n_rel_ents; ao += m.n_active;
+    if (eo > 0x7fffffffLL || ro > 0x7fffffffLL) { set_last_error("csr_concat: edge total overflows int32"); return REGCN_ERR_DIM; }
+  }
+  const regcn_csr_arrays& o = *out;
+  if (!o.src || !o.dst || !o.etype || !o.indeg || !o.norm || !o.rowptr || !o.src_sorted || !o.etype_sorted || !o.eperm || !o.vptr ||
+      !o.sptr || !o.vrow_row || !o.active_pos || !o.active_rows || !o.rel_rowptr || !o.rel_ents || !o.counts) {
+    set_last_error("csr_concat: null pointer in the output index"); return REGCN_ERR_NULL;
+  }
+  a.src = o.src; a.dst = o.dst; a.etype = o.etype; a.indeg = o.indeg; a.norm = o.norm; a.rowptr = o.rowptr;
+  a.src_sorted = o.src_sorted; a.etype_sorted = o.etype_sorted; a.eperm = o.eperm; a.vptr = o.vptr; a.sptr = o.sptr;
+  a.vrow_row = o.vrow_row; a.active_pos = o.active_pos; a.active_rows = o.active_rows; a.rel_rowptr = o.rel_rowptr;
+  a.rel_ents = o.rel_ents; a.counts = o.counts;
+  a.G = G; a.N = N; a.R = R;
+  const int blocks = std::max(1, std::min(64, (N + 255) / 256));
+  launch_k(csr_concat_kernel, dim3(blocks, G), dim3(256), 0, st, a);
+  return check_launch("csr_concat");
 }
 
 }  // namespace regcn

@@ -12,6 +12,7 @@ int csr_build(const int64_t* triples, int T, int N, int R, int* src, int* dst, i
               int* active_pos, int* active_rows, int* rel_rowptr, int* rel_ents, int* counts, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t csr_build_batch_workspace_bytes(const int* T, int L, int N, int R);
 int csr_build_batch(const regcn_csr_arrays* snaps, int L, int N, int R, void* ws, size_t ws_bytes, cudaStream_t st);
+int csr_concat(const regcn_csr_arrays* members, const int* sizes, int G, int N, int R, const regcn_csr_arrays* out, cudaStream_t st);
 int rel_mean_pool(const float* h, const int* rel_rowptr, const int* rel_ents, int R, int d, int nsplit, float* out,
                   float* partial, float* out_hi, float* out_lo, cudaStream_t st);
 int union_aggregate(const float* h, const float* rel, const int* rowptr, const int* src_sorted, const int* etype_sorted,

@@ -82,24 +82,10 @@ def convtrans_decode_rank(model, emb, r_emb, all_t, f_ent, f_rel):
 
 
 @torch.no_grad()
-def evaluate_snapshot(model, glist, all_triples, filter_csr, timers=None, fused=None, shard=None):
-    """Returns (rank, filter_rank) int64 (B,) for the 2*T_q queries `all_triples` (forward + inverse).
-
-    fused (default: on with the tensor-core GEMM): rank through the counting epilogue of the scoring GEMM, never
-    writing the (B,N) score matrix; otherwise the dense predict()-style path.  shard=(lo,hi) restricts the counted
-    candidates (entity-sharded scoring: the caller all-reduces the counts).
-    timers: optional dict of name -> (start_event, end_event) pairs recorded on the current stream."""
-    def mark(name, which):
-        if timers is not None:
-            timers[name][which].record()
-
-    if fused is None:
-        fused = ops.gemm_impl() in ("tc", "tc1") and filter_csr is not None
-    mark("evolve", 0)
-    evolve_embs, _, r_emb, _, _ = model.forward(glist, None, True)
-    mark("evolve", 1)
+def _score_rank(model, emb, r_emb, all_triples, filter_csr, fused, shard, mark):
+    """Scoring + ranking half of one evaluated timestamp; emb is the evolved entity table before the predict-time
+    normalisation (src/rrgcn.py:186-194)."""
     mark("score", 0)
-    emb = evolve_embs[-1]
     if model.layer_norm:
         if hasattr(model, "_c_float"):
             emb = ops.row_map(emb, ops.ROW_TANGENT_NORMALIZE, c=model._c_float)
@@ -128,6 +114,68 @@ def evaluate_snapshot(model, glist, all_triples, filter_csr, timers=None, fused=
     rank, frank = ops.counts_to_ranks(raw, filt)
     mark("rank", 1)
     return rank, frank
+
+
+@torch.no_grad()
+def evaluate_snapshot(model, glist, all_triples, filter_csr, timers=None, fused=None, shard=None):
+    """Returns (rank, filter_rank) int64 (B,) for the 2*T_q queries `all_triples` (forward + inverse).
+
+    fused (default: on with the tensor-core GEMM): rank through the counting epilogue of the scoring GEMM, never
+    writing the (B,N) score matrix; otherwise the dense predict()-style path.  shard=(lo,hi) restricts the counted
+    candidates (entity-sharded scoring: the caller all-reduces the counts).
+    timers: optional dict of name -> (start_event, end_event) pairs recorded on the current stream."""
+    def mark(name, which):
+        if timers is not None:
+            timers[name][which].record()
+
+    if fused is None:
+        fused = ops.gemm_impl() in ("tc", "tc1") and filter_csr is not None
+    mark("evolve", 0)
+    evolve_embs, _, r_emb, _, _ = model.forward(glist, None, True)
+    mark("evolve", 1)
+    return _score_rank(model, evolve_embs[-1], r_emb, all_triples, filter_csr, fused, shard, mark)
+
+
+BATCH_ROWS = 192 * 1024     # entity rows one batched recurrence aims for (timestamps_per_batch)
+
+
+def timestamps_per_batch(model, num_nodes, static_graph=None):
+    """How many consecutive test timestamps test() / evaluate_batch evolve at once.  At TKG sizes (7-23 k entities) the
+    kernels of one timestamp's recurrence are latency-bound; G independent windows as one block-diagonal graph give every
+    launch G times the rows (measured at the ICEWS18 shape: 0.85 ms per timestamp alone, 0.50 ms in batches of 8).
+    REGCN_TEST_BATCH=<n> overrides; 1 = one timestamp per recurrence."""
+    import os
+    ok = hasattr(model, "forward_batch") and model.batch_ok() and not (static_graph is not None and model.use_static)
+    if not ok:
+        return 1
+    env = os.environ.get("REGCN_TEST_BATCH")
+    if env:
+        return max(1, min(16, int(env)))
+    return max(1, min(8, BATCH_ROWS // max(1, int(num_nodes))))
+
+
+@torch.no_grad()
+def evaluate_batch(model, windows, all_triples_list, filter_list, timers=None, fused=None):
+    """evaluate_snapshot for G test timestamps whose history windows are evolved together (model.forward_batch): returns
+    [(rank, filter_rank)] in the order given, each pair identical to evaluate_snapshot(model, windows[g], ...).
+    timers: 'evolve' brackets the batched recurrence, 'score' everything after it."""
+    def mark(name, which):
+        if timers is not None and name in timers:
+            timers[name][which].record()
+
+    def no_mark(name, which):
+        pass
+
+    mark("evolve", 0)
+    states = model.forward_batch(windows)
+    mark("evolve", 1)
+    mark("score", 0)
+    out = []
+    for (emb, r_emb), all_t, f in zip(states, all_triples_list, filter_list):
+        fz = (ops.gemm_impl() in ("tc", "tc1") and f is not None) if fused is None else fused
+        out.append(_score_rank(model, emb, r_emb, all_t, f, fz, None, no_mark))
+    mark("score", 1)
+    return out
 
 
 QUERY_SHARD_MIN = 16384      # smallest query batch whose tower is cut across ranks (see score_rank_sharded)
@@ -352,31 +400,35 @@ def test(model, history_list, test_list, num_rels, num_nodes, use_cuda=True, all
     if multi_step:
         return _test_multi_step(model, input_list, test_list, num_rels, num_nodes, static_graph, dev, topk,
                                 relation_evaluation, return_ranks)
-    cache = SnapshotCache(num_nodes, num_rels, dev, capacity=max(2 * L + 4, 10) + 8)
+    # consecutive test timestamps are independent (ground-truth history, src/main.py:98-100): G of them share one
+    # batched recurrence (timestamps_per_batch / RecurrentRGCN.forward_batch); their decode + rank stays per timestamp
+    G = timestamps_per_batch(model, num_nodes, static_graph) if len(input_list) else 1
+    PREP_DEPTH = 2 if G == 1 else 2 * G   # timestamps whose device-side preparation is in flight ahead of the one(s) evaluated
+    AHEAD = 8           # test snapshots whose edge index is built per batched launch (one CTA each, concurrently): the
+                        # one-CTA build of a single snapshot is 86 us of latency at the ICEWS18 size, eight cost the same
+    cache = SnapshotCache(num_nodes, num_rels, dev, capacity=max(2 * L + 4, 10) + AHEAD + PREP_DEPTH + G)
     fused_ok = ops.gemm_impl() in ("tc", "tc1")
     # ConvTransE / ConvTransR in fp32-parity mode: decode + rank of a timestamp is one C call (same kernels, same ranks)
     one_call = (ops.gemm_impl() == "tc" and ops.score_dtype() == "fp32" and os.environ.get("REGCN_DECODE_ENGINE", "1") != "0"
                 and type(model.decoder_ob).__name__ == "ConvTransE" and type(model.rdecoder).__name__ == "ConvTransR"
                 and model.h_dim % 4 == 0 and model.h_dim <= 256)
     K = len(test_list)
-    # pinned staging, allocated once: two size slots (ping-pong between the step being run and the one being prepared)
-    # and one result area holding [rank | frank | rank_r | frank_r] of every timestamp
-    PREP_DEPTH = 2      # timestamps whose device-side preparation is in flight ahead of the one being evaluated
-    AHEAD = 8           # test snapshots whose edge index is built per batched launch (one CTA each, concurrently): the
-                        # one-CTA build of a single snapshot is 86 us of latency at the ICEWS18 size, eight cost the same
-    size_slots = torch.empty((PREP_DEPTH + 1, 2 + 8 * (L + AHEAD + 2)), dtype=torch.int32, pin_memory=True)
+    # pinned staging, allocated once: size slots (ring over the timestamps being run and the ones being prepared) and one
+    # result area holding [rank | frank | rank_r | frank_r] of every timestamp
+    n_slots = PREP_DEPTH + G + 1
+    size_slots = torch.empty((n_slots, 2 + 8 * (L + AHEAD + 2)), dtype=torch.int32, pin_memory=True)
     offs = [0]
     for snap in test_list:
         offs.append(offs[-1] + 8 * int(snap.shape[0]))
     result_host = torch.empty(max(offs[-1], 1), dtype=torch.int32, pin_memory=True)
     results = []
     # The preparation of a timestamp (H2D copy, index build of the snapshot entering the window, filter-list counting, D2H
-    # of the sizes) is enqueued on the SAME stream, TWO timestamps ahead: when the host is about to enqueue timestamp k+1
-    # the sizes it needs were produced in front of timestamp k's kernels and have long arrived, so the host never blocks on
-    # the GPU and the GPU never waits for the host (with a depth of one the GPU idled ~0.2 ms per step while the host
-    # fetched the sizes and enqueued the next evolution).  A separate preparation stream would also overlap those small
-    # kernels with the evolution, but makes the caching allocator fall back to fresh allocations for every cross-stream
-    # tensor (measured: 2.7-4.7 ms per step); REGCN_PREP_STREAM=1 selects it anyway.
+    # of the sizes) is enqueued on the SAME stream, PREP_DEPTH timestamps ahead: when the host is about to enqueue the next
+    # group the sizes it needs were produced in front of the current group's kernels and have long arrived, so the host
+    # never blocks on the GPU and the GPU never waits for the host (with a depth of one the GPU idled ~0.2 ms per step
+    # while the host fetched the sizes and enqueued the next evolution).  A separate preparation stream would also overlap
+    # those small kernels with the evolution, but makes the caching allocator fall back to fresh allocations for every
+    # cross-stream tensor (measured: 2.7-4.7 ms per step); REGCN_PREP_STREAM=1 selects it anyway.
     # Non multi-step evaluation feeds ground-truth history (src/main.py:98-100), so every window is known up front.
     main_stream = torch.cuda.current_stream()
     prep_stream = main_stream
@@ -392,54 +444,65 @@ def test(model, history_list, test_list, num_rels, num_nodes, use_cuda=True, all
         # test snapshot i joins the window at step i + 1; every AHEAD-th step builds the next AHEAD of them at once
         return list(test_list[j:min(j + AHEAD, K - 1)]) if (j % AHEAD == 0 and len(base)) else []
 
-    queue = [_prepare(cache, window(j), test_list[j], num_rels, dev, size_slots[j % (PREP_DEPTH + 1)], prep_stream,
-                      main_stream, ahead(j)) for j in range(min(PREP_DEPTH, K))]
+    def prepare(j):
+        return _prepare(cache, window(j), test_list[j], num_rels, dev, size_slots[j % n_slots], prep_stream, main_stream,
+                        ahead(j))
+
+    queue = [prepare(j) for j in range(min(PREP_DEPTH, K))]
+    next_j = len(queue)
     _tm = os.environ.get("REGCN_TEST_TIMING") == "1"
     _acc = [0.0] * 6
-    for k in range(K):
-        cur = queue.pop(0)
+    k = 0
+    while k < K:
+        n_g = min(G, K - k)
+        group = [queue.pop(0) for _ in range(n_g)]
         _t0 = time.perf_counter()
-        cur.event.synchronize()
-        if prep_stream is not main_stream:
-            main_stream.wait_event(cur.event)
+        for cur in group:
+            cur.event.synchronize()
+            if prep_stream is not main_stream:
+                main_stream.wait_event(cur.event)
         _t1 = time.perf_counter()
-        f_ent, f_rel = _finish_prepare(cur)
-        all_t = cur.all_t
+        filters = [_finish_prepare(cur) for cur in group]
         _t2 = time.perf_counter()
-        evolve_embs, _, r_emb, _, _ = model.forward(cur.glist, static_graph, True)
-        _t3 = time.perf_counter()
-        emb = evolve_embs[-1]
-        if one_call:
-            packed = convtrans_decode_rank(model, emb, r_emb, all_t, f_ent, f_rel)
+        if n_g > 1:
+            states = model.forward_batch([cur.glist for cur in group])
         else:
-            if model.layer_norm:
-                if hasattr(model, "_c_float"):
-                    emb = ops.row_map(emb, ops.ROW_TANGENT_NORMALIZE, c=model._c_float)
-                else:
-                    emb = ops.row_map(emb, ops.ROW_NORMALIZE)
-            if fused_ok:
-                q, cand, hyp, col_bias = _scoring_operands(model, emb, r_emb, all_t)
-                target = all_t[:, 2].to(torch.int32).contiguous()
-                pa, pe = f_ent.pairs(target)
-                raw, filt, _ = ops.fused_rank_counts(q, cand, target, f_ent.ptr, f_ent.idx, pa, pe, hyp=hyp,
-                                                     col_bias=col_bias, filt_end=f_ent.end)
-                rank, frank = ops.counts_to_ranks(raw, filt)
+            evolve_embs, _, r_emb, _, _ = model.forward(group[0].glist, static_graph, True)
+            states = [(evolve_embs[-1], r_emb)]
+        _t3 = time.perf_counter()
+        for i, (cur, (emb, r_emb), (f_ent, f_rel)) in enumerate(zip(group, states, filters)):
+            all_t = cur.all_t
+            if one_call:
+                packed = convtrans_decode_rank(model, emb, r_emb, all_t, f_ent, f_rel)
             else:
-                score = model.decoder_ob.forward(emb, r_emb, all_t, mode="test")
-                _, _, rank, frank = utils.get_total_rank(all_t, score, None, 1000, rel_predict=0, filter_csr=f_ent)
-            score_rel = model.rdecoder.forward(emb, r_emb, all_t, mode="test")
-            raw_r, filt_r, _ = ops.rank_dense(score_rel, all_t, 1, f_rel.ptr, f_rel.idx, filt_end=f_rel.end)
-            rank_r, frank_r = ops.counts_to_ranks(raw_r, filt_r)
-            packed = torch.cat((rank, frank, rank_r, frank_r)).to(torch.int32)
-        host = result_host[offs[k]:offs[k + 1]]
-        host.copy_(packed, non_blocking=True)                      # this timestamp's result, device -> host
-        results.append(host)
+                if model.layer_norm:
+                    if hasattr(model, "_c_float"):
+                        emb = ops.row_map(emb, ops.ROW_TANGENT_NORMALIZE, c=model._c_float)
+                    else:
+                        emb = ops.row_map(emb, ops.ROW_NORMALIZE)
+                if fused_ok:
+                    q, cand, hyp, col_bias = _scoring_operands(model, emb, r_emb, all_t)
+                    target = all_t[:, 2].to(torch.int32).contiguous()
+                    pa, pe = f_ent.pairs(target)
+                    raw, filt, _ = ops.fused_rank_counts(q, cand, target, f_ent.ptr, f_ent.idx, pa, pe, hyp=hyp,
+                                                         col_bias=col_bias, filt_end=f_ent.end)
+                    rank, frank = ops.counts_to_ranks(raw, filt)
+                else:
+                    score = model.decoder_ob.forward(emb, r_emb, all_t, mode="test")
+                    _, _, rank, frank = utils.get_total_rank(all_t, score, None, 1000, rel_predict=0, filter_csr=f_ent)
+                score_rel = model.rdecoder.forward(emb, r_emb, all_t, mode="test")
+                raw_r, filt_r, _ = ops.rank_dense(score_rel, all_t, 1, f_rel.ptr, f_rel.idx, filt_end=f_rel.end)
+                rank_r, frank_r = ops.counts_to_ranks(raw_r, filt_r)
+                packed = torch.cat((rank, frank, rank_r, frank_r)).to(torch.int32)
+            host = result_host[offs[k + i]:offs[k + i + 1]]
+            host.copy_(packed, non_blocking=True)                      # this timestamp's result, device -> host
+            results.append(host)
         _t4 = time.perf_counter()
-        # the window slides (src/main.py:98-100); prepare the timestamp PREP_DEPTH ahead while the GPU is busy
-        j = k + PREP_DEPTH
-        if j < K:
-            queue.append(_prepare(cache, window(j), test_list[j], num_rels, dev, size_slots[j % (PREP_DEPTH + 1)],
-                                  prep_stream, main_stream, ahead(j)))
+        k += n_g
+        # the window slides (src/main.py:98-100); prepare the timestamps up to PREP_DEPTH ahead while the GPU is busy
+        while next_j < min(K, k + PREP_DEPTH):
+            queue.append(prepare(next_j))
+            next_j += 1
         _t5 = time.perf_counter()
         for _i, _d in enumerate((_t1 - _t0, _t2 - _t1, _t3 - _t2, _t4 - _t3, _t5 - _t4)):
             _acc[_i] += _d

@@ -22,12 +22,16 @@ class _Frame(dict):
 
 
 class SnapshotGraph:
-    def __init__(self, num_nodes, num_rels, triples_dev, _defer_counts=False, _defer_build=False):
+    def __init__(self, num_nodes, num_rels, triples_dev, _defer_counts=False, _defer_build=False, _shell=None):
         self.num_nodes = int(num_nodes)
         self.num_rels = int(num_rels)
-        self.triples = triples_dev  # (T,3) int64 on the device, reference layout
-        self.device = triples_dev.device
-        T = int(triples_dev.shape[0])
+        self.triples = triples_dev  # (T,3) int64 on the device, reference layout (None: index made by concat_graphs)
+        if triples_dev is None:
+            T, self.device = int(_shell[0]), _shell[1]
+            _defer_build = True
+        else:
+            self.device = triples_dev.device
+            T = int(triples_dev.shape[0])
         N, R, E = self.num_nodes, self.num_rels, 2 * T
         self.num_edges = E
         dev = self.device
@@ -66,7 +70,7 @@ class SnapshotGraph:
 
     def _descriptor(self, desc):
         """Fill a struct regcn_csr_arrays with this snapshot's pointers (batched build)."""
-        desc.triples = self.triples.data_ptr()
+        desc.triples = self.triples.data_ptr() if self.triples is not None else None
         desc.T = self.num_edges // 2
         for name in ("src", "dst", "etype", "indeg", "norm", "rowptr", "src_sorted", "etype_sorted", "eperm", "vptr",
                      "sptr", "vrow_row", "active_pos", "active_rows", "rel_rowptr", "rel_ents"):
@@ -199,6 +203,37 @@ def finish_sub_graphs(gs, counts=None):
         for g, c in zip(gs, counts):
             g._set_counts(c)
     return gs
+
+
+def concat_graphs(graphs):
+    """Block-diagonal union of G finished SnapshotGraphs over the same (N, R) as ONE SnapshotGraph over G*N entities and
+    G*R relations (`regcn_csr_concat`, one launch of offset copies): member g's entity v is g*N + v, its relation r < R
+    is g*R + r, the inverse relation R + r is G*R + g*R + r.  This is the graph one recurrence step runs on when G
+    independent history windows are evolved together (evaluate.test: consecutive test timestamps, src/main.py:60-90).
+    No host synchronisation: the members' size counters are already on the host."""
+    import ctypes
+    G = len(graphs)
+    g0 = graphs[0]
+    N, R = g0.num_nodes, g0.num_rels
+    if any(g.num_nodes != N or g.num_rels != R or g.device != g0.device for g in graphs):
+        raise ValueError("concat_graphs: members must share num_nodes, num_rels and device")
+    T = sum(g.num_edges // 2 for g in graphs)
+    out = SnapshotGraph(G * N, G * R, None, _shell=(T, g0.device))
+    descs = (_lib.CsrArrays * G)()
+    for g, dsc in zip(graphs, descs):
+        g._descriptor(dsc)
+    od = _lib.CsrArrays()
+    out._descriptor(od)
+    sizes = (ctypes.c_int32 * (4 * G))()
+    for i, g in enumerate(graphs):
+        sizes[4 * i:4 * i + 4] = [g.n_vrows, g.n_split_chunks, g.n_rel_ents, g.n_active]
+    call("regcn_csr_concat", ctypes.cast(descs, ctypes.c_void_p), ctypes.cast(sizes, ctypes.c_void_p), G, N, R,
+         ctypes.cast(ctypes.pointer(od), ctypes.c_void_p))
+    out._set_counts([sum(g.n_vrows for g in graphs), sum(g.n_split_chunks for g in graphs),
+                     sum(g.n_rel_ents for g in graphs), max(g.max_hub_degree for g in graphs),
+                     sum(g.n_active for g in graphs)])
+    out.members = G
+    return out
 
 
 class SnapshotCache:

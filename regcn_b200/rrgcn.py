@@ -174,20 +174,44 @@ class RecurrentRGCN(nn.Module):
         itab = np.array([self.num_ents, 2 * self.num_rels, d, len(self.rgcn.layers), int(bool(self.layer_norm)), 1],
                         dtype=np.int32)
         self._engine_tab = (ptab, itab, keep)
+        self._engine_heads = ptrs[:5]           # the tables with one row per entity / relation (see _engine_tables_batch)
         self._engine_stamp = stamp
+        self._engine_tab_batch = {}
         return self._engine_tab
 
-    def _forward_engine(self, g_list, h_init=None):
+    def _engine_tables_batch(self, G):
+        """Tables of the recurrence over G independent history windows at once: the per-entity / per-relation tables are
+        tiled G times in the numbering of graph.concat_graphs (entity g*N + v; relation g*R + r, inverse G*R + g*R + r),
+        the weights are shared."""
+        ptab, itab, _ = self._engine_tables()
+        hit = self._engine_tab_batch.get(G)
+        if hit is not None:
+            return hit
+        R = self.num_rels
+        dyn, emb_rel, er_hi, er_lo, gi_static = self._engine_heads
+
+        def tile_rel(t):
+            return torch.cat([t[:R]] * G + [t[R:]] * G).contiguous()
+
+        heads = [dyn.repeat(G, 1).contiguous(), tile_rel(emb_rel), tile_rel(er_hi), tile_rel(er_lo), tile_rel(gi_static)]
+        ptab_g, itab_g = ptab.copy(), itab.copy()
+        for i, t in enumerate(heads):
+            ptab_g[i] = t.data_ptr()
+        itab_g[0], itab_g[1] = G * self.num_ents, 2 * G * R
+        self._engine_tab_batch[G] = (ptab_g, itab_g, heads)
+        return self._engine_tab_batch[G]
+
+    def _forward_engine(self, g_list, h_init=None, members=1):
         import numpy as np
         from . import _lib
-        ptab, itab, _ = self._engine_tables(h_init)
+        ptab, itab, _ = self._engine_tables(h_init) if members == 1 else self._engine_tables_batch(members)
         L = len(g_list)
-        N, R2, d = self.num_ents, 2 * self.num_rels, self.h_dim
+        N, R2, d = members * self.num_ents, 2 * members * self.num_rels, self.h_dim
         dev = self.dynamic_emb.device
         gp = np.concatenate([g.ptr_table for g in g_list]) if L else np.zeros(1, dtype=np.uint64)
         gi = np.concatenate([g.int_table for g in g_list]) if L else np.zeros(1, dtype=np.int32)
         max_split = max([g.n_split_chunks for g in g_list], default=0)
-        rel_nsplit = max([max(1, min(64, g.n_rel_ents // (max(1, self.num_rels) * 512))) for g in g_list], default=1)
+        rel_nsplit = max([max(1, min(64, g.n_rel_ents // (max(1, R2 // 2) * 512))) for g in g_list], default=1)
         need = _lib.load().regcn_regcn_evolve_workspace_bytes(N, R2, d, max_split, rel_nsplit)
         ws = getattr(self, "_engine_ws", None)
         if ws is None or ws.numel() < need or ws.device != dev:
@@ -198,6 +222,32 @@ class RecurrentRGCN(nn.Module):
         _lib.call("regcn_regcn_evolve", ptab.ctypes.data, itab.ctypes.data, gp.ctypes.data, gi.ctypes.data, L,
                   hist.data_ptr(), h0.data_ptr(), rel_nsplit, ws.data_ptr(), ws.numel())
         return [hist[i] for i in range(L)], h0
+
+    def batch_ok(self):
+        """True when forward_batch can evolve several history windows at once (the whole-recurrence engine, no static
+        graph: its initial table is rebuilt per call)."""
+        return self._engine_ok() and not self.use_static
+
+    @torch.no_grad()
+    def forward_batch(self, windows):
+        """Evolve G independent history windows (lists of L SnapshotGraphs each, same L) in ONE recurrence over the
+        block-diagonal union graphs (graph.concat_graphs).  The reference evaluates test timestamps one after the other,
+        each over its own window (src/main.py:60-90); the windows do not depend on each other, so this runs the same
+        kernels at G times the rows per launch.  Returns [(h_g (N,d), r_emb_g (2R,d))] -- row for row what
+        forward(windows[g]) returns as (history_embs[-1], h_0)."""
+        from .graph import concat_graphs
+        G = len(windows)
+        L = len(windows[0])
+        if not self.batch_ok() or L == 0 or any(len(w) != L for w in windows):
+            raise RuntimeError("forward_batch: needs the recurrence engine, no static graph and windows of one length > 0")
+        if G == 1:
+            embs, _, r_emb, _, _ = self.forward(windows[0], None, True)
+            return [(embs[-1], r_emb)]
+        comb = [concat_graphs([w[i] for w in windows]) for i in range(L)]
+        hist, h0 = self._forward_engine(comb, None, members=G)
+        N, R, d = self.num_ents, self.num_rels, self.h_dim
+        rel = h0.view(2, G, R, d).transpose(0, 1).contiguous().view(G, 2 * R, d)
+        return [(hist[-1][g * N:(g + 1) * N], rel[g]) for g in range(G)]
 
     @torch.no_grad()
     def forward(self, g_list, static_graph, use_cuda):

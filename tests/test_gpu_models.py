@@ -371,6 +371,123 @@ def test_evaluation_loop_matches_stepwise_reference_style_loop(kind):
     assert abs(mrrs[1] - ref_mrr) < 1e-7
 
 
+def _offset_union(snaps, n, r):
+    parts = []
+    for g, s in enumerate(snaps):
+        s = np.array(s, dtype=np.int64, copy=True)
+        s[:, 0] += g * n
+        s[:, 2] += g * n
+        s[:, 1] += g * r
+        parts.append(s)
+    return np.concatenate(parts)
+
+
+@pytest.mark.parametrize("shape,G", [("tiny", 3), ("small", 4), ("c1", 8), ("c4", 2)])
+def test_concat_graphs_equals_index_built_on_union_triples(shape, G):
+    """regcn_csr_concat (block-diagonal union of G finished snapshot indices) against regcn_csr_build on the union's
+    triples written out with offset ids: every array the kernels read must be identical, the per-edge arrays in arrival
+    order describe the same multiset of edges.  One member is empty, one has a single triple."""
+    from regcn_b200.graph import concat_graphs
+    R._lib.require_device()
+    n, r, t, _, _ = synth.SHAPES[shape]
+    rng = np.random.default_rng(11)
+    snaps = [synth.make_snapshot(rng, n, r, t, True) for _ in range(G)]
+    snaps[1] = np.zeros((0, 3), dtype=np.int64)
+    if G > 2:
+        snaps[2] = snaps[2][:1]
+    members = [R.build_sub_graph(n, r, s, True, 0) for s in snaps]
+    cat = concat_graphs(members)
+    ref = R.build_sub_graph(G * n, G * r, _offset_union(snaps, n, r), True, 0)
+    assert cat.num_nodes == ref.num_nodes and cat.num_rels == ref.num_rels and cat.num_edges == ref.num_edges
+    assert (cat.n_vrows, cat.n_split_chunks, cat.n_rel_ents, cat.max_hub_degree, cat.n_active) == \
+           (ref.n_vrows, ref.n_split_chunks, ref.n_rel_ents, ref.max_hub_degree, ref.n_active)
+    assert cat._counts[:5].tolist() == ref._counts[:5].tolist()
+    E, N2 = ref.num_edges, ref.num_nodes
+    for name, cnt in (("rowptr", N2 + 1), ("src_sorted", E), ("etype_sorted", E), ("indeg", N2), ("norm", N2),
+                      ("vptr", N2 + 1), ("sptr", N2 + 1), ("vrow_row", ref.n_vrows), ("active_pos", N2),
+                      ("active_rows", ref.n_active), ("rel_rowptr", G * r + 1), ("rel_ents", ref.n_rel_ents)):
+        assert torch.equal(getattr(cat, name)[:cnt], getattr(ref, name)[:cnt]), name
+    key = lambda g_: torch.sort(g_.src[:E].long() * (4 * G * r) * N2 + g_.dst[:E].long() * (4 * G * r) + g_.etype[:E].long())[0]
+    assert torch.equal(key(cat), key(ref))
+    # eperm maps CSR slots to the per-edge arrays of the same index
+    ep = cat.eperm[:E].long()
+    assert torch.equal(cat.src[:E][ep], cat.src_sorted[:E]) and torch.equal(cat.etype[:E][ep], cat.etype_sorted[:E])
+
+
+@pytest.mark.parametrize("shape,G,ln", [("tiny", 2, True), ("small", 5, True), ("c1", 8, True), ("c1", 3, False), ("c4", 4, True)])
+def test_forward_batch_rows_equal_per_window_forward(shape, G, ln):
+    """RecurrentRGCN.forward_batch (G history windows as one block-diagonal recurrence) against forward() window by
+    window.  When every snapshot takes the engine's sparse-snapshot form alone (fewer than half of the entities receive
+    edges, the TKG case) so does the union, and every entity / relation row is bit-identical (same kernels, same per-row
+    arithmetic and order); a member that is dense on its own is evolved in the other, algebraically equal form inside a
+    sparse union, so those shapes are compared at 1e-5."""
+    R._lib.require_device()
+    n, r, t, L, _ = synth.SHAPES[shape]
+    rng = np.random.default_rng(7)
+    snaps = [synth.make_snapshot(rng, n, r, t, True) for _ in range(L + G - 1)]
+    snaps[1] = snaps[1][:0]                                         # an empty snapshot inside some windows
+    model, _ = build_model(dict(kind="regcn", layer_norm=ln, seed=6), n, r)
+    model = model.to(DEV)
+    graphs = [R.build_sub_graph(n, r, s, True, 0) for s in snaps]
+    windows = [graphs[g:g + L] for g in range(G)]
+    single = []
+    for w in windows:
+        hist, _, h0, _, _ = model.forward(w, None, True)
+        single.append((hist[-1].clone(), h0.clone()))
+    exact = all(2 * g.n_active <= n for g in graphs)
+    assert exact == (shape != "tiny")
+    for _ in range(2):
+        states = model.forward_batch(windows)
+        torch.cuda.synchronize()
+        for (h, h0), (hs, h0s) in zip(states, single):
+            if exact:
+                assert torch.equal(h, hs) and torch.equal(h0, h0s)
+            else:
+                assert float((h - hs).abs().max()) <= 1e-5 * max(1.0, float(hs.abs().max()))
+                assert float((h0 - h0s).abs().max()) <= 1e-5 * max(1.0, float(h0s.abs().max()))
+
+
+def test_evaluation_loop_batched_equals_one_timestamp_at_a_time(monkeypatch):
+    """regcn_b200.test() evolving groups of consecutive timestamps together (the default below ~190 k entity rows per
+    batch) returns the ranks of the one-timestamp-per-recurrence loop, for group sizes that do and do not divide the
+    number of test snapshots; evaluate_batch equals evaluate_snapshot."""
+    from regcn_b200 import evaluate, utils
+    R._lib.require_device()
+    st = synth.make_stream("c1", 9, n_test=7)
+    n, r = st["num_ents"], st["num_rels"]
+    model, _ = build_model(dict(kind="regcn", layer_norm=True, seed=9), n, r)
+    model = model.to(DEV)
+    L = len(st["history"])
+    assert evaluate.timestamps_per_batch(model, n) == 8
+    out = {}
+    for flag in ("1", "3", "8"):
+        monkeypatch.setenv("REGCN_TEST_BATCH", flag)
+        out[flag] = R.test(model, st["history"], st["tests"], r, n, True, None, None, None, None, "eval",
+                           test_history_len=L, return_ranks=True)
+    monkeypatch.delenv("REGCN_TEST_BATCH")
+    for flag in ("3", "8"):
+        assert out[flag][0] == out["1"][0]
+        for a, b in zip(out[flag][1], out["1"][1]):
+            assert len(a) == len(b) == 7
+            for x, y in zip(a, b):
+                assert torch.equal(x, y)
+    snaps = list(st["history"]) + list(st["tests"])
+    graphs = [R.build_sub_graph(n, r, s, True, 0) for s in snaps]
+    windows, trip, filt = [], [], []
+    for k in range(3):
+        windows.append(graphs[k:k + L])
+        t_ = torch.from_numpy(st["tests"][k]).to(DEV)
+        inv = t_[:, [2, 1, 0]].clone()
+        inv[:, 1] += r
+        trip.append(torch.cat((t_, inv)).contiguous())
+        filt.append(utils.filter_csr_from_snapshot(trip[-1], 2 * r, 0))
+    res = evaluate.evaluate_batch(model, windows, trip, filt)
+    for k in range(3):
+        rank, frank = evaluate.evaluate_snapshot(model, windows[k], trip[k], filt[k])
+        assert torch.equal(res[k][0], rank) and torch.equal(res[k][1], frank)
+        assert torch.equal(rank.cpu().long(), out["1"][1][0][k]) and torch.equal(frank.cpu().long(), out["1"][1][1][k])
+
+
 def test_one_call_decode_rank_equals_per_op_path(monkeypatch):
     """regcn_convtrans_decode_rank (decode + rank of a timestamp in one C call) against the per-op path of test():
     the same kernels in the same order -> identical ranks, entity and relation, raw and filtered."""
