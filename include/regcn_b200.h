@@ -189,6 +189,11 @@ REGCN_API void regcn_pdl_enable(int on);
 /* two-stream schedule of the evolve engines (default on; REGCN_TWO_STREAM=0 or regcn_two_stream_enable(0): every kernel
  * on the caller's stream, which is also how the per-kernel timings of bench.py's roofline block are taken) */
 REGCN_API void regcn_two_stream_enable(int on);
+/* Data flow of the all-entity GEMMs of regcn_regcn_evolve (sparse-snapshot form): 1 = the entity state is kept as ONE
+ * fp32 copy and split to TF32 (hi, lo) on chip by the GEMM's converter warps (regcn_gemm_tf32_layer_a32), 0 = (hi, lo)
+ * copies in HBM read by TMA, -1 (default) = by size: fp32 from 65 536 entity rows, where those GEMMs are HBM-bound
+ * (REGCN_EVOLVE_A32 sets the initial mode).  Results are bit-identical either way.                                   */
+REGCN_API void regcn_evolve_a32_mode(int mode);
 /* number of kernels this library has launched in the calling process (the snapshot-index build adds ~8 CUB launches per
  * large snapshot that are not counted) */
 REGCN_API long long regcn_kernel_launches(void);

@@ -116,6 +116,25 @@ def main():
                 parts.append(s_)
             comb.append(R.build_sub_graph(G * n, G * r, np.concatenate(parts), True, 0))
         run(what, lambda: mG.forward(comb, None, True), steps)
+    elif what.startswith("c3e"):
+        # the whole batched step: G windows evolved together (forward_batch), then scored and ranked one by one
+        import numpy as np
+        G = int(what[3:])
+        n, r, t, L, tq = synth.SHAPES["c3"]
+        st = synth.make_stream("c3", 0, n_test=G)
+        snaps = list(st["history"]) + list(st["tests"][:G - 1])
+        m, sd = build_product_model(model_cfg("regcn"), n, r, 0)
+        m = m.to(dev)
+        graphs = [R.build_sub_graph(n, r, s_, True, 0) for s_ in snaps]
+        windows, trips, filts = [], [], []
+        for g in range(G):
+            windows.append(graphs[g:g + L])
+            tg = torch.from_numpy(st["tests"][g]).to(dev)
+            ig = tg[:, [2, 1, 0]].clone()
+            ig[:, 1] += r
+            trips.append(torch.cat((tg, ig)).contiguous())
+            filts.append(utils.filter_csr_from_snapshot(trips[-1], 2 * r, 0))
+        run(what, lambda: evaluate.evaluate_batch(m, windows, trips, filts), steps)
     elif what == "c5":
         # BASELINE configs[4]: 1 M entities, 512 relations, 10 M edges per snapshot, L = 3, hyperbolic_uvrgcn + RotH
         import numpy as np

@@ -56,6 +56,7 @@ SIGNATURES = {
     "regcn_gemm_tf32_layer": (_i, [_p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p, _i, _p, _p, _i, _p]),
     "regcn_pdl_enable": (None, [_i]),
     "regcn_two_stream_enable": (None, [_i]),
+    "regcn_evolve_a32_mode": (None, [_i]),
     "regcn_kernel_launches": (ctypes.c_longlong, []),
     "regcn_aggregate_tune": (None, [_i]),
     "regcn_score_count_tf32": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _i, _i, _p, _p, _p, _d, _p, _p, _i, _p]),

@@ -164,6 +164,7 @@ int regcn_gemm_tf32(const float* a_hi, const float* a_lo, int lda, const float* 
 }
 void regcn_pdl_enable(int on) { regcn::pdl_set(on); }
 void regcn_two_stream_enable(int on) { regcn::two_stream_set(on); }
+void regcn_evolve_a32_mode(int mode) { regcn::evolve_a32_set(mode); }
 long long regcn_kernel_launches(void) { return __atomic_load_n(&regcn::g_kernel_launches, __ATOMIC_RELAXED); }
 void regcn_gemm_tf32_tune(int block_n, int stages) { gemm_tf32_tune(block_n, stages); }
 void regcn_aggregate_tune(int impl) { aggregate_tune(impl); }

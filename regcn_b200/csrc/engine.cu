@@ -96,6 +96,14 @@ static bool side_pdl_keep() {
   if (v < 0) { const char* e = getenv("REGCN_SIDE_PDL"); v = (e && e[0] == '1') ? 1 : 0; }
   return v != 0;
 }
+// fp32-A dataflow for the all-entity GEMMs of the sparse-snapshot form (see regcn_regcn_evolve): on from 64 k entity rows,
+// REGCN_EVOLVE_A32=0 / 1 or regcn_evolve_a32_mode(0 / 1) force it off / on, -1 = by size
+static int g_evolve_a32 = -2;          // -2: read REGCN_EVOLVE_A32 on first use; -1 auto, 0 off, 1 on
+void evolve_a32_set(int mode) { g_evolve_a32 = mode < 0 ? -1 : (mode ? 1 : 0); }
+static bool evolve_a32(int N) {
+  if (g_evolve_a32 == -2) { const char* e = getenv("REGCN_EVOLVE_A32"); g_evolve_a32 = e ? (e[0] == '1' ? 1 : e[0] == '0' ? 0 : -1) : -1; }
+  return g_evolve_a32 >= 0 ? g_evolve_a32 != 0 : N >= 65536;
+}
 static int g_two_stream = -1;
 void two_stream_set(int on) { g_two_stream = on ? 1 : 0; }
 static bool two_stream_enabled() {
@@ -177,6 +185,11 @@ int regcn_regcn_evolve(const void* const* mp, const int* mi, const void* const* 
   int* fold = reinterpret_cast<int*>(ws + w.fold);
   if (max_split > 0 && cudaMemsetAsync(fold, 0, w.fold_n * sizeof(int), st) != cudaSuccess) { cudaGetLastError(); fold = nullptr; }
   if (max_split <= 0) fold = nullptr;
+  // Large tables (a recurrence batched over several history windows, or a big graph): the all-entity GEMMs are
+  // HBM-bound, and two thirds of their bytes are the (hi, lo) copies of activations.  There the entity state stays ONE
+  // fp32 copy and the GEMM's converter warps split it on chip (gemm_tf32_layer_a32): 7 instead of 12 row-sized
+  // transfers per snapshot.  Small tables keep the pre-split operands (the TMA-fed main loop has the lower latency).
+  const bool a32 = evolve_a32(N);
   StreamScope scope(two_stream_enabled() ? aux_stream() : nullptr, st);
   AuxStream* aux = scope.aux;
   bool gh_ahead = false;        // gh of the current snapshot was already enqueued on side stream C
@@ -276,25 +289,42 @@ int regcn_regcn_evolve(const void* const* mp, const int* mi, const void* const* 
                                  GI(RG_VPTR), GI(RG_SPTR), GI(RG_VROW_ROW), gn[RGI_N_VROWS], gn[RGI_N_SPLIT_CHUNKS], nullptr,
                                  0.f, N, d, nullptr, ws + w.partial, ws + w.agg_hi, ws + w.agg_lo, GI(RG_ACTIVE_POS), 2 * d,
                                  gn[RGI_MAX_CHUNKS], sB, fold))) return e;
+        // a32: the inactive rows' input is the fp32 state itself (split on chip), their output one fp32 copy; the split
+        // copies of the entity state are then never read.  The NEXT snapshot decides whether it needs them (it may be a
+        // dense one), so the last layer still writes them unless that snapshot takes this form too.
+        const bool next_a32 = a32 && (i + 1 >= L || (gi_[(size_t)(i + 1) * RGI_NUM_INTS + RGI_N_ACTIVE] * 2 <= N));
         if (!last) {
           if (two) { gemm_tf32_sm_hint(0); pdl_suppress(l > 0); }   // later layers must not park CTAs on the free SMs early
-          e = gemm_tf32_layer(x_hi, x_lo, d, F(base + 6), F(base + 7), d, N, ncol, d, d, nullptr, o_hi, o_lo,
-                              l == 0 ? ws + w.Lm : nullptr, d, nullptr, GI(RG_ACTIVE_POS), nullptr, 0, nullptr, nullptr, 0, st);
+          if (a32)
+            e = gemm_tf32_layer_a32(x_raw, d, d, nullptr, nullptr, 0, 0, nullptr, F(base + 6), F(base + 7), d, N, ncol, d, o_raw,
+                                    nullptr, nullptr, l == 0 ? ws + w.Lm : nullptr, d, nullptr, GI(RG_ACTIVE_POS), nullptr, 0,
+                                    nullptr, nullptr, 0, st);
+          else
+            e = gemm_tf32_layer(x_hi, x_lo, d, F(base + 6), F(base + 7), d, N, ncol, d, d, nullptr, o_hi, o_lo,
+                                l == 0 ? ws + w.Lm : nullptr, d, nullptr, GI(RG_ACTIVE_POS), nullptr, 0, nullptr, nullptr, 0, st);
           pdl_suppress(two && side_pdl_off);
           if (e) return e;
           if (two) gemm_tf32_sm_hint(side_hint(N, d, ncol, sm_count));
           if (n_active > 0 &&
               (e = gemm_tf32_layer(ws + w.agg_hi, ws + w.agg_lo, 2 * d, F(base + 4), F(base + 5), 2 * d, n_active, d, 2 * d, d,
-                                   o_raw, o_hi, o_lo, nullptr, 0, arows, nullptr, nullptr, 0, nullptr, nullptr, 0, sB))) return e;
+                                   o_raw, a32 ? nullptr : o_hi, a32 ? nullptr : o_lo, nullptr, 0, arows, nullptr, nullptr, 0,
+                                   nullptr, nullptr, 0, sB))) return e;
         } else {
           float* h_new = hist + (size_t)i * nd;
+          float* n_hi = next_a32 ? nullptr : ws + w.h_hi;
+          float* n_lo = next_a32 ? nullptr : ws + w.h_lo;
           if (two) gemm_tf32_sm_hint(side_hint(N, d, d, sm_count));
           if (n_active > 0 &&
               (e = gemm_tf32(ws + w.agg_hi, ws + w.agg_lo, 2 * d, F(base + 4), F(base + 5), 2 * d, ws + w.P, d, n_active, d,
                              2 * d, nullptr, 0, 3, 1, nullptr, 0, nullptr, 0, sB))) return e;
           if (two) { gemm_tf32_sm_hint(0); pdl_suppress(true); }
-          e = gemm_tf32_layer(x_hi, x_lo, d, F(base + 6), F(base + 7), d, N, d, d, d, h_new, ws + w.h_hi, ws + w.h_lo,
-                              nullptr, 0, nullptr, GI(RG_ACTIVE_POS), ws + w.Lm, d, F(RM_GATE_BIAS), h_raw, layer_norm, st);
+          if (a32)
+            e = gemm_tf32_layer_a32(x_raw, d, d, nullptr, nullptr, 0, 0, nullptr, F(base + 6), F(base + 7), d, N, d, d, h_new,
+                                    n_hi, n_lo, nullptr, 0, nullptr, GI(RG_ACTIVE_POS), ws + w.Lm, d, F(RM_GATE_BIAS), h_raw,
+                                    layer_norm, st);
+          else
+            e = gemm_tf32_layer(x_hi, x_lo, d, F(base + 6), F(base + 7), d, N, d, d, d, h_new, n_hi, n_lo,
+                                nullptr, 0, nullptr, GI(RG_ACTIVE_POS), ws + w.Lm, d, F(RM_GATE_BIAS), h_raw, layer_norm, st);
           pdl_suppress(false);
           if (e) return e;
           if (two) {                                   // join: the active rows need the gate columns (caller's stream) and P (side stream)
@@ -302,8 +332,8 @@ int regcn_regcn_evolve(const void* const* mp, const int* mi, const void* const* 
             scope.b_open = false;
           }
           if (n_active > 0 &&
-              (e = time_gate(ws + w.Lm, F(RM_GATE_BIAS), ws + w.P, h_raw, h_new, n_active, d, layer_norm, d, ws + w.h_hi,
-                             ws + w.h_lo, st, arows, 1))) return e;
+              (e = time_gate(ws + w.Lm, F(RM_GATE_BIAS), ws + w.P, h_raw, h_new, n_active, d, layer_norm, d, n_hi, n_lo, st,
+                             arows, 1))) return e;
           gate_done = true;
         }
       } else if (sparse) {

@@ -87,13 +87,14 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_c, uint64_t desc_a, uint6
       "}" ::"r"(tmem_c), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc) : "memory");
 }
 // K-major, 128B-swizzled tile: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO), version 1, layout type 2.
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+// sw64: rows of 64 bytes (k-blocks of 16 floats), 8-row groups 512 bytes apart, layout type 4 (SWIZZLE_64B).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, bool sw64 = false) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
   d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major), 16 B
-  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset = 1024 B
+  d |= (uint64_t)((sw64 ? 512 : 1024) >> 4) << 32;   // stride byte offset between 8-row groups
   d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  d |= (uint64_t)(sw64 ? 4 : 2) << 61;       // SWIZZLE_64B / SWIZZLE_128B
   return d;
 }
 // MN-major tf32 tile.  For 32-bit operands tcgen05 accepts exactly one MN-major shared-memory layout: 128-byte rows
@@ -181,7 +182,10 @@ struct Params {
   const float* gate_h;        // [*, lay_d] previous entity state
   int gate_norm;              // F.normalize the layer output first (layer_norm)
   // ---- fp32-A mode: A = [seg0 | seg1] along K, each segment an fp32 row-major matrix, rows optionally gathered ----
-  int a_f32;                  // 1: the tensor maps of A are unused, converter warps build the hi / lo tiles
+  int kblk;                   // fp32 elements per k-block row: 32 (128-byte swizzle rows) or 16 (64-byte rows: twice the
+                              // ring slots in the same shared memory -- 3xTF32 tiles of 208-256 columns get 4 instead of 2)
+  int a_f32;                  // 1: the tensor maps of A are unused, converter warps build the hi / lo tiles;
+                              // 2: TMA delivers the fp32 k-block into the stage and the converter warps split it in place
   const float* a_ptr[2];      // segment base pointers (seg1 NULL when a_k[1] == 0)
   int a_ld[2];                // leading dimensions (floats, multiples of 4)
   int a_k[2];                 // segment lengths along K (multiples of 4); p.K = k-block-padded total
@@ -198,8 +202,17 @@ __device__ __forceinline__ void trace_stamp(const Params& p, int slot) {
   }
 }
 
-// sigmoid on the SFU (ex2.approx + rcp.approx, ~2 ulp): the epilogue warps have no spare issue slots for the IEEE path
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// sigmoid on the SFU (ex2.approx + rcp.approx, ~2 ulp; the epilogue warps have no spare issue slots for the IEEE path),
+// without the denormal / huge-divisor fix-ups __expf / __fdividef wrap around the two operations (8 instructions instead
+// of 14): ex2 flushes to +0 for x > ~87 (sigmoid -> 1) and overflows to +inf for x < ~-88 (rcp(inf) = 0)
+__device__ __forceinline__ float lean_sigmoid(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
+// F.rrelu in eval mode as max(x, slope x) (0 < slope < 1): the same value as the select for every finite x, 2 instructions
+__device__ __forceinline__ float rrelu_max(float x) { return fmaxf(x, x * kRReluSlope); }
 
 __device__ __forceinline__ float finish_score(const Params& p, float dot, int row, int col, float scale, float margin) {
   float v = dot;
@@ -223,6 +236,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[8];
   __shared__ __align__(8) uint64_t empty_bar[8];
+  __shared__ __align__(8) uint64_t raw_bar[8];             // a_f32 == 2: TMA (raw fp32 A + B) -> converter warps
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
@@ -230,23 +244,26 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int block_k = p.bf16 ? 2 * BLOCK_K : BLOCK_K;      // elements per 128-byte k-block row
+  const int block_k = p.bf16 ? 2 * BLOCK_K : p.kblk;       // elements per k-block row (128 bytes; 64 with kblk == 16)
   const int total_kb = (p.K + block_k - 1) / block_k;
   const int tiles_mn = p.m_tiles * p.n_tiles;
   const int total_tiles = tiles_mn * p.splits;
 
   // dynamic smem carve-up (1024-byte aligned tiles): per stage [A_hi][A_lo?][B_hi][B_lo?]
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const uint32_t a_bytes = BLOCK_M * BLOCK_K * 4;
-  const uint32_t b_bytes = (uint32_t)p.block_n * BLOCK_K * 4;
+  const uint32_t a_bytes = BLOCK_M * (uint32_t)p.kblk * 4;
+  const uint32_t b_bytes = (uint32_t)p.block_n * (uint32_t)p.kblk * 4;
   const bool three = p.passes == 3;
   const uint32_t stage_bytes = (three ? 2u : 1u) * (a_bytes + b_bytes);
   const uint32_t smem_base = smem_u32(smem);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), p.a_f32 ? 1 + CVT_WARPS : 1);   // TMA (expect_tx) + one arrival per converter warp
+      // a_f32 == 1: TMA (expect_tx, B only) + one arrival per converter warp;  a_f32 == 2: the converter warps alone (they
+      // pass on what TMA delivered under raw_bar)
+      mbar_init(smem_u32(&full_bar[s]), p.a_f32 == 2 ? CVT_WARPS : p.a_f32 ? 1 + CVT_WARPS : 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
+      mbar_init(smem_u32(&raw_bar[s]), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&tmem_full_bar[a]), 1);
@@ -270,8 +287,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
   auto decode = [&](int t, int& m0, int& n0, int& kb_beg, int& kb_end) {
     const int z = t / tiles_mn;
     const int r = t - z * tiles_mn;
-    const int nt = r / p.m_tiles;
-    const int mt = r - nt * p.m_tiles;
+    // the dimension with fewer tiles runs fastest: CTAs working at the same time then share the other operand's tile in L2
+    // (many m-tiles x 2 n-tiles: the A tile, fetched from HBM once; few query tiles x many candidate tiles: the B tile)
+    const bool n_fast = p.n_tiles < p.m_tiles;
+    const int nt = n_fast ? r % p.n_tiles : r / p.m_tiles;
+    const int mt = n_fast ? r / p.n_tiles : r - nt * p.m_tiles;
     m0 = mt * BLOCK_M;
     n0 = EPI == 2 ? m0 : nt * p.block_n;   // pair scores: diagonal tiles only
     kb_beg = z * p.kb_per_split;
@@ -290,12 +310,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         if (pit < 4) trace_stamp(p, 2 + pit);          // producer starts issuing tile pit
         for (int kb = kb_beg; kb < kb_end; ++kb) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-          const uint32_t fb = smem_u32(&full_bar[stage]);
-          mbar_expect_tx(fb, p.a_f32 ? (three ? 2u : 1u) * b_bytes : stage_bytes);
+          const bool raw_a = p.a_f32 == 2;
+          const uint32_t fb = smem_u32(raw_a ? &raw_bar[stage] : &full_bar[stage]);
+          mbar_expect_tx(fb, raw_a ? a_bytes + (three ? 2u : 1u) * b_bytes : p.a_f32 ? (three ? 2u : 1u) * b_bytes : stage_bytes);
           uint32_t dst = smem_base + stage * stage_bytes;
           // fp32-A mode with two K segments: k-blocks never straddle a segment, so the weight columns of segment 1
           // start at a_k[0] (the zero-filled A tail of segment 0 cancels the columns its last k-block overlaps)
-          const int k0 = (p.a_f32 && kb >= p.a_kb0) ? p.a_k[0] + (kb - p.a_kb0) * BLOCK_K : kb * block_k;
+          const int k0 = (p.a_f32 == 1 && kb >= p.a_kb0) ? p.a_k[0] + (kb - p.a_kb0) * BLOCK_K : kb * block_k;
           // K-major operand: one box of 32 k-floats x rows; MN-major operand: boxes of 32 MN-elements x 32 reduction
           // rows, 4096 bytes each (inner coordinate = MN offset)
           auto load_op = [&](const CUtensorMap* tm, int mn, int r0, int nrows, uint32_t bytes) {
@@ -303,7 +324,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
             else tma_load_2d(dst, tm, fb, k0, r0);
             dst += bytes;
           };
-          if (p.a_f32) dst += (three ? 2u : 1u) * a_bytes;        // the converter warps fill the A half of the stage
+          if (raw_a) {                                            // the fp32 tile lands where its hi part will be
+            tma_load_2d(dst, &tm_a_hi, fb, k0, m0);
+            dst += (three ? 2u : 1u) * a_bytes;
+          } else if (p.a_f32) dst += (three ? 2u : 1u) * a_bytes;  // the converter warps fill the A half of the stage
           else {
             load_op(&tm_a_hi, p.a_mn, m0, BLOCK_M, a_bytes);
             if (three) load_op(&tm_a_lo, p.a_mn, m0, BLOCK_M, a_bytes);
@@ -359,18 +383,21 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
               umma_tf32(tmem_acc, da(sa_hi), db(sb_hi), idesc, acc);
               acc = 1;
             }
-          } else
+          } else {
+            const bool sw64 = p.kblk == 16;
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint32_t koff = k * UMMA_K * 4;   // bytes inside the 128-byte swizzle row
-            if (three) {
-              umma_tf32(tmem_acc, make_desc(sa_lo + koff), make_desc(sb_hi + koff), idesc, acc);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              if (k * UMMA_K >= p.kblk) break;        // 64-byte rows hold two K steps
+              const uint32_t koff = k * UMMA_K * 4;   // bytes inside the swizzle row
+              if (three) {
+                umma_tf32(tmem_acc, make_desc(sa_lo + koff, sw64), make_desc(sb_hi + koff, sw64), idesc, acc);
+                acc = 1;
+                umma_tf32(tmem_acc, make_desc(sa_hi + koff, sw64), make_desc(sb_lo + koff, sw64), idesc, acc);
+              }
+              if (p.bf16) umma_f16(tmem_acc, make_desc(sa_hi + koff), make_desc(sb_hi + koff), idesc, acc);   // 16 bf16 = 32 bytes per step
+              else umma_tf32(tmem_acc, make_desc(sa_hi + koff, sw64), make_desc(sb_hi + koff, sw64), idesc, acc);
               acc = 1;
-              umma_tf32(tmem_acc, make_desc(sa_hi + koff), make_desc(sb_lo + koff), idesc, acc);
             }
-            if (p.bf16) umma_f16(tmem_acc, make_desc(sa_hi + koff), make_desc(sb_hi + koff), idesc, acc);   // 16 bf16 = 32 bytes per step
-            else umma_tf32(tmem_acc, make_desc(sa_hi + koff), make_desc(sb_hi + koff), idesc, acc);
-            acc = 1;
           }
           umma_commit(smem_u32(&empty_bar[stage]));      // frees the smem slot once these MMAs retire
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -386,7 +413,49 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     // registers BEFORE the warp waits for the stage of k-block kb to drain: a stage turns around in the time of the
     // split + 32 shared-memory stores, not in a global-memory round trip.  hi = rna_tf32(x) and lo = rna_tf32(x - hi) go
     // to the swizzled places TMA would have written them to; fence.proxy.async publishes them to the tensor core.
-    if (p.a_f32) {
+    if (p.a_f32 == 2) {
+      // Raw-tile form (one K segment, rows not gathered): TMA has put the fp32 k-block where the hi tile belongs, in the
+      // swizzled layout the tensor core reads.  The split is elementwise, so the layout does not matter here: every
+      // thread rewrites its 16-byte chunks in place (hi) and writes the same offsets of the lo tile.  The loads are TMA's
+      // (a whole stage in flight, like the pre-split operands) -- the register-staged form below keeps only 16 KB per SM
+      // in flight, which is latency-bound once the fp32 rows come from HBM.
+      const int tid = (warp - 2) * 32 + lane;
+      constexpr int GRP = 8;                                  // 16-byte chunks a thread holds at a time
+      const int groups = (int)(a_bytes / 16) / (32 * CVT_WARPS * GRP);          // 2 (k-blocks of 32 floats) or 1 (16)
+      int stage_c = 0;
+      uint32_t phase_c = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int m0, n0, kb_beg, kb_end;
+        decode(t, m0, n0, kb_beg, kb_end);
+        for (int kb = kb_beg; kb < kb_end; ++kb) {
+          mbar_wait(smem_u32(&raw_bar[stage_c]), phase_c);
+          const uint32_t base = smem_base + stage_c * stage_bytes + tid * 16;
+          for (int half = 0; half < groups; ++half) {
+            float4 v[GRP];
+#pragma unroll
+            for (int j = 0; j < GRP; ++j) {
+              const uint32_t a = base + (half * GRP + j) * (32 * CVT_WARPS * 16);
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[j].x), "=f"(v[j].y), "=f"(v[j].z), "=f"(v[j].w) : "r"(a) : "memory");
+            }
+#pragma unroll
+            for (int j = 0; j < GRP; ++j) {
+              const uint32_t a = base + (half * GRP + j) * (32 * CVT_WARPS * 16);
+              float4 h, l;
+              h.x = rna_tf32(v[j].x); h.y = rna_tf32(v[j].y); h.z = rna_tf32(v[j].z); h.w = rna_tf32(v[j].w);
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+              if (three) {
+                l.x = rna_tf32(v[j].x - h.x); l.y = rna_tf32(v[j].y - h.y); l.z = rna_tf32(v[j].z - h.z); l.w = rna_tf32(v[j].w - h.w);
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a + a_bytes), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
+              }
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_bar[stage_c])) : "memory");
+          if (++stage_c == p.stages) { stage_c = 0; phase_c ^= 1; }
+        }
+      }
+    } else if (p.a_f32) {
       const int cw = warp - 2;
       const int c16 = lane & 7, rsub = lane >> 3;
       constexpr int RPL = BLOCK_M / CVT_WARPS / 4;        // rows per lane (16)
@@ -461,7 +530,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     constexpr int kParts = EPI_WARPS / 4;
     float* stage = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes) + (warp - EPI_WARP0) * (32 * kStagePitch);
     float scale = 1.f, margin = 0.f;
-    if (EPI != 0 && EPI != 3 && p.hyp) { scale = __ldg(p.scale_margin); margin = __ldg(p.scale_margin + 1); }
+    if (EPI != 0 && EPI != 3 && EPI != 5 && p.hyp) { scale = __ldg(p.scale_margin); margin = __ldg(p.scale_margin + 1); }
     int it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       int m0, n0, kb_beg, kb_end;
@@ -679,28 +748,89 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         }
         if (rv && cnt) atomicAdd(p.raw_count + row, cnt);
       } else if constexpr (EPI == 3) {
-        // Fused layer epilogue, same transposed staging as the store epilogue: per-row quantities (output row, skip
-        // flag, row norm) are computed by the thread that owns the row in TMEM and fetched by shuffle afterwards.
+        // Fused layer epilogue, same transposed staging as the store epilogue: columns < lay_d are layer outputs
+        // rrelu(acc) written as fp32 and / or TF32 split (rows optionally scattered through row_idx, rows owned by the
+        // compact GEMM skipped), columns >= lay_d are stored unchanged to C (gate pre-activations).  Per-row quantities
+        // are computed by the thread that owns the row in TMEM and fetched by shuffle.  (The time-gate form is EPI 5.)
         const bool rv = row < p.M;
         int my_orow = rv ? row : 0;
         int my_skip = rv ? 0 : 1;
         if (rv && p.row_idx) my_orow = __ldg(p.row_idx + row);
         if (rv && p.skip_rows && __ldg(p.skip_rows + row) >= 0) my_skip = 1;
+        const int sub_r = lane >> 3, sub_q = lane & 7, sub_c = sub_q * 4;
+        {
+          // No gate: nothing is read from global memory, and the per-row facts of the 8 rows a lane serves in the
+          // transposed layout (output row, write flags) are fetched once per tile instead of once per 32-column chunk.
+          const unsigned rows_in = __ballot_sync(0xffffffffu, rv) >> sub_r;              // bit 4 i: row 4 i + sub_r < M
+          const unsigned rows_out = __ballot_sync(0xffffffffu, !my_skip) >> sub_r;       // ... and not left to the compact GEMM
+          int orow8[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) orow8[i] = __shfl_sync(0xffffffffu, my_orow, 4 * i + sub_r);
+          for (int c0 = 32 * part; c0 < p.block_n; c0 += 32 * kParts) {
+            float v[32];
+            tmem_ld32(tmem_acc + (uint32_t)c0, v);
+            const int gn0 = n0 + c0;
+            const int ncols = min(32, min(p.block_n - c0, p.N - gn0));
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<float4*>(stage + stage_off(lane, q)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            __syncwarp();
+            const int col = gn0 + sub_c;
+            if (sub_c < ncols) {                               // N and lay_d are multiples of 4: whole float4 or nothing
+              if (col < p.lay_d) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  if ((rows_out >> (4 * i)) & 1u) {
+                    float4 a = *reinterpret_cast<const float4*>(stage + stage_off(4 * i + sub_r, sub_q));
+                    a.x = rrelu_max(a.x); a.y = rrelu_max(a.y); a.z = rrelu_max(a.z); a.w = rrelu_max(a.w);
+                    const size_t o = (size_t)orow8[i] * p.lay_d + col;
+                    if (p.lay_raw) st4(p.lay_raw + o, a);
+                    if (p.lay_hi) {
+                      float4 h, l;
+                      split_tf32_1(a.x, h.x, l.x); split_tf32_1(a.y, h.y, l.y);
+                      split_tf32_1(a.z, h.z, l.z); split_tf32_1(a.w, h.w, l.w);
+                      st4(p.lay_hi + o, h);
+                      st4(p.lay_lo + o, l);
+                    }
+                  }
+                }
+              } else {
+                const int cc = col - p.lay_d;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  if ((rows_in >> (4 * i)) & 1u)
+                    st4(p.C + (size_t)orow8[i] * p.ldc + cc, *reinterpret_cast<const float4*>(stage + stage_off(4 * i + sub_r, sub_q)));
+                }
+              }
+            }
+            __syncwarp();
+          }
+        }
+      } else if constexpr (EPI == 5) {
+        // Time-gate epilogue of a snapshot's last layer, specialised (gemm_tf32_layer picks it when the tile spans the
+        // whole row and all three outputs exist):  h' = h + s (normalize(rrelu(acc)) - h),  s = sigmoid(G + b)
+        // (src/rrgcn.py:176-178 with the UnionRGCNLayer activation, rgcn/layers.py:253-255), written as fp32 + TF32 split.
+        // Same staging as the general layer epilogue; what is different is the instruction count: the per-row facts
+        // (output row, 1/norm, write flag) of the 8 rows a lane serves in the transposed layout are fetched once per
+        // tile, not per 32-column chunk, the sigmoid is two bare SFU operations, the blend one subtract and one FMA.
+        const bool rv = row < p.M;
+        int my_orow = rv ? row : 0;
+        bool my_wr = rv;
+        if (rv && p.row_idx) my_orow = __ldg(p.row_idx + row);
+        if (rv && p.skip_rows && __ldg(p.skip_rows + row) >= 0) my_wr = false;
         float my_nrm = 1.f;
-        const bool gate = p.gate_G != nullptr;
-        if (gate && p.gate_norm) {
-          // pass 1 over the accumulator: |rrelu(acc)|^2 of the whole row (the tile spans all lay_d columns).  The two
-          // warps of a TMEM lane quarter each sum their own 32-column chunks and swap the partial sums through shared
-          // memory (named barrier of the pair, a second one frees the slots); both add them in the same order.
+        if (p.gate_norm) {
           float ss = 0.f;
           for (int c0 = 32 * part; c0 < p.block_n; c0 += 32 * kParts) {
             float v[32];
             tmem_ld32(tmem_acc + (uint32_t)c0, v);
-            const int ncols = min(32, p.lay_d - c0);
+            const int ncols = p.lay_d - c0;
+            if (ncols >= 32) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float r = rreluf_(v[j]);
-              ss = j < ncols ? fmaf(r, r, ss) : ss;
+              for (int j = 0; j < 32; ++j) { const float r = rrelu_max(v[j]); ss = fmaf(r, r, ss); }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) { const float r = rrelu_max(v[j]); ss = j < ncols ? fmaf(r, r, ss) : ss; }
             }
           }
           float* slot = &norm_xchg[0][0];
@@ -713,68 +843,54 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
           my_nrm = 1.0f / fmaxf(sqrtf(tot), 1e-12f);    // F.normalize: x / max(|x|, 1e-12), applied as a multiply
         }
         const int sub_r = lane >> 3, sub_q = lane & 7, sub_c = sub_q * 4;
+        const unsigned wr_all = __ballot_sync(0xffffffffu, my_wr);
+        int orow8[8];
+        float nrm8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          orow8[i] = __shfl_sync(0xffffffffu, my_orow, 4 * i + sub_r);
+          nrm8[i] = __shfl_sync(0xffffffffu, my_nrm, 4 * i + sub_r);
+        }
+        const unsigned wr8 = wr_all >> sub_r;               // bit 4 i: row 4 i + sub_r is written
+        const int ld_h = p.lay_d, ld_g = p.gate_ld;
         for (int c0 = 32 * part; c0 < p.block_n; c0 += 32 * kParts) {
           float v[32];
           tmem_ld32(tmem_acc + (uint32_t)c0, v);
-          const int gn0 = n0 + c0;
-          const int ncols = min(32, min(p.block_n - c0, p.N - gn0));
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             *reinterpret_cast<float4*>(stage + stage_off(lane, q)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
           __syncwarp();
-          const int col = gn0 + sub_c;
-          const bool cvalid = sub_c < ncols;                 // N and lay_d are multiples of 4: whole float4 or nothing
-          const bool is_out = col < p.lay_d;
-          // batch every global load of the chunk first (16 independent float4 loads in flight per thread), then compute
-          float4 g4[8], h4[8];
-          int orow_[8];
-          float nrm_[8];
-          bool wr_[8];
+          const int col = c0 + sub_c;
+          if (col < ld_h) {                                  // lay_d is a multiple of 4: a whole float4 or nothing
+            const float4 b4 = ldg4(p.gate_bias + col);
+            float4 g4[8], h4[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = 4 * i + sub_r;
-            const int orow = __shfl_sync(0xffffffffu, my_orow, r);
-            const int skip = __shfl_sync(0xffffffffu, my_skip, r);
-            nrm_[i] = __shfl_sync(0xffffffffu, my_nrm, r);
-            const bool rowv = (m0 + quarter * 32 + r) < p.M;
-            orow_[i] = orow;
-            // skip_rows only masks the layer-output columns: the gate pre-activations are needed for every row
-            wr_[i] = rowv && cvalid && (is_out ? !skip : true);
-            if (gate && wr_[i] && is_out) {
-              g4[i] = *reinterpret_cast<const float4*>(p.gate_G + (size_t)orow * p.gate_ld + col);
-              h4[i] = *reinterpret_cast<const float4*>(p.gate_h + (size_t)orow * p.lay_d + col);
+            for (int i = 0; i < 8; ++i) {
+              if ((wr8 >> (4 * i)) & 1u) {
+                g4[i] = *reinterpret_cast<const float4*>(p.gate_G + (size_t)orow8[i] * ld_g + col);
+                h4[i] = *reinterpret_cast<const float4*>(p.gate_h + (size_t)orow8[i] * ld_h + col);
+              }
             }
-          }
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (gate && cvalid && is_out) b4 = ldg4(p.gate_bias + col);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (!wr_[i]) continue;
-            const int r = 4 * i + sub_r;
-            float4 a = *reinterpret_cast<const float4*>(stage + stage_off(r, sub_q));
-            if (is_out) {
-              a.x = rreluf_(a.x); a.y = rreluf_(a.y); a.z = rreluf_(a.z); a.w = rreluf_(a.w);
-              const size_t o = (size_t)orow_[i] * p.lay_d + col;
-              if (gate) {
-                if (p.gate_norm) {
-                  const float nrm = nrm_[i];
-                  a.x = a.x * nrm; a.y = a.y * nrm; a.z = a.z * nrm; a.w = a.w * nrm;
+            for (int i = 0; i < 8; ++i) {
+              if ((wr8 >> (4 * i)) & 1u) {
+                float4 a = *reinterpret_cast<const float4*>(stage + stage_off(4 * i + sub_r, sub_q));
+                const float nrm = nrm8[i];
+                a.x = rrelu_max(a.x) * nrm; a.y = rrelu_max(a.y) * nrm; a.z = rrelu_max(a.z) * nrm; a.w = rrelu_max(a.w) * nrm;
+                const float sx = lean_sigmoid(g4[i].x + b4.x), sy = lean_sigmoid(g4[i].y + b4.y);
+                const float sz = lean_sigmoid(g4[i].z + b4.z), sw = lean_sigmoid(g4[i].w + b4.w);
+                a.x = fmaf(sx, a.x - h4[i].x, h4[i].x); a.y = fmaf(sy, a.y - h4[i].y, h4[i].y);
+                a.z = fmaf(sz, a.z - h4[i].z, h4[i].z); a.w = fmaf(sw, a.w - h4[i].w, h4[i].w);
+                const size_t o = (size_t)orow8[i] * ld_h + col;
+                st4(p.lay_raw + o, a);
+                if (p.lay_hi) {                              // uniform: the fp32-A consumers need no split copy
+                  float4 h, l;
+                  split_tf32_1(a.x, h.x, l.x); split_tf32_1(a.y, h.y, l.y);
+                  split_tf32_1(a.z, h.z, l.z); split_tf32_1(a.w, h.w, l.w);
+                  st4(p.lay_hi + o, h);
+                  st4(p.lay_lo + o, l);
                 }
-                const float sx = fast_sigmoid(g4[i].x + b4.x), sy = fast_sigmoid(g4[i].y + b4.y);
-                const float sz = fast_sigmoid(g4[i].z + b4.z), sw = fast_sigmoid(g4[i].w + b4.w);
-                a.x = sx * a.x + (1.0f - sx) * h4[i].x; a.y = sy * a.y + (1.0f - sy) * h4[i].y;
-                a.z = sz * a.z + (1.0f - sz) * h4[i].z; a.w = sw * a.w + (1.0f - sw) * h4[i].w;
               }
-              if (p.lay_raw) st4(p.lay_raw + o, a);
-              if (p.lay_hi) {
-                float4 h, l;
-                split_tf32_1(a.x, h.x, l.x); split_tf32_1(a.y, h.y, l.y);
-                split_tf32_1(a.z, h.z, l.z); split_tf32_1(a.w, h.w, l.w);
-                st4(p.lay_hi + o, h);
-                st4(p.lay_lo + o, l);
-              }
-            } else {
-              st4(p.C + (size_t)orow_[i] * p.ldc + (col - p.lay_d), a);
             }
           }
           __syncwarp();
@@ -896,15 +1012,16 @@ static EncodeTiledFn get_encode() {
 
 // 2-D fp32 row-major [rows, cols] with leading dimension ld; box = 32 floats x box_rows, 128B swizzle, zero OOB fill.
 static int make_map(CUtensorMap* m, const void* ptr, int rows, int cols, int ld, int box_rows, bool bf16 = false,
-                    bool atom32 = false) {
+                    bool atom32 = false, int kblk = BLOCK_K) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_last_error("gemm_tf32: cuTensorMapEncodeTiled entry point unavailable"); return REGCN_ERR_UNSUPPORTED; }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * (bf16 ? 2 : 4)};
-  cuuint32_t box[2] = {(cuuint32_t)(bf16 ? 2 * BLOCK_K : BLOCK_K), (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)(bf16 ? 2 * BLOCK_K : kblk), (cuuint32_t)box_rows};   // kblk 16: 64-byte rows
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : (!bf16 && kblk == 16) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_last_error("gemm_tf32: cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%d", (int)r, rows, cols, ld); return REGCN_ERR_DIM; }
@@ -935,6 +1052,10 @@ int to_bf16(const float* x, void* out, size_t n, cudaStream_t st) {
 }
 
 static int g_force_block_n = 0, g_force_stages = 0;
+// REGCN_A32_TMA=0: fp32-A tiles always through the register-staged converter (A/B switch for profiles/)
+// REGCN_GEMM_KBLK16=0: k-blocks of 32 floats everywhere (A/B switch)
+static const bool g_kblk16 = [] { const char* e = getenv("REGCN_GEMM_KBLK16"); return !(e && e[0] == '0'); }();
+static const bool g_a32_tma = [] { const char* e = getenv("REGCN_A32_TMA"); return !(e && e[0] == '0'); }();
 static int g_hyp_poly = 1;      // 0: the counting epilogue evaluates the IEEE score of every candidate (yardstick / tests)
 void score_count_poly(int on) { g_hyp_poly = on ? 1 : 0; }
 void gemm_tf32_tune(int block_n, int stages) { g_force_block_n = block_n; g_force_stages = stages; }
@@ -1026,6 +1147,7 @@ static void clear_epi(tc::Params& p) {
   p.lay_d = 0; p.lay_raw = nullptr; p.lay_hi = nullptr; p.lay_lo = nullptr; p.row_idx = nullptr; p.skip_rows = nullptr;
   p.gate_G = nullptr; p.gate_ld = 0; p.gate_bias = nullptr; p.gate_h = nullptr; p.gate_norm = 0;
   p.bf16 = 0; p.a_mn = 0; p.b_mn = 0;
+  p.kblk = tc::BLOCK_K;
   p.a_f32 = 0; p.a_ptr[0] = p.a_ptr[1] = nullptr; p.a_ld[0] = p.a_ld[1] = 0; p.a_k[0] = p.a_k[1] = 0;
   p.a_rows[0] = p.a_rows[1] = nullptr; p.a_kb0 = 0;
   p.trace = nullptr;
@@ -1055,10 +1177,26 @@ static int launch_tc(const float* a_hi, const float* a_lo, int lda, const float*
   if (p.a_f32) {
     if (p.a_k[0] + p.a_k[1] != Ktrue) { set_last_error("%s: fp32 A segments %d + %d != K = %d", who, p.a_k[0], p.a_k[1], Ktrue); return REGCN_ERR_DIM; }
     if (p.bf16 || p.a_mn || p.b_mn) { set_last_error("%s: fp32 A takes K-major tf32 operands", who); return REGCN_ERR_UNSUPPORTED; }
-    p.K = BLOCK_K * (p.a_kb0 + (p.a_k[1] + BLOCK_K - 1) / BLOCK_K);
+    // one K segment, rows in place: TMA delivers the fp32 k-blocks, the converter warps split them inside the stage
+    if (g_a32_tma && p.a_k[1] == 0 && !p.a_rows[0] && !(p.a_ld[0] & 3) && !((uintptr_t)p.a_ptr[0] & 15) && p.a_ld[0] >= p.a_k[0]) p.a_f32 = 2;
     a_hi = a_lo = b_hi;                  // placeholders for the checks / unused tensor maps below
     lda = ldb;
   }
+  // tile width first: it decides how many ring slots fit, and with it the k-block width
+  p.block_n = force_block_n > 0 ? force_block_n : pick_block_n(M, N, Ktrue, split_k);
+  if (p.b_mn) {                                         // MN-major B tiles are whole 32-element atoms
+    const int nt = (N + 255) / 256;
+    p.block_n = ((N + nt - 1) / nt + 31) / 32 * 32;
+  }
+  p.kblk = BLOCK_K;
+  {
+    const uint32_t stage32 = (passes == 3 ? 2u : 1u) * (BLOCK_M * BLOCK_K * 4 + (uint32_t)p.block_n * BLOCK_K * 4);
+    // k-blocks of 16 floats (64-byte swizzle rows) when fewer than four 128-byte-row stages fit: the ring is what hides the
+    // L2 / HBM latency of the operand stream, and two slots of 86 KB do not (8.5 us per 128 x 208 tile against 4.6 us of MMA)
+    if (g_kblk16 && !p.bf16 && !p.a_mn && !p.b_mn && p.a_f32 != 1 && split_k <= 1 && SMEM_BUDGET / stage32 < 4) p.kblk = 16;
+  }
+  if (p.a_f32 == 2) p.K = (Ktrue + p.kblk - 1) / p.kblk * p.kblk;
+  else if (p.a_f32) p.K = BLOCK_K * (p.a_kb0 + (p.a_k[1] + BLOCK_K - 1) / BLOCK_K);
   const int K = p.K;
   if (!a_hi || !b_hi || (passes == 3 && (!a_lo || !b_lo))) { set_last_error("%s: null operand", who); return REGCN_ERR_NULL; }
   if (passes != 1 && passes != 3) { set_last_error("%s: passes must be 1 or 3", who); return REGCN_ERR_DIM; }
@@ -1071,18 +1209,13 @@ static int launch_tc(const float* a_hi, const float* a_lo, int lda, const float*
   }
   if (M == 0) return REGCN_OK;
   p.passes = passes;
-  p.block_n = force_block_n > 0 ? force_block_n : pick_block_n(M, N, K, split_k);
   if (p.a_mn || p.b_mn) {
     if (p.bf16 || p.epi != 0) { set_last_error("%s: MN-major operands take fp32 data and the store epilogue", who); return REGCN_ERR_UNSUPPORTED; }
   }
-  if (p.b_mn) {                                         // MN-major B tiles are whole 32-element atoms
-    const int nt = (N + 255) / 256;
-    p.block_n = ((N + nt - 1) / nt + 31) / 32 * 32;
-  }
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * p.block_n) p.tmem_cols <<= 1;     // two accumulator slots
-  const uint32_t stage_bytes = (passes == 3 ? 2u : 1u) * (BLOCK_M * BLOCK_K * 4 + (uint32_t)p.block_n * BLOCK_K * 4);
-  const int block_k = p.bf16 ? 2 * BLOCK_K : BLOCK_K;
+  const uint32_t stage_bytes = (passes == 3 ? 2u : 1u) * (BLOCK_M * (uint32_t)p.kblk * 4 + (uint32_t)p.block_n * (uint32_t)p.kblk * 4);
+  const int block_k = p.bf16 ? 2 * BLOCK_K : p.kblk;
   const int total_kb = (K + block_k - 1) / block_k;
   if (split_k < 1) split_k = 1;
   if (split_k > total_kb) split_k = total_kb;
@@ -1095,13 +1228,15 @@ static int launch_tc(const float* a_hi, const float* a_lo, int lda, const float*
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   int e;
   // K-major operand (rows, K): box of 32 k-floats x tile rows; MN-major operand (K, rows): boxes of 32 columns x 32 rows
-  if ((e = p.b_mn ? make_map(&tb_hi, b_hi, K, N, ldb, BLOCK_K, false, true) : make_map(&tb_hi, b_hi, N, Ktrue, ldb, p.block_n, p.bf16 != 0))) return e;
-  if (p.a_f32) ta_hi = tb_hi;           // never dereferenced: the converter warps build the A tiles
-  else if ((e = p.a_mn ? make_map(&ta_hi, a_hi, K, M, lda, BLOCK_K, false, true) : make_map(&ta_hi, a_hi, M, K, lda, BLOCK_M, p.bf16 != 0))) return e;
+  if ((e = p.b_mn ? make_map(&tb_hi, b_hi, K, N, ldb, BLOCK_K, false, true) : make_map(&tb_hi, b_hi, N, Ktrue, ldb, p.block_n, p.bf16 != 0, false, p.kblk))) return e;
+  if (p.a_f32 == 2) {
+    if ((e = make_map(&ta_hi, p.a_ptr[0], M, p.a_k[0], p.a_ld[0], BLOCK_M, false, false, p.kblk))) return e;
+  } else if (p.a_f32) ta_hi = tb_hi;    // never dereferenced: the converter warps build the A tiles
+  else if ((e = p.a_mn ? make_map(&ta_hi, a_hi, K, M, lda, BLOCK_K, false, true) : make_map(&ta_hi, a_hi, M, K, lda, BLOCK_M, p.bf16 != 0, false, p.kblk))) return e;
   if (passes == 3) {
     if (p.a_f32) ta_lo = tb_hi;
-    else if ((e = p.a_mn ? make_map(&ta_lo, a_lo, K, M, lda, BLOCK_K, false, true) : make_map(&ta_lo, a_lo, M, K, lda, BLOCK_M))) return e;
-    if ((e = p.b_mn ? make_map(&tb_lo, b_lo, K, N, ldb, BLOCK_K, false, true) : make_map(&tb_lo, b_lo, N, Ktrue, ldb, p.block_n))) return e;
+    else if ((e = p.a_mn ? make_map(&ta_lo, a_lo, K, M, lda, BLOCK_K, false, true) : make_map(&ta_lo, a_lo, M, K, lda, BLOCK_M, false, false, p.kblk))) return e;
+    if ((e = p.b_mn ? make_map(&tb_lo, b_lo, K, N, ldb, BLOCK_K, false, true) : make_map(&tb_lo, b_lo, N, Ktrue, ldb, p.block_n, false, false, p.kblk))) return e;
   } else {
     ta_lo = ta_hi; tb_lo = tb_hi;
   }
@@ -1114,6 +1249,7 @@ static int launch_tc(const float* a_hi, const float* a_lo, int lda, const float*
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(gemm_tf32_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(gemm_tf32_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(gemm_tf32_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(gemm_tf32_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     if (ce != cudaSuccess) { set_last_error("%s: cudaFuncSetAttribute failed: %s", who, cudaGetErrorString(ce)); return (int)ce; }
     attr_set = true;
   }
@@ -1152,6 +1288,7 @@ static int launch_tc(const float* a_hi, const float* a_lo, int lda, const float*
     case 1: launch_k(gemm_tf32_kernel<1>, grid, NUM_THREADS, smem, st, ta_hi, ta_lo, tb_hi, tb_lo, p); break;
     case 2: launch_k(gemm_tf32_kernel<2>, grid, NUM_THREADS, smem, st, ta_hi, ta_lo, tb_hi, tb_lo, p); break;
     case 3: launch_k(gemm_tf32_kernel<3>, grid, NUM_THREADS, smem, st, ta_hi, ta_lo, tb_hi, tb_lo, p); break;
+    case 5: launch_k(gemm_tf32_kernel<5>, grid, NUM_THREADS, smem, st, ta_hi, ta_lo, tb_hi, tb_lo, p); break;
     default: launch_k(gemm_tf32_kernel<4>, grid, NUM_THREADS, smem, st, ta_hi, ta_lo, tb_hi, tb_lo, p); break;
   }
   prof_end(PROF_GEMM_TC, alg_flops, st);
@@ -1227,8 +1364,8 @@ int gemm_tf32_layer(const float* a_hi, const float* a_lo, int lda, const float* 
   if (d <= 0 || (d & 3) || (N & 3) || N < d || (N > d && (!gate_out || ld_gate_out < N - d || (ld_gate_out & 3)))) {
     set_last_error("gemm_tf32_layer: bad dims N=%d d=%d", N, d); return REGCN_ERR_DIM;
   }
-  if (gate_G && (N != d || d > 256 || !gate_bias || !gate_h || (gate_ld & 3))) {
-    set_last_error("gemm_tf32_layer: the fused time gate needs N == d <= 256"); return REGCN_ERR_DIM;
+  if (gate_G && (N != d || d > 256 || !gate_bias || !gate_h || (gate_ld & 3) || !out_raw)) {
+    set_last_error("gemm_tf32_layer: the fused time gate needs N == d <= 256 and an fp32 output"); return REGCN_ERR_DIM;
   }
   tc::Params p;
   clear_epi(p);
@@ -1236,6 +1373,7 @@ int gemm_tf32_layer(const float* a_hi, const float* a_lo, int lda, const float* 
   p.C = gate_out; p.ldc = ld_gate_out; p.row_idx = row_idx; p.skip_rows = skip_rows;
   p.gate_G = gate_G; p.gate_ld = gate_ld; p.gate_bias = gate_bias; p.gate_h = gate_h; p.gate_norm = gate_norm;
   const int force_bn = gate_G ? (d + 15) / 16 * 16 : 0;      // one tile must span the whole row for the norm
+  if (gate_G) p.epi = 5;                                     // the time-gate epilogue
   int e = launch_tc(a_hi, a_lo, lda, b_hi, b_lo, ldb, p, 3, 1, force_bn, "gemm_tf32_layer", st);
   if (e) return e;
   return check_launch("gemm_tf32_layer");
@@ -1284,8 +1422,8 @@ int gemm_tf32_layer_a32(const float* a0, int lda0, int k0, const int* rows0, con
   if (d <= 0 || (d & 3) || (N & 3) || N < d || (N > d && (!gate_out || ld_gate_out < N - d || (ld_gate_out & 3)))) {
     set_last_error("gemm_tf32_layer_a32: bad dims N=%d d=%d", N, d); return REGCN_ERR_DIM;
   }
-  if (gate_G && (N != d || d > 256 || !gate_bias || !gate_h || (gate_ld & 3))) {
-    set_last_error("gemm_tf32_layer_a32: the fused time gate needs N == d <= 256"); return REGCN_ERR_DIM;
+  if (gate_G && (N != d || d > 256 || !gate_bias || !gate_h || (gate_ld & 3) || !out_raw)) {
+    set_last_error("gemm_tf32_layer_a32: the fused time gate needs N == d <= 256 and an fp32 output"); return REGCN_ERR_DIM;
   }
   tc::Params p;
   clear_epi(p);
@@ -1295,6 +1433,7 @@ int gemm_tf32_layer_a32(const float* a0, int lda0, int k0, const int* rows0, con
   p.C = gate_out; p.ldc = ld_gate_out; p.row_idx = row_idx; p.skip_rows = skip_rows;
   p.gate_G = gate_G; p.gate_ld = gate_ld; p.gate_bias = gate_bias; p.gate_h = gate_h; p.gate_norm = gate_norm;
   const int force_bn = gate_G ? (d + 15) / 16 * 16 : 0;
+  if (gate_G) p.epi = 5;
   e = launch_tc(nullptr, nullptr, 0, b_hi, b_lo, ldb, p, 3, 1, force_bn, "gemm_tf32_layer_a32", st);
   if (e) return e;
   return check_launch("gemm_tf32_layer_a32");

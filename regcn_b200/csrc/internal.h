@@ -51,6 +51,7 @@ int gemm_tf32_layer_a32(const float* a0, int lda0, int k0, const int* rows0, con
                         int gate_norm, cudaStream_t st);
 void pdl_set(int on);
 void two_stream_set(int on);
+void evolve_a32_set(int mode);
 void gemm_tf32_tune(int block_n, int stages);
 void gemm_tf32_trace(void* dev_buf);
 void gemm_tf32_trace_begin(void* dev_buf, size_t bytes);

@@ -625,6 +625,36 @@ def test_schedule_switches_do_not_change_results():
         assert torch.equal(h, outs[0][0]) and torch.equal(r0, outs[0][1])
 
 
+@pytest.mark.parametrize("shape,ln", [("c1", True), ("c1", False), ("c4", True)])
+def test_fp32_state_dataflow_equals_presplit_dataflow(shape, ln):
+    """regcn_evolve_a32_mode: the all-entity GEMMs reading the fp32 entity state (split on chip by the converter warps)
+    against the (hi, lo) copies read by TMA -- the same operand values reach the tensor core, so the whole recurrence is
+    bit-identical; also through a dense snapshot in the middle of the window (the split copies must be there for it)."""
+    R._lib.require_device()
+    lib = R._lib.load()
+    n, r, t, L, _ = synth.SHAPES[shape]
+    rng = np.random.default_rng(21)
+    snaps = [synth.make_snapshot(rng, n, r, t, True) for _ in range(4)]
+    snaps[2] = synth.make_snapshot(rng, n, r, 6 * n, False)          # dense: most entities receive edges
+    model, _ = build_model(dict(kind="regcn", layer_norm=ln, seed=8), n, r)
+    model = model.to(DEV)
+    glist = [R.build_sub_graph(n, r, s, True, 0) for s in snaps]
+    assert 2 * glist[2].n_active > n and all(2 * glist[i].n_active <= n for i in (0, 1, 3))
+    outs = []
+    try:
+        for mode in (0, 1, 1, 0):
+            lib.regcn_evolve_a32_mode(mode)
+            hist, _, h0, _, _ = model.forward(glist, None, True)
+            torch.cuda.synchronize()
+            outs.append(([h.clone() for h in hist], h0.clone()))
+    finally:
+        lib.regcn_evolve_a32_mode(-1)
+    for hs, h0 in outs[1:]:
+        assert torch.equal(h0, outs[0][1])
+        for a, b in zip(hs, outs[0][0]):
+            assert torch.equal(a, b)
+
+
 def test_edge_cases_empty_and_single_snapshots():
     """Ragged inputs: an EMPTY history snapshot (no edges: every entity takes the evolve-loop path, absent relations
     pool to zero), a single-triple test snapshot (B = 2 queries, BatchNorm eval), a one-snapshot history -- against the
