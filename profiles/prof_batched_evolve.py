@@ -41,7 +41,7 @@ def main():
     dev = torch.device("cuda", 0)
     n, r, t, L, tq = synth.SHAPES[shape]
     rng = np.random.default_rng(0)
-    GMAX = 8
+    GMAX = 16
     snaps = [synth.make_snapshot(rng, n, r, t, True) for _ in range(L + GMAX - 1)]
     m, sd = build_product_model(model_cfg("regcn"), n, r, 0)
     m = m.to(dev)
@@ -69,7 +69,7 @@ def main():
     t1 = timed(lambda: m.forward(graphs[0:L], None, True))
     out["per_timestamp_ms"] = t1
     print(f"G=1: {t1:.3f} ms per timestamp", flush=True)
-    for G in (2, 4, 8):
+    for G in (2, 4, 8, 16):
         mG = batched_model(m, sd, n, r, G, dev)
         comb = []
         for i in range(L):

@@ -136,17 +136,36 @@ __device__ __forceinline__ long long filt_key(const int64_t* __restrict__ triple
   return (long long)((unsigned long long)triples[3 * (size_t)j] << 32) | (triples[3 * (size_t)j + key_col] & 0xffffffffLL);
 }
 
+constexpr int kFiltBlocks = 8;        // lists of up to 32 * kFiltBlocks answers are sorted across the warp
+constexpr int kFiltTile = 2048;       // keys staged in shared memory per pass (16 KB)
+
+// Every CTA scans all B keys: they are packed once per tile into shared memory (the triples are 24-byte records, a key
+// takes two of their fields) and the warps of the CTA -- one query each -- compare against the staged copy.
+__device__ __forceinline__ int filt_stage_keys(const int64_t* __restrict__ triples, int B, int key_col, int tile0,
+                                               long long* __restrict__ skeys) {
+  const int tn = min(kFiltTile, B - tile0);
+  __syncthreads();                                        // the previous tile is no longer read
+  for (int j = threadIdx.x; j < tn; j += blockDim.x) skeys[j] = filt_key(triples, tile0 + j, key_col);
+  __syncthreads();
+  return tn;
+}
+
 __global__ void __launch_bounds__(kFiltThreads) filter_count_kernel(const int64_t* __restrict__ triples, int B, int key_col,
                                                                     int* __restrict__ counts) {
   pdl_grid_sync();
+  __shared__ long long skeys[kFiltTile];
   const int lane = threadIdx.x & 31;
   const int b = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
-  if (b >= B) return;
-  const long long mykey = filt_key(triples, b, key_col);
+  const bool live = b < B;
+  const long long mykey = live ? filt_key(triples, b, key_col) : 0;
   int c = 0;
-  for (int j = lane; j < B; j += 32) c += filt_key(triples, j, key_col) == mykey ? 1 : 0;
+  for (int tile0 = 0; tile0 < B; tile0 += kFiltTile) {
+    const int tn = filt_stage_keys(triples, B, key_col, tile0, skeys);
+    if (live)
+      for (int j = lane; j < tn; j += 32) c += skeys[j] == mykey ? 1 : 0;
+  }
   c = warp_sum_i(c);
-  if (lane == 0) counts[b] = c;
+  if (live && lane == 0) counts[b] = c;
 }
 
 __global__ void __launch_bounds__(kFiltThreads) filter_fill_kernel(const int64_t* __restrict__ triples, int B, int key_col,
@@ -154,26 +173,32 @@ __global__ void __launch_bounds__(kFiltThreads) filter_fill_kernel(const int64_t
                                                                    int* __restrict__ idx, int* __restrict__ end,
                                                                    int* __restrict__ pair_a, int* __restrict__ pair_e) {
   pdl_grid_sync();
+  __shared__ long long skeys[kFiltTile];
   const int lane = threadIdx.x & 31;
   const int b = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
-  if (b >= B) return;
-  const long long mykey = filt_key(triples, b, key_col);
-  const int b0 = beg[b];
+  const bool live = b < B;                        // (every warp of the CTA takes part in staging the keys)
+  const long long mykey = live ? filt_key(triples, b, key_col) : 0;
+  const int b0 = live ? beg[b] : 0;
   int* lst = idx + b0;
   // collect the answers of the matching queries in query order
   int n = 0;
   int mine = 0;                                   // lane i keeps the i-th match (lists of <= 32 stay in registers)
-  for (int j0 = 0; j0 < B; j0 += 32) {
-    const int j = j0 + lane;
-    const bool m = j < B && filt_key(triples, j, key_col) == mykey;
-    const unsigned bal = __ballot_sync(0xffffffffu, m);
-    if (bal) {
-      const int a = m ? (int)triples[3 * (size_t)j + ans_col] : 0;
-      const int pos = n + __popc(bal & ((1u << lane) - 1u));
-      if (m) lst[pos] = a;
-      n += __popc(bal);
+  for (int tile0 = 0; tile0 < B; tile0 += kFiltTile) {
+    const int tn = filt_stage_keys(triples, B, key_col, tile0, skeys);
+    if (!live) continue;
+    for (int j0 = 0; j0 < tn; j0 += 32) {
+      const int j = j0 + lane;
+      const bool m = j < tn && skeys[j] == mykey;
+      const unsigned bal = __ballot_sync(0xffffffffu, m);
+      if (bal) {
+        const int a = m ? (int)triples[3 * (size_t)(tile0 + j) + ans_col] : 0;
+        const int pos = n + __popc(bal & ((1u << lane) - 1u));
+        if (m) lst[pos] = a;
+        n += __popc(bal);
+      }
     }
   }
+  if (!live) return;
   __syncwarp();
   int u;
   if (n <= 32) {
@@ -199,6 +224,61 @@ __global__ void __launch_bounds__(kFiltThreads) filter_fill_kernel(const int64_t
     __syncwarp();
     const int first = lst[0];
     if (lane >= u && lane < n) lst[lane] = first;     // unused tail slots stay valid candidate ids
+    __syncwarp();
+  } else if (n <= 32 * kFiltBlocks) {
+    // medium list (a hub pair / hub entity of a skewed snapshot): the same rank sort with several elements per lane --
+    // element blk*32 + lane lives in val[blk]; one serial insertion sort of 50 elements would cost the whole launch 40 us
+    int val[kFiltBlocks], pos[kFiltBlocks];
+    unsigned keepmask = 0;
+    const int nb = (n + 31) >> 5;
+#pragma unroll
+    for (int blk = 0; blk < kFiltBlocks; ++blk) val[blk] = (blk * 32 + lane < n) ? lst[blk * 32 + lane] : 0x7fffffff;
+#pragma unroll
+    for (int blk = 0; blk < kFiltBlocks; ++blk) {
+      if (blk < nb) {
+        const int i = blk * 32 + lane;
+        bool dup = false;
+#pragma unroll
+        for (int jb = 0; jb < kFiltBlocks; ++jb) {
+          if (jb <= blk) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+              const int o = __shfl_sync(0xffffffffu, val[jb], k);
+              dup |= (jb * 32 + k < i) & (o == val[blk]);
+            }
+          }
+        }
+        if (i < n && !dup) keepmask |= 1u << blk;
+      }
+    }
+    u = 0;
+#pragma unroll
+    for (int blk = 0; blk < kFiltBlocks; ++blk) {
+      pos[blk] = 0;
+      if (blk < nb) {
+        int upos = 0;
+#pragma unroll
+        for (int jb = 0; jb < kFiltBlocks; ++jb) {
+          if (jb < nb) {
+            const unsigned kb = __ballot_sync(0xffffffffu, (keepmask >> jb) & 1u);
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+              const int o = __shfl_sync(0xffffffffu, val[jb], k);
+              upos += (int)((kb >> k) & 1u) & (int)(o < val[blk]);
+            }
+          }
+        }
+        pos[blk] = upos;
+        u += __popc(__ballot_sync(0xffffffffu, (keepmask >> blk) & 1u));
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int blk = 0; blk < kFiltBlocks; ++blk)
+      if ((keepmask >> blk) & 1u) lst[pos[blk]] = val[blk];
+    __syncwarp();
+    const int first = lst[0];
+    for (int i = u + lane; i < n; i += 32) lst[i] = first;     // unused tail slots stay valid candidate ids
     __syncwarp();
   } else {
     // long list (hub query): insertion sort + unique by one lane, in place

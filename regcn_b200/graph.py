@@ -205,12 +205,14 @@ def finish_sub_graphs(gs, counts=None):
     return gs
 
 
-def concat_graphs(graphs):
+def concat_graphs(graphs, out=None):
     """Block-diagonal union of G finished SnapshotGraphs over the same (N, R) as ONE SnapshotGraph over G*N entities and
     G*R relations (`regcn_csr_concat`, one launch of offset copies): member g's entity v is g*N + v, its relation r < R
     is g*R + r, the inverse relation R + r is G*R + g*R + r.  This is the graph one recurrence step runs on when G
     independent history windows are evolved together (evaluate.test: consecutive test timestamps, src/main.py:60-90).
-    No host synchronisation: the members' size counters are already on the host."""
+    No host synchronisation: the members' size counters are already on the host.
+    out: a union graph returned earlier for the same G whose arrays are reused when they are large enough (the caller
+    guarantees that no kernel still reads it on another stream)."""
     import ctypes
     G = len(graphs)
     g0 = graphs[0]
@@ -218,20 +220,28 @@ def concat_graphs(graphs):
     if any(g.num_nodes != N or g.num_rels != R or g.device != g0.device for g in graphs):
         raise ValueError("concat_graphs: members must share num_nodes, num_rels and device")
     T = sum(g.num_edges // 2 for g in graphs)
-    out = SnapshotGraph(G * N, G * R, None, _shell=(T, g0.device))
+    if (out is None or getattr(out, "_cap_T", -1) < T or out.num_nodes != G * N or out.num_rels != G * R
+            or out.device != g0.device):
+        cap = T + T // 4 + 16
+        out = SnapshotGraph(G * N, G * R, None, _shell=(cap, g0.device))
+        out._cap_T = cap
+        out._cdesc = _lib.CsrArrays()
+        out._descriptor(out._cdesc)
+    out.num_edges = 2 * T
     descs = (_lib.CsrArrays * G)()
-    for g, dsc in zip(graphs, descs):
-        g._descriptor(dsc)
-    od = _lib.CsrArrays()
-    out._descriptor(od)
     sizes = (ctypes.c_int32 * (4 * G))()
     for i, g in enumerate(graphs):
-        sizes[4 * i:4 * i + 4] = [g.n_vrows, g.n_split_chunks, g.n_rel_ents, g.n_active]
-    call("regcn_csr_concat", ctypes.cast(descs, ctypes.c_void_p), ctypes.cast(sizes, ctypes.c_void_p), G, N, R,
-         ctypes.cast(ctypes.pointer(od), ctypes.c_void_p))
+        d = g.__dict__.get("_cdesc")
+        if d is None:
+            d = g._cdesc = _lib.CsrArrays()
+            g._descriptor(d)
+        descs[i] = d
+        sizes[4 * i], sizes[4 * i + 1], sizes[4 * i + 2], sizes[4 * i + 3] = g.n_vrows, g.n_split_chunks, g.n_rel_ents, g.n_active
+    call("regcn_csr_concat", ctypes.addressof(descs), ctypes.addressof(sizes), G, N, R, ctypes.addressof(out._cdesc))
     out._set_counts([sum(g.n_vrows for g in graphs), sum(g.n_split_chunks for g in graphs),
                      sum(g.n_rel_ents for g in graphs), max(g.max_hub_degree for g in graphs),
                      sum(g.n_active for g in graphs)])
+    out._ndata = out._edata = out._r2e = None
     out.members = G
     return out
 

@@ -243,7 +243,13 @@ class RecurrentRGCN(nn.Module):
         if G == 1:
             embs, _, r_emb, _, _ = self.forward(windows[0], None, True)
             return [(embs[-1], r_emb)]
-        comb = [concat_graphs([w[i] for w in windows]) for i in range(L)]
+        # the union graphs of the previous call with this G are overwritten in place: every kernel that read them was
+        # enqueued on this stream before (the engine joins its side streams before it returns)
+        pool = self.__dict__.setdefault("_batch_graphs", {})
+        key = (G, torch.cuda.current_stream().cuda_stream)
+        old = pool.get(key, [])
+        comb = [concat_graphs([w[i] for w in windows], old[i] if i < len(old) else None) for i in range(L)]
+        pool[key] = comb
         hist, h0 = self._forward_engine(comb, None, members=G)
         N, R, d = self.num_ents, self.num_rels, self.h_dim
         rel = h0.view(2, G, R, d).transpose(0, 1).contiguous().view(G, 2 * R, d)

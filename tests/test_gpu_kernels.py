@@ -568,7 +568,12 @@ def test_filter_lists_hub_queries_and_duplicates():
     hub = np.stack((np.full(90, 3), np.full(90, 2), rng.integers(0, n, 90)), 1)        # 90 answers, some repeated
     dup = np.array([[5, 1, 9]] * 4 + [[5, 1, 8]] * 2)
     rest = np.stack((rng.integers(0, n, 300), rng.integers(0, r, 300), rng.integers(0, n, 300)), 1)
-    for test in (np.concatenate((hub, dup, rest)).astype(np.int64), np.array([[1, 0, 2]], dtype=np.int64)):
+    # list lengths around the register (32), warp-rank-sort (256) and serial paths, in a query set larger than one
+    # shared-memory key tile (2048): hubs with 32 / 33 / 256 / 300 distinct answers plus repeats
+    sized = [np.stack((np.full(k + 5, 10 + i), np.full(k + 5, i % r), np.concatenate((np.arange(k) * 3 % n if k <= n // 3 else np.arange(k), rng.integers(0, 4, 5)))), 1)
+             for i, k in enumerate((32, 33, 256, 300))]
+    big = np.concatenate(sized + [np.stack((rng.integers(0, n, 1500), rng.integers(0, r, 1500), rng.integers(0, n, 1500)), 1)])
+    for test in (np.concatenate((hub, dup, rest)).astype(np.int64), np.array([[1, 0, 2]], dtype=np.int64), big.astype(np.int64)):
         all_t = restate.add_inverse(test, r)
         for rel_p in (0, 1):
             d = synth.answers_of(test, r, bool(rel_p))
