@@ -39,7 +39,7 @@ static DecodePlan plan_decode(int N, int R2, int d, int B, int C, int P) {
   auto take = [&](size_t bytes) { size_t at = o; o += al256(bytes); return at; };
   const size_t nd = (size_t)N * d * 4, bd = (size_t)B * d * 4, bf = (size_t)B * C * d * 4, pd = (size_t)P * d * 4;
   p.emb_n = take(nd); p.e_all = take(nd); p.e_hi = take(nd); p.e_lo = take(nd);
-  p.f_hi = take(bf); p.f_lo = take(bf);
+  p.f_hi = take(bf); p.f_lo = p.f_hi;     // (one fp32 feature matrix; f_lo kept as an alias)
   p.q = take(bd); p.q_hi = take(bd); p.q_lo = take(bd);
   // the FC GEMM's split-K choice of ConvTransE._tower (regcn_b200/decoder.py)
   int sk = (148 * 2) / (((B + 127) / 128) * ((d + 127) / 128));
@@ -67,16 +67,15 @@ enum { TW_BN0_S = 0, TW_BN0_B, TW_CONV_W, TW_CONV_B, TW_BN1_S, TW_BN1_B, TW_FC_H
 
 static int run_tower(const float* first, const float* second, const int64_t* triples, int col0, int col1, int B, int d,
                      int C, int ksz, const void* const* tw, const DecodePlan& pl, char* ws, int bn2, cudaStream_t st) {
-  float* f_hi = (float*)(ws + pl.f_hi);
-  float* f_lo = (float*)(ws + pl.f_lo);
+  float* feat = (float*)(ws + pl.f_hi);      // the feature map as ONE fp32 matrix: the FC GEMM splits it to TF32 on chip
   float* q = (float*)(ws + pl.q);
   int e = convtranse_features(first, second, triples, col0, col1, B, d, C, ksz, (const float*)tw[TW_BN0_S],
                               (const float*)tw[TW_BN0_B], (const float*)tw[TW_CONV_W], (const float*)tw[TW_CONV_B],
-                              (const float*)tw[TW_BN1_S], (const float*)tw[TW_BN1_B], nullptr, f_hi, f_lo, st);
+                              (const float*)tw[TW_BN1_S], (const float*)tw[TW_BN1_B], feat, nullptr, nullptr, st);
   if (e) return e;
-  e = gemm_tf32(f_hi, f_lo, C * d, (const float*)tw[TW_FC_HI], (const float*)tw[TW_FC_LO], C * d, q, d, B, d, C * d,
-                (const float*)tw[TW_FC_B], 0, 3, pl.split_k, (float*)(ws + pl.gemm_ws),
-                gemm_tf32_workspace_bytes(B, d, pl.split_k), nullptr, 0, st);
+  e = gemm_tf32_a32(feat, C * d, C * d, nullptr, nullptr, 0, 0, nullptr, (const float*)tw[TW_FC_HI],
+                    (const float*)tw[TW_FC_LO], C * d, q, d, B, d, (const float*)tw[TW_FC_B], 0, 3, pl.split_k,
+                    (float*)(ws + pl.gemm_ws), gemm_tf32_workspace_bytes(B, d, pl.split_k), nullptr, 0, st);
   if (e) return e;
   e = affine_relu(q, bn2 ? (const float*)tw[TW_BN2_S] : nullptr, bn2 ? (const float*)tw[TW_BN2_B] : nullptr, B, d, 1, st);
   if (e) return e;

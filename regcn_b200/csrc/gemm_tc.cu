@@ -1193,7 +1193,15 @@ static int launch_tc(const float* a_hi, const float* a_lo, int lda, const float*
     const uint32_t stage32 = (passes == 3 ? 2u : 1u) * (BLOCK_M * BLOCK_K * 4 + (uint32_t)p.block_n * BLOCK_K * 4);
     // k-blocks of 16 floats (64-byte swizzle rows) when fewer than four 128-byte-row stages fit: the ring is what hides the
     // L2 / HBM latency of the operand stream, and two slots of 86 KB do not (8.5 us per 128 x 208 tile against 4.6 us of MMA)
-    if (g_kblk16 && !p.bf16 && !p.a_mn && !p.b_mn && p.a_f32 != 1 && split_k <= 1 && SMEM_BUDGET / stage32 < 4) p.kblk = 16;
+    if (g_kblk16 && !p.bf16 && !p.a_mn && !p.b_mn && p.a_f32 != 1 && SMEM_BUDGET / stage32 < 4) {
+      p.kblk = 16;
+      if (split_k > 1) {
+        // split-K: the caller sized its workspace / reduction for `split_k` parts -- keep the narrow k-blocks only if the
+        // work list they give has exactly that many
+        const int tkb = (Ktrue + 15) / 16, per = (tkb + split_k - 1) / split_k;
+        if ((tkb + per - 1) / per != split_k) p.kblk = BLOCK_K;
+      }
+    }
   }
   if (p.a_f32 == 2) p.K = (Ktrue + p.kblk - 1) / p.kblk * p.kblk;
   else if (p.a_f32) p.K = BLOCK_K * (p.a_kb0 + (p.a_k[1] + BLOCK_K - 1) / BLOCK_K);

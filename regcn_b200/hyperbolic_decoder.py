@@ -53,10 +53,11 @@ class _HypConvBase(nn.Module):
         B = len(triplets)
         feats = ops.convtranse_features(ent_act, second, triplets, col0, col1, _fold_bn(self.bn0),
                                         self.conv1.weight.detach(), self.conv1.bias.detach(), _fold_bn(self.bn1),
-                                        split=ops.gemm_impl() == "tc")
+                                        split=False)
         split_k = max(1, min(16, (148 * 2) // max(1, ((B + 127) // 128) * ((self.fc.out_features + 127) // 128))))
+        # the feature map stays one fp32 matrix (B, 50 d): the FC GEMM splits it to TF32 on chip
         x = ops.gemm(feats, self.fc.weight.detach(), trans_b=True, bias=self.fc.bias.detach(), split_k=split_k,
-                     b_key=(self.fc.weight, "w"))
+                     b_key=(self.fc.weight, "w"), split_a_on_chip=True)
         if always_bn2 or B > 1:
             s, t = _fold_bn(self.bn2)
             ops.affine_relu_(x, s, t, relu=True)

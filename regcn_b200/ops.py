@@ -113,8 +113,11 @@ def _tc_operand(m, need_lo):
     return split_tf32(m)
 
 
-def gemm(a, b, trans_b=False, bias=None, out=None, accumulate=False, split_k=1, b_key=None):
+def gemm(a, b, trans_b=False, bias=None, out=None, accumulate=False, split_k=1, b_key=None, split_a_on_chip=False):
     """C[M,N] (+)= A[M,K] @ (B[K,N] | B[N,K]^T) (+ bias) on the tcgen05 kernel.  torch.mm / F.linear call sites of the path.
+
+    split_a_on_chip: A stays one fp32 matrix in HBM; TMA brings its k-blocks into the operand ring and two converter warps
+    split them to TF32 (hi, lo) there (regcn_gemm_tf32_a32) -- the same operand values, half the bytes of A.
 
     b_key=(owner_tensor, name): B is a static weight; its prepared form (K-major transpose, TF32 split) is cached on
     `owner_tensor` under `name`.  K must be a multiple of 4 (16-byte operand rows for TMA): every contraction of the
@@ -124,7 +127,7 @@ def gemm(a, b, trans_b=False, bias=None, out=None, accumulate=False, split_k=1, 
     if K % 4:
         raise ValueError(f"gemm: reduction length K={K} must be a multiple of 4 (TMA needs 16-byte operand rows); pad the "
                          "operands with zero columns")
-    return _gemm_tc(a, b, trans_b, bias, out, accumulate, split_k, b_key, 3 if impl == "tc" else 1)
+    return _gemm_tc(a, b, trans_b, bias, out, accumulate, split_k, b_key, 3 if impl == "tc" else 1, split_a_on_chip)
 
 
 def gemm_f32_yardstick(a, b, trans_b=False, bias=None, out=None, accumulate=False, split_k=1):
@@ -153,7 +156,7 @@ def gemm_f32_yardstick(a, b, trans_b=False, bias=None, out=None, accumulate=Fals
     return out
 
 
-def _gemm_tc(a, b, trans_b, bias, out, accumulate, split_k, b_key, passes):
+def _gemm_tc(a, b, trans_b, bias, out, accumulate, split_k, b_key, passes, a_on_chip=False):
     a_pre = a if isinstance(a, tuple) else None      # (hi, lo) produced directly by the upstream kernel
     if a_pre is not None:
         a = a_pre[0]
@@ -177,7 +180,13 @@ def _gemm_tc(a, b, trans_b, bias, out, accumulate, split_k, b_key, passes):
                             prep_b)
     else:
         b_hi, b_lo = prep_b()
-    a_hi, a_lo = a_pre if a_pre is not None else _tc_operand(a.detach(), need_lo)
+    a_on_chip = a_on_chip and a_pre is None
+    if a_on_chip:
+        a = a.detach()
+        if a.stride(1) != 1 or a.stride(0) % 4 or a.data_ptr() % 16:
+            a = a.contiguous()
+    else:
+        a_hi, a_lo = a_pre if a_pre is not None else _tc_operand(a.detach(), need_lo)
     if out is None:
         if accumulate:
             raise ValueError("gemm: accumulate needs out")
@@ -192,6 +201,10 @@ def _gemm_tc(a, b, trans_b, bias, out, accumulate, split_k, b_key, passes):
     if split_k > 1:
         ws_bytes = _lib.load().regcn_gemm_tf32_workspace_bytes(M, N, split_k)
         ws = torch.empty(ws_bytes // 4, device=a.device, dtype=F32)
+    if a_on_chip:
+        call("regcn_gemm_tf32_a32", a.data_ptr(), a.stride(0), K, None, None, 4, 0, None, ptr(b_hi), ptr(b_lo), K,
+             out.data_ptr(), out.stride(0), M, N, ptr(bias), int(accumulate), passes, split_k, ptr(ws), ws_bytes, None, 0)
+        return out
     call("regcn_gemm_tf32", ptr(a_hi), ptr(a_lo), K, ptr(b_hi), ptr(b_lo), K, out.data_ptr(), out.stride(0), M, N, K,
          ptr(bias), int(accumulate), passes, split_k, ptr(ws), ws_bytes)
     return out
