@@ -896,13 +896,16 @@ def main():
     lib.regcn_two_stream_enable(1)
     lib.regcn_pdl_enable(1)
     agg_launches = max(1, agg_n_c.value // probe_steps)                  # per batch of G timestamps
-    agg_bytes = agg_launches * G * (808.0 * 2 * T + 808.0 * n + 800.0 * 2 * r)
+    # sparse-snapshot form: the kernel gathers one 800-byte row + 8 bytes of ids per edge and writes the (hi, lo) halves of the
+    # compact [agg | .] operand for the ACTIVE destinations only (plus the relation table); inactive rows are not touched
+    n_act = sum(g_.n_active for g_ in bgraphs[:L + G - 1]) / max(1, L + G - 1)
+    agg_bytes = agg_launches * G * (808.0 * 2 * T + 1600.0 * n_act + 800.0 * 2 * r)
     agg_ms = agg_ms_c.value / probe_steps
     hbm = float(peaks.get("hbm_gbs", 6650.0))
     edge = {"kernel": "regcn::union_aggregate_kernel (split rows folded in-kernel)", "bound": "hbm",
             "launches_per_step": agg_launches / G,
             "ms_per_step_in_kernel": agg_ms / G, "achieved": agg_bytes / (agg_ms * 1e-3) / 1e9 if agg_ms > 0 else 0.0,
-            "peak": hbm, "unit": "GB/s", "note": f"one launch serves {G} timestamps ({G}x3082 edges); still latency-bound at this size, see "
+            "peak": hbm, "unit": "GB/s", "note": f"one launch serves {G} timestamps ({G}x3082 edges, active destinations only); latency-bound at this size, see "
             "edge_kernel_hbm_bound for the HBM-bound stress sizes"}
     edge["frac"] = edge["achieved"] / hbm
 
