@@ -63,6 +63,7 @@ static bool stream_after(cudaStream_t waiter, cudaStream_t src, cudaEvent_t ev) 
   return true;
 }
 void gemm_tf32_sm_hint(int sms);
+void gemm_tf32_grid_cap(int ctas);
 struct StreamScope {
   AuxStream* aux;
   cudaStream_t st;
@@ -76,6 +77,7 @@ struct StreamScope {
     join();
     pdl_suppress(false);
     gemm_tf32_sm_hint(0);
+    gemm_tf32_grid_cap(0);
     if (aux) aux->mu.unlock();
   }
 };
@@ -98,6 +100,14 @@ static bool side_pdl_keep() {
 }
 // fp32-A dataflow for the all-entity GEMMs of the sparse-snapshot form (see regcn_regcn_evolve): on from 64 k entity rows,
 // REGCN_EVOLVE_A32=0 / 1 or regcn_evolve_a32_mode(0 / 1) force it off / on, -1 = by size
+// SMs the side stream gets in the many-round regime (REGCN_SIDE_SMS; 0 = no split).  Measured at 8 ICEWS18-shaped windows
+// per recurrence (profiles/timeline.py c3x8, us per batched recurrence): 0: 3155, 12: 4250, 16: 3942, 24: 3238, 32: 3007,
+// 40: 3041, 48: 3167, 64: 3576 -- the side chain is latency-bound and needs ~a fifth of the machine to keep pace
+static int side_sm_share() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("REGCN_SIDE_SMS"); v = e ? atoi(e) : 32; if (v < 0 || v > 64) v = 32; }
+  return v;
+}
 static int g_evolve_a32 = -2;          // -2: read REGCN_EVOLVE_A32 on first use; -1 auto, 0 off, 1 on
 void evolve_a32_set(int mode) { g_evolve_a32 = mode < 0 ? -1 : (mode ? 1 : 0); }
 static bool evolve_a32(int N) {
@@ -201,6 +211,17 @@ int regcn_regcn_evolve(const void* const* mp, const int* mi, const void* const* 
     if (sm_count <= 0) sm_count = 148;
   }
 
+  // Many-round regime (a batched recurrence: >= 4 tiles per SM in the all-entity GEMMs): the SMs are split between the two
+  // streams -- the all-entity GEMMs get sm_count - side_sms persistent CTAs, the side stream's GEMMs side_sms, and the
+  // side stream's other kernels run on whatever the capped grids leave free.  Small tables keep the balanced whole-machine
+  // grids (their one- or two-round GEMMs leave SMs free by themselves).
+  const int side_sms = side_sm_share();
+  const bool split_sms = side_sms > 0 && (long long)((N + 127) / 128) >= 4LL * sm_count;
+  auto main_knobs = [&]() { gemm_tf32_sm_hint(0); gemm_tf32_grid_cap(split_sms ? sm_count - side_sms : 0); };
+  auto side_knobs = [&](int ncol) {
+    gemm_tf32_sm_hint(split_sms ? side_sms : side_hint(N, d, ncol, sm_count));
+    gemm_tf32_grid_cap(split_sms ? side_sms : 0);
+  };
   for (int i = 0; i < L; ++i) {
     const void* const* g = gp + (size_t)i * RG_NUM_PTRS;
     const int* gn = gi_ + (size_t)i * RGI_NUM_INTS;
@@ -223,7 +244,7 @@ int regcn_regcn_evolve(const void* const* mp, const int* mi, const void* const* 
     if (two) {
       scope.b_open = true;
       side_pdl_off = !side_pdl_keep();
-      gemm_tf32_sm_hint(side_hint(N, d, 2 * d, sm_count));
+      side_knobs(2 * d);
       // kernels launched early park their CTAs on the SMs the other stream needs: the side stream stays plainly ordered
       pdl_suppress(side_pdl_off);
     }
@@ -294,7 +315,7 @@ int regcn_regcn_evolve(const void* const* mp, const int* mi, const void* const* 
         // dense one), so the last layer still writes them unless that snapshot takes this form too.
         const bool next_a32 = a32 && (i + 1 >= L || (gi_[(size_t)(i + 1) * RGI_NUM_INTS + RGI_N_ACTIVE] * 2 <= N));
         if (!last) {
-          if (two) { gemm_tf32_sm_hint(0); pdl_suppress(l > 0); }   // later layers must not park CTAs on the free SMs early
+          if (two) { main_knobs(); pdl_suppress(l > 0); }   // later layers must not park CTAs on the free SMs early
           if (a32)
             e = gemm_tf32_layer_a32(x_raw, d, d, nullptr, nullptr, 0, 0, nullptr, F(base + 6), F(base + 7), d, N, ncol, d, o_raw,
                                     nullptr, nullptr, l == 0 ? ws + w.Lm : nullptr, d, nullptr, GI(RG_ACTIVE_POS), nullptr, 0,
@@ -304,7 +325,7 @@ int regcn_regcn_evolve(const void* const* mp, const int* mi, const void* const* 
                                 l == 0 ? ws + w.Lm : nullptr, d, nullptr, GI(RG_ACTIVE_POS), nullptr, 0, nullptr, nullptr, 0, st);
           pdl_suppress(two && side_pdl_off);
           if (e) return e;
-          if (two) gemm_tf32_sm_hint(side_hint(N, d, ncol, sm_count));
+          if (two) side_knobs(ncol);
           if (n_active > 0 &&
               (e = gemm_tf32_layer(ws + w.agg_hi, ws + w.agg_lo, 2 * d, F(base + 4), F(base + 5), 2 * d, n_active, d, 2 * d, d,
                                    o_raw, a32 ? nullptr : o_hi, a32 ? nullptr : o_lo, nullptr, 0, arows, nullptr, nullptr, 0,
@@ -313,11 +334,11 @@ int regcn_regcn_evolve(const void* const* mp, const int* mi, const void* const* 
           float* h_new = hist + (size_t)i * nd;
           float* n_hi = next_a32 ? nullptr : ws + w.h_hi;
           float* n_lo = next_a32 ? nullptr : ws + w.h_lo;
-          if (two) gemm_tf32_sm_hint(side_hint(N, d, d, sm_count));
+          if (two) side_knobs(d);
           if (n_active > 0 &&
               (e = gemm_tf32(ws + w.agg_hi, ws + w.agg_lo, 2 * d, F(base + 4), F(base + 5), 2 * d, ws + w.P, d, n_active, d,
                              2 * d, nullptr, 0, 3, 1, nullptr, 0, nullptr, 0, sB))) return e;
-          if (two) { gemm_tf32_sm_hint(0); pdl_suppress(true); }
+          if (two) { main_knobs(); pdl_suppress(true); }
           if (a32)
             e = gemm_tf32_layer_a32(x_raw, d, d, nullptr, nullptr, 0, 0, nullptr, F(base + 6), F(base + 7), d, N, d, d, h_new,
                                     n_hi, n_lo, nullptr, 0, nullptr, GI(RG_ACTIVE_POS), ws + w.Lm, d, F(RM_GATE_BIAS), h_raw,
@@ -370,6 +391,7 @@ int regcn_regcn_evolve(const void* const* mp, const int* mi, const void* const* 
     }
     // ---- time gate (K9): h = s(h W_t + b) * [normalize](cur) + (1 - s) * h ----
     gemm_tf32_sm_hint(0);
+    gemm_tf32_grid_cap(0);
     pdl_suppress(false);
     float* h_new = hist + (size_t)i * nd;
     if (!gate_done &&

@@ -1097,6 +1097,11 @@ int gemm_tf32_trace_slots() { return tc::kTraceSlots; }
 // owns most of the machine; they then pick the narrowest tile whose grid still fits the SMs that are left (one wave)
 static thread_local int g_sm_hint = 0;
 void gemm_tf32_sm_hint(int sms) { g_sm_hint = sms; }
+// Grid cap: the next persistent grids use at most this many CTAs (0 = the whole machine).  The evolve engine splits the SMs
+// between its two streams with it when the all-entity GEMMs run many rounds (a 144-CTA persistent grid would otherwise hold
+// every SM for its whole duration and the other stream's chain would run behind it, not beside it).
+static thread_local int g_grid_cap = 0;
+void gemm_tf32_grid_cap(int ctas) { g_grid_cap = ctas > 0 ? ctas : 0; }
 
 static int pick_block_n(int M, int N, int K, int split_k) {
   if (g_force_block_n > 0) return g_force_block_n;
@@ -1274,7 +1279,8 @@ static int launch_tc(const float* a_hi, const float* a_lo, int lda, const float*
   const long long total_tiles = (long long)p.m_tiles * p.n_tiles * p.splits;
   // balanced persistent grid: the smallest grid that needs no more rounds than the whole machine would (360 tiles on
   // 148 SMs take 3 rounds; so do 120 CTAs -- and 28 SMs stay free for whatever runs next to this kernel)
-  const long long rounds = (total_tiles + sms - 1) / sms;
+  const int sms_eff = (g_grid_cap > 0 && g_grid_cap < sms) ? g_grid_cap : sms;
+  const long long rounds = (total_tiles + sms_eff - 1) / sms_eff;
   dim3 grid((unsigned)((total_tiles + rounds - 1) / (rounds > 0 ? rounds : 1)));
   const double alg_flops = p.epi == 2 ? 2.0 * M * (double)Ktrue : 2.0 * M * (double)N * Ktrue;
   if (g_trace) {

@@ -60,6 +60,7 @@ int gemm_tf32_trace_read(int i, int* epi, int* M, int* N, int* K, int* grid, int
 void score_count_poly(int on);
 int gemm_tf32_trace_slots();
 void gemm_tf32_sm_hint(int sms);
+void gemm_tf32_grid_cap(int ctas);
 void aggregate_tune(int impl);
 int score_count_tf32(const float* q_hi, const float* q_lo, const float* e_hi, const float* e_lo, int B, int N, int K,
                      const float* tscore, const int* target, int* raw_count, int col_offset, int hyp, const float* x2,
