@@ -477,6 +477,42 @@ def run_other_configs(dev, flush, hbm_peak):
         all_t = torch.cat((t, inv)).contiguous()
         return model, glist, all_t, utils.filter_csr_from_snapshot(all_t, 2 * r, 0)
 
+    def batched(model, shape, seed=0, steps=3, warm=2):
+        """ms per timestamp with G consecutive timestamps of a stream evolved per recurrence (evaluate.evaluate_batch)."""
+        n, r = synth.SHAPES[shape][0], synth.SHAPES[shape][1]
+        G = evaluate.timestamps_per_batch(model, n)
+        if G <= 1:
+            return None
+        st = synth.make_stream(shape, seed, n_test=G)
+        L = len(st["history"])
+        snaps = list(st["history"]) + list(st["tests"][:G - 1])
+        graphs = [R.build_sub_graph(n, r, s_, True, dev.index or 0) for s_ in snaps]
+        wins, trips, filts = [], [], []
+        for g in range(G):
+            wins.append(graphs[g:g + L])
+            tg = torch.from_numpy(st["tests"][g]).to(dev)
+            ig = tg[:, [2, 1, 0]].clone()
+            ig[:, 1] += r
+            trips.append(torch.cat((tg, ig)).contiguous())
+            filts.append(utils.filter_csr_from_snapshot(trips[-1], 2 * r, 0))
+        for _ in range(warm):
+            evaluate.evaluate_batch(model, wins, trips, filts)
+        torch.cuda.synchronize()
+        tot, ev_ms = 0.0, 0.0
+        for _ in range(steps):
+            flush.fill_(1.0)
+            tm = {"evolve": (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))}
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            evaluate.evaluate_batch(model, wins, trips, filts, tm)
+            b.record()
+            torch.cuda.synchronize()
+            tot += a.elapsed_time(b)
+            ev_ms += tm["evolve"][0].elapsed_time(tm["evolve"][1])
+        nq = sum(int(t_.shape[0]) for t_ in trips)
+        return {"timestamps_per_recurrence": G, "ms_per_step": tot / steps / G, "evolve_ms_per_step": ev_ms / steps / G,
+                "queries_per_s": nq / (tot / steps * 1e-3), "snapshot_steps_per_s": G * L / (ev_ms / steps * 1e-3)}
+
     out = {}
     # configs[1]: Hyperbolic RE-GCN, lgcn encoder + RotH decoder, c = 0.01, ICEWS14s shape, history 3
     try:
@@ -486,7 +522,9 @@ def run_other_configs(dev, flush, hbm_peak):
         out["configs[1] hyperbolic lgcn+roth, ICEWS14s shape"] = {
             "ms_per_step": ms, "queries_per_s": all_t.shape[0] / (ms * 1e-3), "phase_ms": parts,
             "snapshot_steps_per_s": len(glist) / (parts["evolve"] * 1e-3), "gpu_launches_per_step": nl,
-            "shape": "N=7128 R=230 T=250/snapshot L=3 B=500"}
+            "shape": "N=7128 R=230 T=250/snapshot L=3 B=500",
+            "what": "one timestamp per recurrence; `batched` = consecutive timestamps evolved together (test()'s schedule)",
+            "batched": batched(model, "c1")}
         del model, glist
     except Exception as e:  # noqa: BLE001
         out["configs[1] hyperbolic lgcn+roth, ICEWS14s shape"] = {"error": repr(e)[:300]}
@@ -502,7 +540,8 @@ def run_other_configs(dev, flush, hbm_peak):
             out[key] = {"ms_per_step": ms, "queries_per_s": all_t.shape[0] / (ms * 1e-3), "phase_ms": parts,
                         "snapshot_steps_per_s": len(glist) / (parts["evolve"] * 1e-3), "gpu_launches_per_step": nl,
                         "edges_per_s_through_the_aggregate": 2 * len(glist) * E / (parts["evolve"] * 1e-3),
-                        "shape": f"N={n} R={r} E={E}/snapshot L={len(glist)} B={all_t.shape[0]}"}
+                        "shape": f"N={n} R={r} E={E}/snapshot L={len(glist)} B={all_t.shape[0]}",
+                        "batched": batched(model, shp)}
             del model, glist
         except Exception as e:  # noqa: BLE001
             out[key] = {"error": repr(e)[:300]}

@@ -229,20 +229,50 @@ class HyperbolicRecurrentRGCN(nn.Module):
                          float(tre.anchor_beta), float(tre.epsilon), float(tre.radius_mlp.bias.detach().item())],
                         dtype=np.float64)
         self._engine_tab = (ptab, itab, dtab, keep)
+        self._engine_ptr_tensors = ptrs
         self._engine_stamp = stamp
+        self._engine_tab_batch = {}
         return self._engine_tab
 
-    def _forward_engine(self, g_list, h_init=None):
+    def _engine_tables_batch(self, G):
+        """Tables of the recurrence over G independent history windows at once (see RecurrentRGCN._engine_tables_batch):
+        per-entity tables (tangent table, static radii) tiled G times, per-relation tables (relation embeddings, the
+        Lorentz layers' relation blocks) tiled in the numbering of graph.concat_graphs, dense weights shared."""
+        ptab, itab, dtab, _ = self._engine_tables()
+        hit = self._engine_tab_batch.get(G)
+        if hit is not None:
+            return hit
+        R = self.num_rels
+        t = self._engine_ptr_tensors
+
+        def tile_rel(x):
+            return torch.cat([x[:R]] * G + [x[R:]] * G).contiguous()
+
+        heads = {0: t[0].repeat(G, 1).contiguous(), 1: t[1].repeat(G, *([1] * (t[1].dim() - 1))).contiguous()}
+        for i in (2, 3, 4, 5):
+            heads[i] = tile_rel(t[i])
+        if self.encoder_name == "lgcn":
+            for l in range(len(self.rgcn.layers)):
+                w = tile_rel(t[15 + 4 * l])
+                heads[15 + 4 * l] = heads[16 + 4 * l] = w
+        ptab_g, itab_g = ptab.copy(), itab.copy()
+        for i, x in heads.items():
+            ptab_g[i] = x.data_ptr()
+        itab_g[0], itab_g[1] = G * self.num_ents, 2 * G * R
+        self._engine_tab_batch[G] = (ptab_g, itab_g, dtab, heads)
+        return self._engine_tab_batch[G]
+
+    def _forward_engine(self, g_list, h_init=None, members=1):
         import numpy as np
         from . import _lib
-        ptab, itab, dtab, _ = self._engine_tables(h_init)
+        ptab, itab, dtab, _ = self._engine_tables(h_init) if members == 1 else self._engine_tables_batch(members)
         L = len(g_list)
-        N, R2, d = self.num_ents, 2 * self.num_rels, self.h_dim
+        N, R2, d = members * self.num_ents, 2 * members * self.num_rels, self.h_dim
         dev = self.dynamic_emb.device
         gp = np.concatenate([g.ptr_table for g in g_list])
         gi = np.concatenate([g.int_table for g in g_list])
         max_split = max(g.n_split_chunks for g in g_list)
-        rel_nsplit = max(max(1, min(64, g.n_rel_ents // (max(1, self.num_rels) * 512))) for g in g_list)
+        rel_nsplit = max(max(1, min(64, g.n_rel_ents // (max(1, R2 // 2) * 512))) for g in g_list)
         need = _lib.load().regcn_hyp_evolve_workspace_bytes(N, R2, d, max_split, rel_nsplit)
         ws = getattr(self, "_engine_ws", None)
         if ws is None or ws.numel() < need or ws.device != dev:
@@ -253,6 +283,33 @@ class HyperbolicRecurrentRGCN(nn.Module):
         _lib.call("regcn_hyp_evolve", ptab.ctypes.data, itab.ctypes.data, dtab.ctypes.data, gp.ctypes.data,
                   gi.ctypes.data, L, hist.data_ptr(), h0.data_ptr(), rel_nsplit, ws.data_ptr(), ws.numel())
         return [hist[i] for i in range(L)], h0
+
+    def batch_ok(self):
+        """True when forward_batch can evolve several history windows at once (whole-recurrence engine, no static graph)."""
+        return self._engine_ok() and not self.use_static
+
+    @torch.no_grad()
+    def forward_batch(self, windows):
+        """G independent history windows (lists of L SnapshotGraphs, same L) as ONE recurrence over the block-diagonal union
+        graphs -- RecurrentRGCN.forward_batch for the hyperbolic model (hyperbolic_main.py:100-113 evaluates the test
+        timestamps one after the other, each over its own window).  Returns [(h_g (N,d) on the ball, r_emb_g (2R,d))]."""
+        from .graph import concat_graphs
+        G = len(windows)
+        L = len(windows[0])
+        if not self.batch_ok() or L == 0 or any(len(w) != L for w in windows):
+            raise RuntimeError("forward_batch: needs the recurrence engine, no static graph and windows of one length > 0")
+        if G == 1:
+            embs, _, r_emb, _, _ = self.forward(windows[0], None, True)
+            return [(embs[-1], r_emb)]
+        pool = self.__dict__.setdefault("_batch_graphs", {})
+        key = (G, torch.cuda.current_stream().cuda_stream)
+        old = pool.get(key, [])
+        comb = [concat_graphs([w[i] for w in windows], old[i] if i < len(old) else None) for i in range(L)]
+        pool[key] = comb
+        hist, h0 = self._forward_engine(comb, None, members=G)
+        N, R, d = self.num_ents, self.num_rels, self.h_dim
+        rel = h0.view(2, G, R, d).transpose(0, 1).contiguous().view(G, 2 * R, d)
+        return [(hist[-1][g * N:(g + 1) * N], rel[g]) for g in range(G)]
 
     @torch.no_grad()
     def forward(self, g_list, static_graph, use_cuda):

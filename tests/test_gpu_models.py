@@ -447,6 +447,33 @@ def test_forward_batch_rows_equal_per_window_forward(shape, G, ln):
                 assert float((h0 - h0s).abs().max()) <= 1e-5 * max(1.0, float(h0s.abs().max()))
 
 
+@pytest.mark.parametrize("enc,dec,shape,G,ln", [("hyperbolic_uvrgcn", "roth", "c1", 8, False), ("lgcn", "roth", "small_l", 4, False),
+                                                ("hyperbolic_uvrgcn", "hyperbolic_convtranse", "small", 3, True)])
+def test_hyperbolic_forward_batch_rows_equal_per_window_forward(enc, dec, shape, G, ln):
+    """HyperbolicRecurrentRGCN.forward_batch against forward() window by window: the hyperbolic engine has one form per
+    encoder, so every entity row (a point of the ball) and every relation row is bit-identical; the Lorentz layers'
+    per-relation blocks and the static radii are tiled in the union graph's numbering."""
+    R._lib.require_device()
+    n, r, t, L, _ = synth.SHAPES[shape]
+    rng = np.random.default_rng(13)
+    snaps = [synth.make_snapshot(rng, n, r, t, True) for _ in range(L + G - 1)]
+    snaps[2] = snaps[2][:0]
+    model, _ = build_model(dict(kind="hyp", layer_norm=ln, seed=12, encoder=enc, decoder=dec, gamma=0.15), n, r)
+    model = model.to(DEV)
+    graphs = [R.build_sub_graph(n, r, s, True, 0) for s in snaps]
+    windows = [graphs[g:g + L] for g in range(G)]
+    single = []
+    for w in windows:
+        hist, _, h0, _, _ = model.forward(w, None, True)
+        single.append((hist[-1].clone(), h0.clone()))
+    assert model.batch_ok()
+    for _ in range(2):
+        states = model.forward_batch(windows)
+        torch.cuda.synchronize()
+        for (h, h0), (hs, h0s) in zip(states, single):
+            assert torch.equal(h, hs) and torch.equal(h0, h0s)
+
+
 def test_evaluation_loop_batched_equals_one_timestamp_at_a_time(monkeypatch):
     """regcn_b200.test() evolving groups of consecutive timestamps together (the default below ~190 k entity rows per
     batch) returns the ranks of the one-timestamp-per-recurrence loop, for group sizes that do and do not divide the
