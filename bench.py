@@ -332,6 +332,25 @@ def run_stress(dev, hbm_peak, tf_peak, tf32_peak=None):
                                    "frac": b4 / ms / 1e6 / hbm_peak, "split_chunks": g.n_split_chunks,
                                    "note": "the whole working set (6 MB table + 1 MB index) is L2-resident: the launch is "
                                            "latency-bound, the HBM fraction is reported for the record"}
+    # the same kernel on the union graph of 8 such snapshots: what one launch works on when test() evolves 8 timestamps per
+    # recurrence (regcn_csr_concat; 8 x the edges and rows, the table no longer L2-resident)
+    try:
+        from regcn_b200.graph import concat_graphs
+        G8 = 8
+        rng8 = np.random.default_rng(1)
+        members = [g] + [R.build_sub_graph(cn, cr, synth.make_snapshot(rng8, cn, cr, ct, zipf=True), True, dev.index or 0)
+                         for _ in range(G8 - 1)]
+        gu = concat_graphs(members)
+        hu, relu_ = torch.randn(G8 * cn, d, device=dev), torch.randn(2 * G8 * cr, d, device=dev)
+        ou = torch.empty(G8 * cn, d, device=dev)
+        ms8 = med(lambda: ops.union_aggregate(hu, relu_, gu, out=ou))
+        b8 = 808.0 * gu.num_edges + 808.0 * G8 * cn + 800.0 * 2 * G8 * cr
+        out["edge_kernel_c4_dense"]["union_of_8_snapshots"] = {
+            "shape": f"N={G8 * cn} E={gu.num_edges} 2R={2 * G8 * cr}", "ms": ms8, "algorithmic_bytes_per_launch": b8,
+            "achieved": b8 / ms8 / 1e6, "frac": b8 / ms8 / 1e6 / hbm_peak, "split_chunks": gu.n_split_chunks}
+        del members, gu, hu, ou
+    except Exception as e:  # noqa: BLE001
+        out["edge_kernel_c4_dense"]["union_of_8_snapshots"] = {"error": repr(e)[:200]}
     del g, h4, o4
     tf32 = tf32_peak["burst"] if tf32_peak else tf_peak / 2
     score = {"kernel": "regcn::tc::gemm_tf32_kernel<1> (counting epilogue, no score matrix)", "bound": "tensor",

@@ -36,6 +36,14 @@ constexpr int EPI_WARPS = 8;           // epilogue warps: 2 per TMEM lane quarte
 constexpr int CVT_WARPS = 2;           // A-operand converter warps (fp32-A mode)
 constexpr int EPI_WARP0 = 2 + CVT_WARPS;   // first epilogue warp; a multiple of 4 so that warp % 4 is the TMEM lane quarter
 constexpr int NUM_THREADS = 32 * (EPI_WARP0 + EPI_WARPS);
+// The time-gate epilogue (EPI 5) is a latency-bound instruction stream (profiles/r02_ncu_le1_batched.txt): it runs with THREE
+// warps per TMEM lane quarter = per warp scheduler (512 threads, 128 registers each) instead of two.
+template <int EPI> constexpr int epi_warps() { return EPI == 5 ? 12 : EPI_WARPS; }
+template <int EPI> constexpr int num_threads() { return 32 * (EPI_WARP0 + epi_warps<EPI>()); }
+constexpr uint32_t staging_bytes(int warps) { return (uint32_t)warps * 32 * 32 * 4; }       // one 32 x 32 fp32 tile per epilogue warp
+// operand-ring budget: what is left of the 227 KB (232 448 B) per CTA after 2 KB of static shared memory, the alignment slack
+// and the epilogue staging
+constexpr uint32_t ring_budget(int warps) { return warps == EPI_WARPS ? 192u * 1024u : 232448u - 2048u - 1024u - staging_bytes(warps); }
 constexpr uint32_t SMEM_BUDGET = 192 * 1024;   // operand ring; + 32 KB of epilogue staging + alignment slack <= 227 KB
 constexpr int kStagePitch = 32;                                      // floats per row of an epilogue staging tile (XOR-swizzled)
 constexpr uint32_t STAGING_BYTES = EPI_WARPS * 32 * kStagePitch * 4; // one 32 x 32 fp32 tile per epilogue warp
@@ -227,7 +235,7 @@ __device__ __forceinline__ float finish_score(const Params& p, float dot, int ro
 //   TMEM slots  tmem_full[a] / tmem_empty[a] MMA issuer   <-> epilogue     (2 accumulators of block_n columns)
 // so the epilogue of tile i (TMEM -> registers -> global / counting) overlaps the main loop of tile i+1.
 template <int EPI>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(num_threads<EPI>(), 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                  const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                  const Params p) {
@@ -240,7 +248,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float norm_xchg[EPI_WARPS / 4][BLOCK_M];      // EPI 3: row-norm partial sums of the two warps of a lane quarter
+  constexpr int EW = epi_warps<EPI>();                     // epilogue warps of this instantiation
+  __shared__ float norm_xchg[EW / 4][BLOCK_M];             // EPI 5: row-norm partial sums of the warps of a lane quarter
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -267,7 +276,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&tmem_full_bar[a]), 1);
-      mbar_init(smem_u32(&tmem_empty_bar[a]), 32 * EPI_WARPS);     // every epilogue thread arrives
+      mbar_init(smem_u32(&tmem_empty_bar[a]), 32 * EW);     // every epilogue thread arrives
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -455,7 +464,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
           if (++stage_c == p.stages) { stage_c = 0; phase_c ^= 1; }
         }
       }
-    } else if (p.a_f32) {
+    } else if (EPI != 5 && p.a_f32) {       // (the 128-register time-gate instantiation takes fp32 A in the raw-tile form only)
       const int cw = warp - 2;
       const int c16 = lane & 7, rsub = lane >> 3;
       constexpr int RPL = BLOCK_M / CVT_WARPS / 4;        // rows per lane (16)
@@ -527,7 +536,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     // ===================== epilogue: TMEM -> registers -> global / counts =====================
     const int quarter = warp & 3;                      // TMEM lanes [32*quarter, 32*quarter+32)
     const int part = (warp - EPI_WARP0) >> 2;                  // which share of the 32-column chunks this warp takes
-    constexpr int kParts = EPI_WARPS / 4;
+    constexpr int kParts = EW / 4;
     float* stage = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes) + (warp - EPI_WARP0) * (32 * kStagePitch);
     float scale = 1.f, margin = 0.f;
     if (EPI != 0 && EPI != 3 && EPI != 5 && p.hyp) { scale = __ldg(p.scale_margin); margin = __ldg(p.scale_margin + 1); }
@@ -863,32 +872,38 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
           const int col = c0 + sub_c;
           if (col < ld_h) {                                  // lay_d is a multiple of 4: a whole float4 or nothing
             const float4 b4 = ldg4(p.gate_bias + col);
-            float4 g4[8], h4[8];
+            // two groups of 4 rows: 8 float4 loads in flight per thread (the instantiation lives in 128 registers)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              if ((wr8 >> (4 * i)) & 1u) {
-                g4[i] = *reinterpret_cast<const float4*>(p.gate_G + (size_t)orow8[i] * ld_g + col);
-                h4[i] = *reinterpret_cast<const float4*>(p.gate_h + (size_t)orow8[i] * ld_h + col);
+            for (int half = 0; half < 2; ++half) {
+              float4 g4[4], h4[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int i = 4 * half + j;
+                if ((wr8 >> (4 * i)) & 1u) {
+                  g4[j] = *reinterpret_cast<const float4*>(p.gate_G + (size_t)orow8[i] * ld_g + col);
+                  h4[j] = *reinterpret_cast<const float4*>(p.gate_h + (size_t)orow8[i] * ld_h + col);
+                }
               }
-            }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              if ((wr8 >> (4 * i)) & 1u) {
-                float4 a = *reinterpret_cast<const float4*>(stage + stage_off(4 * i + sub_r, sub_q));
-                const float nrm = nrm8[i];
-                a.x = rrelu_max(a.x) * nrm; a.y = rrelu_max(a.y) * nrm; a.z = rrelu_max(a.z) * nrm; a.w = rrelu_max(a.w) * nrm;
-                const float sx = lean_sigmoid(g4[i].x + b4.x), sy = lean_sigmoid(g4[i].y + b4.y);
-                const float sz = lean_sigmoid(g4[i].z + b4.z), sw = lean_sigmoid(g4[i].w + b4.w);
-                a.x = fmaf(sx, a.x - h4[i].x, h4[i].x); a.y = fmaf(sy, a.y - h4[i].y, h4[i].y);
-                a.z = fmaf(sz, a.z - h4[i].z, h4[i].z); a.w = fmaf(sw, a.w - h4[i].w, h4[i].w);
-                const size_t o = (size_t)orow8[i] * ld_h + col;
-                st4(p.lay_raw + o, a);
-                if (p.lay_hi) {                              // uniform: the fp32-A consumers need no split copy
-                  float4 h, l;
-                  split_tf32_1(a.x, h.x, l.x); split_tf32_1(a.y, h.y, l.y);
-                  split_tf32_1(a.z, h.z, l.z); split_tf32_1(a.w, h.w, l.w);
-                  st4(p.lay_hi + o, h);
-                  st4(p.lay_lo + o, l);
+              for (int j = 0; j < 4; ++j) {
+                const int i = 4 * half + j;
+                if ((wr8 >> (4 * i)) & 1u) {
+                  float4 a = *reinterpret_cast<const float4*>(stage + stage_off(4 * i + sub_r, sub_q));
+                  const float nrm = nrm8[i];
+                  a.x = rrelu_max(a.x) * nrm; a.y = rrelu_max(a.y) * nrm; a.z = rrelu_max(a.z) * nrm; a.w = rrelu_max(a.w) * nrm;
+                  const float sx = lean_sigmoid(g4[j].x + b4.x), sy = lean_sigmoid(g4[j].y + b4.y);
+                  const float sz = lean_sigmoid(g4[j].z + b4.z), sw = lean_sigmoid(g4[j].w + b4.w);
+                  a.x = fmaf(sx, a.x - h4[j].x, h4[j].x); a.y = fmaf(sy, a.y - h4[j].y, h4[j].y);
+                  a.z = fmaf(sz, a.z - h4[j].z, h4[j].z); a.w = fmaf(sw, a.w - h4[j].w, h4[j].w);
+                  const size_t o = (size_t)orow8[i] * ld_h + col;
+                  st4(p.lay_raw + o, a);
+                  if (p.lay_hi) {                              // uniform: the fp32-A consumers need no split copy
+                    float4 h, l;
+                    split_tf32_1(a.x, h.x, l.x); split_tf32_1(a.y, h.y, l.y);
+                    split_tf32_1(a.z, h.z, l.z); split_tf32_1(a.w, h.w, l.w);
+                    st4(p.lay_hi + o, h);
+                    st4(p.lay_lo + o, l);
+                  }
                 }
               }
             }
@@ -1183,7 +1198,8 @@ static int launch_tc(const float* a_hi, const float* a_lo, int lda, const float*
     if (p.a_k[0] + p.a_k[1] != Ktrue) { set_last_error("%s: fp32 A segments %d + %d != K = %d", who, p.a_k[0], p.a_k[1], Ktrue); return REGCN_ERR_DIM; }
     if (p.bf16 || p.a_mn || p.b_mn) { set_last_error("%s: fp32 A takes K-major tf32 operands", who); return REGCN_ERR_UNSUPPORTED; }
     // one K segment, rows in place: TMA delivers the fp32 k-blocks, the converter warps split them inside the stage
-    if (g_a32_tma && p.a_k[1] == 0 && !p.a_rows[0] && !(p.a_ld[0] & 3) && !((uintptr_t)p.a_ptr[0] & 15) && p.a_ld[0] >= p.a_k[0]) p.a_f32 = 2;
+    if ((g_a32_tma || p.epi == 5) && p.a_k[1] == 0 && !p.a_rows[0] && !(p.a_ld[0] & 3) && !((uintptr_t)p.a_ptr[0] & 15) && p.a_ld[0] >= p.a_k[0]) p.a_f32 = 2;
+    if (p.epi == 5 && p.a_f32 != 2) { set_last_error("%s: the fused time gate takes fp32 A as one K segment with its rows in place", who); return REGCN_ERR_UNSUPPORTED; }
     a_hi = a_lo = b_hi;                  // placeholders for the checks / unused tensor maps below
     lda = ldb;
   }
@@ -1234,7 +1250,8 @@ static int launch_tc(const float* a_hi, const float* a_lo, int lda, const float*
   if (split_k > total_kb) split_k = total_kb;
   p.kb_per_split = (total_kb + split_k - 1) / split_k;
   split_k = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
-  p.stages = (int)(SMEM_BUDGET / stage_bytes);
+  const int ew = p.epi == 5 ? epi_warps<5>() : EPI_WARPS;                 // epilogue warps of the instantiation that will run
+  p.stages = (int)(ring_budget(ew) / stage_bytes);
   if (p.stages > 8) p.stages = 8;
   if (g_force_stages > 0 && g_force_stages < p.stages) p.stages = g_force_stages;
   if (p.stages < (p.a_f32 ? 2 : 1)) { set_last_error("%s: tile does not fit in shared memory", who); return REGCN_ERR_UNSUPPORTED; }
@@ -1253,7 +1270,7 @@ static int launch_tc(const float* a_hi, const float* a_lo, int lda, const float*
   } else {
     ta_lo = ta_hi; tb_lo = tb_hi;
   }
-  const size_t smem = (size_t)p.stages * stage_bytes + 1024 + STAGING_BYTES;
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024 + staging_bytes(ew);
   static bool attr_set = false;
   if (!attr_set) {
     const int mx = (int)(SMEM_BUDGET + 1024 + STAGING_BYTES);   // + 2 KB of static shared memory = the 227 KB limit
@@ -1262,7 +1279,8 @@ static int launch_tc(const float* a_hi, const float* a_lo, int lda, const float*
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(gemm_tf32_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(gemm_tf32_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(gemm_tf32_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(gemm_tf32_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(gemm_tf32_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     (int)(ring_budget(epi_warps<5>()) + 1024 + staging_bytes(epi_warps<5>())));
     if (ce != cudaSuccess) { set_last_error("%s: cudaFuncSetAttribute failed: %s", who, cudaGetErrorString(ce)); return (int)ce; }
     attr_set = true;
   }
@@ -1302,7 +1320,7 @@ static int launch_tc(const float* a_hi, const float* a_lo, int lda, const float*
     case 1: launch_k(gemm_tf32_kernel<1>, grid, NUM_THREADS, smem, st, ta_hi, ta_lo, tb_hi, tb_lo, p); break;
     case 2: launch_k(gemm_tf32_kernel<2>, grid, NUM_THREADS, smem, st, ta_hi, ta_lo, tb_hi, tb_lo, p); break;
     case 3: launch_k(gemm_tf32_kernel<3>, grid, NUM_THREADS, smem, st, ta_hi, ta_lo, tb_hi, tb_lo, p); break;
-    case 5: launch_k(gemm_tf32_kernel<5>, grid, NUM_THREADS, smem, st, ta_hi, ta_lo, tb_hi, tb_lo, p); break;
+    case 5: launch_k(gemm_tf32_kernel<5>, grid, num_threads<5>(), smem, st, ta_hi, ta_lo, tb_hi, tb_lo, p); break;
     default: launch_k(gemm_tf32_kernel<4>, grid, NUM_THREADS, smem, st, ta_hi, ta_lo, tb_hi, tb_lo, p); break;
   }
   prof_end(PROF_GEMM_TC, alg_flops, st);
