@@ -319,6 +319,11 @@ REGCN_API int regcn_apply_filter(float* S, int64_t ld, int B, int N, const int64
  * regcn_filter_count / regcn_filter_fill build them from the query triples themselves (time-aware filtering,
  * rgcn/utils.py:264-304): key = (col 0, key_col), answers = ans_col; counts -> exclusive scan (caller) -> fill,
  * which also emits the (query, candidate) pair lists of the fused rank path (B target pairs first).           */
+/* One-call preparation of a test snapshot's queries (src/main.py:60-74, src/rrgcn.py:184-186): all_t (2T,3) = the triples
+ * followed by their inverses (o, r + R, s); counts (2, 2T) = regcn_filter_count of all_t for key_col 1 (entity filter) and 2
+ * (relation filter); beg (2, 2T) = their exclusive scans (the list offsets regcn_filter_fill takes); totals (2) = slot totals. */
+REGCN_API int regcn_queries_prepare(const int64_t* triples, int T, int R, int64_t* all_t, int32_t* counts, int32_t* beg,
+                                    int32_t* totals, void* stream);
 REGCN_API int regcn_filter_count(const int64_t* triples, int B, int key_col, int32_t* counts, void* stream);
 REGCN_API int regcn_filter_fill(const int64_t* triples, int B, int key_col, int ans_col, const int32_t* beg, int32_t* idx,
                       int32_t* end, int32_t* pair_a, int32_t* pair_e, void* stream);

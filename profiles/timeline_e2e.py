@@ -42,6 +42,8 @@ busy += cur_e - cur_s
 print(f"device busy (any stream) {busy / steps:.0f} us per step, idle {(t1 - t0 - busy) / steps:.0f} us per step")
 gaps.sort(reverse=True)
 print("largest idle gaps (us, at):", [(round(g, 1), round(a)) for g, a in gaps[:12]])
+json.dump([{"t": round(e["ts"] - t0, 1), "dur": round(e["dur"], 1), "s": e["args"].get("stream"), "name": e["name"].replace("regcn::", "").split("(")[0][:60]}
+           for e in ev], open("gpurun_out/timeline_e2e.json", "w"))
 agg = {}
 for e in ev:
     nm = e["name"].replace("regcn::", "").split("(")[0][:60]

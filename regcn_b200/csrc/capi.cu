@@ -238,6 +238,10 @@ int regcn_filter_correct(int B, const int32_t* filt_ptr, const int32_t* filt_idx
   return filter_correct(B, filt_ptr, filt_idx, target, pair_score, raw_count, col_lo, col_hi, filt_count, filt_end,
                         ST(stream));
 }
+int regcn_queries_prepare(const int64_t* triples, int T, int R, int64_t* all_t, int32_t* counts, int32_t* beg, int32_t* totals,
+                          void* stream) {
+  return queries_prepare(triples, T, R, all_t, counts, beg, totals, ST(stream));
+}
 int regcn_filter_count(const int64_t* triples, int B, int key_col, int32_t* counts, void* stream) {
   return filter_count(triples, B, key_col, counts, ST(stream));
 }

@@ -118,6 +118,7 @@ int rank_count(const float* S, int64_t ld, int B, int N, const int64_t* triples,
                const int* filt_idx, int col_offset, const float* target_score, int* raw_count, int* filt_count,
                const int* filt_end, cudaStream_t st);
 int filter_count(const int64_t* triples, int B, int key_col, int* counts, cudaStream_t st);
+int queries_prepare(const int64_t* triples, int T, int R, int64_t* all_t, int* counts, int* beg, int* totals, cudaStream_t st);
 int filter_fill(const int64_t* triples, int B, int key_col, int ans_col, const int* beg, int* idx, int* end, int* pair_a,
                 int* pair_e, cudaStream_t st);
 int mean_f32(const float* x, int n, float* out, cudaStream_t st);

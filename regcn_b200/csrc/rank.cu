@@ -303,6 +303,81 @@ __global__ void __launch_bounds__(kFiltThreads) filter_fill_kernel(const int64_t
   }
 }
 
+// ---- one-call preparation of a test snapshot's queries (src/main.py:60-74 before predict / get_total_rank) ----------
+// all_t = [triples ; (o, r + R, s)] (src/rrgcn.py:184-186), the match counts of both filter keys and their exclusive
+// scans: what regcn_b200.test() needs on the device before it can size the filter lists of a timestamp.  Three launches
+// instead of ~14 framework operations (flip / add / cat / 2 x {count, cumsum, subtract, slice}).
+__global__ void __launch_bounds__(256) queries_inverse_kernel(const int64_t* __restrict__ triples, int T, int R,
+                                                              int64_t* __restrict__ all_t) {
+  pdl_grid_sync();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T) return;
+  const int64_t s = triples[3 * (size_t)i], r = triples[3 * (size_t)i + 1], o = triples[3 * (size_t)i + 2];
+  int64_t* f = all_t + 3 * (size_t)i;
+  int64_t* b = all_t + 3 * ((size_t)T + i);
+  f[0] = s; f[1] = r; f[2] = o;
+  b[0] = o; b[1] = r + R; b[2] = s;
+}
+
+__global__ void __launch_bounds__(kFiltThreads) filter_count2_kernel(const int64_t* __restrict__ triples, int B,
+                                                                     int* __restrict__ counts) {
+  pdl_grid_sync();
+  __shared__ long long skeys[kFiltTile];
+  const int key_col = 1 + (int)blockIdx.y;                 // y = 0: entity filter (h, r); y = 1: relation filter (h, t)
+  const int lane = threadIdx.x & 31;
+  const int b = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+  const bool live = b < B;
+  const long long mykey = live ? filt_key(triples, b, key_col) : 0;
+  int c = 0;
+  for (int tile0 = 0; tile0 < B; tile0 += kFiltTile) {
+    const int tn = filt_stage_keys(triples, B, key_col, tile0, skeys);
+    if (live)
+      for (int j = lane; j < tn; j += 32) c += skeys[j] == mykey ? 1 : 0;
+  }
+  c = warp_sum_i(c);
+  if (live && lane == 0) counts[(size_t)blockIdx.y * B + b] = c;
+}
+
+// exclusive scan of counts[y][0..B) into beg[y][0..B), totals[y] = sum; one 1024-thread CTA per y
+__global__ void __launch_bounds__(1024) filter_scan2_kernel(const int* __restrict__ counts, int B, int* __restrict__ beg,
+                                                            int* __restrict__ totals) {
+  pdl_grid_sync();
+  __shared__ int wsum[32];
+  const int* c = counts + (size_t)blockIdx.y * B;
+  int* o = beg + (size_t)blockIdx.y * B;
+  const int per = (B + 1023) / 1024;
+  const int lo = min(B, (int)threadIdx.x * per), hi = min(B, lo + per);
+  int s = 0;
+  for (int i = lo; i < hi; ++i) s += c[i];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int inc = s;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += v; }
+  if (lane == 31) wsum[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    int v = wsum[lane];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += u; }
+    wsum[lane] = v;
+  }
+  __syncthreads();
+  int run = inc - s + (w > 0 ? wsum[w - 1] : 0);          // exclusive prefix of this thread's slice
+  for (int i = lo; i < hi; ++i) { o[i] = run; run += c[i]; }
+  if (threadIdx.x == 1023) totals[blockIdx.y] = wsum[31];
+}
+
+int queries_prepare(const int64_t* triples, int T, int R, int64_t* all_t, int* counts, int* beg, int* totals, cudaStream_t st) {
+  if (!triples || !all_t || !counts || !beg || !totals) { set_last_error("queries_prepare: null pointer"); return REGCN_ERR_NULL; }
+  if (T <= 0 || R <= 0 || T > (1 << 24)) { set_last_error("queries_prepare: bad dims T=%d R=%d", T, R); return REGCN_ERR_DIM; }
+  const int B = 2 * T;
+  launch_k(queries_inverse_kernel, (unsigned)((T + 255) / 256), 256, 0, st, triples, T, R, all_t);
+  launch_k(filter_count2_kernel, dim3((unsigned)(((size_t)B * 32 + kFiltThreads - 1) / kFiltThreads), 2), dim3(kFiltThreads), 0, st,
+           (const int64_t*)all_t, B, counts);
+  launch_k(filter_scan2_kernel, dim3(1, 2), dim3(1024), 0, st, (const int*)counts, B, beg, totals);
+  return check_launch("queries_prepare");
+}
+
 int filter_count(const int64_t* triples, int B, int key_col, int* counts, cudaStream_t st) {
   if (!triples || !counts) { set_last_error("filter_count: null pointer"); return REGCN_ERR_NULL; }
   if (key_col < 1 || key_col > 2) { set_last_error("filter_count: key_col must be 1 or 2"); return REGCN_ERR_DIM; }

@@ -265,7 +265,7 @@ def evaluate_from_host(model, history_host, test_host, num_nodes, num_rels, devi
 class _Prepared:
     """Inputs of one evaluated timestamp whose device-side preparation is enqueued but whose sizes are still on the way
     to the host (pinned buffer + event)."""
-    __slots__ = ("glist", "new_graphs", "all_t", "pf_ent", "pf_rel", "sizes_host", "event")
+    __slots__ = ("glist", "new_graphs", "all_t", "pf_ent", "pf_rel", "sizes_host", "event", "totals")
 
 
 def _prepare(cache, input_list, test_snap, num_rels, device, sizes_slot, prep_stream, main_stream, ahead=()):
@@ -283,14 +283,19 @@ def _prepare(cache, input_list, test_snap, num_rels, device, sizes_slot, prep_st
         p.glist = glist[:len(input_list)]
         t = test_snap if isinstance(test_snap, torch.Tensor) else torch.from_numpy(test_snap)
         test = t.to(device, non_blocking=True)
-        inv = test.flip(1)
-        inv[:, 1] = inv[:, 1] + num_rels
-        p.all_t = torch.cat((test, inv)).contiguous()
-        p.pf_ent, p.pf_rel = utils.filter_lists_begin(p.all_t, 0), utils.filter_lists_begin(p.all_t, 1)
-        parts = [p.pf_ent.total, p.pf_rel.total]
-        if p.new_graphs:
-            parts.append(pending_counts(p.new_graphs).flatten())
-        sizes = torch.cat(parts)
+        if 0 < test.shape[0] <= 16384:
+            # inverse triples, both filter-list count passes and their scans in one C call
+            p.all_t, p.pf_ent, p.pf_rel, totals = utils.queries_prepare(test, num_rels)
+            sizes = torch.cat((totals, pending_counts(p.new_graphs).flatten())) if p.new_graphs else totals
+        else:
+            inv = test.flip(1)
+            inv[:, 1] = inv[:, 1] + num_rels
+            p.all_t = torch.cat((test, inv)).contiguous()
+            p.pf_ent, p.pf_rel = utils.filter_lists_begin(p.all_t, 0), utils.filter_lists_begin(p.all_t, 1)
+            parts = [p.pf_ent.total, p.pf_rel.total]
+            if p.new_graphs:
+                parts.append(pending_counts(p.new_graphs).flatten())
+            sizes = torch.cat(parts)
         p.sizes_host = sizes_slot[:sizes.numel()]
         p.sizes_host.copy_(sizes, non_blocking=True)
         p.event = torch.cuda.Event()
@@ -302,13 +307,20 @@ def _prepare(cache, input_list, test_snap, num_rels, device, sizes_slot, prep_st
     return p
 
 
-def _finish_prepare(p):
+def _finish_prepare(p, filters=True):
+    """Read the sizes of a prepared timestamp and finalise its graphs; with filters=False the two filter lists are left
+    for _finish_filters (so that their fill launches can be enqueued BEHIND the evolution that only needs the graphs)."""
     from .graph import finish_sub_graphs
     p.event.synchronize()
     sizes = p.sizes_host.tolist()
     if p.new_graphs:
         finish_sub_graphs(p.new_graphs, [sizes[2 + 8 * i:10 + 8 * i] for i in range(len(p.new_graphs))])
-    return p.pf_ent.finish(sizes[0]), p.pf_rel.finish(sizes[1])
+    p.totals = (sizes[0], sizes[1])
+    return _finish_filters(p) if filters else None
+
+
+def _finish_filters(p):
+    return p.pf_ent.finish(p.totals[0]), p.pf_rel.finish(p.totals[1])
 
 
 @torch.no_grad()
@@ -464,13 +476,15 @@ def test(model, history_list, test_list, num_rels, num_nodes, use_cuda=True, all
             if prep_stream is not main_stream:
                 main_stream.wait_event(cur.event)
         _t1 = time.perf_counter()
-        filters = [_finish_prepare(cur) for cur in group]
+        for cur in group:
+            _finish_prepare(cur, filters=False)
         _t2 = time.perf_counter()
         if n_g > 1:
             states = model.forward_batch([cur.glist for cur in group])
         else:
             evolve_embs, _, r_emb, _, _ = model.forward(group[0].glist, static_graph, True)
             states = [(evolve_embs[-1], r_emb)]
+        filters = [_finish_filters(cur) for cur in group]      # the fill launches queue up behind the evolution
         _t3 = time.perf_counter()
         # the next group's preparation goes behind this evolution and in front of its decodes: its sizes are on the host
         # when the next iteration asks for them (in steady state it was already prepared one iteration earlier)

@@ -21,6 +21,11 @@ class _Frame(dict):
     pass
 
 
+# arrays of one snapshot's index, in arena order (norm, float32, follows them)
+_VIEWS = ("src", "dst", "etype", "indeg", "rowptr", "src_sorted", "etype_sorted", "eperm", "vptr", "sptr", "vrow_row",
+          "active_pos", "rel_rowptr", "rel_ents", "_counts", "active_rows")
+
+
 class SnapshotGraph:
     def __init__(self, num_nodes, num_rels, triples_dev, _defer_counts=False, _defer_build=False, _shell=None):
         self.num_nodes = int(num_nodes)
@@ -35,38 +40,46 @@ class SnapshotGraph:
         N, R, E = self.num_nodes, self.num_rels, 2 * T
         self.num_edges = E
         dev = self.device
-        # one arena for every int32 array of the index (a single allocation per snapshot)
+        # one arena for every int32 array of the index (a single allocation per snapshot); the per-array tensor views are
+        # made on first access (_VIEWS / __getattr__): the evaluation loop only ever needs their addresses
         sizes = [E, E, E, N, N + 1, E, E, E, N + 1, N + 1, min(N, E) + E // AGG_CHUNK + 1, N, R + 1, E, 8, min(N, E)]
         offs, tot = [], 0
         for n in sizes:
             offs.append(tot)
             tot += (max(int(n), 1) + 3) // 4 * 4          # keep every view 16-byte aligned
         arena = torch.empty(tot + N, device=dev, dtype=I32)
-        v = [arena[o:o + max(int(n), 1)] for o, n in zip(offs, sizes)]
-        (self.src, self.dst, self.etype, self.indeg, self.rowptr, self.src_sorted, self.etype_sorted, self.eperm,
-         self.vptr, self.sptr, self.vrow_row, self.active_pos, self.rel_rowptr, self.rel_ents, self._counts,
-         self.active_rows) = v
-        self.norm = arena[tot:tot + N].view(torch.float32)
         self._arena = arena
+        self._layout = {name: (o, max(int(n), 1)) for name, o, n in zip(_VIEWS, offs, sizes)}
+        self._layout["norm"] = (tot, N)
+        base = arena.data_ptr()
+        self._addr = {name: base + 4 * o for name, (o, _) in self._layout.items()}
         if not _defer_build:
             ws_bytes = _lib.load().regcn_csr_build_workspace_bytes(T, N, R)
             ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
-            call("regcn_csr_build", ptr(triples_dev), T, N, R, self.src.data_ptr(), self.dst.data_ptr(),
-                 self.etype.data_ptr(), self.indeg.data_ptr(), self.norm.data_ptr(), self.rowptr.data_ptr(),
-                 self.src_sorted.data_ptr(), self.etype_sorted.data_ptr(), self.eperm.data_ptr(), self.vptr.data_ptr(),
-                 self.sptr.data_ptr(), self.vrow_row.data_ptr(), self.active_pos.data_ptr(), self.active_rows.data_ptr(),
-                 self.rel_rowptr.data_ptr(),
-                 self.rel_ents.data_ptr(), self._counts.data_ptr(), ptr(ws), ws_bytes)
+            a = self._addr
+            call("regcn_csr_build", ptr(triples_dev), T, N, R, a["src"], a["dst"], a["etype"], a["indeg"], a["norm"], a["rowptr"],
+                 a["src_sorted"], a["etype_sorted"], a["eperm"], a["vptr"], a["sptr"], a["vrow_row"], a["active_pos"],
+                 a["active_rows"], a["rel_rowptr"], a["rel_ents"], a["_counts"], ptr(ws), ws_bytes)
         self._ndata = None
         self._edata = None
         self._r2e = None
-        self.ptr_table = np.array([t.data_ptr() for t in (self.rowptr, self.src_sorted, self.etype_sorted, self.indeg,
-                                                          self.norm, self.vptr, self.sptr, self.vrow_row,
-                                                          self.rel_rowptr, self.rel_ents, self.active_pos,
-                                                          self.active_rows)],
+        self.ptr_table = np.array([self._addr[k] for k in ("rowptr", "src_sorted", "etype_sorted", "indeg", "norm", "vptr", "sptr",
+                                                          "vrow_row", "rel_rowptr", "rel_ents", "active_pos", "active_rows")],
                                   dtype=np.uint64)
         if not _defer_counts and not _defer_build:
             self._set_counts(self._counts.tolist())          # the one host sync of graph construction
+
+    def __getattr__(self, name):
+        # tensor view of one array of the index, created on first access (only reached when the attribute is missing)
+        lay = self.__dict__.get("_layout")
+        if lay is not None and name in lay:
+            o, n = lay[name]
+            v = self._arena[o:o + n]
+            if name == "norm":
+                v = v.view(torch.float32)
+            self.__dict__[name] = v
+            return v
+        raise AttributeError(name)
 
     def _descriptor(self, desc):
         """Fill a struct regcn_csr_arrays with this snapshot's pointers (batched build)."""
@@ -74,8 +87,8 @@ class SnapshotGraph:
         desc.T = self.num_edges // 2
         for name in ("src", "dst", "etype", "indeg", "norm", "rowptr", "src_sorted", "etype_sorted", "eperm", "vptr",
                      "sptr", "vrow_row", "active_pos", "active_rows", "rel_rowptr", "rel_ents"):
-            setattr(desc, name, getattr(self, name).data_ptr())
-        desc.counts = self._counts.data_ptr()
+            setattr(desc, name, self._addr[name])
+        desc.counts = self._addr["_counts"]
 
     def _set_counts(self, c):
         self.n_vrows, self.n_split_chunks, self.n_rel_ents, self.max_hub_degree, self.n_active = c[:5]
@@ -228,19 +241,17 @@ def concat_graphs(graphs, out=None):
         out._cdesc = _lib.CsrArrays()
         out._descriptor(out._cdesc)
     out.num_edges = 2 * T
-    descs = (_lib.CsrArrays * G)()
-    sizes = (ctypes.c_int32 * (4 * G))()
-    for i, g in enumerate(graphs):
-        d = g.__dict__.get("_cdesc")
-        if d is None:
-            d = g._cdesc = _lib.CsrArrays()
-            g._descriptor(d)
-        descs[i] = d
-        sizes[4 * i], sizes[4 * i + 1], sizes[4 * i + 2], sizes[4 * i + 3] = g.n_vrows, g.n_split_chunks, g.n_rel_ents, g.n_active
-    call("regcn_csr_concat", ctypes.addressof(descs), ctypes.addressof(sizes), G, N, R, ctypes.addressof(out._cdesc))
-    out._set_counts([sum(g.n_vrows for g in graphs), sum(g.n_split_chunks for g in graphs),
-                     sum(g.n_rel_ents for g in graphs), max(g.max_hub_degree for g in graphs),
-                     sum(g.n_active for g in graphs)])
+    for g in graphs:                                   # per-member descriptor and size row, made once per snapshot
+        if "_cdesc" not in g.__dict__:
+            g._cdesc = _lib.CsrArrays()
+            g._descriptor(g._cdesc)
+            g._sz5 = np.array([g.n_vrows, g.n_split_chunks, g.n_rel_ents, g.n_active, g.max_hub_degree], dtype=np.int32)
+    descs = (_lib.CsrArrays * G)(*[g._cdesc for g in graphs])
+    sz = np.stack([g._sz5 for g in graphs])
+    sizes = np.ascontiguousarray(sz[:, :4])
+    call("regcn_csr_concat", ctypes.addressof(descs), sizes.ctypes.data, G, N, R, ctypes.addressof(out._cdesc))
+    tot = sz.sum(axis=0)
+    out._set_counts([int(tot[0]), int(tot[1]), int(tot[2]), int(sz[:, 4].max()), int(tot[3])])
     out._ndata = out._edata = out._r2e = None
     out.members = G
     return out

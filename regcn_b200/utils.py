@@ -121,6 +121,31 @@ def filter_lists_begin(all_triples, rel_predict=0):
     return _PendingFilter(all_triples.contiguous(), rel_predict)
 
 
+def queries_prepare(test_triples, num_rels):
+    """Device-side preparation of one test snapshot in ONE C call (`regcn_queries_prepare`): returns (all_triples,
+    pending_entity_filter, pending_relation_filter, totals) -- all_triples = the (T,3) int64 device triples followed by
+    their inverses (src/rrgcn.py:184-186), the two filter objects are in the state filter_lists_begin leaves them in
+    (counts and offsets on the device), totals (2,) int32 = the slot totals their finish() needs from the host."""
+    from ._lib import call, ptr
+    t = test_triples.contiguous()
+    T = int(t.shape[0])
+    B = 2 * T
+    dev = t.device
+    all_t = torch.empty((B, 3), device=dev, dtype=torch.int64)
+    work = torch.empty(4 * B + 2, device=dev, dtype=torch.int32)          # counts (2,B) | offsets (2,B) | totals (2)
+    counts, beg, totals = work[:2 * B].view(2, B), work[2 * B:4 * B].view(2, B), work[4 * B:]
+    call("regcn_queries_prepare", ptr(t), T, int(num_rels), ptr(all_t), ptr(counts), ptr(beg), ptr(totals))
+    out = []
+    for rel_predict in (0, 1):
+        pf = _PendingFilter.__new__(_PendingFilter)
+        pf.triples, pf.B = all_t, B
+        pf.key_col, pf.ans_col = (2, 1) if rel_predict else (1, 2)
+        pf.beg = beg[rel_predict]
+        pf.total = totals[rel_predict:rel_predict + 1]
+        out.append(pf)
+    return all_t, out[0], out[1], totals
+
+
 def filter_lists_from_queries(all_triples, rel_predict=0):
     """Kernel-built time-aware filter lists for the queries themselves (the test snapshot incl. inverses): two
     launches + one scan + one host read of the slot total; also yields the fused-rank pair lists.  All-pairs scan
