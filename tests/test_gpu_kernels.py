@@ -593,6 +593,30 @@ def test_filter_lists_hub_queries_and_duplicates():
                 assert (rows[sl] == q).all() and set(cand[sl].tolist()) == set(lists[q])
 
 
+def test_queries_prepare_equals_stepwise_preparation():
+    """regcn_queries_prepare (inverse triples + both filter count passes + their scans in one call) against the framework
+    operations it replaces (flip / add / cat, regcn_filter_count + cumsum), incl. more queries than one 1024-thread scan
+    slice per thread and a single triple."""
+    R, _ = _ops()
+    from regcn_b200 import utils
+    rng = np.random.default_rng(3)
+    for T, n, r in ((1, 50, 4), (37, 50, 4), (1457, 23033, 256), (5000, 300, 7)):
+        tri = np.stack((rng.integers(0, n, T), rng.integers(0, r, T), rng.integers(0, n, T)), 1).astype(np.int64)
+        t = torch.from_numpy(tri).to(DEV)
+        all_t, pf_e, pf_r, totals = utils.queries_prepare(t, r)
+        ref_all = torch.from_numpy(restate.add_inverse(tri, r)).to(DEV)
+        assert torch.equal(all_t, ref_all)
+        for pf, rel_p in ((pf_e, 0), (pf_r, 1)):
+            old = utils.filter_lists_begin(ref_all, rel_p)
+            assert torch.equal(pf.beg, old.beg) and int(pf.total) == int(old.total)
+            assert a_lists(pf.finish()) == a_lists(old.finish())
+        assert totals.tolist() == [int(pf_e.total), int(pf_r.total)]
+
+
+def a_lists(f):
+    return f.lists()
+
+
 # ----------------------------------------------------------------------------------------- tcgen05 GEMM
 @pytest.mark.parametrize("impl,rtol", [("tc", 1e-4), ("tc1", 4e-3)])
 @pytest.mark.parametrize("M,N,K,trans_b,bias,split_k", [
