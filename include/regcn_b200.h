@@ -199,6 +199,9 @@ REGCN_API void regcn_evolve_a32_mode(int mode);
 REGCN_API long long regcn_kernel_launches(void);
 /* tuning knob for experiments: force the N tile (multiple of 16, <= 256; 0 = automatic) and cap the pipeline depth */
 REGCN_API void regcn_gemm_tf32_tune(int block_n, int stages);
+/* Persistent-grid cap of the calling thread's next GEMM launches: at most `ctas` CTAs (0 = the whole machine).  The evolve
+ * engine uses it to split the SMs between its two streams; profiles/ uses it to separate per-SM from chip-wide limits. */
+REGCN_API void regcn_gemm_tf32_grid_cap(int ctas);
 /* fp32-A variants of regcn_gemm_tf32 / regcn_gemm_tf32_layer: the A operand is ONE fp32 copy in memory,
  *   A[m, :] = [ a0[rows0 ? rows0[m] : m, 0:k0] | a1[rows1 ? rows1[m] : m, 0:k1] ]      (k1 = 0: one segment)
  * and is split into the TF32 (hi, lo) pair inside shared memory by converter warps of the GEMM kernel, bit-identically

@@ -19,8 +19,8 @@ lib = _lib.load()
 _lib.require_device()
 dev = torch.device("cuda", 0)
 SLOTS = lib.regcn_gemm_tf32_trace_slots()
-N, d, R2 = 23033, 200, 512
-n_act = 1560
+N, d, R2 = int(os.environ.get("REGCN_TRACE_ROWS", "23033")), 200, 512      # REGCN_TRACE_ROWS=184264: 8 windows per recurrence
+n_act = 1560 * max(1, N // 23033)
 rng = torch.Generator(device=dev)
 rng.manual_seed(0)
 
@@ -171,9 +171,17 @@ def main():
              ("store 23033x400x200", store400), ("store 23033x200x200", store200),
              ("store 23033x200x200 1-pass", store200_1pass), ("GRU gh 512x600x200 +bias", gru_gh),
              ("compact0 1560x200x400 scatter-epilogue", compact0), ("compact1 1560x200x400 store", compact1)]
+    cap = int(os.environ.get("REGCN_TRACE_CAP", "0"))          # persistent-grid cap: per-SM vs chip-wide limits
+    only = os.environ.get("REGCN_TRACE_ONLY")
+    lib.regcn_gemm_tf32_grid_cap(cap)
     for name, fn in cases:
+        if only and only not in name:
+            continue
         us = timed(fn)
-        res.append(describe(name, trace(fn), us))
+        res.append(describe(name + (f" [grid cap {cap}]" if cap else ""), trace(fn), us))
+    lib.regcn_gemm_tf32_grid_cap(0)
+    if only:
+        return
     # tile-shape sensitivity of the two big layer GEMMs
     for bn, st in ((208, 0), (128, 0), (104, 0), (64, 0)):
         lib.regcn_gemm_tf32_tune(bn, st)

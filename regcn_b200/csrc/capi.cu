@@ -167,6 +167,7 @@ void regcn_two_stream_enable(int on) { regcn::two_stream_set(on); }
 void regcn_evolve_a32_mode(int mode) { regcn::evolve_a32_set(mode); }
 long long regcn_kernel_launches(void) { return __atomic_load_n(&regcn::g_kernel_launches, __ATOMIC_RELAXED); }
 void regcn_gemm_tf32_tune(int block_n, int stages) { gemm_tf32_tune(block_n, stages); }
+void regcn_gemm_tf32_grid_cap(int ctas) { regcn::gemm_tf32_grid_cap(ctas); }
 void regcn_aggregate_tune(int impl) { aggregate_tune(impl); }
 int regcn_gemm_tf32_a32(const float* a0, int lda0, int k0, const int32_t* rows0, const float* a1, int lda1, int k1,
                         const int32_t* rows1, const float* b_hi, const float* b_lo, int ldb, float* C, int ldc, int M, int N,
