@@ -755,14 +755,17 @@ def main():
         return evaluate.evaluate_batch(model, windows[:count], trip_l[:count], filt_l[:count], tm)
 
     def timed_batches(steps, warmup):
-        """`steps` timestamps in batches of G (the last one smaller), L2 flushed between batches (untimed)."""
-        for _ in range(max(2, -(-warmup // G))):
-            run_batch(G)
+        """`steps` timestamps in ceil(steps / G) batches of equal size (+-1), L2 flushed between batches (untimed)."""
+        n_batches = -(-steps // G)
+        sizes = [steps // n_batches + (1 if i < steps % n_batches else 0) for i in range(n_batches)]
+        # warm-up in the batch sizes of the timed region (a new size builds its union-graph arrays and tiled tables once)
+        for cnt in sorted(set(sizes)):
+            for _ in range(max(2, -(-warmup // cnt))):
+                run_batch(cnt)
         barrier()
         pairs, tms = [], []
         done = 0
-        while done < steps:
-            cnt = min(G, steps - done)
+        for cnt in sizes:
             flush.fill_(1.0)
             tm = {k: (ev(), ev()) for k in (("evolve", "score", "rank") if G == 1 else ("evolve", "score"))}
             a, b = ev(), ev()

@@ -352,6 +352,21 @@ REGCN_API int regcn_regcn_evolve(const void* const* model_ptrs, const int* model
                        const int* graph_ints, int L, float* hist, float* h0_out, int rel_nsplit, void* workspace,
                        size_t workspace_bytes, void* stream);
 
+/* Shared-trajectory form of the same recurrence for G history windows of ONE model evolved together
+ * (RecurrentRGCN.forward_batch; the evaluation loop of src/main.py:60-90 re-runs src/rrgcn.py:142-180 per test timestamp
+ * over windows that do not depend on each other).  Tables and graphs are those of regcn_regcn_evolve in the numbering of
+ * regcn_csr_concat (N = G N0 entity rows, entity (g, v) = row g N0 + v).  A row without in-edges is updated from its own
+ * state only and all windows start from one table, so the all-entity products run over N0 shared rows plus the rows that
+ * have been active in their window so far (compact, bit-identical per row) instead of G N0 rows.  Output: h_final (N, d) =
+ * history_embs[-1] of every window, h0_out as above; intermediate history_embs are not produced.  sum_active / max_active
+ * = sum / maximum of graph_ints[RGI_N_ACTIVE] over the L snapshots.  REGCN_ERR_UNSUPPORTED (nothing enqueued) unless
+ * n_layers >= 2, self_loop and every snapshot has n_active <= N / 2: callers then use regcn_regcn_evolve.            */
+REGCN_API size_t regcn_regcn_evolve_shared_workspace_bytes(int N0, int G, int R2, int d, int max_split_chunks, int rel_nsplit,
+                                                           long long sum_active, int max_active);
+REGCN_API int regcn_regcn_evolve_shared(const void* const* model_ptrs, const int* model_ints, const void* const* graph_ptrs,
+                              const int* graph_ints, int L, int G, float* h_final, float* h0_out, int rel_nsplit,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- whole-recurrence orchestration, hyperbolic: HyperbolicRecurrentRGCN.forward, hyperbolic_model.py:722-890
  * (encoders hyperbolic_uvrgcn = 0 and lgcn = 1, self_loop, no skip connection, fixed curvature).  Same calling
  * convention as regcn_regcn_evolve plus a double table for the scalars.                                         */

@@ -43,6 +43,8 @@ SIGNATURES = {
     "regcn_gemm_tf32": (_i, [_p, _p, _i, _p, _p, _i, _p, _i, _i, _i, _i, _p, _i, _i, _i, _p, _sz, _p]),
     "regcn_regcn_evolve_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "regcn_regcn_evolve": (_i, [_p, _p, _p, _p, _i, _p, _p, _i, _p, _sz, _p]),
+    "regcn_regcn_evolve_shared_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, ctypes.c_longlong, _i]),
+    "regcn_regcn_evolve_shared": (_i, [_p, _p, _p, _p, _i, _i, _p, _p, _i, _p, _sz, _p]),
     "regcn_gemm_tf32_tune": (None, [_i, _i]),
     "regcn_gemm_tf32_grid_cap": (None, [_i]),
     "regcn_gemm_tf32_a32": (_i, [_p, _i, _i, _p, _p, _i, _i, _p, _p, _p, _i, _p, _i, _i, _i, _p, _i, _i, _i, _p, _sz, _p, _i, _p]),

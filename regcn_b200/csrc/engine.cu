@@ -402,6 +402,253 @@ int regcn_regcn_evolve(const void* const* mp, const int* mi, const void* const* 
   return REGCN_OK;
 }
 
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
+// Shared-trajectory form of the batched recurrence (RecurrentRGCN.forward_batch: G history windows of one model as ONE
+// recurrence over the block-diagonal union graph, N = G N0 entity rows).
+//
+// The update of a row WITHOUT in-edges is row-local -- x' = rrelu(x W_evolve) per layer, then the time gate against its
+// own previous state (rgcn/layers.py:240-255, src/rrgcn.py:176-178) -- and every window starts from the same table
+// (src/rrgcn.py:154).  So until entity v first receives an edge in window g, row (g, v) holds exactly the state U_i[v]
+// that v has in every other window where it has not been touched either: the all-entity products of a step are needed
+// for N0 shared rows plus the rows that HAVE been active in their window, not for G N0 rows (ICEWS18 shape, 8 windows of
+// 6 snapshots: 36 % of the rows on average).  The entity state is therefore kept compact (rowops.cu
+// shared_rows_update): rows [0, N0) = the shared trajectory, one further row per (window, entity) from its first
+// activity on, in order of arrival.  The all-entity GEMMs run over the compact rows (contiguous: same TMA-fed kernels,
+// same per-row arithmetic, so every row is bit-identical to the full computation); the edge kernels keep the union
+// numbering and gather from a union-numbered table that only ever holds the rows of the CURRENT step's active
+// entities (every gathered row is an active one: each edge source is also a destination).  Only the last step's state
+// is expanded to union numbering (h_final); intermediate history_embs are not produced.
+// Preconditions (else REGCN_ERR_UNSUPPORTED, callers fall back to regcn_regcn_evolve): >= 2 layers, self_loop, every
+// snapshot in the sparse form (n_active <= N / 2).
+// ---------------------------------------------------------------------------------------------------------
+namespace regcn {
+struct SharedWs {
+  size_t xm_hi, xm_lo, gi, gh, h0_hi, h0_lo, agg_hi, agg_lo, P, Lm, o_c[2], h_c[2], x_full, o_full[2], partial, rel_partial, fold, fold_n;
+  size_t cpos, apos, act, count, total;
+  long long cap;
+};
+static SharedWs plan_shared(int N0, int G, int R2, int d, int max_split_chunks, int rel_nsplit, long long sum_active, int max_active) {
+  SharedWs w;
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off += al(n); return o; };
+  const long long N = (long long)N0 * G;
+  w.cap = N0 + (sum_active < N ? sum_active : N);
+  const size_t rd = (size_t)R2 * d, cd = (size_t)w.cap * d, nd = (size_t)N * d;
+  const size_t ma = (size_t)(max_active > 0 ? max_active : 1);
+  w.xm_hi = take(rd); w.xm_lo = take(rd);
+  w.gi = take(rd * 3); w.gh = take(rd * 3);
+  w.h0_hi = take(rd); w.h0_lo = take(rd);
+  w.agg_hi = take(ma * 2 * d); w.agg_lo = take(ma * 2 * d);
+  w.P = take(ma * d);
+  w.Lm = take(cd);
+  for (int k = 0; k < 2; ++k) { w.o_c[k] = take(cd); w.h_c[k] = take(cd); }
+  w.x_full = take(nd);
+  for (int k = 0; k < 2; ++k) w.o_full[k] = take(nd);
+  w.partial = take((size_t)(max_split_chunks > 0 ? max_split_chunks : 1) * (d + 1));
+  w.rel_partial = take(rel_nsplit > 1 ? (size_t)(R2 / 2) * rel_nsplit * d : 1);
+  w.fold_n = (size_t)(max_split_chunks > 0 ? max_split_chunks : 1);
+  w.fold = take(w.fold_n);
+  w.cpos = take((size_t)N); w.apos = take((size_t)w.cap); w.act = take(ma); w.count = take(64);
+  w.total = off * sizeof(float);
+  return w;
+}
+// SMs for the side stream in the shared-trajectory form (REGCN_SHARED_SIDE_SMS; 0 = balanced whole-machine grids).  With
+// a third of the rows in the all-entity GEMMs the chain of small kernels is the longer one and wants more of the machine
+// than in regcn_regcn_evolve.  Measured (B200, ICEWS18 shape, us per timestamp at 8 / 12 / 16 windows per recurrence;
+// profiles/time_batched_forward.py): 24 SMs 349 / - / -, 32: 305, 40: 285 / - / 225, 48: 279 / 235 / 220, 56: 261 / 225 / 210,
+// 64: 265 / 228 / 208, 72: 271 / 229 / 207, 80: 279; balanced grids: 271.
+static int shared_side_sms() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("REGCN_SHARED_SIDE_SMS"); v = e ? atoi(e) : 60; if (v < 0 || v > 96) v = 60; }
+  return v;
+}
+}  // namespace regcn
+
+extern "C" {
+
+size_t regcn_regcn_evolve_shared_workspace_bytes(int N0, int G, int R2, int d, int max_split_chunks, int rel_nsplit,
+                                                 long long sum_active, int max_active) {
+  return plan_shared(N0, G, R2, d, max_split_chunks, rel_nsplit < 1 ? 1 : rel_nsplit, sum_active, max_active).total;
+}
+
+int regcn_regcn_evolve_shared(const void* const* mp, const int* mi, const void* const* gp, const int* gi_, int L, int G,
+                              float* h_final, float* h0_out, int rel_nsplit, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!mp || !mi || !gp || !gi_ || !h_final || !h0_out || !workspace) { set_last_error("regcn_evolve_shared: null pointer"); return REGCN_ERR_NULL; }
+  const int N = mi[RMI_NUM_ENTS], R2 = mi[RMI_NUM_RELS2], d = mi[RMI_DIM], nl = mi[RMI_NUM_LAYERS];
+  const int layer_norm = mi[RMI_LAYER_NORM], self_loop = mi[RMI_SELF_LOOP];
+  if (N <= 0 || G < 1 || N % G || R2 <= 0 || (R2 & 1) || d <= 0 || (d & 3) || d > 256 || nl < 1 || nl > 8 || L < 1) {
+    set_last_error("regcn_evolve_shared: bad dims N=%d G=%d R2=%d d=%d layers=%d L=%d", N, G, R2, d, nl, L); return REGCN_ERR_DIM;
+  }
+  if (!self_loop || nl < 2) { set_last_error("regcn_evolve_shared: needs self_loop and >= 2 layers"); return REGCN_ERR_UNSUPPORTED; }
+  const int N0 = N / G;
+  int max_split = 0, max_active = 0;
+  long long sum_active = 0;
+  for (int i = 0; i < L; ++i) {
+    const int* gn = gi_ + (size_t)i * RGI_NUM_INTS;
+    if (gn[RGI_N_SPLIT_CHUNKS] > max_split) max_split = gn[RGI_N_SPLIT_CHUNKS];
+    if (gn[RGI_N_ACTIVE] > max_active) max_active = gn[RGI_N_ACTIVE];
+    if ((long long)gn[RGI_N_ACTIVE] * 2 > N) { set_last_error("regcn_evolve_shared: snapshot %d is not sparse (%d active of %d rows)", i, gn[RGI_N_ACTIVE], N); return REGCN_ERR_UNSUPPORTED; }
+    sum_active += gn[RGI_N_ACTIVE];
+  }
+  if (rel_nsplit < 1) rel_nsplit = 1;
+  const SharedWs w = plan_shared(N0, G, R2, d, max_split, rel_nsplit, sum_active, max_active);
+  if (workspace_bytes < w.total) { set_last_error("regcn_evolve_shared: workspace %zu < %zu", workspace_bytes, w.total); return REGCN_ERR_WORKSPACE; }
+  float* ws = (float*)workspace;
+  auto F = [&](int k) { return (const float*)mp[k]; };
+  int* cpos = reinterpret_cast<int*>(ws + w.cpos);
+  int* apos = reinterpret_cast<int*>(ws + w.apos);
+  int* act_c = reinterpret_cast<int*>(ws + w.act);
+  int* count = reinterpret_cast<int*>(ws + w.count);
+  int* fold = reinterpret_cast<int*>(ws + w.fold);
+  int e;
+
+  // ---- shared rows of step 0: F.normalize(dynamic_emb) if layer_norm (src/rrgcn.py:154); no window row exists yet ----
+  float* h_cur = ws + w.h_c[0];
+  float* h_nxt = ws + w.h_c[1];
+  if (layer_norm) {
+    if ((e = row_map(F(RM_DYNAMIC_EMB), h_cur, N0, d, 0, 1.0, nullptr, nullptr, nullptr, st))) return e;
+  } else if (cudaMemcpyAsync(h_cur, F(RM_DYNAMIC_EMB), (size_t)N0 * d * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+    cudaGetLastError(); set_last_error("regcn_evolve_shared: copy of the initial table failed"); return REGCN_ERR_UNSUPPORTED;
+  }
+  if (cudaMemsetAsync(cpos, 0xFF, (size_t)N * sizeof(int), st) != cudaSuccess ||
+      cudaMemsetAsync(count, 0, sizeof(int), st) != cudaSuccess) { cudaGetLastError(); set_last_error("regcn_evolve_shared: memset failed"); return REGCN_ERR_UNSUPPORTED; }
+  if (max_split > 0 && cudaMemsetAsync(fold, 0, w.fold_n * sizeof(int), st) != cudaSuccess) { cudaGetLastError(); fold = nullptr; }
+  if (max_split <= 0) fold = nullptr;
+  const float* h0_raw = F(RM_EMB_REL);
+  const float* h0_hi = F(RM_EMB_REL_HI);
+  const float* h0_lo = F(RM_EMB_REL_LO);
+
+  StreamScope scope(two_stream_enabled() ? aux_stream() : nullptr, st);
+  AuxStream* aux = scope.aux;
+  bool gh_ahead = false;
+  int sm_count = 148;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (sm_count <= 0) sm_count = 148;
+  }
+  const int side_sms = shared_side_sms();
+  long long rows_bound = N0;              // compact rows that can exist after this step's update (host-side bound)
+  for (int i = 0; i < L; ++i) {
+    const void* const* g = gp + (size_t)i * RG_NUM_PTRS;
+    const int* gn = gi_ + (size_t)i * RGI_NUM_INTS;
+    auto GI = [&](int k) { return (const int*)g[k]; };
+    const int n_active = gn[RGI_N_ACTIVE];
+    rows_bound += n_active;
+    const int Mc = (int)(rows_bound < w.cap ? rows_bound : w.cap);
+    const int* arows = GI(RG_ACTIVE_ROWS);
+    // ---- compact rows of this step's active entities; their state published in union numbering ----
+    if (cudaMemsetAsync(apos, 0xFF, (size_t)Mc * sizeof(int), st) != cudaSuccess) { cudaGetLastError(); set_last_error("regcn_evolve_shared: memset failed"); return REGCN_ERR_UNSUPPORTED; }
+    if ((e = shared_rows_update(arows, n_active, N0, d, cpos, count, h_cur, ws + w.x_full, act_c, apos, st))) return e;
+
+    bool two = aux != nullptr && N >= 4096;
+    bool side_pdl_off = false;
+    if (two) {
+      two = stream_after(aux->sb, st, aux->fork);
+      if (!two) scope.join();
+    }
+    cudaStream_t sB = two ? aux->sb : st;
+    // SM split between the streams: the compact all-entity GEMMs get sm_count - side_sms persistent CTAs when they run
+    // at least two rounds on them, the side chain the rest
+    const bool split_sms = two && side_sms > 0 && (long long)((Mc + 127) / 128) * 2 >= 2LL * (sm_count - side_sms);
+    auto main_knobs = [&]() { gemm_tf32_sm_hint(0); gemm_tf32_grid_cap(split_sms ? sm_count - side_sms : 0); };
+    auto side_knobs = [&](int ncol) {
+      gemm_tf32_sm_hint(split_sms ? side_sms : side_hint(Mc, d, ncol, sm_count));
+      gemm_tf32_grid_cap(split_sms ? side_sms : 0);
+    };
+    if (two) {
+      scope.b_open = true;
+      side_pdl_off = !side_pdl_keep();
+      side_knobs(2 * d);
+      pdl_suppress(side_pdl_off);
+    }
+    // ---- relation evolution (K2, K3): as in regcn_regcn_evolve, entity rows read from the published table ----
+    if (!gh_ahead) {
+      cudaStream_t sG = sB;
+      if (two && cudaStreamWaitEvent(aux->sc, aux->fork, 0) == cudaSuccess) { sG = aux->sc; scope.c_open = true; }
+      if ((e = gemm_tf32(h0_hi, h0_lo, d, F(RM_WHH_HI), F(RM_WHH_LO), d, ws + w.gh, 3 * d, R2, 3 * d, d, F(RM_B_HH), 0, 3, 1,
+                         nullptr, 0, nullptr, 0, sG))) return e;
+      gh_ahead = sG != sB;
+    }
+    if ((e = rel_mean_pool(ws + w.x_full, GI(RG_REL_ROWPTR), GI(RG_REL_ENTS), R2 / 2, d, rel_nsplit, nullptr, ws + w.rel_partial,
+                           ws + w.xm_hi, ws + w.xm_lo, sB))) return e;
+    if ((e = gemm_tf32(ws + w.xm_hi, ws + w.xm_lo, d, F(RM_WIH_R_HI), F(RM_WIH_R_LO), d, ws + w.gi, 3 * d, R2, 3 * d, d,
+                       nullptr, 0, 3, 1, nullptr, 0, F(RM_GI_STATIC), 3 * d, sB))) return e;
+    if (gh_ahead) {
+      if (!stream_after(sB, aux->sc, aux->c_done)) cudaStreamSynchronize(aux->sc);
+      scope.c_open = false;
+      gh_ahead = false;
+    }
+    if ((e = gru_gate(ws + w.gi, ws + w.gh, h0_raw, h0_out, R2, d, layer_norm, ws + w.h0_hi, ws + w.h0_lo, sB))) return e;
+    h0_raw = h0_out; h0_hi = ws + w.h0_hi; h0_lo = ws + w.h0_lo;
+    if (two && i + 1 < L && stream_after(aux->sc, sB, aux->h0_ready)) {
+      scope.c_open = true;
+      if ((e = gemm_tf32(h0_hi, h0_lo, d, F(RM_WHH_HI), F(RM_WHH_LO), d, ws + w.gh, 3 * d, R2, 3 * d, d, F(RM_B_HH), 0, 3,
+                         1, nullptr, 0, nullptr, 0, aux->sc))) return e;
+      gh_ahead = true;
+    }
+    // ---- entity evolution ----
+    const float* xa_full = ws + w.x_full;        // union-numbered input of the layer (active rows only)
+    const float* xa_c = h_cur;                   // compact input of the layer (all compact rows)
+    for (int l = 0; l < nl; ++l) {
+      const int base = RM_LAYER0 + RM_LAYER_STRIDE * l;
+      const bool last = l == nl - 1;
+      const int ncol = (l == 0 ? 2 : 1) * d;           // [W_evolve (| W_time)]
+      if ((e = union_aggregate(xa_full, h0_raw, GI(RG_ROWPTR), GI(RG_SRC_SORTED), GI(RG_ETYPE_SORTED), (const float*)g[RG_NORM],
+                               GI(RG_VPTR), GI(RG_SPTR), GI(RG_VROW_ROW), gn[RGI_N_VROWS], gn[RGI_N_SPLIT_CHUNKS], nullptr,
+                               0.f, N, d, nullptr, ws + w.partial, ws + w.agg_hi, ws + w.agg_lo, GI(RG_ACTIVE_POS), 2 * d,
+                               gn[RGI_MAX_CHUNKS], sB, fold))) return e;
+      if (!last) {
+        float* oc = ws + w.o_c[l & 1];
+        float* of = ws + w.o_full[l & 1];
+        if (two) { main_knobs(); pdl_suppress(l > 0); }
+        e = gemm_tf32_layer_a32(xa_c, d, d, nullptr, nullptr, 0, 0, nullptr, F(base + 6), F(base + 7), d, Mc, ncol, d, oc,
+                                nullptr, nullptr, l == 0 ? ws + w.Lm : nullptr, d, nullptr, apos, nullptr, 0, nullptr, nullptr,
+                                0, st);
+        pdl_suppress(two && side_pdl_off);
+        if (e) return e;
+        if (two) side_knobs(ncol);
+        if (n_active > 0 &&
+            (e = gemm_tf32_layer(ws + w.agg_hi, ws + w.agg_lo, 2 * d, F(base + 4), F(base + 5), 2 * d, n_active, d, 2 * d, d,
+                                 of, nullptr, nullptr, nullptr, 0, arows, nullptr, nullptr, 0, nullptr, nullptr, 0, sB))) return e;
+        xa_full = of; xa_c = oc;
+      } else {
+        if (two) side_knobs(d);
+        if (n_active > 0 &&
+            (e = gemm_tf32(ws + w.agg_hi, ws + w.agg_lo, 2 * d, F(base + 4), F(base + 5), 2 * d, ws + w.P, d, n_active, d,
+                           2 * d, nullptr, 0, 3, 1, nullptr, 0, nullptr, 0, sB))) return e;
+        if (two) { main_knobs(); pdl_suppress(true); }
+        e = gemm_tf32_layer_a32(xa_c, d, d, nullptr, nullptr, 0, 0, nullptr, F(base + 6), F(base + 7), d, Mc, d, d, h_nxt,
+                                nullptr, nullptr, nullptr, 0, nullptr, apos, ws + w.Lm, d, F(RM_GATE_BIAS), h_cur, layer_norm, st);
+        pdl_suppress(false);
+        if (e) return e;
+        if (two) {
+          if (!stream_after(st, sB, aux->b_done)) cudaStreamSynchronize(sB);
+          scope.b_open = false;
+        }
+        // active rows: gate columns and previous state at their compact rows, P in the order of active_rows
+        if (n_active > 0 &&
+            (e = time_gate(ws + w.Lm, F(RM_GATE_BIAS), ws + w.P, h_cur, h_nxt, n_active, d, layer_norm, d, nullptr, nullptr, st,
+                           act_c, 1))) return e;
+      }
+    }
+    gemm_tf32_sm_hint(0);
+    gemm_tf32_grid_cap(0);
+    pdl_suppress(false);
+    float* t = h_cur; h_cur = h_nxt; h_nxt = t;
+  }
+  return shared_rows_expand(h_cur, cpos, N, N0, d, h_final, st);
+}
+
+}  // extern "C"
+
+extern "C" {
+
 // ---------------------------------------------------------------------------------------------------------
 // Hyperbolic recurrence (HyperbolicRecurrentRGCN.forward, hyperbolic_model.py:722-890) in one call.
 // Encoder 0 = hyperbolic_uvrgcn (radius-weighted union aggregate + W_n GEMM), 1 = lgcn (Lorentz centroid).

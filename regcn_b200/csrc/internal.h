@@ -92,6 +92,9 @@ int union_combine(const float* P, const float* L, const int* indeg, const float*
 int time_gate(const float* G, const float* bias, const float* cur, const float* h, float* out, int N, int d,
               int normalize_cur, int ldg, float* out_hi, float* out_lo, cudaStream_t st, const int* row_idx = nullptr,
               int act = 0);
+int shared_rows_update(const int* active_rows, int n_active, int N0, int d, int* cpos, int* count, float* h_c, float* x_full,
+                       int* act_c, int* apos_c, cudaStream_t st);
+int shared_rows_expand(const float* h_c, const int* cpos, int N, int N0, int d, float* out, cudaStream_t st);
 int hyp_init(const float* emb, const float* radius_static, int N, int d, int normalize, int on_manifold, double c,
              float rmin, float rmax, float* out, cudaStream_t st);
 int hyp_tangent(const float* h, int N, int d, double c, float* ht, float* pt, float* radius, float* ht_hi,

@@ -214,6 +214,74 @@ int time_gate(const float* G, const float* bias, const float* cur, const float* 
   return check_launch("time_gate");
 }
 
+// ---- shared-trajectory evolution (engine.cu: regcn_regcn_evolve_shared) ------------------------------------------
+// G history windows evolved as one recurrence keep their entity state COMPACT: rows [0, N0) are the trajectory every
+// entity follows until it first receives an edge in its window (the inactive-row update is row-local, and all windows
+// start from the same table, so that trajectory is shared by all G windows); a row (g, v) of the union numbering gets
+// its own compact row the first time it is active.  One warp per active row of the step: assigns the compact row
+// (first activity: copies the shared row), publishes the row's state to the union-numbered table the edge kernels
+// gather from, and records the compact positions of the step's active rows.
+__global__ void __launch_bounds__(256) shared_rows_update_kernel(const int* __restrict__ active_rows, int n_active, int N0,
+                                                                 int d, int* __restrict__ cpos, int* __restrict__ count,
+                                                                 float* __restrict__ h_c, float* __restrict__ x_full,
+                                                                 int* __restrict__ act_c, int* __restrict__ apos_c) {
+  pdl_grid_sync();
+  const int lane = threadIdx.x & 31;
+  const int i = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+  if (i >= n_active) return;
+  const int a = __ldg(active_rows + i);
+  int p = 0, fresh = 0;
+  if (lane == 0) {
+    p = cpos[a];
+    if (p < 0) {
+      p = N0 + atomicAdd(count, 1);
+      cpos[a] = p;
+      fresh = 1;
+    }
+    act_c[i] = p;
+    apos_c[p] = i;
+  }
+  p = __shfl_sync(0xffffffffu, p, 0);
+  fresh = __shfl_sync(0xffffffffu, fresh, 0);
+  const float4* src = reinterpret_cast<const float4*>(h_c + (size_t)(fresh ? a % N0 : p) * d);
+  float4* own = reinterpret_cast<float4*>(h_c + (size_t)p * d);
+  float4* pub = reinterpret_cast<float4*>(x_full + (size_t)a * d);
+  for (int k = lane; k < (d >> 2); k += 32) {
+    const float4 v = src[k];
+    if (fresh) own[k] = v;
+    pub[k] = v;
+  }
+}
+
+// out[r] = h_c[cpos[r] >= 0 ? cpos[r] : r mod N0]: the union-numbered table of the last step
+__global__ void __launch_bounds__(256) shared_rows_expand_kernel(const float* __restrict__ h_c, const int* __restrict__ cpos,
+                                                                 int N, int N0, int d, float* __restrict__ out) {
+  pdl_grid_sync();
+  const int lane = threadIdx.x & 31;
+  const int r = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+  if (r >= N) return;
+  const int p = __ldg(cpos + r);
+  const float4* src = reinterpret_cast<const float4*>(h_c + (size_t)(p >= 0 ? p : r % N0) * d);
+  float4* dst = reinterpret_cast<float4*>(out + (size_t)r * d);
+  for (int k = lane; k < (d >> 2); k += 32) dst[k] = src[k];
+}
+
+int shared_rows_update(const int* active_rows, int n_active, int N0, int d, int* cpos, int* count, float* h_c, float* x_full,
+                       int* act_c, int* apos_c, cudaStream_t st) {
+  if (!active_rows || !cpos || !count || !h_c || !x_full || !act_c || !apos_c) { set_last_error("shared_rows_update: null pointer"); return REGCN_ERR_NULL; }
+  if (int e = check_d("shared_rows_update", d)) return e;
+  if (n_active <= 0) return REGCN_OK;
+  launch_k(shared_rows_update_kernel, row_grid(n_active), 256, 0, st, active_rows, n_active, N0, d, cpos, count, h_c, x_full, act_c, apos_c);
+  return check_launch("shared_rows_update");
+}
+int shared_rows_expand(const float* h_c, const int* cpos, int N, int N0, int d, float* out, cudaStream_t st) {
+  if (!h_c || !cpos || !out) { set_last_error("shared_rows_expand: null pointer"); return REGCN_ERR_NULL; }
+  if (int e = check_d("shared_rows_expand", d)) return e;
+  if (N <= 0) return REGCN_OK;
+  launch_k(shared_rows_expand_kernel, row_grid(N), 256, 0, st, h_c, cpos, N, N0, d, out);
+  return check_launch("shared_rows_expand");
+}
+
 // ---- K8: hyperbolic init / tangent prep / gate + radius evolution ------------------------------
 struct RadiusCfg {
   float rmin, rmax, rs_cap;   // _static_radius: min(clamp(rs, rmin, rmax), 1/sqrt(c) - 1e-6)   hyperbolic_model.py:715-720

@@ -151,6 +151,11 @@ def timestamps_per_batch(model, num_nodes, static_graph=None):
     env = os.environ.get("REGCN_TEST_BATCH")
     if env:
         return max(1, min(16, int(env)))
+    if hasattr(model, "_forward_engine_shared") and os.environ.get("REGCN_SHARED_ROWS", "1") != "0":
+        # shared-trajectory engine (regcn_regcn_evolve_shared): the all-entity products run over the rows touched so far,
+        # not G N rows, and the shared rows are amortised over the windows (ICEWS18 shape: 261 / 225 / 208 us per
+        # timestamp at 8 / 12 / 16 windows)
+        return max(1, min(16, 2 * BATCH_ROWS // max(1, int(num_nodes))))
     return max(1, min(8, BATCH_ROWS // max(1, int(num_nodes))))
 
 
@@ -462,13 +467,14 @@ def test(model, history_list, test_list, num_rels, num_nodes, use_cuda=True, all
 
     # start-up: only the first group is prepared in front of the first evolution (every prepare costs ~0.2 ms of host time
     # during which the GPU has nothing to do); the following groups are prepared behind it, see the two top-ups below
-    queue = [prepare(j) for j in range(min(G if G > 1 else PREP_DEPTH, K))]
+    G_FIRST = min(G, 4)   # the first group is short: its preparation is host time in front of an idle GPU
+    queue = [prepare(j) for j in range(min(G_FIRST if G > 1 else PREP_DEPTH, K))]
     next_j = len(queue)
     _tm = os.environ.get("REGCN_TEST_TIMING") == "1"
     _acc = [0.0] * 6
     k = 0
     while k < K:
-        n_g = min(G, K - k)
+        n_g = min(G if k else G_FIRST, K - k)
         group = [queue.pop(0) for _ in range(n_g)]
         _t0 = time.perf_counter()
         for cur in group:

@@ -4,6 +4,8 @@
 Per history snapshot (src/rrgcn.py:159-179): relation mean-pool (K2) -> relation GRU (K3) ->
 2 x UnionRGCNLayer (K4 aggregate + node GEMMs + K5 combine) -> time gate (K9).
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -223,6 +225,35 @@ class RecurrentRGCN(nn.Module):
                   hist.data_ptr(), h0.data_ptr(), rel_nsplit, ws.data_ptr(), ws.numel())
         return [hist[i] for i in range(L)], h0
 
+    def _forward_engine_shared(self, g_list, members):
+        """regcn_regcn_evolve_shared: the recurrence over `members` windows with the entity state kept compact (one shared
+        row per entity until it is first active in its window).  Returns (h_final (G N, d), h0) or None when the
+        preconditions do not hold (a dense snapshot, one layer) -- the caller then runs the plain engine."""
+        import numpy as np
+        from . import _lib
+        G = members
+        n_act = [int(g.n_active) for g in g_list]
+        N, R2, d = G * self.num_ents, 2 * G * self.num_rels, self.h_dim
+        if len(self.rgcn.layers) < 2 or any(2 * a > N for a in n_act) or os.environ.get("REGCN_SHARED_ROWS", "1") == "0":
+            return None
+        ptab, itab, _ = self._engine_tables_batch(G)
+        dev = self.dynamic_emb.device
+        gp = np.concatenate([g.ptr_table for g in g_list])
+        gi = np.concatenate([g.int_table for g in g_list])
+        max_split = max([g.n_split_chunks for g in g_list], default=0)
+        rel_nsplit = max([max(1, min(64, g.n_rel_ents // (max(1, R2 // 2) * 512))) for g in g_list], default=1)
+        need = _lib.load().regcn_regcn_evolve_shared_workspace_bytes(self.num_ents, G, R2, d, max_split, rel_nsplit,
+                                                                     sum(n_act), max(n_act))
+        ws = getattr(self, "_engine_ws_shared", None)
+        if ws is None or ws.numel() < need or ws.device != dev:
+            ws = torch.empty(int(need * 1.25), device=dev, dtype=torch.uint8)
+            self._engine_ws_shared = ws
+        h_final = torch.empty((N, d), device=dev, dtype=torch.float32)
+        h0 = torch.empty((R2, d), device=dev, dtype=torch.float32)
+        _lib.call("regcn_regcn_evolve_shared", ptab.ctypes.data, itab.ctypes.data, gp.ctypes.data, gi.ctypes.data,
+                  len(g_list), G, h_final.data_ptr(), h0.data_ptr(), rel_nsplit, ws.data_ptr(), ws.numel())
+        return h_final, h0
+
     def batch_ok(self):
         """True when forward_batch can evolve several history windows at once (the whole-recurrence engine, no static
         graph: its initial table is rebuilt per call)."""
@@ -250,10 +281,15 @@ class RecurrentRGCN(nn.Module):
         old = pool.get(key, [])
         comb = [concat_graphs([w[i] for w in windows], old[i] if i < len(old) else None) for i in range(L)]
         pool[key] = comb
-        hist, h0 = self._forward_engine(comb, None, members=G)
+        shared = self._forward_engine_shared(comb, G)
+        if shared is not None:
+            h_last, h0 = shared
+        else:
+            hist, h0 = self._forward_engine(comb, None, members=G)
+            h_last = hist[-1]
         N, R, d = self.num_ents, self.num_rels, self.h_dim
         rel = h0.view(2, G, R, d).transpose(0, 1).contiguous().view(G, 2 * R, d)
-        return [(hist[-1][g * N:(g + 1) * N], rel[g]) for g in range(G)]
+        return [(h_last[g * N:(g + 1) * N], rel[g]) for g in range(G)]
 
     @torch.no_grad()
     def forward(self, g_list, static_graph, use_cuda):

@@ -447,6 +447,49 @@ def test_forward_batch_rows_equal_per_window_forward(shape, G, ln):
                 assert float((h0 - h0s).abs().max()) <= 1e-5 * max(1.0, float(h0s.abs().max()))
 
 
+@pytest.mark.parametrize("shape,G,ln,layers", [("c1", 8, True, 2), ("c1", 5, False, 3), ("small", 3, True, 2), ("c3", 8, True, 2)])
+def test_forward_batch_shared_rows_equal_full_rows(shape, G, ln, layers, monkeypatch):
+    """regcn_regcn_evolve_shared (entity state compact: one shared row per entity until it is first active in its window)
+    against the full block-diagonal recurrence and against forward() window by window: bit-identical entity and relation
+    rows.  Entities recur across snapshots (rows active in several steps, rows that go quiet again), one snapshot of the
+    stream is empty, and the call is repeated (compact positions are handed out in arrival order, results must not
+    depend on it)."""
+    R._lib.require_device()
+    n, r, t, L, _ = synth.SHAPES[shape]
+    rng = np.random.default_rng(11)
+    snaps = [synth.make_snapshot(rng, n, r, t, True) for _ in range(L + G - 1)]
+    hubs = rng.integers(0, n, size=(max(4, t // 10), 1))
+    for k in range(0, len(snaps), 2):                               # the same entities in every other snapshot
+        snaps[k] = np.concatenate([snaps[k], np.concatenate([hubs, rng.integers(0, r, size=hubs.shape), np.roll(hubs, 1, 0)], 1)])
+    snaps[2] = snaps[2][:0]
+    model, _ = build_model(dict(kind="regcn", layer_norm=ln, seed=9), n, r)
+    if layers != 2:
+        import regcn_b200 as RR
+        model = RR.RecurrentRGCN("convtranse", "uvrgcn", n, r, 0, 0, 200, "sub", 3, num_bases=100, num_basis=-1,
+                                 num_hidden_layers=layers, dropout=0.2, self_loop=True, skip_connect=False, layer_norm=ln,
+                                 input_dropout=0.2, hidden_dropout=0.2, feat_dropout=0.2, entity_prediction=True,
+                                 relation_prediction=True, use_cuda=True, gpu=0)
+        model.load_state_dict(synth.fill_state_dict(model.state_dict(), 9))
+        model.eval()
+    model = model.to(DEV)
+    graphs = [R.build_sub_graph(n, r, s, True, 0) for s in snaps]
+    assert all(2 * g.n_active <= n for g in graphs)
+    windows = [graphs[g:g + L] for g in range(G)]
+    monkeypatch.setenv("REGCN_SHARED_ROWS", "0")
+    full = [(h.clone(), h0.clone()) for h, h0 in model.forward_batch(windows)]
+    monkeypatch.setenv("REGCN_SHARED_ROWS", "1")
+    calls = R._lib.launch_count
+    assert model._forward_engine_shared.__func__ is type(model)._forward_engine_shared
+    for _ in range(3):
+        states = model.forward_batch(windows)
+        torch.cuda.synchronize()
+        for (h, h0), (hf, h0f) in zip(states, full):
+            assert torch.equal(h, hf) and torch.equal(h0, h0f)
+    assert getattr(model, "_engine_ws_shared", None) is not None and R._lib.launch_count > calls
+    hist, _, h0, _, _ = model.forward(windows[-1], None, True)
+    assert torch.equal(states[-1][0], hist[-1]) and torch.equal(states[-1][1], h0)
+
+
 @pytest.mark.parametrize("enc,dec,shape,G,ln", [("hyperbolic_uvrgcn", "roth", "c1", 8, False), ("lgcn", "roth", "small_l", 4, False),
                                                 ("hyperbolic_uvrgcn", "hyperbolic_convtranse", "small", 3, True)])
 def test_hyperbolic_forward_batch_rows_equal_per_window_forward(enc, dec, shape, G, ln):
@@ -475,27 +518,34 @@ def test_hyperbolic_forward_batch_rows_equal_per_window_forward(enc, dec, shape,
 
 
 def test_evaluation_loop_batched_equals_one_timestamp_at_a_time(monkeypatch):
-    """regcn_b200.test() evolving groups of consecutive timestamps together (the default below ~190 k entity rows per
-    batch) returns the ranks of the one-timestamp-per-recurrence loop, for group sizes that do and do not divide the
-    number of test snapshots; evaluate_batch equals evaluate_snapshot."""
+    """regcn_b200.test() evolving groups of consecutive timestamps together (the default: up to 16 per recurrence with the
+    shared-trajectory engine, 8 without; the first group of a call is 4) returns the ranks of the
+    one-timestamp-per-recurrence loop, for group sizes that do and do not divide the number of test snapshots, with and
+    without the shared-trajectory engine; evaluate_batch equals evaluate_snapshot."""
     from regcn_b200 import evaluate, utils
     R._lib.require_device()
-    st = synth.make_stream("c1", 9, n_test=7)
+    st = synth.make_stream("c1", 9, n_test=23)
     n, r = st["num_ents"], st["num_rels"]
     model, _ = build_model(dict(kind="regcn", layer_norm=True, seed=9), n, r)
     model = model.to(DEV)
     L = len(st["history"])
+    assert evaluate.timestamps_per_batch(model, n) == 16
+    monkeypatch.setenv("REGCN_SHARED_ROWS", "0")
     assert evaluate.timestamps_per_batch(model, n) == 8
     out = {}
-    for flag in ("1", "3", "8"):
-        monkeypatch.setenv("REGCN_TEST_BATCH", flag)
+    for flag in ("1", "3", "8", "8s", "16s"):
+        monkeypatch.setenv("REGCN_TEST_BATCH", flag.rstrip("s"))
+        monkeypatch.setenv("REGCN_SHARED_ROWS", "1" if flag.endswith("s") else "0")
         out[flag] = R.test(model, st["history"], st["tests"], r, n, True, None, None, None, None, "eval",
                            test_history_len=L, return_ranks=True)
     monkeypatch.delenv("REGCN_TEST_BATCH")
-    for flag in ("3", "8"):
+    monkeypatch.delenv("REGCN_SHARED_ROWS")
+    out["default"] = R.test(model, st["history"], st["tests"], r, n, True, None, None, None, None, "eval",
+                            test_history_len=L, return_ranks=True)
+    for flag in ("3", "8", "8s", "16s", "default"):
         assert out[flag][0] == out["1"][0]
         for a, b in zip(out[flag][1], out["1"][1]):
-            assert len(a) == len(b) == 7
+            assert len(a) == len(b) == 23
             for x, y in zip(a, b):
                 assert torch.equal(x, y)
     snaps = list(st["history"]) + list(st["tests"])
