@@ -285,6 +285,24 @@ REGCN_API int regcn_convtranse_features(const float* ent, const float* second, c
                               int B, int d, int C, int ksz, const float* bn0_scale, const float* bn0_shift,
                               const float* conv_w, const float* conv_b, const float* bn1_scale,
                               const float* bn1_shift, float* F, float* F_hi, float* F_lo, void* stream);
+/* The tower up to and including the fully-connected layer in ONE GEMM (src/decoder.py:81-93: bn0 -> conv1d(2 -> C, k = 3) ->
+ * bn1 -> relu -> fc): out (B, N) = W_fc . features + bias with the (B, C d) feature map computed inside the operand ring of
+ * the tcgen05 GEMM instead of written and read back.  w_hi / w_lo (N, ldw >= 16 C ceil(d / 16)) = fc.weight in the order
+ * the reduction is walked in, blocks of 16 positions outermost (regcn_convtrans_fc_pack_weight, once per weight).  Split-K over
+ * equal shares of the reduction; batch_total >= B = size of the whole query batch when B rows are one slice of it (the
+ * split follows the whole batch so that a row does not depend on the cut; 0 = B).  ws: regcn_convtrans_fc_workspace_bytes.
+ * Tail (src/decoder.py:92-95), folded into the split-K reduction: out = [relu]([bn2_scale *] (fc + bias) [+ bn2_shift]),
+ * bn2_* NULL = no BatchNorm (the B == 1 rule); out_hi / out_lo (B, N), optional = TF32 split of out for the scoring GEMM.
+ * REGCN_ERR_UNSUPPORTED unless kernel size 3, d % 4 == 0, C <= 64, N % 4 == 0 (callers then use regcn_convtranse_features +
+ * regcn_gemm_tf32_a32).                                                                                             */
+REGCN_API int regcn_convtrans_fc_pack_weight(const float* fc_weight, int N, int C, int d, float* w_hi, float* w_lo, void* stream);
+REGCN_API size_t regcn_convtrans_fc_workspace_bytes(int batch_total, int N);
+REGCN_API int regcn_convtrans_fc(const float* x0, const float* x1, const int64_t* triples, int col0, int col1, int B,
+                       int batch_total, int d, int C, int ksz, const float* bn0_scale, const float* bn0_shift,
+                       const float* conv_w, const float* conv_b, const float* bn1_scale, const float* bn1_shift,
+                       const float* w_hi, const float* w_lo, int ldw, int N, const float* bias, const float* bn2_scale,
+                       const float* bn2_shift, int relu, float* out, int ldc, float* out_hi, float* out_lo, float* ws,
+                       size_t ws_bytes, void* stream);
 REGCN_API int regcn_affine_relu(float* x, const float* scale, const float* shift, int M, int d, int relu, void* stream);
 
 /* ---- K12 RotH / MuRP / RotHRel query builder: hyperbolic_decoder.py:744-765,1064-1086,1243-1251 - */
@@ -523,9 +541,10 @@ REGCN_API int regcn_gemm_tf32_mn(const float* a_hi, const float* a_lo, int lda, 
  * src/decoder.py:29-52,78-100, rgcn/utils.py:136-166 as called from src/main.py:71-74): [F.normalize] -> tanh(E) ->
  * entity tower -> fused score/count over all N entities + filter correction -> relation tower -> (B,2R) scores ->
  * raw/filtered relation ranks.  packed (4*B int32) = [rank | filter_rank | rank_rel | filter_rank_rel], 1-based.
- * tower_ent / tower_rel: HOST arrays of 11 device pointers {bn0 scale, bn0 shift, conv weight (C,2,k), conv bias,
- * bn1 scale, bn1 shift, fc weight hi, fc weight lo (d, C*d), fc bias, bn2 scale, bn2 shift} (eval-mode BatchNorm folded
- * to scale/shift).  fe_* / fr_*: the entity / relation filter lists (ptr, idx, end as built by regcn_filter_count /
+ * tower_ent / tower_rel: HOST arrays of 13 device pointers {bn0 scale, bn0 shift, conv weight (C,2,k), conv bias,
+ * bn1 scale, bn1 shift, fc weight hi, fc weight lo (d, C*d), fc bias, bn2 scale, bn2 shift, fc weight hi, lo packed by
+ * regcn_convtrans_fc_pack_weight} (eval-mode BatchNorm folded to scale/shift; the packed pair is read when the tower runs
+ * as regcn_convtrans_fc: kernel size 3, d % 4 == 0, C <= 64, REGCN_FUSED_TOWER != 0 -- else it may repeat the plain pair).  fe_* / fr_*: the entity / relation filter lists (ptr, idx, end as built by regcn_filter_count /
  * regcn_filter_fill); pair_a / pair_e (P >= B): the (query, candidate) pairs regcn_filter_fill emits.
  * Same kernels and arithmetic as the per-op entry points, so ranks are bit-identical to calling those in sequence. */
 REGCN_API size_t regcn_convtrans_decode_rank_workspace_bytes(int N, int R2, int d, int B, int C, int P);

@@ -83,6 +83,10 @@ SIGNATURES = {
     "regcn_hyp_tangent": (_i, [_p, _i, _i, _d, _p, _p, _p, _p]),
     "regcn_hyp_time_gate": (_i, [_p] * 6 + [_f, _i, _i, _i, _i, _d, _f, _f, _f, _f, _p, _p]),
     "regcn_convtranse_features": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i] + [_p] * 9 + [_p]),
+    "regcn_convtrans_fc_pack_weight": (_i, [_p, _i, _i, _i, _p, _p, _p]),
+    "regcn_convtrans_fc_workspace_bytes": (_sz, [_i, _i]),
+    "regcn_convtrans_fc": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _i,
+                                _p, _i, _p, _p, _p, _sz, _p]),
     "regcn_affine_relu": (_i, [_p, _p, _p, _i, _i, _i, _p]),
     "regcn_gather_log0": (_i, [_p, _p, _i, _i, _i, _i, _d, _p, _p]),
     "regcn_hyp_query": (_i, [_p] * 5 + [_i, _i, _i, _d, _p, _p, _p]),

@@ -287,6 +287,20 @@ int regcn_convtranse_features(const float* ent, const float* second, const int64
   return convtranse_features(ent, second, triples, col0, col1, B, d, C, ksz, bn0_scale, bn0_shift, conv_w, conv_b,
                              bn1_scale, bn1_shift, F, F_hi, F_lo, ST(stream));
 }
+int regcn_convtrans_fc_pack_weight(const float* fc_weight, int N, int C, int d, float* w_hi, float* w_lo, void* stream) {
+  return convfc_pack_weight(fc_weight, N, C, d, w_hi, w_lo, ST(stream));
+}
+size_t regcn_convtrans_fc_workspace_bytes(int batch_total, int N) { return convtrans_fc_workspace_bytes(batch_total, N); }
+int regcn_convtrans_fc(const float* x0, const float* x1, const int64_t* triples, int col0, int col1, int B, int batch_total,
+                       int d, int C, int ksz, const float* bn0_scale, const float* bn0_shift, const float* conv_w,
+                       const float* conv_b, const float* bn1_scale, const float* bn1_shift, const float* w_hi,
+                       const float* w_lo, int ldw, int N, const float* bias, const float* bn2_scale, const float* bn2_shift,
+                       int relu, float* out, int ldc, float* out_hi, float* out_lo, float* ws, size_t ws_bytes,
+                       void* stream) {
+  return convtrans_fc(x0, x1, triples, col0, col1, B, d, C, ksz, bn0_scale, bn0_shift, conv_w, conv_b, bn1_scale, bn1_shift,
+                      w_hi, w_lo, ldw, N, bias, out, ldc, ws, ws_bytes, ST(stream), batch_total, bn2_scale, bn2_shift, relu,
+                      out_hi, out_lo);
+}
 int regcn_affine_relu(float* x, const float* scale, const float* shift, int M, int d, int relu, void* stream) {
   return affine_relu(x, scale, shift, M, d, relu, ST(stream));
 }

@@ -7,6 +7,7 @@
 // allocator calls per timestamp (the loop is host-bound at ICEWS sizes).
 #include "common.cuh"
 #include "internal.h"
+#include <stdlib.h>
 
 namespace regcn {
 
@@ -27,10 +28,16 @@ __global__ void pack_ranks_kernel(const int* __restrict__ raw, const int* __rest
 }
 
 static inline size_t al256(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
+// REGCN_FUSED_TOWER=0: feature map through memory (regcn_convtranse_features + FC GEMM), as regcn_b200/decoder.py reads it
+static bool fused_tower() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("REGCN_FUSED_TOWER"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
 
 struct DecodePlan {
   size_t emb_n, e_all, e_hi, e_lo, f_hi, f_lo, q, q_hi, q_lo, gemm_ws, a_hi, a_lo, b_hi, b_lo, ps, target, raw, filt,
-      r_hi, r_lo, score_rel, tscore_r, raw_r, filt_r, total;
+      r_hi, r_lo, score_rel, tscore_r, raw_r, filt_r, total, gemm_ws_bytes;
   int split_k;
 };
 static DecodePlan plan_decode(int N, int R2, int d, int B, int C, int P) {
@@ -46,7 +53,11 @@ static DecodePlan plan_decode(int N, int R2, int d, int B, int C, int P) {
   sk = sk < 1 ? 1 : (sk > 16 ? 16 : sk);
   const int kmax = (C * d) / 512 > 1 ? (C * d) / 512 : 1;
   p.split_k = sk < kmax ? sk : kmax;
-  p.gemm_ws = take(gemm_tf32_workspace_bytes(B, d, p.split_k));
+  {
+    const size_t a = gemm_tf32_workspace_bytes(B, d, p.split_k), b = convtrans_fc_workspace_bytes(B, d);
+    p.gemm_ws_bytes = a > b ? a : b;
+  }
+  p.gemm_ws = take(p.gemm_ws_bytes);
   p.a_hi = take(pd); p.a_lo = take(pd); p.b_hi = take(pd); p.b_lo = take(pd);
   p.ps = take((size_t)P * 4);
   p.target = take((size_t)B * 4); p.raw = take((size_t)B * 4); p.filt = take((size_t)B * 4);
@@ -62,14 +73,26 @@ size_t convtrans_decode_rank_workspace_bytes(int N, int R2, int d, int B, int C,
 }
 
 // tower parameter block of one decoder (device pointers): bn0 scale, shift (2) | conv weight (C,2,k), bias (C) |
-// bn1 scale, shift (C) | fc weight hi, lo (d, C*d) | fc bias (d) | bn2 scale, shift (d)
-enum { TW_BN0_S = 0, TW_BN0_B, TW_CONV_W, TW_CONV_B, TW_BN1_S, TW_BN1_B, TW_FC_HI, TW_FC_LO, TW_FC_B, TW_BN2_S, TW_BN2_B, TW_NUM };
+// bn1 scale, shift (C) | fc weight hi, lo (d, C*d) | fc bias (d) | bn2 scale, shift (d) | fc weight hi, lo in the
+// reduction order of the fused tower (regcn_convtrans_fc_pack_weight; only read when that path runs)
+enum { TW_BN0_S = 0, TW_BN0_B, TW_CONV_W, TW_CONV_B, TW_BN1_S, TW_BN1_B, TW_FC_HI, TW_FC_LO, TW_FC_B, TW_BN2_S, TW_BN2_B, TW_FCZ_HI, TW_FCZ_LO, TW_NUM };
 
 static int run_tower(const float* first, const float* second, const int64_t* triples, int col0, int col1, int B, int d,
                      int C, int ksz, const void* const* tw, const DecodePlan& pl, char* ws, int bn2, cudaStream_t st) {
   float* feat = (float*)(ws + pl.f_hi);      // the feature map as ONE fp32 matrix: the FC GEMM splits it to TF32 on chip
   float* q = (float*)(ws + pl.q);
-  int e = convtranse_features(first, second, triples, col0, col1, B, d, C, ksz, (const float*)tw[TW_BN0_S],
+  int e;
+  if (fused_tower() && ksz == 3 && !(d & 3) && C <= 64) {
+    // the feature map is computed inside the FC GEMM's operand ring (gemm_tc.cu, conv-producer mode): never written
+    e = convtrans_fc(first, second, triples, col0, col1, B, d, C, ksz, (const float*)tw[TW_BN0_S], (const float*)tw[TW_BN0_B],
+                     (const float*)tw[TW_CONV_W], (const float*)tw[TW_CONV_B], (const float*)tw[TW_BN1_S],
+                     (const float*)tw[TW_BN1_B], (const float*)tw[TW_FCZ_HI], (const float*)tw[TW_FCZ_LO], 16 * C * ((d + 15) / 16), d,
+                     (const float*)tw[TW_FC_B], q, d, (float*)(ws + pl.gemm_ws), pl.gemm_ws_bytes, st, 0,
+                     bn2 ? (const float*)tw[TW_BN2_S] : nullptr, bn2 ? (const float*)tw[TW_BN2_B] : nullptr, 1,
+                     (float*)(ws + pl.q_hi), (float*)(ws + pl.q_lo));
+    return e;
+  }
+  e = convtranse_features(first, second, triples, col0, col1, B, d, C, ksz, (const float*)tw[TW_BN0_S],
                               (const float*)tw[TW_BN0_B], (const float*)tw[TW_CONV_W], (const float*)tw[TW_CONV_B],
                               (const float*)tw[TW_BN1_S], (const float*)tw[TW_BN1_B], feat, nullptr, nullptr, st);
   if (e) return e;

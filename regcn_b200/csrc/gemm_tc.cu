@@ -199,8 +199,34 @@ struct Params {
   int a_k[2];                 // segment lengths along K (multiples of 4); p.K = k-block-padded total
   const int* a_rows[2];       // tile row m reads source row a_rows[s][m] (NULL: m)
   int a_kb0;                  // k-blocks of segment 0 = ceil(a_k[0] / 32)
+  // ---- conv-producer mode (a_f32 == 3, EPI 0): the A operand of the ConvTransE / ConvTransR fully-connected layer is never
+  //      materialised.  A[b, c*d + i] = relu(bn1(conv1d_k3(bn0([x0[idx0[b]]; x1[idx1[b]]]))))[c, i] (src/decoder.py:81-90,
+  //      eval-mode BatchNorm folded to scale / shift) is computed by the converter warps straight into the operand ring.
+  //      K is walked in units (z, c) = (block of 16 positions, channel), z-major: the 128 x 18 input window of a position
+  //      block is staged in shared memory once per ~C units.  The weight is given in the same order (convfc_pack_weight:
+  //      W'[n, 16 (z C + c) + j] = W[n, c d + 16 z + j], zero where 16 z + j >= d), so the B stream is a plain contiguous
+  //      K walk with 64-byte aligned boxes; a split-K slice is a contiguous range of units. ----
+  const float* cv_x0;         // [*, cv_d] first input table (entity rows)
+  const float* cv_x1;         // [*, cv_d] second input table (relation rows / entity rows)
+  const int64_t* cv_triples;  // [M, 3] query triples: row b reads cv_x0[triples[b][cv_col0]] and cv_x1[triples[b][cv_col1]]
+  int cv_col0, cv_col1;
+  const float* cv_bn0_s;      // (2) bn0 scale, (2) shift
+  const float* cv_bn0_t;
+  const float* cv_w;          // (C, 2, 3) conv weight
+  const float* cv_b;          // (C) conv bias
+  const float* cv_bn1_s;      // (C) bn1 scale, shift
+  const float* cv_bn1_t;
+  int cv_C, cv_d, cv_zb;      // channels, positions per row, position blocks = ceil(d / 16)
   unsigned long long* trace;  // optional in-kernel timeline: [gridDim.x][kTraceSlots] %globaltimer stamps (NULL = off)
 };
+constexpr int kConvPitch = 20;                                   // floats per staged input row: 18 used (positions 16 z - 1 .. 16 z + 16)
+constexpr int kConvMaxC = 64;
+constexpr int kConvWarps = 8;                                    // producer warps of the conv mode: warps 2 .. 9
+// The staged inputs (2 x 128 x kConvPitch floats = 20 KB) live in the epilogue staging slices of the first five epilogue
+// warps: those warps are producers while a tile's main loop runs and only transpose accumulator chunks through their slices
+// after every producer has passed the tile's last k-block.  Extra shared memory: the per-channel constants.
+constexpr uint32_t kConvBytes = kConvMaxC * 9 * 4 + 256;
+static_assert(2 * 128 * kConvPitch * 4 <= 5 * 32 * 32 * 4, "staged conv inputs must fit the staging slices of five epilogue warps");
 constexpr int kTraceSlots = 48;
 __device__ __forceinline__ void trace_stamp(const Params& p, int slot) {
   if (p.trace) {
@@ -254,7 +280,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int block_k = p.bf16 ? 2 * BLOCK_K : p.kblk;       // elements per k-block row (128 bytes; 64 with kblk == 16)
-  const int total_kb = (p.K + block_k - 1) / block_k;
+  const int total_kb = p.a_f32 == 3 ? p.cv_C * p.cv_zb : (p.K + block_k - 1) / block_k;
   const int tiles_mn = p.m_tiles * p.n_tiles;
   const int total_tiles = tiles_mn * p.splits;
 
@@ -270,7 +296,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     for (int s = 0; s < p.stages; ++s) {
       // a_f32 == 1: TMA (expect_tx, B only) + one arrival per converter warp;  a_f32 == 2: the converter warps alone (they
       // pass on what TMA delivered under raw_bar)
-      mbar_init(smem_u32(&full_bar[s]), p.a_f32 == 2 ? CVT_WARPS : p.a_f32 ? 1 + CVT_WARPS : 1);
+      mbar_init(smem_u32(&full_bar[s]), p.a_f32 == 3 ? 1 + kConvWarps : p.a_f32 == 2 ? CVT_WARPS : p.a_f32 ? 1 + CVT_WARPS : 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
       mbar_init(smem_u32(&raw_bar[s]), 1);
     }
@@ -303,8 +329,112 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     const int mt = n_fast ? r / p.n_tiles : r - nt * p.m_tiles;
     m0 = mt * BLOCK_M;
     n0 = EPI == 2 ? m0 : nt * p.block_n;   // pair scores: diagonal tiles only
-    kb_beg = z * p.kb_per_split;
-    kb_end = min(total_kb, kb_beg + p.kb_per_split);
+    if (p.a_f32 == 3) {          // conv-producer mode: equal shares of the (position block, channel) units
+      kb_beg = (int)((long long)z * total_kb / p.splits);
+      kb_end = (int)((long long)(z + 1) * total_kb / p.splits);
+    } else {
+      kb_beg = z * p.kb_per_split;
+      kb_end = min(total_kb, kb_beg + p.kb_per_split);
+    }
+  };
+
+  // ---- conv-producer mode (a_f32 == 3, see Params): kConvWarps warps (the two converter warps and the first six epilogue
+  //      warps, which have nothing to do while a tile's main loop runs) compute the A k-blocks of a tile's units.
+  //      thread <-> (16-byte chunk q of the 64-byte k-block row, rows rb and rb + 64).  The arithmetic of an element is that
+  //      of convtranse_features_kernel (same fused multiply-adds in the same order). ----
+  int cv_stage = 0, cv_m0 = -1, cv_z = -1;
+  uint32_t cv_phase = 0;
+  auto conv_produce = [&](int m0, int kb_beg, int kb_end) {
+    if constexpr (EPI == 0) {
+      const int tid = (warp - 2) * 32 + lane;                 // 0 .. 32 kConvWarps - 1
+      float* cin = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes);            // aliases epilogue staging
+      float* cpar = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes + staging_bytes(EW));
+      const int C = p.cv_C, d = p.cv_d;
+      if (cv_m0 < 0) {
+        for (int i = tid; i < C; i += 32 * kConvWarps) {
+#pragma unroll
+          for (int k = 0; k < 6; ++k) cpar[i * 9 + k] = __ldg(p.cv_w + i * 6 + k);
+          cpar[i * 9 + 6] = __ldg(p.cv_b + i);
+          cpar[i * 9 + 7] = __ldg(p.cv_bn1_s + i);
+          cpar[i * 9 + 8] = __ldg(p.cv_bn1_t + i);
+        }
+      }
+      const int q = tid & 3, rb = tid >> 2;
+      constexpr int kRowStep = 8 * kConvWarps;                 // rows covered by the producers per pass
+      for (int kb = kb_beg; kb < kb_end; ++kb) {
+        const int zz = kb / C, c = kb - zz * C;
+        if (m0 != cv_m0 || zz != cv_z) {
+          // stage bn0([x0; x1]) of positions 16 z - 1 .. 16 z + 16 (zero outside the row: the conv's padding) for the 128
+          // query rows of the tile (thread <-> row, table); every producer has finished reading the previous window
+          asm volatile("bar.sync 8, %0;" ::"r"(32 * kConvWarps) : "memory");
+          const int pz = 16 * zz;
+          for (int item = tid; item < 2 * BLOCK_M; item += 32 * kConvWarps) {
+          const int r = item >> 1, tab = item & 1;
+          const int gm = m0 + r;
+          const bool rv = gm < p.M;
+          const int64_t idx = rv ? p.cv_triples[3 * (size_t)gm + (tab ? p.cv_col1 : p.cv_col0)] : 0;
+          const float* src = (tab ? p.cv_x1 : p.cv_x0) + (size_t)idx * d;
+          const float sc = __ldg((tab ? p.cv_bn0_s + 1 : p.cv_bn0_s)), sh = __ldg((tab ? p.cv_bn0_t + 1 : p.cv_bn0_t));
+          float* dst = cin + (tab * BLOCK_M + r) * kConvPitch;
+          float4 v[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            v[k] = (rv && pz + 4 * k < d) ? __ldg(reinterpret_cast<const float4*>(src + pz + 4 * k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float lft = (rv && pz > 0) ? __ldg(src + pz - 1) : 0.f;
+          const float rgt = (rv && pz + 16 < d) ? __ldg(src + pz + 16) : 0.f;
+          dst[0] = (rv && pz > 0) ? fmaf(lft, sc, sh) : 0.f;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const bool in = rv && pz + 4 * k < d;
+            dst[1 + 4 * k] = in ? fmaf(v[k].x, sc, sh) : 0.f;
+            dst[2 + 4 * k] = in ? fmaf(v[k].y, sc, sh) : 0.f;
+            dst[3 + 4 * k] = in ? fmaf(v[k].z, sc, sh) : 0.f;
+            dst[4 + 4 * k] = in ? fmaf(v[k].w, sc, sh) : 0.f;
+          }
+          dst[17] = (rv && pz + 16 < d) ? fmaf(rgt, sc, sh) : 0.f;
+          }
+          asm volatile("bar.sync 8, %0;" ::"r"(32 * kConvWarps) : "memory");
+          cv_m0 = m0; cv_z = zz;
+        }
+        const float* w = cpar + c * 9;
+        const float w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4], w5 = w[5], cb = w[6], bs = w[7], bt = w[8];
+        const bool chunk_in = 16 * zz + 4 * q < d;       // d % 4 == 0: a chunk lies inside the row or outside it
+        mbar_wait(smem_u32(&empty_bar[cv_stage]), cv_phase ^ 1);
+        const uint32_t a_hi = smem_base + cv_stage * stage_bytes;
+#pragma unroll
+        for (int j = 0; j < BLOCK_M / kRowStep; ++j) {
+          const int r = rb + kRowStep * j;
+          float4 h = make_float4(0.f, 0.f, 0.f, 0.f), l = h;
+          if (chunk_in) {
+            const float* p0 = cin + r * kConvPitch + 4 * q;
+            const float* p1 = p0 + BLOCK_M * kConvPitch;
+            const float4 x4 = *reinterpret_cast<const float4*>(p0);
+            const float4 y4 = *reinterpret_cast<const float4*>(p1);
+            const float a0[6] = {x4.x, x4.y, x4.z, x4.w, p0[4], p0[5]};
+            const float a1[6] = {y4.x, y4.y, y4.z, y4.w, p1[4], p1[5]};
+            float o[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              float acc = cb;
+              acc = fmaf(w0, a0[u], acc); acc = fmaf(w1, a0[u + 1], acc); acc = fmaf(w2, a0[u + 2], acc);
+              acc = fmaf(w3, a1[u], acc); acc = fmaf(w4, a1[u + 1], acc); acc = fmaf(w5, a1[u + 2], acc);
+              o[u] = fmaxf(fmaf(acc, bs, bt), 0.f);
+            }
+            h.x = rna_tf32(o[0]); h.y = rna_tf32(o[1]); h.z = rna_tf32(o[2]); h.w = rna_tf32(o[3]);
+            l.x = rna_tf32(o[0] - h.x); l.y = rna_tf32(o[1] - h.y); l.z = rna_tf32(o[2] - h.z); l.w = rna_tf32(o[3] - h.w);
+          }
+          // 64-byte swizzle: 16-byte chunk index XOR address bits [7, 9) = (row >> 1) & 3
+          const uint32_t ph = a_hi + r * 64 + ((q ^ ((r >> 1) & 3)) << 4);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ph), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+          if (three)
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ph + a_bytes), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_bar[cv_stage])) : "memory");
+        if (++cv_stage == p.stages) { cv_stage = 0; cv_phase ^= 1; }
+      }
+    }
   };
 
   if (warp == 0) {
@@ -464,6 +594,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
           if (++stage_c == p.stages) { stage_c = 0; phase_c ^= 1; }
         }
       }
+    } else if (EPI == 0 && p.a_f32 == 3) {
+      // Conv-producer form: these two warps and the first kConvWarps - 2 epilogue warps build the A tiles (conv_produce)
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int m0, n0, kb_beg, kb_end;
+        decode(t, m0, n0, kb_beg, kb_end);
+        conv_produce(m0, kb_beg, kb_end);
+      }
     } else if (EPI != 5 && p.a_f32) {       // (the 128-register time-gate instantiation takes fp32 A in the raw-tile form only)
       const int cw = warp - 2;
       const int c16 = lane & 7, rsub = lane >> 3;
@@ -544,6 +681,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       int m0, n0, kb_beg, kb_end;
       decode(t, m0, n0, kb_beg, kb_end);
+      if (EPI == 0 && p.a_f32 == 3 && warp < 2 + kConvWarps) conv_produce(m0, kb_beg, kb_end);   // idle until the tile is done
       const int slot = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       const int row = m0 + quarter * 32 + lane;
@@ -1170,6 +1308,8 @@ static void clear_epi(tc::Params& p) {
   p.kblk = tc::BLOCK_K;
   p.a_f32 = 0; p.a_ptr[0] = p.a_ptr[1] = nullptr; p.a_ld[0] = p.a_ld[1] = 0; p.a_k[0] = p.a_k[1] = 0;
   p.a_rows[0] = p.a_rows[1] = nullptr; p.a_kb0 = 0;
+  p.cv_x0 = p.cv_x1 = nullptr; p.cv_triples = nullptr; p.cv_col0 = p.cv_col1 = 0; p.cv_bn0_s = p.cv_bn0_t = nullptr;
+  p.cv_w = p.cv_b = p.cv_bn1_s = p.cv_bn1_t = nullptr; p.cv_C = p.cv_d = p.cv_zb = 0;
   p.trace = nullptr;
 }
 
@@ -1194,7 +1334,12 @@ static int launch_tc(const float* a_hi, const float* a_lo, int lda, const float*
   using namespace tc;
   const int M = p.M, N = p.N;
   const int Ktrue = p.K;                 // reduction length of B (the weights); fp32-A mode pads every segment to k-blocks
-  if (p.a_f32) {
+  const bool conv = p.a_f32 == 3;          // conv-producer mode: the converter warps compute the A tiles (see Params)
+  if (conv) {
+    if (p.epi != 0 || passes != 3) { set_last_error("%s: the conv-producer mode takes the store epilogue and 3 passes", who); return REGCN_ERR_UNSUPPORTED; }
+    a_hi = a_lo = b_hi;
+    lda = ldb;
+  } else if (p.a_f32) {
     if (p.a_k[0] + p.a_k[1] != Ktrue) { set_last_error("%s: fp32 A segments %d + %d != K = %d", who, p.a_k[0], p.a_k[1], Ktrue); return REGCN_ERR_DIM; }
     if (p.bf16 || p.a_mn || p.b_mn) { set_last_error("%s: fp32 A takes K-major tf32 operands", who); return REGCN_ERR_UNSUPPORTED; }
     // one K segment, rows in place: TMA delivers the fp32 k-blocks, the converter warps split them inside the stage
@@ -1224,8 +1369,9 @@ static int launch_tc(const float* a_hi, const float* a_lo, int lda, const float*
       }
     }
   }
+  if (conv) p.kblk = 16;
   if (p.a_f32 == 2) p.K = (Ktrue + p.kblk - 1) / p.kblk * p.kblk;
-  else if (p.a_f32) p.K = BLOCK_K * (p.a_kb0 + (p.a_k[1] + BLOCK_K - 1) / BLOCK_K);
+  else if (p.a_f32 == 1) p.K = BLOCK_K * (p.a_kb0 + (p.a_k[1] + BLOCK_K - 1) / BLOCK_K);
   const int K = p.K;
   if (!a_hi || !b_hi || (passes == 3 && (!a_lo || !b_lo))) { set_last_error("%s: null operand", who); return REGCN_ERR_NULL; }
   if (passes != 1 && passes != 3) { set_last_error("%s: passes must be 1 or 3", who); return REGCN_ERR_DIM; }
@@ -1245,13 +1391,13 @@ static int launch_tc(const float* a_hi, const float* a_lo, int lda, const float*
   while (p.tmem_cols < 2 * p.block_n) p.tmem_cols <<= 1;     // two accumulator slots
   const uint32_t stage_bytes = (passes == 3 ? 2u : 1u) * (BLOCK_M * (uint32_t)p.kblk * 4 + (uint32_t)p.block_n * (uint32_t)p.kblk * 4);
   const int block_k = p.bf16 ? 2 * BLOCK_K : p.kblk;
-  const int total_kb = (K + block_k - 1) / block_k;
+  const int total_kb = conv ? p.cv_C * p.cv_zb : (K + block_k - 1) / block_k;
   if (split_k < 1) split_k = 1;
   if (split_k > total_kb) split_k = total_kb;
   p.kb_per_split = (total_kb + split_k - 1) / split_k;
-  split_k = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
+  if (!conv) split_k = (total_kb + p.kb_per_split - 1) / p.kb_per_split;     // (conv mode: equal shares of the units, any count)
   const int ew = p.epi == 5 ? epi_warps<5>() : EPI_WARPS;                 // epilogue warps of the instantiation that will run
-  p.stages = (int)(ring_budget(ew) / stage_bytes);
+  p.stages = (int)((ring_budget(ew) - (conv ? kConvBytes : 0u)) / stage_bytes);
   if (p.stages > 8) p.stages = 8;
   if (g_force_stages > 0 && g_force_stages < p.stages) p.stages = g_force_stages;
   if (p.stages < (p.a_f32 ? 2 : 1)) { set_last_error("%s: tile does not fit in shared memory", who); return REGCN_ERR_UNSUPPORTED; }
@@ -1270,7 +1416,7 @@ static int launch_tc(const float* a_hi, const float* a_lo, int lda, const float*
   } else {
     ta_lo = ta_hi; tb_lo = tb_hi;
   }
-  const size_t smem = (size_t)p.stages * stage_bytes + 1024 + staging_bytes(ew);
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024 + staging_bytes(ew) + (conv ? kConvBytes : 0u);
   static bool attr_set = false;
   if (!attr_set) {
     const int mx = (int)(SMEM_BUDGET + 1024 + STAGING_BYTES);   // + 2 KB of static shared memory = the 227 KB limit
@@ -1443,6 +1589,132 @@ int gemm_tf32_a32(const float* a0, int lda0, int k0, const int* rows0, const flo
     launch_k(splitk_reduce_kernel, (unsigned)((total + 255) / 256), 256, 0, st, ws, sk, C, ldc, M, N, bias, accumulate);
   }
   return check_launch("gemm_tf32_a32");
+}
+
+// ---- ConvTransE / ConvTransR query tower up to the fully-connected layer in ONE GEMM (src/decoder.py:78-93):
+//   out[b, :] = W_fc . vec(relu(bn1(conv1d_k3(bn0([x0[t[b][col0]]; x1[t[b][col1]]]))))) + bias
+// The (B, C d) feature map is computed inside the operand ring (Params: conv-producer mode) instead of being written
+// and read back (117 MB per tower at the ICEWS18 shape).  Split-K over equal shares of the (position block, channel)
+// units; partials are folded in split order by splitk_reduce_kernel (deterministic).
+// fc.weight (N, C d) -> the unit order of the conv-producer GEMM, split to TF32:
+//   out[n, 16 (z C + c) + j] = W[n, c d + 16 z + j]   (zero where 16 z + j >= d),   row length zb C 16, zb = ceil(d / 16)
+__global__ void convfc_pack_weight_kernel(const float* __restrict__ w, int N, int C, int d, int zb, float* __restrict__ hi,
+                                          float* __restrict__ lo) {
+  pdl_grid_sync();
+  const size_t total = (size_t)N * zb * C * 16;
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int j = (int)(i & 15);
+  const size_t u = i >> 4;
+  const int c = (int)(u % C);
+  const size_t u2 = u / C;
+  const int z = (int)(u2 % zb);
+  const size_t n = u2 / zb;
+  const int pos = 16 * z + j;
+  const float v = pos < d ? w[n * (size_t)C * d + (size_t)c * d + pos] : 0.f;
+  float h, l;
+  split_tf32_1(v, h, l);
+  hi[i] = h;
+  lo[i] = l;
+}
+int convfc_pack_weight(const float* w, int N, int C, int d, float* hi, float* lo, cudaStream_t st) {
+  if (!w || !hi || !lo) { set_last_error("convfc_pack_weight: null pointer"); return REGCN_ERR_NULL; }
+  if (N <= 0 || C <= 0 || d <= 0) { set_last_error("convfc_pack_weight: bad dims"); return REGCN_ERR_DIM; }
+  const size_t total = (size_t)N * ((d + 15) / 16) * C * 16;
+  launch_k(convfc_pack_weight_kernel, (unsigned)((total + 255) / 256), 256, 0, st, w, N, C, d, (d + 15) / 16, hi, lo);
+  return check_launch("convfc_pack_weight");
+}
+int affine_relu(float* x, const float* scale, const float* shift, int M, int d, int relu, cudaStream_t st);   // decoder.cu
+// split-K fold of the fused tower with its tail: out = [relu]([scale *] (sum_z ws[z] + bias) [+ shift]), optional TF32 split
+// of the result for the scoring GEMM (one pass instead of splitk_reduce + affine_relu + split_tf32); split order fixed
+__global__ void convfc_finish_kernel(const float* __restrict__ ws, int splits, int M, int N, const float* __restrict__ bias,
+                                     const float* __restrict__ scale, const float* __restrict__ shift, int relu,
+                                     float* __restrict__ out, int ldc, float* __restrict__ out_hi, float* __restrict__ out_lo) {
+  pdl_grid_sync();
+  const size_t total4 = (size_t)M * N / 4;
+  const size_t i4 = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i4 >= total4) return;
+  const size_t i = i4 * 4;
+  const int col = (int)(i % N);
+  const size_t row = i / N;
+  float4 a = *reinterpret_cast<const float4*>(ws + i);
+  for (int z = 1; z < splits; ++z) a = f4_add(a, *reinterpret_cast<const float4*>(ws + (size_t)z * M * N + i));
+  if (bias) a = f4_add(a, ldg4(bias + col));
+  if (scale) {
+    const float4 s4 = ldg4(scale + col), t4 = ldg4(shift + col);
+    a.x = fmaf(a.x, s4.x, t4.x); a.y = fmaf(a.y, s4.y, t4.y); a.z = fmaf(a.z, s4.z, t4.z); a.w = fmaf(a.w, s4.w, t4.w);
+  }
+  if (relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+  st4(out + row * ldc + col, a);
+  if (out_hi) {
+    float4 h, l;
+    split_tf32_1(a.x, h.x, l.x); split_tf32_1(a.y, h.y, l.y); split_tf32_1(a.z, h.z, l.z); split_tf32_1(a.w, h.w, l.w);
+    st4(out_hi + i, h);
+    st4(out_lo + i, l);
+  }
+}
+int convtrans_fc_splits(int B) {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  const int m_tiles = (B + tc::BLOCK_M - 1) / tc::BLOCK_M;
+  int s = sms / (m_tiles > 0 ? m_tiles : 1);
+  return s < 1 ? 1 : (s > 16 ? 16 : s);
+}
+size_t convtrans_fc_workspace_bytes(int B, int N) { return gemm_tf32_workspace_bytes(B, N, convtrans_fc_splits(B)) + 256; }
+int convtrans_fc(const float* x0, const float* x1, const int64_t* triples, int col0, int col1, int B, int d, int C, int ksz,
+                 const float* bn0_scale, const float* bn0_shift, const float* conv_w, const float* conv_b,
+                 const float* bn1_scale, const float* bn1_shift, const float* w_hi, const float* w_lo, int ldw, int N,
+                 const float* bias, float* out, int ldc, float* ws, size_t ws_bytes, cudaStream_t st, int batch_total,
+                 const float* act_scale, const float* act_shift, int relu, float* out_hi, float* out_lo) {
+  if ((act_scale && !act_shift) || (out_hi && !out_lo) || (ldc & 3)) { set_last_error("convtrans_fc: bad tail arguments"); return REGCN_ERR_NULL; }
+  if (!x0 || !x1 || !triples || !bn0_scale || !bn0_shift || !conv_w || !conv_b || !bn1_scale || !bn1_shift || !w_hi || !w_lo || !out) {
+    set_last_error("convtrans_fc: null pointer"); return REGCN_ERR_NULL;
+  }
+  if (B <= 0) return REGCN_OK;
+  const int zb = (d + 15) / 16;
+  if (ksz != 3 || d <= 0 || (d & 3) || C <= 0 || C > tc::kConvMaxC || N <= 0 || (N & 3) || ldc < N || ldw < zb * C * 16 ||
+      (((uintptr_t)x0 | (uintptr_t)x1) & 15) || col0 < 0 || col0 > 2 || col1 < 0 || col1 > 2) {
+    set_last_error("convtrans_fc: unsupported shape d=%d C=%d k=%d N=%d (kernel 3, d %% 4 == 0, C <= %d)", d, C, ksz, N, tc::kConvMaxC);
+    return REGCN_ERR_UNSUPPORTED;
+  }
+  tc::Params p;
+  clear_epi(p);
+  p.a_f32 = 3;
+  p.cv_x0 = x0; p.cv_x1 = x1; p.cv_triples = triples; p.cv_col0 = col0; p.cv_col1 = col1;
+  p.cv_bn0_s = bn0_scale; p.cv_bn0_t = bn0_shift; p.cv_w = conv_w; p.cv_b = conv_b; p.cv_bn1_s = bn1_scale; p.cv_bn1_t = bn1_shift;
+  p.cv_C = C; p.cv_d = d; p.cv_zb = (d + 15) / 16;
+  p.C = out; p.ldc = ldc; p.M = B; p.N = N; p.K = zb * C * 16; p.bias = bias;
+  int sk = convtrans_fc_splits(batch_total > B ? batch_total : B);   // a slice of a sharded batch splits like the whole batch
+  if (sk > C * p.cv_zb) sk = C * p.cv_zb;
+  if (sk > 1) {
+    if (!ws || ws_bytes < gemm_tf32_workspace_bytes(B, N, sk)) { set_last_error("convtrans_fc: split-K workspace too small"); return REGCN_ERR_WORKSPACE; }
+    p.ws = ws;
+  }
+  const int bn = N <= 256 ? (N + 15) / 16 * 16 : 256;
+  int e = launch_tc(nullptr, nullptr, 0, w_hi, w_lo, ldw, p, 3, sk, bn, "convtrans_fc", st);
+  if (e) return e;
+  if (sk > 1) {
+    const size_t total4 = (size_t)B * N / 4;
+    launch_k(convfc_finish_kernel, (unsigned)((total4 + 255) / 256), 256, 0, st, (const float*)ws, sk, B, N, bias, act_scale, act_shift,
+             relu, out, ldc, out_hi, out_lo);
+    return check_launch("convtrans_fc");
+  }
+  // one slice: the GEMM wrote out (+ bias) itself
+  if ((e = check_launch("convtrans_fc"))) return e;
+  if (act_scale || relu) {
+    if (ldc != N) { set_last_error("convtrans_fc: the tail needs a dense output when the GEMM runs unsplit"); return REGCN_ERR_UNSUPPORTED; }
+    if ((e = affine_relu(out, act_scale, act_shift, B, N, relu, st))) return e;
+  }
+  if (out_hi) {
+    if (ldc != N) { set_last_error("convtrans_fc: the tail needs a dense output when the GEMM runs unsplit"); return REGCN_ERR_UNSUPPORTED; }
+    return split_tf32(out, out_hi, out_lo, (size_t)B * N, st);
+  }
+  return REGCN_OK;
 }
 
 int gemm_tf32_layer_a32(const float* a0, int lda0, int k0, const int* rows0, const float* a1, int lda1, int k1,

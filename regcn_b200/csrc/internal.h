@@ -106,6 +106,15 @@ int convtranse_features(const float* ent, const float* second, const int64_t* tr
                         int d, int C, int ksz, const float* bn0_scale, const float* bn0_shift, const float* conv_w,
                         const float* conv_b, const float* bn1_scale, const float* bn1_shift, float* F, float* F_hi,
                         float* F_lo, cudaStream_t st);
+int convfc_pack_weight(const float* w, int N, int C, int d, float* hi, float* lo, cudaStream_t st);
+int convtrans_fc_splits(int B);
+size_t convtrans_fc_workspace_bytes(int B, int N);
+int convtrans_fc(const float* x0, const float* x1, const int64_t* triples, int col0, int col1, int B, int d, int C, int ksz,
+                 const float* bn0_scale, const float* bn0_shift, const float* conv_w, const float* conv_b,
+                 const float* bn1_scale, const float* bn1_shift, const float* w_hi, const float* w_lo, int ldw, int N,
+                 const float* bias, float* out, int ldc, float* ws, size_t ws_bytes, cudaStream_t st, int batch_total = 0,
+                 const float* act_scale = nullptr, const float* act_shift = nullptr, int relu = 0, float* out_hi = nullptr,
+                 float* out_lo = nullptr);
 int affine_relu(float* x, const float* scale, const float* shift, int M, int d, int relu, cudaStream_t st);
 int gather_log0(const float* E, const int64_t* triples, int col, int B, int d, int project, double c, float* out,
                 cudaStream_t st);

@@ -57,6 +57,13 @@ class _ConvTransBase(nn.Module):
         split-K factor of the FC and the B == 1 rule of bn2 then follow the whole batch, so a row's value does not depend
         on how the batch was cut."""
         B = len(triplets) if batch_total is None else int(batch_total)
+        if ops.gemm_impl() == "tc" and ops.convtrans_fc_ok(ent_act.shape[1], self.conv1.weight, self.fc.out_features):
+            # the feature map is computed inside the FC GEMM's operand ring (regcn_convtrans_fc): never written or read
+            x = ops.convtrans_fc(ent_act, second, triplets, col0, col1, _fold_bn(self.bn0), self.conv1.weight.detach(),
+                                 self.conv1.bias.detach(), _fold_bn(self.bn1), self.fc.weight,
+                                 self.fc.bias.detach(), batch_total=B,
+                                 bn2=_fold_bn(self.bn2) if (always_bn2 or B > 1) else None, relu=True)
+            return x
         feats = ops.convtranse_features(ent_act, second, triplets, col0, col1, _fold_bn(self.bn0),
                                         self.conv1.weight.detach(), self.conv1.bias.detach(), _fold_bn(self.bn1),
                                         split=False)

@@ -28,7 +28,7 @@ def _scoring_operands(model, emb, r_emb, all_triples):
 
 
 def _tower_table(dec):
-    """Host array of the 11 device pointers regcn_convtrans_decode_rank takes per decoder (include/regcn_b200.h), rebuilt
+    """Host array of the 13 device pointers regcn_convtrans_decode_rank takes per decoder (include/regcn_b200.h), rebuilt
     when any of the module's tensors changes (version / storage)."""
     import numpy as np
     from .decoder import _fold_bn
@@ -47,7 +47,13 @@ def _tower_table(dec):
         cb = dec.conv1.bias.detach().contiguous()
         fw_hi, fw_lo = ops.split_tf32(dec.fc.weight.detach().contiguous())
         fb = dec.fc.bias.detach().contiguous()
-    keep = [s0, b0, cw, cb, s1, b1, fw_hi, fw_lo, fb, s2, b2]
+        C_, _, ksz_ = cw.shape
+        d_ = dec.fc.in_features // C_
+        if ops.convtrans_fc_ok(d_, cw, dec.fc.out_features):
+            fz_hi, fz_lo = ops.convtrans_fc_weight(dec.fc.weight, C_, d_)     # reduction order of the fused tower
+        else:
+            fz_hi, fz_lo = fw_hi, fw_lo
+    keep = [s0, b0, cw, cb, s1, b1, fw_hi, fw_lo, fb, s2, b2, fz_hi, fz_lo]
     tab = np.array([t.data_ptr() for t in keep], dtype=np.uint64)
     dec.__dict__["_regcn_tower_tab"] = (stamp, (tab, keep))
     return tab, keep

@@ -359,6 +359,49 @@ def convtranse_features(ent, second, triples, col0, col1, bn0, conv_w, conv_b, b
     return out
 
 
+def convtrans_fc_ok(d, conv_w, n_out):
+    """Shapes regcn_convtrans_fc takes (kernel size 3, d % 4 == 0, at most 64 channels); REGCN_FUSED_TOWER=0 turns it off."""
+    import os
+    C, _, ksz = conv_w.shape
+    return ksz == 3 and d % 4 == 0 and C <= 64 and n_out % 4 == 0 and os.environ.get("REGCN_FUSED_TOWER", "1") != "0"
+
+
+def convtrans_fc_weight(fc_w, C, d):
+    """fc.weight (n_out, C d) in the reduction order of regcn_convtrans_fc (blocks of 16 positions outermost), TF32 split;
+    cached on the Parameter until it changes."""
+    def build():
+        w = fc_w.detach().contiguous()
+        n_out = w.shape[0]
+        kp = 16 * C * ((d + 15) // 16)
+        hi = torch.empty((n_out, kp), device=w.device, dtype=F32)
+        lo = torch.empty((n_out, kp), device=w.device, dtype=F32)
+        call("regcn_convtrans_fc_pack_weight", ptr(w), n_out, C, d, ptr(hi), ptr(lo))
+        return hi, lo
+    return cached(fc_w, ("convfc", C, d, tuple(fc_w.shape)), build)
+
+
+def convtrans_fc(ent, second, triples, col0, col1, bn0, conv_w, conv_b, bn1, fc_w, fc_b, batch_total=None, bn2=None,
+                 relu=False):
+    """bn0 -> conv1d -> bn1 -> relu -> fc in one tcgen05 GEMM whose A operand (the feature map) is computed inside the
+    operand ring (regcn_convtrans_fc).  fc_w: the fc.weight Parameter itself (its TF32 split is cached on it, shared with
+    ops.gemm(..., b_key=(fc_w, "w"))).  bn2 = (scale, shift) / relu: the tower's tail folded into the split-K reduction.
+    Returns the (B, n_out) activations."""
+    B = triples.shape[0]
+    d = ent.shape[1]
+    C, _, ksz = conv_w.shape
+    n_out = fc_w.shape[0]
+    w_hi, w_lo = convtrans_fc_weight(fc_w, C, d)
+    total = int(batch_total) if batch_total else B
+    ws_bytes = _lib.load().regcn_convtrans_fc_workspace_bytes(total, n_out)
+    ws = torch.empty(ws_bytes // 4 + 1, device=ent.device, dtype=F32)
+    out = torch.empty((B, n_out), device=ent.device, dtype=F32)
+    call("regcn_convtrans_fc", ptr(ent), ptr(second), ptr(triples), col0, col1, B, total, d, C, ksz, ptr(bn0[0]), ptr(bn0[1]),
+         ptr(conv_w.contiguous()), ptr(conv_b), ptr(bn1[0]), ptr(bn1[1]), ptr(w_hi), ptr(w_lo), w_hi.shape[1], n_out, ptr(fc_b),
+         ptr(bn2[0]) if bn2 is not None else None, ptr(bn2[1]) if bn2 is not None else None, int(relu), ptr(out), n_out,
+         None, None, ptr(ws), ws_bytes)
+    return out
+
+
 def affine_relu_(x, scale, shift, relu=True):
     M, d = x.shape
     call("regcn_affine_relu", ptr(x), ptr(scale), ptr(shift), M, d, int(relu))

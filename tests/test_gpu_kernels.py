@@ -478,6 +478,57 @@ def test_convtranse_tower_and_hyp_query_vs_oracle():
     assert ok, worst
 
 
+@pytest.mark.parametrize("B,n,d,C,nout,cols", [(77, 300, 200, 50, 200, (0, 1)), (2914, 5000, 200, 50, 200, (0, 2)),
+                                               (1, 40, 200, 50, 200, (0, 1)), (300, 64, 72, 7, 40, (2, 1)),
+                                               (129, 64, 16, 64, 16, (0, 2))])
+def test_convtrans_fc_fused_tower_vs_fp64_and_feature_map_path(B, n, d, C, nout, cols):
+    """regcn_convtrans_fc (bn0 -> conv1d -> bn1 -> relu -> fc with the feature map computed inside the GEMM's operand ring)
+    against an fp64 evaluation of src/decoder.py:81-91 and against the path that writes the feature map
+    (regcn_convtranse_features + the fp32-A GEMM): same element arithmetic, another summation order of the FC.  Row tails
+    (B % 128), a last position block of 8 valid columns (d = 200, 72), d = 16 (one block) and 64 channels are covered."""
+    R, ops = _ops()
+    import torch.nn.functional as F_
+    gen = torch.Generator().manual_seed(B + d)
+    ent = torch.randn(n, d, generator=gen)
+    sec = torch.randn(n, d, generator=gen)
+    tri = torch.stack([torch.randint(0, n, (B,), generator=gen) for _ in range(3)], 1)
+    bn0 = (torch.rand(2, generator=gen) + 0.5, torch.randn(2, generator=gen) * 0.1)
+    bn1 = (torch.rand(C, generator=gen) + 0.5, torch.randn(C, generator=gen) * 0.1)
+    cw = torch.randn(C, 2, 3, generator=gen) * 0.4
+    cb = torch.randn(C, generator=gen) * 0.1
+    fw = torch.nn.Parameter(torch.randn(nout, C * d, generator=gen) / (C * d) ** 0.5)
+    fb = torch.randn(nout, generator=gen) * 0.1
+    x = torch.stack([ent[tri[:, cols[0]]], sec[tri[:, cols[1]]]], 1).double()
+    x = x * bn0[0].double()[None, :, None] + bn0[1].double()[None, :, None]
+    y = F_.conv1d(x, cw.double(), cb.double(), padding=1)
+    y = torch.relu(y * bn1[0].double()[None, :, None] + bn1[1].double()[None, :, None]).reshape(B, -1)
+    ref = y @ fw.detach().double().t() + fb.double()
+    cu = lambda t: t.to(DEV).contiguous()
+    fw_d = torch.nn.Parameter(cu(fw.detach()))
+    bn0d, bn1d = (cu(bn0[0]), cu(bn0[1])), (cu(bn1[0]), cu(bn1[1]))
+    assert ops.convtrans_fc_ok(d, cw, nout)
+    out = ops.convtrans_fc(cu(ent), cu(sec), cu(tri), cols[0], cols[1], bn0d, cu(cw), cu(cb), bn1d, fw_d, cu(fb))
+    out2 = ops.convtrans_fc(cu(ent), cu(sec), cu(tri), cols[0], cols[1], bn0d, cu(cw), cu(cb), bn1d, fw_d, cu(fb))
+    assert torch.equal(out, out2)                                     # deterministic (fixed split order)
+    feats = ops.convtranse_features(cu(ent), cu(sec), cu(tri), cols[0], cols[1], bn0d, cu(cw), cu(cb), bn1d, split=False)
+    old = ops.gemm(feats, fw_d.detach(), trans_b=True, bias=cu(fb), split_k=4 if C * d >= 2048 else 1, split_a_on_chip=True)
+    scale = float(ref.abs().max())
+    err_new = float((out.double().cpu() - ref).abs().max()) / scale
+    err_old = float((old.double().cpu() - ref).abs().max()) / scale
+    assert err_new <= max(2e-6, 2.0 * err_old), (err_new, err_old)
+    # the tower's tail (bn2 -> relu) folded into the split-K reduction
+    bn2 = (cu(torch.rand(nout, generator=gen) + 0.5), cu(torch.randn(nout, generator=gen) * 0.1))
+    tail = ops.convtrans_fc(cu(ent), cu(sec), cu(tri), cols[0], cols[1], bn0d, cu(cw), cu(cb), bn1d, fw_d, cu(fb), bn2=bn2,
+                            relu=True)
+    want = torch.relu(out.double() * bn2[0].double() + bn2[1].double())
+    assert float((tail.double() - want).abs().max()) <= 1e-6 * max(1.0, float(want.abs().max()))
+    if B > 1:
+        # a slice of a sharded batch splits like the whole batch: rows do not depend on the cut
+        part = ops.convtrans_fc(cu(ent), cu(sec), cu(tri[:B // 2]), cols[0], cols[1], bn0d, cu(cw), cu(cb), bn1d, fw_d, cu(fb),
+                                batch_total=B)
+        assert torch.equal(part, out[:B // 2])
+
+
 @pytest.mark.parametrize("decoder", ["roth", "murp", "hyperbolic_convtranse"])
 def test_hyperbolic_decoders_vs_oracle(decoder):
     R, ops = _ops()
