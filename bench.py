@@ -898,8 +898,11 @@ def main():
         ns = float(t_out.max() - t_in.min())
         tot_ns += ns
         tot_fl += fl_.value
-        key = f"{names.get(e_.value, e_.value)} {m_.value}x{n_.value}x{k_.value}"
-        d_ = inst.setdefault(key, {"launches": 0, "us": 0.0, "flops": 0.0, "grid": g_.value})
+        # one row per (epilogue, N, K): the row counts of the compact all-entity GEMMs differ from launch to launch
+        key = f"{names.get(e_.value, 'time gate' if e_.value == 5 else e_.value)} Mx{'M' if e_.value == 2 else n_.value}x{k_.value}"
+        d_ = inst.setdefault(key, {"launches": 0, "us": 0.0, "flops": 0.0, "grid": g_.value, "m_min": m_.value, "m_max": m_.value})
+        d_["m_min"], d_["m_max"] = min(d_["m_min"], m_.value), max(d_["m_max"], m_.value)
+        d_["grid"] = max(d_["grid"], g_.value)
         d_["launches"] += 1
         d_["us"] += ns / 1e3
         d_["flops"] += fl_.value
@@ -915,7 +918,8 @@ def main():
     for key, d_ in sorted(inst.items(), key=lambda kv: -kv[1]["us"]):
         us = d_["us"] / d_["launches"]
         alg = d_["flops"] / d_["launches"] / (us * 1e-6) / 1e12
-        per_instance.append({"gemm": key, "grid": d_["grid"], "launches_per_step": d_["launches"] / (probe_steps * G), "us": us,
+        per_instance.append({"gemm": key, "rows_M": [d_["m_min"], d_["m_max"]], "grid": d_["grid"],
+                             "launches_per_step": d_["launches"] / (probe_steps * G), "us": us,
                              "algorithmic_tflops": alg, "frac": alg / peak_tf})
     traffic = None
     try:
@@ -941,8 +945,10 @@ def main():
                 "per_instance": per_instance,
                 "note": f"fp32-parity mode issues {passes} TF32 MMAs per algorithmic MAC (lo.hi + hi.lo + hi.hi), so the "
                         f"algorithmic fraction of the bf16 peak cannot exceed 1/(2*{passes}) = {1.0 / (2 * passes):.3f}; the "
-                        f"evolution GEMMs ({G} x 23033 rows x 200..400 columns per launch) are L2-operand- and epilogue-bound, "
-                        f"see per_instance and scoring_kernel"}
+                        f"evolution GEMMs (shared-trajectory engine: 23033 shared rows + the rows touched so far in the {G} "
+                        f"windows, x 200..400 columns per launch) are operand-feed- and epilogue-bound, the fully-connected "
+                        f"layer of the query tower computes its A operand (the conv feature map) on chip; see per_instance "
+                        f"(us = mean per launch) and scoring_kernel"}
     # edge kernel (HBM-bound) at this workload: CUDA events around the aggregate launches of single-stream probe steps
     lib.regcn_two_stream_enable(0)
     lib.regcn_pdl_enable(0)
@@ -1159,8 +1165,14 @@ def main():
                 "run": {"parallelism": f"timestamp-dp{world}", "l2": "256 MiB buffer written between timed batches (untimed); "
                         "one batch also streams > 1 GB", "timestamps_per_batch": G,
                         "batching": "the windows of G consecutive test timestamps are evolved as one block-diagonal recurrence "
-                                    "(regcn_csr_concat + RecurrentRGCN.forward_batch), scored and ranked per timestamp; "
-                                    "results are identical to one recurrence per timestamp (tests)",
+                                    "(regcn_csr_concat + RecurrentRGCN.forward_batch; K steps run as ceil(K/G) batches of equal "
+                                    "size), scored and ranked per timestamp; results are identical to one recurrence per "
+                                    "timestamp (tests).  The recurrence is the shared-trajectory engine "
+                                    "(regcn_regcn_evolve_shared): a row without in-edges is updated from its own state only and "
+                                    "all windows start from one table, so the all-entity products run once for the N shared rows "
+                                    "plus once per (window, entity) row that has been active in its window so far -- every row "
+                                    "bit-identical to the full G N-row recurrence (tests); all of it inside the timed region, "
+                                    "nothing is cached across batches",
                         "gemm_impl": ops.gemm_impl(), "reference_arm": "oracle/_ref staged" if reference_available()
                         else "oracle/_ref missing: the CPU arm falls back to the oracle port"},
                 "snapshot_steps_per_s": world * L / (evolve_ms * 1e-3), "evolve_ms_per_step": evolve_ms,

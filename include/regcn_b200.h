@@ -256,6 +256,11 @@ REGCN_API void regcn_aggregate_tune(int impl);
  * 6 exp_0(normalize(log_0 x)), 7 identity, 8 exp_0(rrelu(x)); sumsq (optional, M): |out|^2 per row; out may be NULL
  * when only sumsq is wanted.                                                                    */
 REGCN_API int regcn_row_map(const float* x, float* out, int M, int d, int mode, double c, float* sumsq, void* stream);
+/* the same map, also emitting the TF32 split (out_hi, out_lo) of the result for a consumer GEMM (no separate split pass);
+ * mode 9 = tanh(x / max(|x|, 1e-12)): predict-time F.normalize (src/rrgcn.py:190) and the ConvTransE activation
+ * (src/decoder.py:79) in one pass */
+REGCN_API int regcn_row_map_split(const float* x, float* out, float* out_hi, float* out_lo, int M, int d, int mode, double c,
+                        void* stream);
 
 /* ---- K3 GRU gates: nn.GRUCell at src/rrgcn.py:133,168-174; hyperbolic_model.py:408,815-824 ----- */
 REGCN_API int regcn_gru_gate(const float* gi, const float* gh, const float* hprev, float* out, int M, int d,

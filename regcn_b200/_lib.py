@@ -76,6 +76,7 @@ SIGNATURES = {
     "regcn_hyp_evolve_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "regcn_hyp_evolve": (_i, [_p, _p, _p, _p, _p, _i, _p, _p, _i, _p, _sz, _p]),
     "regcn_row_map": (_i, [_p, _p, _i, _i, _i, _d, _p, _p]),
+    "regcn_row_map_split": (_i, [_p, _p, _p, _p, _i, _i, _i, _d, _p]),
     "regcn_gru_gate": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
     "regcn_union_combine": (_i, [_p] * 6 + [_i, _i, _i, _i, _d, _p, _p, _p, _p]),
     "regcn_time_gate": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p]),

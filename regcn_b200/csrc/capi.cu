@@ -250,6 +250,10 @@ int regcn_filter_fill(const int64_t* triples, int B, int key_col, int ans_col, c
                       int32_t* end, int32_t* pair_a, int32_t* pair_e, void* stream) {
   return filter_fill(triples, B, key_col, ans_col, beg, idx, end, pair_a, pair_e, ST(stream));
 }
+int regcn_row_map_split(const float* x, float* out, float* out_hi, float* out_lo, int M, int d, int mode, double c,
+                        void* stream) {
+  return row_map(x, out, M, d, mode, c, nullptr, out_hi, out_lo, ST(stream));
+}
 int regcn_row_map(const float* x, float* out, int M, int d, int mode, double c, float* sumsq, void* stream) {
   return row_map(x, out, M, d, mode, c, sumsq, nullptr, nullptr, ST(stream));
 }

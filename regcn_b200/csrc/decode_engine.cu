@@ -118,15 +118,11 @@ int convtrans_decode_rank(const float* emb, const float* r_emb, const int64_t* t
   char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
   int e;
   // [F.normalize] (src/rrgcn.py:190) and tanh of the entity table (src/decoder.py:30,79), with its TF32 split
-  const float* src = emb;
-  if (layer_norm) {
-    if ((e = row_map(emb, (float*)(ws + pl.emb_n), N, d, 0, 1.0, nullptr, nullptr, nullptr, st))) return e;
-    src = (const float*)(ws + pl.emb_n);
-  }
   float* e_all = (float*)(ws + pl.e_all);
   float* e_hi = (float*)(ws + pl.e_hi);
   float* e_lo = (float*)(ws + pl.e_lo);
-  if ((e = row_map(src, e_all, N, d, 1, 1.0, nullptr, e_hi, e_lo, st))) return e;
+  // one pass: row_map mode 9 = tanh(normalize(x)) (the same two steps on the row held in registers), mode 1 = tanh
+  if ((e = row_map(emb, e_all, N, d, layer_norm ? 9 : 1, 1.0, nullptr, e_hi, e_lo, st))) return e;
   // ---- entity head: query tower, pair scores, counting GEMM, filter correction ------------------------------------
   if ((e = run_tower(e_all, r_emb, triples, 0, 1, B, d, C, ksz, tower_ent, pl, ws, B > 1, st))) return e;
   const float* q_hi = (const float*)(ws + pl.q_hi);

@@ -1446,7 +1446,8 @@ static int launch_tc(const float* a_hi, const float* a_lo, int lda, const float*
   const int sms_eff = (g_grid_cap > 0 && g_grid_cap < sms) ? g_grid_cap : sms;
   const long long rounds = (total_tiles + sms_eff - 1) / sms_eff;
   dim3 grid((unsigned)((total_tiles + rounds - 1) / (rounds > 0 ? rounds : 1)));
-  const double alg_flops = p.epi == 2 ? 2.0 * M * (double)Ktrue : 2.0 * M * (double)N * Ktrue;
+  const int Kalg = conv ? p.cv_C * p.cv_d : Ktrue;        // (the packed weight of the conv mode pads every row to 16 positions)
+  const double alg_flops = p.epi == 2 ? 2.0 * M * (double)Kalg : 2.0 * M * (double)N * Kalg;
   if (g_trace) {
     std::lock_guard<std::mutex> g(g_trace_mu);
     if (g_trace && grid.x <= (unsigned)kTraceCtas) {
@@ -1454,7 +1455,7 @@ static int launch_tc(const float* a_hi, const float* a_lo, int lda, const float*
       p.trace = g_trace + rec * (size_t)kTraceCtas * kTraceSlots;
       if (g_trace_recs.size() < g_trace_cap || g_trace_cap == 1) {
         if (g_trace_cap == 1) g_trace_recs.clear();
-        g_trace_recs.push_back(TraceRec{p.epi, M, N, Ktrue, (int)grid.x, passes, alg_flops});
+        g_trace_recs.push_back(TraceRec{p.epi, M, N, Kalg, (int)grid.x, passes, alg_flops});
       } else {
         p.trace = nullptr;                               // session full: later launches are not recorded
       }

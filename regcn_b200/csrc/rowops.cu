@@ -28,6 +28,8 @@ static inline int check_d(const char* who, int d) {
 // mode 6: out = exp_0(normalize(log_0(x)))            (predict-time layer_norm, hyperbolic_model.py:926-929)
 // mode 7: identity; with out == NULL only the row |x|^2 is produced
 // mode 8: out = exp_0(rrelu(x))                       (HyperbolicRGCNLayer tail, hyperbolic_layers.py:149-159)
+// mode 9: out = tanh(x / max(|x|,1e-12))              (predict-time F.normalize + ConvTransE activation in one pass,
+//                                                      src/rrgcn.py:190 + src/decoder.py:79)
 // sumsq (optional): |out|^2 per row (for the norm/dot form of the hyperbolic scores)
 template <int RV>
 __global__ void __launch_bounds__(256) row_map_kernel(const float* __restrict__ x, float* __restrict__ out, int M, int d,
@@ -46,6 +48,7 @@ __global__ void __launch_bounds__(256) row_map_kernel(const float* __restrict__ 
     case 5: row_project(r, cv); break;
     case 6: row_log0(r, cv); row_l2normalize(r); row_exp0(r, cv); break;
     case 8: r.map([](float a) { return rreluf_(a); }); row_exp0(r, cv); break;
+    case 9: row_l2normalize(r); r.map([](float a) { return tanhf(a); }); break;
     default: break;  // mode 7: identity (row |x|^2 only)
   }
   if (out) r.store(out + (size_t)row * d, nvec, lane);
@@ -60,7 +63,7 @@ int row_map(const float* x, float* out, int M, int d, int mode, double c, float*
             cudaStream_t st) {
   if (!x || (!out && !sumsq && !out_hi) || (out_hi && !out_lo)) { set_last_error("row_map: null pointer"); return REGCN_ERR_NULL; }
   if (int e = check_d("row_map", d)) return e;
-  if (mode < 0 || mode > 8) { set_last_error("row_map: bad mode %d", mode); return REGCN_ERR_DIM; }
+  if (mode < 0 || mode > 9) { set_last_error("row_map: bad mode %d", mode); return REGCN_ERR_DIM; }
   if (M <= 0) return REGCN_OK;
   Curv cv = make_curv(c > 0 ? c : 1.0);
   if (d <= 128) launch_k(row_map_kernel<1>, row_grid(M), 256, 0, st, x, out, M, d, mode, cv, sumsq, out_hi, out_lo);

@@ -90,10 +90,13 @@ class ConvTransE(_ConvTransBase):
                          kernel_size)
 
     @torch.no_grad()
-    def query(self, embedding, emb_rel, triplets, batch_total=None):
-        """Returns (tanh(E), Q): the activated entity table and the (B,d) query matrix of the dot scoring."""
+    def query(self, embedding, emb_rel, triplets, batch_total=None, normalize=False):
+        """Returns (tanh(E), Q): the activated entity table and the (B,d) query matrix of the dot scoring.
+        normalize: `embedding` is the evolved table BEFORE the predict-time F.normalize (src/rrgcn.py:190), applied here in
+        the same pass as the tanh."""
         self._check_eval()
-        e_all = ops.row_map(embedding, ops.ROW_TANH)
+        e_all = ops.row_map(embedding, ops.ROW_NORMALIZE_TANH if normalize else ops.ROW_TANH,
+                            split=ops.gemm_impl() == "tc" and ops.score_dtype() == "fp32")
         q = self._tower(e_all, emb_rel.contiguous(), triplets, 0, 1, always_bn2=False, batch_total=batch_total)
         return e_all, q
 

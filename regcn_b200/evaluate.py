@@ -8,13 +8,15 @@ import torch
 from . import ops, utils
 
 
-def _scoring_operands(model, emb, r_emb, all_triples):
-    """(q, cand, hyp, col_bias) of the entity decoder: everything the scoring GEMM needs except the GEMM itself."""
+def _scoring_operands(model, emb, r_emb, all_triples, normalize=False):
+    """(q, cand, hyp, col_bias) of the entity decoder: everything the scoring GEMM needs except the GEMM itself.
+    normalize (ConvTransE only): emb is the evolved table before the predict-time F.normalize, folded into the tanh pass."""
     dec = model.decoder_ob
     name = type(dec).__name__
     if name == "ConvTransE":
-        e_all, q = dec.query(emb, r_emb, all_triples)
+        e_all, q = dec.query(emb, r_emb, all_triples, normalize=normalize)
         return q, e_all, None, None
+    assert not normalize
     if name == "HyperbolicConvTransE":
         et = ops.row_map(emb, ops.ROW_LEAKY_TANH_LOG0, c=dec.c)
         q = dec._tower(et, r_emb.contiguous(), all_triples, 0, 1, always_bn2=False)
@@ -92,13 +94,14 @@ def _score_rank(model, emb, r_emb, all_triples, filter_csr, fused, shard, mark):
     """Scoring + ranking half of one evaluated timestamp; emb is the evolved entity table before the predict-time
     normalisation (src/rrgcn.py:186-194)."""
     mark("score", 0)
-    if model.layer_norm:
+    fold_norm = bool(model.layer_norm) and fused and type(model.decoder_ob).__name__ == "ConvTransE"
+    if model.layer_norm and not fold_norm:
         if hasattr(model, "_c_float"):
             emb = ops.row_map(emb, ops.ROW_TANGENT_NORMALIZE, c=model._c_float)
         else:
             emb = ops.row_map(emb, ops.ROW_NORMALIZE)
     if fused:
-        q, cand, hyp, col_bias = _scoring_operands(model, emb, r_emb, all_triples)
+        q, cand, hyp, col_bias = _scoring_operands(model, emb, r_emb, all_triples, normalize=fold_norm)
         target = all_triples[:, 2].to(torch.int32).contiguous()
         pa, pe = filter_csr.pairs(target)
         mark("score", 1)

@@ -263,7 +263,7 @@ def lorentz_aggregate(ht, weight, rel, g, num_bases, c):
 
 # --------------------------------------------------------------------------- row maps
 ROW_NORMALIZE, ROW_TANH, ROW_LEAKY_TANH_LOG0, ROW_LOG0, ROW_EXP0, ROW_PROJECT, ROW_TANGENT_NORMALIZE, ROW_IDENTITY, \
-    ROW_RRELU_EXP0 = range(9)
+    ROW_RRELU_EXP0, ROW_NORMALIZE_TANH = range(10)
 
 
 def row_sumsq(x):
@@ -275,11 +275,18 @@ def row_sumsq(x):
     return ss
 
 
-def row_map(x, mode, c=1.0, want_sumsq=False, out=None):
+def row_map(x, mode, c=1.0, want_sumsq=False, out=None, split=False):
+    """split=True: the TF32 (hi, lo) pair of the result is produced in the same pass and rides on the returned tensor as
+    `_regcn_split` (consumed by fused_rank_counts instead of a separate split kernel)."""
     x = _f32(x, "x")
     M, d = x.shape
     if out is None:
         out = torch.empty_like(x)
+    if split and not want_sumsq:
+        hi, lo = torch.empty_like(out), torch.empty_like(out)
+        call("regcn_row_map_split", ptr(x), ptr(out), ptr(hi), ptr(lo), M, d, mode, float(c))
+        out._regcn_split = (hi, lo)
+        return out
     ss = torch.empty(M, device=x.device, dtype=F32) if want_sumsq else None
     call("regcn_row_map", ptr(x), ptr(out), M, d, mode, float(c), ptr(ss))
     return (out, ss) if want_sumsq else out
@@ -511,6 +518,8 @@ def fused_rank_counts(q, cand, target, filt_ptr, filt_idx, pair_a, pair_e, hyp=N
         call("regcn_gather_rows2", ptr(e_hi), None, ptr(pair_e), P, K // 2, ptr(b_hi), None)
     else:
         q_hi, q_lo = _tc_operand(q.detach(), passes == 3)
+        if cand_split is None and passes == 3:
+            cand_split = getattr(cand, "_regcn_split", None)       # produced with the table (row_map(split=True))
         e_hi, e_lo = cand_split if cand_split is not None else _tc_operand(cand.detach(), passes == 3)
         a_hi = torch.empty((P, K), device=dev, dtype=F32)
         b_hi = torch.empty((P, K), device=dev, dtype=F32)
