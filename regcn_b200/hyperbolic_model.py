@@ -311,8 +311,22 @@ class HyperbolicRecurrentRGCN(nn.Module):
         rel = h0.view(2, G, R, d).transpose(0, 1).contiguous().view(G, 2 * R, d)
         return [(hist[-1][g * N:(g + 1) * N], rel[g]) for g in range(G)]
 
-    @torch.no_grad()
     def forward(self, g_list, static_graph, use_cuda):
+        """hyperbolic_model.py:722-890.  In train() mode with autograd enabled the outputs carry gradients (the
+        kernel-backed autograd nodes of regcn_b200.train_hyp, the ones get_loss() trains through); otherwise the
+        one-call inference engine."""
+        if self.training and torch.is_grad_enabled():
+            from . import train, train_hyp
+            train.begin_step()
+            with torch.enable_grad():
+                hist, h0, static_emb = train_hyp.hyp_evolve(self, g_list, static_graph)
+            self.h_0 = h0
+            self.h = hist[-1] if hist else None
+            return hist, static_emb, h0, [], []
+        return self._forward_eval(g_list, static_graph, use_cuda)
+
+    @torch.no_grad()
+    def _forward_eval(self, g_list, static_graph, use_cuda):
         gate_list, degree_list = [], []
         static_emb = None
         if self.use_static and static_graph is not None:

@@ -291,8 +291,23 @@ class RecurrentRGCN(nn.Module):
         rel = h0.view(2, G, R, d).transpose(0, 1).contiguous().view(G, 2 * R, d)
         return [(h_last[g * N:(g + 1) * N], rel[g]) for g in range(G)]
 
-    @torch.no_grad()
     def forward(self, g_list, static_graph, use_cuda):
+        """src/rrgcn.py:142-180: (history_embs, static_emb, h_0, gate_list, degree_list).  In train() mode with autograd
+        enabled the outputs carry gradients (layer dropout active), as the reference's do: the recurrence runs on the
+        kernel-backed autograd nodes of regcn_b200.train (the same ones get_loss() trains through).  Otherwise: the
+        one-call inference engine."""
+        if self.training and torch.is_grad_enabled():
+            from . import train
+            train.begin_step()
+            with torch.enable_grad():
+                hist, h0, static_emb = train.regcn_evolve(self, g_list, static_graph)
+            self.h_0 = h0
+            self.h = hist[-1] if hist else None
+            return hist, static_emb, h0, [], []
+        return self._forward_eval(g_list, static_graph, use_cuda)
+
+    @torch.no_grad()
+    def _forward_eval(self, g_list, static_graph, use_cuda):
         gate_list, degree_list = [], []
         static_emb = None
         if self.use_static:

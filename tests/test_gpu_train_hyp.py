@@ -295,3 +295,29 @@ def test_hyperbolic_convtrans_forward_in_train_mode(which):
     mine = [ed.grad, rd.grad] + [params[k].grad for k in names]
     assert all(g is not None for g in mine), [k for k, g in zip(["dE", "drel"] + names, mine) if g is None]
     _cmp(mine, [ec.grad, rc.grad] + [P[k].grad for k in names], ["dE", "drel"] + names)
+
+
+def test_hyperbolic_forward_in_train_mode_carries_gradients():
+    """HyperbolicRecurrentRGCN.forward() in train() mode with autograd on returns history embeddings with gradients (the
+    autograd nodes get_loss() trains through); with dropout 0 the values equal the inference engine's."""
+    import regcn_b200 as R
+    from oracle import synth
+    from tests.helpers import build_model, close
+    case = synth.make_case("small", 4)
+    n, r = case["num_ents"], case["num_rels"]
+    m, _ = build_model(dict(kind="hyp", layer_norm=False, seed=4, encoder="hyperbolic_uvrgcn", decoder="roth", gamma=0.15), n, r)
+    m = m.to("cuda")
+    for layer in m.rgcn.layers:
+        if getattr(layer, "dropout", None) is not None:
+            layer.dropout.p = 0.0
+    glist = [R.build_sub_graph(n, r, s, True, 0) for s in case["history"]]
+    hist_e, _, h0_e, _, _ = m.forward(glist, None, True)
+    m.train()
+    hist, _, h0, _, _ = m.forward(glist, None, True)
+    assert hist[-1].requires_grad and h0.requires_grad
+    ok, worst = close(hist[-1].detach().cpu().numpy(), hist_e[-1].cpu().numpy(), rtol=5e-5)
+    assert ok, worst
+    (hist[-1].square().sum() + h0.square().sum()).backward()
+    g = m.dynamic_emb.grad
+    assert g is not None and bool(torch.isfinite(g).all()) and float(g.abs().max()) > 0
+    assert m.time_gate_weight.grad is not None and float(m.time_gate_weight.grad.abs().max()) > 0
