@@ -1,7 +1,9 @@
 """R-GCN layers with the reference's constructor / forward signatures and parameter names
 (rgcn/layers.py:7-91 RGCNLayer, :147-179 RGCNBlockLayer, :182-279 UnionRGCNLayer), computing on the
-sm_100a kernels.  Inference path only in this round: dropout layers are kept for state-dict / API
-parity and are the identity in eval(); calling a layer in training mode with dropout > 0 raises.
+sm_100a kernels.  eval(): the inference kernels under no_grad (dropout = identity).  train(): UnionRGCNLayer runs on the
+kernel-backed autograd nodes of regcn_b200/train.py (dropout, gradients, the live skip gate when prev_h is given); the
+layers without backward kernels of their own (RGCNBlockLayer outside the static-graph path) raise instead of returning
+values without gradients.
 """
 import torch
 import torch.nn as nn
@@ -61,25 +63,31 @@ class UnionRGCNLayer(nn.Module):
             self._loop_cat_key = key
         return self._loop_cat_val
 
-    def _forward_train(self, g, emb_rel):
+    def _forward_train(self, g, emb_rel, prev_h=None):
         """train() mode with gradients and dropout: the kernel-backed autograd nodes RecurrentRGCN's training path uses
-        (regcn_b200/train.py), for a caller that drives the layer itself (rgcn/layers.py:222-255)."""
+        (regcn_b200/train.py), for a caller that drives the layer itself (rgcn/layers.py:222-255).  prev_h: the LIVE skip
+        gate (rgcn/layers.py:234-245): sigmoid(prev_h W_s + b_s) mixes the node representation with prev_h in front of
+        the activation -- the time-gate node without its normalisation."""
         from . import train as T
         with torch.enable_grad():
             h = g.ndata['h']
             p = float(self.dropout.p) if self.dropout is not None else 0.0
             P = T.linear(T.union_aggregate(h, emb_rel, g), self.weight_neighbor, None, True)
             L = T.linear(h, torch.cat((self.loop_weight, self.evolve_loop_weight), dim=1), None, True)
-            out = T.union_combine(P, L, g, p)
+            if prev_h is None:
+                out = T.union_combine(P, L, g, p)
+            else:
+                S = T.linear(prev_h, self.skip_connect_weight, None, True)
+                out = T.rrelu_drop(T.time_gate(S, self.skip_connect_bias, T.union_sum(P, L, g), prev_h, False), p)
         g.ndata['h'] = out
         return out
 
     @torch.no_grad()
     def forward(self, g, prev_h, emb_rel):
-        if (self.training and self.self_loop and self.activation is F.rrelu
-                and not (len(prev_h) != 0 and self.skip_connect)):
+        if self.training and self.self_loop and self.activation is F.rrelu:
             self.rel_emb = emb_rel
-            return self._forward_train(g, emb_rel)
+            live = len(prev_h) != 0 and self.skip_connect
+            return self._forward_train(g, emb_rel, prev_h if live else None)
         _no_train_dropout(self)
         self.rel_emb = emb_rel
         h = g.ndata['h']

@@ -265,6 +265,25 @@ class _UnionCombine(torch.autograd.Function):
         return dP, dL, None, None
 
 
+class _UnionSum(torch.autograd.Function):
+    """P + where(indeg>0, L[:, :d], L[:, d:]) without activation: the node representation in front of a LIVE skip gate
+    (rgcn/layers.py:236-245)."""
+
+    @staticmethod
+    def forward(ctx, P, L, g):
+        out, _, _ = ops.union_combine(P.contiguous(), L.contiguous(), g.indeg, act=0)
+        ctx.g = g
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        N, d = dout.shape
+        dP = torch.empty((N, d), device=dout.device, dtype=F32)
+        dL = torch.empty((N, 2 * d), device=dout.device, dtype=F32)
+        call("regcn_union_combine_bwd", None, ptr(dout.contiguous()), ptr(ctx.g.indeg), N, d, 0.0, ptr(dP), ptr(dL))
+        return dP, dL, None
+
+
 class _TimeGate(torch.autograd.Function):
     """h' = s(G+b) [normalize](cur) + (1 - s(G+b)) h   (src/rrgcn.py:176-178)."""
 
@@ -633,6 +652,8 @@ def static_embedding(model, static_graph):
 rel_mean_pool = _RelMeanPool.apply
 union_aggregate = _UnionAggregate.apply
 union_combine = _UnionCombine.apply
+union_sum = _UnionSum.apply
+rrelu_drop = _RReluDrop.apply
 time_gate = _TimeGate.apply
 gru_gate = _GRUGate.apply
 normalize = _Normalize.apply

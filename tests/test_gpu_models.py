@@ -214,8 +214,7 @@ def test_layer_signatures_drop_in():
     ref = restate.block_layer(h.double(), o, blk.weight.detach().cpu().double(), 100, d)
     ok, worst = close(out.cpu().numpy(), ref.numpy())
     assert ok, worst
-    # train() mode: the layer runs on the kernel-backed autograd nodes (dropout 0.2 applied, gradients flow); with a LIVE
-    # skip gate (prev_h given) it refuses loudly instead of silently skipping the dropout
+    # train() mode: the layer runs on the kernel-backed autograd nodes (dropout 0.2 applied, gradients flow)
     hd = h.to(DEV).requires_grad_(True)
     g.ndata['h'] = hd
     out_t = layer.train()(g, [], rel.to(DEV))
@@ -228,9 +227,31 @@ def test_layer_signatures_drop_in():
     assert torch.allclose(out_t.detach()[kept], out_e[kept] / 0.8, rtol=1e-5, atol=1e-6)
     out_t.sum().backward()
     assert hd.grad is not None and layer.weight_neighbor.grad is not None and layer.loop_weight.grad is not None
-    g.ndata['h'] = h.to(DEV)
-    with pytest.raises(NotImplementedError):
-        layer.train()(g, prev.to(DEV), rel.to(DEV))
+    # LIVE skip gate in train() mode (rgcn/layers.py:234-245): values (dropout 0) and gradients against torch autograd
+    # over the fp64 oracle
+    layer.dropout.p = 0.0
+    for q in layer.parameters():
+        q.grad = None
+    hd = h.to(DEV).requires_grad_(True)
+    pd = prev.to(DEV).requires_grad_(True)
+    g.ndata['h'] = hd
+    out_s = layer.train()(g, pd, rel.to(DEV))
+    w = torch.randn(n, d, generator=torch.Generator().manual_seed(3))
+    (out_s * w.to(DEV)).sum().backward()
+    Pd = {k: v.detach().cpu().double().requires_grad_(True) for k, v in layer.state_dict().items()}
+    h64, p64 = h.double().requires_grad_(True), prev.double().requires_grad_(True)
+    ref_s = restate.union_layer(h64, rel.double(), o, Pd["weight_neighbor"], Pd["loop_weight"], Pd["evolve_loop_weight"],
+                                skip=(Pd["skip_connect_weight"], Pd["skip_connect_bias"]), prev_h=p64)
+    ok, worst = close(out_s.detach().cpu().numpy(), ref_s.detach().numpy())
+    assert ok, worst
+    (ref_s * w.double()).sum().backward()
+    pairs = [(hd.grad, h64.grad), (pd.grad, p64.grad)] + [(getattr(layer, k).grad, Pd[k].grad) for k in
+             ("weight_neighbor", "loop_weight", "evolve_loop_weight", "skip_connect_weight", "skip_connect_bias")]
+    for mine, ref_g in pairs:
+        assert mine is not None
+        l2 = float((mine.detach().cpu().double() - ref_g).norm() / ref_g.norm())
+        assert l2 <= 2e-3, l2            # (one rrelu mask within rounding of zero moves a 500 x 200 gradient by ~1e-3)
+    layer.dropout.p = 0.2
 
 
 @pytest.mark.parametrize("kind", ["regcn", "hyp_uv_roth", "hyp_uv_convtranse", "hyp_lgcn_murp", "hyp_uv_roth_flags",
