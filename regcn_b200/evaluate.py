@@ -476,14 +476,32 @@ def test(model, history_list, test_list, num_rels, num_nodes, use_cuda=True, all
 
     # start-up: only the first group is prepared in front of the first evolution (every prepare costs ~0.2 ms of host time
     # during which the GPU has nothing to do); the following groups are prepared behind it, see the two top-ups below
-    G_FIRST = min(G, 4)   # the first group is short: its preparation is host time in front of an idle GPU
+    # Group sizes of the call.  The first groups ramp up (4, 8, then equal shares of the rest in groups of at most G): the
+    # preparation of a group is ~0.1 ms of host time per timestamp with nothing but the previous group's decodes for the
+    # GPU to run meanwhile -- one group of 4 in front of one of 16 left it idle ~1.4 ms twice per call.
+    if G > 1:
+        sizes, left = [], K
+        for cap in (4, 8):
+            if left > 0 and cap < G:
+                sizes.append(min(cap, left))
+                left -= sizes[-1]
+        n_rest = -(-left // G)
+        sizes += [left // n_rest + (1 if i < left % n_rest else 0) for i in range(n_rest)] if left > 0 else []
+    else:
+        sizes = [1] * K
+    starts = [0]
+    for n_ in sizes:
+        starts.append(starts[-1] + n_)
+    G_FIRST = sizes[0] if sizes else 1
     queue = [prepare(j) for j in range(min(G_FIRST if G > 1 else PREP_DEPTH, K))]
     next_j = len(queue)
     _tm = os.environ.get("REGCN_TEST_TIMING") == "1"
     _acc = [0.0] * 6
     k = 0
+    gi_ = 0
     while k < K:
-        n_g = min(G if k else G_FIRST, K - k)
+        n_g = sizes[gi_]
+        gi_ += 1
         group = [queue.pop(0) for _ in range(n_g)]
         _t0 = time.perf_counter()
         for cur in group:
@@ -501,12 +519,16 @@ def test(model, history_list, test_list, num_rels, num_nodes, use_cuda=True, all
             states = [(evolve_embs[-1], r_emb)]
         filters = [_finish_filters(cur) for cur in group]      # the fill launches queue up behind the evolution
         _t3 = time.perf_counter()
-        # the next group's preparation goes behind this evolution and in front of its decodes: its sizes are on the host
-        # when the next iteration asks for them (in steady state it was already prepared one iteration earlier)
-        while next_j < min(K, k + n_g + (G if G > 1 else 0)):
-            queue.append(prepare(next_j))
-            next_j += 1
+        # the next group's preparation goes behind this evolution, interleaved with this group's decodes: every prepare
+        # costs ~0.1 ms of host time, and with a decode (~0.4 ms of kernels) enqueued in front of each few of them the GPU
+        # has work while the host issues them (at the start of a call nothing else is queued: 16 preparations in a row left
+        # the GPU idle for ~2 ms).  Their sizes are on the host when the next iteration asks for them (in steady state they
+        # were already prepared one iteration earlier).
+        prep_target = min(K, starts[min(gi_ + 1, len(sizes))]) if G > 1 else min(K, k + n_g)   # through the next group
+        prep_each = -(-max(0, prep_target - next_j) // max(1, n_g // 2))       # all of them within the first half of the decodes:
+        # the host asks for their sizes at the top of the next iteration, when the GPU still has the second half queued
         _t3b = time.perf_counter()
+        _tprep = 0.0
         for i, (cur, (emb, r_emb), (f_ent, f_rel)) in enumerate(zip(group, states, filters)):
             all_t = cur.all_t
             if one_call:
@@ -534,14 +556,23 @@ def test(model, history_list, test_list, num_rels, num_nodes, use_cuda=True, all
             host = result_host[offs[k + i]:offs[k + i + 1]]
             host.copy_(packed, non_blocking=True)                      # this timestamp's result, device -> host
             results.append(host)
+            _tp0 = time.perf_counter()
+            for _ in range(prep_each):
+                if next_j < prep_target:
+                    queue.append(prepare(next_j))
+                    next_j += 1
+            _tprep += time.perf_counter() - _tp0
+        while next_j < prep_target:
+            queue.append(prepare(next_j))
+            next_j += 1
         _t4 = time.perf_counter()
         k += n_g
         # the window slides (src/main.py:98-100); prepare the timestamps up to PREP_DEPTH ahead while the GPU is busy
-        while next_j < min(K, k + PREP_DEPTH):
+        while G == 1 and next_j < min(K, k + PREP_DEPTH):
             queue.append(prepare(next_j))
             next_j += 1
         _t5 = time.perf_counter()
-        for _i, _d in enumerate((_t1 - _t0, _t2 - _t1, _t3 - _t2, _t4 - _t3b, _t5 - _t4 + _t3b - _t3)):
+        for _i, _d in enumerate((_t1 - _t0, _t2 - _t1, _t3 - _t2, _t4 - _t3b - _tprep, _t5 - _t4 + _t3b - _t3 + _tprep)):
             _acc[_i] += _d
     if _tm and K:
         print("test() host ms/step: wait %.3f finish %.3f forward %.3f decode+rank %.3f prepare %.3f" %
