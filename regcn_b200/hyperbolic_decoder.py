@@ -51,6 +51,11 @@ class _HypConvBase(nn.Module):
         if self.training:
             raise NotImplementedError("regcn_b200 decoders: the standalone forward() is the inference path (folded BatchNorm, no dropout); batch-statistics BatchNorm, dropout and gradients run through the model's get_loss() (regcn_b200/train.py, train_hyp.py)")
         B = len(triplets)
+        if ops.gemm_impl() == "tc" and ops.convtrans_fc_ok(ent_act.shape[1], self.conv1.weight, self.fc.out_features):
+            # one GEMM whose A operand (the conv feature map) is computed on chip; bn2 + relu in its split-K reduction
+            return ops.convtrans_fc(ent_act, second, triplets, col0, col1, _fold_bn(self.bn0), self.conv1.weight.detach(),
+                                    self.conv1.bias.detach(), _fold_bn(self.bn1), self.fc.weight, self.fc.bias.detach(),
+                                    bn2=_fold_bn(self.bn2) if (always_bn2 or B > 1) else None, relu=True)
         feats = ops.convtranse_features(ent_act, second, triplets, col0, col1, _fold_bn(self.bn0),
                                         self.conv1.weight.detach(), self.conv1.bias.detach(), _fold_bn(self.bn1),
                                         split=False)

@@ -193,7 +193,7 @@ def test_union_aggregate_large_vs_torch():
     ref = torch.zeros(n, d, device=DEV, dtype=torch.float64).index_add_(0, g.dst[:E].long(), msg)
     ref *= g.norm.double().view(-1, 1)
     err = (out.double() - ref).abs()
-    assert bool((err <= 2e-4 * torch.clamp(ref.abs(), min=1.0)).all()), float(err.max())
+    assert bool((err <= 1e-4 * torch.clamp(ref.abs(), min=1.0)).all()), float(err.max())
     # linearity in h (size-independent property): agg(h1 + h2, rel) = agg(h1, rel) + agg(h2, 0)
     h2 = torch.randn(n, d, device=DEV)
     lhs = ops.union_aggregate(h + h2, rel, g)
@@ -414,7 +414,7 @@ def test_hyperbolic_row_kernels_vs_oracle(layer_norm, residual):
         hn = restate.apply_radius(hn, rs, c)
     out = ops.hyp_time_gate(h2.to(DEV), pt, G.to(DEV), b.to(DEV), rs_raw.to(DEV), w.view(-1).to(DEV), rb, layer_norm,
                             residual, c, rmin, rmax, beta, eps_r)
-    ok, worst = close(out.cpu().numpy(), hn.numpy(), rtol=2e-4)
+    ok, worst = close(out.cpu().numpy(), hn.numpy(), rtol=1e-4)
     assert ok, worst
 
 
@@ -445,7 +445,7 @@ def test_block_and_lorentz_aggregate_vs_oracle(nb):
     agg = ops.lorentz_aggregate(ht, W.to(DEV), rel.to(DEV), g, nb, c)
     L = ops.gemm(ht, torch.cat((wl, we), 1).to(DEV))
     out, _, _ = ops.union_combine(agg, L, g.indeg, act=1, hyper=True, c=c)
-    ok, worst = close(out.cpu().numpy(), ref_l.numpy(), rtol=2e-4)
+    ok, worst = close(out.cpu().numpy(), ref_l.numpy(), rtol=1e-4)
     assert ok, worst
 
 
@@ -465,16 +465,16 @@ def test_convtranse_tower_and_hyp_query_vs_oracle():
     P = {k: v.float() for k, v in sd.items() if v.is_floating_point()}
     ref = restate.convtranse_scores(P, emb, rel, tri.numpy())
     out = m.decoder_ob(emb.to(DEV), rel.to(DEV), tri.to(DEV), mode="test")
-    ok, worst = close(out.cpu().numpy(), ref.numpy(), rtol=2e-4)
+    ok, worst = close(out.cpu().numpy(), ref.numpy(), rtol=1e-4)
     assert ok, worst
     ref = restate.convtransr_scores(P, emb, rel, tri.numpy())
     out = m.rdecoder(emb.to(DEV), rel.to(DEV), tri.to(DEV), mode="test")
-    ok, worst = close(out.cpu().numpy(), ref.numpy(), rtol=2e-4)
+    ok, worst = close(out.cpu().numpy(), ref.numpy(), rtol=1e-4)
     assert ok, worst
     # single-query batch skips bn2 (src/decoder.py:93-94)
     ref1 = restate.convtranse_scores(P, emb, rel, tri[:1].numpy())
     out1 = m.decoder_ob(emb.to(DEV), rel.to(DEV), tri[:1].contiguous().to(DEV), mode="test")
-    ok, worst = close(out1.cpu().numpy(), ref1.numpy(), rtol=2e-4)
+    ok, worst = close(out1.cpu().numpy(), ref1.numpy(), rtol=1e-4)
     assert ok, worst
 
 
@@ -549,12 +549,12 @@ def test_hyperbolic_decoders_vs_oracle(decoder):
     ref = fn[0](P, emb, rel, tri.numpy(), c)
     ref = ref[0] if isinstance(ref, tuple) else ref
     out = m.decoder_ob(emb.to(DEV), rel.to(DEV), tri.to(DEV), mode="test")
-    ok, worst = close(out.cpu().numpy(), ref.numpy(), rtol=2e-4)
+    ok, worst = close(out.cpu().numpy(), ref.numpy(), rtol=1e-4)
     assert ok, worst
     ref = fn[1](P, emb, rel, tri.numpy(), c)
     ref = ref[0] if isinstance(ref, tuple) else ref
     out = m.rdecoder(emb.to(DEV), rel.to(DEV), tri.to(DEV), mode="test")
-    ok, worst = close(out.cpu().numpy(), ref.numpy(), rtol=2e-4)
+    ok, worst = close(out.cpu().numpy(), ref.numpy(), rtol=1e-4)
     assert ok, worst
 
 
@@ -689,7 +689,7 @@ def test_gemm_tcgen05_vs_fp64(impl, rtol, M, N, K, trans_b, bias, split_k):
     try:
         out = ops.gemm(a.to(DEV), b.to(DEV), trans_b=trans_b, bias=bv.to(DEV) if bias else None, split_k=split_k)
         torch.cuda.synchronize()
-        tol = rtol * max(1.0, (K / 200.0) ** 0.5) * 4
+        tol = rtol * max(1.0, (K / 200.0) ** 0.5) * (4 if K > 2048 else 2)   # (unit-variance operands: the sum of |a||b| grows with K, 3xTF32 keeps ~2^-21 of it)
         err = (out.cpu().double() - ref).abs()
         scale = torch.clamp(ref.abs(), min=1.0) if impl == "tc" else torch.clamp(ref.abs(), min=float(K) ** 0.5)
         assert bool((err <= tol * scale).all()), float((err / scale).max())

@@ -50,9 +50,9 @@ def test_model_matches_reference_golden(name):
         for i, h in enumerate(hist):
             ok, worst = close(h.cpu().numpy(), z["hist"][i])
             assert ok, f"hist[{i}] worst ratio {worst}"
-        ok, worst = close(score.cpu().numpy(), z["score"], rtol=2e-4)
+        ok, worst = close(score.cpu().numpy(), z["score"], rtol=1e-4)
         assert ok, f"score worst ratio {worst}"
-        ok, worst = close(score_rel.cpu().numpy(), z["score_rel"], rtol=2e-4)
+        ok, worst = close(score_rel.cpu().numpy(), z["score_rel"], rtol=1e-4)
         assert ok, f"score_rel worst ratio {worst}"
         ref_score = torch.from_numpy(z["score"]).to(DEV)
         fm, m, rank, frank = utils.get_total_rank(all_t, ref_score, all_ans, 1000, rel_predict=0)
@@ -68,15 +68,15 @@ def test_model_matches_reference_golden(name):
         assert ok, f"hist_last worst ratio {worst}"
         ok, worst = close(hist[0][rows].cpu().numpy(), z["hist_first_rows"])
         assert ok, f"hist_first worst ratio {worst}"
-        ok, worst = close(score[qrows][:, rows].cpu().numpy(), z["score_block"], rtol=2e-4)
+        ok, worst = close(score[qrows][:, rows].cpu().numpy(), z["score_block"], rtol=1e-4)
         assert ok, f"score block worst ratio {worst}"
-        ok, worst = close(score_rel[qrows].cpu().numpy(), z["score_rel_qrows"], rtol=2e-4)
+        ok, worst = close(score_rel[qrows].cpu().numpy(), z["score_rel_qrows"], rtol=1e-4)
         assert ok, f"score_rel worst ratio {worst}"
-        ok, worst = close(score.double().sum(1).cpu().numpy(), z["score_rowsum"], rtol=2e-4,
+        ok, worst = close(score.double().sum(1).cpu().numpy(), z["score_rowsum"], rtol=1e-4,
                           atol_scale=float(np.abs(z["score_absmax"]).max()) * 50)
         assert ok, f"score row-sum worst ratio {worst}"
         if "score_full_rows" in z.files:                     # complete score rows of 16 queries (every candidate)
-            ok, worst = close(score[torch.as_tensor(z["full_qrows"]).to(DEV)].cpu().numpy(), z["score_full_rows"], rtol=2e-4)
+            ok, worst = close(score[torch.as_tensor(z["full_qrows"]).to(DEV)].cpu().numpy(), z["score_full_rows"], rtol=1e-4)
             assert ok, f"full score rows worst ratio {worst}"
     # end-to-end ranks on our own scores: report-level agreement (fp32 re-association flips near-ties)
     _, _, rank, frank = utils.get_total_rank(all_t, score, all_ans, 1000, rel_predict=0,
@@ -771,14 +771,14 @@ def test_edge_cases_empty_and_single_snapshots():
     all_t, score, score_rel = model.predict(glist, r, None, torch.from_numpy(case["test"]).to(DEV), True)
     graphs = [restate.build_edges(s, n, r) for s in hist]
     o_t, o_score, o_rel, _, _ = restate.regcn_predict(sd, graphs, r, case["test"], layer_norm=True)
-    ok, worst = close(score.cpu().numpy(), o_score.numpy(), rtol=2e-4)
+    ok, worst = close(score.cpu().numpy(), o_score.numpy(), rtol=1e-4)
     assert ok, worst
-    ok, worst = close(score_rel.cpu().numpy(), o_rel.numpy(), rtol=2e-4)
+    ok, worst = close(score_rel.cpu().numpy(), o_rel.numpy(), rtol=1e-4)
     assert ok, worst
     one = case["test"][:1]
     _, s1, _ = model.predict(glist, r, None, torch.from_numpy(one).to(DEV), True)
     _, o1, _, _, _ = restate.regcn_predict(sd, graphs, r, one, layer_norm=True)
-    ok, worst = close(s1.cpu().numpy(), o1.numpy(), rtol=2e-4)
+    ok, worst = close(s1.cpu().numpy(), o1.numpy(), rtol=1e-4)
     assert ok and s1.shape == (2, n), worst
     mrrs = R.test(model, hist, [one, case["test"]], r, n, True, test_history_len=3)
     assert all(np.isfinite(v) and 0 < v <= 1 for v in mrrs)
