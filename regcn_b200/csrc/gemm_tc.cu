@@ -202,8 +202,8 @@ struct Params {
   // ---- conv-producer mode (a_f32 == 3, EPI 0): the A operand of the ConvTransE / ConvTransR fully-connected layer is never
   //      materialised.  A[b, c*d + i] = relu(bn1(conv1d_k3(bn0([x0[idx0[b]]; x1[idx1[b]]]))))[c, i] (src/decoder.py:81-90,
   //      eval-mode BatchNorm folded to scale / shift) is computed by the converter warps straight into the operand ring.
-  //      K is walked in units (z, c) = (block of 16 positions, channel), z-major: the 128 x 18 input window of a position
-  //      block is staged in shared memory once per ~C units.  The weight is given in the same order (convfc_pack_weight:
+  //      K is walked in units (z, c) = (block of 16 positions, channel), z-major: a producer thread keeps the inputs of its
+  //      (two rows, 4-position chunk) of a position block in registers for the ~C units that use them.  The weight is given in the same order (convfc_pack_weight:
   //      W'[n, 16 (z C + c) + j] = W[n, c d + 16 z + j], zero where 16 z + j >= d), so the B stream is a plain contiguous
   //      K walk with 64-byte aligned boxes; a split-K slice is a contiguous range of units. ----
   const float* cv_x0;         // [*, cv_d] first input table (entity rows)
@@ -219,14 +219,11 @@ struct Params {
   int cv_C, cv_d, cv_zb;      // channels, positions per row, position blocks = ceil(d / 16)
   unsigned long long* trace;  // optional in-kernel timeline: [gridDim.x][kTraceSlots] %globaltimer stamps (NULL = off)
 };
-constexpr int kConvPitch = 20;                                   // floats per staged input row: 18 used (positions 16 z - 1 .. 16 z + 16)
 constexpr int kConvMaxC = 64;
 constexpr int kConvWarps = 8;                                    // producer warps of the conv mode: warps 2 .. 9
-// The staged inputs (2 x 128 x kConvPitch floats = 20 KB) live in the epilogue staging slices of the first five epilogue
-// warps: those warps are producers while a tile's main loop runs and only transpose accumulator chunks through their slices
-// after every producer has passed the tile's last k-block.  Extra shared memory: the per-channel constants.
-constexpr uint32_t kConvBytes = kConvMaxC * 9 * 4 + 256;
-static_assert(2 * 128 * kConvPitch * 4 <= 5 * 32 * 32 * 4, "staged conv inputs must fit the staging slices of five epilogue warps");
+// Extra shared memory of the conv mode: the per-channel constants (12 floats each).  The inputs of a position block live in
+// the producer threads' registers (two rows x two tables x six positions).
+constexpr uint32_t kConvBytes = kConvMaxC * 12 * 4 + 256;
 constexpr int kTraceSlots = 48;
 __device__ __forceinline__ void trace_stamp(const Params& p, int slot) {
   if (p.trace) {
@@ -344,80 +341,82 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
   //      of convtranse_features_kernel (same fused multiply-adds in the same order). ----
   int cv_stage = 0, cv_m0 = -1, cv_z = -1;
   uint32_t cv_phase = 0;
+  float cv_in[2][2][6];                                       // [row j][table][positions 16 z + 4 q - 1 .. + 4], bn0 applied
+  int cv_idx[2][2] = {{-1, -1}, {-1, -1}};                     // source rows of the thread's two tile rows in both tables (-1: past M)
   auto conv_produce = [&](int m0, int kb_beg, int kb_end) {
     if constexpr (EPI == 0) {
       const int tid = (warp - 2) * 32 + lane;                 // 0 .. 32 kConvWarps - 1
-      float* cin = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes);            // aliases epilogue staging
       float* cpar = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes + staging_bytes(EW));
       const int C = p.cv_C, d = p.cv_d;
       if (cv_m0 < 0) {
+        // per-channel constants, 12 floats per channel: {w0 w1 w2 w3} {w4 w5 conv_b bn1_s} {bn1_t - - -}
         for (int i = tid; i < C; i += 32 * kConvWarps) {
 #pragma unroll
-          for (int k = 0; k < 6; ++k) cpar[i * 9 + k] = __ldg(p.cv_w + i * 6 + k);
-          cpar[i * 9 + 6] = __ldg(p.cv_b + i);
-          cpar[i * 9 + 7] = __ldg(p.cv_bn1_s + i);
-          cpar[i * 9 + 8] = __ldg(p.cv_bn1_t + i);
+          for (int k = 0; k < 6; ++k) cpar[i * 12 + k] = __ldg(p.cv_w + i * 6 + k);
+          cpar[i * 12 + 6] = __ldg(p.cv_b + i);
+          cpar[i * 12 + 7] = __ldg(p.cv_bn1_s + i);
+          cpar[i * 12 + 8] = __ldg(p.cv_bn1_t + i);
         }
+        asm volatile("bar.sync 8, %0;" ::"r"(32 * kConvWarps) : "memory");
       }
       const int q = tid & 3, rb = tid >> 2;
-      constexpr int kRowStep = 8 * kConvWarps;                 // rows covered by the producers per pass
+      constexpr int kRowStep = 8 * kConvWarps;                 // rows covered by the producers per pass (64: two rows a thread)
+      static_assert(BLOCK_M / kRowStep == 2, "a producer thread holds the inputs of two rows");
       for (int kb = kb_beg; kb < kb_end; ++kb) {
         const int zz = kb / C, c = kb - zz * C;
+        if (m0 != cv_m0) {
+          // rows of this tile: source row ids in both input tables
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int gm = m0 + rb + kRowStep * j;
+            const bool rv = gm < p.M;
+            cv_idx[j][0] = rv ? (int)p.cv_triples[3 * (size_t)gm + p.cv_col0] : -1;
+            cv_idx[j][1] = rv ? (int)p.cv_triples[3 * (size_t)gm + p.cv_col1] : -1;
+          }
+        }
         if (m0 != cv_m0 || zz != cv_z) {
-          // stage bn0([x0; x1]) of positions 16 z - 1 .. 16 z + 16 (zero outside the row: the conv's padding) for the 128
-          // query rows of the tile (thread <-> row, table); every producer has finished reading the previous window
-          asm volatile("bar.sync 8, %0;" ::"r"(32 * kConvWarps) : "memory");
-          const int pz = 16 * zz;
-          for (int item = tid; item < 2 * BLOCK_M; item += 32 * kConvWarps) {
-          const int r = item >> 1, tab = item & 1;
-          const int gm = m0 + r;
-          const bool rv = gm < p.M;
-          const int64_t idx = rv ? p.cv_triples[3 * (size_t)gm + (tab ? p.cv_col1 : p.cv_col0)] : 0;
-          const float* src = (tab ? p.cv_x1 : p.cv_x0) + (size_t)idx * d;
-          const float sc = __ldg((tab ? p.cv_bn0_s + 1 : p.cv_bn0_s)), sh = __ldg((tab ? p.cv_bn0_t + 1 : p.cv_bn0_t));
-          float* dst = cin + (tab * BLOCK_M + r) * kConvPitch;
-          float4 v[4];
+          // bn0([x0; x1]) of positions 16 z + 4 q - 1 .. 16 z + 4 q + 4 of the thread's two rows, kept in registers for the C
+          // units of this position block (zero outside the row: the conv's padding)
+          const int pos = 16 * zz + 4 * q;
+          const float s0 = __ldg(p.cv_bn0_s), t0 = __ldg(p.cv_bn0_t), s1 = __ldg(p.cv_bn0_s + 1), t1 = __ldg(p.cv_bn0_t + 1);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            v[k] = (rv && pz + 4 * k < d) ? __ldg(reinterpret_cast<const float4*>(src + pz + 4 * k)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          const float lft = (rv && pz > 0) ? __ldg(src + pz - 1) : 0.f;
-          const float rgt = (rv && pz + 16 < d) ? __ldg(src + pz + 16) : 0.f;
-          dst[0] = (rv && pz > 0) ? fmaf(lft, sc, sh) : 0.f;
+          for (int j = 0; j < 2; ++j) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const bool in = rv && pz + 4 * k < d;
-            dst[1 + 4 * k] = in ? fmaf(v[k].x, sc, sh) : 0.f;
-            dst[2 + 4 * k] = in ? fmaf(v[k].y, sc, sh) : 0.f;
-            dst[3 + 4 * k] = in ? fmaf(v[k].z, sc, sh) : 0.f;
-            dst[4 + 4 * k] = in ? fmaf(v[k].w, sc, sh) : 0.f;
+            for (int tab = 0; tab < 2; ++tab) {
+              const float* src = (tab ? p.cv_x1 : p.cv_x0) + (size_t)(cv_idx[j][tab] < 0 ? 0 : cv_idx[j][tab]) * d;
+              const float sc = tab ? s1 : s0, sh = tab ? t1 : t0;
+              const bool in = cv_idx[j][tab] >= 0 && pos < d;
+              const float4 v = in ? __ldg(reinterpret_cast<const float4*>(src + pos)) : make_float4(0.f, 0.f, 0.f, 0.f);
+              const float lft = (in && pos > 0) ? __ldg(src + pos - 1) : 0.f;
+              const float rgt = (in && pos + 4 < d) ? __ldg(src + pos + 4) : 0.f;
+              cv_in[j][tab][0] = (in && pos > 0) ? fmaf(lft, sc, sh) : 0.f;
+              cv_in[j][tab][1] = in ? fmaf(v.x, sc, sh) : 0.f;
+              cv_in[j][tab][2] = in ? fmaf(v.y, sc, sh) : 0.f;
+              cv_in[j][tab][3] = in ? fmaf(v.z, sc, sh) : 0.f;
+              cv_in[j][tab][4] = in ? fmaf(v.w, sc, sh) : 0.f;
+              cv_in[j][tab][5] = (in && pos + 4 < d) ? fmaf(rgt, sc, sh) : 0.f;
+            }
           }
-          dst[17] = (rv && pz + 16 < d) ? fmaf(rgt, sc, sh) : 0.f;
-          }
-          asm volatile("bar.sync 8, %0;" ::"r"(32 * kConvWarps) : "memory");
           cv_m0 = m0; cv_z = zz;
         }
-        const float* w = cpar + c * 9;
-        const float w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4], w5 = w[5], cb = w[6], bs = w[7], bt = w[8];
+        const float4 wa = *reinterpret_cast<const float4*>(cpar + c * 12);
+        const float4 wb = *reinterpret_cast<const float4*>(cpar + c * 12 + 4);
+        const float bt = cpar[c * 12 + 8];
+        const float w0 = wa.x, w1 = wa.y, w2 = wa.z, w3 = wa.w, w4 = wb.x, w5 = wb.y, cb = wb.z, bs = wb.w;
         const bool chunk_in = 16 * zz + 4 * q < d;       // d % 4 == 0: a chunk lies inside the row or outside it
         mbar_wait(smem_u32(&empty_bar[cv_stage]), cv_phase ^ 1);
         const uint32_t a_hi = smem_base + cv_stage * stage_bytes;
 #pragma unroll
-        for (int j = 0; j < BLOCK_M / kRowStep; ++j) {
+        for (int j = 0; j < 2; ++j) {
           const int r = rb + kRowStep * j;
           float4 h = make_float4(0.f, 0.f, 0.f, 0.f), l = h;
           if (chunk_in) {
-            const float* p0 = cin + r * kConvPitch + 4 * q;
-            const float* p1 = p0 + BLOCK_M * kConvPitch;
-            const float4 x4 = *reinterpret_cast<const float4*>(p0);
-            const float4 y4 = *reinterpret_cast<const float4*>(p1);
-            const float a0[6] = {x4.x, x4.y, x4.z, x4.w, p0[4], p0[5]};
-            const float a1[6] = {y4.x, y4.y, y4.z, y4.w, p1[4], p1[5]};
             float o[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               float acc = cb;
-              acc = fmaf(w0, a0[u], acc); acc = fmaf(w1, a0[u + 1], acc); acc = fmaf(w2, a0[u + 2], acc);
-              acc = fmaf(w3, a1[u], acc); acc = fmaf(w4, a1[u + 1], acc); acc = fmaf(w5, a1[u + 2], acc);
+              acc = fmaf(w0, cv_in[j][0][u], acc); acc = fmaf(w1, cv_in[j][0][u + 1], acc); acc = fmaf(w2, cv_in[j][0][u + 2], acc);
+              acc = fmaf(w3, cv_in[j][1][u], acc); acc = fmaf(w4, cv_in[j][1][u + 1], acc); acc = fmaf(w5, cv_in[j][1][u + 2], acc);
               o[u] = fmaxf(fmaf(acc, bs, bt), 0.f);
             }
             h.x = rna_tf32(o[0]); h.y = rna_tf32(o[1]); h.z = rna_tf32(o[2]); h.w = rna_tf32(o[3]);
