@@ -737,6 +737,8 @@ def main():
     # recurrence (evaluate.timestamps_per_batch: consecutive timestamps do not depend on each other), then scored and
     # ranked one by one.  A step stays ONE evaluated timestamp: K steps = ceil(K/G) batched calls.
     G = evaluate.timestamps_per_batch(model, n)
+    if G > 1:
+        G = -(-args.steps // -(-args.steps // G))                  # the batch size the timed region runs (K steps = equal batches)
     bstream = synth.make_stream(args.workload, rank, n_test=G)     # timestamp 0 == `case`
     bsnaps = list(bstream["history"]) + list(bstream["tests"][:G - 1])
     bgraphs = glist + [R.build_sub_graph(n, r, s, True, local) for s in bsnaps[L:]]
@@ -822,8 +824,8 @@ def main():
     # its test snapshot host->device, builds the edge index of the snapshot that entered the window, evolves, ranks
     # entities and relations (raw + time-filtered) and copies the four rank vectors device->host.
     e2e_steps = max(3, min(args.steps, 32))          # one test() call over up to 32 timestamps (ICEWS18's test split has 34)
-    if G > 1:
-        e2e_steps = -(-e2e_steps // G) * G           # whole batches of G timestamps
+    if G > 1 and args.steps >= 16:
+        e2e_steps = 32                               # (test() forms its own groups: 4, 8, then equal shares of the rest)
     e2e_warm = max(L + 1, min(args.warmup, 3))       # the window must have turned over once (steady-state cache)
     e2e_reps = 3                                     # the loop is timed three times over fresh snapshots: median
     stream = synth.make_stream(args.workload, 1000 + rank, n_test=e2e_warm + (1 + e2e_reps) * e2e_steps)

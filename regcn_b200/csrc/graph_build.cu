@@ -507,7 +507,7 @@ int csr_build_batch(const regcn_csr_arrays* snaps, int L, int N, int R, void* ws
 // relation->entity lists keep their member-local order and are shifted by the totals of the members before them.
 // One launch; pure copies with offsets (a few hundred KB per member).
 // =====================================================================================================================
-constexpr int kConcatMax = 16;
+constexpr int kConcatMax = 32;     // (ConcatArgs = 5.8 KB of kernel parameters: CUDA >= 12.1 / sm_70+ take up to 32 KB)
 
 struct ConcatMember {
   const int* src; const int* dst; const int* etype; const int* indeg; const float* norm; const int* rowptr;

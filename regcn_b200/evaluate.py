@@ -159,12 +159,12 @@ def timestamps_per_batch(model, num_nodes, static_graph=None):
         return 1
     env = os.environ.get("REGCN_TEST_BATCH")
     if env:
-        return max(1, min(16, int(env)))
+        return max(1, min(32, int(env)))
     if hasattr(model, "_forward_engine_shared") and os.environ.get("REGCN_SHARED_ROWS", "1") != "0":
         # shared-trajectory engine (regcn_regcn_evolve_shared): the all-entity products run over the rows touched so far,
         # not G N rows, and the shared rows are amortised over the windows (ICEWS18 shape: 261 / 225 / 208 us per
         # timestamp at 8 / 12 / 16 windows)
-        return max(1, min(16, 2 * BATCH_ROWS // max(1, int(num_nodes))))
+        return max(1, min(32, 4 * BATCH_ROWS // max(1, int(num_nodes))))
     return max(1, min(8, BATCH_ROWS // max(1, int(num_nodes))))
 
 

@@ -181,12 +181,13 @@ class RecurrentRGCN(nn.Module):
         self._engine_tab_batch = {}
         return self._engine_tab
 
-    def _engine_tables_batch(self, G):
+    def _engine_tables_batch(self, G, tile_entities=True):
         """Tables of the recurrence over G independent history windows at once: the per-entity / per-relation tables are
         tiled G times in the numbering of graph.concat_graphs (entity g*N + v; relation g*R + r, inverse G*R + g*R + r),
-        the weights are shared."""
+        the weights are shared.  tile_entities=False (the shared-trajectory engine reads the first N rows only): the
+        entity table is passed as it is instead of G copies of it."""
         ptab, itab, _ = self._engine_tables()
-        hit = self._engine_tab_batch.get(G)
+        hit = self._engine_tab_batch.get((G, tile_entities))
         if hit is not None:
             return hit
         R = self.num_rels
@@ -195,13 +196,15 @@ class RecurrentRGCN(nn.Module):
         def tile_rel(t):
             return torch.cat([t[:R]] * G + [t[R:]] * G).contiguous()
 
-        heads = [dyn.repeat(G, 1).contiguous(), tile_rel(emb_rel), tile_rel(er_hi), tile_rel(er_lo), tile_rel(gi_static)]
+        other = self._engine_tab_batch.get((G, not tile_entities))
+        rel_heads = other[2][1:] if other is not None else [tile_rel(emb_rel), tile_rel(er_hi), tile_rel(er_lo), tile_rel(gi_static)]
+        heads = [dyn.repeat(G, 1).contiguous() if tile_entities else dyn] + list(rel_heads)
         ptab_g, itab_g = ptab.copy(), itab.copy()
         for i, t in enumerate(heads):
             ptab_g[i] = t.data_ptr()
         itab_g[0], itab_g[1] = G * self.num_ents, 2 * G * R
-        self._engine_tab_batch[G] = (ptab_g, itab_g, heads)
-        return self._engine_tab_batch[G]
+        self._engine_tab_batch[(G, tile_entities)] = (ptab_g, itab_g, heads)
+        return self._engine_tab_batch[(G, tile_entities)]
 
     def _forward_engine(self, g_list, h_init=None, members=1):
         import numpy as np
@@ -236,7 +239,7 @@ class RecurrentRGCN(nn.Module):
         N, R2, d = G * self.num_ents, 2 * G * self.num_rels, self.h_dim
         if len(self.rgcn.layers) < 2 or any(2 * a > N for a in n_act) or os.environ.get("REGCN_SHARED_ROWS", "1") == "0":
             return None
-        ptab, itab, _ = self._engine_tables_batch(G)
+        ptab, itab, _ = self._engine_tables_batch(G, tile_entities=False)
         dev = self.dynamic_emb.device
         gp = np.concatenate([g.ptr_table for g in g_list])
         gi = np.concatenate([g.int_table for g in g_list])

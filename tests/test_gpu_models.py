@@ -539,7 +539,7 @@ def test_hyperbolic_forward_batch_rows_equal_per_window_forward(enc, dec, shape,
 
 
 def test_evaluation_loop_batched_equals_one_timestamp_at_a_time(monkeypatch):
-    """regcn_b200.test() evolving groups of consecutive timestamps together (the default: up to 16 per recurrence with the
+    """regcn_b200.test() evolving groups of consecutive timestamps together (the default: up to 32 per recurrence with the
     shared-trajectory engine, 8 without; a call ramps up through groups of 4 and 8) returns the ranks of the
     one-timestamp-per-recurrence loop, for group sizes that do and do not divide the number of test snapshots, with and
     without the shared-trajectory engine; evaluate_batch equals evaluate_snapshot."""
@@ -550,11 +550,11 @@ def test_evaluation_loop_batched_equals_one_timestamp_at_a_time(monkeypatch):
     model, _ = build_model(dict(kind="regcn", layer_norm=True, seed=9), n, r)
     model = model.to(DEV)
     L = len(st["history"])
-    assert evaluate.timestamps_per_batch(model, n) == 16
+    assert evaluate.timestamps_per_batch(model, n) == 32
     monkeypatch.setenv("REGCN_SHARED_ROWS", "0")
     assert evaluate.timestamps_per_batch(model, n) == 8
     out = {}
-    for flag in ("1", "3", "8", "8s", "16s"):
+    for flag in ("1", "3", "8", "8s", "16s", "20s"):
         monkeypatch.setenv("REGCN_TEST_BATCH", flag.rstrip("s"))
         monkeypatch.setenv("REGCN_SHARED_ROWS", "1" if flag.endswith("s") else "0")
         out[flag] = R.test(model, st["history"], st["tests"], r, n, True, None, None, None, None, "eval",
@@ -563,7 +563,7 @@ def test_evaluation_loop_batched_equals_one_timestamp_at_a_time(monkeypatch):
     monkeypatch.delenv("REGCN_SHARED_ROWS")
     out["default"] = R.test(model, st["history"], st["tests"], r, n, True, None, None, None, None, "eval",
                             test_history_len=L, return_ranks=True)
-    for flag in ("3", "8", "8s", "16s", "default"):
+    for flag in ("3", "8", "8s", "16s", "20s", "default"):
         assert out[flag][0] == out["1"][0]
         for a, b in zip(out[flag][1], out["1"][1]):
             assert len(a) == len(b) == 23
