@@ -633,9 +633,11 @@ REGCN_API int regcn_attn_mix_bwd(const float* w, int w_bcast, const float* u, co
                        void* stream);
 
 /* LorentzRGCNLayer aggregate backward (lgcn encoder in training; hyperbolic_layers.py:589-625, hyperbolic_ops.py:492-518,
- * 563-581), 2x2 relation blocks (num_bases = d/2).  gout (N,d) = dL/d(aggregate output).  dht (N,d); part_rel
- * (S, R2, d) and part_w (S, R2, 2d) with S = regcn_lorentz_bwd_splits(): per-split partial sums of drel / dW, to be
- * summed over S (regcn_col_sum).  type_* : edges grouped by relation type (regcn_group_by_key).
+ * 563-581); num_bases relation blocks of sb x sb, sb = d / num_bases (2x2: chunk-local register kernels; any other size,
+ * e.g. 10x10 where the reference clamps num_bases to 2R (:559-561): generic kernels with the (d, sb) gradient of a relation
+ * accumulated in shared memory, REGCN_ERR_UNSUPPORTED above 200 KB).  gout (N,d) = dL/d(aggregate output).  dht (N,d);
+ * part_rel (S, R2, d) and part_w (S, R2, d sb) with S = regcn_lorentz_bwd_splits(): per-split partial sums of drel / dW,
+ * to be summed over S (regcn_col_sum).  type_* : edges grouped by relation type (regcn_group_by_key).
  * workspace: regcn_lorentz_aggregate_bwd_workspace_bytes(N, R2, d).                                                */
 REGCN_API size_t regcn_lorentz_aggregate_bwd_workspace_bytes(int N, int R2, int d);
 REGCN_API int regcn_lorentz_bwd_splits(void);

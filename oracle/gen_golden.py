@@ -372,14 +372,26 @@ HYP_TRAIN_CASES = {
                                         layer_norm=False, gamma=0.15),
     "hyptrain_lgcn_convtranse_small_s10_ln": dict(kind="hyp", shape="small_l", seed=10, encoder="lgcn",
                                                   decoder="hyperbolic_convtranse", layer_norm=True, gamma=0.15),
+    # num_bases clamped to 2R = 10 (hyperbolic_layers.py:559-561): relation blocks of 20x20
+    "hyptrain_lgcn_roth_tiny_l_s17": dict(kind="hyp", shape="tiny_l", seed=17, encoder="lgcn", decoder="roth",
+                                          layer_norm=False, gamma=0.15),
+    "hyptrain_lgcn_skip_tiny_l_s18_ln": dict(kind="hyp", shape="tiny_l", seed=18, encoder="lgcn",
+                                             decoder="hyperbolic_convtranse", layer_norm=True, gamma=0.15,
+                                             skip_connect=True),
 }
 
 
-def run_hyp_train(ref_utils, HyperbolicRecurrentRGCN):
+def run_hyp_train(ref_utils, HyperbolicRecurrentRGCN, only=()):
     """tests/golden/train_hyp.npz: one optimisation step of the UNMODIFIED hyperbolic reference (get_loss in train() mode
-    with every dropout 0, loss = 0.7 l_e + 0.3 l_r + l_static + l_radius, clip_grad_norm_(1.0), Adam)."""
+    with every dropout 0, loss = 0.7 l_e + 0.3 l_r + l_static + l_radius, clip_grad_norm_(1.0), Adam).  With case names
+    after --hyp-train only those are (re)generated and merged into the existing file."""
     out = {}
+    if only:
+        with np.load(os.path.join(GOLDEN, "train_hyp.npz")) as z:
+            out = {k: z[k] for k in z.files if k.split(".")[0] not in only}
     for name, cfg in HYP_TRAIN_CASES.items():
+        if only and name not in only:
+            continue
         case = synth.make_case(cfg["shape"], cfg["seed"])
         n, r = case["num_ents"], case["num_rels"]
         st_cfg, sg, n_srel, n_words = cfg.get("static"), None, 0, 0
@@ -474,7 +486,7 @@ def main(argv):
     if len(argv) > 1 and argv[1] == "--losses":
         return run_losses(ref_utils, RecurrentRGCN, HyperbolicRecurrentRGCN)
     if len(argv) > 1 and argv[1] == "--hyp-train":
-        return run_hyp_train(ref_utils, HyperbolicRecurrentRGCN)
+        return run_hyp_train(ref_utils, HyperbolicRecurrentRGCN, tuple(argv[2:]))
     if len(argv) > 1 and argv[1] == "--construct-snap":
         return run_construct_snap(ref_utils)
     if len(argv) > 1 and argv[1] == "--static":

@@ -1064,8 +1064,8 @@ int rel_mean_pool(const float* h, const int* rel_rowptr, const int* rel_ents, in
 // ---------------------------------------------------------------------------------------------------------------------
 // K7 backward (lgcn encoder in training; hyperbolic_layers.py:589-625, ops:492-518,563-581).  The centroid weights are
 // equal inside a node, so d(out_v)/d(mL_e) is ONE (d+1)-vector G_v per destination: a node kernel produces it, the edge
-// kernels recompute every message and push G through to_lorentz and exp_0.  num_bases blocks of 2x2 only (the
-// reference's 100 bases at d = 200).
+// kernels recompute every message and push G through to_lorentz and exp_0.  2x2 relation blocks (the reference's 100
+// bases at d = 200) stay chunk-local in registers; any other block size takes the generic variants (SB == 0).
 // ---------------------------------------------------------------------------------------------------------------------
 template <int RV>
 __device__ __forceinline__ void lorentz_edge_forward(const WarpRow<RV>& m, const Curv& cv, float& f, float& D, float& mn) {
@@ -1101,7 +1101,7 @@ __device__ __forceinline__ void lorentz_message_grad(WarpRow<RV>& m, float g0, c
   m.zip(dp, [=](float mm, float dd) { return s * dd + coef * mm; });
 }
 
-template <int RV>
+template <int RV, int SB>
 __global__ void __launch_bounds__(256) lorentz_node_grad_kernel(
     const float* __restrict__ ht, const float* __restrict__ W, const float* __restrict__ rel,
     const int* __restrict__ rowptr, const int* __restrict__ src_sorted, const int* __restrict__ etype_sorted,
@@ -1120,12 +1120,13 @@ __global__ void __launch_bounds__(256) lorentz_node_grad_kernel(
     if (lane == 0) G0[row] = 0.f;
     return;
   }
-  const size_t wstride = (size_t)nb * 4;
+  const int sb = d / nb;
+  const size_t wstride = (size_t)d * sb;
   float acc0 = 0.f;
   for (int p = b; p < e; ++p) {
     const int s = __ldg(src_sorted + p), t = __ldg(etype_sorted + p);
     WarpRow<RV> m;
-    lorentz_message<RV, 2>(m, ht + (size_t)s * d, W + (size_t)t * wstride, rel + (size_t)t * d, nvec, lane, 2);
+    lorentz_message<RV, SB>(m, ht + (size_t)s * d, W + (size_t)t * wstride, rel + (size_t)t * d, nvec, lane, sb);
     float f, D, mn;
     lorentz_edge_forward(m, cv, f, D, mn);
     const float nsq = (mn * f) * (mn * f);
@@ -1180,19 +1181,22 @@ __global__ void __launch_bounds__(256) lorentz_node_grad_kernel(
 
 // dht[u] = sum over the in-edges (w -> u, r') of row u of W[inv r']^T dm(u -> w, inv r')   (the graph holds every edge with
 // its inverse, so the forward CSR enumerates u's out-edges too)
-template <int RV>
+template <int RV, int SB>
 __global__ void __launch_bounds__(256) lorentz_grad_src_kernel(
     const float* __restrict__ ht, const float* __restrict__ W, const float* __restrict__ rel,
     const int* __restrict__ rowptr, const int* __restrict__ src_sorted, const int* __restrict__ etype_sorted,
     const float* __restrict__ G0, const float* __restrict__ G, int N, int d, int nb, int R, Curv cv,
     float* __restrict__ dht) {
   pdl_grid_sync();
+  __shared__ __align__(16) float dms[SB == 2 ? 4 : 8 * 256];     // generic blocks: a warp's dm, read across lanes
   const int lane = threadIdx.x & 31;
   const int row = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
   if (row >= N) return;
   const int nvec = d >> 2;
   const int b = __ldg(rowptr + row), e = __ldg(rowptr + row + 1);
-  const size_t wstride = (size_t)nb * 4;
+  const int sb = d / nb;
+  const size_t wstride = (size_t)d * sb;
+  float* dmw = dms + (SB == 2 ? 0 : (threadIdx.x >> 5) * 256);
   WarpRow<RV> acc;
   acc.zero();
   for (int p = b; p < e; ++p) {
@@ -1200,19 +1204,43 @@ __global__ void __launch_bounds__(256) lorentz_grad_src_kernel(
     const int ti = t < R ? t + R : t - R;
     const float* wp = W + (size_t)ti * wstride;
     WarpRow<RV> m, g;
-    lorentz_message<RV, 2>(m, ht + (size_t)row * d, wp, rel + (size_t)ti * d, nvec, lane, 2);
+    lorentz_message<RV, SB>(m, ht + (size_t)row * d, wp, rel + (size_t)ti * d, nvec, lane, sb);
     g.load_plain(G + (size_t)w * d, nvec, lane);
     lorentz_message_grad(m, __ldg(G0 + w), g, cv);         // m <- dm
+    if (SB == 2) {
 #pragma unroll
-    for (int i = 0; i < RV; ++i) {
-      const int c = lane + i * kWarp;
-      if (c < nvec) {
-        const float4 w0 = ldg4(wp + 8 * c), w1 = ldg4(wp + 8 * c + 4);
-        const float4 dm = m.v[i];
-        acc.v[i].x += w0.x * dm.x + w0.y * dm.y;
-        acc.v[i].y += w0.z * dm.x + w0.w * dm.y;
-        acc.v[i].z += w1.x * dm.z + w1.y * dm.w;
-        acc.v[i].w += w1.z * dm.z + w1.w * dm.w;
+      for (int i = 0; i < RV; ++i) {
+        const int c = lane + i * kWarp;
+        if (c < nvec) {
+          const float4 w0 = ldg4(wp + 8 * c), w1 = ldg4(wp + 8 * c + 4);
+          const float4 dm = m.v[i];
+          acc.v[i].x += w0.x * dm.x + w0.y * dm.y;
+          acc.v[i].y += w0.z * dm.x + w0.w * dm.y;
+          acc.v[i].z += w1.x * dm.z + w1.y * dm.w;
+          acc.v[i].w += w1.z * dm.z + w1.w * dm.w;
+        }
+      }
+    } else {
+      // dx[j] = sum_o W[j][o] dm[block(j) * sb + o]  (row j of the (d, sb) weight of this relation)
+      __syncwarp();
+      m.store(dmw, nvec, lane);
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < RV; ++i) {
+        const int c = lane + i * kWarp;
+        if (c < nvec) {
+          float o4[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int j = 4 * c + q;
+            const float* dmb = dmw + (j / sb) * sb;
+            const float* wr = wp + (size_t)j * sb;
+            float a = 0.f;
+            for (int o = 0; o < sb; ++o) a = fmaf(__ldg(wr + o), dmb[o], a);
+            o4[q] = a;
+          }
+          acc.v[i].x += o4[0]; acc.v[i].y += o4[1]; acc.v[i].z += o4[2]; acc.v[i].w += o4[3];
+        }
       }
     }
   }
@@ -1282,8 +1310,72 @@ __global__ void __launch_bounds__(256) lorentz_grad_type_kernel(
   }
 }
 
+// Generic block size sb = d / nb (the reference clamps num_bases to 2R, hyperbolic_layers.py:559-561: 10x10 blocks on
+// a 10-relation dataset): dW[r] is a (d, sb) matrix, dW[j][o] = sum_e x_e[j] dm_e[block(j) sb + o].  CTA = (type, split);
+// per round its 8 warps recompute dm of 8 edges into shared memory, then all threads add the round's outer products to
+// the shared (d, sb) accumulator in warp order (fixed summation order: bit-reproducible).
+template <int RV>
+__global__ void __launch_bounds__(256) lorentz_grad_type_generic_kernel(
+    const float* __restrict__ ht, const float* __restrict__ W, const float* __restrict__ rel,
+    const int* __restrict__ type_rowptr, const int* __restrict__ type_src, const int* __restrict__ type_dst,
+    const float* __restrict__ G0, const float* __restrict__ G, int d, int nb, int R2, Curv cv,
+    float* __restrict__ part_rel, float* __restrict__ part_w) {
+  pdl_grid_sync();
+  extern __shared__ __align__(16) float gsm[];                  // xs [8][d] | dm [8][d] | accW [d * sb] | accR [d]
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int r = blockIdx.x, sp = blockIdx.y;
+  const int nvec = d >> 2;
+  const int sb = d / nb;
+  const int nW = d * sb;
+  float* xs = gsm;
+  float* dmsm = gsm + 8 * d;
+  float* accW = gsm + 16 * d;
+  float* accR = accW + nW;
+  for (int i = threadIdx.x; i < nW + d; i += 256) accW[i] = 0.f;
+  const int tb = __ldg(type_rowptr + r), te = __ldg(type_rowptr + r + 1);
+  const int per = (te - tb + kLorentzSplit - 1) / kLorentzSplit;
+  const int e0 = tb + sp * per, e1 = min(te, e0 + per);
+  const float* wp = W + (size_t)r * nW;
+  for (int base = e0; base < e1; base += 8) {
+    const int e = base + wid;
+    WarpRow<RV> m, x;
+    if (e < e1) {
+      const int u = __ldg(type_src + e), v = __ldg(type_dst + e);
+      WarpRow<RV> g;
+      x.load_plain(ht + (size_t)u * d, nvec, lane);
+      lorentz_message<RV, 0>(m, ht + (size_t)u * d, wp, rel + (size_t)r * d, nvec, lane, sb);
+      g.load_plain(G + (size_t)v * d, nvec, lane);
+      lorentz_message_grad(m, __ldg(G0 + v), g, cv);
+    } else {
+      m.zero(); x.zero();
+    }
+    __syncthreads();                              // the previous round's outer products are done
+    x.store(xs + wid * d, nvec, lane);
+    m.store(dmsm + wid * d, nvec, lane);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nW; i += 256) {
+      const int j = i / sb, o = i - j * sb;
+      const int bo = (j / sb) * sb + o;
+      float a = accW[i];
+#pragma unroll
+      for (int w = 0; w < 8; ++w) a = fmaf(xs[w * d + j], dmsm[w * d + bo], a);
+      accW[i] = a;
+    }
+    for (int i = threadIdx.x; i < d; i += 256) {
+      float a = accR[i];
+#pragma unroll
+      for (int w = 0; w < 8; ++w) a += dmsm[w * d + i];
+      accR[i] = a;
+    }
+  }
+  __syncthreads();
+  const size_t pr = (size_t)sp * R2 + r;
+  for (int i = threadIdx.x; i < nW; i += 256) part_w[pr * nW + i] = accW[i];
+  for (int i = threadIdx.x; i < d; i += 256) part_rel[pr * d + i] = accR[i];
+}
+
 size_t lorentz_aggregate_bwd_workspace_bytes(int N, int R2, int d) {
-  return ((size_t)N * (d + 1) + (size_t)kLorentzSplit * R2 * 3 * d) * sizeof(float) + 1024;
+  return ((size_t)N * (d + 1) + (size_t)kLorentzSplit * R2 * 3 * d) * sizeof(float) + 1024;   // G, G0 (+ slack)
 }
 int lorentz_aggregate_bwd(const float* ht, const float* W, const float* rel, const float* gout, const int* rowptr,
                           const int* src_sorted, const int* etype_sorted, const float* norm, const int* type_rowptr,
@@ -1291,7 +1383,7 @@ int lorentz_aggregate_bwd(const float* ht, const float* W, const float* rel, con
                           float* part_rel, float* part_w, float* ws, size_t ws_bytes, cudaStream_t st) {
   if (!ht || !W || !rel || !gout || !rowptr || !src_sorted || !etype_sorted || !norm || !type_rowptr || !type_src ||
       !type_dst || !dht || !part_rel || !part_w || !ws) { set_last_error("lorentz_aggregate_bwd: null pointer"); return REGCN_ERR_NULL; }
-  if (d <= 0 || (d & 3) || d > 256 || nb * 2 != d || (R2 & 1)) { set_last_error("lorentz_aggregate_bwd: needs 2x2 blocks (num_bases = d/2), d%%4==0, d<=256"); return REGCN_ERR_UNSUPPORTED; }
+  if (d <= 0 || (d & 3) || d > 256 || nb <= 0 || d % nb || (R2 & 1)) { set_last_error("lorentz_aggregate_bwd: needs d%%4==0, d<=256, num_bases dividing d (d=%d nb=%d)", d, nb); return REGCN_ERR_UNSUPPORTED; }
   if (ws_bytes < (size_t)N * (d + 1) * sizeof(float)) { set_last_error("lorentz_aggregate_bwd: workspace too small"); return REGCN_ERR_WORKSPACE; }
   if (N <= 0) return REGCN_OK;
   Curv cv = make_curv(c);
@@ -1299,13 +1391,31 @@ int lorentz_aggregate_bwd(const float* ht, const float* W, const float* rel, con
   float* G0 = ws + (size_t)N * d;
   const unsigned grid = (unsigned)(((size_t)N * 32 + 255) / 256);
   dim3 tgrid((unsigned)R2, (unsigned)kLorentzSplit);
+  const int sb = d / nb;
+  if (sb != 2) {
+    // generic relation blocks: (d, sb) gradient accumulator of a relation in shared memory
+    const size_t smem = ((size_t)17 * d + (size_t)d * sb) * sizeof(float);
+    if (smem > 200 * 1024) { set_last_error("lorentz_aggregate_bwd: relation blocks of %dx%d at d=%d need %zu bytes of shared memory", sb, sb, d, smem); return REGCN_ERR_UNSUPPORTED; }
+    if (d <= 128) {
+      cudaFuncSetAttribute(lorentz_grad_type_generic_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      launch_k(lorentz_node_grad_kernel<1, 0>, grid, 256, 0, st, ht, W, rel, rowptr, src_sorted, etype_sorted, norm, gout, N, d, nb, cv, G0, G);
+      launch_k(lorentz_grad_src_kernel<1, 0>, grid, 256, 0, st, ht, W, rel, rowptr, src_sorted, etype_sorted, (const float*)G0, (const float*)G, N, d, nb, R2 / 2, cv, dht);
+      launch_k(lorentz_grad_type_generic_kernel<1>, tgrid, 256, smem, st, ht, W, rel, type_rowptr, type_src, type_dst, (const float*)G0, (const float*)G, d, nb, R2, cv, part_rel, part_w);
+    } else {
+      cudaFuncSetAttribute(lorentz_grad_type_generic_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      launch_k(lorentz_node_grad_kernel<2, 0>, grid, 256, 0, st, ht, W, rel, rowptr, src_sorted, etype_sorted, norm, gout, N, d, nb, cv, G0, G);
+      launch_k(lorentz_grad_src_kernel<2, 0>, grid, 256, 0, st, ht, W, rel, rowptr, src_sorted, etype_sorted, (const float*)G0, (const float*)G, N, d, nb, R2 / 2, cv, dht);
+      launch_k(lorentz_grad_type_generic_kernel<2>, tgrid, 256, smem, st, ht, W, rel, type_rowptr, type_src, type_dst, (const float*)G0, (const float*)G, d, nb, R2, cv, part_rel, part_w);
+    }
+    return check_launch("lorentz_aggregate_bwd");
+  }
   if (d <= 128) {
-    launch_k(lorentz_node_grad_kernel<1>, grid, 256, 0, st, ht, W, rel, rowptr, src_sorted, etype_sorted, norm, gout, N, d, nb, cv, G0, G);
-    launch_k(lorentz_grad_src_kernel<1>, grid, 256, 0, st, ht, W, rel, rowptr, src_sorted, etype_sorted, (const float*)G0, (const float*)G, N, d, nb, R2 / 2, cv, dht);
+    launch_k(lorentz_node_grad_kernel<1, 2>, grid, 256, 0, st, ht, W, rel, rowptr, src_sorted, etype_sorted, norm, gout, N, d, nb, cv, G0, G);
+    launch_k(lorentz_grad_src_kernel<1, 2>, grid, 256, 0, st, ht, W, rel, rowptr, src_sorted, etype_sorted, (const float*)G0, (const float*)G, N, d, nb, R2 / 2, cv, dht);
     launch_k(lorentz_grad_type_kernel<1>, tgrid, 256, (size_t)8 * 3 * 32 * sizeof(float4), st, ht, W, rel, type_rowptr, type_src, type_dst, (const float*)G0, (const float*)G, d, nb, R2, cv, part_rel, part_w);
   } else {
-    launch_k(lorentz_node_grad_kernel<2>, grid, 256, 0, st, ht, W, rel, rowptr, src_sorted, etype_sorted, norm, gout, N, d, nb, cv, G0, G);
-    launch_k(lorentz_grad_src_kernel<2>, grid, 256, 0, st, ht, W, rel, rowptr, src_sorted, etype_sorted, (const float*)G0, (const float*)G, N, d, nb, R2 / 2, cv, dht);
+    launch_k(lorentz_node_grad_kernel<2, 2>, grid, 256, 0, st, ht, W, rel, rowptr, src_sorted, etype_sorted, norm, gout, N, d, nb, cv, G0, G);
+    launch_k(lorentz_grad_src_kernel<2, 2>, grid, 256, 0, st, ht, W, rel, rowptr, src_sorted, etype_sorted, (const float*)G0, (const float*)G, N, d, nb, R2 / 2, cv, dht);
     launch_k(lorentz_grad_type_kernel<2>, tgrid, 256, (size_t)8 * 3 * 64 * sizeof(float4), st, ht, W, rel, type_rowptr, type_src, type_dst, (const float*)G0, (const float*)G, d, nb, R2, cv, part_rel, part_w);
   }
   return check_launch("lorentz_aggregate_bwd");

@@ -229,7 +229,8 @@ def hyp_union_layer(layer, g, h_in, h0, c, training):
 
 class _LorentzAggregate(torch.autograd.Function):
     """LorentzRGCNLayer message passing (hyperbolic_layers.py:589-625, 665-672): per-edge blockdiag(W[r]) ht[u] + rel[r]
-    -> exp_0 -> to_lorentz, per-node Lorentz centroid -> to_poincare -> log_0 -> clamp.  2x2 relation blocks in training."""
+    -> exp_0 -> to_lorentz, per-node Lorentz centroid -> to_poincare -> log_0 -> clamp.  Any block size dividing d (the
+    reference clamps num_bases to 2R, :559-561: 2x2 blocks at 100 bases, 10x10 on a 10-relation dataset)."""
 
     @staticmethod
     def forward(ctx, ht, weight, rel, g, num_bases, c):
@@ -250,7 +251,7 @@ class _LorentzAggregate(torch.autograd.Function):
         type_rowptr, type_src, type_dst = T._block_index(g)
         dht = torch.empty_like(ht)
         part_rel = torch.empty((S, R2 * d), device=dev, dtype=F32)
-        part_w = torch.empty((S, R2 * 2 * d), device=dev, dtype=F32)
+        part_w = torch.empty((S, R2 * d * (d // ctx.nb)), device=dev, dtype=F32)
         nb = lib.regcn_lorentz_aggregate_bwd_workspace_bytes(N, R2, d)
         ws = T._ws(dev, nb, slot=2)
         call("regcn_lorentz_aggregate_bwd", ptr(ht), ptr(weight), ptr(rel), ptr(gout.contiguous()), ptr(g.rowptr),
@@ -284,9 +285,8 @@ def hyp_evolve(model, g_list, static_graph=None):
     # inert for hyperbolic_uvrgcn; LorentzRGCNCell does (hyperbolic_src/hyperbolic_layers.py:737-740)
     if model.encoder_name not in ("hyperbolic_uvrgcn", "lgcn") or any(not l.self_loop for l in model.rgcn.layers):
         raise NotImplementedError("regcn_b200.train_hyp: hyperbolic_uvrgcn / lgcn with self_loop")
-    if model.encoder_name == "lgcn" and any(2 * l.num_bases != model.h_dim for l in model.rgcn.layers):
-        raise NotImplementedError("regcn_b200.train_hyp: the lgcn encoder trains with 2x2 relation blocks (num_bases = h_dim/2, "
-                                  "the reference's 100 bases at h_dim 200)")
+    if model.encoder_name == "lgcn" and any(model.h_dim % l.num_bases for l in model.rgcn.layers):
+        raise ValueError("regcn_b200.train_hyp: lgcn needs num_bases (clamped to 2R) to divide h_dim")
     layer_fn = hyp_union_layer if model.encoder_name == "hyperbolic_uvrgcn" else lorentz_layer
     c = model._c_float
     cell = model.relation_gru

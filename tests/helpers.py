@@ -172,6 +172,12 @@ HYP_TRAIN_CASES = {
                                         layer_norm=False, gamma=0.15),
     "hyptrain_lgcn_convtranse_small_s10_ln": dict(kind="hyp", shape="small_l", seed=10, encoder="lgcn",
                                                   decoder="hyperbolic_convtranse", layer_norm=True, gamma=0.15),
+    # num_bases clamped to 2R = 10 (hyperbolic_layers.py:559-561): relation blocks of 20x20
+    "hyptrain_lgcn_roth_tiny_l_s17": dict(kind="hyp", shape="tiny_l", seed=17, encoder="lgcn", decoder="roth",
+                                          layer_norm=False, gamma=0.15),
+    "hyptrain_lgcn_skip_tiny_l_s18_ln": dict(kind="hyp", shape="tiny_l", seed=18, encoder="lgcn",
+                                             decoder="hyperbolic_convtranse", layer_norm=True, gamma=0.15,
+                                             skip_connect=True),
 }
 
 

@@ -123,6 +123,47 @@ def test_hyperbolic_union_layer_backward():
          [hc.grad, rc.grad] + [w.grad for w in Wc], ["dh", "drel", "dW_n", "dW_loop", "dW_evolve"])
 
 
+@pytest.mark.parametrize("d,nb", [(200, 100), (200, 50), (200, 10), (200, 1), (64, 16), (64, 4), (128, 2)])
+def test_lorentz_layer_backward_any_block_size(d, nb):
+    """One LorentzRGCNLayer (lgcn) in train() mode against torch autograd over the fp64 oracle: relation blocks of 2x2 (the
+    chunk-local kernels) and of 4x4 ... dxd (the generic kernels; num_bases clamped to 2R, hyperbolic_layers.py:559-561),
+    both register widths (d <= 128 / d > 128)."""
+    R._lib.require_device()
+    case = synth.make_case("small_l", 6)
+    n, r = case["num_ents"], case["num_rels"]
+    g = R.build_sub_graph(n, r, case["history"][1], True, 0)
+    og = restate.build_edges(case["history"][1], n, r)
+    rng = np.random.default_rng(100 * d + nb)
+    sb = d // nb
+    h = rng.standard_normal((n, d)) * rng.uniform(0.02, 0.25, size=(n, 1))
+    rel = rng.standard_normal((2 * r, d)) * 0.2
+    W = rng.standard_normal((2 * r, nb * sb * sb)) * (0.5 / np.sqrt(sb))
+    wl, we = rng.standard_normal((d, d)) * 0.1, rng.standard_normal((d, d)) * 0.1
+    go = rng.standard_normal((n, d))
+    layer = R.LorentzRGCNLayer(d, d, 2 * r, num_bases=nb, c=C, activation=torch.nn.functional.rrelu, self_loop=True,
+                               dropout=0.0).to(DEV)
+    assert layer.num_bases == nb
+    with torch.no_grad():
+        for p_, w in zip((layer.weight, layer.loop_weight, layer.evolve_loop_weight), (W, wl, we)):
+            p_.copy_(torch.as_tensor(w, dtype=torch.float32))
+    hd, rd = _leaf(h), _leaf(rel)
+    out = train_hyp.lorentz_layer(layer, g, hd, rd, C, True)
+    out.backward(torch.as_tensor(go, dtype=torch.float32, device=DEV))
+    hc, rc, Wc, wlc, wec = (torch.tensor(a, dtype=torch.float64, requires_grad=True) for a in (h, rel, W, wl, we))
+    outc = restate.lorentz_layer(hc, rc, og, Wc, wlc, wec, C, nb)
+    outc.backward(torch.as_tensor(go))
+    ok, worst = close(out.detach().cpu().numpy(), outc.detach().numpy())
+    assert ok, worst
+    _cmp([hd.grad, rd.grad, layer.weight.grad, layer.loop_weight.grad, layer.evolve_loop_weight.grad],
+         [hc.grad, rc.grad, Wc.grad, wlc.grad, wec.grad], ["dh", "drel", "dW_blocks", "dW_loop", "dW_evolve"])
+    # bit-reproducible (fixed summation order in every kernel of the backward)
+    g1 = layer.weight.grad.clone()
+    layer.weight.grad = None
+    hd2, rd2 = _leaf(h), _leaf(rel)
+    train_hyp.lorentz_layer(layer, g, hd2, rd2, C, True).backward(torch.as_tensor(go, dtype=torch.float32, device=DEV))
+    assert torch.equal(g1, layer.weight.grad) and torch.equal(hd.grad, hd2.grad)
+
+
 @pytest.mark.parametrize("name", sorted(HYP_TRAIN_CASES))
 def test_hyperbolic_train_step_matches_reference(name):
     """One optimisation step of HyperbolicRecurrentRGCN (get_loss in train() mode -> backward -> clip -> Adam) against the
