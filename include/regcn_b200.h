@@ -353,6 +353,12 @@ REGCN_API int regcn_queries_prepare(const int64_t* triples, int T, int R, int64_
 REGCN_API int regcn_filter_count(const int64_t* triples, int B, int key_col, int32_t* counts, void* stream);
 REGCN_API int regcn_filter_fill(const int64_t* triples, int B, int key_col, int ans_col, const int32_t* beg, int32_t* idx,
                       int32_t* end, int32_t* pair_a, int32_t* pair_e, void* stream);
+/* Both filter lists of a timestamp's queries in ONE launch (what regcn_b200.test() needs per timestamp, src/main.py:71-74:
+ * entity ranks filtered by key (h, r) -> answers t, relation ranks by key (h, t) -> answers r): the *_e arguments are
+ * regcn_filter_fill(key_col 1, ans_col 2), the *_r arguments regcn_filter_fill(key_col 2, ans_col 1); identical lists.  */
+REGCN_API int regcn_filter_fill2(const int64_t* triples, int B, const int32_t* beg_e, int32_t* idx_e, int32_t* end_e,
+                       int32_t* pair_a_e, int32_t* pair_e_e, const int32_t* beg_r, int32_t* idx_r, int32_t* end_r,
+                       int32_t* pair_a_r, int32_t* pair_e_r, void* stream);
 
 /* ---- whole-recurrence orchestration: RecurrentRGCN.forward, src/rrgcn.py:142-180 (uvrgcn, self_loop, no skip) ---
  * One call enqueues every kernel of the L-snapshot recurrence on `stream`.  Inputs are pointer / int tables:

@@ -30,11 +30,11 @@ for t in tests[:2]:
     # back to back (how test() enqueues them)
     def both():
         for _ in range(12):
-            pe.finish(tot[0]); pr.finish(tot[1])
+            utils.filter_lists_finish2(pe, tot[0], pr, tot[1])
     us_b, _ = timed(both, 5)
     le = (fe.end - fe.ptr).cpu(); lr = (fr.end - fr.ptr).cpu()
     ce = (pe.beg[1:] - pe.beg[:-1]).cpu(); cr = (pr.beg[1:] - pr.beg[:-1]).cpu()
-    print(f"B={all_t.shape[0]} prepare {us:.1f} us, fill ent {us_e:.1f} us, fill rel {us_r:.1f} us, 24 fills back to back {us_b / 12:.1f} us per timestamp")
+    print(f"B={all_t.shape[0]} prepare {us:.1f} us, fill ent {us_e:.1f} us, fill rel {us_r:.1f} us, 12 x regcn_filter_fill2 back to back {us_b / 12:.1f} us per timestamp")
     print("  matches per query (ent) max", int(ce.max()), "mean %.2f" % float(ce.float().mean()), " >32:", int((ce > 32).sum()), " >256:", int((ce > 256).sum()),
           "| (rel) max", int(cr.max()), "mean %.2f" % float(cr.float().mean()), " >32:", int((cr > 32).sum()), " >256:", int((cr > 256).sum()))
     print("  unique per query (ent) max", int(le.max()), "(rel) max", int(lr.max()))

@@ -100,6 +100,7 @@ SIGNATURES = {
     "regcn_queries_prepare": (_i, [_p, _i, _i, _p, _p, _p, _p, _p]),
     "regcn_filter_count": (_i, [_p, _i, _i, _p, _p]),
     "regcn_filter_fill": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "regcn_filter_fill2": (_i, [_p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     # ---- training (csrc/backward.cu)
     "regcn_csr_gather_sum": (_i, [_p, _i, _p, _p, _p, _p, _i, _i, _i, _p, _i, _i, _p, _f, _p, _p]),
     "regcn_group_by_key_workspace_bytes": (_sz, [_i]),

@@ -250,6 +250,11 @@ int regcn_filter_fill(const int64_t* triples, int B, int key_col, int ans_col, c
                       int32_t* end, int32_t* pair_a, int32_t* pair_e, void* stream) {
   return filter_fill(triples, B, key_col, ans_col, beg, idx, end, pair_a, pair_e, ST(stream));
 }
+int regcn_filter_fill2(const int64_t* triples, int B, const int32_t* beg_e, int32_t* idx_e, int32_t* end_e, int32_t* pair_a_e,
+                       int32_t* pair_e_e, const int32_t* beg_r, int32_t* idx_r, int32_t* end_r, int32_t* pair_a_r,
+                       int32_t* pair_e_r, void* stream) {
+  return filter_fill2(triples, B, beg_e, idx_e, end_e, pair_a_e, pair_e_e, beg_r, idx_r, end_r, pair_a_r, pair_e_r, ST(stream));
+}
 int regcn_row_map_split(const float* x, float* out, float* out_hi, float* out_lo, int M, int d, int mode, double c,
                         void* stream) {
   return row_map(x, out, M, d, mode, c, nullptr, out_hi, out_lo, ST(stream));

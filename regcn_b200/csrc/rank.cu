@@ -168,32 +168,59 @@ __global__ void __launch_bounds__(kFiltThreads) filter_count_kernel(const int64_
   if (live && lane == 0) counts[b] = c;
 }
 
-__global__ void __launch_bounds__(kFiltThreads) filter_fill_kernel(const int64_t* __restrict__ triples, int B, int key_col,
-                                                                   int ans_col, const int* __restrict__ beg,
-                                                                   int* __restrict__ idx, int* __restrict__ end,
-                                                                   int* __restrict__ pair_a, int* __restrict__ pair_e) {
+// One filter list set: key (col 0, key_col) -> answers ans_col, offsets beg, outputs idx / end / pairs.
+struct FiltFill {
+  int key_col, ans_col;
+  const int* beg;
+  int* idx;
+  int* end;
+  int* pair_a;
+  int* pair_e;
+};
+constexpr int kFillTile = 3072;       // (key, answer) records staged per pass: 36 KB; one pass for a TKG timestamp
+
+// grid.y selects the list set (the entity and the relation filter of a timestamp are filled by ONE launch: each was a
+// ~17 us latency chain of its own).  Keys AND answers are staged, so a match costs no global load; the common short list
+// (<= 32 matches) never touches global memory before its final stores: matches are compacted through a 32-slot
+// shared-memory line per warp, rank-sorted + uniqued over shuffles, and idx / pair lists are written from registers.
+__global__ void __launch_bounds__(kFiltThreads) filter_fill_kernel(const int64_t* __restrict__ triples, int B, FiltFill f0,
+                                                                   FiltFill f1) {
   pdl_grid_sync();
-  __shared__ long long skeys[kFiltTile];
-  const int lane = threadIdx.x & 31;
+  __shared__ long long skeys[kFillTile];
+  __shared__ int sans[kFillTile];
+  __shared__ int wl[kFiltThreads / 32][32];
+  const FiltFill f = blockIdx.y ? f1 : f0;
+  const int key_col = f.key_col, ans_col = f.ans_col;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int b = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
   const bool live = b < B;                        // (every warp of the CTA takes part in staging the keys)
   const long long mykey = live ? filt_key(triples, b, key_col) : 0;
-  const int b0 = live ? beg[b] : 0;
-  int* lst = idx + b0;
+  const int b0 = live ? __ldg(f.beg + b) : 0;
+  int* lst = f.idx + b0;
+  int* pair_a = f.pair_a;
+  int* pair_e = f.pair_e;
   // collect the answers of the matching queries in query order
   int n = 0;
-  int mine = 0;                                   // lane i keeps the i-th match (lists of <= 32 stay in registers)
-  for (int tile0 = 0; tile0 < B; tile0 += kFiltTile) {
-    const int tn = filt_stage_keys(triples, B, key_col, tile0, skeys);
+  for (int tile0 = 0; tile0 < B; tile0 += kFillTile) {
+    const int tn = min(kFillTile, B - tile0);
+    __syncthreads();                                        // the previous tile is no longer read
+    for (int j = threadIdx.x; j < tn; j += blockDim.x) {
+      skeys[j] = filt_key(triples, tile0 + j, key_col);
+      sans[j] = (int)triples[3 * (size_t)(tile0 + j) + ans_col];
+    }
+    __syncthreads();
     if (!live) continue;
+#pragma unroll 4
     for (int j0 = 0; j0 < tn; j0 += 32) {
       const int j = j0 + lane;
       const bool m = j < tn && skeys[j] == mykey;
       const unsigned bal = __ballot_sync(0xffffffffu, m);
       if (bal) {
-        const int a = m ? (int)triples[3 * (size_t)(tile0 + j) + ans_col] : 0;
         const int pos = n + __popc(bal & ((1u << lane) - 1u));
-        if (m) lst[pos] = a;
+        if (m) {
+          if (pos < 32) wl[wid][pos] = sans[j];
+          else lst[pos] = sans[j];
+        }
         n += __popc(bal);
       }
     }
@@ -202,7 +229,7 @@ __global__ void __launch_bounds__(kFiltThreads) filter_fill_kernel(const int64_t
   __syncwarp();
   int u;
   if (n <= 32) {
-    mine = lane < n ? lst[lane] : 0x7fffffff;
+    const int mine = lane < n ? wl[wid][lane] : 0x7fffffff;   // lane i keeps the i-th match
     // duplicate = an equal value at a smaller lane; unique position = #{distinct values below mine}
     bool dup = false;
 #pragma unroll
@@ -219,13 +246,23 @@ __global__ void __launch_bounds__(kFiltThreads) filter_fill_kernel(const int64_t
       upos += od & (int)(o < mine);
     }
     u = __popc(__ballot_sync(0xffffffffu, keep));
-    __syncwarp();
+    int first = mine;                                          // smallest answer: fills the unused tail slots
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
     if (keep) lst[upos] = mine;
-    __syncwarp();
-    const int first = lst[0];
-    if (lane >= u && lane < n) lst[lane] = first;     // unused tail slots stay valid candidate ids
-    __syncwarp();
-  } else if (n <= 32 * kFiltBlocks) {
+    if (lane >= u && lane < n) lst[lane] = first;              // unused tail slots stay valid candidate ids
+    if (lane == 0) f.end[b] = b0 + u;
+    if (pair_a) {
+      if (lane == 0) { pair_a[b] = b; pair_e[b] = (int)triples[3 * (size_t)b + ans_col]; }
+      if (lane < n) pair_a[B + b0 + lane] = b;
+      if (keep) pair_e[B + b0 + upos] = mine;
+      if (lane >= u && lane < n) pair_e[B + b0 + lane] = first;
+    }
+    return;
+  }
+  if (lane < 32) lst[lane] = wl[wid][lane];                    // longer lists are finished in place
+  __syncwarp();
+  if (n <= 32 * kFiltBlocks) {
     // medium list (a hub pair / hub entity of a skewed snapshot): the same rank sort with several elements per lane --
     // element blk*32 + lane lives in val[blk]; one serial insertion sort of 50 elements would cost the whole launch 40 us
     int val[kFiltBlocks], pos[kFiltBlocks];
@@ -296,7 +333,7 @@ __global__ void __launch_bounds__(kFiltThreads) filter_fill_kernel(const int64_t
     u = __shfl_sync(0xffffffffu, u, 0);
     __syncwarp();
   }
-  if (lane == 0) end[b] = b0 + u;
+  if (lane == 0) f.end[b] = b0 + u;
   if (pair_a) {
     if (lane == 0) { pair_a[b] = b; pair_e[b] = (int)triples[3 * (size_t)b + ans_col]; }
     for (int i = lane; i < n; i += 32) { pair_a[B + b0 + i] = b; pair_e[B + b0 + i] = lst[i]; }
@@ -386,13 +423,28 @@ int filter_count(const int64_t* triples, int B, int key_col, int* counts, cudaSt
   return check_launch("filter_count");
 }
 
+static bool filt_fill_ok(const FiltFill& f) {
+  return f.beg && f.idx && f.end && !(f.pair_a && !f.pair_e) && f.key_col >= 1 && f.key_col <= 2 && f.ans_col >= 1 &&
+         f.ans_col <= 2 && f.key_col != f.ans_col;
+}
+
 int filter_fill(const int64_t* triples, int B, int key_col, int ans_col, const int* beg, int* idx, int* end, int* pair_a,
                 int* pair_e, cudaStream_t st) {
-  if (!triples || !beg || !idx || !end || (pair_a && !pair_e)) { set_last_error("filter_fill: null pointer"); return REGCN_ERR_NULL; }
-  if (key_col < 1 || key_col > 2 || ans_col < 1 || ans_col > 2 || key_col == ans_col) { set_last_error("filter_fill: bad columns"); return REGCN_ERR_DIM; }
+  const FiltFill f{key_col, ans_col, beg, idx, end, pair_a, pair_e};
+  if (!triples || !filt_fill_ok(f)) { set_last_error("filter_fill: null pointer or bad columns (key_col / ans_col are 1 and 2)"); return triples && beg && idx && end ? REGCN_ERR_DIM : REGCN_ERR_NULL; }
   if (B <= 0) return REGCN_OK;
-  launch_k(filter_fill_kernel, (unsigned)(((size_t)B * 32 + kFiltThreads - 1) / kFiltThreads), kFiltThreads, 0, st, triples, B, key_col, ans_col, beg, idx, end, pair_a, pair_e);
+  launch_k(filter_fill_kernel, dim3((unsigned)(((size_t)B * 32 + kFiltThreads - 1) / kFiltThreads), 1), dim3(kFiltThreads), 0, st, triples, B, f, f);
   return check_launch("filter_fill");
+}
+
+// entity filter (key (h, r) -> answers t) and relation filter (key (h, t) -> answers r) of the same queries in one launch
+int filter_fill2(const int64_t* triples, int B, const int* beg_e, int* idx_e, int* end_e, int* pair_a_e, int* pair_e_e,
+                 const int* beg_r, int* idx_r, int* end_r, int* pair_a_r, int* pair_e_r, cudaStream_t st) {
+  const FiltFill fe{1, 2, beg_e, idx_e, end_e, pair_a_e, pair_e_e}, fr{2, 1, beg_r, idx_r, end_r, pair_a_r, pair_e_r};
+  if (!triples || !filt_fill_ok(fe) || !filt_fill_ok(fr)) { set_last_error("filter_fill2: null pointer"); return REGCN_ERR_NULL; }
+  if (B <= 0) return REGCN_OK;
+  launch_k(filter_fill_kernel, dim3((unsigned)(((size_t)B * 32 + kFiltThreads - 1) / kFiltThreads), 2), dim3(kFiltThreads), 0, st, triples, B, fe, fr);
+  return check_launch("filter_fill2");
 }
 
 int gather_target_score(const float* S, int64_t ld, int B, int N, const int64_t* triples, int target_col, int col_offset,

@@ -334,7 +334,7 @@ def _finish_prepare(p, filters=True):
 
 
 def _finish_filters(p):
-    return p.pf_ent.finish(p.totals[0]), p.pf_rel.finish(p.totals[1])
+    return utils.filter_lists_finish2(p.pf_ent, p.totals[0], p.pf_rel, p.totals[1])
 
 
 @torch.no_grad()

@@ -117,6 +117,26 @@ class _PendingFilter:
         return FilterCSR(self.beg, idx, end, pairs=(pa, pe))
 
 
+def filter_lists_finish2(pf_ent, total_ent, pf_rel, total_rel):
+    """finish() of the entity and the relation filter of the same queries as ONE launch (`regcn_filter_fill2`); all
+    outputs live in one allocation.  Returns (FilterCSR entity, FilterCSR relation), identical to the two finish() calls."""
+    from ._lib import call, ptr
+    if pf_ent.triples is not pf_rel.triples or pf_ent.key_col != 1 or pf_rel.key_col != 2:
+        return pf_ent.finish(total_ent), pf_rel.finish(total_rel)
+    B, dev = pf_ent.B, pf_ent.triples.device
+    te, tr = int(total_ent), int(total_rel)
+    ne, nr = max(te, 1), max(tr, 1)
+    buf = torch.empty(ne + nr + 2 * B + 2 * (B + te) + 2 * (B + tr), device=dev, dtype=torch.int32)
+    parts, o = [], 0
+    for n in (ne, B, B + te, B + te, nr, B, B + tr, B + tr):
+        parts.append(buf[o:o + n])
+        o += n
+    idx_e, end_e, pa_e, pe_e, idx_r, end_r, pa_r, pe_r = parts
+    call("regcn_filter_fill2", ptr(pf_ent.triples), B, ptr(pf_ent.beg), ptr(idx_e), ptr(end_e), ptr(pa_e), ptr(pe_e),
+         ptr(pf_rel.beg), ptr(idx_r), ptr(end_r), ptr(pa_r), ptr(pe_r))
+    return (FilterCSR(pf_ent.beg, idx_e, end_e, pairs=(pa_e, pe_e)), FilterCSR(pf_rel.beg, idx_r, end_r, pairs=(pa_r, pe_r)))
+
+
 def filter_lists_begin(all_triples, rel_predict=0):
     return _PendingFilter(all_triples.contiguous(), rel_predict)
 

@@ -631,6 +631,10 @@ def test_filter_lists_hub_queries_and_duplicates():
             a = utils.filter_csr_from_dict(torch.as_tensor(all_t), d, rel_predict=rel_p, device=DEV)
             b = utils.filter_lists_from_queries(_t(all_t, torch.int64), rel_p)
             assert a.lists() == b.lists()
+            pfs = [utils.filter_lists_begin(_t(all_t, torch.int64), k) for k in (0, 1)]
+            pfs[1].triples = pfs[0].triples
+            two = utils.filter_lists_finish2(pfs[0], int(pfs[0].total), pfs[1], int(pfs[1].total))[rel_p]
+            assert two.lists() == b.lists() and all(torch.equal(x, y) for x, y in zip(two.pairs(None), b.pairs(None)))
             B = all_t.shape[0]
             pa, pe = b.pairs(None)
             assert pa[:B].cpu().tolist() == list(range(B))
@@ -662,6 +666,11 @@ def test_queries_prepare_equals_stepwise_preparation():
             assert torch.equal(pf.beg, old.beg) and int(pf.total) == int(old.total)
             assert a_lists(pf.finish()) == a_lists(old.finish())
         assert totals.tolist() == [int(pf_e.total), int(pf_r.total)]
+        # both lists in one launch (regcn_filter_fill2, what test() calls per timestamp) == the two single fills
+        tot = totals.tolist()
+        for one, two in zip((pf_e.finish(tot[0]), pf_r.finish(tot[1])), utils.filter_lists_finish2(pf_e, tot[0], pf_r, tot[1])):
+            assert torch.equal(one.idx, two.idx) and torch.equal(one.end, two.end) and torch.equal(one.ptr, two.ptr)
+            assert all(torch.equal(x, y) for x, y in zip(one.pairs(None), two.pairs(None)))
 
 
 def a_lists(f):

@@ -329,14 +329,12 @@ def test_get_loss_matches_reference(name):
     assert len(mine) == len(ref)
     np.testing.assert_allclose(mine, ref, rtol=1e-4, atol=1e-6)
     if cfg["kind"] != "regcn":
-        # training mode: both encoders train with every decoder and flag (tests/test_gpu_train_hyp.py); lgcn blocks other
-        # than 2x2 refuse loudly instead of returning a loss without gradients
-        if cfg["encoder"] == "lgcn" and cfg["shape"] == "tiny_l":                                   # 20x20 relation blocks
-            with pytest.raises(NotImplementedError):
-                model.train().get_loss(glist, torch.from_numpy(case["test"]).to(DEV), None, True)
-        else:
-            tl = model.train().get_loss(glist, torch.from_numpy(case["test"]).to(DEV), None, True)
-            assert len(tl) == 4 and tl[0].requires_grad and all(bool(torch.isfinite(x).all()) for x in tl)
+        # training mode: both encoders train with every decoder and flag (tests/test_gpu_train_hyp.py), lgcn with relation
+        # blocks of any size (tiny_l: 20x20)
+        tl = model.train().get_loss(glist, torch.from_numpy(case["test"]).to(DEV), None, True)
+        assert len(tl) == 4 and tl[0].requires_grad and all(bool(torch.isfinite(x).all()) for x in tl)
+        (tl[0] + tl[1] + tl[2] + tl[3]).backward()
+        assert all(bool(torch.isfinite(p.grad).all()) for p in model.parameters() if p.grad is not None)
 
 
 def test_fused_ce_equals_dense_ce():
