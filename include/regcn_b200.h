@@ -350,6 +350,13 @@ REGCN_API int regcn_apply_filter(float* S, int64_t ld, int B, int N, const int64
  * (relation filter); beg (2, 2T) = their exclusive scans (the list offsets regcn_filter_fill takes); totals (2) = slot totals. */
 REGCN_API int regcn_queries_prepare(const int64_t* triples, int T, int R, int64_t* all_t, int32_t* counts, int32_t* beg,
                                     int32_t* totals, void* stream);
+/* The same for the n <= 32 test snapshots of a group of timestamps in three launches (regcn_b200.test() evolves consecutive
+ * timestamps together and prepares a group at once).  triples_cat (toff[n], 3): the snapshots back to back; toff (n+1, HOST):
+ * rows in front of snapshot g, toff[0] = 0, every snapshot non-empty.  Snapshot g's outputs: all_t_cat + 3 * 2 toff[g]
+ * (2 T_g rows), counts_cat / beg_cat + 4 toff[g] (each (2, 2 T_g)), totals + 2 g -- array for array what
+ * regcn_queries_prepare writes for that snapshot alone.                                                              */
+REGCN_API int regcn_queries_prepare_batch(const int64_t* triples_cat, const int32_t* toff, int n, int R, int64_t* all_t_cat,
+                                int32_t* counts_cat, int32_t* beg_cat, int32_t* totals, void* stream);
 REGCN_API int regcn_filter_count(const int64_t* triples, int B, int key_col, int32_t* counts, void* stream);
 REGCN_API int regcn_filter_fill(const int64_t* triples, int B, int key_col, int ans_col, const int32_t* beg, int32_t* idx,
                       int32_t* end, int32_t* pair_a, int32_t* pair_e, void* stream);

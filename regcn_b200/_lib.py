@@ -98,6 +98,7 @@ SIGNATURES = {
     "regcn_counts_to_ranks": (_i, [_p, _p, _i, _p, _p, _p]),
     "regcn_apply_filter": (_i, [_p, _i64, _i, _i, _p, _i, _p, _p, _i, _p, _p]),
     "regcn_queries_prepare": (_i, [_p, _i, _i, _p, _p, _p, _p, _p]),
+    "regcn_queries_prepare_batch": (_i, [_p, _p, _i, _i, _p, _p, _p, _p, _p]),
     "regcn_filter_count": (_i, [_p, _i, _i, _p, _p]),
     "regcn_filter_fill": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
     "regcn_filter_fill2": (_i, [_p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),

@@ -243,6 +243,10 @@ int regcn_queries_prepare(const int64_t* triples, int T, int R, int64_t* all_t, 
                           void* stream) {
   return queries_prepare(triples, T, R, all_t, counts, beg, totals, ST(stream));
 }
+int regcn_queries_prepare_batch(const int64_t* triples_cat, const int32_t* toff, int n, int R, int64_t* all_t_cat,
+                                int32_t* counts_cat, int32_t* beg_cat, int32_t* totals, void* stream) {
+  return queries_prepare_batch(triples_cat, toff, n, R, all_t_cat, counts_cat, beg_cat, totals, ST(stream));
+}
 int regcn_filter_count(const int64_t* triples, int B, int key_col, int32_t* counts, void* stream) {
   return filter_count(triples, B, key_col, counts, ST(stream));
 }

@@ -131,6 +131,8 @@ int rank_count(const float* S, int64_t ld, int B, int N, const int64_t* triples,
                const int* filt_end, cudaStream_t st);
 int filter_count(const int64_t* triples, int B, int key_col, int* counts, cudaStream_t st);
 int queries_prepare(const int64_t* triples, int T, int R, int64_t* all_t, int* counts, int* beg, int* totals, cudaStream_t st);
+int queries_prepare_batch(const int64_t* triples_cat, const int* toff, int n, int R, int64_t* all_t_cat, int* counts_cat,
+                          int* beg_cat, int* totals, cudaStream_t st);
 int filter_fill2(const int64_t* triples, int B, const int* beg_e, int* idx_e, int* end_e, int* pair_a_e, int* pair_e_e,
                  const int* beg_r, int* idx_r, int* end_r, int* pair_a_r, int* pair_e_r, cudaStream_t st);
 int filter_fill(const int64_t* triples, int B, int key_col, int ans_col, const int* beg, int* idx, int* end, int* pair_a,

@@ -404,6 +404,107 @@ __global__ void __launch_bounds__(1024) filter_scan2_kernel(const int* __restric
   if (threadIdx.x == 1023) totals[blockIdx.y] = wsum[31];
 }
 
+// ---- the same for the n test snapshots of a group in three launches (grid.z = snapshot) -------------------------------
+// triples_cat (sum T, 3): the snapshots back to back, toff[g] = rows in front of snapshot g.  Snapshot g's outputs sit at
+// all_t_cat + 3 * 2 toff[g] (2 T_g rows), counts_cat / beg_cat + 4 toff[g] ((2, 2 T_g) each), totals + 2 g.
+constexpr int kPrepBatchMax = 32;
+struct QPrepBatch {
+  int n;
+  int toff[kPrepBatchMax + 1];
+};
+
+__global__ void __launch_bounds__(256) queries_inverse_batch_kernel(const int64_t* __restrict__ triples_cat, int R,
+                                                                    int64_t* __restrict__ all_t_cat, QPrepBatch qb) {
+  pdl_grid_sync();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= qb.toff[qb.n]) return;
+  int g = 0;
+  while (i >= qb.toff[g + 1]) ++g;
+  const int T = qb.toff[g + 1] - qb.toff[g], li = i - qb.toff[g];
+  const int64_t s = triples_cat[3 * (size_t)i], r = triples_cat[3 * (size_t)i + 1], o = triples_cat[3 * (size_t)i + 2];
+  int64_t* f = all_t_cat + 3 * ((size_t)2 * qb.toff[g] + li);
+  int64_t* b = f + 3 * (size_t)T;
+  f[0] = s; f[1] = r; f[2] = o;
+  b[0] = o; b[1] = r + R; b[2] = s;
+}
+
+// 1024 threads: every CTA stages all keys of its snapshot, so 32 queries per CTA read a quarter of what 8 would
+__global__ void __launch_bounds__(1024) filter_count2_batch_kernel(const int64_t* __restrict__ all_t_cat,
+                                                                           int* __restrict__ counts_cat, QPrepBatch qb) {
+  pdl_grid_sync();
+  __shared__ long long skeys[kFiltTile];
+  const int g = blockIdx.z;
+  const int B = 2 * (qb.toff[g + 1] - qb.toff[g]);
+  if ((size_t)blockIdx.x * (blockDim.x / 32) >= (size_t)B) return;        // (whole CTA: the grid is sized for the largest snapshot)
+  const int64_t* triples = all_t_cat + 3 * (size_t)2 * qb.toff[g];
+  int* counts = counts_cat + (size_t)4 * qb.toff[g];
+  const int key_col = 1 + (int)blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int b = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+  const bool live = b < B;
+  const long long mykey = live ? filt_key(triples, b, key_col) : 0;
+  int c = 0;
+  for (int tile0 = 0; tile0 < B; tile0 += kFiltTile) {
+    const int tn = filt_stage_keys(triples, B, key_col, tile0, skeys);
+    if (live)
+      for (int j = lane; j < tn; j += 32) c += skeys[j] == mykey ? 1 : 0;
+  }
+  c = warp_sum_i(c);
+  if (live && lane == 0) counts[(size_t)blockIdx.y * B + b] = c;
+}
+
+__global__ void __launch_bounds__(1024) filter_scan2_batch_kernel(const int* __restrict__ counts_cat, int* __restrict__ beg_cat,
+                                                                  int* __restrict__ totals, QPrepBatch qb) {
+  pdl_grid_sync();
+  __shared__ int wsum[32];
+  const int g = blockIdx.z;
+  const int B = 2 * (qb.toff[g + 1] - qb.toff[g]);
+  const int* c = counts_cat + (size_t)4 * qb.toff[g] + (size_t)blockIdx.y * B;
+  int* o = beg_cat + (size_t)4 * qb.toff[g] + (size_t)blockIdx.y * B;
+  const int per = (B + 1023) / 1024;
+  const int lo = min(B, (int)threadIdx.x * per), hi = min(B, lo + per);
+  int s = 0;
+  for (int i = lo; i < hi; ++i) s += c[i];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int inc = s;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += v; }
+  if (lane == 31) wsum[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    int v = wsum[lane];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, d); if (lane >= d) v += u; }
+    wsum[lane] = v;
+  }
+  __syncthreads();
+  int run = inc - s + (w > 0 ? wsum[w - 1] : 0);
+  for (int i = lo; i < hi; ++i) { o[i] = run; run += c[i]; }
+  if (threadIdx.x == 1023) totals[2 * g + blockIdx.y] = wsum[31];
+}
+
+int queries_prepare_batch(const int64_t* triples_cat, const int* toff, int n, int R, int64_t* all_t_cat, int* counts_cat,
+                          int* beg_cat, int* totals, cudaStream_t st) {
+  if (!triples_cat || !toff || !all_t_cat || !counts_cat || !beg_cat || !totals) { set_last_error("queries_prepare_batch: null pointer"); return REGCN_ERR_NULL; }
+  if (n <= 0 || n > kPrepBatchMax || R <= 0) { set_last_error("queries_prepare_batch: 1..%d snapshots per call (n=%d), R=%d", kPrepBatchMax, n, R); return REGCN_ERR_DIM; }
+  QPrepBatch qb;
+  qb.n = n;
+  int maxT = 0;
+  for (int g = 0; g <= kPrepBatchMax; ++g) qb.toff[g] = toff[g <= n ? g : n];
+  if (qb.toff[0] != 0) { set_last_error("queries_prepare_batch: toff[0] must be 0"); return REGCN_ERR_DIM; }
+  for (int g = 0; g < n; ++g) {
+    const int T = qb.toff[g + 1] - qb.toff[g];
+    if (T <= 0 || T > (1 << 24)) { set_last_error("queries_prepare_batch: snapshot %d has %d triples", g, T); return REGCN_ERR_DIM; }
+    maxT = T > maxT ? T : maxT;
+  }
+  const int total = qb.toff[n];
+  launch_k(queries_inverse_batch_kernel, (unsigned)((total + 255) / 256), 256, 0, st, triples_cat, R, all_t_cat, qb);
+  launch_k(filter_count2_batch_kernel, dim3((unsigned)(((size_t)2 * maxT * 32 + 1023) / 1024), 2, (unsigned)n),
+           dim3(1024), 0, st, (const int64_t*)all_t_cat, counts_cat, qb);
+  launch_k(filter_scan2_batch_kernel, dim3(1, 2, (unsigned)n), dim3(1024), 0, st, (const int*)counts_cat, beg_cat, totals, qb);
+  return check_launch("queries_prepare_batch");
+}
+
 int queries_prepare(const int64_t* triples, int T, int R, int64_t* all_t, int* counts, int* beg, int* totals, cudaStream_t st) {
   if (!triples || !all_t || !counts || !beg || !totals) { set_last_error("queries_prepare: null pointer"); return REGCN_ERR_NULL; }
   if (T <= 0 || R <= 0 || T > (1 << 24)) { set_last_error("queries_prepare: bad dims T=%d R=%d", T, R); return REGCN_ERR_DIM; }

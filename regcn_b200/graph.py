@@ -185,8 +185,21 @@ def build_sub_graphs(num_nodes, num_rels, triples_list, device, sync=True):
     device: call `finish_sub_graphs(gs)` (or pass them through `pending_counts`) before using the graphs."""
     import ctypes
     _lib.require_device()
-    gs = [SnapshotGraph(num_nodes, num_rels, t.to(device, non_blocking=True).contiguous(), _defer_build=True)
-          for t in triples_list]
+    dev_t = [None] * len(triples_list)
+    host = [i for i, t in enumerate(triples_list) if not t.is_cuda and t.dtype == torch.int64 and t.dim() == 2 and t.shape[0] > 0]
+    if len(host) > 2:
+        # several host snapshots (the start of a test() call uploads the whole history window): ONE staged copy instead of
+        # one ~25 us host-side copy call each; the pinned staging block comes from torch's caching host allocator
+        sizes = [int(triples_list[i].numel()) for i in host]
+        stage = torch.empty(sum(sizes), dtype=torch.int64, pin_memory=True)
+        torch.cat([triples_list[i].reshape(-1) for i in host], out=stage)
+        on_dev = stage.to(device, non_blocking=True)
+        o = 0
+        for i, n in zip(host, sizes):
+            dev_t[i] = on_dev[o:o + n].view(-1, 3)
+            o += n
+    gs = [SnapshotGraph(num_nodes, num_rels, (t.to(device, non_blocking=True) if d is None else d).contiguous(), _defer_build=True)
+          for t, d in zip(triples_list, dev_t)]
     if gs:
         L = len(gs)
         descs = (_lib.CsrArrays * L)()
@@ -268,10 +281,12 @@ class SnapshotCache:
         self.num_nodes, self.num_rels, self.device, self.capacity = int(num_nodes), int(num_rels), device, int(capacity)
         self._graphs = {}          # id(array) -> (array (kept alive), SnapshotGraph)
 
-    def ensure(self, snapshots):
+    def ensure(self, snapshots, device_copies=None):
         """Graphs of `snapshots` (list of (T,3) int64 numpy arrays / tensors), building the missing ones in one batched
         call WITHOUT reading their size counters back.  Returns (graphs, new_graphs): call finish_sub_graphs(new_graphs,
-        counts) (or let `finish` do it) before the graphs are used."""
+        counts) (or let `finish` do it) before the graphs are used.  device_copies: {id(snapshot): (T,3) int64 device
+        tensor} for snapshots whose triples are already in HBM (a test snapshot was uploaded as the queries of its own
+        timestamp before it slides into a history window): no second upload."""
         missing = [s for s in snapshots if id(s) not in self._graphs]
         new = []
         if missing:
@@ -280,7 +295,9 @@ class SnapshotCache:
                 if id(s) not in seen:
                     seen.add(id(s))
                     uniq.append(s)
-            tens = [s if isinstance(s, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(s, dtype=np.int64))
+            have = device_copies or {}
+            tens = [have[id(s)] if id(s) in have else
+                    (s if isinstance(s, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(s, dtype=np.int64)))
                     for s in uniq]
             new = build_sub_graphs(self.num_nodes, self.num_rels, tens, self.device, sync=False)
             for s, g in zip(uniq, new):

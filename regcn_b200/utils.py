@@ -166,6 +166,43 @@ def queries_prepare(test_triples, num_rels):
     return all_t, out[0], out[1], totals
 
 
+def queries_prepare_batch(triples_cat, Ts, num_rels):
+    """`queries_prepare` for the test snapshots of a GROUP of timestamps in one C call / three launches
+    (`regcn_queries_prepare_batch`).  triples_cat: (sum Ts, 3) int64 device tensor, the snapshots back to back; Ts: their
+    row counts (all > 0, at most 32 of them).  Returns ([(all_triples, pending_entity_filter, pending_relation_filter)],
+    totals (n, 2) int32 on the device) -- member g is what queries_prepare returns for snapshot g alone."""
+    import ctypes
+    from ._lib import call, ptr
+    n = len(Ts)
+    toff = [0]
+    for T in Ts:
+        toff.append(toff[-1] + int(T))
+    tot = toff[-1]
+    dev = triples_cat.device
+    t = triples_cat.contiguous()
+    all_t = torch.empty((2 * tot, 3), device=dev, dtype=torch.int64)
+    work = torch.empty(8 * tot + 2 * n, device=dev, dtype=torch.int32)      # counts (4 tot) | offsets (4 tot) | totals (n, 2)
+    counts, beg, totals = work[:4 * tot], work[4 * tot:8 * tot], work[8 * tot:].view(n, 2)
+    toff_c = (ctypes.c_int32 * (n + 1))(*toff)
+    call("regcn_queries_prepare_batch", ptr(t), ctypes.cast(toff_c, ctypes.c_void_p), n, int(num_rels), ptr(all_t), ptr(counts),
+         ptr(beg), ptr(totals))
+    out = []
+    for g in range(n):
+        B = 2 * int(Ts[g])
+        a = all_t[2 * toff[g]:2 * toff[g + 1]]
+        bg = beg[4 * toff[g]:4 * toff[g + 1]].view(2, B)
+        pfs = []
+        for rel_predict in (0, 1):
+            pf = _PendingFilter.__new__(_PendingFilter)
+            pf.triples, pf.B = a, B
+            pf.key_col, pf.ans_col = (2, 1) if rel_predict else (1, 2)
+            pf.beg = bg[rel_predict]
+            pf.total = totals[g, rel_predict:rel_predict + 1]
+            pfs.append(pf)
+        out.append((a, pfs[0], pfs[1]))
+    return out, totals
+
+
 def filter_lists_from_queries(all_triples, rel_predict=0):
     """Kernel-built time-aware filter lists for the queries themselves (the test snapshot incl. inverses): two
     launches + one scan + one host read of the slot total; also yields the fused-rank pair lists.  All-pairs scan

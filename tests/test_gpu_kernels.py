@@ -677,6 +677,29 @@ def a_lists(f):
     return f.lists()
 
 
+def test_queries_prepare_batch_equals_per_snapshot_calls():
+    """regcn_queries_prepare_batch (the test snapshots of a group of timestamps in three launches) against one
+    regcn_queries_prepare per snapshot: inverse triples, list offsets, totals and the filled lists, incl. snapshots of one
+    triple, of more queries than one key tile, and the maximum of 32 members."""
+    R, _ = _ops()
+    from regcn_b200 import utils
+    rng = np.random.default_rng(5)
+    for Ts, n, r in (((1,), 50, 4), ((37, 1, 5000, 12), 300, 7), (tuple(int(x) for x in rng.integers(1, 1600, 32)), 23033, 256)):
+        snaps = [np.stack((rng.integers(0, n, T), rng.integers(0, r, T), rng.integers(0, n, T)), 1).astype(np.int64) for T in Ts]
+        cat = torch.from_numpy(np.concatenate(snaps)).to(DEV)
+        members, totals = utils.queries_prepare_batch(cat, list(Ts), r)
+        tot = totals.tolist()
+        for g, (snap, (all_t, pf_e, pf_r)) in enumerate(zip(snaps, members)):
+            one_all, one_e, one_r, one_tot = utils.queries_prepare(torch.from_numpy(snap).to(DEV), r)
+            assert torch.equal(all_t, one_all) and tot[g] == one_tot.tolist()
+            assert torch.equal(pf_e.beg, one_e.beg) and torch.equal(pf_r.beg, one_r.beg)
+            for mine, ref in zip(utils.filter_lists_finish2(pf_e, tot[g][0], pf_r, tot[g][1]),
+                                 (one_e.finish(one_tot.tolist()[0]), one_r.finish(one_tot.tolist()[1]))):
+                assert torch.equal(mine.idx, ref.idx) and torch.equal(mine.end, ref.end)
+    with pytest.raises(Exception):
+        utils.queries_prepare_batch(cat, [1] * 33, r)
+
+
 # ----------------------------------------------------------------------------------------- tcgen05 GEMM
 @pytest.mark.parametrize("impl,rtol", [("tc", 1e-4), ("tc1", 4e-3)])
 @pytest.mark.parametrize("M,N,K,trans_b,bias,split_k", [

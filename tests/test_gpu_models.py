@@ -561,7 +561,11 @@ def test_evaluation_loop_batched_equals_one_timestamp_at_a_time(monkeypatch):
     monkeypatch.delenv("REGCN_SHARED_ROWS")
     out["default"] = R.test(model, st["history"], st["tests"], r, n, True, None, None, None, None, "eval",
                             test_history_len=L, return_ranks=True)
-    for flag in ("3", "8", "8s", "16s", "20s", "default"):
+    monkeypatch.setenv("REGCN_PREP_BATCH", "1")           # one batched preparation per group instead of one per timestamp
+    out["default_p"] = R.test(model, st["history"], st["tests"], r, n, True, None, None, None, None, "eval",
+                              test_history_len=L, return_ranks=True)
+    monkeypatch.delenv("REGCN_PREP_BATCH")
+    for flag in ("3", "8", "8s", "16s", "20s", "default", "default_p"):
         assert out[flag][0] == out["1"][0]
         for a, b in zip(out[flag][1], out["1"][1]):
             assert len(a) == len(b) == 23
