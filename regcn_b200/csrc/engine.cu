@@ -458,11 +458,13 @@ static SharedWs plan_shared(int N0, int G, int R2, int d, int max_split_chunks, 
 // a third of the rows in the all-entity GEMMs the chain of small kernels is the longer one and wants more of the machine
 // than in regcn_regcn_evolve.  Measured (B200, ICEWS18 shape, us per timestamp at 8 / 12 / 16 windows per recurrence;
 // profiles/time_batched_forward.py): 24 SMs 349 / - / -, 32: 305, 40: 285 / - / 225, 48: 279 / 235 / 220, 56: 261 / 225 / 210,
-// 64: 265 / 228 / 208, 72: 271 / 229 / 207, 80: 279; balanced grids: 271.
-static int shared_side_sms() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("REGCN_SHARED_SIDE_SMS"); v = e ? atoi(e) : 60; if (v < 0 || v > 96) v = 60; }
-  return v;
+// 64: 265 / 228 / 208, 72: 271 / 229 / 207, 80: 279; balanced grids: 271.  Re-measured with up to 32 windows (16 / 30 windows):
+// 48: 236 / 200, 60: 224 / 191, 72: 218 / 191, 84: 231 / 199, 96: 255 / 221, balanced grids: 223 / 185 -- from ~24 windows
+// on both chains are many-round GEMM work and whole-machine grids on both streams win.
+static int shared_side_sms(int G) {
+  static int v = -2;
+  if (v == -2) { const char* e = getenv("REGCN_SHARED_SIDE_SMS"); v = e ? atoi(e) : -1; if (v < -1 || v > 96) v = -1; }
+  return v >= 0 ? v : (G >= 24 ? 0 : G > 12 ? 72 : 60);
 }
 }  // namespace regcn
 
@@ -532,7 +534,7 @@ int regcn_regcn_evolve_shared(const void* const* mp, const int* mi, const void* 
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
     if (sm_count <= 0) sm_count = 148;
   }
-  const int side_sms = shared_side_sms();
+  const int side_sms = shared_side_sms(G);
   long long rows_bound = N0;              // compact rows that can exist after this step's update (host-side bound)
   for (int i = 0; i < L; ++i) {
     const void* const* g = gp + (size_t)i * RG_NUM_PTRS;
