@@ -165,7 +165,10 @@ def timestamps_per_batch(model, num_nodes, static_graph=None):
         # not G N rows, and the shared rows are amortised over the windows (ICEWS18 shape: 261 / 225 / 208 us per
         # timestamp at 8 / 12 / 16 windows)
         return max(1, min(32, 4 * BATCH_ROWS // max(1, int(num_nodes))))
-    return max(1, min(8, BATCH_ROWS // max(1, int(num_nodes))))
+    # full block-diagonal recurrence (the hyperbolic model; RE-GCN outside the shared engine's preconditions): measured at
+    # the ICEWS14s shape (lgcn / hyperbolic_uvrgcn, profiles/time_batched_forward_hyp.py) 732 / 669 us per timestamp alone,
+    # 301 / 321 at 8 windows, 241 / 266 at 16, 219 / 243 at 24
+    return max(1, min(24, BATCH_ROWS // max(1, int(num_nodes))))
 
 
 @torch.no_grad()

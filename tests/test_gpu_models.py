@@ -550,7 +550,7 @@ def test_evaluation_loop_batched_equals_one_timestamp_at_a_time(monkeypatch):
     L = len(st["history"])
     assert evaluate.timestamps_per_batch(model, n) == 32
     monkeypatch.setenv("REGCN_SHARED_ROWS", "0")
-    assert evaluate.timestamps_per_batch(model, n) == 8
+    assert evaluate.timestamps_per_batch(model, n) == 24
     out = {}
     for flag in ("1", "3", "8", "8s", "16s", "20s"):
         monkeypatch.setenv("REGCN_TEST_BATCH", flag.rstrip("s"))
