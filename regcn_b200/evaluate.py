@@ -555,12 +555,15 @@ def test(model, history_list, test_list, num_rels, num_nodes, use_cuda=True, all
 
     # start-up: only the first group is prepared in front of the first evolution (every prepare costs ~0.2 ms of host time
     # during which the GPU has nothing to do); the following groups are prepared behind it, see the two top-ups below
-    # Group sizes of the call.  The first groups ramp up (4, 8, then equal shares of the rest in groups of at most G): the
+    # Group sizes of the call: a short first group (8), then equal shares of the rest in groups of at most G.  The
     # preparation of a group is ~0.1 ms of host time per timestamp with nothing but the previous group's decodes for the
-    # GPU to run meanwhile -- one group of 4 in front of one of 16 left it idle ~1.4 ms twice per call.
+    # GPU to run meanwhile, and the evolution is cheaper per timestamp the more windows share a recurrence (ICEWS18 shape:
+    # 259 / 209 / 184 us at 10 / 20 / 30 windows).  Measured, ms per timestamp of a 32-timestamp call (profiles/e2e_loop.py;
+    # REGCN_TEST_RAMP = first group sizes): "4,8" (the ramp used before: groups 4, 8, 20) 0.774, "4,12" 0.767, "2,6" 0.761,
+    # "4" 0.747, "6" 0.747, "8" (groups 8, 24) 0.743.
     if G > 1:
         sizes, left = [], K
-        for cap in (4, 8):
+        for cap in tuple(int(x) for x in os.environ.get("REGCN_TEST_RAMP", "8").split(",") if x):
             if left > 0 and cap < G:
                 sizes.append(min(cap, left))
                 left -= sizes[-1]

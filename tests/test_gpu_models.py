@@ -538,7 +538,7 @@ def test_hyperbolic_forward_batch_rows_equal_per_window_forward(enc, dec, shape,
 
 def test_evaluation_loop_batched_equals_one_timestamp_at_a_time(monkeypatch):
     """regcn_b200.test() evolving groups of consecutive timestamps together (the default: up to 32 per recurrence with the
-    shared-trajectory engine, 8 without; a call ramps up through groups of 4 and 8) returns the ranks of the
+    shared-trajectory engine, 24 without; a call starts with a group of 8) returns the ranks of the
     one-timestamp-per-recurrence loop, for group sizes that do and do not divide the number of test snapshots, with and
     without the shared-trajectory engine; evaluate_batch equals evaluate_snapshot."""
     from regcn_b200 import evaluate, utils
