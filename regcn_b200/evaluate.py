@@ -576,9 +576,10 @@ def test(model, history_list, test_list, num_rels, num_nodes, use_cuda=True, all
         starts.append(starts[-1] + n_)
     G_FIRST = sizes[0] if sizes else 1
     # REGCN_PREP_BATCH=1: a whole group is prepared by ONE batched call (_prepare_group; its sizes travel in one pinned slot
-    # of the ring).  Opt-in: under a profiler it removes ~50 us of stream gaps per timestamp and 0.6 ms of call start-up,
-    # in an un-profiled run the per-timestamp preparation hides behind the decodes just as well (0.765 vs 0.773 ms per
-    # timestamp at the ICEWS18 shape) and the per-call pinned staging makes the first calls of a process slower.
+    # of the ring).  Opt-in: once a process has run ~5 calls it is the faster schedule (0.705-0.716 vs 0.743-0.756 ms per
+    # timestamp at the ICEWS18 shape with groups of 8 + 24), but during the first calls the index build of 13-24 snapshots
+    # in one go (SnapshotCache.ensure: one arena allocation per snapshot while the caching allocator's pool still grows)
+    # stalls the host for 50-70 ms at a time (0.8-2.3 ms per timestamp) -- measured, not fixed: DESIGN 11.2.
     batched = G > 1 and prep_stream is main_stream and os.environ.get("REGCN_PREP_BATCH", "0") == "1"
     group_slots = torch.empty((4, 2 * 32 + 8 * (L + 32 + 2)), dtype=torch.int32, pin_memory=True) if batched else None
     n_ranges = [0]
