@@ -364,7 +364,9 @@ def _prepare_group(cache, windows, test_snaps, num_rels, device, sizes_slot, sta
         if stage is None or stage.numel() != 3 * sum(Ts):
             stage = torch.empty(3 * sum(Ts), dtype=torch.int64, pin_memory=True)
         torch.cat([t.reshape(-1) for t in tens], out=stage)
-        cat = stage.to(device, non_blocking=True).view(-1, 3)
+        cat = torch.empty((stage.numel() + 65535) // 65536 * 65536, device=device, dtype=torch.int64)[:stage.numel()]
+        cat.copy_(stage, non_blocking=True)
+        cat = cat.view(-1, 3)
     else:
         cat = torch.cat([t.to(device, non_blocking=True) for t in tens])
     if on_device is not None:
@@ -576,10 +578,9 @@ def test(model, history_list, test_list, num_rels, num_nodes, use_cuda=True, all
         starts.append(starts[-1] + n_)
     G_FIRST = sizes[0] if sizes else 1
     # REGCN_PREP_BATCH=1: a whole group is prepared by ONE batched call (_prepare_group; its sizes travel in one pinned slot
-    # of the ring).  Opt-in: once a process has run ~5 calls it is the faster schedule (0.705-0.716 vs 0.743-0.756 ms per
-    # timestamp at the ICEWS18 shape with groups of 8 + 24), but during the first calls the index build of 13-24 snapshots
-    # in one go (SnapshotCache.ensure: one arena allocation per snapshot while the caching allocator's pool still grows)
-    # stalls the host for 50-70 ms at a time (0.8-2.3 ms per timestamp) -- measured, not fixed: DESIGN 11.2.
+    # of the ring).  Opt-in: it is the faster schedule in the median (0.71-0.72 vs 0.743-0.756 ms per timestamp at the
+    # ICEWS18 shape with groups of 8 + 24), but a few calls per process still stall on the host (0.8-3 ms per timestamp;
+    # device allocations while kernels are queued) where the per-timestamp preparation never does: DESIGN 11.2.
     batched = G > 1 and prep_stream is main_stream and os.environ.get("REGCN_PREP_BATCH", "0") == "1"
     group_slots = torch.empty((4, 2 * 32 + 8 * (L + 32 + 2)), dtype=torch.int32, pin_memory=True) if batched else None
     n_ranges = [0]

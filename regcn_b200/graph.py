@@ -27,7 +27,16 @@ _VIEWS = ("src", "dst", "etype", "indeg", "rowptr", "src_sorted", "etype_sorted"
 
 
 class SnapshotGraph:
-    def __init__(self, num_nodes, num_rels, triples_dev, _defer_counts=False, _defer_build=False, _shell=None):
+    @staticmethod
+    def _arena_sizes(N, R, E):
+        return [E, E, E, N, N + 1, E, E, E, N + 1, N + 1, min(N, E) + E // AGG_CHUNK + 1, N, R + 1, E, 8, min(N, E)]
+
+    @staticmethod
+    def arena_ints(N, R, T):
+        """int32 words of one snapshot's index arena (what __init__ allocates)."""
+        return sum((max(int(n), 1) + 3) // 4 * 4 for n in SnapshotGraph._arena_sizes(int(N), int(R), 2 * int(T))) + int(N)
+
+    def __init__(self, num_nodes, num_rels, triples_dev, _defer_counts=False, _defer_build=False, _shell=None, _arena=None):
         self.num_nodes = int(num_nodes)
         self.num_rels = int(num_rels)
         self.triples = triples_dev  # (T,3) int64 on the device, reference layout (None: index made by concat_graphs)
@@ -42,12 +51,13 @@ class SnapshotGraph:
         dev = self.device
         # one arena for every int32 array of the index (a single allocation per snapshot); the per-array tensor views are
         # made on first access (_VIEWS / __getattr__): the evaluation loop only ever needs their addresses
-        sizes = [E, E, E, N, N + 1, E, E, E, N + 1, N + 1, min(N, E) + E // AGG_CHUNK + 1, N, R + 1, E, 8, min(N, E)]
+        sizes = self._arena_sizes(N, R, E)
         offs, tot = [], 0
         for n in sizes:
             offs.append(tot)
             tot += (max(int(n), 1) + 3) // 4 * 4          # keep every view 16-byte aligned
-        arena = torch.empty(tot + N, device=dev, dtype=I32)
+        # _arena: a slice of a buffer shared by the snapshots of one batched build (build_sub_graphs)
+        arena = _arena if _arena is not None else torch.empty(tot + N, device=dev, dtype=I32)
         self._arena = arena
         self._layout = {name: (o, max(int(n), 1)) for name, o, n in zip(_VIEWS, offs, sizes)}
         self._layout["norm"] = (tot, N)
@@ -198,8 +208,20 @@ def build_sub_graphs(num_nodes, num_rels, triples_list, device, sync=True):
         for i, n in zip(host, sizes):
             dev_t[i] = on_dev[o:o + n].view(-1, 3)
             o += n
-    gs = [SnapshotGraph(num_nodes, num_rels, (t.to(device, non_blocking=True) if d is None else d).contiguous(), _defer_build=True)
-          for t, d in zip(triples_list, dev_t)]
+    arenas = [None] * len(triples_list)
+    if len(triples_list) > 2:
+        # one allocation for the arenas of the batch, in a size class that repeats from call to call (a fresh size per
+        # snapshot keeps the caching allocator growing its pool -- a device allocation while kernels are queued stalls the
+        # host -- through the first calls of a process)
+        need = [(SnapshotGraph.arena_ints(num_nodes, num_rels, t.shape[0]) + 63) // 64 * 64 for t in triples_list]
+        chunk = 1 << 20
+        big = torch.empty((sum(need) + chunk - 1) // chunk * chunk, device=device, dtype=I32)
+        o = 0
+        for i, n_ in enumerate(need):
+            arenas[i] = big[o:o + n_]
+            o += n_
+    gs = [SnapshotGraph(num_nodes, num_rels, (t.to(device, non_blocking=True) if d is None else d).contiguous(), _defer_build=True,
+                        _arena=a) for t, d, a in zip(triples_list, dev_t, arenas)]
     if gs:
         L = len(gs)
         descs = (_lib.CsrArrays * L)()

@@ -180,9 +180,10 @@ def queries_prepare_batch(triples_cat, Ts, num_rels):
     tot = toff[-1]
     dev = triples_cat.device
     t = triples_cat.contiguous()
-    all_t = torch.empty((2 * tot, 3), device=dev, dtype=torch.int64)
-    work = torch.empty(8 * tot + 2 * n, device=dev, dtype=torch.int32)      # counts (4 tot) | offsets (4 tot) | totals (n, 2)
-    counts, beg, totals = work[:4 * tot], work[4 * tot:8 * tot], work[8 * tot:].view(n, 2)
+    cap = (tot + 8191) // 8192 * 8192            # allocation sizes that repeat from call to call (caching allocator)
+    all_t = torch.empty((2 * cap, 3), device=dev, dtype=torch.int64)[:2 * tot]
+    work = torch.empty(8 * cap + 64, device=dev, dtype=torch.int32)      # counts (4 tot) | offsets (4 tot) | totals (n, 2)
+    counts, beg, totals = work[:4 * tot], work[4 * tot:8 * tot], work[8 * tot:8 * tot + 2 * n].view(n, 2)
     toff_c = (ctypes.c_int32 * (n + 1))(*toff)
     call("regcn_queries_prepare_batch", ptr(t), ctypes.cast(toff_c, ctypes.c_void_p), n, int(num_rels), ptr(all_t), ptr(counts),
          ptr(beg), ptr(totals))
