@@ -577,11 +577,11 @@ def test(model, history_list, test_list, num_rels, num_nodes, use_cuda=True, all
     for n_ in sizes:
         starts.append(starts[-1] + n_)
     G_FIRST = sizes[0] if sizes else 1
-    # REGCN_PREP_BATCH=1: a whole group is prepared by ONE batched call (_prepare_group; its sizes travel in one pinned slot
-    # of the ring).  Opt-in: it is the faster schedule in the median (0.71-0.72 vs 0.743-0.756 ms per timestamp at the
-    # ICEWS18 shape with groups of 8 + 24), but a few calls per process still stall on the host (0.8-3 ms per timestamp;
-    # device allocations while kernels are queued) where the per-timestamp preparation never does: DESIGN 11.2.
-    batched = G > 1 and prep_stream is main_stream and os.environ.get("REGCN_PREP_BATCH", "0") == "1"
+    # A whole group is prepared by ONE batched call (_prepare_group; its sizes travel in one pinned slot of the ring):
+    # 0.70-0.72 vs 0.743-0.756 ms per timestamp at the ICEWS18 shape with groups of 8 + 24 (30 calls, no outlier; it needs
+    # the device allocations of the batch in size classes that repeat from call to call -- a fresh cudaMalloc while kernels
+    # are queued stalls the host for tens of ms: DESIGN 11.2).  REGCN_PREP_BATCH=0: one preparation per timestamp.
+    batched = G > 1 and prep_stream is main_stream and os.environ.get("REGCN_PREP_BATCH", "1") != "0"
     group_slots = torch.empty((4, 2 * 32 + 8 * (L + 32 + 2)), dtype=torch.int32, pin_memory=True) if batched else None
     n_ranges = [0]
     on_device = {}

@@ -214,7 +214,7 @@ def build_sub_graphs(num_nodes, num_rels, triples_list, device, sync=True):
         # snapshot keeps the caching allocator growing its pool -- a device allocation while kernels are queued stalls the
         # host -- through the first calls of a process)
         need = [(SnapshotGraph.arena_ints(num_nodes, num_rels, t.shape[0]) + 63) // 64 * 64 for t in triples_list]
-        chunk = 1 << 20
+        chunk = 1 << 23                               # 32 MB steps: a 24-snapshot ICEWS18-shaped batch is ~18 MB
         big = torch.empty((sum(need) + chunk - 1) // chunk * chunk, device=device, dtype=I32)
         o = 0
         for i, n_ in enumerate(need):
@@ -230,7 +230,7 @@ def build_sub_graphs(num_nodes, num_rels, triples_list, device, sync=True):
         Ts = (ctypes.c_int32 * L)(*[g.num_edges // 2 for g in gs])
         lib = _lib.load()
         ws_bytes = lib.regcn_csr_build_batch_workspace_bytes(Ts, L, int(num_nodes), int(num_rels))
-        ws = torch.empty(max(ws_bytes, 1), device=gs[0].device, dtype=torch.uint8)
+        ws = torch.empty((max(ws_bytes, 1) + (1 << 22) - 1) >> 22 << 22, device=gs[0].device, dtype=torch.uint8)
         call("regcn_csr_build_batch", ctypes.cast(descs, ctypes.c_void_p), L, int(num_nodes), int(num_rels), ptr(ws),
              ws_bytes)
         if sync:

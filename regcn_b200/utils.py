@@ -180,7 +180,7 @@ def queries_prepare_batch(triples_cat, Ts, num_rels):
     tot = toff[-1]
     dev = triples_cat.device
     t = triples_cat.contiguous()
-    cap = (tot + 8191) // 8192 * 8192            # allocation sizes that repeat from call to call (caching allocator)
+    cap = (tot + 65535) // 65536 * 65536         # allocation sizes that repeat from call to call (caching allocator)
     all_t = torch.empty((2 * cap, 3), device=dev, dtype=torch.int64)[:2 * tot]
     work = torch.empty(8 * cap + 64, device=dev, dtype=torch.int32)      # counts (4 tot) | offsets (4 tot) | totals (n, 2)
     counts, beg, totals = work[:4 * tot], work[4 * tot:8 * tot], work[8 * tot:8 * tot + 2 * n].view(n, 2)

@@ -561,7 +561,7 @@ def test_evaluation_loop_batched_equals_one_timestamp_at_a_time(monkeypatch):
     monkeypatch.delenv("REGCN_SHARED_ROWS")
     out["default"] = R.test(model, st["history"], st["tests"], r, n, True, None, None, None, None, "eval",
                             test_history_len=L, return_ranks=True)
-    monkeypatch.setenv("REGCN_PREP_BATCH", "1")           # one batched preparation per group instead of one per timestamp
+    monkeypatch.setenv("REGCN_PREP_BATCH", "0")           # one preparation per timestamp instead of one batch per group
     out["default_p"] = R.test(model, st["history"], st["tests"], r, n, True, None, None, None, None, "eval",
                               test_history_len=L, return_ranks=True)
     monkeypatch.delenv("REGCN_PREP_BATCH")
