@@ -57,6 +57,8 @@ class SnapshotGraph:
             offs.append(tot)
             tot += (max(int(n), 1) + 3) // 4 * 4          # keep every view 16-byte aligned
         # _arena: a slice of a buffer shared by the snapshots of one batched build (build_sub_graphs)
+        if _arena is not None and (_arena.numel() < tot + N or _arena.dtype != I32 or _arena.data_ptr() % 16):
+            raise ValueError("SnapshotGraph: the shared arena slice is too small or misaligned")
         arena = _arena if _arena is not None else torch.empty(tot + N, device=dev, dtype=I32)
         self._arena = arena
         self._layout = {name: (o, max(int(n), 1)) for name, o, n in zip(_VIEWS, offs, sizes)}
