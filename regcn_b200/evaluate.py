@@ -171,6 +171,22 @@ def timestamps_per_batch(model, num_nodes, static_graph=None):
     return max(1, min(24, BATCH_ROWS // max(1, int(num_nodes))))
 
 
+def group_sizes(K, G, ramp="8"):
+    """How test() cuts K consecutive test timestamps into groups that share one recurrence: the short first groups named
+    by `ramp` (comma-separated sizes, each used only while it is below G), then the rest in equal shares of at most G."""
+    if G <= 1:
+        return [1] * K
+    sizes, left = [], K
+    for cap in (int(x) for x in str(ramp).split(",") if x.strip()):
+        if left > 0 and 0 < cap < G:
+            sizes.append(min(cap, left))
+            left -= sizes[-1]
+    if left > 0:
+        n_rest = -(-left // G)
+        sizes += [left // n_rest + (1 if i < left % n_rest else 0) for i in range(n_rest)]
+    return sizes
+
+
 @torch.no_grad()
 def evaluate_batch(model, windows, all_triples_list, filter_list, timers=None, fused=None):
     """evaluate_snapshot for G test timestamps whose history windows are evolved together (model.forward_batch): returns
@@ -563,16 +579,7 @@ def test(model, history_list, test_list, num_rels, num_nodes, use_cuda=True, all
     # 259 / 209 / 184 us at 10 / 20 / 30 windows).  Measured, ms per timestamp of a 32-timestamp call (profiles/e2e_loop.py;
     # REGCN_TEST_RAMP = first group sizes): "4,8" (the ramp used before: groups 4, 8, 20) 0.774, "4,12" 0.767, "2,6" 0.761,
     # "4" 0.747, "6" 0.747, "8" (groups 8, 24) 0.743.
-    if G > 1:
-        sizes, left = [], K
-        for cap in tuple(int(x) for x in os.environ.get("REGCN_TEST_RAMP", "8").split(",") if x):
-            if left > 0 and cap < G:
-                sizes.append(min(cap, left))
-                left -= sizes[-1]
-        n_rest = -(-left // G)
-        sizes += [left // n_rest + (1 if i < left % n_rest else 0) for i in range(n_rest)] if left > 0 else []
-    else:
-        sizes = [1] * K
+    sizes = group_sizes(K, G, os.environ.get("REGCN_TEST_RAMP", "8"))
     starts = [0]
     for n_ in sizes:
         starts.append(starts[-1] + n_)

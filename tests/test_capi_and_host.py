@@ -159,3 +159,21 @@ def test_dataset_reader_round_trip(tmp_path):
         assert (ref.num_nodes, ref.num_rels) == (data.num_nodes, data.num_rels)
         for split in ("train", "valid", "test"):
             assert np.array_equal(np.asarray(getattr(ref, split)), getattr(data, split))
+
+
+def test_group_sizes_of_the_evaluation_loop():
+    """evaluate.group_sizes: every timestamp in exactly one group, no group above G, ramp sizes only while below G."""
+    from regcn_b200.evaluate import group_sizes
+    assert group_sizes(32, 32) == [8, 24]
+    assert group_sizes(32, 32, "4,8") == [4, 8, 20]
+    assert group_sizes(5, 32) == [5]
+    assert group_sizes(0, 32) == []
+    assert group_sizes(7, 1) == [1] * 7
+    assert group_sizes(100, 32) == [8, 31, 31, 30]
+    assert group_sizes(20, 8) == [7, 7, 6]                # a ramp step that is not below G is skipped
+    assert group_sizes(20, 8, "") == [7, 7, 6]
+    for K in range(0, 80):
+        for G in (1, 2, 8, 24, 32):
+            for ramp in ("8", "4,8", "2", ""):
+                sz = group_sizes(K, G, ramp)
+                assert sum(sz) == K and all(0 < s <= max(G, 1) for s in sz)
